@@ -1,0 +1,233 @@
+/*
+ * bam_gpu.h -- C ABI of the B200-native BaM hot path.
+ *
+ * This is the drop-in boundary: everything a host written in Fortran
+ * (ISO_C_BINDING, see bindings/bam_gpu_binding.f90), C or C++ needs to replace
+ *   - the sampler callback  Posterior_wrapper      (src/BaM_tools.f90:3467-3517)
+ *   - the engine calls      BaM_Fit / BaM_Prediction (src/BaM_tools.f90:545-623, 882-1135)
+ *   - the envelope pass     BaM_ProcessSpag        (src/BaM_tools.f90:1292-1432)
+ * of the reference.  Plain pointers and sizes only; all matrices are COLUMN-MAJOR
+ * exactly as Fortran passes them; integers are int32_t (mik), reals are double
+ * (mrk).  Every call returns `int err` with the reference's convention
+ * (0 OK, >0 error, <0 warning; src/BaM_tools.f90:175) and fills `mess`
+ * (caller-owned, at least BAMGPU_MESS_LEN bytes, NUL terminated).
+ *
+ * The same `bamgpu_problem` description is consumed by the CPU oracle
+ * (oracle/bam_oracle.h), which is test infrastructure only.
+ */
+#ifndef BAM_GPU_H
+#define BAM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAMGPU_MESS_LEN 250
+#define BAMGPU_PRIOR_NPAR 4            /* stride of the flattened prior-parameter tables */
+#define BAMGPU_UNDEF_RN (-999999999.0) /* DMSL undefRN: value of fx when !feas or isnull */
+#define BAMGPU_NENV 7                  /* Median q2.5 q97.5 q16 q84 Mean Stdev (src/BaM_tools.f90:1309-1315) */
+
+/* Model catalogue: ModelLibrary_tools.f90:79-112 (ID strings without the "MDL_" prefix). */
+enum bamgpu_model {
+    BAMGPU_MDL_LINEAR = 1,    /* Linear_model.f90:62-101 */
+    BAMGPU_MDL_BARATIN = 2,   /* BaRatin_model.f90:67-436 */
+    BAMGPU_MDL_SEDIMENT = 3,  /* SedimentTransport_model.f90:100-607 */
+    BAMGPU_MDL_TEXTFILE = 4,  /* TextFile_model.f90:231-309,1035-1098 */
+    BAMGPU_MDL_VEGETATION = 5 /* Vegetation_model.f90:87-569 */
+};
+
+/* Prior / distribution families (BMSL Distribution_tools names). */
+enum bamgpu_dist {
+    BAMGPU_DIST_GAUSSIAN = 1,
+    BAMGPU_DIST_UNIFORM = 2,
+    BAMGPU_DIST_TRIANGLE = 3,
+    BAMGPU_DIST_LOGNORMAL = 4,
+    BAMGPU_DIST_EXPONENTIAL = 5,
+    BAMGPU_DIST_FLATPRIOR = 6,
+    BAMGPU_DIST_FLATPRIOR_POS = 7, /* 'FlatPrior+' */
+    BAMGPU_DIST_FLATPRIOR_NEG = 8  /* 'FlatPrior-' */
+};
+
+/* Remnant sigma functions: Sigmafunk_Apply, src/BaM_tools.f90:3521-3571. */
+enum bamgpu_sigmafunc {
+    BAMGPU_SIG_CONSTANT = 1,
+    BAMGPU_SIG_LINEAR = 2,
+    BAMGPU_SIG_PROPORTIONAL = 3,
+    BAMGPU_SIG_POWER = 4,
+    BAMGPU_SIG_EXPONENTIAL = 5,
+    BAMGPU_SIG_GAUSSIAN = 6
+};
+
+/* Parameter types: src/BaM_tools.f90:118. */
+enum bamgpu_partype { BAMGPU_PAR_FIX = -1, BAMGPU_PAR_STD = 0, BAMGPU_PAR_VAR = 1 };
+
+/* Sediment options (SedimentTransport_model.f90:30-48), carried in xtra_i. */
+enum bamgpu_sed_formula { BAMGPU_SED_MPM = 1, BAMGPU_SED_CAMENEN = 2, BAMGPU_SED_NIELSEN = 3, BAMGPU_SED_SMART = 4 };
+enum bamgpu_sed_css { BAMGPU_CSS_CONSTANT = 1, BAMGPU_CSS_SOULSBY = 2, BAMGPU_CSS_SW = 3 };
+enum bamgpu_sed_ppo { BAMGPU_PPO_FIX = 1, BAMGPU_PPO_IN = 2, BAMGPU_PPO_PAR = 3 };
+enum bamgpu_sed_co { BAMGPU_CO_FIX = 1, BAMGPU_CO_PAR = 2 };
+
+/* Vegetation growth formulas (Vegetation_model.f90:25-30), carried in xtra_i[0]. */
+enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YIN3 = 3, BAMGPU_VEG_YIN1_TEMPORAL = 4 };
+
+/*
+ * The immutable problem description = the reference's module globals INFER + MODEL
+ * after LoadBamObjects (src/BaM_tools.f90:73-101,133-420; ModelLibrary_tools.f90:114-126).
+ * The callee copies everything it needs during bamgpu_create (as LoadBamObjects
+ * does at :213-229); the caller keeps ownership of every pointer.
+ */
+typedef struct bamgpu_problem {
+    const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" (optionally "MDL_"-prefixed) */
+    int32_t nobs, nX, nY, ntheta;
+
+    /* calibration data, nobs x nX / nobs x nY, column-major (INFER%X .. INFER%Ybindx) */
+    const double* X;
+    const double* Xu;
+    const double* Xb;
+    const int32_t* Xbindx;
+    const double* Y;
+    const double* Yu;
+    const double* Yb;
+    const int32_t* Ybindx;
+
+    /* model parameters theta (INFER%theta), size ntheta */
+    const int32_t* partype;  /* bamgpu_partype */
+    const int32_t* nval;     /* 1 for FIX/STD, number of distinct values for VAR */
+    const double* fix_value; /* init(1), used for FIX parameters only */
+    const int32_t* var_indx; /* nobs x ntheta column-major, 1-based; may be NULL if no VAR parameter */
+
+    /* flattened priors of the fitted theta (INFER%Prior_theta, size nFit = sum nval of non-FIX) */
+    const int32_t* prior_theta_dist;
+    const double* prior_theta_par; /* nFit x BAMGPU_PRIOR_NPAR, row per parameter */
+
+    /* remnant-error (structural) model per output */
+    const int32_t* sigma_func; /* nY, bamgpu_sigmafunc */
+    const int32_t* nremnant;   /* nY */
+    const int32_t* prior_gamma_dist; /* sum(nremnant) */
+    const double* prior_gamma_par;   /* sum(nremnant) x BAMGPU_PRIOR_NPAR */
+
+    /* optional Gaussian-copula matrix (C^-1 - I), k x k, k = nFit + sum(nremnant); NULL if absent
+       (INFER%priorM, src/BaM_tools.f90:386-414; order of rows: theta first, then gamma, :3084-3101) */
+    const double* priorM;
+
+    /* model-specific xtra (ModelLibrary_tools.f90:436-544):
+       BaRatin    : xtra_i = control matrix ncontrol x ncontrol, column-major (n_xtra_i = ncontrol^2)
+       Sediment   : xtra_i = {formula, css, co, ppo_d, ppo_s, ppo_v, ppo_g}; xtra_d = pseudoval[4]
+       TextFile   : xtra_text = content of the model text file (TextFile_model.f90:946-978)
+       Vegetation : xtra_i = {growth formula, nYear, itmax}; xtra_d = {xscale, fscale, tolX, tolF}
+       Linear     : none */
+    const int32_t* xtra_i;
+    int32_t n_xtra_i;
+    const double* xtra_d;
+    int32_t n_xtra_d;
+    const char* xtra_text;
+
+    double mv;          /* missing-value code of Y, -9999 (src/BaM_tools.f90:100) */
+    double unfeas_flag; /* -666.666 (ModelLibrary_tools.f90:124) */
+} bamgpu_problem;
+
+/* Sizes derived at create time (INFER%nFit, nInfer, nDpar ...; src/BaM_tools.f90:336,346-379). */
+typedef struct bamgpu_sizes {
+    int32_t nFit;    /* fitted theta values */
+    int32_t nGamma;  /* sum(nremnant) */
+    int32_t nLatent; /* sum(nXerror): inferred "true" inputs */
+    int32_t nXbias;  /* sum(nXb) */
+    int32_t nYbias;  /* sum(nYb) */
+    int32_t nInfer;  /* P = length of a parameter vector */
+    int32_t nDpar;   /* derived parameters per vector (model nDpar x number of VAR combinations) */
+    int32_t nCombo;  /* distinct VAR combinations (size of INFER%DparIndx) */
+    int32_t nState;
+} bamgpu_sizes;
+
+typedef struct bamgpu_handle bamgpu_t;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+
+/* replaces LoadBamObjects (src/BaM_tools.f90:133-143): validates, derives the vector layout,
+   uploads the tables to HBM of CUDA device `device`.  Fails (err>0) if no CUDA device. */
+int bamgpu_create(bamgpu_t** h, const bamgpu_problem* p, int device, char* mess);
+void bamgpu_destroy(bamgpu_t* h);
+int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s);
+
+/* name -> enum helpers (return 0 when the name is unknown) */
+int bamgpu_dist_id(const char* name);
+int bamgpu_dist_npar(int dist);
+int bamgpu_sigmafunc_id(const char* name);
+int bamgpu_sigmafunc_npar(int sigmafunc);
+int bamgpu_model_id(const char* name);
+
+/* C (k x k correlation, unit diagonal) -> M = C^-1 - I, as LoadBamObjects does with
+   choles_invrt (src/BaM_tools.f90:398-414).  err=1 if not positive definite. */
+int bamgpu_prior_corr_to_M(int k, const double* C, double* M, char* mess);
+
+/* ---- log-posterior: replaces Posterior_wrapper (src/BaM_tools.f90:3467-3517) ---------- */
+
+/* K parameter vectors, x is P x K column-major (vector k at x + k*P), HOST memory.
+   fx[K]; feas[K], isnull[K] (0/1); dpar is nDpar x K column-major or NULL. */
+int bamgpu_logpost(bamgpu_t* h, int K, const double* x, double* fx, int32_t* feas, int32_t* isnull,
+                   double* dpar, char* mess);
+/* prior / likelihood / hyper split, for DIC (src/BaM_tools.f90:1626-1646) and tests */
+int bamgpu_logpost_parts(bamgpu_t* h, int K, const double* x, double* prior, double* lkh, double* hyper,
+                         int32_t* feas, int32_t* isnull, char* mess);
+
+/* resident variant: upload once, evaluate many times with everything in HBM */
+int bamgpu_chains_upload(bamgpu_t* h, int K, const double* x, char* mess);
+int bamgpu_logpost_resident(bamgpu_t* h, char* mess); /* asynchronous on the handle's stream */
+int bamgpu_chains_download(bamgpu_t* h, double* fx, int32_t* feas, int32_t* isnull, double* dpar, char* mess);
+int bamgpu_sync(bamgpu_t* h, char* mess);
+
+/* ---- sampler: replaces BaM_Fit + Adaptive_Metro_OAAT (src/BaM_tools.f90:545-623) ------- */
+
+/* K chains in lockstep, one-at-a-time adaptive Metropolis.  start/start_std are P x K.
+   Rows kept: iterations it with it > burn and (it-burn) % keep_every == 0 (it = 1..nAdapt*nCycles);
+   out_rows is (P + 1 + nDpar) x nKeep x K (chain-major blocks; row = [x, logpost, dpar]) or NULL.
+   Final states are left resident (bamgpu_chains_download) and running per-chain moments of the
+   kept rows are accumulated for bamgpu_moments. */
+int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std, int nAdapt, int nCycles,
+               double MinMoveRate, double MaxMoveRate, double DownMult, double UpMult, uint64_t seed,
+               int burn, int keep_every, double* out_rows, int64_t* n_keep, char* mess);
+
+/* per-chain moments of the kept rows: count[K], mean[P x K], m2[P x K] (sum of squared deviations).
+   If dev_ptrs != 0 the three pointers are DEVICE pointers (for an NCCL all-gather across ranks). */
+int bamgpu_moments(bamgpu_t* h, double* count, double* mean, double* m2, int dev_ptrs, char* mess);
+/* Gelman-Rubin potential scale reduction from (gathered) per-chain moments; host arrays. */
+int bamgpu_rhat(int K, int P, const double* count, const double* mean, const double* m2, double* rhat,
+                char* mess);
+
+/* ---- prediction: replaces BaM_Prediction + BaM_ProcessSpag ----------------------------- */
+
+/* mc   : Nrep x P column-major (the cooked MCMC matrix), HOST; may be NULL if maxpost run
+   mode : P (maxpost), used when !doParametric (theta) -- gamma always comes from mc (:1085)
+   xspag: nX pointers, matrix i is nobs_pred x nspag[i] column-major
+   t0,t1: half-open range of prediction inputs handled by this call (multi-GPU shards inputs)
+   env  : (t1-t0) x 7 x nY column-major per output, or NULL
+   spag : (t1-t0) x Nrep x nY ("transposed" layout: one row per input), or NULL
+   Noise for (rep, t, y) is a pure function of (seed, rep, t, y): results do not depend on sharding. */
+int bamgpu_predict(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                   const double* const* xspag, const int32_t* nspag, int doParametric,
+                   const int32_t* doRemnant, uint64_t seed, int t0, int t1, double* env, double* spag,
+                   char* mess);
+
+/* resident variant for measurement: the sample matrix and inputs stay in HBM between calls */
+int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                          const double* const* xspag, const int32_t* nspag, char* mess);
+int bamgpu_predict_resident(bamgpu_t* h, int doParametric, const int32_t* doRemnant, uint64_t seed, int t0,
+                            int t1, char* mess);
+int bamgpu_predict_download(bamgpu_t* h, double* env, char* mess);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+
+/* number of kernel launches issued by this handle since creation, and the device time (ms) of the
+   last resident evaluation's dominant kernel measured with CUDA events on the handle's stream */
+int64_t bamgpu_launch_count(const bamgpu_t* h);
+double bamgpu_last_kernel_ms(const bamgpu_t* h);
+/* FP64 DFMA peak micro-benchmark (register-resident FMA chains), TFLOP/s counting 2 flop per DFMA */
+int bamgpu_fp64_peak(int device, double* tflops, char* mess);
+const char* bamgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAM_GPU_H */

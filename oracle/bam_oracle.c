@@ -1,0 +1,1379 @@
+/*
+ * bam_oracle.c -- CPU restatement (ORACLE) of BaM's hot path.  TEST INFRASTRUCTURE ONLY
+ * (see bam_oracle.h for who may use it and for the parity status).
+ *
+ * Plain C99, IEEE double, libm.  The loop order, the early exits and the order in which terms
+ * are accumulated follow the reference (i-major / j-minor likelihood sum, prior -> likelihood
+ * -> hyper, j-major hyper sum) so that this file is a line-by-line restatement of
+ *   src/BaM_tools.f90:3006-3571 (posterior), :4115-4177 (theta expansion / VAR), :4202-4242 and
+ *   :3386-3463 (vector layout), :882-1135 and :1292-1432 (prediction / envelopes),
+ *   src/ModelLibrary_tools.f90:237-434 (dispatch + infeasible-row flagging),
+ *   src/Models/{BaRatin,Linear,SedimentTransport,TextFile}_model.f90.
+ * Compile with -ffp-contract=off: the reference is built by gfortran without FMA contraction.
+ */
+#include "bam_oracle.h"
+
+#include <ctype.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXCONTROL 16
+#define MAXVMCODE 512
+#define MAXVMIMMED 128
+#define MAXVMOUT 8
+#define MAXVMSTACK 64
+
+static const double LOG_SQRT_2PI = 0.91893853320467274178; /* 0.5*log(2*pi) */
+static const double SQRT_2PI = 2.50662827463100050242;
+
+typedef struct {
+    int ncode, nimmed, stacksize;
+    int32_t code[MAXVMCODE];
+    double immed[MAXVMIMMED];
+} vm_prog;
+
+struct oracle_handle {
+    int model;
+    int n, nX, nY, ntheta;
+    double *X, *Xu, *Xb, *Y, *Yu, *Yb;
+    int32_t *Xbindx, *Ybindx;
+    int32_t *partype, *nval, *theta_off; /* theta_off: 0-based offset in the fitted vector, -1 for FIX */
+    double* fix_value;
+    int32_t* var_indx; /* n x ntheta, 1-based; all ones if no VAR */
+    int nVar;
+    int32_t *pt_dist, *pg_dist;
+    double *pt_par, *pg_par;
+    int32_t *sigma_func, *nremnant, *gamma_off; /* gamma_off: offset inside the gamma block */
+    double* priorM;
+    int kM;
+    int32_t* xtra_i;
+    int n_xtra_i;
+    double* xtra_d;
+    int n_xtra_d;
+    double mv, unfeas;
+    /* derived */
+    int nFit, nGamma, nLatent, nXbTot, nYbTot, P, nDparModel, nDpar, nCombo, nState;
+    int32_t *nXb, *nYb, *off_xb, *off_yb; /* offsets in the full vector */
+    int32_t* Xerror;
+    int32_t* latIdx;   /* n x nX: position in the full vector or -1 */
+    int32_t* comboOf;  /* n: combo id of each observation */
+    int32_t* comboRow; /* nCombo: first observation (0-based) of each combo = INFER%DparIndx - 1 */
+    /* model specifics */
+    int ncontrol;
+    int32_t M[MAXCONTROL * MAXCONTROL]; /* row-major M[r*ncontrol+c] */
+    int sed_formula, sed_css, sed_co, sed_ppo[4];
+    double sed_pseudo[4];
+    int vm_nin, vm_npar, vm_nout;
+    vm_prog vm[MAXVMOUT];
+};
+
+static void setmess(char* mess, const char* s) {
+    if (!mess) return;
+    strncpy(mess, s, BAMGPU_MESS_LEN - 1);
+    mess[BAMGPU_MESS_LEN - 1] = 0;
+}
+
+static void* dup_mem(const void* src, size_t bytes) {
+    void* p = malloc(bytes ? bytes : 1);
+    if (src && bytes) memcpy(p, src, bytes);
+    return p;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Distributions (BMSL Distribution_tools -- un-vendored; conventions as declared in SURVEY App. E)
+ * ------------------------------------------------------------------------------------------ */
+
+static double norm_cdf(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
+
+/* Phi^-1: Abramowitz-Stegun 26.2.23 start, Halley iterations on erfc to full double precision. */
+double oracle_normal_quantile(double p) {
+    if (!(p > 0.0 && p < 1.0)) return NAN;
+    int upper = p > 0.5;
+    double q = upper ? 1.0 - p : p; /* exact for p in [0.5,1] */
+    if (q == 0.5) return 0.0;
+    double t = sqrt(-2.0 * log(q));
+    double z = -(t - (2.515517 + t * (0.802853 + t * 0.010328)) /
+                         (1.0 + t * (1.432788 + t * (0.189269 + t * 0.001308))));
+    for (int it = 0; it < 12; ++it) {
+        double e = norm_cdf(z) - q;
+        double u = e * SQRT_2PI * exp(0.5 * z * z);
+        double dz = u / (1.0 + 0.5 * z * u);
+        z -= dz;
+        if (fabs(dz) <= 1e-16 * fabs(z)) break;
+    }
+    return upper ? -z : z;
+}
+
+int oracle_logpdf(int dist, const double* par, double x, double* lp, int* feas, int* isnull) {
+    *feas = 1;
+    *isnull = 0;
+    *lp = BAMGPU_UNDEF_RN;
+    switch (dist) {
+        case BAMGPU_DIST_GAUSSIAN: {
+            double mu = par[0], s = par[1];
+            if (!(s > 0.0)) { *feas = 0; return 0; }
+            double z = (x - mu) / s;
+            *lp = -LOG_SQRT_2PI - log(s) - 0.5 * z * z;
+            return 0;
+        }
+        case BAMGPU_DIST_UNIFORM: {
+            double a = par[0], b = par[1];
+            if (!(b > a)) { *feas = 0; return 0; }
+            if (x < a || x > b) { *isnull = 1; return 0; }
+            *lp = -log(b - a);
+            return 0;
+        }
+        case BAMGPU_DIST_TRIANGLE: {
+            double pk = par[0], a = par[1], b = par[2];
+            if (!(b > a) || pk < a || pk > b) { *feas = 0; return 0; }
+            if (x < a || x > b) { *isnull = 1; return 0; }
+            double d;
+            if (x <= pk) d = (pk > a) ? 2.0 * (x - a) / ((b - a) * (pk - a)) : 2.0 / (b - a);
+            else d = (b > pk) ? 2.0 * (b - x) / ((b - a) * (b - pk)) : 2.0 / (b - a);
+            if (!(d > 0.0)) { *isnull = 1; return 0; }
+            *lp = log(d);
+            return 0;
+        }
+        case BAMGPU_DIST_LOGNORMAL: {
+            double mu = par[0], s = par[1];
+            if (!(s > 0.0)) { *feas = 0; return 0; }
+            if (!(x > 0.0)) { *isnull = 1; return 0; }
+            double lx = log(x);
+            double z = (lx - mu) / s;
+            *lp = -LOG_SQRT_2PI - log(s) - lx - 0.5 * z * z;
+            return 0;
+        }
+        case BAMGPU_DIST_EXPONENTIAL: {
+            double x0 = par[0], sc = par[1];
+            if (!(sc > 0.0)) { *feas = 0; return 0; }
+            if (x < x0) { *isnull = 1; return 0; }
+            *lp = -log(sc) - (x - x0) / sc;
+            return 0;
+        }
+        case BAMGPU_DIST_FLATPRIOR: *lp = 0.0; return 0;
+        case BAMGPU_DIST_FLATPRIOR_POS:
+            if (x > 0.0) *lp = 0.0; else *isnull = 1;
+            return 0;
+        case BAMGPU_DIST_FLATPRIOR_NEG:
+            if (x < 0.0) *lp = 0.0; else *isnull = 1;
+            return 0;
+        default: *feas = 0; return 1;
+    }
+}
+
+int oracle_cdf(int dist, const double* par, double x, double* u, int* feas) {
+    *feas = 1;
+    *u = BAMGPU_UNDEF_RN;
+    switch (dist) {
+        case BAMGPU_DIST_GAUSSIAN:
+            if (!(par[1] > 0.0)) { *feas = 0; return 0; }
+            *u = norm_cdf((x - par[0]) / par[1]);
+            return 0;
+        case BAMGPU_DIST_UNIFORM:
+            if (!(par[1] > par[0])) { *feas = 0; return 0; }
+            if (x <= par[0]) *u = 0.0;
+            else if (x >= par[1]) *u = 1.0;
+            else *u = (x - par[0]) / (par[1] - par[0]);
+            return 0;
+        case BAMGPU_DIST_TRIANGLE: {
+            double pk = par[0], a = par[1], b = par[2];
+            if (!(b > a) || pk < a || pk > b) { *feas = 0; return 0; }
+            if (x <= a) *u = 0.0;
+            else if (x >= b) *u = 1.0;
+            else if (x <= pk) *u = (x - a) * (x - a) / ((b - a) * (pk - a));
+            else *u = 1.0 - (b - x) * (b - x) / ((b - a) * (b - pk));
+            return 0;
+        }
+        case BAMGPU_DIST_LOGNORMAL:
+            if (!(par[1] > 0.0)) { *feas = 0; return 0; }
+            if (!(x > 0.0)) *u = 0.0;
+            else *u = norm_cdf((log(x) - par[0]) / par[1]);
+            return 0;
+        case BAMGPU_DIST_EXPONENTIAL:
+            if (!(par[1] > 0.0)) { *feas = 0; return 0; }
+            if (x <= par[0]) *u = 0.0;
+            else *u = 1.0 - exp(-(x - par[0]) / par[1]);
+            return 0;
+        default: /* flat priors have no cdf: infeasible in a copula */
+            *feas = 0;
+            return 0;
+    }
+}
+
+/* Gcop_getV, src/BaM_tools.f90:4246-4269: v = qnorm(cdf(x)); quantile failure -> infeasible */
+static int gcop_getv(int dist, const double* par, double x, double* v, int* feas) {
+    double u;
+    int err = oracle_cdf(dist, par, x, &u, feas);
+    if (err > 0) { *feas = 0; return err; }
+    if (!*feas) return 0;
+    if (!(u > 0.0 && u < 1.0)) { *feas = 0; return 0; }
+    *v = oracle_normal_quantile(u);
+    return 0;
+}
+
+/* Sigmafunk_Apply, src/BaM_tools.f90:3521-3571 */
+static double sigmafunk(int funk, const double* par, double Y) {
+    double ay = fabs(Y);
+    switch (funk) {
+        case BAMGPU_SIG_CONSTANT: return par[0];
+        case BAMGPU_SIG_LINEAR: return par[0] + par[1] * ay;
+        case BAMGPU_SIG_PROPORTIONAL: return par[0] * ay;
+        case BAMGPU_SIG_POWER: return par[0] + par[1] * pow(ay, par[2]);
+        case BAMGPU_SIG_EXPONENTIAL: return par[0] + (par[2] - par[0]) * (1.0 - exp(-(ay / par[1])));
+        case BAMGPU_SIG_GAUSSIAN: {
+            double r = ay / par[1];
+            return par[0] + (par[2] - par[0]) * (1.0 - exp(-(r * r)));
+        }
+    }
+    return NAN;
+}
+
+static int sigmafunk_npar(int funk) {
+    switch (funk) {
+        case BAMGPU_SIG_CONSTANT: return 1;
+        case BAMGPU_SIG_LINEAR: return 2;
+        case BAMGPU_SIG_PROPORTIONAL: return 1;
+        case BAMGPU_SIG_POWER: return 3;
+        case BAMGPU_SIG_EXPONENTIAL: return 3;
+        case BAMGPU_SIG_GAUSSIAN: return 3;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * TextFile model: formula compiler + stack VM (TextFile_model.f90:208-309, 551-857)
+ * ------------------------------------------------------------------------------------------ */
+
+enum { cImmed = 1, cNeg, cAdd, cSub, cMul, cDiv, cPow, cAbs, cExp, cLog10, cLog, cSqrt, cSinh, cCosh, cTanh,
+       cSin, cCos, cTan, cAsin, cAcos, cAtan, cIs0, cIsPos, cIsNeg, cIsSPos, cIsSNeg, VarBegin };
+static const char* const FUNCS[] = {"abs", "exp", "log10", "log", "sqrt", "sinh", "cosh", "tanh", "sin", "cos",
+                                    "tan", "asin", "acos", "atan", "is0", "ispos", "isneg", "isspos", "issneg"};
+#define NFUNCS 19
+static const char OPS[] = "+-*/^";
+
+typedef struct {
+    const char* F; /* condensed formula */
+    const char* const* var;
+    int nvar;
+    int32_t* code;
+    int maxcode, ncode;
+    double* immed;
+    int maximmed, nimmed;
+    int sp, stacksize;
+    int err;
+} vm_comp;
+
+/* MathFunctionIndex (:463-482): first catalogue entry that is a case-insensitive prefix of s[0..len) */
+static int math_function_index(const char* s, int len) {
+    for (int j = 0; j < NFUNCS; ++j) {
+        int k = (int)strlen(FUNCS[j]);
+        if (k > len) continue; /* the reference compares a blank-padded, shorter string: never equal */
+        int ok = 1;
+        for (int q = 0; q < k; ++q)
+            if (tolower((unsigned char)s[q]) != FUNCS[j][q]) { ok = 0; break; }
+        if (ok) return cAbs + j;
+    }
+    return 0;
+}
+
+/* VariableIndex (:484-515): name runs until one of "+-*^/) " */
+static int variable_index(const vm_comp* c, const char* s, int len) {
+    int in = 0;
+    while (in < len && !strchr("+-*/^) ", s[in])) ++in;
+    for (int j = 0; j < c->nvar; ++j)
+        if ((int)strlen(c->var[j]) == in && strncmp(s, c->var[j], in) == 0) return j + 1;
+    return 0;
+}
+
+static int completely_enclosed(const char* F, int b, int e) { /* :621-642, 0-based inclusive */
+    if (b > e || F[b] != '(' || F[e] != ')') return 0;
+    int k = 0;
+    for (int j = b + 1; j <= e - 1; ++j) {
+        if (F[j] == '(') ++k;
+        else if (F[j] == ')') --k;
+        if (k < 0) break;
+    }
+    return k == 0;
+}
+
+static int is_binary_op(const char* F, int j) { /* :740-778 */
+    if (F[j] == '+' || F[j] == '-') {
+        if (j == 0) return 0;
+        if (strchr("+-*/^(", F[j - 1])) return 0;
+        if (isdigit((unsigned char)F[j + 1]) && strchr("eEdD", F[j - 1])) {
+            int Dflag = 0, Pflag = 0;
+            int k = j - 1;
+            while (k > 0) {
+                --k;
+                if (isdigit((unsigned char)F[k])) Dflag = 1;
+                else if (F[k] == '.') {
+                    if (Pflag) break;
+                    Pflag = 1;
+                } else break;
+            }
+            if (Dflag && (k == 0 || strchr("+-*/^(", F[k]))) return 0;
+        }
+    }
+    return 1;
+}
+
+static void add_byte(vm_comp* c, int32_t b) {
+    if (c->ncode >= c->maxcode) { c->err = 1; return; }
+    c->code[c->ncode++] = b;
+}
+
+/* RealNum (:780-853): [+|-][nnn][.nnn][e|E|d|D[+|-]nnn] at the start of s */
+static double real_num(const char* s, int len, int* ok) {
+    char buf[128];
+    int in = 0, Bflag = 1, InMan = 0, Pflag = 0, Eflag = 0, InExp = 0, DInMan = 0, DInExp = 0;
+    while (in < len) {
+        char ch = s[in];
+        if (ch == '+' || ch == '-') {
+            if (Bflag) { InMan = 1; Bflag = 0; }
+            else if (Eflag) { InExp = 1; Eflag = 0; }
+            else break;
+        } else if (isdigit((unsigned char)ch)) {
+            if (Bflag) { InMan = 1; Bflag = 0; }
+            else if (Eflag) { InExp = 1; Eflag = 0; }
+            if (InMan) DInMan = 1;
+            if (InExp) DInExp = 1;
+        } else if (ch == '.') {
+            if (Bflag) { Pflag = 1; InMan = 1; Bflag = 0; }
+            else if (InMan && !Pflag) Pflag = 1;
+            else break;
+        } else if (ch == 'e' || ch == 'E' || ch == 'd' || ch == 'D') {
+            if (InMan) { Eflag = 1; InMan = 0; }
+            else break;
+        } else break;
+        ++in;
+    }
+    int bad = (in < 1) || !DInMan || ((Eflag || InExp) && !DInExp) || in >= (int)sizeof(buf);
+    if (bad) { *ok = 0; return 0.0; }
+    for (int q = 0; q < in; ++q) buf[q] = (s[q] == 'd' || s[q] == 'D') ? 'e' : s[q];
+    buf[in] = 0;
+    *ok = 1;
+    return strtod(buf, NULL);
+}
+
+static void compile_substr(vm_comp* c, int b, int e) { /* CompileSubstr :644-738 (0-based inclusive) */
+    const char* F = c->F;
+    if (c->err || b > e) { c->err = 1; return; }
+    if (F[b] == '+') { compile_substr(c, b + 1, e); return; }              /* case 1 */
+    if (completely_enclosed(F, b, e)) { compile_substr(c, b + 1, e - 1); return; } /* case 2 */
+    if (isalpha((unsigned char)F[b])) {
+        int n = math_function_index(F + b, e - b + 1);
+        if (n > 0) {
+            const char* par = memchr(F + b, '(', e - b + 1);
+            if (par) {
+                int b2 = (int)(par - F);
+                if (completely_enclosed(F, b2, e)) { /* case 3 */
+                    compile_substr(c, b2 + 1, e - 1);
+                    add_byte(c, n);
+                    return;
+                }
+            }
+        }
+    } else if (F[b] == '-') {
+        if (completely_enclosed(F, b + 1, e)) { /* case 4 */
+            compile_substr(c, b + 2, e - 1);
+            add_byte(c, cNeg);
+            return;
+        } else if (b + 1 <= e && isalpha((unsigned char)F[b + 1])) {
+            int n = math_function_index(F + b + 1, e - b);
+            if (n > 0) {
+                const char* par = memchr(F + b + 1, '(', e - b);
+                if (par) {
+                    int b2 = (int)(par - F);
+                    if (completely_enclosed(F, b2, e)) { /* case 5 */
+                        compile_substr(c, b2 + 1, e - 1);
+                        add_byte(c, n);
+                        add_byte(c, cNeg);
+                        return;
+                    }
+                }
+            }
+        }
+    }
+    for (int io = 0; io < 5; ++io) { /* increasing priority + - * / ^ ; right-most occurrence first */
+        int k = 0;
+        for (int j = e; j >= b; --j) {
+            if (F[j] == ')') ++k;
+            else if (F[j] == '(') --k;
+            if (k == 0 && F[j] == OPS[io] && is_binary_op(F, j)) {
+                if (io >= 2 && F[b] == '-') { /* case 6 */
+                    compile_substr(c, b + 1, e);
+                    add_byte(c, cNeg);
+                    return;
+                }
+                compile_substr(c, b, j - 1); /* case 7 */
+                compile_substr(c, j + 1, e);
+                add_byte(c, cAdd + io);
+                c->sp -= 1;
+                return;
+            }
+        }
+    }
+    int b2 = b;
+    if (F[b] == '-') ++b2;
+    int n = 0;
+    if (b2 <= e && (isdigit((unsigned char)F[b2]) || F[b2] == '.')) {
+        int ok;
+        double r = real_num(F + b2, e - b2 + 1, &ok);
+        if (!ok || c->nimmed >= c->maximmed) { c->err = 1; return; }
+        c->immed[c->nimmed++] = r;
+        n = cImmed;
+    } else if (b2 <= e) {
+        n = variable_index(c, F + b2, e - b2 + 1);
+        if (n > 0) n = VarBegin + n - 1;
+    }
+    if (n == 0) { c->err = 1; return; }
+    add_byte(c, n);
+    c->sp += 1;
+    if (c->sp > c->stacksize) c->stacksize += 1;
+    if (b2 > b) add_byte(c, cNeg);
+}
+
+int oracle_textfile_compile(const char* formula, const char* const* varnames, int nvar, int32_t* code,
+                            int maxcode, double* immed, int maximmed, int* nimmed, int* stacksize) {
+    /* parsef (:208-229): '**' -> '^', strip blanks */
+    size_t L = strlen(formula);
+    char* F = (char*)malloc(L + 1);
+    size_t m = 0;
+    for (size_t i = 0; i < L; ++i) {
+        if (formula[i] == '*' && i + 1 < L && formula[i + 1] == '*') { F[m++] = '^'; ++i; continue; }
+        if (formula[i] == ' ' || formula[i] == '\t' || formula[i] == '\r' || formula[i] == '\n') continue;
+        F[m++] = formula[i];
+    }
+    F[m] = 0;
+    if (m == 0) { free(F); return -1; }
+    int par = 0;
+    for (size_t i = 0; i < m; ++i) { /* minimal syntax check: parentheses */
+        if (F[i] == '(') ++par;
+        if (F[i] == ')') --par;
+        if (par < 0) { free(F); return -1; }
+    }
+    if (par != 0) { free(F); return -1; }
+    vm_comp c;
+    memset(&c, 0, sizeof c);
+    c.F = F; c.var = varnames; c.nvar = nvar; c.code = code; c.maxcode = maxcode;
+    c.immed = immed; c.maximmed = maximmed;
+    compile_substr(&c, 0, (int)m - 1);
+    free(F);
+    if (c.err) return -1;
+    *nimmed = c.nimmed;
+    *stacksize = c.stacksize;
+    return c.ncode;
+}
+
+/* evalf (:231-309).  Returns error type (0 OK). */
+static int vm_eval(const vm_prog* p, const double* val, double* res) {
+    double st[MAXVMSTACK];
+    int sp = -1, dp = 0;
+    for (int ip = 0; ip < p->ncode; ++ip) {
+        int op = p->code[ip];
+        switch (op) {
+            case cImmed: st[++sp] = p->immed[dp++]; break;
+            case cNeg: st[sp] = -st[sp]; break;
+            case cAdd: st[sp - 1] = st[sp - 1] + st[sp]; --sp; break;
+            case cSub: st[sp - 1] = st[sp - 1] - st[sp]; --sp; break;
+            case cMul: st[sp - 1] = st[sp - 1] * st[sp]; --sp; break;
+            case cDiv:
+                if (st[sp] == 0.0) { *res = 0.0; return 1; }
+                st[sp - 1] = st[sp - 1] / st[sp]; --sp; break;
+            case cPow: st[sp - 1] = pow(st[sp - 1], st[sp]); --sp; break;
+            case cAbs: st[sp] = fabs(st[sp]); break;
+            case cExp: st[sp] = exp(st[sp]); break;
+            case cLog10:
+                if (st[sp] <= 0.0) { *res = 0.0; return 3; }
+                st[sp] = log10(st[sp]); break;
+            case cLog:
+                if (st[sp] <= 0.0) { *res = 0.0; return 3; }
+                st[sp] = log(st[sp]); break;
+            case cSqrt:
+                if (st[sp] < 0.0) { *res = 0.0; return 3; }
+                st[sp] = sqrt(st[sp]); break;
+            case cSinh: st[sp] = sinh(st[sp]); break;
+            case cCosh: st[sp] = cosh(st[sp]); break;
+            case cTanh: st[sp] = tanh(st[sp]); break;
+            case cSin: st[sp] = sin(st[sp]); break;
+            case cCos: st[sp] = cos(st[sp]); break;
+            case cTan: st[sp] = tan(st[sp]); break;
+            case cAsin:
+                if (st[sp] < -1.0 || st[sp] > 1.0) { *res = 0.0; return 4; }
+                st[sp] = asin(st[sp]); break;
+            case cAcos:
+                if (st[sp] < -1.0 || st[sp] > 1.0) { *res = 0.0; return 4; }
+                st[sp] = acos(st[sp]); break;
+            case cAtan: st[sp] = atan(st[sp]); break;
+            case cIs0: st[sp] = (st[sp] == 0.0) ? 1.0 : 0.0; break;
+            case cIsPos: st[sp] = (st[sp] >= 0.0) ? 1.0 : 0.0; break;
+            case cIsNeg: st[sp] = (st[sp] <= 0.0) ? 1.0 : 0.0; break;
+            case cIsSPos: st[sp] = (st[sp] > 0.0) ? 1.0 : 0.0; break;
+            case cIsSNeg: st[sp] = (st[sp] < 0.0) ? 1.0 : 0.0; break;
+            default: st[++sp] = val[op - VarBegin]; break;
+        }
+    }
+    *res = st[0];
+    return 0;
+}
+
+/* split one list-directed record into items (comma / blank separated, quotes stripped, '!' ends it) */
+static int split_items(const char* line, char items[][64], int maxitems) {
+    int n = 0;
+    const char* s = line;
+    while (*s && n < maxitems) {
+        while (*s == ' ' || *s == '\t' || *s == ',' || *s == '\r') ++s;
+        if (!*s || *s == '\n' || *s == '!') break;
+        int m = 0;
+        if (*s == '"' || *s == '\'') {
+            char q = *s++;
+            while (*s && *s != q && m < 63) items[n][m++] = *s++;
+            if (*s == q) ++s;
+        } else {
+            while (*s && !strchr(" \t,\r\n!", *s) && m < 63) items[n][m++] = *s++;
+        }
+        items[n][m] = 0;
+        ++n;
+    }
+    return n;
+}
+
+static const char* next_line(const char* s, char* buf, int bufsz) {
+    if (!s || !*s) return NULL;
+    int m = 0;
+    while (*s && *s != '\n') {
+        if (m < bufsz - 1) buf[m++] = *s;
+        ++s;
+    }
+    buf[m] = 0;
+    if (*s == '\n') ++s;
+    return s;
+}
+
+/* TxtMdl_load + TxtMdl_define (TextFile_model.f90:897-1033) from the text of the model file */
+static int textfile_load(oracle_t* o, const char* text, char* mess) {
+    char line[4096];
+    char items[64][64];
+    char names[64][64];
+    const char* vp[64];
+    const char* s = text;
+    if (!s) { setmess(mess, "oracle: TextFile model needs xtra_text"); return 1; }
+    s = next_line(s, line, sizeof line);
+    if (!s) goto bad;
+    int nIN = atoi(line);
+    s = next_line(s, line, sizeof line);
+    if (!s) goto bad;
+    int nv = 0;
+    if (nIN > 0) {
+        int k = split_items(line, items, 64);
+        if (k < nIN) goto bad;
+        for (int i = 0; i < nIN; ++i) strcpy(names[nv++], items[i]);
+    }
+    s = next_line(s, line, sizeof line);
+    if (!s) goto bad;
+    int nPAR = atoi(line);
+    s = next_line(s, line, sizeof line);
+    if (!s) goto bad;
+    if (nPAR > 0) {
+        int k = split_items(line, items, 64);
+        if (k < nPAR) goto bad;
+        for (int i = 0; i < nPAR; ++i) strcpy(names[nv++], items[i]);
+    }
+    s = next_line(s, line, sizeof line);
+    if (!s) goto bad;
+    int nOUT = atoi(line);
+    if (nOUT <= 0 || nOUT > MAXVMOUT) goto bad;
+    for (int i = 0; i < nv; ++i) vp[i] = names[i];
+    o->vm_nin = nIN; o->vm_npar = nPAR; o->vm_nout = nOUT;
+    for (int k = 0; k < nOUT; ++k) {
+        s = next_line(s, line, sizeof line);
+        if (!s && k < nOUT - 1) goto bad;
+        char* excl = strchr(line, '!');
+        if (excl) *excl = 0;
+        vm_prog* p = &o->vm[k];
+        p->ncode = oracle_textfile_compile(line, vp, nv, p->code, MAXVMCODE, p->immed, MAXVMIMMED, &p->nimmed,
+                                           &p->stacksize);
+        if (p->ncode < 0 || p->stacksize > MAXVMSTACK) {
+            setmess(mess, "oracle: TxtMdl_define: Syntax error");
+            return 5;
+        }
+        if (!s) break;
+    }
+    return 0;
+bad:
+    setmess(mess, "oracle: TxtMdl_load: problem reading model text");
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Models.  X is n x nX column-major with leading dimension ldx.  Y n x nY, leading dim ldy.
+ * vfeas[n] row feasibility.  Returns err.
+ * ------------------------------------------------------------------------------------------ */
+
+/* ApplyContinuity, BaRatin_model.f90:330-396 */
+static int baratin_continuity(const oracle_t* o, const double* a, const double* c, const double* k, double* b) {
+    int nc = o->ncontrol;
+    if (a[0] <= 0.0 || c[0] == 0.0) return 0;
+    b[0] = k[0];
+    for (int j = 1; j < nc; ++j) {
+        if (k[j] <= k[j - 1]) return 0;
+        for (int i = 0; i < j; ++i)
+            if (k[j] < b[i]) return 0;
+        if (a[j] <= 0.0 || c[j] == 0.0) return 0;
+        double som = 0.0;
+        for (int i = 0; i < j; ++i)
+            som = som + (double)(o->M[(j - 1) * nc + i] - o->M[j * nc + i]) * a[i] * pow(k[j] - b[i], c[i]);
+        if (som < 0.0) return 0;
+        b[j] = k[j] - pow((1.0 / a[j]) * som, 1.0 / c[j]);
+    }
+    return 1;
+}
+
+/* BaRatin_Apply + BaRatin_computeQ + GetHRange, BaRatin_model.f90:67-137,194-252,398-436 */
+static void baratin_apply(const oracle_t* o, int n, const double* H, const double* theta, double* Q, double* b,
+                          int32_t* vfeas) {
+    int nc = o->ncontrol;
+    double k[MAXCONTROL], a[MAXCONTROL], c[MAXCONTROL];
+    for (int i = 0; i < nc; ++i) { k[i] = theta[3 * i]; a[i] = theta[3 * i + 1]; c[i] = theta[3 * i + 2]; }
+    if (!baratin_continuity(o, a, c, k, b)) {
+        for (int t = 0; t < n; ++t) vfeas[t] = 0;
+        return;
+    }
+    for (int t = 0; t < n; ++t) {
+        double h = H[t];
+        int range = nc;
+        for (int i = 0; i < nc; ++i)
+            if (h < k[i]) { range = i; break; }
+        double q = 0.0;
+        for (int i = 0; i < range; ++i) {
+            if (o->M[(range - 1) * nc + i] == 1) {
+                if ((h - b[i]) < 0.0) { q = 0.0; break; }
+                q = q + a[i] * pow(h - b[i], c[i]);
+            } else {
+                if ((h - b[i]) < 0.0) { vfeas[t] = 0; break; }
+            }
+        }
+        Q[t] = q;
+    }
+}
+
+/* LM_Apply, Linear_model.f90:62-101: Y = matmul(X, reshape(theta,(nX,nY))) */
+static void linear_apply(const oracle_t* o, int n, const double* X, int ldx, const double* theta, double* Y,
+                         int ldy) {
+    for (int t = 0; t < n; ++t)
+        for (int y = 0; y < o->nY; ++y) {
+            double s = 0.0;
+            for (int x = 0; x < o->nX; ++x) s = s + X[t + (size_t)x * ldx] * theta[y * o->nX + x];
+            Y[t + (size_t)y * ldy] = s;
+        }
+}
+
+static int sed_nbase(int f) { return (f == BAMGPU_SED_MPM || f == BAMGPU_SED_NIELSEN) ? 2 : 3; }
+static int sed_ncoeff(int css) { return css == BAMGPU_CSS_SOULSBY ? 4 : (css == BAMGPU_CSS_SW ? 3 : 0); }
+
+/* Sediment_Apply + GetAllPar + CSS_Apply, SedimentTransport_model.f90:100-192,251-310,525-607 */
+static void sediment_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
+                           int32_t* vfeas) {
+    int nbase = sed_nbase(o->sed_formula), ncoeff = sed_ncoeff(o->sed_css);
+    for (int t = 0; t < n; ++t) {
+        int bad = 0;
+        for (int x = 0; x < o->nX; ++x)
+            if (IN[t + (size_t)x * ldx] <= 0.0) bad = 1;
+        if (bad) { vfeas[t] = 0; continue; }
+        /* GetAllPar */
+        double base[3], pseudo[4], coeff[4], cte = BAMGPU_UNDEF_RN;
+        int ktheta = 0, kin = 2;
+        for (int i = 0; i < nbase; ++i) base[i] = theta[ktheta++];
+        if (o->sed_css == BAMGPU_CSS_CONSTANT) cte = theta[ktheta++];
+        for (int i = 0; i < 4; ++i) {
+            if (o->sed_ppo[i] == BAMGPU_PPO_FIX) pseudo[i] = o->sed_pseudo[i];
+            else if (o->sed_ppo[i] == BAMGPU_PPO_PAR) pseudo[i] = theta[ktheta++];
+            else pseudo[i] = IN[t + (size_t)(kin++) * ldx];
+        }
+        if (o->sed_css != BAMGPU_CSS_CONSTANT) {
+            if (o->sed_co == BAMGPU_CO_PAR)
+                for (int i = 0; i < ncoeff; ++i) coeff[i] = theta[ktheta++];
+            else if (o->sed_css == BAMGPU_CSS_SOULSBY) { coeff[0] = 0.3; coeff[1] = 1.2; coeff[2] = 0.055; coeff[3] = 0.02; }
+            else { coeff[0] = 0.24; coeff[1] = 0.055; coeff[2] = 0.02; }
+        }
+        double d = pseudo[0], s = pseudo[1], v = pseudo[2], g = pseudo[3];
+        /* CSS_Apply */
+        if (d <= 0.0 || s <= 0.0 || v <= 0.0 || g <= 0.0) { vfeas[t] = 0; continue; }
+        double css;
+        if (o->sed_css == BAMGPU_CSS_CONSTANT) css = cte;
+        else {
+            double SD = pow(g * (s - 1.0) / (v * v), 1.0 / 3.0) * d;
+            if (o->sed_css == BAMGPU_CSS_SOULSBY)
+                css = (coeff[0] / (1.0 + coeff[1] * SD)) * coeff[2] * (1.0 - exp(-1.0 * coeff[3] * SD));
+            else
+                css = (coeff[0] / SD) * coeff[1] * (1.0 - exp(-1.0 * coeff[2] * SD));
+        }
+        if (s <= 1.0) { vfeas[t] = 0; continue; }
+        double in1 = IN[t], in2 = IN[t + (size_t)ldx];
+        double tau = (in1 * in2) / ((s - 1.0) * d);
+        if (tau <= 0.0) { vfeas[t] = 0; continue; }
+        if (tau <= css) { OUT[t] = 0.0; continue; }
+        double dim = sqrt(g * (s - 1.0) * (d * d * d));
+        switch (o->sed_formula) {
+            case BAMGPU_SED_MPM: OUT[t] = dim * base[0] * pow(tau - css, base[1]); break;
+            case BAMGPU_SED_CAMENEN: OUT[t] = dim * base[0] * pow(tau, base[1]) * exp(-1.0 * base[2] * (css / tau)); break;
+            case BAMGPU_SED_NIELSEN: OUT[t] = dim * base[0] * pow(tau, base[1]) * (tau - css); break;
+            case BAMGPU_SED_SMART:
+                OUT[t] = dim * base[0] * pow(in2, base[1]) * pow(s - 1.0, 1.0 / 6.0) * pow(d, 1.0 / 6.0) *
+                         pow(g, -0.5) * pow(tau, base[2]) * (tau - css);
+                break;
+        }
+    }
+}
+
+/* TxtMdl_Apply, TextFile_model.f90:1035-1098 */
+static void textfile_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
+                           int ldy, int32_t* vfeas) {
+    double val[128];
+    for (int p = 0; p < o->vm_npar; ++p) val[o->vm_nin + p] = theta[p];
+    for (int t = 0; t < n; ++t) {
+        for (int x = 0; x < o->vm_nin; ++x) val[x] = IN[t + (size_t)x * ldx];
+        for (int k = 0; k < o->vm_nout; ++k) {
+            double r;
+            int e = vm_eval(&o->vm[k], val, &r);
+            if (e > 0 || r != r) { vfeas[t] = 0; r = BAMGPU_UNDEF_RN; }
+            OUT[t + (size_t)k * ldy] = r;
+        }
+    }
+}
+
+/* ApplyModel, ModelLibrary_tools.f90:237-434: init to unfeasFlag, dispatch, flag infeasible rows.
+   Returns feas = all(vfeas) through *feas. */
+static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const double* fullTheta, double* Y,
+                       int ldy, double* dparModel, int32_t* vfeas, int* feas) {
+    for (int t = 0; t < n; ++t) vfeas[t] = 1;
+    for (int y = 0; y < o->nY; ++y)
+        for (int t = 0; t < n; ++t) Y[t + (size_t)y * ldy] = o->unfeas;
+    for (int d = 0; d < o->nDparModel; ++d) dparModel[d] = o->unfeas;
+    switch (o->model) {
+        case BAMGPU_MDL_LINEAR: linear_apply(o, n, X, ldx, fullTheta, Y, ldy); break;
+        case BAMGPU_MDL_BARATIN: baratin_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
+        case BAMGPU_MDL_SEDIMENT: sediment_apply(o, n, X, ldx, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_TEXTFILE: textfile_apply(o, n, X, ldx, fullTheta, Y, ldy, vfeas); break;
+        default: return 1;
+    }
+    int all = 1;
+    for (int t = 0; t < n; ++t)
+        if (!vfeas[t]) {
+            all = 0;
+            for (int y = 0; y < o->nY; ++y) Y[t + (size_t)y * ldy] = o->unfeas;
+        }
+    *feas = all;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * create / layout  (LoadBamObjects, src/BaM_tools.f90:133-420)
+ * ------------------------------------------------------------------------------------------ */
+
+static int model_from_name(const char* name) {
+    if (!name) return 0;
+    if (strncmp(name, "MDL_", 4) == 0) name += 4;
+    if (!strcmp(name, "Linear")) return BAMGPU_MDL_LINEAR;
+    if (!strcmp(name, "BaRatin")) return BAMGPU_MDL_BARATIN;
+    if (!strcmp(name, "Sediment")) return BAMGPU_MDL_SEDIMENT;
+    if (!strcmp(name, "TextFile")) return BAMGPU_MDL_TEXTFILE;
+    if (!strcmp(name, "Vegetation")) return BAMGPU_MDL_VEGETATION;
+    return 0;
+}
+
+int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
+    if (mess) mess[0] = 0;
+    oracle_t* o = (oracle_t*)calloc(1, sizeof *o);
+    o->model = model_from_name(p->model_id);
+    if (!o->model || o->model == BAMGPU_MDL_VEGETATION) {
+        setmess(mess, "oracle: ApplyModel: Fatal: Unavailable [model%ID]");
+        free(o);
+        return 1;
+    }
+    int n = o->n = p->nobs, nX = o->nX = p->nX, nY = o->nY = p->nY, nt = o->ntheta = p->ntheta;
+    size_t sx = (size_t)n * nX, sy = (size_t)n * nY;
+    o->X = dup_mem(p->X, sx * 8); o->Xu = dup_mem(p->Xu, sx * 8); o->Xb = dup_mem(p->Xb, sx * 8);
+    o->Xbindx = dup_mem(p->Xbindx, sx * 4);
+    o->Y = dup_mem(p->Y, sy * 8); o->Yu = dup_mem(p->Yu, sy * 8); o->Yb = dup_mem(p->Yb, sy * 8);
+    o->Ybindx = dup_mem(p->Ybindx, sy * 4);
+    o->partype = dup_mem(p->partype, nt * 4); o->nval = dup_mem(p->nval, nt * 4);
+    o->fix_value = dup_mem(p->fix_value, nt * 8);
+    o->theta_off = malloc((nt + 1) * 4);
+    o->nFit = 0; o->nVar = 0;
+    for (int i = 0; i < nt; ++i) {
+        if (o->partype[i] == BAMGPU_PAR_FIX) o->theta_off[i] = -1;
+        else { o->theta_off[i] = o->nFit; o->nFit += o->nval[i]; }
+        if (o->partype[i] == BAMGPU_PAR_VAR) o->nVar++;
+    }
+    o->var_indx = malloc(((size_t)n * nt + 1) * 4);
+    for (size_t q = 0; q < (size_t)n * nt; ++q) o->var_indx[q] = (p->var_indx && o->nVar) ? p->var_indx[q] : 1;
+    for (int i = 0; i < nt; ++i)
+        for (int t = 0; t < n; ++t) {
+            int v = o->var_indx[t + (size_t)i * n];
+            if (o->partype[i] != BAMGPU_PAR_VAR) v = o->var_indx[t + (size_t)i * n] = 1;
+            if (v <= 0 || v > o->nval[i]) { setmess(mess, "oracle: Config_Finalize: VAR index out of range"); return 1; }
+        }
+    o->sigma_func = dup_mem(p->sigma_func, nY * 4); o->nremnant = dup_mem(p->nremnant, nY * 4);
+    o->gamma_off = malloc((nY + 1) * 4);
+    o->nGamma = 0;
+    for (int j = 0; j < nY; ++j) {
+        if (sigmafunk_npar(o->sigma_func[j]) != o->nremnant[j]) { setmess(mess, "oracle: wrong number of remnant parameters"); return 1; }
+        o->gamma_off[j] = o->nGamma; o->nGamma += o->nremnant[j];
+    }
+    o->pt_dist = dup_mem(p->prior_theta_dist, o->nFit * 4);
+    o->pt_par = dup_mem(p->prior_theta_par, (size_t)o->nFit * BAMGPU_PRIOR_NPAR * 8);
+    o->pg_dist = dup_mem(p->prior_gamma_dist, o->nGamma * 4);
+    o->pg_par = dup_mem(p->prior_gamma_par, (size_t)o->nGamma * BAMGPU_PRIOR_NPAR * 8);
+    o->kM = o->nFit + o->nGamma;
+    o->priorM = p->priorM ? dup_mem(p->priorM, (size_t)o->kM * o->kM * 8) : NULL;
+    o->xtra_i = dup_mem(p->xtra_i, (size_t)p->n_xtra_i * 4); o->n_xtra_i = p->n_xtra_i;
+    o->xtra_d = dup_mem(p->xtra_d, (size_t)p->n_xtra_d * 8); o->n_xtra_d = p->n_xtra_d;
+    o->mv = p->mv; o->unfeas = p->unfeas_flag;
+
+    /* latent inputs, biases: :230-253 */
+    o->Xerror = calloc(nX + 1, 4); o->latIdx = malloc((sx + 1) * 4);
+    o->nXb = calloc(nX + 1, 4); o->nYb = calloc(nY + 1, 4);
+    o->off_xb = calloc(nX + 1, 4); o->off_yb = calloc(nY + 1, 4);
+    int pos = o->nFit + o->nGamma;
+    o->nLatent = 0;
+    for (int j = 0; j < nX; ++j)
+        for (int i = 0; i < n; ++i) {
+            size_t q = i + (size_t)j * n;
+            if (o->Xu[q] > 0.0) { o->latIdx[q] = pos++; o->nLatent++; o->Xerror[j] = 1; }
+            else o->latIdx[q] = -1;
+        }
+    o->nXbTot = o->nYbTot = 0;
+    for (int j = 0; j < nX; ++j) {
+        int mx = 0;
+        for (int i = 0; i < n; ++i) if (o->Xbindx[i + (size_t)j * n] > mx) mx = o->Xbindx[i + (size_t)j * n];
+        o->nXb[j] = mx; o->off_xb[j] = pos; pos += mx; o->nXbTot += mx;
+    }
+    for (int j = 0; j < nY; ++j) { /* NOTE: Packer layout (:4235-4240); UnfoldParVector's cursor quirk (:3460) not reproduced */
+        int mx = 0;
+        for (int i = 0; i < n; ++i) if (o->Ybindx[i + (size_t)j * n] > mx) mx = o->Ybindx[i + (size_t)j * n];
+        o->nYb[j] = mx; o->off_yb[j] = pos; pos += mx; o->nYbTot += mx;
+    }
+    o->P = pos;
+
+    /* model xtra + nDpar: XtraSetup, ModelLibrary_tools.f90:546-760 */
+    o->nDparModel = 0; o->nState = 0;
+    switch (o->model) {
+        case BAMGPU_MDL_LINEAR:
+            if (nt != nX * nY) { setmess(mess, "oracle: Linear: ntheta /= nX*nY"); return 1; }
+            break;
+        case BAMGPU_MDL_BARATIN: {
+            int nc = nt / 3;
+            if (nX != 1 || nY != 1 || nt != 3 * nc || nc < 1 || nc > MAXCONTROL || p->n_xtra_i != nc * nc) {
+                setmess(mess, "oracle: BaRatin_Apply:Fatal:Incorrect size [theta]"); return 1;
+            }
+            o->ncontrol = nc;
+            for (int r = 0; r < nc; ++r)
+                for (int c = 0; c < nc; ++c) o->M[r * nc + c] = p->xtra_i[r + c * nc];
+            o->nDparModel = nc;
+            break;
+        }
+        case BAMGPU_MDL_SEDIMENT: {
+            if (p->n_xtra_i != 7 || p->n_xtra_d != 4 || nY != 1) { setmess(mess, "oracle: Sediment: bad xtra"); return 1; }
+            o->sed_formula = p->xtra_i[0]; o->sed_css = p->xtra_i[1]; o->sed_co = p->xtra_i[2];
+            int np = sed_nbase(o->sed_formula) + (o->sed_css == BAMGPU_CSS_CONSTANT ? 1 : 0), nin = 2;
+            for (int i = 0; i < 4; ++i) {
+                o->sed_ppo[i] = p->xtra_i[3 + i]; o->sed_pseudo[i] = p->xtra_d[i];
+                if (o->sed_ppo[i] == BAMGPU_PPO_PAR) ++np;
+                if (o->sed_ppo[i] == BAMGPU_PPO_IN) ++nin;
+            }
+            if (o->sed_css != BAMGPU_CSS_CONSTANT && o->sed_co == BAMGPU_CO_PAR) np += sed_ncoeff(o->sed_css);
+            if (np != nt || nin != nX) { setmess(mess, "oracle: Sediment: wrong size [theta] or [IN]"); return 1; }
+            break;
+        }
+        case BAMGPU_MDL_TEXTFILE: {
+            int e = textfile_load(o, p->xtra_text, mess);
+            if (e) return e;
+            if (o->vm_nin != nX || o->vm_npar != nt || o->vm_nout != nY) { setmess(mess, "oracle: TextFile: size mismatch"); return 1; }
+            break;
+        }
+    }
+
+    /* VAR combinations: :346-379 (order of first appearance) */
+    o->comboOf = malloc((n + 1) * 4);
+    o->comboRow = malloc((n + 1) * 4);
+    o->nCombo = 0;
+    if (o->nVar == 0 || n == 0) {
+        o->nCombo = 1; o->comboRow[0] = 0;
+        for (int t = 0; t < n; ++t) o->comboOf[t] = 0;
+    } else {
+        for (int t = 0; t < n; ++t) {
+            int found = -1;
+            for (int k = 0; k < o->nCombo && found < 0; ++k) {
+                int r = o->comboRow[k], same = 1;
+                for (int i = 0; i < nt && same; ++i)
+                    if (o->var_indx[t + (size_t)i * n] != o->var_indx[r + (size_t)i * n]) same = 0;
+                if (same) found = k;
+            }
+            if (found < 0) { found = o->nCombo; o->comboRow[o->nCombo++] = t; }
+            o->comboOf[t] = found;
+        }
+    }
+    o->nDpar = o->nDparModel * o->nCombo;
+    *out = o;
+    return 0;
+}
+
+void oracle_destroy(oracle_t* o) {
+    if (!o) return;
+    free(o->X); free(o->Xu); free(o->Xb); free(o->Y); free(o->Yu); free(o->Yb); free(o->Xbindx); free(o->Ybindx);
+    free(o->partype); free(o->nval); free(o->theta_off); free(o->fix_value); free(o->var_indx);
+    free(o->pt_dist); free(o->pg_dist); free(o->pt_par); free(o->pg_par); free(o->sigma_func); free(o->nremnant);
+    free(o->gamma_off); free(o->priorM); free(o->xtra_i); free(o->xtra_d); free(o->nXb); free(o->nYb);
+    free(o->off_xb); free(o->off_yb); free(o->Xerror); free(o->latIdx); free(o->comboOf); free(o->comboRow);
+    free(o);
+}
+
+int oracle_get_sizes(const oracle_t* o, bamgpu_sizes* s) {
+    s->nFit = o->nFit; s->nGamma = o->nGamma; s->nLatent = o->nLatent; s->nXbias = o->nXbTot; s->nYbias = o->nYbTot;
+    s->nInfer = o->P; s->nDpar = o->nDpar; s->nCombo = o->nCombo; s->nState = o->nState;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * log-posterior
+ * ------------------------------------------------------------------------------------------ */
+
+/* fullTheta for observation t (ApplyModel_BaM, src/BaM_tools.f90:4133-4159) */
+static void full_theta(const oracle_t* o, const double* theta_fit, int t, double* full) {
+    for (int i = 0; i < o->ntheta; ++i) {
+        if (o->partype[i] == BAMGPU_PAR_FIX) full[i] = o->fix_value[i];
+        else full[i] = theta_fit[o->theta_off[i] + (o->n > 0 ? o->var_indx[t + (size_t)i * o->n] : 1) - 1];
+    }
+}
+
+/* GetPriorLogPdf, src/BaM_tools.f90:3006-3138 */
+static int prior_logpdf(const oracle_t* o, const double* x, double* prior, int* feas, int* isnull) {
+    const double* theta = x;
+    const double* gamma = x + o->nFit;
+    double pr = 0.0, lp;
+    *feas = 1; *isnull = 0;
+    for (int j = 0; j < o->nY; ++j) { /* remnant parameters first (:3062-3069) */
+        double s = 0.0; /* GetLogPrior = sum of the log-pdfs of one list */
+        for (int m = 0; m < o->nremnant[j]; ++m) {
+            int g = o->gamma_off[j] + m;
+            int e = oracle_logpdf(o->pg_dist[g], o->pg_par + (size_t)g * BAMGPU_PRIOR_NPAR, gamma[g], &lp, feas, isnull);
+            if (e > 0) { *feas = 0; return e; }
+            if (!*feas || *isnull) return 0;
+            s = s + lp;
+        }
+        pr = pr + s;
+    }
+    {
+        double s = 0.0;
+        for (int k = 0; k < o->nFit; ++k) { /* theta (:3072-3077) */
+            int e = oracle_logpdf(o->pt_dist[k], o->pt_par + (size_t)k * BAMGPU_PRIOR_NPAR, theta[k], &lp, feas, isnull);
+            if (e > 0) { *feas = 0; return e; }
+            if (!*feas || *isnull) return 0;
+            s = s + lp;
+        }
+        pr = pr + s;
+    }
+    if (o->priorM) { /* Gaussian copula (:3080-3112): theta first, then gamma */
+        int k = o->kM;
+        double* v = (double*)malloc((size_t)k * 8);
+        for (int i = 0; i < o->nFit; ++i) {
+            gcop_getv(o->pt_dist[i], o->pt_par + (size_t)i * BAMGPU_PRIOR_NPAR, theta[i], &v[i], feas);
+            if (!*feas) { free(v); return 0; }
+        }
+        for (int g = 0; g < o->nGamma; ++g) {
+            gcop_getv(o->pg_dist[g], o->pg_par + (size_t)g * BAMGPU_PRIOR_NPAR, gamma[g], &v[o->nFit + g], feas);
+            if (!*feas) { free(v); return 0; }
+        }
+        /* dot_product(matmul(v,M),v): w_c = sum_r v_r M(r,c) */
+        double q = 0.0;
+        for (int c = 0; c < k; ++c) {
+            double w = 0.0;
+            for (int r = 0; r < k; ++r) w = w + v[r] * o->priorM[r + (size_t)c * k];
+            q = q + w * v[c];
+        }
+        pr = pr - 0.5 * q;
+        free(v);
+    }
+    static const double n01[2] = {0.0, 1.0};
+    for (int j = 0; j < o->nX; ++j)
+        for (int i = 0; i < o->nXb[j]; ++i) {
+            oracle_logpdf(BAMGPU_DIST_GAUSSIAN, n01, x[o->off_xb[j] + i], &lp, feas, isnull);
+            pr = pr + lp;
+        }
+    for (int j = 0; j < o->nY; ++j)
+        for (int i = 0; i < o->nYb[j]; ++i) {
+            oracle_logpdf(BAMGPU_DIST_GAUSSIAN, n01, x[o->off_yb[j] + i], &lp, feas, isnull);
+            pr = pr + lp;
+        }
+    *prior = pr;
+    return 0;
+}
+
+/* ApplyModel_BaM on the calibration data (src/BaM_tools.f90:4115-4177) */
+static int apply_model_bam(const oracle_t* o, const double* Xtrue, const double* theta_fit, double* bigY,
+                           double* dpar, int32_t* vfeas, int* feas) {
+    int n = o->n;
+    double full[256], dmod[MAXCONTROL + 64];
+    for (int d = 0; d < o->nDpar; ++d) dpar[d] = o->unfeas;
+    if (o->nVar == 0) {
+        full_theta(o, theta_fit, 0, full);
+        int e = apply_model(o, n, Xtrue, n, full, bigY, n, dpar, vfeas, feas);
+        return e;
+    }
+    int k = 0;
+    double xrow[16], yrow[16];
+    for (int t = 0; t < n; ++t) { /* one model call per observation (:4152-4174) */
+        full_theta(o, theta_fit, t, full);
+        for (int j = 0; j < o->nX; ++j) xrow[j] = Xtrue[t + (size_t)j * n];
+        int32_t vf;
+        int e = apply_model(o, 1, xrow, 1, full, yrow, 1, dmod, &vf, feas);
+        if (e > 0) return e;
+        if (!*feas) return 0;
+        for (int j = 0; j < o->nY; ++j) bigY[t + (size_t)j * n] = yrow[j];
+        if (k < o->nCombo && t == o->comboRow[k]) {
+            for (int d = 0; d < o->nDparModel; ++d) dpar[k * o->nDparModel + d] = dmod[d];
+            ++k;
+        }
+    }
+    *feas = 1;
+    return 0;
+}
+
+int oracle_logpost(const oracle_t* o, const double* x, double* fx, double* prior_out, double* lkh_out,
+                   double* hyper_out, int32_t* feas_out, int32_t* isnull_out, double* dpar_out, int use_ld,
+                   char* mess) {
+    int n = o->n, nX = o->nX, nY = o->nY;
+    int feas = 1, isnull = 0;
+    double prior = BAMGPU_UNDEF_RN, lkh = BAMGPU_UNDEF_RN, hyper = BAMGPU_UNDEF_RN;
+    if (mess) mess[0] = 0;
+    *fx = BAMGPU_UNDEF_RN;
+    double* dpar = (double*)malloc(((size_t)o->nDpar + 1) * 8);
+    for (int d = 0; d < o->nDpar; ++d) dpar[d] = o->unfeas;
+    /* UnfoldParVector (:3386-3463): Xtrue = X copy, latent cells from x, un-bias non-latent biased cells */
+    double* Xtrue = (double*)malloc(((size_t)n * nX + 1) * 8);
+    memcpy(Xtrue, o->X, (size_t)n * nX * 8);
+    for (int j = 0; j < nX; ++j)
+        for (int i = 0; i < n; ++i) {
+            size_t q = i + (size_t)j * n;
+            if (o->latIdx[q] >= 0) Xtrue[q] = x[o->latIdx[q]];
+        }
+    for (int j = 0; j < nX; ++j) {
+        if (o->nXb[j] == 0) continue;
+        for (int i = 0; i < n; ++i) {
+            size_t q = i + (size_t)j * n;
+            if (o->Xbindx[q] > 0 && o->Xu[q] == 0.0) Xtrue[q] = o->X[q] - o->Xb[q] * x[o->off_xb[j] + o->Xbindx[q] - 1];
+        }
+    }
+    double* bigY = (double*)malloc(((size_t)n * nY + 1) * 8);
+    int32_t* vfeas = (int32_t*)malloc(((size_t)n + 1) * 4);
+    int err = 0;
+
+    /* GetPostLogPdf (:3310-3382): prior, likelihood, hyper with early exits */
+    err = prior_logpdf(o, x, &prior, &feas, &isnull);
+    if (err > 0) { feas = 0; goto done; }
+    if (!feas || isnull) goto done;
+
+    { /* GetLogLikelihood (:3142-3229) */
+        err = apply_model_bam(o, Xtrue, x, bigY, dpar, vfeas, &feas);
+        if (err > 0) { setmess(mess, "oracle: ApplyModel failed"); feas = 0; goto done; }
+        if (!feas) goto done;
+        const double* gamma = x + o->nFit;
+        double acc = 0.0;
+        long double accl = 0.0L;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < nY; ++j) {
+                size_t q = i + (size_t)j * n;
+                if (o->Y[q] == o->mv) continue;
+                double yhat = bigY[q];
+                double sig = sigmafunk(o->sigma_func[j], gamma + o->gamma_off[j], yhat);
+                if (sig <= 0.0) { feas = 0; goto done; }
+                sig = sqrt(o->Yu[q] * o->Yu[q] + sig * sig);
+                double mu = yhat;
+                if (o->Ybindx[q] != 0) mu = yhat + o->Yb[q] * x[o->off_yb[j] + o->Ybindx[q] - 1];
+                if (!(sig > 0.0)) { feas = 0; goto done; } /* GetPdf(GAUSS): feas <=> sigma>0 */
+                double z = (o->Y[q] - mu) / sig;
+                double lp = -LOG_SQRT_2PI - log(sig) - 0.5 * z * z;
+                acc = acc + lp;
+                accl += (long double)lp;
+            }
+        lkh = use_ld ? (double)accl : acc;
+    }
+    { /* GetHyperLogPdf (:3233-3306): j-major */
+        double acc = 0.0;
+        long double accl = 0.0L;
+        for (int j = 0; j < nX; ++j) {
+            if (!o->Xerror[j]) continue;
+            for (int i = 0; i < n; ++i) {
+                size_t q = i + (size_t)j * n;
+                if (o->Xu[q] == 0.0) continue;
+                double mu = Xtrue[q];
+                if (o->Xbindx[q] != 0) mu = Xtrue[q] + o->Xb[q] * x[o->off_xb[j] + o->Xbindx[q] - 1];
+                if (!(o->Xu[q] > 0.0)) { feas = 0; goto done; }
+                double z = (o->X[q] - mu) / o->Xu[q];
+                double lp = -LOG_SQRT_2PI - log(o->Xu[q]) - 0.5 * z * z;
+                acc = acc + lp;
+                accl += (long double)lp;
+            }
+        }
+        hyper = use_ld ? (double)accl : acc;
+    }
+    *fx = use_ld ? (double)((long double)prior + (long double)lkh + (long double)hyper) : prior + lkh + hyper;
+done:
+    if (prior_out) *prior_out = prior;
+    if (lkh_out) *lkh_out = lkh;
+    if (hyper_out) *hyper_out = hyper;
+    *feas_out = feas;
+    *isnull_out = isnull;
+    if (dpar_out) memcpy(dpar_out, dpar, (size_t)o->nDpar * 8);
+    free(dpar); free(Xtrue); free(bigY); free(vfeas);
+    return err > 0 ? err : 0;
+}
+
+int oracle_logpost_batch(const oracle_t* o, int K, const double* x, double* fx, int32_t* feas, int32_t* isnull,
+                         double* dpar, int nthreads, char* mess) {
+    int err = 0;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int k = 0; k < K; ++k) {
+        char m[BAMGPU_MESS_LEN];
+        int e = oracle_logpost(o, x + (size_t)k * o->P, &fx[k], NULL, NULL, NULL, &feas[k], &isnull[k],
+                               dpar ? dpar + (size_t)k * o->nDpar : NULL, 0, m);
+        if (e > 0) {
+#pragma omp critical
+            { err = e; setmess(mess, m); }
+        }
+    }
+    return err;
+}
+
+int oracle_apply_model(const oracle_t* o, int n, const double* X, const double* theta_fit, double* Y, double* dpar,
+                       int32_t* feas_rows, char* mess) {
+    if (o->nVar) { setmess(mess, "oracle: prediction with VAR parameters is not allowed (BaM_Message 13)"); return 1; }
+    double full[256], dmod[MAXCONTROL + 64];
+    full_theta(o, theta_fit, 0, full);
+    int feas;
+    int e = apply_model(o, n, X, n, full, Y, n, dmod, feas_rows, &feas);
+    if (dpar) for (int d = 0; d < o->nDparModel; ++d) dpar[d] = dmod[d];
+    return e;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * RNG: Philox4x32-10 counter-based generator (Salmon et al. 2011), Box-Muller normals.
+ * Specified here; the device implements the same specification independently.
+ * ------------------------------------------------------------------------------------------ */
+
+void oracle_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* 53-bit uniform in (0,1): ((hi>>5)*2^26 + (lo>>6) + 0.5) / 2^53 */
+static double u53(uint32_t hi, uint32_t lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+double oracle_uniform(uint64_t seed, uint64_t a, uint32_t b, uint32_t c) {
+    uint32_t w[4];
+    oracle_philox4x32((uint32_t)a, (uint32_t)(a >> 32), b, c, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    return u53(w[0], w[1]);
+}
+
+double oracle_normal(uint64_t seed, uint64_t a, uint32_t b, uint32_t c) {
+    uint32_t w[4];
+    oracle_philox4x32((uint32_t)a, (uint32_t)(a >> 32), b, c, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    double u1 = u53(w[0], w[1]), u2 = u53(w[2], w[3]);
+    return sqrt(-2.0 * log(u1)) * cos(6.28318530717958647692 * u2);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Prediction + envelopes
+ * ------------------------------------------------------------------------------------------ */
+
+static int cmp_double(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+/* GetEmpiricalQuantile (BMSL, un-vendored): DECLARED CONVENTION = Hazen plotting positions
+   pp_i=(i-0.5)/n with linear interpolation, clamped to the extremes. */
+static double hazen_quantile(const double* xs, int64_t n, double p) {
+    double h = p * (double)n + 0.5; /* 1-based fractional rank */
+    if (h <= 1.0) return xs[0];
+    if (h >= (double)n) return xs[n - 1];
+    int64_t i = (int64_t)floor(h);
+    double frac = h - (double)i;
+    return xs[i - 1] + frac * (xs[i] - xs[i - 1]);
+}
+
+/* one column: src/BaM_tools.f90:1393-1421 */
+void oracle_envelope(const double* col, int64_t nrep, double unfeas, double* env) {
+    static const double probs[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
+    int64_t nbad = 0;
+    for (int64_t r = 0; r < nrep; ++r)
+        if (col[r] == unfeas || col[r] != col[r]) ++nbad;
+    double* arr = (double*)malloc(((size_t)nrep + 1) * 8);
+    int64_t m = 0;
+    if ((double)nbad / (double)nrep < 0.75) {
+        for (int64_t r = 0; r < nrep; ++r)
+            if (!(col[r] == unfeas || col[r] != col[r])) arr[m++] = col[r];
+    } else {
+        for (int64_t r = 0; r < nrep; ++r) arr[m++] = col[r];
+    }
+    int anybad = 0;
+    for (int64_t r = 0; r < m; ++r)
+        if (arr[r] == unfeas || arr[r] != arr[r]) anybad = 1;
+    if (anybad || m == 0) {
+        for (int s = 0; s < BAMGPU_NENV; ++s) env[s] = unfeas;
+    } else {
+        qsort(arr, (size_t)m, sizeof(double), cmp_double);
+        for (int s = 0; s < 5; ++s) env[s] = hazen_quantile(arr, m, probs[s]);
+        double sum = 0.0;
+        for (int64_t r = 0; r < m; ++r) sum += arr[r];
+        double mean = sum / (double)m, ss = 0.0;
+        for (int64_t r = 0; r < m; ++r) ss += (arr[r] - mean) * (arr[r] - mean);
+        env[5] = mean;
+        env[6] = (m > 1) ? sqrt(ss / (double)(m - 1)) : unfeas;
+    }
+    free(arr);
+}
+
+int oracle_predict(const oracle_t* o, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                   const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
+                   uint64_t seed, int t0, int t1, double* env, double* spag_out, int nthreads, char* mess) {
+    if (mess) mess[0] = 0;
+    if (o->nVar) { setmess(mess, "oracle: BaM_Prediction: VAR parameters not allowed (BaM_Message 13)"); return 1; }
+    int nT = t1 - t0, nX = o->nX, nY = o->nY;
+    if (nT <= 0 || Nrep <= 0) return 0;
+    int anyRem = 0;
+    for (int y = 0; y < nY; ++y) anyRem |= doRemnant[y];
+    if ((doParametric || anyRem) && !mc) { setmess(mess, "oracle: BaM_Prediction: mcmc matrix required"); return 1; }
+    double* spag = spag_out ? spag_out : (double*)malloc((size_t)Nrep * nT * nY * 8);
+    int err = 0;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64_t rep = 0; rep < Nrep; ++rep) { /* the rep loop, :1034-1108 */
+        double* X = (double*)malloc(((size_t)nT * nX + 1) * 8);
+        double* Ys = (double*)malloc(((size_t)nT * nY + 1) * 8);
+        int32_t* vf = (int32_t*)malloc(((size_t)nT + 1) * 4);
+        double theta[256], full[256], dmod[MAXCONTROL + 64];
+        for (int i = 0; i < nX; ++i) { /* indx = modulo(rep, nspag), 1-based rep (:1049) */
+            int64_t col = rep % nspag[i];
+            for (int t = 0; t < nT; ++t) X[t + (size_t)i * nT] = xspag[i][(size_t)col * nobs_pred + t0 + t];
+        }
+        for (int k = 0; k < o->nFit; ++k) theta[k] = doParametric ? mc[rep + (size_t)k * Nrep] : mode[k];
+        full_theta(o, theta, 0, full);
+        int feas;
+        int e = apply_model(o, nT, X, nT, full, Ys, nT, dmod, vf, &feas);
+        if (e > 0) {
+#pragma omp critical
+            err = e;
+        }
+        for (int y = 0; y < nY; ++y) {
+            if (doRemnant[y]) {
+                double gam[8];
+                for (int m = 0; m < o->nremnant[y]; ++m)
+                    gam[m] = mc[rep + (size_t)(o->nFit + o->gamma_off[y] + m) * Nrep];
+                for (int t = 0; t < nT; ++t) {
+                    double v = Ys[t + (size_t)y * nT];
+                    if (v == o->unfeas) continue;
+                    double sig = sigmafunk(o->sigma_func[y], gam, v);
+                    if (sig > 0.0) /* Generate(GAUSS,(0,sig)) feasible iff sig>0 (:1095-1102) */
+                        Ys[t + (size_t)y * nT] = v + sig * oracle_normal(seed, (uint64_t)rep, (uint32_t)(t0 + t), (uint32_t)y);
+                }
+            }
+            for (int t = 0; t < nT; ++t) spag[(size_t)y * Nrep * nT + (size_t)t * Nrep + rep] = Ys[t + (size_t)y * nT];
+        }
+        free(X); free(Ys); free(vf);
+    }
+    if (env && Nrep >= 2) {
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 8)
+        for (int64_t q = 0; q < (int64_t)nT * nY; ++q) {
+            int y = (int)(q / nT), t = (int)(q % nT);
+            double e7[BAMGPU_NENV];
+            oracle_envelope(spag + (size_t)y * Nrep * nT + (size_t)t * Nrep, Nrep, o->unfeas, e7);
+            for (int s = 0; s < BAMGPU_NENV; ++s) env[(size_t)y * BAMGPU_NENV * nT + (size_t)s * nT + t] = e7[s];
+        }
+    }
+    if (!spag_out) free(spag);
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Sampler: Adaptive_Metro_OAAT (BMSL MCMCStrategy_tools, un-vendored; semantics as declared in
+ * SURVEY.md App. E).  RNG counters: proposal of chain c, iteration it (0-based over the whole run),
+ * component i uses normal(seed, c, it, 2i) and uniform(seed, c, it, 2i+1).
+ * ------------------------------------------------------------------------------------------ */
+int oracle_fit(const oracle_t* o, int K, const double* start, const double* start_std, int nAdapt, int nCycles,
+               double MinMoveRate, double MaxMoveRate, double DownMult, double UpMult, uint64_t seed, int burn,
+               int keep_every, double* out_rows, int64_t* n_keep, double* final_x, double* final_std, char* mess) {
+    int P = o->P, nD = o->nDpar;
+    int64_t nIter = (int64_t)nAdapt * nCycles;
+    if (keep_every < 1) keep_every = 1;
+    int64_t nKeep = (nIter > burn) ? (nIter - burn) / keep_every : 0;
+    if (n_keep) *n_keep = nKeep;
+    int rowlen = P + 1 + nD;
+    int err = 0;
+    for (int c = 0; c < K && !err; ++c) {
+        double* x = (double*)malloc((size_t)P * 8);
+        double* cand = (double*)malloc((size_t)P * 8);
+        double* sd = (double*)malloc((size_t)P * 8);
+        double* dpar = (double*)malloc(((size_t)nD + 1) * 8);
+        double* dcand = (double*)malloc(((size_t)nD + 1) * 8);
+        int* moves = (int*)calloc(P, sizeof(int));
+        memcpy(x, start + (size_t)c * P, (size_t)P * 8);
+        memcpy(sd, start_std + (size_t)c * P, (size_t)P * 8);
+        double fx, fc;
+        int32_t feas, isnull;
+        oracle_logpost(o, x, &fx, NULL, NULL, NULL, &feas, &isnull, dpar, 0, mess);
+        if (!feas || isnull) { setmess(mess, "oracle: Adaptive_Metro_OAAT: unfeasible starting point"); err = 1; }
+        int64_t it = 0, kept = 0;
+        for (int cyc = 0; cyc < nCycles && !err; ++cyc) {
+            memset(moves, 0, (size_t)P * sizeof(int));
+            for (int a = 0; a < nAdapt; ++a, ++it) {
+                for (int i = 0; i < P; ++i) {
+                    memcpy(cand, x, (size_t)P * 8);
+                    cand[i] = x[i] + sd[i] * oracle_normal(seed, (uint64_t)c, (uint32_t)it, (uint32_t)(2 * i));
+                    oracle_logpost(o, cand, &fc, NULL, NULL, NULL, &feas, &isnull, dcand, 0, mess);
+                    if (feas && !isnull) {
+                        double u = oracle_uniform(seed, (uint64_t)c, (uint32_t)it, (uint32_t)(2 * i + 1));
+                        if (log(u) < fc - fx) {
+                            x[i] = cand[i]; fx = fc; memcpy(dpar, dcand, (size_t)nD * 8); moves[i]++;
+                        }
+                    }
+                }
+                int64_t it1 = it + 1;
+                if (out_rows && it1 > burn && (it1 - burn) % keep_every == 0 && kept < nKeep) {
+                    double* row = out_rows + ((size_t)c * nKeep + kept) * rowlen;
+                    memcpy(row, x, (size_t)P * 8);
+                    row[P] = fx;
+                    memcpy(row + P + 1, dpar, (size_t)nD * 8);
+                    ++kept;
+                }
+            }
+            for (int i = 0; i < P; ++i) {
+                double rate = (double)moves[i] / (double)nAdapt;
+                if (rate <= MinMoveRate) sd[i] *= DownMult;
+                if (rate >= MaxMoveRate) sd[i] *= UpMult;
+            }
+        }
+        if (final_x) memcpy(final_x + (size_t)c * P, x, (size_t)P * 8);
+        if (final_std) memcpy(final_std + (size_t)c * P, sd, (size_t)P * 8);
+        free(x); free(cand); free(sd); free(dpar); free(dcand); free(moves);
+    }
+    return err;
+}
