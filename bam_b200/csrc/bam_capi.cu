@@ -1,0 +1,437 @@
+// bam_capi.cu -- extern "C" entry points of include/bam_gpu.h.
+#include <cstring>
+#include <string>
+
+#include "bam_handle.h"
+
+namespace {
+
+void setmess(char* mess, const std::string& s) {
+    if (!mess) return;
+    strncpy(mess, s.c_str(), BAMGPU_MESS_LEN - 1);
+    mess[BAMGPU_MESS_LEN - 1] = 0;
+}
+
+template <class T>
+T* upload(bamgpu_handle* h, const T* src, size_t count) {
+    if (count == 0) return nullptr;
+    T* d = nullptr;
+    BAM_CUDA(cudaMalloc(&d, sizeof(T) * count));
+    h->owned.push_back(d);
+    BAM_CUDA(cudaMemcpy(d, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+    return d;
+}
+
+template <class F>
+int guarded(char* mess, F&& f) {
+    if (mess) mess[0] = 0;
+    try {
+        return f();
+    } catch (const bam::CudaError& e) {
+        setmess(mess, e.what);
+        return 1;
+    } catch (const std::exception& e) {
+        setmess(mess, e.what());
+        return 1;
+    }
+}
+
+void ensure_sampler_capacity(bamgpu_handle* h, int K, long long nKeep, bool rows) {
+    const DevProblem& p = h->dp;
+    auto re = [&](auto*& ptr, size_t bytes) {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        BAM_CUDA(cudaMalloc(&ptr, bytes ? bytes : 8));
+    };
+    const size_t KP = (size_t)K * p.P;
+    re(h->d_std, KP * 8); re(h->d_fxcur, (size_t)K * 8); re(h->d_dparcur, (size_t)K * std::max(p.nDpar, 1) * 8);
+    re(h->d_moves, KP * 4); re(h->d_mcount, (size_t)K * 8); re(h->d_mmean, KP * 8); re(h->d_mm2, KP * 8);
+    if (rows) {
+        const size_t need = (size_t)K * nKeep * (p.P + 1 + p.nDpar);
+        if (need > h->rowsCap) { re(h->d_rows, need * 8); h->rowsCap = need; }
+    }
+}
+
+void free_prediction(bamgpu_handle* h) {
+    auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(h->d_mc); fr(h->d_mode); fr(h->d_ptab); fr(h->d_pstatus); fr(h->d_xspagPtrs); fr(h->d_nspag);
+    for (auto& q : h->d_xspag) if (q) cudaFree(q);
+    h->d_xspag.clear();
+    h->predNspag.clear();
+    h->predNrep = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bamgpu_version(void) { return "bam_b200 0.1 (sm_100a)"; }
+
+int bamgpu_dist_id(const char* name) { return bam::dist_from_name(name); }
+int bamgpu_dist_npar(int dist) { return bam::dist_npar(dist); }
+int bamgpu_sigmafunc_id(const char* name) { return bam::sigmafunc_from_name(name); }
+int bamgpu_sigmafunc_npar(int f) { return bam::sigmafunc_npar(f); }
+int bamgpu_model_id(const char* name) { return bam::model_from_name(name); }
+
+int bamgpu_prior_corr_to_M(int k, const double* C, double* M, char* mess) {
+    std::string m;
+    int e = bam::prior_corr_to_M(k, C, M, m);
+    setmess(mess, m);
+    return e;
+}
+
+int bamgpu_rhat(int K, int P, const double* count, const double* mean, const double* m2, double* rhat, char* mess) {
+    if (mess) mess[0] = 0;
+    bam::rhat_from_moments(K, P, count, mean, m2, rhat);
+    return 0;
+}
+
+int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* mess) {
+    *out = nullptr;
+    return guarded(mess, [&]() -> int {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw bam::CudaError{"bamgpu_create: no CUDA device available (this library has no CPU path)"};
+        if (device < 0 || device >= ndev) throw bam::CudaError{"bamgpu_create: invalid device ordinal"};
+        auto* h = new bamgpu_handle();
+        std::string m;
+        int e = bam::build_layout(*pb, h->L, m);
+        if (e) { setmess(mess, m); delete h; return e; }
+        const bam::HostLayout& L = h->L;
+        if (L.nX > BAM_MAXX || L.nY > BAM_MAXY || L.ntheta > BAM_MAXTHETA || L.nGamma > BAM_MAXGAMMA ||
+            (pb->priorM && L.nFit + L.nGamma > BAM_MAXCOPULA) || L.vmMaxStack > BAM_VMSTACK) {
+            delete h;
+            throw bam::CudaError{"bamgpu_create: problem exceeds the compiled limits (nX,nY<=8, ntheta<=40, copula<=96)"};
+        }
+        h->device = device;
+        BAM_CUDA(cudaSetDevice(device));
+        BAM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        BAM_CUDA(cudaEventCreate(&h->ev0));
+        BAM_CUDA(cudaEventCreate(&h->ev1));
+
+        DevProblem& d = h->dp;
+        memset(&d, 0, sizeof d);
+        d.model = L.model; d.n = L.n; d.nX = L.nX; d.nY = L.nY; d.ntheta = L.ntheta;
+        d.nFit = L.nFit; d.nGamma = L.nGamma; d.nLatent = L.nLatent; d.P = L.P; d.nCombo = L.nCombo;
+        d.nDparModel = L.nDparModel; d.nDpar = L.nDpar;
+        d.nDer = L.nDparModel;
+        // table layout
+        d.tabGamma = 0;
+        d.tabXb = L.nGamma;
+        d.tabYb = d.tabXb + L.nXbTot;
+        d.tabCombo = d.tabYb + L.nYbTot;
+        d.comboStride = L.ntheta + d.nDer;
+        d.tabStride = d.tabCombo + L.nCombo * d.comboStride;
+        const size_t sx = (size_t)L.n * L.nX, sy = (size_t)L.n * L.nY;
+        d.X = upload(h, pb->X, sx); d.Xu = upload(h, pb->Xu, sx); d.Xb = upload(h, pb->Xb, sx);
+        d.Xbindx = upload(h, pb->Xbindx, sx);
+        d.Y = upload(h, pb->Y, sy); d.Yu = upload(h, pb->Yu, sy); d.Yb = upload(h, pb->Yb, sy);
+        d.Ybindx = upload(h, pb->Ybindx, sy);
+        d.comboOf = upload(h, L.comboOf.data(), L.comboOf.size());
+        d.comboSrc = upload(h, L.comboSrc.data(), L.comboSrc.size());
+        d.latIdx = L.hasLatent ? upload(h, L.latIdx.data(), L.latIdx.size()) : nullptr;
+        for (int i = 0; i < L.ntheta; ++i) d.fixv[i] = L.fixv[i];
+        d.hasLatent = L.hasLatent; d.hasXbias = L.hasXbias; d.hasYbias = L.hasYbias;
+        d.hyperInfeasible = L.hyperInfeasible; d.hasMissing = L.hasMissing;
+        int txb = d.tabXb, tyb = d.tabYb;
+        for (int j = 0; j < L.nX; ++j) {
+            d.Xerror[j] = L.Xerror[j]; d.nXb[j] = L.nXb[j]; d.offXb[j] = L.offXb[j]; d.tabOffXb[j] = txb; txb += L.nXb[j];
+        }
+        for (int j = 0; j < L.nY; ++j) {
+            d.nYb[j] = L.nYb[j]; d.offYb[j] = L.offYb[j]; d.tabOffYb[j] = tyb; tyb += L.nYb[j];
+            d.sigfunc[j] = L.sigfunc[j]; d.nrem[j] = L.nrem[j]; d.gamOff[j] = L.gamOff[j];
+        }
+        d.ptDist = upload(h, pb->prior_theta_dist, (size_t)L.nFit);
+        d.ptPar = upload(h, pb->prior_theta_par, (size_t)L.nFit * BAMGPU_PRIOR_NPAR);
+        d.pgDist = upload(h, pb->prior_gamma_dist, (size_t)L.nGamma);
+        d.pgPar = upload(h, pb->prior_gamma_par, (size_t)L.nGamma * BAMGPU_PRIOR_NPAR);
+        d.kM = L.nFit + L.nGamma;
+        d.priorM = pb->priorM ? upload(h, pb->priorM, (size_t)d.kM * d.kM) : nullptr;
+        d.mv = pb->mv; d.unfeas = pb->unfeas_flag;
+        d.ncontrol = L.ncontrol; d.ctrlMask = L.ctrlMask;
+        d.sedFormula = L.sed[0]; d.sedCss = L.sed[1]; d.sedCo = L.sed[2];
+        for (int i = 0; i < 4; ++i) { d.sedPpo[i] = L.sed[3 + i]; d.sedPseudo[i] = L.sedPseudo[i]; }
+        if (L.model == BAMGPU_MDL_TEXTFILE) {
+            d.vmCode = upload(h, L.vmCode.data(), L.vmCode.size());
+            d.vmImmed = upload(h, L.vmImmed.data(), L.vmImmed.size());
+            for (int k = 0; k < L.nY; ++k) { d.vmNcode[k] = L.vmNcode[k]; d.vmCodeOff[k] = L.vmCodeOff[k]; d.vmImmedOff[k] = L.vmImmedOff[k]; }
+            d.vmNin = L.nX; d.vmNpar = L.ntheta;
+        }
+        *out = h;
+        return 0;
+    });
+}
+
+void bamgpu_destroy(bamgpu_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->owned) cudaFree(p);
+    auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(h->d_x); fr(h->d_tab); fr(h->d_part); fr(h->d_prior); fr(h->d_lkh); fr(h->d_hyper); fr(h->d_fx); fr(h->d_dpar);
+    fr(h->d_status); fr(h->d_delta); fr(h->d_std); fr(h->d_fxcur); fr(h->d_dparcur); fr(h->d_moves); fr(h->d_mcount);
+    fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_env);
+    free_prediction(h);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s) {
+    const bam::HostLayout& L = h->L;
+    s->nFit = L.nFit; s->nGamma = L.nGamma; s->nLatent = L.nLatent; s->nXbias = L.nXbTot; s->nYbias = L.nYbTot;
+    s->nInfer = L.P; s->nDpar = L.nDpar; s->nCombo = L.nCombo; s->nState = L.nState;
+    return 0;
+}
+
+int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset) {
+    h->chainOffset = offset;
+    return 0;
+}
+
+// ---- log-posterior -------------------------------------------------------------------------------
+
+int bamgpu_chains_upload(bamgpu_t* h, int K, const double* x, char* mess) {
+    return guarded(mess, [&]() -> int {
+        if (K < 1) throw bam::CudaError{"bamgpu: K must be >= 1"};
+        BAM_CUDA(cudaSetDevice(h->device));
+        bam::ensure_chain_capacity(h, K);
+        h->K = K;
+        BAM_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)K * h->dp.P, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    });
+}
+
+int bamgpu_logpost_resident(bamgpu_t* h, char* mess) {
+    return guarded(mess, [&]() -> int {
+        if (h->K < 1) throw bam::CudaError{"bamgpu: no resident chains (call bamgpu_chains_upload first)"};
+        BAM_CUDA(cudaSetDevice(h->device));
+        bam::launch_logpost(h, h->K, h->d_x, -1, nullptr, true);
+        return 0;
+    });
+}
+
+int bamgpu_sync(bamgpu_t* h, char* mess) {
+    return guarded(mess, [&]() -> int {
+        BAM_CUDA(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        if (cudaEventQuery(h->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->lastMs = ms;
+        cudaGetLastError();
+        return 0;
+    });
+}
+
+static void download_flags(bamgpu_t* h, int K, int32_t* feas, int32_t* isnull) {
+    std::vector<int> st(K);
+    BAM_CUDA(cudaMemcpyAsync(st.data(), h->d_status, sizeof(int) * K, cudaMemcpyDeviceToHost, h->stream));
+    BAM_CUDA(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < K; ++k) {
+        // priority of the reference's early exits: prior (infeasible | null) -> likelihood -> hyper
+        const int s = st[k];
+        int f = 1, z = 0;
+        if (s & ST_PRIOR_INFEAS) f = 0;
+        else if (s & ST_PRIOR_NULL) z = 1;
+        else if (s & (ST_LKH_INFEAS | ST_HYPER_INFEAS)) f = 0;
+        if (feas) feas[k] = f;
+        if (isnull) isnull[k] = z;
+    }
+}
+
+int bamgpu_chains_download(bamgpu_t* h, double* fx, int32_t* feas, int32_t* isnull, double* dpar, char* mess) {
+    return guarded(mess, [&]() -> int {
+        const int K = h->K;
+        BAM_CUDA(cudaSetDevice(h->device));
+        if (fx) BAM_CUDA(cudaMemcpyAsync(fx, h->d_fx, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+        if (dpar && h->dp.nDpar > 0)
+            BAM_CUDA(cudaMemcpyAsync(dpar, h->d_dpar, sizeof(double) * (size_t)K * h->dp.nDpar, cudaMemcpyDeviceToHost, h->stream));
+        download_flags(h, K, feas, isnull);
+        return 0;
+    });
+}
+
+int bamgpu_logpost(bamgpu_t* h, int K, const double* x, double* fx, int32_t* feas, int32_t* isnull, double* dpar,
+                   char* mess) {
+    int e = bamgpu_chains_upload(h, K, x, mess);
+    if (e) return e;
+    e = bamgpu_logpost_resident(h, mess);
+    if (e) return e;
+    return bamgpu_chains_download(h, fx, feas, isnull, dpar, mess);
+}
+
+int bamgpu_logpost_parts(bamgpu_t* h, int K, const double* x, double* prior, double* lkh, double* hyper, int32_t* feas,
+                         int32_t* isnull, char* mess) {
+    int e = bamgpu_chains_upload(h, K, x, mess);
+    if (e) return e;
+    e = bamgpu_logpost_resident(h, mess);
+    if (e) return e;
+    return guarded(mess, [&]() -> int {
+        if (prior) BAM_CUDA(cudaMemcpyAsync(prior, h->d_prior, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+        if (lkh) BAM_CUDA(cudaMemcpyAsync(lkh, h->d_lkh, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+        if (hyper) BAM_CUDA(cudaMemcpyAsync(hyper, h->d_hyper, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+        download_flags(h, K, feas, isnull);
+        return 0;
+    });
+}
+
+// ---- sampler ----------------------------------------------------------------------------------------
+
+int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std, int nAdapt, int nCycles,
+               double MinMoveRate, double MaxMoveRate, double DownMult, double UpMult, uint64_t seed, int burn,
+               int keep_every, double* out_rows, int64_t* n_keep, char* mess) {
+    int e = bamgpu_chains_upload(h, K, start, mess);
+    if (e) return e;
+    return guarded(mess, [&]() -> int {
+        if (nAdapt < 1 || nCycles < 1) throw bam::CudaError{"Config_Read_MCMC: nAdapt and nCycles must be >= 1"};
+        if (keep_every < 1) keep_every = 1;
+        if (burn < 0) burn = 0;
+        const long long nIter = (long long)nAdapt * nCycles;
+        const long long nKeep = nIter > burn ? (nIter - burn) / keep_every : 0;
+        if (n_keep) *n_keep = nKeep;
+        ensure_sampler_capacity(h, K, nKeep, out_rows != nullptr);
+        BAM_CUDA(cudaMemcpyAsync(h->d_std, start_std, sizeof(double) * (size_t)K * h->dp.P, cudaMemcpyHostToDevice, h->stream));
+        bam::launch_fit(h, K, nAdapt, nCycles, MinMoveRate, MaxMoveRate, DownMult, UpMult, seed, burn, keep_every,
+                        out_rows != nullptr, nKeep);
+        if (out_rows && nKeep > 0)
+            BAM_CUDA(cudaMemcpyAsync(out_rows, h->d_rows, sizeof(double) * (size_t)K * nKeep * (h->dp.P + 1 + h->dp.nDpar),
+                                     cudaMemcpyDeviceToHost, h->stream));
+        BAM_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    });
+}
+
+int bamgpu_moments(bamgpu_t* h, double* count, double* mean, double* m2, int dev_ptrs, char* mess) {
+    return guarded(mess, [&]() -> int {
+        if (!h->haveMoments) throw bam::CudaError{"bamgpu_moments: run bamgpu_fit first"};
+        const size_t K = h->K, KP = K * h->dp.P;
+        const cudaMemcpyKind kind = dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        BAM_CUDA(cudaMemcpyAsync(count, h->d_mcount, K * 8, kind, h->stream));
+        BAM_CUDA(cudaMemcpyAsync(mean, h->d_mmean, KP * 8, kind, h->stream));
+        BAM_CUDA(cudaMemcpyAsync(m2, h->d_mm2, KP * 8, kind, h->stream));
+        BAM_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    });
+}
+
+// ---- prediction ---------------------------------------------------------------------------------------
+
+int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                          const double* const* xspag, const int32_t* nspag, char* mess) {
+    return guarded(mess, [&]() -> int {
+        BAM_CUDA(cudaSetDevice(h->device));
+        if (Nrep < 1 || nobs_pred < 1) throw bam::CudaError{"BaM_Prediction: empty prediction"};
+        free_prediction(h);
+        const DevProblem& p = h->dp;
+        h->predNrep = Nrep; h->predNobs = nobs_pred;
+        if (mc) {
+            BAM_CUDA(cudaMalloc(&h->d_mc, sizeof(double) * (size_t)Nrep * p.P));
+            BAM_CUDA(cudaMemcpyAsync(h->d_mc, mc, sizeof(double) * (size_t)Nrep * p.P, cudaMemcpyHostToDevice, h->stream));
+        }
+        if (mode) {
+            BAM_CUDA(cudaMalloc(&h->d_mode, sizeof(double) * std::max(p.P, 1)));
+            BAM_CUDA(cudaMemcpyAsync(h->d_mode, mode, sizeof(double) * p.P, cudaMemcpyHostToDevice, h->stream));
+        }
+        std::vector<double*> ptrs(p.nX);
+        for (int i = 0; i < p.nX; ++i) {
+            if (nspag[i] < 1) throw bam::CudaError{"BaM_ReadSpag: nspag must be >= 1"};
+            double* d = nullptr;
+            const size_t cnt = (size_t)nobs_pred * nspag[i];
+            BAM_CUDA(cudaMalloc(&d, sizeof(double) * cnt));
+            BAM_CUDA(cudaMemcpyAsync(d, xspag[i], sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+            h->d_xspag.push_back(d);
+            h->predNspag.push_back(nspag[i]);
+            ptrs[i] = d;
+        }
+        BAM_CUDA(cudaMalloc(&h->d_xspagPtrs, sizeof(double*) * p.nX));
+        BAM_CUDA(cudaMemcpyAsync(h->d_xspagPtrs, ptrs.data(), sizeof(double*) * p.nX, cudaMemcpyHostToDevice, h->stream));
+        BAM_CUDA(cudaMalloc(&h->d_nspag, sizeof(int) * p.nX));
+        BAM_CUDA(cudaMemcpyAsync(h->d_nspag, nspag, sizeof(int) * p.nX, cudaMemcpyHostToDevice, h->stream));
+        BAM_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    });
+}
+
+int bamgpu_predict_resident(bamgpu_t* h, int doParametric, const int32_t* doRemnant, uint64_t seed, int t0, int t1,
+                            char* mess) {
+    return guarded(mess, [&]() -> int {
+        BAM_CUDA(cudaSetDevice(h->device));
+        if (h->predNrep < 1) throw bam::CudaError{"bamgpu_predict_resident: call bamgpu_predict_upload first"};
+        if (t0 < 0 || t1 > h->predNobs || t0 >= t1) throw bam::CudaError{"bamgpu_predict: bad input range [t0,t1)"};
+        bam::launch_predict(h, doParametric, doRemnant, seed, t0, t1, nullptr);
+        return 0;
+    });
+}
+
+int bamgpu_predict_download(bamgpu_t* h, double* env, char* mess) {
+    return guarded(mess, [&]() -> int {
+        const size_t cnt = (size_t)(h->predT1 - h->predT0) * BAMGPU_NENV * h->dp.nY;
+        if (h->predNrep >= 2)
+            BAM_CUDA(cudaMemcpyAsync(env, h->d_env, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        BAM_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    });
+}
+
+int bamgpu_predict(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                   const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
+                   uint64_t seed, int t0, int t1, double* env, double* spag, char* mess) {
+    int e = bamgpu_predict_upload(h, Nrep, mc, mode, nobs_pred, xspag, nspag, mess);
+    if (e) return e;
+    e = guarded(mess, [&]() -> int {
+        if (t0 < 0 || t1 > nobs_pred || t0 >= t1) throw bam::CudaError{"bamgpu_predict: bad input range [t0,t1)"};
+        bam::launch_predict(h, doParametric, doRemnant, seed, t0, t1, spag);
+        return 0;
+    });
+    if (e) return e;
+    if (env) return bamgpu_predict_download(h, env, mess);
+    return bamgpu_sync(h, mess);
+}
+
+// ---- measurement --------------------------------------------------------------------------------------
+
+int64_t bamgpu_launch_count(const bamgpu_t* h) { return h->launches; }
+double bamgpu_last_kernel_ms(const bamgpu_t* h) { return h->lastMs; }
+
+int bamgpu_pin(void* ptr, size_t bytes) { return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1; }
+int bamgpu_unpin(void* ptr) { return cudaHostUnregister(ptr) == cudaSuccess ? 0 : 1; }
+
+}  // extern "C"
+
+// ---- FP64 peak micro-benchmark: register-resident independent DFMA chains ---------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int bamgpu_fp64_peak(int device, double* tflops, char* mess) {
+    return guarded(mess, [&]() -> int {
+        BAM_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        BAM_CUDA(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 8192;
+        double* d = nullptr;
+        BAM_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)blocks * threads));
+        cudaEvent_t e0, e1;
+        BAM_CUDA(cudaEventCreate(&e0));
+        BAM_CUDA(cudaEventCreate(&e1));
+        double best = 0.0;
+        for (int rep = 0; rep < 5; ++rep) {
+            BAM_CUDA(cudaEventRecord(e0));
+            dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+            BAM_CUDA(cudaEventRecord(e1));
+            BAM_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            BAM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            const double fl = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+        *tflops = best;
+        return 0;
+    });
+}

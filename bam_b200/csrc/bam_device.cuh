@@ -1,0 +1,215 @@
+// bam_device.cuh -- device-side problem description and math shared by all kernels.
+//
+// DevProblem is the HBM-resident, immutable image of the reference's INFER + MODEL globals
+// (src/BaM_tools.f90:73-101; ModelLibrary_tools.f90:114-126).  It is passed BY VALUE to every
+// kernel (a few hundred bytes of kernel-parameter space); the big tables it points to are
+// column-major exactly as Fortran holds them, so a warp reading 32 consecutive observations
+// of one variable issues one 256-byte coalesced request.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bam_gpu.h"
+
+#define BAM_MAXX 8
+#define BAM_MAXY 8
+#define BAM_MAXTHETA 40
+#define BAM_MAXCTRL 8
+#define BAM_MAXGAMMA 24
+#define BAM_MAXCOPULA 96
+#define BAM_VMSTACK 24
+
+// chain status bits (priority order of the reference's early exits, GetPostLogPdf :3310-3382)
+#define ST_PRIOR_INFEAS 1
+#define ST_PRIOR_NULL 2
+#define ST_LKH_INFEAS 4
+#define ST_HYPER_INFEAS 8
+
+struct DevProblem {
+    int model;
+    int n, nX, nY, ntheta;
+    int nFit, nGamma, nLatent, P, nCombo, nDparModel, nDpar;
+    // per-chain table row: [gamma | xbias | ybias | nCombo x (ntheta full theta + nDer derived)]
+    int tabStride, tabGamma, tabXb, tabYb, tabCombo, comboStride, nDer;
+    const double *X, *Xu, *Xb, *Y, *Yu, *Yb;
+    const int *Xbindx, *Ybindx;
+    const int* comboOf;   // n : VAR-combination id of each observation
+    const int* comboSrc;  // nCombo x ntheta : position in the parameter vector, or -1 for FIX
+    const int* latIdx;    // n x nX : position of the latent "true input" in the vector, or -1
+    double fixv[BAM_MAXTHETA];
+    int hasLatent, hasXbias, hasYbias, hyperInfeasible, hasMissing;
+    int Xerror[BAM_MAXX], nXb[BAM_MAXX], offXb[BAM_MAXX], tabOffXb[BAM_MAXX];
+    int nYb[BAM_MAXY], offYb[BAM_MAXY], tabOffYb[BAM_MAXY];
+    int sigfunc[BAM_MAXY], nrem[BAM_MAXY], gamOff[BAM_MAXY];
+    const int *ptDist, *pgDist;
+    const double *ptPar, *pgPar;
+    const double* priorM;
+    int kM;
+    double mv, unfeas;
+    // BaRatin
+    int ncontrol;
+    unsigned long long ctrlMask;  // bit (r*8+c) = ControlMatrix(r+1,c+1)
+    // Sediment
+    int sedFormula, sedCss, sedCo, sedPpo[4];
+    double sedPseudo[4];
+    // TextFile
+    const int* vmCode;
+    const double* vmImmed;
+    int vmNcode[BAM_MAXY], vmCodeOff[BAM_MAXY], vmImmedOff[BAM_MAXY], vmNin, vmNpar;
+};
+
+#define BAM_LOG_SQRT_2PI 0.91893853320467274178
+
+// ---------------------------------------------------------------------------------------------
+// distributions (BMSL Distribution_tools; conventions declared in SURVEY.md App. E / DESIGN.md)
+// ---------------------------------------------------------------------------------------------
+
+// log N(x; mu, s) ; the caller guarantees s > 0
+__device__ __forceinline__ double gauss_logpdf(double x, double mu, double s) {
+    double z = (x - mu) / s;
+    return -BAM_LOG_SQRT_2PI - log(s) - 0.5 * z * z;
+}
+
+// returns 0 OK; sets feas/isnull like BMSL GetPdf(loga=.true.)
+__device__ inline void dist_logpdf(int dist, const double* __restrict__ par, double x, double& lp, bool& feas,
+                                   bool& isnull) {
+    feas = true;
+    isnull = false;
+    lp = BAMGPU_UNDEF_RN;
+    switch (dist) {
+        case BAMGPU_DIST_GAUSSIAN: {
+            double s = par[1];
+            if (!(s > 0.0)) { feas = false; return; }
+            lp = gauss_logpdf(x, par[0], s);
+            return;
+        }
+        case BAMGPU_DIST_UNIFORM: {
+            double a = par[0], b = par[1];
+            if (!(b > a)) { feas = false; return; }
+            if (x < a || x > b) { isnull = true; return; }
+            lp = -log(b - a);
+            return;
+        }
+        case BAMGPU_DIST_TRIANGLE: {
+            double pk = par[0], a = par[1], b = par[2];
+            if (!(b > a) || pk < a || pk > b) { feas = false; return; }
+            if (x < a || x > b) { isnull = true; return; }
+            double d;
+            if (x <= pk) d = (pk > a) ? 2.0 * (x - a) / ((b - a) * (pk - a)) : 2.0 / (b - a);
+            else d = (b > pk) ? 2.0 * (b - x) / ((b - a) * (b - pk)) : 2.0 / (b - a);
+            if (!(d > 0.0)) { isnull = true; return; }
+            lp = log(d);
+            return;
+        }
+        case BAMGPU_DIST_LOGNORMAL: {
+            double s = par[1];
+            if (!(s > 0.0)) { feas = false; return; }
+            if (!(x > 0.0)) { isnull = true; return; }
+            double lx = log(x);
+            double z = (lx - par[0]) / s;
+            lp = -BAM_LOG_SQRT_2PI - log(s) - lx - 0.5 * z * z;
+            return;
+        }
+        case BAMGPU_DIST_EXPONENTIAL: {
+            double sc = par[1];
+            if (!(sc > 0.0)) { feas = false; return; }
+            if (x < par[0]) { isnull = true; return; }
+            lp = -log(sc) - (x - par[0]) / sc;
+            return;
+        }
+        case BAMGPU_DIST_FLATPRIOR: lp = 0.0; return;
+        case BAMGPU_DIST_FLATPRIOR_POS:
+            if (x > 0.0) lp = 0.0; else isnull = true;
+            return;
+        case BAMGPU_DIST_FLATPRIOR_NEG:
+            if (x < 0.0) lp = 0.0; else isnull = true;
+            return;
+        default: feas = false; return;
+    }
+}
+
+__device__ inline void dist_cdf(int dist, const double* __restrict__ par, double x, double& u, bool& feas) {
+    feas = true;
+    u = 0.0;
+    switch (dist) {
+        case BAMGPU_DIST_GAUSSIAN:
+            if (!(par[1] > 0.0)) { feas = false; return; }
+            u = normcdf((x - par[0]) / par[1]);
+            return;
+        case BAMGPU_DIST_UNIFORM:
+            if (!(par[1] > par[0])) { feas = false; return; }
+            if (x <= par[0]) u = 0.0;
+            else if (x >= par[1]) u = 1.0;
+            else u = (x - par[0]) / (par[1] - par[0]);
+            return;
+        case BAMGPU_DIST_TRIANGLE: {
+            double pk = par[0], a = par[1], b = par[2];
+            if (!(b > a) || pk < a || pk > b) { feas = false; return; }
+            if (x <= a) u = 0.0;
+            else if (x >= b) u = 1.0;
+            else if (x <= pk) u = (x - a) * (x - a) / ((b - a) * (pk - a));
+            else u = 1.0 - (b - x) * (b - x) / ((b - a) * (b - pk));
+            return;
+        }
+        case BAMGPU_DIST_LOGNORMAL:
+            if (!(par[1] > 0.0)) { feas = false; return; }
+            if (!(x > 0.0)) u = 0.0;
+            else u = normcdf((log(x) - par[0]) / par[1]);
+            return;
+        case BAMGPU_DIST_EXPONENTIAL:
+            if (!(par[1] > 0.0)) { feas = false; return; }
+            if (x <= par[0]) u = 0.0;
+            else u = 1.0 - exp(-(x - par[0]) / par[1]);
+            return;
+        default: feas = false; return;
+    }
+}
+
+// Sigmafunk_Apply, src/BaM_tools.f90:3521-3571
+__device__ __forceinline__ double sigmafunk(int funk, const double* par, double Y) {
+    double ay = fabs(Y);
+    switch (funk) {
+        case BAMGPU_SIG_CONSTANT: return par[0];
+        case BAMGPU_SIG_LINEAR: return fma(par[1], ay, par[0]);
+        case BAMGPU_SIG_PROPORTIONAL: return par[0] * ay;
+        case BAMGPU_SIG_POWER: return par[0] + par[1] * pow(ay, par[2]);
+        case BAMGPU_SIG_EXPONENTIAL: return par[0] + (par[2] - par[0]) * (1.0 - exp(-(ay / par[1])));
+        default: {  // Gaussian
+            double r = ay / par[1];
+            return par[0] + (par[2] - par[0]) * (1.0 - exp(-(r * r)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller.  Same specification as the oracle (oracle/bam_oracle.c), written
+// independently: counter = (a_lo, a_hi, b, c), key = (seed_lo, seed_hi).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                              uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t a, uint32_t b, uint32_t c) {
+    uint32_t c0 = (uint32_t)a, c1 = (uint32_t)(a >> 32), c2 = b, c3 = c;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return u53(c0, c1);
+}
+
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t a, uint32_t b, uint32_t c) {
+    uint32_t c0 = (uint32_t)a, c1 = (uint32_t)(a >> 32), c2 = b, c3 = c;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    double u1 = u53(c0, c1), u2 = u53(c2, c3);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}

@@ -1,0 +1,91 @@
+// bam_handle.h -- the opaque bamgpu_t: one GPU-resident problem + its chain / prediction workspaces.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "bam_device.cuh"
+#include "bam_host.h"
+
+#define BAM_BLOCK 256
+
+struct LogpostPlan {
+    int TX = 256, TY = 1;  // block = TX observation lanes x TY chain rows
+    int CT = 32;           // chains per block tile
+    int nTiles = 0;        // observation tiles
+    size_t smem = 0;
+};
+
+struct bamgpu_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bam::HostLayout L;
+    DevProblem dp;
+    std::vector<void*> owned;  // device allocations that live as long as the handle
+
+    // ---- chain workspace (capacity Kcap vectors) ----
+    int Kcap = 0, K = 0;
+    double* d_x = nullptr;      // P x K (vector k at k*P)
+    double* d_tab = nullptr;    // tabStride x K
+    double* d_part = nullptr;   // 2 x K x nTiles
+    double *d_prior = nullptr, *d_lkh = nullptr, *d_hyper = nullptr, *d_fx = nullptr, *d_dpar = nullptr;
+    int* d_status = nullptr;
+    LogpostPlan plan;
+    long long chainOffset = 0;  // global index of local chain 0 (multi-GPU sharding; RNG streams)
+
+    // ---- sampler state ----
+    double *d_std = nullptr, *d_delta = nullptr, *d_fxcur = nullptr, *d_dparcur = nullptr;
+    int* d_moves = nullptr;
+    double *d_mcount = nullptr, *d_mmean = nullptr, *d_mm2 = nullptr;  // per-chain running moments
+    double* d_rows = nullptr;
+    size_t rowsCap = 0;
+    bool haveMoments = false;
+
+    // ---- prediction workspace ----
+    long long predNrep = 0;
+    int predNobs = 0;
+    double *d_mc = nullptr, *d_mode = nullptr;
+    std::vector<double*> d_xspag;
+    std::vector<int> predNspag;
+    double** d_xspagPtrs = nullptr;
+    int* d_nspag = nullptr;
+    double* d_ptab = nullptr;  // per-replication parameter table
+    int* d_pstatus = nullptr;
+    double* d_V = nullptr;     // materialised spaghetti tile: Nrep x tileT per output
+    size_t vCap = 0;
+    double* d_env = nullptr;   // nT x 7 x nY of the last resident prediction
+    int predT0 = 0, predT1 = 0;
+    size_t envCap = 0;
+
+    // ---- measurement ----
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double lastMs = 0.0;
+    long long launches = 0;
+};
+
+// internal entry points shared between translation units
+namespace bam {
+
+struct CudaError {
+    std::string what;
+};
+#define BAM_CUDA(call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            throw bam::CudaError{std::string(#call) + ": " + cudaGetErrorString(e_)};                   \
+    } while (0)
+
+void ensure_chain_capacity(bamgpu_handle* h, int K);
+// evaluate K vectors at d_x (optionally with component `comp` of every vector shifted by d_delta[k]);
+// results in d_prior/d_lkh/d_hyper/d_fx/d_status/d_dpar.  Asynchronous on h->stream.
+void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain);
+
+void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, double maxMR, double downMult,
+                double upMult, unsigned long long seed, int burn, int keepEvery, bool storeRows, long long nKeep);
+
+void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, unsigned long long seed, int t0, int t1,
+                    double* h_spag /* host, may be null */);
+
+}  // namespace bam

@@ -1,0 +1,545 @@
+// bam_host.cpp -- host-side layout derivation and the TextFile formula compiler.
+#include "bam_host.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+
+namespace bam {
+
+// ------------------------------------------------------------------------------------------------
+// catalogues
+// ------------------------------------------------------------------------------------------------
+int model_from_name(const char* name) {
+    if (!name) return 0;
+    std::string s(name);
+    if (s.rfind("MDL_", 0) == 0) s = s.substr(4);
+    if (s == "Linear") return BAMGPU_MDL_LINEAR;
+    if (s == "BaRatin") return BAMGPU_MDL_BARATIN;
+    if (s == "Sediment") return BAMGPU_MDL_SEDIMENT;
+    if (s == "TextFile") return BAMGPU_MDL_TEXTFILE;
+    if (s == "Vegetation") return BAMGPU_MDL_VEGETATION;
+    return 0;
+}
+
+int dist_from_name(const char* name) {
+    if (!name) return 0;
+    static const struct { const char* n; int id; } tab[] = {
+        {"Gaussian", BAMGPU_DIST_GAUSSIAN},   {"Uniform", BAMGPU_DIST_UNIFORM},
+        {"Triangle", BAMGPU_DIST_TRIANGLE},   {"LogNormal", BAMGPU_DIST_LOGNORMAL},
+        {"Exponential", BAMGPU_DIST_EXPONENTIAL}, {"FlatPrior", BAMGPU_DIST_FLATPRIOR},
+        {"FlatPrior+", BAMGPU_DIST_FLATPRIOR_POS}, {"FlatPrior-", BAMGPU_DIST_FLATPRIOR_NEG}};
+    for (auto& t : tab)
+        if (!strcmp(name, t.n)) return t.id;
+    return 0;
+}
+
+int dist_npar(int d) {
+    switch (d) {
+        case BAMGPU_DIST_GAUSSIAN: case BAMGPU_DIST_UNIFORM: case BAMGPU_DIST_LOGNORMAL: case BAMGPU_DIST_EXPONENTIAL: return 2;
+        case BAMGPU_DIST_TRIANGLE: return 3;
+        case BAMGPU_DIST_FLATPRIOR: case BAMGPU_DIST_FLATPRIOR_POS: case BAMGPU_DIST_FLATPRIOR_NEG: return 0;
+    }
+    return -1;
+}
+
+int sigmafunc_from_name(const char* name) {
+    if (!name) return 0;
+    static const char* names[] = {"Constant", "Linear", "Proportional", "Power", "Exponential", "Gaussian"};
+    for (int i = 0; i < 6; ++i)
+        if (!strcmp(name, names[i])) return i + 1;
+    return 0;
+}
+
+int sigmafunc_npar(int f) {  // Sigmafunk_GetParNumber, src/BaM_tools.f90:3575-3620
+    static const int np[] = {-1, 1, 2, 1, 3, 3, 3};
+    return (f >= 1 && f <= 6) ? np[f] : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TextFile formula compiler.  Semantics of R. Schmehl's fparser as modified in the reference
+// (TextFile_model.f90:644-738): split at the RIGHT-MOST base-level binary occurrence of the
+// lowest-priority operator, testing operators in the order + - * / ^.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+enum Op { IMMED = 1, NEG, ADD, SUB, MUL, DIV, POW, ABS_, EXP_, LOG10_, LOG_, SQRT_, SINH_, COSH_, TANH_, SIN_, COS_,
+          TAN_, ASIN_, ACOS_, ATAN_, IS0, ISPOS, ISNEG, ISSPOS, ISSNEG, VARBEGIN };
+
+const char* kFuncs[] = {"abs", "exp", "log10", "log", "sqrt", "sinh", "cosh", "tanh", "sin", "cos", "tan", "asin",
+                        "acos", "atan", "is0", "ispos", "isneg", "isspos", "issneg"};
+const char kOps[] = {'+', '-', '*', '/', '^'};
+
+struct Compiler {
+    std::string F;
+    const std::vector<std::string>& vars;
+    VmProgram out;
+    int sp = 0;
+
+    Compiler(const std::string& f, const std::vector<std::string>& v) : F(f), vars(v) {}
+
+    static bool in(char c, const char* set) { return c && strchr(set, c) != nullptr; }
+
+    int funcAt(int b, int e) const {  // catalogue entry that prefixes F[b..e] (case-insensitive)
+        for (int j = 0; j < 19; ++j) {
+            int k = (int)strlen(kFuncs[j]);
+            if (k > e - b + 1) continue;
+            bool ok = true;
+            for (int q = 0; q < k && ok; ++q) ok = std::tolower((unsigned char)F[b + q]) == kFuncs[j][q];
+            if (ok) return ABS_ + j;
+        }
+        return 0;
+    }
+
+    bool enclosed(int b, int e) const {
+        if (b > e || F[b] != '(' || F[e] != ')') return false;
+        int depth = 0;
+        for (int j = b + 1; j < e; ++j) {
+            if (F[j] == '(') ++depth;
+            else if (F[j] == ')') --depth;
+            if (depth < 0) break;
+        }
+        return depth == 0;
+    }
+
+    bool binaryAt(int j) const {
+        char c = F[j];
+        if (c != '+' && c != '-') return true;
+        if (j == 0) return false;
+        if (in(F[j - 1], "+-*/^(")) return false;
+        if (j + 1 < (int)F.size() && std::isdigit((unsigned char)F[j + 1]) && in(F[j - 1], "eEdD")) {
+            bool digit = false, point = false;
+            int k = j - 1;
+            while (k > 0) {
+                --k;
+                if (std::isdigit((unsigned char)F[k])) digit = true;
+                else if (F[k] == '.') {
+                    if (point) break;
+                    point = true;
+                } else break;
+            }
+            if (digit && (k == 0 || in(F[k], "+-*/^("))) return false;
+        }
+        return true;
+    }
+
+    void byte(int b) { out.code.push_back(b); }
+
+    double number(int b, int e) {  // [nnn][.nnn][e|E|d|D[+|-]nnn]
+        int i = b;
+        bool mant = false, expo = false;
+        while (i <= e && (std::isdigit((unsigned char)F[i]) || F[i] == '.')) { mant |= std::isdigit((unsigned char)F[i]) != 0; ++i; }
+        if (i <= e && in(F[i], "eEdD")) {
+            int s = i + 1;
+            if (s <= e && (F[s] == '+' || F[s] == '-')) ++s;
+            int q = s;
+            while (q <= e && std::isdigit((unsigned char)F[q])) { expo = true; ++q; }
+            if (!expo) throw std::runtime_error("Syntax error");
+            i = q;
+        }
+        if (!mant) throw std::runtime_error("Syntax error");
+        std::string t = F.substr(b, i - b);
+        for (auto& ch : t)
+            if (ch == 'd' || ch == 'D') ch = 'e';
+        return strtod(t.c_str(), nullptr);
+    }
+
+    int variable(int b, int e) const {
+        int i = b;
+        while (i <= e && !in(F[i], "+-*/^) ")) ++i;
+        std::string name = F.substr(b, i - b);
+        for (size_t j = 0; j < vars.size(); ++j)
+            if (vars[j] == name) return (int)j + 1;
+        return 0;
+    }
+
+    void emit(int b, int e) {
+        if (b > e) throw std::runtime_error("Syntax error");
+        if (F[b] == '+') return emit(b + 1, e);
+        if (enclosed(b, e)) return emit(b + 1, e - 1);
+        if (std::isalpha((unsigned char)F[b])) {
+            int fn = funcAt(b, e);
+            if (fn) {
+                size_t par = F.find('(', b);
+                if (par != std::string::npos && (int)par <= e && enclosed((int)par, e)) {
+                    emit((int)par + 1, e - 1);
+                    byte(fn);
+                    return;
+                }
+            }
+        } else if (F[b] == '-') {
+            if (enclosed(b + 1, e)) {
+                emit(b + 2, e - 1);
+                byte(NEG);
+                return;
+            }
+            if (b + 1 <= e && std::isalpha((unsigned char)F[b + 1])) {
+                int fn = funcAt(b + 1, e);
+                if (fn) {
+                    size_t par = F.find('(', b + 1);
+                    if (par != std::string::npos && (int)par <= e && enclosed((int)par, e)) {
+                        emit((int)par + 1, e - 1);
+                        byte(fn);
+                        byte(NEG);
+                        return;
+                    }
+                }
+            }
+        }
+        for (int io = 0; io < 5; ++io) {
+            int depth = 0;
+            for (int j = e; j >= b; --j) {
+                if (F[j] == ')') ++depth;
+                else if (F[j] == '(') --depth;
+                if (depth == 0 && F[j] == kOps[io] && binaryAt(j)) {
+                    if (io >= 2 && F[b] == '-') {
+                        emit(b + 1, e);
+                        byte(NEG);
+                        return;
+                    }
+                    emit(b, j - 1);
+                    emit(j + 1, e);
+                    byte(ADD + io);
+                    --sp;
+                    return;
+                }
+            }
+        }
+        int b2 = (F[b] == '-') ? b + 1 : b;
+        if (b2 > e) throw std::runtime_error("Syntax error");
+        if (std::isdigit((unsigned char)F[b2]) || F[b2] == '.') {
+            out.immed.push_back(number(b2, e));
+            byte(IMMED);
+        } else {
+            int v = variable(b2, e);
+            if (!v) throw std::runtime_error("Syntax error");
+            byte(VARBEGIN + v - 1);
+        }
+        ++sp;
+        if (sp > out.stackSize) out.stackSize = sp;
+        if (b2 > b) byte(NEG);
+    }
+};
+
+std::vector<std::string> list_items(const std::string& line) {  // one list-directed record
+    std::vector<std::string> out;
+    size_t i = 0, n = line.size();
+    while (i < n) {
+        char c = line[i];
+        if (c == ' ' || c == '\t' || c == ',' || c == '\r') { ++i; continue; }
+        if (c == '!') break;
+        if (c == '"' || c == '\'') {
+            size_t j = line.find(c, i + 1);
+            if (j == std::string::npos) j = n;
+            out.push_back(line.substr(i + 1, j - i - 1));
+            i = j + 1;
+        } else {
+            size_t j = i;
+            while (j < n && !strchr(" \t,\r!", line[j])) ++j;
+            out.push_back(line.substr(i, j - i));
+            i = j;
+        }
+    }
+    return out;
+}
+
+}  // namespace
+
+VmProgram compile_formula(const std::string& formula, const std::vector<std::string>& vars) {
+    std::string f;
+    for (size_t i = 0; i < formula.size(); ++i) {
+        char c = formula[i];
+        if (c == '*' && i + 1 < formula.size() && formula[i + 1] == '*') { f.push_back('^'); ++i; continue; }
+        if (c == ' ' || c == '\t' || c == '\r' || c == '\n') continue;
+        f.push_back(c);
+    }
+    if (f.empty()) throw std::runtime_error("Syntax error");
+    int depth = 0;
+    for (char c : f) {
+        if (c == '(') ++depth;
+        if (c == ')') --depth;
+        if (depth < 0) throw std::runtime_error("Syntax error");
+    }
+    if (depth != 0) throw std::runtime_error("Syntax error");
+    Compiler c(f, vars);
+    c.emit(0, (int)f.size() - 1);
+    return c.out;
+}
+
+TextFileModel parse_textfile_model(const std::string& text) {
+    TextFileModel m;
+    std::istringstream is(text);
+    std::string line;
+    auto need = [&](std::string& l) {
+        if (!std::getline(is, l)) throw std::runtime_error("TxtMdl_load:problem reading model text");
+    };
+    need(line);
+    int nIN = atoi(line.c_str());
+    if (nIN < 0) throw std::runtime_error("TxtMdl_load:negative nIN not allowed");
+    need(line);
+    if (nIN > 0) {
+        auto it = list_items(line);
+        if ((int)it.size() < nIN) throw std::runtime_error("TxtMdl_load:problem reading model text");
+        m.inNames.assign(it.begin(), it.begin() + nIN);
+    }
+    need(line);
+    int nPAR = atoi(line.c_str());
+    if (nPAR < 0) throw std::runtime_error("TxtMdl_load:negative nPAR not allowed");
+    need(line);
+    if (nPAR > 0) {
+        auto it = list_items(line);
+        if ((int)it.size() < nPAR) throw std::runtime_error("TxtMdl_load:problem reading model text");
+        m.parNames.assign(it.begin(), it.begin() + nPAR);
+    }
+    need(line);
+    int nOUT = atoi(line.c_str());
+    if (nOUT <= 0) throw std::runtime_error("TxtMdl_load:nOUT should be at least one");
+    std::vector<std::string> vars = m.inNames;
+    vars.insert(vars.end(), m.parNames.begin(), m.parNames.end());
+    for (int k = 0; k < nOUT; ++k) {
+        need(line);
+        size_t ex = line.find('!');
+        if (ex != std::string::npos) line = line.substr(0, ex);
+        m.formulas.push_back(line);
+        m.progs.push_back(compile_formula(line, vars));
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------
+int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
+    L = HostLayout();
+    L.model = model_from_name(p.model_id);
+    if (!L.model) { mess = "ApplyModel: Fatal: Unavailable [model%ID]"; return 1; }
+    if (L.model == BAMGPU_MDL_VEGETATION) { mess = "bamgpu: model Vegetation is recognised but not built yet (see DESIGN.md)"; return 1; }
+    const int n = L.n = p.nobs, nX = L.nX = p.nX, nY = L.nY = p.nY, nt = L.ntheta = p.ntheta;
+    if (n < 0 || nX < 1 || nY < 1 || nt < 0) { mess = "LoadBamObjects: size mismatch in input data"; return 1; }
+    if (n > 0 && (!p.X || !p.Xu || !p.Xb || !p.Xbindx || !p.Y || !p.Yu || !p.Yb || !p.Ybindx)) {
+        mess = "LoadBamObjects: NULL data array"; return 1;
+    }
+    L.partype.assign(p.partype, p.partype + nt);
+    L.nval.assign(p.nval, p.nval + nt);
+    L.fixv.assign(p.fix_value, p.fix_value + nt);
+    L.thetaOff.assign(nt, -1);
+    for (int i = 0; i < nt; ++i) {
+        if (L.partype[i] == BAMGPU_PAR_FIX) continue;
+        if (L.partype[i] != BAMGPU_PAR_STD && L.partype[i] != BAMGPU_PAR_VAR) { mess = "Config_Finalize: STOK parameters not implemented yet"; return 1; }
+        if (L.nval[i] < 1) { mess = "Config_Finalize: nval < 1"; return 1; }
+        L.thetaOff[i] = L.nFit;
+        L.nFit += L.nval[i];
+        if (L.partype[i] == BAMGPU_PAR_VAR) ++L.nVar;
+    }
+    if (L.nVar && !p.var_indx) { mess = "Config_Finalize: VAR parameter without index series"; return 1; }
+    L.sigfunc.assign(p.sigma_func, p.sigma_func + nY);
+    L.nrem.assign(p.nremnant, p.nremnant + nY);
+    L.gamOff.assign(nY, 0);
+    for (int j = 0; j < nY; ++j) {
+        if (sigmafunc_npar(L.sigfunc[j]) < 0) { mess = "Sigmafunk_Apply: unknown remnant sigma function"; return 1; }
+        if (sigmafunc_npar(L.sigfunc[j]) != L.nrem[j]) { mess = "Config_Read_RemnantSigma: wrong number of parameters for the sigma function"; return 1; }
+        L.gamOff[j] = L.nGamma;
+        L.nGamma += L.nrem[j];
+    }
+    for (int k = 0; k < L.nFit; ++k)
+        if (dist_npar(p.prior_theta_dist[k]) < 0) { mess = "GetLogPrior: unknown prior distribution"; return 1; }
+    for (int k = 0; k < L.nGamma; ++k)
+        if (dist_npar(p.prior_gamma_dist[k]) < 0) { mess = "GetLogPrior: unknown prior distribution"; return 1; }
+
+    // latent inputs and biases (:230-253); vector layout = Packer (:4202-4242)
+    L.Xerror.assign(nX, 0); L.nXb.assign(nX, 0); L.nYb.assign(nY, 0); L.offXb.assign(nX, 0); L.offYb.assign(nY, 0);
+    L.latIdx.assign((size_t)n * nX, -1);
+    int pos = L.nFit + L.nGamma;
+    for (int j = 0; j < nX; ++j)
+        for (int i = 0; i < n; ++i) {
+            size_t q = i + (size_t)j * n;
+            double xu = p.Xu[q];
+            if (xu > 0.0) { L.latIdx[q] = pos++; ++L.nLatent; L.Xerror[j] = 1; }
+        }
+    for (int j = 0; j < nX; ++j)  // a negative Xu in an error-affected column makes GetHyperLogPdf infeasible (:3288-3300)
+        if (L.Xerror[j])
+            for (int i = 0; i < n; ++i)
+                if (p.Xu[i + (size_t)j * n] < 0.0) L.hyperInfeasible = true;
+    L.hasLatent = L.nLatent > 0;
+    for (int j = 0; j < nX; ++j) {
+        int mx = 0;
+        for (int i = 0; i < n; ++i) mx = std::max(mx, (int)p.Xbindx[i + (size_t)j * n]);
+        L.nXb[j] = mx; L.offXb[j] = pos; pos += mx; L.nXbTot += mx;
+    }
+    for (int j = 0; j < nY; ++j) {
+        int mx = 0;
+        for (int i = 0; i < n; ++i) mx = std::max(mx, (int)p.Ybindx[i + (size_t)j * n]);
+        L.nYb[j] = mx; L.offYb[j] = pos; pos += mx; L.nYbTot += mx;
+    }
+    L.hasXbias = L.nXbTot > 0;
+    L.hasYbias = L.nYbTot > 0;
+    L.P = pos;
+    for (size_t q = 0; q < (size_t)n * nY; ++q)
+        if (p.Y[q] == p.mv) { L.hasMissing = true; break; }
+
+    // model xtra (XtraRead / XtraSetup, ModelLibrary_tools.f90:436-760)
+    switch (L.model) {
+        case BAMGPU_MDL_LINEAR:
+            if (nt != nX * nY) { mess = "LM_Apply: size mismatch [theta]"; return 1; }
+            break;
+        case BAMGPU_MDL_BARATIN: {
+            int nc = nt / 3;
+            if (nX != 1 || nY != 1 || nc < 1 || nt != 3 * nc || p.n_xtra_i != nc * nc) { mess = "BaRatin_Apply:Fatal:Incorrect size [theta]"; return 1; }
+            if (nc > 8) { mess = "bamgpu: BaRatin supports at most 8 controls"; return 1; }
+            L.ncontrol = nc;
+            auto M = [&](int r, int c) { return p.xtra_i[r + c * nc]; };
+            // CheckControlMatrix, BaRatin_model.f90:254-322
+            for (int r = 0; r < nc; ++r)
+                for (int c = 0; c < nc; ++c) {
+                    if (M(r, c) != 0 && M(r, c) != 1) { mess = "BaRatin_XtraRead:invalid control matrix"; return 1; }
+                    if (c > r && M(r, c) > 0) { mess = "BaRatin_XtraRead:invalid control matrix"; return 1; }
+                    if (M(r, c)) L.ctrlMask |= 1ull << (r * 8 + c);
+                }
+            for (int r = 1; r < nc; ++r) {
+                int act = 0;
+                for (int c = 0; c < nc; ++c) act += (M(r, c) - M(r - 1, c) > 0);
+                if (act != 1) { mess = "BaRatin_XtraRead:invalid control matrix"; return 1; }
+            }
+            for (int r = 0; r < nc; ++r)
+                if (M(r, r) != 1) { mess = "BaRatin_XtraRead:invalid control matrix"; return 1; }
+            L.nDparModel = nc;
+            break;
+        }
+        case BAMGPU_MDL_SEDIMENT: {
+            if (p.n_xtra_i != 7 || p.n_xtra_d != 4 || nY != 1) { mess = "Sediment_XtraRead:problem reading xtra"; return 1; }
+            for (int i = 0; i < 7; ++i) L.sed[i] = p.xtra_i[i];
+            for (int i = 0; i < 4; ++i) L.sedPseudo[i] = p.xtra_d[i];
+            if (L.sed[0] < 1 || L.sed[0] > 4) { mess = "Sediment_Apply:Fatal:Unavailable [ID]"; return 1; }
+            if (L.sed[1] < 1 || L.sed[1] > 3) { mess = "CSS_Apply:Fatal:Unavailable [ID]"; return 1; }
+            if (L.sed[2] < 1 || L.sed[2] > 2) { mess = "GetAllpar:Fatal:Unavailable [CO]"; return 1; }
+            int np = ((L.sed[0] == BAMGPU_SED_MPM || L.sed[0] == BAMGPU_SED_NIELSEN) ? 2 : 3) + (L.sed[1] == BAMGPU_CSS_CONSTANT ? 1 : 0);
+            int nin = 2;
+            for (int i = 0; i < 4; ++i) {
+                if (L.sed[3 + i] < 1 || L.sed[3 + i] > 3) { mess = "GetAllpar:Fatal:Unavailable [PPO]"; return 1; }
+                if (L.sed[3 + i] == BAMGPU_PPO_PAR) ++np;
+                if (L.sed[3 + i] == BAMGPU_PPO_IN) ++nin;
+            }
+            if (L.sed[1] != BAMGPU_CSS_CONSTANT && L.sed[2] == BAMGPU_CO_PAR) np += (L.sed[1] == BAMGPU_CSS_SOULSBY ? 4 : 3);
+            if (np != nt || nin != nX) { mess = "Sediment_Apply: wrong size [theta] or [IN]"; return 1; }
+            break;
+        }
+        case BAMGPU_MDL_TEXTFILE: {
+            if (!p.xtra_text) { mess = "TxtMdl_load:problem opening file"; return 1; }
+            try {
+                L.txt = parse_textfile_model(p.xtra_text);
+            } catch (const std::exception& e) {
+                mess = std::string("TxtMdl_define:") + e.what();
+                return 5;
+            }
+            if ((int)L.txt.inNames.size() != nX || (int)L.txt.parNames.size() != nt || (int)L.txt.progs.size() != nY) {
+                mess = "TxtMdl_Apply: size mismatch between the model text and nX/nPar/nY"; return 1;
+            }
+            for (auto& pr : L.txt.progs) {
+                L.vmCodeOff.push_back((int)L.vmCode.size());
+                L.vmImmedOff.push_back((int)L.vmImmed.size());
+                L.vmNcode.push_back((int)pr.code.size());
+                L.vmCode.insert(L.vmCode.end(), pr.code.begin(), pr.code.end());
+                L.vmImmed.insert(L.vmImmed.end(), pr.immed.begin(), pr.immed.end());
+                L.vmMaxStack = std::max(L.vmMaxStack, pr.stackSize);
+            }
+            break;
+        }
+    }
+
+    // VAR combinations in order of first appearance (:346-379); L(t,i) = offset_i + indx_i(t) (:326-334)
+    L.comboOf.assign(n, 0);
+    L.comboRow.clear();
+    std::vector<int32_t> key(nt, 1);
+    std::vector<std::vector<int32_t>> combos;
+    if (L.nVar == 0 || n == 0) {
+        combos.push_back(std::vector<int32_t>(nt, 1));
+        L.comboRow.push_back(0);
+    } else {
+        for (int t = 0; t < n; ++t) {
+            for (int i = 0; i < nt; ++i) {
+                key[i] = (L.partype[i] == BAMGPU_PAR_VAR) ? p.var_indx[t + (size_t)i * n] : 1;
+                if (key[i] < 1 || key[i] > L.nval[i]) { mess = "Config_Finalize: index of a VAR parameter out of [1,nval]"; return 1; }
+            }
+            int found = -1;
+            for (size_t k = 0; k < combos.size() && found < 0; ++k)
+                if (combos[k] == key) found = (int)k;
+            if (found < 0) { found = (int)combos.size(); combos.push_back(key); L.comboRow.push_back(t); }
+            L.comboOf[t] = found;
+        }
+    }
+    L.nCombo = (int)combos.size();
+    L.comboSrc.assign((size_t)L.nCombo * nt, -1);
+    for (int k = 0; k < L.nCombo; ++k)
+        for (int i = 0; i < nt; ++i)
+            if (L.partype[i] != BAMGPU_PAR_FIX) L.comboSrc[(size_t)k * nt + i] = L.thetaOff[i] + combos[k][i] - 1;
+    L.nDpar = L.nDparModel * L.nCombo;
+    mess.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small dense helpers
+// ------------------------------------------------------------------------------------------------
+int prior_corr_to_M(int k, const double* C, double* M, std::string& mess) {
+    for (int i = 0; i < k; ++i)
+        if (C[i + (size_t)i * k] != 1.0) { mess = "LoadBamObjects: diagonal terms of the prior correlation matrix should be equal to 1"; return 1; }
+    // Cholesky C = L L^T (lower), then C^-1 = L^-T L^-1
+    std::vector<double> Lm((size_t)k * k, 0.0), Li((size_t)k * k, 0.0);
+    for (int j = 0; j < k; ++j) {
+        double d = C[j + (size_t)j * k];
+        for (int q = 0; q < j; ++q) d -= Lm[j + (size_t)q * k] * Lm[j + (size_t)q * k];
+        if (!(d > 0.0)) { mess = "LoadBamObjects: prior correlation matrix is not positive definite"; return 1; }
+        Lm[j + (size_t)j * k] = sqrt(d);
+        for (int i = j + 1; i < k; ++i) {
+            double s = C[i + (size_t)j * k];
+            for (int q = 0; q < j; ++q) s -= Lm[i + (size_t)q * k] * Lm[j + (size_t)q * k];
+            Lm[i + (size_t)j * k] = s / Lm[j + (size_t)j * k];
+        }
+    }
+    for (int c = 0; c < k; ++c) {  // Li = L^-1 by forward substitution
+        for (int r = c; r < k; ++r) {
+            double s = (r == c) ? 1.0 : 0.0;
+            for (int q = c; q < r; ++q) s -= Lm[r + (size_t)q * k] * Li[q + (size_t)c * k];
+            Li[r + (size_t)c * k] = s / Lm[r + (size_t)r * k];
+        }
+    }
+    for (int r = 0; r < k; ++r)
+        for (int c = 0; c < k; ++c) {
+            double s = 0.0;
+            for (int q = std::max(r, c); q < k; ++q) s += Li[q + (size_t)r * k] * Li[q + (size_t)c * k];
+            M[r + (size_t)c * k] = s - (r == c ? 1.0 : 0.0);
+        }
+    return 0;
+}
+
+void rhat_from_moments(int K, int P, const double* count, const double* mean, const double* m2, double* rhat) {
+    // Gelman & Rubin (1992): W = mean within-chain variance, B/n = variance of chain means
+    for (int j = 0; j < P; ++j) {
+        double nbar = 0.0, gm = 0.0, W = 0.0;
+        int used = 0;
+        for (int c = 0; c < K; ++c) {
+            if (count[c] < 2.0) continue;
+            ++used;
+            nbar += count[c];
+            gm += mean[(size_t)c * P + j];
+            W += m2[(size_t)c * P + j] / (count[c] - 1.0);
+        }
+        if (used < 2) { rhat[j] = NAN; continue; }
+        nbar /= used; gm /= used; W /= used;
+        double Bn = 0.0;
+        for (int c = 0; c < K; ++c) {
+            if (count[c] < 2.0) continue;
+            double d = mean[(size_t)c * P + j] - gm;
+            Bn += d * d;
+        }
+        Bn /= (used - 1);
+        double varplus = (nbar - 1.0) / nbar * W + Bn;
+        rhat[j] = (W > 0.0) ? sqrt(varplus / W) : NAN;
+    }
+}
+
+}  // namespace bam

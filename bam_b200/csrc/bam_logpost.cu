@@ -1,0 +1,369 @@
+// bam_logpost.cu -- batched log-posterior for K parameter vectors x all observations.
+//
+// Replaces Posterior_wrapper -> UnfoldParVector -> GetPostLogPdf -> {GetPriorLogPdf, GetLogLikelihood
+// (ApplyModel_BaM + Sigmafunk_Apply + GetPdf per term), GetHyperLogPdf} (src/BaM_tools.f90:3006-3517,
+// 4115-4177) with three kernels:
+//
+//   K2 logpost_prep     one thread per vector: priors (+ Gaussian copula, bias priors) in the reference's
+//                       sequential order with its early exits; expands theta for every VAR combination
+//                       (FIX filled in) and runs the per-parameter-set model pre-pass (BaRatin continuity)
+//                       ONCE per combination instead of once per observation; writes the per-chain table.
+//   K1 logpost_main     grid = (observation tiles) x (chain tiles).  A thread owns one observation: its
+//                       X/Y/Yu/... live in registers and are re-used for every chain of the tile, so the
+//                       observation tables are read from HBM once per chain tile (24-28 B per observation
+//                       shared by CT chains).  The chain tile's tables are staged in shared memory; all
+//                       lanes of a warp read the same entry (broadcast).  Model + sigma function +
+//                       Gaussian log-pdf (+ hyper term of latent inputs) are fused; a warp-shuffle tree
+//                       and a fixed-order cross-warp sum give one partial per (tile, chain):
+//                       deterministic, no atomics on doubles.
+//   K1b logpost_final   one thread per vector: sums the tile partials in fixed order, applies the
+//                       early-exit priority prior -> likelihood -> hyper, writes fx / flags.
+#include <algorithm>
+#include <cstdio>
+
+#include "bam_handle.h"
+#include "bam_models.cuh"
+
+namespace {
+
+// value q of vector c, with the optional single-component candidate shift
+__device__ __forceinline__ double xval(const double* __restrict__ x, size_t base, int q, int comp, double dl) {
+    double v = x[base + q];
+    return (q == comp) ? v + dl : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: prior + per-chain table
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* __restrict__ x, int K, int comp,
+                                                    const double* __restrict__ delta, double* __restrict__ tab,
+                                                    double* __restrict__ prior_out, int* __restrict__ status,
+                                                    double* __restrict__ dpar) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    const size_t base = (size_t)c * p.P;
+    const double dl = (comp >= 0) ? delta[c] : 0.0;
+    int st = 0;
+    double prior = 0.0, lp;
+    bool feas = true, isnull = false;
+
+    // GetPriorLogPdf (:3006-3138): remnant parameters first, then theta
+    for (int j = 0; j < p.nY && !st; ++j) {
+        double s = 0.0;
+        for (int m = 0; m < p.nrem[j]; ++m) {
+            const int g = p.gamOff[j] + m;
+            dist_logpdf(p.pgDist[g], p.pgPar + (size_t)g * BAMGPU_PRIOR_NPAR, xval(x, base, p.nFit + g, comp, dl), lp,
+                        feas, isnull);
+            if (!feas) { st = ST_PRIOR_INFEAS; break; }
+            if (isnull) { st = ST_PRIOR_NULL; break; }
+            s = s + lp;
+        }
+        prior = prior + s;
+    }
+    if (!st) {
+        double s = 0.0;
+        for (int k = 0; k < p.nFit; ++k) {
+            dist_logpdf(p.ptDist[k], p.ptPar + (size_t)k * BAMGPU_PRIOR_NPAR, xval(x, base, k, comp, dl), lp, feas,
+                        isnull);
+            if (!feas) { st = ST_PRIOR_INFEAS; break; }
+            if (isnull) { st = ST_PRIOR_NULL; break; }
+            s = s + lp;
+        }
+        prior = prior + s;
+    }
+    if (!st && p.priorM != nullptr) {  // Gaussian copula (:3080-3112), v = qnorm(cdf(x)) (Gcop_getV :4246)
+        double v[BAM_MAXCOPULA];
+        const int k = p.kM;
+        for (int i = 0; i < k && !st; ++i) {
+            double u;
+            bool f;
+            if (i < p.nFit) dist_cdf(p.ptDist[i], p.ptPar + (size_t)i * BAMGPU_PRIOR_NPAR, xval(x, base, i, comp, dl), u, f);
+            else dist_cdf(p.pgDist[i - p.nFit], p.pgPar + (size_t)(i - p.nFit) * BAMGPU_PRIOR_NPAR,
+                          xval(x, base, i, comp, dl), u, f);
+            if (!f || !(u > 0.0 && u < 1.0)) { st = ST_PRIOR_INFEAS; break; }
+            v[i] = normcdfinv(u);
+        }
+        if (!st) {
+            double q = 0.0;
+            for (int cc = 0; cc < k; ++cc) {
+                double w = 0.0;
+                for (int r = 0; r < k; ++r) w = w + v[r] * p.priorM[r + (size_t)cc * k];
+                q = q + w * v[cc];
+            }
+            prior = prior - 0.5 * q;
+        }
+    }
+    if (!st) {  // N(0,1) priors of the input / output biases (:3116-3135)
+        for (int j = 0; j < p.nX; ++j)
+            for (int i = 0; i < p.nXb[j]; ++i) prior = prior + gauss_logpdf(xval(x, base, p.offXb[j] + i, comp, dl), 0.0, 1.0);
+        for (int j = 0; j < p.nY; ++j)
+            for (int i = 0; i < p.nYb[j]; ++i) prior = prior + gauss_logpdf(xval(x, base, p.offYb[j] + i, comp, dl), 0.0, 1.0);
+    }
+
+    // per-chain table
+    double* row = tab + (size_t)c * p.tabStride;
+    for (int g = 0; g < p.nGamma; ++g) row[p.tabGamma + g] = xval(x, base, p.nFit + g, comp, dl);
+    for (int j = 0; j < p.nX; ++j)
+        for (int i = 0; i < p.nXb[j]; ++i) row[p.tabOffXb[j] + i] = xval(x, base, p.offXb[j] + i, comp, dl);
+    for (int j = 0; j < p.nY; ++j)
+        for (int i = 0; i < p.nYb[j]; ++i) row[p.tabOffYb[j] + i] = xval(x, base, p.offYb[j] + i, comp, dl);
+    double th[BAM_MAXTHETA], der[BAM_MAXCTRL];
+    for (int k = 0; k < p.nCombo; ++k) {  // ApplyModel_BaM theta expansion (:4133-4159), once per combination
+        double* cr = row + p.tabCombo + (size_t)k * p.comboStride;
+        for (int i = 0; i < p.ntheta; ++i) {
+            const int src = p.comboSrc[(size_t)k * p.ntheta + i];
+            th[i] = (src < 0) ? p.fixv[i] : xval(x, base, src, comp, dl);
+            cr[i] = th[i];
+        }
+        for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
+        const bool ok = model_prepare(p, th, der);
+        if (!ok) st |= ST_LKH_INFEAS;
+        for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
+        if (dpar != nullptr)
+            for (int d = 0; d < p.nDparModel; ++d) dpar[(size_t)c * p.nDpar + k * p.nDparModel + d] = ok ? der[d] : p.unfeas;
+    }
+    prior_out[c] = prior;
+    status[c] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: fused model + likelihood (+ hyper)
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NX, int NY>
+__global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const double* __restrict__ x, int K, int CT, int TX,
+                                                          const double* __restrict__ tab, const int* status,
+                                                          double* __restrict__ part, int* statusOut, int comp,
+                                                          const double* __restrict__ delta) {
+    extern __shared__ double sm[];
+    const int tabStride = p.tabStride;
+    double* stab = sm;                        // CT x tabStride
+    const int warpsPerRow = TX >> 5;
+    double* red = sm + (size_t)CT * tabStride;  // [2][warpsPerRow][CT]
+    int* sst = (int*)(red + 2 * warpsPerRow * CT);  // CT chain status
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX, TY = BAM_BLOCK / TX;
+    const int lane = tid & 31, wrow = tx >> 5;
+    const int c0 = blockIdx.y * CT;
+    const int nc = min(CT, K - c0);
+    for (int idx = tid; idx < nc * tabStride; idx += BAM_BLOCK) stab[idx] = tab[(size_t)c0 * tabStride + idx];
+    for (int idx = tid; idx < nc; idx += BAM_BLOCK) sst[idx] = status[c0 + idx];
+    __syncthreads();
+
+    const int n = p.n;
+    const int i = blockIdx.x * TX + tx;
+    const bool act = i < n;
+    // this thread's observation, kept in registers for all chains of the tile
+    double xo[NX], xu[NX], xb[NX], yo[NY], yu[NY], yb[NY];
+    int xbi[NX], ybi[NY], lat[NX], combo = 0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) { xo[j] = 0; xu[j] = 0; xb[j] = 0; xbi[j] = 0; lat[j] = -1; }
+#pragma unroll
+    for (int j = 0; j < NY; ++j) { yo[j] = 0; yu[j] = 0; yb[j] = 0; ybi[j] = 0; }
+    if (act) {
+        combo = (p.nCombo > 1) ? p.comboOf[i] : 0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            const size_t q = i + (size_t)j * n;
+            xo[j] = p.X[q];
+            if (p.hasLatent) { xu[j] = p.Xu[q]; lat[j] = p.latIdx[q]; }
+            if (p.hasXbias) { xb[j] = p.Xb[q]; xbi[j] = p.Xbindx[q]; }
+        }
+#pragma unroll
+        for (int j = 0; j < NY; ++j) {
+            const size_t q = i + (size_t)j * n;
+            yo[j] = p.Y[q];
+            yu[j] = p.Yu[q];
+            if (p.hasYbias) { yb[j] = p.Yb[q]; ybi[j] = p.Ybindx[q]; }
+        }
+    }
+
+    for (int cc = ty; cc < nc; cc += TY) {
+        const int c = c0 + cc;
+        const double* __restrict__ row = stab + (size_t)cc * tabStride;
+        double lk = 0.0, hy = 0.0;
+        bool bad = false, badh = false;
+        if (act && sst[cc] == 0) {
+            const double dl = (comp >= 0) ? delta[c] : 0.0;
+            // UnfoldParVector (:3429-3452): latent cell from the vector, else un-bias the observed input
+            double xt[NX];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                double v = xo[j];
+                if (p.hasLatent && lat[j] >= 0) {
+                    v = x[(size_t)c * p.P + lat[j]];
+                    if (lat[j] == comp) v += dl;
+                } else if (p.hasXbias && xbi[j] > 0) {
+                    v = xo[j] - xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
+                }
+                xt[j] = v;
+            }
+            const double* __restrict__ th = row + p.tabCombo + (size_t)combo * p.comboStride;
+            double yh[NY];
+            const bool ok = model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh);
+            if (!ok) bad = true;
+            else {
+#pragma unroll
+                for (int j = 0; j < NY; ++j) {  // GetLogLikelihood inner loop (:3204-3227)
+                    if (p.hasMissing && yo[j] == p.mv) continue;
+                    double sig = sigmafunk(p.sigfunc[j], row + p.tabGamma + p.gamOff[j], yh[j]);
+                    if (!(sig > 0.0)) { bad = true; continue; }
+                    sig = sqrt(yu[j] * yu[j] + sig * sig);
+                    double mu = yh[j];
+                    if (p.hasYbias && ybi[j] != 0) mu = yh[j] + yb[j] * row[p.tabOffYb[j] + ybi[j] - 1];
+                    lk += gauss_logpdf(yo[j], mu, sig);
+                }
+                if (p.hasLatent) {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) {  // GetHyperLogPdf (:3285-3303)
+                        if (xu[j] == 0.0) continue;
+                        if (!(xu[j] > 0.0)) { badh = true; continue; }
+                        double mu = xt[j];
+                        if (p.hasXbias && xbi[j] != 0) mu = xt[j] + xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
+                        hy += gauss_logpdf(xo[j], mu, xu[j]);
+                    }
+                }
+            }
+        }
+        // warp tree (fixed order) -> one value per (warp, chain)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lk += __shfl_down_sync(0xffffffffu, lk, off);
+        if (p.hasLatent) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) hy += __shfl_down_sync(0xffffffffu, hy, off);
+        }
+        const unsigned anyBad = __ballot_sync(0xffffffffu, bad), anyBadH = __ballot_sync(0xffffffffu, badh);
+        if (lane == 0) {
+            red[(size_t)wrow * CT + cc] = lk;
+            red[(size_t)(warpsPerRow + wrow) * CT + cc] = hy;
+            if (anyBad | anyBadH) atomicOr(&statusOut[c], (anyBad ? ST_LKH_INFEAS : 0) | (anyBadH ? ST_HYPER_INFEAS : 0));
+        }
+    }
+    __syncthreads();
+    for (int cc = tid; cc < nc; cc += BAM_BLOCK) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < warpsPerRow; ++w) {
+            a += red[(size_t)w * CT + cc];
+            b += red[(size_t)(warpsPerRow + w) * CT + cc];
+        }
+        const size_t o = ((size_t)blockIdx.x * K + (c0 + cc)) * 2;
+        part[o] = a;
+        part[o + 1] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b: final sum + early-exit priority (GetPostLogPdf :3358-3380)
+// ------------------------------------------------------------------------------------------------
+__global__ void logpost_final(DevProblem p, int K, int nTiles, const double* __restrict__ part,
+                              const double* __restrict__ prior, int* __restrict__ status, double* __restrict__ lkh,
+                              double* __restrict__ hyper, double* __restrict__ fx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < nTiles; ++t) {
+        const size_t o = ((size_t)t * K + c) * 2;
+        a += part[o];
+        b += part[o + 1];
+    }
+    int st = status[c];
+    if (p.hyperInfeasible && !(st & (ST_PRIOR_INFEAS | ST_PRIOR_NULL | ST_LKH_INFEAS))) st |= ST_HYPER_INFEAS;
+    status[c] = st;
+    lkh[c] = a;
+    hyper[c] = b;
+    fx[c] = st ? BAMGPU_UNDEF_RN : (prior[c] + a + b);
+}
+
+using MainKernel = void (*)(DevProblem, const double*, int, int, int, const double*, const int*, double*, int*, int,
+                            const double*);
+
+template <int MODEL>
+MainKernel pick_nxny(int nX, int nY) {
+#define PICK(a, b) \
+    if (nX == a && nY == b) return logpost_main<MODEL, a, b>;
+    PICK(1, 1) PICK(2, 1) PICK(3, 1) PICK(4, 1) PICK(1, 2) PICK(2, 2) PICK(3, 2) PICK(4, 2)
+#undef PICK
+    return nullptr;
+}
+
+MainKernel pick_main(int model, int nX, int nY) {
+    switch (model) {
+        case BAMGPU_MDL_BARATIN: return (nX == 1 && nY == 1) ? logpost_main<BAMGPU_MDL_BARATIN, 1, 1> : nullptr;
+        case BAMGPU_MDL_LINEAR: return pick_nxny<BAMGPU_MDL_LINEAR>(nX, nY);
+        case BAMGPU_MDL_TEXTFILE: return pick_nxny<BAMGPU_MDL_TEXTFILE>(nX, nY);
+        case BAMGPU_MDL_SEDIMENT:
+            if (nY != 1) return nullptr;
+            switch (nX) {
+                case 2: return logpost_main<BAMGPU_MDL_SEDIMENT, 2, 1>;
+                case 3: return logpost_main<BAMGPU_MDL_SEDIMENT, 3, 1>;
+                case 4: return logpost_main<BAMGPU_MDL_SEDIMENT, 4, 1>;
+                case 5: return logpost_main<BAMGPU_MDL_SEDIMENT, 5, 1>;
+                case 6: return logpost_main<BAMGPU_MDL_SEDIMENT, 6, 1>;
+            }
+            return nullptr;
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+namespace bam {
+
+static void make_plan(bamgpu_handle* h, int K) {
+    LogpostPlan& pl = h->plan;
+    const int n = std::max(h->L.n, 1);
+    pl.TX = n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32));
+    pl.TY = BAM_BLOCK / pl.TX;
+    pl.nTiles = (n + pl.TX - 1) / pl.TX;
+    const int stride = h->dp.tabStride;
+    // chains per tile: as many as fit in ~40 KB of shared memory, at most 64, a multiple of TY,
+    // but keep at least ~4 blocks per SM in flight when K is small
+    int ct = 64;
+    while (ct > pl.TY && (size_t)ct * stride * 8 > 40 * 1024) ct >>= 1;
+    while (ct > pl.TY && (long long)pl.nTiles * ((K + ct - 1) / ct) < 148 * 4) ct >>= 1;
+    ct = std::max(ct, pl.TY);
+    pl.CT = ct;
+    pl.smem = ((size_t)ct * stride + 2 * (pl.TX / 32) * ct) * 8 + (size_t)ct * 4;
+}
+
+void ensure_chain_capacity(bamgpu_handle* h, int K) {
+    if (K <= h->Kcap) { make_plan(h, K); return; }
+    auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(h->d_x); fr(h->d_tab); fr(h->d_part); fr(h->d_prior); fr(h->d_lkh); fr(h->d_hyper); fr(h->d_fx); fr(h->d_dpar);
+    fr(h->d_status); fr(h->d_delta);
+    const DevProblem& p = h->dp;
+    make_plan(h, K);
+    BAM_CUDA(cudaMalloc(&h->d_x, sizeof(double) * (size_t)K * p.P));
+    BAM_CUDA(cudaMalloc(&h->d_tab, sizeof(double) * (size_t)K * p.tabStride));
+    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * std::max(h->plan.nTiles, 1)));
+    BAM_CUDA(cudaMalloc(&h->d_prior, sizeof(double) * K));
+    BAM_CUDA(cudaMalloc(&h->d_lkh, sizeof(double) * K));
+    BAM_CUDA(cudaMalloc(&h->d_hyper, sizeof(double) * K));
+    BAM_CUDA(cudaMalloc(&h->d_fx, sizeof(double) * K));
+    BAM_CUDA(cudaMalloc(&h->d_dpar, sizeof(double) * (size_t)K * std::max(p.nDpar, 1)));
+    BAM_CUDA(cudaMalloc(&h->d_status, sizeof(int) * K));
+    BAM_CUDA(cudaMalloc(&h->d_delta, sizeof(double) * K));
+    h->Kcap = K;
+}
+
+void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain) {
+    const DevProblem& p = h->dp;
+    const LogpostPlan& pl = h->plan;
+    MainKernel kern = pick_main(p.model, p.nX, p.nY);
+    if (!kern) throw CudaError{"bamgpu: no kernel instantiated for this (model, nX, nY)"};
+    logpost_prep<<<(K + 127) / 128, 128, 0, h->stream>>>(p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status,
+                                                         h->d_dpar);
+    if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
+    if (timeMain) BAM_CUDA(cudaEventRecord(h->ev0, h->stream));
+    if (p.n > 0)
+        kern<<<grid, BAM_BLOCK, pl.smem, h->stream>>>(p, d_x, K, pl.CT, pl.TX, h->d_tab, h->d_status, h->d_part, h->d_status,
+                                                       comp, d_delta);
+    if (timeMain) BAM_CUDA(cudaEventRecord(h->ev1, h->stream));
+    logpost_final<<<(K + 127) / 128, 128, 0, h->stream>>>(p, K, p.n > 0 ? pl.nTiles : 0, h->d_part, h->d_prior, h->d_status,
+                                                          h->d_lkh, h->d_hyper, h->d_fx);
+    h->launches += (p.n > 0) ? 3 : 2;
+    BAM_CUDA(cudaGetLastError());
+}
+
+}  // namespace bam

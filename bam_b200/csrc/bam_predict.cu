@@ -1,0 +1,523 @@
+// bam_predict.cu -- K4: propagation of MCMC samples through the model + streamed envelopes.
+//
+// Replaces the replication loop of BaM_Prediction (src/BaM_tools.f90:1034-1108) and the envelope pass
+// of BaM_ProcessSpag (:1393-1426).  The reference writes every simulated value to a text file, reads
+// the whole file back, and quicksorts each column; here
+//
+//   pred_prep   one thread per replication: theta (from the sample, or the maxpost mode) with FIX
+//               filled in, the per-parameter-set model pre-pass, gamma of the replication -> table.
+//   pred_main   thread <-> replication (its parameters sit in a private shared-memory column, loaded
+//               once), loop over the prediction inputs of the tile (inputs broadcast).  Model, optional
+//               structural-error noise N(0, sigma(gamma, Y)) from a counter-based Philox stream keyed
+//               by (seed, rep, t, y).  Consecutive lanes = consecutive replications, so the stores to
+//               the tile V[t][rep] are coalesced.  Only one tile of inputs is ever materialised.
+//   envelope_*  per prediction input: drop infeasible / NaN values when they are < 75 %, exact
+//               empirical quantiles (0.5, 0.025, 0.975, 0.16, 0.84), mean, standard deviation.
+//               Small Nrep: the column is sorted in shared memory (bitonic).  Large Nrep: exact
+//               selection by multi-level linear histograms over the HBM tile (no full sort).
+#include <algorithm>
+#include <cfloat>
+
+#include "bam_handle.h"
+#include "bam_models.cuh"
+
+namespace {
+
+struct PredArgs {
+    long long Nrep;
+    int nobsPred, t0, nT;       // this tile: inputs [t0, t0+nT)
+    int doParametric;
+    int doRemnant[BAM_MAXY];
+    unsigned long long seed;
+    int stride;                 // doubles per replication in the table: [gamma | full theta | derived]
+};
+
+__global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const double* __restrict__ mc,
+                                                 const double* __restrict__ mode, double* __restrict__ tab,
+                                                 int* __restrict__ status) {
+    const long long rep = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep >= a.Nrep) return;
+    double* row = tab + (size_t)rep * a.stride;
+    // gamma always comes from the sample, even when !doParametric (reference quirk, :1085)
+    for (int g = 0; g < p.nGamma; ++g) row[g] = mc ? mc[rep + (size_t)(p.nFit + g) * a.Nrep] : 0.0;
+    double th[BAM_MAXTHETA], der[BAM_MAXCTRL];
+    for (int i = 0; i < p.ntheta; ++i) {
+        const int src = p.comboSrc[i];
+        if (src < 0) th[i] = p.fixv[i];
+        else th[i] = a.doParametric ? mc[rep + (size_t)src * a.Nrep] : mode[src];
+        row[p.nGamma + i] = th[i];
+    }
+    for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
+    const bool ok = model_prepare(p, th, der);
+    for (int d = 0; d < p.nDer; ++d) row[p.nGamma + p.ntheta + d] = der[d];
+    status[rep] = ok ? 0 : 1;
+}
+
+template <int MODEL, int NX, int NY>
+__global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a, const double* __restrict__ tab,
+                                                       const int* __restrict__ status, double* const* __restrict__ xspag,
+                                                       const int* __restrict__ nspag, double* __restrict__ V) {
+    extern __shared__ double sm[];  // [stride][BAM_BLOCK] : parameter k of thread t at sm[k*BLOCK + t]
+    const int tid = threadIdx.x;
+    const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
+    const bool act = rep < a.Nrep;
+    const int stride = a.stride;
+    if (act)
+        for (int k = 0; k < stride; ++k) sm[k * BAM_BLOCK + tid] = tab[(size_t)rep * stride + k];
+    const bool setOk = act ? (status[rep] == 0) : false;
+    const int tBeg = blockIdx.y * 32, tEnd = min(a.nT, tBeg + 32);
+    const double* xp[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const int col = act ? (int)(rep % nspag[j]) : 0;  // indx = modulo(rep, nspag) with 1-based rep (:1049)
+        xp[j] = xspag[j] + (size_t)col * a.nobsPred + a.t0;
+    }
+    if (!act) return;
+    // this replication's full theta + derived values: private copy, loaded once for all inputs of the tile
+    double loc[BAM_MAXTHETA + BAM_MAXCTRL];
+    const int np = p.ntheta + p.nDer;
+    for (int k = 0; k < np; ++k) loc[k] = sm[(p.nGamma + k) * BAM_BLOCK + tid];
+    for (int t = tBeg; t < tEnd; ++t) {
+        double xin[NX], y[NY];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) xin[j] = xp[j][t];
+        bool ok = setOk;
+        if (ok) ok = model_apply<MODEL, NX, NY>(p, xin, loc, loc + p.ntheta, y);
+#pragma unroll
+        for (int j = 0; j < NY; ++j) {
+            double v = ok ? y[j] : p.unfeas;  // ApplyModel flags infeasible rows (ModelLibrary_tools.f90:419-432)
+            if (a.doRemnant[j] && v != p.unfeas) {
+                double gam[3];
+                for (int m = 0; m < p.nrem[j] && m < 3; ++m) gam[m] = sm[(p.gamOff[j] + m) * BAM_BLOCK + tid];
+                const double sig = sigmafunk(p.sigfunc[j], gam, v);
+                if (sig > 0.0) v = v + sig * philox_normal(a.seed, (uint64_t)rep, (unsigned)(a.t0 + t), (unsigned)j);
+            }
+            V[((size_t)j * a.nT + t) * a.Nrep + rep] = v;
+        }
+    }
+}
+
+// ---- envelopes ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double hazen(const double* xs, long long n, double pr) {
+    // GetEmpiricalQuantile (BMSL, un-vendored): declared convention = Hazen plotting positions
+    const double hh = pr * (double)n + 0.5;
+    if (hh <= 1.0) return xs[0];
+    if (hh >= (double)n) return xs[n - 1];
+    const long long i = (long long)floor(hh);
+    const double frac = hh - (double)i;
+    return xs[i - 1] + frac * (xs[i] - xs[i - 1]);
+}
+
+// block-wide deterministic sum (fixed tree)
+__device__ double block_sum(double v, double* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (tid == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += scratch[i];
+    if (tid == 0) scratch[0] = s;
+    __syncthreads();
+    s = scratch[0];
+    __syncthreads();
+    return s;
+}
+
+// one block per column (input t, output y); column fits in shared memory (npad = pow2 >= Nrep)
+__global__ void __launch_bounds__(BAM_BLOCK) envelope_smem(long long Nrep, int npad, int nT, double unfeas,
+                                                           const double* __restrict__ V, double* __restrict__ env) {
+    extern __shared__ double s[];  // npad values + 32 scratch
+    double* scratch = s + npad;
+    __shared__ int nbadS, mS;
+    const int tid = threadIdx.x;
+    const int colId = blockIdx.x;  // y*nT + t
+    const double* col = V + (size_t)colId * Nrep;
+    if (tid == 0) { nbadS = 0; mS = 0; }
+    __syncthreads();
+    int nb = 0;
+    for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
+        const double v = col[r];
+        if (v == unfeas || v != v) ++nb;
+    }
+    if (nb) atomicAdd(&nbadS, nb);
+    __syncthreads();
+    const int nbad = nbadS;
+    const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
+    const int y = colId / nT, t = colId % nT;
+    double* out = env + (size_t)y * BAMGPU_NENV * nT + t;
+    if (!drop && nbad > 0) {  // too many bad values: flag the row (:1402-1404)
+        if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
+        return;
+    }
+    // load (bad values, if any, become +inf and sort to the end)
+    for (int r = tid; r < npad; r += BAM_BLOCK) {
+        double v = (r < Nrep) ? col[r] : INFINITY;
+        if (v == unfeas || v != v) v = INFINITY;
+        s[r] = v;
+    }
+    const long long m = Nrep - nbad;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += BAM_BLOCK) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double a = s[i], b = s[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (m <= 0) {
+        if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
+        return;
+    }
+    double part = 0.0;
+    for (long long r = tid; r < m; r += BAM_BLOCK) part += s[r];
+    const double mean = block_sum(part, scratch) / (double)m;
+    part = 0.0;
+    for (long long r = tid; r < m; r += BAM_BLOCK) { const double d = s[r] - mean; part += d * d; }
+    const double ss = block_sum(part, scratch);
+    if (tid == 0) {
+        const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
+        for (int q = 0; q < 5; ++q) out[(size_t)q * nT] = hazen(s, m, pr[q]);
+        out[(size_t)5 * nT] = mean;
+        out[(size_t)6 * nT] = (m > 1) ? sqrt(ss / (double)(m - 1)) : unfeas;
+    }
+}
+
+// ---- large Nrep: exact selection with two levels of linear histograms + a final gather ------------
+//
+// Level 0: min / max / count of good values.  Level 1: NB equal-width bins on [min,max]; for each of
+// the 10 order statistics needed (two neighbours per quantile) find its bin and the rank inside it.
+// Level 2: the same inside each selected bin.  Final: gather the (few) values that fall in the selected
+// level-2 bins, sort them in shared memory, pick the order statistics.  bin(v) is a monotone function of
+// v, so the selection is exact; ties and degenerate ranges are handled by the width==0 shortcut.
+#define SEL_NB 1024
+#define SEL_NT 10
+#define SEL_GATHER 2048
+
+struct SelState {
+    double lo[SEL_NT], hi[SEL_NT];   // current value interval of each target
+    long long rank[SEL_NT];          // 0-based rank of the target inside the interval
+    long long below[SEL_NT];
+};
+
+__device__ __forceinline__ int lin_bin(double v, double lo, double scale) {
+    int b = (int)((v - lo) * scale);
+    return b < 0 ? 0 : (b >= SEL_NB ? SEL_NB - 1 : b);
+}
+
+__global__ void __launch_bounds__(BAM_BLOCK) envelope_select(long long Nrep, int nT, double unfeas,
+                                                             const double* __restrict__ V, double* __restrict__ env) {
+    __shared__ unsigned hist[SEL_NB];
+    __shared__ double scratch[32];
+    __shared__ double gath[SEL_GATHER];
+    __shared__ SelState st;
+    __shared__ double sMin, sMax;
+    __shared__ long long sBad;
+    __shared__ int sCnt, sOverflow;
+    const int tid = threadIdx.x;
+    const int colId = blockIdx.x;
+    const double* col = V + (size_t)colId * Nrep;
+    const int y = colId / nT, t = colId % nT;
+    double* out = env + (size_t)y * BAMGPU_NENV * nT + t;
+
+    // level 0: min, max, #bad, sum
+    double mn = INFINITY, mx = -INFINITY, sum = 0.0;
+    long long nb = 0;
+    for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
+        const double v = col[r];
+        if (v == unfeas || v != v) { ++nb; continue; }
+        mn = fmin(mn, v); mx = fmax(mx, v); sum += v;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        nb += __shfl_xor_sync(0xffffffffu, nb, off);
+    }
+    if ((tid & 31) == 0) { scratch[tid >> 5] = mn; }
+    __syncthreads();
+    if (tid == 0) { double v = INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmin(v, scratch[i]); sMin = v; }
+    __syncthreads();
+    if ((tid & 31) == 0) { scratch[tid >> 5] = mx; }
+    __syncthreads();
+    if (tid == 0) { double v = -INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmax(v, scratch[i]); sMax = v; }
+    __syncthreads();
+    if ((tid & 31) == 0) { scratch[tid >> 5] = (double)nb; }
+    __syncthreads();
+    if (tid == 0) { double v = 0; for (int i = 0; i < BAM_BLOCK / 32; ++i) v += scratch[i]; sBad = (long long)v; }
+    __syncthreads();
+    const long long nbad = sBad;
+    const bool drop = (double)nbad / (double)Nrep < 0.75;
+    if ((!drop && nbad > 0) || nbad == Nrep) {
+        if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
+        return;
+    }
+    const long long m = Nrep - nbad;
+    const double mean = block_sum(sum, scratch) / (double)m;
+    double part = 0.0;
+    for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
+        const double v = col[r];
+        if (v == unfeas || v != v) continue;
+        const double d = v - mean;
+        part += d * d;
+    }
+    const double ss = block_sum(part, scratch);
+
+    // the 10 target ranks (0-based): i-1 and i of each Hazen quantile
+    const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
+    if (tid == 0) {
+        for (int q = 0; q < 5; ++q) {
+            const double hh = pr[q] * (double)m + 0.5;
+            long long i0, i1;
+            if (hh <= 1.0) i0 = i1 = 0;
+            else if (hh >= (double)m) i0 = i1 = m - 1;
+            else { const long long i = (long long)floor(hh); i0 = i - 1; i1 = i; }
+            st.rank[2 * q] = i0; st.rank[2 * q + 1] = i1;
+            for (int k = 0; k < 2; ++k) { st.lo[2 * q + k] = sMin; st.hi[2 * q + k] = sMax; }
+        }
+    }
+    __syncthreads();
+    double result[SEL_NT];
+    for (int k = 0; k < SEL_NT; ++k) {
+        // targets are processed one at a time; an interval shared with the previous target is re-used
+        double lo = st.lo[k], hi = st.hi[k];
+        long long rank = st.rank[k];
+        double val = lo;
+        for (int level = 0; level < 64; ++level) {
+            if (!(hi > lo)) { val = lo; break; }
+            const double scale = (double)SEL_NB / (hi - lo);
+            for (int b = tid; b < SEL_NB; b += BAM_BLOCK) hist[b] = 0;
+            if (tid == 0) { sCnt = 0; sOverflow = 0; }
+            __syncthreads();
+            // count values inside [lo,hi] per bin
+            for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
+                const double v = col[r];
+                if (v == unfeas || v != v) continue;
+                if (v < lo || v > hi) continue;
+                atomicAdd(&hist[lin_bin(v, lo, scale)], 1u);
+            }
+            __syncthreads();
+            // locate the bin of `rank` (serial scan by thread 0: 1024 steps)
+            __shared__ int sBin;
+            __shared__ long long sBefore, sInBin;
+            if (tid == 0) {
+                long long acc = 0;
+                int b = 0;
+                for (; b < SEL_NB; ++b) {
+                    if (acc + hist[b] > rank) break;
+                    acc += hist[b];
+                }
+                if (b >= SEL_NB) b = SEL_NB - 1;
+                sBin = b; sBefore = acc; sInBin = hist[b];
+            }
+            __syncthreads();
+            const int bsel = sBin;
+            const long long inBin = sInBin;
+            rank -= sBefore;
+            if (inBin <= SEL_GATHER) {
+                // gather the bin, sort, pick
+                for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
+                    const double v = col[r];
+                    if (v == unfeas || v != v) continue;
+                    if (v < lo || v > hi) continue;
+                    if (lin_bin(v, lo, scale) == bsel) {
+                        const int pos = atomicAdd(&sCnt, 1);
+                        if (pos < SEL_GATHER) gath[pos] = v;
+                    }
+                }
+                __syncthreads();
+                const int cnt = min(sCnt, SEL_GATHER);
+                int npad = 1;
+                while (npad < cnt) npad <<= 1;
+                for (int i = cnt + tid; i < npad; i += BAM_BLOCK) gath[i] = INFINITY;
+                __syncthreads();
+                for (int kk = 2; kk <= npad; kk <<= 1)
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        for (int i = tid; i < npad; i += BAM_BLOCK) {
+                            const int ixj = i ^ j;
+                            if (ixj > i) {
+                                const double a = gath[i], b = gath[ixj];
+                                const bool up = ((i & kk) == 0);
+                                if ((a > b) == up) { gath[i] = b; gath[ixj] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                val = gath[rank < cnt ? rank : cnt - 1];
+                __syncthreads();
+                break;
+            }
+            // refine: new interval = value range of the selected bin (computed exactly from the data)
+            double bmn = INFINITY, bmx = -INFINITY;
+            for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
+                const double v = col[r];
+                if (v == unfeas || v != v) continue;
+                if (v < lo || v > hi) continue;
+                if (lin_bin(v, lo, scale) == bsel) { bmn = fmin(bmn, v); bmx = fmax(bmx, v); }
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                bmn = fmin(bmn, __shfl_xor_sync(0xffffffffu, bmn, off));
+                bmx = fmax(bmx, __shfl_xor_sync(0xffffffffu, bmx, off));
+            }
+            __syncthreads();
+            if ((tid & 31) == 0) scratch[tid >> 5] = bmn;
+            __syncthreads();
+            if (tid == 0) { double v = INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmin(v, scratch[i]); sMin = v; }
+            __syncthreads();
+            if ((tid & 31) == 0) scratch[tid >> 5] = bmx;
+            __syncthreads();
+            if (tid == 0) { double v = -INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmax(v, scratch[i]); sMax = v; }
+            __syncthreads();
+            lo = sMin; hi = sMax;
+            val = lo;
+            __syncthreads();
+        }
+        result[k] = val;
+    }
+    if (tid == 0) {
+        for (int q = 0; q < 5; ++q) {
+            const double hh = pr[q] * (double)m + 0.5;
+            double qv;
+            if (hh <= 1.0 || hh >= (double)m) qv = result[2 * q];
+            else {
+                const long long i = (long long)floor(hh);
+                const double frac = hh - (double)i;
+                qv = result[2 * q] + frac * (result[2 * q + 1] - result[2 * q]);
+            }
+            out[(size_t)q * nT] = qv;
+        }
+        out[(size_t)5 * nT] = mean;
+        out[(size_t)6 * nT] = (m > 1) ? sqrt(ss / (double)(m - 1)) : unfeas;
+    }
+}
+
+using PredKernel = void (*)(DevProblem, PredArgs, const double*, const int*, double* const*, const int*, double*);
+
+template <int MODEL>
+PredKernel pick_nxny(int nX, int nY) {
+#define PICK(a, b) \
+    if (nX == a && nY == b) return pred_main<MODEL, a, b>;
+    PICK(1, 1) PICK(2, 1) PICK(3, 1) PICK(4, 1) PICK(1, 2) PICK(2, 2) PICK(3, 2) PICK(4, 2)
+#undef PICK
+    return nullptr;
+}
+
+PredKernel pick_pred(int model, int nX, int nY) {
+    switch (model) {
+        case BAMGPU_MDL_BARATIN: return (nX == 1 && nY == 1) ? pred_main<BAMGPU_MDL_BARATIN, 1, 1> : nullptr;
+        case BAMGPU_MDL_LINEAR: return pick_nxny<BAMGPU_MDL_LINEAR>(nX, nY);
+        case BAMGPU_MDL_TEXTFILE: return pick_nxny<BAMGPU_MDL_TEXTFILE>(nX, nY);
+        case BAMGPU_MDL_SEDIMENT:
+            if (nY != 1) return nullptr;
+            switch (nX) {
+                case 2: return pred_main<BAMGPU_MDL_SEDIMENT, 2, 1>;
+                case 3: return pred_main<BAMGPU_MDL_SEDIMENT, 3, 1>;
+                case 4: return pred_main<BAMGPU_MDL_SEDIMENT, 4, 1>;
+                case 5: return pred_main<BAMGPU_MDL_SEDIMENT, 5, 1>;
+                case 6: return pred_main<BAMGPU_MDL_SEDIMENT, 6, 1>;
+            }
+            return nullptr;
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+namespace bam {
+
+void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, unsigned long long seed, int t0, int t1,
+                    double* h_spag) {
+    const DevProblem& p = h->dp;
+    if (h->L.nVar) throw CudaError{"BaM_Prediction: prediction with VAR parameters is not allowed (BaM_Message 13)"};
+    PredKernel kern = pick_pred(p.model, p.nX, p.nY);
+    if (!kern) throw CudaError{"bamgpu: no prediction kernel instantiated for this (model, nX, nY)"};
+    const long long Nrep = h->predNrep;
+    const int nTall = t1 - t0, nY = p.nY;
+    if (nTall <= 0 || Nrep <= 0) return;
+    bool anyRem = false;
+    for (int y = 0; y < nY; ++y) anyRem |= doRemnant[y] != 0;
+    if ((doParametric || anyRem) && !h->d_mc) throw CudaError{"BaM_Prediction: an MCMC sample is required"};
+    if (!doParametric && !h->d_mode && p.nFit > 0) throw CudaError{"BaM_Prediction: maxpost vector required"};
+    cudaStream_t s = h->stream;
+
+    PredArgs a;
+    a.Nrep = Nrep; a.nobsPred = h->predNobs; a.doParametric = doParametric; a.seed = seed;
+    for (int y = 0; y < BAM_MAXY; ++y) a.doRemnant[y] = (y < nY) ? doRemnant[y] : 0;
+    a.stride = p.nGamma + p.ntheta + p.nDer;
+
+    // table + envelope output
+    if (!h->d_ptab) {
+        BAM_CUDA(cudaMalloc(&h->d_ptab, sizeof(double) * (size_t)Nrep * a.stride));
+        BAM_CUDA(cudaMalloc(&h->d_pstatus, sizeof(int) * (size_t)Nrep));
+    }
+    const size_t envNeed = (size_t)nTall * BAMGPU_NENV * nY;
+    if (envNeed > h->envCap) {
+        if (h->d_env) cudaFree(h->d_env);
+        BAM_CUDA(cudaMalloc(&h->d_env, sizeof(double) * envNeed));
+        h->envCap = envNeed;
+    }
+    h->predT0 = t0; h->predT1 = t1;
+
+    // tile of inputs: at most ~2 GiB of materialised values
+    const size_t budget = (size_t)2 << 30;
+    long long tileT = (long long)(budget / (sizeof(double) * (size_t)Nrep * nY));
+    tileT = std::max<long long>(32, std::min<long long>(tileT / 32 * 32, ((long long)nTall + 31) / 32 * 32));
+    if (h_spag) tileT = std::max<long long>(tileT, 32);
+    const size_t vNeed = (size_t)tileT * Nrep * nY;
+    if (vNeed > h->vCap) {
+        if (h->d_V) cudaFree(h->d_V);
+        BAM_CUDA(cudaMalloc(&h->d_V, sizeof(double) * vNeed));
+        h->vCap = vNeed;
+    }
+
+    pred_prep<<<(unsigned)((Nrep + 127) / 128), 128, 0, s>>>(p, a, h->d_mc, h->d_mode, h->d_ptab, h->d_pstatus);
+    h->launches += 1;
+    const size_t smemMain = sizeof(double) * (size_t)a.stride * BAM_BLOCK;
+    if (smemMain > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMain));
+
+    int npad = 1;
+    while (npad < Nrep && npad < (1 << 30)) npad <<= 1;
+    const bool smallN = Nrep <= 16384;
+    const size_t smemEnv = sizeof(double) * ((size_t)npad + 32);
+    if (smallN && smemEnv > 48 * 1024)
+        BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEnv));
+
+    BAM_CUDA(cudaEventRecord(h->ev0, s));
+    for (int tt = 0; tt < nTall; tt += (int)tileT) {
+        const int nT = std::min<long long>(tileT, nTall - tt);
+        a.t0 = t0 + tt; a.nT = nT;
+        dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + 31) / 32);
+        kern<<<grid, BAM_BLOCK, smemMain, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspagPtrs, h->d_nspag, h->d_V);
+        h->launches += 1;
+        if (Nrep >= 2) {
+            // envelopes of this tile go to a compact [y][7][nT] scratch, then into the full [y][7][nTall] array
+            double* envTile = nullptr;
+            BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nY, s));
+            if (smallN) envelope_smem<<<nT * nY, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
+            else envelope_select<<<nT * nY, BAM_BLOCK, 0, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile);
+            h->launches += 1;
+            for (int y = 0; y < nY; ++y)
+                BAM_CUDA(cudaMemcpy2DAsync(h->d_env + ((size_t)y * BAMGPU_NENV * nTall + tt), sizeof(double) * nTall,
+                                           envTile + (size_t)y * BAMGPU_NENV * nT, sizeof(double) * nT,
+                                           sizeof(double) * nT, BAMGPU_NENV, cudaMemcpyDeviceToDevice, s));
+            BAM_CUDA(cudaFreeAsync(envTile, s));
+        }
+        if (h_spag) {  // host layout: [y][t][rep] over the whole [t0,t1) range
+            for (int y = 0; y < nY; ++y)
+                BAM_CUDA(cudaMemcpyAsync(h_spag + ((size_t)y * nTall + tt) * Nrep, h->d_V + (size_t)y * nT * Nrep,
+                                         sizeof(double) * (size_t)nT * Nrep, cudaMemcpyDeviceToHost, s));
+            BAM_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    BAM_CUDA(cudaEventRecord(h->ev1, s));
+    BAM_CUDA(cudaGetLastError());
+}
+
+}  // namespace bam

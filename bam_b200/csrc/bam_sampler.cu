@@ -1,0 +1,147 @@
+// bam_sampler.cu -- K3: batched one-at-a-time adaptive Metropolis, K chains in lockstep.
+//
+// Replaces BMSL's sequential Adaptive_Metro_OAAT as called by BaM_Fit (src/BaM_tools.f90:615-621).
+// Declared semantics (BMSL is un-vendored): for every cycle { moves=0; nAdapt
+// iterations of { for each component i: candidate = x + std_i*N(0,1) on component i; accept with
+// probability min(1, exp(f(cand)-f(x))) if feasible and non-null }; one row [x, f(x), Dpar] per
+// iteration; then std_i *= DownMult if rate_i <= MinMoveRate, *= UpMult if rate_i >= MaxMoveRate }.
+// RNG = Philox4x32-10 keyed by the seed, counter (global chain index, iteration, 2*i | 2*i+1): a
+// chain's trajectory does not depend on K, on the GPU count or on launch geometry.
+//
+// K5: Welford running moments {count, mean, M2} per (chain, component) over the kept rows; they feed
+// the Gelman-Rubin diagnostic (all-gathered across ranks by the caller, NCCL).
+#include "bam_handle.h"
+
+namespace {
+
+__global__ void propose_kernel(int K, int P, int comp, unsigned long long seed, long long chainOffset, unsigned it,
+                               const double* __restrict__ sd, double* __restrict__ delta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    delta[c] = sd[(size_t)c * P + comp] * philox_normal(seed, (uint64_t)(chainOffset + c), it, 2u * (unsigned)comp);
+}
+
+__global__ void accept_kernel(int K, int P, int nDpar, int comp, unsigned long long seed, long long chainOffset,
+                              unsigned it, const double* __restrict__ delta, const double* __restrict__ fxCand,
+                              const int* __restrict__ stCand, const double* __restrict__ dparCand, double* __restrict__ x,
+                              double* __restrict__ fxCur, double* __restrict__ dparCur, int* __restrict__ moves) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    if (stCand[c] != 0) return;  // infeasible or null candidate: rejected
+    const double u = philox_uniform(seed, (uint64_t)(chainOffset + c), it, 2u * (unsigned)comp + 1u);
+    if (log(u) < fxCand[c] - fxCur[c]) {
+        x[(size_t)c * P + comp] += delta[c];
+        fxCur[c] = fxCand[c];
+        for (int d = 0; d < nDpar; ++d) dparCur[(size_t)c * nDpar + d] = dparCand[(size_t)c * nDpar + d];
+        moves[(size_t)c * P + comp] += 1;
+    }
+}
+
+__global__ void init_state_kernel(int K, int nDpar, const double* __restrict__ fx, const double* __restrict__ dpar,
+                                  const int* __restrict__ st, double* __restrict__ fxCur, double* __restrict__ dparCur,
+                                  int* __restrict__ nBad) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    fxCur[c] = fx[c];
+    for (int d = 0; d < nDpar; ++d) dparCur[(size_t)c * nDpar + d] = dpar[(size_t)c * nDpar + d];
+    if (st[c] != 0) atomicAdd(nBad, 1);
+}
+
+// one kept iteration: store the row and update the running moments; one thread per (chain, column)
+__global__ void record_kernel(int K, int P, int nDpar, long long keepIdx, long long nKeep, const double* __restrict__ x,
+                              const double* __restrict__ fxCur, const double* __restrict__ dparCur,
+                              double* __restrict__ rows, double* __restrict__ mcount, double* __restrict__ mmean,
+                              double* __restrict__ mm2) {
+    const int rowlen = P + 1 + nDpar;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)K * rowlen) return;
+    const int c = (int)(q / rowlen), j = (int)(q % rowlen);
+    double v;
+    if (j < P) v = x[(size_t)c * P + j];
+    else if (j == P) v = fxCur[c];
+    else v = dparCur[(size_t)c * nDpar + (j - P - 1)];
+    if (rows) rows[((size_t)c * nKeep + keepIdx) * rowlen + j] = v;
+    if (j < P) {  // Welford
+        const double cnt = (double)(keepIdx + 1);
+        const size_t o = (size_t)c * P + j;
+        const double m = mmean[o], d = v - m, mn = m + d / cnt;
+        mmean[o] = mn;
+        mm2[o] += d * (v - mn);
+        if (j == 0) mcount[c] = cnt;
+    }
+}
+
+__global__ void adapt_kernel(int K, int P, int nAdapt, double minMR, double maxMR, double downMult, double upMult,
+                             double* __restrict__ sd, int* __restrict__ moves) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)K * P) return;
+    const double rate = (double)moves[q] / (double)nAdapt;
+    double s = sd[q];
+    if (rate <= minMR) s *= downMult;
+    if (rate >= maxMR) s *= upMult;
+    sd[q] = s;
+    moves[q] = 0;
+}
+
+}  // namespace
+
+namespace bam {
+
+void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, double maxMR, double downMult,
+                double upMult, unsigned long long seed, int burn, int keepEvery, bool storeRows, long long nKeep) {
+    const DevProblem& p = h->dp;
+    const int P = p.P, nD = p.nDpar;
+    cudaStream_t s = h->stream;
+    const int TB = 128, gK = (K + TB - 1) / TB;
+    const long long KP = (long long)K * P, Krow = (long long)K * (P + 1 + nD);
+
+    BAM_CUDA(cudaMemsetAsync(h->d_moves, 0, sizeof(int) * KP, s));
+    BAM_CUDA(cudaMemsetAsync(h->d_mcount, 0, sizeof(double) * K, s));
+    BAM_CUDA(cudaMemsetAsync(h->d_mmean, 0, sizeof(double) * KP, s));
+    BAM_CUDA(cudaMemsetAsync(h->d_mm2, 0, sizeof(double) * KP, s));
+
+    // f(start): must be feasible (the reference aborts otherwise)
+    launch_logpost(h, K, h->d_x, -1, nullptr, false);
+    int* d_nbad = nullptr;
+    BAM_CUDA(cudaMalloc(&d_nbad, sizeof(int)));
+    BAM_CUDA(cudaMemsetAsync(d_nbad, 0, sizeof(int), s));
+    init_state_kernel<<<gK, TB, 0, s>>>(K, nD, h->d_fx, h->d_dpar, h->d_status, h->d_fxcur, h->d_dparcur, d_nbad);
+    int nbad = 0;
+    BAM_CUDA(cudaMemcpyAsync(&nbad, d_nbad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BAM_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_nbad);
+    h->launches += 1;
+    if (nbad > 0) throw CudaError{"Adaptive_Metro_OAAT: unfeasible starting point for " + std::to_string(nbad) + " chain(s)"};
+
+    long long it = 0, kept = 0;
+    for (int cyc = 0; cyc < nCycles; ++cyc) {
+        for (int a = 0; a < nAdapt; ++a, ++it) {
+            for (int i = 0; i < P; ++i) {
+                propose_kernel<<<gK, TB, 0, s>>>(K, P, i, seed, h->chainOffset, (unsigned)it, h->d_std, h->d_delta);
+                launch_logpost(h, K, h->d_x, i, h->d_delta, false);
+                accept_kernel<<<gK, TB, 0, s>>>(K, P, nD, i, seed, h->chainOffset, (unsigned)it, h->d_delta, h->d_fx,
+                                                h->d_status, h->d_dpar, h->d_x, h->d_fxcur, h->d_dparcur, h->d_moves);
+                h->launches += 2;
+            }
+            const long long it1 = it + 1;
+            if (it1 > burn && (it1 - burn) % keepEvery == 0 && kept < nKeep) {
+                record_kernel<<<(unsigned)((Krow + 255) / 256), 256, 0, s>>>(K, P, nD, kept, nKeep, h->d_x, h->d_fxcur,
+                                                                             h->d_dparcur, storeRows ? h->d_rows : nullptr,
+                                                                             h->d_mcount, h->d_mmean, h->d_mm2);
+                ++kept;
+                h->launches += 1;
+            }
+        }
+        adapt_kernel<<<(unsigned)((KP + 255) / 256), 256, 0, s>>>(K, P, nAdapt, minMR, maxMR, downMult, upMult, h->d_std,
+                                                                  h->d_moves);
+        h->launches += 1;
+        BAM_CUDA(cudaGetLastError());
+    }
+    // leave the final state consistent for bamgpu_chains_download
+    BAM_CUDA(cudaMemcpyAsync(h->d_fx, h->d_fxcur, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
+    BAM_CUDA(cudaMemcpyAsync(h->d_dpar, h->d_dparcur, sizeof(double) * (size_t)K * std::max(nD, 1), cudaMemcpyDeviceToDevice, s));
+    BAM_CUDA(cudaMemsetAsync(h->d_status, 0, sizeof(int) * K, s));
+    h->haveMoments = true;
+}
+
+}  // namespace bam

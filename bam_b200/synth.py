@@ -1,0 +1,203 @@
+"""Synthetic workloads of the BASELINE.json configs, seed 20261019.
+
+These only build *inputs* (numpy); they contain no compute path.  Used by bench.py and by the
+tests (so that the parity tests and the bench run the same shapes).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .capi import PARTYPE, SED_CO, SED_CSS, SED_FORMULA, SED_PPO, Problem
+
+SEED = 20261019
+
+# priors of tests/BaM_BaRatin_SPD (Config_Model.txt, Config_k1_VAR.txt, Config_k2_VAR.txt, Config_RemnantSigma.txt)
+_SPD_K1_SD = [0.5, 0.62, 0.71, 0.8, 0.87]
+_SPD_K2 = [1.05, 1.08, 1.11, 1.15, 1.19]
+_SPD_CONTROL = [[1, 0, 0], [0, 1, 0], [0, 1, 1]]
+
+
+def _baratin_q(H, k, a, c, M):
+    """numpy BaRatin used only to synthesise observations."""
+    nc = len(k)
+    b = np.zeros(nc)
+    b[0] = k[0]
+    for j in range(1, nc):
+        som = sum((M[j - 1][i] - M[j][i]) * a[i] * (k[j] - b[i]) ** c[i] for i in range(j))
+        b[j] = k[j] - (som / a[j]) ** (1.0 / c[j])
+    Q = np.zeros_like(H)
+    rng_idx = np.sum(H[:, None] >= np.asarray(k)[None, :], axis=1)
+    for r in range(1, nc + 1):
+        sel = rng_idx == r
+        for i in range(r):
+            if M[r - 1][i]:
+                Q[sel] += a[i] * np.maximum(H[sel] - b[i], 0.0) ** c[i]
+    return Q
+
+
+def baratin_spd(nobs: int = 100_000, copula: bool = False, seed: int = SEED):
+    """cfg 2: BaRatin, 3 controls, 5 periods, VAR k1 and k2 (multi-period rating curves).
+
+    Returns (Problem, truth vector of length 19)."""
+    rng = np.random.default_rng(seed)
+    nper = 5
+    period = 1 + (nper * np.arange(nobs)) // max(nobs, 1)
+    H = rng.uniform(-0.5, 3.0, nobs)
+    a = [14.17, 26.52, 31.82]
+    c = [1.5, 1.67, 1.67]
+    k1, k3 = -0.6, 1.2
+    gam = (0.1, 0.05)
+    Q = np.zeros(nobs)
+    for p in range(nper):
+        sel = period == p + 1
+        Q[sel] = _baratin_q(H[sel], [k1, _SPD_K2[p], k3], a, c, _SPD_CONTROL)
+    uQ = 0.05 * Q + 0.01
+    Qobs = Q + rng.standard_normal(nobs) * np.sqrt(uQ**2 + (gam[0] + gam[1] * Q) ** 2)
+    ntheta = 9
+    partype = [PARTYPE["VAR"], 0, 0, PARTYPE["VAR"], 0, 0, 0, 0, 0]
+    nval = [nper, 1, 1, nper, 1, 1, 1, 1, 1]
+    var_indx = np.ones((nobs, ntheta), dtype=np.int32)
+    var_indx[:, 0] = period
+    var_indx[:, 3] = period
+    priors = ([("Gaussian", [-0.6, s]) for s in _SPD_K1_SD] + [("Gaussian", [14.17, 5.01]), ("Gaussian", [1.5, 0.025])]
+              + [("Gaussian", [k, 0.3]) for k in _SPD_K2] + [("Gaussian", [26.52, 8.4]), ("Gaussian", [1.67, 0.025]),
+                                                             ("Gaussian", [1.2, 0.2]), ("Gaussian", [31.82, 10.93]),
+                                                             ("Gaussian", [1.67, 0.025])])
+    priorM = None
+    if copula:
+        k = 19
+        C = np.eye(k)
+        for i in range(nper):
+            for j in range(nper):
+                if i != j:
+                    C[i, j] = 0.8 ** abs(i - j)
+                    C[7 + i, 7 + j] = 0.6 ** abs(i - j)
+        priorM = np.linalg.inv(C) - np.eye(k)
+    prob = Problem("BaRatin", H, Qobs, Yu=uQ, partype=partype, nval=nval, var_indx=var_indx, priors_theta=priors,
+                   sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000]), ("Uniform", [0, 1000])], priorM=priorM,
+                   xtra_i=np.asarray(_SPD_CONTROL, dtype=np.int32).flatten(order="F"))
+    truth = np.array([k1] * nper + [a[0], c[0]] + _SPD_K2 + [a[1], c[1], k3, a[2], c[2], gam[0], gam[1]])
+    return prob, truth
+
+
+def feasible_starts(truth, K: int, rel: float = 0.01, seed: int = SEED + 1, check=None):
+    """K starting vectors = truth * (1 + rel * N(0,1)), redrawn until `check(x)` says feasible."""
+    rng = np.random.default_rng(seed)
+    truth = np.asarray(truth, dtype=np.float64)
+    x = truth * (1.0 + rel * rng.standard_normal((K, truth.size)))
+    if check is not None:
+        for _ in range(50):
+            bad = ~check(x)
+            if not bad.any():
+                break
+            x[bad] = truth * (1.0 + rel * rng.standard_normal((int(bad.sum()), truth.size)))
+    return x
+
+
+def spd_start_check(x):
+    """k2_p < k3 and k1 < k2 for every period (the only way a 1 % perturbation turns infeasible)."""
+    x = np.asarray(x)
+    return (x[:, 7:12].max(axis=1) < x[:, 14]) & (x[:, 0:5].max(axis=1) < x[:, 7:12].min(axis=1)) & (x[:, 17] > 0)
+
+
+def linear_latent(nobs: int = 1_000_000, seed: int = SEED):
+    """cfg 3: Linear nX=nY=2 with input uncertainty on every cell -> 2*nobs latent inputs."""
+    rng = np.random.default_rng(seed)
+    Xtrue = rng.standard_normal((nobs, 2))
+    Xu = np.full((nobs, 2), 0.1)
+    Xobs = Xtrue + rng.standard_normal((nobs, 2)) * Xu
+    theta = np.array([1.0, -2.0, 0.5, 3.0])  # column-major (nX, nY)
+    Yhat = Xtrue @ theta.reshape(2, 2, order="F")
+    Yu = np.full((nobs, 2), 0.05)
+    gam = (0.1, 0.02)
+    Y = Yhat + rng.standard_normal((nobs, 2)) * np.sqrt(Yu**2 + (gam[0] + gam[1] * np.abs(Yhat)) ** 2)
+    prob = Problem("Linear", Xobs, Y, Yu=Yu, Xu=Xu, partype=[0, 0, 0, 0],
+                   priors_theta=[("Gaussian", [0, 10])] * 4, sigma_func=["Linear", "Linear"],
+                   priors_gamma=[("Uniform", [0, 100])] * 4)
+    truth = np.concatenate([theta, [gam[0], gam[1], gam[0], gam[1]], Xtrue.flatten(order="F")])
+    return prob, truth
+
+
+def textfile_latent(nobs: int = 100_000, seed: int = SEED):
+    """cfg 3 twin: TextFile 'a*T+b' with input uncertainty (tests/BaM_TextFile_InputUncertainty shape)."""
+    rng = np.random.default_rng(seed)
+    T = rng.uniform(5.0, 50.0, nobs)
+    Tu = np.full(nobs, 1.0)
+    Tobs = T + rng.standard_normal(nobs) * Tu
+    a, b = 2.0, 1.0
+    Yhat = a * T + b
+    Yu = np.full(nobs, 0.5)
+    gam = (0.5, 0.05)
+    Y = Yhat + rng.standard_normal(nobs) * np.sqrt(Yu**2 + (gam[0] + gam[1] * np.abs(Yhat)) ** 2)
+    text = "1\nT\n2\na,b\n1\na*T+b   ! concentration\n"
+    prob = Problem("TextFile", Tobs, Y, Yu=Yu, Xu=Tu, partype=[0, 0], priors_theta=[("Gaussian", [0, 10])] * 2,
+                   sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 100])] * 2, xtra_text=text)
+    truth = np.concatenate([[a, b, gam[0], gam[1]], T])
+    return prob, truth
+
+
+def sediment_camenen(nobs: int = 812, seed: int = SEED):
+    """cfg 4: Sediment Camenen + Soulsby, d and s as inputs (tests/BaM_Sediment_Camenen_X4 options)."""
+    rng = np.random.default_rng(seed)
+    h = rng.uniform(0.02, 0.5, nobs)
+    S0 = rng.uniform(1e-3, 8e-3, nobs)
+    d = rng.choice([3.05e-4, 5.06e-4, 1.0e-3], nobs)
+    s = np.full(nobs, 2.65)
+    X = np.column_stack([h, S0, d, s])
+    theta = np.array([12.0, 1.5, 4.5])
+    v, g = 1e-6, 9.81
+    SD = (g * (s - 1) / v**2) ** (1 / 3) * d
+    css = (0.3 / (1 + 1.2 * SD)) * 0.055 * (1 - np.exp(-0.02 * SD))
+    tau = h * S0 / ((s - 1) * d)
+    q = np.sqrt(g * (s - 1) * d**3) * theta[0] * tau ** theta[1] * np.exp(-theta[2] * css / tau)
+    q[tau <= css] = 0.0
+    gam = (1e-4, 0.1)
+    Y = q + rng.standard_normal(nobs) * (gam[0] + gam[1] * q)
+    prob = Problem("Sediment", X, Y, partype=[0, 0, 0],
+                   priors_theta=[("Gaussian", [12, 6]), ("Gaussian", [1.5, 0.5]), ("Gaussian", [4.5, 2])],
+                   sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1]), ("Uniform", [0, 10])],
+                   xtra_i=[SED_FORMULA["Camenen"], SED_CSS["Soulsby"], SED_CO["FIX"], SED_PPO["IN"], SED_PPO["IN"],
+                           SED_PPO["FIX"], SED_PPO["FIX"]], xtra_d=[5.06e-4, 2.65, 1e-6, 9.81])
+    truth = np.concatenate([theta, gam])
+    return prob, truth
+
+
+def sediment_posterior(Nrep: int, seed: int = SEED + 4):
+    """cfg 4 posterior sample: theta ~ N((12,1.5,4.5), diag(1,0.05,0.3)^2) truncated > 0, gamma ~ |N|."""
+    rng = np.random.default_rng(seed)
+    th = np.abs(np.array([12.0, 1.5, 4.5]) + rng.standard_normal((Nrep, 3)) * np.array([1.0, 0.05, 0.3]))
+    gm = np.abs(np.array([1e-4, 0.1]) + rng.standard_normal((Nrep, 2)) * np.array([2e-5, 0.01]))
+    return np.column_stack([th, gm])
+
+
+def baratin_2c(nobs: int = 38, seed: int = SEED):
+    """cfg 1/5 model: 2-control BaRatin with the priors of tests/BaM_BaRatin; synthetic gaugings."""
+    rng = np.random.default_rng(seed)
+    H = rng.uniform(-0.3, 4.0, nobs)
+    k, a, c = [-0.5, 1.5], [53.0, 144.0], [1.5, 1.67]
+    Q = _baratin_q(H, k, a, c, [[1, 0], [0, 1]])
+    uQ = 0.05 * Q + 0.1
+    gam = (1.0, 0.1)
+    Qobs = Q + rng.standard_normal(nobs) * np.sqrt(uQ**2 + (gam[0] + gam[1] * Q) ** 2)
+    priors = [("Gaussian", [-0.5, 0.25]), ("Gaussian", [53, 10]), ("Gaussian", [1.5, 0.025]), ("Gaussian", [1.5, 0.5]),
+              ("Gaussian", [144, 45]), ("Gaussian", [1.67, 0.025])]
+    prob = Problem("BaRatin", H, Qobs, Yu=uQ, partype=[0] * 6, priors_theta=priors, sigma_func=["Linear"],
+                   priors_gamma=[("Uniform", [0, 1000]), ("Uniform", [0, 1000])], xtra_i=[1, 0, 0, 1])
+    truth = np.array([k[0], a[0], c[0], k[1], a[1], c[1], gam[0], gam[1]])
+    return prob, truth
+
+
+def baratin_spaghetti(Nrep: int = 1_000_000, nobs: int = 100_000, nspag: int = 1, seed: int = SEED + 5):
+    """cfg 5: Nrep posterior rows ~ N(maxpost, (2 % of value)^2), feasibility filtered; stage series
+    H_t = 0.5 + 1.5 sin^2(pi t / 5000) + 0.05 N(0,1); optionally nspag noisy copies."""
+    rng = np.random.default_rng(seed)
+    maxpost = np.array([-0.5, 53.0, 1.5, 1.5, 144.0, 1.67, 1.0, 0.1])
+    mc = maxpost * (1.0 + 0.02 * rng.standard_normal((Nrep, maxpost.size)))
+    mc[:, 6:] = np.abs(mc[:, 6:])
+    t = np.arange(nobs)
+    H = 0.5 + 1.5 * np.sin(np.pi * t / 5000.0) ** 2 + 0.05 * rng.standard_normal(nobs)
+    if nspag > 1:
+        Hs = H[:, None] + 0.01 * rng.standard_normal((nobs, nspag))
+    else:
+        Hs = H.reshape(-1, 1)
+    return mc, maxpost, Hs

@@ -18,6 +18,7 @@
 #ifndef BAM_GPU_H
 #define BAM_GPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -150,6 +151,9 @@ typedef struct bamgpu_handle bamgpu_t;
 int bamgpu_create(bamgpu_t** h, const bamgpu_problem* p, int device, char* mess);
 void bamgpu_destroy(bamgpu_t* h);
 int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s);
+/* global index of this handle's chain 0 (multi-GPU: chains are sharded across ranks and the RNG
+   streams are keyed by the GLOBAL chain index, so results do not depend on the GPU count) */
+int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset);
 
 /* name -> enum helpers (return 0 when the name is unknown) */
 int bamgpu_dist_id(const char* name);
@@ -203,7 +207,7 @@ int bamgpu_rhat(int K, int P, const double* count, const double* mean, const dou
    xspag: nX pointers, matrix i is nobs_pred x nspag[i] column-major
    t0,t1: half-open range of prediction inputs handled by this call (multi-GPU shards inputs)
    env  : (t1-t0) x 7 x nY column-major per output, or NULL
-   spag : (t1-t0) x Nrep x nY ("transposed" layout: one row per input), or NULL
+   spag : Nrep x (t1-t0) x nY column-major (Fortran Spag(nrep,nobs), src/BaM_tools.f90:1327), or NULL
    Noise for (rep, t, y) is a pure function of (seed, rep, t, y): results do not depend on sharding. */
 int bamgpu_predict(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
                    const double* const* xspag, const int32_t* nspag, int doParametric,
@@ -225,6 +229,9 @@ int64_t bamgpu_launch_count(const bamgpu_t* h);
 double bamgpu_last_kernel_ms(const bamgpu_t* h);
 /* FP64 DFMA peak micro-benchmark (register-resident FMA chains), TFLOP/s counting 2 flop per DFMA */
 int bamgpu_fp64_peak(int device, double* tflops, char* mess);
+/* page-lock / unlock a caller-owned host buffer so the H2D / D2H copies of the calls above are DMA copies */
+int bamgpu_pin(void* ptr, size_t bytes);
+int bamgpu_unpin(void* ptr);
 const char* bamgpu_version(void);
 
 #ifdef __cplusplus

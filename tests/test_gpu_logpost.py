@@ -1,0 +1,191 @@
+"""GPU parity tests of the log-posterior (K1/K2) against the CPU oracle, through the C ABI.
+
+Tolerance (BASELINE.json north_star (a)): |gpu - oracle| <= 1e-12 relative.  The sum over observations
+is a tree on the GPU and sequential in the oracle, so the comparison uses the bound of SURVEY.md
+section 7: |gpu - long-double oracle| <= max(1e-12*scale, |double oracle - long-double oracle|), with
+scale = max(|lp|, sum of |terms|/n ...) approximated by |prior|+|lkh|+|hyper|.
+Feasibility / null flags (integer work) must be identical.
+"""
+import numpy as np
+import pytest
+
+from bam_b200 import synth
+from bam_b200.capi import BamGpu
+from oracle.oracle_api import Oracle
+from tests.helpers import perturbed_vectors, problem_from_fixture
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def check_parity(prob, x, tol=TOL, nthreads=8):
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.P == o.P and g.nDpar == o.nDpar
+    fx, feas, isnull, dpar = g.logpost(x, want_dpar=True)
+    pr, lk, hy, feas2, isnull2 = g.logpost_parts(x)
+    ofx, ofeas, oisnull, odpar = o.logpost(x, nthreads=nthreads, want_dpar=True)
+    assert (feas == ofeas).all() and (isnull == oisnull).all(), "feasibility flags differ"
+    assert (feas2 == ofeas).all() and (isnull2 == oisnull).all()
+    ok = (ofeas == 1) & (oisnull == 0)
+    assert ok.sum() >= max(1, len(ok) // 4), "too few feasible vectors for a meaningful test"
+    opr, olk, ohy, _, _ = o.logpost_parts(x[ok][:8], long_double=True)
+    scale = np.abs(ofx[ok])
+    err = np.abs(fx[ok] - ofx[ok]) / np.maximum(scale, 1e-300)
+    assert err.max() <= tol, f"log-posterior parity {err.max():.3e} > {tol}"
+    # parts, against the long-double arbiter
+    sel = np.flatnonzero(ok)[:8]
+    for a, b in ((pr[sel], opr), (lk[sel], olk), (hy[sel], ohy)):
+        assert (np.abs(a - b) <= tol * np.maximum(np.abs(b), 1.0)).all()
+    assert (fx[~ok] == -999999999.0).all()
+    if g.nDpar:
+        assert np.allclose(dpar[ok], odpar[ok], rtol=1e-13, atol=0)
+    return err.max()
+
+
+@pytest.mark.parametrize("name", ["baratin", "baratin_spd", "regression_x2y2", "sediment_camenen_x4",
+                                  "sediment_mpm_x2", "textfile_inputuncertainty"])
+def test_reference_workspaces(name):
+    prob, d = problem_from_fixture(name)
+    x = perturbed_vectors(d["start"], 96, rel=0.03, seed=1)
+    check_parity(prob, x)
+
+
+def test_spd_without_copula():
+    prob, d = problem_from_fixture("baratin_spd", with_copula=False)
+    check_parity(prob, perturbed_vectors(d["start"], 64, rel=0.03, seed=2))
+
+
+def test_flags_and_infeasible_vectors():
+    prob, d = problem_from_fixture("baratin")
+    x = perturbed_vectors(d["start"], 32, rel=0.01, seed=3)
+    x[1, 6] = -1.0            # gamma1 outside its Uniform prior -> isnull
+    x[2, 3] = -1.0            # k2 < k1 -> infeasible continuity
+    x[3, 6] = 0.0; x[3, 7] = 0.0   # sigma == 0 -> infeasible
+    x[4, 1] = -5.0            # a1 <= 0
+    x[5, 6] = -1.0; x[5, 3] = -1.0  # null prior wins over infeasible model (prior is evaluated first)
+    g, o = BamGpu(prob), Oracle(prob)
+    fx, feas, isnull = g.logpost(x)
+    ofx, ofeas, oisnull = o.logpost(x)
+    assert (feas == ofeas).all() and (isnull == oisnull).all()
+    assert (feas[1], isnull[1]) == (1, 1) and (feas[2], isnull[2]) == (0, 0) and feas[3] == 0 and feas[4] == 0
+    assert (feas[5], isnull[5]) == (1, 1)
+
+
+def test_biases_and_latent_inputs():
+    """X random error (latent inputs), X bias, Y bias together (BaM_BaRatin_QbiasHbias shape)."""
+    rng = np.random.default_rng(5)
+    prob0, truth = synth.baratin_2c(nobs=300, seed=11)
+    n = 300
+    Xu = np.where(rng.random(n) < 0.5, 0.02, 0.0).reshape(-1, 1)
+    Xbindx = rng.integers(0, 3, n).reshape(-1, 1)
+    Xb = np.where(Xbindx > 0, 0.01, 0.0)
+    Ybindx = rng.integers(0, 4, n).reshape(-1, 1)
+    Yb = np.where(Ybindx > 0, 0.05 * np.abs(prob0.Y), 0.0)
+    Y = prob0.Y.copy()
+    Y[7, 0] = -9999.0  # a missing value is skipped (src/BaM_tools.f90:3207)
+    from bam_b200.capi import Problem
+
+    prob = Problem("BaRatin", prob0.X, Y, Yu=prob0.Yu, Xu=Xu, Xb=Xb, Xbindx=Xbindx, Yb=Yb, Ybindx=Ybindx,
+                   partype=[0] * 6, priors_theta=[("Gaussian", [t, abs(t) * 0.2 + 0.1]) for t in truth[:6]],
+                   sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000]), ("LogNormal", [-2.0, 1.0])],
+                   xtra_i=[1, 0, 0, 1])
+    o = Oracle(prob)
+    nlat = int((Xu > 0).sum())
+    assert o.sizes.nLatent == nlat and o.sizes.nXbias == 2 and o.sizes.nYbias == 3
+    start = np.concatenate([truth, prob0.X[Xu[:, 0] > 0, 0], np.zeros(5)])
+    x = perturbed_vectors(start, 48, rel=0.01, seed=6)
+    x[:, -5:] = 0.3 * rng.standard_normal((48, 5))
+    check_parity(prob, x)
+
+
+@pytest.mark.parametrize("funk,gam", [("Constant", [0.7]), ("Proportional", [0.2]), ("Power", [0.3, 0.1, 0.8]),
+                                      ("Exponential", [0.2, 5.0, 1.5]), ("Gaussian", [0.2, 5.0, 1.5])])
+def test_all_sigma_functions(funk, gam):
+    from bam_b200.capi import Problem
+
+    prob0, truth = synth.baratin_2c(nobs=200, seed=12)
+    prob = Problem("BaRatin", prob0.X, prob0.Y, Yu=prob0.Yu, partype=[0] * 6,
+                   priors_theta=[("Gaussian", [t, abs(t) * 0.2 + 0.1]) for t in truth[:6]], sigma_func=[funk],
+                   priors_gamma=[("Uniform", [0, 100])] * len(gam), xtra_i=[1, 0, 0, 1])
+    x = perturbed_vectors(np.concatenate([truth[:6], gam]), 32, rel=0.01, seed=7)
+    check_parity(prob, x)
+
+
+def test_all_prior_families_and_fix():
+    from bam_b200.capi import Problem
+
+    prob0, truth = synth.baratin_2c(nobs=120, seed=13)
+    priors = [("Triangle", [-0.5, -2.0, 1.0]), ("LogNormal", [4.0, 0.5]), ("Exponential", [1.0, 2.0]),
+              ("FlatPrior", []), ("FlatPrior+", [])]
+    prob = Problem("BaRatin", prob0.X, prob0.Y, Yu=prob0.Yu, partype=[0, 0, 0, 0, 0, -1],
+                   fix_value=[0, 0, 0, 0, 0, 1.67], priors_theta=priors, sigma_func=["Linear"],
+                   priors_gamma=[("Uniform", [0, 1000]), ("FlatPrior+", [])], xtra_i=[1, 0, 0, 1])
+    start = np.concatenate([truth[:5], truth[6:]])
+    x = perturbed_vectors(start, 48, rel=0.02, seed=8)
+    x[3, 1] = -1.0  # LogNormal at x<=0 -> null
+    x[4, 6] = -0.1  # FlatPrior+ at x<=0 -> null
+    check_parity(prob, x)
+
+
+def test_cfg2_synthetic_medium():
+    """BaRatin_SPD synthetic (cfg 2 generator) at a size the oracle finishes in seconds; with copula."""
+    prob, truth = synth.baratin_spd(nobs=20000, copula=True)
+    x = synth.feasible_starts(truth, 24, check=synth.spd_start_check)
+    check_parity(prob, x)
+
+
+def test_cfg3_linear_latent_medium():
+    prob, truth = synth.linear_latent(nobs=4000)
+    x = perturbed_vectors(truth, 6, rel=0.01, seed=9)
+    check_parity(prob, x)
+
+
+def test_cfg3_textfile_latent_medium():
+    prob, truth = synth.textfile_latent(nobs=3000)
+    x = perturbed_vectors(truth, 6, rel=0.005, seed=10)
+    check_parity(prob, x)
+
+
+def test_cfg4_sediment_medium():
+    prob, truth = synth.sediment_camenen(nobs=5000)
+    x = perturbed_vectors(truth, 16, rel=0.02, seed=11)
+    check_parity(prob, x)
+
+
+def test_small_and_ragged_sizes():
+    """n = 1, 31, 33, 257 observations (tile edges) and K = 1, 3, 65 vectors (chain-tile edges)."""
+    for n in (1, 31, 33, 257):
+        prob, truth = synth.baratin_2c(nobs=n, seed=20 + n)
+        for K in (1, 3, 65):
+            check_parity(prob, perturbed_vectors(truth, K, rel=0.01, seed=n + K))
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE size (4096 chains x 100k gaugings): size-independent properties.
+    (1) additivity: the likelihood over all observations equals the sum over two disjoint halves;
+    (2) batch independence: a vector evaluated alone equals the same vector inside the batch (bitwise);
+    (3) spot parity of 4 vectors against the oracle."""
+    n, K = 100_000, 4096
+    prob, truth = synth.baratin_spd(nobs=n)
+    x = synth.feasible_starts(truth, K, check=synth.spd_start_check)
+    g = BamGpu(prob)
+    pr, lk, hy, feas, isnull = g.logpost_parts(x)
+    assert feas.all() and not isnull.any()
+    from bam_b200.capi import Problem
+
+    def half(sel):
+        return Problem("BaRatin", prob.X[sel], prob.Y[sel], Yu=prob.Yu[sel], partype=prob.partype, nval=prob.nval,
+                       var_indx=prob.var_indx[sel], priors_theta=[(int(d), list(p)) for d, p in
+                                                                  zip(prob.prior_theta_dist, prob.prior_theta_par)],
+                       sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000])] * 2, xtra_i=prob.xtra_i)
+
+    idx = np.arange(n)
+    lkA = BamGpu(half(idx % 2 == 0)).logpost_parts(x)[1]
+    lkB = BamGpu(half(idx % 2 == 1)).logpost_parts(x)[1]
+    assert (np.abs(lkA + lkB - lk) <= 1e-12 * np.abs(lk)).all()
+    fx_all = g.logpost(x)[0]
+    for k in (0, 17, 4095):
+        assert g.logpost(x[k])[0][0] == fx_all[k]
+    o = Oracle(prob)
+    ofx = o.logpost(x[:4], nthreads=4)[0]
+    assert (np.abs(fx_all[:4] - ofx) <= 1e-12 * np.abs(ofx)).all()

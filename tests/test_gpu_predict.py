@@ -1,0 +1,161 @@
+"""GPU parity tests of the prediction path (K4 + envelopes) against the CPU oracle.
+
+(b) of BASELINE.json's north_star: deterministic propagation of a fixed sample agrees within 1e-12
+relative; integer selections (control activation / range, X-spaghetti column, infeasible flags) are
+bit-exact -- checked through the pattern of zeros and of unfeasFlag values, which must be identical.
+The structural-error noise is a pure function of (seed, rep, t, y) on both sides (Philox4x32-10)."""
+import numpy as np
+import pytest
+
+from bam_b200 import synth
+from bam_b200.capi import BamGpu
+from oracle.oracle_api import Oracle
+from tests.helpers import load_fixture, problem_from_fixture
+
+pytestmark = pytest.mark.gpu
+FLAG = -666.666
+
+
+def cmp_spag(a, b, tol=1e-12):
+    assert a.shape == b.shape
+    assert ((a == FLAG) == (b == FLAG)).all(), "infeasible pattern differs"
+    assert ((a == 0.0) == (b == 0.0)).all(), "Q == 0 pattern (range / control activation) differs"
+    m = a != FLAG
+    scale = np.maximum(np.abs(b[m]), 1e-6)
+    err = np.abs(a[m] - b[m]) / scale
+    assert err.max() <= tol, err.max()
+
+
+def cmp_env(a, b, tol=1e-12):
+    assert ((a == FLAG) == (b == FLAG)).all()
+    m = b != FLAG
+    scale = np.maximum(np.abs(b[m]), 1e-6)
+    assert (np.abs(a[m] - b[m]) / scale).max() <= tol
+
+
+def baratin_case(Nrep, seed=3):
+    prob, d = problem_from_fixture("baratin")
+    rng = np.random.default_rng(seed)
+    start = np.array(d["start"])
+    mc = start * (1.0 + 0.03 * rng.standard_normal((Nrep, start.size)))
+    mc[:, 6:] = np.abs(mc[:, 6:])
+    mc[5, 3] = -2.0  # k2 < k1: the whole replication is infeasible -> a row of flags
+    return prob, mc, start
+
+
+def test_baratin_workspace_experiments():
+    """The 4 posterior experiments of tests/BaM_BaRatin/Config_Pred_*.txt: grid with parametric U,
+    grid with total U, limnigraph maxpost, noisy limnigraph (100 X-spaghettis) with total U."""
+    prob, mc, mode = baratin_case(500)
+    pin = load_fixture("baratin_pred_inputs")
+    hgrid = np.asarray(pin["Hgrid"])
+    limni = np.asarray(pin["Limni"])
+    noisy = np.asarray(pin["Limni_noisy_colmajor"]).reshape(pin["Limni_noisy_shape"][::-1]).T
+    g, o = BamGpu(prob), Oracle(prob)
+    for xs, dop, dor in ((hgrid, 1, [0]), (hgrid, 1, [1]), (noisy, 1, [1]), (limni, 0, [1])):
+        env, spag = g.predict(mc, mode, [xs], dop, dor, seed=42, want_spag=True)
+        oenv, ospag = o.predict(mc, mode, [xs], dop, dor, seed=42, want_spag=True, nthreads=8)
+        cmp_spag(spag, ospag)
+        cmp_env(env, oenv)
+    # maxpost run: Nrep = 1, no envelope (src/BaM_tools.f90:958-960,1382)
+    _, spag = g.predict(None, mode, [limni], 0, [0], want_env=False, want_spag=True)
+    _, ospag = o.predict(None, mode, [limni], 0, [0], want_env=False, want_spag=True)
+    cmp_spag(spag, ospag)
+
+
+def test_input_sharding_is_invisible():
+    """Prediction inputs sharded across ranks ([t0,t1) slices) give bitwise the same columns."""
+    prob, mc, mode = baratin_case(300)
+    H = np.linspace(-1, 6, 301)
+    g = BamGpu(prob)
+    env, spag = g.predict(mc, mode, [H], 1, [1], seed=9, want_spag=True)
+    e1, s1 = g.predict(mc, mode, [H], 1, [1], seed=9, t0=0, t1=150, want_spag=True)
+    e2, s2 = g.predict(mc, mode, [H], 1, [1], seed=9, t0=150, t1=301, want_spag=True)
+    assert (np.concatenate([s1, s2], axis=1) == spag).all()
+    assert (np.concatenate([e1, e2], axis=2) == env).all()
+
+
+def test_envelope_bad_value_rule():
+    """< 75 % infeasible replications are dropped, >= 75 % flags the row (src/BaM_tools.f90:1393-1404)."""
+    prob, mc, mode = baratin_case(200)
+    mc2 = mc.copy()
+    mc2[:160, 3] = -2.0  # 80 % infeasible
+    H = np.linspace(-1, 6, 40)
+    g, o = BamGpu(prob), Oracle(prob)
+    env, _ = g.predict(mc2, mode, [H], 1, [0])
+    oenv, _ = o.predict(mc2, mode, [H], 1, [0])
+    assert (env == FLAG).all() and (oenv == FLAG).all()
+    mc3 = mc.copy()
+    mc3[:100, 3] = -2.0  # 50 % infeasible -> dropped
+    env, _ = g.predict(mc3, mode, [H], 1, [0])
+    oenv, _ = o.predict(mc3, mode, [H], 1, [0])
+    cmp_env(env, oenv)
+    assert (env != FLAG).all()
+
+
+def test_sediment_and_linear_and_textfile():
+    prob, truth = synth.sediment_camenen(nobs=50)
+    mc = synth.sediment_posterior(700)
+    X = [prob.X[:, j].copy() for j in range(4)]
+    X[0][3] = -1.0  # a non-positive input makes that row infeasible for every replication
+    g, o = BamGpu(prob), Oracle(prob)
+    for dor in ([0], [1]):
+        env, spag = g.predict(mc, truth, X, 1, dor, seed=5, want_spag=True)
+        oenv, ospag = o.predict(mc, truth, X, 1, dor, seed=5, want_spag=True, nthreads=8)
+        cmp_spag(spag, ospag)
+        cmp_env(env, oenv)
+    # Linear 2x2, two outputs, remnant noise on the second only
+    prob, d = problem_from_fixture("regression_x2y2")
+    rng = np.random.default_rng(2)
+    mc = np.abs(rng.standard_normal((64, 8))) + 0.1
+    Xs = [rng.standard_normal((30, 3)), rng.standard_normal((30, 1))]
+    g, o = BamGpu(prob), Oracle(prob)
+    env, spag = g.predict(mc, mc[0], Xs, 1, [0, 1], seed=8, want_spag=True)
+    oenv, ospag = o.predict(mc, mc[0], Xs, 1, [0, 1], seed=8, want_spag=True)
+    cmp_spag(spag, ospag)
+    cmp_env(env, oenv)
+    # TextFile a*T+b (no latent inputs at prediction time)
+    prob, d = problem_from_fixture("textfile_inputuncertainty")
+    P = len(d["start"])
+    mc = np.tile(np.asarray(d["start"]), (40, 1)) * (1 + 0.05 * rng.standard_normal((40, P)))
+    mc[:, 2:4] = np.abs(mc[:, 2:4])
+    T = np.linspace(0, 60, 25)
+    g, o = BamGpu(prob), Oracle(prob)
+    env, spag = g.predict(mc, mc[0], [T], 1, [1], seed=3, want_spag=True)
+    oenv, ospag = o.predict(mc, mc[0], [T], 1, [1], seed=3, want_spag=True)
+    cmp_spag(spag, ospag)
+    cmp_env(env, oenv)
+
+
+def test_large_sample_selection_path():
+    """Nrep above the shared-memory sort limit uses the histogram selection: exact order statistics."""
+    prob, d = problem_from_fixture("baratin")
+    mc, mode, Hs = synth.baratin_spaghetti(Nrep=40000, nobs=24, nspag=1)
+    mc[:9000, 3] = -2.0  # 22 % infeasible replications are dropped before the quantiles
+    g, o = BamGpu(prob), Oracle(prob)
+    for dor in ([0], [1]):
+        env, _ = g.predict(mc, mode, [Hs], 1, dor, seed=77)
+        oenv, _ = o.predict(mc, mode, [Hs], 1, dor, seed=77, nthreads=8)
+        cmp_env(env, oenv)
+    # heavy ties: every replication identical -> all quantiles equal, sd = 0
+    mc_same = np.tile(mode, (20000, 1))
+    env, _ = g.predict(mc_same, mode, [Hs], 1, [0])
+    assert (env[0, 0] == env[0, 1]).all() and (env[0, 6] == 0).all()
+
+
+def test_full_size_properties():
+    """BASELINE-sized sample (10^6 replications) on a few inputs: (1) envelopes without noise are
+    monotone in H for a rating curve; (2) quantile ordering q2.5 <= q16 <= median <= q84 <= q97.5;
+    (3) resident path == host path."""
+    prob, d = problem_from_fixture("baratin")
+    mc, mode, Hs = synth.baratin_spaghetti(Nrep=1_000_000, nobs=64, nspag=1)
+    Hs = np.sort(Hs, axis=0)
+    g = BamGpu(prob)
+    env, _ = g.predict(mc, mode, [Hs], 1, [0])
+    assert (np.diff(env[0, 0]) >= 0).all()
+    env, _ = g.predict(mc, mode, [Hs], 1, [1], seed=1)
+    q = env[0]
+    assert (q[1] <= q[3]).all() and (q[3] <= q[0]).all() and (q[0] <= q[4]).all() and (q[4] <= q[2]).all()
+    g.predict_upload(mc, mode, [Hs])
+    g.predict_resident(1, [1], seed=1)
+    assert (g.predict_download() == env).all()

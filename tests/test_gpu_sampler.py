@@ -1,0 +1,97 @@
+"""GPU tests of the batched adaptive-Metropolis sampler (K3) and the moments / Gelman-Rubin (K5).
+
+(c) of BASELINE.json's north_star: the sampler is stochastic -> statistical agreement.  Because the
+device and the oracle share the RNG specification (Philox counters keyed by chain / iteration /
+component), short runs can also be compared trajectory by trajectory."""
+import numpy as np
+import pytest
+
+from bam_b200 import synth
+from bam_b200.capi import BamGpu
+from oracle.oracle_api import Oracle
+from tests.helpers import problem_from_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def start_std(start, K, factor=0.1):
+    s = np.tile(np.asarray(start, dtype=np.float64), (K, 1))
+    sd = np.where(s != 0, factor * np.abs(s), 0.1)  # Config_Read_MCMC default (:2459-2471)
+    return s, sd
+
+
+def test_short_trajectories_match_oracle():
+    prob, d = problem_from_fixture("baratin")
+    K = 6
+    s, sd = start_std(d["start"], K)
+    g, o = BamGpu(prob), Oracle(prob)
+    rows = g.fit(s, sd, nAdapt=10, nCycles=4, seed=11)
+    orow, ofx, ostd = o.fit(s, sd, nAdapt=10, nCycles=4, seed=11)
+    assert rows.shape == orow.shape == (K, 40, 8 + 1 + 2)
+    # identical accept/reject decisions -> identical states up to libm/libdevice rounding of fx
+    assert np.allclose(rows[:, :, :8], orow[:, :, :8], rtol=1e-12, atol=0)
+    assert np.allclose(rows[:, :, 8], orow[:, :, 8], rtol=1e-12)
+    assert np.allclose(rows[:, :, 9:], orow[:, :, 9:], rtol=1e-12)
+    # chains differ from each other (independent streams) and moved
+    assert not np.allclose(rows[0, -1, :8], rows[1, -1, :8])
+    fx, feas, isnull, dpar = g.chains_download(want_dpar=True)
+    assert np.allclose(fx, orow[:, -1, 8], rtol=1e-12) and feas.all()
+    cnt, mean, m2 = g.moments()
+    assert (cnt == 40).all()
+    assert np.allclose(mean, rows[:, :, :8].mean(axis=1), rtol=1e-11)
+    assert np.allclose(m2, ((rows[:, :, :8] - mean[:, None, :]) ** 2).sum(axis=1), rtol=1e-8, atol=1e-14)
+
+
+def test_burn_and_thinning_and_var_params():
+    prob, d = problem_from_fixture("baratin_spd", with_copula=True)
+    K = 4
+    s, sd = start_std(d["start"], K, 0.05)
+    g, o = BamGpu(prob), Oracle(prob)
+    rows = g.fit(s, sd, nAdapt=5, nCycles=4, seed=3, burn=6, keep_every=3)
+    orow, _, _ = o.fit(s, sd, nAdapt=5, nCycles=4, seed=3, burn=6, keep_every=3)
+    assert rows.shape == orow.shape == (K, 4, 19 + 1 + 15)
+    assert np.allclose(rows, orow, rtol=1e-11, atol=1e-13)
+
+
+def test_posterior_statistics_and_rhat():
+    """Statistical agreement: many short GPU chains vs. the oracle sampler on the same posterior."""
+    prob, truth = synth.baratin_2c(nobs=60, seed=4)
+    K = 256
+    s, sd = start_std(truth, K, 0.05)
+    g, o = BamGpu(prob), Oracle(prob)
+    rows = g.fit(s, sd, nAdapt=50, nCycles=12, seed=5, burn=300, keep_every=1)
+    cnt, mean, m2 = g.moments()
+    rhat = g.rhat(cnt, mean, m2)
+    assert (rhat < 1.2).all(), rhat
+    gm = rows[:, :, :8].reshape(-1, 8)
+    orow, _, _ = o.fit(s[:24], sd[:24], nAdapt=50, nCycles=12, seed=99, burn=300, keep_every=1)
+    om = orow[:, :, :8].reshape(-1, 8)
+    # posterior means agree within a few Monte-Carlo standard errors of the smaller (oracle) sample
+    se = om.std(axis=0) / np.sqrt(24 * 300 / 20.0)
+    assert (np.abs(gm.mean(axis=0) - om.mean(axis=0)) < 6 * se).all()
+    for q in (0.16, 0.5, 0.84):
+        assert (np.abs(np.quantile(gm, q, axis=0) - np.quantile(om, q, axis=0)) < 8 * se).all()
+
+
+def test_infeasible_start_is_an_error():
+    from bam_b200.capi import BamError
+
+    prob, d = problem_from_fixture("baratin")
+    s, sd = start_std(d["start"], 3)
+    s[1, 3] = -2.0
+    with pytest.raises(BamError) as e:
+        BamGpu(prob).fit(s, sd, nAdapt=2, nCycles=1)
+    assert "unfeasible starting point" in str(e.value)
+
+
+def test_chain_offset_makes_sharding_invisible():
+    """Chains sharded over ranks: rank r runs chains [r*K/2, (r+1)*K/2) with chain offset -> same rows."""
+    prob, d = problem_from_fixture("baratin")
+    K = 8
+    s, sd = start_std(d["start"], K)
+    g = BamGpu(prob)
+    rows = g.fit(s, sd, nAdapt=6, nCycles=2, seed=21)
+    g2 = BamGpu(prob)
+    g2.lib.bamgpu_set_chain_offset(g2.h, 4)
+    rows_b = g2.fit(s[4:], sd[4:], nAdapt=6, nCycles=2, seed=21)
+    assert (rows_b == rows[4:]).all()

@@ -1,0 +1,176 @@
+"""CPU tests of the oracle: pinned against everything the reference offers for this path
+(SURVEY.md 8c): known-answer columns in the sediment data files, control matrices / VAR index
+columns, and the independent surveyor restatement of SURVEY.md App. F."""
+import numpy as np
+import pytest
+
+from oracle import oracle_api
+from oracle.oracle_api import Oracle
+from tests.helpers import load_fixture, problem_from_fixture
+
+
+# SURVEY.md App. F (independent scratch restatement, sequential python sums)
+APP_F = {
+    "baratin": dict(fx=-208.221439619687, lkh=-192.240250729638, prior=-15.981188890049, b2=0.47563645511404),
+    "sediment_camenen_x4": dict(fx=2843.24519325832, lkh=2894.82100383739, prior=-51.5758105790742),
+    "regression_x2y2": dict(fx=-306.503863198421, lkh=-252.165941407072, prior=-54.3379217913487),
+}
+
+
+@pytest.mark.parametrize("name", sorted(APP_F))
+def test_logpost_matches_independent_restatement(name):
+    p, d = problem_from_fixture(name)
+    r = Oracle(p).logpost_one(d["start"])
+    ref = APP_F[name]
+    assert r["feas"] == 1 and r["isnull"] == 0
+    for key in ("fx", "lkh", "prior"):
+        assert abs(r[key] - ref[key]) <= 2e-12 * abs(ref[key]), (key, r[key], ref[key])
+    if "b2" in ref:
+        assert abs(r["dpar"][1] - ref["b2"]) < 1e-13
+        assert r["dpar"][0] == d["start"][0]  # b1 = k1 exactly (BaRatin_model.f90:375)
+
+
+def test_long_double_arbiter_agrees():
+    for name in APP_F:
+        p, d = problem_from_fixture(name)
+        o = Oracle(p)
+        a, b = o.logpost_one(d["start"]), o.logpost_one(d["start"], long_double=True)
+        assert abs(a["fx"] - b["fx"]) <= 1e-12 * abs(a["fx"])
+
+
+def test_sediment_known_answer_columns():
+    """tests/BaM_Sediment_Camenen_X4/XY.BAD carries tau, qsCL, sediment_D, tau_cr_soulsby (3 digits).
+    tau and D pin the inputs/units; qsCL was generated with the ADDITIVE Soulsby formula while the
+    reference CODE multiplies the two terms (SedimentTransport_model.f90:302 vs :39-40).  Parity
+    target is the code; the discrepancy is asserted explicitly so that it stays documented."""
+    p, d = problem_from_fixture("sediment_camenen_x4")
+    n, ncol = d["nobs"], d["data_ncol"]
+    W = np.asarray(d["data_table"]).reshape(ncol, n).T
+    h, S0, dd, s, v, g, qs, tau_col, qsCL, SD_col, css_col = W.T
+    tau = h * S0 / ((s - 1.0) * dd)
+    SD = (g * (s - 1.0) / v**2) ** (1.0 / 3.0) * dd
+    assert np.allclose(tau, tau_col, rtol=1.5e-2)  # inputs and answers are printed with 3 digits
+    assert np.allclose(SD, SD_col, rtol=6e-3)
+    css_add = 0.3 / (1 + 1.2 * SD) + 0.055 * (1 - np.exp(-0.02 * SD))
+    css_mul = (0.3 / (1 + 1.2 * SD)) * 0.055 * (1 - np.exp(-0.02 * SD))
+    assert np.allclose(css_add, css_col, rtol=1.5e-2)
+    o = Oracle(p)
+    theta = np.array([12.0, 1.5, 4.5])
+    Y, feas, _ = o.apply_model(np.column_stack([h, S0, dd, s]), theta)
+    assert feas.all()
+    code = np.sqrt(g * (s - 1) * dd**3) * 12.0 * tau**1.5 * np.exp(-4.5 * css_mul / tau)
+    assert np.allclose(Y[:, 0], code, rtol=1e-13)
+    # undo the css difference -> the data file's qsCL (3 significant digits)
+    as_file = Y[:, 0] * np.exp(-4.5 * (css_add - css_mul) / tau)
+    assert np.allclose(as_file, qsCL, rtol=4e-2)
+
+
+def test_spd_fixture_structure():
+    """control matrix / VAR index column / prior correlation of tests/BaM_BaRatin_SPD"""
+    p, d = problem_from_fixture("baratin_spd")
+    o = Oracle(p)
+    assert d["xtra_i"] == [1, 0, 0, 0, 1, 1, 0, 0, 1]  # column-major [[1,0,0],[0,1,0],[0,1,1]]
+    assert (o.sizes.nFit, o.sizes.nGamma, o.sizes.nInfer, o.sizes.nCombo, o.sizes.nDpar) == (17, 2, 19, 5, 15)
+    vi = np.asarray(d["var_indx"]).reshape(9, d["nobs"]).T
+    assert set(np.unique(vi[:, 0])) == {1, 2, 3, 4, 5} and (vi[:, 0] == vi[:, 3]).all()
+    C = np.asarray(d["priorC"]).reshape(19, 19)
+    assert np.allclose(C, C.T) and np.allclose(np.diag(C), 1.0)
+    r = o.logpost_one(d["start"])
+    assert r["feas"] == 1
+    # b3 = k3 because range 3 keeps control 2 and adds control 3 (BaRatin_model.f90:386-393)
+    assert all(r["dpar"][3 * k + 2] == 1.2 for k in range(5))
+    # copula term changes the prior, not the likelihood
+    p0, _ = problem_from_fixture("baratin_spd", with_copula=False)
+    r0 = Oracle(p0).logpost_one(d["start"])
+    assert r0["lkh"] == r["lkh"] and r0["prior"] != r["prior"]
+
+
+def test_early_exit_flags():
+    p, d = problem_from_fixture("baratin")
+    o = Oracle(p)
+    x = np.array(d["start"])
+    bad = x.copy(); bad[6] = -1.0          # gamma1 outside Uniform(0,1000) -> isnull, feas stays true
+    r = o.logpost_one(bad)
+    assert (r["feas"], r["isnull"]) == (1, 1) and r["fx"] == -999999999.0
+    bad = x.copy(); bad[3] = -1.0          # k2 < k1 -> continuity infeasible
+    r = o.logpost_one(bad)
+    assert (r["feas"], r["isnull"]) == (0, 0)
+    bad = x.copy(); bad[6] = 0.0; bad[7] = 0.0   # sigma = 0 -> infeasible (src/BaM_tools.f90:3210)
+    assert o.logpost_one(bad)["feas"] == 0
+
+
+def test_baratin_range_boundaries():
+    """H == k_i belongs to the upper range (strict <, BaRatin_model.f90:427); below k1 -> Q = 0."""
+    p, d = problem_from_fixture("baratin")
+    o = Oracle(p)
+    th = np.array(d["start"][:6])
+    H = np.array([-1.0, -0.5, np.nextafter(-0.5, 1), 1.5, np.nextafter(1.5, -1), 3.0])
+    Y, feas, dpar = o.apply_model(H, th)
+    b2 = dpar[1]
+    assert Y[0, 0] == 0.0 and Y[1, 0] == 0.0  # (H-b1)=0 -> 53*0**1.5 = 0
+    assert Y[3, 0] == 144.0 * (1.5 - b2) ** 1.67          # range 2: control 2 only
+    assert Y[4, 0] == 53.0 * (H[4] + 0.5) ** 1.5          # still range 1
+    assert abs(Y[3, 0] - Y[4, 0]) < 1e-9 * Y[3, 0]        # continuity at k2
+    assert feas.all()
+
+
+def test_textfile_compiler_semantics():
+    """a+b-c -> a+(b-c); a*b/c -> a*(b/c); a^b^c -> (a^b)^c; leading minus negates the product
+    (TextFile_model.f90:702-726)."""
+    from bam_b200.capi import Problem
+
+    def ev(formula, vals):
+        text = f"3\nx,y,z\n0\n\n1\n{formula}\n"
+        p = Problem("TextFile", np.array([vals]), np.array([[0.0]]), partype=[], priors_theta=[],
+                    sigma_func=["Constant"], priors_gamma=[("FlatPrior", [])], xtra_text=text)
+        Y, feas, _ = Oracle(p).apply_model(np.array([vals]), np.array([]))
+        return Y[0, 0], feas[0]
+
+    x, y, z = 0.1, 0.2, 0.3
+    assert ev("x+y-z", (x, y, z))[0] == x + (y - z)
+    assert ev("x-y+z", (x, y, z))[0] == (x - y) + z
+    assert ev("x*y/z", (x, y, z))[0] == x * (y / z)
+    assert ev("x**y**z", (x, y, z))[0] == (x**y) ** z
+    assert ev("-x*y", (x, y, z))[0] == -(x * y)
+    assert ev("-x^2", (3.0, y, z))[0] == -9.0
+    assert ev("2.5e-1*x+exp(-y)", (x, y, z))[0] == 2.5e-1 * x + np.exp(-y)
+    assert ev("Abs(-x)+SQRT(y)", (x, y, z))[0] == abs(-x) + np.sqrt(y)
+    assert ev("ispos(x)*is0(y-y)+issneg(z)", (x, y, z))[0] == 1.0
+    assert ev("x/(y-y)", (x, y, z))[1] == 0      # division by zero -> row infeasible
+    assert ev("log(-x)", (x, y, z))[1] == 0
+    assert ev("sqrt(-x)", (x, y, z))[1] == 0
+    assert ev("asin(x+2)", (x, y, z))[1] == 0
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors)."""
+    assert oracle_api.philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert oracle_api.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert oracle_api.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_normal_stream_moments_and_quantile():
+    z = np.array([oracle_api.normal(7, i, 3, 1) for i in range(20000)])
+    assert abs(z.mean()) < 0.03 and abs(z.std() - 1.0) < 0.03
+    u = np.array([oracle_api.uniform(7, i, 0, 0) for i in range(20000)])
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    from scipy.stats import norm
+    for p in (1e-12, 1e-6, 0.025, 0.3, 0.5, 0.7, 0.975, 1 - 1e-9):
+        assert abs(oracle_api.normal_quantile(p) - norm.ppf(p)) <= 1e-12 * max(1.0, abs(norm.ppf(p)))
+
+
+def test_envelope_rule():
+    """< 75 % bad -> dropped; >= 75 % bad -> row of flags (src/BaM_tools.f90:1393-1404); Hazen quantiles."""
+    f = -666.666
+    col = np.arange(1.0, 101.0)
+    e = oracle_api.envelope(col)
+    assert e[0] == 50.5 and abs(e[5] - 50.5) < 1e-12 and abs(e[6] - col.std(ddof=1)) < 1e-12
+    assert abs(e[1] - (0.025 * 100 + 0.5 - 3 + 3)) < 1e-12  # h = 3.0 -> x_3 = 3
+    c2 = col.copy(); c2[:70] = f
+    e2 = oracle_api.envelope(c2)
+    assert e2[0] == np.median(col[70:]) and (e2 != f).all()
+    c3 = col.copy(); c3[:75] = f
+    assert (oracle_api.envelope(c3) == f).all()
+    c4 = col.copy(); c4[3] = np.nan
+    assert np.isfinite(oracle_api.envelope(c4)).all()
