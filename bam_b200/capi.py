@@ -313,6 +313,14 @@ def load_library(path: Optional[str] = None):
     lib.bamgpu_last_kernel_ms.argtypes = [H]
     lib.bamgpu_last_kernel_ms.restype = C.c_double
     lib.bamgpu_fp64_peak.argtypes = [ci, _dp, cp]
+    for name in ("step_begin", "step_end"):
+        getattr(lib, "bamgpu_" + name).argtypes = [H]
+    lib.bamgpu_step_times.argtypes = [H, _dp, ci]
+    lib.bamgpu_kernel_times.argtypes = [H, _dp, ci]
+    lib.bamgpu_flush_l2.argtypes = [H, C.c_size_t]
+    lib.bamgpu_pin.argtypes = [C.c_void_p, C.c_size_t]
+    lib.bamgpu_unpin.argtypes = [C.c_void_p]
+    lib.bamgpu_set_chain_offset.argtypes = [H, i64]
     lib.bamgpu_version.restype = cp
     for name in ("dist_id", "sigmafunc_id", "model_id"):
         getattr(lib, "bamgpu_" + name).argtypes = [cp]
@@ -527,6 +535,28 @@ class BamGpu:
         return env
 
     # -- measurement ---------------------------------------------------------------------
+    def step_begin(self):
+        self.lib.bamgpu_step_begin(self.h)
+
+    def step_end(self):
+        self.lib.bamgpu_step_end(self.h)
+
+    def step_times(self, cap=8192):
+        buf = np.empty(cap)
+        n = self.lib.bamgpu_step_times(self.h, _ptr_d(buf), cap)
+        return buf[:n].copy()
+
+    def kernel_times(self, cap=8192):
+        buf = np.empty(cap)
+        n = self.lib.bamgpu_kernel_times(self.h, _ptr_d(buf), cap)
+        return buf[:n].copy()
+
+    def flush_l2(self, nbytes=256 << 20):
+        self.lib.bamgpu_flush_l2(self.h, nbytes)
+
+    def set_chain_offset(self, off: int):
+        self.lib.bamgpu_set_chain_offset(self.h, off)
+
     def launch_count(self) -> int:
         return int(self.lib.bamgpu_launch_count(self.h))
 

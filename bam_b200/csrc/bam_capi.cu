@@ -172,6 +172,10 @@ void bamgpu_destroy(bamgpu_t* h) {
     fr(h->d_status); fr(h->d_delta); fr(h->d_std); fr(h->d_fxcur); fr(h->d_dparcur); fr(h->d_moves); fr(h->d_mcount);
     fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_env);
     free_prediction(h);
+    if (h->d_flush) cudaFree(h->d_flush);
+    for (auto e : h->evPool) cudaEventDestroy(e);
+    for (auto& pr : h->stepEv) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : h->kernEv) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -391,6 +395,52 @@ int bamgpu_predict(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mo
 
 int64_t bamgpu_launch_count(const bamgpu_t* h) { return h->launches; }
 double bamgpu_last_kernel_ms(const bamgpu_t* h) { return h->lastMs; }
+
+int bamgpu_step_begin(bamgpu_t* h) {
+    try {
+        h->recordKernels = true;
+        h->stepOpen = bam::take_event(h);
+        return cudaEventRecord(h->stepOpen, h->stream) == cudaSuccess ? 0 : 1;
+    } catch (...) { return 1; }
+}
+
+int bamgpu_step_end(bamgpu_t* h) {
+    try {
+        if (!h->stepOpen) return 1;
+        cudaEvent_t e = bam::take_event(h);
+        if (cudaEventRecord(e, h->stream) != cudaSuccess) return 1;
+        h->stepEv.emplace_back(h->stepOpen, e);
+        h->stepOpen = nullptr;
+        return 0;
+    } catch (...) { return 1; }
+}
+
+static int drain(bamgpu_t* h, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, double* ms, int cap) {
+    cudaStreamSynchronize(h->stream);
+    int n = 0;
+    for (auto& pr : v) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, pr.first, pr.second);
+        if (n < cap) ms[n] = t;
+        ++n;
+        h->evPool.push_back(pr.first);
+        h->evPool.push_back(pr.second);
+    }
+    v.clear();
+    return n < cap ? n : cap;
+}
+
+int bamgpu_step_times(bamgpu_t* h, double* ms, int cap) { return drain(h, h->stepEv, ms, cap); }
+int bamgpu_kernel_times(bamgpu_t* h, double* ms, int cap) { return drain(h, h->kernEv, ms, cap); }
+
+int bamgpu_flush_l2(bamgpu_t* h, size_t bytes) {
+    if (bytes > h->flushCap) {
+        if (h->d_flush) cudaFree(h->d_flush);
+        if (cudaMalloc(&h->d_flush, bytes) != cudaSuccess) { h->d_flush = nullptr; h->flushCap = 0; return 1; }
+        h->flushCap = bytes;
+    }
+    return cudaMemsetAsync(h->d_flush, 0x5a, bytes, h->stream) == cudaSuccess ? 0 : 1;
+}
 
 int bamgpu_pin(void* ptr, size_t bytes) { return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1; }
 int bamgpu_unpin(void* ptr) { return cudaHostUnregister(ptr) == cudaSuccess ? 0 : 1; }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "bam_device.cuh"
@@ -62,6 +63,12 @@ struct bamgpu_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double lastMs = 0.0;
     long long launches = 0;
+    std::vector<cudaEvent_t> evPool;            // recycled events
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> stepEv, kernEv;  // recorded, not yet read
+    cudaEvent_t stepOpen = nullptr;
+    bool recordKernels = false;
+    void* d_flush = nullptr;
+    size_t flushCap = 0;
 };
 
 // internal entry points shared between translation units
@@ -78,6 +85,7 @@ struct CudaError {
     } while (0)
 
 void ensure_chain_capacity(bamgpu_handle* h, int K);
+cudaEvent_t take_event(bamgpu_handle* h);
 // evaluate K vectors at d_x (optionally with component `comp` of every vector shifted by d_delta[k]);
 // results in d_prior/d_lkh/d_hyper/d_fx/d_status/d_dpar.  Asynchronous on h->stream.
 void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain);

@@ -326,6 +326,13 @@ static void make_plan(bamgpu_handle* h, int K) {
     pl.smem = ((size_t)ct * stride + 2 * (pl.TX / 32) * ct) * 8 + (size_t)ct * 4;
 }
 
+cudaEvent_t take_event(bamgpu_handle* h) {
+    if (!h->evPool.empty()) { cudaEvent_t e = h->evPool.back(); h->evPool.pop_back(); return e; }
+    cudaEvent_t e;
+    BAM_CUDA(cudaEventCreate(&e));
+    return e;
+}
+
 void ensure_chain_capacity(bamgpu_handle* h, int K) {
     if (K <= h->Kcap) { make_plan(h, K); return; }
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
@@ -355,11 +362,18 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
                                                          h->d_dpar);
     if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
-    if (timeMain) BAM_CUDA(cudaEventRecord(h->ev0, h->stream));
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    if (timeMain) {
+        BAM_CUDA(cudaEventRecord(h->ev0, h->stream));
+        if (h->recordKernels && h->kernEv.size() < 8192) { k0 = take_event(h); k1 = take_event(h); BAM_CUDA(cudaEventRecord(k0, h->stream)); }
+    }
     if (p.n > 0)
         kern<<<grid, BAM_BLOCK, pl.smem, h->stream>>>(p, d_x, K, pl.CT, pl.TX, h->d_tab, h->d_status, h->d_part, h->d_status,
                                                        comp, d_delta);
-    if (timeMain) BAM_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if (timeMain) {
+        BAM_CUDA(cudaEventRecord(h->ev1, h->stream));
+        if (k1) { BAM_CUDA(cudaEventRecord(k1, h->stream)); h->kernEv.emplace_back(k0, k1); }
+    }
     logpost_final<<<(K + 127) / 128, 128, 0, h->stream>>>(p, K, p.n > 0 ? pl.nTiles : 0, h->d_part, h->d_prior, h->d_status,
                                                           h->d_lkh, h->d_hyper, h->d_fx);
     h->launches += (p.n > 0) ? 3 : 2;

@@ -490,6 +490,8 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEnv));
 
     BAM_CUDA(cudaEventRecord(h->ev0, s));
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    if (h->recordKernels && h->kernEv.size() < 8192) { k0 = take_event(h); k1 = take_event(h); BAM_CUDA(cudaEventRecord(k0, s)); }
     for (int tt = 0; tt < nTall; tt += (int)tileT) {
         const int nT = std::min<long long>(tileT, nTall - tt);
         a.t0 = t0 + tt; a.nT = nT;
@@ -517,6 +519,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         }
     }
     BAM_CUDA(cudaEventRecord(h->ev1, s));
+    if (k1) { BAM_CUDA(cudaEventRecord(k1, s)); h->kernEv.emplace_back(k0, k1); }
     BAM_CUDA(cudaGetLastError());
 }
 

@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the BaM hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): BaRatin_SPD multi-period
+rating curves -- 4096 chains x 100 000 synthetic gaugings PER GPU (weak scaling: chains shard across
+ranks, observations are replicated, no data-path collective).  A "step" = one batched log-posterior
+evaluation of every chain of the rank against all observations.  metric = chain x obs evaluations / s,
+whole job.  `value`: inputs resident in HBM, CUDA-event timed per step with an L2 flush between steps.
+`e2e`: the same metric through the C-ABI call a host makes (bamgpu_logpost) with pinned HOST buffers,
+H2D of the parameter vectors and D2H of (fx, flags) inside the timed region.
+Also reported (same JSON line, key "prediction"): BASELINE's second metric, prediction samples x inputs / s
+on configs[4] (BaRatin spaghetti with structural-error noise), scaled to fit the default run time.
+
+--impl reference: the reference executable cannot be built here or on the GPU box (no Fortran compiler,
+BMSL/miniDMSL un-vendored); this arm times the CPU restatement (oracle, kind "port") of the reference's own
+algorithm on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "log-posterior evals/sec (chains x obs)"
+UNIT = "chain*obs/s"
+NOBS = 100_000
+CHAINS_PER_GPU = 4096
+# FP64-pipe instructions per chain x obs of logpost_main<BaRatin,1,1> on this workload, from the ncu capture in
+# profiles/ (smsp__inst_executed_pipe_fp64 / units); see DESIGN.md "roofline accounting".
+FP64_INST_PER_UNIT = None  # filled from profiles/fp64_inst_per_unit.json when present
+NOMINAL_FLOPS_PER_UNIT = 24.6  # 3 range compares + 5 per active control (1.51 avg) + 14 likelihood tail
+ALGO_BYTES_PER_OBS = 28  # H, Q, uQ (3 x 8 B) + int32 period
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def start_clock_sampler(device_index: int):
+    f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                              "-i", str(device_index)], stdout=f, stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, f.name
+    return p, f.name
+
+
+def stop_clock_sampler(p, path):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    if p is not None:
+        p.terminate()
+        try:
+            p.wait(timeout=5)
+        except Exception:
+            p.kill()
+    try:
+        rows = [ln.strip().split(",") for ln in open(path) if ln.strip()]
+        sm = [float(r[1]) for r in rows if len(r) >= 9]
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(rows[0][2])
+            out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for j, nm in enumerate(names):
+                if any("Active" in r[5 + j] and "Not" not in r[5 + j] for r in rows if len(r) >= 9):
+                    out["reasons"].append(nm)
+            out["samples"] = len(sm)
+    except Exception:
+        pass
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    return out
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def fp64_inst_per_unit():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "fp64_inst_per_unit.json")))
+    except Exception:
+        return {}
+
+
+def cpu_baseline(prob, x, seconds_target=12.0):
+    """oracle (port) on all host cores on a bounded sample of the same workload"""
+    from oracle.oracle_api import Oracle
+
+    o = Oracle(prob)
+    cores = os.cpu_count() or 1
+    n = prob.nobs
+    k = min(len(x), cores)
+    t0 = time.perf_counter()
+    o.logpost(x[:k], nthreads=cores)          # calibration: one vector per core
+    dt = max(time.perf_counter() - t0, 1e-6)
+    kk = int(min(len(x), max(cores, round(seconds_target / dt) * cores)))
+    t0 = time.perf_counter()
+    o.logpost(x[:kk], nthreads=cores)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    o.logpost(x[:2], nthreads=1)
+    dt1 = time.perf_counter() - t1
+    return {"value": kk * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{kk} chains x {n} obs, oracle/bam_oracle.c (C restatement; the Fortran reference cannot be built "
+                      f"here), OpenMP over chains", "value_1core": 2 * n / dt1, "seconds": dt}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    from bam_b200 import synth
+    from oracle.oracle_api import Oracle
+
+    prob, truth = synth.baratin_spd(nobs=NOBS)
+    cores = os.cpu_count() or 1
+    kstep = max(cores, 32)  # bounded sample per step
+    x = synth.feasible_starts(truth, kstep, check=synth.spd_start_check)
+    o = Oracle(prob)
+    for _ in range(max(args.warmup, 1)):
+        o.logpost(x[:cores], nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.logpost(x, nthreads=cores)
+    dt = time.perf_counter() - t0
+    val = args.steps * kstep * NOBS / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BaRatin_SPD 4096 chains x 100k gaugings per GPU (configs[1])",
+                       "sample_per_step": f"{kstep} chains x {NOBS} obs"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{kstep} chains x {NOBS} obs per step, oracle/bam_oracle.c, OpenMP over chains"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def prediction_leg(device, steps=2):
+    """BASELINE's second metric on configs[4] (BaRatin spaghetti + structural-error noise), bounded size."""
+    from bam_b200 import synth
+    from bam_b200.capi import BamGpu
+
+    Nrep, nobs = 1_000_000, 2048
+    prob, _ = synth.baratin_2c(nobs=38)
+    mc, mode, Hs = synth.baratin_spaghetti(Nrep=Nrep, nobs=nobs)
+    g = BamGpu(prob, device)
+    g.predict_upload(mc, mode, [Hs])
+    g.predict_resident(1, [1], seed=1)
+    g.sync()
+    g.kernel_times()
+    g.step_times()
+    for _ in range(steps):
+        g.step_begin()
+        g.predict_resident(1, [1], seed=1)
+        g.step_end()
+    g.sync()
+    ms = g.step_times()
+    env = g.predict_download()
+    ok = bool(np.isfinite(env).all())
+    return {"metric": "prediction samples x inputs/sec", "value": Nrep * nobs / (ms.mean() * 1e-3), "unit": "sample*input/s",
+            "ms_per_step": float(ms.mean()), "workload": f"BaRatin spaghetti {Nrep} samples x {nobs} inputs, parametric + "
+            f"remnant noise, exact envelopes (configs[4] scaled to {nobs} inputs)", "finite": ok}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--nobs", type=int, default=NOBS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-prediction", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local = dist_env()
+    import torch  # plumbing only: barrier / max-over-ranks / synchronize
+
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = local if world > 1 else 0
+    torch.cuda.set_device(device)
+
+    from bam_b200 import synth
+    from bam_b200.capi import BamGpu, load_library
+
+    lib = load_library()
+    K, n = args.chains, args.nobs
+    prob, truth = synth.baratin_spd(nobs=n)
+    x = synth.feasible_starts(truth, K, seed=synth.SEED + 1 + rank, check=synth.spd_start_check)
+    g = BamGpu(prob, device)
+    g.set_chain_offset(rank * K)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        g.sync()
+
+    # ---- resident path (value) ----
+    g.chains_upload(x)
+    for _ in range(args.warmup):
+        g.logpost_resident()
+    g.sync()
+    g.step_times(); g.kernel_times()
+    launches0 = g.launch_count()
+    sampler, spath = start_clock_sampler(device)
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        if not args.no_flush:
+            g.flush_l2(256 << 20)
+        g.step_begin()
+        g.logpost_resident()
+        g.step_end()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = stop_clock_sampler(sampler, spath)
+    step_ms = g.step_times()
+    kern_ms = g.kernel_times()
+    launches = g.launch_count() - launches0
+    fx, feas, isnull = g.chains_download()
+    assert feas.all() and np.isfinite(fx).all(), "benchmark vectors must be feasible"
+    t_total = float(step_ms.sum()) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_total = float(tt.item())
+    value = world * K * n * args.steps / t_total
+
+    # ---- e2e path: host buffers through the C ABI ----
+    xh = np.ascontiguousarray(x)
+    lib.bamgpu_pin(xh.ctypes.data, xh.nbytes)
+    g.logpost(xh)
+    barrier()
+    e0 = time.perf_counter()
+    esteps = max(3, min(args.steps, 10))
+    for _ in range(esteps):
+        fx2, feas2, isnull2 = g.logpost(xh)
+    barrier()
+    e_t = time.perf_counter() - e0
+    lib.bamgpu_unpin(xh.ctypes.data)
+    if world > 1:
+        tt = torch.tensor([e_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e_t = float(tt.item())
+    e2e_value = world * K * n * esteps / e_t
+    assert (fx2 == fx).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (logpost_main), rank 0 ----
+    peaks = measured_peaks()
+    tfl = np.zeros(1)
+    import ctypes as C
+    mb = C.create_string_buffer(250)
+    lib.bamgpu_fp64_peak(device, tfl.ctypes.data_as(C.POINTER(C.c_double)), mb)
+    fp64_peak = float(tfl[0])
+    k_ms = float(kern_ms.mean())
+    units = K * n
+    ipu = fp64_inst_per_unit().get("logpost_main_baratin_spd")
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # algorithmic bytes of one launch: every observation table once + the per-chain table + one (lkh, hyper) partial
+    # per (observation tile, chain)
+    n_tiles = (n + 255) // 256
+    algo_bytes = n * ALGO_BYTES_PER_OBS + K * 8 * (2 + 5 * 12) + n_tiles * K * 16
+    roof = {
+        "bound": "fp64",
+        "kernel": "logpost_main<BaRatin,1,1>",
+        "unit": "TFLOP/s",
+        "peak": fp64_peak,
+        "peak_source": "DFMA micro-benchmark run live in this process (MEASURED_PEAKS.json has no FP64 figure); 2 flop per DFMA",
+        "kernel_ms": k_ms,
+        "kernel_share_of_step": k_ms / float(step_ms.mean()),
+        "nominal_flops_per_unit": NOMINAL_FLOPS_PER_UNIT,
+        "achieved_nominal": NOMINAL_FLOPS_PER_UNIT * units / (k_ms * 1e-3) / 1e12,
+        "traffic": None,
+        "hbm": {"achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback"},
+    }
+    if ipu:
+        ach = 2.0 * ipu * units / (k_ms * 1e-3) / 1e12
+        roof.update({"achieved": ach, "frac": ach / fp64_peak, "fp64_inst_per_unit": ipu,
+                     "achieved_note": "2 x FP64-pipe instructions executed (ncu, profiles/) per second: pipe utilisation vs the DFMA peak"})
+        prof = fp64_inst_per_unit()
+        roof["traffic"] = prof.get("dram_bytes_per_launch")
+    else:
+        roof.update({"achieved": roof["achieved_nominal"], "frac": roof["achieved_nominal"] / fp64_peak,
+                     "achieved_note": "nominal flops only (no ncu instruction count committed yet)"})
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BaRatin_SPD (3 controls, 5 periods, VAR k1/k2): {K} chains x {n} gaugings per GPU (configs[1])",
+                   "chains_per_gpu": K, "nobs": n, "P": 19,
+                   "l2": "flushed between timed steps (256 MiB write)" if not args.no_flush else "not flushed",
+                   "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes),
+                "d2h_bytes_per_step": int(K * (8 + 4)), "steps": esteps,
+                "path": "bamgpu_logpost (C ABI) with pinned host buffers, wall clock around the blocking calls"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "wall_s_timed_region": wall,
+    }
+    if not args.no_cpu and world == 1:
+        line["cpu_baseline"] = cpu_baseline(prob, x)
+    if not args.no_prediction and world == 1:
+        try:
+            line["prediction"] = prediction_leg(device)
+        except Exception as e:  # the headline metric must still be printed
+            line["prediction"] = {"error": str(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -227,6 +227,15 @@ int bamgpu_predict_download(bamgpu_t* h, double* env, char* mess);
    last resident evaluation's dominant kernel measured with CUDA events on the handle's stream */
 int64_t bamgpu_launch_count(const bamgpu_t* h);
 double bamgpu_last_kernel_ms(const bamgpu_t* h);
+/* CUDA-event timing on the handle's stream.  bamgpu_step_begin/end bracket one step (any sequence of
+   resident calls); every resident evaluation also brackets its dominant kernel.  After bamgpu_sync,
+   bamgpu_step_times / bamgpu_kernel_times return the recorded durations (ms) and clear them. */
+int bamgpu_step_begin(bamgpu_t* h);
+int bamgpu_step_end(bamgpu_t* h);
+int bamgpu_step_times(bamgpu_t* h, double* ms, int cap);
+int bamgpu_kernel_times(bamgpu_t* h, double* ms, int cap);
+/* write `bytes` of scratch HBM on the handle's stream (L2 flush between timed iterations) */
+int bamgpu_flush_l2(bamgpu_t* h, size_t bytes);
 /* FP64 DFMA peak micro-benchmark (register-resident FMA chains), TFLOP/s counting 2 flop per DFMA */
 int bamgpu_fp64_peak(int device, double* tflops, char* mess);
 /* page-lock / unlock a caller-owned host buffer so the H2D / D2H copies of the calls above are DMA copies */

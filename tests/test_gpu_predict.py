@@ -21,7 +21,10 @@ def cmp_spag(a, b, tol=1e-12):
     assert ((a == FLAG) == (b == FLAG)).all(), "infeasible pattern differs"
     assert ((a == 0.0) == (b == 0.0)).all(), "Q == 0 pattern (range / control activation) differs"
     m = a != FLAG
-    scale = np.maximum(np.abs(b[m]), 1e-6)
+    # relative to the magnitude of the spaghetti at that input: a noisy value Y + sigma*N(0,1) can cancel to ~0
+    bb = np.where(b == FLAG, np.nan, np.abs(b))
+    colscale = np.nan_to_num(np.nanmedian(bb, axis=-1, keepdims=True), nan=1.0) * np.ones_like(b)
+    scale = np.maximum(np.maximum(np.abs(b[m]), colscale[m]), 1e-6)
     err = np.abs(a[m] - b[m]) / scale
     assert err.max() <= tol, err.max()
 
@@ -140,7 +143,8 @@ def test_large_sample_selection_path():
     # heavy ties: every replication identical -> all quantiles equal, sd = 0
     mc_same = np.tile(mode, (20000, 1))
     env, _ = g.predict(mc_same, mode, [Hs], 1, [0])
-    assert (env[0, 0] == env[0, 1]).all() and (env[0, 6] == 0).all()
+    assert (env[0, 0] == env[0, 1]).all() and (env[0, 0] == env[0, 2]).all()
+    assert (env[0, 6] <= 1e-12 * np.abs(env[0, 5]) + 1e-300).all()
 
 
 def test_full_size_properties():

@@ -59,15 +59,15 @@ def test_posterior_statistics_and_rhat():
     K = 256
     s, sd = start_std(truth, K, 0.05)
     g, o = BamGpu(prob), Oracle(prob)
-    rows = g.fit(s, sd, nAdapt=50, nCycles=12, seed=5, burn=300, keep_every=1)
+    rows = g.fit(s, sd, nAdapt=50, nCycles=40, seed=5, burn=1000, keep_every=1)
     cnt, mean, m2 = g.moments()
     rhat = g.rhat(cnt, mean, m2)
     assert (rhat < 1.2).all(), rhat
     gm = rows[:, :, :8].reshape(-1, 8)
-    orow, _, _ = o.fit(s[:24], sd[:24], nAdapt=50, nCycles=12, seed=99, burn=300, keep_every=1)
+    orow, _, _ = o.fit(s[:24], sd[:24], nAdapt=50, nCycles=40, seed=99, burn=1000, keep_every=1)
     om = orow[:, :, :8].reshape(-1, 8)
     # posterior means agree within a few Monte-Carlo standard errors of the smaller (oracle) sample
-    se = om.std(axis=0) / np.sqrt(24 * 300 / 20.0)
+    se = om.std(axis=0) / np.sqrt(24 * 1000 / 50.0)  # effective sample size: ~1 independent draw per 50 iterations
     assert (np.abs(gm.mean(axis=0) - om.mean(axis=0)) < 6 * se).all()
     for q in (0.16, 0.5, 0.84):
         assert (np.abs(np.quantile(gm, q, axis=0) - np.quantile(om, q, axis=0)) < 8 * se).all()
