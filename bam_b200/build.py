@@ -73,7 +73,7 @@ def build_driver(force: bool = False) -> str | None:
     if not os.path.isdir(hostdir):
         return None
     srcs = sorted(os.path.join(hostdir, f) for f in os.listdir(hostdir) if f.endswith(".cpp"))
-    if not srcs:
+    if not srcs or not os.path.exists(os.path.join(hostdir, "bam_gpu_main.cpp")):
         return None
     exe = os.path.join(HERE, "bam_gpu")
     so = os.path.join(HERE, "libbam_gpu.so")

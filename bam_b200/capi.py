@@ -321,6 +321,7 @@ def load_library(path: Optional[str] = None):
     lib.bamgpu_pin.argtypes = [C.c_void_p, C.c_size_t]
     lib.bamgpu_unpin.argtypes = [C.c_void_p]
     lib.bamgpu_set_chain_offset.argtypes = [H, i64]
+    lib.bamgpu_set_option.argtypes = [H, cp, ci]
     lib.bamgpu_version.restype = cp
     for name in ("dist_id", "sigmafunc_id", "model_id"):
         getattr(lib, "bamgpu_" + name).argtypes = [cp]
@@ -553,6 +554,10 @@ class BamGpu:
 
     def flush_l2(self, nbytes=256 << 20):
         self.lib.bamgpu_flush_l2(self.h, nbytes)
+
+    def set_option(self, name: str, value: int):
+        if self.lib.bamgpu_set_option(self.h, name.encode(), int(value)) != 0:
+            raise ValueError(f"unknown option {name}")
 
     def set_chain_offset(self, off: int):
         self.lib.bamgpu_set_chain_offset(self.h, off)

@@ -1,4 +1,6 @@
 // bam_capi.cu -- extern "C" entry points of include/bam_gpu.h.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -114,7 +116,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         d.model = L.model; d.n = L.n; d.nX = L.nX; d.nY = L.nY; d.ntheta = L.ntheta;
         d.nFit = L.nFit; d.nGamma = L.nGamma; d.nLatent = L.nLatent; d.P = L.P; d.nCombo = L.nCombo;
         d.nDparModel = L.nDparModel; d.nDpar = L.nDpar;
-        d.nDer = L.nDparModel;
+        d.nDer = (L.model == BAMGPU_MDL_BARATIN) ? 2 * L.ncontrol : L.nDparModel;  // BaRatin: b_i and log a_i
         // table layout
         d.tabGamma = 0;
         d.tabXb = L.nGamma;
@@ -123,11 +125,52 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         d.comboStride = L.ntheta + d.nDer;
         d.tabStride = d.tabCombo + L.nCombo * d.comboStride;
         const size_t sx = (size_t)L.n * L.nX, sy = (size_t)L.n * L.nY;
-        d.X = upload(h, pb->X, sx); d.Xu = upload(h, pb->Xu, sx); d.Xb = upload(h, pb->Xb, sx);
-        d.Xbindx = upload(h, pb->Xbindx, sx);
-        d.Y = upload(h, pb->Y, sy); d.Yu = upload(h, pb->Yu, sy); d.Yb = upload(h, pb->Yb, sy);
-        d.Ybindx = upload(h, pb->Ybindx, sy);
-        d.comboOf = upload(h, L.comboOf.data(), L.comboOf.size());
+        // Observation order on the device.  The log-likelihood is a sum over observations, so any fixed order is
+        // valid; sorting by (VAR combination, first input) makes the lanes of a warp agree on the combination (the
+        // shared-memory table reads become broadcasts) and on the stage range of BaRatin (no divergent pow counts).
+        // Not done when latent inputs exist: their per-chain values are read coalesced in the original order.
+        std::vector<int> perm(L.n);
+        for (int i = 0; i < L.n; ++i) perm[i] = i;
+        if (!L.hasLatent && L.n > 1)
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+                if (L.comboOf[a] != L.comboOf[b]) return L.comboOf[a] < L.comboOf[b];
+                return pb->X[a] < pb->X[b];
+            });
+        auto permD = [&](const double* src, int ncol) {
+            std::vector<double> v((size_t)L.n * ncol);
+            for (int j = 0; j < ncol; ++j)
+                for (int i = 0; i < L.n; ++i) v[i + (size_t)j * L.n] = src[perm[i] + (size_t)j * L.n];
+            return v;
+        };
+        auto permI = [&](const int32_t* src, int ncol) {
+            std::vector<int32_t> v((size_t)L.n * ncol);
+            for (int j = 0; j < ncol; ++j)
+                for (int i = 0; i < L.n; ++i) v[i + (size_t)j * L.n] = src[perm[i] + (size_t)j * L.n];
+            return v;
+        };
+        d.X = upload(h, permD(pb->X, L.nX).data(), sx); d.Xu = upload(h, permD(pb->Xu, L.nX).data(), sx);
+        d.Xb = upload(h, permD(pb->Xb, L.nX).data(), sx); d.Xbindx = upload(h, permI(pb->Xbindx, L.nX).data(), sx);
+        d.Y = upload(h, permD(pb->Y, L.nY).data(), sy); d.Yu = upload(h, permD(pb->Yu, L.nY).data(), sy);
+        d.Yb = upload(h, permD(pb->Yb, L.nY).data(), sy); d.Ybindx = upload(h, permI(pb->Ybindx, L.nY).data(), sy);
+        d.comboOf = upload(h, permI(L.comboOf.data(), 1).data(), L.comboOf.size());
+        {   // combination segments of the sorted observation order (only meaningful when sorted, i.e. no latent inputs)
+            std::vector<int> start(L.nCombo + 1, L.n);
+            std::vector<int32_t> sortedCombo = permI(L.comboOf.data(), 1);
+            for (int i = L.n - 1; i >= 0; --i) start[sortedCombo[i]] = i;
+            for (int v = L.nCombo - 1; v >= 0; --v) start[v] = std::min(start[v], start[v + 1]);
+            if (L.n == 0) start.assign(L.nCombo + 1, 0);
+            d.comboStart = upload(h, start.data(), start.size());
+            // tables of the table-driven log / exp (bam_fastmath.cuh), computed in long double
+            std::vector<double> lt(2 * 128), et(64);
+            for (int i = 0; i < 128; ++i) {
+                const long double c = 1.0L + (i + 0.5L) / 128.0L;
+                lt[2 * i] = (double)(1.0L / c);
+                lt[2 * i + 1] = (double)(-logl((long double)lt[2 * i]));
+            }
+            for (int j = 0; j < 64; ++j) et[j] = (double)exp2l(j / 64.0L);
+            d.logTab = reinterpret_cast<const double2*>(upload(h, lt.data(), lt.size()));
+            d.expTab = upload(h, et.data(), et.size());
+        }
         d.comboSrc = upload(h, L.comboSrc.data(), L.comboSrc.size());
         d.latIdx = L.hasLatent ? upload(h, L.latIdx.data(), L.latIdx.size()) : nullptr;
         for (int i = 0; i < L.ntheta; ++i) d.fixv[i] = L.fixv[i];
@@ -187,6 +230,11 @@ int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s) {
     s->nFit = L.nFit; s->nGamma = L.nGamma; s->nLatent = L.nLatent; s->nXbias = L.nXbTot; s->nYbias = L.nYbTot;
     s->nInfer = L.P; s->nDpar = L.nDpar; s->nCombo = L.nCombo; s->nState = L.nState;
     return 0;
+}
+
+int bamgpu_set_option(bamgpu_t* h, const char* name, int value) {
+    if (!strcmp(name, "force_generic")) { h->forceGeneric = value != 0; return 0; }
+    return 1;
 }
 
 int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset) {

@@ -15,6 +15,7 @@
 #define BAM_MAXY 8
 #define BAM_MAXTHETA 40
 #define BAM_MAXCTRL 8
+#define BAM_MAXDER 16  /* per-parameter-set derived values kept in the chain table (BaRatin: b_i and log a_i) */
 #define BAM_MAXGAMMA 24
 #define BAM_MAXCOPULA 96
 #define BAM_VMSTACK 24
@@ -34,6 +35,9 @@ struct DevProblem {
     const double *X, *Xu, *Xb, *Y, *Yu, *Yb;
     const int *Xbindx, *Ybindx;
     const int* comboOf;   // n : VAR-combination id of each observation
+    const int* comboStart;  // nCombo+1 : observations are stored sorted by combination; combo v = [start[v], start[v+1])
+    const double2* logTab;  // 128 x (1/c_i, -log(1/c_i)), c_i = 1 + (i+0.5)/128 : table-driven log (bam_fastmath.cuh)
+    const double* expTab;   // 64 x 2^(j/64)                                    : table-driven exp
     const int* comboSrc;  // nCombo x ntheta : position in the parameter vector, or -1 for FIX
     const int* latIdx;    // n x nX : position of the latent "true input" in the vector, or -1
     double fixv[BAM_MAXTHETA];
@@ -63,6 +67,25 @@ struct DevProblem {
 // ---------------------------------------------------------------------------------------------
 // distributions (BMSL Distribution_tools; conventions declared in SURVEY.md App. E / DESIGN.md)
 // ---------------------------------------------------------------------------------------------
+
+// 1/v for a positive, normal v: MUFU.RCP64H seed + two Newton steps (relative error ~1e-16); replaces the
+// IEEE division (~35 instructions with its slow path) in the likelihood tail
+__device__ __forceinline__ double fast_rcp_pos(double v) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+    double e = fma(-v, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-v, r, 1.0);
+    return fma(r, e, r);
+}
+
+// log N(y; mu, sqrt(v)) given the VARIANCE v > 0: -log sqrt(2 pi) - 0.5 log v - 0.5 (y-mu)^2 / v.
+// Same quantity as gauss_logpdf(y, mu, sqrt(v)) without the square root and the division.
+__device__ __forceinline__ double gauss_logpdf_var(double y, double mu, double v) {
+    const double r = y - mu;
+    const double t = fma(r * r, fast_rcp_pos(v), log(v));
+    return fma(-0.5, t, -BAM_LOG_SQRT_2PI);
+}
 
 // log N(x; mu, s) ; the caller guarantees s > 0
 __device__ __forceinline__ double gauss_logpdf(double x, double mu, double s) {

@@ -33,7 +33,8 @@ struct bamgpu_handle {
     double *d_prior = nullptr, *d_lkh = nullptr, *d_hyper = nullptr, *d_fx = nullptr, *d_dpar = nullptr;
     int* d_status = nullptr;
     LogpostPlan plan;
-    long long chainOffset = 0;  // global index of local chain 0 (multi-GPU sharding; RNG streams)
+    long long chainOffset = 0;
+    bool forceGeneric = false;  // tests: disable the specialised fast kernels  // global index of local chain 0 (multi-GPU sharding; RNG streams)
 
     // ---- sampler state ----
     double *d_std = nullptr, *d_delta = nullptr, *d_fxcur = nullptr, *d_dparcur = nullptr;

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstdio>
 
+#include "bam_fastmath.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* 
         for (int i = 0; i < p.nXb[j]; ++i) row[p.tabOffXb[j] + i] = xval(x, base, p.offXb[j] + i, comp, dl);
     for (int j = 0; j < p.nY; ++j)
         for (int i = 0; i < p.nYb[j]; ++i) row[p.tabOffYb[j] + i] = xval(x, base, p.offYb[j] + i, comp, dl);
-    double th[BAM_MAXTHETA], der[BAM_MAXCTRL];
+    double th[BAM_MAXTHETA], der[BAM_MAXDER];
     for (int k = 0; k < p.nCombo; ++k) {  // ApplyModel_BaM theta expansion (:4133-4159), once per combination
         double* cr = row + p.tabCombo + (size_t)k * p.comboStride;
         for (int i = 0; i < p.ntheta; ++i) {
@@ -208,10 +209,10 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
                     if (p.hasMissing && yo[j] == p.mv) continue;
                     double sig = sigmafunk(p.sigfunc[j], row + p.tabGamma + p.gamOff[j], yh[j]);
                     if (!(sig > 0.0)) { bad = true; continue; }
-                    sig = sqrt(yu[j] * yu[j] + sig * sig);
+                    const double var = fma(yu[j], yu[j], sig * sig);  // sigma_Y^2 + sigma_remnant^2 (:3213)
                     double mu = yh[j];
                     if (p.hasYbias && ybi[j] != 0) mu = yh[j] + yb[j] * row[p.tabOffYb[j] + ybi[j] - 1];
-                    lk += gauss_logpdf(yo[j], mu, sig);
+                    lk += gauss_logpdf_var(yo[j], mu, var);
                 }
                 if (p.hasLatent) {
 #pragma unroll
@@ -272,6 +273,121 @@ __global__ void logpost_final(DevProblem p, int K, int nTiles, const double* __r
     lkh[c] = a;
     hyper[c] = b;
     fx[c] = st ? BAMGPU_UNDEF_RN : (prior[c] + a + b);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K1 fast path: BaRatin, chain-parallel ("thread = chain") with observations broadcast from shared memory.
+//
+// Used for the headline configuration (many chains, no latent inputs / biases, Constant | Linear |
+// Proportional remnant sigma).  A thread owns one chain: the parameters of the current VAR combination
+// (k, b, c, log a) live in registers; a block of 256 chains walks one tile of observations that was staged
+// ONCE in shared memory (H, Q, uQ^2): every shared-memory read is a broadcast.  The likelihood partial of a
+// chain is accumulated in a register -- no shuffles, no cross-warp reduction -- and written coalesced.
+// Lanes of a warp evaluate the same observation for neighbouring chains, so they agree on the stage range
+// except within the posterior spread of the activation stages k: divergence is negligible.
+// a_i (H-b_i)^c_i = texp(c_i tlog(H-b_i) + log a_i) and -0.5 log(v) via tlog: ~60 FP64-pipe instructions per
+// chain x observation against ~330 for the libdevice pow/log/sqrt/div formulation.
+// ------------------------------------------------------------------------------------------------
+template <int NC, int SIGF>
+__global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p, int K, int TOBS, const double* __restrict__ tab,
+                                                                    const int* status, double* __restrict__ part,
+                                                                    int* statusOut) {
+    extern __shared__ double sm[];
+    double2* sLog = reinterpret_cast<double2*>(sm);  // 128 x 16 B
+    double* sExp = sm + 2 * BAM_LOGTAB_N;            // 64
+    double* sH = sExp + BAM_EXPTAB_N;
+    double* sY = sH + TOBS;
+    double* sV = sY + TOBS;                          // uQ^2, or -1 for a missing observation
+
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * TOBS;
+    const int nt = min(TOBS, p.n - i0);
+    for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) sLog[i] = p.logTab[i];
+    for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExp[i] = p.expTab[i];
+    for (int i = tid; i < nt; i += BAM_BLOCK) {
+        const double y = p.Y[i0 + i], u = p.Yu[i0 + i];
+        sH[i] = p.X[i0 + i];
+        sY[i] = y;
+        sV[i] = (p.hasMissing && y == p.mv) ? -1.0 : u * u;
+    }
+    __syncthreads();
+    const int c = blockIdx.y * BAM_BLOCK + tid;
+    if (c >= K) return;
+    const size_t o = ((size_t)blockIdx.x * K + c) * 2;
+    part[o + 1] = 0.0;
+    if (status[c] != 0) { part[o] = 0.0; return; }
+    const double* __restrict__ row = tab + (size_t)c * p.tabStride;
+    const double g1 = row[p.tabGamma], g2 = (SIGF == BAMGPU_SIG_LINEAR) ? row[p.tabGamma + 1] : 0.0;
+    const unsigned long long mask = p.ctrlMask;
+    double acc = 0.0;
+    bool bad = false;
+
+    for (int v = 0; v < p.nCombo; ++v) {
+        const int lo = max(i0, __ldg(p.comboStart + v)) - i0, hi = min(i0 + nt, __ldg(p.comboStart + v + 1)) - i0;
+        if (lo >= hi) continue;
+        const double* __restrict__ cr = row + p.tabCombo + (size_t)v * p.comboStride;
+        double k[NC], b[NC], cc[NC], la[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) { k[j] = cr[3 * j]; cc[j] = cr[3 * j + 2]; b[j] = cr[3 * NC + j]; la[j] = cr[4 * NC + j]; }
+#pragma unroll 2
+        for (int i = lo; i < hi; ++i) {
+            const double h = sH[i], v2 = sV[i];
+            if (v2 < 0.0) continue;
+            int r = 0;  // GetHRange (BaRatin_model.f90:398-436): k is increasing, so range = #{k_j <= H}
+#pragma unroll
+            for (int j = 0; j < NC; ++j) r += (h >= k[j]) ? 1 : 0;
+            double q = 0.0;
+            if (r > 0) {
+                const unsigned rowm = (unsigned)(mask >> ((r - 1) * 8)) & 0xffu;
+                bool done = false;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {  // BaRatin_computeQ range_loop (:236-249), same exit order
+                    if (j < r && !done) {
+                        const double d = h - b[j];
+                        if ((rowm >> j) & 1u) {
+                            if (d < 0.0) { q = 0.0; done = true; }
+                            else q += texp(fma(cc[j], tlog(d, sLog), la[j]), sExp);
+                        } else if (d < 0.0) { bad = true; done = true; }
+                    }
+                }
+            }
+            double sig;
+            if (SIGF == BAMGPU_SIG_CONSTANT) sig = g1;
+            else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(g2, fabs(q), g1);
+            else sig = g1 * fabs(q);
+            if (!(sig > 0.0)) { bad = true; continue; }
+            const double var = fma(sig, sig, v2);
+            const double res = sY[i] - q;
+            const double t = fma(res * res, fast_rcp_pos(var), tlog(var, sLog));
+            acc += fma(-0.5, t, -BAM_LOG_SQRT_2PI);
+        }
+    }
+    part[o] = acc;
+    if (bad) atomicOr(&statusOut[c], ST_LKH_INFEAS);
+}
+
+using FastKernel = void (*)(DevProblem, int, int, const double*, const int*, double*, int*);
+
+template <int NC>
+FastKernel pick_fast_sig(int sigf) {
+    switch (sigf) {
+        case BAMGPU_SIG_CONSTANT: return logpost_baratin_cb<NC, BAMGPU_SIG_CONSTANT>;
+        case BAMGPU_SIG_LINEAR: return logpost_baratin_cb<NC, BAMGPU_SIG_LINEAR>;
+        case BAMGPU_SIG_PROPORTIONAL: return logpost_baratin_cb<NC, BAMGPU_SIG_PROPORTIONAL>;
+    }
+    return nullptr;
+}
+
+FastKernel pick_fast(const DevProblem& p, int K) {
+    if (p.model != BAMGPU_MDL_BARATIN || p.hasLatent || p.hasXbias || p.hasYbias || K < 128 || p.nCombo > 4096) return nullptr;
+    switch (p.ncontrol) {
+        case 1: return pick_fast_sig<1>(p.sigfunc[0]);
+        case 2: return pick_fast_sig<2>(p.sigfunc[0]);
+        case 3: return pick_fast_sig<3>(p.sigfunc[0]);
+        case 4: return pick_fast_sig<4>(p.sigfunc[0]);
+    }
+    return nullptr;
 }
 
 using MainKernel = void (*)(DevProblem, const double*, int, int, int, const double*, const int*, double*, int*, int,
@@ -358,23 +474,35 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     const LogpostPlan& pl = h->plan;
     MainKernel kern = pick_main(p.model, p.nX, p.nY);
     if (!kern) throw CudaError{"bamgpu: no kernel instantiated for this (model, nX, nY)"};
+    FastKernel fast = (p.n > 0 && !h->forceGeneric) ? pick_fast(p, K) : nullptr;
     logpost_prep<<<(K + 127) / 128, 128, 0, h->stream>>>(p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status,
                                                          h->d_dpar);
-    if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     if (timeMain) {
         BAM_CUDA(cudaEventRecord(h->ev0, h->stream));
         if (h->recordKernels && h->kernEv.size() < 8192) { k0 = take_event(h); k1 = take_event(h); BAM_CUDA(cudaEventRecord(k0, h->stream)); }
     }
-    if (p.n > 0)
+    int nTiles = pl.nTiles;
+    if (fast) {
+        // observations per block: large tiles amortise the staging, but keep >= ~6 blocks per SM in flight
+        int tobs = 1024;
+        const int chainBlocks = (K + BAM_BLOCK - 1) / BAM_BLOCK;
+        while (tobs > 128 && (long long)chainBlocks * ((p.n + tobs - 1) / tobs) < 148 * 6) tobs >>= 1;
+        nTiles = (p.n + tobs - 1) / tobs;
+        const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 3 * (size_t)tobs);
+        dim3 grid(nTiles, chainBlocks);
+        fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_tab, h->d_status, h->d_part, h->d_status);
+    } else if (p.n > 0) {
+        if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
         kern<<<grid, BAM_BLOCK, pl.smem, h->stream>>>(p, d_x, K, pl.CT, pl.TX, h->d_tab, h->d_status, h->d_part, h->d_status,
                                                        comp, d_delta);
+    }
     if (timeMain) {
         BAM_CUDA(cudaEventRecord(h->ev1, h->stream));
         if (k1) { BAM_CUDA(cudaEventRecord(k1, h->stream)); h->kernEv.emplace_back(k0, k1); }
     }
-    logpost_final<<<(K + 127) / 128, 128, 0, h->stream>>>(p, K, p.n > 0 ? pl.nTiles : 0, h->d_part, h->d_prior, h->d_status,
+    logpost_final<<<(K + 127) / 128, 128, 0, h->stream>>>(p, K, p.n > 0 ? nTiles : 0, h->d_part, h->d_prior, h->d_status,
                                                           h->d_lkh, h->d_hyper, h->d_fx);
     h->launches += (p.n > 0) ? 3 : 2;
     BAM_CUDA(cudaGetLastError());

@@ -31,6 +31,9 @@ __device__ inline bool baratin_prepare(const DevProblem& p, const double* th, do
         if (som < 0.0) return false;
         b[j] = kj - pow((1.0 / aj) * som, 1.0 / cj);
     }
+    // der[nc + i] = log a_i (every a_i > 0 here): lets the per-observation kernel evaluate
+    // a_i (H-b_i)^c_i as exp(c_i log(H-b_i) + log a_i), ~2x fewer FP64 instructions than pow()
+    for (int i = 0; i < nc; ++i) b[nc + i] = log(th[3 * i + 1]);
     return true;
 }
 
@@ -49,7 +52,8 @@ __device__ __forceinline__ bool baratin_apply(const DevProblem& p, double H, con
             double d = H - b[i];
             if ((row >> i) & 1u) {
                 if (d < 0.0) { q = 0.0; break; }
-                q = q + th[3 * i + 1] * pow(d, th[3 * i + 2]);
+                // a_i d^c_i; d == 0 gives log = -inf -> exp(-inf) = 0 for c > 0, +inf for c < 0, as pow() does
+                q = q + exp(fma(th[3 * i + 2], log(d), b[nc + i]));
             } else if (d < 0.0) { ok = false; break; }
         }
     }

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const
     double* row = tab + (size_t)rep * a.stride;
     // gamma always comes from the sample, even when !doParametric (reference quirk, :1085)
     for (int g = 0; g < p.nGamma; ++g) row[g] = mc ? mc[rep + (size_t)(p.nFit + g) * a.Nrep] : 0.0;
-    double th[BAM_MAXTHETA], der[BAM_MAXCTRL];
+    double th[BAM_MAXTHETA], der[BAM_MAXDER];
     for (int i = 0; i < p.ntheta; ++i) {
         const int src = p.comboSrc[i];
         if (src < 0) th[i] = p.fixv[i];
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
     }
     if (!act) return;
     // this replication's full theta + derived values: private copy, loaded once for all inputs of the tile
-    double loc[BAM_MAXTHETA + BAM_MAXCTRL];
+    double loc[BAM_MAXTHETA + BAM_MAXDER];
     const int np = p.ntheta + p.nDer;
     for (int k = 0; k < np; ++k) loc[k] = sm[(p.nGamma + k) * BAM_BLOCK + tid];
     for (int t = tBeg; t < tEnd; ++t) {

@@ -154,6 +154,8 @@ int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s);
 /* global index of this handle's chain 0 (multi-GPU: chains are sharded across ranks and the RNG
    streams are keyed by the GLOBAL chain index, so results do not depend on the GPU count) */
 int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset);
+/* tuning / test switches: "force_generic" (1 = never use the specialised fast kernels). err=1 if unknown. */
+int bamgpu_set_option(bamgpu_t* h, const char* name, int value);
 
 /* name -> enum helpers (return 0 when the name is unknown) */
 int bamgpu_dist_id(const char* name);

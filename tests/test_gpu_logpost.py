@@ -189,3 +189,46 @@ def test_full_size_properties_cfg2():
     o = Oracle(prob)
     ofx = o.logpost(x[:4], nthreads=4)[0]
     assert (np.abs(fx_all[:4] - ofx) <= 1e-12 * np.abs(ofx)).all()
+
+
+@pytest.mark.parametrize("name,copula", [("baratin", False), ("baratin_spd", True), ("baratin_spd", False)])
+def test_chain_parallel_fast_path(name, copula):
+    """K >= 128 BaRatin problems without latent inputs / biases run the chain-parallel kernel with the
+    table-driven log/exp: same flags, 1e-12 parity against the oracle and against the generic kernel."""
+    prob, d = problem_from_fixture(name, with_copula=copula)
+    x = perturbed_vectors(d["start"], 300, rel=0.03, seed=4)
+    x[7, 3 if name == "baratin" else 7] = -5.0   # infeasible continuity for one vector
+    x[9, len(d["start"]) - 2] = -1.0             # gamma1 < 0: null prior
+    check_parity(prob, x)
+    g = BamGpu(prob)
+    fast = g.logpost(x)
+    g.set_option("force_generic", 1)
+    gen = g.logpost(x)
+    assert (fast[1] == gen[1]).all() and (fast[2] == gen[2]).all()
+    ok = fast[1] == 1
+    assert (np.abs(fast[0][ok] - gen[0][ok]) <= 1e-12 * np.abs(gen[0][ok])).all()
+
+
+def test_fast_path_edge_observations():
+    """H exactly on an activation stage (upper range), H == b1 (zero discharge through log(0) = -inf),
+    H below every control (Q = 0), missing Y, 1..4 controls, Constant / Proportional sigma."""
+    from bam_b200.capi import Problem
+
+    rng = np.random.default_rng(3)
+    for nc, funk, gam in ((1, "Constant", [0.8]), (2, "Proportional", [0.3]), (3, "Linear", [0.5, 0.1]),
+                          (4, "Linear", [0.5, 0.1])):
+        k = np.array([-0.5, 0.7, 1.9, 3.1])[:nc]
+        a = np.array([20.0, 35.0, 50.0, 65.0])[:nc]
+        c = np.array([1.5, 1.67, 1.67, 2.0])[:nc]
+        M = np.tril(np.ones((nc, nc), dtype=np.int32))  # every control stays active once activated
+        theta = np.column_stack([k, a, c]).ravel()
+        H = np.concatenate([rng.uniform(-1.0, 4.5, 500), k, [-0.5, np.nextafter(-0.5, 1), -3.0]])
+        Y = np.abs(rng.standard_normal(H.size)) * 50 + 1.0
+        Y[5] = -9999.0
+        Yu = 0.05 * Y
+        prob = Problem("BaRatin", H, Y, Yu=np.abs(Yu), partype=[0] * (3 * nc),
+                       priors_theta=[("Gaussian", [t, abs(t) * 0.3 + 0.1]) for t in theta], sigma_func=[funk],
+                       priors_gamma=[("Uniform", [0, 100])] * len(gam), xtra_i=M.flatten(order="F"))
+        x = perturbed_vectors(np.concatenate([theta, gam]), 200, rel=0.01, seed=nc)
+        x[0] = np.concatenate([theta, gam])  # exact k: H == k rows hit the boundary bit-exactly
+        check_parity(prob, x)
