@@ -1,52 +1,75 @@
 // bam_fastmath.cuh -- table-driven double-precision log / exp for the FP64-bound kernels.
 //
-// Why: the hot loops are bound by the FP64 pipe (64 lanes / SM).  libdevice's log() costs 29 FP64-pipe
-// instructions (+ ~30 others, 22 of them UMOVs that re-materialise constants), exp() 16, pow() ~90.  With a
-// 128-entry reciprocal table (log) and a 64-entry 2^(j/64) table (exp) staged in shared memory, the polynomial
-// degrees drop to 6 and 5:  tlog = 10 FP64 instructions, texp = 12.
+// Why: the hot loops are bound by the FP64 pipe (64 lanes / SM) and, next, by instruction issue.  libdevice's
+// log() costs 29 FP64-pipe instructions (+ ~30 others, 22 of them UMOVs that re-materialise constants), exp() 16,
+// pow() ~90.  With a 256-entry reciprocal table (log) and a 256-entry 2^(j/256) table (exp) staged in shared
+// memory the polynomial degrees drop to 5 and 4:  tlog = 8 FP64 instructions, texp = 9, no FP64 compares.
+// Polynomial coefficients come from __constant__ memory so that they are DFMA operands (c[bank][offset]) instead
+// of immediates that ptxas materialises with UMOV pairs inside the loop.
 //
-// Accuracy (validated on the host against long-double libm over 2e7 points, see tests/test_fastmath.py and
-// DESIGN.md): tlog |abs error| <= 4e-15 for |log x| <= 20 (<= 5e-16 for |log x| <= 3), texp relative error
-// <= 2.4e-16.  Both are far inside the 1e-12 parity budget.  Domain: tlog x > 0 normal, or x == 0 (-> -inf);
-// texp any finite x, +-inf; results that would be denormal are flushed to 0.
+// Accuracy (host emulation against long-double libm over 2e7 points: tests/test_fastmath.py):
+// tlog |abs error| <= 4e-15 for |log x| <= 20 (<= 5e-16 for |log x| <= 3); texp relative error <= 3e-16.
+// Domain: tlog x > 0 and normal, or x == 0 (-> -inf).  texp: any x; |x| >= 708 takes a (rare) slow branch.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
-#define BAM_LOGTAB_N 128
-#define BAM_EXPTAB_N 64
+#define BAM_LOGTAB_N 256
+#define BAM_EXPTAB_N 256
+
+// [0..3] log1p: 1/5, -1/4, 1/3, -1/2   [4] ln2   [5] 256/ln2   [6] -ln2/256 hi   [7] -ln2/256 lo
+// [8..10] exp: 1/24, 1/6, 1/2          [11] 1.5*2^52
+__constant__ double kFM[12] = {0.2,
+                               -0.25,
+                               1.0 / 3.0,
+                               -0.5,
+                               0.693147180559945309417232,
+                               369.32993046757463,
+                               -0.0027076061523985118,
+                               -2.1663774597568432e-11,
+                               1.0 / 24.0,
+                               1.0 / 6.0,
+                               0.5,
+                               6755399441055744.0};
 
 __device__ __forceinline__ double tlog(double x, const double2* __restrict__ lt) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
-    const int e = (hi >> 20) - 1023;
-    const double2 t = lt[(hi >> 13) & (BAM_LOGTAB_N - 1)];
+    const double2 t = lt[(hi >> 12) & (BAM_LOGTAB_N - 1)];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);  // mantissa in [1,2)
-    const double r = fma(m, t.x, -1.0);                                       // |r| < 2^-8
-    double q = fma(-1.0 / 6.0, r, 0.2);                                       // log1p(r), degree 6
-    q = fma(q, r, -0.25);
-    q = fma(q, r, 1.0 / 3.0);
-    q = fma(q, r, -0.5);
+    const double r = fma(m, t.x, -1.0);                                       // |r| < 2^-9
+    double q = fma(kFM[0], r, kFM[1]);                                        // log1p(r), degree 5
+    q = fma(q, r, kFM[2]);
+    q = fma(q, r, kFM[3]);
     const double pr = fma(q, r * r, r);
-    const double s = fma((double)e, 0.693147180559945309417232, t.y);
-    const double res = s + pr;
-    return (x == 0.0) ? -CUDART_INF_F : res;
+    const double s = fma((double)((hi >> 20) - 1023), kFM[4], t.y);
+    double res = s + pr;
+    if ((hi | lo) == 0) res = -CUDART_INF_F;  // log(0): integer test, keeps the FP64 pipe free of compares
+    return res;
 }
 
 __device__ __forceinline__ double texp(double x, const double* __restrict__ et) {
-    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest integer in the low word
-    const double t = fma(x, 92.332482616893657, MAGIC);      // x * 64/ln2
+    const double t = fma(x, kFM[5], kFM[11]);  // x * 256/ln2, rounded to an integer in the low word
     const int ki = __double2loint(t);
-    const double kd = t - MAGIC;
-    double r = fma(kd, -0.010830424667801708, x);            // ln2/64 split hi (28 bits) / lo
-    r = fma(kd, -2.8447437476806321e-11, r);
+    const double kd = t - kFM[11];
+    double r = fma(kd, kFM[6], x);             // ln2/256 split hi (26 bits) / lo
+    r = fma(kd, kFM[7], r);
     const double T = et[ki & (BAM_EXPTAB_N - 1)];
-    double q = fma(1.0 / 120.0, r, 1.0 / 24.0);              // e^r - 1, degree 5, |r| <= ln2/128
-    q = fma(q, r, 1.0 / 6.0);
-    q = fma(q, r, 0.5);
+    double q = fma(kFM[8], r, kFM[9]);         // e^r - 1, degree 4, |r| <= ln2/512
+    q = fma(q, r, kFM[10]);
     q = fma(q, r, 1.0);
     double res = fma(T, q * r, T);
-    res = __hiloint2double(__double2hiint(res) + ((ki >> 6) << 20), __double2loint(res));  // * 2^(ki/64)
-    if (x < -708.0) res = 0.0;
-    if (!(x <= 709.0)) res = x + CUDART_INF_F;                  // +big -> inf, NaN -> NaN
+    res = __hiloint2double(__double2hiint(res) + ((ki >> 8) << 20), __double2loint(res));  // * 2^(ki/256)
+    if (((unsigned)__double2hiint(x) & 0x7fffffffu) >= 0x40862000u) {  // |x| >= 708, inf or NaN: rare
+        if (x < 0.0) res = 0.0;
+        else res = x + CUDART_INF_F;
+    }
     return res;
+}
+
+// 1/v for a positive normal v: MUFU.RCP64H seed (>= 20 bits) + one cubic step  r0 (1 + e + e^2), e = 1 - v r0
+__device__ __forceinline__ double trcp(double v) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(v));
+    const double e = fma(-v, r0, 1.0);
+    return fma(r0, fma(e, e, e), r0);
 }

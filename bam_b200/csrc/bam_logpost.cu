@@ -333,23 +333,22 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p,
 #pragma unroll 2
         for (int i = lo; i < hi; ++i) {
             const double h = sH[i], v2 = sV[i];
-            if (v2 < 0.0) continue;
+            if (__double2hiint(v2) < 0) continue;  // missing observation (flagged -1)
             int r = 0;  // GetHRange (BaRatin_model.f90:398-436): k is increasing, so range = #{k_j <= H}
 #pragma unroll
             for (int j = 0; j < NC; ++j) r += (h >= k[j]) ? 1 : 0;
             double q = 0.0;
-            if (r > 0) {
-                const unsigned rowm = (unsigned)(mask >> ((r - 1) * 8)) & 0xffu;
-                bool done = false;
+            const unsigned rowm = (r > 0) ? ((unsigned)(mask >> ((r - 1) * 8)) & 0xffu) : 0u;
+            bool done = false;
 #pragma unroll
-                for (int j = 0; j < NC; ++j) {  // BaRatin_computeQ range_loop (:236-249), same exit order
-                    if (j < r && !done) {
-                        const double d = h - b[j];
-                        if ((rowm >> j) & 1u) {
-                            if (d < 0.0) { q = 0.0; done = true; }
-                            else q += texp(fma(cc[j], tlog(d, sLog), la[j]), sExp);
-                        } else if (d < 0.0) { bad = true; done = true; }
-                    }
+            for (int j = 0; j < NC; ++j) {  // BaRatin_computeQ range_loop (:236-249), same exit order
+                if (j < r && !done) {
+                    const double d = h - b[j];
+                    const bool neg = __double2hiint(d) < 0;  // d < 0 (d is never -0: x - x = +0)
+                    if ((rowm >> j) & 1u) {
+                        if (neg) { q = 0.0; done = true; }
+                        else q += texp(fma(cc[j], tlog(d, sLog), la[j]), sExp);
+                    } else if (neg) { bad = true; done = true; }
                 }
             }
             double sig;
@@ -359,7 +358,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p,
             if (!(sig > 0.0)) { bad = true; continue; }
             const double var = fma(sig, sig, v2);
             const double res = sY[i] - q;
-            const double t = fma(res * res, fast_rcp_pos(var), tlog(var, sLog));
+            const double t = fma(res * res, trcp(var), tlog(var, sLog));
             acc += fma(-0.5, t, -BAM_LOG_SQRT_2PI);
         }
     }
@@ -485,7 +484,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     int nTiles = pl.nTiles;
     if (fast) {
         // observations per block: large tiles amortise the staging, but keep >= ~6 blocks per SM in flight
-        int tobs = 1024;
+        int tobs = 256;
         const int chainBlocks = (K + BAM_BLOCK - 1) / BAM_BLOCK;
         while (tobs > 128 && (long long)chainBlocks * ((p.n + tobs - 1) / tobs) < 148 * 6) tobs >>= 1;
         nTiles = (p.n + tobs - 1) / tobs;

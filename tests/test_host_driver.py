@@ -1,0 +1,133 @@
+"""The C++ host driver `bam_gpu` (bam_b200/csrc/host): config reader cross-checked against the
+independent Python reader that produced the golden fixtures, and (GPU) a full run that writes the
+reference's result files."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.helpers import load_fixture
+from tests.workspace_writer import write_workspace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "bam_b200", "bam_gpu")
+FIXTURES = ["baratin", "baratin_spd", "regression_x2y2", "sediment_camenen_x4", "sediment_mpm_x2",
+            "textfile_inputuncertainty"]
+DIST = {"Gaussian": 1, "Uniform": 2, "Triangle": 3, "LogNormal": 4, "Exponential": 5, "FlatPrior": 6, "FlatPrior+": 7,
+        "FlatPrior-": 8}
+SIG = {"Constant": 1, "Linear": 2, "Proportional": 3, "Power": 4, "Exponential": 5, "Gaussian": 6}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    from bam_b200 import build
+
+    build.build_all()
+    assert os.path.exists(EXE)
+
+
+def dump(cfg):
+    out = cfg + ".json"
+    r = subprocess.run([EXE, "-cf", cfg, "--dump-problem", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return json.load(open(out))
+
+
+def compare(d, fx):
+    n = fx["nobs"]
+    assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == (fx["model_id"], n, fx["nX"], fx["nY"])
+    for key in ("X", "Xu", "Xb", "Y", "Yu", "Yb"):
+        assert np.array_equal(np.asarray(d[key]), np.asarray(fx[key])), key
+    for key in ("Xbindx", "Ybindx", "partype", "nval"):
+        assert list(d[key]) == list(fx[key]), key
+    if fx.get("var_indx") is not None:
+        assert list(d["var_indx"]) == list(fx["var_indx"])
+    assert list(d["prior_theta_dist"]) == [DIST[p[0]] for p in fx["priors_theta"]]
+    assert list(d["prior_gamma_dist"]) == [DIST[p[0]] for p in fx["priors_gamma"]]
+    par = np.asarray(d["prior_theta_par"]).reshape(-1, 4)
+    for row, (_, p) in zip(par, fx["priors_theta"]):
+        assert list(row[: len(p)]) == list(p)
+    assert list(d["sigma_func"]) == [SIG[s] for s in fx["sigma_func"]]
+    assert list(d["xtra_i"]) == list(fx["xtra_i"]) and np.allclose(d["xtra_d"], fx["xtra_d"], rtol=0, atol=0)
+    assert np.array_equal(np.asarray(d["start"]), np.asarray(fx["start"]))
+    if fx.get("priorC") is not None:
+        k = int(round(len(fx["priorC"]) ** 0.5))
+        C = np.asarray(fx["priorC"]).reshape(k, k).T
+        M = np.asarray(d["priorM"]).reshape(k, k).T
+        assert np.allclose(M, np.linalg.inv(C) - np.eye(k), rtol=1e-9, atol=1e-9)
+    # jump std: stdFactor*|x0| (0.1 if zero), latent X -> Xu, biases -> 0.1 (src/BaM_tools.f90:605-606,2459-2471)
+    f = fx["mcmc"]["MultFactor"]
+    nfg = len(fx["priors_theta"]) + len(fx["priors_gamma"])
+    exp = [f * abs(v) if f * abs(v) != 0 else 0.1 for v in fx["start"][:nfg]]
+    assert np.allclose(d["start_std"][:nfg], exp, rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_config_reader_roundtrip(name, tmp_path):
+    fx = load_fixture(name)
+    cfg, _ = write_workspace(fx, str(tmp_path), name="WS_" + name)
+    compare(dump(cfg), fx)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference workspaces only exist in the build container")
+@pytest.mark.parametrize("cfg,name", [("Config_BaM_BaRatin.txt", "baratin"), ("Config_BaM_BaRatin_SPD.txt", "baratin_spd"),
+                                      ("Config_BaM_Regression_X2Y2.txt", "regression_x2y2"),
+                                      ("Config_BaM_TextFile_InputUncertainty.txt", "textfile_inputuncertainty")])
+def test_config_reader_on_shipped_workspaces(cfg, name):
+    """the reference's own example workspaces, Windows path separators included"""
+    compare_d = dump_ref(cfg)
+    compare(compare_d, load_fixture(name))
+
+
+def dump_ref(cfg):
+    out = f"/tmp/_dump_{cfg}.json"
+    r = subprocess.run([EXE, "-cf", os.path.join("/root/reference/tests", cfg), "--dump-problem", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return json.load(open(out))
+
+
+def test_cli_version_and_errors(tmp_path):
+    r = subprocess.run([EXE, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and "version" in r.stdout
+    r = subprocess.run([EXE, "-cf", str(tmp_path / "missing.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "FATAL ERROR" in r.stderr
+
+
+def read_table(path):
+    lines = open(path).read().splitlines()
+    head = [lines[0][i:i + 15].strip() for i in range(0, len(lines[0]), 15)]
+    rows = np.array([[float(ln[i:i + 15]) for i in range(0, len(ln), 15)] for ln in lines[1:] if ln.strip()])
+    return head, rows
+
+
+@pytest.mark.gpu
+def test_full_run_writes_reference_files(tmp_path):
+    fx = load_fixture("baratin")
+    H = np.linspace(-1, 6, 41)
+    cfg, ws = write_workspace(fx, str(tmp_path), name="RUN", nAdapt=20, nCycles=10, do_pred=True,
+                              pred=[dict(X=H, doParametric=True, doRemnant=True), dict(X=H, doParametric=False, doRemnant=False),
+                                    dict(X=H, doParametric=True, doRemnant=False, nsim=50)])
+    r = subprocess.run([EXE, "-cf", cfg, "-sd", "7", "--chains", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    head, rows = read_table(os.path.join(ws, "Results_MCMC.txt"))
+    assert head == ["k1", "a1", "c1", "k2", "a2", "c2", "Y1_gamma1", "Y1_gamma2", "LogPost", "b1", "b2"]
+    assert rows.shape == (200, 11) and np.isfinite(rows).all()
+    assert np.allclose(rows[:, 9], rows[:, 0], rtol=1e-6)  # b1 = k1, 7 significant digits (e15.6)
+    _, cooked = read_table(os.path.join(ws, "Results_MCMC_Cooked.txt"))
+    assert cooked.shape == (4 * 50, 11)  # burn 50 %, slim 2, 4 chains pooled
+    lines = open(os.path.join(ws, "Results_Summary.txt")).read().splitlines()
+    assert len(lines) == 17 and lines[1].startswith("N") and lines[16].startswith("MaxPost")
+    assert open(os.path.join(ws, "Config_MCMC.txt.monitor")).read().strip() == "200/200"
+    _, rhat = read_table(os.path.join(ws, "Results_Rhat.txt"))
+    assert rhat.shape == (1, 8)
+    head, env = read_table(os.path.join(ws, "Y_1.env"))
+    assert head == ["Median", "q2.5", "q97.5", "q16", "q84", "Mean", "Stdev"] and env.shape == (41, 7)
+    assert (env[:, 1] <= env[:, 0]).all() and (env[:, 0] <= env[:, 2]).all()
+    spag = np.loadtxt(os.path.join(ws, "Y_1.spag"))
+    assert spag.shape == (41, 200)  # transposed: one row per input
+    mp = np.loadtxt(os.path.join(ws, "Y_2.spag"))
+    assert mp.shape == (41,) and not os.path.exists(os.path.join(ws, "Y_2.env"))  # maxpost: Nrep = 1, no envelope
+    assert np.loadtxt(os.path.join(ws, "Y_3.spag")).shape == (41, 50)  # prior prediction with nsim = 50
