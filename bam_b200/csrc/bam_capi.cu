@@ -161,13 +161,13 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
             if (L.n == 0) start.assign(L.nCombo + 1, 0);
             d.comboStart = upload(h, start.data(), start.size());
             // tables of the table-driven log / exp (bam_fastmath.cuh), computed in long double
-            std::vector<double> lt(2 * 128), et(64);
-            for (int i = 0; i < 128; ++i) {
-                const long double c = 1.0L + (i + 0.5L) / 128.0L;
+            std::vector<double> lt(2 * BAM_LOGTAB_N), et(BAM_EXPTAB_N);
+            for (int i = 0; i < BAM_LOGTAB_N; ++i) {
+                const long double c = 1.0L + (i + 0.5L) / (long double)BAM_LOGTAB_N;
                 lt[2 * i] = (double)(1.0L / c);
                 lt[2 * i + 1] = (double)(-logl((long double)lt[2 * i]));
             }
-            for (int j = 0; j < 64; ++j) et[j] = (double)exp2l(j / 64.0L);
+            for (int j = 0; j < BAM_EXPTAB_N; ++j) et[j] = (double)exp2l(j / (long double)BAM_EXPTAB_N);
             d.logTab = reinterpret_cast<const double2*>(upload(h, lt.data(), lt.size()));
             d.expTab = upload(h, et.data(), et.size());
         }

@@ -19,6 +19,8 @@
 #define BAM_MAXGAMMA 24
 #define BAM_MAXCOPULA 96
 #define BAM_VMSTACK 24
+#define BAM_LOGTAB_N 256  /* table-driven log: reciprocal table entries (bam_fastmath.cuh) */
+#define BAM_EXPTAB_N 256  /* table-driven exp: 2^(j/N) entries */
 
 // chain status bits (priority order of the reference's early exits, GetPostLogPdf :3310-3382)
 #define ST_PRIOR_INFEAS 1
@@ -36,8 +38,8 @@ struct DevProblem {
     const int *Xbindx, *Ybindx;
     const int* comboOf;   // n : VAR-combination id of each observation
     const int* comboStart;  // nCombo+1 : observations are stored sorted by combination; combo v = [start[v], start[v+1])
-    const double2* logTab;  // 128 x (1/c_i, -log(1/c_i)), c_i = 1 + (i+0.5)/128 : table-driven log (bam_fastmath.cuh)
-    const double* expTab;   // 64 x 2^(j/64)                                    : table-driven exp
+    const double2* logTab;  // BAM_LOGTAB_N x (1/c_i, -log(1/c_i)), c_i = 1 + (i+0.5)/N : table-driven log (bam_fastmath.cuh)
+    const double* expTab;   // BAM_EXPTAB_N x 2^(j/N)                                    : table-driven exp
     const int* comboSrc;  // nCombo x ntheta : position in the parameter vector, or -1 for FIX
     const int* latIdx;    // n x nX : position of the latent "true input" in the vector, or -1
     double fixv[BAM_MAXTHETA];

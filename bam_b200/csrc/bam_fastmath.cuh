@@ -14,8 +14,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
-#define BAM_LOGTAB_N 256
-#define BAM_EXPTAB_N 256
+#include "bam_device.cuh"  // BAM_LOGTAB_N, BAM_EXPTAB_N
 
 // [0..3] log1p: 1/5, -1/4, 1/3, -1/2   [4] ln2   [5] 256/ln2   [6] -ln2/256 hi   [7] -ln2/256 lo
 // [8..10] exp: 1/24, 1/6, 1/2          [11] 1.5*2^52

@@ -457,7 +457,7 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     make_plan(h, K);
     BAM_CUDA(cudaMalloc(&h->d_x, sizeof(double) * (size_t)K * p.P));
     BAM_CUDA(cudaMalloc(&h->d_tab, sizeof(double) * (size_t)K * p.tabStride));
-    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * std::max(h->plan.nTiles, 1)));
+    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * std::max(std::max(h->plan.nTiles, (h->L.n + 127) / 128), 1)));
     BAM_CUDA(cudaMalloc(&h->d_prior, sizeof(double) * K));
     BAM_CUDA(cudaMalloc(&h->d_lkh, sizeof(double) * K));
     BAM_CUDA(cudaMalloc(&h->d_hyper, sizeof(double) * K));
