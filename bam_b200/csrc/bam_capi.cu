@@ -124,41 +124,48 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         d.tabCombo = d.tabYb + L.nYbTot;
         d.comboStride = L.ntheta + d.nDer;
         d.tabStride = d.tabCombo + L.nCombo * d.comboStride;
-        const size_t sx = (size_t)L.n * L.nX, sy = (size_t)L.n * L.nY;
         // Observation order on the device.  The log-likelihood is a sum over observations, so any fixed order is
         // valid; sorting by (VAR combination, first input) makes the lanes of a warp agree on the combination (the
         // shared-memory table reads become broadcasts) and on the stage range of BaRatin (no divergent pow counts).
         // Not done when latent inputs exist: their per-chain values are read coalesced in the original order.
-        std::vector<int> perm(L.n);
-        for (int i = 0; i < L.n; ++i) perm[i] = i;
-        if (!L.hasLatent && L.n > 1)
+        // With a single output and no latent inputs, an observation whose Y is the missing-value code contributes
+        // nothing to the posterior (:3207): it is dropped from the device tables (nDev <= n) instead of being tested
+        // in the inner loop.
+        std::vector<int> perm;
+        for (int i = 0; i < L.n; ++i)
+            if (!(L.nY == 1 && !L.hasLatent && pb->Y[i] == pb->mv)) perm.push_back(i);
+        const int nDev = (int)perm.size();
+        const bool dropped = nDev != L.n;
+        if (!L.hasLatent && nDev > 1)
             std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
                 if (L.comboOf[a] != L.comboOf[b]) return L.comboOf[a] < L.comboOf[b];
                 return pb->X[a] < pb->X[b];
             });
         auto permD = [&](const double* src, int ncol) {
-            std::vector<double> v((size_t)L.n * ncol);
+            std::vector<double> v((size_t)nDev * ncol + 1);
             for (int j = 0; j < ncol; ++j)
-                for (int i = 0; i < L.n; ++i) v[i + (size_t)j * L.n] = src[perm[i] + (size_t)j * L.n];
+                for (int i = 0; i < nDev; ++i) v[i + (size_t)j * nDev] = src[perm[i] + (size_t)j * L.n];
             return v;
         };
         auto permI = [&](const int32_t* src, int ncol) {
-            std::vector<int32_t> v((size_t)L.n * ncol);
+            std::vector<int32_t> v((size_t)nDev * ncol + 1);
             for (int j = 0; j < ncol; ++j)
-                for (int i = 0; i < L.n; ++i) v[i + (size_t)j * L.n] = src[perm[i] + (size_t)j * L.n];
+                for (int i = 0; i < nDev; ++i) v[i + (size_t)j * nDev] = src[perm[i] + (size_t)j * L.n];
             return v;
         };
-        d.X = upload(h, permD(pb->X, L.nX).data(), sx); d.Xu = upload(h, permD(pb->Xu, L.nX).data(), sx);
-        d.Xb = upload(h, permD(pb->Xb, L.nX).data(), sx); d.Xbindx = upload(h, permI(pb->Xbindx, L.nX).data(), sx);
-        d.Y = upload(h, permD(pb->Y, L.nY).data(), sy); d.Yu = upload(h, permD(pb->Yu, L.nY).data(), sy);
-        d.Yb = upload(h, permD(pb->Yb, L.nY).data(), sy); d.Ybindx = upload(h, permI(pb->Ybindx, L.nY).data(), sy);
-        d.comboOf = upload(h, permI(L.comboOf.data(), 1).data(), L.comboOf.size());
+        const size_t sxd = (size_t)nDev * L.nX, syd = (size_t)nDev * L.nY;
+        d.X = upload(h, permD(pb->X, L.nX).data(), sxd); d.Xu = upload(h, permD(pb->Xu, L.nX).data(), sxd);
+        d.Xb = upload(h, permD(pb->Xb, L.nX).data(), sxd); d.Xbindx = upload(h, permI(pb->Xbindx, L.nX).data(), sxd);
+        d.Y = upload(h, permD(pb->Y, L.nY).data(), syd); d.Yu = upload(h, permD(pb->Yu, L.nY).data(), syd);
+        d.Yb = upload(h, permD(pb->Yb, L.nY).data(), syd); d.Ybindx = upload(h, permI(pb->Ybindx, L.nY).data(), syd);
+        d.comboOf = upload(h, permI(L.comboOf.data(), 1).data(), (size_t)nDev);
+        d.n = nDev;
         {   // combination segments of the sorted observation order (only meaningful when sorted, i.e. no latent inputs)
-            std::vector<int> start(L.nCombo + 1, L.n);
+            std::vector<int> start(L.nCombo + 1, nDev);
             std::vector<int32_t> sortedCombo = permI(L.comboOf.data(), 1);
-            for (int i = L.n - 1; i >= 0; --i) start[sortedCombo[i]] = i;
+            for (int i = nDev - 1; i >= 0; --i) start[sortedCombo[i]] = i;
             for (int v = L.nCombo - 1; v >= 0; --v) start[v] = std::min(start[v], start[v + 1]);
-            if (L.n == 0) start.assign(L.nCombo + 1, 0);
+            if (nDev == 0) start.assign(L.nCombo + 1, 0);
             d.comboStart = upload(h, start.data(), start.size());
             // tables of the table-driven log / exp (bam_fastmath.cuh), computed in long double
             std::vector<double> lt(2 * BAM_LOGTAB_N), et(BAM_EXPTAB_N);
@@ -175,7 +182,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         d.latIdx = L.hasLatent ? upload(h, L.latIdx.data(), L.latIdx.size()) : nullptr;
         for (int i = 0; i < L.ntheta; ++i) d.fixv[i] = L.fixv[i];
         d.hasLatent = L.hasLatent; d.hasXbias = L.hasXbias; d.hasYbias = L.hasYbias;
-        d.hyperInfeasible = L.hyperInfeasible; d.hasMissing = L.hasMissing;
+        d.hyperInfeasible = L.hyperInfeasible; d.hasMissing = L.hasMissing && !dropped;
         int txb = d.tabXb, tyb = d.tabYb;
         for (int j = 0; j < L.nX; ++j) {
             d.Xerror[j] = L.Xerror[j]; d.nXb[j] = L.nXb[j]; d.offXb[j] = L.offXb[j]; d.tabOffXb[j] = txb; txb += L.nXb[j];

@@ -268,6 +268,7 @@ __global__ void logpost_final(DevProblem p, int K, int nTiles, const double* __r
         b += part[o + 1];
     }
     int st = status[c];
+    if (!st && !(a == a && b == b)) st |= ST_LKH_INFEAS;  // a NaN sum (e.g. NaN sigma) is an infeasible vector
     if (p.hyperInfeasible && !(st & (ST_PRIOR_INFEAS | ST_PRIOR_NULL | ST_LKH_INFEAS))) st |= ST_HYPER_INFEAS;
     status[c] = st;
     lkh[c] = a;
@@ -293,12 +294,12 @@ template <int NC, int SIGF>
 __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p, int K, int TOBS, const double* __restrict__ tab,
                                                                     const int* status, double* __restrict__ part,
                                                                     int* statusOut) {
-    extern __shared__ double sm[];
-    double2* sLog = reinterpret_cast<double2*>(sm);  // 128 x 16 B
-    double* sExp = sm + 2 * BAM_LOGTAB_N;            // 64
+    extern __shared__ __align__(16) double sm[];
+    double2* sLog = reinterpret_cast<double2*>(sm);  // BAM_LOGTAB_N x 16 B
+    double* sExp = sm + 2 * BAM_LOGTAB_N;
     double* sH = sExp + BAM_EXPTAB_N;
     double* sY = sH + TOBS;
-    double* sV = sY + TOBS;                          // uQ^2, or -1 for a missing observation
+    double* sV = sY + TOBS;                          // uQ^2
 
     const int tid = threadIdx.x;
     const int i0 = blockIdx.x * TOBS;
@@ -306,10 +307,10 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p,
     for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) sLog[i] = p.logTab[i];
     for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExp[i] = p.expTab[i];
     for (int i = tid; i < nt; i += BAM_BLOCK) {
-        const double y = p.Y[i0 + i], u = p.Yu[i0 + i];
+        const double u = p.Yu[i0 + i];
         sH[i] = p.X[i0 + i];
-        sY[i] = y;
-        sV[i] = (p.hasMissing && y == p.mv) ? -1.0 : u * u;
+        sY[i] = p.Y[i0 + i];
+        sV[i] = u * u;
     }
     __syncthreads();
     const int c = blockIdx.y * BAM_BLOCK + tid;
@@ -319,7 +320,11 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p,
     if (status[c] != 0) { part[o] = 0.0; return; }
     const double* __restrict__ row = tab + (size_t)c * p.tabStride;
     const double g1 = row[p.tabGamma], g2 = (SIGF == BAMGPU_SIG_LINEAR) ? row[p.tabGamma + 1] : 0.0;
-    const unsigned long long mask = p.ctrlMask;
+    // control matrix as nibbles: nibble r = row r-1 (nibble 0 = no control: H below every activation stage)
+    unsigned mask4 = 0;
+#pragma unroll
+    for (int r = 1; r <= NC; ++r) mask4 |= ((unsigned)(p.ctrlMask >> ((r - 1) * 8)) & 0xfu) << (4 * r);
+    const unsigned lt = smem_addr(sLog), et = smem_addr(sExp);
     double acc = 0.0;
     bool bad = false;
 
@@ -330,37 +335,88 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p,
         double k[NC], b[NC], cc[NC], la[NC];
 #pragma unroll
         for (int j = 0; j < NC; ++j) { k[j] = cr[3 * j]; cc[j] = cr[3 * j + 2]; b[j] = cr[3 * NC + j]; la[j] = cr[4 * NC + j]; }
-#pragma unroll 2
-        for (int i = lo; i < hi; ++i) {
-            const double h = sH[i], v2 = sV[i];
-            if (__double2hiint(v2) < 0) continue;  // missing observation (flagged -1)
-            int r = 0;  // GetHRange (BaRatin_model.f90:398-436): k is increasing, so range = #{k_j <= H}
+
+        // GetHRange (BaRatin_model.f90:398-436): k is increasing, so range = #{k_j <= H}
+        auto range = [&](double h) -> int {
+            int r = 0;
 #pragma unroll
             for (int j = 0; j < NC; ++j) r += (h >= k[j]) ? 1 : 0;
-            double q = 0.0;
-            const unsigned rowm = (r > 0) ? ((unsigned)(mask >> ((r - 1) * 8)) & 0xffu) : 0u;
-            bool done = false;
+            return r;
+        };
+        auto next_stage = [&](int r) -> double {  // k[r], or +inf above the last activation stage
+            double kn = CUDART_INF_F;
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {  // BaRatin_computeQ range_loop (:236-249), same exit order
-                if (j < r && !done) {
-                    const double d = h - b[j];
-                    const bool neg = __double2hiint(d) < 0;  // d < 0 (d is never -0: x - x = +0)
-                    if ((rowm >> j) & 1u) {
-                        if (neg) { q = 0.0; done = true; }
-                        else q += texp(fma(cc[j], tlog(d, sLog), la[j]), sExp);
-                    } else if (neg) { bad = true; done = true; }
-                }
-            }
+            for (int j = NC - 1; j >= 0; --j) kn = (r == j) ? k[j] : kn;
+            return kn;
+        };
+        // BaRatin_computeQ (:236-249).  For a parameter set that passed ApplyContinuity every control j < range has
+        // H >= k_(range) >= k_j >= b_j (k increasing, b_j <= k_j, and k_j >= b_i for i < j are exactly the feasibility
+        // tests of :380-391), so H - b_j >= 0 holds in floating point as well: the "H-b<0" exits of the reference can
+        // never fire here and the loop reduces to the sum over the active controls.
+        auto q_checked = [&](double h, unsigned m) -> double {
+            double q = 0.0;
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+                if ((m >> j) & 1u) q += texp(fma(cc[j], tlog(h - b[j], lt), la[j]), et);
+            return q;
+        };
+        // Gaussian log-density of one observation given Q (GetLogLikelihood :3208-3225), variance form.  A
+        // non-positive sigma makes the vector infeasible (:3210): flagged through the sign of (high word - 1), the
+        // (garbage) contribution is still accumulated because the sum of an infeasible vector is never read.
+        int badAcc = 0;
+        auto tail = [&](double q, double y, double v2) {
             double sig;
             if (SIGF == BAMGPU_SIG_CONSTANT) sig = g1;
             else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(g2, fabs(q), g1);
             else sig = g1 * fabs(q);
-            if (!(sig > 0.0)) { bad = true; continue; }
+            { const int hs = __double2hiint(sig); badAcc |= hs | (hs - 1); }  // negative iff sig <= 0 (or denormal)
             const double var = fma(sig, sig, v2);
-            const double res = sY[i] - q;
-            const double t = fma(res * res, trcp(var), tlog(var, sLog));
+            const double res = y - q;
+            const double t = fma(res * res, trcp(var), tlog_pos(var, lt));
             acc += fma(-0.5, t, -BAM_LOG_SQRT_2PI);
+        };
+
+        // observations are sorted by stage inside a combination, so the range only moves up: keep (row mask, next
+        // activation stage) in registers and re-derive them only when an observation crosses the next stage.
+        int r = range(sH[lo]);
+        unsigned m = (mask4 >> (4 * r)) & 0xfu;
+        double knext = next_stage(r);
+        int i = lo;
+        for (; i + 1 < hi; i += 2) {  // two observations per iteration: independent dependency chains (ILP 2)
+            const double h0 = sH[i], h1 = sH[i + 1];
+            double q0, q1;
+            if (h1 >= knext) {  // rare: a stage boundary inside the pair
+                q0 = q_checked(h0, (mask4 >> (4 * range(h0))) & 0xfu);
+                r = range(h1);
+                m = (mask4 >> (4 * r)) & 0xfu;
+                knext = next_stage(r);
+                q1 = q_checked(h1, m);
+            } else {
+                unsigned oor = 0;
+                q0 = 0.0;
+                q1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NC; ++j)
+                    if ((m >> j) & 1u) {
+                        const double x0 = fma(cc[j], tlog(h0 - b[j], lt), la[j]);
+                        const double x1 = fma(cc[j], tlog(h1 - b[j], lt), la[j]);
+                        oor = max(oor, max((unsigned)__double2hiint(x0) & 0x7fffffffu, (unsigned)__double2hiint(x1) & 0x7fffffffu));
+                        q0 += texp_inrange(x0, et);
+                        q1 += texp_inrange(x1, et);
+                    }
+                if (oor >= BAM_EXP_OOR) {  // rare: H == b exactly (log 0) or an overflowing power
+                    q0 = q_checked(h0, m);
+                    q1 = q_checked(h1, m);
+                }
+            }
+            tail(q0, sY[i], sV[i]);
+            tail(q1, sY[i + 1], sV[i + 1]);
         }
+        if (i < hi) {
+            const double h0 = sH[i];
+            tail(q_checked(h0, (mask4 >> (4 * range(h0))) & 0xfu), sY[i], sV[i]);
+        }
+        bad |= badAcc < 0;
     }
     part[o] = acc;
     if (bad) atomicOr(&statusOut[c], ST_LKH_INFEAS);
@@ -379,7 +435,7 @@ FastKernel pick_fast_sig(int sigf) {
 }
 
 FastKernel pick_fast(const DevProblem& p, int K) {
-    if (p.model != BAMGPU_MDL_BARATIN || p.hasLatent || p.hasXbias || p.hasYbias || K < 128 || p.nCombo > 4096) return nullptr;
+    if (p.model != BAMGPU_MDL_BARATIN || p.hasLatent || p.hasXbias || p.hasYbias || p.hasMissing || K < 128 || p.nCombo > 4096) return nullptr;
     switch (p.ncontrol) {
         case 1: return pick_fast_sig<1>(p.sigfunc[0]);
         case 2: return pick_fast_sig<2>(p.sigfunc[0]);
@@ -426,7 +482,7 @@ namespace bam {
 
 static void make_plan(bamgpu_handle* h, int K) {
     LogpostPlan& pl = h->plan;
-    const int n = std::max(h->L.n, 1);
+    const int n = std::max(h->dp.n, 1);
     pl.TX = n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32));
     pl.TY = BAM_BLOCK / pl.TX;
     pl.nTiles = (n + pl.TX - 1) / pl.TX;
@@ -457,7 +513,7 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     make_plan(h, K);
     BAM_CUDA(cudaMalloc(&h->d_x, sizeof(double) * (size_t)K * p.P));
     BAM_CUDA(cudaMalloc(&h->d_tab, sizeof(double) * (size_t)K * p.tabStride));
-    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * std::max(std::max(h->plan.nTiles, (h->L.n + 127) / 128), 1)));
+    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * std::max(std::max(h->plan.nTiles, (h->dp.n + 127) / 128), 1)));
     BAM_CUDA(cudaMalloc(&h->d_prior, sizeof(double) * K));
     BAM_CUDA(cudaMalloc(&h->d_lkh, sizeof(double) * K));
     BAM_CUDA(cudaMalloc(&h->d_hyper, sizeof(double) * K));
