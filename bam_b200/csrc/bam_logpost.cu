@@ -256,17 +256,31 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
 // ------------------------------------------------------------------------------------------------
 // K1b: final sum + early-exit priority (GetPostLogPdf :3358-3380)
 // ------------------------------------------------------------------------------------------------
-__global__ void logpost_final(DevProblem p, int K, int nTiles, const double* __restrict__ part,
-                              const double* __restrict__ prior, int* __restrict__ status, double* __restrict__ lkh,
-                              double* __restrict__ hyper, double* __restrict__ fx) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= K) return;
+#define FINAL_STRIPES 8
+__global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final(DevProblem p, int K, int nTiles, const double* __restrict__ part,
+                                                              const double* __restrict__ prior, int* __restrict__ status,
+                                                              double* __restrict__ lkh, double* __restrict__ hyper,
+                                                              double* __restrict__ fx) {
+    // 32 chains per block; FINAL_STRIPES warps each sum every FINAL_STRIPES-th tile, then a fixed-order combine:
+    // deterministic, and 8x more loads in flight than one thread per chain.
+    __shared__ double sa[FINAL_STRIPES][32], sb[FINAL_STRIPES][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     double a = 0.0, b = 0.0;
-    for (int t = 0; t < nTiles; ++t) {
-        const size_t o = ((size_t)t * K + c) * 2;
-        a += part[o];
-        b += part[o + 1];
-    }
+    if (c < K)
+        for (int t = w; t < nTiles; t += FINAL_STRIPES) {
+            const double2 v = *reinterpret_cast<const double2*>(part + ((size_t)t * K + c) * 2);
+            a += v.x;
+            b += v.y;
+        }
+    sa[w][lane] = a;
+    sb[w][lane] = b;
+    __syncthreads();
+    if (w != 0 || c >= K) return;
+    a = 0.0;
+    b = 0.0;
+#pragma unroll
+    for (int s = 0; s < FINAL_STRIPES; ++s) { a += sa[s][lane]; b += sb[s][lane]; }
     int st = status[c];
     if (!st && !(a == a && b == b)) st |= ST_LKH_INFEAS;  // a NaN sum (e.g. NaN sigma) is an infeasible vector
     if (p.hyperInfeasible && !(st & (ST_PRIOR_INFEAS | ST_PRIOR_NULL | ST_LKH_INFEAS))) st |= ST_HYPER_INFEAS;
@@ -275,7 +289,6 @@ __global__ void logpost_final(DevProblem p, int K, int nTiles, const double* __r
     hyper[c] = b;
     fx[c] = st ? BAMGPU_UNDEF_RN : (prior[c] + a + b);
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // K1 fast path: BaRatin, chain-parallel ("thread = chain") with observations broadcast from shared memory.
@@ -290,6 +303,9 @@ __global__ void logpost_final(DevProblem p, int K, int nTiles, const double* __r
 // a_i (H-b_i)^c_i = texp(c_i tlog(H-b_i) + log a_i) and -0.5 log(v) via tlog: ~60 FP64-pipe instructions per
 // chain x observation against ~330 for the libdevice pow/log/sqrt/div formulation.
 // ------------------------------------------------------------------------------------------------
+#ifndef BAM_CB_ILP
+#define BAM_CB_ILP 4
+#endif
 template <int NC, int SIGF>
 __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p, int K, int TOBS, const double* __restrict__ tab,
                                                                     const int* status, double* __restrict__ part,
@@ -382,39 +398,45 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p,
         unsigned m = (mask4 >> (4 * r)) & 0xfu;
         double knext = next_stage(r);
         int i = lo;
-        for (; i + 1 < hi; i += 2) {  // two observations per iteration: independent dependency chains (ILP 2)
-            const double h0 = sH[i], h1 = sH[i + 1];
-            double q0, q1;
-            if (h1 >= knext) {  // rare: a stage boundary inside the pair
-                q0 = q_checked(h0, (mask4 >> (4 * range(h0))) & 0xfu);
-                r = range(h1);
+        for (; i + (BAM_CB_ILP - 1) < hi; i += BAM_CB_ILP) {  // ILP observations per iteration: independent chains
+            double hh[BAM_CB_ILP], qq[BAM_CB_ILP];
+#pragma unroll
+            for (int u = 0; u < BAM_CB_ILP; ++u) hh[u] = sH[i + u];
+            if (hh[BAM_CB_ILP - 1] >= knext) {  // rare: a stage boundary inside the group
+#pragma unroll
+                for (int u = 0; u < BAM_CB_ILP; ++u) qq[u] = q_checked(hh[u], (mask4 >> (4 * range(hh[u]))) & 0xfu);
+                r = range(hh[BAM_CB_ILP - 1]);
                 m = (mask4 >> (4 * r)) & 0xfu;
                 knext = next_stage(r);
-                q1 = q_checked(h1, m);
             } else {
                 unsigned oor = 0;
-                q0 = 0.0;
-                q1 = 0.0;
+#pragma unroll
+                for (int u = 0; u < BAM_CB_ILP; ++u) qq[u] = 0.0;
 #pragma unroll
                 for (int j = 0; j < NC; ++j)
                     if ((m >> j) & 1u) {
-                        const double x0 = fma(cc[j], tlog(h0 - b[j], lt), la[j]);
-                        const double x1 = fma(cc[j], tlog(h1 - b[j], lt), la[j]);
-                        oor = max(oor, max((unsigned)__double2hiint(x0) & 0x7fffffffu, (unsigned)__double2hiint(x1) & 0x7fffffffu));
-                        q0 += texp_inrange(x0, et);
-                        q1 += texp_inrange(x1, et);
+                        double xx[BAM_CB_ILP];
+#pragma unroll
+                        for (int u = 0; u < BAM_CB_ILP; ++u) {
+                            xx[u] = fma(cc[j], tlog(hh[u] - b[j], lt), la[j]);
+                            oor = max(oor, (unsigned)__double2hiint(xx[u]) & 0x7fffffffu);
+                        }
+#pragma unroll
+                        for (int u = 0; u < BAM_CB_ILP; ++u) qq[u] += texp_inrange(xx[u], et);
                     }
                 if (oor >= BAM_EXP_OOR) {  // rare: H == b exactly (log 0) or an overflowing power
-                    q0 = q_checked(h0, m);
-                    q1 = q_checked(h1, m);
+#pragma unroll
+                    for (int u = 0; u < BAM_CB_ILP; ++u) qq[u] = q_checked(hh[u], m);
                 }
             }
-            tail(q0, sY[i], sV[i]);
-            tail(q1, sY[i + 1], sV[i + 1]);
+#pragma unroll
+            for (int u = 0; u < BAM_CB_ILP; ++u) tail(qq[u], sY[i + u], sV[i + u]);
         }
-        if (i < hi) {
+        for (; i < hi; ++i) {
             const double h0 = sH[i];
             tail(q_checked(h0, (mask4 >> (4 * range(h0))) & 0xfu), sY[i], sV[i]);
+        }
+        if (hi > lo) {  // leave the tracked range consistent for the next tile segment (not needed: state is per segment)
         }
         bad |= badAcc < 0;
     }
@@ -557,8 +579,8 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         BAM_CUDA(cudaEventRecord(h->ev1, h->stream));
         if (k1) { BAM_CUDA(cudaEventRecord(k1, h->stream)); h->kernEv.emplace_back(k0, k1); }
     }
-    logpost_final<<<(K + 127) / 128, 128, 0, h->stream>>>(p, K, p.n > 0 ? nTiles : 0, h->d_part, h->d_prior, h->d_status,
-                                                          h->d_lkh, h->d_hyper, h->d_fx);
+    logpost_final<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, p.n > 0 ? nTiles : 0, h->d_part, h->d_prior,
+                                                                       h->d_status, h->d_lkh, h->d_hyper, h->d_fx);
     h->launches += (p.n > 0) ? 3 : 2;
     BAM_CUDA(cudaGetLastError());
 }

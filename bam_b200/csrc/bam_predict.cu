@@ -214,7 +214,9 @@ __device__ __forceinline__ int lin_bin(double v, double lo, double scale) {
 }
 
 __global__ void __launch_bounds__(BAM_BLOCK) envelope_select(long long Nrep, int nT, double unfeas,
-                                                             const double* __restrict__ V, double* __restrict__ env) {
+                                                             const double* __restrict__ V, double* __restrict__ env,
+                                                             const int* __restrict__ only) {
+    if (only != nullptr && only[blockIdx.x] == 0) return;  // second chance for the columns envelope_select2 gave up
     __shared__ unsigned hist[SEL_NB];
     __shared__ double scratch[32];
     __shared__ double gath[SEL_GATHER];
@@ -398,6 +400,262 @@ __global__ void __launch_bounds__(BAM_BLOCK) envelope_select(long long Nrep, int
     }
 }
 
+// ---- large Nrep, fast path: all 10 order statistics with 4 reads of the column ---------------------------------
+//
+// pass A  min / max / #bad / sum                                   (1 read)
+// pass B  2048-bin histogram on [min,max]  +  sum (v-mean)^2        (1 read)   -> bin and residual rank per target
+// pass C  1024-bin sub-histogram inside every selected bin (<= 10)  (1 read)   -> sub-bin and residual rank
+// pass D  gather the members of the selected sub-bins (<= 256 each), sort, pick (1 read)
+// A target whose sub-bin still holds more than 256 values (heavy ties / pathological clustering) is resolved by
+// the multi-level routine of envelope_select on its own (rare).  bin functions are monotone in v => exact.
+#define S2_NB1 2048
+#define S2_NB2 1024
+#define S2_CAP 256
+#define S2_THREADS 512
+
+__device__ __forceinline__ int s2_bin(double v, double lo, double scale, int nb) {
+    int b = (int)((v - lo) * scale);
+    return b < 0 ? 0 : (b >= nb ? nb - 1 : b);
+}
+
+__device__ double s2_block_sum(double v, double* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < S2_THREADS / 32; ++i) s += scratch[i];
+        scratch[32] = s;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, int nT, double unfeas,
+                                                               const double* __restrict__ V, double* __restrict__ env,
+                                                               int* __restrict__ needSlow) {
+    extern __shared__ __align__(16) unsigned char s2raw[];
+    unsigned* hist = reinterpret_cast<unsigned*>(s2raw);                  // max(NB1, 10*NB2) counters = 40 KB
+    double* gath = reinterpret_cast<double*>(s2raw + sizeof(unsigned) * SEL_NT * S2_NB2);  // 10 x CAP doubles = 20 KB
+    __shared__ double scratch[40];
+    __shared__ short slotOfBin[S2_NB1];
+    __shared__ long long tRank[SEL_NT], tBefore[SEL_NT];
+    __shared__ int tBin1[SEL_NT], tSlot[SEL_NT], tBin2[SEL_NT], tList[SEL_NT], nSlots, nLists, gCount[SEL_NT], listSlot[SEL_NT],
+        listBin2[SEL_NT];
+    __shared__ double slotLo[SEL_NT], slotScale[SEL_NT], tVal[SEL_NT];
+    __shared__ unsigned prefix[S2_THREADS];
+    const int tid = threadIdx.x;
+    const int colId = blockIdx.x;
+    const double* col = V + (size_t)colId * Nrep;
+    const int y = colId / nT, t = colId % nT;
+    double* out = env + (size_t)y * BAMGPU_NENV * nT + t;
+    if (tid == 0) needSlow[colId] = 0;
+
+    // ---- pass A
+    double mn = INFINITY, mx = -INFINITY, sum = 0.0, nb = 0.0;
+    for (long long r = tid; r < Nrep; r += S2_THREADS) {
+        const double v = col[r];
+        if (v == unfeas || v != v) { nb += 1.0; continue; }
+        mn = fmin(mn, v); mx = fmax(mx, v); sum += v;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((tid & 31) == 0) { scratch[tid >> 5] = mn; }
+    __syncthreads();
+    if (tid == 0) { double v = INFINITY; for (int i = 0; i < S2_THREADS / 32; ++i) v = fmin(v, scratch[i]); scratch[33] = v; }
+    __syncthreads();
+    mn = scratch[33];
+    __syncthreads();
+    if ((tid & 31) == 0) { scratch[tid >> 5] = mx; }
+    __syncthreads();
+    if (tid == 0) { double v = -INFINITY; for (int i = 0; i < S2_THREADS / 32; ++i) v = fmax(v, scratch[i]); scratch[34] = v; }
+    __syncthreads();
+    mx = scratch[34];
+    const long long nbad = (long long)s2_block_sum(nb, scratch);
+    const bool drop = (double)nbad / (double)Nrep < 0.75;
+    if ((!drop && nbad > 0) || nbad == Nrep) {
+        if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
+        return;
+    }
+    const long long m = Nrep - nbad;
+    const double mean = s2_block_sum(sum, scratch) / (double)m;
+
+    // ---- pass B: level-1 histogram + sum of squares
+    const double scale1 = (mx > mn) ? (double)S2_NB1 / (mx - mn) : 0.0;
+    for (int b = tid; b < S2_NB1; b += S2_THREADS) { hist[b] = 0; slotOfBin[b] = -1; }
+    __syncthreads();
+    double part = 0.0;
+    for (long long r = tid; r < Nrep; r += S2_THREADS) {
+        const double v = col[r];
+        if (v == unfeas || v != v) continue;
+        const double d = v - mean;
+        part += d * d;
+        atomicAdd(&hist[s2_bin(v, mn, scale1, S2_NB1)], 1u);
+    }
+    const double ss = s2_block_sum(part, scratch);
+    // exclusive prefix over the 2048 bins (4 bins per thread + scan of the 512 partials)
+    {
+        unsigned loc[S2_NB1 / S2_THREADS], acc = 0;
+#pragma unroll
+        for (int q = 0; q < S2_NB1 / S2_THREADS; ++q) { loc[q] = hist[tid * (S2_NB1 / S2_THREADS) + q]; acc += loc[q]; }
+        prefix[tid] = acc;
+        __syncthreads();
+        for (int off = 1; off < S2_THREADS; off <<= 1) {
+            unsigned add = (tid >= off) ? prefix[tid - off] : 0;
+            __syncthreads();
+            prefix[tid] += add;
+            __syncthreads();
+        }
+        unsigned base = prefix[tid] - acc;
+#pragma unroll
+        for (int q = 0; q < S2_NB1 / S2_THREADS; ++q) { const unsigned c0 = loc[q]; hist[tid * (S2_NB1 / S2_THREADS) + q] = base; base += c0; }
+        __syncthreads();  // hist[b] = number of values in bins < b
+    }
+    const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
+    if (tid < SEL_NT) {
+        const int q = tid >> 1;
+        const double hh = pr[q] * (double)m + 0.5;
+        long long rk;
+        if (hh <= 1.0) rk = 0;
+        else if (hh >= (double)m) rk = m - 1;
+        else rk = (long long)floor(hh) - 1 + (tid & 1);
+        // largest bin b with hist[b] <= rk  (binary search on the exclusive prefix)
+        int lo = 0, hi = S2_NB1 - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((long long)hist[mid] <= rk) lo = mid; else hi = mid - 1;
+        }
+        tBin1[tid] = lo;
+        tBefore[tid] = hist[lo];
+        tRank[tid] = rk - hist[lo];
+    }
+    __syncthreads();
+    if (tid == 0) {  // distinct level-1 bins -> slots
+        int ns = 0;
+        for (int k = 0; k < SEL_NT; ++k) {
+            int sl = -1;
+            for (int j = 0; j < ns; ++j)
+                if (slotOfBin[tBin1[k]] == j) sl = j;
+            if (sl < 0) {
+                sl = ns++;
+                slotOfBin[tBin1[k]] = (short)sl;
+                // value range of the bin (approximate edges are fine: clamping keeps the sub-bin function monotone)
+                const double w = (mx - mn) / (double)S2_NB1;
+                slotLo[sl] = mn + w * (double)tBin1[k];
+                slotScale[sl] = (w > 0.0) ? (double)S2_NB2 / w : 0.0;
+            }
+            tSlot[k] = sl;
+        }
+        nSlots = ns;
+    }
+    __syncthreads();
+    const bool degenerate = !(mx > mn);
+    if (!degenerate) {
+        // ---- pass C: level-2 histograms of the selected bins
+        for (int b = tid; b < SEL_NT * S2_NB2; b += S2_THREADS) hist[b] = 0;
+        __syncthreads();
+        for (long long r = tid; r < Nrep; r += S2_THREADS) {
+            const double v = col[r];
+            if (v == unfeas || v != v) continue;
+            const int sl = slotOfBin[s2_bin(v, mn, scale1, S2_NB1)];
+            if (sl >= 0) atomicAdd(&hist[sl * S2_NB2 + s2_bin(v, slotLo[sl], slotScale[sl], S2_NB2)], 1u);
+        }
+        __syncthreads();
+        if (tid < SEL_NT) {  // serial scan of one 1024-bin histogram per target
+            const unsigned* hsl = hist + tSlot[tid] * S2_NB2;
+            long long acc = 0;
+            int b = 0;
+            for (; b < S2_NB2; ++b) {
+                if (acc + hsl[b] > tRank[tid]) break;
+                acc += hsl[b];
+            }
+            if (b >= S2_NB2) b = S2_NB2 - 1;
+            tBin2[tid] = b;
+            tRank[tid] -= acc;
+            gCount[tid] = (int)min((unsigned)0x7fffffff, hsl[b]);  // members of the selected sub-bin
+        }
+        __syncthreads();
+        if (tid == 0) {  // distinct (slot, sub-bin) -> gather lists
+            int nl = 0;
+            for (int k = 0; k < SEL_NT; ++k) {
+                int li = -1;
+                for (int j = 0; j < nl; ++j)
+                    if (listSlot[j] == tSlot[k] && listBin2[j] == tBin2[k]) li = j;
+                if (li < 0) { li = nl++; listSlot[li] = tSlot[k]; listBin2[li] = tBin2[k]; }
+                tList[k] = li;
+            }
+            nLists = nl;
+        }
+        __syncthreads();
+        __shared__ int lCount[SEL_NT];
+        if (tid < SEL_NT) lCount[tid] = 0;
+        __syncthreads();
+        // ---- pass D: gather
+        for (long long r = tid; r < Nrep; r += S2_THREADS) {
+            const double v = col[r];
+            if (v == unfeas || v != v) continue;
+            const int sl = slotOfBin[s2_bin(v, mn, scale1, S2_NB1)];
+            if (sl < 0) continue;
+            const int b2 = s2_bin(v, slotLo[sl], slotScale[sl], S2_NB2);
+            for (int j = 0; j < nLists; ++j)
+                if (listSlot[j] == sl && listBin2[j] == b2) {
+                    const int pos = atomicAdd(&lCount[j], 1);
+                    if (pos < S2_CAP) gath[j * S2_CAP + pos] = v;
+                }
+        }
+        __syncthreads();
+        // sort every list (bitonic, padded with +inf) -- one list at a time, whole block
+        for (int j = 0; j < nLists; ++j) {
+            const int cnt = min(lCount[j], S2_CAP);
+            double* g = gath + j * S2_CAP;
+            for (int i = cnt + tid; i < S2_CAP; i += S2_THREADS) g[i] = INFINITY;
+            __syncthreads();
+            for (int kk = 2; kk <= S2_CAP; kk <<= 1)
+                for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                    for (int i = tid; i < S2_CAP; i += S2_THREADS) {
+                        const int ixj = i ^ jj;
+                        if (ixj > i) {
+                            const double a = g[i], b = g[ixj];
+                            const bool up = ((i & kk) == 0);
+                            if ((a > b) == up) { g[i] = b; g[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+        }
+        if (tid < SEL_NT) {
+            const int j = tList[tid];
+            if (lCount[j] <= S2_CAP) tVal[tid] = gath[j * S2_CAP + (int)tRank[tid]];
+            else tVal[tid] = NAN;  // unresolved: too many members (ties): slow path
+        }
+    } else if (tid < SEL_NT) tVal[tid] = mn;
+    __syncthreads();
+    if (tid == 0) {
+        bool slow = false;
+        for (int k = 0; k < SEL_NT; ++k) slow |= (tVal[k] != tVal[k]);
+        if (slow) { needSlow[colId] = 1; return; }
+        needSlow[colId] = 0;
+        for (int q = 0; q < 5; ++q) {
+            const double hh = pr[q] * (double)m + 0.5;
+            double qv;
+            if (hh <= 1.0 || hh >= (double)m) qv = tVal[2 * q];
+            else {
+                const long long i = (long long)floor(hh);
+                const double frac = hh - (double)i;
+                qv = tVal[2 * q] + frac * (tVal[2 * q + 1] - tVal[2 * q]);
+            }
+            out[(size_t)q * nT] = qv;
+        }
+        out[(size_t)5 * nT] = mean;
+        out[(size_t)6 * nT] = (m > 1) ? sqrt(ss / (double)(m - 1)) : unfeas;
+    }
+}
+
 using PredKernel = void (*)(DevProblem, PredArgs, const double*, const int*, double* const*, const int*, double*);
 
 template <int MODEL>
@@ -466,7 +724,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     h->predT0 = t0; h->predT1 = t1;
 
     // tile of inputs: at most ~2 GiB of materialised values
-    const size_t budget = (size_t)2 << 30;
+    const size_t budget = (size_t)8 << 30;
     long long tileT = (long long)(budget / (sizeof(double) * (size_t)Nrep * nY));
     tileT = std::max<long long>(32, std::min<long long>(tileT / 32 * 32, ((long long)nTall + 31) / 32 * 32));
     if (h_spag) tileT = std::max<long long>(tileT, 32);
@@ -489,6 +747,8 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     if (smallN && smemEnv > 48 * 1024)
         BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEnv));
 
+    const size_t smemSel2 = sizeof(unsigned) * SEL_NT * S2_NB2 + sizeof(double) * SEL_NT * S2_CAP;
+    if (!smallN) BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel2));
     BAM_CUDA(cudaEventRecord(h->ev0, s));
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     if (h->recordKernels && h->kernEv.size() < 8192) { k0 = take_event(h); k1 = take_event(h); BAM_CUDA(cudaEventRecord(k0, s)); }
@@ -503,7 +763,14 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             double* envTile = nullptr;
             BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nY, s));
             if (smallN) envelope_smem<<<nT * nY, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
-            else envelope_select<<<nT * nY, BAM_BLOCK, 0, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile);
+            else {
+                int* needSlow = nullptr;
+                BAM_CUDA(cudaMallocAsync(&needSlow, sizeof(int) * (size_t)nT * nY, s));
+                envelope_select2<<<nT * nY, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
+                envelope_select<<<nT * nY, BAM_BLOCK, 0, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
+                BAM_CUDA(cudaFreeAsync(needSlow, s));
+                h->launches += 1;
+            }
             h->launches += 1;
             for (int y = 0; y < nY; ++y)
                 BAM_CUDA(cudaMemcpy2DAsync(h->d_env + ((size_t)y * BAMGPU_NENV * nTall + tt), sizeof(double) * nTall,
