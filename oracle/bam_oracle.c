@@ -1320,7 +1320,8 @@ int oracle_predict(const oracle_t* o, int64_t Nrep, const double* mc, const doub
  * ------------------------------------------------------------------------------------------ */
 int oracle_fit(const oracle_t* o, int K, const double* start, const double* start_std, int nAdapt, int nCycles,
                double MinMoveRate, double MaxMoveRate, double DownMult, double UpMult, uint64_t seed, int burn,
-               int keep_every, double* out_rows, int64_t* n_keep, double* final_x, double* final_std, char* mess) {
+               int keep_every, double* out_rows, int64_t* n_keep, double* final_x, double* final_std,
+               int64_t chain_offset, char* mess) {
     int P = o->P, nD = o->nDpar;
     int64_t nIter = (int64_t)nAdapt * nCycles;
     if (keep_every < 1) keep_every = 1;
@@ -1347,10 +1348,10 @@ int oracle_fit(const oracle_t* o, int K, const double* start, const double* star
             for (int a = 0; a < nAdapt; ++a, ++it) {
                 for (int i = 0; i < P; ++i) {
                     memcpy(cand, x, (size_t)P * 8);
-                    cand[i] = x[i] + sd[i] * oracle_normal(seed, (uint64_t)c, (uint32_t)it, (uint32_t)(2 * i));
+                    cand[i] = x[i] + sd[i] * oracle_normal(seed, (uint64_t)(chain_offset + c), (uint32_t)it, (uint32_t)(2 * i));
                     oracle_logpost(o, cand, &fc, NULL, NULL, NULL, &feas, &isnull, dcand, 0, mess);
                     if (feas && !isnull) {
-                        double u = oracle_uniform(seed, (uint64_t)c, (uint32_t)it, (uint32_t)(2 * i + 1));
+                        double u = oracle_uniform(seed, (uint64_t)(chain_offset + c), (uint32_t)it, (uint32_t)(2 * i + 1));
                         if (log(u) < fc - fx) {
                             x[i] = cand[i]; fx = fc; memcpy(dpar, dcand, (size_t)nD * 8); moves[i]++;
                         }

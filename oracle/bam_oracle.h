@@ -59,7 +59,8 @@ void oracle_envelope(const double* col, int64_t nrep, double unfeas_flag, double
 /* Adaptive_Metro_OAAT (BMSL, recalled semantics: SURVEY.md App. E), same RNG streams as the device */
 int oracle_fit(const oracle_t* o, int K, const double* start, const double* start_std, int nAdapt, int nCycles,
                double MinMoveRate, double MaxMoveRate, double DownMult, double UpMult, uint64_t seed, int burn,
-               int keep_every, double* out_rows, int64_t* n_keep, double* final_x, double* final_std, char* mess);
+               int keep_every, double* out_rows, int64_t* n_keep, double* final_x, double* final_std,
+               int64_t chain_offset /* global index of chain 0 (sharding across ranks) */, char* mess);
 
 /* RNG primitives shared (by specification, not by code) with the device */
 void oracle_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,

@@ -43,7 +43,7 @@ def load():
     lib.oracle_predict.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, ci, _ip, u64, ci, ci, _dp, _dp, ci, cp]
     lib.oracle_envelope.argtypes = [_dp, i64, d, _dp]
     lib.oracle_envelope.restype = None
-    lib.oracle_fit.argtypes = [H, ci, _dp, _dp, ci, ci, d, d, d, d, u64, ci, ci, _dp, C.POINTER(i64), _dp, _dp, cp]
+    lib.oracle_fit.argtypes = [H, ci, _dp, _dp, ci, ci, d, d, d, d, u64, ci, ci, _dp, C.POINTER(i64), _dp, _dp, i64, cp]
     lib.oracle_normal.argtypes = [u64, u64, C.c_uint32, C.c_uint32]
     lib.oracle_normal.restype = d
     lib.oracle_uniform.argtypes = [u64, u64, C.c_uint32, C.c_uint32]
@@ -163,7 +163,7 @@ class Oracle:
         return env, spag
 
     def fit(self, start, start_std, nAdapt, nCycles, MinMoveRate=0.1, MaxMoveRate=0.5, DownMult=0.9, UpMult=1.1,
-            seed=1, burn=0, keep_every=1):
+            seed=1, burn=0, keep_every=1, chain_offset=0):
         start = np.asarray(start, dtype=np.float64)
         K = 1 if start.ndim == 1 else start.shape[0]
         s = _vec(K, self.P, start)
@@ -176,7 +176,7 @@ class Oracle:
         mess = C.create_string_buffer(MESS_LEN)
         _check(self.lib.oracle_fit(self.h, K, _ptr_d(s), _ptr_d(sd), nAdapt, nCycles, MinMoveRate, MaxMoveRate, DownMult,
                                    UpMult, seed, burn, keep_every, _ptr_d(rows), C.byref(nk), _ptr_d(fx), _ptr_d(fstd),
-                                   mess), mess)
+                                   chain_offset, mess), mess)
         return rows, fx, fstd
 
 
