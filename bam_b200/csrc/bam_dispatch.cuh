@@ -1,0 +1,14 @@
+// bam_dispatch.cuh -- the (model, nX, nY) combinations the templated kernels are instantiated for.
+// One list, used by the log-posterior, sampler and prediction translation units.
+#pragma once
+#include "../../include/bam_gpu.h"
+
+#define BAM_FOR_EACH_INSTANCE(X)                                                                            \
+    X(BAMGPU_MDL_BARATIN, 1, 1)                                                                             \
+    X(BAMGPU_MDL_LINEAR, 1, 1) X(BAMGPU_MDL_LINEAR, 2, 1) X(BAMGPU_MDL_LINEAR, 3, 1) X(BAMGPU_MDL_LINEAR, 4, 1)   \
+    X(BAMGPU_MDL_LINEAR, 1, 2) X(BAMGPU_MDL_LINEAR, 2, 2) X(BAMGPU_MDL_LINEAR, 3, 2) X(BAMGPU_MDL_LINEAR, 4, 2)   \
+    X(BAMGPU_MDL_TEXTFILE, 1, 1) X(BAMGPU_MDL_TEXTFILE, 2, 1) X(BAMGPU_MDL_TEXTFILE, 3, 1)                   \
+    X(BAMGPU_MDL_TEXTFILE, 4, 1) X(BAMGPU_MDL_TEXTFILE, 1, 2) X(BAMGPU_MDL_TEXTFILE, 2, 2)                   \
+    X(BAMGPU_MDL_TEXTFILE, 3, 2) X(BAMGPU_MDL_TEXTFILE, 4, 2)                                               \
+    X(BAMGPU_MDL_SEDIMENT, 2, 1) X(BAMGPU_MDL_SEDIMENT, 3, 1) X(BAMGPU_MDL_SEDIMENT, 4, 1)                   \
+    X(BAMGPU_MDL_SEDIMENT, 5, 1) X(BAMGPU_MDL_SEDIMENT, 6, 1)

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstdio>
 
+#include "bam_dispatch.cuh"
 #include "bam_fastmath.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
@@ -470,31 +471,11 @@ FastKernel pick_fast(const DevProblem& p, int K) {
 using MainKernel = void (*)(DevProblem, const double*, int, int, int, const double*, const int*, double*, int*, int,
                             const double*);
 
-template <int MODEL>
-MainKernel pick_nxny(int nX, int nY) {
-#define PICK(a, b) \
-    if (nX == a && nY == b) return logpost_main<MODEL, a, b>;
-    PICK(1, 1) PICK(2, 1) PICK(3, 1) PICK(4, 1) PICK(1, 2) PICK(2, 2) PICK(3, 2) PICK(4, 2)
-#undef PICK
-    return nullptr;
-}
-
 MainKernel pick_main(int model, int nX, int nY) {
-    switch (model) {
-        case BAMGPU_MDL_BARATIN: return (nX == 1 && nY == 1) ? logpost_main<BAMGPU_MDL_BARATIN, 1, 1> : nullptr;
-        case BAMGPU_MDL_LINEAR: return pick_nxny<BAMGPU_MDL_LINEAR>(nX, nY);
-        case BAMGPU_MDL_TEXTFILE: return pick_nxny<BAMGPU_MDL_TEXTFILE>(nX, nY);
-        case BAMGPU_MDL_SEDIMENT:
-            if (nY != 1) return nullptr;
-            switch (nX) {
-                case 2: return logpost_main<BAMGPU_MDL_SEDIMENT, 2, 1>;
-                case 3: return logpost_main<BAMGPU_MDL_SEDIMENT, 3, 1>;
-                case 4: return logpost_main<BAMGPU_MDL_SEDIMENT, 4, 1>;
-                case 5: return logpost_main<BAMGPU_MDL_SEDIMENT, 5, 1>;
-                case 6: return logpost_main<BAMGPU_MDL_SEDIMENT, 6, 1>;
-            }
-            return nullptr;
-    }
+#define X(M, A, B) \
+    if (model == M && nX == A && nY == B) return logpost_main<M, A, B>;
+    BAM_FOR_EACH_INSTANCE(X)
+#undef X
     return nullptr;
 }
 

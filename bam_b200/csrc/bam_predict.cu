@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cfloat>
 
+#include "bam_dispatch.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
 
@@ -658,31 +659,11 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
 
 using PredKernel = void (*)(DevProblem, PredArgs, const double*, const int*, double* const*, const int*, double*);
 
-template <int MODEL>
-PredKernel pick_nxny(int nX, int nY) {
-#define PICK(a, b) \
-    if (nX == a && nY == b) return pred_main<MODEL, a, b>;
-    PICK(1, 1) PICK(2, 1) PICK(3, 1) PICK(4, 1) PICK(1, 2) PICK(2, 2) PICK(3, 2) PICK(4, 2)
-#undef PICK
-    return nullptr;
-}
-
 PredKernel pick_pred(int model, int nX, int nY) {
-    switch (model) {
-        case BAMGPU_MDL_BARATIN: return (nX == 1 && nY == 1) ? pred_main<BAMGPU_MDL_BARATIN, 1, 1> : nullptr;
-        case BAMGPU_MDL_LINEAR: return pick_nxny<BAMGPU_MDL_LINEAR>(nX, nY);
-        case BAMGPU_MDL_TEXTFILE: return pick_nxny<BAMGPU_MDL_TEXTFILE>(nX, nY);
-        case BAMGPU_MDL_SEDIMENT:
-            if (nY != 1) return nullptr;
-            switch (nX) {
-                case 2: return pred_main<BAMGPU_MDL_SEDIMENT, 2, 1>;
-                case 3: return pred_main<BAMGPU_MDL_SEDIMENT, 3, 1>;
-                case 4: return pred_main<BAMGPU_MDL_SEDIMENT, 4, 1>;
-                case 5: return pred_main<BAMGPU_MDL_SEDIMENT, 5, 1>;
-                case 6: return pred_main<BAMGPU_MDL_SEDIMENT, 6, 1>;
-            }
-            return nullptr;
-    }
+#define X(M, A, B) \
+    if (model == M && nX == A && nY == B) return pred_main<M, A, B>;
+    BAM_FOR_EACH_INSTANCE(X)
+#undef X
     return nullptr;
 }
 

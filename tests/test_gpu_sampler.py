@@ -95,3 +95,24 @@ def test_chain_offset_makes_sharding_invisible():
     g2.lib.bamgpu_set_chain_offset(g2.h, 4)
     rows_b = g2.fit(s[4:], sd[4:], nAdapt=6, nCycles=2, seed=21)
     assert (rows_b == rows[4:]).all()
+
+
+def test_persistent_and_launch_per_proposal_paths_agree():
+    """Small data sets run the persistent warp-per-chain kernel, large ones one launch per proposal:
+    same RNG streams and accept rule -> the same chains (up to the rounding of differently ordered sums)."""
+    prob, d = problem_from_fixture("baratin_spd", with_copula=True)
+    K = 5
+    s, sd = start_std(d["start"], K, 0.05)
+    g = BamGpu(prob)
+    rows_p = g.fit(s, sd, nAdapt=6, nCycles=3, seed=13)
+    cnt_p, mean_p, m2_p = g.moments()
+    g2 = BamGpu(prob)
+    g2.set_option("force_generic", 1)
+    rows_g = g2.fit(s, sd, nAdapt=6, nCycles=3, seed=13)
+    cnt_g, mean_g, m2_g = g2.moments()
+    assert g.launch_count() < g2.launch_count() / 10
+    assert np.allclose(rows_p, rows_g, rtol=1e-11, atol=1e-13)
+    assert np.allclose(mean_p, mean_g, rtol=1e-11) and (cnt_p == cnt_g).all()
+    assert np.allclose(m2_p, m2_g, rtol=1e-7, atol=1e-13)
+    fx_p = g.chains_download()[0]
+    assert np.allclose(fx_p, rows_p[:, -1, 19], rtol=1e-12)
