@@ -116,7 +116,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         d.model = L.model; d.n = L.n; d.nX = L.nX; d.nY = L.nY; d.ntheta = L.ntheta;
         d.nFit = L.nFit; d.nGamma = L.nGamma; d.nLatent = L.nLatent; d.P = L.P; d.nCombo = L.nCombo;
         d.nDparModel = L.nDparModel; d.nDpar = L.nDpar;
-        d.nDer = (L.model == BAMGPU_MDL_BARATIN) ? 2 * L.ncontrol : L.nDparModel;  // BaRatin: b_i and log a_i
+        d.nDer = L.nDer;
         // table layout
         d.tabGamma = 0;
         d.tabXb = L.nGamma;
@@ -136,7 +136,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
             if (!(L.nY == 1 && !L.hasLatent && pb->Y[i] == pb->mv)) perm.push_back(i);
         const int nDev = (int)perm.size();
         const bool dropped = nDev != L.n;
-        if (!L.hasLatent && nDev > 1)
+        if (!L.hasLatent && nDev > 1 && L.model != BAMGPU_MDL_VEGETATION)  // Vegetation: the series order matters
             std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
                 if (L.comboOf[a] != L.comboOf[b]) return L.comboOf[a] < L.comboOf[b];
                 return pb->X[a] < pb->X[b];
@@ -201,6 +201,8 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         d.ncontrol = L.ncontrol; d.ctrlMask = L.ctrlMask;
         d.sedFormula = L.sed[0]; d.sedCss = L.sed[1]; d.sedCo = L.sed[2];
         for (int i = 0; i < 4; ++i) { d.sedPpo[i] = L.sed[3 + i]; d.sedPseudo[i] = L.sedPseudo[i]; }
+        d.vegGrowth = L.vegGrowth; d.vegNYear = L.vegNYear; d.vegItmax = L.vegItmax;
+        d.vegXscale = L.vegOpt[0]; d.vegFscale = L.vegOpt[1]; d.vegTolX = L.vegOpt[2]; d.vegTolF = L.vegOpt[3];
         if (L.model == BAMGPU_MDL_TEXTFILE) {
             d.vmCode = upload(h, L.vmCode.data(), L.vmCode.size());
             d.vmImmed = upload(h, L.vmImmed.data(), L.vmImmed.size());

@@ -15,7 +15,8 @@
 #define BAM_MAXY 8
 #define BAM_MAXTHETA 40
 #define BAM_MAXCTRL 8
-#define BAM_MAXDER 16  /* per-parameter-set derived values kept in the chain table (BaRatin: b_i and log a_i) */
+#define BAM_MAXDER 64  /* per-parameter-set derived values kept in the chain table (BaRatin: b_i and log a_i; Vegetation: 1+6 nYear) */
+#define BAM_VEG_MAXYEAR 10
 #define BAM_MAXGAMMA 24
 #define BAM_MAXCOPULA 96
 #define BAM_VMSTACK 24
@@ -62,6 +63,9 @@ struct DevProblem {
     const int* vmCode;
     const double* vmImmed;
     int vmNcode[BAM_MAXY], vmCodeOff[BAM_MAXY], vmImmedOff[BAM_MAXY], vmNin, vmNpar;
+    // Vegetation
+    int vegGrowth, vegNYear, vegItmax;
+    double vegXscale, vegFscale, vegTolX, vegTolF;
 };
 
 #define BAM_LOG_SQRT_2PI 0.91893853320467274178

@@ -11,4 +11,6 @@
     X(BAMGPU_MDL_TEXTFILE, 4, 1) X(BAMGPU_MDL_TEXTFILE, 1, 2) X(BAMGPU_MDL_TEXTFILE, 2, 2)                   \
     X(BAMGPU_MDL_TEXTFILE, 3, 2) X(BAMGPU_MDL_TEXTFILE, 4, 2)                                               \
     X(BAMGPU_MDL_SEDIMENT, 2, 1) X(BAMGPU_MDL_SEDIMENT, 3, 1) X(BAMGPU_MDL_SEDIMENT, 4, 1)                   \
-    X(BAMGPU_MDL_SEDIMENT, 5, 1) X(BAMGPU_MDL_SEDIMENT, 6, 1)
+    X(BAMGPU_MDL_SEDIMENT, 5, 1) X(BAMGPU_MDL_SEDIMENT, 6, 1)                                               \
+    X(BAMGPU_MDL_VEGETATION, 2, 4) X(BAMGPU_MDL_VEGETATION, 2, 5)                                           \
+    X(BAMGPU_MDL_VEGETATION, 4, 4) X(BAMGPU_MDL_VEGETATION, 4, 5)

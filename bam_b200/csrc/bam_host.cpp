@@ -317,7 +317,6 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
     L = HostLayout();
     L.model = model_from_name(p.model_id);
     if (!L.model) { mess = "ApplyModel: Fatal: Unavailable [model%ID]"; return 1; }
-    if (L.model == BAMGPU_MDL_VEGETATION) { mess = "bamgpu: model Vegetation is recognised but not built yet (see DESIGN.md)"; return 1; }
     const int n = L.n = p.nobs, nX = L.nX = p.nX, nY = L.nY = p.nY, nt = L.ntheta = p.ntheta;
     if (n < 0 || nX < 1 || nY < 1 || nt < 0) { mess = "LoadBamObjects: size mismatch in input data"; return 1; }
     if (n > 0 && (!p.X || !p.Xu || !p.Xb || !p.Xbindx || !p.Y || !p.Yu || !p.Yb || !p.Ybindx)) {
@@ -448,7 +447,35 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             }
             break;
         }
+        case BAMGPU_MDL_VEGETATION: {  // Vegetation_XtraRead (Vegetation_model.f90:244-289), GetParNumber (:46-86)
+            if (p.n_xtra_i != 3 || p.n_xtra_d != 4) { mess = "Vegetation_XtraRead:problem reading xtra"; return 1; }
+            L.vegGrowth = p.xtra_i[0]; L.vegNYear = p.xtra_i[1]; L.vegItmax = p.xtra_i[2];
+            for (int i = 0; i < 4; ++i) L.vegOpt[i] = p.xtra_d[i];
+            if (L.vegGrowth < 1 || L.vegGrowth > 4) { mess = "GetNpar_growth:Fatal:Unavailable [growthFormula]"; return 1; }
+            const bool temporal = L.vegGrowth == BAMGPU_VEG_YIN1_TEMPORAL;
+            if (L.vegNYear < 1 || L.vegNYear > 10) { mess = "bamgpu: Vegetation supports 1..10 years"; return 1; }
+            const int np = 5 + 2 + (temporal ? 3 : 4) + (temporal ? 1 : L.vegNYear);
+            if (nt != np) { mess = "Vegetation_Apply:wrong size[theta]"; return 1; }
+            if (nX != (temporal ? 2 : 4) || (nY != 4 && nY != 5)) { mess = "Vegetation_Apply: wrong number of input or output columns"; return 1; }
+            if (!temporal) {
+                // the degree-day scan needs the whole series: a VAR parameter makes the reference call the model one
+                // row at a time (:4152-4174), which ends in "empty year" (:432-436); latent / biased inputs would make
+                // the series chain-dependent
+                if (L.nVar) { mess = "Apply_growth:Fatal:empty year, currently unsupported (VAR parameters with a temperature-driven growth formula)"; return 1; }
+                if (L.hasLatent || L.hasXbias) { mess = "bamgpu: Vegetation with temperature-driven growth does not support input errors"; return 1; }
+                for (int y = 0; y < L.vegNYear && n > 0; ++y) {
+                    bool any = false;
+                    for (int i = 0; i < n && !any; ++i) any = std::floor(p.X[i]) == (double)y;
+                    if (!any) { mess = "Apply_growth:Fatal:empty year, currently unsupported"; return 1; }
+                }
+            }
+            L.nDparModel = temporal ? 1 : L.vegNYear + 1;
+            L.nDer = temporal ? 3 : 1 + 6 * L.vegNYear;
+            break;
+        }
     }
+    if (L.model == BAMGPU_MDL_BARATIN) L.nDer = 2 * L.ncontrol;  // b_i and log a_i
+    else if (L.model != BAMGPU_MDL_VEGETATION) L.nDer = L.nDparModel;
 
     // VAR combinations in order of first appearance (:346-379); L(t,i) = offset_i + indx_i(t) (:326-334)
     L.comboOf.assign(n, 0);

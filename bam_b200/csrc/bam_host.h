@@ -51,6 +51,9 @@ struct HostLayout {
     std::vector<double> vmImmed;
     std::vector<int32_t> vmNcode, vmCodeOff, vmImmedOff;
     int vmMaxStack = 0;
+    int vegGrowth = 0, vegNYear = 0, vegItmax = 0;
+    double vegOpt[4] = {0, 0, 0, 0};  // xscale, fscale, tolX, tolF
+    int nDer = 0;  // derived values per (parameter set, combination) kept in the device table
 };
 
 // Validates `p` and derives the layout.  Returns err (0 OK, >0 error) and fills mess.

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* 
     for (int j = 0; j < p.nY; ++j)
         for (int i = 0; i < p.nYb[j]; ++i) row[p.tabOffYb[j] + i] = xval(x, base, p.offYb[j] + i, comp, dl);
     double th[BAM_MAXTHETA], der[BAM_MAXDER];
+    const double* xc[BAM_MAXX];
+    for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
     for (int k = 0; k < p.nCombo; ++k) {  // ApplyModel_BaM theta expansion (:4133-4159), once per combination
         double* cr = row + p.tabCombo + (size_t)k * p.comboStride;
         for (int i = 0; i < p.ntheta; ++i) {
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* 
             cr[i] = th[i];
         }
         for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
-        const bool ok = model_prepare(p, th, der);
+        const bool ok = model_prepare(p, th, der, xc, p.n);
         if (!ok) st |= ST_LKH_INFEAS;
         for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
         if (dpar != nullptr)

@@ -204,12 +204,193 @@ __device__ inline bool textfile_eval(const DevProblem& p, int k, const double* i
 }
 
 // -------------------------------------------------------------------------------------------
+// Vegetation (Vegetation_model.f90:87-569).  theta = (B,S0,n1,b1,c1 | chi,U_chi | growth pars | gmax).
+// Per parameter set (vegetation_prepare): feasibility + growth-curve constants; for the temperature-driven
+// formulas this is the per-year degree-day scan of Apply_growth (:420-532) over the WHOLE input series.
+// der layout: [0] B sqrt(S0)/n1 (Dpar 1); temporal: [1] alpha, [2] t_f;
+//             else [1+i] T_m of year i (Dpar 2..), then per year 5 values at [1+nYear+5i]: t_b, t_e, t_f, alpha, g==0 flag.
+// -------------------------------------------------------------------------------------------
+#define BAM_VEG_PI 3.14159265358979323846
+#define BAM_VEG_GRAVITY 9.81
+
+__device__ inline bool vegetation_prepare(const DevProblem& p, const double* th, double* der, const double* const* xc,
+                                          int nser) {
+    const bool temporal = p.vegGrowth == BAMGPU_VEG_YIN1_TEMPORAL;
+    const int nG = temporal ? 3 : 4, nGmax = temporal ? 1 : p.vegNYear;
+    const double B = th[0], S0 = th[1], n1 = th[2], c1 = th[4], chi = th[5], U_chi = th[6];
+    const double* par = th + 7;
+    const double* gmax = th + 7 + nG;
+    der[0] = (S0 >= 0.0) ? B * sqrt(S0) / n1 : BAMGPU_UNDEF_RN;
+    bool badg = false;
+    for (int i = 0; i < nGmax; ++i) badg |= gmax[i] < 0.0;
+    if (B <= 0.0 || S0 <= 0.0 || n1 <= 0.0 || c1 <= 0.0 || chi < -2.0 || chi > 0.0 || U_chi <= 0.0 || badg) return false;
+    if (temporal) {  // :395-419
+        const double t0 = par[0], ti = par[1], tmax = par[2];
+        if (t0 <= 0.0 || ti <= 0.0 || tmax <= 0.0 || t0 >= 1.0 || ti >= 1.0 || tmax >= 1.0 || t0 >= ti || ti >= tmax) return false;
+        der[1] = (tmax - t0) / (tmax - ti);
+        der[2] = 2.0 * tmax - ti;
+        return true;
+    }
+    const double Tmin = par[0], Tb = par[1], Te = par[2];
+    const int nYear = p.vegNYear;
+    for (int i = 0; i < nYear; ++i) der[1 + i] = BAMGPU_UNDEF_RN;
+    if (Te <= Tb) return false;
+    const double *time = xc[0], *Traw = xc[2], *Tsmooth = xc[3];
+    for (int i = 0; i < nYear; ++i) {
+        // pass 1: degree-day sum in order of appearance; first crossings of T_b, T_e (and of T_m for Yin1)
+        double cumul = 0.0, prev = (double)i, time_b = 0.0, time_e = 0.0, time_m = 0.0, last = 0.0;
+        bool gotB = false, gotE = false, gotM = false;
+        int m = 0;
+        for (int j = 0; j < nser; ++j) {
+            const double tj = time[j];
+            if (floor(tj) != (double)i) continue;
+            const double tr = Traw[j];
+            if (tr >= Tmin) cumul = cumul + 365.0 * (tj - prev) * (tr - Tmin);
+            prev = tj;
+            last = tj;
+            ++m;
+            if (!gotB && cumul >= Tb) { gotB = true; time_b = tj; }
+            if (!gotE && cumul >= Te) { gotE = true; time_e = tj; }
+            if (p.vegGrowth == BAMGPU_VEG_YIN1 && !gotM && Tsmooth[j] >= par[3]) { gotM = true; time_m = tj; }
+        }
+        if (m == 0) return false;  // "empty year": an error in the reference (:432-436); checked on the host where possible
+        if (!gotE) return false;
+        double* yr = der + 1 + nYear + 5 * i;
+        yr[0] = time_b; yr[1] = time_e; yr[2] = 0.0; yr[3] = 0.0; yr[4] = gotB ? 0.0 : 1.0;
+        if (!gotB) continue;  // no growth this year
+        double alpha, time_f;
+        if (p.vegGrowth == BAMGPU_VEG_YIN1) {
+            if (!gotM) return false;
+            if (time_m <= time_b) time_m = time_b;
+            if (time_m >= time_e) return false;
+            alpha = (time_e - time_b) / (time_e - time_m);
+            time_f = 2.0 * time_e - time_m;
+        } else if (p.vegGrowth == BAMGPU_VEG_YIN2) {
+            if (par[3] <= 0.0) return false;
+            alpha = par[3];
+            time_f = time_e + (time_e - time_b) / alpha;
+            time_m = ((alpha - 1.0) * time_f + 2.0 * time_b) / (alpha + 1.0);
+        } else {
+            if (par[3] <= 0.0) return false;
+            time_f = time_e + par[3];
+            alpha = (time_e - time_b) / (time_f - time_e);
+            time_m = ((alpha - 1.0) * time_f + 2.0 * time_b) / (alpha + 1.0);
+        }
+        if (time_m < time_b) time_m = time_b;
+        if (alpha <= 0.0 || time_m >= time_e || time_f > last) return false;
+        yr[2] = time_f; yr[3] = alpha;
+        // pass 2: optimal temperature = smoothed temperature at the first point with time >= t_m
+        for (int j = 0; j < nser; ++j) {
+            const double tj = time[j];
+            if (floor(tj) != (double)i) continue;
+            if (tj >= time_m) { der[1 + i] = Tsmooth[j]; break; }
+        }
+    }
+    return true;
+}
+
+// Vegetation_fNewton (:536-569)
+__device__ __forceinline__ void veg_fnewton(double x, double Q0, double gam, double gam2, double chi, double& f, double& df) {
+    double m = pow(x, chi) / gam2;
+    if (1.0 < m) m = 1.0;
+    f = x * x + (gam * (x * x) * m) - Q0 * Q0;
+    if (m == 1.0) df = 2.0 * x * (1.0 + gam);
+    else df = 2.0 * x + (gam / gam2 * (2.0 + chi) * pow(x, 1.0 + chi));
+}
+
+// znewton on [0, Q0]: declared convention (miniDMSL is un-vendored), identical to oracle/bam_oracle.c:veg_znewton
+__device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, double gam2, double chi, double& root) {
+    double fl, fh, df, f, xl, xh;
+    const double x1 = 0.0, x2 = Q0;
+    veg_fnewton(x1, Q0, gam, gam2, chi, fl, df);
+    veg_fnewton(x2, Q0, gam, gam2, chi, fh, df);
+    int fcalls = 2;
+    if (fl == 0.0) { root = x1; return fcalls <= p.vegItmax; }
+    if (fh == 0.0) { root = x2; return fcalls <= p.vegItmax; }
+    if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) return false;
+    if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
+    double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
+    veg_fnewton(rts, Q0, gam, gam2, chi, f, df);
+    ++fcalls;
+    for (int j = 0; j < p.vegItmax; ++j) {
+        if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+            dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
+        } else {
+            dxold = dx; dx = f / df; rts = rts - dx;
+        }
+        const bool convx = fabs(dx) <= p.vegTolX * p.vegXscale;
+        veg_fnewton(rts, Q0, gam, gam2, chi, f, df);
+        ++fcalls;
+        if (f < 0.0) xl = rts; else xh = rts;
+        if (convx || fabs(f) <= p.vegTolF * p.vegFscale) break;
+    }
+    for (int j = 0; j < 3 && f != 0.0 && df > 0.0; ++j) {  // polish to the root itself
+        const double lo = fmin(xl, xh), hi = fmax(xl, xh);
+        double xn = rts - f / df;
+        xn = fmin(fmax(xn, lo), hi);
+        if (xn == rts) break;
+        rts = xn;
+        veg_fnewton(rts, Q0, gam, gam2, chi, f, df);
+        if (f < 0.0) xl = rts; else xh = rts;
+    }
+    root = rts;
+    return fcalls <= p.vegItmax;
+}
+
+template <int NX, int NY>
+__device__ inline bool vegetation_apply(const DevProblem& p, const double* in, const double* __restrict__ th,
+                                        const double* __restrict__ der, double* out) {
+    const double time = in[0], h = in[1];
+    double g, g0, cosg, sing;
+    if (p.vegGrowth == BAMGPU_VEG_YIN1_TEMPORAL) {
+        const double t0 = th[7], tmax = th[9], alf = der[1], tf = der[2];
+        const double tt = time - floor(time);
+        if (tt >= t0 && tt <= tf) g0 = (pow((tt - t0) / (tmax - t0), alf)) * (tf - tt) / (tf - tmax);
+        else g0 = 0.0;
+        cosg = cos(g0 * BAM_VEG_PI);
+        sing = (tt <= tmax) ? sin(g0 * BAM_VEG_PI) : -1.0 * sin(g0 * BAM_VEG_PI);
+        g = th[10] * g0;
+    } else {
+        const int nYear = p.vegNYear;
+        const double fy = floor(time);
+        if (fy >= 0.0 && fy < (double)nYear) {
+            const int i = (int)fy;
+            const double* yr = der + 1 + nYear + 5 * i;
+            const double time_b = yr[0], time_e = yr[1], time_f = yr[2], alpha = yr[3];
+            if (yr[4] != 0.0 || time <= time_b || time >= time_f) g0 = 0.0;
+            else g0 = pow((time - time_b) / (time_e - time_b), alpha) * (time_f - time) / (time_f - time_e);
+            g = g0 * th[11 + i];
+            cosg = cos(g0 * BAM_VEG_PI);
+            sing = (time <= time_e) ? sin(g0 * BAM_VEG_PI) : -1.0 * sin(g0 * BAM_VEG_PI);
+        } else g = g0 = cosg = sing = BAMGPU_UNDEF_RN;  // a point outside every year keeps the initial undefRN (:380)
+    }
+    if (NY > 1) out[1] = g;
+    if (NY > 2) out[2] = cosg;
+    if (NY > 3) out[3] = sing;
+    if (NY > 4) out[4] = g0;
+    const double y = h - th[3];
+    if (y <= 0.0) { out[0] = 0.0; return true; }
+    const double Q0 = der[0] * pow(y, th[4]);
+    if (g <= 0.0) { out[0] = Q0; return true; }
+    const double chi = th[5];
+    const double gam = (g * pow(y, 1.0 / 3.0)) / (8.0 * BAM_VEG_GRAVITY * (th[2] * th[2]));
+    const double gam2 = pow(th[0], chi) * pow(y, chi) * pow(th[6], chi);
+    double q;
+    if (!veg_root(p, Q0, gam, gam2, chi, q)) return false;
+    out[0] = q;
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
 // dispatch
 // -------------------------------------------------------------------------------------------
 
-// once per (parameter set, VAR combination): derived values + feasibility
-__device__ inline bool model_prepare(const DevProblem& p, const double* th, double* der) {
+// once per (parameter set, VAR combination): derived values + feasibility.  xc[j] = column j of the input series
+// the parameter set will be applied to (nser rows): only whole-series models (Vegetation) look at it.
+__device__ inline bool model_prepare(const DevProblem& p, const double* th, double* der, const double* const* xc,
+                                     int nser) {
     if (p.model == BAMGPU_MDL_BARATIN) return baratin_prepare(p, th, der);
+    if (p.model == BAMGPU_MDL_VEGETATION) return vegetation_prepare(p, th, der, xc, nser);
     return true;
 }
 
@@ -224,6 +405,8 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return true;
     } else if (MODEL == BAMGPU_MDL_SEDIMENT) {
         return sediment_apply<NX>(p, x, th, y[0]);
+    } else if (MODEL == BAMGPU_MDL_VEGETATION) {
+        return vegetation_apply<NX, NY>(p, x, th, der, y);
     } else {
         bool ok = true;
 #pragma unroll

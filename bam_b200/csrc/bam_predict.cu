@@ -34,7 +34,8 @@ struct PredArgs {
 };
 
 __global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const double* __restrict__ mc,
-                                                 const double* __restrict__ mode, double* __restrict__ tab,
+                                                 const double* __restrict__ mode, double* const* __restrict__ xspag,
+                                                 const int* __restrict__ nspag, double* __restrict__ tab,
                                                  int* __restrict__ status) {
     const long long rep = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (rep >= a.Nrep) return;
@@ -49,7 +50,10 @@ __global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const
         row[p.nGamma + i] = th[i];
     }
     for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
-    const bool ok = model_prepare(p, th, der);
+    // whole-series models scan the complete input series of this replication (column rep mod nspag, :1049)
+    const double* xc[BAM_MAXX];
+    for (int j = 0; j < p.nX; ++j) xc[j] = xspag[j] + (size_t)(rep % nspag[j]) * a.nobsPred;
+    const bool ok = model_prepare(p, th, der, xc, a.nobsPred);
     for (int d = 0; d < p.nDer; ++d) row[p.nGamma + p.ntheta + d] = der[d];
     status[rep] = ok ? 0 : 1;
 }
@@ -716,7 +720,8 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         h->vCap = vNeed;
     }
 
-    pred_prep<<<(unsigned)((Nrep + 127) / 128), 128, 0, s>>>(p, a, h->d_mc, h->d_mode, h->d_ptab, h->d_pstatus);
+    pred_prep<<<(unsigned)((Nrep + 127) / 128), 128, 0, s>>>(p, a, h->d_mc, h->d_mode, h->d_xspagPtrs, h->d_nspag, h->d_ptab,
+                                                             h->d_pstatus);
     h->launches += 1;
     const size_t smemMain = sizeof(double) * (size_t)a.stride * BAM_BLOCK;
     if (smemMain > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMain));

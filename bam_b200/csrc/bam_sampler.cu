@@ -164,6 +164,8 @@ __device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, 
         for (int i = lane; i < p.nYb[j]; i += 32) tab[p.tabOffYb[j] + i] = xs[p.offYb[j] + i];
     for (int k = lane; k < p.nCombo; k += 32) {
         double th[BAM_MAXTHETA], der[BAM_MAXDER];
+        const double* xc[BAM_MAXX];
+        for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
         double* cr = tab + p.tabCombo + (size_t)k * p.comboStride;
         for (int i = 0; i < p.ntheta; ++i) {
             const int src = p.comboSrc[(size_t)k * p.ntheta + i];
@@ -171,7 +173,7 @@ __device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, 
             cr[i] = th[i];
         }
         for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
-        if (!model_prepare(p, th, der)) st |= ST_LKH_INFEAS;
+        if (!model_prepare(p, th, der, xc, p.n)) st |= ST_LKH_INFEAS;
         for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
     }
     st = __reduce_or_sync(0xffffffffu, st);

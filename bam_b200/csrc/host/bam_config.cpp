@@ -342,6 +342,18 @@ void load_workspace(const std::string& configFile, Workspace& w) {
         std::stringstream ss;
         ss << is.rdbuf();
         w.xtraText = ss.str();
+    } else if (w.modelID == "Vegetation") {  // Vegetation_XtraRead (Vegetation_model.f90:244-289)
+        Cursor s(xf);
+        const std::string gf = s.str();
+        int gid = 0;
+        const char* names[] = {"Growth_Yin1", "Growth_Yin2", "Growth_Yin3", "Growth_Yin1_temporal"};
+        for (int k = 0; k < 4; ++k)
+            if (gf == names[k]) gid = k + 1;
+        if (!gid) fail("GetNpar_growth:Fatal:Unavailable [growthFormula] '" + gf + "'");
+        w.xtraI.push_back(gid);
+        w.xtraI.push_back(s.integer());                          // nYear
+        for (int k = 0; k < 4; ++k) w.xtraD.push_back(s.num());  // Newton xscale, fscale, tolX, tolF (one per line)
+        w.xtraI.push_back(s.integer());                          // Newton itmax
     } else if (w.modelID == "Linear") {
     } else {
         fail("ApplyModel: Fatal: Unavailable [model%ID] '" + w.modelID + "' (not on the GPU hot path yet)");
@@ -514,6 +526,10 @@ void Workspace::make_headers(const bamgpu_sizes& s, int nDparModel) {  // GetHea
     std::vector<std::string> dn;
     if (modelID == "BaRatin")
         for (int i = 1; i <= nDparModel; ++i) dn.push_back("b" + std::to_string(i));
+    if (modelID == "Vegetation") {  // ModelLibrary_tools.f90:625-638
+        dn.push_back("a1");
+        for (int i = 2; i <= nDparModel; ++i) dn.push_back("Topt_" + std::to_string(i));
+    }
     const bool hasVar = std::any_of(partype.begin(), partype.end(), [](int t) { return t == 1; });
     if (!hasVar) headers.insert(headers.end(), dn.begin(), dn.end());
     else

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .capi import PARTYPE, SED_CO, SED_CSS, SED_FORMULA, SED_PPO, Problem
+from .capi import PARTYPE, SED_CO, SED_CSS, SED_FORMULA, SED_PPO, VEG_GROWTH, Problem
 
 SEED = 20261019
 
@@ -201,3 +201,80 @@ def baratin_spaghetti(Nrep: int = 1_000_000, nobs: int = 100_000, nspag: int = 1
     else:
         Hs = H.reshape(-1, 1)
     return mc, maxpost, Hs
+
+
+def vegetation(nobs: int = 600, growth: str = "Growth_Yin1_temporal", nyear: int = 3, var_gmax: bool = False,
+               nY: int = 5, seed: int = SEED + 6):
+    """Vegetation-affected rating curve (tests/BaM_Vegetation_static shape; theta with U_chi as the CODE expects,
+    Vegetation_model.f90:40-41,156-181).  Inputs: time (years), stage [, raw and smoothed temperature].
+    Outputs: Q (observed with noise), g / cos / sin / g0 (g observed, the rest missing).  Returns (Problem, truth)."""
+    rng = np.random.default_rng(seed)
+    temporal = growth == "Growth_Yin1_temporal"
+    time = np.sort(rng.uniform(0.0, nyear, nobs))
+    for y in range(nyear):  # make sure every year starts and ends with a point
+        time[np.searchsorted(time, y)] = y + 0.002
+        time[np.searchsorted(time, y + 1) - 1] = y + 0.998
+    tt = time - np.floor(time)
+    h = 1.6 + 0.8 * np.sin(2 * np.pi * (tt - 0.1)) ** 2 + 0.2 * rng.random(nobs)
+    Ts = 10.0 + 10.0 * np.sin(2 * np.pi * (tt - 0.25))
+    Tr = Ts + rng.standard_normal(nobs)
+    base = [25.0, 0.001, 0.02, 1.0, 1.67, -0.5, 0.5]
+    if temporal:
+        gpar, ng = [0.2, 0.45, 0.7], 1
+        X = np.column_stack([time, h])
+    else:
+        gpar = {"Growth_Yin1": [5.0, 200.0, 1500.0, 15.0], "Growth_Yin2": [5.0, 200.0, 1500.0, 2.0],
+                "Growth_Yin3": [5.0, 200.0, 1500.0, 0.2]}[growth]
+        ng = nyear
+        X = np.column_stack([time, h, Tr, Ts])
+    gmax = [1.0 + 0.2 * i for i in range(ng)]
+    theta = np.array(base + gpar + gmax)
+    ntheta = theta.size
+    partype = [0] * ntheta
+    nval = [1] * ntheta
+    var_indx = None
+    pri = [("Gaussian", [25, 5]), ("Gaussian", [0.001, 0.01]), ("Gaussian", [0.02, 0.01]), ("Gaussian", [1.0, 0.5]),
+           ("Gaussian", [1.67, 0.025]), ("Uniform", [-1, 0]), ("LogNormal", [-0.7, 0.5])]
+    if temporal:
+        pri += [("Uniform", [0, 1])] * 3
+    else:
+        pri += [("Gaussian", [5, 5]), ("Gaussian", [200, 100]), ("Gaussian", [1500, 500]),
+                ("Gaussian", [gpar[3], abs(gpar[3])])]
+    truth_theta = list(theta)
+    if var_gmax and temporal:  # gmax varies from year to year (Config_VAR_gmax.txt)
+        partype[-1] = PARTYPE["VAR"]
+        nval[-1] = nyear
+        var_indx = np.ones((nobs, ntheta), dtype=np.int32)
+        var_indx[:, -1] = 1 + np.floor(time).astype(np.int32)
+        gm = [1.0 + 0.3 * i for i in range(nyear)]
+        pri += [("Uniform", [0, 100])] * nyear
+        truth_theta = list(theta[:-1]) + gm
+    else:
+        pri += [("Uniform", [0, 100])] * ng
+    # observations: generated with a plain numpy forward model good to ~1e-6 (only used to make data)
+    gm_t = np.asarray(truth_theta[-(nyear if (var_gmax and temporal) else ng):])
+    yy = np.maximum(h - 1.0, 0.0)
+    Q0 = 25.0 * np.sqrt(0.001) / 0.02 * yy**1.67
+    if temporal:
+        t0, ti, tm = gpar
+        alf, tf = (tm - t0) / (tm - ti), 2 * tm - ti
+        g0 = np.where((tt >= t0) & (tt <= tf), np.abs((tt - t0) / (tm - t0)) ** alf * (tf - tt) / (tf - tm), 0.0)
+        g = g0 * (gm_t[np.floor(time).astype(int)] if (var_gmax and temporal) else gm_t[0])
+    else:
+        g0 = np.where((tt > 0.3) & (tt < 0.9), np.sin(np.pi * (tt - 0.3) / 0.6) ** 2, 0.0)
+        g = g0 * gm_t[np.floor(time).astype(int)]
+    Q = Q0 / np.sqrt(1.0 + g * yy ** (1 / 3) / (8 * 9.81 * 0.02**2) * 0.5)
+    uQ = 0.03 * Q + 0.05
+    Qobs = Q + rng.standard_normal(nobs) * np.sqrt(uQ**2 + (0.5 + 0.05 * Q) ** 2)
+    Y = np.full((nobs, nY), -9999.0)
+    Y[:, 0] = Qobs
+    Y[:, 1] = g + 0.05 * rng.standard_normal(nobs)
+    Yu = np.zeros((nobs, nY))
+    Yu[:, 0] = uQ
+    sig = ["Linear"] + ["Constant"] * (nY - 1)
+    pg = [("Uniform", [0, 1000]), ("Uniform", [0, 1000])] + [("Uniform", [0, 1000])] * (nY - 1)
+    prob = Problem("Vegetation", X, Y, Yu=Yu, partype=partype, nval=nval, var_indx=var_indx, priors_theta=pri,
+                   sigma_func=sig, priors_gamma=pg,
+                   xtra_i=[VEG_GROWTH[growth], nyear, 100], xtra_d=[5.0, 1000.0, 1e-5, 1e-10])
+    truth = np.array(truth_theta + [0.5, 0.05] + [0.1] * (nY - 1))
+    return prob, truth

@@ -8,7 +8,7 @@
  *   src/BaM_tools.f90:3006-3571 (posterior), :4115-4177 (theta expansion / VAR), :4202-4242 and
  *   :3386-3463 (vector layout), :882-1135 and :1292-1432 (prediction / envelopes),
  *   src/ModelLibrary_tools.f90:237-434 (dispatch + infeasible-row flagging),
- *   src/Models/{BaRatin,Linear,SedimentTransport,TextFile}_model.f90.
+ *   src/Models/{BaRatin,Linear,SedimentTransport,TextFile,Vegetation}_model.f90.
  * Compile with -ffp-contract=off: the reference is built by gfortran without FMA contraction.
  */
 #include "bam_oracle.h"
@@ -70,6 +70,8 @@ struct oracle_handle {
     double sed_pseudo[4];
     int vm_nin, vm_npar, vm_nout;
     vm_prog vm[MAXVMOUT];
+    int veg_growth, veg_nyear, veg_itmax;          /* Vegetation xtra (Vegetation_XtraRead :244-289) */
+    double veg_xscale, veg_fscale, veg_tolx, veg_tolf;
 };
 
 static void setmess(char* mess, const char* s) {
@@ -731,6 +733,218 @@ static void sediment_apply(const oracle_t* o, int n, const double* IN, int ldx, 
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Vegetation (Vegetation_model.f90)
+ * ------------------------------------------------------------------------------------------ */
+#define VEG_MAXYEAR 16
+static const double VEG_PI = 3.14159265358979323846; /* utilities_dmsl_kit pi */
+static const double VEG_GRAVITY = 9.81;              /* :129 */
+
+static int veg_ngrowth(int growth) { return growth == BAMGPU_VEG_YIN1_TEMPORAL ? 3 : 4; } /* GetNpar_growth :296-330 */
+
+/* Vegetation_fNewton, Vegetation_model.f90:536-569: f(x) = x^2 + gamma x^2 min(1, x^chi/gamma2) - Q0^2 */
+static void veg_fnewton(double x, double Q0, double gam, double gam2, double chi, double* fx, double* dfdx) {
+    double m = pow(x, chi) / gam2;
+    if (1.0 < m) m = 1.0; /* min(1., .) */
+    *fx = x * x + (gam * pow(x, 2.0) * m) - Q0 * Q0;
+    if (m == 1.0) *dfdx = 2.0 * x * (1.0 + gam);
+    else *dfdx = 2.0 * x + (gam / gam2 * (2.0 + chi) * pow(x, 1.0 + chi));
+}
+
+/* znewton (miniDMSL numerix_dmsl_kit, UN-VENDORED; declared convention = Numerical-Recipes "rtsafe": Newton from
+   the mid-point of the bracket, bisection whenever the Newton step leaves the bracket or converges too slowly;
+   stop when |dx| <= tolX*xscale or |f| <= tolF*fscale; fcalls counts every evaluation of f).
+   After that stop the root is POLISHED by up to 3 more clamped Newton steps: the reference's own answer is only
+   defined up to its tolerances (path unknown), so the restatement and the device both return the root itself
+   (|polished - reference| <= the reference's tolerance).  Returns 0 OK, 1 = not bracketed. */
+static int veg_znewton(double Q0, double gam, double gam2, double chi, double x1, double x2, double tolX, double tolF,
+                       double xscale, double fscale, int itmax, double* xroot, int* fcalls) {
+    double fl, fh, df, f, xl, xh;
+    veg_fnewton(x1, Q0, gam, gam2, chi, &fl, &df);
+    veg_fnewton(x2, Q0, gam, gam2, chi, &fh, &df);
+    *fcalls = 2;
+    if (fl == 0.0) { *xroot = x1; return 0; }
+    if (fh == 0.0) { *xroot = x2; return 0; }
+    if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) { *xroot = BAMGPU_UNDEF_RN; return 1; }
+    if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
+    double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
+    veg_fnewton(rts, Q0, gam, gam2, chi, &f, &df);
+    ++*fcalls;
+    for (int j = 0; j < itmax; ++j) {
+        if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+            dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
+        } else {
+            dxold = dx; dx = f / df; rts = rts - dx;
+        }
+        int convx = fabs(dx) <= tolX * xscale;
+        veg_fnewton(rts, Q0, gam, gam2, chi, &f, &df);
+        ++*fcalls;
+        if (f < 0.0) xl = rts; else xh = rts;
+        if (convx || fabs(f) <= tolF * fscale) break;
+    }
+    for (int j = 0; j < 3 && f != 0.0 && df > 0.0; ++j) { /* polish */
+        double lo = xl < xh ? xl : xh, hi = xl < xh ? xh : xl;
+        double xn = rts - f / df;
+        if (xn < lo) xn = lo;
+        if (xn > hi) xn = hi;
+        if (xn == rts) break;
+        rts = xn;
+        veg_fnewton(rts, Q0, gam, gam2, chi, &f, &df);
+        if (f < 0.0) xl = rts; else xh = rts;
+    }
+    *xroot = rts;
+    return 0;
+}
+
+/* Apply_growth, Vegetation_model.f90:345-534.  Returns 0 if the whole parameter set is infeasible. */
+static int veg_apply_growth(const oracle_t* o, int n, const double* time, const double* Traw, const double* Tsmooth,
+                            const double* par, const double* gmax, double* g, double* g0, double* cosg, double* sing,
+                            double* Tm, int* err) {
+    *err = 0;
+    for (int i = 0; i < n; ++i) g[i] = g0[i] = cosg[i] = sing[i] = BAMGPU_UNDEF_RN;
+    if (o->veg_growth == BAMGPU_VEG_YIN1_TEMPORAL) { /* :395-419 */
+        double t0 = par[0], ti = par[1], tmax = par[2];
+        if (t0 <= 0.0 || ti <= 0.0 || tmax <= 0.0 || t0 >= 1.0 || ti >= 1.0 || tmax >= 1.0 || t0 >= ti || ti >= tmax) return 0;
+        double alf = (tmax - t0) / (tmax - ti), tf = 2.0 * tmax - ti;
+        for (int i = 0; i < n; ++i) {
+            double tt = time[i] - floor(time[i]);
+            if (tt >= t0 && tt <= tf) g0[i] = (pow((tt - t0) / (tmax - t0), alf)) * (tf - tt) / (tf - tmax);
+            else g0[i] = 0.0;
+            cosg[i] = cos(g0[i] * VEG_PI);
+            if (tt <= tmax) sing[i] = sin(g0[i] * VEG_PI);
+            else sing[i] = -1.0 * sin(g0[i] * VEG_PI);
+            g[i] = gmax[0] * g0[i];
+        }
+        return 1;
+    }
+    double Tmin = par[0], Tb = par[1], Te = par[2];
+    int nYear = o->veg_nyear;
+    for (int i = 0; i < nYear; ++i) Tm[i] = BAMGPU_UNDEF_RN;
+    if (Te <= Tb) return 0;
+    double* tim = (double*)malloc(((size_t)n + 1) * 5 * sizeof(double));
+    double *temp = tim + n, *stemp = temp + n, *cum = stemp + n, *foog0 = cum + n;
+    int ok = 1;
+    for (int i = 0; i < nYear && ok; ++i) {
+        int m = 0;
+        for (int j = 0; j < n; ++j)
+            if (floor(time[j]) == (double)i) { tim[m] = time[j]; temp[m] = Traw[j]; stemp[m] = Tsmooth[j]; ++m; }
+        if (m == 0) { *err = 1; break; } /* "empty year, currently unsupported" :432-436 */
+        double cumul = 0.0; /* degree-days :447-453 */
+        if (temp[0] >= Tmin) cumul = cumul + 365.0 * (tim[0] - (double)i) * (temp[0] - Tmin);
+        cum[0] = cumul;
+        for (int j = 1; j < m; ++j) {
+            if (temp[j] >= Tmin) cumul = cumul + 365.0 * (tim[j] - tim[j - 1]) * (temp[j] - Tmin);
+            cum[j] = cumul;
+        }
+        int gnull = 0, k;
+        double time_b = 0.0, time_e = 0.0, time_m = 0.0, time_f = 0.0, alpha = 0.0;
+        for (k = 0; k < m && !(cum[k] >= Tb); ++k) {}
+        if (k < m) time_b = tim[k]; else gnull = 1;
+        for (k = 0; k < m && !(cum[k] >= Te); ++k) {}
+        if (k < m) time_e = tim[k]; else { ok = 0; break; }
+        if (gnull) {
+            for (int j = 0; j < m; ++j) foog0[j] = 0.0;
+        } else {
+            switch (o->veg_growth) {
+                case BAMGPU_VEG_YIN1:
+                    Tm[i] = par[3];
+                    for (k = 0; k < m && !(stemp[k] >= Tm[i]); ++k) {}
+                    if (k < m) time_m = tim[k]; else { ok = 0; }
+                    if (!ok) break;
+                    if (time_m <= time_b) time_m = time_b;
+                    if (time_m >= time_e) { ok = 0; break; }
+                    alpha = (time_e - time_b) / (time_e - time_m);
+                    time_f = 2.0 * time_e - time_m;
+                    break;
+                case BAMGPU_VEG_YIN2:
+                    if (par[3] <= 0.0) { ok = 0; break; }
+                    alpha = par[3];
+                    time_f = time_e + (time_e - time_b) / alpha;
+                    time_m = ((alpha - 1.0) * time_f + 2.0 * time_b) / (alpha + 1.0);
+                    break;
+                default: /* Yin3 */
+                    if (par[3] <= 0.0) { ok = 0; break; }
+                    time_f = time_e + par[3];
+                    alpha = (time_e - time_b) / (time_f - time_e);
+                    time_m = ((alpha - 1.0) * time_f + 2.0 * time_b) / (alpha + 1.0);
+                    break;
+            }
+            if (!ok) break;
+            if (time_m < time_b) time_m = time_b;
+            if (alpha <= 0.0 || time_m >= time_e || time_f > tim[m - 1]) { ok = 0; break; }
+            for (k = 0; k < m && !(tim[k] >= time_m); ++k) {}
+            Tm[i] = stemp[k < m ? k : m - 1];
+            for (int j = 0; j < m; ++j) {
+                if (tim[j] <= time_b) { foog0[j] = 0.0; continue; }
+                if (tim[j] >= time_f) { foog0[j] = 0.0; continue; }
+                foog0[j] = pow((tim[j] - time_b) / (time_e - time_b), alpha) * (time_f - tim[j]) / (time_f - time_e);
+            }
+        }
+        k = 0;
+        for (int j = 0; j < n; ++j)
+            if (floor(time[j]) == (double)i) {
+                g0[j] = foog0[k];
+                g[j] = g0[j] * gmax[i];
+                cosg[j] = cos(foog0[k] * VEG_PI);
+                if (tim[k] <= time_e) sing[j] = sin(foog0[k] * VEG_PI);
+                else sing[j] = -1.0 * sin(foog0[k] * VEG_PI);
+                ++k;
+            }
+    }
+    free(tim);
+    return ok && !*err;
+}
+
+/* Vegetation_Apply, Vegetation_model.f90:87-243.  OUT columns: Q, g, cos, sin, g0 (the first nY of them). */
+static int vegetation_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
+                            int ldy, double* Dpar, int32_t* vfeas) {
+    const int temporal = o->veg_growth == BAMGPU_VEG_YIN1_TEMPORAL;
+    const int nG = veg_ngrowth(o->veg_growth), nGmax = temporal ? 1 : o->veg_nyear;
+    const double *time = IN, *h = IN + (size_t)ldx, *Traw = temporal ? NULL : IN + 2 * (size_t)ldx,
+                 *Tsmooth = temporal ? NULL : IN + 3 * (size_t)ldx;
+    double B = theta[0], S0 = theta[1], n1 = theta[2], b1 = theta[3], c1 = theta[4], chi = theta[5], U_chi = theta[6];
+    const double* growthPar = theta + 7;
+    const double* gmax = theta + 7 + nG;
+    for (int t = 0; t < n; ++t)
+        for (int y = 0; y < o->nY; ++y) OUT[t + (size_t)y * ldy] = BAMGPU_UNDEF_RN;
+    Dpar[0] = (S0 >= 0.0) ? B * sqrt(S0) / n1 : BAMGPU_UNDEF_RN;
+    int badg = 0;
+    for (int i = 0; i < nGmax; ++i) badg |= gmax[i] < 0.0;
+    if (B <= 0.0 || S0 <= 0.0 || n1 <= 0.0 || c1 <= 0.0 || chi < -2.0 || chi > 0.0 || U_chi <= 0.0 || badg) {
+        for (int t = 0; t < n; ++t) vfeas[t] = 0;
+        return 0;
+    }
+    double* g = (double*)malloc(((size_t)n + 1) * 4 * sizeof(double));
+    double *g0 = g + n, *cosg = g0 + n, *sing = cosg + n, Tm[VEG_MAXYEAR];
+    int err = 0;
+    if (!veg_apply_growth(o, n, time, Traw, Tsmooth, growthPar, gmax, g, g0, cosg, sing, Tm, &err)) {
+        free(g);
+        if (err) return 1;
+        for (int t = 0; t < n; ++t) vfeas[t] = 0;
+        return 0;
+    }
+    if (!temporal)
+        for (int i = 0; i < o->veg_nyear; ++i) Dpar[1 + i] = Tm[i];
+    const double* cols[4] = {g, cosg, sing, g0};
+    for (int y = 1; y < o->nY && y < 5; ++y)
+        for (int t = 0; t < n; ++t) OUT[t + (size_t)y * ldy] = cols[y - 1][t];
+    for (int t = 0; t < n; ++t) { /* discharge :202-240 */
+        double y = h[t] - b1, Q;
+        if (y <= 0.0) { OUT[t] = 0.0; continue; }
+        double Q0 = ((B * sqrt(S0)) / n1) * pow(y, c1);
+        if (g[t] <= 0.0) { OUT[t] = Q0; continue; }
+        double gam = (g[t] * pow(y, 1.0 / 3.0)) / (8.0 * VEG_GRAVITY * (n1 * n1));
+        double gam2 = pow(B, chi) * pow(y, chi) * pow(U_chi, chi);
+        int fcalls = 0;
+        int e = veg_znewton(Q0, gam, gam2, chi, 0.0, Q0, o->veg_tolx, o->veg_tolf, o->veg_xscale, o->veg_fscale,
+                            o->veg_itmax, &Q, &fcalls);
+        if (e > 0 || fcalls > o->veg_itmax) { vfeas[t] = 0; continue; }
+        OUT[t] = Q;
+    }
+    free(g);
+    return 0;
+}
+
 /* TxtMdl_Apply, TextFile_model.f90:1035-1098 */
 static void textfile_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
                            int ldy, int32_t* vfeas) {
@@ -760,6 +974,9 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         case BAMGPU_MDL_BARATIN: baratin_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
         case BAMGPU_MDL_SEDIMENT: sediment_apply(o, n, X, ldx, fullTheta, Y, vfeas); break;
         case BAMGPU_MDL_TEXTFILE: textfile_apply(o, n, X, ldx, fullTheta, Y, ldy, vfeas); break;
+        case BAMGPU_MDL_VEGETATION:
+            if (vegetation_apply(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas)) return 1;
+            break;
         default: return 1;
     }
     int all = 1;
@@ -791,7 +1008,7 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
     if (mess) mess[0] = 0;
     oracle_t* o = (oracle_t*)calloc(1, sizeof *o);
     o->model = model_from_name(p->model_id);
-    if (!o->model || o->model == BAMGPU_MDL_VEGETATION) {
+    if (!o->model) {
         setmess(mess, "oracle: ApplyModel: Fatal: Unavailable [model%ID]");
         free(o);
         return 1;
@@ -895,6 +1112,19 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             int e = textfile_load(o, p->xtra_text, mess);
             if (e) return e;
             if (o->vm_nin != nX || o->vm_npar != nt || o->vm_nout != nY) { setmess(mess, "oracle: TextFile: size mismatch"); return 1; }
+            break;
+        }
+        case BAMGPU_MDL_VEGETATION: { /* xtra_i = {growth, nYear, itmax}; xtra_d = {xscale, fscale, tolX, tolF} */
+            if (p->n_xtra_i != 3 || p->n_xtra_d != 4) { setmess(mess, "oracle: Vegetation_XtraRead: bad xtra"); return 1; }
+            o->veg_growth = p->xtra_i[0]; o->veg_nyear = p->xtra_i[1]; o->veg_itmax = p->xtra_i[2];
+            o->veg_xscale = p->xtra_d[0]; o->veg_fscale = p->xtra_d[1]; o->veg_tolx = p->xtra_d[2]; o->veg_tolf = p->xtra_d[3];
+            if (o->veg_growth < 1 || o->veg_growth > 4) { setmess(mess, "oracle: GetNpar_growth:Fatal:Unavailable [growthFormula]"); return 1; }
+            int temporal = o->veg_growth == BAMGPU_VEG_YIN1_TEMPORAL;
+            if (o->veg_nyear < 1 || o->veg_nyear > VEG_MAXYEAR) { setmess(mess, "oracle: Vegetation: nYear out of range"); return 1; }
+            int np = 5 + 2 + veg_ngrowth(o->veg_growth) + (temporal ? 1 : o->veg_nyear); /* GetParNumber :46-86 */
+            if (nt != np) { setmess(mess, "oracle: Vegetation_Apply:wrong size[theta]"); return 1; }
+            if (nX != (temporal ? 2 : 4) || nY < 1 || nY > 5) { setmess(mess, "oracle: Vegetation: wrong nX or nY"); return 1; }
+            o->nDparModel = temporal ? 1 : o->veg_nyear + 1; /* ModelLibrary_tools.f90:625-632 */
             break;
         }
     }

@@ -174,3 +174,73 @@ def test_envelope_rule():
     assert (oracle_api.envelope(c3) == f).all()
     c4 = col.copy(); c4[3] = np.nan
     assert np.isfinite(oracle_api.envelope(c4)).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Vegetation: known-answer columns of the reference's own tests/BaM_Vegetation/SyntheticData.txt
+# (tests/golden/make_vegetation_fixture.py explains how the generator's parameters were recovered)
+# ---------------------------------------------------------------------------------------------------
+def _vegetation_fixture_problem():
+    from bam_b200.capi import VEG_GROWTH, Problem
+
+    d = load_fixture("vegetation_synthetic")
+    n, nyear = d["nobs"], d["nYear"]
+    X = np.column_stack([d["time"], d["stage"], d["Temp"], d["Temp"]])
+    Y = np.column_stack([d["Q"], d["g"], d["cosg"], d["sing"], d["g0"]])
+    nt = len(d["theta"])
+    nw = d["newton"]
+    prob = Problem("Vegetation", X, Y, partype=[0] * nt, priors_theta=[("FlatPrior", [])] * nt,
+                   sigma_func=["Constant"] * 5, priors_gamma=[("FlatPrior", [])] * 5,
+                   xtra_i=[VEG_GROWTH[d["growth"]], nyear, int(nw[4])], xtra_d=nw[:4])
+    return prob, d, X, Y, n
+
+
+def test_vegetation_known_answer_columns():
+    prob, d, X, Y, n = _vegetation_fixture_problem()
+    o = Oracle(prob)
+    Yh, feas, dpar = o.apply_model(X, np.asarray(d["theta"]))
+    assert feas.all()
+    # the file prints 9-10 significant digits; the time column is rounded too, which moves the single sample that
+    # sits on t_f (g0 = 0 in the file) by 2e-8
+    tfrac = X[:, 0] - np.floor(X[:, 0])
+    # the time column is rounded to 1e-9; on the steep declining limb (t_e < t <= t_f = t_e + 35 days) the factor
+    # (t_f - t) is small, so that rounding alone moves g0 by up to ~2e-7: looser bound there, file precision elsewhere
+    edge = (tfrac > 164.5 / 365.0 + 1e-8) & (tfrac < 199.5 / 365.0 + 1e-8)
+    assert 60 <= edge.sum() <= 72
+    for j, name in enumerate(["Q", "g", "cosg", "sing", "g0"]):
+        e = np.abs(Yh[:, j] - Y[:, j]) / np.maximum(np.abs(Y[:, j]), 1.0)
+        season = (tfrac > 106.5 / 365.0) & ~edge & (tfrac < 0.5)  # rising limb: dg0/dt ~ 10/year x 5e-10
+        assert e[~edge & ~season].max() <= 2e-9, (name, e[~edge & ~season].max())  # no vegetation: Q = Q0
+        assert e[season].max() <= 3e-8, (name, e[season].max())
+        assert e[edge].max() <= 3e-7, (name, e[edge].max())
+    assert (Yh[:, 1] > 0).sum() > 100  # the growth season is really exercised
+    # the degree-day sum of Apply_growth against the file's Tcumul column at the two crossings it selects
+    tc, t = np.asarray(d["Tcumul"]), np.asarray(d["time"])
+    yr0 = np.floor(t) == 0
+    tb = t[yr0][np.argmax(tc[yr0] >= 10.0)]
+    te = t[yr0][np.argmax(tc[yr0] >= 200.0)]
+    g0 = np.asarray(d["g0"])
+    assert g0[yr0][t[yr0] <= tb].max() == 0.0 and abs(g0[yr0][t[yr0] == te][0] - 1.0) < 1e-9
+    assert abs(dpar[0] - 10.0 * np.sqrt(0.001) * 35.0) < 1e-12
+
+
+def test_vegetation_newton_root_is_the_root():
+    """bending branch (chi < 0): the restated znewton returns the root of Vegetation_fNewton (:559) to rounding"""
+    from bam_b200 import synth
+
+    prob, truth = synth.vegetation(nobs=300, growth="Growth_Yin1_temporal")
+    o = Oracle(prob)
+    th = truth[:prob.nFit]
+    Yh, feas, _ = o.apply_model(prob.X, th)
+    assert feas.all()
+    B, S0, n1, b1, c1, chi, U = th[:7]
+    y = prob.X[:, 1] - b1
+    g = Yh[:, 1]
+    sel = (y > 0) & (g > 0)
+    Q0 = B * np.sqrt(S0) / n1 * y[sel] ** c1
+    gam = g[sel] * y[sel] ** (1.0 / 3.0) / (8 * 9.81 * n1 * n1)
+    gam2 = B**chi * y[sel] ** chi * U**chi
+    x = Yh[sel, 0]
+    f = x * x + gam * x * x * np.minimum(1.0, x**chi / gam2) - Q0 * Q0
+    assert sel.sum() > 50 and np.max(np.abs(f) / (Q0 * Q0)) < 1e-14
+    assert (np.minimum(1.0, x**chi / gam2) < 1.0).any() and (x < Q0).all()
