@@ -242,3 +242,13 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t a, uint3
     double u1 = u53(c0, c1), u2 = u53(c2, c3);
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
+
+// Structural-error noise of the prediction path (specification in bam_fastmath.cuh): inputs 2m and 2m+1 share one
+// Philox block; the even one takes the cosine, the odd one the sine branch of Box-Muller.
+__device__ __forceinline__ double philox_normal_pred(uint64_t seed, uint64_t rep, uint32_t t, uint32_t y) {
+    uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = t >> 1, c3 = y;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = u53(c0, c1), u2 = u53(c2, c3);
+    const double r = sqrt(-2.0 * log(u1));
+    return r * ((t & 1u) ? sinpi(2.0 * u2) : cospi(2.0 * u2));
+}

@@ -110,3 +110,93 @@ __device__ __forceinline__ double trcp(double v) {
     const double e = fma(-v, r0, 1.0);
     return fma(r0, fma(e, e, e), r0);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Structural-error noise of the prediction path: Box-Muller PAIRS from one Philox4x32-10 block.
+//
+// Specification (shared with oracle/bam_oracle.c:oracle_normal_pair): for replication `rep`, prediction input t and
+// output y,   (u1,u2) = two 53-bit uniforms of Philox(seed; counter = (rep_lo, rep_hi, t>>1, y)),
+//             z(t) = sqrt(-2 ln u1) * (t even ? cos(2 pi u2) : sin(2 pi u2)).
+// Two consecutive inputs share one Philox block, one log and one square root.
+// FP64-pipe cost per pair of normals: uniforms 8, tlog 8, sqrt 8, sincos 23 -> ~25 per normal (libdevice: ~110).
+// ---------------------------------------------------------------------------------------------------------------
+
+// [0..5] sin kernel S1..S6, [6..11] cos kernel C1..C6 (fdlibm k_sin.c / k_cos.c minimax sets, |x| <= pi/4),
+// [12] pi, [13] 1.5*2^52 (rint), [14] 2^78, [15] 2^52
+__constant__ double kFN[16] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                               2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+                               4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                               -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11,
+                               3.14159265358979323846,      6755399441055744.0,          302231454903657293676544.0,
+                               4503599627370496.0};
+
+// (N + 0.5) with N = (hi >> 5) * 2^26 + (lo >> 6) (53 bits): the numerator of u53() in bam_device.cuh, built with
+// magic-number adds instead of integer->double conversions.  Same rounding as u53: the integer sum is exact, the
+// +0.5 rounds to nearest even once N >= 2^52.  u = result * 2^-53.
+__device__ __forceinline__ double u53_numerator(uint32_t hi, uint32_t lo) {
+    const double dh = __hiloint2double(0x44D00000, (int)(hi >> 5)) - kFN[14];  // (hi>>5) * 2^26, exact
+    const double dl = __hiloint2double(0x43300000, (int)(lo >> 6)) - kFN[15];  // (lo>>6), exact
+    return (dh + dl) + 0.5;
+}
+
+// sqrt(x) for a positive normal x: MUFU.RSQ64H seed (>= 20 bits), one Goldschmidt step (>= 40 bits), one
+// correction g += (x - g^2) h: result within 1 ulp.  7 FP64 instructions (IEEE sqrt(): ~15 with its slow path).
+__device__ __forceinline__ double tsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    const double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+
+// sin(pi a), cos(pi a) for a in [0, 2]
+__device__ __forceinline__ void tsincospi(double a, double& s, double& c) {
+    const double t = fma(a, 2.0, kFN[13]);
+    const int q = __double2loint(t);           // rint(2a) in 0..4
+    const double kd = t - kFN[13];
+    const double x = fma(kd, -0.5, a) * kFN[12];  // pi * (a - q/2), |x| <= pi/4
+    const double z = x * x;
+    double ps = fma(kFN[5], z, kFN[4]);
+    ps = fma(ps, z, kFN[3]);
+    ps = fma(ps, z, kFN[2]);
+    ps = fma(ps, z, kFN[1]);
+    ps = fma(ps, z, kFN[0]);
+    const double sn = fma(x * z, ps, x);
+    double pc = fma(kFN[11], z, kFN[10]);
+    pc = fma(pc, z, kFN[9]);
+    pc = fma(pc, z, kFN[8]);
+    pc = fma(pc, z, kFN[7]);
+    pc = fma(pc, z, kFN[6]);
+    const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+    // quadrant: angle = q*pi/2 + x
+    const double s0 = (q & 1) ? cs : sn, c0 = (q & 1) ? sn : cs;
+    const unsigned sneg = (unsigned)q & 2u, cneg = (unsigned)(q + 1) & 2u;
+    s = __hiloint2double((int)((unsigned)__double2hiint(s0) ^ (sneg << 30)), __double2loint(s0));
+    c = __hiloint2double((int)((unsigned)__double2hiint(c0) ^ (cneg << 30)), __double2loint(c0));
+}
+
+// the pair (z_even, z_odd) of standard normals for (seed, rep, tpair = t>>1, y); `lt` = shared log table
+__device__ __forceinline__ void normal_pair_fast(uint64_t seed, uint64_t rep, uint32_t tpair, uint32_t y, unsigned lt,
+                                                 double& z0, double& z1) {
+    uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = tpair, c3 = y;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double n1 = u53_numerator(c0, c1), n2 = u53_numerator(c2, c3);
+    // u1 = n1 * 2^-53 through the exponent field (integer subtract, exact)
+    const double u1 = __hiloint2double(__double2hiint(n1) - (53 << 20), __double2loint(n1));
+    double L;
+    if (__double2hiint(n1) >= 0x433FF800) {
+        // u1 within 2^-10 of 1 (probability 1e-3): the table-driven log has ABSOLUTE error ~1e-16, not enough
+        // relative accuracy when log(u1) -> 0
+        L = log(u1);
+    } else {
+        L = tlog_pos(u1, lt);  // |L| >= 9.7e-4
+    }
+    const double r = tsqrt_pos(-2.0 * L);
+    double s, c;
+    tsincospi(n2 * (2.0 / 9007199254740992.0), s, c);
+    z0 = r * c;
+    z1 = r * s;
+}

@@ -34,6 +34,7 @@ struct bamgpu_handle {
     int* d_status = nullptr;
     LogpostPlan plan;
     long long chainOffset = 0;
+    bool noSelect3 = false;     // tests: skip the 2-read envelope selection
     bool forceGeneric = false;  // tests: disable the specialised fast kernels  // global index of local chain 0 (multi-GPU sharding; RNG streams)
 
     // ---- sampler state ----

@@ -19,6 +19,7 @@
 #include <cfloat>
 
 #include "bam_dispatch.cuh"
+#include "bam_fastmath.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
 
@@ -95,11 +96,109 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
                 double gam[3];
                 for (int m = 0; m < p.nrem[j] && m < 3; ++m) gam[m] = sm[(p.gamOff[j] + m) * BAM_BLOCK + tid];
                 const double sig = sigmafunk(p.sigfunc[j], gam, v);
-                if (sig > 0.0) v = v + sig * philox_normal(a.seed, (uint64_t)rep, (unsigned)(a.t0 + t), (unsigned)j);
+                if (sig > 0.0) v = v + sig * philox_normal_pred(a.seed, (uint64_t)rep, (unsigned)(a.t0 + t), (unsigned)j);
             }
             V[((size_t)j * a.nT + t) * a.Nrep + rep] = v;
         }
     }
+}
+
+// ---- K4 fast path: BaRatin spaghetti (cfg 5) -------------------------------------------------------------------
+//
+// thread <-> replication with its parameter set (k, b, c, log a per control, gamma) in REGISTERS; the block walks a
+// tile of PF_TT prediction inputs (staged once in shared memory when all replications share one input series).
+// a_i (H-b_i)^c_i = texp(c_i tlog(H-b_i) + log a_i) with the table-driven functions of bam_fastmath.cuh, the
+// structural-error noise from Box-Muller pairs (one Philox block, one log and one sqrt per TWO inputs).
+// As in the log-posterior fast path the "H-b<0" exits of BaRatin_computeQ cannot fire for a parameter set that
+// passed ApplyContinuity, so Q is the plain sum over the active controls of the stage range.
+// ~60 FP64-pipe instructions per (replication, input) against ~330 for the libdevice formulation of pred_main.
+#define PF_TT 64
+template <int NC, int SIGF, bool NOISE>
+__global__ void __launch_bounds__(BAM_BLOCK) pred_baratin_fast(DevProblem p, PredArgs a, const double* __restrict__ tab,
+                                                               const int* __restrict__ status,
+                                                               const double* __restrict__ xs, int nspag,
+                                                               double* __restrict__ V) {
+    __shared__ __align__(16) double sLogT[2 * BAM_LOGTAB_N];
+    __shared__ double sExpT[BAM_EXPTAB_N];
+    __shared__ double sH[PF_TT];
+    const int tid = threadIdx.x;
+    const int tBeg = blockIdx.y * PF_TT, nt = min(PF_TT, a.nT - tBeg);
+    for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) reinterpret_cast<double2*>(sLogT)[i] = p.logTab[i];
+    for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExpT[i] = p.expTab[i];
+    if (nspag == 1)
+        for (int i = tid; i < nt; i += BAM_BLOCK) sH[i] = xs[a.t0 + tBeg + i];
+    __syncthreads();
+    const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
+    if (rep >= a.Nrep) return;
+    double* out = V + (size_t)tBeg * a.Nrep + rep;
+    if (status[rep] != 0) {  // infeasible parameter set: the whole replication is flagged (ModelLibrary_tools.f90:419-432)
+        for (int t = 0; t < nt; ++t) __stcs(out + (size_t)t * a.Nrep, p.unfeas);
+        return;
+    }
+    const double* __restrict__ row = tab + (size_t)rep * a.stride;
+    const double g1 = row[0], g2 = (SIGF == BAMGPU_SIG_LINEAR) ? row[1] : 0.0;
+    const double* __restrict__ th = row + p.nGamma;
+    double k[NC], b[NC], cc[NC], la[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) { k[j] = th[3 * j]; cc[j] = th[3 * j + 2]; b[j] = th[3 * NC + j]; la[j] = th[4 * NC + j]; }
+    unsigned mask4 = 0;
+#pragma unroll
+    for (int r = 1; r <= NC; ++r) mask4 |= ((unsigned)(p.ctrlMask >> ((r - 1) * 8)) & 0xfu) << (4 * r);
+    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT);
+    const double* __restrict__ xcol = xs + (size_t)(rep % nspag) * a.nobsPred + a.t0 + tBeg;
+    unsigned lastPair = 0xffffffffu;
+    double z0 = 0.0, z1 = 0.0;
+    for (int t = 0; t < nt; ++t) {
+        const double h = (nspag == 1) ? sH[t] : __ldg(xcol + t);
+        int r = 0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) r += (h >= k[j]) ? 1 : 0;  // GetHRange: k increasing
+        const unsigned m = (mask4 >> (4 * r)) & 0xfu;
+        double q = 0.0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+            if ((m >> j) & 1u) q += texp(fma(cc[j], tlog(h - b[j], lt), la[j]), et);
+        double v = q;
+        if (NOISE) {
+            const unsigned tg = (unsigned)(a.t0 + tBeg + t);
+            if ((tg >> 1) != lastPair) {
+                lastPair = tg >> 1;
+                normal_pair_fast(a.seed, (uint64_t)rep, lastPair, 0u, lt, z0, z1);
+            }
+            double sig;
+            if (SIGF == BAMGPU_SIG_CONSTANT) sig = g1;
+            else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(g2, fabs(q), g1);
+            else sig = g1 * fabs(q);
+            if (sig > 0.0) v = fma(sig, (tg & 1u) ? z1 : z0, q);
+        }
+        __stcs(out + (size_t)t * a.Nrep, v);
+    }
+}
+
+using PredFastKernel = void (*)(DevProblem, PredArgs, const double*, const int*, const double*, int, double*);
+
+template <int NC, int SIGF>
+PredFastKernel pick_pred_fast_noise(bool noise) {
+    return noise ? pred_baratin_fast<NC, SIGF, true> : pred_baratin_fast<NC, SIGF, false>;
+}
+template <int NC>
+PredFastKernel pick_pred_fast_sig(int sigf, bool noise) {
+    switch (sigf) {
+        case BAMGPU_SIG_CONSTANT: return pick_pred_fast_noise<NC, BAMGPU_SIG_CONSTANT>(noise);
+        case BAMGPU_SIG_LINEAR: return pick_pred_fast_noise<NC, BAMGPU_SIG_LINEAR>(noise);
+        case BAMGPU_SIG_PROPORTIONAL: return pick_pred_fast_noise<NC, BAMGPU_SIG_PROPORTIONAL>(noise);
+    }
+    return nullptr;
+}
+PredFastKernel pick_pred_fast(const DevProblem& p, bool noise, long long Nrep) {
+    if (p.model != BAMGPU_MDL_BARATIN || Nrep < 1024) return nullptr;
+    switch (p.ncontrol) {
+        case 1: return pick_pred_fast_sig<1>(p.sigfunc[0], noise);
+        case 2: return pick_pred_fast_sig<2>(p.sigfunc[0], noise);
+        case 3: return pick_pred_fast_sig<3>(p.sigfunc[0], noise);
+        case 4: return pick_pred_fast_sig<4>(p.sigfunc[0], noise);
+    }
+    return nullptr;
 }
 
 // ---- envelopes ------------------------------------------------------------------------------------
@@ -441,7 +540,11 @@ __device__ double s2_block_sum(double v, double* scratch) {
 
 __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, int nT, double unfeas,
                                                                const double* __restrict__ V, double* __restrict__ env,
-                                                               int* __restrict__ needSlow) {
+                                                               int* __restrict__ needSlow, const int* __restrict__ only) {
+    if (only != nullptr && only[blockIdx.x] == 0) {  // already resolved by envelope_select3
+        if (threadIdx.x == 0) needSlow[blockIdx.x] = 0;
+        return;
+    }
     extern __shared__ __align__(16) unsigned char s2raw[];
     unsigned* hist = reinterpret_cast<unsigned*>(s2raw);                  // max(NB1, 10*NB2) counters = 40 KB
     double* gath = reinterpret_cast<double*>(s2raw + sizeof(unsigned) * SEL_NT * S2_NB2);  // 10 x CAP doubles = 20 KB
@@ -661,6 +764,257 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
     }
 }
 
+// ---- large Nrep, 2-read path: all 10 order statistics with TWO reads of the column ---------------------------------
+//
+// phase 0  strided subsample of 2048 values, sorted in shared memory: bin range [lo,hi] = its 0.5 % / 99.5 % points
+//          (the targets are the 2.5 % .. 97.5 % quantiles and their neighbours), pivot = its median.  Values outside
+//          [lo,hi] are CLAMPED into the two edge bins: the bin function stays monotone, so the selection stays exact
+//          whatever the subsample looks like; a bad subsample only costs a fallback.
+// pass B   16384-bin histogram in shared memory + #bad + sum (v-pivot) + sum (v-pivot)^2     (1 read)
+//          -> m, mean, variance (shifted-data formula), bin and residual rank of every target
+// pass C   gather the members of the <= 10 selected bins (<= S3_CAP each), sort, pick       (1 read)
+// A selected bin with more than S3_CAP members is still resolved when all its members are equal (ties: e.g. Q = 0
+// below the first activation stage); anything else is flagged for the 4-read kernel envelope_select2.
+#define S3_NB 16384
+#define S3_SAMPLE 2048
+#define S3_CAP 512 /* power of two: the lists are sorted in place by a bitonic network */
+#define S3_THREADS 512
+
+__device__ __forceinline__ int s3_bin(double v, double lo, double scale) {
+    if (v < lo) return 0;
+    const double f = (v - lo) * scale;
+    return (f >= (double)(S3_NB - 2)) ? S3_NB - 1 : 1 + (int)f;
+}
+
+__device__ __forceinline__ unsigned long long s3_key(double v) {  // order-preserving map double -> uint64
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+}
+
+__device__ double s3_block_sum(double v, double* scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < S3_THREADS / 32; ++i) s += scratch[i];
+        scratch[32] = s;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, int nT, double unfeas,
+                                                               const double* __restrict__ V, double* __restrict__ env,
+                                                               int* __restrict__ needSlow) {
+    extern __shared__ __align__(16) unsigned char s3raw[];  // 64 KB: sample (16 KB) -> histogram (64 KB) -> gather lists (40 KB)
+    double* smp = reinterpret_cast<double*>(s3raw);
+    unsigned* hist = reinterpret_cast<unsigned*>(s3raw);
+    double* gath = reinterpret_cast<double*>(s3raw);
+    __shared__ double scratch[40];
+    __shared__ unsigned bitmap[S3_NB / 32];
+    __shared__ unsigned prefix[S3_THREADS];
+    __shared__ long long tRank[SEL_NT];
+    __shared__ int tBin[SEL_NT], tList[SEL_NT], listBin[SEL_NT], listCnt[SEL_NT], listOver[SEL_NT], gCnt[SEL_NT], nLists, nGood;
+    __shared__ unsigned long long listMin[SEL_NT], listMax[SEL_NT];
+    __shared__ double tVal[SEL_NT];
+    const int tid = threadIdx.x;
+    const int colId = blockIdx.x;
+    const double* col = V + (size_t)colId * Nrep;
+    const int y = colId / nT, t = colId % nT;
+    double* out = env + (size_t)y * BAMGPU_NENV * nT + t;
+
+    // ---- phase 0: subsample
+    if (tid == 0) nGood = 0;
+    __syncthreads();
+    const long long stride = Nrep / S3_SAMPLE;
+    int good = 0;
+    for (int i = tid; i < S3_SAMPLE; i += S3_THREADS) {
+        double v = col[(long long)i * stride];
+        if (v == unfeas || v != v) v = INFINITY; else ++good;
+        smp[i] = v;
+    }
+    if (good) atomicAdd(&nGood, good);
+    __syncthreads();
+    for (int kk = 2; kk <= S3_SAMPLE; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < S3_SAMPLE; i += S3_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double a = smp[i], b = smp[ixj];
+                    const bool up = ((i & kk) == 0);
+                    if ((a > b) == up) { smp[i] = b; smp[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const int ns = nGood;
+    if (ns < 256) {  // mostly bad values: leave it to the general kernels
+        if (tid == 0) needSlow[colId] = 1;
+        return;
+    }
+    const double lo = smp[ns / 200], hi = smp[ns - 1 - ns / 200], pivot = smp[ns / 2];
+    __syncthreads();
+    if (!(hi > lo) || !(hi - lo < INFINITY)) {
+        if (tid == 0) needSlow[colId] = 1;
+        return;
+    }
+    const double scale = (double)(S3_NB - 2) / (hi - lo);
+
+    // ---- pass B
+    for (int b = tid; b < S3_NB; b += S3_THREADS) hist[b] = 0;
+    for (int b = tid; b < S3_NB / 32; b += S3_THREADS) bitmap[b] = 0;
+    __syncthreads();
+    double s1 = 0.0, s2 = 0.0, nb = 0.0;
+    for (long long r = tid; r < Nrep; r += S3_THREADS) {
+        const double v = __ldcs(col + r);
+        if (v == unfeas || v != v) { nb += 1.0; continue; }
+        const double d = v - pivot;
+        s1 += d;
+        s2 = fma(d, d, s2);
+        atomicAdd(&hist[s3_bin(v, lo, scale)], 1u);
+    }
+    const long long nbad = (long long)s3_block_sum(nb, scratch);
+    const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
+    if ((!drop && nbad > 0) || nbad == Nrep) {
+        if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
+        if (tid == 0) needSlow[colId] = 0;
+        return;
+    }
+    const long long m = Nrep - nbad;
+    const double S1 = s3_block_sum(s1, scratch), S2 = s3_block_sum(s2, scratch);
+    const double mean = pivot + S1 / (double)m;
+    const double ss = fmax(S2 - S1 * (S1 / (double)m), 0.0);
+    {   // exclusive prefix over the bins: 32 consecutive bins per thread + scan of the 512 partials
+        constexpr int PER = S3_NB / S3_THREADS;
+        unsigned acc = 0;
+        for (int q = 0; q < PER; ++q) acc += hist[tid * PER + q];
+        prefix[tid] = acc;
+        __syncthreads();
+        for (int off = 1; off < S3_THREADS; off <<= 1) {
+            const unsigned add = (tid >= off) ? prefix[tid - off] : 0;
+            __syncthreads();
+            prefix[tid] += add;
+            __syncthreads();
+        }
+        unsigned base = prefix[tid] - acc;
+        for (int q = 0; q < PER; ++q) { const unsigned c0 = hist[tid * PER + q]; hist[tid * PER + q] = base; base += c0; }
+        __syncthreads();  // hist[b] = number of good values in bins < b
+    }
+    const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
+    if (tid < SEL_NT) {
+        const int q = tid >> 1;
+        const double hh = pr[q] * (double)m + 0.5;
+        long long rk;
+        if (hh <= 1.0) rk = 0;
+        else if (hh >= (double)m) rk = m - 1;
+        else rk = (long long)floor(hh) - 1 + (tid & 1);
+        int a0 = 0, a1 = S3_NB - 1;  // largest bin b with hist[b] <= rk
+        while (a0 < a1) {
+            const int mid = (a0 + a1 + 1) >> 1;
+            if ((long long)hist[mid] <= rk) a0 = mid; else a1 = mid - 1;
+        }
+        tBin[tid] = a0;
+        tRank[tid] = rk - hist[a0];
+        gCnt[tid] = (int)(((a0 + 1 < S3_NB) ? hist[a0 + 1] : (unsigned)m) - hist[a0]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nl = 0;
+        for (int k = 0; k < SEL_NT; ++k) {
+            int li = -1;
+            for (int j = 0; j < nl; ++j)
+                if (listBin[j] == tBin[k]) li = j;
+            if (li < 0) {
+                li = nl++;
+                listBin[li] = tBin[k];
+                listCnt[li] = 0;
+                listOver[li] = gCnt[k] > S3_CAP;
+                listMin[li] = 0xffffffffffffffffull;
+                listMax[li] = 0ull;
+                bitmap[tBin[k] >> 5] |= 1u << (tBin[k] & 31);
+            }
+            tList[k] = li;
+        }
+        nLists = nl;
+    }
+    __syncthreads();  // the histogram is dead from here on: its memory becomes the gather lists
+
+    // ---- pass C: gather
+    const int nl = nLists;
+    for (long long r = tid; r < Nrep; r += S3_THREADS) {
+        const double v = __ldcs(col + r);
+        if (v == unfeas || v != v) continue;
+        const int b = s3_bin(v, lo, scale);
+        if (!((bitmap[b >> 5] >> (b & 31)) & 1u)) continue;
+        for (int j = 0; j < nl; ++j)
+            if (listBin[j] == b) {
+                if (listOver[j]) {
+                    const unsigned long long key = s3_key(v);
+                    atomicMin(&listMin[j], key);
+                    atomicMax(&listMax[j], key);
+                } else {
+                    const int pos = atomicAdd(&listCnt[j], 1);
+                    gath[j * S3_CAP + pos] = v;
+                }
+            }
+    }
+    __syncthreads();
+    for (int j = 0; j < nl; ++j) {  // sort every list (bitonic, padded with +inf), whole block
+        if (listOver[j]) continue;
+        const int cnt = listCnt[j];
+        int npad = 2;
+        while (npad < cnt) npad <<= 1;
+        double* g = gath + j * S3_CAP;
+        for (int i = cnt + tid; i < npad; i += S3_THREADS) g[i] = INFINITY;
+        __syncthreads();
+        for (int kk = 2; kk <= npad; kk <<= 1)
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                for (int i = tid; i < npad; i += S3_THREADS) {
+                    const int ixj = i ^ jj;
+                    if (ixj > i) {
+                        const double a = g[i], b = g[ixj];
+                        const bool up = ((i & kk) == 0);
+                        if ((a > b) == up) { g[i] = b; g[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    if (tid < SEL_NT) {
+        const int j = tList[tid];
+        if (!listOver[j]) tVal[tid] = gath[j * S3_CAP + (int)tRank[tid]];
+        else if (listMin[j] == listMax[j]) {  // every member of the bin is the same value
+            const unsigned long long kx = listMin[j];
+            const unsigned long long bits = (kx >> 63) ? (kx ^ 0x8000000000000000ull) : ~kx;
+            tVal[tid] = __longlong_as_double((long long)bits);
+        } else tVal[tid] = NAN;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bool slow = false;
+        for (int k = 0; k < SEL_NT; ++k) slow |= (tVal[k] != tVal[k]);
+        needSlow[colId] = slow ? 1 : 0;
+        if (slow) return;
+        for (int q = 0; q < 5; ++q) {
+            const double hh = pr[q] * (double)m + 0.5;
+            double qv;
+            if (hh <= 1.0 || hh >= (double)m) qv = tVal[2 * q];
+            else {
+                const long long i = (long long)floor(hh);
+                const double frac = hh - (double)i;
+                qv = tVal[2 * q] + frac * (tVal[2 * q + 1] - tVal[2 * q]);
+            }
+            out[(size_t)q * nT] = qv;
+        }
+        out[(size_t)5 * nT] = mean;
+        out[(size_t)6 * nT] = (m > 1) ? sqrt(ss / (double)(m - 1)) : unfeas;
+    }
+}
+
 using PredKernel = void (*)(DevProblem, PredArgs, const double*, const int*, double* const*, const int*, double*);
 
 PredKernel pick_pred(int model, int nX, int nY) {
@@ -734,15 +1088,27 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEnv));
 
     const size_t smemSel2 = sizeof(unsigned) * SEL_NT * S2_NB2 + sizeof(double) * SEL_NT * S2_CAP;
-    if (!smallN) BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel2));
+    const size_t smemSel3 = sizeof(unsigned) * S3_NB;
+    // the 2-read selection resolves bins of <= S3_CAP members: worth trying while the densest bin stays below that
+    const bool trySel3 = !smallN && Nrep <= 3000000 && !h->noSelect3;
+    if (!smallN) {
+        BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel2));
+        BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel3));
+    }
+    PredFastKernel fastK = (!h->forceGeneric && p.nX == 1 && p.nY == 1) ? pick_pred_fast(p, anyRem, Nrep) : nullptr;
     BAM_CUDA(cudaEventRecord(h->ev0, s));
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     if (h->recordKernels && h->kernEv.size() < 8192) { k0 = take_event(h); k1 = take_event(h); BAM_CUDA(cudaEventRecord(k0, s)); }
     for (int tt = 0; tt < nTall; tt += (int)tileT) {
         const int nT = std::min<long long>(tileT, nTall - tt);
         a.t0 = t0 + tt; a.nT = nT;
-        dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + 31) / 32);
-        kern<<<grid, BAM_BLOCK, smemMain, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspagPtrs, h->d_nspag, h->d_V);
+        if (fastK) {
+            dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + PF_TT - 1) / PF_TT);
+            fastK<<<grid, BAM_BLOCK, 0, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspag[0], h->predNspag[0], h->d_V);
+        } else {
+            dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + 31) / 32);
+            kern<<<grid, BAM_BLOCK, smemMain, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspagPtrs, h->d_nspag, h->d_V);
+        }
         h->launches += 1;
         if (Nrep >= 2) {
             // envelopes of this tile go to a compact [y][7][nT] scratch, then into the full [y][7][nTall] array
@@ -750,11 +1116,17 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nY, s));
             if (smallN) envelope_smem<<<nT * nY, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
             else {
-                int* needSlow = nullptr;
+                int *need3 = nullptr, *needSlow = nullptr;
                 BAM_CUDA(cudaMallocAsync(&needSlow, sizeof(int) * (size_t)nT * nY, s));
-                envelope_select2<<<nT * nY, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
+                if (trySel3) {
+                    BAM_CUDA(cudaMallocAsync(&need3, sizeof(int) * (size_t)nT * nY, s));
+                    envelope_select3<<<nT * nY, S3_THREADS, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
+                    h->launches += 1;
+                }
+                envelope_select2<<<nT * nY, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow, need3);
                 envelope_select<<<nT * nY, BAM_BLOCK, 0, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
                 BAM_CUDA(cudaFreeAsync(needSlow, s));
+                if (need3) BAM_CUDA(cudaFreeAsync(need3, s));
                 h->launches += 1;
             }
             h->launches += 1;

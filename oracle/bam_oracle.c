@@ -1430,6 +1430,17 @@ double oracle_normal(uint64_t seed, uint64_t a, uint32_t b, uint32_t c) {
     return sqrt(-2.0 * log(u1)) * cos(6.28318530717958647692 * u2);
 }
 
+/* Structural-error noise of the prediction (the reference draws it from BMSL's generator, un-vendored: only the
+   distribution is shared).  Declared specification: inputs 2m and 2m+1 of replication rep / output y share one
+   Philox block (counter (rep, t>>1, y)); Box-Muller, cosine branch for even t, sine branch for odd t. */
+double oracle_normal_pred(uint64_t seed, uint64_t rep, uint32_t t, uint32_t y) {
+    uint32_t w[4];
+    oracle_philox4x32((uint32_t)rep, (uint32_t)(rep >> 32), t >> 1, y, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    double u1 = u53(w[0], w[1]), u2 = u53(w[2], w[3]);
+    double r = sqrt(-2.0 * log(u1));
+    return r * ((t & 1u) ? sin(6.28318530717958647692 * u2) : cos(6.28318530717958647692 * u2));
+}
+
 /* ------------------------------------------------------------------------------------------
  * Prediction + envelopes
  * ------------------------------------------------------------------------------------------ */
@@ -1523,7 +1534,7 @@ int oracle_predict(const oracle_t* o, int64_t Nrep, const double* mc, const doub
                     if (v == o->unfeas) continue;
                     double sig = sigmafunk(o->sigma_func[y], gam, v);
                     if (sig > 0.0) /* Generate(GAUSS,(0,sig)) feasible iff sig>0 (:1095-1102) */
-                        Ys[t + (size_t)y * nT] = v + sig * oracle_normal(seed, (uint64_t)rep, (uint32_t)(t0 + t), (uint32_t)y);
+                        Ys[t + (size_t)y * nT] = v + sig * oracle_normal_pred(seed, (uint64_t)rep, (uint32_t)(t0 + t), (uint32_t)y);
                 }
             }
             for (int t = 0; t < nT; ++t) spag[(size_t)y * Nrep * nT + (size_t)t * Nrep + rep] = Ys[t + (size_t)y * nT];

@@ -67,6 +67,8 @@ void oracle_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint3
                        uint32_t out[4]);
 double oracle_normal(uint64_t seed, uint64_t a, uint32_t b, uint32_t c);  /* N(0,1) for counter (a,b,c) */
 double oracle_uniform(uint64_t seed, uint64_t a, uint32_t b, uint32_t c); /* U(0,1) */
+/* prediction noise for (replication, input t, output y): Box-Muller pairs, see bam_oracle.c */
+double oracle_normal_pred(uint64_t seed, uint64_t rep, uint32_t t, uint32_t y);
 
 /* distribution helpers exposed for tests */
 double oracle_normal_quantile(double p);

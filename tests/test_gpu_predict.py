@@ -163,3 +163,81 @@ def test_full_size_properties():
     g.predict_upload(mc, mode, [Hs])
     g.predict_resident(1, [1], seed=1)
     assert (g.predict_download() == env).all()
+
+
+def test_fast_baratin_kernel_against_oracle():
+    """the register-resident BaRatin spaghetti kernel (table-driven log/exp, Box-Muller pairs) vs the oracle:
+    1e-12 on every value, identical zero / flag patterns; shared and per-replication input series; odd shard
+    starts (a noise pair straddles the shard boundary)."""
+    prob, d = problem_from_fixture("baratin")
+    for nspag in (1, 7):
+        mc, mode, Hs = synth.baratin_spaghetti(Nrep=3000, nobs=150, nspag=nspag)
+        Hs[::9] -= 2.0      # stages below the first activation stage: Q == 0 exactly
+        mc[11, 3] = -2.0    # infeasible replication
+        mc[12, 6] = 0.0; mc[12, 7] = 0.0  # sigma == 0: no noise added (Generate infeasible, :1095-1102)
+        g, o = BamGpu(prob), Oracle(prob)
+        for dop, dor, (t0, t1) in ((1, [1], (0, 150)), (1, [0], (0, 150)), (1, [1], (37, 120)), (0, [1], (0, 150))):
+            env, spag = g.predict(mc, mode, [Hs], dop, dor, seed=5, t0=t0, t1=t1, want_spag=True)
+            oenv, ospag = o.predict(mc, mode, [Hs], dop, dor, seed=5, t0=t0, t1=t1, want_spag=True, nthreads=8)
+            cmp_spag(spag, ospag)
+            cmp_env(env, oenv)
+        # the generic kernel (libdevice pow / log / cospi) gives the same spaghetti to 1e-12
+        g2 = BamGpu(prob)
+        g2.set_option("force_generic", 1)
+        _, s1 = g.predict(mc, mode, [Hs], 1, [1], seed=6, want_env=False, want_spag=True)
+        _, s2 = g2.predict(mc, mode, [Hs], 1, [1], seed=6, want_env=False, want_spag=True)
+        cmp_spag(s1, s2)
+
+
+@pytest.mark.parametrize("three_controls", [False, True])
+def test_fast_baratin_kernel_sigma_functions_and_controls(three_controls):
+    from bam_b200.capi import Problem
+
+    rng = np.random.default_rng(4)
+    if three_controls:
+        truth = np.array([-0.6, 14.17, 1.5, 1.08, 26.52, 1.67, 1.2, 31.82, 1.67])
+        ctrl = np.asarray([[1, 0, 0], [0, 1, 0], [0, 1, 1]], dtype=np.int32).flatten(order="F")
+    else:
+        truth = np.array([-0.5, 53.0, 1.5, 1.5, 144.0, 1.67])
+        ctrl = [1, 0, 0, 1]
+    H = rng.uniform(-1.0, 3.0, 90)
+    for funk, gam in (("Constant", [0.7]), ("Proportional", [0.2]), ("Linear", [0.5, 0.1])):
+        prob = Problem("BaRatin", H, np.zeros(90), partype=[0] * truth.size,
+                       priors_theta=[("FlatPrior", [])] * truth.size, sigma_func=[funk],
+                       priors_gamma=[("FlatPrior", [])] * len(gam), xtra_i=ctrl)
+        full = np.concatenate([truth, gam])
+        mc = full * (1.0 + 0.02 * rng.standard_normal((2048, full.size)))
+        g, o = BamGpu(prob), Oracle(prob)
+        env, spag = g.predict(mc, full, [H], 1, [1], seed=9, want_spag=True)
+        oenv, ospag = o.predict(mc, full, [H], 1, [1], seed=9, want_spag=True, nthreads=8)
+        cmp_spag(spag, ospag)
+        cmp_env(env, oenv)
+
+
+def test_two_read_selection_ties_zeros_and_fallbacks():
+    """envelope_select3 (subsample-guided 16384-bin histogram + gather) against the oracle's sort, on columns that
+    stress it: a block of exact zeros (ties inside a selected bin), 30 % dropped replications, an almost constant
+    column; and the same envelopes from the 4-read kernel alone."""
+    prob, d = problem_from_fixture("baratin")
+    mc, mode, Hs = synth.baratin_spaghetti(Nrep=60000, nobs=20, nspag=1)
+    Hs[3] = -0.52   # just around k1 ~ N(-0.5, 2 %): about half of the replications give Q == 0 exactly
+    Hs[4] = -3.0    # every replication gives 0: constant column
+    mc[1000:19000, 3] = -2.0  # 30 % infeasible replications
+    g, o = BamGpu(prob), Oracle(prob)
+    g4 = BamGpu(prob)
+    g4.set_option("no_select3", 1)
+    for dor in ([0], [1]):
+        env, _ = g.predict(mc, mode, [Hs], 1, dor, seed=13)
+        oenv, _ = o.predict(mc, mode, [Hs], 1, dor, seed=13, nthreads=8)
+        cmp_env(env, oenv)
+        env4, _ = g4.predict(mc, mode, [Hs], 1, dor, seed=13)
+        q, q4 = env[0, :5], env4[0, :5]
+        assert (q == q4).all()  # order statistics are exact on both paths
+        assert np.allclose(env[0, 5:], env4[0, 5:], rtol=1e-12, atol=1e-300)
+    # clustered values with a few far outliers (the subsample's range does not cover the column)
+    mc2 = np.tile(mode, (50000, 1))
+    mc2[:, 1] *= 1.0 + 1e-9 * np.arange(50000)
+    mc2[::5000, 1] *= 50.0
+    env, _ = g.predict(mc2, mode, [Hs], 1, [0])
+    oenv, _ = o.predict(mc2, mode, [Hs], 1, [0], nthreads=8)
+    cmp_env(env, oenv)
