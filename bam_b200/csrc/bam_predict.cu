@@ -113,17 +113,19 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
 // passed ApplyContinuity, so Q is the plain sum over the active controls of the stage range.
 // ~60 FP64-pipe instructions per (replication, input) against ~330 for the libdevice formulation of pred_main.
 #define PF_TT 64
+#define PF_SMEM (sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + PF_TT))
 template <int NC, int SIGF, bool NOISE>
-__global__ void __launch_bounds__(BAM_BLOCK) pred_baratin_fast(DevProblem p, PredArgs a, const double* __restrict__ tab,
-                                                               const int* __restrict__ status,
-                                                               const double* __restrict__ xs, int nspag,
-                                                               double* __restrict__ V) {
-    __shared__ __align__(16) double sLogT[2 * BAM_LOGTAB_N];
-    __shared__ double sExpT[BAM_EXPTAB_N];
-    __shared__ double sH[PF_TT];
+__global__ void __launch_bounds__(BAM_BLOCK, 4) pred_baratin_fast(DevProblem p, PredArgs a, const double* __restrict__ tab,
+                                                                  const int* __restrict__ status,
+                                                                  const double* __restrict__ xs, int nspag,
+                                                                  double* __restrict__ V) {
+    extern __shared__ __align__(16) double pfsm[];
+    double2* sLogT = reinterpret_cast<double2*>(pfsm);
+    double* sExpT = pfsm + 2 * BAM_LOGTAB_N;
+    double* sH = sExpT + BAM_EXPTAB_N;
     const int tid = threadIdx.x;
     const int tBeg = blockIdx.y * PF_TT, nt = min(PF_TT, a.nT - tBeg);
-    for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) reinterpret_cast<double2*>(sLogT)[i] = p.logTab[i];
+    for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) sLogT[i] = p.logTab[i];
     for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExpT[i] = p.expTab[i];
     if (nspag == 1)
         for (int i = tid; i < nt; i += BAM_BLOCK) sH[i] = xs[a.t0 + tBeg + i];
@@ -144,34 +146,75 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_baratin_fast(DevProblem p, Pre
     unsigned mask4 = 0;
 #pragma unroll
     for (int r = 1; r <= NC; ++r) mask4 |= ((unsigned)(p.ctrlMask >> ((r - 1) * 8)) & 0xfu) << (4 * r);
-    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT);
+    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT), ht = smem_addr(sH);
     const double* __restrict__ xcol = xs + (size_t)(rep % nspag) * a.nobsPred + a.t0 + tBeg;
-    unsigned lastPair = 0xffffffffu;
-    double z0 = 0.0, z1 = 0.0;
-    for (int t = 0; t < nt; ++t) {
-        const double h = (nspag == 1) ? sH[t] : __ldg(xcol + t);
+    const bool shared = nspag == 1;
+
+    auto stage = [&](int t) -> double { return shared ? lds_f64(ht + 8u * (unsigned)t) : __ldg(xcol + t); };
+    auto amask = [&](double h) -> unsigned {  // GetHRange (k increasing) -> row of the control matrix
         int r = 0;
 #pragma unroll
-        for (int j = 0; j < NC; ++j) r += (h >= k[j]) ? 1 : 0;  // GetHRange: k increasing
-        const unsigned m = (mask4 >> (4 * r)) & 0xfu;
+        for (int j = 0; j < NC; ++j) r += (h >= k[j]) ? 1 : 0;
+        return (mask4 >> (4 * r)) & 0xfu;
+    };
+    auto q_checked = [&](double h, unsigned m) -> double {
         double q = 0.0;
 #pragma unroll
         for (int j = 0; j < NC; ++j)
             if ((m >> j) & 1u) q += texp(fma(cc[j], tlog(h - b[j], lt), la[j]), et);
+        return q;
+    };
+    auto finish = [&](int t, double q, double z) {
         double v = q;
         if (NOISE) {
-            const unsigned tg = (unsigned)(a.t0 + tBeg + t);
-            if ((tg >> 1) != lastPair) {
-                lastPair = tg >> 1;
-                normal_pair_fast(a.seed, (uint64_t)rep, lastPair, 0u, lt, z0, z1);
-            }
             double sig;
             if (SIGF == BAMGPU_SIG_CONSTANT) sig = g1;
             else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(g2, fabs(q), g1);
             else sig = g1 * fabs(q);
-            if (sig > 0.0) v = fma(sig, (tg & 1u) ? z1 : z0, q);
+            if (sig > 0.0) v = fma(sig, z, q);
         }
         __stcs(out + (size_t)t * a.Nrep, v);
+    };
+    // two inputs per iteration: they share one Box-Muller pair and give the FP64 pipe two independent chains
+    auto two = [&](int t, double zA, double zB) {
+        const double hA = stage(t), hB = stage(t + 1);
+        const unsigned mA = amask(hA), mB = amask(hB);
+        double qA = 0.0, qB = 0.0;
+        unsigned oor = 0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            if ((mA >> j) & 1u) {
+                const double x = fma(cc[j], tlog(hA - b[j], lt), la[j]);
+                oor = max(oor, (unsigned)__double2hiint(x) & 0x7fffffffu);
+                qA += texp_inrange(x, et);
+            }
+            if ((mB >> j) & 1u) {
+                const double x = fma(cc[j], tlog(hB - b[j], lt), la[j]);
+                oor = max(oor, (unsigned)__double2hiint(x) & 0x7fffffffu);
+                qB += texp_inrange(x, et);
+            }
+        }
+        if (oor >= BAM_EXP_OOR) { qA = q_checked(hA, mA); qB = q_checked(hB, mB); }  // rare: H == b or overflow
+        finish(t, qA, zA);
+        finish(t + 1, qB, zB);
+    };
+    const unsigned tg0 = (unsigned)(a.t0 + tBeg);
+    double z0 = 0.0, z1 = 0.0;
+    int t = 0;
+    if ((tg0 & 1u) && nt > 0) {  // the tile starts on the odd member of a pair
+        if (NOISE) normal_pair_fast(a.seed, (uint64_t)rep, tg0 >> 1, 0u, lt, z0, z1);
+        const double h = stage(0);
+        finish(0, q_checked(h, amask(h)), z1);
+        t = 1;
+    }
+    for (; t + 1 < nt; t += 2) {
+        if (NOISE) normal_pair_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 1, 0u, lt, z0, z1);
+        two(t, z0, z1);
+    }
+    if (t < nt) {
+        if (NOISE) normal_pair_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 1, 0u, lt, z0, z1);
+        const double h = stage(t);
+        finish(t, q_checked(h, amask(h)), z0);
     }
 }
 
@@ -807,6 +850,28 @@ __device__ double s3_block_sum(double v, double* scratch) {
     return scratch[32];
 }
 
+// Column walkers of envelope_select3: 128-bit streaming loads, four independent requests per thread in flight
+// (the passes are pure HBM streams; with one 8-byte load per thread and iteration they were latency-bound at
+// 2.3 TB/s).  `f(v)` is applied to every value exactly once; the order does not matter to the callers.
+template <class F>
+__device__ __forceinline__ void s3_for_each(const double* __restrict__ col, long long Nrep, F f) {
+    const int tid = threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(col) & 15) == 0) {
+        const double2* __restrict__ c2 = reinterpret_cast<const double2*>(col);
+        const long long n2 = Nrep >> 1;
+        long long i = tid;
+        for (; i + 3 * S3_THREADS < n2; i += 4 * S3_THREADS) {
+            const double2 a = __ldcs(c2 + i), b = __ldcs(c2 + i + S3_THREADS), c = __ldcs(c2 + i + 2 * S3_THREADS),
+                          d = __ldcs(c2 + i + 3 * S3_THREADS);
+            f(a.x); f(a.y); f(b.x); f(b.y); f(c.x); f(c.y); f(d.x); f(d.y);
+        }
+        for (; i < n2; i += S3_THREADS) { const double2 a = __ldcs(c2 + i); f(a.x); f(a.y); }
+        if ((Nrep & 1) && tid == 0) f(col[Nrep - 1]);
+    } else {
+        for (long long r = tid; r < Nrep; r += S3_THREADS) f(__ldcs(col + r));
+    }
+}
+
 __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, int nT, double unfeas,
                                                                const double* __restrict__ V, double* __restrict__ env,
                                                                int* __restrict__ needSlow) {
@@ -869,14 +934,13 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
     for (int b = tid; b < S3_NB / 32; b += S3_THREADS) bitmap[b] = 0;
     __syncthreads();
     double s1 = 0.0, s2 = 0.0, nb = 0.0;
-    for (long long r = tid; r < Nrep; r += S3_THREADS) {
-        const double v = __ldcs(col + r);
-        if (v == unfeas || v != v) { nb += 1.0; continue; }
+    s3_for_each(col, Nrep, [&](double v) {
+        if (v == unfeas || v != v) { nb += 1.0; return; }
         const double d = v - pivot;
         s1 += d;
         s2 = fma(d, d, s2);
         atomicAdd(&hist[s3_bin(v, lo, scale)], 1u);
-    }
+    });
     const long long nbad = (long long)s3_block_sum(nb, scratch);
     const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
     if ((!drop && nbad > 0) || nbad == Nrep) {
@@ -945,11 +1009,10 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
 
     // ---- pass C: gather
     const int nl = nLists;
-    for (long long r = tid; r < Nrep; r += S3_THREADS) {
-        const double v = __ldcs(col + r);
-        if (v == unfeas || v != v) continue;
+    s3_for_each(col, Nrep, [&](double v) {
+        if (v == unfeas || v != v) return;
         const int b = s3_bin(v, lo, scale);
-        if (!((bitmap[b >> 5] >> (b & 31)) & 1u)) continue;
+        if (!((bitmap[b >> 5] >> (b & 31)) & 1u)) return;
         for (int j = 0; j < nl; ++j)
             if (listBin[j] == b) {
                 if (listOver[j]) {
@@ -961,7 +1024,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
                     gath[j * S3_CAP + pos] = v;
                 }
             }
-    }
+    });
     __syncthreads();
     for (int j = 0; j < nl; ++j) {  // sort every list (bitonic, padded with +inf), whole block
         if (listOver[j]) continue;
@@ -1104,7 +1167,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         a.t0 = t0 + tt; a.nT = nT;
         if (fastK) {
             dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + PF_TT - 1) / PF_TT);
-            fastK<<<grid, BAM_BLOCK, 0, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspag[0], h->predNspag[0], h->d_V);
+            fastK<<<grid, BAM_BLOCK, PF_SMEM, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspag[0], h->predNspag[0], h->d_V);
         } else {
             dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + 31) / 32);
             kern<<<grid, BAM_BLOCK, smemMain, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspagPtrs, h->d_nspag, h->d_V);
