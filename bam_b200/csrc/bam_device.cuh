@@ -243,12 +243,14 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t a, uint3
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
-// Structural-error noise of the prediction path (specification in bam_fastmath.cuh): inputs 2m and 2m+1 share one
-// Philox block; the even one takes the cosine, the odd one the sine branch of Box-Muller.
+// Structural-error noise of the prediction path (specification in bam_fastmath.cuh): inputs 4q..4q+3 share one
+// Philox block; words (0,1) serve inputs 4q, 4q+1 and words (2,3) inputs 4q+2, 4q+3; the even input takes the
+// cosine, the odd one the sine branch of Box-Muller; uniforms are (w + 0.5) 2^-32.
 __device__ __forceinline__ double philox_normal_pred(uint64_t seed, uint64_t rep, uint32_t t, uint32_t y) {
-    uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = t >> 1, c3 = y;
+    uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = t >> 2, c3 = y;
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double u1 = u53(c0, c1), u2 = u53(c2, c3);
+    const uint32_t wa = (t & 2u) ? c2 : c0, wb = (t & 2u) ? c3 : c1;
+    const double u1 = ((double)wa + 0.5) * (1.0 / 4294967296.0), u2 = ((double)wb + 0.5) * (1.0 / 4294967296.0);
     const double r = sqrt(-2.0 * log(u1));
     return r * ((t & 1u) ? sinpi(2.0 * u2) : cospi(2.0 * u2));
 }

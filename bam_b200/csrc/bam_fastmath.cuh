@@ -112,32 +112,29 @@ __device__ __forceinline__ double trcp(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Structural-error noise of the prediction path: Box-Muller PAIRS from one Philox4x32-10 block.
+// Structural-error noise of the prediction path: Box-Muller pairs, FOUR normals from one Philox4x32-10 block.
 //
-// Specification (shared with oracle/bam_oracle.c:oracle_normal_pair): for replication `rep`, prediction input t and
-// output y,   (u1,u2) = two 53-bit uniforms of Philox(seed; counter = (rep_lo, rep_hi, t>>1, y)),
-//             z(t) = sqrt(-2 ln u1) * (t even ? cos(2 pi u2) : sin(2 pi u2)).
-// Two consecutive inputs share one Philox block, one log and one square root.
-// FP64-pipe cost per pair of normals: uniforms 8, tlog 8, sqrt 8, sincos 23 -> ~25 per normal (libdevice: ~110).
+// Specification (shared with oracle/bam_oracle.c:oracle_normal_pred and bam_device.cuh:philox_normal_pred): for
+// replication `rep`, prediction input t and output y,
+//     (w0,w1,w2,w3) = Philox4x32-10(key = seed; counter = (rep_lo, rep_hi, t>>2, y)),   p = (t>>1)&1,
+//     u1 = (w[2p] + 0.5) 2^-32,  u2 = (w[2p+1] + 0.5) 2^-32,
+//     z(t) = sqrt(-2 ln u1) * (t even ? cos(2 pi u2) : sin(2 pi u2)).
+// 32-bit uniforms (|z| <= 6.7) are the resolution class of the generators the reference itself draws from; four
+// consecutive inputs share one Philox block, two share one log and one square root.
+// FP64-pipe cost per normal: ~2 (uniforms) + 4 (tlog) + 3.5 (sqrt) + 11.5 (sincos) + 0.5 = ~22 (libdevice: ~110).
 // ---------------------------------------------------------------------------------------------------------------
 
 // [0..5] sin kernel S1..S6, [6..11] cos kernel C1..C6 (fdlibm k_sin.c / k_cos.c minimax sets, |x| <= pi/4),
-// [12] pi, [13] 1.5*2^52 (rint), [14] 2^78, [15] 2^52
+// [12] pi, [13] 1.5*2^52 (rint), [14] 2^52 - 0.5
 __constant__ double kFN[16] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
                                2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10,
                                4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11,
-                               3.14159265358979323846,      6755399441055744.0,          302231454903657293676544.0,
-                               4503599627370496.0};
+                               3.14159265358979323846,      6755399441055744.0,          4503599627370495.5,
+                               0.0};
 
-// (N + 0.5) with N = (hi >> 5) * 2^26 + (lo >> 6) (53 bits): the numerator of u53() in bam_device.cuh, built with
-// magic-number adds instead of integer->double conversions.  Same rounding as u53: the integer sum is exact, the
-// +0.5 rounds to nearest even once N >= 2^52.  u = result * 2^-53.
-__device__ __forceinline__ double u53_numerator(uint32_t hi, uint32_t lo) {
-    const double dh = __hiloint2double(0x44D00000, (int)(hi >> 5)) - kFN[14];  // (hi>>5) * 2^26, exact
-    const double dl = __hiloint2double(0x43300000, (int)(lo >> 6)) - kFN[15];  // (lo>>6), exact
-    return (dh + dl) + 0.5;
-}
+// w + 0.5 as a double (exact): magic-number add instead of an integer -> double conversion
+__device__ __forceinline__ double u32_plus_half(uint32_t w) { return __hiloint2double(0x43300000, (int)w) - kFN[14]; }
 
 // sqrt(x) for a positive normal x: MUFU.RSQ64H seed (>= 20 bits), one Goldschmidt step (>= 40 bits), one
 // correction g += (x - g^2) h: result within 1 ulp.  7 FP64 instructions (IEEE sqrt(): ~15 with its slow path).
@@ -178,16 +175,13 @@ __device__ __forceinline__ void tsincospi(double a, double& s, double& c) {
     c = __hiloint2double((int)((unsigned)__double2hiint(c0) ^ (cneg << 30)), __double2loint(c0));
 }
 
-// the pair (z_even, z_odd) of standard normals for (seed, rep, tpair = t>>1, y); `lt` = shared log table
-__device__ __forceinline__ void normal_pair_fast(uint64_t seed, uint64_t rep, uint32_t tpair, uint32_t y, unsigned lt,
-                                                 double& z0, double& z1) {
-    uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = tpair, c3 = y;
-    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double n1 = u53_numerator(c0, c1), n2 = u53_numerator(c2, c3);
-    // u1 = n1 * 2^-53 through the exponent field (integer subtract, exact)
-    const double u1 = __hiloint2double(__double2hiint(n1) - (53 << 20), __double2loint(n1));
+// the Box-Muller pair (z_even, z_odd) from two Philox words; `lt` = shared log table
+__device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, unsigned lt, double& z0, double& z1) {
+    const double n1 = u32_plus_half(wa), n2 = u32_plus_half(wb);
+    // u1 = n1 * 2^-32 through the exponent field (integer subtract, exact)
+    const double u1 = __hiloint2double(__double2hiint(n1) - (32 << 20), __double2loint(n1));
     double L;
-    if (__double2hiint(n1) >= 0x433FF800) {
+    if (wa >= 0xFFC00000u) {
         // u1 within 2^-10 of 1 (probability 1e-3): the table-driven log has ABSOLUTE error ~1e-16, not enough
         // relative accuracy when log(u1) -> 0
         L = log(u1);
@@ -196,7 +190,16 @@ __device__ __forceinline__ void normal_pair_fast(uint64_t seed, uint64_t rep, ui
     }
     const double r = tsqrt_pos(-2.0 * L);
     double s, c;
-    tsincospi(n2 * (2.0 / 9007199254740992.0), s, c);
+    tsincospi(n2 * (2.0 / 4294967296.0), s, c);
     z0 = r * c;
     z1 = r * s;
+}
+
+// the four normals z(4q), z(4q+1), z(4q+2), z(4q+3) of (seed, rep, quad q = t>>2, y)
+__device__ __forceinline__ void normal_quad_fast(uint64_t seed, uint64_t rep, uint32_t quad, uint32_t y, unsigned lt,
+                                                 double z[4]) {
+    uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = quad, c3 = y;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    box_muller_fast(c0, c1, lt, z[0], z[1]);
+    box_muller_fast(c2, c3, lt, z[2], z[3]);
 }

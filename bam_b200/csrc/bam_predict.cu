@@ -108,14 +108,17 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
 // thread <-> replication with its parameter set (k, b, c, log a per control, gamma) in REGISTERS; the block walks a
 // tile of PF_TT prediction inputs (staged once in shared memory when all replications share one input series).
 // a_i (H-b_i)^c_i = texp(c_i tlog(H-b_i) + log a_i) with the table-driven functions of bam_fastmath.cuh, the
-// structural-error noise from Box-Muller pairs (one Philox block, one log and one sqrt per TWO inputs).
+// structural-error noise from Box-Muller pairs (one Philox block per FOUR inputs, one log and one sqrt per two).
 // As in the log-posterior fast path the "H-b<0" exits of BaRatin_computeQ cannot fire for a parameter set that
 // passed ApplyContinuity, so Q is the plain sum over the active controls of the stage range.
 // ~60 FP64-pipe instructions per (replication, input) against ~330 for the libdevice formulation of pred_main.
 #define PF_TT 64
+#ifndef PF_MINB
+#define PF_MINB 4
+#endif
 #define PF_SMEM (sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + PF_TT))
 template <int NC, int SIGF, bool NOISE>
-__global__ void __launch_bounds__(BAM_BLOCK, 4) pred_baratin_fast(DevProblem p, PredArgs a, const double* __restrict__ tab,
+__global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProblem p, PredArgs a, const double* __restrict__ tab,
                                                                   const int* __restrict__ status,
                                                                   const double* __restrict__ xs, int nspag,
                                                                   double* __restrict__ V) {
@@ -199,23 +202,22 @@ __global__ void __launch_bounds__(BAM_BLOCK, 4) pred_baratin_fast(DevProblem p, 
         finish(t + 1, qB, zB);
     };
     const unsigned tg0 = (unsigned)(a.t0 + tBeg);
-    double z0 = 0.0, z1 = 0.0;
-    int t = 0;
-    if ((tg0 & 1u) && nt > 0) {  // the tile starts on the odd member of a pair
-        if (NOISE) normal_pair_fast(a.seed, (uint64_t)rep, tg0 >> 1, 0u, lt, z0, z1);
-        const double h = stage(0);
-        finish(0, q_checked(h, amask(h)), z1);
-        t = 1;
-    }
-    for (; t + 1 < nt; t += 2) {
-        if (NOISE) normal_pair_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 1, 0u, lt, z0, z1);
-        two(t, z0, z1);
-    }
-    if (t < nt) {
-        if (NOISE) normal_pair_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 1, 0u, lt, z0, z1);
+    double z[4] = {0.0, 0.0, 0.0, 0.0};
+    auto single = [&](int t) {  // head / tail of a tile that does not start or end on a multiple of four inputs
+        const unsigned tg = tg0 + (unsigned)t;
+        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, tg >> 2, 0u, lt, z);
         const double h = stage(t);
-        finish(t, q_checked(h, amask(h)), z0);
+        const double zz = (tg & 2u) ? ((tg & 1u) ? z[3] : z[2]) : ((tg & 1u) ? z[1] : z[0]);
+        finish(t, q_checked(h, amask(h)), zz);
+    };
+    int t = 0;
+    for (; t < nt && ((tg0 + (unsigned)t) & 3u); ++t) single(t);
+    for (; t + 3 < nt; t += 4) {  // four inputs share one Philox block, two share one log and one sqrt
+        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 2, 0u, lt, z);
+        two(t, z[0], z[1]);
+        two(t + 2, z[2], z[3]);
     }
+    for (; t < nt; ++t) single(t);
 }
 
 using PredFastKernel = void (*)(DevProblem, PredArgs, const double*, const int*, const double*, int, double*);

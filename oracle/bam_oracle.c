@@ -1431,12 +1431,14 @@ double oracle_normal(uint64_t seed, uint64_t a, uint32_t b, uint32_t c) {
 }
 
 /* Structural-error noise of the prediction (the reference draws it from BMSL's generator, un-vendored: only the
-   distribution is shared).  Declared specification: inputs 2m and 2m+1 of replication rep / output y share one
-   Philox block (counter (rep, t>>1, y)); Box-Muller, cosine branch for even t, sine branch for odd t. */
+   distribution is shared).  Declared specification: inputs 4q..4q+3 of replication rep / output y share one
+   Philox block (counter (rep, t>>2, y)); words (0,1) serve inputs 4q and 4q+1, words (2,3) inputs 4q+2 and 4q+3;
+   uniforms are (w + 0.5) 2^-32; Box-Muller, cosine branch for even t, sine branch for odd t. */
 double oracle_normal_pred(uint64_t seed, uint64_t rep, uint32_t t, uint32_t y) {
     uint32_t w[4];
-    oracle_philox4x32((uint32_t)rep, (uint32_t)(rep >> 32), t >> 1, y, (uint32_t)seed, (uint32_t)(seed >> 32), w);
-    double u1 = u53(w[0], w[1]), u2 = u53(w[2], w[3]);
+    oracle_philox4x32((uint32_t)rep, (uint32_t)(rep >> 32), t >> 2, y, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    uint32_t wa = (t & 2u) ? w[2] : w[0], wb = (t & 2u) ? w[3] : w[1];
+    double u1 = ((double)wa + 0.5) * (1.0 / 4294967296.0), u2 = ((double)wb + 0.5) * (1.0 / 4294967296.0);
     double r = sqrt(-2.0 * log(u1));
     return r * ((t & 1u) ? sin(6.28318530717958647692 * u2) : cos(6.28318530717958647692 * u2));
 }
