@@ -92,6 +92,8 @@ cudaEvent_t take_event(bamgpu_handle* h);
 // results in d_prior/d_lkh/d_hyper/d_fx/d_status/d_dpar.  Asynchronous on h->stream.
 void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain);
 
+void launch_table(bamgpu_handle* h, int K, const double* d_x);
+
 void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, double maxMR, double downMult,
                 double upMult, unsigned long long seed, int burn, int keepEvery, bool storeRows, long long nKeep);
 

@@ -529,6 +529,13 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     h->Kcap = K;
 }
 
+// only K2: the per-chain tables (gamma, biases, expanded theta + derived values) of the vectors at d_x
+void launch_table(bamgpu_handle* h, int K, const double* d_x) {
+    logpost_prep<<<(K + 127) / 128, 128, 0, h->stream>>>(h->dp, d_x, K, -1, nullptr, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
+    h->launches += 1;
+    BAM_CUDA(cudaGetLastError());
+}
+
 void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain) {
     const DevProblem& p = h->dp;
     const LogpostPlan& pl = h->plan;

@@ -310,6 +310,124 @@ __global__ void __launch_bounds__(32 * WS_WARPS) sampler_warp(DevProblem p, Warp
     if (lane == 0) a.fxcur[c] = fxc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3l: one-launch sweep over ALL latent "true input" components (cfg 3: 2 x 10^6 per chain).
+//
+// Every model on this path is pointwise, so given (theta, gamma, biases) the posterior factorises over
+// observations: the latent inputs of observation i only enter its own likelihood terms and its own hyper terms
+// (GetLogLikelihood :3204-3227, GetHyperLogPdf :3285-3303).  The one-at-a-time updates of latent components that
+// belong to DIFFERENT observations therefore commute, and
+//     f(candidate) - f(current) = [lkh_i + hyper_i](candidate) - [lkh_i + hyper_i](current)
+// needs O(1) work instead of a pass over all observations.  thread <-> (chain, observation); the latent inputs of
+// one observation are visited in column order, which is exactly the order in which the reference's vector layout
+// (Packer :4202-4242: column-major over (i,j)) visits them as far as observation i can tell.  Same Philox streams
+// as every other path (normal: (chain, it, 2 comp), uniform: (chain, it, 2 comp + 1)), same accept rule.
+// Per latent component: 8 B read + 8 B written of state, 8 B jump scale, 8 B move counter: HBM-leaning FP64 work.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NX, int NY>
+__device__ __forceinline__ bool local_logpost(const DevProblem& p, const double* xt, const double* xo, const double* xu,
+                                              const double* xb, const int* xbi, const double* yo, const double* yu,
+                                              const double* yb, const int* ybi, const double* __restrict__ row,
+                                              const double* __restrict__ th, double& val) {
+    double yh[NY];
+    if (!model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh)) return false;
+    double lk = 0.0;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+        if (p.hasMissing && yo[j] == p.mv) continue;
+        const double sig = sigmafunk(p.sigfunc[j], row + p.tabGamma + p.gamOff[j], yh[j]);
+        if (!(sig > 0.0)) return false;
+        double mu = yh[j];
+        if (p.hasYbias && ybi[j] != 0) mu = yh[j] + yb[j] * row[p.tabOffYb[j] + ybi[j] - 1];
+        lk += gauss_logpdf_var(yo[j], mu, fma(yu[j], yu[j], sig * sig));
+    }
+    double hy = 0.0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        if (!(xu[j] > 0.0)) continue;
+        double mu = xt[j];
+        if (p.hasXbias && xbi[j] != 0) mu = xt[j] + xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
+        hy += gauss_logpdf(xo[j], mu, xu[j]);
+    }
+    val = lk + hy;
+    return val == val;
+}
+
+template <int MODEL, int NX, int NY>
+__global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, unsigned long long seed,
+                                                          long long chainOffset, unsigned it, double* __restrict__ x,
+                                                          const double* __restrict__ sd, int* __restrict__ moves,
+                                                          const double* __restrict__ tab) {
+    extern __shared__ double lsm[];  // table row of this chain
+    const int c = blockIdx.y;
+    for (int q = threadIdx.x; q < p.tabStride; q += BAM_BLOCK) lsm[q] = tab[(size_t)c * p.tabStride + q];
+    __syncthreads();
+    const int n = p.n;
+    const int i = blockIdx.x * BAM_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    double xo[NX], xu[NX], xb[NX], yo[NY], yu[NY], yb[NY], xt[NX];
+    int xbi[NX], ybi[NY], lat[NX];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const size_t q = i + (size_t)j * n;
+        xo[j] = p.X[q]; xu[j] = p.Xu[q]; lat[j] = p.latIdx[q];
+        xb[j] = 0.0; xbi[j] = 0;
+        if (p.hasXbias) { xb[j] = p.Xb[q]; xbi[j] = p.Xbindx[q]; }
+        any |= lat[j] >= 0;
+    }
+    if (!any) return;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+        const size_t q = i + (size_t)j * n;
+        yo[j] = p.Y[q]; yu[j] = p.Yu[q];
+        yb[j] = 0.0; ybi[j] = 0;
+        if (p.hasYbias) { yb[j] = p.Yb[q]; ybi[j] = p.Ybindx[q]; }
+    }
+    const double* __restrict__ row = lsm;
+    const int combo = (p.nCombo > 1) ? p.comboOf[i] : 0;
+    const double* __restrict__ th = row + p.tabCombo + (size_t)combo * p.comboStride;
+    const size_t base = (size_t)c * p.P;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {  // UnfoldParVector (:3429-3452)
+        double v = xo[j];
+        if (lat[j] >= 0) v = x[base + lat[j]];
+        else if (p.hasXbias && xbi[j] > 0) v = xo[j] - xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
+        xt[j] = v;
+    }
+    double cur;
+    if (!local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, row, th, cur)) return;  // cannot happen for a feasible state
+    const unsigned long long gc = (unsigned long long)(chainOffset + c);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        if (lat[j] < 0) continue;
+        const unsigned comp = (unsigned)lat[j];
+        const double old = xt[j];
+        xt[j] = old + sd[base + comp] * philox_normal(seed, gc, it, 2u * comp);
+        double cand;
+        bool acc = false;
+        if (local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, row, th, cand)) {
+            const double u = philox_uniform(seed, gc, it, 2u * comp + 1u);
+            acc = log(u) < cand - cur;
+        }
+        if (acc) {
+            cur = cand;
+            x[base + comp] = xt[j];
+            moves[base + comp] += 1;
+        } else xt[j] = old;
+    }
+}
+
+using LatentKernel = void (*)(DevProblem, int, unsigned long long, long long, unsigned, double*, const double*, int*,
+                              const double*);
+LatentKernel pick_latent_sweep(int model, int nX, int nY) {
+#define X(M, A, B) \
+    if (model == M && nX == A && nY == B) return latent_sweep<M, A, B>;
+    BAM_FOR_EACH_INSTANCE(X)
+#undef X
+    return nullptr;
+}
+
 using WarpSamplerKernel = void (*)(DevProblem, WarpSamplerArgs);
 WarpSamplerKernel pick_warp_sampler(int model, int nX, int nY) {
 #define X(M, A, B) \
@@ -375,15 +493,32 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
         return;
     }
 
+    // components visited with one launch set per proposal: everything except the latent inputs when the one-launch
+    // sweep applies (vector order: theta | gamma | latent inputs | X biases | Y biases, Packer :4202-4242)
+    LatentKernel lk = (p.hasLatent && !h->forceGeneric) ? pick_latent_sweep(p.model, p.nX, p.nY) : nullptr;
+    const int latBeg = p.nFit + p.nGamma, latEnd = latBeg + p.nLatent;
+    auto propose_one = [&](int i, long long it) {
+        propose_kernel<<<gK, TB, 0, s>>>(K, P, i, seed, h->chainOffset, (unsigned)it, h->d_std, h->d_delta);
+        launch_logpost(h, K, h->d_x, i, h->d_delta, false);
+        accept_kernel<<<gK, TB, 0, s>>>(K, P, nD, i, seed, h->chainOffset, (unsigned)it, h->d_delta, h->d_fx,
+                                        h->d_status, h->d_dpar, h->d_x, h->d_fxcur, h->d_dparcur, h->d_moves);
+        h->launches += 2;
+    };
     long long it = 0, kept = 0;
     for (int cyc = 0; cyc < nCycles; ++cyc) {
         for (int a = 0; a < nAdapt; ++a, ++it) {
-            for (int i = 0; i < P; ++i) {
-                propose_kernel<<<gK, TB, 0, s>>>(K, P, i, seed, h->chainOffset, (unsigned)it, h->d_std, h->d_delta);
-                launch_logpost(h, K, h->d_x, i, h->d_delta, false);
-                accept_kernel<<<gK, TB, 0, s>>>(K, P, nD, i, seed, h->chainOffset, (unsigned)it, h->d_delta, h->d_fx,
-                                                h->d_status, h->d_dpar, h->d_x, h->d_fxcur, h->d_dparcur, h->d_moves);
-                h->launches += 2;
+            for (int i = 0; i < (lk ? latBeg : P); ++i) propose_one(i, it);
+            if (lk) {
+                // the table of the CURRENT state (theta, gamma, biases of every chain), then the sweep, then the
+                // full log-posterior of the swept state becomes the current one
+                launch_table(h, K, h->d_x);
+                dim3 grid((p.n + BAM_BLOCK - 1) / BAM_BLOCK, K);
+                lk<<<grid, BAM_BLOCK, sizeof(double) * p.tabStride, s>>>(p, K, seed, h->chainOffset, (unsigned)it, h->d_x,
+                                                                        h->d_std, h->d_moves, h->d_tab);
+                launch_logpost(h, K, h->d_x, -1, nullptr, false);
+                BAM_CUDA(cudaMemcpyAsync(h->d_fxcur, h->d_fx, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
+                h->launches += 1;
+                for (int i = latEnd; i < P; ++i) propose_one(i, it);
             }
             const long long it1 = it + 1;
             if (it1 > burn && (it1 - burn) % keepEvery == 0 && kept < nKeep) {

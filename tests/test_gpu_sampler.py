@@ -116,3 +116,63 @@ def test_persistent_and_launch_per_proposal_paths_agree():
     assert np.allclose(m2_p, m2_g, rtol=1e-7, atol=1e-13)
     fx_p = g.chains_download()[0]
     assert np.allclose(fx_p, rows_p[:, -1, 19], rtol=1e-12)
+
+
+def _latent_problem(n=40, seed=3):
+    """Linear 2x2 with input errors on most cells, an X bias on the others (cfg 3 shape, small)."""
+    from bam_b200.capi import Problem
+
+    rng = np.random.default_rng(seed)
+    prob0, truth0 = synth.linear_latent(nobs=n, seed=seed)
+    Xu = np.array(prob0.Xu)
+    Xu[::7, 1] = 0.0  # a few cells without random error
+    Xbindx = np.zeros((n, 2), dtype=np.int32)
+    Xbindx[::7, 1] = 1
+    Xb = np.where(Xbindx > 0, 0.05, 0.0)
+    prob = Problem("Linear", prob0.X, prob0.Y, Yu=prob0.Yu, Xu=Xu, Xb=Xb, Xbindx=Xbindx, partype=[0, 0, 0, 0],
+                   priors_theta=[("Gaussian", [0, 10])] * 4, sigma_func=["Linear", "Linear"],
+                   priors_gamma=[("Uniform", [0, 100])] * 4)
+    lat = np.asarray(prob0.X).flatten(order="F")[(Xu > 0).flatten(order="F")]
+    start = np.concatenate([truth0[:8], lat, [0.0]])
+    sd = np.concatenate([0.05 * np.abs(truth0[:8]), Xu.flatten(order="F")[(Xu > 0).flatten(order="F")], [0.1]])
+    return prob, start, sd
+
+
+def test_latent_sweep_equals_full_posterior_oaat():
+    """cfg 3: the one-launch sweep over all latent inputs uses the LOCAL posterior difference of one observation;
+    the oracle runs the reference's one-at-a-time loop with a FULL posterior evaluation per component.  Same RNG
+    streams -> same accept / reject decisions -> same chains (up to the rounding of the differently summed fx)."""
+    prob, start, sd = _latent_problem()
+    K = 5
+    s = np.tile(start, (K, 1))
+    sdev = np.tile(sd, (K, 1))
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.sizes.nLatent == start.size - 9 and g.sizes.nXbias == 1
+    rows = g.fit(s, sdev, nAdapt=6, nCycles=3, seed=17)
+    orow, _, ostd = o.fit(s, sdev, nAdapt=6, nCycles=3, seed=17)
+    assert rows.shape == orow.shape
+    P = start.size
+    assert np.allclose(rows[:, :, :P], orow[:, :, :P], rtol=1e-10, atol=1e-12)
+    assert np.allclose(rows[:, :, P], orow[:, :, P], rtol=1e-10)
+    # the latent inputs really moved, and the launch-per-proposal path gives the same chains
+    assert (np.abs(rows[:, -1, 8:P - 1] - s[:, 8:P - 1]) > 0).mean() > 0.5
+    g2 = BamGpu(prob)
+    g2.set_option("force_generic", 1)
+    rows2 = g2.fit(s, sdev, nAdapt=6, nCycles=3, seed=17)
+    assert np.allclose(rows, rows2, rtol=1e-10, atol=1e-12)
+    assert g.launch_count() < g2.launch_count() / 5
+
+
+def test_latent_sweep_textfile_and_moments():
+    prob, truth = synth.textfile_latent(nobs=300)
+    K = 8
+    s = np.tile(truth, (K, 1))
+    sd = np.concatenate([0.02 * np.abs(truth[:4]), np.full(300, 1.0)])
+    g = BamGpu(prob)
+    rows = g.fit(s, np.tile(sd, (K, 1)), nAdapt=20, nCycles=5, seed=5)
+    assert np.isfinite(rows).all()
+    cnt, mean, m2 = g.moments()
+    assert (cnt == 100).all() and np.allclose(mean, rows[:, :, :304].mean(axis=1), rtol=1e-10, atol=1e-12)
+    # latent inputs stay within a few input standard deviations of the observed inputs
+    z = (rows[:, -1, 4:304] - np.asarray(prob.X)[:, 0]) / 1.0
+    assert np.abs(z).max() < 6 and z.std() > 0.2
