@@ -296,6 +296,7 @@ def load_library(path: Optional[str] = None):
     u64, i64, ci, cp = C.c_uint64, C.c_int64, C.c_int, C.c_char_p
     lib.bamgpu_logpost.argtypes = [H, ci, _dp, _dp, _ip, _ip, _dp, cp]
     lib.bamgpu_logpost_parts.argtypes = [H, ci, _dp, _dp, _dp, _dp, _ip, _ip, cp]
+    lib.bamgpu_calibration_run.argtypes = [H, C.POINTER(CProblem), _dp, _dp, _dp, _ip, cp]
     lib.bamgpu_chains_upload.argtypes = [H, ci, _dp, cp]
     lib.bamgpu_logpost_resident.argtypes = [H, cp]
     lib.bamgpu_chains_download.argtypes = [H, _dp, _ip, _ip, _dp, cp]
@@ -438,6 +439,19 @@ class BamGpu:
         return fx, feas, isnull
 
     # -- sampler -------------------------------------------------------------------------
+    def calibration_run(self, x):
+        """GetSim_calibration: (Xtrue n x nX, Ysim n x nY, feas) for one parameter vector."""
+        pr = self.problem
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        Xtrue = np.empty((pr.nobs, pr.nX), order="F")
+        Ysim = np.empty((pr.nobs, pr.nY), order="F")
+        feas = C.c_int32(0)
+        mess = C.create_string_buffer(MESS_LEN)
+        cs = pr.c_struct()
+        _check(self.lib.bamgpu_calibration_run(self.h, C.byref(cs), _ptr_d(x), _ptr_d(Xtrue), _ptr_d(Ysim),
+                                               C.byref(feas), mess), mess)
+        return Xtrue, Ysim, bool(feas.value)
+
     def fit(self, start, start_std, nAdapt, nCycles, MinMoveRate=0.1, MaxMoveRate=0.5, DownMult=0.9, UpMult=1.1,
             seed=1, burn=0, keep_every=1, want_rows=True):
         start = np.asarray(start, dtype=np.float64)

@@ -336,6 +336,48 @@ int bamgpu_logpost_parts(bamgpu_t* h, int K, const double* x, double* prior, dou
     });
 }
 
+int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* pb, const double* x, double* Xtrue, double* Ysim,
+                           int32_t* feas, char* mess) {
+    return guarded(mess, [&]() -> int {
+        BAM_CUDA(cudaSetDevice(h->device));
+        const bam::HostLayout& L = h->L;
+        const int n = L.n, nX = L.nX, nY = L.nY;
+        if (pb->nobs != n || pb->nX != nX || pb->nY != nY) throw bam::CudaError{"bamgpu_calibration_run: the problem does not match the handle"};
+        if (feas) *feas = 0;
+        if (n == 0) { if (feas) *feas = 1; return 0; }
+        // UnfoldParVector (:3429-3452): latent cells from the vector, biased non-latent cells un-biased
+        std::vector<double> xt((size_t)n * nX);
+        for (int j = 0; j < nX; ++j)
+            for (int i = 0; i < n; ++i) {
+                const size_t q = i + (size_t)j * n;
+                double v = pb->X[q];
+                if (L.latIdx[q] >= 0) v = x[L.latIdx[q]];
+                else if (pb->Xbindx[q] > 0 && L.nXb[j] > 0) v = pb->X[q] - pb->Xb[q] * x[L.offXb[j] + pb->Xbindx[q] - 1];
+                xt[q] = v;
+            }
+        if (Xtrue) std::copy(xt.begin(), xt.end(), Xtrue);
+        double *d_x1 = nullptr, *d_xt = nullptr, *d_y = nullptr;
+        int* d_combo = nullptr;
+        BAM_CUDA(cudaMalloc(&d_x1, sizeof(double) * L.P));
+        BAM_CUDA(cudaMalloc(&d_xt, sizeof(double) * xt.size()));
+        BAM_CUDA(cudaMalloc(&d_y, sizeof(double) * (size_t)n * nY));
+        BAM_CUDA(cudaMalloc(&d_combo, sizeof(int) * n));
+        BAM_CUDA(cudaMemcpyAsync(d_x1, x, sizeof(double) * L.P, cudaMemcpyHostToDevice, h->stream));
+        BAM_CUDA(cudaMemcpyAsync(d_xt, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice, h->stream));
+        BAM_CUDA(cudaMemcpyAsync(d_combo, L.comboOf.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        const int nbad = bam::launch_calibration_run(h, d_x1, n, d_xt, d_combo, d_y);
+        if (nbad < 0) {  // infeasible parameter set: every row is flagged (ApplyModel :419-432)
+            for (size_t q = 0; q < (size_t)n * nY; ++q) Ysim[q] = pb->unfeas_flag;
+        } else {
+            BAM_CUDA(cudaMemcpyAsync(Ysim, d_y, sizeof(double) * (size_t)n * nY, cudaMemcpyDeviceToHost, h->stream));
+            BAM_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        cudaFree(d_x1); cudaFree(d_xt); cudaFree(d_y); cudaFree(d_combo);
+        if (feas) *feas = nbad == 0;
+        return 0;
+    });
+}
+
 // ---- sampler ----------------------------------------------------------------------------------------
 
 int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std, int nAdapt, int nCycles,

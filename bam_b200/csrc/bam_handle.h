@@ -93,6 +93,8 @@ cudaEvent_t take_event(bamgpu_handle* h);
 void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain);
 
 void launch_table(bamgpu_handle* h, int K, const double* d_x);
+int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const double* d_xtrue, const int* d_combo,
+                           double* d_ysim);
 
 void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, double maxMR, double downMult,
                 double upMult, unsigned long long seed, int burn, int keepEvery, bool storeRows, long long nKeep);

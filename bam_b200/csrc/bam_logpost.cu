@@ -481,6 +481,38 @@ MainKernel pick_main(int model, int nX, int nY) {
     return nullptr;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// GetSim_calibration (src/BaM_tools.f90:3619-3680): the model outputs on the calibration inputs for ONE parameter
+// vector, in the caller's observation order (the device tables of the handle are sorted / compacted, so this
+// kernel works on temporaries built from the caller's own arrays).  thread <-> observation.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int NX, int NY>
+__global__ void __launch_bounds__(BAM_BLOCK) calib_sim(DevProblem p, int n, const double* __restrict__ Xtrue,
+                                                       const int* __restrict__ comboOf, const double* __restrict__ row,
+                                                       double* __restrict__ Ysim, int* __restrict__ nBad) {
+    const int i = blockIdx.x * BAM_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    double xt[NX], yh[NY];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) xt[j] = Xtrue[i + (size_t)j * n];
+    const int combo = (p.nCombo > 1) ? comboOf[i] : 0;
+    const double* th = row + p.tabCombo + (size_t)combo * p.comboStride;
+    const bool ok = model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh);
+    if (!ok) atomicAdd(nBad, 1);
+#pragma unroll
+    for (int j = 0; j < NY; ++j) Ysim[i + (size_t)j * n] = ok ? yh[j] : p.unfeas;  // ModelLibrary_tools.f90:419-432
+}
+
+using CalibKernel = void (*)(DevProblem, int, const double*, const int*, const double*, double*, int*);
+CalibKernel pick_calib(int model, int nX, int nY) {
+#define X(M, A, B) \
+    if (model == M && nX == A && nY == B) return calib_sim<M, A, B>;
+    BAM_FOR_EACH_INSTANCE(X)
+#undef X
+    return nullptr;
+}
+
 }  // namespace
 
 namespace bam {
@@ -527,6 +559,35 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     BAM_CUDA(cudaMalloc(&h->d_status, sizeof(int) * K));
     BAM_CUDA(cudaMalloc(&h->d_delta, sizeof(double) * K));
     h->Kcap = K;
+}
+
+// one vector through the model on n caller-ordered observations (d_xtrue: n x nX, d_combo: n); returns #infeasible rows
+// or -1 when the parameter set itself is infeasible / null
+int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const double* d_xtrue, const int* d_combo,
+                           double* d_ysim) {
+    const DevProblem& p0 = h->dp;
+    CalibKernel kern = pick_calib(p0.model, p0.nX, p0.nY);
+    if (!kern) throw CudaError{"bamgpu: no kernel instantiated for this (model, nX, nY)"};
+    double *tab = nullptr, *prior = nullptr, *dpar = nullptr;
+    int *status = nullptr;
+    BAM_CUDA(cudaMalloc(&tab, sizeof(double) * std::max(p0.tabStride, 1)));
+    BAM_CUDA(cudaMalloc(&prior, sizeof(double)));
+    BAM_CUDA(cudaMalloc(&dpar, sizeof(double) * std::max(p0.nDpar, 1)));
+    BAM_CUDA(cudaMalloc(&status, 2 * sizeof(int)));
+    BAM_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int), h->stream));
+    // whole-series models (Vegetation) scan the input series in prep: point the problem image at the caller's series
+    DevProblem p = p0;
+    p.X = d_xtrue;
+    p.n = n;
+    logpost_prep<<<1, 128, 0, h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
+    kern<<<(n + BAM_BLOCK - 1) / BAM_BLOCK, BAM_BLOCK, 0, h->stream>>>(p, n, d_xtrue, d_combo, tab, d_ysim, status + 1);
+    int st[2] = {0, 0};
+    BAM_CUDA(cudaMemcpyAsync(st, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    BAM_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(tab); cudaFree(prior); cudaFree(dpar); cudaFree(status);
+    h->launches += 2;
+    BAM_CUDA(cudaGetLastError());
+    return (st[0] & ST_LKH_INFEAS) ? -1 : st[1];
 }
 
 // only K2: the per-chain tables (gamma, biases, expanded theta + derived values) of the vectors at d_x

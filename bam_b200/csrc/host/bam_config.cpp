@@ -423,7 +423,12 @@ void load_workspace(const std::string& configFile, Workspace& w) {
         Cursor k(w.dir + w.fCooking);
         w.cookFile = k.str(); w.burnFactor = k.num(); w.nSlim = k.integer();
     }
-    if (exists(w.dir + w.fSummary)) { Cursor s(w.dir + w.fSummary); w.summaryFile = s.str(); }
+    if (exists(w.dir + w.fSummary)) {
+        Cursor s(w.dir + w.fSummary);
+        w.summaryFile = s.str();
+        if (s.more()) { auto it = s.next(); if (!it.empty()) w.dicFile = it[0]; }          // absent -> no DIC (back-compatibility)
+        if (s.more()) { auto it = s.next(); if (!it.empty()) w.xtendedMcmcFile = it[0]; }  // absent -> no extended MCMC file
+    }
     if (exists(w.dir + w.fResidual)) { Cursor s(w.dir + w.fResidual); w.residualFile = s.str(); }
     // Config_Read_Pred_Master (:2694-2739)
     if (w.doPred && exists(w.dir + w.fPredMaster)) {

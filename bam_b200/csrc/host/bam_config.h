@@ -79,6 +79,7 @@ struct Workspace {
     double burnFactor = 0.5;
     int nSlim = 10;
     std::string summaryFile = "Results_Summary.txt", residualFile = "Results_Residuals.txt";
+    std::string dicFile, xtendedMcmcFile;  // optional 2nd / 3rd record of Config_Summary (Config_Read_Summary :2682-2687)
     std::vector<std::string> predConfigs;
 
     // flattened views handed to the C ABI (filled by finalize())

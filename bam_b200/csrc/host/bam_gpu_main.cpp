@@ -6,7 +6,8 @@
 // LoadBamObjects -> [MCMC -> cook] -> [summary] -> [predictions].  The reference runs ONE chain; here
 // `--chains K` runs K chains in lockstep on the GPU (K=1 is the like-for-like setting), Results_MCMC.txt
 // holds chain 1, the cooked file pools the burnt/slimmed rows of all chains and Results_Rhat.txt (new)
-// reports the Gelman-Rubin statistic.  Residual diagnostics and DIC are not written yet.
+// reports the Gelman-Rubin statistic.  Residual diagnostics (BaM_Residual) and DIC (BaM_computeDIC) re-use the
+// device kernels through bamgpu_calibration_run / bamgpu_logpost_parts.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -242,6 +243,94 @@ int main(int argc, char** argv) {
                 fprintf(f, "%s\n", line.c_str());
             }
             fclose(f);
+        }
+        if (w.doSummary && nCooked && !w.dicFile.empty()) {  // BaM_computeDIC (:1526-1682)
+            std::vector<double> X((size_t)nCooked * P), prior(nCooked), lkh(nCooked), hyper(nCooked), dev(nCooked);
+            std::vector<int32_t> feas(nCooked), isnull(nCooked);
+            for (size_t r = 0; r < nCooked; ++r) std::copy(cooked.begin() + r * rowlen, cooked.begin() + r * rowlen + P, X.begin() + r * P);
+            check(bamgpu_logpost_parts(h, (int)nCooked, X.data(), prior.data(), lkh.data(), hyper.data(), feas.data(), isnull.data(), mess), mess);
+            size_t best = 0;
+            for (size_t r = 0; r < nCooked; ++r) {
+                if (!feas[r] || isnull[r]) throw std::runtime_error("BaM_computeDIC: unfeasible or null prior / hyper density for an MCMC sample (BaM_Message 16/17)");
+                const double lp = cooked[r * rowlen + P];
+                lkh[r] = lp - prior[r] - hyper[r];  // :1634 -- from the stored log-posterior, as the reference does
+                dev[r] = -2.0 * lkh[r];
+                if (lp > cooked[best * rowlen + P]) best = r;
+            }
+            if (!w.xtendedMcmcFile.empty()) {
+                std::vector<std::string> hd(w.headers.begin(), w.headers.begin() + P);
+                for (auto s2 : {"LogPost", "LogPrior", "LogHyper", "LogLkh", "Deviance"}) hd.push_back(s2);
+                std::vector<double> ext(nCooked * (size_t)(P + 5));
+                for (size_t r = 0; r < nCooked; ++r) {
+                    double* o = ext.data() + r * (P + 5);
+                    std::copy(X.begin() + r * P, X.begin() + (r + 1) * P, o);
+                    o[P] = cooked[r * rowlen + P]; o[P + 1] = prior[r]; o[P + 2] = hyper[r]; o[P + 3] = lkh[r]; o[P + 4] = dev[r];
+                }
+                write_table(w.dir + w.xtendedMcmcFile, hd, ext, nCooked, P + 5);
+            }
+            double st[15];
+            stats15(dev, st);
+            const double Dmean = st[4], Dmed = st[5], Ds = st[10], Dvar = st[11], Dmax = dev[best];
+            FILE* f = fopen((w.dir + w.dicFile).c_str(), "w");
+            if (!f) throw std::runtime_error("problem opening file " + w.dir + w.dicFile);
+            const std::pair<const char*, double> rowsD[8] = {{"DIC1", 2.0 * Dmean - Dmax}, {"DIC2", Dmax + Dvar}, {"DIC3", Dmean + 0.5 * Dvar},
+                                                             {"D(maxpost)", Dmax}, {"E[D]", Dmean}, {"VAR[D]", Dvar},
+                                                             {"MEDIAN[D]", Dmed}, {"SDEV[D]", Ds}};
+            for (auto& rd : rowsD) fprintf(f, "%s%s\n", a15(rd.first).c_str(), e15_6(rd.second).c_str());
+            fclose(f);
+        }
+        if (w.doResidual && nCooked) {  // BaM_Residual (:754-878)
+            const size_t n = (size_t)w.nobs;
+            std::vector<double> Xtrue(n * w.nX), Ysim(n * w.nY), Yunb(w.Y), res(n * w.nY), stdres(n * w.nY);
+            int32_t feas = 0;
+            check(bamgpu_calibration_run(h, &pb, maxpost.data(), Xtrue.data(), Ysim.data(), &feas, mess), mess);
+            if (!feas) throw std::runtime_error("BaM_Residual: unfeasible [maxpost] parameter vector (BaM_Message 5)");
+            int k = sz.nFit + sz.nGamma + sz.nLatent + sz.nXbias;
+            for (int j = 0; j < w.nY; ++j) {  // un-biased outputs (:801-811)
+                int nyb = 0;
+                for (size_t i = 0; i < n; ++i) nyb = std::max(nyb, (int)w.Ybindx[i + j * n]);
+                if (!nyb) continue;
+                for (size_t i = 0; i < n; ++i)
+                    if (w.Ybindx[i + j * n] > 0 && w.Y[i + j * n] != -9999.0)
+                        Yunb[i + j * n] = w.Y[i + j * n] - w.Yb[i + j * n] * maxpost[k + w.Ybindx[i + j * n] - 1];
+                k += nyb;
+            }
+            k = sz.nFit;
+            for (int j = 0; j < w.nY; ++j) {  // residuals and standardised residuals (:816-830)
+                const double* g = maxpost.data() + k;
+                k += w.nremnant[j];
+                for (size_t i = 0; i < n; ++i) {
+                    const size_t q = i + j * n;
+                    if (w.Y[q] == -9999.0) { res[q] = stdres[q] = -9999.0; continue; }
+                    const double ys = Ysim[q], ay = std::fabs(ys);
+                    double sig;
+                    switch (w.sigmaFunc[j]) {  // Sigmafunk_Apply (:3521-3571)
+                        case BAMGPU_SIG_CONSTANT: sig = g[0]; break;
+                        case BAMGPU_SIG_LINEAR: sig = g[0] + g[1] * ay; break;
+                        case BAMGPU_SIG_PROPORTIONAL: sig = g[0] * ay; break;
+                        case BAMGPU_SIG_POWER: sig = g[0] + g[1] * std::pow(ay, g[2]); break;
+                        case BAMGPU_SIG_EXPONENTIAL: sig = g[0] + (g[2] - g[0]) * (1.0 - std::exp(-(ay / g[1]))); break;
+                        default: sig = g[0] + (g[2] - g[0]) * (1.0 - std::exp(-((ay / g[1]) * (ay / g[1])))); break;
+                    }
+                    res[q] = Yunb[q] - ys;
+                    stdres[q] = res[q] / std::sqrt(sig * sig + w.Yu[q] * w.Yu[q]);
+                }
+            }
+            std::vector<std::string> hd;
+            for (int i = 1; i <= w.nX; ++i) hd.push_back("X" + std::to_string(i) + "_obs");
+            for (int i = 1; i <= w.nX; ++i) hd.push_back("X" + std::to_string(i) + "_true");
+            for (auto sfx : {"_obs", "_unbiased", "_sim", "_res", "_stdres"})
+                for (int i = 1; i <= w.nY; ++i) hd.push_back("Y" + std::to_string(i) + sfx);
+            const size_t ncol = hd.size();
+            std::vector<double> tab(n * ncol);
+            for (size_t i = 0; i < n; ++i) {
+                size_t c = 0;
+                for (int j = 0; j < w.nX; ++j) tab[i * ncol + c++] = w.X[i + j * n];
+                for (int j = 0; j < w.nX; ++j) tab[i * ncol + c++] = Xtrue[i + j * n];
+                for (const std::vector<double>* src : {&w.Y, &Yunb, &Ysim, &res, &stdres})
+                    for (int j = 0; j < w.nY; ++j) tab[i * ncol + c++] = (*src)[i + j * n];
+            }
+            write_table(w.dir + w.residualFile, hd, tab, n, ncol);
         }
         // prediction experiments (src/BaM_main.f90:449-530)
         for (auto& pf : w.predConfigs) {

@@ -154,7 +154,8 @@ int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s);
 /* global index of this handle's chain 0 (multi-GPU: chains are sharded across ranks and the RNG
    streams are keyed by the GLOBAL chain index, so results do not depend on the GPU count) */
 int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset);
-/* tuning / test switches: "force_generic" (1 = never use the specialised fast kernels). err=1 if unknown. */
+/* tuning / test switches: "force_generic" (1 = never use the specialised fast kernels), "no_select3" (1 = skip the
+   2-read envelope selection).  err=1 if unknown. */
 int bamgpu_set_option(bamgpu_t* h, const char* name, int value);
 
 /* name -> enum helpers (return 0 when the name is unknown) */
@@ -177,6 +178,13 @@ int bamgpu_logpost(bamgpu_t* h, int K, const double* x, double* fx, int32_t* fea
 /* prior / likelihood / hyper split, for DIC (src/BaM_tools.f90:1626-1646) and tests */
 int bamgpu_logpost_parts(bamgpu_t* h, int K, const double* x, double* prior, double* lkh, double* hyper,
                          int32_t* feas, int32_t* isnull, char* mess);
+
+/* replaces GetSim_calibration (src/BaM_tools.f90:3619-3680), the model run behind BaM_Residual (:754-878):
+   one vector x (P) through the model on the calibration inputs of `p` (the same description the handle was created
+   from; caller order).  Xtrue (nobs x nX, may be NULL) receives the unfolded "true" inputs, Ysim (nobs x nY) the
+   outputs (rows of unfeas_flag where the model is infeasible); *feas = 1 iff every row is feasible. */
+int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* p, const double* x, double* Xtrue, double* Ysim,
+                           int32_t* feas, char* mess);
 
 /* resident variant: upload once, evaluate many times with everything in HBM */
 int bamgpu_chains_upload(bamgpu_t* h, int K, const double* x, char* mess);

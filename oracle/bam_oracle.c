@@ -1365,6 +1365,30 @@ done:
     return err > 0 ? err : 0;
 }
 
+/* GetSim_calibration (src/BaM_tools.f90:3619-3680): Xtrue (n x nX) and Ysim (n x nY) for one vector */
+int oracle_calibration_run(const oracle_t* o, const double* x, double* Xtrue, double* Ysim, int32_t* feas_out, char* mess) {
+    int n = o->n, nX = o->nX;
+    if (mess) mess[0] = 0;
+    double* xt = (double*)malloc(((size_t)n * nX + 1) * 8);
+    memcpy(xt, o->X, (size_t)n * nX * 8);
+    for (int j = 0; j < nX; ++j)
+        for (int i = 0; i < n; ++i) {
+            size_t q = i + (size_t)j * n;
+            if (o->latIdx[q] >= 0) xt[q] = x[o->latIdx[q]];
+            else if (o->nXb[j] > 0 && o->Xbindx[q] > 0) xt[q] = o->X[q] - o->Xb[q] * x[o->off_xb[j] + o->Xbindx[q] - 1];
+        }
+    if (Xtrue) memcpy(Xtrue, xt, (size_t)n * nX * 8);
+    double* dpar = (double*)malloc(((size_t)o->nDpar + 1) * 8);
+    int32_t* vfeas = (int32_t*)malloc(((size_t)n + 1) * 4);
+    int feas = 1;
+    for (size_t q = 0; q < (size_t)n * o->nY; ++q) Ysim[q] = o->unfeas;
+    int e = apply_model_bam(o, xt, x, Ysim, dpar, vfeas, &feas);
+    *feas_out = feas;
+    free(xt); free(dpar); free(vfeas);
+    if (e > 0) setmess(mess, "oracle: ApplyModel failed");
+    return e > 0 ? e : 0;
+}
+
 int oracle_logpost_batch(const oracle_t* o, int K, const double* x, double* fx, int32_t* feas, int32_t* isnull,
                          double* dpar, int nthreads, char* mess) {
     int err = 0;

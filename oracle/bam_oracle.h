@@ -37,6 +37,9 @@ int oracle_get_sizes(const oracle_t* o, bamgpu_sizes* s);
 int oracle_logpost(const oracle_t* o, const double* x, double* fx, double* prior, double* lkh, double* hyper,
                    int32_t* feas, int32_t* isnull, double* dpar, int use_long_double, char* mess);
 
+/* GetSim_calibration (src/BaM_tools.f90:3619-3680) */
+int oracle_calibration_run(const oracle_t* o, const double* x, double* Xtrue, double* Ysim, int32_t* feas, char* mess);
+
 /* K vectors (P x K), nthreads OpenMP threads over vectors (1 = the serial reference analogue). */
 int oracle_logpost_batch(const oracle_t* o, int K, const double* x, double* fx, int32_t* feas, int32_t* isnull,
                          double* dpar, int nthreads, char* mess);

@@ -40,6 +40,7 @@ def load():
     lib.oracle_logpost.argtypes = [H, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, ci, cp]
     lib.oracle_logpost_batch.argtypes = [H, ci, _dp, _dp, _ip, _ip, _dp, ci, cp]
     lib.oracle_apply_model.argtypes = [H, ci, _dp, _dp, _dp, _dp, _ip, cp]
+    lib.oracle_calibration_run.argtypes = [H, _dp, _dp, _dp, _ip, cp]
     lib.oracle_predict.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, ci, _ip, u64, ci, ci, _dp, _dp, ci, cp]
     lib.oracle_envelope.argtypes = [_dp, i64, d, _dp]
     lib.oracle_envelope.restype = None
@@ -122,6 +123,16 @@ class Oracle:
         r = [self.logpost_one(v, long_double) for v in x]
         g = lambda k: np.array([q[k] for q in r])  # noqa: E731
         return g("prior"), g("lkh"), g("hyper"), g("feas").astype(np.int32), g("isnull").astype(np.int32)
+
+    def calibration_run(self, x):
+        pr = self.problem
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        Xtrue = np.empty((pr.nobs, pr.nX), order="F")
+        Ysim = np.empty((pr.nobs, pr.nY), order="F")
+        feas = C.c_int32(0)
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(self.lib.oracle_calibration_run(self.h, _ptr_d(x), _ptr_d(Xtrue), _ptr_d(Ysim), C.byref(feas), mess), mess)
+        return Xtrue, Ysim, bool(feas.value)
 
     def apply_model(self, X, theta_fit):
         X = np.asarray(X, dtype=np.float64)

@@ -131,3 +131,56 @@ def test_full_run_writes_reference_files(tmp_path):
     mp = np.loadtxt(os.path.join(ws, "Y_2.spag"))
     assert mp.shape == (41,) and not os.path.exists(os.path.join(ws, "Y_2.env"))  # maxpost: Nrep = 1, no envelope
     assert np.loadtxt(os.path.join(ws, "Y_3.spag")).shape == (41, 50)  # prior prediction with nsim = 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["baratin", "textfile_inputuncertainty", "baratin_spd"])
+def test_residuals_and_dic_files(name, tmp_path):
+    """BaM_Residual (:754-878) and BaM_computeDIC (:1526-1682) on top of the device kernels: the residual table
+    against the oracle's calibration run at the written maxpost, the DIC identities against the extended MCMC."""
+    from bam_b200.capi import BamGpu
+    from oracle.oracle_api import Oracle
+    from tests.helpers import problem_from_fixture
+
+    fx = load_fixture(name)
+    cfg, ws = write_workspace(fx, str(tmp_path), name="RD", nAdapt=10, nCycles=6, do_dic=True, do_residual=True)
+    r = subprocess.run([EXE, "-cf", cfg, "-sd", "3", "--chains", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    prob, _ = problem_from_fixture(name)
+    o = Oracle(prob)
+    P = o.P
+    head, cooked = read_table(os.path.join(ws, "Results_MCMC_Cooked.txt"))
+    # ---- DIC
+    hx, ext = read_table(os.path.join(ws, "Results_MCMC_Xtended.txt"))
+    assert hx[P:] == ["LogPost", "LogPrior", "LogHyper", "LogLkh", "Deviance"] and ext.shape == (cooked.shape[0], P + 5)
+    lp, pr, hy, lk, dev = (ext[:, P + i] for i in range(5))
+    assert np.allclose(lk, lp - pr - hy, rtol=1e-5, atol=2e-3) and np.allclose(dev, -2 * lk, rtol=1e-5)  # e15.6: 6 digits
+    opr, olk, ohy, ofe, onu = o.logpost_parts(cooked[:6, :P])  # the file holds 7 digits of every parameter
+    assert ofe.all()
+    dic = dict((ln[:15].strip(), float(ln[15:])) for ln in open(os.path.join(ws, "Results_DIC.txt")).read().splitlines())
+    assert list(dic) == ["DIC1", "DIC2", "DIC3", "D(maxpost)", "E[D]", "VAR[D]", "MEDIAN[D]", "SDEV[D]"]
+    k = int(np.argmax(lp))
+    assert np.isclose(dic["E[D]"], dev.mean(), rtol=1e-5) and np.isclose(dic["VAR[D]"], dev.var(ddof=1), rtol=1e-4)
+    assert np.isclose(dic["D(maxpost)"], dev[k], rtol=1e-5)
+    assert np.isclose(dic["DIC1"], 2 * dic["E[D]"] - dic["D(maxpost)"], rtol=1e-5)
+    assert np.isclose(dic["DIC3"], 0.5 * (dic["DIC1"] + dic["DIC2"]), rtol=1e-5)
+    # ---- residuals: device calibration run vs oracle at full precision, then the written table
+    g = BamGpu(prob)
+    x = cooked[k, :P]
+    Xt, Ys, feas = g.calibration_run(x)
+    oXt, oYs, ofeas = o.calibration_run(x)
+    assert feas and ofeas and np.array_equal(Xt, oXt)
+    assert np.allclose(Ys, oYs, rtol=1e-12, atol=1e-300)
+    hr, res = read_table(os.path.join(ws, "Results_Residuals.txt"))
+    nX, nY, n = prob.nX, prob.nY, prob.nobs
+    assert res.shape == (n, 2 * nX + 5 * nY) and hr[0] == "X1_obs" and hr[-1] == f"Y{nY}_stdres"
+    Ysim_file = res[:, 2 * nX + 2 * nY:2 * nX + 3 * nY]
+    # the driver's maxpost carries full precision, the cooked file 7 digits: compare loosely with the oracle run
+    ok = np.asarray(prob.Y) != -9999.0
+    assert np.allclose(Ysim_file, oYs, rtol=2e-3, atol=1e-6)
+    resid = res[:, 2 * nX + 3 * nY:2 * nX + 4 * nY]
+    yunb = res[:, 2 * nX + nY:2 * nX + 2 * nY]
+    assert np.allclose(resid[ok], (yunb - Ysim_file)[ok], rtol=1e-4, atol=1e-5 * np.abs(yunb[ok]).max())
+    assert (resid[~ok] == -9999.0).all()
+    std = res[:, 2 * nX + 4 * nY:]
+    assert np.isfinite(std[ok]).all() and np.abs(std[ok]).max() < 50

@@ -12,7 +12,7 @@ def _par_block(name, init, dist, pars):
 
 
 def write_workspace(fx: dict, root: str, name: str = "WS", nAdapt=None, nCycles=None, do_pred=False, pred=None,
-                    windows_paths=True):
+                    windows_paths=True, do_dic=False, do_residual=False):
     ws = os.path.join(root, name)
     os.makedirs(ws, exist_ok=True)
     n, nX, nY = fx["nobs"], fx["nX"], fx["nY"]
@@ -112,9 +112,11 @@ def write_workspace(fx: dict, root: str, name: str = "WS", nAdapt=None, nCycles=
         repr(m["MaxMoveRate"]), repr(m["DownMult"]), repr(m["UpMult"]), "0", "**** cosmetics ****",
         repr(m["MultFactor"]), "0.1", "0.1"]) + "\n")
     open(os.path.join(ws, "Config_Cooking.txt"), "w").write('"Results_MCMC_Cooked.txt"\n0.5\n2\n')
-    open(os.path.join(ws, "Config_Summary.txt"), "w").write('"Results_Summary.txt"\n')
+    open(os.path.join(ws, "Config_Summary.txt"), "w").write(
+        '"Results_Summary.txt"\n' + ('"Results_DIC.txt"\n"Results_MCMC_Xtended.txt"\n' if do_dic else ""))
     open(os.path.join(ws, "Config_Residuals.txt"), "w").write('"Results_Residuals.txt"\n')
-    open(os.path.join(ws, "Config_RunOptions.txt"), "w").write(f".true.\n.true.\n.false.\n{'.true.' if do_pred else '.false.'}\n")
+    open(os.path.join(ws, "Config_RunOptions.txt"), "w").write(
+        f".true.\n.true.\n{'.true.' if do_residual else '.false.'}\n{'.true.' if do_pred else '.false.'}\n")
     plines = ["0"]
     if do_pred and pred:
         plines = [str(len(pred))]
