@@ -1162,11 +1162,17 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     }
     PredFastKernel fastK = (!h->forceGeneric && p.nX == 1 && p.nY == 1) ? pick_pred_fast(p, anyRem, Nrep) : nullptr;
     BAM_CUDA(cudaEventRecord(h->ev0, s));
-    cudaEvent_t k0 = nullptr, k1 = nullptr;
-    if (h->recordKernels && h->kernEv.size() < 8192) { k0 = take_event(h); k1 = take_event(h); BAM_CUDA(cudaEventRecord(k0, s)); }
+    // measurement: per tile two bracketed intervals, [propagation kernel] and [envelope kernels]
+    auto mark = [&]() -> cudaEvent_t {
+        if (!h->recordKernels || h->kernEv.size() >= 8192) return nullptr;
+        cudaEvent_t e = take_event(h);
+        BAM_CUDA(cudaEventRecord(e, s));
+        return e;
+    };
     for (int tt = 0; tt < nTall; tt += (int)tileT) {
         const int nT = std::min<long long>(tileT, nTall - tt);
         a.t0 = t0 + tt; a.nT = nT;
+        cudaEvent_t kp0 = mark();
         if (fastK) {
             dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + PF_TT - 1) / PF_TT);
             fastK<<<grid, BAM_BLOCK, PF_SMEM, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspag[0], h->predNspag[0], h->d_V);
@@ -1175,7 +1181,10 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             kern<<<grid, BAM_BLOCK, smemMain, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspagPtrs, h->d_nspag, h->d_V);
         }
         h->launches += 1;
+        cudaEvent_t kp1 = mark();
+        if (kp0 && kp1) h->kernEv.emplace_back(kp0, kp1);
         if (Nrep >= 2) {
+            cudaEvent_t ke0 = mark();
             // envelopes of this tile go to a compact [y][7][nT] scratch, then into the full [y][7][nTall] array
             double* envTile = nullptr;
             BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nY, s));
@@ -1195,6 +1204,8 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                 h->launches += 1;
             }
             h->launches += 1;
+            cudaEvent_t ke1 = mark();
+            if (ke0 && ke1) h->kernEv.emplace_back(ke0, ke1);
             for (int y = 0; y < nY; ++y)
                 BAM_CUDA(cudaMemcpy2DAsync(h->d_env + ((size_t)y * BAMGPU_NENV * nTall + tt), sizeof(double) * nTall,
                                            envTile + (size_t)y * BAMGPU_NENV * nT, sizeof(double) * nT,
@@ -1209,7 +1220,6 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         }
     }
     BAM_CUDA(cudaEventRecord(h->ev1, s));
-    if (k1) { BAM_CUDA(cudaEventRecord(k1, s)); h->kernEv.emplace_back(k0, k1); }
     BAM_CUDA(cudaGetLastError());
 }
 

@@ -479,12 +479,16 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
         a.x = h->d_x; a.sd = h->d_std; a.fxcur = h->d_fxcur; a.dparcur = h->d_dparcur;
         a.rows = storeRows ? h->d_rows : nullptr; a.mcount = h->d_mcount; a.mmean = h->d_mmean; a.mm2 = h->d_mm2;
         a.moves = h->d_moves;
+        cudaEvent_t f0 = take_event(h), f1 = take_event(h);  // the iterations as one timed "step" (bamgpu_step_times)
+        BAM_CUDA(cudaEventRecord(f0, s));
         for (int cyc = 0; cyc < nCycles; ++cyc) {
             a.it0 = (long long)cyc * nAdapt;
             a.nIterChunk = nAdapt;
             wk<<<(K + WS_WARPS - 1) / WS_WARPS, 32 * WS_WARPS, wsSmem, s>>>(p, a);
             h->launches += 1;
         }
+        BAM_CUDA(cudaEventRecord(f1, s));
+        if (h->stepEv.size() < 8192) h->stepEv.emplace_back(f0, f1);
         BAM_CUDA(cudaGetLastError());
         BAM_CUDA(cudaMemcpyAsync(h->d_fx, h->d_fxcur, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
         BAM_CUDA(cudaMemcpyAsync(h->d_dpar, h->d_dparcur, sizeof(double) * (size_t)K * std::max(nD, 1), cudaMemcpyDeviceToDevice, s));
@@ -505,6 +509,8 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
         h->launches += 2;
     };
     long long it = 0, kept = 0;
+    cudaEvent_t f0 = take_event(h), f1 = take_event(h);  // the iterations as one timed "step" (bamgpu_step_times)
+    BAM_CUDA(cudaEventRecord(f0, s));
     for (int cyc = 0; cyc < nCycles; ++cyc) {
         for (int a = 0; a < nAdapt; ++a, ++it) {
             for (int i = 0; i < (lk ? latBeg : P); ++i) propose_one(i, it);
@@ -534,6 +540,8 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
         h->launches += 1;
         BAM_CUDA(cudaGetLastError());
     }
+    BAM_CUDA(cudaEventRecord(f1, s));
+    if (h->stepEv.size() < 8192) h->stepEv.emplace_back(f0, f1);
     // leave the final state consistent for bamgpu_chains_download
     BAM_CUDA(cudaMemcpyAsync(h->d_fx, h->d_fxcur, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
     BAM_CUDA(cudaMemcpyAsync(h->d_dpar, h->d_dparcur, sizeof(double) * (size_t)K * std::max(nD, 1), cudaMemcpyDeviceToDevice, s));

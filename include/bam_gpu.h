@@ -198,7 +198,8 @@ int bamgpu_sync(bamgpu_t* h, char* mess);
    Rows kept: iterations it with it > burn and (it-burn) % keep_every == 0 (it = 1..nAdapt*nCycles);
    out_rows is (P + 1 + nDpar) x nKeep x K (chain-major blocks; row = [x, logpost, dpar]) or NULL.
    Final states are left resident (bamgpu_chains_download) and running per-chain moments of the
-   kept rows are accumulated for bamgpu_moments. */
+   kept rows are accumulated for bamgpu_moments.  The device time of the iteration loop is recorded as one
+   step (bamgpu_step_times). */
 int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std, int nAdapt, int nCycles,
                double MinMoveRate, double MaxMoveRate, double DownMult, double UpMult, uint64_t seed,
                int burn, int keep_every, double* out_rows, int64_t* n_keep, char* mess);
