@@ -77,6 +77,20 @@ interface
         type(c_ptr), intent(in) :: xspag(*); integer(c_int), intent(in) :: nspag(*), doRemnant(*)
         type(c_ptr), value :: env, spag; character(kind=c_char) :: mess(*)
     end function
+    ! prior / likelihood / hyper split of K vectors: the loop body of BaM_computeDIC (src/BaM_tools.f90:1626-1646)
+    integer(c_int) function bamgpu_logpost_parts(h, K, x, prior, lkh, hyper, feas, isnull, mess) &
+                                                 bind(C, name='bamgpu_logpost_parts')
+        import; type(c_ptr), value :: h; integer(c_int), value :: K
+        real(c_double), intent(in) :: x(*); real(c_double), intent(out) :: prior(*), lkh(*), hyper(*)
+        integer(c_int), intent(out) :: feas(*), isnull(*); character(kind=c_char) :: mess(*)
+    end function
+    ! replaces GetSim_calibration (src/BaM_tools.f90:3619-3680), the model run behind BaM_Residual (:794)
+    integer(c_int) function bamgpu_calibration_run(h, p, x, Xtrue, Ysim, feas, mess) &
+                                                   bind(C, name='bamgpu_calibration_run')
+        import; type(c_ptr), value :: h; type(bamgpu_problem), intent(in) :: p
+        real(c_double), intent(in) :: x(*); real(c_double), intent(out) :: Xtrue(*), Ysim(*)
+        integer(c_int), intent(out) :: feas; character(kind=c_char) :: mess(*)
+    end function
     integer(c_int) function bamgpu_moments(h, cnt, mean, m2, dev_ptrs, mess) bind(C, name='bamgpu_moments')
         import; type(c_ptr), value :: h; real(c_double), intent(out) :: cnt(*), mean(*), m2(*)
         integer(c_int), value :: dev_ptrs; character(kind=c_char) :: mess(*)
