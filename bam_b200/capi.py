@@ -36,6 +36,8 @@ SED_FORMULA = {"MPM": 1, "Camenen": 2, "Nielsen": 3, "Smart": 4}
 SED_CSS = {"Constant": 1, "Soulsby": 2, "SoulsbyWhitehouse": 3}
 SED_PPO = {"FIX": 1, "IN": 2, "PAR": 3}
 SED_CO = {"FIX": 1, "PAR": 2}
+SWOT_ID = {"SWOT_hS": 1, "SWOT_hSB": 2}
+ORTHO_DISTO = {"None": 1, "Radial": 2}
 VEG_GROWTH = {"Growth_Yin1": 1, "Growth_Yin2": 2, "Growth_Yin3": 3, "Growth_Yin1_temporal": 4}
 
 _dp = C.POINTER(C.c_double)

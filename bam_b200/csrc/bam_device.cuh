@@ -63,6 +63,8 @@ struct DevProblem {
     const int* vmCode;
     const double* vmImmed;
     int vmNcode[BAM_MAXY], vmCodeOff[BAM_MAXY], vmImmedOff[BAM_MAXY], vmNin, vmNpar;
+    // SWOT {variant}, Orthorectification {distortion id, npar}
+    int modelOpt[4];
     // Vegetation
     int vegGrowth, vegNYear, vegItmax;
     double vegXscale, vegFscale, vegTolX, vegTolF;

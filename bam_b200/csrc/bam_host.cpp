@@ -23,6 +23,11 @@ int model_from_name(const char* name) {
     if (s == "Sediment") return BAMGPU_MDL_SEDIMENT;
     if (s == "TextFile") return BAMGPU_MDL_TEXTFILE;
     if (s == "Vegetation") return BAMGPU_MDL_VEGETATION;
+    if (s == "SuspendedLoad") return BAMGPU_MDL_SUSPENDEDLOAD;
+    if (s == "SWOT") return BAMGPU_MDL_SWOT;
+    if (s == "SGD") return BAMGPU_MDL_SGD;
+    if (s == "Orthorectification") return BAMGPU_MDL_ORTHO;
+    if (s == "Recession_h") return BAMGPU_MDL_RECESSION_H;
     return 0;
 }
 
@@ -474,7 +479,31 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             break;
         }
     }
+    switch (L.model) {  // second-wave pointwise models (GetParNumber / XtraRead of each module)
+        case BAMGPU_MDL_SUSPENDEDLOAD:
+            if (nt != 5 || nX != 1 || nY != 1) { mess = "SuspendedLoad_Apply: wrong size [theta], nX or nY"; return 1; }
+            break;
+        case BAMGPU_MDL_SGD:
+            if (nt != 5 || nX != 2 || nY != 1) { mess = "SGD_Apply: wrong size [theta], nX or nY"; return 1; }
+            break;
+        case BAMGPU_MDL_RECESSION_H:
+            if (nt != 4 || nX != 1 || nY != 1) { mess = "Recession_h_Apply: wrong size [theta], nX or nY"; return 1; }
+            break;
+        case BAMGPU_MDL_SWOT:
+            if (p.n_xtra_i != 1 || (p.xtra_i[0] != BAMGPU_SWOT_HS && p.xtra_i[0] != BAMGPU_SWOT_HSB)) { mess = "SWOT_Apply: Fatal: Unavailable [ID]"; return 1; }
+            L.modelOpt[0] = p.xtra_i[0];
+            if (nt != 5 || nX != (p.xtra_i[0] == BAMGPU_SWOT_HS ? 2 : 3) || nY != 1) { mess = "SWOT_Apply: wrong size [theta], nX or nY"; return 1; }
+            break;
+        case BAMGPU_MDL_ORTHO:
+            if (p.n_xtra_i != 2 || (p.xtra_i[0] != BAMGPU_DISTO_NONE && p.xtra_i[0] != BAMGPU_DISTO_RADIAL) || p.xtra_i[1] < 0) { mess = "Disto_Apply:Fatal:Unavailable [Disto_ID]"; return 1; }
+            L.modelOpt[0] = p.xtra_i[0]; L.modelOpt[1] = p.xtra_i[1];
+            if (nt != 11 + p.xtra_i[1] || nX != 3 || nY != 2) { mess = "Ortho_Apply: wrong size [theta], nX or nY"; return 1; }
+            L.nDparModel = 20;  // rotation matrix + ortho parameters (ModelLibrary_tools.f90:608-613)
+            break;
+        default: break;
+    }
     if (L.model == BAMGPU_MDL_BARATIN) L.nDer = 2 * L.ncontrol;  // b_i and log a_i
+    else if (L.model == BAMGPU_MDL_ORTHO) L.nDer = 22;           // Dpar + the two focal lengths in pixels
     else if (L.model != BAMGPU_MDL_VEGETATION) L.nDer = L.nDparModel;
 
     // VAR combinations in order of first appearance (:346-379); L(t,i) = offset_i + indx_i(t) (:326-334)

@@ -53,6 +53,7 @@ struct HostLayout {
     int vmMaxStack = 0;
     int vegGrowth = 0, vegNYear = 0, vegItmax = 0;
     double vegOpt[4] = {0, 0, 0, 0};  // xscale, fscale, tolX, tolF
+    int modelOpt[4] = {0, 0, 0, 0};  // SWOT: {variant}; Orthorectification: {distortion id, number of distortion parameters}
     int nDer = 0;  // derived values per (parameter set, combination) kept in the device table
 };
 

@@ -382,6 +382,96 @@ __device__ inline bool vegetation_apply(const DevProblem& p, const double* in, c
 }
 
 // -------------------------------------------------------------------------------------------
+// Second-wave pointwise models
+// -------------------------------------------------------------------------------------------
+
+// SuspendedLoad_Apply (SuspendedLoad_model.f90:38-116): Qs = t1 (h-t2)^t3 / (h-t4)^t5
+__device__ __forceinline__ bool suspendedload_apply(double h, const double* __restrict__ th, double& out) {
+    if (h < th[1] || h < th[3]) return false;
+    const double num = pow(h - th[1], th[2]), den = pow(h - th[3], th[4]);
+    out = th[0] * (num / den);
+    return true;
+}
+
+// SWOT_Apply (SWOT_model.f90:73-148): Q = K (B-B0) sqrt(S-S0) (h-h0)^M ; variant hS: B = theta2, B0 = 0
+template <int NX>
+__device__ __forceinline__ bool swot_apply(const DevProblem& p, const double* in, const double* __restrict__ th, double& out) {
+    const double K = th[0], S0 = th[2], h0 = th[3], M = th[4];
+    double Bt, B0;
+    if (p.modelOpt[0] == BAMGPU_SWOT_HS) { Bt = th[1]; B0 = 0.0; }
+    else { Bt = in[NX > 2 ? 2 : 0]; B0 = th[1]; }
+    if (Bt - B0 < 0.0 || in[1] - S0 < 0.0) return false;
+    if (in[0] - h0 <= 0.0) { out = 0.0; return true; }
+    out = K * (Bt - B0) * sqrt(in[1] - S0) * pow(in[0] - h0, M);
+    return true;
+}
+
+// SGD_Apply (StageGradientDischarge_model.f90:57-113)
+__device__ __forceinline__ bool sgd_apply(const double* in, const double* __restrict__ th, double& out) {
+    const double K = th[0], B = th[1], S0 = th[2], h0 = th[3], M = th[4];
+    const double h = in[0], dhdt = in[1];
+    if (h - h0 <= 0.0) return false;
+    const double Q0 = K * B * sqrt(S0) * pow(h - h0, M);
+    const double c = M * K * sqrt(S0) * pow(h - h0, M - 1.0);
+    const double corr = 1.0 + (1.0 / (c * S0)) * dhdt;
+    if (corr <= 0.0) return false;
+    out = Q0 * sqrt(corr);
+    return true;
+}
+
+// Recession_h_Apply (Recession_model.f90:36-94): normalised two-exponential recession
+__device__ __forceinline__ bool recession_apply(double t, const double* __restrict__ th, double& out) {
+    out = th[0] * exp(-th[1] * t) + (1.0 - th[0] - th[2]) * exp(-th[3] * t) + th[2];
+    return true;
+}
+
+// Ortho_Apply (Orthorectification_model.f90:66-190).  der[0..19] = Dpar (r11..r33, a1..a4, b1..b4, c1..c3),
+// der[20] = f / pixel width, der[21] = f / pixel height.
+__device__ inline bool ortho_prepare(const double* th, double* der) {
+    const double x0 = th[0], y0 = th[1], z0 = th[2], azim = th[3], roll = th[4], tilt = th[5], f = th[6], c0 = th[7],
+                 l0 = th[8], lambda = th[9], k = th[10];
+    const double pc = lambda, pl = k * pc;
+    if (pc <= 0.0 || pl <= 0.0 || k <= 0.0) return false;
+    const double ac = f / pc, al = f / pl;
+    const double r11 = cos(azim) * cos(roll) + sin(azim) * cos(tilt) * sin(roll);
+    const double r12 = -1.0 * sin(azim) * cos(roll) + cos(azim) * cos(tilt) * sin(roll);
+    const double r13 = sin(tilt) * sin(roll);
+    const double r21 = -1.0 * cos(azim) * sin(roll) + sin(azim) * cos(tilt) * cos(roll);
+    const double r22 = sin(azim) * sin(roll) + cos(azim) * cos(tilt) * cos(roll);
+    const double r23 = sin(tilt) * cos(roll);
+    const double r31 = sin(azim) * sin(tilt), r32 = cos(azim) * sin(tilt), r33 = -1.0 * cos(tilt);
+    const double alpha = r31 * x0 + r32 * y0 + r33 * z0;
+    if (alpha == 0.0) return false;
+    const double a1 = (ac * r21 - r31 * c0) / alpha, a2 = (ac * r22 - r32 * c0) / alpha, a3 = (ac * r23 - r33 * c0) / alpha;
+    const double a4 = -1.0 * (a1 * x0 + a2 * y0 + a3 * z0);
+    const double b1 = (al * r11 - r31 * l0) / alpha, b2 = (al * r12 - r32 * l0) / alpha, b3 = (al * r13 - r33 * l0) / alpha;
+    const double b4 = -1.0 * (b1 * x0 + b2 * y0 + b3 * z0);
+    const double vals[22] = {r11, r12, r13, r21, r22, r23, r31, r32, r33, a1, a2, a3, a4, b1, b2, b3, b4,
+                             -1.0 * r31 / alpha, -1.0 * r32 / alpha, -1.0 * r33 / alpha, ac, al};
+    for (int i = 0; i < 22; ++i) der[i] = vals[i];
+    return true;
+}
+
+__device__ inline bool ortho_apply(const DevProblem& p, const double* in, const double* __restrict__ th,
+                                   const double* __restrict__ der, double* out) {
+    const double dx = in[0] - th[0], dy = in[1] - th[1], dz = in[2] - th[2];
+    const double denom = der[6] * dx + der[7] * dy + der[8] * dz;
+    if (denom == 0.0) return false;
+    const double c0 = th[7], l0 = th[8];
+    const double c = c0 - der[20] * (der[3] * dx + der[4] * dy + der[5] * dz) / denom;
+    const double l = l0 - der[21] * (der[0] * dx + der[1] * dy + der[2] * dz) / denom;
+    if (p.modelOpt[0] == BAMGPU_DISTO_NONE) { out[0] = c; out[1] = l; return true; }
+    // Disto_Apply, radial (:271-280): d = 1 + sum_i theta(11+i) r^(2i)
+    const double r = sqrt((c - c0) * (c - c0) + (l - l0) * (l - l0));
+    const double r2 = r * r;
+    double d = 1.0, rp = 1.0;
+    for (int i = 0; i < p.modelOpt[1]; ++i) { rp = rp * r2; d = d + th[11 + i] * rp; }
+    out[0] = c0 + d * (c - c0);
+    out[1] = l0 + d * (l - l0);
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
 // dispatch
 // -------------------------------------------------------------------------------------------
 
@@ -391,6 +481,11 @@ __device__ inline bool model_prepare(const DevProblem& p, const double* th, doub
                                      int nser) {
     if (p.model == BAMGPU_MDL_BARATIN) return baratin_prepare(p, th, der);
     if (p.model == BAMGPU_MDL_VEGETATION) return vegetation_prepare(p, th, der, xc, nser);
+    if (p.model == BAMGPU_MDL_ORTHO) return ortho_prepare(th, der);
+    // parameter-set feasibility of the pointwise second-wave models
+    if (p.model == BAMGPU_MDL_SUSPENDEDLOAD) return !(th[0] <= 0.0 || th[2] <= 0.0 || th[4] <= 0.0);  // SuspendedLoad_model.f90:96-99
+    if (p.model == BAMGPU_MDL_SWOT) return !(th[0] <= 0.0 || th[4] <= 0.0);                             // SWOT_model.f90:128-130
+    if (p.model == BAMGPU_MDL_SGD) return !(th[0] <= 0.0 || th[4] <= 0.0 || th[1] <= 0.0 || th[2] <= 0.0);  // SGD :94-96
     return true;
 }
 
@@ -407,6 +502,16 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return sediment_apply<NX>(p, x, th, y[0]);
     } else if (MODEL == BAMGPU_MDL_VEGETATION) {
         return vegetation_apply<NX, NY>(p, x, th, der, y);
+    } else if (MODEL == BAMGPU_MDL_SUSPENDEDLOAD) {
+        return suspendedload_apply(x[0], th, y[0]);
+    } else if (MODEL == BAMGPU_MDL_SWOT) {
+        return swot_apply<NX>(p, x, th, y[0]);
+    } else if (MODEL == BAMGPU_MDL_SGD) {
+        return sgd_apply(x, th, y[0]);
+    } else if (MODEL == BAMGPU_MDL_RECESSION_H) {
+        return recession_apply(x[0], th, y[0]);
+    } else if (MODEL == BAMGPU_MDL_ORTHO) {
+        return ortho_apply(p, x, th, der, y);
     } else {
         bool ok = true;
 #pragma unroll

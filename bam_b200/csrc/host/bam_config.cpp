@@ -354,7 +354,20 @@ void load_workspace(const std::string& configFile, Workspace& w) {
         w.xtraI.push_back(s.integer());                          // nYear
         for (int k = 0; k < 4; ++k) w.xtraD.push_back(s.num());  // Newton xscale, fscale, tolX, tolF (one per line)
         w.xtraI.push_back(s.integer());                          // Newton itmax
-    } else if (w.modelID == "Linear") {
+    } else if (w.modelID == "SWOT") {  // SWOT_XtraRead (SWOT_model.f90:150-182): model variant
+        Cursor s(xf);
+        const std::string id = s.str();
+        if (id == "SWOT_hS") w.xtraI.push_back(BAMGPU_SWOT_HS);
+        else if (id == "SWOT_hSB") w.xtraI.push_back(BAMGPU_SWOT_HSB);
+        else fail("SWOT_Apply: Fatal: Unavailable [ID] '" + id + "'");
+    } else if (w.modelID == "Orthorectification") {  // Ortho_XtraRead (Orthorectification_model.f90:192-230)
+        Cursor s(xf);
+        const std::string id = s.str();
+        if (id == "None") w.xtraI.push_back(BAMGPU_DISTO_NONE);
+        else if (id == "Radial") w.xtraI.push_back(BAMGPU_DISTO_RADIAL);
+        else fail("Disto_Apply:Fatal:Unavailable [Disto_ID] '" + id + "'");
+        w.xtraI.push_back(s.integer());
+    } else if (w.modelID == "Linear" || w.modelID == "SuspendedLoad" || w.modelID == "SGD" || w.modelID == "Recession_h") {
     } else {
         fail("ApplyModel: Fatal: Unavailable [model%ID] '" + w.modelID + "' (not on the GPU hot path yet)");
     }
@@ -531,6 +544,10 @@ void Workspace::make_headers(const bamgpu_sizes& s, int nDparModel) {  // GetHea
     std::vector<std::string> dn;
     if (modelID == "BaRatin")
         for (int i = 1; i <= nDparModel; ++i) dn.push_back("b" + std::to_string(i));
+    if (modelID == "Orthorectification")  // ModelLibrary_tools.f90:608-613
+        for (auto nm : {"r11", "r12", "r13", "r21", "r22", "r23", "r31", "r32", "r33", "a1", "a2", "a3", "a4", "b1", "b2",
+                        "b3", "b4", "c1", "c2", "c3"})
+            dn.push_back(nm);
     if (modelID == "Vegetation") {  // ModelLibrary_tools.f90:625-638
         dn.push_back("a1");
         for (int i = 2; i <= nDparModel; ++i) dn.push_back("Topt_" + std::to_string(i));

@@ -278,3 +278,78 @@ def vegetation(nobs: int = 600, growth: str = "Growth_Yin1_temporal", nyear: int
                    xtra_i=[VEG_GROWTH[growth], nyear, 100], xtra_d=[5.0, 1000.0, 1e-5, 1e-10])
     truth = np.array(truth_theta + [0.5, 0.05] + [0.1] * (nY - 1))
     return prob, truth
+
+
+def second_wave(model: str, nobs: int = 400, seed: int = SEED + 7, **kw):
+    """Synthetic problems for the second-wave pointwise models.
+    Returns (Problem, truth vector)."""
+    from .capi import ORTHO_DISTO, SWOT_ID
+
+    rng = np.random.default_rng(seed)
+    flat = lambda k: [("FlatPrior", [])] * k  # noqa: E731
+    if model == "SuspendedLoad":  # Qs = t1 (h-t2)^t3 / (h-t4)^t5
+        th = np.array([2.0, 0.2, 2.5, -0.5, 1.2])
+        h = rng.uniform(0.1, 4.0, nobs)  # a few stages below t2: infeasible rows -> infeasible vector unless avoided
+        h = np.maximum(h, 0.25)
+        q = th[0] * (h - th[1]) ** th[2] / (h - th[3]) ** th[4]
+        X, xtra = h.reshape(-1, 1), {}
+        pri = [("LogNormal", [0.7, 1.0]), ("Gaussian", [0.2, 0.1]), ("Gaussian", [2.5, 0.5]), ("Gaussian", [-0.5, 0.3]),
+               ("Gaussian", [1.2, 0.3])]
+    elif model == "SWOT":
+        variant = kw.get("variant", "SWOT_hSB")
+        th = np.array([30.0, 5.0 if variant == "SWOT_hSB" else 80.0, 1e-5, 1.0, 1.67])
+        h = rng.uniform(0.5, 6.0, nobs)
+        S = rng.uniform(5e-5, 3e-4, nobs)
+        B = rng.uniform(60.0, 120.0, nobs)
+        Bt, B0 = (B, th[1]) if variant == "SWOT_hSB" else (th[1], 0.0)
+        q = np.where(h > th[3], th[0] * (Bt - B0) * np.sqrt(S - th[2]) * np.abs(h - th[3]) ** th[4], 0.0)
+        X = np.column_stack([h, S, B]) if variant == "SWOT_hSB" else np.column_stack([h, S])
+        xtra = dict(xtra_i=[SWOT_ID[variant]])
+        pri = [("Gaussian", [30, 10]), ("Gaussian", [th[1], 0.3 * th[1]]), ("Gaussian", [1e-5, 1e-5]), ("Gaussian", [1, 0.5]),
+               ("Gaussian", [1.67, 0.1])]
+    elif model == "SGD":
+        th = np.array([30.0, 50.0, 1e-3, 0.5, 1.67])
+        h = rng.uniform(0.8, 5.0, nobs)
+        dhdt = rng.normal(0.0, 2e-5, nobs)
+        q0 = th[0] * th[1] * np.sqrt(th[2]) * (h - th[3]) ** th[4]
+        c = th[4] * th[0] * np.sqrt(th[2]) * (h - th[3]) ** (th[4] - 1)
+        q = q0 * np.sqrt(np.maximum(1 + dhdt / (c * th[2]), 1e-3))
+        X, xtra = np.column_stack([h, dhdt]), {}
+        pri = [("Gaussian", [30, 10]), ("Gaussian", [50, 10]), ("LogNormal", [-6.9, 0.5]), ("Gaussian", [0.5, 0.2]),
+               ("Gaussian", [1.67, 0.1])]
+    elif model == "Recession_h":
+        th = np.array([0.5, 2.0, 0.1, 0.2])
+        t = np.sort(rng.uniform(0.0, 20.0, nobs))
+        q = th[0] * np.exp(-th[1] * t) + (1 - th[0] - th[2]) * np.exp(-th[3] * t) + th[2]
+        X, xtra = t.reshape(-1, 1), {}
+        pri = [("Uniform", [0, 1]), ("LogNormal", [0.7, 1.0]), ("Uniform", [0, 1]), ("LogNormal", [-1.6, 1.0])]
+    elif model == "Orthorectification":
+        npd = int(kw.get("disto_npar", 2))
+        disto = "Radial" if npd > 0 else "None"
+        th = np.array([10.0, -1.0, 12.6, 3.14, -1.57, -1.0, 0.01, 960.0, 540.0, 5e-6, 1.0] + [1e-8, -1e-15][:npd])
+        xyz = np.column_stack([rng.uniform(-20, 5, nobs), rng.uniform(5, 40, nobs), rng.uniform(0, 2, nobs)])
+        X = xyz
+        xtra = dict(xtra_i=[ORTHO_DISTO[disto], npd])
+        pri = ([("Gaussian", [v, 0.1 * abs(v) + 1e-9]) for v in th[:11]] + [("Gaussian", [0, 1e-7]), ("Gaussian", [0, 1e-14])][:npd])
+        q = None
+    else:
+        raise ValueError(model)
+    nt = th.size
+    if model == "Orthorectification":
+        # observations: generated through a throw-away numpy forward model (rotation + projection, no distortion)
+        az, ro, ti = th[3], th[4], th[5]
+        R = np.array([[np.cos(az) * np.cos(ro) + np.sin(az) * np.cos(ti) * np.sin(ro), -np.sin(az) * np.cos(ro) + np.cos(az) * np.cos(ti) * np.sin(ro), np.sin(ti) * np.sin(ro)],
+                      [-np.cos(az) * np.sin(ro) + np.sin(az) * np.cos(ti) * np.cos(ro), np.sin(az) * np.sin(ro) + np.cos(az) * np.cos(ti) * np.cos(ro), np.sin(ti) * np.cos(ro)],
+                      [np.sin(az) * np.sin(ti), np.cos(az) * np.sin(ti), -np.cos(ti)]])
+        d = (X - th[:3]) @ R.T
+        c = th[7] - (th[6] / th[9]) * d[:, 1] / d[:, 2]
+        l = th[8] - (th[6] / (th[10] * th[9])) * d[:, 0] / d[:, 2]
+        Y = np.column_stack([c, l]) + rng.standard_normal((nobs, 2))
+        prob = Problem(model, X, Y, partype=[0] * nt, priors_theta=pri, sigma_func=["Constant", "Constant"],
+                       priors_gamma=[("Uniform", [0, 100])] * 2, **xtra)
+        return prob, np.concatenate([th, [1.0, 1.0]])
+    uq = 0.03 * np.abs(q) + 1e-3 * np.abs(q).mean()
+    Y = q + rng.standard_normal(nobs) * np.sqrt(uq**2 + (0.01 * np.abs(q).mean() + 0.05 * np.abs(q)) ** 2)
+    prob = Problem(model, X, Y, Yu=uq, partype=[0] * nt, priors_theta=pri, sigma_func=["Linear"],
+                   priors_gamma=[("Uniform", [0, 1e6])] * 2, **xtra)
+    return prob, np.concatenate([th, [0.01 * np.abs(q).mean(), 0.05]])

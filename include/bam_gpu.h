@@ -36,7 +36,13 @@ enum bamgpu_model {
     BAMGPU_MDL_BARATIN = 2,   /* BaRatin_model.f90:67-436 */
     BAMGPU_MDL_SEDIMENT = 3,  /* SedimentTransport_model.f90:100-607 */
     BAMGPU_MDL_TEXTFILE = 4,  /* TextFile_model.f90:231-309,1035-1098 */
-    BAMGPU_MDL_VEGETATION = 5 /* Vegetation_model.f90:87-569 */
+    BAMGPU_MDL_VEGETATION = 5,    /* Vegetation_model.f90:87-569 */
+    /* second wave: pointwise closed forms behind the same kernels */
+    BAMGPU_MDL_SUSPENDEDLOAD = 6, /* SuspendedLoad_model.f90:38-116 */
+    BAMGPU_MDL_SWOT = 7,          /* SWOT_model.f90:73-148 */
+    BAMGPU_MDL_SGD = 8,           /* StageGradientDischarge_model.f90:57-113 */
+    BAMGPU_MDL_ORTHO = 9,         /* Orthorectification_model.f90:66-288 ("Orthorectification") */
+    BAMGPU_MDL_RECESSION_H = 10   /* Recession_model.f90:36-94 ("Recession_h") */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -70,6 +76,10 @@ enum bamgpu_sed_css { BAMGPU_CSS_CONSTANT = 1, BAMGPU_CSS_SOULSBY = 2, BAMGPU_CS
 enum bamgpu_sed_ppo { BAMGPU_PPO_FIX = 1, BAMGPU_PPO_IN = 2, BAMGPU_PPO_PAR = 3 };
 enum bamgpu_sed_co { BAMGPU_CO_FIX = 1, BAMGPU_CO_PAR = 2 };
 
+/* SWOT variants (SWOT_model.f90:29-30), xtra_i[0]; distortion functions of Orthorectification (:28-30), xtra_i[0] */
+enum bamgpu_swot_id { BAMGPU_SWOT_HS = 1, BAMGPU_SWOT_HSB = 2 };
+enum bamgpu_ortho_disto { BAMGPU_DISTO_NONE = 1, BAMGPU_DISTO_RADIAL = 2 };
+
 /* Vegetation growth formulas (Vegetation_model.f90:25-30), carried in xtra_i[0]. */
 enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YIN3 = 3, BAMGPU_VEG_YIN1_TEMPORAL = 4 };
 
@@ -80,7 +90,8 @@ enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YI
  * does at :213-229); the caller keeps ownership of every pointer.
  */
 typedef struct bamgpu_problem {
-    const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" (optionally "MDL_"-prefixed) */
+    const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
+                             "Orthorectification" | "Recession_h" (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 
     /* calibration data, nobs x nX / nobs x nY, column-major (INFER%X .. INFER%Ybindx) */
@@ -118,7 +129,9 @@ typedef struct bamgpu_problem {
        Sediment   : xtra_i = {formula, css, co, ppo_d, ppo_s, ppo_v, ppo_g}; xtra_d = pseudoval[4]
        TextFile   : xtra_text = content of the model text file (TextFile_model.f90:946-978)
        Vegetation : xtra_i = {growth formula, nYear, itmax}; xtra_d = {xscale, fscale, tolX, tolF}
-       Linear     : none */
+       SWOT       : xtra_i = {bamgpu_swot_id}
+       Orthorectification : xtra_i = {bamgpu_ortho_disto, number of distortion parameters}
+       Linear, SuspendedLoad, SGD, Recession_h : none */
     const int32_t* xtra_i;
     int32_t n_xtra_i;
     const double* xtra_d;

@@ -70,6 +70,7 @@ struct oracle_handle {
     double sed_pseudo[4];
     int vm_nin, vm_npar, vm_nout;
     vm_prog vm[MAXVMOUT];
+    int model_opt[4];                              /* SWOT {variant}; Orthorectification {distortion id, npar} */
     int veg_growth, veg_nyear, veg_itmax;          /* Vegetation xtra (Vegetation_XtraRead :244-289) */
     double veg_xscale, veg_fscale, veg_tolx, veg_tolf;
 };
@@ -945,6 +946,116 @@ static int vegetation_apply(const oracle_t* o, int n, const double* IN, int ldx,
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Second-wave pointwise models
+ * ------------------------------------------------------------------------------------------ */
+
+/* SuspendedLoad_Apply, SuspendedLoad_model.f90:38-116 */
+static void suspendedload_apply(int n, const double* h, const double* theta, double* Qs, int32_t* vfeas) {
+    if (theta[0] <= 0.0 || theta[2] <= 0.0 || theta[4] <= 0.0) {
+        for (int i = 0; i < n; ++i) vfeas[i] = 0;
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (h[i] < theta[1] || h[i] < theta[3]) { vfeas[i] = 0; continue; }
+        double num = pow(h[i] - theta[1], theta[2]), den = pow(h[i] - theta[3], theta[4]);
+        Qs[i] = theta[0] * (num / den);
+    }
+}
+
+/* SWOT_Apply, SWOT_model.f90:73-148 */
+static void swot_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT, int32_t* vfeas) {
+    double K = theta[0], S0 = theta[2], h0 = theta[3], M = theta[4], B0 = 0.0;
+    int hS = o->model_opt[0] == BAMGPU_SWOT_HS;
+    if (!hS) B0 = theta[1];
+    if (K <= 0.0 || M <= 0.0) {
+        for (int t = 0; t < n; ++t) vfeas[t] = 0;
+        return;
+    }
+    for (int t = 0; t < n; ++t) {
+        double ht = IN[t], St = IN[t + (size_t)ldx], Bt = hS ? theta[1] : IN[t + 2 * (size_t)ldx];
+        if (Bt - B0 < 0.0 || St - S0 < 0.0) { vfeas[t] = 0; continue; }
+        if (ht - h0 <= 0.0) { OUT[t] = 0.0; continue; }
+        OUT[t] = K * (Bt - B0) * sqrt(St - S0) * pow(ht - h0, M);
+    }
+}
+
+/* SGD_Apply, StageGradientDischarge_model.f90:57-113 */
+static void sgd_apply(int n, const double* IN, int ldx, const double* theta, double* OUT, int32_t* vfeas) {
+    double K = theta[0], B = theta[1], S0 = theta[2], h0 = theta[3], M = theta[4];
+    if (K <= 0.0 || M <= 0.0 || B <= 0.0 || S0 <= 0.0) {
+        for (int t = 0; t < n; ++t) vfeas[t] = 0;
+        return;
+    }
+    for (int t = 0; t < n; ++t) {
+        double h = IN[t], dhdt = IN[t + (size_t)ldx];
+        if (h - h0 <= 0.0) { vfeas[t] = 0; continue; }
+        double Q0 = K * B * sqrt(S0) * pow(h - h0, M);
+        double c = M * K * sqrt(S0) * pow(h - h0, M - 1.0);
+        double corr = 1.0 + (1.0 / (c * S0)) * dhdt;
+        if (corr <= 0.0) { vfeas[t] = 0; continue; }
+        OUT[t] = Q0 * sqrt(corr);
+    }
+}
+
+/* Recession_h_Apply, Recession_model.f90:36-94 (normalised, two exponentials) */
+static void recession_apply(int n, const double* time, const double* theta, double* h) {
+    for (int t = 0; t < n; ++t)
+        h[t] = theta[0] * exp(-theta[1] * time[t]) + (1 - theta[0] - theta[2]) * exp(-theta[3] * time[t]) + theta[2];
+}
+
+/* Ortho_Apply + Disto_Apply, Orthorectification_model.f90:66-288 */
+static void ortho_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT, int ldy,
+                        double* Dpar, int32_t* vfeas) {
+    double x0 = theta[0], y0 = theta[1], z0 = theta[2], azim = theta[3], roll = theta[4], tilt = theta[5], f = theta[6],
+           c0 = theta[7], l0 = theta[8], lambda = theta[9], k = theta[10];
+    double pc = lambda, pl = k * pc;
+    int bad = (pc <= 0.0 || pl <= 0.0 || k <= 0.0);
+    double ac = 0, al = 0, r11 = 0, r12 = 0, r13 = 0, r21 = 0, r22 = 0, r23 = 0, r31 = 0, r32 = 0, r33 = 0;
+    if (!bad) {
+        ac = f / pc; al = f / pl;
+        r11 = cos(azim) * cos(roll) + sin(azim) * cos(tilt) * sin(roll);
+        r12 = -1.0 * sin(azim) * cos(roll) + cos(azim) * cos(tilt) * sin(roll);
+        r13 = sin(tilt) * sin(roll);
+        r21 = -1.0 * cos(azim) * sin(roll) + sin(azim) * cos(tilt) * cos(roll);
+        r22 = sin(azim) * sin(roll) + cos(azim) * cos(tilt) * cos(roll);
+        r23 = sin(tilt) * cos(roll);
+        r31 = sin(azim) * sin(tilt); r32 = cos(azim) * sin(tilt); r33 = -1.0 * cos(tilt);
+        double alpha = r31 * x0 + r32 * y0 + r33 * z0;
+        if (alpha == 0.0) bad = 1;
+        else {
+            double a1 = (ac * r21 - r31 * c0) / alpha, a2 = (ac * r22 - r32 * c0) / alpha, a3 = (ac * r23 - r33 * c0) / alpha;
+            double a4 = -1.0 * (a1 * x0 + a2 * y0 + a3 * z0);
+            double b1 = (al * r11 - r31 * l0) / alpha, b2 = (al * r12 - r32 * l0) / alpha, b3 = (al * r13 - r33 * l0) / alpha;
+            double b4 = -1.0 * (b1 * x0 + b2 * y0 + b3 * z0);
+            double v[20] = {r11, r12, r13, r21, r22, r23, r31, r32, r33, a1, a2, a3, a4, b1, b2, b3, b4,
+                            -1.0 * r31 / alpha, -1.0 * r32 / alpha, -1.0 * r33 / alpha};
+            memcpy(Dpar, v, sizeof v);
+        }
+    }
+    if (bad) {
+        for (int i = 0; i < n; ++i) vfeas[i] = 0;
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        double x = IN[i], y = IN[i + (size_t)ldx], z = IN[i + 2 * (size_t)ldx];
+        double denom = r31 * (x - x0) + r32 * (y - y0) + r33 * (z - z0);
+        if (denom == 0.0) { vfeas[i] = 0; continue; }
+        double c = c0 - ac * (r21 * (x - x0) + r22 * (y - y0) + r23 * (z - z0)) / denom;
+        double l = l0 - al * (r11 * (x - x0) + r12 * (y - y0) + r13 * (z - z0)) / denom;
+        if (o->model_opt[0] == BAMGPU_DISTO_NONE) { OUT[i] = c; OUT[i + (size_t)ldy] = l; continue; }
+        double r = sqrt((c - c0) * (c - c0) + (l - l0) * (l - l0));
+        double d = 1.0;
+        for (int q = 1; q <= o->model_opt[1]; ++q) {
+            double rp = 1.0; /* r**(2*q): integer power */
+            for (int m = 0; m < 2 * q; ++m) rp = rp * r;
+            d = d + theta[10 + q] * rp;
+        }
+        OUT[i] = c0 + d * (c - c0);
+        OUT[i + (size_t)ldy] = l0 + d * (l - l0);
+    }
+}
+
 /* TxtMdl_Apply, TextFile_model.f90:1035-1098 */
 static void textfile_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
                            int ldy, int32_t* vfeas) {
@@ -977,6 +1088,11 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         case BAMGPU_MDL_VEGETATION:
             if (vegetation_apply(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas)) return 1;
             break;
+        case BAMGPU_MDL_SUSPENDEDLOAD: suspendedload_apply(n, X, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_SWOT: swot_apply(o, n, X, ldx, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_SGD: sgd_apply(n, X, ldx, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_RECESSION_H: recession_apply(n, X, fullTheta, Y); break;
+        case BAMGPU_MDL_ORTHO: ortho_apply(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas); break;
         default: return 1;
     }
     int all = 1;
@@ -1001,6 +1117,11 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "Sediment")) return BAMGPU_MDL_SEDIMENT;
     if (!strcmp(name, "TextFile")) return BAMGPU_MDL_TEXTFILE;
     if (!strcmp(name, "Vegetation")) return BAMGPU_MDL_VEGETATION;
+    if (!strcmp(name, "SuspendedLoad")) return BAMGPU_MDL_SUSPENDEDLOAD;
+    if (!strcmp(name, "SWOT")) return BAMGPU_MDL_SWOT;
+    if (!strcmp(name, "SGD")) return BAMGPU_MDL_SGD;
+    if (!strcmp(name, "Orthorectification")) return BAMGPU_MDL_ORTHO;
+    if (!strcmp(name, "Recession_h")) return BAMGPU_MDL_RECESSION_H;
     return 0;
 }
 
@@ -1127,6 +1248,22 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             o->nDparModel = temporal ? 1 : o->veg_nyear + 1; /* ModelLibrary_tools.f90:625-632 */
             break;
         }
+        case BAMGPU_MDL_SUSPENDEDLOAD: case BAMGPU_MDL_SGD:
+            if (nt != 5 || nY != 1) { setmess(mess, "oracle: wrong size [theta]"); return 1; }
+            break;
+        case BAMGPU_MDL_RECESSION_H:
+            if (nt != 4 || nX != 1 || nY != 1) { setmess(mess, "oracle: wrong size [theta]"); return 1; }
+            break;
+        case BAMGPU_MDL_SWOT:
+            if (p->n_xtra_i != 1 || nt != 5 || nY != 1) { setmess(mess, "oracle: SWOT: bad xtra or sizes"); return 1; }
+            o->model_opt[0] = p->xtra_i[0];
+            if (nX != (o->model_opt[0] == BAMGPU_SWOT_HS ? 2 : 3)) { setmess(mess, "oracle: SWOT: wrong nX"); return 1; }
+            break;
+        case BAMGPU_MDL_ORTHO:
+            if (p->n_xtra_i != 2 || nX != 3 || nY != 2 || nt != 11 + p->xtra_i[1]) { setmess(mess, "oracle: Ortho: bad xtra or sizes"); return 1; }
+            o->model_opt[0] = p->xtra_i[0]; o->model_opt[1] = p->xtra_i[1];
+            o->nDparModel = 20;
+            break;
     }
 
     /* VAR combinations: :346-379 (order of first appearance) */

@@ -1,0 +1,75 @@
+"""GPU parity tests of the second-wave pointwise models against the CPU oracle:
+SuspendedLoad, SWOT (hS / hSB), SGD, Recession_h, Orthorectification (no / radial distortion).
+Same bar as the first wave: log-posterior 1e-12 relative, identical feasibility flags, prediction spaghetti and
+envelopes 1e-12, short sampler runs trajectory-identical."""
+import numpy as np
+import pytest
+
+from bam_b200 import synth
+from bam_b200.capi import BamGpu
+from oracle.oracle_api import Oracle
+from tests.test_gpu_logpost import check_parity
+from tests.test_gpu_predict import cmp_env, cmp_spag
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("SuspendedLoad", {}), ("SWOT", dict(variant="SWOT_hS")), ("SWOT", dict(variant="SWOT_hSB")), ("SGD", {}),
+         ("Recession_h", {}), ("Orthorectification", dict(disto_npar=0)), ("Orthorectification", dict(disto_npar=2))]
+
+
+@pytest.mark.parametrize("model,kw", CASES)
+def test_logpost_prediction_sampler(model, kw):
+    prob, truth = synth.second_wave(model, nobs=500, **kw)
+    x = synth.feasible_starts(truth, 48, rel=0.01, seed=2)
+    x[3, 0] = -abs(x[3, 0]) - 1.0 if model != "Recession_h" else x[3, 0]  # K / theta1 <= 0 (or pixel size for Ortho below)
+    if model == "Orthorectification":
+        x[3] = truth
+        x[3, 9] = -1e-6  # negative pixel size
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.nDpar == (20 if model == "Orthorectification" else 0)
+    check_parity(prob, x)
+    # prediction: propagate a small sample through the model on the calibration inputs
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.005 * rng.standard_normal((200, truth.size)))
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(prob.nX)]
+    dor = [1] * prob.nY
+    env, spag = g.predict(mc, truth, xs, 1, dor, seed=4, want_spag=True)
+    oenv, ospag = o.predict(mc, truth, xs, 1, dor, seed=4, want_spag=True, nthreads=8)
+    if model == "Orthorectification":
+        # pixel coordinates c = c0 - (f/pc) * (..)/(..) with c0 ~ 1000: a coordinate near 0 is a cancellation, so the
+        # tolerance is relative to the image scale, not to |value|
+        assert ((spag == -666.666) == (ospag == -666.666)).all()
+        assert np.max(np.abs(spag - ospag) / np.maximum(np.abs(ospag), 1000.0)) <= 1e-12
+        assert np.max(np.abs(env - oenv) / np.maximum(np.abs(oenv), 1000.0)) <= 1e-12
+    else:
+        cmp_spag(spag, ospag)
+        cmp_env(env, oenv)
+    # a short sampler run follows the oracle's trajectory
+    s = np.tile(truth, (3, 1))
+    sd = 0.01 * np.abs(s) + 1e-12
+    rows = g.fit(s, sd, nAdapt=4, nCycles=2, seed=5)
+    orows = o.fit(s, sd, nAdapt=4, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+    # residual run
+    Xt, Ys, feas = g.calibration_run(truth)
+    oXt, oYs, ofeas = o.calibration_run(truth)
+    assert feas == ofeas and np.allclose(Ys, oYs, rtol=1e-12, atol=1e-300)
+
+
+def test_row_infeasibility_patterns():
+    """per-row exits: SuspendedLoad h < t2 (:104), SWOT S < S0 (:137) and h <= h0 -> Q = 0 (:138), SGD h <= h0 (:100)"""
+    for model, kw, col, val in (("SuspendedLoad", {}, 0, 0.0), ("SWOT", dict(variant="SWOT_hS"), 1, -1.0), ("SGD", {}, 0, 0.1)):
+        prob, truth = synth.second_wave(model, nobs=60, **kw)
+        X = np.array(prob.X)
+        xs = [X[:, j].copy() for j in range(prob.nX)]
+        xs[col][5] = val
+        if model == "SWOT":
+            xs[0][7] = 0.5  # below h0 = 1: discharge exactly zero, row feasible
+        g, o = BamGpu(prob), Oracle(prob)
+        mc = np.tile(truth, (40, 1))
+        _, spag = g.predict(mc, truth, xs, 1, [0], want_env=False, want_spag=True)
+        _, ospag = o.predict(mc, truth, xs, 1, [0], want_env=False, want_spag=True)
+        cmp_spag(spag, ospag)
+        assert (spag[0, 5] == -666.666).all()
+        if model == "SWOT":
+            assert (spag[0, 7] == 0.0).all()

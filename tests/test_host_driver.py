@@ -81,6 +81,13 @@ def test_config_reader_on_shipped_workspaces(cfg, name):
     compare(compare_d, load_fixture(name))
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference workspaces only exist in the build container")
+def test_config_reader_on_shipped_second_wave_workspace():
+    d = dump_ref("Config_BaM_Orthorectification.txt")
+    assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == ("Orthorectification", 19, 3, 2)
+    assert list(d["xtra_i"]) == [1, 0] and len(d["partype"]) == 11  # "None" distortion, 0 distortion parameters
+
+
 def dump_ref(cfg):
     out = f"/tmp/_dump_{cfg}.json"
     r = subprocess.run([EXE, "-cf", os.path.join("/root/reference/tests", cfg), "--dump-problem", out],
