@@ -28,6 +28,7 @@ namespace {
 struct PredArgs {
     long long Nrep;
     int nobsPred, t0, nT;       // this tile: inputs [t0, t0+nT)
+    int tBase;                  // first input of the whole call (per-input scratch is indexed from it)
     int doParametric;
     int doRemnant[BAM_MAXY];
     unsigned long long seed;
@@ -242,6 +243,151 @@ PredFastKernel pick_pred_fast(const DevProblem& p, bool noise, long long Nrep) {
         case 2: return pick_pred_fast_sig<2>(p.sigfunc[0], noise);
         case 3: return pick_pred_fast_sig<3>(p.sigfunc[0], noise);
         case 4: return pick_pred_fast_sig<4>(p.sigfunc[0], noise);
+    }
+    return nullptr;
+}
+
+// ---- K4 fast path: Sediment (cfg 4) -----------------------------------------------------------------------------
+//
+// When the pseudo-parameters d, s, nu, g are inputs or fixed values and the critical-shear-stress coefficients are
+// fixed (the shipped BaM_Sediment* option files), everything in Sediment_Apply except three numbers per replication
+// depends on the prediction INPUT only:
+//     MPM      dim t1 (tau-css)^t2                  Camenen  dim t1 tau^t2 exp(-t3 css/tau)
+//     Nielsen  dim t1 tau^t2 (tau-css)              Smart    dim t1 S0^t2 (s-1)^(1/6) d^(1/6) g^(-1/2) tau^t3 (tau-css)
+// all have the form  t1 * B(input) * exp(t2 * L1(input) + t3 * L2(input)).  `sed_obs_prep` evaluates (B, L1, L2) and
+// the row status (infeasible inputs / tau <= css -> 0) once per input with the reference's libm-class functions
+// (SedimentTransport_model.f90:155-187,290-304); `pred_sediment_fast` then spends one table-driven exp per
+// (replication, input) instead of three pow, two exp, a cube root and a square root: ~330 -> ~12 FP64 instructions
+// for the model (plus ~24 for the noise).
+struct SedObs { double B, L1, L2, st; };  // st: 0 normal, 1 -> value 0 (tau <= css), 2 infeasible row
+
+template <int NX>
+__global__ void sed_obs_prep(DevProblem p, int nobsPred, int t0, int nT, double* const* __restrict__ xspag,
+                             SedObs* __restrict__ obs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nT) return;
+    double in[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) in[j] = xspag[j][t0 + t];
+    SedObs o{0.0, 0.0, 0.0, 2.0};
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) ok &= in[j] > 0.0;
+    double pseudo[4];
+    int kin = 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (p.sedPpo[i] == BAMGPU_PPO_FIX) pseudo[i] = p.sedPseudo[i];
+        else { pseudo[i] = (kin < NX) ? in[kin < NX ? kin : 0] : 0.0; ++kin; }
+    }
+    const double d = pseudo[0], s = pseudo[1], v = pseudo[2], g = pseudo[3];
+    ok = ok && d > 0.0 && s > 0.0 && v > 0.0 && g > 0.0 && s > 1.0;
+    if (ok) {
+        const double SD = pow(g * (s - 1.0) / (v * v), 1.0 / 3.0) * d;
+        const double css = (p.sedCss == BAMGPU_CSS_SOULSBY) ? (0.3 / (1.0 + 1.2 * SD)) * 0.055 * (1.0 - exp(-1.0 * 0.02 * SD))
+                                                           : (0.24 / SD) * 0.055 * (1.0 - exp(-1.0 * 0.02 * SD));
+        const double tau = (in[0] * in[1]) / ((s - 1.0) * d);
+        if (tau > 0.0) {
+            if (tau <= css) o.st = 1.0;
+            else {
+                const double dim = sqrt(g * (s - 1.0) * (d * d * d));
+                o.st = 0.0;
+                switch (p.sedFormula) {
+                    case BAMGPU_SED_MPM: o.B = dim; o.L1 = log(tau - css); break;
+                    case BAMGPU_SED_CAMENEN: o.B = dim; o.L1 = log(tau); o.L2 = -1.0 * (css / tau); break;
+                    case BAMGPU_SED_NIELSEN: o.B = dim * (tau - css); o.L1 = log(tau); break;
+                    default:
+                        o.B = dim * pow(s - 1.0, 1.0 / 6.0) * pow(d, 1.0 / 6.0) * pow(g, -0.5) * (tau - css);
+                        o.L1 = log(in[1]); o.L2 = log(tau);
+                        break;
+                }
+            }
+        }
+    }
+    obs[t] = o;
+}
+
+template <int SIGF, bool NOISE>
+__global__ void __launch_bounds__(BAM_BLOCK, 4) pred_sediment_fast(DevProblem p, PredArgs a, const double* __restrict__ mc,
+                                                                   const double* __restrict__ mode,
+                                                                   const SedObs* __restrict__ obs, double* __restrict__ V) {
+    extern __shared__ __align__(16) double pfsm[];
+    double2* sLogT = reinterpret_cast<double2*>(pfsm);
+    double* sExpT = pfsm + 2 * BAM_LOGTAB_N;
+    SedObs* sObs = reinterpret_cast<SedObs*>(sExpT + BAM_EXPTAB_N);
+    const int tid = threadIdx.x;
+    const int tBeg = blockIdx.y * PF_TT, nt = min(PF_TT, a.nT - tBeg);
+    for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) sLogT[i] = p.logTab[i];
+    for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExpT[i] = p.expTab[i];
+    for (int i = tid; i < nt; i += BAM_BLOCK) sObs[i] = obs[a.t0 - a.tBase + tBeg + i];
+    __syncthreads();
+    const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
+    if (rep >= a.Nrep) return;
+    double* out = V + (size_t)tBeg * a.Nrep + rep;
+    // theta (FIX filled in, :1054-1063) and gamma of this replication, straight from the sample matrix
+    double th[3];
+    const int nbase = (p.sedFormula == BAMGPU_SED_MPM || p.sedFormula == BAMGPU_SED_NIELSEN) ? 2 : 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        th[i] = 0.0;
+        if (i < nbase) {
+            const int src = p.comboSrc[i];
+            th[i] = (src < 0) ? p.fixv[i] : (a.doParametric ? mc[rep + (size_t)src * a.Nrep] : mode[src]);
+        }
+    }
+    const double e1 = th[1], e2 = (p.sedFormula == BAMGPU_SED_CAMENEN || p.sedFormula == BAMGPU_SED_SMART) ? th[2] : 0.0;
+    double g1 = 0.0, g2 = 0.0;
+    if (NOISE) {
+        g1 = mc[rep + (size_t)p.nFit * a.Nrep];
+        if (SIGF == BAMGPU_SIG_LINEAR) g2 = mc[rep + (size_t)(p.nFit + 1) * a.Nrep];
+    }
+    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT);
+    const unsigned tg0 = (unsigned)(a.t0 + tBeg);
+    double z[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned lastQuad = 0xffffffffu;
+    for (int t = 0; t < nt; ++t) {
+        const SedObs o = sObs[t];
+        const unsigned tg = tg0 + (unsigned)t;
+        if (NOISE && (tg >> 2) != lastQuad) {
+            lastQuad = tg >> 2;
+            normal_quad_fast(a.seed, (uint64_t)rep, lastQuad, 0u, lt, z);
+        }
+        double v;
+        if (o.st == 2.0) v = p.unfeas;
+        else {
+            const double q = (o.st == 1.0) ? 0.0 : o.B * th[0] * texp(fma(e1, o.L1, e2 * o.L2), et);
+            v = q;
+            if (NOISE) {
+                double sig;
+                if (SIGF == BAMGPU_SIG_CONSTANT) sig = g1;
+                else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(g2, fabs(q), g1);
+                else sig = g1 * fabs(q);
+                const double zz = (tg & 2u) ? ((tg & 1u) ? z[3] : z[2]) : ((tg & 1u) ? z[1] : z[0]);
+                if (sig > 0.0) v = fma(sig, zz, q);
+            }
+        }
+        __stcs(out + (size_t)t * a.Nrep, v);
+    }
+}
+
+using SedFastKernel = void (*)(DevProblem, PredArgs, const double*, const double*, const SedObs*, double*);
+using SedPrepKernel = void (*)(DevProblem, int, int, int, double* const*, SedObs*);
+
+SedFastKernel pick_sed_fast(int sigf, bool noise) {
+    switch (sigf) {
+        case BAMGPU_SIG_CONSTANT: return noise ? pred_sediment_fast<BAMGPU_SIG_CONSTANT, true> : pred_sediment_fast<BAMGPU_SIG_CONSTANT, false>;
+        case BAMGPU_SIG_LINEAR: return noise ? pred_sediment_fast<BAMGPU_SIG_LINEAR, true> : pred_sediment_fast<BAMGPU_SIG_LINEAR, false>;
+        case BAMGPU_SIG_PROPORTIONAL: return noise ? pred_sediment_fast<BAMGPU_SIG_PROPORTIONAL, true> : pred_sediment_fast<BAMGPU_SIG_PROPORTIONAL, false>;
+    }
+    return nullptr;
+}
+SedPrepKernel pick_sed_prep(int nX) {
+    switch (nX) {
+        case 2: return sed_obs_prep<2>;
+        case 3: return sed_obs_prep<3>;
+        case 4: return sed_obs_prep<4>;
+        case 5: return sed_obs_prep<5>;
+        case 6: return sed_obs_prep<6>;
     }
     return nullptr;
 }
@@ -822,8 +968,6 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
 // below the first activation stage); anything else is flagged for the 4-read kernel envelope_select2.
 #define S3_NB 16384
 #define S3_SAMPLE 2048
-#define S3_CAP 512 /* power of two: the lists are sorted in place by a bitonic network */
-#define S3_THREADS 512
 
 __device__ __forceinline__ int s3_bin(double v, double lo, double scale) {
     if (v < lo) return 0;
@@ -836,6 +980,7 @@ __device__ __forceinline__ unsigned long long s3_key(double v) {  // order-prese
     return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
 }
 
+template <int NTHR>
 __device__ double s3_block_sum(double v, double* scratch) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -845,7 +990,7 @@ __device__ double s3_block_sum(double v, double* scratch) {
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
-        for (int i = 0; i < S3_THREADS / 32; ++i) s += scratch[i];
+        for (int i = 0; i < NTHR / 32; ++i) s += scratch[i];
         scratch[32] = s;
     }
     __syncthreads();
@@ -855,26 +1000,29 @@ __device__ double s3_block_sum(double v, double* scratch) {
 // Column walkers of envelope_select3: 128-bit streaming loads, four independent requests per thread in flight
 // (the passes are pure HBM streams; with one 8-byte load per thread and iteration they were latency-bound at
 // 2.3 TB/s).  `f(v)` is applied to every value exactly once; the order does not matter to the callers.
-template <class F>
+template <int NTHR, class F>
 __device__ __forceinline__ void s3_for_each(const double* __restrict__ col, long long Nrep, F f) {
     const int tid = threadIdx.x;
     if ((reinterpret_cast<uintptr_t>(col) & 15) == 0) {
         const double2* __restrict__ c2 = reinterpret_cast<const double2*>(col);
         const long long n2 = Nrep >> 1;
         long long i = tid;
-        for (; i + 3 * S3_THREADS < n2; i += 4 * S3_THREADS) {
-            const double2 a = __ldcs(c2 + i), b = __ldcs(c2 + i + S3_THREADS), c = __ldcs(c2 + i + 2 * S3_THREADS),
-                          d = __ldcs(c2 + i + 3 * S3_THREADS);
+        for (; i + 3 * NTHR < n2; i += 4 * NTHR) {
+            const double2 a = __ldcs(c2 + i), b = __ldcs(c2 + i + NTHR), c = __ldcs(c2 + i + 2 * NTHR),
+                          d = __ldcs(c2 + i + 3 * NTHR);
             f(a.x); f(a.y); f(b.x); f(b.y); f(c.x); f(c.y); f(d.x); f(d.y);
         }
-        for (; i < n2; i += S3_THREADS) { const double2 a = __ldcs(c2 + i); f(a.x); f(a.y); }
+        for (; i < n2; i += NTHR) { const double2 a = __ldcs(c2 + i); f(a.x); f(a.y); }
         if ((Nrep & 1) && tid == 0) f(col[Nrep - 1]);
     } else {
-        for (long long r = tid; r < Nrep; r += S3_THREADS) f(__ldcs(col + r));
+        for (long long r = tid; r < Nrep; r += NTHR) f(__ldcs(col + r));
     }
 }
 
-__global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, int nT, double unfeas,
+// CAP = capacity of a gather list (power of two: the lists are sorted in place by a bitonic network), NTHR = block size.
+// <512, 512>: 64 KB of shared memory, 3 blocks per SM (Nrep <= 3e6); <2048, 1024>: 160 KB, 1 block per SM (Nrep <= 1.2e7).
+template <int CAP, int NTHR>
+__global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT, double unfeas,
                                                                const double* __restrict__ V, double* __restrict__ env,
                                                                int* __restrict__ needSlow) {
     extern __shared__ __align__(16) unsigned char s3raw[];  // 64 KB: sample (16 KB) -> histogram (64 KB) -> gather lists (40 KB)
@@ -883,7 +1031,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
     double* gath = reinterpret_cast<double*>(s3raw);
     __shared__ double scratch[40];
     __shared__ unsigned bitmap[S3_NB / 32];
-    __shared__ unsigned prefix[S3_THREADS];
+    __shared__ unsigned prefix[NTHR];
     __shared__ long long tRank[SEL_NT];
     __shared__ int tBin[SEL_NT], tList[SEL_NT], listBin[SEL_NT], listCnt[SEL_NT], listOver[SEL_NT], gCnt[SEL_NT], nLists, nGood;
     __shared__ unsigned long long listMin[SEL_NT], listMax[SEL_NT];
@@ -899,7 +1047,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
     __syncthreads();
     const long long stride = Nrep / S3_SAMPLE;
     int good = 0;
-    for (int i = tid; i < S3_SAMPLE; i += S3_THREADS) {
+    for (int i = tid; i < S3_SAMPLE; i += NTHR) {
         double v = col[(long long)i * stride];
         if (v == unfeas || v != v) v = INFINITY; else ++good;
         smp[i] = v;
@@ -908,7 +1056,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
     __syncthreads();
     for (int kk = 2; kk <= S3_SAMPLE; kk <<= 1)
         for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < S3_SAMPLE; i += S3_THREADS) {
+            for (int i = tid; i < S3_SAMPLE; i += NTHR) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
                     const double a = smp[i], b = smp[ixj];
@@ -932,18 +1080,18 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
     const double scale = (double)(S3_NB - 2) / (hi - lo);
 
     // ---- pass B
-    for (int b = tid; b < S3_NB; b += S3_THREADS) hist[b] = 0;
-    for (int b = tid; b < S3_NB / 32; b += S3_THREADS) bitmap[b] = 0;
+    for (int b = tid; b < S3_NB; b += NTHR) hist[b] = 0;
+    for (int b = tid; b < S3_NB / 32; b += NTHR) bitmap[b] = 0;
     __syncthreads();
     double s1 = 0.0, s2 = 0.0, nb = 0.0;
-    s3_for_each(col, Nrep, [&](double v) {
+    s3_for_each<NTHR>(col, Nrep, [&](double v) {
         if (v == unfeas || v != v) { nb += 1.0; return; }
         const double d = v - pivot;
         s1 += d;
         s2 = fma(d, d, s2);
         atomicAdd(&hist[s3_bin(v, lo, scale)], 1u);
     });
-    const long long nbad = (long long)s3_block_sum(nb, scratch);
+    const long long nbad = (long long)s3_block_sum<NTHR>(nb, scratch);
     const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
     if ((!drop && nbad > 0) || nbad == Nrep) {
         if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
@@ -951,16 +1099,16 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
         return;
     }
     const long long m = Nrep - nbad;
-    const double S1 = s3_block_sum(s1, scratch), S2 = s3_block_sum(s2, scratch);
+    const double S1 = s3_block_sum<NTHR>(s1, scratch), S2 = s3_block_sum<NTHR>(s2, scratch);
     const double mean = pivot + S1 / (double)m;
     const double ss = fmax(S2 - S1 * (S1 / (double)m), 0.0);
     {   // exclusive prefix over the bins: 32 consecutive bins per thread + scan of the 512 partials
-        constexpr int PER = S3_NB / S3_THREADS;
+        constexpr int PER = S3_NB / NTHR;
         unsigned acc = 0;
         for (int q = 0; q < PER; ++q) acc += hist[tid * PER + q];
         prefix[tid] = acc;
         __syncthreads();
-        for (int off = 1; off < S3_THREADS; off <<= 1) {
+        for (int off = 1; off < NTHR; off <<= 1) {
             const unsigned add = (tid >= off) ? prefix[tid - off] : 0;
             __syncthreads();
             prefix[tid] += add;
@@ -998,7 +1146,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
                 li = nl++;
                 listBin[li] = tBin[k];
                 listCnt[li] = 0;
-                listOver[li] = gCnt[k] > S3_CAP;
+                listOver[li] = gCnt[k] > CAP;
                 listMin[li] = 0xffffffffffffffffull;
                 listMax[li] = 0ull;
                 bitmap[tBin[k] >> 5] |= 1u << (tBin[k] & 31);
@@ -1011,7 +1159,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
 
     // ---- pass C: gather
     const int nl = nLists;
-    s3_for_each(col, Nrep, [&](double v) {
+    s3_for_each<NTHR>(col, Nrep, [&](double v) {
         if (v == unfeas || v != v) return;
         const int b = s3_bin(v, lo, scale);
         if (!((bitmap[b >> 5] >> (b & 31)) & 1u)) return;
@@ -1023,7 +1171,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
                     atomicMax(&listMax[j], key);
                 } else {
                     const int pos = atomicAdd(&listCnt[j], 1);
-                    gath[j * S3_CAP + pos] = v;
+                    gath[j * CAP + pos] = v;
                 }
             }
     });
@@ -1033,12 +1181,12 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
         const int cnt = listCnt[j];
         int npad = 2;
         while (npad < cnt) npad <<= 1;
-        double* g = gath + j * S3_CAP;
-        for (int i = cnt + tid; i < npad; i += S3_THREADS) g[i] = INFINITY;
+        double* g = gath + j * CAP;
+        for (int i = cnt + tid; i < npad; i += NTHR) g[i] = INFINITY;
         __syncthreads();
         for (int kk = 2; kk <= npad; kk <<= 1)
             for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                for (int i = tid; i < npad; i += S3_THREADS) {
+                for (int i = tid; i < npad; i += NTHR) {
                     const int ixj = i ^ jj;
                     if (ixj > i) {
                         const double a = g[i], b = g[ixj];
@@ -1051,7 +1199,7 @@ __global__ void __launch_bounds__(S3_THREADS) envelope_select3(long long Nrep, i
     }
     if (tid < SEL_NT) {
         const int j = tList[tid];
-        if (!listOver[j]) tVal[tid] = gath[j * S3_CAP + (int)tRank[tid]];
+        if (!listOver[j]) tVal[tid] = gath[j * CAP + (int)tRank[tid]];
         else if (listMin[j] == listMax[j]) {  // every member of the bin is the same value
             const unsigned long long kx = listMin[j];
             const unsigned long long bits = (kx >> 63) ? (kx ^ 0x8000000000000000ull) : ~kx;
@@ -1127,8 +1275,11 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     }
     h->predT0 = t0; h->predT1 = t1;
 
-    // tile of inputs: at most ~2 GiB of materialised values
-    const size_t budget = (size_t)8 << 30;
+    // tile of inputs: the materialised values take at most a third of the free HBM (capped at 48 GiB).  The envelope
+    // kernels run one block per column, so a tile should hold several times 148 columns when Nrep is large.
+    size_t freeB = 0, totalB = 0;
+    BAM_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((freeB + h->vCap * sizeof(double)) / 3, (size_t)48 << 30));
     long long tileT = (long long)(budget / (sizeof(double) * (size_t)Nrep * nY));
     tileT = std::max<long long>(32, std::min<long long>(tileT / 32 * 32, ((long long)nTall + 31) / 32 * 32));
     if (h_spag) tileT = std::max<long long>(tileT, 32);
@@ -1153,14 +1304,33 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEnv));
 
     const size_t smemSel2 = sizeof(unsigned) * SEL_NT * S2_NB2 + sizeof(double) * SEL_NT * S2_CAP;
-    const size_t smemSel3 = sizeof(unsigned) * S3_NB;
-    // the 2-read selection resolves bins of <= S3_CAP members: worth trying while the densest bin stays below that
-    const bool trySel3 = !smallN && Nrep <= 3000000 && !h->noSelect3;
+    // the 2-read selection resolves bins of <= CAP members: worth trying while the densest of its 16384 bins stays below
+    // that (a Gaussian column peaks at ~1.1e-4 Nrep per bin); two instantiations, see envelope_select3
+    const bool sel3Big = Nrep > 3000000;
+    const size_t smemSel3 = std::max(sizeof(unsigned) * S3_NB, sizeof(double) * SEL_NT * (sel3Big ? 2048 : 512));
+    const bool trySel3 = !smallN && Nrep <= 12000000 && !h->noSelect3;
     if (!smallN) {
         BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel2));
-        BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel3));
+        if (sel3Big) BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select3<2048, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel3));
+        else BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select3<512, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel3));
     }
     PredFastKernel fastK = (!h->forceGeneric && p.nX == 1 && p.nY == 1) ? pick_pred_fast(p, anyRem, Nrep) : nullptr;
+    // Sediment fast path: pseudo-parameters FIX / IN, fixed css coefficients, one input series for all replications
+    SedFastKernel sedK = nullptr;
+    SedObs* d_sedObs = nullptr;
+    if (!h->forceGeneric && p.model == BAMGPU_MDL_SEDIMENT && Nrep >= 1024 && p.sedCss != BAMGPU_CSS_CONSTANT &&
+        p.sedCo == BAMGPU_CO_FIX && (doParametric || h->d_mode)) {
+        bool okPath = true;
+        for (int i = 0; i < 4; ++i) okPath &= p.sedPpo[i] != BAMGPU_PPO_PAR;
+        for (int i = 0; i < p.nX; ++i) okPath &= h->predNspag[i] == 1;
+        if (okPath) sedK = pick_sed_fast(p.sigfunc[0], anyRem);
+        if (sedK) {
+            BAM_CUDA(cudaMallocAsync(&d_sedObs, sizeof(SedObs) * (size_t)nTall, s));
+            pick_sed_prep(p.nX)<<<(nTall + 127) / 128, 128, 0, s>>>(p, h->predNobs, t0, nTall, h->d_xspagPtrs, d_sedObs);
+            h->launches += 1;
+        }
+    }
+    a.tBase = t0;
     BAM_CUDA(cudaEventRecord(h->ev0, s));
     // measurement: per tile two bracketed intervals, [propagation kernel] and [envelope kernels]
     auto mark = [&]() -> cudaEvent_t {
@@ -1173,7 +1343,11 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         const int nT = std::min<long long>(tileT, nTall - tt);
         a.t0 = t0 + tt; a.nT = nT;
         cudaEvent_t kp0 = mark();
-        if (fastK) {
+        if (sedK) {
+            dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + PF_TT - 1) / PF_TT);
+            sedK<<<grid, BAM_BLOCK, sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N) + sizeof(SedObs) * PF_TT, s>>>(
+                p, a, h->d_mc, h->d_mode, d_sedObs, h->d_V);
+        } else if (fastK) {
             dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + PF_TT - 1) / PF_TT);
             fastK<<<grid, BAM_BLOCK, PF_SMEM, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspag[0], h->predNspag[0], h->d_V);
         } else {
@@ -1194,7 +1368,8 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                 BAM_CUDA(cudaMallocAsync(&needSlow, sizeof(int) * (size_t)nT * nY, s));
                 if (trySel3) {
                     BAM_CUDA(cudaMallocAsync(&need3, sizeof(int) * (size_t)nT * nY, s));
-                    envelope_select3<<<nT * nY, S3_THREADS, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
+                    if (sel3Big) envelope_select3<2048, 1024><<<nT * nY, 1024, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
+                    else envelope_select3<512, 512><<<nT * nY, 512, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
                     h->launches += 1;
                 }
                 envelope_select2<<<nT * nY, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow, need3);
@@ -1219,6 +1394,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             BAM_CUDA(cudaStreamSynchronize(s));
         }
     }
+    if (d_sedObs) BAM_CUDA(cudaFreeAsync(d_sedObs, s));
     BAM_CUDA(cudaEventRecord(h->ev1, s));
     BAM_CUDA(cudaGetLastError());
 }

