@@ -234,7 +234,7 @@ def run_reference(args):
     return 0
 
 
-def prediction_leg(device, fp64_peak, hbm_peak, steps=3):
+def prediction_leg(device, fp64_peak, hbm_peak, steps=2):
     """BASELINE's second metric on configs[4] (BaRatin spaghetti + structural-error noise), bounded size.
 
     Two kernels dominate: the propagation kernel (FP64-pipe bound) and the envelope selection (HBM bound: it reads
@@ -243,18 +243,16 @@ def prediction_leg(device, fp64_peak, hbm_peak, steps=3):
     from bam_b200 import synth
     from bam_b200.capi import BamGpu
 
-    Nrep, nobs = 1_000_000, 2048
+    Nrep, nobs = 1_000_000, 100_000
     prob, _ = synth.baratin_2c(nobs=38)
     mc, mode, Hs = synth.baratin_spaghetti(Nrep=Nrep, nobs=nobs)
     g = BamGpu(prob, device)
     g.predict_upload(mc, mode, [Hs])
-    for _ in range(2):
-        g.predict_resident(1, [1], seed=1)
+    g.predict_resident(1, [1], seed=1)
     g.sync()
     g.kernel_times()
     g.step_times()
     for _ in range(steps):
-        g.flush_l2(256 << 20)
         g.step_begin()
         g.predict_resident(1, [1], seed=1)
         g.step_end()
@@ -266,7 +264,8 @@ def prediction_leg(device, fp64_peak, hbm_peak, steps=3):
     pairs = Nrep * nobs
     out = {"metric": "prediction samples x inputs/sec", "value": pairs / (ms.mean() * 1e-3), "unit": "sample*input/s",
            "ms_per_step": float(ms.mean()), "workload": f"BaRatin spaghetti {Nrep} samples x {nobs} inputs, parametric + "
-           f"remnant noise, exact envelopes (configs[4] scaled to {nobs} inputs); tile of 16 GB materialised, L2 flushed",
+           f"remnant noise, exact envelopes (configs[4], full size: {8 * Nrep * nobs / 1e9:.0f} GB of spaghetti materialised in "
+           f"tiles of <= 48 GiB, far larger than L2)",
            "finite": ok}
     if km.size >= 2 * steps:
         kp, ke = float(km[0::2].sum()) / steps, float(km[1::2].sum()) / steps  # summed over the tiles of a step
@@ -320,7 +319,29 @@ def sediment_prediction_leg(device, hbm_peak, Nrep=10_000_000, steps=2):
             "finite": bool(np.isfinite(g.predict_download()).all())}
 
 
-def latent_sampler_leg(device, n=200_000, K=32, iters=4):
+def small_sampler_leg(device):
+    """configs[0]: the reference's own tests/BaM_BaRatin workspace (38 gaugings, P = 8), adaptive Metropolis with the
+    persistent warp-per-chain kernel; K = 1 is like-for-like with the reference's single chain."""
+    from bam_b200.capi import BamGpu
+    from tests.helpers import problem_from_fixture
+
+    prob, d = problem_from_fixture("baratin")
+    out = {"workload": "tests/BaM_BaRatin (38 gaugings, 8 components), Config_MCMC shape: cycles of 100 iterations"}
+    for K, nC in ((4096, 50), (1, 200)):
+        g = BamGpu(prob, device)
+        s = np.tile(np.asarray(d["start"]), (K, 1))
+        sd = 0.1 * np.abs(s)
+        g.fit(s, sd, nAdapt=10, nCycles=1, want_rows=False)
+        g.step_times()
+        g.fit(s, sd, nAdapt=100, nCycles=nC, seed=3, want_rows=False)
+        ms = float(g.step_times()[-1])
+        nprop = K * 100 * nC * g.P
+        out[f"K{K}"] = {"iterations": 100 * nC, "ms": ms, "proposals_per_s": nprop / (ms * 1e-3),
+                        "chain_obs_per_s": nprop * prob.nobs / (ms * 1e-3)}
+    return out
+
+
+def latent_sampler_leg(device, n=1_000_000, K=64, iters=4):
     """configs[2] (Regression with input uncertainty): adaptive Metropolis over theta, gamma AND 2n latent inputs per
     chain; the latent inputs are swept by one kernel launch with O(1) local posterior differences.  Bounded size."""
     from bam_b200 import synth
@@ -525,6 +546,10 @@ def main():
             line["prediction_sediment"] = sediment_prediction_leg(device, hbm_peak)
         except Exception as e:
             line["prediction_sediment"] = {"error": str(e)}
+        try:
+            line["sampler_small"] = small_sampler_leg(device)
+        except Exception as e:
+            line["sampler_small"] = {"error": str(e)}
         try:
             line["latent_sampler"] = latent_sampler_leg(device)
         except Exception as e:
