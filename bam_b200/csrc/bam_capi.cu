@@ -202,6 +202,9 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         d.sedFormula = L.sed[0]; d.sedCss = L.sed[1]; d.sedCo = L.sed[2];
         for (int i = 0; i < 4; ++i) { d.sedPpo[i] = L.sed[3 + i]; d.sedPseudo[i] = L.sedPseudo[i]; }
         for (int i = 0; i < 4; ++i) d.modelOpt[i] = L.modelOpt[i];
+        d.modelOptD = L.modelOptD;
+        d.hcsN = (int)(L.hcsTab.size() / 4);
+        d.hcsTab = d.hcsN ? upload(h, L.hcsTab.data(), L.hcsTab.size()) : nullptr;
         d.vegGrowth = L.vegGrowth; d.vegNYear = L.vegNYear; d.vegItmax = L.vegItmax;
         d.vegXscale = L.vegOpt[0]; d.vegFscale = L.vegOpt[1]; d.vegTolX = L.vegOpt[2]; d.vegTolF = L.vegOpt[3];
         if (L.model == BAMGPU_MDL_TEXTFILE) {

@@ -65,6 +65,9 @@ struct DevProblem {
     int vmNcode[BAM_MAXY], vmCodeOff[BAM_MAXY], vmImmedOff[BAM_MAXY], vmNin, vmNpar;
     // SWOT {variant}, Orthorectification {distortion id, npar}
     int modelOpt[4];
+    double modelOptD;
+    const double* hcsTab;  // HydraulicControl_section: 4 x hcsN (h | A | w | h + A/(2w))
+    int hcsN;
     // Vegetation
     int vegGrowth, vegNYear, vegItmax;
     double vegXscale, vegFscale, vegTolX, vegTolF;

@@ -28,6 +28,8 @@ int model_from_name(const char* name) {
     if (s == "SGD") return BAMGPU_MDL_SGD;
     if (s == "Orthorectification") return BAMGPU_MDL_ORTHO;
     if (s == "Recession_h") return BAMGPU_MDL_RECESSION_H;
+    if (s == "HydraulicControl_section") return BAMGPU_MDL_HCS;
+    if (s == "Segmentation") return BAMGPU_MDL_SEGMENTATION;
     return 0;
 }
 
@@ -500,9 +502,32 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             if (nt != 11 + p.xtra_i[1] || nX != 3 || nY != 2) { mess = "Ortho_Apply: wrong size [theta], nX or nY"; return 1; }
             L.nDparModel = 20;  // rotation matrix + ortho parameters (ModelLibrary_tools.f90:608-613)
             break;
+        case BAMGPU_MDL_HCS: {  // HydraulicControl_section_XtraRead / _Setup (:114-260): h-A-w table, >= 3 rows
+            const int np = p.n_xtra_d / 3;
+            if (np < 3 || p.n_xtra_d != 3 * np) { mess = "HydraulicControl_section_Setup:invalid h-A-w matrix: at least 3 points are required"; return 1; }
+            if (nt != 2 || nX != 1 || nY != 1) { mess = "HydraulicControl_section_Apply: wrong size [theta], nX or nY"; return 1; }
+            L.hcsTab.assign((size_t)4 * np, 0.0);  // h | A | w | h + A/(2w)
+            for (int i = 0; i < np; ++i) {
+                const double hh = p.xtra_d[i], A = p.xtra_d[i + np], ww = p.xtra_d[i + 2 * np];
+                L.hcsTab[i] = hh; L.hcsTab[i + np] = A; L.hcsTab[i + 2 * np] = ww;
+                L.hcsTab[i + 3 * np] = hh + 0.5 * (i == 0 ? 0.0 : A / ww);
+            }
+            break;
+        }
+        case BAMGPU_MDL_SEGMENTATION: {  // Segmentation_XtraRead (:142-180)
+            if (p.n_xtra_i != 3 || p.n_xtra_d != 1) { mess = "Segmentation_XtraRead:problem reading xtra"; return 1; }
+            const int nS = p.xtra_i[0];
+            if (nS < 1 || nt != 2 * nS - 1 || nX != 1 || nY != 1) { mess = "Segmentation_Apply: Fatal: incorrect size [theta]"; return 1; }
+            if (p.xtra_i[2] != 1 && p.xtra_i[2] != 2) { mess = "Segmentation_Apply: Fatal: Unavailable [option]"; return 1; }
+            if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: Segmentation is a whole-series model: VAR parameters and input errors are not supported"; return 1; }
+            L.modelOpt[0] = nS; L.modelOpt[1] = p.xtra_i[1]; L.modelOpt[2] = p.xtra_i[2];
+            L.modelOptD = p.xtra_d[0];
+            break;
+        }
         default: break;
     }
     if (L.model == BAMGPU_MDL_BARATIN) L.nDer = 2 * L.ncontrol;  // b_i and log a_i
+    else if (L.model == BAMGPU_MDL_SEGMENTATION) L.nDer = std::max(L.modelOpt[0] - 1, 0);  // the shift times tau
     else if (L.model == BAMGPU_MDL_ORTHO) L.nDer = 22;           // Dpar + the two focal lengths in pixels
     else if (L.model != BAMGPU_MDL_VEGETATION) L.nDer = L.nDparModel;
 

@@ -53,7 +53,9 @@ struct HostLayout {
     int vmMaxStack = 0;
     int vegGrowth = 0, vegNYear = 0, vegItmax = 0;
     double vegOpt[4] = {0, 0, 0, 0};  // xscale, fscale, tolX, tolF
-    int modelOpt[4] = {0, 0, 0, 0};  // SWOT: {variant}; Orthorectification: {distortion id, number of distortion parameters}
+    int modelOpt[4] = {0, 0, 0, 0};  // SWOT: {variant}; Orthorectification: {distortion id, npar}; Segmentation: {nS, nmin, option}
+    double modelOptD = 0.0;          // Segmentation: tmin
+    std::vector<double> hcsTab;      // HydraulicControl_section: h | A | w | h + A/(2w), p rows each
     int nDer = 0;  // derived values per (parameter set, combination) kept in the device table
 };
 

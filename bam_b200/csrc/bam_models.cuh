@@ -471,6 +471,74 @@ __device__ inline bool ortho_apply(const DevProblem& p, const double* in, const 
     return true;
 }
 
+// HydraulicControl_section_Apply (HydraulicControl_section_model.f90:40-112): critical-section control from a
+// bathymetry table (h, A, w); the critical stage solves h + A/(2w) = H by linear interpolation of the table.
+__device__ inline bool hcs_apply(const DevProblem& p, double H, const double* __restrict__ th, double& out) {
+    const int np = p.hcsN;
+    const double* __restrict__ hh = p.hcsTab;
+    const double* __restrict__ AA = p.hcsTab + np;
+    const double* __restrict__ lhs = p.hcsTab + 3 * np;
+    if (H <= hh[0]) { out = 0.0; return true; }
+    if (H >= hh[np - 1]) return false;
+    int k1 = -1;  // maxloc(fx, mask = fx <= 0): first position of the largest non-positive fx
+    double best = 0.0;
+    for (int i = 0; i < np; ++i) {
+        const double fx = lhs[i] - H;
+        if (fx <= 0.0 && (k1 < 0 || fx > best)) { k1 = i; best = fx; }
+    }
+    const int k2 = k1 + 1;
+    if (k1 < 0 || k2 >= np) return false;
+    const double x1 = hh[k1], x2 = hh[k2];
+    double y1 = lhs[k1] - H, y2 = lhs[k2] - H;
+    const double hc = (x1 * y2 - x2 * y1) / (y2 - y1);
+    y1 = AA[k1]; y2 = AA[k2];
+    const double Ahc = (y1 * (x2 - hc) + y2 * (hc - x1)) / (x2 - x1);
+    out = th[0] * sqrt(2.0 * th[1] * (H - hc)) * Ahc;
+    return true;
+}
+
+// Segmentation_Apply (Segmentation_model.f90:52-140): theta = (mu_1..mu_nS, nS-1 shift times | durations).
+// Per parameter set: shift times tau (-> der), feasibility incl. the >= nmin points per segment test, which scans the
+// whole input series; per observation: Y = mu(segment), segment = first i with t < tau_i (GettRange :182-215).
+__device__ inline bool segmentation_prepare(const DevProblem& p, const double* th, double* der, const double* time, int nser) {
+    const int nS = p.modelOpt[0], nmin = p.modelOpt[1], option = p.modelOpt[2];
+    if (nS == 1) return true;
+    double prev = 0.0, acc = 0.0;
+    for (int i = 0; i < nS - 1; ++i) {
+        double dur, tau;
+        if (option == 1) { tau = th[nS + i]; dur = (i == 0) ? 1.0 : tau - prev; }
+        else { dur = th[nS + i]; acc = acc + dur; tau = acc; }
+        if (dur <= 0.0 || dur <= p.modelOptD) return false;
+        der[i] = tau;
+        prev = tau;
+    }
+    double tmax = -INFINITY;
+    for (int j = 0; j < nser; ++j) tmax = fmax(tmax, time[j]);
+    for (int i = 0; i < nS - 1; ++i)
+        if (der[i] >= tmax) return false;
+    int cnt[BAM_MAXTHETA];
+    for (int i = 0; i < nS; ++i) cnt[i] = 0;
+    for (int j = 0; j < nser; ++j) {
+        int seg = nS - 1;
+        for (int i = 0; i < nS - 1; ++i)
+            if (time[j] < der[i]) { seg = i; break; }
+        ++cnt[seg];
+    }
+    for (int i = 0; i < nS; ++i)
+        if (cnt[i] < nmin) return false;
+    return true;
+}
+
+__device__ __forceinline__ bool segmentation_apply(const DevProblem& p, double t, const double* __restrict__ th,
+                                                   const double* __restrict__ der, double& out) {
+    const int nS = p.modelOpt[0];
+    int seg = nS - 1;
+    for (int i = 0; i < nS - 1; ++i)
+        if (t < der[i]) { seg = i; break; }
+    out = th[seg];
+    return true;
+}
+
 // -------------------------------------------------------------------------------------------
 // dispatch
 // -------------------------------------------------------------------------------------------
@@ -482,6 +550,8 @@ __device__ inline bool model_prepare(const DevProblem& p, const double* th, doub
     if (p.model == BAMGPU_MDL_BARATIN) return baratin_prepare(p, th, der);
     if (p.model == BAMGPU_MDL_VEGETATION) return vegetation_prepare(p, th, der, xc, nser);
     if (p.model == BAMGPU_MDL_ORTHO) return ortho_prepare(th, der);
+    if (p.model == BAMGPU_MDL_SEGMENTATION) return segmentation_prepare(p, th, der, xc[0], nser);
+    if (p.model == BAMGPU_MDL_HCS) return !(th[0] <= 0.0 || th[1] <= 0.0);  // HydraulicControl_section_model.f90:70-72
     // parameter-set feasibility of the pointwise second-wave models
     if (p.model == BAMGPU_MDL_SUSPENDEDLOAD) return !(th[0] <= 0.0 || th[2] <= 0.0 || th[4] <= 0.0);  // SuspendedLoad_model.f90:96-99
     if (p.model == BAMGPU_MDL_SWOT) return !(th[0] <= 0.0 || th[4] <= 0.0);                             // SWOT_model.f90:128-130
@@ -512,6 +582,10 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return recession_apply(x[0], th, y[0]);
     } else if (MODEL == BAMGPU_MDL_ORTHO) {
         return ortho_apply(p, x, th, der, y);
+    } else if (MODEL == BAMGPU_MDL_HCS) {
+        return hcs_apply(p, x[0], th, y[0]);
+    } else if (MODEL == BAMGPU_MDL_SEGMENTATION) {
+        return segmentation_apply(p, x[0], th, der, y[0]);
     } else {
         bool ok = true;
 #pragma unroll

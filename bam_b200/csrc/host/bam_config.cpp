@@ -216,7 +216,14 @@ void load_workspace(const std::string& configFile, Workspace& w) {
         // workspace given relative to the config file's directory (as the shipped tests/Config_BaM_*.txt)
         size_t cut = configFile.find_last_of('/');
         std::string base = cut == std::string::npos ? std::string("") : configFile.substr(0, cut + 1);
-        w.dir = base + w.dir;
+        const std::string rel = w.dir;
+        w.dir = base + rel;
+        if (!exists(w.dir + ".") && !base.empty()) {
+            // a Config_BaM.txt stored INSIDE its workspace and written for a run from the parent directory
+            // (tests/BaM_Segmentation/Config_BaM.txt names "BaM_Segmentation/")
+            const size_t cut2 = base.find_last_of('/', base.size() - 2);
+            w.dir = (cut2 == std::string::npos ? std::string("") : base.substr(0, cut2 + 1)) + rel;
+        }
     }
     w.fRunOptions = c.str(); w.fModel = c.str(); w.fXtra = c.str(); w.fData = c.str();
     w.fRemnant = list_items(c.raw());
@@ -367,6 +374,25 @@ void load_workspace(const std::string& configFile, Workspace& w) {
         else if (id == "Radial") w.xtraI.push_back(BAMGPU_DISTO_RADIAL);
         else fail("Disto_Apply:Fatal:Unavailable [Disto_ID] '" + id + "'");
         w.xtraI.push_back(s.integer());
+    } else if (w.modelID == "HydraulicControl_section") {  // h-A-w matrix, one row per line (:114-150)
+        std::vector<std::vector<double>> rows;
+        for (auto& l : read_lines(xf)) {
+            auto it = list_items(l);
+            if (it.empty()) continue;
+            if (it.size() < 3) fail("HydraulicControl_section_XtraRead:problem reading file " + xf);
+            rows.push_back({to_double(it[0]), to_double(it[1]), to_double(it[2])});
+        }
+        const size_t np = rows.size();
+        w.xtraD.assign(3 * np, 0.0);
+        for (size_t i = 0; i < np; ++i)
+            for (int c = 0; c < 3; ++c) w.xtraD[i + c * np] = rows[i][c];
+    } else if (w.modelID == "Segmentation") {  // Segmentation_XtraRead (:142-180): nS, tmin, nmin, option
+        Cursor s(xf);
+        const int nS = s.integer();
+        const double tmin = s.num();
+        const int nmin = s.integer(), option = s.integer();
+        w.xtraI = {nS, nmin, option};
+        w.xtraD = {tmin};
     } else if (w.modelID == "Linear" || w.modelID == "SuspendedLoad" || w.modelID == "SGD" || w.modelID == "Recession_h") {
     } else {
         fail("ApplyModel: Fatal: Unavailable [model%ID] '" + w.modelID + "' (not on the GPU hot path yet)");

@@ -332,6 +332,32 @@ def second_wave(model: str, nobs: int = 400, seed: int = SEED + 7, **kw):
         xtra = dict(xtra_i=[ORTHO_DISTO[disto], npd])
         pri = ([("Gaussian", [v, 0.1 * abs(v) + 1e-9]) for v in th[:11]] + [("Gaussian", [0, 1e-7]), ("Gaussian", [0, 1e-14])][:npd])
         q = None
+    elif model == "HydraulicControl_section":
+        # bathymetry table of a parabolic-ish section: h increasing, A and w increasing, A/w increasing
+        hh = np.linspace(0.0, 5.0, kw.get("ntab", 60))
+        ww = 4.0 + 6.0 * hh
+        AA = 4.0 * hh + 3.0 * hh**2
+        th = np.array([1.0, 9.81])
+        H = rng.uniform(-0.2, 6.0, nobs)  # a few stages below the lowest point (Q = 0); a stage above the table is an infeasible row
+        H = np.minimum(H, 4.9)
+        lhs = hh + 0.5 * np.where(hh > 0, AA / np.maximum(ww, 1e-300), 0.0)
+        hc = np.interp(np.clip(H, lhs[0], lhs[-1]), lhs, hh)
+        q = np.where(H > 0, th[0] * np.sqrt(2 * th[1] * np.maximum(H - hc, 0)) * np.interp(hc, hh, AA), 0.0)
+        X = H.reshape(-1, 1)
+        xtra = dict(xtra_d=np.column_stack([hh, AA, ww]).flatten(order="F"))
+        pri = [("LogNormal", [0, 0.2]), ("Gaussian", [9.81, 0.01])]
+    elif model == "Segmentation":
+        nS, option = int(kw.get("nS", 3)), int(kw.get("option", 1))
+        t = np.sort(rng.uniform(0.0, 100.0, nobs))
+        mu = [1.0, 3.0, 2.0, 4.0][:nS]
+        tau = [30.0, 65.0, 85.0][: nS - 1]
+        shifts = tau if option == 1 else list(np.diff([0.0] + tau))
+        th = np.array(mu + shifts)
+        seg = np.searchsorted(np.asarray(tau), t, side="right")
+        q = np.asarray(mu)[seg]
+        X = t.reshape(-1, 1)
+        xtra = dict(xtra_i=[nS, int(kw.get("nmin", 3)), option], xtra_d=[float(kw.get("tmin", 0.5))])  # option 1 sets duration(1) = 1, so tmin must stay below 1 (:86,95)
+        pri = [("Gaussian", [2, 5])] * nS + [("Uniform", [0, 100])] * (nS - 1)
     else:
         raise ValueError(model)
     nt = th.size

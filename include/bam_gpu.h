@@ -42,7 +42,9 @@ enum bamgpu_model {
     BAMGPU_MDL_SWOT = 7,          /* SWOT_model.f90:73-148 */
     BAMGPU_MDL_SGD = 8,           /* StageGradientDischarge_model.f90:57-113 */
     BAMGPU_MDL_ORTHO = 9,         /* Orthorectification_model.f90:66-288 ("Orthorectification") */
-    BAMGPU_MDL_RECESSION_H = 10   /* Recession_model.f90:36-94 ("Recession_h") */
+    BAMGPU_MDL_RECESSION_H = 10,  /* Recession_model.f90:36-94 ("Recession_h") */
+    BAMGPU_MDL_HCS = 11,          /* HydraulicControl_section_model.f90:40-112 ("HydraulicControl_section") */
+    BAMGPU_MDL_SEGMENTATION = 12  /* Segmentation_model.f90:52-140 (whole-series model: segment sizes are checked) */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -91,7 +93,8 @@ enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YI
  */
 typedef struct bamgpu_problem {
     const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
-                             "Orthorectification" | "Recession_h" (optionally "MDL_"-prefixed) */
+                             "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation"
+                             (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 
     /* calibration data, nobs x nX / nobs x nY, column-major (INFER%X .. INFER%Ybindx) */
@@ -131,6 +134,8 @@ typedef struct bamgpu_problem {
        Vegetation : xtra_i = {growth formula, nYear, itmax}; xtra_d = {xscale, fscale, tolX, tolF}
        SWOT       : xtra_i = {bamgpu_swot_id}
        Orthorectification : xtra_i = {bamgpu_ortho_disto, number of distortion parameters}
+       HydraulicControl_section : xtra_d = the h-A-w matrix, p x 3 column-major (n_xtra_d = 3p)
+       Segmentation : xtra_i = {nS, nmin, option}; xtra_d = {tmin}
        Linear, SuspendedLoad, SGD, Recession_h : none */
     const int32_t* xtra_i;
     int32_t n_xtra_i;

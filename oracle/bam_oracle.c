@@ -70,7 +70,9 @@ struct oracle_handle {
     double sed_pseudo[4];
     int vm_nin, vm_npar, vm_nout;
     vm_prog vm[MAXVMOUT];
-    int model_opt[4];                              /* SWOT {variant}; Orthorectification {distortion id, npar} */
+    int model_opt[4];  /* SWOT {variant}; Orthorectification {distortion id, npar}; Segmentation {nS, nmin, option} */
+    double model_optd; /* Segmentation tmin */
+    int hcs_n;         /* HydraulicControl_section: rows of the h-A-w table (xtra_d, p x 3) */
     int veg_growth, veg_nyear, veg_itmax;          /* Vegetation xtra (Vegetation_XtraRead :244-289) */
     double veg_xscale, veg_fscale, veg_tolx, veg_tolf;
 };
@@ -1056,6 +1058,80 @@ static void ortho_apply(const oracle_t* o, int n, const double* IN, int ldx, con
     }
 }
 
+/* HydraulicControl_section_Apply, HydraulicControl_section_model.f90:40-112 */
+static void hcs_apply(const oracle_t* o, int n, const double* H, const double* theta, double* Q, int32_t* vfeas) {
+    int p = o->hcs_n;
+    const double *hh = o->xtra_d, *AA = o->xtra_d + p, *ww = o->xtra_d + 2 * p;
+    double coeff = theta[0], g = theta[1];
+    if (coeff <= 0.0 || g <= 0.0) {
+        for (int i = 0; i < n; ++i) vfeas[i] = 0;
+        return;
+    }
+    double* lhs = (double*)malloc((size_t)p * 2 * sizeof(double));
+    double* fx = lhs + p;
+    for (int i = 0; i < p; ++i) lhs[i] = hh[i] + 0.5 * (i == 0 ? 0.0 : AA[i] / ww[i]);
+    for (int i = 0; i < n; ++i) {
+        if (H[i] <= hh[0]) { Q[i] = 0.0; continue; }
+        if (H[i] >= hh[p - 1]) { vfeas[i] = 0; continue; }
+        int k1 = -1;
+        for (int k = 0; k < p; ++k) {
+            fx[k] = lhs[k] - H[i];
+            if (fx[k] <= 0.0 && (k1 < 0 || fx[k] > fx[k1])) k1 = k; /* maxloc(fx, mask=fx<=0): first maximum */
+        }
+        int k2 = k1 + 1;
+        if (k1 < 0 || k2 >= p) { vfeas[i] = 0; continue; }
+        double x1 = hh[k1], x2 = hh[k2], y1 = fx[k1], y2 = fx[k2];
+        double hc = (x1 * y2 - x2 * y1) / (y2 - y1);
+        y1 = AA[k1]; y2 = AA[k2];
+        double Ahc = (y1 * (x2 - hc) + y2 * (hc - x1)) / (x2 - x1);
+        Q[i] = coeff * sqrt(2.0 * g * (H[i] - hc)) * Ahc;
+    }
+    free(lhs);
+}
+
+/* Segmentation_Apply, Segmentation_model.f90:52-140.  Returns 0 when the parameter set is infeasible. */
+static int segmentation_apply(const oracle_t* o, int nt, const double* time, const double* theta, double* Y) {
+    int nS = o->model_opt[0], nmin = o->model_opt[1], option = o->model_opt[2];
+    double tmin = o->model_optd;
+    if (nS == 1) {
+        for (int i = 0; i < nt; ++i) Y[i] = theta[0];
+        return 1;
+    }
+    double tau[64], duration[64];
+    if (option == 1) {
+        for (int i = 0; i < nS - 1; ++i) tau[i] = theta[nS + i];
+        duration[0] = 1.0;
+        for (int i = 1; i < nS - 1; ++i) duration[i] = tau[i] - tau[i - 1];
+    } else {
+        double acc = 0.0;
+        for (int i = 0; i < nS - 1; ++i) { duration[i] = theta[nS + i]; acc = acc + duration[i]; tau[i] = acc; }
+    }
+    for (int i = 0; i < nS - 1; ++i)
+        if (duration[i] <= 0.0) return 0;
+    for (int i = 0; i < nS - 1; ++i)
+        if (duration[i] <= tmin) return 0;
+    double tmax = -HUGE_VAL;
+    for (int i = 0; i < nt; ++i) if (time[i] > tmax) tmax = time[i];
+    for (int i = 0; i < nS - 1; ++i)
+        if (tau[i] >= tmax) return 0;
+    int cnt[64] = {0};
+    int* seg = (int*)malloc(((size_t)nt + 1) * sizeof(int));
+    for (int i = 0; i < nt; ++i) {
+        int r = nS - 1;
+        for (int k = 0; k < nS - 1; ++k)
+            if (time[i] < tau[k]) { r = k; break; }
+        seg[i] = r;
+        cnt[r]++;
+    }
+    int ok = 1;
+    for (int k = 0; k < nS; ++k)
+        if (cnt[k] < nmin) ok = 0;
+    if (ok)
+        for (int i = 0; i < nt; ++i) Y[i] = theta[seg[i]];
+    free(seg);
+    return ok;
+}
+
 /* TxtMdl_Apply, TextFile_model.f90:1035-1098 */
 static void textfile_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
                            int ldy, int32_t* vfeas) {
@@ -1093,6 +1169,11 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         case BAMGPU_MDL_SGD: sgd_apply(n, X, ldx, fullTheta, Y, vfeas); break;
         case BAMGPU_MDL_RECESSION_H: recession_apply(n, X, fullTheta, Y); break;
         case BAMGPU_MDL_ORTHO: ortho_apply(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas); break;
+        case BAMGPU_MDL_HCS: hcs_apply(o, n, X, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_SEGMENTATION:
+            if (!segmentation_apply(o, n, X, fullTheta, Y))
+                for (int t = 0; t < n; ++t) vfeas[t] = 0; /* scalar feas=.false. (ModelLibrary_tools.f90:362-364) */
+            break;
         default: return 1;
     }
     int all = 1;
@@ -1122,6 +1203,8 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "SGD")) return BAMGPU_MDL_SGD;
     if (!strcmp(name, "Orthorectification")) return BAMGPU_MDL_ORTHO;
     if (!strcmp(name, "Recession_h")) return BAMGPU_MDL_RECESSION_H;
+    if (!strcmp(name, "HydraulicControl_section")) return BAMGPU_MDL_HCS;
+    if (!strcmp(name, "Segmentation")) return BAMGPU_MDL_SEGMENTATION;
     return 0;
 }
 
@@ -1263,6 +1346,15 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             if (p->n_xtra_i != 2 || nX != 3 || nY != 2 || nt != 11 + p->xtra_i[1]) { setmess(mess, "oracle: Ortho: bad xtra or sizes"); return 1; }
             o->model_opt[0] = p->xtra_i[0]; o->model_opt[1] = p->xtra_i[1];
             o->nDparModel = 20;
+            break;
+        case BAMGPU_MDL_HCS:
+            o->hcs_n = p->n_xtra_d / 3;
+            if (o->hcs_n < 3 || p->n_xtra_d != 3 * o->hcs_n || nt != 2 || nX != 1 || nY != 1) { setmess(mess, "oracle: HydraulicControl_section: bad xtra or sizes"); return 1; }
+            break;
+        case BAMGPU_MDL_SEGMENTATION:
+            if (p->n_xtra_i != 3 || p->n_xtra_d != 1 || nX != 1 || nY != 1 || nt != 2 * p->xtra_i[0] - 1 || p->xtra_i[0] > 32) { setmess(mess, "oracle: Segmentation: bad xtra or sizes"); return 1; }
+            o->model_opt[0] = p->xtra_i[0]; o->model_opt[1] = p->xtra_i[1]; o->model_opt[2] = p->xtra_i[2];
+            o->model_optd = p->xtra_d[0];
             break;
     }
 

@@ -14,14 +14,21 @@ from tests.test_gpu_predict import cmp_env, cmp_spag
 pytestmark = pytest.mark.gpu
 
 CASES = [("SuspendedLoad", {}), ("SWOT", dict(variant="SWOT_hS")), ("SWOT", dict(variant="SWOT_hSB")), ("SGD", {}),
-         ("Recession_h", {}), ("Orthorectification", dict(disto_npar=0)), ("Orthorectification", dict(disto_npar=2))]
+         ("Recession_h", {}), ("Orthorectification", dict(disto_npar=0)), ("Orthorectification", dict(disto_npar=2)),
+         ("HydraulicControl_section", {}), ("Segmentation", dict(nS=3, option=1)), ("Segmentation", dict(nS=4, option=2)),
+         ("Segmentation", dict(nS=1))]
 
 
 @pytest.mark.parametrize("model,kw", CASES)
 def test_logpost_prediction_sampler(model, kw):
     prob, truth = synth.second_wave(model, nobs=500, **kw)
     x = synth.feasible_starts(truth, 48, rel=0.01, seed=2)
-    x[3, 0] = -abs(x[3, 0]) - 1.0 if model != "Recession_h" else x[3, 0]  # K / theta1 <= 0 (or pixel size for Ortho below)
+    if model not in ("Recession_h", "Segmentation"):
+        x[3, 0] = -abs(x[3, 0]) - 1.0  # K / theta1 <= 0 (or pixel size for Ortho below)
+    if model == "Segmentation" and kw.get("nS", 3) > 1:
+        nS = kw["nS"]
+        x[3, nS] = 1e9 if kw["option"] == 1 else -1.0  # shift after the last time (:96) / negative duration (:94)
+        x[4, nS] = 0.01                                # first segment holds fewer than nmin points (:102-104)
     if model == "Orthorectification":
         x[3] = truth
         x[3, 9] = -1e-6  # negative pixel size
@@ -58,7 +65,8 @@ def test_logpost_prediction_sampler(model, kw):
 
 def test_row_infeasibility_patterns():
     """per-row exits: SuspendedLoad h < t2 (:104), SWOT S < S0 (:137) and h <= h0 -> Q = 0 (:138), SGD h <= h0 (:100)"""
-    for model, kw, col, val in (("SuspendedLoad", {}, 0, 0.0), ("SWOT", dict(variant="SWOT_hS"), 1, -1.0), ("SGD", {}, 0, 0.1)):
+    for model, kw, col, val in (("SuspendedLoad", {}, 0, 0.0), ("SWOT", dict(variant="SWOT_hS"), 1, -1.0), ("SGD", {}, 0, 0.1),
+                                ("HydraulicControl_section", {}, 0, 5.5)):  # stage above the bathymetry table (:84)
         prob, truth = synth.second_wave(model, nobs=60, **kw)
         X = np.array(prob.X)
         xs = [X[:, j].copy() for j in range(prob.nX)]
@@ -73,3 +81,16 @@ def test_row_infeasibility_patterns():
         assert (spag[0, 5] == -666.666).all()
         if model == "SWOT":
             assert (spag[0, 7] == 0.0).all()
+
+
+def test_segmentation_and_hcs_prediction_uses_the_prediction_series():
+    """whole-series feasibility of Segmentation is evaluated on the series the model is applied to (:96,102-104):
+    a prediction grid that leaves a segment empty flags every replication"""
+    prob, truth = synth.second_wave("Segmentation", nobs=200, nS=3, option=1)
+    g, o = BamGpu(prob), Oracle(prob)
+    mc = np.tile(truth, (50, 1))
+    for grid in (np.linspace(0, 100, 40), np.linspace(0, 50, 40)):  # the second grid never reaches the 2nd shift
+        env, spag = g.predict(mc, truth, [grid], 1, [0], want_spag=True)
+        oenv, ospag = o.predict(mc, truth, [grid], 1, [0], want_spag=True)
+        assert (spag == ospag).all() and (env == oenv).all()  # piecewise-constant outputs: exact
+    assert (spag == -666.666).all() and (env == -666.666).all()

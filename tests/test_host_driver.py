@@ -86,10 +86,16 @@ def test_config_reader_on_shipped_second_wave_workspace():
     d = dump_ref("Config_BaM_Orthorectification.txt")
     assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == ("Orthorectification", 19, 3, 2)
     assert list(d["xtra_i"]) == [1, 0] and len(d["partype"]) == 11  # "None" distortion, 0 distortion parameters
+    d = dump_ref("Config_BaM_HydraulicControl_section.txt")
+    assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == ("HydraulicControl_section", 6, 1, 1)
+    tab = np.asarray(d["xtra_d"]).reshape(3, -1)  # h | A | w
+    assert tab.shape[1] >= 3 and (np.diff(tab[0]) >= 0).all() and (tab[1, 1:] > 0).all()
+    d = dump_ref(os.path.join("BaM_Segmentation", "Config_BaM.txt"))  # a Config_BaM.txt stored inside its workspace
+    assert (d["model_id"], d["nobs"]) == ("Segmentation", 110) and list(d["xtra_i"]) == [2, 2, 1]
 
 
 def dump_ref(cfg):
-    out = f"/tmp/_dump_{cfg}.json"
+    out = "/tmp/_dump_" + cfg.replace("/", "_") + ".json"
     r = subprocess.run([EXE, "-cf", os.path.join("/root/reference/tests", cfg), "--dump-problem", out],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
