@@ -306,11 +306,14 @@ __global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final(DevProblem p
 // a_i (H-b_i)^c_i = texp(c_i tlog(H-b_i) + log a_i) and -0.5 log(v) via tlog: ~60 FP64-pipe instructions per
 // chain x observation against ~330 for the libdevice pow/log/sqrt/div formulation.
 // ------------------------------------------------------------------------------------------------
+#ifndef BAM_CB_MINB
+#define BAM_CB_MINB 2
+#endif
 #ifndef BAM_CB_ILP
 #define BAM_CB_ILP 4
 #endif
 template <int NC, int SIGF>
-__global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_baratin_cb(DevProblem p, int K, int TOBS, const double* __restrict__ tab,
+__global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(DevProblem p, int K, int TOBS, const double* __restrict__ tab,
                                                                     const int* status, double* __restrict__ part,
                                                                     int* statusOut) {
     extern __shared__ __align__(16) double sm[];
