@@ -182,6 +182,14 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
         }
     }
 
+    // hyper term of a latent input: log N(xo; mu, xu) = -log sqrt(2 pi) - log xu - 0.5 ((xo - mu) / xu)^2; log xu and
+    // 1 / xu belong to the observation, not to the chain: computed once per thread
+    double hyC[NX], hyR[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        hyC[j] = 0.0; hyR[j] = 0.0;
+        if (p.hasLatent && xu[j] > 0.0) { hyC[j] = -BAM_LOG_SQRT_2PI - log(xu[j]); hyR[j] = 1.0 / xu[j]; }
+    }
     for (int cc = ty; cc < nc; cc += TY) {
         const int c = c0 + cc;
         const double* __restrict__ row = stab + (size_t)cc * tabStride;
@@ -224,7 +232,8 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
                         if (!(xu[j] > 0.0)) { badh = true; continue; }
                         double mu = xt[j];
                         if (p.hasXbias && xbi[j] != 0) mu = xt[j] + xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
-                        hy += gauss_logpdf(xo[j], mu, xu[j]);
+                        const double z = (xo[j] - mu) * hyR[j];
+                        hy += fma(-0.5 * z, z, hyC[j]);
                     }
                 }
             }

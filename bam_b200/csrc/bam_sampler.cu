@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(32 * WS_WARPS) sampler_warp(DevProblem p, Warp
 template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool local_logpost(const DevProblem& p, const double* xt, const double* xo, const double* xu,
                                               const double* xb, const int* xbi, const double* yo, const double* yu,
-                                              const double* yb, const int* ybi, const double* __restrict__ row,
-                                              const double* __restrict__ th, double& val) {
+                                              const double* yb, const int* ybi, const double* hyC, const double* hyR,
+                                              const double* __restrict__ row, const double* __restrict__ th, double& val) {
     double yh[NY];
     if (!model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh)) return false;
     double lk = 0.0;
@@ -347,7 +347,8 @@ __device__ __forceinline__ bool local_logpost(const DevProblem& p, const double*
         if (!(xu[j] > 0.0)) continue;
         double mu = xt[j];
         if (p.hasXbias && xbi[j] != 0) mu = xt[j] + xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
-        hy += gauss_logpdf(xo[j], mu, xu[j]);
+        const double z = (xo[j] - mu) * hyR[j];
+        hy += fma(-0.5 * z, z, hyC[j]);  // hyC = -log sqrt(2 pi) - log xu, hyR = 1 / xu: per observation, not per proposal
     }
     val = lk + hy;
     return val == val;
@@ -395,8 +396,14 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
         else if (p.hasXbias && xbi[j] > 0) v = xo[j] - xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
         xt[j] = v;
     }
+    double hyC[NX], hyR[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        hyC[j] = 0.0; hyR[j] = 0.0;
+        if (xu[j] > 0.0) { hyC[j] = -BAM_LOG_SQRT_2PI - log(xu[j]); hyR[j] = 1.0 / xu[j]; }
+    }
     double cur;
-    if (!local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, row, th, cur)) return;  // cannot happen for a feasible state
+    if (!local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, cur)) return;  // cannot happen for a feasible state
     const unsigned long long gc = (unsigned long long)(chainOffset + c);
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
         xt[j] = old + sd[base + comp] * philox_normal(seed, gc, it, 2u * comp);
         double cand;
         bool acc = false;
-        if (local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, row, th, cand)) {
+        if (local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, cand)) {
             const double u = philox_uniform(seed, gc, it, 2u * comp + 1u);
             acc = log(u) < cand - cur;
         }
