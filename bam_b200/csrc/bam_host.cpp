@@ -30,6 +30,7 @@ int model_from_name(const char* name) {
     if (s == "Recession_h") return BAMGPU_MDL_RECESSION_H;
     if (s == "HydraulicControl_section") return BAMGPU_MDL_HCS;
     if (s == "Segmentation") return BAMGPU_MDL_SEGMENTATION;
+    if (s == "BaRatinBAC") return BAMGPU_MDL_BARATINBAC;
     return 0;
 }
 
@@ -392,7 +393,8 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
         case BAMGPU_MDL_LINEAR:
             if (nt != nX * nY) { mess = "LM_Apply: size mismatch [theta]"; return 1; }
             break;
-        case BAMGPU_MDL_BARATIN: {
+        case BAMGPU_MDL_BARATIN:
+        case BAMGPU_MDL_BARATINBAC: {
             int nc = nt / 3;
             if (nX != 1 || nY != 1 || nc < 1 || nt != 3 * nc || p.n_xtra_i != nc * nc) { mess = "BaRatin_Apply:Fatal:Incorrect size [theta]"; return 1; }
             if (nc > 8) { mess = "bamgpu: BaRatin supports at most 8 controls"; return 1; }
@@ -413,6 +415,27 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             for (int r = 0; r < nc; ++r)
                 if (M(r, r) != 1) { mess = "BaRatin_XtraRead:invalid control matrix"; return 1; }
             L.nDparModel = nc;
+            if (L.model == BAMGPU_MDL_BARATINBAC) {  // BaRatinBAC_XtraRead (:150-235): hmax + the extra matrix constraints
+                if (p.n_xtra_d != 1) { mess = "BaRatinBAC_XtraRead:problem reading file (hmax)"; return 1; }
+                L.modelOptD = p.xtra_d[0];
+                for (int i = 1; i < nc; ++i) {
+                    int s0 = 0, s1 = 0;
+                    for (int c = 0; c < nc; ++c) { s0 += M(i - 1, c); s1 += M(i, c); }
+                    if (s1 < s0) { mess = "BaRatinBAC_XtraRead:FATAL: the number of active controls is not allowed to decrease when stage increases. Use original BaRatin for such configuration."; return 1; }
+                    bool same = true;
+                    for (int c = 0; c < i; ++c) same &= M(i, c) == M(i - 1, c);
+                    if (same && M(i, i) == 1 && M(i - 1, i) == 0) continue;  // control addition
+                    if (M(i - 1, i - 1) == 1 && M(i - 1, i) == 0 && M(i, i - 1) == 0 && M(i, i) == 1) {  // replacement
+                        bool rest = true;
+                        for (int c = 0; c + 1 < i; ++c) rest &= M(i, c) == M(i - 1, c);
+                        if (!rest) { mess = "BaRatinBAC_XtraRead:FATAL: unsupported control matrix: unsupported control replacement."; return 2; }
+                        continue;
+                    }
+                    mess = "BaRatinBAC_XtraRead:FATAL: unsupported control matrix.";
+                    return 3;
+                }
+                L.nDparModel = 2 * nc;  // activation stages k and their type (ModelLibrary_tools.f90:593-602)
+            }
             break;
         }
         case BAMGPU_MDL_SEDIMENT: {
@@ -527,6 +550,7 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
         default: break;
     }
     if (L.model == BAMGPU_MDL_BARATIN) L.nDer = 2 * L.ncontrol;  // b_i and log a_i
+    else if (L.model == BAMGPU_MDL_BARATINBAC) L.nDer = 2 * L.ncontrol;  // k_i and ktype_i
     else if (L.model == BAMGPU_MDL_SEGMENTATION) L.nDer = std::max(L.modelOpt[0] - 1, 0);  // the shift times tau
     else if (L.model == BAMGPU_MDL_ORTHO) L.nDer = 22;           // Dpar + the two focal lengths in pixels
     else if (L.model != BAMGPU_MDL_VEGETATION) L.nDer = L.nDparModel;

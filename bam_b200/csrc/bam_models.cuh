@@ -62,6 +62,145 @@ __device__ __forceinline__ bool baratin_apply(const DevProblem& p, double H, con
 }
 
 // -------------------------------------------------------------------------------------------
+// BaRatinBAC (BaRatinBAC_model.f90:96-666): theta = (b_i, a_i, c_i); the activation stages k_i follow from the
+// continuity of the rating curve: k_i = b_i when control i is ADDED, the root of
+//     f(x) = c2 log(x-b2) - c1 log(x-b1) - log(a1/a2)        (fContinuity :521-526)
+// when control i REPLACES control i-1 (SolveContinuity :396-518, cases I-VI).  der = [k_i | ktype_i].
+// -------------------------------------------------------------------------------------------
+#define BAM_BAC_EPS 1.1920928955078125e-07 /* epsilon(1.): the reference uses the SINGLE-precision epsilon (:400) */
+
+__device__ __forceinline__ double bac_f(double x, double a1, double b1, double c1, double a2, double b2, double c2) {
+    return c2 * log(x - b2) - c1 * log(x - b1) - log(a1 / a2);
+}
+__device__ __forceinline__ double bac_df(double x, double b1, double c1, double b2, double c2) {
+    return (c2 / (x - b2)) - (c1 / (x - b1));
+}
+
+// findRoot (:603-636) -> znewton with tolX = 1e-4, tolF = 1e-6, unit scales, itmax = 10000; same declared convention
+// as the Vegetation solver (rtsafe + polish; miniDMSL is un-vendored), identical to oracle/bam_oracle.c:bac_find_root
+__device__ inline bool bac_find_root(double a1, double b1, double c1, double a2, double b2, double c2, double x1, double x2,
+                                     double fl, double fh, double& root) {
+    if (fl == 0.0) { root = x1; return true; }
+    if (fh == 0.0) { root = x2; return true; }
+    if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) return false;
+    double xl, xh;
+    if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
+    double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
+    double f = bac_f(rts, a1, b1, c1, a2, b2, c2), df = bac_df(rts, b1, c1, b2, c2);
+    for (int j = 0; j < 10000; ++j) {
+        if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+            dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
+        } else {
+            dxold = dx; dx = f / df; rts = rts - dx;
+        }
+        const bool convx = fabs(dx) <= 1e-4;
+        f = bac_f(rts, a1, b1, c1, a2, b2, c2);
+        df = bac_df(rts, b1, c1, b2, c2);
+        if (f < 0.0) xl = rts; else xh = rts;
+        if (convx || fabs(f) <= 1e-6) break;
+    }
+    for (int j = 0; j < 4 && f != 0.0 && df != 0.0; ++j) {  // polish to the root itself
+        const double lo = fmin(xl, xh), hi = fmax(xl, xh);
+        double xn = rts - f / df;
+        xn = fmin(fmax(xn, lo), hi);
+        if (xn == rts) break;
+        rts = xn;
+        f = bac_f(rts, a1, b1, c1, a2, b2, c2);
+        df = bac_df(rts, b1, c1, b2, c2);
+        if (f < 0.0) xl = rts; else xh = rts;
+    }
+    root = rts;
+    return root == root;
+}
+
+// SolveContinuity (:396-518); returns the number of roots (0 | 1)
+__device__ inline int bac_solve(double a1, double b1, double c1, double a2, double b2, double c2, double lbound, double hbound,
+                                double& root, int& troot) {
+    const double eps = BAM_BAC_EPS;
+    troot = 0;
+    if (fabs(c1 - c2) <= eps) {  // case I
+        if (fabs(a1 - a2) <= eps) return 0;
+        const double foo1 = pow(a1, 1.0 / c1), foo2 = pow(a2, 1.0 / c1);
+        root = (foo2 * b2 - foo1 * b1) / (foo2 - foo1);
+        if (root > lbound && root < hbound) { troot = 1; return 1; }
+        return 0;
+    }
+    if (fabs(b1 - b2) <= eps) {  // case II
+        root = b1 + pow(a1 / a2, 1.0 / (c2 - c1));
+        if (root > lbound && root < hbound) { troot = 2; return 1; }
+        return 0;
+    }
+    const double x0 = (c2 * b1 - c1 * b2) / (c2 - c1);
+    if (x0 <= lbound) {  // case III: monotonic within the bounds
+        const double f1 = bac_f(lbound + eps, a1, b1, c1, a2, b2, c2), f2 = bac_f(hbound, a1, b1, c1, a2, b2, c2);
+        if (f1 * f2 > 0.0) return 0;
+        if (bac_find_root(a1, b1, c1, a2, b2, c2, lbound + eps, hbound, f1, f2, root)) { troot = 3; return 1; }
+        return 0;
+    }
+    const double fx0 = bac_f(x0, a1, b1, c1, a2, b2, c2);
+    if (fabs(fx0) <= eps) { root = x0; troot = 5; return 1; }  // case V
+    if ((c2 > c1 && fx0 > 0.0) || (c2 < c1 && fx0 < 0.0)) { troot = 6; return 0; }  // case VI
+    troot = 4;  // case IV: keep the largest of the two roots
+    if (x0 >= hbound) return 0;
+    const double f2 = bac_f(hbound, a1, b1, c1, a2, b2, c2);
+    if (f2 * fx0 > 0.0) return 0;
+    return bac_find_root(a1, b1, c1, a2, b2, c2, x0, hbound, fx0, f2, root) ? 1 : 0;
+}
+
+// ApplyContinuity (:237-394): der[0..nc) = k, der[nc..2nc) = ktype
+__device__ inline bool baratinbac_prepare(const DevProblem& p, const double* th, double* der) {
+    const int nc = p.ncontrol;
+    for (int i = 0; i < nc; ++i)
+        if (th[3 * i + 1] <= 0.0 || th[3 * i + 2] == 0.0) return false;
+    der[0] = th[0];
+    der[nc] = 0.0;
+    for (int j = nc - 1; j >= 1; --j) {  // from the highest control down
+        const double bj = th[3 * j], bjm = th[3 * (j - 1)];
+        const double lbound = fmax(bj, bjm);
+        const double hbound = (j == nc - 1) ? p.modelOptD : der[j + 1];
+        bool addition = true;
+        for (int i = 0; i < j; ++i)
+            addition &= ((p.ctrlMask >> (j * 8 + i)) & 1ull) == ((p.ctrlMask >> ((j - 1) * 8 + i)) & 1ull);
+        if (addition) { der[j] = bj; der[nc + j] = 0.0; }
+        else {
+            double root = 0.0;
+            int troot = 0;
+            if (bac_solve(th[3 * (j - 1) + 1], bjm, th[3 * (j - 1) + 2], th[3 * j + 1], bj, th[3 * j + 2], lbound, hbound, root, troot) == 0)
+                return false;
+            der[j] = root;
+            der[nc + j] = (double)troot;
+        }
+        if (der[j] >= hbound) return false;
+        for (int i = 0; i < j; ++i)
+            if (der[j] < th[3 * i]) return false;
+    }
+    return true;
+}
+
+// BaRatin_computeQ (BaRatin_model.f90:194-252) with b from theta and k from der
+__device__ __forceinline__ bool baratinbac_apply(const DevProblem& p, double H, const double* __restrict__ th,
+                                                 const double* __restrict__ k, double& Q) {
+    const int nc = p.ncontrol;
+    int range = nc;
+    for (int i = 0; i < nc; ++i)
+        if (H < k[i]) { range = i; break; }
+    double q = 0.0;
+    bool ok = true;
+    if (range > 0) {
+        const unsigned row = (unsigned)((p.ctrlMask >> ((range - 1) * 8)) & 0xffull);
+        for (int i = 0; i < range; ++i) {
+            const double d = H - th[3 * i];
+            if ((row >> i) & 1u) {
+                if (d < 0.0) { q = 0.0; break; }
+                q = q + th[3 * i + 1] * pow(d, th[3 * i + 2]);
+            } else if (d < 0.0) { ok = false; break; }
+        }
+    }
+    Q = q;
+    return ok;
+}
+
+// -------------------------------------------------------------------------------------------
 // Linear (Linear_model.f90:62-101): Y = X . reshape(theta,(nX,nY))
 // -------------------------------------------------------------------------------------------
 template <int NX, int NY>
@@ -548,6 +687,7 @@ __device__ __forceinline__ bool segmentation_apply(const DevProblem& p, double t
 __device__ inline bool model_prepare(const DevProblem& p, const double* th, double* der, const double* const* xc,
                                      int nser) {
     if (p.model == BAMGPU_MDL_BARATIN) return baratin_prepare(p, th, der);
+    if (p.model == BAMGPU_MDL_BARATINBAC) return baratinbac_prepare(p, th, der);
     if (p.model == BAMGPU_MDL_VEGETATION) return vegetation_prepare(p, th, der, xc, nser);
     if (p.model == BAMGPU_MDL_ORTHO) return ortho_prepare(th, der);
     if (p.model == BAMGPU_MDL_SEGMENTATION) return segmentation_prepare(p, th, der, xc[0], nser);
@@ -582,6 +722,8 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return recession_apply(x[0], th, y[0]);
     } else if (MODEL == BAMGPU_MDL_ORTHO) {
         return ortho_apply(p, x, th, der, y);
+    } else if (MODEL == BAMGPU_MDL_BARATINBAC) {
+        return baratinbac_apply(p, x[0], th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_HCS) {
         return hcs_apply(p, x[0], th, y[0]);
     } else if (MODEL == BAMGPU_MDL_SEGMENTATION) {

@@ -331,6 +331,23 @@ void load_workspace(const std::string& configFile, Workspace& w) {
             if ((int)rows[r].size() < nc) fail("BaRatin_XtraRead:problem reading file " + xf);
             for (int cc = 0; cc < nc; ++cc) w.xtraI[r + (size_t)cc * nc] = rows[r][cc];
         }
+    } else if (w.modelID == "BaRatinBAC") {  // BaRatinBAC_XtraRead (:150-180): n-1 matrix rows, then hmax
+        std::vector<std::vector<double>> rows;
+        for (auto& l : read_lines(xf)) {
+            auto it = list_items(l);
+            if (it.empty()) continue;
+            std::vector<double> r;
+            for (auto& s : it) r.push_back(to_double(s));
+            rows.push_back(r);
+        }
+        if (rows.size() < 2) fail("BaRatinBAC_XtraRead:problem reading file " + xf);
+        const int nc = (int)rows.size() - 1;
+        w.xtraI.assign((size_t)nc * nc, 0);
+        for (int r = 0; r < nc; ++r) {
+            if ((int)rows[r].size() < nc) fail("BaRatinBAC_XtraRead:problem reading file " + xf);
+            for (int cc = 0; cc < nc; ++cc) w.xtraI[r + (size_t)cc * nc] = (int)std::lround(rows[r][cc]);
+        }
+        w.xtraD = {rows[nc][0]};
     } else if (w.modelID == "Sediment") {  // Sediment_XtraRead (SedimentTransport_model.f90:193-245)
         Cursor s(xf);
         auto pick = [&](const std::string& v, std::initializer_list<const char*> names, const char* what) {
@@ -570,6 +587,10 @@ void Workspace::make_headers(const bamgpu_sizes& s, int nDparModel) {  // GetHea
     std::vector<std::string> dn;
     if (modelID == "BaRatin")
         for (int i = 1; i <= nDparModel; ++i) dn.push_back("b" + std::to_string(i));
+    if (modelID == "BaRatinBAC") {  // ModelLibrary_tools.f90:593-602
+        for (int i = 1; i <= nDparModel / 2; ++i) dn.push_back("k" + std::to_string(i));
+        for (int i = 1; i <= nDparModel / 2; ++i) dn.push_back("ktype" + std::to_string(i));
+    }
     if (modelID == "Orthorectification")  // ModelLibrary_tools.f90:608-613
         for (auto nm : {"r11", "r12", "r13", "r21", "r22", "r23", "r31", "r32", "r33", "a1", "a2", "a3", "a4", "b1", "b2",
                         "b3", "b4", "c1", "c2", "c3"})

@@ -379,3 +379,31 @@ def second_wave(model: str, nobs: int = 400, seed: int = SEED + 7, **kw):
     prob = Problem(model, X, Y, Yu=uq, partype=[0] * nt, priors_theta=pri, sigma_func=["Linear"],
                    priors_gamma=[("Uniform", [0, 1e6])] * 2, **xtra)
     return prob, np.concatenate([th, [0.01 * np.abs(q).mean(), 0.05]])
+
+
+def baratin_bac(nobs: int = 300, seed: int = SEED + 8, hmax: float = 6.0):
+    """BaRatinBAC: the 3-control matrix of tests/BaM_BaRatinBAC (control 2 REPLACES control 1, control 3 is ADDED),
+    theta = (b, a, c) per control.  Returns (Problem, truth)."""
+    rng = np.random.default_rng(seed)
+    M = [[1, 0, 0], [0, 1, 0], [0, 1, 1]]
+    b, a, c = [-0.6, -0.1, 1.2], [14.17, 26.52, 31.82], [1.5, 1.67, 1.67]
+    # activation stages: k1 = b1; k2 solves a1 (k-b1)^c1 = a2 (k-b2)^c2 (replacement); k3 = b3 (addition)
+    from scipy.optimize import brentq
+    k2 = brentq(lambda x: c[1] * np.log(x - b[1]) - c[0] * np.log(x - b[0]) - np.log(a[0] / a[1]), -0.1 + 1e-9, 1.2)
+    H = rng.uniform(-1.0, 4.0, nobs)
+    Q = np.zeros(nobs)
+    r1 = (H >= b[0]) & (H < k2)
+    r2 = (H >= k2) & (H < b[2])
+    r3 = H >= b[2]
+    Q[r1] = a[0] * (H[r1] - b[0]) ** c[0]
+    Q[r2] = a[1] * (H[r2] - b[1]) ** c[1]
+    Q[r3] = a[1] * (H[r3] - b[1]) ** c[1] + a[2] * (H[r3] - b[2]) ** c[2]
+    uQ = 0.05 * Q + 0.05
+    gam = (0.5, 0.05)
+    Qobs = Q + rng.standard_normal(nobs) * np.sqrt(uQ**2 + (gam[0] + gam[1] * Q) ** 2)
+    th = np.array([b[0], a[0], c[0], b[1], a[1], c[1], b[2], a[2], c[2]])
+    pri = [("Gaussian", [v, 0.2 * abs(v) + 0.05]) for v in th]
+    prob = Problem("BaRatinBAC", H, Qobs, Yu=uQ, partype=[0] * 9, priors_theta=pri, sigma_func=["Linear"],
+                   priors_gamma=[("Uniform", [0, 1000])] * 2, xtra_i=np.asarray(M, dtype=np.int32).flatten(order="F"),
+                   xtra_d=[hmax])
+    return prob, np.concatenate([th, gam])

@@ -44,7 +44,8 @@ enum bamgpu_model {
     BAMGPU_MDL_ORTHO = 9,         /* Orthorectification_model.f90:66-288 ("Orthorectification") */
     BAMGPU_MDL_RECESSION_H = 10,  /* Recession_model.f90:36-94 ("Recession_h") */
     BAMGPU_MDL_HCS = 11,          /* HydraulicControl_section_model.f90:40-112 ("HydraulicControl_section") */
-    BAMGPU_MDL_SEGMENTATION = 12  /* Segmentation_model.f90:52-140 (whole-series model: segment sizes are checked) */
+    BAMGPU_MDL_SEGMENTATION = 12, /* Segmentation_model.f90:52-140 (whole-series model: segment sizes are checked) */
+    BAMGPU_MDL_BARATINBAC = 13    /* BaRatinBAC_model.f90:96-666: BaRatin in the b-a-c parameterisation */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -93,7 +94,7 @@ enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YI
  */
 typedef struct bamgpu_problem {
     const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
-                             "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation"
+                             "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC"
                              (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 
@@ -129,6 +130,7 @@ typedef struct bamgpu_problem {
 
     /* model-specific xtra (ModelLibrary_tools.f90:436-544):
        BaRatin    : xtra_i = control matrix ncontrol x ncontrol, column-major (n_xtra_i = ncontrol^2)
+       BaRatinBAC : the same matrix; xtra_d = {hmax} (upper bound of the highest activation stage)
        Sediment   : xtra_i = {formula, css, co, ppo_d, ppo_s, ppo_v, ppo_g}; xtra_d = pseudoval[4]
        TextFile   : xtra_text = content of the model text file (TextFile_model.f90:946-978)
        Vegetation : xtra_i = {growth formula, nYear, itmax}; xtra_d = {xscale, fscale, tolX, tolF}

@@ -667,6 +667,141 @@ static void baratin_apply(const oracle_t* o, int n, const double* H, const doubl
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * BaRatinBAC (BaRatinBAC_model.f90:96-666)
+ * ------------------------------------------------------------------------------------------ */
+static const double BAC_EPS = 1.1920928955078125e-07; /* epsilon(1.) -- single precision (:400) */
+
+static double bac_f(double x, double a1, double b1, double c1, double a2, double b2, double c2) { /* fContinuity :521 */
+    return c2 * log(x - b2) - c1 * log(x - b1) - log(a1 / a2);
+}
+static double bac_df(double x, double b1, double c1, double b2, double c2) { /* dfContinuity :528 */
+    return (c2 / (x - b2)) - (c1 / (x - b1));
+}
+
+/* findRoot (:603-636): znewton(tolX=1e-4, tolF=1e-6, xscale=fscale=1, itmax=10000); declared convention as for the
+   Vegetation solver (rtsafe, then the root is polished). */
+static int bac_find_root(double a1, double b1, double c1, double a2, double b2, double c2, double x1, double x2, double fl,
+                         double fh, double* root) {
+    if (fl == 0.0) { *root = x1; return 1; }
+    if (fh == 0.0) { *root = x2; return 1; }
+    if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) return 0;
+    double xl, xh;
+    if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
+    double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
+    double f = bac_f(rts, a1, b1, c1, a2, b2, c2), df = bac_df(rts, b1, c1, b2, c2);
+    for (int j = 0; j < 10000; ++j) {
+        if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+            dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
+        } else {
+            dxold = dx; dx = f / df; rts = rts - dx;
+        }
+        int convx = fabs(dx) <= 1e-4;
+        f = bac_f(rts, a1, b1, c1, a2, b2, c2);
+        df = bac_df(rts, b1, c1, b2, c2);
+        if (f < 0.0) xl = rts; else xh = rts;
+        if (convx || fabs(f) <= 1e-6) break;
+    }
+    for (int j = 0; j < 4 && f != 0.0 && df != 0.0; ++j) {
+        double lo = xl < xh ? xl : xh, hi = xl < xh ? xh : xl;
+        double xn = rts - f / df;
+        if (xn < lo) xn = lo;
+        if (xn > hi) xn = hi;
+        if (xn == rts) break;
+        rts = xn;
+        f = bac_f(rts, a1, b1, c1, a2, b2, c2);
+        df = bac_df(rts, b1, c1, b2, c2);
+        if (f < 0.0) xl = rts; else xh = rts;
+    }
+    *root = rts;
+    return rts == rts;
+}
+
+/* SolveContinuity (:396-518) */
+static int bac_solve(double a1, double b1, double c1, double a2, double b2, double c2, double lbound, double hbound,
+                     double* root, int* troot) {
+    const double eps = BAC_EPS;
+    *troot = 0;
+    if (fabs(c1 - c2) <= eps) {
+        if (fabs(a1 - a2) <= eps) return 0;
+        double foo1 = pow(a1, 1.0 / c1), foo2 = pow(a2, 1.0 / c1);
+        *root = (foo2 * b2 - foo1 * b1) / (foo2 - foo1);
+        if (*root > lbound && *root < hbound) { *troot = 1; return 1; }
+        return 0;
+    }
+    if (fabs(b1 - b2) <= eps) {
+        *root = b1 + pow(a1 / a2, 1.0 / (c2 - c1));
+        if (*root > lbound && *root < hbound) { *troot = 2; return 1; }
+        return 0;
+    }
+    double x0 = (c2 * b1 - c1 * b2) / (c2 - c1);
+    if (x0 <= lbound) {
+        double f1 = bac_f(lbound + eps, a1, b1, c1, a2, b2, c2), f2 = bac_f(hbound, a1, b1, c1, a2, b2, c2);
+        if (f1 * f2 > 0.0) return 0;
+        if (bac_find_root(a1, b1, c1, a2, b2, c2, lbound + eps, hbound, f1, f2, root)) { *troot = 3; return 1; }
+        return 0;
+    }
+    double fx0 = bac_f(x0, a1, b1, c1, a2, b2, c2);
+    if (fabs(fx0) <= eps) { *root = x0; *troot = 5; return 1; }
+    if ((c2 > c1 && fx0 > 0.0) || (c2 < c1 && fx0 < 0.0)) { *troot = 6; return 0; }
+    *troot = 4;
+    if (x0 >= hbound) return 0;
+    double f2 = bac_f(hbound, a1, b1, c1, a2, b2, c2);
+    if (f2 * fx0 > 0.0) return 0;
+    return bac_find_root(a1, b1, c1, a2, b2, c2, x0, hbound, fx0, f2, root);
+}
+
+/* BaRatinBAC_Apply (:96-149) = ApplyContinuity (:237-394) + BaRatin_computeQ (BaRatin_model.f90:194-252) */
+static void baratinbac_apply(const oracle_t* o, int n, const double* H, const double* theta, double* Q, double* Dpar,
+                             int32_t* vfeas) {
+    int nc = o->ncontrol, ok = 1;
+    double b[MAXCONTROL], a[MAXCONTROL], c[MAXCONTROL], k[MAXCONTROL], kt[MAXCONTROL];
+    for (int i = 0; i < nc; ++i) { b[i] = theta[3 * i]; a[i] = theta[3 * i + 1]; c[i] = theta[3 * i + 2]; }
+    for (int i = 0; i < nc; ++i)
+        if (a[i] <= 0.0 || c[i] == 0.0) ok = 0;
+    if (ok) {
+        k[0] = b[0]; kt[0] = 0.0;
+        for (int j = nc - 1; j >= 1 && ok; --j) {
+            double lbound = b[j] > b[j - 1] ? b[j] : b[j - 1];
+            double hbound = (j == nc - 1) ? o->model_optd : k[j + 1];
+            int addition = 1;
+            for (int i = 0; i < j; ++i)
+                if (o->M[j * nc + i] != o->M[(j - 1) * nc + i]) addition = 0;
+            if (addition) { k[j] = b[j]; kt[j] = 0.0; }
+            else {
+                double root = 0.0;
+                int troot = 0;
+                if (!bac_solve(a[j - 1], b[j - 1], c[j - 1], a[j], b[j], c[j], lbound, hbound, &root, &troot)) { ok = 0; break; }
+                k[j] = root; kt[j] = (double)troot;
+            }
+            if (k[j] >= hbound) { ok = 0; break; }
+            for (int i = 0; i < j; ++i)
+                if (k[j] < b[i]) ok = 0;
+        }
+    }
+    if (!ok) {
+        for (int t = 0; t < n; ++t) vfeas[t] = 0;
+        return;
+    }
+    for (int i = 0; i < nc; ++i) { Dpar[i] = k[i]; Dpar[nc + i] = kt[i]; }
+    for (int t = 0; t < n; ++t) {
+        double h = H[t];
+        int range = nc;
+        for (int i = 0; i < nc; ++i)
+            if (h < k[i]) { range = i; break; }
+        double q = 0.0;
+        for (int i = 0; i < range; ++i) {
+            if (o->M[(range - 1) * nc + i] == 1) {
+                if ((h - b[i]) < 0.0) { q = 0.0; break; }
+                q = q + a[i] * pow(h - b[i], c[i]);
+            } else {
+                if ((h - b[i]) < 0.0) { vfeas[t] = 0; break; }
+            }
+        }
+        Q[t] = q;
+    }
+}
+
 /* LM_Apply, Linear_model.f90:62-101: Y = matmul(X, reshape(theta,(nX,nY))) */
 static void linear_apply(const oracle_t* o, int n, const double* X, int ldx, const double* theta, double* Y,
                          int ldy) {
@@ -1170,6 +1305,7 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         case BAMGPU_MDL_RECESSION_H: recession_apply(n, X, fullTheta, Y); break;
         case BAMGPU_MDL_ORTHO: ortho_apply(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas); break;
         case BAMGPU_MDL_HCS: hcs_apply(o, n, X, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_BARATINBAC: baratinbac_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
         case BAMGPU_MDL_SEGMENTATION:
             if (!segmentation_apply(o, n, X, fullTheta, Y))
                 for (int t = 0; t < n; ++t) vfeas[t] = 0; /* scalar feas=.false. (ModelLibrary_tools.f90:362-364) */
@@ -1205,6 +1341,7 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "Recession_h")) return BAMGPU_MDL_RECESSION_H;
     if (!strcmp(name, "HydraulicControl_section")) return BAMGPU_MDL_HCS;
     if (!strcmp(name, "Segmentation")) return BAMGPU_MDL_SEGMENTATION;
+    if (!strcmp(name, "BaRatinBAC")) return BAMGPU_MDL_BARATINBAC;
     return 0;
 }
 
@@ -1288,6 +1425,7 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
         case BAMGPU_MDL_LINEAR:
             if (nt != nX * nY) { setmess(mess, "oracle: Linear: ntheta /= nX*nY"); return 1; }
             break;
+        case BAMGPU_MDL_BARATINBAC:
         case BAMGPU_MDL_BARATIN: {
             int nc = nt / 3;
             if (nX != 1 || nY != 1 || nt != 3 * nc || nc < 1 || nc > MAXCONTROL || p->n_xtra_i != nc * nc) {
@@ -1297,6 +1435,11 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             for (int r = 0; r < nc; ++r)
                 for (int c = 0; c < nc; ++c) o->M[r * nc + c] = p->xtra_i[r + c * nc];
             o->nDparModel = nc;
+            if (o->model == BAMGPU_MDL_BARATINBAC) {
+                if (p->n_xtra_d != 1) { setmess(mess, "oracle: BaRatinBAC: hmax missing"); return 1; }
+                o->model_optd = p->xtra_d[0];
+                o->nDparModel = 2 * nc;
+            }
             break;
         }
         case BAMGPU_MDL_SEDIMENT: {

@@ -94,3 +94,31 @@ def test_segmentation_and_hcs_prediction_uses_the_prediction_series():
         oenv, ospag = o.predict(mc, truth, [grid], 1, [0], want_spag=True)
         assert (spag == ospag).all() and (env == oenv).all()  # piecewise-constant outputs: exact
     assert (spag == -666.666).all() and (env == -666.666).all()
+
+
+def test_baratinbac():
+    """b-a-c parameterisation: per-parameter-set root finding for the activation stage of a REPLACED control
+    (SolveContinuity cases I-VI), then the BaRatin discharge equation.  Derived parameters = (k_i, ktype_i)."""
+    prob, truth = synth.baratin_bac(nobs=400)
+    x = synth.feasible_starts(truth, 64, rel=0.01, seed=4)
+    x[3, 1] = -1.0                  # a1 <= 0 (:266-268)
+    x[4, 3] = 3.0                   # b2 above b3: the replacement root falls beyond its upper bound -> infeasible
+    x[5, 5] = x[5, 2]               # c2 == c1: case I (explicit root)
+    x[6, 3] = x[6, 0]               # b2 == b1: case II (explicit root)
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.nDpar == 6
+    check_parity(prob, x)
+    fx, feas, isnull, dpar = g.logpost(x, want_dpar=True)
+    assert feas[0] == 1 and feas[3] == 0 and feas[4] == 0
+    assert list(dpar[0, 3:]) == [0.0, 3.0, 0.0] or list(dpar[0, 3:]) == [0.0, 4.0, 0.0]  # ktype: addition, root case, addition
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.005 * rng.standard_normal((300, truth.size)))
+    H = np.linspace(-1.5, 5.0, 120)
+    env, spag = g.predict(mc, truth, [H], 1, [1], seed=4, want_spag=True)
+    oenv, ospag = o.predict(mc, truth, [H], 1, [1], seed=4, want_spag=True, nthreads=8)
+    cmp_spag(spag, ospag)
+    cmp_env(env, oenv)
+    s = np.tile(truth, (3, 1))
+    rows = g.fit(s, 0.01 * np.abs(s), nAdapt=4, nCycles=2, seed=5)
+    orows = o.fit(s, 0.01 * np.abs(s), nAdapt=4, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)

@@ -90,6 +90,17 @@ def test_config_reader_on_shipped_second_wave_workspace():
     assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == ("HydraulicControl_section", 6, 1, 1)
     tab = np.asarray(d["xtra_d"]).reshape(3, -1)  # h | A | w
     assert tab.shape[1] >= 3 and (np.diff(tab[0]) >= 0).all() and (tab[1, 1:] > 0).all()
+    # BaRatinBAC ships without a top-level Config_BaM file: point one at the workspace
+    cfg = "/tmp/_Config_BaM_BaRatinBAC.txt"
+    open(cfg, "w").write("\n".join(['"/root/reference/tests/BaM_BaRatinBAC/"', '"Config_RunOptions.txt"', '"Config_Model.txt"',
+                                    '"Config_ControlMatrix.txt"', '"Config_Data.txt"', '"Config_RemnantSigma.txt"', '"Config_MCMC.txt"',
+                                    '"Config_Cooking.txt"', '"Config_Summary.txt"', '"Config_Residuals.txt"',
+                                    '"Config_Pred_Master.txt"']) + "\n")
+    out = cfg + ".json"
+    r = subprocess.run([EXE, "-cf", cfg, "--dump-problem", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = json.load(open(out))
+    assert (d["model_id"], d["nobs"]) == ("BaRatinBAC", 104) and list(d["xtra_i"]) == [1, 0, 0, 0, 1, 1, 0, 0, 1] and d["xtra_d"] == [5]
     d = dump_ref(os.path.join("BaM_Segmentation", "Config_BaM.txt"))  # a Config_BaM.txt stored inside its workspace
     assert (d["model_id"], d["nobs"]) == ("Segmentation", 110) and list(d["xtra_i"]) == [2, 2, 1]
 

@@ -244,3 +244,42 @@ def test_vegetation_newton_root_is_the_root():
     f = x * x + gam * x * x * np.minimum(1.0, x**chi / gam2) - Q0 * Q0
     assert sel.sum() > 50 and np.max(np.abs(f) / (Q0 * Q0)) < 1e-14
     assert (np.minimum(1.0, x**chi / gam2) < 1.0).any() and (x < Q0).all()
+
+
+def test_baratinbac_is_consistent_with_baratin():
+    """Two parameterisations of the same rating curve, restated from two different reference modules
+    (BaRatin_model.f90 k-a-c, BaRatinBAC_model.f90 b-a-c): feeding BaRatin's derived offsets b back into BaRatinBAC
+    must return the original activation stages k (root of the continuity equation for the REPLACED control, b itself
+    for the ADDED one) and the same discharges."""
+    from bam_b200.capi import Problem
+
+    for name, ktypes in (("baratin", [0, 3]), ("baratin_spd", None)):
+        prob, fx = problem_from_fixture(name, with_copula=False)
+        o = Oracle(prob)
+        x = np.asarray(fx["start"], dtype=np.float64)
+        _, feas, _, dpar = o.logpost(x.reshape(1, -1), want_dpar=True)
+        assert feas[0] == 1
+        nc = prob.ntheta // 3
+        if name == "baratin_spd":  # first VAR combination: k1_1, k2_1
+            th = np.array([x[0], x[5], x[6], x[7], x[12], x[13], x[14], x[15], x[16]])
+            b = dpar[0][:3]
+        else:
+            th, b = x[:6], dpar[0][:2]
+        k, a, c = th[0::3], th[1::3], th[2::3]
+        bac_theta = np.column_stack([b, a, c]).flatten()
+        H = np.linspace(float(k[0]) - 0.5, 4.0, 200)
+        M = np.asarray(prob.xtra_i)
+        pb = Problem("BaRatinBAC", H, np.zeros_like(H), partype=[0] * (3 * nc), priors_theta=[("FlatPrior", [])] * (3 * nc),
+                     sigma_func=["Constant"], priors_gamma=[("FlatPrior", [])], xtra_i=M, xtra_d=[50.0])
+        pk = Problem("BaRatin", H, np.zeros_like(H), partype=[0] * (3 * nc), priors_theta=[("FlatPrior", [])] * (3 * nc),
+                     sigma_func=["Constant"], priors_gamma=[("FlatPrior", [])], xtra_i=M)
+        Yb, fb, dpb = Oracle(pb).apply_model(H, bac_theta)
+        Yk, fk, dpk = Oracle(pk).apply_model(H, th)
+        assert fb.all() and fk.all()
+        assert np.allclose(dpb[:nc], k, rtol=1e-11, atol=1e-12), (dpb[:nc], k)
+        assert np.allclose(dpk[:nc], b, rtol=0, atol=0)
+        # discharges agree except within rounding of a stage boundary
+        away = np.min(np.abs(H[:, None] - k[None, :]), axis=1) > 1e-9
+        assert np.allclose(Yb[away, 0], Yk[away, 0], rtol=1e-12, atol=1e-12)
+        if ktypes is not None:
+            assert list(dpb[nc:2 * nc]) == ktypes
