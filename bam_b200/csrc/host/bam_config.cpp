@@ -207,6 +207,110 @@ std::vector<double> read_matrix(const std::string& file, int nrow, int ncol, int
     return M;
 }
 
+// Xtra (ModelLibrary_tools.f90 XtraRead :436-544): fills w.xtraI / w.xtraD / w.xtraText from the model's Xtra file
+static void read_xtra(Workspace& w) {
+    const std::string xf = w.dir + fix_sep(w.fXtra);
+    if (w.modelID == "BaRatin") {  // BaRatin_XtraRead: square 0/1 matrix, size = number of rows
+        std::vector<std::vector<int>> rows;
+        for (auto& l : read_lines(xf)) {
+            auto it = list_items(l);
+            if (it.empty()) continue;
+            std::vector<int> r;
+            for (auto& s : it) r.push_back((int)std::lround(to_double(s)));
+            rows.push_back(r);
+        }
+        int nc = (int)rows.size();
+        w.xtraI.assign((size_t)nc * nc, 0);
+        for (int r = 0; r < nc; ++r) {
+            if ((int)rows[r].size() < nc) fail("BaRatin_XtraRead:problem reading file " + xf);
+            for (int cc = 0; cc < nc; ++cc) w.xtraI[r + (size_t)cc * nc] = rows[r][cc];
+        }
+    } else if (w.modelID == "BaRatinBAC") {  // BaRatinBAC_XtraRead (:150-180): n-1 matrix rows, then hmax
+        std::vector<std::vector<double>> rows;
+        for (auto& l : read_lines(xf)) {
+            auto it = list_items(l);
+            if (it.empty()) continue;
+            std::vector<double> r;
+            for (auto& s : it) r.push_back(to_double(s));
+            rows.push_back(r);
+        }
+        if (rows.size() < 2) fail("BaRatinBAC_XtraRead:problem reading file " + xf);
+        const int nc = (int)rows.size() - 1;
+        w.xtraI.assign((size_t)nc * nc, 0);
+        for (int r = 0; r < nc; ++r) {
+            if ((int)rows[r].size() < nc) fail("BaRatinBAC_XtraRead:problem reading file " + xf);
+            for (int cc = 0; cc < nc; ++cc) w.xtraI[r + (size_t)cc * nc] = (int)std::lround(rows[r][cc]);
+        }
+        w.xtraD = {rows[nc][0]};
+    } else if (w.modelID == "Sediment") {  // Sediment_XtraRead (SedimentTransport_model.f90:193-245)
+        Cursor s(xf);
+        auto pick = [&](const std::string& v, std::initializer_list<const char*> names, const char* what) {
+            int k = 1;
+            for (auto nm : names) { if (v == nm) return k; ++k; }
+            fail(std::string("Sediment: Fatal:Unavailable [") + what + "] '" + v + "'");
+        };
+        w.xtraI.push_back(pick(s.str(), {"MPM", "Camenen", "Nielsen", "Smart"}, "ID"));
+        w.xtraI.push_back(pick(s.str(), {"Constant", "Soulsby", "SoulsbyWhitehouse"}, "CSS_ID"));
+        w.xtraI.push_back(pick(s.str(), {"FIX", "PAR"}, "CO"));
+        for (auto& o : s.strs(4)) w.xtraI.push_back(pick(o, {"FIX", "IN", "PAR"}, "PPO"));
+        w.xtraD = s.nums(4);
+    } else if (w.modelID == "TextFile") {
+        std::ifstream is(xf);
+        if (!is) fail("TxtMdl_load:problem opening file " + xf);
+        std::stringstream ss;
+        ss << is.rdbuf();
+        w.xtraText = ss.str();
+    } else if (w.modelID == "Vegetation") {  // Vegetation_XtraRead (Vegetation_model.f90:244-289)
+        Cursor s(xf);
+        const std::string gf = s.str();
+        int gid = 0;
+        const char* names[] = {"Growth_Yin1", "Growth_Yin2", "Growth_Yin3", "Growth_Yin1_temporal"};
+        for (int k = 0; k < 4; ++k)
+            if (gf == names[k]) gid = k + 1;
+        if (!gid) fail("GetNpar_growth:Fatal:Unavailable [growthFormula] '" + gf + "'");
+        w.xtraI.push_back(gid);
+        w.xtraI.push_back(s.integer());                          // nYear
+        for (int k = 0; k < 4; ++k) w.xtraD.push_back(s.num());  // Newton xscale, fscale, tolX, tolF (one per line)
+        w.xtraI.push_back(s.integer());                          // Newton itmax
+    } else if (w.modelID == "SWOT") {  // SWOT_XtraRead (SWOT_model.f90:150-182): model variant
+        Cursor s(xf);
+        const std::string id = s.str();
+        if (id == "SWOT_hS") w.xtraI.push_back(BAMGPU_SWOT_HS);
+        else if (id == "SWOT_hSB") w.xtraI.push_back(BAMGPU_SWOT_HSB);
+        else fail("SWOT_Apply: Fatal: Unavailable [ID] '" + id + "'");
+    } else if (w.modelID == "Orthorectification") {  // Ortho_XtraRead (Orthorectification_model.f90:192-230)
+        Cursor s(xf);
+        const std::string id = s.str();
+        if (id == "None") w.xtraI.push_back(BAMGPU_DISTO_NONE);
+        else if (id == "Radial") w.xtraI.push_back(BAMGPU_DISTO_RADIAL);
+        else fail("Disto_Apply:Fatal:Unavailable [Disto_ID] '" + id + "'");
+        w.xtraI.push_back(s.integer());
+    } else if (w.modelID == "HydraulicControl_section") {  // h-A-w matrix, one row per line (:114-150)
+        std::vector<std::vector<double>> rows;
+        for (auto& l : read_lines(xf)) {
+            auto it = list_items(l);
+            if (it.empty()) continue;
+            if (it.size() < 3) fail("HydraulicControl_section_XtraRead:problem reading file " + xf);
+            rows.push_back({to_double(it[0]), to_double(it[1]), to_double(it[2])});
+        }
+        const size_t np = rows.size();
+        w.xtraD.assign(3 * np, 0.0);
+        for (size_t i = 0; i < np; ++i)
+            for (int c = 0; c < 3; ++c) w.xtraD[i + c * np] = rows[i][c];
+    } else if (w.modelID == "Segmentation") {  // Segmentation_XtraRead (:142-180): nS, tmin, nmin, option
+        Cursor s(xf);
+        const int nS = s.integer();
+        const double tmin = s.num();
+        const int nmin = s.integer(), option = s.integer();
+        w.xtraI = {nS, nmin, option};
+        w.xtraD = {tmin};
+    } else if (w.modelID == "Linear" || w.modelID == "SuspendedLoad" || w.modelID == "SGD" || w.modelID == "Recession_h") {
+    } else {
+        fail("ApplyModel: Fatal: Unavailable [model%ID] '" + w.modelID + "' (not on the GPU hot path yet)");
+    }
+
+}
+
 void load_workspace(const std::string& configFile, Workspace& w) {
     // Config_Read (:1963-2040)
     Cursor c(configFile);
@@ -314,106 +418,7 @@ void load_workspace(const std::string& configFile, Workspace& w) {
         }
     }
 
-    // Xtra (ModelLibrary_tools.f90 XtraRead :436-544)
-    const std::string xf = w.dir + fix_sep(w.fXtra);
-    if (w.modelID == "BaRatin") {  // BaRatin_XtraRead: square 0/1 matrix, size = number of rows
-        std::vector<std::vector<int>> rows;
-        for (auto& l : read_lines(xf)) {
-            auto it = list_items(l);
-            if (it.empty()) continue;
-            std::vector<int> r;
-            for (auto& s : it) r.push_back((int)std::lround(to_double(s)));
-            rows.push_back(r);
-        }
-        int nc = (int)rows.size();
-        w.xtraI.assign((size_t)nc * nc, 0);
-        for (int r = 0; r < nc; ++r) {
-            if ((int)rows[r].size() < nc) fail("BaRatin_XtraRead:problem reading file " + xf);
-            for (int cc = 0; cc < nc; ++cc) w.xtraI[r + (size_t)cc * nc] = rows[r][cc];
-        }
-    } else if (w.modelID == "BaRatinBAC") {  // BaRatinBAC_XtraRead (:150-180): n-1 matrix rows, then hmax
-        std::vector<std::vector<double>> rows;
-        for (auto& l : read_lines(xf)) {
-            auto it = list_items(l);
-            if (it.empty()) continue;
-            std::vector<double> r;
-            for (auto& s : it) r.push_back(to_double(s));
-            rows.push_back(r);
-        }
-        if (rows.size() < 2) fail("BaRatinBAC_XtraRead:problem reading file " + xf);
-        const int nc = (int)rows.size() - 1;
-        w.xtraI.assign((size_t)nc * nc, 0);
-        for (int r = 0; r < nc; ++r) {
-            if ((int)rows[r].size() < nc) fail("BaRatinBAC_XtraRead:problem reading file " + xf);
-            for (int cc = 0; cc < nc; ++cc) w.xtraI[r + (size_t)cc * nc] = (int)std::lround(rows[r][cc]);
-        }
-        w.xtraD = {rows[nc][0]};
-    } else if (w.modelID == "Sediment") {  // Sediment_XtraRead (SedimentTransport_model.f90:193-245)
-        Cursor s(xf);
-        auto pick = [&](const std::string& v, std::initializer_list<const char*> names, const char* what) {
-            int k = 1;
-            for (auto nm : names) { if (v == nm) return k; ++k; }
-            fail(std::string("Sediment: Fatal:Unavailable [") + what + "] '" + v + "'");
-        };
-        w.xtraI.push_back(pick(s.str(), {"MPM", "Camenen", "Nielsen", "Smart"}, "ID"));
-        w.xtraI.push_back(pick(s.str(), {"Constant", "Soulsby", "SoulsbyWhitehouse"}, "CSS_ID"));
-        w.xtraI.push_back(pick(s.str(), {"FIX", "PAR"}, "CO"));
-        for (auto& o : s.strs(4)) w.xtraI.push_back(pick(o, {"FIX", "IN", "PAR"}, "PPO"));
-        w.xtraD = s.nums(4);
-    } else if (w.modelID == "TextFile") {
-        std::ifstream is(xf);
-        if (!is) fail("TxtMdl_load:problem opening file " + xf);
-        std::stringstream ss;
-        ss << is.rdbuf();
-        w.xtraText = ss.str();
-    } else if (w.modelID == "Vegetation") {  // Vegetation_XtraRead (Vegetation_model.f90:244-289)
-        Cursor s(xf);
-        const std::string gf = s.str();
-        int gid = 0;
-        const char* names[] = {"Growth_Yin1", "Growth_Yin2", "Growth_Yin3", "Growth_Yin1_temporal"};
-        for (int k = 0; k < 4; ++k)
-            if (gf == names[k]) gid = k + 1;
-        if (!gid) fail("GetNpar_growth:Fatal:Unavailable [growthFormula] '" + gf + "'");
-        w.xtraI.push_back(gid);
-        w.xtraI.push_back(s.integer());                          // nYear
-        for (int k = 0; k < 4; ++k) w.xtraD.push_back(s.num());  // Newton xscale, fscale, tolX, tolF (one per line)
-        w.xtraI.push_back(s.integer());                          // Newton itmax
-    } else if (w.modelID == "SWOT") {  // SWOT_XtraRead (SWOT_model.f90:150-182): model variant
-        Cursor s(xf);
-        const std::string id = s.str();
-        if (id == "SWOT_hS") w.xtraI.push_back(BAMGPU_SWOT_HS);
-        else if (id == "SWOT_hSB") w.xtraI.push_back(BAMGPU_SWOT_HSB);
-        else fail("SWOT_Apply: Fatal: Unavailable [ID] '" + id + "'");
-    } else if (w.modelID == "Orthorectification") {  // Ortho_XtraRead (Orthorectification_model.f90:192-230)
-        Cursor s(xf);
-        const std::string id = s.str();
-        if (id == "None") w.xtraI.push_back(BAMGPU_DISTO_NONE);
-        else if (id == "Radial") w.xtraI.push_back(BAMGPU_DISTO_RADIAL);
-        else fail("Disto_Apply:Fatal:Unavailable [Disto_ID] '" + id + "'");
-        w.xtraI.push_back(s.integer());
-    } else if (w.modelID == "HydraulicControl_section") {  // h-A-w matrix, one row per line (:114-150)
-        std::vector<std::vector<double>> rows;
-        for (auto& l : read_lines(xf)) {
-            auto it = list_items(l);
-            if (it.empty()) continue;
-            if (it.size() < 3) fail("HydraulicControl_section_XtraRead:problem reading file " + xf);
-            rows.push_back({to_double(it[0]), to_double(it[1]), to_double(it[2])});
-        }
-        const size_t np = rows.size();
-        w.xtraD.assign(3 * np, 0.0);
-        for (size_t i = 0; i < np; ++i)
-            for (int c = 0; c < 3; ++c) w.xtraD[i + c * np] = rows[i][c];
-    } else if (w.modelID == "Segmentation") {  // Segmentation_XtraRead (:142-180): nS, tmin, nmin, option
-        Cursor s(xf);
-        const int nS = s.integer();
-        const double tmin = s.num();
-        const int nmin = s.integer(), option = s.integer();
-        w.xtraI = {nS, nmin, option};
-        w.xtraD = {tmin};
-    } else if (w.modelID == "Linear" || w.modelID == "SuspendedLoad" || w.modelID == "SGD" || w.modelID == "Recession_h") {
-    } else {
-        fail("ApplyModel: Fatal: Unavailable [model%ID] '" + w.modelID + "' (not on the GPU hot path yet)");
-    }
+    read_xtra(w);
 
     // flatten for the C ABI
     for (auto& p : w.theta) {
@@ -491,6 +496,48 @@ void load_workspace(const std::string& configFile, Workspace& w) {
         Cursor pm(w.dir + w.fPredMaster);
         int np = pm.integer();
         for (int i = 0; i < np; ++i) w.predConfigs.push_back(pm.str());
+    }
+}
+
+// Config_Read_oneRun (:2042-2092) + Config_Read_Inputs (:2294-2330) + BaM_ReadInputs (:1196-1240): workspace, model
+// config, xtra config, inputs config {data file, header lines, nobs, ncol}.  The model is run ONCE at the initial
+// values of Config_Model (src/BaM_main.f90:215-247); there is no calibration data and no remnant model.
+void load_onerun(const std::string& configFile, Workspace& w, std::vector<double>& Xin, int& nIn) {
+    Cursor c(configFile);
+    w.dir = fix_sep(c.str());
+    if (!w.dir.empty() && w.dir.back() != '/') w.dir += '/';
+    if (!exists(w.dir + ".")) {
+        size_t cut = configFile.find_last_of('/');
+        w.dir = (cut == std::string::npos ? std::string("") : configFile.substr(0, cut + 1)) + w.dir;
+    }
+    w.fModel = c.str(); w.fXtra = c.str();
+    const std::string fInputs = c.str();
+    {
+        Cursor m(w.dir + w.fModel);
+        w.modelID = m.str();
+        w.nX = m.integer(); w.nY = m.integer(); w.ntheta = m.integer();
+        for (int i = 0; i < w.ntheta; ++i) w.theta.push_back(read_par(m));
+    }
+    read_xtra(w);
+    Cursor d(w.dir + fix_sep(fInputs));
+    const std::string dataFile = resolve(w, d.str());
+    const int nhead = d.integer();
+    nIn = d.integer();
+    const int ncol = d.integer();
+    std::vector<double> W = read_matrix(dataFile, nIn, ncol, nhead);
+    if (ncol < w.nX) fail("BaM_ReadInputs: fewer columns than model inputs in " + dataFile);
+    Xin.assign(W.begin(), W.begin() + (size_t)nIn * w.nX);  // the first nX columns (column-major)
+    // every parameter takes its first initial value and is handed to the library as FIX: nothing is inferred
+    w.nobs = 0;
+    for (auto& pr : w.theta) {
+        w.partype.push_back(-1); w.nval.push_back(1);
+        w.fixValue.push_back(pr.init.empty() ? 0.0 : pr.init[0]);
+    }
+    for (int j = 0; j < w.nY; ++j) {  // placeholder remnant model (never used: no noise, no likelihood)
+        w.sigmaFunc.push_back(BAMGPU_SIG_CONSTANT); w.nremnant.push_back(1);
+        w.priorGammaDist.push_back(BAMGPU_DIST_FLATPRIOR);
+        for (int q = 0; q < BAMGPU_PRIOR_NPAR; ++q) w.priorGammaPar.push_back(0.0);
+        w.gamma0.push_back(1.0);
     }
 }
 

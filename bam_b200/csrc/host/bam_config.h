@@ -94,6 +94,8 @@ struct Workspace {
 
 // throws std::runtime_error with the reference's style of message on failure
 void load_workspace(const std::string& configFile, Workspace& w);
+// --onerun mode (src/BaM_main.f90:215-247): model + xtra + an input file; Xin = nIn x nX column-major
+void load_onerun(const std::string& configFile, Workspace& w, std::vector<double>& Xin, int& nIn);
 PredConfig read_pred_config(const Workspace& w, const std::string& file);
 std::vector<double> read_matrix(const std::string& file, int nrow, int ncol, int nskip);  // column-major
 std::string resolve(const Workspace& w, const std::string& name);

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <numeric>
 #include <random>
@@ -120,9 +121,10 @@ static bool prior_draw(const Prior& pr, std::mt19937_64& g, double& x, double& m
 }
 
 int main(int argc, char** argv) {
-    std::string cfg = "Config_BaM.txt", dump;
+    std::string cfg = "Config_BaM.txt", dump, priorFile, yFile;
     unsigned long long seed = 20261019ull;
     int K = 1, device = 0;
+    bool savePrior = false, earlyStop = false, oneRun = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto need = [&](const char* what) -> std::string {
@@ -131,18 +133,50 @@ int main(int argc, char** argv) {
         };
         if (a == "-cf" || a == "--config") cfg = need("a path to a file");
         else if (a == "-sd" || a == "--seed") seed = strtoull(need("the seed as an integer number").c_str(), nullptr, 10);
+        else if (a == "-sp" || a == "--saveprior") { savePrior = true; priorFile = need("a file name"); }
+        else if (a == "-rd" || a == "--random") seed = (unsigned long long)std::random_device{}() * 2654435761ull + (unsigned long long)time(nullptr);
+        else if (a == "-dr" || a == "--dontrun") earlyStop = true;
+        else if (a == "-or" || a == "--onerun") { oneRun = true; yFile = need("a file name"); }
         else if (a == "--chains") K = atoi(need("a number of chains").c_str());
         else if (a == "--device") device = atoi(need("a device ordinal").c_str());
         else if (a == "--dump-problem") dump = need("a file name");
         else if (a == "-v" || a == "--version") { printf(" version: %s\n", kVersion); return 0; }
         else if (a == "-h" || a == "--help") {
-            printf("usage: bam_gpu [-cf Config_BaM.txt] [-sd seed] [--chains K] [--device d] [--dump-problem file.json]\n");
+            printf("usage: bam_gpu [-cf Config_BaM.txt] [-sd seed | -rd] [-sp priorfile] [-dr] [-or Yfile] [--chains K] [--device d]\n"
+                   "               [--dump-problem file.json] [-v] [-h]\n"
+                   "  -cf, --config     main configuration file (default Config_BaM.txt)\n"
+                   "  -sd, --seed       seed of the random streams;  -rd, --random: seed from the clock\n"
+                   "  -sp, --saveprior  save the prior sample of prior-prediction experiments in this file (workspace-relative)\n"
+                   "  -dr, --dontrun    read the configuration, write INFO_BaM.txt and stop\n"
+                   "  -or, --onerun     run the model once at the initial parameter values on an input file, write Y to Yfile\n"
+                   "  --chains K        number of MCMC chains run in lockstep on the GPU (the reference runs 1)\n");
             return 0;
         } else { fprintf(stderr, "Unrecognized command-line option: %s\n", a.c_str()); return 1; }
     }
     bamgpu_t* h = nullptr;
     try {
         Workspace w;
+        if (oneRun) {  // src/BaM_main.f90:215-247
+            std::vector<double> Xin;
+            int nIn = 0;
+            load_onerun(cfg, w, Xin, nIn);
+            char mess[BAMGPU_MESS_LEN];
+            bamgpu_problem pb = w.problem();
+            check(bamgpu_create(&h, &pb, device, mess), mess);
+            std::vector<const double*> xp(w.nX);
+            std::vector<int32_t> ns(w.nX, 1), dr(w.nY, 0);
+            for (int i = 0; i < w.nX; ++i) xp[i] = Xin.data() + (size_t)i * nIn;
+            std::vector<double> mode(w.gamma0), spag((size_t)nIn * w.nY);  // vector = [gamma] only: every theta is FIX
+            check(bamgpu_predict(h, 1, nullptr, mode.data(), nIn, xp.data(), ns.data(), 0, dr.data(), seed, 0, nIn, nullptr, spag.data(), mess), mess);
+            std::vector<std::string> hd;
+            for (int j = 1; j <= w.nY; ++j) hd.push_back("Y" + std::to_string(j));
+            std::vector<double> tab((size_t)nIn * w.nY);
+            for (int t = 0; t < nIn; ++t)
+                for (int j = 0; j < w.nY; ++j) tab[(size_t)t * w.nY + j] = spag[(size_t)j * nIn + t];
+            write_table(w.dir + yFile, hd, tab, (size_t)nIn, (size_t)w.nY);  // BaM_WriteOutputs (:1244-1288)
+            bamgpu_destroy(h);
+            return 0;
+        }
         load_workspace(cfg, w);
         if (!dump.empty()) {
             std::ofstream(dump) << dump_problem_json(w);
@@ -164,6 +198,7 @@ int main(int argc, char** argv) {
                 fclose(f);
             }
         }
+        if (earlyStop) { bamgpu_destroy(h); return 0; }  // "-dr": the user just wanted INFO_BaM.txt (src/BaM_main.f90:308)
         std::vector<double> cooked;  // pooled rows [x, logpost, dpar]
         size_t nCooked = 0;
         const std::string cookPath = w.dir + w.cookFile;
@@ -364,6 +399,13 @@ int main(int argc, char** argv) {
                         for (auto& pr : p.prior) fill(pr);
                 for (auto& r : w.remnant)
                     for (auto& pr : r.prior) fill(pr);
+                if (savePrior && !priorFile.empty()) {  // BaM_Prediction :984-1004: header + one row per prior draw
+                    std::vector<std::string> hd(w.headers.begin(), w.headers.begin() + k);
+                    std::vector<double> tab((size_t)Nrep * k);
+                    for (long long r = 0; r < Nrep; ++r)
+                        for (int c = 0; c < k; ++c) tab[(size_t)r * k + c] = mc[r + (size_t)c * Nrep];
+                    write_table(w.dir + priorFile, hd, tab, (size_t)Nrep, (size_t)k);
+                }
             } else if (!isMaxpost) {
                 if (!nCooked) throw std::runtime_error("BaM_Prediction: no MCMC sample available");
                 Nrep = (long long)nCooked;

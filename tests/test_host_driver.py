@@ -208,3 +208,38 @@ def test_residuals_and_dic_files(name, tmp_path):
     assert (resid[~ok] == -9999.0).all()
     std = res[:, 2 * nX + 4 * nY:]
     assert np.isfinite(std[ok]).all() and np.abs(std[ok]).max() < 50
+
+
+@pytest.mark.gpu
+def test_onerun_dontrun_saveprior_modes(tmp_path):
+    """the remaining command-line modes of BaM_main (src/BaM_main.f90:100-160): --onerun (model run at the initial
+    values, :215-247), --dontrun (INFO_BaM.txt only, :308), --saveprior (prior sample of a prior prediction, :984-1004)"""
+    from oracle.oracle_api import Oracle
+    from tests.helpers import problem_from_fixture
+
+    fx = load_fixture("baratin")
+    H = np.linspace(-1, 6, 41)
+    cfg, ws = write_workspace(fx, str(tmp_path), name="OR", nAdapt=5, nCycles=2, do_pred=True,
+                              pred=[dict(X=H, doParametric=True, doRemnant=False, nsim=30)])
+    # --onerun
+    np.savetxt(os.path.join(ws, "Hin.txt"), np.column_stack([H, 2 * H]), header="H junk", comments="")
+    open(os.path.join(ws, "Config_Inputs.txt"), "w").write('"Hin.txt"\n1\n41\n2\n')
+    xtra = open(cfg).read().splitlines()[3].split('"')[1]  # 4th record of Config_BaM: the model's Xtra file
+    one = os.path.join(str(tmp_path), "Config_OneRun.txt")
+    open(one, "w").write(f'"{ws}/"\n"Config_Model.txt"\n"{xtra}"\n"Config_Inputs.txt"\n')
+    r = subprocess.run([EXE, "-cf", one, "-or", "Y_onerun.txt"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    head, Y = read_table(os.path.join(ws, "Y_onerun.txt"))
+    prob, _ = problem_from_fixture("baratin")
+    Yo, feas, _ = Oracle(prob).apply_model(H, np.asarray(fx["start"])[:6])
+    assert head == ["Y1"] and Y.shape == (41, 1) and np.allclose(Y[:, 0], Yo[:, 0], rtol=1e-5, atol=1e-9)  # e15.6: 6 digits
+    # --dontrun: only INFO_BaM.txt
+    r = subprocess.run([EXE, "-cf", cfg, "-dr"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(os.path.join(ws, "INFO_BaM.txt")) and not os.path.exists(os.path.join(ws, "Results_MCMC.txt"))
+    # --saveprior with a prior-prediction experiment (nsim = 30)
+    r = subprocess.run([EXE, "-cf", cfg, "-sd", "5", "-sp", "PriorSample.txt"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hp, pri = read_table(os.path.join(ws, "PriorSample.txt"))
+    assert hp[:3] == ["k1", "a1", "c1"] and pri.shape == (30, 8)
+    assert abs(pri[:, 1].mean() - 53.0) < 10.0  # a1 ~ N(53, 10) in Config_Model of tests/BaM_BaRatin
