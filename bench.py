@@ -363,6 +363,80 @@ def latent_sampler_leg(device, n=1_000_000, K=64, iters=4):
                     "full log-posterior (n observations) per component, the sweep kernel needs O(1) per latent input"}
 
 
+def multi_gpu_legs(device, rank, world, dist, torch):
+    """N > 1: the two places where the path exchanges data, through NCCL over NVLink.
+    (1) prediction inputs shard across ranks ([t0,t1) slices, samples replicated); every rank owns whole columns, so
+        the exact quantiles need no exchange; the envelope slices are all-gathered.  STRONG scaling: the experiment is
+        fixed (10^6 samples x 10^5 inputs), time = max over ranks (CUDA events) + the gather.
+    (2) chains shard across ranks; per-chain moments {count, mean, M2} are all-gathered from DEVICE buffers filled by
+        bamgpu_moments(dev_ptrs=1) and the Gelman-Rubin statistic is computed redundantly on every rank."""
+    from bam_b200 import synth
+    from bam_b200.capi import BamGpu
+    from tests.helpers import problem_from_fixture
+
+    out = {}
+    # ---- (1) sharded prediction
+    Nrep, nobs = 1_000_000, 100_000
+    prob, _ = synth.baratin_2c(nobs=38)
+    mc, mode, Hs = synth.baratin_spaghetti(Nrep=Nrep, nobs=nobs)
+    per = (nobs + world - 1) // world
+    t0, t1 = rank * per, min(nobs, (rank + 1) * per)
+    g = BamGpu(prob, device)
+    g.predict_upload(mc, mode, [Hs])
+    g.predict_resident(1, [1], seed=1, t0=t0, t1=t1)
+    g.sync(); g.step_times(); g.kernel_times()
+    dist.barrier(); torch.cuda.synchronize()
+    g.step_begin()
+    g.predict_resident(1, [1], seed=1, t0=t0, t1=t1)
+    g.step_end()
+    g.sync()
+    ms = float(g.step_times()[-1])
+    env = torch.from_numpy(np.ascontiguousarray(g.predict_download()[0].T)).cuda()  # (t1-t0) x 7
+    pad = torch.zeros(per, 7, dtype=torch.float64, device="cuda")
+    pad[: t1 - t0] = env
+    gathered = torch.empty(world * per, 7, dtype=torch.float64, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dist.all_gather_into_tensor(gathered, pad)
+    e1.record()
+    torch.cuda.synchronize()
+    tt = torch.tensor([ms, e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    full = gathered[:nobs].cpu().numpy()
+    out["prediction"] = {"metric": "prediction samples x inputs/sec", "value": Nrep * nobs / ((tt[0].item() + tt[1].item()) * 1e-3),
+                         "unit": "sample*input/s", "scaling": "strong", "ms_compute_max_over_ranks": tt[0].item(),
+                         "ms_envelope_allgather_nccl": tt[1].item(),
+                         "workload": f"BaRatin spaghetti {Nrep} samples x {nobs} inputs sharded by input over {world} GPUs",
+                         "finite": bool(np.isfinite(full).all()), "median_checksum": float(full[:, 0].sum())}
+    del g
+    # ---- (2) sharded sampler + NCCL all-gather of the moments
+    prob, d = problem_from_fixture("baratin")
+    K = 4096
+    g = BamGpu(prob, device)
+    g.set_chain_offset(rank * K)
+    s0 = np.tile(np.asarray(d["start"]), (K, 1))
+    g.fit(s0, 0.1 * np.abs(s0), nAdapt=100, nCycles=20, seed=3, want_rows=False)
+    P = g.P
+    cnt = torch.empty(K, dtype=torch.float64, device="cuda")
+    mean = torch.empty(K, P, dtype=torch.float64, device="cuda")
+    m2 = torch.empty(K, P, dtype=torch.float64, device="cuda")
+    g.moments_device(cnt.data_ptr(), mean.data_ptr(), m2.data_ptr())
+    gc = torch.empty(world * K, dtype=torch.float64, device="cuda")
+    gm = torch.empty(world * K, P, dtype=torch.float64, device="cuda")
+    g2 = torch.empty(world * K, P, dtype=torch.float64, device="cuda")
+    e0.record()
+    dist.all_gather_into_tensor(gc, cnt)
+    dist.all_gather_into_tensor(gm, mean)
+    dist.all_gather_into_tensor(g2, m2)
+    e1.record()
+    torch.cuda.synchronize()
+    rhat = g.rhat(gc.cpu().numpy(), gm.cpu().numpy(), g2.cpu().numpy())
+    out["sampler"] = {"workload": f"tests/BaM_BaRatin, {K} chains per GPU x 2000 iterations, chains sharded over {world} GPUs",
+                      "ms_fit_loop": float(g.step_times()[-1]), "ms_moments_allgather_nccl": e0.elapsed_time(e1),
+                      "chains_total": world * K, "rhat_max": float(np.nanmax(rhat))}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -478,6 +552,12 @@ def main():
     e2e_value = world * K * n * esteps / e_t
     assert (fx2 == fx).all()
 
+    multi = None
+    if world > 1 and not args.no_prediction:
+        try:
+            multi = multi_gpu_legs(device, rank, world, dist, torch)
+        except Exception as e:  # every rank must reach the barriers below
+            multi = {"error": str(e)}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -537,6 +617,8 @@ def main():
                 "path": "bamgpu_logpost (C ABI) with pinned host buffers, wall clock around the blocking calls"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "wall_s_timed_region": wall,
     }
+    if multi is not None:
+        line["multi_gpu"] = multi
     if not args.no_prediction and world == 1:
         try:
             line["prediction"] = prediction_leg(device, fp64_peak, hbm_peak)
