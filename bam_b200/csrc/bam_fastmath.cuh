@@ -103,6 +103,16 @@ __device__ __forceinline__ double texp(double x, unsigned et) {
     return res;
 }
 
+// log N(y; mu, sqrt(v)) given the variance v > 0, with the table-driven log (libdevice log() costs ~60 instructions,
+// 22 of them constant materialisations); v outside the normal range (denormal, inf, NaN) takes the libdevice path
+__device__ __forceinline__ double gauss_logpdf_var_t(double y, double mu, double v, unsigned lt) {
+    const double r = y - mu;
+    const unsigned hi = (unsigned)__double2hiint(v);
+    const double lg = (hi - 0x00100000u < 0x7fe00000u) ? tlog_pos(v, lt) : log(v);
+    const double t = fma(r * r, fast_rcp_pos(v), lg);
+    return fma(-0.5, t, -BAM_LOG_SQRT_2PI);
+}
+
 // 1/v for a positive normal v: MUFU.RCP64H seed (>= 20 bits) + one cubic step  r0 (1 + e + e^2), e = 1 - v r0
 __device__ __forceinline__ double trcp(double v) {
     double r0;

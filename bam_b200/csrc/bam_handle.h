@@ -16,6 +16,7 @@ struct LogpostPlan {
     int CT = 32;           // chains per block tile
     int nTiles = 0;        // observation tiles
     size_t smem = 0;
+    int logOff = 0;        // offset (in doubles) of the log table inside the dynamic shared memory
 };
 
 struct bamgpu_handle {

@@ -137,15 +137,18 @@ template <int MODEL, int NX, int NY>
 __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const double* __restrict__ x, int K, int CT, int TX,
                                                           const double* __restrict__ tab, const int* status,
                                                           double* __restrict__ part, int* statusOut, int comp,
-                                                          const double* __restrict__ delta) {
+                                                          const double* __restrict__ delta, int smemLogOff) {
     extern __shared__ double sm[];
     const int tabStride = p.tabStride;
     double* stab = sm;                        // CT x tabStride
     const int warpsPerRow = TX >> 5;
     double* red = sm + (size_t)CT * tabStride;  // [2][warpsPerRow][CT]
     int* sst = (int*)(red + 2 * warpsPerRow * CT);  // CT chain status
+    double2* sLogT = reinterpret_cast<double2*>(sm + smemLogOff);  // table of the table-driven log (16-byte aligned)
 
     const int tid = threadIdx.x;
+    for (int q = tid; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
+    const unsigned lt = smem_addr(sLogT);
     const int tx = tid % TX, ty = tid / TX, TY = BAM_BLOCK / TX;
     const int lane = tid & 31, wrow = tx >> 5;
     const int c0 = blockIdx.y * CT;
@@ -190,11 +193,29 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
         hyC[j] = 0.0; hyR[j] = 0.0;
         if (p.hasLatent && xu[j] > 0.0) { hyC[j] = -BAM_LOG_SQRT_2PI - log(xu[j]); hyR[j] = 1.0 / xu[j]; }
     }
+    // latent "true" inputs are per-chain state in HBM (16 B per chain x observation in cfg 3): the values of the NEXT
+    // chain of the tile are requested before the current chain is evaluated, so the load latency overlaps the math
+    double xlat[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) xlat[j] = 0.0;
+    if (p.hasLatent && act && ty < nc) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            if (lat[j] >= 0) xlat[j] = x[(size_t)(c0 + ty) * p.P + lat[j]];
+    }
     for (int cc = ty; cc < nc; cc += TY) {
         const int c = c0 + cc;
         const double* __restrict__ row = stab + (size_t)cc * tabStride;
         double lk = 0.0, hy = 0.0;
         bool bad = false, badh = false;
+        double xnext[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) xnext[j] = 0.0;
+        if (p.hasLatent && act && cc + TY < nc) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                if (lat[j] >= 0) xnext[j] = x[(size_t)(c + TY) * p.P + lat[j]];
+        }
         if (act && sst[cc] == 0) {
             const double dl = (comp >= 0) ? delta[c] : 0.0;
             // UnfoldParVector (:3429-3452): latent cell from the vector, else un-bias the observed input
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
             for (int j = 0; j < NX; ++j) {
                 double v = xo[j];
                 if (p.hasLatent && lat[j] >= 0) {
-                    v = x[(size_t)c * p.P + lat[j]];
+                    v = xlat[j];
                     if (lat[j] == comp) v += dl;
                 } else if (p.hasXbias && xbi[j] > 0) {
                     v = xo[j] - xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
@@ -223,7 +244,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
                     const double var = fma(yu[j], yu[j], sig * sig);  // sigma_Y^2 + sigma_remnant^2 (:3213)
                     double mu = yh[j];
                     if (p.hasYbias && ybi[j] != 0) mu = yh[j] + yb[j] * row[p.tabOffYb[j] + ybi[j] - 1];
-                    lk += gauss_logpdf_var(yo[j], mu, var);
+                    lk += gauss_logpdf_var_t(yo[j], mu, var, lt);
                 }
                 if (p.hasLatent) {
 #pragma unroll
@@ -238,6 +259,8 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
                 }
             }
         }
+#pragma unroll
+        for (int j = 0; j < NX; ++j) xlat[j] = xnext[j];
         // warp tree (fixed order) -> one value per (warp, chain)
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) lk += __shfl_down_sync(0xffffffffu, lk, off);
@@ -500,7 +523,7 @@ FastKernel pick_fast(const DevProblem& p, int K) {
 }
 
 using MainKernel = void (*)(DevProblem, const double*, int, int, int, const double*, const int*, double*, int*, int,
-                            const double*);
+                            const double*, int);
 
 MainKernel pick_main(int model, int nX, int nY) {
 #define X(M, A, B) \
@@ -560,7 +583,10 @@ static void make_plan(bamgpu_handle* h, int K) {
     while (ct > pl.TY && (long long)pl.nTiles * ((K + ct - 1) / ct) < 148 * 4) ct >>= 1;
     ct = std::max(ct, pl.TY);
     pl.CT = ct;
-    pl.smem = ((size_t)ct * stride + 2 * (pl.TX / 32) * ct) * 8 + (size_t)ct * 4;
+    // [chain tables | cross-warp partials | chain status (int)] then, 16-byte aligned, the 4 KB log table
+    const size_t head = ((size_t)ct * stride + 2 * (pl.TX / 32) * ct) * 8 + (size_t)ct * 4;
+    pl.logOff = (int)((head + 15) / 16 * 2);  // in doubles
+    pl.smem = (size_t)pl.logOff * 8 + sizeof(double) * 2 * BAM_LOGTAB_N;
 }
 
 cudaEvent_t take_event(bamgpu_handle* h) {
@@ -653,7 +679,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
         kern<<<grid, BAM_BLOCK, pl.smem, h->stream>>>(p, d_x, K, pl.CT, pl.TX, h->d_tab, h->d_status, h->d_part, h->d_status,
-                                                       comp, d_delta);
+                                                       comp, d_delta, pl.logOff);
     }
     if (timeMain) {
         BAM_CUDA(cudaEventRecord(h->ev1, h->stream));

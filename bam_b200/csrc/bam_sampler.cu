@@ -11,6 +11,7 @@
 // K5: Welford running moments {count, mean, M2} per (chain, component) over the kept rows; they feed
 // the Gelman-Rubin diagnostic (all-gathered across ranks by the caller, NCCL).
 #include "bam_dispatch.cuh"
+#include "bam_fastmath.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
 
@@ -328,7 +329,8 @@ template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool local_logpost(const DevProblem& p, const double* xt, const double* xo, const double* xu,
                                               const double* xb, const int* xbi, const double* yo, const double* yu,
                                               const double* yb, const int* ybi, const double* hyC, const double* hyR,
-                                              const double* __restrict__ row, const double* __restrict__ th, double& val) {
+                                              const double* __restrict__ row, const double* __restrict__ th, unsigned lt,
+                                              double& val) {
     double yh[NY];
     if (!model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh)) return false;
     double lk = 0.0;
@@ -339,7 +341,7 @@ __device__ __forceinline__ bool local_logpost(const DevProblem& p, const double*
         if (!(sig > 0.0)) return false;
         double mu = yh[j];
         if (p.hasYbias && ybi[j] != 0) mu = yh[j] + yb[j] * row[p.tabOffYb[j] + ybi[j] - 1];
-        lk += gauss_logpdf_var(yo[j], mu, fma(yu[j], yu[j], sig * sig));
+        lk += gauss_logpdf_var_t(yo[j], mu, fma(yu[j], yu[j], sig * sig), lt);
     }
     double hy = 0.0;
 #pragma unroll
@@ -359,10 +361,14 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
                                                           long long chainOffset, unsigned it, double* __restrict__ x,
                                                           const double* __restrict__ sd, int* __restrict__ moves,
                                                           const double* __restrict__ tab) {
-    extern __shared__ double lsm[];  // table row of this chain
+    extern __shared__ __align__(16) double lsm[];  // [log table (4 KB) | table row of this chain]
+    double2* sLogT = reinterpret_cast<double2*>(lsm);
+    double* srow = lsm + 2 * BAM_LOGTAB_N;
     const int c = blockIdx.y;
-    for (int q = threadIdx.x; q < p.tabStride; q += BAM_BLOCK) lsm[q] = tab[(size_t)c * p.tabStride + q];
+    for (int q = threadIdx.x; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
+    for (int q = threadIdx.x; q < p.tabStride; q += BAM_BLOCK) srow[q] = tab[(size_t)c * p.tabStride + q];
     __syncthreads();
+    const unsigned lt = smem_addr(sLogT);
     const int n = p.n;
     const int i = blockIdx.x * BAM_BLOCK + threadIdx.x;
     if (i >= n) return;
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
         yb[j] = 0.0; ybi[j] = 0;
         if (p.hasYbias) { yb[j] = p.Yb[q]; ybi[j] = p.Ybindx[q]; }
     }
-    const double* __restrict__ row = lsm;
+    const double* __restrict__ row = srow;
     const int combo = (p.nCombo > 1) ? p.comboOf[i] : 0;
     const double* __restrict__ th = row + p.tabCombo + (size_t)combo * p.comboStride;
     const size_t base = (size_t)c * p.P;
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
         if (xu[j] > 0.0) { hyC[j] = -BAM_LOG_SQRT_2PI - log(xu[j]); hyR[j] = 1.0 / xu[j]; }
     }
     double cur;
-    if (!local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, cur)) return;  // cannot happen for a feasible state
+    if (!local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, lt, cur)) return;  // cannot happen for a feasible state
     const unsigned long long gc = (unsigned long long)(chainOffset + c);
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
         xt[j] = old + sd[base + comp] * philox_normal(seed, gc, it, 2u * comp);
         double cand;
         bool acc = false;
-        if (local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, cand)) {
+        if (local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, lt, cand)) {
             const double u = philox_uniform(seed, gc, it, 2u * comp + 1u);
             acc = log(u) < cand - cur;
         }
@@ -526,7 +532,7 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
                 // full log-posterior of the swept state becomes the current one
                 launch_table(h, K, h->d_x);
                 dim3 grid((p.n + BAM_BLOCK - 1) / BAM_BLOCK, K);
-                lk<<<grid, BAM_BLOCK, sizeof(double) * p.tabStride, s>>>(p, K, seed, h->chainOffset, (unsigned)it, h->d_x,
+                lk<<<grid, BAM_BLOCK, sizeof(double) * (p.tabStride + 2 * BAM_LOGTAB_N), s>>>(p, K, seed, h->chainOffset, (unsigned)it, h->d_x,
                                                                         h->d_std, h->d_moves, h->d_tab);
                 launch_logpost(h, K, h->d_x, -1, nullptr, false);
                 BAM_CUDA(cudaMemcpyAsync(h->d_fxcur, h->d_fx, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
