@@ -167,6 +167,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
             for (int v = L.nCombo - 1; v >= 0; --v) start[v] = std::min(start[v], start[v + 1]);
             if (nDev == 0) start.assign(L.nCombo + 1, 0);
             d.comboStart = upload(h, start.data(), start.size());
+            h->comboStartHost = start;
             // tables of the table-driven log / exp (bam_fastmath.cuh), computed in long double
             std::vector<double> lt(2 * BAM_LOGTAB_N), et(BAM_EXPTAB_N);
             for (int i = 0; i < BAM_LOGTAB_N; ++i) {
@@ -227,6 +228,9 @@ void bamgpu_destroy(bamgpu_t* h) {
     fr(h->d_x); fr(h->d_tab); fr(h->d_part); fr(h->d_prior); fr(h->d_lkh); fr(h->d_hyper); fr(h->d_fx); fr(h->d_dpar);
     fr(h->d_status); fr(h->d_delta); fr(h->d_std); fr(h->d_fxcur); fr(h->d_dparcur); fr(h->d_moves); fr(h->d_mcount);
     fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_env);
+    fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0); fr(h->d_lkCcur); fr(h->d_lkCcand);
+    for (auto*& q : h->d_compTiles) fr(q);
+    for (auto*& q : h->d_compAffected) fr(q);
     free_prediction(h);
     if (h->d_flush) cudaFree(h->d_flush);
     for (auto e : h->evPool) cudaEventDestroy(e);
@@ -248,6 +252,7 @@ int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s) {
 int bamgpu_set_option(bamgpu_t* h, const char* name, int value) {
     if (!strcmp(name, "force_generic")) { h->forceGeneric = value != 0; return 0; }
     if (!strcmp(name, "no_select3")) { h->noSelect3 = value != 0; return 0; }
+    if (!strcmp(name, "no_partial")) { h->noPartial = value != 0; return 0; }
     return 1;
 }
 

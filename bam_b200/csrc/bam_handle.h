@@ -34,7 +34,17 @@ struct bamgpu_handle {
     double *d_prior = nullptr, *d_lkh = nullptr, *d_hyper = nullptr, *d_fx = nullptr, *d_dpar = nullptr;
     int* d_status = nullptr;
     LogpostPlan plan;
+    // fast-path tiling: tiles never straddle VAR combinations, so per-combination likelihood sums exist and a
+    // proposal on a VAR parameter only re-evaluates the tiles of the combinations it touches (bam_logpost.cu)
+    int fpTobs = 0, fpTiles = 0;
+    int *d_fpStart = nullptr, *d_fpEnd = nullptr, *d_fpCombo = nullptr, *d_fpComboTile0 = nullptr;
+    std::vector<int> comboStartHost, fpComboTile0;
+    double *d_lkCcur = nullptr, *d_lkCcand = nullptr;  // nCombo x Kcap: per-combination log-likelihood of the current / candidate state
+    std::vector<int*> d_compTiles, d_compAffected;      // per vector component: tile ids / 0-1 flag per combination (lazy)
+    std::vector<int> compTileCnt;
+    bool lkCvalid = false;
     long long chainOffset = 0;
+    bool noPartial = false;     // tests / measurement: always re-evaluate every observation in the sampler
     bool noSelect3 = false;     // tests: skip the 2-read envelope selection
     bool forceGeneric = false;  // tests: disable the specialised fast kernels  // global index of local chain 0 (multi-GPU sharding; RNG streams)
 
@@ -91,7 +101,9 @@ void ensure_chain_capacity(bamgpu_handle* h, int K);
 cudaEvent_t take_event(bamgpu_handle* h);
 // evaluate K vectors at d_x (optionally with component `comp` of every vector shifted by d_delta[k]);
 // results in d_prior/d_lkh/d_hyper/d_fx/d_status/d_dpar.  Asynchronous on h->stream.
-void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain);
+void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain,
+                    bool partial = false);
+bool fast_path_keeps_combo_sums(const bamgpu_handle* h, int K);
 
 void launch_table(bamgpu_handle* h, int K, const double* d_x);
 int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const double* d_xtrue, const int* d_combo,

@@ -325,6 +325,51 @@ __global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final(DevProblem p
     fx[c] = st ? BAMGPU_UNDEF_RN : (prior[c] + a + b);
 }
 
+// K1b for the fast path: per-combination sums (fixed stripes inside a combination, combinations in order), so that
+//   * a full and a partial evaluation of the same state give bitwise the same log-posterior, and
+//   * a proposal on a VAR parameter re-uses the cached sums of the combinations it does not touch.
+__global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final_combo(DevProblem p, int K, const int* __restrict__ comboTile0,
+                                                                    const double* __restrict__ part,
+                                                                    const double* __restrict__ prior, int* __restrict__ status,
+                                                                    const int* __restrict__ affected,
+                                                                    const double* __restrict__ lkCcur, double* __restrict__ lkCcand,
+                                                                    double* __restrict__ lkh, double* __restrict__ hyper,
+                                                                    double* __restrict__ fx) {
+    __shared__ double sa[FINAL_STRIPES][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    double total = 0.0;
+    for (int v = 0; v < p.nCombo; ++v) {
+        const bool redo = affected == nullptr || affected[v] != 0;  // uniform over the block
+        if (redo) {
+            double a = 0.0;
+            if (c < K)
+                for (int t = comboTile0[v] + w; t < comboTile0[v + 1]; t += FINAL_STRIPES) a += part[((size_t)t * K + c) * 2];
+            sa[w][lane] = a;
+            __syncthreads();
+            if (w == 0 && c < K) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < FINAL_STRIPES; ++q) s += sa[q][lane];
+                lkCcand[(size_t)v * K + c] = s;
+                total += s;
+            }
+            __syncthreads();
+        } else if (w == 0 && c < K) {
+            const double s = lkCcur[(size_t)v * K + c];
+            lkCcand[(size_t)v * K + c] = s;
+            total += s;
+        }
+    }
+    if (w != 0 || c >= K) return;
+    int st = status[c];
+    if (!st && !(total == total)) st |= ST_LKH_INFEAS;
+    status[c] = st;
+    lkh[c] = total;
+    hyper[c] = 0.0;
+    fx[c] = st ? BAMGPU_UNDEF_RN : (prior[c] + total + 0.0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 fast path: BaRatin, chain-parallel ("thread = chain") with observations broadcast from shared memory.
 //
@@ -345,7 +390,9 @@ __global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final(DevProblem p
 #define BAM_CB_ILP 4
 #endif
 template <int NC, int SIGF>
-__global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(DevProblem p, int K, int TOBS, const double* __restrict__ tab,
+__global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(DevProblem p, int K, int TOBS, const int* __restrict__ tStart,
+                                                                    const int* __restrict__ tEnd, const int* __restrict__ tCombo,
+                                                                    const int* __restrict__ tileIds, const double* __restrict__ tab,
                                                                     const int* status, double* __restrict__ part,
                                                                     int* statusOut) {
     extern __shared__ __align__(16) double sm[];
@@ -356,8 +403,10 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(Dev
     double* sV = sY + TOBS;                          // uQ^2
 
     const int tid = threadIdx.x;
-    const int i0 = blockIdx.x * TOBS;
-    const int nt = min(TOBS, p.n - i0);
+    // tiles never straddle VAR combinations (host tile table); with a tile list only the listed tiles are evaluated
+    const int tile = tileIds ? tileIds[blockIdx.x] : blockIdx.x;
+    const int i0 = tStart[tile];
+    const int nt = tEnd[tile] - i0;
     for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) sLog[i] = p.logTab[i];
     for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExp[i] = p.expTab[i];
     for (int i = tid; i < nt; i += BAM_BLOCK) {
@@ -369,7 +418,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(Dev
     __syncthreads();
     const int c = blockIdx.y * BAM_BLOCK + tid;
     if (c >= K) return;
-    const size_t o = ((size_t)blockIdx.x * K + c) * 2;
+    const size_t o = ((size_t)tile * K + c) * 2;
     part[o + 1] = 0.0;
     if (status[c] != 0) { part[o] = 0.0; return; }
     const double* __restrict__ row = tab + (size_t)c * p.tabStride;
@@ -387,10 +436,10 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(Dev
     bool bad = false;
     int cnt = 0;
 
-    for (int v = 0; v < p.nCombo; ++v) {
-        const int lo = max(i0, __ldg(p.comboStart + v)) - i0, hi = min(i0 + nt, __ldg(p.comboStart + v + 1)) - i0;
-        cnt += max(hi - lo, 0);
-        if (lo >= hi) continue;
+    {
+        const int v = tCombo[tile];
+        const int lo = 0, hi = nt;
+        cnt = nt;
         const double* __restrict__ cr = row + p.tabCombo + (size_t)v * p.comboStride;
         double k[NC], b[NC], cc[NC], la[NC];
 #pragma unroll
@@ -486,8 +535,6 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(Dev
             const double h0 = sH[i];
             tail(q_checked(h0, (mask4 >> (4 * range(h0))) & 0xfu), sY[i], sV[i], pmu[0]);
         }
-        if (hi > lo) {  // leave the tracked range consistent for the next tile segment (not needed: state is per segment)
-        }
         bad |= badAcc < 0;
     }
     // sum_i log N(y_i; q_i, sqrt(var_i)) = -cnt log sqrt(2 pi) - 0.5 [ sum log var_i + sum res_i^2 / var_i ]
@@ -499,7 +546,8 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(Dev
     if (bad) atomicOr(&statusOut[c], ST_LKH_INFEAS);
 }
 
-using FastKernel = void (*)(DevProblem, int, int, const double*, const int*, double*, int*);
+using FastKernel = void (*)(DevProblem, int, int, const int*, const int*, const int*, const int*, const double*, const int*,
+                            double*, int*);
 
 template <int NC>
 FastKernel pick_fast_sig(int sigf) {
@@ -589,6 +637,66 @@ static void make_plan(bamgpu_handle* h, int K) {
     pl.smem = (size_t)pl.logOff * 8 + sizeof(double) * 2 * BAM_LOGTAB_N;
 }
 
+#define BAM_FP_MAXCOMBO 64
+
+bool fast_path_keeps_combo_sums(const bamgpu_handle* h, int K) {
+    return !h->forceGeneric && h->dp.n > 0 && pick_fast(h->dp, K) != nullptr && h->dp.nCombo <= BAM_FP_MAXCOMBO;
+}
+
+// tiles of at most `tobs` observations that never straddle two VAR combinations (observations are stored sorted by
+// combination): tile table on the device, tile range of every combination on host and device
+static void ensure_fast_tiles(bamgpu_handle* h, int tobs) {
+    if (h->fpTobs == tobs && h->d_fpStart) return;
+    auto fr = [](auto*& q) { if (q) cudaFree(q); q = nullptr; };
+    fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0);
+    for (auto*& q : h->d_compTiles) fr(q);
+    for (auto*& q : h->d_compAffected) fr(q);
+    h->d_compTiles.clear(); h->d_compAffected.clear(); h->compTileCnt.clear();
+    const int nCombo = h->dp.nCombo;
+    std::vector<int> ts, te, tc;
+    h->fpComboTile0.assign(nCombo + 1, 0);
+    for (int v = 0; v < nCombo; ++v) {
+        h->fpComboTile0[v] = (int)ts.size();
+        for (int i = h->comboStartHost[v]; i < h->comboStartHost[v + 1]; i += tobs) {
+            ts.push_back(i); te.push_back(std::min(i + tobs, h->comboStartHost[v + 1])); tc.push_back(v);
+        }
+    }
+    h->fpComboTile0[nCombo] = (int)ts.size();
+    h->fpTiles = (int)ts.size();
+    h->fpTobs = tobs;
+    auto up = [&](int*& d, const std::vector<int>& v) {
+        BAM_CUDA(cudaMalloc(&d, sizeof(int) * std::max<size_t>(v.size(), 1)));
+        BAM_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, h->stream));
+    };
+    up(h->d_fpStart, ts); up(h->d_fpEnd, te); up(h->d_fpCombo, tc); up(h->d_fpComboTile0, h->fpComboTile0);
+    BAM_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+    h->lkCvalid = false;
+}
+
+// tile list and affected-combination flags of one vector component (built on first use).  A fitted theta value
+// touches the combinations whose parameter set reads it (HostLayout::comboSrc); gamma touches all of them.
+static void ensure_comp_tiles(bamgpu_handle* h, int comp) {
+    const HostLayout& L = h->L;
+    if (h->d_compTiles.empty()) {
+        h->d_compTiles.assign(L.P, nullptr); h->d_compAffected.assign(L.P, nullptr); h->compTileCnt.assign(L.P, -1);
+    }
+    if (h->compTileCnt[comp] >= 0) return;
+    std::vector<int> aff(L.nCombo, comp >= L.nFit ? 1 : 0), tiles;
+    if (comp < L.nFit)
+        for (int k = 0; k < L.nCombo; ++k)
+            for (int i = 0; i < L.ntheta; ++i)
+                if (L.comboSrc[(size_t)k * L.ntheta + i] == comp) aff[k] = 1;
+    for (int k = 0; k < L.nCombo; ++k)
+        if (aff[k])
+            for (int t = h->fpComboTile0[k]; t < h->fpComboTile0[k + 1]; ++t) tiles.push_back(t);
+    BAM_CUDA(cudaMalloc(&h->d_compTiles[comp], sizeof(int) * std::max<size_t>(tiles.size(), 1)));
+    BAM_CUDA(cudaMalloc(&h->d_compAffected[comp], sizeof(int) * L.nCombo));
+    BAM_CUDA(cudaMemcpyAsync(h->d_compTiles[comp], tiles.data(), sizeof(int) * tiles.size(), cudaMemcpyHostToDevice, h->stream));
+    BAM_CUDA(cudaMemcpyAsync(h->d_compAffected[comp], aff.data(), sizeof(int) * L.nCombo, cudaMemcpyHostToDevice, h->stream));
+    BAM_CUDA(cudaStreamSynchronize(h->stream));
+    h->compTileCnt[comp] = (int)tiles.size();
+}
+
 cudaEvent_t take_event(bamgpu_handle* h) {
     if (!h->evPool.empty()) { cudaEvent_t e = h->evPool.back(); h->evPool.pop_back(); return e; }
     cudaEvent_t e;
@@ -600,12 +708,17 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     if (K <= h->Kcap) { make_plan(h, K); return; }
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(h->d_x); fr(h->d_tab); fr(h->d_part); fr(h->d_prior); fr(h->d_lkh); fr(h->d_hyper); fr(h->d_fx); fr(h->d_dpar);
-    fr(h->d_status); fr(h->d_delta);
+    fr(h->d_status); fr(h->d_delta); fr(h->d_lkCcur); fr(h->d_lkCcand);
+    h->lkCvalid = false;
     const DevProblem& p = h->dp;
     make_plan(h, K);
     BAM_CUDA(cudaMalloc(&h->d_x, sizeof(double) * (size_t)K * p.P));
     BAM_CUDA(cudaMalloc(&h->d_tab, sizeof(double) * (size_t)K * p.tabStride));
-    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * std::max(std::max(h->plan.nTiles, (h->dp.n + 127) / 128), 1)));
+    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * (std::max(std::max(h->plan.nTiles, (h->dp.n + 127) / 128), 1) + p.nCombo)));
+    if (p.nCombo <= BAM_FP_MAXCOMBO) {
+        BAM_CUDA(cudaMalloc(&h->d_lkCcur, sizeof(double) * (size_t)K * p.nCombo));
+        BAM_CUDA(cudaMalloc(&h->d_lkCcand, sizeof(double) * (size_t)K * p.nCombo));
+    }
     BAM_CUDA(cudaMalloc(&h->d_prior, sizeof(double) * K));
     BAM_CUDA(cudaMalloc(&h->d_lkh, sizeof(double) * K));
     BAM_CUDA(cudaMalloc(&h->d_hyper, sizeof(double) * K));
@@ -652,7 +765,7 @@ void launch_table(bamgpu_handle* h, int K, const double* d_x) {
     BAM_CUDA(cudaGetLastError());
 }
 
-void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain) {
+void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta, bool timeMain, bool partial) {
     const DevProblem& p = h->dp;
     const LogpostPlan& pl = h->plan;
     MainKernel kern = pick_main(p.model, p.nX, p.nY);
@@ -666,15 +779,33 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         if (h->recordKernels && h->kernEv.size() < 8192) { k0 = take_event(h); k1 = take_event(h); BAM_CUDA(cudaEventRecord(k0, h->stream)); }
     }
     int nTiles = pl.nTiles;
+    bool comboFinal = false;
+    const int* d_affected = nullptr;
     if (fast) {
         // observations per block: large tiles amortise the staging, but keep >= ~6 blocks per SM in flight
         int tobs = 256;
         const int chainBlocks = (K + BAM_BLOCK - 1) / BAM_BLOCK;
         while (tobs > 128 && (long long)chainBlocks * ((p.n + tobs - 1) / tobs) < 148 * 6) tobs >>= 1;
-        nTiles = (p.n + tobs - 1) / tobs;
+        ensure_fast_tiles(h, tobs);
+        nTiles = h->fpTiles;
+        comboFinal = p.nCombo <= BAM_FP_MAXCOMBO;
+        // a proposal that touches only some VAR combinations re-evaluates only their tiles (the cached sums of the
+        // current state cover the rest); needs the cache to describe the CURRENT state: the sampler guarantees it
+        const int* d_tiles = nullptr;
+        int launchTiles = nTiles;
+        if (partial && comboFinal && comp >= 0 && comp < h->L.P && h->lkCvalid && p.nCombo > 1) {
+            ensure_comp_tiles(h, comp);
+            if (h->compTileCnt[comp] < nTiles) {
+                d_tiles = h->d_compTiles[comp];
+                launchTiles = h->compTileCnt[comp];
+                d_affected = h->d_compAffected[comp];
+            }
+        }
         const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 3 * (size_t)tobs);
-        dim3 grid(nTiles, chainBlocks);
-        fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_tab, h->d_status, h->d_part, h->d_status);
+        dim3 grid(std::max(launchTiles, 1), chainBlocks);
+        if (launchTiles > 0)
+            fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_fpStart, h->d_fpEnd, h->d_fpCombo, d_tiles, h->d_tab,
+                                                       h->d_status, h->d_part, h->d_status);
     } else if (p.n > 0) {
         if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
@@ -685,8 +816,13 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         BAM_CUDA(cudaEventRecord(h->ev1, h->stream));
         if (k1) { BAM_CUDA(cudaEventRecord(k1, h->stream)); h->kernEv.emplace_back(k0, k1); }
     }
-    logpost_final<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, p.n > 0 ? nTiles : 0, h->d_part, h->d_prior,
-                                                                       h->d_status, h->d_lkh, h->d_hyper, h->d_fx);
+    if (comboFinal)
+        logpost_final_combo<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, h->d_fpComboTile0, h->d_part, h->d_prior,
+                                                                                 h->d_status, d_affected, h->d_lkCcur, h->d_lkCcand,
+                                                                                 h->d_lkh, h->d_hyper, h->d_fx);
+    else
+        logpost_final<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, p.n > 0 ? nTiles : 0, h->d_part, h->d_prior,
+                                                                           h->d_status, h->d_lkh, h->d_hyper, h->d_fx);
     h->launches += (p.n > 0) ? 3 : 2;
     BAM_CUDA(cudaGetLastError());
 }

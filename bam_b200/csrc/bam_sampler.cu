@@ -27,7 +27,8 @@ __global__ void propose_kernel(int K, int P, int comp, unsigned long long seed, 
 __global__ void accept_kernel(int K, int P, int nDpar, int comp, unsigned long long seed, long long chainOffset,
                               unsigned it, const double* __restrict__ delta, const double* __restrict__ fxCand,
                               const int* __restrict__ stCand, const double* __restrict__ dparCand, double* __restrict__ x,
-                              double* __restrict__ fxCur, double* __restrict__ dparCur, int* __restrict__ moves) {
+                              double* __restrict__ fxCur, double* __restrict__ dparCur, int* __restrict__ moves,
+                              int nCombo, const double* __restrict__ lkCcand, double* __restrict__ lkCcur) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= K) return;
     if (stCand[c] != 0) return;  // infeasible or null candidate: rejected
@@ -37,6 +38,9 @@ __global__ void accept_kernel(int K, int P, int nDpar, int comp, unsigned long l
         fxCur[c] = fxCand[c];
         for (int d = 0; d < nDpar; ++d) dparCur[(size_t)c * nDpar + d] = dparCand[(size_t)c * nDpar + d];
         moves[(size_t)c * P + comp] += 1;
+        // per-combination likelihood sums of the accepted state (fast path with partial re-evaluation)
+        if (lkCcur != nullptr)
+            for (int v = 0; v < nCombo; ++v) lkCcur[(size_t)v * K + c] = lkCcand[(size_t)v * K + c];
     }
 }
 
@@ -514,11 +518,19 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
     // sweep applies (vector order: theta | gamma | latent inputs | X biases | Y biases, Packer :4202-4242)
     LatentKernel lk = (p.hasLatent && !h->forceGeneric) ? pick_latent_sweep(p.model, p.nX, p.nY) : nullptr;
     const int latBeg = p.nFit + p.nGamma, latEnd = latBeg + p.nLatent;
+    // fast path (BaRatin, many chains): per-combination likelihood sums of the current state are kept, so that a
+    // proposal on a VAR parameter only re-evaluates the observations of the combinations it touches
+    const bool comboSums = fast_path_keeps_combo_sums(h, K) && !lk && !h->noPartial;
+    if (comboSums) {  // the full evaluation of the start point above left its sums in d_lkCcand
+        BAM_CUDA(cudaMemcpyAsync(h->d_lkCcur, h->d_lkCcand, sizeof(double) * (size_t)K * p.nCombo, cudaMemcpyDeviceToDevice, s));
+        h->lkCvalid = true;
+    }
     auto propose_one = [&](int i, long long it) {
         propose_kernel<<<gK, TB, 0, s>>>(K, P, i, seed, h->chainOffset, (unsigned)it, h->d_std, h->d_delta);
-        launch_logpost(h, K, h->d_x, i, h->d_delta, false);
+        launch_logpost(h, K, h->d_x, i, h->d_delta, false, comboSums);
         accept_kernel<<<gK, TB, 0, s>>>(K, P, nD, i, seed, h->chainOffset, (unsigned)it, h->d_delta, h->d_fx,
-                                        h->d_status, h->d_dpar, h->d_x, h->d_fxcur, h->d_dparcur, h->d_moves);
+                                        h->d_status, h->d_dpar, h->d_x, h->d_fxcur, h->d_dparcur, h->d_moves, p.nCombo,
+                                        comboSums ? h->d_lkCcand : nullptr, comboSums ? h->d_lkCcur : nullptr);
         h->launches += 2;
     };
     long long it = 0, kept = 0;
@@ -555,6 +567,7 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
     }
     BAM_CUDA(cudaEventRecord(f1, s));
     if (h->stepEv.size() < 8192) h->stepEv.emplace_back(f0, f1);
+    h->lkCvalid = false;
     // leave the final state consistent for bamgpu_chains_download
     BAM_CUDA(cudaMemcpyAsync(h->d_fx, h->d_fxcur, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
     BAM_CUDA(cudaMemcpyAsync(h->d_dpar, h->d_dparcur, sizeof(double) * (size_t)K * std::max(nD, 1), cudaMemcpyDeviceToDevice, s));

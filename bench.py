@@ -341,6 +341,24 @@ def small_sampler_leg(device):
     return out
 
 
+def cfg2_sampler_leg(g, x, K, n, iters=5):
+    """configs[1] as the user runs it: the batched adaptive-Metropolis sampler on the headline problem (4096 chains x
+    100 000 gaugings, 19 components).  A proposal on a VAR parameter (k1 / k2 of one period) only re-evaluates the
+    gaugings of that period; the per-combination sums of the current state cover the rest."""
+    sd = 0.002 * np.abs(x) + 1e-6
+    out = {"workload": f"BaRatin_SPD sampler, {K} chains x {n} gaugings, {g.P} components per iteration"}
+    for name, flag in (("full_reevaluation", 1), ("partial_reevaluation", 0)):
+        g.set_option("no_partial", flag)
+        g.fit(x, sd, nAdapt=1, nCycles=1, seed=1, want_rows=False)
+        g.step_times()
+        g.fit(x, sd, nAdapt=iters, nCycles=1, seed=2, want_rows=False)
+        ms = float(g.step_times()[-1]) / iters
+        out[name] = {"ms_per_iteration": ms, "proposals_per_s": K * g.P / (ms * 1e-3),
+                     "chain_obs_per_s_equivalent": K * g.P * n / (ms * 1e-3)}
+    g.set_option("no_partial", 0)
+    return out
+
+
 def latent_sampler_leg(device, n=1_000_000, K=64, iters=4):
     """configs[2] (Regression with input uncertainty): adaptive Metropolis over theta, gamma AND 2n latent inputs per
     chain; the latent inputs are swept by one kernel launch with O(1) local posterior differences.  Bounded size."""
@@ -628,6 +646,10 @@ def main():
             line["prediction_sediment"] = sediment_prediction_leg(device, hbm_peak)
         except Exception as e:
             line["prediction_sediment"] = {"error": str(e)}
+        try:
+            line["sampler_cfg2"] = cfg2_sampler_leg(g, x, K, n)
+        except Exception as e:
+            line["sampler_cfg2"] = {"error": str(e)}
         try:
             line["sampler_small"] = small_sampler_leg(device)
         except Exception as e:
