@@ -16,4 +16,5 @@
     X(BAMGPU_MDL_VEGETATION, 4, 4) X(BAMGPU_MDL_VEGETATION, 4, 5)                                           \
     X(BAMGPU_MDL_SUSPENDEDLOAD, 1, 1) X(BAMGPU_MDL_SWOT, 2, 1) X(BAMGPU_MDL_SWOT, 3, 1)                     \
     X(BAMGPU_MDL_SGD, 2, 1) X(BAMGPU_MDL_ORTHO, 3, 2) X(BAMGPU_MDL_RECESSION_H, 1, 1)                       \
-    X(BAMGPU_MDL_HCS, 1, 1) X(BAMGPU_MDL_SEGMENTATION, 1, 1) X(BAMGPU_MDL_BARATINBAC, 1, 1)
+    X(BAMGPU_MDL_HCS, 1, 1) X(BAMGPU_MDL_SEGMENTATION, 1, 1) X(BAMGPU_MDL_BARATINBAC, 1, 1)                 \
+    X(BAMGPU_MDL_SFD, 2, 1)

@@ -31,6 +31,7 @@ int model_from_name(const char* name) {
     if (s == "HydraulicControl_section") return BAMGPU_MDL_HCS;
     if (s == "Segmentation") return BAMGPU_MDL_SEGMENTATION;
     if (s == "BaRatinBAC") return BAMGPU_MDL_BARATINBAC;
+    if (s == "SFD") return BAMGPU_MDL_SFD;
     return 0;
 }
 
@@ -537,6 +538,14 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             }
             break;
         }
+        case BAMGPU_MDL_SFD:  // SFD_XtraRead (StageFallDischarge_model.f90:191-247)
+            if (p.n_xtra_i != 2 || p.n_xtra_d != 5 || p.xtra_i[0] != 1) { mess = "SFD_Apply: Fatal: Unavailable [ID]"; return 1; }
+            if (nt != 8 || nX != 2 || nY != 1) { mess = "SFD_Apply: wrong size [theta], nX or nY"; return 1; }
+            L.vegItmax = p.xtra_i[1];
+            for (int i = 0; i < 4; ++i) L.vegOpt[i] = p.xtra_d[1 + i];  // xscale, fscale, tolX, tolF (shared Newton option slots)
+            L.modelOptD = p.xtra_d[0];                                   // upper bound of the search interval
+            L.nState = 1;
+            break;
         case BAMGPU_MDL_SEGMENTATION: {  // Segmentation_XtraRead (:142-180)
             if (p.n_xtra_i != 3 || p.n_xtra_d != 1) { mess = "Segmentation_XtraRead:problem reading xtra"; return 1; }
             const int nS = p.xtra_i[0];

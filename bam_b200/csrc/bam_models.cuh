@@ -679,6 +679,68 @@ __device__ __forceinline__ bool segmentation_apply(const DevProblem& p, double t
 }
 
 // -------------------------------------------------------------------------------------------
+// SFD (StageFallDischarge_model.f90:80-283, SFD_Val_General): twin-gauge rating curve.  theta = (KB, h0, M, L, h0',
+// KBS0, delta, M').  Per observation the transition stage kappa between the variable-slope and the channel-control
+// regime solves  KB (x-h0)^M sqrt((x-h2-delta)/L) = KBS0 (x-h0')^M'  (fNewton_Val_General :253-283) on
+// [max(h0,h0',h2+delta)+0.001, upperbound] by znewton (declared convention as for Vegetation: rtsafe + polish).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sfd_fnewton(double x, const double* __restrict__ th, double h2, double& f, double& df) {
+    const double s = sqrt((x - h2 - th[6]) / th[3]);
+    f = th[0] * pow(x - th[1], th[2]) * s - th[5] * pow(x - th[4], th[7]);
+    df = th[0] * pow(x - th[1], th[2] - 1.0) / (2.0 * th[3] * s) *
+             ((2.0 * th[2] + 1.0) * x - (2.0 * th[2] * (h2 + th[6]) + th[1])) -
+         th[5] * th[7] * pow(x - th[4], th[7] - 1.0);
+}
+
+__device__ inline bool sfd_apply(const DevProblem& p, const double* in, const double* __restrict__ th, double& out) {
+    const double h1 = in[0], h2 = in[1];
+    const double KB = th[0], h0 = th[1], M = th[2], L = th[3], h0p = th[4], KBS0 = th[5], delta = th[6], Mp = th[7];
+    if (h1 - h2 - delta <= 0.0) return false;
+    if (h1 - h0 <= 0.0 || h2 - h0p <= 0.0) { out = 0.0; return true; }
+    const double x1 = fmax(fmax(h0, h0p), h2 + delta) + 0.001, x2 = p.modelOptD;
+    double fl, fh, df, f, xl, xh;
+    sfd_fnewton(x1, th, h2, fl, df);
+    sfd_fnewton(x2, th, h2, fh, df);
+    int fcalls = 2;
+    double kappa;
+    if (fl == 0.0) kappa = x1;
+    else if (fh == 0.0) kappa = x2;
+    else {
+        if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) return false;  // znewton err > 0: root not bracketed
+        if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
+        double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
+        sfd_fnewton(rts, th, h2, f, df);
+        ++fcalls;
+        for (int j = 0; j < p.vegItmax; ++j) {
+            if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+                dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
+            } else {
+                dxold = dx; dx = f / df; rts = rts - dx;
+            }
+            const bool convx = fabs(dx) <= p.vegTolX * p.vegXscale;
+            sfd_fnewton(rts, th, h2, f, df);
+            ++fcalls;
+            if (f < 0.0) xl = rts; else xh = rts;
+            if (convx || fabs(f) <= p.vegTolF * p.vegFscale) break;
+        }
+        for (int j = 0; j < 3 && f != 0.0 && df != 0.0; ++j) {  // polish
+            const double lo = fmin(xl, xh), hi = fmax(xl, xh);
+            double xn = rts - f / df;
+            xn = fmin(fmax(xn, lo), hi);
+            if (xn == rts) break;
+            rts = xn;
+            sfd_fnewton(rts, th, h2, f, df);
+            if (f < 0.0) xl = rts; else xh = rts;
+        }
+        kappa = rts;
+    }
+    if (fcalls > p.vegItmax || !(kappa == kappa)) return false;
+    if (h1 <= kappa) out = (KB * pow(h1 - h0, M)) * sqrt((h1 - h2 - delta) / L);  // variable-slope model
+    else out = KBS0 * pow(h1 - h0p, Mp);                                       // standard channel model
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
 // dispatch
 // -------------------------------------------------------------------------------------------
 
@@ -691,6 +753,8 @@ __device__ inline bool model_prepare(const DevProblem& p, const double* th, doub
     if (p.model == BAMGPU_MDL_VEGETATION) return vegetation_prepare(p, th, der, xc, nser);
     if (p.model == BAMGPU_MDL_ORTHO) return ortho_prepare(th, der);
     if (p.model == BAMGPU_MDL_SEGMENTATION) return segmentation_prepare(p, th, der, xc[0], nser);
+    if (p.model == BAMGPU_MDL_SFD)  // StageFallDischarge_model.f90:141-143
+        return !(th[0] <= 0.0 || th[2] <= 0.0 || th[3] <= 0.0 || th[5] <= 0.0 || th[7] <= 0.0);
     if (p.model == BAMGPU_MDL_HCS) return !(th[0] <= 0.0 || th[1] <= 0.0);  // HydraulicControl_section_model.f90:70-72
     // parameter-set feasibility of the pointwise second-wave models
     if (p.model == BAMGPU_MDL_SUSPENDEDLOAD) return !(th[0] <= 0.0 || th[2] <= 0.0 || th[4] <= 0.0);  // SuspendedLoad_model.f90:96-99
@@ -724,6 +788,8 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return ortho_apply(p, x, th, der, y);
     } else if (MODEL == BAMGPU_MDL_BARATINBAC) {
         return baratinbac_apply(p, x[0], th, der, y[0]);
+    } else if (MODEL == BAMGPU_MDL_SFD) {
+        return sfd_apply(p, x, th, y[0]);
     } else if (MODEL == BAMGPU_MDL_HCS) {
         return hcs_apply(p, x[0], th, y[0]);
     } else if (MODEL == BAMGPU_MDL_SEGMENTATION) {

@@ -272,6 +272,12 @@ static void read_xtra(Workspace& w) {
         w.xtraI.push_back(s.integer());                          // nYear
         for (int k = 0; k < 4; ++k) w.xtraD.push_back(s.num());  // Newton xscale, fscale, tolX, tolF (one per line)
         w.xtraI.push_back(s.integer());                          // Newton itmax
+    } else if (w.modelID == "SFD") {  // SFD_XtraRead (StageFallDischarge_model.f90:191-247)
+        Cursor s(xf);
+        const std::string id = s.str();
+        if (id != "SFD_Val_General") fail("SFD_Apply: Fatal: Unavailable [ID] '" + id + "'");
+        for (int k = 0; k < 5; ++k) w.xtraD.push_back(s.num());  // upper bound, xscale, fscale, xtol, ftol
+        w.xtraI = {1, s.integer()};                               // maxiter
     } else if (w.modelID == "SWOT") {  // SWOT_XtraRead (SWOT_model.f90:150-182): model variant
         Cursor s(xf);
         const std::string id = s.str();

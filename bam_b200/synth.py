@@ -407,3 +407,22 @@ def baratin_bac(nobs: int = 300, seed: int = SEED + 8, hmax: float = 6.0):
                    priors_gamma=[("Uniform", [0, 1000])] * 2, xtra_i=np.asarray(M, dtype=np.int32).flatten(order="F"),
                    xtra_d=[hmax])
     return prob, np.concatenate([th, gam])
+
+
+def sfd(nobs: int = 300, seed: int = SEED + 9):
+    """SFD (twin-gauge stage-fall-discharge, SFD_Val_General) with the parameter values of tests/BaM_SFD."""
+    rng = np.random.default_rng(seed)
+    th = np.array([6000.0, -5.0, 1.6667, 3900.0, -5.0, 171.0, -0.01, 1.6667])
+    h2 = rng.uniform(1.0, 3.0, nobs)
+    h1 = h2 + rng.uniform(0.02, 1.5, nobs)
+    # throw-away forward model for the observations: the smaller of the two regimes is a fair proxy
+    qv = th[0] * (h1 - th[1]) ** th[2] * np.sqrt((h1 - h2 - th[6]) / th[3])
+    qc = th[5] * (h1 - th[4]) ** th[7]
+    q = np.minimum(qv, qc)
+    uq = 0.05 * q
+    Y = q + rng.standard_normal(nobs) * np.sqrt(uq**2 + (10.0 + 0.05 * q) ** 2)
+    pri = [("Gaussian", [6000, 901.5]), ("Gaussian", [-5, 1]), ("Gaussian", [1.6667, 0.025]), ("Gaussian", [3900, 50]),
+           ("Gaussian", [-5, 1]), ("Gaussian", [171, 46]), ("Gaussian", [0, 0.025]), ("Gaussian", [1.6667, 0.025])]
+    prob = Problem("SFD", np.column_stack([h1, h2]), Y, Yu=uq, partype=[0] * 8, priors_theta=pri, sigma_func=["Linear"],
+                   priors_gamma=[("Uniform", [0, 10000])] * 2, xtra_i=[1, 100], xtra_d=[20.0, 5.0, 1000.0, 1e-5, 1e-10])
+    return prob, np.concatenate([th, [10.0, 0.05]])

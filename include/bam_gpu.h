@@ -45,7 +45,9 @@ enum bamgpu_model {
     BAMGPU_MDL_RECESSION_H = 10,  /* Recession_model.f90:36-94 ("Recession_h") */
     BAMGPU_MDL_HCS = 11,          /* HydraulicControl_section_model.f90:40-112 ("HydraulicControl_section") */
     BAMGPU_MDL_SEGMENTATION = 12, /* Segmentation_model.f90:52-140 (whole-series model: segment sizes are checked) */
-    BAMGPU_MDL_BARATINBAC = 13    /* BaRatinBAC_model.f90:96-666: BaRatin in the b-a-c parameterisation */
+    BAMGPU_MDL_BARATINBAC = 13,   /* BaRatinBAC_model.f90:96-666: BaRatin in the b-a-c parameterisation */
+    BAMGPU_MDL_SFD = 14           /* StageFallDischarge_model.f90:80-283 (SFD_Val_General); the transition stage kappa
+                                     (the model's only state variable) is computed but not exported by this ABI yet */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -94,7 +96,7 @@ enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YI
  */
 typedef struct bamgpu_problem {
     const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
-                             "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC"
+                             "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC" | "SFD"
                              (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 
@@ -138,6 +140,7 @@ typedef struct bamgpu_problem {
        Orthorectification : xtra_i = {bamgpu_ortho_disto, number of distortion parameters}
        HydraulicControl_section : xtra_d = the h-A-w matrix, p x 3 column-major (n_xtra_d = 3p)
        Segmentation : xtra_i = {nS, nmin, option}; xtra_d = {tmin}
+       SFD        : xtra_i = {1 (SFD_Val_General), itmax}; xtra_d = {upperbound, xscale, fscale, tolX, tolF}
        Linear, SuspendedLoad, SGD, Recession_h : none */
     const int32_t* xtra_i;
     int32_t n_xtra_i;

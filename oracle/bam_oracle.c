@@ -802,6 +802,72 @@ static void baratinbac_apply(const oracle_t* o, int n, const double* H, const do
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * SFD (StageFallDischarge_model.f90:80-283), SFD_Val_General
+ * ------------------------------------------------------------------------------------------ */
+static void sfd_fnewton(double x, const double* th, double h2, double* f, double* df) { /* fNewton_Val_General :253-283 */
+    double s = sqrt((x - h2 - th[6]) / th[3]);
+    *f = th[0] * pow(x - th[1], th[2]) * s - th[5] * pow(x - th[4], th[7]);
+    *df = th[0] * pow(x - th[1], th[2] - 1.0) / (2.0 * th[3] * s) *
+              ((2.0 * th[2] + 1.0) * x - (2.0 * th[2] * (h2 + th[6]) + th[1])) -
+          th[5] * th[7] * pow(x - th[4], th[7] - 1.0);
+}
+
+static void sfd_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* th, double* OUT, int32_t* vfeas) {
+    double KB = th[0], h0 = th[1], M = th[2], L = th[3], h0p = th[4], KBS0 = th[5], delta = th[6], Mp = th[7];
+    if (KB <= 0.0 || M <= 0.0 || L <= 0.0 || KBS0 <= 0.0 || Mp <= 0.0) {
+        for (int t = 0; t < n; ++t) vfeas[t] = 0;
+        return;
+    }
+    for (int t = 0; t < n; ++t) {
+        double h1 = IN[t], h2 = IN[t + (size_t)ldx];
+        if (h1 - h2 - delta <= 0.0) { vfeas[t] = 0; continue; }
+        if (h1 - h0 <= 0.0 || h2 - h0p <= 0.0) { OUT[t] = 0.0; continue; }
+        double m = h0 > h0p ? h0 : h0p;
+        if (h2 + delta > m) m = h2 + delta;
+        double x1 = m + 0.001, x2 = o->model_optd;
+        double fl, fh, df, f, xl, xh, kappa;
+        sfd_fnewton(x1, th, h2, &fl, &df);
+        sfd_fnewton(x2, th, h2, &fh, &df);
+        int fcalls = 2;
+        if (fl == 0.0) kappa = x1;
+        else if (fh == 0.0) kappa = x2;
+        else {
+            if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) { vfeas[t] = 0; continue; }
+            if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
+            double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
+            sfd_fnewton(rts, th, h2, &f, &df);
+            ++fcalls;
+            for (int j = 0; j < o->veg_itmax; ++j) {
+                if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+                    dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
+                } else {
+                    dxold = dx; dx = f / df; rts = rts - dx;
+                }
+                int convx = fabs(dx) <= o->veg_tolx * o->veg_xscale;
+                sfd_fnewton(rts, th, h2, &f, &df);
+                ++fcalls;
+                if (f < 0.0) xl = rts; else xh = rts;
+                if (convx || fabs(f) <= o->veg_tolf * o->veg_fscale) break;
+            }
+            for (int j = 0; j < 3 && f != 0.0 && df != 0.0; ++j) {
+                double lo = xl < xh ? xl : xh, hi = xl < xh ? xh : xl;
+                double xn = rts - f / df;
+                if (xn < lo) xn = lo;
+                if (xn > hi) xn = hi;
+                if (xn == rts) break;
+                rts = xn;
+                sfd_fnewton(rts, th, h2, &f, &df);
+                if (f < 0.0) xl = rts; else xh = rts;
+            }
+            kappa = rts;
+        }
+        if (fcalls > o->veg_itmax || kappa != kappa) { vfeas[t] = 0; continue; }
+        if (h1 <= kappa) OUT[t] = (KB * pow(h1 - h0, M)) * sqrt((h1 - h2 - delta) / L);
+        else OUT[t] = KBS0 * pow(h1 - h0p, Mp);
+    }
+}
+
 /* LM_Apply, Linear_model.f90:62-101: Y = matmul(X, reshape(theta,(nX,nY))) */
 static void linear_apply(const oracle_t* o, int n, const double* X, int ldx, const double* theta, double* Y,
                          int ldy) {
@@ -1306,6 +1372,7 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         case BAMGPU_MDL_ORTHO: ortho_apply(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas); break;
         case BAMGPU_MDL_HCS: hcs_apply(o, n, X, fullTheta, Y, vfeas); break;
         case BAMGPU_MDL_BARATINBAC: baratinbac_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
+        case BAMGPU_MDL_SFD: sfd_apply(o, n, X, ldx, fullTheta, Y, vfeas); break;
         case BAMGPU_MDL_SEGMENTATION:
             if (!segmentation_apply(o, n, X, fullTheta, Y))
                 for (int t = 0; t < n; ++t) vfeas[t] = 0; /* scalar feas=.false. (ModelLibrary_tools.f90:362-364) */
@@ -1342,6 +1409,7 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "HydraulicControl_section")) return BAMGPU_MDL_HCS;
     if (!strcmp(name, "Segmentation")) return BAMGPU_MDL_SEGMENTATION;
     if (!strcmp(name, "BaRatinBAC")) return BAMGPU_MDL_BARATINBAC;
+    if (!strcmp(name, "SFD")) return BAMGPU_MDL_SFD;
     return 0;
 }
 
@@ -1489,6 +1557,13 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             if (p->n_xtra_i != 2 || nX != 3 || nY != 2 || nt != 11 + p->xtra_i[1]) { setmess(mess, "oracle: Ortho: bad xtra or sizes"); return 1; }
             o->model_opt[0] = p->xtra_i[0]; o->model_opt[1] = p->xtra_i[1];
             o->nDparModel = 20;
+            break;
+        case BAMGPU_MDL_SFD:
+            if (p->n_xtra_i != 2 || p->n_xtra_d != 5 || nt != 8 || nX != 2 || nY != 1) { setmess(mess, "oracle: SFD: bad xtra or sizes"); return 1; }
+            o->veg_itmax = p->xtra_i[1];
+            o->model_optd = p->xtra_d[0]; o->veg_xscale = p->xtra_d[1]; o->veg_fscale = p->xtra_d[2];
+            o->veg_tolx = p->xtra_d[3]; o->veg_tolf = p->xtra_d[4];
+            o->nState = 1;
             break;
         case BAMGPU_MDL_HCS:
             o->hcs_n = p->n_xtra_d / 3;

@@ -122,3 +122,31 @@ def test_baratinbac():
     rows = g.fit(s, 0.01 * np.abs(s), nAdapt=4, nCycles=2, seed=5)
     orows = o.fit(s, 0.01 * np.abs(s), nAdapt=4, nCycles=2, seed=5)[0]
     assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+
+
+def test_sfd():
+    """twin-gauge rating curve: per-observation Newton for the transition stage, then one of two regimes"""
+    prob, truth = synth.sfd(nobs=400)
+    x = synth.feasible_starts(truth, 48, rel=0.005, seed=4)
+    x[3, 0] = -1.0   # KB <= 0
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.sizes.nState == 1
+    check_parity(prob, x)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.003 * rng.standard_normal((200, truth.size)))
+    h1 = np.linspace(0.5, 7.0, 80)
+    h2 = np.full(80, 1.93)
+    h2[5] = 9.0  # fall h1 - h2 - delta <= 0: infeasible row (:147)
+    env, spag = g.predict(mc, truth, [h1, h2], 1, [1], seed=4, want_spag=True)
+    oenv, ospag = o.predict(mc, truth, [h1, h2], 1, [1], seed=4, want_spag=True, nthreads=8)
+    cmp_spag(spag, ospag)
+    cmp_env(env, oenv)
+    assert (spag[0, 5] == -666.666).all()
+    # both regimes occur along the rating curve
+    _, det = g.predict(None, truth, [h1, h2], 0, [0], want_env=False, want_spag=True)
+    qv = truth[0] * (h1 - truth[1]) ** truth[2] * np.sqrt(np.maximum(h1 - h2 - truth[6], 0) / truth[3])
+    qc = truth[5] * (h1 - truth[4]) ** truth[7]
+    ok = det[0, :, 0] != -666.666
+    isv = np.isclose(det[0, ok, 0], qv[ok], rtol=1e-9)
+    isc = np.isclose(det[0, ok, 0], qc[ok], rtol=1e-9)
+    assert (isv | isc).all() and isv.any() and isc.any()

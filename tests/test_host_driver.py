@@ -90,6 +90,9 @@ def test_config_reader_on_shipped_second_wave_workspace():
     assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == ("HydraulicControl_section", 6, 1, 1)
     tab = np.asarray(d["xtra_d"]).reshape(3, -1)  # h | A | w
     assert tab.shape[1] >= 3 and (np.diff(tab[0]) >= 0).all() and (tab[1, 1:] > 0).all()
+    d = dump_ref("Config_BaM_SFD.txt")
+    assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == ("SFD", 68, 2, 1) and list(d["xtra_i"]) == [1, 100]
+    assert d["xtra_d"] == [20, 5, 1000, 1e-05, 1e-10]
     # BaRatinBAC ships without a top-level Config_BaM file: point one at the workspace
     cfg = "/tmp/_Config_BaM_BaRatinBAC.txt"
     open(cfg, "w").write("\n".join(['"/root/reference/tests/BaM_BaRatinBAC/"', '"Config_RunOptions.txt"', '"Config_Model.txt"',
