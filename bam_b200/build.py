@@ -17,7 +17,8 @@ OBJ = os.path.join(HERE, "build")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "g++"]
-LIB_SOURCES = ["bam_capi.cu", "bam_logpost.cu", "bam_sampler.cu", "bam_predict.cu", "bam_host.cpp"]
+LIB_SOURCES = ["bam_capi.cu", "bam_logpost.cu", "bam_sampler.cu", "bam_sampler_warp_a.cu", "bam_sampler_warp_b.cu",
+               "bam_sampler_warp_c.cu", "bam_latent.cu", "bam_predict.cu", "bam_host.cpp"]
 
 
 def _newer(src_list, target):
@@ -58,7 +59,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             jobs.append([NVCC] + NVFLAGS + extra + ["-c", s, "-o", o])
     logs = []
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(len(jobs), 6)) as ex:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), 10)) as ex:
             logs = list(ex.map(_run, jobs))
     so = os.path.join(HERE, "libbam_gpu.so")
     if jobs or not os.path.exists(so):

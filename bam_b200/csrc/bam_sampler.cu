@@ -14,6 +14,7 @@
 #include "bam_fastmath.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
+#include "bam_sampler_kernels.h"
 
 namespace {
 
@@ -90,369 +91,6 @@ __global__ void adapt_kernel(int K, int P, int nAdapt, double minMR, double maxM
     moves[q] = 0;
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// K3p: persistent sampler for small data sets (the reference's own workspaces have 38..812 observations).
-//
-// With few observations a launch per proposal is pure launch latency, so the whole Metropolis loop runs inside
-// one kernel: ONE WARP PER CHAIN, lanes stride over the observations (and over parameters for the priors),
-// the chain's vector / table / jump scales live in shared memory, accept / reject, move counters, scale
-// adaptation, row recording and the Welford moments all happen in the kernel.  One launch covers a chunk of
-// iterations (a cycle), so the host can keep the reference's .monitor file alive between launches.
-// Same RNG streams and the same accept rule as the launch-per-proposal path: both give the same chains up to
-// the rounding of the (differently ordered) sums.
-// ------------------------------------------------------------------------------------------------
-#define WS_WARPS 4       /* chains per block */
-#define WS_MAXP 64       /* vector length limit of this path (no latent inputs) */
-
-struct WarpSamplerArgs {
-    int K, nIterChunk, nAdapt;
-    long long it0, burn, keepEvery, nKeep;
-    double minMR, maxMR, downMult, upMult;
-    unsigned long long seed;
-    long long chainOffset;
-    double *x, *sd, *fxcur, *dparcur, *rows, *mcount, *mmean, *mm2;
-    int* moves;
-};
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
-
-// log-posterior of the vector xs (shared memory) for one chain, computed by one warp.  Returns status bits.
-template <int MODEL, int NX, int NY>
-__device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, double* vcop, double& fx) {
-    const int lane = threadIdx.x & 31;
-    int st = 0;
-    // ---- prior (GetPriorLogPdf :3006-3138): parameters spread over lanes
-    double pr = 0.0;
-    const int npar = p.nFit + p.nGamma;
-    for (int k = lane; k < npar; k += 32) {
-        double lp;
-        bool feas, isnull;
-        if (k < p.nFit) dist_logpdf(p.ptDist[k], p.ptPar + (size_t)k * BAMGPU_PRIOR_NPAR, xs[k], lp, feas, isnull);
-        else dist_logpdf(p.pgDist[k - p.nFit], p.pgPar + (size_t)(k - p.nFit) * BAMGPU_PRIOR_NPAR, xs[k], lp, feas, isnull);
-        if (!feas) st |= ST_PRIOR_INFEAS;
-        else if (isnull) st |= ST_PRIOR_NULL;
-        else pr += lp;
-    }
-    if (p.priorM != nullptr) {
-        for (int k = lane; k < npar; k += 32) {
-            double u;
-            bool f;
-            if (k < p.nFit) dist_cdf(p.ptDist[k], p.ptPar + (size_t)k * BAMGPU_PRIOR_NPAR, xs[k], u, f);
-            else dist_cdf(p.pgDist[k - p.nFit], p.pgPar + (size_t)(k - p.nFit) * BAMGPU_PRIOR_NPAR, xs[k], u, f);
-            if (!f || !(u > 0.0 && u < 1.0)) { st |= ST_PRIOR_INFEAS; vcop[k] = 0.0; }
-            else vcop[k] = normcdfinv(u);
-        }
-        __syncwarp();
-        double q = 0.0;
-        for (int cc = lane; cc < npar; cc += 32) {
-            double w = 0.0;
-            for (int r = 0; r < npar; ++r) w = w + vcop[r] * p.priorM[r + (size_t)cc * npar];
-            q += w * vcop[cc];
-        }
-        pr -= 0.5 * q;
-    }
-    for (int j = 0; j < p.nX; ++j)
-        for (int i = lane; i < p.nXb[j]; i += 32) pr += gauss_logpdf(xs[p.offXb[j] + i], 0.0, 1.0);
-    for (int j = 0; j < p.nY; ++j)
-        for (int i = lane; i < p.nYb[j]; i += 32) pr += gauss_logpdf(xs[p.offYb[j] + i], 0.0, 1.0);
-    pr = warp_sum(pr);
-    // ---- per-chain table (as logpost_prep)
-    for (int g = lane; g < p.nGamma; g += 32) tab[p.tabGamma + g] = xs[p.nFit + g];
-    for (int j = 0; j < p.nX; ++j)
-        for (int i = lane; i < p.nXb[j]; i += 32) tab[p.tabOffXb[j] + i] = xs[p.offXb[j] + i];
-    for (int j = 0; j < p.nY; ++j)
-        for (int i = lane; i < p.nYb[j]; i += 32) tab[p.tabOffYb[j] + i] = xs[p.offYb[j] + i];
-    for (int k = lane; k < p.nCombo; k += 32) {
-        double th[BAM_MAXTHETA], der[BAM_MAXDER];
-        const double* xc[BAM_MAXX];
-        for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
-        double* cr = tab + p.tabCombo + (size_t)k * p.comboStride;
-        for (int i = 0; i < p.ntheta; ++i) {
-            const int src = p.comboSrc[(size_t)k * p.ntheta + i];
-            th[i] = (src < 0) ? p.fixv[i] : xs[src];
-            cr[i] = th[i];
-        }
-        for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
-        if (!model_prepare(p, th, der, xc, p.n)) st |= ST_LKH_INFEAS;
-        for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
-    }
-    st = __reduce_or_sync(0xffffffffu, st);
-    __syncwarp();
-    double lk = 0.0;
-    if (!st) {
-        // ---- likelihood (GetLogLikelihood :3142-3229): lanes stride over the observations
-        const int n = p.n;
-        bool bad = false;
-        for (int i = lane; i < n; i += 32) {
-            double xt[NX], yh[NY];
-#pragma unroll
-            for (int j = 0; j < NX; ++j) {
-                const size_t q = i + (size_t)j * n;
-                double v = p.X[q];
-                if (p.hasXbias) {
-                    const int bi = p.Xbindx[q];
-                    if (bi > 0) v = v - p.Xb[q] * tab[p.tabOffXb[j] + bi - 1];
-                }
-                xt[j] = v;
-            }
-            const int combo = (p.nCombo > 1) ? p.comboOf[i] : 0;
-            const double* th = tab + p.tabCombo + (size_t)combo * p.comboStride;
-            if (!model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh)) { bad = true; continue; }
-#pragma unroll
-            for (int j = 0; j < NY; ++j) {
-                const size_t q = i + (size_t)j * n;
-                const double yo = p.Y[q];
-                if (p.hasMissing && yo == p.mv) continue;
-                const double sig = sigmafunk(p.sigfunc[j], tab + p.tabGamma + p.gamOff[j], yh[j]);
-                if (!(sig > 0.0)) { bad = true; continue; }
-                const double yu = p.Yu[q];
-                double mu = yh[j];
-                if (p.hasYbias) {
-                    const int bi = p.Ybindx[q];
-                    if (bi != 0) mu = yh[j] + p.Yb[q] * tab[p.tabOffYb[j] + bi - 1];
-                }
-                lk += gauss_logpdf_var(yo, mu, fma(yu, yu, sig * sig));
-            }
-        }
-        if (__any_sync(0xffffffffu, bad)) st |= ST_LKH_INFEAS;
-        lk = warp_sum(lk);
-        if (!(lk == lk)) st |= ST_LKH_INFEAS;
-    }
-    fx = st ? BAMGPU_UNDEF_RN : pr + lk;
-    return st;
-}
-
-template <int MODEL, int NX, int NY>
-__global__ void __launch_bounds__(32 * WS_WARPS) sampler_warp(DevProblem p, WarpSamplerArgs a) {
-    extern __shared__ double wsm[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c = blockIdx.x * WS_WARPS + w;
-    if (c >= a.K) return;
-    const int P = p.P, nD = p.nDpar;
-    const int perWarp = 2 * P + p.tabStride + p.kM + 2;  // xs | sd | tab | copula v
-    double* xs = wsm + (size_t)w * perWarp;
-    double* sd = xs + P;
-    double* tab = sd + P;
-    double* vcop = tab + p.tabStride;
-    for (int j = lane; j < P; j += 32) { xs[j] = a.x[(size_t)c * P + j]; sd[j] = a.sd[(size_t)c * P + j]; }
-    int mv0 = (lane < P) ? a.moves[(size_t)c * P + lane] : 0;           // move counter of component lane
-    int mv1 = (lane + 32 < P) ? a.moves[(size_t)c * P + lane + 32] : 0; // and of component lane+32
-    double fxc = a.fxcur[c];
-    __syncwarp();
-    const unsigned long long gc = (unsigned long long)(a.chainOffset + c);
-    for (int itl = 0; itl < a.nIterChunk; ++itl) {
-        const long long it = a.it0 + itl;
-        for (int i = 0; i < P; ++i) {
-            const double old = xs[i];
-            const double delta = sd[i] * philox_normal(a.seed, gc, (unsigned)it, 2u * (unsigned)i);
-            __syncwarp();
-            if (lane == 0) xs[i] = old + delta;
-            __syncwarp();
-            double fc;
-            const int st = warp_logpost<MODEL, NX, NY>(p, xs, tab, vcop, fc);
-            bool acc = false;
-            if (st == 0) {
-                const double u = philox_uniform(a.seed, gc, (unsigned)it, 2u * (unsigned)i + 1u);
-                acc = log(u) < fc - fxc;
-            }
-            if (acc) {
-                fxc = fc;
-                if (lane == (i & 31)) { if (i < 32) ++mv0; else ++mv1; }
-                // derived parameters of the accepted state: the b's sit in the table
-                for (int d = lane; d < nD; d += 32) {
-                    const int k = d / p.nDparModel, q = d % p.nDparModel;
-                    a.dparcur[(size_t)c * nD + d] = tab[p.tabCombo + (size_t)k * p.comboStride + p.ntheta + q];
-                }
-            } else {
-                __syncwarp();
-                if (lane == 0) xs[i] = old;
-            }
-            __syncwarp();
-        }
-        const long long it1 = it + 1;
-        if (it1 > a.burn && (it1 - a.burn) % a.keepEvery == 0) {
-            const long long kept = (it1 - a.burn) / a.keepEvery - 1;
-            if (kept < a.nKeep) {
-                const int rowlen = P + 1 + nD;
-                if (a.rows) {
-                    double* row = a.rows + ((size_t)c * a.nKeep + kept) * rowlen;
-                    for (int j = lane; j < P; j += 32) row[j] = xs[j];
-                    if (lane == 0) row[P] = fxc;
-                    for (int d = lane; d < nD; d += 32) row[P + 1 + d] = a.dparcur[(size_t)c * nD + d];
-                }
-                const double cnt = (double)(kept + 1);
-                for (int j = lane; j < P; j += 32) {  // Welford
-                    const size_t o = (size_t)c * P + j;
-                    const double v = xs[j], m = a.mmean[o], d = v - m, mn = m + d / cnt;
-                    a.mmean[o] = mn;
-                    a.mm2[o] += d * (v - mn);
-                }
-                if (lane == 0) a.mcount[c] = cnt;
-            }
-        }
-        if (it1 % a.nAdapt == 0) {  // end of a cycle: scale adaptation (App. E)
-            for (int j = lane; j < P; j += 32) {
-                const int mvj = (j < 32) ? mv0 : mv1;
-                const double rate = (double)mvj / (double)a.nAdapt;
-                double s = sd[j];
-                if (rate <= a.minMR) s *= a.downMult;
-                if (rate >= a.maxMR) s *= a.upMult;
-                sd[j] = s;
-            }
-            mv0 = 0;
-            mv1 = 0;
-            __syncwarp();
-        }
-    }
-    for (int j = lane; j < P; j += 32) { a.x[(size_t)c * P + j] = xs[j]; a.sd[(size_t)c * P + j] = sd[j]; }
-    if (lane < P) a.moves[(size_t)c * P + lane] = mv0;
-    if (lane + 32 < P) a.moves[(size_t)c * P + lane + 32] = mv1;
-    if (lane == 0) a.fxcur[c] = fxc;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3l: one-launch sweep over ALL latent "true input" components (cfg 3: 2 x 10^6 per chain).
-//
-// Every model on this path is pointwise, so given (theta, gamma, biases) the posterior factorises over
-// observations: the latent inputs of observation i only enter its own likelihood terms and its own hyper terms
-// (GetLogLikelihood :3204-3227, GetHyperLogPdf :3285-3303).  The one-at-a-time updates of latent components that
-// belong to DIFFERENT observations therefore commute, and
-//     f(candidate) - f(current) = [lkh_i + hyper_i](candidate) - [lkh_i + hyper_i](current)
-// needs O(1) work instead of a pass over all observations.  thread <-> (chain, observation); the latent inputs of
-// one observation are visited in column order, which is exactly the order in which the reference's vector layout
-// (Packer :4202-4242: column-major over (i,j)) visits them as far as observation i can tell.  Same Philox streams
-// as every other path (normal: (chain, it, 2 comp), uniform: (chain, it, 2 comp + 1)), same accept rule.
-// Per latent component: 8 B read + 8 B written of state, 8 B jump scale, 8 B move counter: HBM-leaning FP64 work.
-// ------------------------------------------------------------------------------------------------
-template <int MODEL, int NX, int NY>
-__device__ __forceinline__ bool local_logpost(const DevProblem& p, const double* xt, const double* xo, const double* xu,
-                                              const double* xb, const int* xbi, const double* yo, const double* yu,
-                                              const double* yb, const int* ybi, const double* hyC, const double* hyR,
-                                              const double* __restrict__ row, const double* __restrict__ th, unsigned lt,
-                                              double& val) {
-    double yh[NY];
-    if (!model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh)) return false;
-    double lk = 0.0;
-#pragma unroll
-    for (int j = 0; j < NY; ++j) {
-        if (p.hasMissing && yo[j] == p.mv) continue;
-        const double sig = sigmafunk(p.sigfunc[j], row + p.tabGamma + p.gamOff[j], yh[j]);
-        if (!(sig > 0.0)) return false;
-        double mu = yh[j];
-        if (p.hasYbias && ybi[j] != 0) mu = yh[j] + yb[j] * row[p.tabOffYb[j] + ybi[j] - 1];
-        lk += gauss_logpdf_var_t(yo[j], mu, fma(yu[j], yu[j], sig * sig), lt);
-    }
-    double hy = 0.0;
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-        if (!(xu[j] > 0.0)) continue;
-        double mu = xt[j];
-        if (p.hasXbias && xbi[j] != 0) mu = xt[j] + xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
-        const double z = (xo[j] - mu) * hyR[j];
-        hy += fma(-0.5 * z, z, hyC[j]);  // hyC = -log sqrt(2 pi) - log xu, hyR = 1 / xu: per observation, not per proposal
-    }
-    val = lk + hy;
-    return val == val;
-}
-
-template <int MODEL, int NX, int NY>
-__global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, unsigned long long seed,
-                                                          long long chainOffset, unsigned it, double* __restrict__ x,
-                                                          const double* __restrict__ sd, int* __restrict__ moves,
-                                                          const double* __restrict__ tab) {
-    extern __shared__ __align__(16) double lsm[];  // [log table (4 KB) | table row of this chain]
-    double2* sLogT = reinterpret_cast<double2*>(lsm);
-    double* srow = lsm + 2 * BAM_LOGTAB_N;
-    const int c = blockIdx.y;
-    for (int q = threadIdx.x; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
-    for (int q = threadIdx.x; q < p.tabStride; q += BAM_BLOCK) srow[q] = tab[(size_t)c * p.tabStride + q];
-    __syncthreads();
-    const unsigned lt = smem_addr(sLogT);
-    const int n = p.n;
-    const int i = blockIdx.x * BAM_BLOCK + threadIdx.x;
-    if (i >= n) return;
-    double xo[NX], xu[NX], xb[NX], yo[NY], yu[NY], yb[NY], xt[NX];
-    int xbi[NX], ybi[NY], lat[NX];
-    bool any = false;
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-        const size_t q = i + (size_t)j * n;
-        xo[j] = p.X[q]; xu[j] = p.Xu[q]; lat[j] = p.latIdx[q];
-        xb[j] = 0.0; xbi[j] = 0;
-        if (p.hasXbias) { xb[j] = p.Xb[q]; xbi[j] = p.Xbindx[q]; }
-        any |= lat[j] >= 0;
-    }
-    if (!any) return;
-#pragma unroll
-    for (int j = 0; j < NY; ++j) {
-        const size_t q = i + (size_t)j * n;
-        yo[j] = p.Y[q]; yu[j] = p.Yu[q];
-        yb[j] = 0.0; ybi[j] = 0;
-        if (p.hasYbias) { yb[j] = p.Yb[q]; ybi[j] = p.Ybindx[q]; }
-    }
-    const double* __restrict__ row = srow;
-    const int combo = (p.nCombo > 1) ? p.comboOf[i] : 0;
-    const double* __restrict__ th = row + p.tabCombo + (size_t)combo * p.comboStride;
-    const size_t base = (size_t)c * p.P;
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {  // UnfoldParVector (:3429-3452)
-        double v = xo[j];
-        if (lat[j] >= 0) v = x[base + lat[j]];
-        else if (p.hasXbias && xbi[j] > 0) v = xo[j] - xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
-        xt[j] = v;
-    }
-    double hyC[NX], hyR[NX];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-        hyC[j] = 0.0; hyR[j] = 0.0;
-        if (xu[j] > 0.0) { hyC[j] = -BAM_LOG_SQRT_2PI - log(xu[j]); hyR[j] = 1.0 / xu[j]; }
-    }
-    double cur;
-    if (!local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, lt, cur)) return;  // cannot happen for a feasible state
-    const unsigned long long gc = (unsigned long long)(chainOffset + c);
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-        if (lat[j] < 0) continue;
-        const unsigned comp = (unsigned)lat[j];
-        const double old = xt[j];
-        xt[j] = old + sd[base + comp] * philox_normal(seed, gc, it, 2u * comp);
-        double cand;
-        bool acc = false;
-        if (local_logpost<MODEL, NX, NY>(p, xt, xo, xu, xb, xbi, yo, yu, yb, ybi, hyC, hyR, row, th, lt, cand)) {
-            const double u = philox_uniform(seed, gc, it, 2u * comp + 1u);
-            acc = log(u) < cand - cur;
-        }
-        if (acc) {
-            cur = cand;
-            x[base + comp] = xt[j];
-            moves[base + comp] += 1;
-        } else xt[j] = old;
-    }
-}
-
-using LatentKernel = void (*)(DevProblem, int, unsigned long long, long long, unsigned, double*, const double*, int*,
-                              const double*);
-LatentKernel pick_latent_sweep(int model, int nX, int nY) {
-#define X(M, A, B) \
-    if (model == M && nX == A && nY == B) return latent_sweep<M, A, B>;
-    BAM_FOR_EACH_INSTANCE(X)
-#undef X
-    return nullptr;
-}
-
-using WarpSamplerKernel = void (*)(DevProblem, WarpSamplerArgs);
-WarpSamplerKernel pick_warp_sampler(int model, int nX, int nY) {
-#define X(M, A, B) \
-    if (model == M && nX == A && nY == B) return sampler_warp<M, A, B>;
-    BAM_FOR_EACH_INSTANCE(X)
-#undef X
-    return nullptr;
-}
 
 }  // namespace
 
