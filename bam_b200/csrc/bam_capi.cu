@@ -103,7 +103,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         if (L.nX > BAM_MAXX || L.nY > BAM_MAXY || L.ntheta > BAM_MAXTHETA || L.nGamma > BAM_MAXGAMMA ||
             (pb->priorM && L.nFit + L.nGamma > BAM_MAXCOPULA) || L.vmMaxStack > BAM_VMSTACK) {
             delete h;
-            throw bam::CudaError{"bamgpu_create: problem exceeds the compiled limits (nX,nY<=8, ntheta<=40, copula<=96)"};
+            throw bam::CudaError{"bamgpu_create: problem exceeds the compiled limits (nX,nY<=8, ntheta<=160, copula<=96)"};
         }
         h->device = device;
         BAM_CUDA(cudaSetDevice(device));
@@ -136,7 +136,13 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
             if (!(L.nY == 1 && !L.hasLatent && pb->Y[i] == pb->mv)) perm.push_back(i);
         const int nDev = (int)perm.size();
         const bool dropped = nDev != L.n;
-        if (!L.hasLatent && nDev > 1 && L.model != BAMGPU_MDL_VEGETATION)  // Vegetation: the series order matters
+        // Mixture: output row r is built from input row xsrc[r] (pack order of its event, bam::mixture_rows); pairing the
+        // rows here makes the model pointwise for every kernel.  Identity for all other models.
+        std::vector<int> xsrc(L.n), xelt;
+        for (int i = 0; i < L.n; ++i) xsrc[i] = i;
+        const bool mixture = L.model == BAMGPU_MDL_MIXTURE && L.n > 0;
+        if (mixture && bam::mixture_rows(L.n, pb->X, L.modelOpt[1], L.modelOpt[2], xsrc, xelt, m)) { setmess(mess, m); delete h; return 1; }
+        if (!L.hasLatent && nDev > 1 && L.model != BAMGPU_MDL_VEGETATION && !mixture)  // Vegetation: the series order matters
             std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
                 if (L.comboOf[a] != L.comboOf[b]) return L.comboOf[a] < L.comboOf[b];
                 return pb->X[a] < pb->X[b];
@@ -153,9 +159,30 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
                 for (int i = 0; i < nDev; ++i) v[i + (size_t)j * nDev] = src[perm[i] + (size_t)j * L.n];
             return v;
         };
+        auto permXD = [&](const double* src, int ncol) {  // X-side tables: row perm[i] of the OUTPUT order reads input row xsrc[.]
+            std::vector<double> v((size_t)nDev * ncol + 1);
+            for (int j = 0; j < ncol; ++j)
+                for (int i = 0; i < nDev; ++i) v[i + (size_t)j * nDev] = src[xsrc[perm[i]] + (size_t)j * L.n];
+            return v;
+        };
+        auto permXI = [&](const int32_t* src, int ncol) {
+            std::vector<int32_t> v((size_t)nDev * ncol + 1);
+            for (int j = 0; j < ncol; ++j)
+                for (int i = 0; i < nDev; ++i) v[i + (size_t)j * nDev] = src[xsrc[perm[i]] + (size_t)j * L.n];
+            return v;
+        };
         const size_t sxd = (size_t)nDev * L.nX, syd = (size_t)nDev * L.nY;
-        d.X = upload(h, permD(pb->X, L.nX).data(), sxd); d.Xu = upload(h, permD(pb->Xu, L.nX).data(), sxd);
-        d.Xb = upload(h, permD(pb->Xb, L.nX).data(), sxd); d.Xbindx = upload(h, permI(pb->Xbindx, L.nX).data(), sxd);
+        {
+            std::vector<double> xd = permXD(pb->X, L.nX);
+            if (mixture)
+                for (int i = 0; i < nDev; ++i) {  // exact integers: event of the output block, position within the event
+                    xd[i] = (double)(perm[i] / L.modelOpt[2] + 1);
+                    xd[i + (size_t)nDev] = (double)xelt[perm[i]];
+                }
+            d.X = upload(h, xd.data(), sxd);
+        }
+        d.Xu = upload(h, permXD(pb->Xu, L.nX).data(), sxd);
+        d.Xb = upload(h, permXD(pb->Xb, L.nX).data(), sxd); d.Xbindx = upload(h, permXI(pb->Xbindx, L.nX).data(), sxd);
         d.Y = upload(h, permD(pb->Y, L.nY).data(), syd); d.Yu = upload(h, permD(pb->Yu, L.nY).data(), syd);
         d.Yb = upload(h, permD(pb->Yb, L.nY).data(), syd); d.Ybindx = upload(h, permI(pb->Ybindx, L.nY).data(), syd);
         d.comboOf = upload(h, permI(L.comboOf.data(), 1).data(), (size_t)nDev);
@@ -180,7 +207,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
             d.expTab = upload(h, et.data(), et.size());
         }
         d.comboSrc = upload(h, L.comboSrc.data(), L.comboSrc.size());
-        d.latIdx = L.hasLatent ? upload(h, L.latIdx.data(), L.latIdx.size()) : nullptr;
+        d.latIdx = L.hasLatent ? upload(h, permXI(L.latIdx.data(), L.nX).data(), L.latIdx.size()) : nullptr;  // hasLatent: perm is the identity
         for (int i = 0; i < L.ntheta; ++i) d.fixv[i] = L.fixv[i];
         d.hasLatent = L.hasLatent; d.hasXbias = L.hasXbias; d.hasYbias = L.hasYbias;
         d.hyperInfeasible = L.hyperInfeasible; d.hasMissing = L.hasMissing && !dropped;
@@ -365,6 +392,16 @@ int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* pb, const double* 
                 xt[q] = v;
             }
         if (Xtrue) std::copy(xt.begin(), xt.end(), Xtrue);
+        if (L.model == BAMGPU_MDL_MIXTURE) {  // pair input rows with output rows (see bamgpu_create)
+            std::vector<int> src, elt;
+            std::string m;
+            if (bam::mixture_rows(n, xt.data(), L.modelOpt[1], L.modelOpt[2], src, elt, m)) throw bam::CudaError{m};
+            std::vector<double> xp(xt.size());
+            for (int j = 0; j < nX; ++j)
+                for (int i = 0; i < n; ++i) xp[i + (size_t)j * n] = xt[src[i] + (size_t)j * n];
+            for (int i = 0; i < n; ++i) { xp[i] = (double)(i / L.modelOpt[2] + 1); xp[i + (size_t)n] = (double)elt[i]; }
+            xt.swap(xp);
+        }
         double *d_x1 = nullptr, *d_xt = nullptr, *d_y = nullptr;
         int* d_combo = nullptr;
         BAM_CUDA(cudaMalloc(&d_x1, sizeof(double) * L.P));
@@ -445,12 +482,35 @@ int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const dou
             BAM_CUDA(cudaMemcpyAsync(h->d_mode, mode, sizeof(double) * p.P, cudaMemcpyHostToDevice, h->stream));
         }
         std::vector<double*> ptrs(p.nX);
+        // Mixture: pair input rows with output rows from the event column (which must be a single series)
+        std::vector<int> msrc, melt;
+        std::vector<double> mbuf;
+        const bool mixture = p.model == BAMGPU_MDL_MIXTURE;
+        if (mixture) {
+            std::string m;
+            if (nspag[0] != 1) throw bam::CudaError{"bamgpu: Mixture: the event column of a prediction must be a single series (nspag = 1)"};
+            if (bam::mixture_rows(nobs_pred, xspag[0], p.modelOpt[1], p.modelOpt[2], msrc, melt, m)) throw bam::CudaError{m};
+        }
         for (int i = 0; i < p.nX; ++i) {
             if (nspag[i] < 1) throw bam::CudaError{"BaM_ReadSpag: nspag must be >= 1"};
             double* d = nullptr;
             const size_t cnt = (size_t)nobs_pred * nspag[i];
             BAM_CUDA(cudaMalloc(&d, sizeof(double) * cnt));
-            BAM_CUDA(cudaMemcpyAsync(d, xspag[i], sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+            const double* srcp = xspag[i];
+            if (mixture) {
+                mbuf.resize(cnt);
+                for (int c = 0; c < nspag[i]; ++c)
+                    for (int r = 0; r < nobs_pred; ++r) {
+                        double v = xspag[i][msrc[r] + (size_t)c * nobs_pred];
+                        if (i == 0) v = (double)(r / p.modelOpt[2] + 1);
+                        if (i == 1) v = (double)melt[r];
+                        mbuf[r + (size_t)c * nobs_pred] = v;
+                    }
+                srcp = mbuf.data();
+                BAM_CUDA(cudaStreamSynchronize(h->stream));  // mbuf is reused for the next column
+            }
+            BAM_CUDA(cudaMemcpyAsync(d, srcp, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+            if (mixture) BAM_CUDA(cudaStreamSynchronize(h->stream));
             h->d_xspag.push_back(d);
             h->predNspag.push_back(nspag[i]);
             ptrs[i] = d;

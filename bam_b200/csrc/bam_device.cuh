@@ -13,7 +13,7 @@
 
 #define BAM_MAXX 8
 #define BAM_MAXY 8
-#define BAM_MAXTHETA 40
+#define BAM_MAXTHETA 160  /* Mixture: nS*nEvt+nElt weights (tests/BaM_Mixture: 148) */
 #define BAM_MAXCTRL 8
 #define BAM_MAXDER 64  /* per-parameter-set derived values kept in the chain table (BaRatin: b_i and log a_i; Vegetation: 1+6 nYear) */
 #define BAM_VEG_MAXYEAR 10
@@ -63,7 +63,7 @@ struct DevProblem {
     const int* vmCode;
     const double* vmImmed;
     int vmNcode[BAM_MAXY], vmCodeOff[BAM_MAXY], vmImmedOff[BAM_MAXY], vmNin, vmNpar;
-    // SWOT {variant}, Orthorectification {distortion id, npar}
+    // SWOT {variant}, Orthorectification {distortion id, npar}, Segmentation {nS, nmin, option}, Mixture {nS, nEvt, nElt, missing}
     int modelOpt[4];
     double modelOptD;
     const double* hcsTab;  // HydraulicControl_section: 4 x hcsN (h | A | w | h + A/(2w))

@@ -32,6 +32,7 @@ int model_from_name(const char* name) {
     if (s == "Segmentation") return BAMGPU_MDL_SEGMENTATION;
     if (s == "BaRatinBAC") return BAMGPU_MDL_BARATINBAC;
     if (s == "SFD") return BAMGPU_MDL_SFD;
+    if (s == "Mixture") return BAMGPU_MDL_MIXTURE;
     return 0;
 }
 
@@ -546,6 +547,23 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             L.modelOptD = p.xtra_d[0];                                   // upper bound of the search interval
             L.nState = 1;
             break;
+        case BAMGPU_MDL_MIXTURE: {  // Mixture_XtraRead (:137-190), Mixture_GetParNumber (:33-72)
+            if (p.n_xtra_i != 4) { mess = "Mixture_XtraRead:problem reading xtra"; return 1; }
+            const int nS = p.xtra_i[0], nEvt = p.xtra_i[1], nElt = p.xtra_i[2], miss = p.xtra_i[3] != 0;
+            if (nS < 1 || nEvt < 1 || nElt < 1 || nt != (miss ? nS * nEvt + nElt : (nS - 1) * nEvt) || nX != 2 + nS || nY != 1) {
+                mess = "Mixture_Apply: wrong size [theta], nX or nY"; return 1;
+            }
+            if (nEvt > 64) { mess = "bamgpu: Mixture supports at most 64 events"; return 1; }
+            if (L.nVar) { mess = "bamgpu: Mixture is a whole-series model: VAR parameters are not supported"; return 1; }
+            if (L.Xerror[0] || L.nXb[0]) { mess = "bamgpu: Mixture: the event column (first input) must be free of input errors"; return 1; }
+            L.modelOpt[0] = nS; L.modelOpt[1] = nEvt; L.modelOpt[2] = nElt; L.modelOpt[3] = miss;
+            L.nDparModel = nEvt;  // LastWeight1..nEvt (ModelLibrary_tools.f90:580-586)
+            if (n > 0) {
+                std::vector<int> src, elt;
+                if (mixture_rows(n, p.X, nEvt, nElt, src, elt, mess)) return 1;
+            }
+            break;
+        }
         case BAMGPU_MDL_SEGMENTATION: {  // Segmentation_XtraRead (:142-180)
             if (p.n_xtra_i != 3 || p.n_xtra_d != 1) { mess = "Segmentation_XtraRead:problem reading xtra"; return 1; }
             const int nS = p.xtra_i[0];
@@ -592,6 +610,22 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             if (L.partype[i] != BAMGPU_PAR_FIX) L.comboSrc[(size_t)k * nt + i] = L.thetaOff[i] + combos[k][i] - 1;
     L.nDpar = L.nDparModel * L.nCombo;
     mess.clear();
+    return 0;
+}
+
+int mixture_rows(int n, const double* evt, int nEvt, int nElt, std::vector<int>& src, std::vector<int>& elt, std::string& mess) {
+    if ((long long)nEvt * nElt != n) { mess = "Mixture_Apply: the number of rows is not nEvt*nElt"; return 1; }
+    src.assign(n, 0);
+    elt.assign(n, 0);
+    std::vector<int> cnt(nEvt, 0);
+    for (int t = 0; t < n; ++t) {
+        const long j = std::lround(evt[t]);  // nint(X(:,1))
+        if (j < 1 || j > nEvt) continue;     // a row of no event is never packed
+        const int e = cnt[j - 1]++;
+        if (e < nElt) { src[(j - 1) * nElt + e] = t; elt[(j - 1) * nElt + e] = e + 1; }
+    }
+    for (int j = 0; j < nEvt; ++j)
+        if (cnt[j] != nElt) { mess = "Mixture_Apply: an event does not have nElt rows"; return 1; }
     return 0;
 }
 

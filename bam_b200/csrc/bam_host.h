@@ -59,6 +59,11 @@ struct HostLayout {
     int nDer = 0;  // derived values per (parameter set, combination) kept in the device table
 };
 
+// Mixture (Mixture_model.f90:119-123): output row (j-1)*nElt+e is built from the e-th input row whose event column
+// (rounded) is j.  src[r] = that input row, elt[r] = e (1-based).  Returns 0, or 1 (mess set) when an event does not
+// have exactly nElt rows or the series is not nEvt*nElt long (array-size mismatches in the reference).
+int mixture_rows(int n, const double* evt, int nEvt, int nElt, std::vector<int>& src, std::vector<int>& elt, std::string& mess);
+
 // Validates `p` and derives the layout.  Returns err (0 OK, >0 error) and fills mess.
 int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess);
 

@@ -741,6 +741,52 @@ __device__ inline bool sfd_apply(const DevProblem& p, const double* in, const do
 }
 
 // -------------------------------------------------------------------------------------------
+// Mixture (Mixture_model.f90:74-135): Y = sum_i w_{j,i} X_i per event j, the weights of an event in [0,1] and summing to
+// one (the last one is derived); with a missing source, + w_last * theta(nEvt nS + e) for element e.  The reference
+// builds output row (j-1) nElt + e from the e-th INPUT row of event j (pack order); the host pairs the rows once at
+// creation (bam::mixture_rows), so that here the model is pointwise: x[0] = event, x[1] = element position within the
+// event (both 1-based), x[2..] = source concentrations.  der[j] = last weight of event j (the derived parameters).
+// -------------------------------------------------------------------------------------------
+__device__ inline bool mixture_prepare(const DevProblem& p, const double* th, double* der) {
+    const int nS = p.modelOpt[0], nEvt = p.modelOpt[1], missing = p.modelOpt[3];
+    for (int j = 0; j < nEvt; ++j) {
+        double s = 0.0, last;
+        bool bad = false;
+        if (missing) {
+            for (int i = 0; i < nS; ++i) { const double w = th[j * nS + i]; s = s + w; bad |= (w < 0.0 || w > 1.0); }
+            if (s > 1.0) return false;
+            last = 1.0 - s;
+        } else {
+            for (int i = 0; i < nS - 1; ++i) { const double w = th[j * (nS - 1) + i]; s = s + w; bad |= (w < 0.0 || w > 1.0); }
+            last = 1.0 - s;
+            bad |= (last < 0.0 || last > 1.0);
+        }
+        if (bad) return false;
+        der[j] = last;
+    }
+    return true;
+}
+
+template <int NX>
+__device__ __forceinline__ bool mixture_apply(const DevProblem& p, const double* x, const double* __restrict__ th,
+                                              const double* __restrict__ der, double& out) {
+    constexpr int nS = NX - 2;
+    const int nEvt = p.modelOpt[1], missing = p.modelOpt[3];
+    const int j = (int)x[0] - 1, e = (int)x[1] - 1;
+    const double last = der[j];
+    const double* __restrict__ w = th + (missing ? j * nS : j * (nS - 1));
+    double y = 0.0;
+#pragma unroll
+    for (int i = 0; i < nS; ++i) {
+        const double wi = (missing || i < nS - 1) ? w[i] : last;
+        y = y + x[2 + i] * wi;
+    }
+    if (missing) y = y + last * th[nEvt * nS + e];
+    out = y;
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
 // dispatch
 // -------------------------------------------------------------------------------------------
 
@@ -753,6 +799,7 @@ __device__ inline bool model_prepare(const DevProblem& p, const double* th, doub
     if (p.model == BAMGPU_MDL_VEGETATION) return vegetation_prepare(p, th, der, xc, nser);
     if (p.model == BAMGPU_MDL_ORTHO) return ortho_prepare(th, der);
     if (p.model == BAMGPU_MDL_SEGMENTATION) return segmentation_prepare(p, th, der, xc[0], nser);
+    if (p.model == BAMGPU_MDL_MIXTURE) return mixture_prepare(p, th, der);
     if (p.model == BAMGPU_MDL_SFD)  // StageFallDischarge_model.f90:141-143
         return !(th[0] <= 0.0 || th[2] <= 0.0 || th[3] <= 0.0 || th[5] <= 0.0 || th[7] <= 0.0);
     if (p.model == BAMGPU_MDL_HCS) return !(th[0] <= 0.0 || th[1] <= 0.0);  // HydraulicControl_section_model.f90:70-72
@@ -794,6 +841,8 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return hcs_apply(p, x[0], th, y[0]);
     } else if (MODEL == BAMGPU_MDL_SEGMENTATION) {
         return segmentation_apply(p, x[0], th, der, y[0]);
+    } else if (MODEL == BAMGPU_MDL_MIXTURE) {
+        return mixture_apply<NX>(p, x, th, der, y[0]);
     } else {
         bool ok = true;
 #pragma unroll

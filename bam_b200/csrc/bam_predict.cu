@@ -33,6 +33,7 @@ struct PredArgs {
     int doRemnant[BAM_MAXY];
     unsigned long long seed;
     int stride;                 // doubles per replication in the table: [gamma | full theta | derived]
+    int stage;                  // pred_main: stage the table rows of the block in shared memory (stride * 2 KB fits)
 };
 
 __global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const double* __restrict__ mc,
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
     const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
     const bool act = rep < a.Nrep;
     const int stride = a.stride;
-    if (act)
+    // a.stage == 0 (stride too large for shared memory, e.g. Mixture with its 148 weights): read the table row directly
+    if (act && a.stage)
         for (int k = 0; k < stride; ++k) sm[k * BAM_BLOCK + tid] = tab[(size_t)rep * stride + k];
     const bool setOk = act ? (status[rep] == 0) : false;
     const int tBeg = blockIdx.y * 32, tEnd = min(a.nT, tBeg + 32);
@@ -83,7 +85,8 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
     // this replication's full theta + derived values: private copy, loaded once for all inputs of the tile
     double loc[BAM_MAXTHETA + BAM_MAXDER];
     const int np = p.ntheta + p.nDer;
-    for (int k = 0; k < np; ++k) loc[k] = sm[(p.nGamma + k) * BAM_BLOCK + tid];
+    if (a.stage) for (int k = 0; k < np; ++k) loc[k] = sm[(p.nGamma + k) * BAM_BLOCK + tid];
+    else for (int k = 0; k < np; ++k) loc[k] = tab[(size_t)rep * stride + p.nGamma + k];
     for (int t = tBeg; t < tEnd; ++t) {
         double xin[NX], y[NY];
 #pragma unroll
@@ -95,7 +98,8 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
             double v = ok ? y[j] : p.unfeas;  // ApplyModel flags infeasible rows (ModelLibrary_tools.f90:419-432)
             if (a.doRemnant[j] && v != p.unfeas) {
                 double gam[3];
-                for (int m = 0; m < p.nrem[j] && m < 3; ++m) gam[m] = sm[(p.gamOff[j] + m) * BAM_BLOCK + tid];
+                for (int m = 0; m < p.nrem[j] && m < 3; ++m)
+                    gam[m] = a.stage ? sm[(p.gamOff[j] + m) * BAM_BLOCK + tid] : tab[(size_t)rep * stride + p.gamOff[j] + m];
                 const double sig = sigmafunk(p.sigfunc[j], gam, v);
                 if (sig > 0.0) v = v + sig * philox_normal_pred(a.seed, (uint64_t)rep, (unsigned)(a.t0 + t), (unsigned)j);
             }
@@ -1261,6 +1265,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     a.Nrep = Nrep; a.nobsPred = h->predNobs; a.doParametric = doParametric; a.seed = seed;
     for (int y = 0; y < BAM_MAXY; ++y) a.doRemnant[y] = (y < nY) ? doRemnant[y] : 0;
     a.stride = p.nGamma + p.ntheta + p.nDer;
+    a.stage = sizeof(double) * (size_t)a.stride * BAM_BLOCK <= 96 * 1024;
 
     // table + envelope output
     if (!h->d_ptab) {
@@ -1293,7 +1298,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     pred_prep<<<(unsigned)((Nrep + 127) / 128), 128, 0, s>>>(p, a, h->d_mc, h->d_mode, h->d_xspagPtrs, h->d_nspag, h->d_ptab,
                                                              h->d_pstatus);
     h->launches += 1;
-    const size_t smemMain = sizeof(double) * (size_t)a.stride * BAM_BLOCK;
+    const size_t smemMain = a.stage ? sizeof(double) * (size_t)a.stride * BAM_BLOCK : 0;
     if (smemMain > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMain));
 
     int npad = 1;

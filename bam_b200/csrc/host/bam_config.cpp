@@ -2,6 +2,7 @@
 #include "bam_config.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -310,6 +311,15 @@ static void read_xtra(Workspace& w) {
         const int nmin = s.integer(), option = s.integer();
         w.xtraI = {nS, nmin, option};
         w.xtraD = {tmin};
+    } else if (w.modelID == "Mixture") {  // Mixture_XtraRead (Mixture_model.f90:137-190): nS, nEvt, nElt, missingSource
+        Cursor s(xf);
+        const int nS = s.integer(), nEvt = s.integer(), nElt = s.integer();
+        std::string flag = s.str();  // Fortran logical: T, F, .true., .false. (any case)
+        size_t q = 0;
+        while (q < flag.size() && flag[q] == '.') ++q;
+        const char c0 = q < flag.size() ? (char)std::tolower((unsigned char)flag[q]) : ' ';
+        if (c0 != 't' && c0 != 'f') fail("Mixture_XtraRead:problem reading file " + xf);
+        w.xtraI = {nS, nEvt, nElt, c0 == 't' ? 1 : 0};
     } else if (w.modelID == "Linear" || w.modelID == "SuspendedLoad" || w.modelID == "SGD" || w.modelID == "Recession_h") {
     } else {
         fail("ApplyModel: Fatal: Unavailable [model%ID] '" + w.modelID + "' (not on the GPU hot path yet)");

@@ -381,6 +381,43 @@ def second_wave(model: str, nobs: int = 400, seed: int = SEED + 7, **kw):
     return prob, np.concatenate([th, [0.01 * np.abs(q).mean(), 0.05]])
 
 
+def mixture(nS: int = 3, nEvt: int = 6, nElt: int = 9, missing: bool = True, shuffle: bool = True, seed: int = SEED + 11):
+    """Mixture (Mixture_model.f90): nEvt events x nElt elements, nS sources; rows optionally interleaved across events so
+    that the reference's pack() pairing (e-th input row of event j -> output row (j-1)*nElt+e) is exercised.
+    Returns (Problem, truth)."""
+    rng = np.random.default_rng(seed)
+    n = nEvt * nElt
+    evt = np.repeat(np.arange(1, nEvt + 1), nElt)
+    elt = np.tile(np.arange(1, nElt + 1), nEvt)
+    if shuffle:
+        o = rng.permutation(n)
+        evt, elt = evt[o], elt[o]
+    src = rng.uniform(0.3, 2.0, (n, nS))
+    if missing:
+        w = rng.dirichlet(np.ones(nS + 1), nEvt)[:, :nS] * 0.9  # sum < 1: the rest goes to the missing source
+        miss = rng.uniform(0.5, 1.5, nElt)
+        th = np.concatenate([w.ravel(), miss])
+        pri = [("Uniform", [0, 1])] * (nS * nEvt) + [("FlatPrior+", [])] * nElt
+    else:
+        wf = rng.dirichlet(np.ones(nS), nEvt)
+        w = wf[:, : nS - 1]
+        th = w.ravel()
+        pri = [("Uniform", [0, 1])] * ((nS - 1) * nEvt)
+    # truth in the reference's own output order: row (j-1)*nElt+e = e-th input row of event j
+    y = np.zeros(n)
+    for j in range(nEvt):
+        rows = np.flatnonzero(evt == j + 1)
+        wj = w[j] if missing else np.append(w[j], 1.0 - w[j].sum())
+        y[j * nElt:(j + 1) * nElt] = src[rows] @ wj
+        if missing:
+            y[j * nElt:(j + 1) * nElt] += (1.0 - w[j].sum()) * miss
+    X = np.column_stack([evt.astype(float), elt.astype(float), src])
+    Y = y + 0.02 * rng.standard_normal(n)
+    prob = Problem("Mixture", X, Y, partype=[0] * th.size, priors_theta=pri, sigma_func=["Linear"],
+                   priors_gamma=[("Uniform", [0, 1000])] * 2, xtra_i=[nS, nEvt, nElt, int(missing)])
+    return prob, np.concatenate([th, [0.02, 0.01]])
+
+
 def baratin_bac(nobs: int = 300, seed: int = SEED + 8, hmax: float = 6.0):
     """BaRatinBAC: the 3-control matrix of tests/BaM_BaRatinBAC (control 2 REPLACES control 1, control 3 is ADDED),
     theta = (b, a, c) per control.  Returns (Problem, truth)."""

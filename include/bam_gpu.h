@@ -46,8 +46,10 @@ enum bamgpu_model {
     BAMGPU_MDL_HCS = 11,          /* HydraulicControl_section_model.f90:40-112 ("HydraulicControl_section") */
     BAMGPU_MDL_SEGMENTATION = 12, /* Segmentation_model.f90:52-140 (whole-series model: segment sizes are checked) */
     BAMGPU_MDL_BARATINBAC = 13,   /* BaRatinBAC_model.f90:96-666: BaRatin in the b-a-c parameterisation */
-    BAMGPU_MDL_SFD = 14           /* StageFallDischarge_model.f90:80-283 (SFD_Val_General); the transition stage kappa
+    BAMGPU_MDL_SFD = 14,          /* StageFallDischarge_model.f90:80-283 (SFD_Val_General); the transition stage kappa
                                      (the model's only state variable) is computed but not exported by this ABI yet */
+    BAMGPU_MDL_MIXTURE = 15       /* Mixture_model.f90:74-135: per-event weighted sum of source concentrations; output
+                                     rows are event x element blocks (row (j-1)*nElt+e = e-th input row of event j) */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -141,6 +143,7 @@ typedef struct bamgpu_problem {
        HydraulicControl_section : xtra_d = the h-A-w matrix, p x 3 column-major (n_xtra_d = 3p)
        Segmentation : xtra_i = {nS, nmin, option}; xtra_d = {tmin}
        SFD        : xtra_i = {1 (SFD_Val_General), itmax}; xtra_d = {upperbound, xscale, fscale, tolX, tolF}
+       Mixture    : xtra_i = {nS, nEvt, nElt, missingSource (0|1)} (Mixture_XtraRead, Mixture_model.f90:137-190)
        Linear, SuspendedLoad, SGD, Recession_h : none */
     const int32_t* xtra_i;
     int32_t n_xtra_i;

@@ -1333,6 +1333,44 @@ static int segmentation_apply(const oracle_t* o, int nt, const double* time, con
     return ok;
 }
 
+/* Mixture_Apply, Mixture_model.f90:74-135.  Output rows are event x element blocks: row (j-1)*nElt+e is the e-th
+   input row whose event column (X(:,1), rounded) equals j -- pack() order.  Returns 0 when the parameter set is
+   infeasible (scalar feas), -1 when an event does not have exactly nElt rows (an array-size mismatch in the reference). */
+static int mixture_apply(const oracle_t* o, int n, const double* X, int ldx, const double* theta, double* Y,
+                         double* theta_last) {
+    const int nS = o->model_opt[0], nEvt = o->model_opt[1], nElt = o->model_opt[2], missing = o->model_opt[3];
+    for (int t = 0; t < n; ++t) Y[t] = BAMGPU_UNDEF_RN;
+    for (int j = 0; j < nEvt; ++j) theta_last[j] = BAMGPU_UNDEF_RN;
+    for (int j = 0; j < nEvt; ++j) {
+        double w[64], last, s = 0.0;
+        if (missing) {
+            for (int i = 0; i < nS; ++i) { w[i] = theta[j * nS + i]; s = s + w[i]; }
+            if (s > 1.0) return 0;
+            last = 1.0 - s;
+        } else {
+            for (int i = 0; i < nS - 1; ++i) { w[i] = theta[j * (nS - 1) + i]; s = s + w[i]; }
+            w[nS - 1] = 1.0 - s;
+            last = w[nS - 1];
+        }
+        for (int i = 0; i < nS; ++i)
+            if (w[i] < 0.0 || w[i] > 1.0) return 0;
+        int e = 0;
+        for (int t = 0; t < n; ++t) {
+            if (lround(X[t]) != j + 1) continue;
+            if (e < nElt && j * nElt + e < n) {
+                double y = 0.0; /* matmul(sources, dummytheta): accumulation over the sources in order */
+                for (int i = 0; i < nS; ++i) y = y + X[t + (size_t)(2 + i) * ldx] * w[i];
+                if (missing) y = y + last * theta[nEvt * nS + e];
+                Y[j * nElt + e] = y;
+            }
+            ++e;
+        }
+        if (e != nElt) return -1;
+        theta_last[j] = last;
+    }
+    return 1;
+}
+
 /* TxtMdl_Apply, TextFile_model.f90:1035-1098 */
 static void textfile_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
                            int ldy, int32_t* vfeas) {
@@ -1373,6 +1411,13 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         case BAMGPU_MDL_HCS: hcs_apply(o, n, X, fullTheta, Y, vfeas); break;
         case BAMGPU_MDL_BARATINBAC: baratinbac_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
         case BAMGPU_MDL_SFD: sfd_apply(o, n, X, ldx, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_MIXTURE: {
+            int r = mixture_apply(o, n, X, ldx, fullTheta, Y, dparModel);
+            if (r < 0) return 1;
+            if (!r)
+                for (int t = 0; t < n; ++t) vfeas[t] = 0;
+            break;
+        }
         case BAMGPU_MDL_SEGMENTATION:
             if (!segmentation_apply(o, n, X, fullTheta, Y))
                 for (int t = 0; t < n; ++t) vfeas[t] = 0; /* scalar feas=.false. (ModelLibrary_tools.f90:362-364) */
@@ -1410,6 +1455,7 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "Segmentation")) return BAMGPU_MDL_SEGMENTATION;
     if (!strcmp(name, "BaRatinBAC")) return BAMGPU_MDL_BARATINBAC;
     if (!strcmp(name, "SFD")) return BAMGPU_MDL_SFD;
+    if (!strcmp(name, "Mixture")) return BAMGPU_MDL_MIXTURE;
     return 0;
 }
 
@@ -1569,6 +1615,15 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             o->hcs_n = p->n_xtra_d / 3;
             if (o->hcs_n < 3 || p->n_xtra_d != 3 * o->hcs_n || nt != 2 || nX != 1 || nY != 1) { setmess(mess, "oracle: HydraulicControl_section: bad xtra or sizes"); return 1; }
             break;
+        case BAMGPU_MDL_MIXTURE: { /* Mixture_GetParNumber (:33-72), XtraSetup (ModelLibrary_tools.f90:580-586) */
+            if (p->n_xtra_i != 4) { setmess(mess, "oracle: Mixture: bad xtra"); return 1; }
+            int nS = p->xtra_i[0], nEvt = p->xtra_i[1], nElt = p->xtra_i[2], miss = p->xtra_i[3] != 0;
+            if (nS < 1 || nS > 62 || nEvt < 1 || nEvt > 64 || nElt < 1 || nX != 2 + nS || nY != 1 ||
+                nt != (miss ? nS * nEvt + nElt : (nS - 1) * nEvt) || nt > 256) { setmess(mess, "oracle: Mixture: bad sizes"); return 1; }
+            o->model_opt[0] = nS; o->model_opt[1] = nEvt; o->model_opt[2] = nElt; o->model_opt[3] = miss;
+            o->nDparModel = nEvt;
+            break;
+        }
         case BAMGPU_MDL_SEGMENTATION:
             if (p->n_xtra_i != 3 || p->n_xtra_d != 1 || nX != 1 || nY != 1 || nt != 2 * p->xtra_i[0] - 1 || p->xtra_i[0] > 32) { setmess(mess, "oracle: Segmentation: bad xtra or sizes"); return 1; }
             o->model_opt[0] = p->xtra_i[0]; o->model_opt[1] = p->xtra_i[1]; o->model_opt[2] = p->xtra_i[2];

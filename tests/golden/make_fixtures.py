@@ -160,6 +160,9 @@ def load_workspace(cfg_name):
     elif model_id == "TextFile":
         with open(path(ws, f_xtra)) as f:
             xtra_text = f.read()
+    elif model_id == "Mixture":  # Mixture_XtraRead (Mixture_model.f90:137-190): nS, nEvt, nElt, missingSource
+        s = read_lines(path(ws, f_xtra))
+        xtra_i = [int(items(s[i])[0]) for i in range(3)] + [1 if items(s[3])[0].strip(".").lower().startswith("t") else 0]
 
     # ---- optional prior correlation (src/BaM_main.f90:22,302; src/BaM_tools.f90:386-414)
     priorC = None
@@ -203,6 +206,7 @@ WORKSPACES = {
     "sediment_camenen_x4": None,  # built below: no top-level Config_BaM for it
     "sediment_mpm_x2": "Config_BaM_Sediment.txt",
     "textfile_inputuncertainty": "Config_BaM_TextFile_InputUncertainty.txt",
+    "mixture": "Config_BaM_Mixture.txt",
 }
 
 

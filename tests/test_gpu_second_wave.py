@@ -150,3 +150,50 @@ def test_sfd():
     isv = np.isclose(det[0, ok, 0], qv[ok], rtol=1e-9)
     isc = np.isclose(det[0, ok, 0], qc[ok], rtol=1e-9)
     assert (isv | isc).all() and isv.any() and isc.any()
+
+
+@pytest.mark.parametrize("missing,shuffle", [(True, True), (False, True), (True, False)])
+def test_mixture(missing, shuffle):
+    """Mixture (Mixture_model.f90:74-135): rows interleaved across events exercise the pack() pairing of input and output
+    rows; weights above one / negative / summing above one are infeasible parameter sets."""
+    prob, truth = synth.mixture(nS=3, nEvt=6, nElt=9, missing=missing, shuffle=shuffle)
+    nt = prob.ntheta
+    x = synth.feasible_starts(truth, 40, rel=0.01, seed=2)
+    x[3, 0] = 1.3                      # a weight above one: null under the Uniform(0,1) prior
+    x[4, 0], x[4, 1] = 0.8, 0.7        # sum of an event's weights above one: infeasible model run (:112 / derived weight < 0)
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.nDpar == 6 and o.nDpar == 6
+    check_parity(prob, x)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.005 * rng.standard_normal((150, truth.size)))
+    mc[7, 0], mc[7, 1] = 0.8, 0.7      # an infeasible replication: its column of the spaghetti is flagged
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(prob.nX)]
+    env, spag = g.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True)
+    oenv, ospag = o.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True, nthreads=8)
+    cmp_spag(spag, ospag)
+    cmp_env(env, oenv)
+    s = np.tile(truth, (3, 1))
+    sd = 0.01 * np.abs(s) + 1e-12
+    rows = g.fit(s, sd, nAdapt=3, nCycles=2, seed=5)
+    orows = o.fit(s, sd, nAdapt=3, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+    Xt, Ys, feas = g.calibration_run(truth)
+    oXt, oYs, ofeas = o.calibration_run(truth)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-13, atol=0) and np.array_equal(Xt, oXt)
+    assert nt == (3 * 6 + 9 if missing else 2 * 6)
+
+
+def test_mixture_reference_workspace():
+    """tests/BaM_Mixture: 148 weights + 2 remnant parameters, 351 rows (27 events x 13 elements)"""
+    from tests.helpers import perturbed_vectors, problem_from_fixture
+
+    prob, d = problem_from_fixture("mixture")
+    x = perturbed_vectors(d["start"], 64, rel=0.02, seed=1)
+    check_parity(prob, x)
+    g, o = BamGpu(prob), Oracle(prob)
+    mc = perturbed_vectors(d["start"], 300, rel=0.01, seed=2)
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(prob.nX)]
+    env, spag = g.predict(mc, np.asarray(d["start"]), xs, 1, [1], seed=9, want_spag=True)
+    oenv, ospag = o.predict(mc, np.asarray(d["start"]), xs, 1, [1], seed=9, want_spag=True, nthreads=8)
+    cmp_spag(spag, ospag)
+    cmp_env(env, oenv)

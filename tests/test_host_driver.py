@@ -14,7 +14,7 @@ from tests.workspace_writer import write_workspace
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "bam_b200", "bam_gpu")
 FIXTURES = ["baratin", "baratin_spd", "regression_x2y2", "sediment_camenen_x4", "sediment_mpm_x2",
-            "textfile_inputuncertainty"]
+            "textfile_inputuncertainty", "mixture"]
 DIST = {"Gaussian": 1, "Uniform": 2, "Triangle": 3, "LogNormal": 4, "Exponential": 5, "FlatPrior": 6, "FlatPrior+": 7,
         "FlatPrior-": 8}
 SIG = {"Constant": 1, "Linear": 2, "Proportional": 3, "Power": 4, "Exponential": 5, "Gaussian": 6}
@@ -74,7 +74,8 @@ def test_config_reader_roundtrip(name, tmp_path):
 @pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference workspaces only exist in the build container")
 @pytest.mark.parametrize("cfg,name", [("Config_BaM_BaRatin.txt", "baratin"), ("Config_BaM_BaRatin_SPD.txt", "baratin_spd"),
                                       ("Config_BaM_Regression_X2Y2.txt", "regression_x2y2"),
-                                      ("Config_BaM_TextFile_InputUncertainty.txt", "textfile_inputuncertainty")])
+                                      ("Config_BaM_TextFile_InputUncertainty.txt", "textfile_inputuncertainty"),
+                                      ("Config_BaM_Mixture.txt", "mixture")])
 def test_config_reader_on_shipped_workspaces(cfg, name):
     """the reference's own example workspaces, Windows path separators included"""
     compare_d = dump_ref(cfg)

@@ -283,3 +283,67 @@ def test_baratinbac_is_consistent_with_baratin():
         assert np.allclose(Yb[away, 0], Yk[away, 0], rtol=1e-12, atol=1e-12)
         if ktypes is not None:
             assert list(dpb[nc:2 * nc]) == ktypes
+
+
+def _mixture_numpy(X, th, nS, nEvt, nElt, missing):
+    """Independent numpy restatement of Mixture_Apply (Mixture_model.f90:110-133), pack() pairing included."""
+    evt = np.rint(X[:, 0]).astype(int)
+    Y, last = np.zeros(nEvt * nElt), np.zeros(nEvt)
+    for j in range(nEvt):
+        w = th[j * nS:(j + 1) * nS] if missing else np.append(th[j * (nS - 1):(j + 1) * (nS - 1)], 0.0)
+        if not missing:
+            w[-1] = 1.0 - np.sum(w[:-1])
+        last[j] = 1.0 - np.sum(w) if missing else w[-1]
+        rows = np.flatnonzero(evt == j + 1)
+        Y[j * nElt:(j + 1) * nElt] = X[rows, 2:] @ w + (last[j] * th[nEvt * nS:] if missing else 0.0)
+    return Y, last
+
+
+def test_mixture_on_the_reference_workspace():
+    """tests/BaM_Mixture (5 sources, 27 events, 13 elements, missing source: 148 weights): the workspace ships no
+    known-answer column, so the restatement is pinned on its DATA through an independent numpy statement of
+    Mixture_Apply, at the configured starting point and at random feasible weights."""
+    prob, fx = problem_from_fixture("mixture")
+    assert (prob.nobs, prob.nX, prob.ntheta) == (351, 7, 148) and list(fx["xtra_i"]) == [5, 27, 13, 1]
+    o = Oracle(prob)
+    assert o.sizes.nDpar == 27 and o.sizes.nInfer == 150
+    X = np.asarray(fx["X"]).reshape(7, 351).T
+    rng = np.random.default_rng(5)
+    th0 = np.asarray(fx["start"][:148])
+    th1 = np.concatenate([(rng.dirichlet(np.ones(6), 27)[:, :5]).ravel(), rng.uniform(0.5, 2.0, 13)])
+    for th in (th0, th1):
+        Y, feas, dpar = o.apply_model(X, th)
+        Yn, last = _mixture_numpy(X, th, 5, 27, 13, True)
+        assert feas.all()
+        assert np.max(np.abs(Y[:, 0] - Yn) / np.abs(Yn)) <= 4e-16 * 8
+        assert np.max(np.abs(dpar[:27] - last)) <= 2e-16
+    r = o.logpost_one(fx["start"])
+    assert r["feas"] == 1 and r["isnull"] == 0 and np.isfinite(r["fx"])
+    # infeasible weights: a weight above one, a negative weight, weights of one event summing above one (:112,120)
+    for pos, val in ((3, 1.2), (7, -0.1), (10, 0.9)):
+        th = th0.copy()
+        th[pos] = val
+        if pos == 10:
+            th[11] = 0.9
+        assert not o.apply_model(X, th)[1].any()
+        x = np.asarray(fx["start"], dtype=np.float64).copy()
+        x[:148] = th
+        rr = o.logpost_one(x)
+        assert rr["feas"] == 0 or rr["isnull"] == 1  # Uniform(0,1) prior: null before the model is run
+
+
+@pytest.mark.parametrize("missing", [True, False])
+def test_mixture_row_pairing(missing):
+    """rows interleaved across events: output row (j-1)*nElt+e is the e-th INPUT row of event j (pack order)"""
+    from bam_b200 import synth
+
+    prob, truth = synth.mixture(nS=3, nEvt=5, nElt=7, missing=missing, shuffle=True)
+    X = np.asarray(prob.X)
+    th = truth[:prob.ntheta]
+    Y, feas, dpar = Oracle(prob).apply_model(X, th)
+    Yn, last = _mixture_numpy(X, th, 3, 5, 7, missing)
+    assert feas.all() and np.max(np.abs(Y[:, 0] - Yn)) <= 1e-15 and np.max(np.abs(dpar[:5] - last)) <= 2e-16
+    if not missing:  # derived last weight outside [0,1]
+        bad = th.copy()
+        bad[0], bad[1] = 0.7, 0.6
+        assert not Oracle(prob).apply_model(X, bad)[1].any()

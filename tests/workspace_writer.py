@@ -98,6 +98,9 @@ def write_workspace(fx: dict, root: str, name: str = "WS", nAdapt=None, nCycles=
             "\n" + ",".join(repr(float(v)) for v in fx["xtra_d"]) + "\n")
     elif fx["model_id"] == "TextFile":
         open(os.path.join(ws, xf), "w").write(fx["xtra_text"])
+    elif fx["model_id"] == "Mixture":
+        xi = fx["xtra_i"]
+        open(os.path.join(ws, xf), "w").write(f"{xi[0]} ! nS\n{xi[1]} ! nEvt\n{xi[2]} ! nElt\n{'.true.' if xi[3] else '.false.'} ! missing source\n")
     else:
         open(os.path.join(ws, xf), "w").write("\n")
 
