@@ -108,6 +108,15 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         h->device = device;
         BAM_CUDA(cudaSetDevice(device));
         BAM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        {   // stream-ordered scratch (cudaMallocAsync in the prediction loop): keep freed blocks in the pool across
+            // synchronisations instead of returning them to the driver (default threshold 0 -> re-mapping every step)
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        }
         BAM_CUDA(cudaEventCreate(&h->ev0));
         BAM_CUDA(cudaEventCreate(&h->ev1));
 
@@ -208,6 +217,17 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         }
         d.comboSrc = upload(h, L.comboSrc.data(), L.comboSrc.size());
         d.latIdx = L.hasLatent ? upload(h, permXI(L.latIdx.data(), L.nX).data(), L.latIdx.size()) : nullptr;  // hasLatent: perm is the identity
+        if (L.hasLatent && (long long)L.nLatent == (long long)L.n * L.nX) {  // chain-independent parts of the hyper term
+            std::vector<double> inv((size_t)L.n * L.nX), hc(L.n, 0.0);
+            for (int j = 0; j < L.nX; ++j)
+                for (int i = 0; i < L.n; ++i) {
+                    const double xu = pb->Xu[xsrc[i] + (size_t)j * L.n];
+                    inv[i + (size_t)j * L.n] = 1.0 / xu;
+                    hc[i] += -BAM_LOG_SQRT_2PI - std::log(xu);
+                }
+            d.XuInv = upload(h, inv.data(), inv.size());
+            d.hyC = upload(h, hc.data(), hc.size());
+        }
         for (int i = 0; i < L.ntheta; ++i) d.fixv[i] = L.fixv[i];
         d.hasLatent = L.hasLatent; d.hasXbias = L.hasXbias; d.hasYbias = L.hasYbias;
         d.hyperInfeasible = L.hyperInfeasible; d.hasMissing = L.hasMissing && !dropped;

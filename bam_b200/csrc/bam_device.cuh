@@ -43,6 +43,8 @@ struct DevProblem {
     const double* expTab;   // BAM_EXPTAB_N x 2^(j/N)                                    : table-driven exp
     const int* comboSrc;  // nCombo x ntheta : position in the parameter vector, or -1 for FIX
     const int* latIdx;    // n x nX : position of the latent "true input" in the vector, or -1
+    const double* XuInv;  // n x nX : 1 / Xu          } only when EVERY input cell is latent (logpost_linear_latent),
+    const double* hyC;    // n : sum_j -log sqrt(2 pi) - log Xu(i,j)  } else nullptr
     double fixv[BAM_MAXTHETA];
     int hasLatent, hasXbias, hasYbias, hyperInfeasible, hasMissing;
     int Xerror[BAM_MAXX], nXb[BAM_MAXX], offXb[BAM_MAXX], tabOffXb[BAM_MAXX];

@@ -289,6 +289,146 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 fast path for cfg 3: Linear model, EVERY input cell latent (TextFile_InputUncertainty / Regression with input
+// uncertainty), no biases, no missing Y, one sigma function.  Per (chain, observation) the path must read the chain's
+// own "true" inputs (8 NX bytes: HBM-leaning), so the kernel is organised around those loads:
+//   * block = 256 threads x LL_OPT observations each (stride 256: coalesced) x a tile of LL_CT chains;
+//   * the observation's (Xobs, 1/Xu, Y, Yu^2) sit in registers for all chains of the tile; the chains' theta and gamma
+//     are broadcast reads from shared memory; the 2 LL_CT (likelihood, hyper) sums stay in REGISTERS across the
+//     thread's observations, so the cross-thread reduction (shuffle tree + fixed-order cross-warp sum) is paid once
+//     per LL_OPT x LL_CT units instead of once per unit as in logpost_main;
+//   * the LL_CT x NX loads of one observation are independent: 2 LL_CT requests in flight per thread;
+//   * blockIdx.x walks the chain tiles, so the blocks that share an observation tile run together and the
+//     observation tables are served by L2.
+// Same arithmetic as logpost_main (GetLogLikelihood :3204-3227, GetHyperLogPdf :3285-3303) except that the
+// chain-independent constants (-log sqrt(2 pi) - log Xu per cell) are summed once per thread and the factor -1/2 is
+// applied to the thread's sum: results agree to ~1e-15 relative, not bitwise.
+// Algorithmic bytes per (chain, observation): 8 NX (latent inputs); observation tables 8 (2 NX + 2 NY) / LL_CT.
+// ------------------------------------------------------------------------------------------------
+#define LL_CT 8
+#define LL_OPT 8
+template <int NX, int NY, int SIGF>
+__global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_linear_latent(DevProblem p, const double* __restrict__ x, int K,
+                                                                      const double* __restrict__ tab,
+                                                                      const int* __restrict__ status,
+                                                                      double* __restrict__ part, int* statusOut) {
+    constexpr int NG = (SIGF == BAMGPU_SIG_LINEAR) ? 2 : 1;
+    __shared__ double sth[LL_CT][NX * NY];
+    __shared__ double sg[LL_CT][NG * NY];
+    __shared__ int sst[LL_CT];
+    __shared__ double red[BAM_BLOCK / 32][2 * LL_CT];
+    __shared__ __align__(16) double2 sLogT[BAM_LOGTAB_N];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * LL_CT, nc = min(LL_CT, K - c0);
+    for (int q = tid; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
+    for (int q = tid; q < LL_CT * NX * NY; q += BAM_BLOCK) {
+        const int cc = q / (NX * NY), i = q % (NX * NY);
+        sth[cc][i] = (cc < nc) ? tab[(size_t)(c0 + cc) * p.tabStride + p.tabCombo + i] : 0.0;
+    }
+    for (int q = tid; q < LL_CT * NG * NY; q += BAM_BLOCK) {
+        const int cc = q / (NG * NY), i = q % (NG * NY), j = i / NG, m = i % NG;
+        sg[cc][i] = (cc < nc) ? tab[(size_t)(c0 + cc) * p.tabStride + p.tabGamma + p.gamOff[j] + m] : 0.0;
+    }
+    if (tid < LL_CT) sst[tid] = (tid < nc) ? status[c0 + tid] : 1;
+    __syncthreads();
+    const unsigned lt = smem_addr(sLogT);
+    const int n = p.n;
+    const size_t latBase = (size_t)p.nFit + p.nGamma;  // every cell latent: cell (i, j) sits at latBase + j n + i (Packer :4202-4242)
+    const double* __restrict__ xrow[LL_CT];
+#pragma unroll
+    for (int cc = 0; cc < LL_CT; ++cc) xrow[cc] = x + (size_t)(c0 + min(cc, nc - 1)) * p.P + latBase;
+    bool live[LL_CT];
+#pragma unroll
+    for (int cc = 0; cc < LL_CT; ++cc) live[cc] = sst[cc] == 0;
+
+    double accL[LL_CT], accH[LL_CT];
+#pragma unroll
+    for (int cc = 0; cc < LL_CT; ++cc) { accL[cc] = 0.0; accH[cc] = 0.0; }
+    double hyConst = 0.0;  // sum over this thread's cells of -log sqrt(2 pi) - log Xu (DevProblem::hyC)
+    int nObs = 0;
+    unsigned badMask = 0;
+    const int i0 = blockIdx.y * (BAM_BLOCK * LL_OPT) + tid;
+#pragma unroll 1
+    for (int o = 0; o < LL_OPT; ++o) {
+        const int i = i0 + o * BAM_BLOCK;
+        if (i >= n) break;
+        double xo[NX], hr[NX], yo[NY], yu2[NY];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            xo[j] = p.X[i + (size_t)j * n];
+            hr[j] = p.XuInv[i + (size_t)j * n];
+        }
+        hyConst += p.hyC[i];
+#pragma unroll
+        for (int j = 0; j < NY; ++j) {
+            yo[j] = p.Y[i + (size_t)j * n];
+            const double yu = p.Yu[i + (size_t)j * n];
+            yu2[j] = yu * yu;
+        }
+        ++nObs;
+        double xl[LL_CT][NX];
+#pragma unroll
+        for (int cc = 0; cc < LL_CT; ++cc)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) xl[cc][j] = __ldcs(xrow[cc] + (size_t)j * n + i);
+#pragma unroll
+        for (int cc = 0; cc < LL_CT; ++cc) {
+            if (!live[cc]) continue;
+            double T = 0.0;
+#pragma unroll
+            for (int j = 0; j < NY; ++j) {
+                double yh = 0.0;  // LM_Apply: Y = X . reshape(theta, (nX, nY))
+#pragma unroll
+                for (int k = 0; k < NX; ++k) yh = yh + xl[cc][k] * sth[cc][j * NX + k];
+                double sig;
+                if (SIGF == BAMGPU_SIG_CONSTANT) sig = sg[cc][j];
+                else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(sg[cc][2 * j + 1], fabs(yh), sg[cc][2 * j]);
+                else sig = sg[cc][j] * fabs(yh);
+                if (!(sig > 0.0)) { badMask |= 1u << cc; continue; }
+                const double v = fma(sig, sig, yu2[j]);
+                const double r = yo[j] - yh;
+                const unsigned hi = (unsigned)__double2hiint(v);
+                const double lg = (hi - 0x00100000u < 0x7fe00000u) ? tlog_pos(v, lt) : log(v);
+                T += fma(r * r, fast_rcp_pos(v), lg);
+            }
+            accL[cc] += T;
+            double H = 0.0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                const double z = (xo[j] - xl[cc][j]) * hr[j];
+                H = fma(z, z, H);
+            }
+            accH[cc] += H;
+        }
+    }
+    // thread sums -> log-densities, then the block reduction (fixed tree, fixed order)
+#pragma unroll
+    for (int cc = 0; cc < LL_CT; ++cc) {
+        double a = live[cc] ? fma(-0.5, accL[cc], -BAM_LOG_SQRT_2PI * (double)(NY * nObs)) : 0.0;
+        double b = live[cc] ? fma(-0.5, accH[cc], hyConst) : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, off);
+            b += __shfl_down_sync(0xffffffffu, b, off);
+        }
+        if (lane == 0) { red[warp][2 * cc] = a; red[warp][2 * cc + 1] = b; }
+    }
+    const unsigned anyBad = __reduce_or_sync(0xffffffffu, badMask);
+    if (lane == 0 && anyBad)
+        for (int cc = 0; cc < nc; ++cc)
+            if ((anyBad >> cc) & 1u) atomicOr(&statusOut[c0 + cc], ST_LKH_INFEAS);
+    __syncthreads();
+    if (tid < 2 * LL_CT) {
+        const int cc = tid >> 1;
+        if (cc < nc) {
+            double a = 0.0;
+            for (int w = 0; w < BAM_BLOCK / 32; ++w) a += red[w][tid];
+            part[((size_t)blockIdx.y * K + (c0 + cc)) * 2 + (tid & 1)] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1b: final sum + early-exit priority (GetPostLogPdf :3358-3380)
 // ------------------------------------------------------------------------------------------------
 #define FINAL_STRIPES 8
@@ -617,6 +757,33 @@ CalibKernel pick_calib(int model, int nX, int nY) {
 
 namespace bam {
 
+using LatentKernel = void (*)(DevProblem, const double*, int, const double*, const int*, double*, int*);
+template <int NX, int NY>
+static LatentKernel pick_latent_sig(int sigf) {
+    switch (sigf) {
+        case BAMGPU_SIG_CONSTANT: return logpost_linear_latent<NX, NY, BAMGPU_SIG_CONSTANT>;
+        case BAMGPU_SIG_LINEAR: return logpost_linear_latent<NX, NY, BAMGPU_SIG_LINEAR>;
+        case BAMGPU_SIG_PROPORTIONAL: return logpost_linear_latent<NX, NY, BAMGPU_SIG_PROPORTIONAL>;
+    }
+    return nullptr;
+}
+// eligibility of the cfg-3 fast path (see logpost_linear_latent); comp = component shifted by a proposal, or -1
+static LatentKernel pick_latent(const bamgpu_handle* h, int comp) {
+    const DevProblem& p = h->dp;
+    const HostLayout& L = h->L;
+    if (h->forceGeneric || p.model != BAMGPU_MDL_LINEAR || !p.hasLatent || p.n < 1 || !p.XuInv) return nullptr;
+    if ((long long)L.nLatent != (long long)p.n * p.nX || p.n != L.n) return nullptr;  // every cell latent, table order = Packer order
+    if (p.hasXbias || p.hasYbias || p.hasMissing || p.hyperInfeasible || p.nCombo != 1) return nullptr;
+    if (comp >= p.nFit + p.nGamma) return nullptr;  // a shifted latent cell is applied by logpost_main
+    for (int j = 1; j < p.nY; ++j)
+        if (p.sigfunc[j] != p.sigfunc[0]) return nullptr;
+    if (p.nX == 1 && p.nY == 1) return pick_latent_sig<1, 1>(p.sigfunc[0]);
+    if (p.nX == 2 && p.nY == 1) return pick_latent_sig<2, 1>(p.sigfunc[0]);
+    if (p.nX == 1 && p.nY == 2) return pick_latent_sig<1, 2>(p.sigfunc[0]);
+    if (p.nX == 2 && p.nY == 2) return pick_latent_sig<2, 2>(p.sigfunc[0]);
+    return nullptr;
+}
+
 static void make_plan(bamgpu_handle* h, int K) {
     LogpostPlan& pl = h->plan;
     const int n = std::max(h->dp.n, 1);
@@ -806,6 +973,10 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         if (launchTiles > 0)
             fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_fpStart, h->d_fpEnd, h->d_fpCombo, d_tiles, h->d_tab,
                                                        h->d_status, h->d_part, h->d_status);
+    } else if (LatentKernel lk = pick_latent(h, comp)) {
+        nTiles = (p.n + BAM_BLOCK * LL_OPT - 1) / (BAM_BLOCK * LL_OPT);
+        dim3 grid((K + LL_CT - 1) / LL_CT, nTiles);
+        lk<<<grid, BAM_BLOCK, 0, h->stream>>>(p, d_x, K, h->d_tab, h->d_status, h->d_part, h->d_status);
     } else if (p.n > 0) {
         if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
