@@ -305,10 +305,17 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
 // applied to the thread's sum: results agree to ~1e-15 relative, not bitwise.
 // Algorithmic bytes per (chain, observation): 8 NX (latent inputs); observation tables 8 (2 NX + 2 NY) / LL_CT.
 // ------------------------------------------------------------------------------------------------
-#define LL_CT 8
-#define LL_OPT 8
+#ifndef LL_CT
+#define LL_CT 4
+#endif
+#ifndef LL_OPT
+#define LL_OPT 16
+#endif
+#ifndef LL_MINB
+#define LL_MINB 2
+#endif
 template <int NX, int NY, int SIGF>
-__global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_linear_latent(DevProblem p, const double* __restrict__ x, int K,
+__global__ void __launch_bounds__(BAM_BLOCK, LL_MINB) logpost_linear_latent(DevProblem p, const double* __restrict__ x, int K,
                                                                       const double* __restrict__ tab,
                                                                       const int* __restrict__ status,
                                                                       double* __restrict__ part, int* statusOut) {
@@ -337,44 +344,64 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_linear_latent(DevProblem
     const double* __restrict__ xrow[LL_CT];
 #pragma unroll
     for (int cc = 0; cc < LL_CT; ++cc) xrow[cc] = x + (size_t)(c0 + min(cc, nc - 1)) * p.P + latBase;
-    bool live[LL_CT];
-#pragma unroll
-    for (int cc = 0; cc < LL_CT; ++cc) live[cc] = sst[cc] == 0;
 
     double accL[LL_CT], accH[LL_CT];
 #pragma unroll
     for (int cc = 0; cc < LL_CT; ++cc) { accL[cc] = 0.0; accH[cc] = 0.0; }
+    unsigned sgnAcc[LL_CT], zerAcc[LL_CT];
+#pragma unroll
+    for (int cc = 0; cc < LL_CT; ++cc) { sgnAcc[cc] = 0u; zerAcc[cc] = 0xffffffffu; }
     double hyConst = 0.0;  // sum over this thread's cells of -log sqrt(2 pi) - log Xu (DevProblem::hyC)
     int nObs = 0;
     unsigned badMask = 0;
     const int i0 = blockIdx.y * (BAM_BLOCK * LL_OPT) + tid;
+    // software pipeline: the tables and the LL_CT x NX latent inputs of observation o+1 are requested before
+    // observation o is evaluated, so the HBM latency overlaps ~LL_CT x 130 instructions of arithmetic
+    double xoN[NX], hrN[NX], yoN[NY], yuN[NY], hcN = 0.0, xlN[LL_CT][NX];
+    auto request = [&](int i) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            xoN[j] = p.X[i + (size_t)j * n];
+            hrN[j] = p.XuInv[i + (size_t)j * n];
+        }
+#pragma unroll
+        for (int j = 0; j < NY; ++j) {
+            yoN[j] = p.Y[i + (size_t)j * n];
+            yuN[j] = p.Yu[i + (size_t)j * n];
+        }
+        hcN = p.hyC[i];
+#pragma unroll
+        for (int cc = 0; cc < LL_CT; ++cc)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) xlN[cc][j] = __ldcs(xrow[cc] + (size_t)j * n + i);
+    };
+    if (i0 < n) request(i0);
 #pragma unroll 1
     for (int o = 0; o < LL_OPT; ++o) {
         const int i = i0 + o * BAM_BLOCK;
         if (i >= n) break;
-        double xo[NX], hr[NX], yo[NY], yu2[NY];
+        double xo[NX], hr[NX], yo[NY], yu2[NY], xl[LL_CT][NX];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) {
-            xo[j] = p.X[i + (size_t)j * n];
-            hr[j] = p.XuInv[i + (size_t)j * n];
-        }
-        hyConst += p.hyC[i];
+        for (int j = 0; j < NX; ++j) { xo[j] = xoN[j]; hr[j] = hrN[j]; }
 #pragma unroll
-        for (int j = 0; j < NY; ++j) {
-            yo[j] = p.Y[i + (size_t)j * n];
-            const double yu = p.Yu[i + (size_t)j * n];
-            yu2[j] = yu * yu;
-        }
-        ++nObs;
-        double xl[LL_CT][NX];
+        for (int j = 0; j < NY; ++j) { yo[j] = yoN[j]; yu2[j] = yuN[j] * yuN[j]; }
+        hyConst += hcN;
 #pragma unroll
         for (int cc = 0; cc < LL_CT; ++cc)
 #pragma unroll
-            for (int j = 0; j < NX; ++j) xl[cc][j] = __ldcs(xrow[cc] + (size_t)j * n + i);
-#pragma unroll
-        for (int cc = 0; cc < LL_CT; ++cc) {
-            if (!live[cc]) continue;
-            double T = 0.0;
+            for (int j = 0; j < NX; ++j) xl[cc][j] = xlN[cc][j];
+        ++nObs;
+        if (o + 1 < LL_OPT && i + BAM_BLOCK < n) request(i + BAM_BLOCK);
+        // straight-line code for all LL_CT chains (no branches: the scheduler interleaves the independent chains); a
+        // chain that is already infeasible is computed like the others and discarded at the end.
+        // sigma > 0 is tracked per chain on the integer words of sigma (OR of the sign bits, minimum of hi|lo): a NaN
+        // sigma needs no test, it ends in a NaN sum, which logpost_final flags like logpost_main's explicit test.
+        // NY == 2: the two outputs share ONE log and ONE reciprocal through the product of their variances,
+        //   log v0 + log v1 + r0^2/v0 + r1^2/v1 = log(v0 v1) + (r0^2 v1 + r1^2 v0) / (v0 v1);
+        // a product outside the normal range (never with sane variances) re-evaluates the observation per output.
+        double T[LL_CT];
+        unsigned rng = 0;
+        auto outputs = [&](int cc, double* v, double* r2) {
 #pragma unroll
             for (int j = 0; j < NY; ++j) {
                 double yh = 0.0;  // LM_Apply: Y = X . reshape(theta, (nX, nY))
@@ -384,14 +411,31 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_linear_latent(DevProblem
                 if (SIGF == BAMGPU_SIG_CONSTANT) sig = sg[cc][j];
                 else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(sg[cc][2 * j + 1], fabs(yh), sg[cc][2 * j]);
                 else sig = sg[cc][j] * fabs(yh);
-                if (!(sig > 0.0)) { badMask |= 1u << cc; continue; }
-                const double v = fma(sig, sig, yu2[j]);
+                sgnAcc[cc] |= (unsigned)__double2hiint(sig);
+                zerAcc[cc] = min(zerAcc[cc], (unsigned)__double2hiint(sig) | (unsigned)__double2loint(sig));
+                v[j] = fma(sig, sig, yu2[j]);
                 const double r = yo[j] - yh;
-                const unsigned hi = (unsigned)__double2hiint(v);
-                const double lg = (hi - 0x00100000u < 0x7fe00000u) ? tlog_pos(v, lt) : log(v);
-                T += fma(r * r, fast_rcp_pos(v), lg);
+                r2[j] = r * r;
             }
-            accL[cc] += T;
+        };
+#pragma unroll
+        for (int cc = 0; cc < LL_CT; ++cc) {
+            double v[NY], r2[NY];
+            outputs(cc, v, r2);
+            if (NY == 2) {
+                const double vp = v[0] * v[1];
+                const double rp = trcp(vp);
+                rng = max(rng, (unsigned)__double2hiint(vp) - 0x00100000u);
+                T[cc] = fma(fma(r2[0], v[1], r2[1] * v[0]), rp, tlog_pos(vp, lt));
+            } else {
+                double t = 0.0;
+#pragma unroll
+                for (int j = 0; j < NY; ++j) {
+                    rng = max(rng, (unsigned)__double2hiint(v[j]) - 0x00100000u);
+                    t += fma(r2[j], trcp(v[j]), tlog_pos(v[j], lt));
+                }
+                T[cc] = t;
+            }
             double H = 0.0;
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
@@ -400,12 +444,31 @@ __global__ void __launch_bounds__(BAM_BLOCK, 2) logpost_linear_latent(DevProblem
             }
             accH[cc] += H;
         }
+        if (rng >= 0x7fe00000u) {  // rare
+#pragma unroll
+            for (int cc = 0; cc < LL_CT; ++cc) {
+                double v[NY], r2[NY], t = 0.0;
+                outputs(cc, v, r2);
+#pragma unroll
+                for (int j = 0; j < NY; ++j) {
+                    if ((unsigned)__double2hiint(v[j]) - 0x00100000u >= 0x7fe00000u) badMask |= 1u << cc;  // as a NaN sum in logpost_main
+                    t += fma(r2[j], trcp(v[j]), tlog_pos(v[j], lt));
+                }
+                T[cc] = t;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < LL_CT; ++cc) accL[cc] += T[cc];
     }
+#pragma unroll
+    for (int cc = 0; cc < LL_CT; ++cc)
+        if (nObs > 0 && ((sgnAcc[cc] & 0x80000000u) || zerAcc[cc] == 0u)) badMask |= 1u << cc;
     // thread sums -> log-densities, then the block reduction (fixed tree, fixed order)
 #pragma unroll
     for (int cc = 0; cc < LL_CT; ++cc) {
-        double a = live[cc] ? fma(-0.5, accL[cc], -BAM_LOG_SQRT_2PI * (double)(NY * nObs)) : 0.0;
-        double b = live[cc] ? fma(-0.5, accH[cc], hyConst) : 0.0;
+        const bool live = sst[cc] == 0;
+        double a = live ? fma(-0.5, accL[cc], -BAM_LOG_SQRT_2PI * (double)(NY * nObs)) : 0.0;
+        double b = live ? fma(-0.5, accH[cc], hyConst) : 0.0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             a += __shfl_down_sync(0xffffffffu, a, off);

@@ -359,6 +359,39 @@ def cfg2_sampler_leg(g, x, K, n, iters=5):
     return out
 
 
+def latent_logpost_leg(device, hbm_peak, n=1_000_000, K=64, steps=10):
+    """configs[2] (Regression_X2Y2 shape with input uncertainty, 10^6 observations): log-posterior of K chains whose
+    vectors each carry 2n latent "true" inputs.  The path must read 16 B of chain-private latent inputs per
+    (chain, observation), so it is reported against the HBM roofline; L2 is flushed between timed steps."""
+    from bam_b200 import synth
+    from bam_b200.capi import BamGpu
+
+    prob, truth = synth.linear_latent(nobs=n)
+    rng = np.random.default_rng(1)
+    x = np.tile(truth, (K, 1))
+    x[:, :8] *= 1.0 + 0.01 * rng.standard_normal((K, 8))
+    x[:, 8:] += 0.05 * rng.standard_normal((K, 2 * n)).astype(np.float64)
+    g = BamGpu(prob, device)
+    g.chains_upload(x)
+    for _ in range(3):
+        g.logpost_resident()
+    g.sync(); g.step_times(); g.kernel_times()
+    for _ in range(steps):
+        g.flush_l2()
+        g.step_begin(); g.logpost_resident(); g.step_end()
+    g.sync()
+    ms, km = g.step_times(), g.kernel_times()
+    fx, feas, _ = g.chains_download()
+    k_ms = float(km.mean())
+    algo = 16.0 * K * n + 72.0 * n  # latent inputs + the observation tables (X, 1/Xu, Y, Yu, hyper constant) once: L2 serves the chain tiles
+    return {"metric": "log-posterior evals/sec (chains x obs)", "value": K * n / (float(ms.mean()) * 1e-3), "unit": "chain*obs/s",
+            "workload": f"Linear 2x2, {n} obs, every input cell latent (P = {g.P}), {K} chains (configs[2] shape)",
+            "ms_per_step": float(ms.mean()), "feasible": bool(feas.all()),
+            "kernel": {"name": "logpost_linear_latent<2,2,Linear>", "ms": k_ms, "bound": "hbm", "algorithmic_bytes": algo,
+                       "achieved": algo / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": algo / (k_ms * 1e-3) / 1e9 / hbm_peak}}
+
+
 def latent_sampler_leg(device, n=1_000_000, K=64, iters=4):
     """configs[2] (Regression with input uncertainty): adaptive Metropolis over theta, gamma AND 2n latent inputs per
     chain; the latent inputs are swept by one kernel launch with O(1) local posterior differences.  Bounded size."""
@@ -654,6 +687,10 @@ def main():
             line["sampler_small"] = small_sampler_leg(device)
         except Exception as e:
             line["sampler_small"] = {"error": str(e)}
+        try:
+            line["latent_logpost"] = latent_logpost_leg(device, hbm_peak)
+        except Exception as e:
+            line["latent_logpost"] = {"error": str(e)}
         try:
             line["latent_sampler"] = latent_sampler_leg(device)
         except Exception as e:
