@@ -299,6 +299,7 @@ def load_library(path: Optional[str] = None):
     lib.bamgpu_logpost.argtypes = [H, ci, _dp, _dp, _ip, _ip, _dp, cp]
     lib.bamgpu_logpost_parts.argtypes = [H, ci, _dp, _dp, _dp, _dp, _ip, _ip, cp]
     lib.bamgpu_calibration_run.argtypes = [H, C.POINTER(CProblem), _dp, _dp, _dp, _ip, cp]
+    lib.bamgpu_calibration_run_states.argtypes = [H, C.POINTER(CProblem), _dp, _dp, _dp, _dp, _ip, cp]
     lib.bamgpu_chains_upload.argtypes = [H, ci, _dp, cp]
     lib.bamgpu_logpost_resident.argtypes = [H, cp]
     lib.bamgpu_chains_download.argtypes = [H, _dp, _ip, _ip, _dp, cp]
@@ -308,6 +309,7 @@ def load_library(path: Optional[str] = None):
     lib.bamgpu_moments.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, ci, cp]
     lib.bamgpu_rhat.argtypes = [ci, ci, _dp, _dp, _dp, _dp, cp]
     lib.bamgpu_predict.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, ci, _ip, u64, ci, ci, _dp, _dp, cp]
+    lib.bamgpu_predict_states.argtypes = lib.bamgpu_predict.argtypes
     lib.bamgpu_predict_upload.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, cp]
     lib.bamgpu_predict_resident.argtypes = [H, ci, _ip, u64, ci, ci, cp]
     lib.bamgpu_predict_download.argtypes = [H, _dp, cp]
@@ -454,6 +456,20 @@ class BamGpu:
                                                C.byref(feas), mess), mess)
         return Xtrue, Ysim, bool(feas.value)
 
+    def calibration_run_states(self, x):
+        """as calibration_run, plus the state variables (n x nState): (Xtrue, Ysim, state, feas)"""
+        pr = self.problem
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        Xtrue = np.empty((pr.nobs, pr.nX), order="F")
+        Ysim = np.empty((pr.nobs, pr.nY), order="F")
+        state = np.empty((pr.nobs, self.sizes.nState), order="F")
+        feas = C.c_int32(0)
+        mess = C.create_string_buffer(MESS_LEN)
+        cs = pr.c_struct()
+        _check(self.lib.bamgpu_calibration_run_states(self.h, C.byref(cs), _ptr_d(x), _ptr_d(Xtrue), _ptr_d(Ysim),
+                                                      _ptr_d(state), C.byref(feas), mess), mess)
+        return Xtrue, Ysim, state, bool(feas.value)
+
     def fit(self, start, start_std, nAdapt, nCycles, MinMoveRate=0.1, MaxMoveRate=0.5, DownMult=0.9, UpMult=1.1,
             seed=1, burn=0, keep_every=1, want_rows=True):
         start = np.asarray(start, dtype=np.float64)
@@ -508,7 +524,8 @@ class BamGpu:
         return mats, ptrs, nspag
 
     def predict(self, mc, mode, xspag, doParametric, doRemnant, seed=1, t0=0, t1=None, want_env=True,
-                want_spag=False):
+                want_spag=False, states=False):
+        """states=True: the nState state variables follow the nY outputs in env / spag (bamgpu_predict_states)"""
         nobs_pred = np.asarray(xspag[0]).shape[0]
         t1 = nobs_pred if t1 is None else t1
         mats, ptrs, nspag = self._xspag(xspag, nobs_pred)
@@ -519,11 +536,11 @@ class BamGpu:
             Nrep = 1
         mode = None if mode is None else np.ascontiguousarray(mode, dtype=np.float64)
         dr = np.asarray(doRemnant, dtype=np.int32)
-        nT, nY = t1 - t0, self.problem.nY
+        nT, nY = t1 - t0, self.problem.nY + (self.sizes.nState if states else 0)
         env = np.empty((nY, NENV, nT)) if want_env else None
         spag = np.empty((nY, nT, Nrep)) if want_spag else None
         mess = C.create_string_buffer(MESS_LEN)
-        _check(self.lib.bamgpu_predict(self.h, Nrep, _ptr_d(mc), _ptr_d(mode), nobs_pred, ptrs, _ptr_i(nspag),
+        _check((self.lib.bamgpu_predict_states if states else self.lib.bamgpu_predict)(self.h, Nrep, _ptr_d(mc), _ptr_d(mode), nobs_pred, ptrs, _ptr_i(nspag),
                                        int(doParametric), _ptr_i(dr), seed, t0, t1,
                                        _ptr_d(env) if want_env else C.cast(None, _dp),
                                        _ptr_d(spag) if want_spag else C.cast(None, _dp), mess), mess)

@@ -394,6 +394,11 @@ int bamgpu_logpost_parts(bamgpu_t* h, int K, const double* x, double* prior, dou
 
 int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* pb, const double* x, double* Xtrue, double* Ysim,
                            int32_t* feas, char* mess) {
+    return bamgpu_calibration_run_states(h, pb, x, Xtrue, Ysim, nullptr, feas, mess);
+}
+
+int bamgpu_calibration_run_states(bamgpu_t* h, const bamgpu_problem* pb, const double* x, double* Xtrue, double* Ysim,
+                                  double* state, int32_t* feas, char* mess) {
     return guarded(mess, [&]() -> int {
         BAM_CUDA(cudaSetDevice(h->device));
         const bam::HostLayout& L = h->L;
@@ -422,8 +427,10 @@ int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* pb, const double* 
             for (int i = 0; i < n; ++i) { xp[i] = (double)(i / L.modelOpt[2] + 1); xp[i + (size_t)n] = (double)elt[i]; }
             xt.swap(xp);
         }
-        double *d_x1 = nullptr, *d_xt = nullptr, *d_y = nullptr;
+        double *d_x1 = nullptr, *d_xt = nullptr, *d_y = nullptr, *d_st = nullptr;
         int* d_combo = nullptr;
+        const int nS = state ? L.nState : 0;
+        if (nS > 0) BAM_CUDA(cudaMalloc(&d_st, sizeof(double) * (size_t)n * nS));
         BAM_CUDA(cudaMalloc(&d_x1, sizeof(double) * L.P));
         BAM_CUDA(cudaMalloc(&d_xt, sizeof(double) * xt.size()));
         BAM_CUDA(cudaMalloc(&d_y, sizeof(double) * (size_t)n * nY));
@@ -431,14 +438,17 @@ int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* pb, const double* 
         BAM_CUDA(cudaMemcpyAsync(d_x1, x, sizeof(double) * L.P, cudaMemcpyHostToDevice, h->stream));
         BAM_CUDA(cudaMemcpyAsync(d_xt, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice, h->stream));
         BAM_CUDA(cudaMemcpyAsync(d_combo, L.comboOf.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
-        const int nbad = bam::launch_calibration_run(h, d_x1, n, d_xt, d_combo, d_y);
+        const int nbad = bam::launch_calibration_run(h, d_x1, n, d_xt, d_combo, d_y, d_st);
         if (nbad < 0) {  // infeasible parameter set: every row is flagged (ApplyModel :419-432)
             for (size_t q = 0; q < (size_t)n * nY; ++q) Ysim[q] = pb->unfeas_flag;
+            for (size_t q = 0; q < (size_t)n * nS; ++q) state[q] = pb->unfeas_flag;
         } else {
             BAM_CUDA(cudaMemcpyAsync(Ysim, d_y, sizeof(double) * (size_t)n * nY, cudaMemcpyDeviceToHost, h->stream));
+            if (nS > 0) BAM_CUDA(cudaMemcpyAsync(state, d_st, sizeof(double) * (size_t)n * nS, cudaMemcpyDeviceToHost, h->stream));
             BAM_CUDA(cudaStreamSynchronize(h->stream));
         }
         cudaFree(d_x1); cudaFree(d_xt); cudaFree(d_y); cudaFree(d_combo);
+        if (d_st) cudaFree(d_st);
         if (feas) *feas = nbad == 0;
         return 0;
     });
@@ -557,7 +567,7 @@ int bamgpu_predict_resident(bamgpu_t* h, int doParametric, const int32_t* doRemn
 
 int bamgpu_predict_download(bamgpu_t* h, double* env, char* mess) {
     return guarded(mess, [&]() -> int {
-        const size_t cnt = (size_t)(h->predT1 - h->predT0) * BAMGPU_NENV * h->dp.nY;
+        const size_t cnt = (size_t)(h->predT1 - h->predT0) * BAMGPU_NENV * (h->predNout > 0 ? h->predNout : h->dp.nY);
         if (h->predNrep >= 2)
             BAM_CUDA(cudaMemcpyAsync(env, h->d_env, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
         BAM_CUDA(cudaStreamSynchronize(h->stream));
@@ -573,6 +583,21 @@ int bamgpu_predict(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mo
     e = guarded(mess, [&]() -> int {
         if (t0 < 0 || t1 > nobs_pred || t0 >= t1) throw bam::CudaError{"bamgpu_predict: bad input range [t0,t1)"};
         bam::launch_predict(h, doParametric, doRemnant, seed, t0, t1, spag);
+        return 0;
+    });
+    if (e) return e;
+    if (env) return bamgpu_predict_download(h, env, mess);
+    return bamgpu_sync(h, mess);
+}
+
+int bamgpu_predict_states(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                          const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
+                          uint64_t seed, int t0, int t1, double* env, double* spag, char* mess) {
+    int e = bamgpu_predict_upload(h, Nrep, mc, mode, nobs_pred, xspag, nspag, mess);
+    if (e) return e;
+    e = guarded(mess, [&]() -> int {
+        if (t0 < 0 || t1 > nobs_pred || t0 >= t1) throw bam::CudaError{"bamgpu_predict: bad input range [t0,t1)"};
+        bam::launch_predict(h, doParametric, doRemnant, seed, t0, t1, spag, true);
         return 0;
     });
     if (e) return e;

@@ -70,6 +70,7 @@ struct bamgpu_handle {
     size_t vCap = 0;
     double* d_env = nullptr;   // nT x 7 x nY of the last resident prediction
     int predT0 = 0, predT1 = 0;
+    int predNout = 0;  // outputs (+ state variables) of the last prediction: rows of d_env
     size_t envCap = 0;
 
     // ---- measurement ----
@@ -107,12 +108,12 @@ bool fast_path_keeps_combo_sums(const bamgpu_handle* h, int K);
 
 void launch_table(bamgpu_handle* h, int K, const double* d_x);
 int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const double* d_xtrue, const int* d_combo,
-                           double* d_ysim);
+                           double* d_ysim, double* d_state /* n x nState, may be null */);
 
 void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, double maxMR, double downMult,
                 double upMult, unsigned long long seed, int burn, int keepEvery, bool storeRows, long long nKeep);
 
 void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, unsigned long long seed, int t0, int t1,
-                    double* h_spag /* host, may be null */);
+                    double* h_spag /* host, may be null */, bool withStates = false);
 
 }  // namespace bam

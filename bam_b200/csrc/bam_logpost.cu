@@ -793,21 +793,26 @@ MainKernel pick_main(int model, int nX, int nY) {
 template <int MODEL, int NX, int NY>
 __global__ void __launch_bounds__(BAM_BLOCK) calib_sim(DevProblem p, int n, const double* __restrict__ Xtrue,
                                                        const int* __restrict__ comboOf, const double* __restrict__ row,
-                                                       double* __restrict__ Ysim, int* __restrict__ nBad) {
+                                                       double* __restrict__ Ysim, double* __restrict__ state,
+                                                       int* __restrict__ nBad) {
     const int i = blockIdx.x * BAM_BLOCK + threadIdx.x;
     if (i >= n) return;
-    double xt[NX], yh[NY];
+    constexpr int NS = model_nstate(MODEL);
+    double xt[NX], yh[NY], st[NS > 0 ? NS : 1];
 #pragma unroll
     for (int j = 0; j < NX; ++j) xt[j] = Xtrue[i + (size_t)j * n];
     const int combo = (p.nCombo > 1) ? comboOf[i] : 0;
     const double* th = row + p.tabCombo + (size_t)combo * p.comboStride;
-    const bool ok = model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh);
+    const bool ok = model_apply_s<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh, st);
     if (!ok) atomicAdd(nBad, 1);
 #pragma unroll
     for (int j = 0; j < NY; ++j) Ysim[i + (size_t)j * n] = ok ? yh[j] : p.unfeas;  // ModelLibrary_tools.f90:419-432
+    if (state != nullptr)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) state[i + (size_t)j * n] = ok ? st[j] : p.unfeas;
 }
 
-using CalibKernel = void (*)(DevProblem, int, const double*, const int*, const double*, double*, int*);
+using CalibKernel = void (*)(DevProblem, int, const double*, const int*, const double*, double*, double*, int*);
 CalibKernel pick_calib(int model, int nX, int nY) {
 #define X(M, A, B) \
     if (model == M && nX == A && nY == B) return calib_sim<M, A, B>;
@@ -820,9 +825,9 @@ CalibKernel pick_calib(int model, int nX, int nY) {
 
 namespace bam {
 
-using LatentKernel = void (*)(DevProblem, const double*, int, const double*, const int*, double*, int*);
+using LatentLogpostKernel = void (*)(DevProblem, const double*, int, const double*, const int*, double*, int*);
 template <int NX, int NY>
-static LatentKernel pick_latent_sig(int sigf) {
+static LatentLogpostKernel pick_latent_sig(int sigf) {
     switch (sigf) {
         case BAMGPU_SIG_CONSTANT: return logpost_linear_latent<NX, NY, BAMGPU_SIG_CONSTANT>;
         case BAMGPU_SIG_LINEAR: return logpost_linear_latent<NX, NY, BAMGPU_SIG_LINEAR>;
@@ -831,7 +836,7 @@ static LatentKernel pick_latent_sig(int sigf) {
     return nullptr;
 }
 // eligibility of the cfg-3 fast path (see logpost_linear_latent); comp = component shifted by a proposal, or -1
-static LatentKernel pick_latent(const bamgpu_handle* h, int comp) {
+static LatentLogpostKernel pick_latent(const bamgpu_handle* h, int comp) {
     const DevProblem& p = h->dp;
     const HostLayout& L = h->L;
     if (h->forceGeneric || p.model != BAMGPU_MDL_LINEAR || !p.hasLatent || p.n < 1 || !p.XuInv) return nullptr;
@@ -962,7 +967,7 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
 // one vector through the model on n caller-ordered observations (d_xtrue: n x nX, d_combo: n); returns #infeasible rows
 // or -1 when the parameter set itself is infeasible / null
 int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const double* d_xtrue, const int* d_combo,
-                           double* d_ysim) {
+                           double* d_ysim, double* d_state) {
     const DevProblem& p0 = h->dp;
     CalibKernel kern = pick_calib(p0.model, p0.nX, p0.nY);
     if (!kern) throw CudaError{"bamgpu: no kernel instantiated for this (model, nX, nY)"};
@@ -978,7 +983,7 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
     p.X = d_xtrue;
     p.n = n;
     logpost_prep<<<1, 128, 0, h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
-    kern<<<(n + BAM_BLOCK - 1) / BAM_BLOCK, BAM_BLOCK, 0, h->stream>>>(p, n, d_xtrue, d_combo, tab, d_ysim, status + 1);
+    kern<<<(n + BAM_BLOCK - 1) / BAM_BLOCK, BAM_BLOCK, 0, h->stream>>>(p, n, d_xtrue, d_combo, tab, d_ysim, d_state, status + 1);
     int st[2] = {0, 0};
     BAM_CUDA(cudaMemcpyAsync(st, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     BAM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1036,7 +1041,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         if (launchTiles > 0)
             fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_fpStart, h->d_fpEnd, h->d_fpCombo, d_tiles, h->d_tab,
                                                        h->d_status, h->d_part, h->d_status);
-    } else if (LatentKernel lk = pick_latent(h, comp)) {
+    } else if (LatentLogpostKernel lk = pick_latent(h, comp)) {
         nTiles = (p.n + BAM_BLOCK * LL_OPT - 1) / (BAM_BLOCK * LL_OPT);
         dim3 grid((K + LL_CT - 1) / LL_CT, nTiles);
         lk<<<grid, BAM_BLOCK, 0, h->stream>>>(p, d_x, K, h->d_tab, h->d_status, h->d_part, h->d_status);

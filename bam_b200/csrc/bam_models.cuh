@@ -692,9 +692,12 @@ __device__ __forceinline__ void sfd_fnewton(double x, const double* __restrict__
          th[5] * th[7] * pow(x - th[4], th[7] - 1.0);
 }
 
-__device__ inline bool sfd_apply(const DevProblem& p, const double* in, const double* __restrict__ th, double& out) {
+// kappaOut: the state variable (transition stage); stays undefRN on the rows that never solve for it (:126,143-144)
+__device__ inline bool sfd_apply(const DevProblem& p, const double* in, const double* __restrict__ th, double& out,
+                                 double* kappaOut = nullptr) {
     const double h1 = in[0], h2 = in[1];
     const double KB = th[0], h0 = th[1], M = th[2], L = th[3], h0p = th[4], KBS0 = th[5], delta = th[6], Mp = th[7];
+    if (kappaOut) *kappaOut = BAMGPU_UNDEF_RN;
     if (h1 - h2 - delta <= 0.0) return false;
     if (h1 - h0 <= 0.0 || h2 - h0p <= 0.0) { out = 0.0; return true; }
     const double x1 = fmax(fmax(h0, h0p), h2 + delta) + 0.001, x2 = p.modelOptD;
@@ -735,6 +738,7 @@ __device__ inline bool sfd_apply(const DevProblem& p, const double* in, const do
         kappa = rts;
     }
     if (fcalls > p.vegItmax || !(kappa == kappa)) return false;
+    if (kappaOut) *kappaOut = kappa;
     if (h1 <= kappa) out = (KB * pow(h1 - h0, M)) * sqrt((h1 - h2 - delta) / L);  // variable-slope model
     else out = KBS0 * pow(h1 - h0p, Mp);                                       // standard channel model
     return true;
@@ -849,4 +853,15 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         for (int k = 0; k < NY; ++k) ok = textfile_eval<NX>(p, k, x, th, y[k]) && ok;
         return ok;
     }
+}
+
+// state variables (ModelLibrary_tools.f90 XtraSetup: model%nState): only SFD has one on this path (kappa)
+__host__ __device__ constexpr int model_nstate(int model) { return model == BAMGPU_MDL_SFD ? 1 : 0; }
+
+// model_apply + the state variables of the observation (st[model_nstate(MODEL)])
+template <int MODEL, int NX, int NY>
+__device__ __forceinline__ bool model_apply_s(const DevProblem& p, const double* x, const double* __restrict__ th,
+                                              const double* __restrict__ der, double* y, double* st) {
+    if (MODEL == BAMGPU_MDL_SFD) return sfd_apply(p, x, th, y[0], st);
+    return model_apply<MODEL, NX, NY>(p, x, th, der, y);
 }

@@ -33,6 +33,7 @@ struct PredArgs {
     int doRemnant[BAM_MAXY];
     unsigned long long seed;
     int stride;                 // doubles per replication in the table: [gamma | full theta | derived]
+    int nStateOut;              // state variables written after the nY outputs (0 | model_nstate)
     int stage;                  // pred_main: stage the table rows of the block in shared memory (stride * 2 KB fits)
 };
 
@@ -88,11 +89,15 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
     if (a.stage) for (int k = 0; k < np; ++k) loc[k] = sm[(p.nGamma + k) * BAM_BLOCK + tid];
     else for (int k = 0; k < np; ++k) loc[k] = tab[(size_t)rep * stride + p.nGamma + k];
     for (int t = tBeg; t < tEnd; ++t) {
-        double xin[NX], y[NY];
+        constexpr int NS = model_nstate(MODEL);
+        double xin[NX], y[NY], st[NS > 0 ? NS : 1];
 #pragma unroll
         for (int j = 0; j < NX; ++j) xin[j] = xp[j][t];
         bool ok = setOk;
-        if (ok) ok = model_apply<MODEL, NX, NY>(p, xin, loc, loc + p.ntheta, y);
+        if (ok) ok = model_apply_s<MODEL, NX, NY>(p, xin, loc, loc + p.ntheta, y, st);
+        if (NS > 0 && a.nStateOut > 0)
+#pragma unroll
+            for (int j = 0; j < NS; ++j) V[((size_t)(NY + j) * a.nT + t) * a.Nrep + rep] = ok ? st[j] : p.unfeas;
 #pragma unroll
         for (int j = 0; j < NY; ++j) {
             double v = ok ? y[j] : p.unfeas;  // ApplyModel flags infeasible rows (ModelLibrary_tools.f90:419-432)
@@ -1247,13 +1252,15 @@ PredKernel pick_pred(int model, int nX, int nY) {
 namespace bam {
 
 void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, unsigned long long seed, int t0, int t1,
-                    double* h_spag) {
+                    double* h_spag, bool withStates) {
     const DevProblem& p = h->dp;
     if (h->L.nVar) throw CudaError{"BaM_Prediction: prediction with VAR parameters is not allowed (BaM_Message 13)"};
     PredKernel kern = pick_pred(p.model, p.nX, p.nY);
     if (!kern) throw CudaError{"bamgpu: no prediction kernel instantiated for this (model, nX, nY)"};
     const long long Nrep = h->predNrep;
-    const int nTall = t1 - t0, nY = p.nY;
+    // state variables (only SFD's kappa on this path) are extra output columns after the nY outputs: no remnant noise,
+    // same envelope rule (BaM_Prediction :1071-1075,1121-1132)
+    const int nTall = t1 - t0, nY = p.nY, nS = withStates ? model_nstate(p.model) : 0, nOut = nY + nS;
     if (nTall <= 0 || Nrep <= 0) return;
     bool anyRem = false;
     for (int y = 0; y < nY; ++y) anyRem |= doRemnant[y] != 0;
@@ -1265,6 +1272,8 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     a.Nrep = Nrep; a.nobsPred = h->predNobs; a.doParametric = doParametric; a.seed = seed;
     for (int y = 0; y < BAM_MAXY; ++y) a.doRemnant[y] = (y < nY) ? doRemnant[y] : 0;
     a.stride = p.nGamma + p.ntheta + p.nDer;
+    a.nStateOut = nS;
+    h->predNout = nOut;
     a.stage = sizeof(double) * (size_t)a.stride * BAM_BLOCK <= 96 * 1024;
 
     // table + envelope output
@@ -1272,7 +1281,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         BAM_CUDA(cudaMalloc(&h->d_ptab, sizeof(double) * (size_t)Nrep * a.stride));
         BAM_CUDA(cudaMalloc(&h->d_pstatus, sizeof(int) * (size_t)Nrep));
     }
-    const size_t envNeed = (size_t)nTall * BAMGPU_NENV * nY;
+    const size_t envNeed = (size_t)nTall * BAMGPU_NENV * nOut;
     if (envNeed > h->envCap) {
         if (h->d_env) cudaFree(h->d_env);
         BAM_CUDA(cudaMalloc(&h->d_env, sizeof(double) * envNeed));
@@ -1285,10 +1294,10 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     size_t freeB = 0, totalB = 0;
     BAM_CUDA(cudaMemGetInfo(&freeB, &totalB));
     const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((freeB + h->vCap * sizeof(double)) / 3, (size_t)48 << 30));
-    long long tileT = (long long)(budget / (sizeof(double) * (size_t)Nrep * nY));
+    long long tileT = (long long)(budget / (sizeof(double) * (size_t)Nrep * nOut));
     tileT = std::max<long long>(32, std::min<long long>(tileT / 32 * 32, ((long long)nTall + 31) / 32 * 32));
     if (h_spag) tileT = std::max<long long>(tileT, 32);
-    const size_t vNeed = (size_t)tileT * Nrep * nY;
+    const size_t vNeed = (size_t)tileT * Nrep * nOut;
     if (vNeed > h->vCap) {
         if (h->d_V) cudaFree(h->d_V);
         BAM_CUDA(cudaMalloc(&h->d_V, sizeof(double) * vNeed));
@@ -1366,19 +1375,19 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             cudaEvent_t ke0 = mark();
             // envelopes of this tile go to a compact [y][7][nT] scratch, then into the full [y][7][nTall] array
             double* envTile = nullptr;
-            BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nY, s));
-            if (smallN) envelope_smem<<<nT * nY, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
+            BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nOut, s));
+            if (smallN) envelope_smem<<<nT * nOut, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
             else {
                 int *need3 = nullptr, *needSlow = nullptr;
-                BAM_CUDA(cudaMallocAsync(&needSlow, sizeof(int) * (size_t)nT * nY, s));
+                BAM_CUDA(cudaMallocAsync(&needSlow, sizeof(int) * (size_t)nT * nOut, s));
                 if (trySel3) {
-                    BAM_CUDA(cudaMallocAsync(&need3, sizeof(int) * (size_t)nT * nY, s));
-                    if (sel3Big) envelope_select3<2048, 1024><<<nT * nY, 1024, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
-                    else envelope_select3<512, 512><<<nT * nY, 512, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
+                    BAM_CUDA(cudaMallocAsync(&need3, sizeof(int) * (size_t)nT * nOut, s));
+                    if (sel3Big) envelope_select3<2048, 1024><<<nT * nOut, 1024, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
+                    else envelope_select3<512, 512><<<nT * nOut, 512, smemSel3, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, need3);
                     h->launches += 1;
                 }
-                envelope_select2<<<nT * nY, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow, need3);
-                envelope_select<<<nT * nY, BAM_BLOCK, 0, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
+                envelope_select2<<<nT * nOut, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow, need3);
+                envelope_select<<<nT * nOut, BAM_BLOCK, 0, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
                 BAM_CUDA(cudaFreeAsync(needSlow, s));
                 if (need3) BAM_CUDA(cudaFreeAsync(need3, s));
                 h->launches += 1;
@@ -1386,14 +1395,14 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             h->launches += 1;
             cudaEvent_t ke1 = mark();
             if (ke0 && ke1) h->kernEv.emplace_back(ke0, ke1);
-            for (int y = 0; y < nY; ++y)
+            for (int y = 0; y < nOut; ++y)
                 BAM_CUDA(cudaMemcpy2DAsync(h->d_env + ((size_t)y * BAMGPU_NENV * nTall + tt), sizeof(double) * nTall,
                                            envTile + (size_t)y * BAMGPU_NENV * nT, sizeof(double) * nT,
                                            sizeof(double) * nT, BAMGPU_NENV, cudaMemcpyDeviceToDevice, s));
             BAM_CUDA(cudaFreeAsync(envTile, s));
         }
         if (h_spag) {  // host layout: [y][t][rep] over the whole [t0,t1) range
-            for (int y = 0; y < nY; ++y)
+            for (int y = 0; y < nOut; ++y)
                 BAM_CUDA(cudaMemcpyAsync(h_spag + ((size_t)y * nTall + tt) * Nrep, h->d_V + (size_t)y * nT * Nrep,
                                          sizeof(double) * (size_t)nT * Nrep, cudaMemcpyDeviceToHost, s));
             BAM_CUDA(cudaStreamSynchronize(s));

@@ -557,7 +557,7 @@ void load_onerun(const std::string& configFile, Workspace& w, std::vector<double
     }
 }
 
-PredConfig read_pred_config(const Workspace& w, const std::string& file) {
+PredConfig read_pred_config(const Workspace& w, const std::string& file, int nState) {
     Cursor c(w.dir + fix_sep(file));
     PredConfig p;
     p.xspagFiles = c.strs(w.nX);
@@ -571,6 +571,20 @@ PredConfig read_pred_config(const Workspace& w, const std::string& file) {
     p.doEnvelop = c.bools(w.nY);
     p.envFiles = c.strs(w.nY);
     p.printCounter = to_bool(c.str());
+    p.doState.assign(nState, 0);
+    if (nState > 0 && c.more()) {  // :2808-2826 (a file without the section: BaM_ConsoleMessage 19, states skipped)
+        try {
+            p.doState = c.bools(nState);
+        } catch (const std::exception&) {
+            p.doState.assign(nState, 0);
+        }
+        if (std::any_of(p.doState.begin(), p.doState.end(), [](int v) { return v != 0; })) {
+            p.sspagFiles = c.strs(nState);
+            p.doTransposeS = c.bools(nState);
+            p.doEnvelopS = c.bools(nState);
+            p.envFilesS = c.strs(nState);
+        }
+    }
     return p;
 }
 

@@ -53,6 +53,9 @@ struct PredConfig {  // Config_Read_Pred, :2743-2830
     std::vector<int> doTranspose, doEnvelop;
     std::vector<std::string> envFiles;
     bool printCounter = false;
+    // state variables (:2808-2826): read only when the model has states; a missing section = no state prediction
+    std::vector<int> doState, doTransposeS, doEnvelopS;
+    std::vector<std::string> sspagFiles, envFilesS;
 };
 
 struct Workspace {
@@ -96,7 +99,7 @@ struct Workspace {
 void load_workspace(const std::string& configFile, Workspace& w);
 // --onerun mode (src/BaM_main.f90:215-247): model + xtra + an input file; Xin = nIn x nX column-major
 void load_onerun(const std::string& configFile, Workspace& w, std::vector<double>& Xin, int& nIn);
-PredConfig read_pred_config(const Workspace& w, const std::string& file);
+PredConfig read_pred_config(const Workspace& w, const std::string& file, int nState = 0);
 std::vector<double> read_matrix(const std::string& file, int nrow, int ncol, int nskip);  // column-major
 std::string resolve(const Workspace& w, const std::string& name);
 std::vector<std::string> list_items(const std::string& line);

@@ -120,6 +120,12 @@ static bool prior_draw(const Prior& pr, std::mt19937_64& g, double& x, double& m
     return false;  // flat priors cannot be sampled (BaM_Message 8)
 }
 
+// model%StateName (XtraSetup, ModelLibrary_tools.f90:617-621)
+static std::string state_name(const std::string& modelID, int i) {
+    if (modelID == "SFD" && i == 0) return "TransitionStage";
+    return "State" + std::to_string(i + 1);
+}
+
 int main(int argc, char** argv) {
     std::string cfg = "Config_BaM.txt", dump, priorFile, yFile;
     unsigned long long seed = 20261019ull;
@@ -317,8 +323,10 @@ int main(int argc, char** argv) {
         if (w.doResidual && nCooked) {  // BaM_Residual (:754-878)
             const size_t n = (size_t)w.nobs;
             std::vector<double> Xtrue(n * w.nX), Ysim(n * w.nY), Yunb(w.Y), res(n * w.nY), stdres(n * w.nY);
+            std::vector<double> state(n * (size_t)sz.nState);
             int32_t feas = 0;
-            check(bamgpu_calibration_run(h, &pb, maxpost.data(), Xtrue.data(), Ysim.data(), &feas, mess), mess);
+            check(bamgpu_calibration_run_states(h, &pb, maxpost.data(), Xtrue.data(), Ysim.data(),
+                                                sz.nState ? state.data() : nullptr, &feas, mess), mess);
             if (!feas) throw std::runtime_error("BaM_Residual: unfeasible [maxpost] parameter vector (BaM_Message 5)");
             int k = sz.nFit + sz.nGamma + sz.nLatent + sz.nXbias;
             for (int j = 0; j < w.nY; ++j) {  // un-biased outputs (:801-811)
@@ -356,6 +364,7 @@ int main(int argc, char** argv) {
             for (int i = 1; i <= w.nX; ++i) hd.push_back("X" + std::to_string(i) + "_true");
             for (auto sfx : {"_obs", "_unbiased", "_sim", "_res", "_stdres"})
                 for (int i = 1; i <= w.nY; ++i) hd.push_back("Y" + std::to_string(i) + sfx);
+            for (int i = 0; i < sz.nState; ++i) hd.push_back(state_name(w.modelID, i));  // model%StateName (:860-862)
             const size_t ncol = hd.size();
             std::vector<double> tab(n * ncol);
             for (size_t i = 0; i < n; ++i) {
@@ -364,12 +373,15 @@ int main(int argc, char** argv) {
                 for (int j = 0; j < w.nX; ++j) tab[i * ncol + c++] = Xtrue[i + j * n];
                 for (const std::vector<double>* src : {&w.Y, &Yunb, &Ysim, &res, &stdres})
                     for (int j = 0; j < w.nY; ++j) tab[i * ncol + c++] = (*src)[i + j * n];
+                for (int j = 0; j < sz.nState; ++j) tab[i * ncol + c++] = state[i + j * n];
             }
             write_table(w.dir + w.residualFile, hd, tab, n, ncol);
         }
         // prediction experiments (src/BaM_main.f90:449-530)
         for (auto& pf : w.predConfigs) {
-            PredConfig pc = read_pred_config(w, pf);
+            PredConfig pc = read_pred_config(w, pf, sz.nState);
+            const bool anyState = std::any_of(pc.doState.begin(), pc.doState.end(), [](int v) { return v != 0; });
+            const int nOut = w.nY + (anyState ? sz.nState : 0);
             std::vector<std::vector<double>> xs(w.nX);
             std::vector<const double*> xp(w.nX);
             for (int i = 0; i < w.nX; ++i) {
@@ -413,16 +425,23 @@ int main(int argc, char** argv) {
                 for (long long r = 0; r < Nrep; ++r)
                     for (int c = 0; c < P; ++c) mc[r + (size_t)c * Nrep] = cooked[r * rowlen + c];
             }
-            std::vector<double> env((size_t)pc.nobs * BAMGPU_NENV * w.nY), spag((size_t)pc.nobs * Nrep * w.nY);
+            std::vector<double> env((size_t)pc.nobs * BAMGPU_NENV * nOut), spag((size_t)pc.nobs * Nrep * nOut);
             std::vector<int32_t> dr(pc.doRemnant.begin(), pc.doRemnant.end()), ns(pc.nspag.begin(), pc.nspag.end());
-            check(bamgpu_predict(h, Nrep, mc.empty() ? nullptr : mc.data(), mode.data(), pc.nobs, xp.data(), ns.data(), pc.doParametric,
+            check((anyState ? bamgpu_predict_states : bamgpu_predict)(h, Nrep, mc.empty() ? nullptr : mc.data(), mode.data(), pc.nobs, xp.data(), ns.data(), pc.doParametric,
                                  dr.data(), seed + 1000, 0, pc.nobs, Nrep >= 2 ? env.data() : nullptr, spag.data(), mess), mess);
             write_monitor(w.dir + pf + ".monitor", Nrep, Nrep);
-            for (int y = 0; y < w.nY; ++y) {
-                FILE* f = fopen((w.dir + pc.yspagFiles[y]).c_str(), "w");
-                if (!f) throw std::runtime_error("problem opening file " + w.dir + pc.yspagFiles[y]);
+            for (int y = 0; y < nOut; ++y) {  // outputs, then the requested state variables (:1071-1075,1121-1132)
+                const bool isState = y >= w.nY;
+                const int q = isState ? y - w.nY : y;
+                if (isState && !pc.doState[q]) continue;
+                const std::string spagFile = isState ? pc.sspagFiles[q] : pc.yspagFiles[q];
+                const std::string envFile = isState ? pc.envFilesS[q] : pc.envFiles[q];
+                const bool doTr = isState ? pc.doTransposeS[q] != 0 : pc.doTranspose[q] != 0;
+                const bool doEnv = isState ? pc.doEnvelopS[q] != 0 : pc.doEnvelop[q] != 0;
+                FILE* f = fopen((w.dir + spagFile).c_str(), "w");
+                if (!f) throw std::runtime_error("problem opening file " + w.dir + spagFile);
                 const double* S = spag.data() + (size_t)y * pc.nobs * Nrep;  // [t][rep]
-                if (pc.doTranspose[y]) {  // one row per input, Nrep values (:1369-1380)
+                if (doTr) {  // one row per input, Nrep values (:1369-1380)
                     for (int t = 0; t < pc.nobs; ++t) {
                         for (long long r = 0; r < Nrep; ++r) fputs(e15_6(S[(size_t)t * Nrep + r]).c_str(), f);
                         fputc('\n', f);
@@ -434,10 +453,10 @@ int main(int argc, char** argv) {
                     }
                 }
                 fclose(f);
-                if (pc.doEnvelop[y] && Nrep >= 2) {  // :1334-1340,1424
+                if (doEnv && Nrep >= 2) {  // :1334-1340,1424
                     static const char* hd[7] = {"Median", "q2.5", "q97.5", "q16", "q84", "Mean", "Stdev"};
-                    FILE* e = fopen((w.dir + pc.envFiles[y]).c_str(), "w");
-                    if (!e) throw std::runtime_error("problem opening file " + w.dir + pc.envFiles[y]);
+                    FILE* e = fopen((w.dir + envFile).c_str(), "w");
+                    if (!e) throw std::runtime_error("problem opening file " + w.dir + envFile);
                     std::string line;
                     for (auto s : hd) line += a15(s);
                     fprintf(e, "%s\n", line.c_str());

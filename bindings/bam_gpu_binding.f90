@@ -77,6 +77,15 @@ interface
         type(c_ptr), intent(in) :: xspag(*); integer(c_int), intent(in) :: nspag(*), doRemnant(*)
         type(c_ptr), value :: env, spag; character(kind=c_char) :: mess(*)
     end function
+    ! the same with the state spaghetti (src/BaM_tools.f90:1071-1075,1121-1132): the nState state variables follow the
+    ! nY outputs in env / spag
+    integer(c_int) function bamgpu_predict_states(h, Nrep, mc, mode, nobs_pred, xspag, nspag, doParametric, doRemnant, &
+                                                  seed, t0, t1, env, spag, mess) bind(C, name='bamgpu_predict_states')
+        import; type(c_ptr), value :: h; integer(c_int64_t), value :: Nrep, seed
+        type(c_ptr), value :: mc, mode; integer(c_int), value :: nobs_pred, doParametric, t0, t1
+        type(c_ptr), intent(in) :: xspag(*); integer(c_int), intent(in) :: nspag(*), doRemnant(*)
+        type(c_ptr), value :: env, spag; character(kind=c_char) :: mess(*)
+    end function
     ! prior / likelihood / hyper split of K vectors: the loop body of BaM_computeDIC (src/BaM_tools.f90:1626-1646)
     integer(c_int) function bamgpu_logpost_parts(h, K, x, prior, lkh, hyper, feas, isnull, mess) &
                                                  bind(C, name='bamgpu_logpost_parts')
@@ -89,6 +98,13 @@ interface
                                                    bind(C, name='bamgpu_calibration_run')
         import; type(c_ptr), value :: h; type(bamgpu_problem), intent(in) :: p
         real(c_double), intent(in) :: x(*); real(c_double), intent(out) :: Xtrue(*), Ysim(*)
+        integer(c_int), intent(out) :: feas; character(kind=c_char) :: mess(*)
+    end function
+    ! GetSim_calibration with its `state` argument (the state columns of Results_Residuals, :793-794,860-873)
+    integer(c_int) function bamgpu_calibration_run_states(h, p, x, Xtrue, Ysim, state, feas, mess) &
+                                                          bind(C, name='bamgpu_calibration_run_states')
+        import; type(c_ptr), value :: h; type(bamgpu_problem), intent(in) :: p
+        real(c_double), intent(in) :: x(*); real(c_double), intent(out) :: Xtrue(*), Ysim(*), state(*)
         integer(c_int), intent(out) :: feas; character(kind=c_char) :: mess(*)
     end function
     integer(c_int) function bamgpu_moments(h, cnt, mean, m2, dev_ptrs, mess) bind(C, name='bamgpu_moments')

@@ -46,8 +46,8 @@ enum bamgpu_model {
     BAMGPU_MDL_HCS = 11,          /* HydraulicControl_section_model.f90:40-112 ("HydraulicControl_section") */
     BAMGPU_MDL_SEGMENTATION = 12, /* Segmentation_model.f90:52-140 (whole-series model: segment sizes are checked) */
     BAMGPU_MDL_BARATINBAC = 13,   /* BaRatinBAC_model.f90:96-666: BaRatin in the b-a-c parameterisation */
-    BAMGPU_MDL_SFD = 14,          /* StageFallDischarge_model.f90:80-283 (SFD_Val_General); the transition stage kappa
-                                     (the model's only state variable) is computed but not exported by this ABI yet */
+    BAMGPU_MDL_SFD = 14,          /* StageFallDischarge_model.f90:80-283 (SFD_Val_General); the transition stage kappa is
+                                     the model's state variable (bamgpu_predict_states, bamgpu_calibration_run_states) */
     BAMGPU_MDL_MIXTURE = 15       /* Mixture_model.f90:74-135: per-event weighted sum of source concentrations; output
                                      rows are event x element blocks (row (j-1)*nElt+e = e-th input row of event j) */
 };
@@ -211,6 +211,11 @@ int bamgpu_logpost_parts(bamgpu_t* h, int K, const double* x, double* prior, dou
    outputs (rows of unfeas_flag where the model is infeasible); *feas = 1 iff every row is feasible. */
 int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* p, const double* x, double* Xtrue, double* Ysim,
                            int32_t* feas, char* mess);
+/* the same with the model's state variables (GetSim_calibration's `state`, the state columns of Results_Residuals,
+   src/BaM_tools.f90:793-794,860-873): state is nobs x nState (bamgpu_sizes.nState; SFD: the transition stage kappa),
+   rows of unfeas_flag where the model is infeasible, undefRN where the model does not define the state. */
+int bamgpu_calibration_run_states(bamgpu_t* h, const bamgpu_problem* p, const double* x, double* Xtrue, double* Ysim,
+                                  double* state, int32_t* feas, char* mess);
 
 /* resident variant: upload once, evaluate many times with everything in HBM */
 int bamgpu_chains_upload(bamgpu_t* h, int K, const double* x, char* mess);
@@ -250,6 +255,12 @@ int bamgpu_predict(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mo
                    const double* const* xspag, const int32_t* nspag, int doParametric,
                    const int32_t* doRemnant, uint64_t seed, int t0, int t1, double* env, double* spag,
                    char* mess);
+/* bamgpu_predict with the state spaghetti / envelopes of BaM_Prediction (src/BaM_tools.f90:1071-1075,1121-1132): the
+   model's state variables are nState extra outputs placed AFTER the nY outputs, without structural-error noise:
+   env is 7 x (t1-t0) x (nY + nState), spag (t1-t0)*Nrep x (nY + nState) in the layout of bamgpu_predict. */
+int bamgpu_predict_states(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                          const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
+                          uint64_t seed, int t0, int t1, double* env, double* spag, char* mess);
 
 /* resident variant for measurement: the sample matrix and inputs stay in HBM between calls */
 int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,

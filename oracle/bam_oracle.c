@@ -813,7 +813,11 @@ static void sfd_fnewton(double x, const double* th, double h2, double* f, double
           th[5] * th[7] * pow(x - th[4], th[7] - 1.0);
 }
 
-static void sfd_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* th, double* OUT, int32_t* vfeas) {
+/* kappa (nullable): the state variable, undefRN where it is never solved for (:126) */
+static void sfd_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* th, double* OUT, int32_t* vfeas,
+                      double* kappa_out) {
+    if (kappa_out)
+        for (int t = 0; t < n; ++t) kappa_out[t] = BAMGPU_UNDEF_RN;
     double KB = th[0], h0 = th[1], M = th[2], L = th[3], h0p = th[4], KBS0 = th[5], delta = th[6], Mp = th[7];
     if (KB <= 0.0 || M <= 0.0 || L <= 0.0 || KBS0 <= 0.0 || Mp <= 0.0) {
         for (int t = 0; t < n; ++t) vfeas[t] = 0;
@@ -863,6 +867,7 @@ static void sfd_apply(const oracle_t* o, int n, const double* IN, int ldx, const
             kappa = rts;
         }
         if (fcalls > o->veg_itmax || kappa != kappa) { vfeas[t] = 0; continue; }
+        if (kappa_out) kappa_out[t] = kappa;
         if (h1 <= kappa) OUT[t] = (KB * pow(h1 - h0, M)) * sqrt((h1 - h2 - delta) / L);
         else OUT[t] = KBS0 * pow(h1 - h0p, Mp);
     }
@@ -1389,8 +1394,8 @@ static void textfile_apply(const oracle_t* o, int n, const double* IN, int ldx, 
 
 /* ApplyModel, ModelLibrary_tools.f90:237-434: init to unfeasFlag, dispatch, flag infeasible rows.
    Returns feas = all(vfeas) through *feas. */
-static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const double* fullTheta, double* Y,
-                       int ldy, double* dparModel, int32_t* vfeas, int* feas) {
+static int apply_model_s(const oracle_t* o, int n, const double* X, int ldx, const double* fullTheta, double* Y,
+                         int ldy, double* dparModel, int32_t* vfeas, int* feas, double* state /* n x nState, ld = ldy, or NULL */) {
     for (int t = 0; t < n; ++t) vfeas[t] = 1;
     for (int y = 0; y < o->nY; ++y)
         for (int t = 0; t < n; ++t) Y[t + (size_t)y * ldy] = o->unfeas;
@@ -1410,7 +1415,7 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         case BAMGPU_MDL_ORTHO: ortho_apply(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas); break;
         case BAMGPU_MDL_HCS: hcs_apply(o, n, X, fullTheta, Y, vfeas); break;
         case BAMGPU_MDL_BARATINBAC: baratinbac_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
-        case BAMGPU_MDL_SFD: sfd_apply(o, n, X, ldx, fullTheta, Y, vfeas); break;
+        case BAMGPU_MDL_SFD: sfd_apply(o, n, X, ldx, fullTheta, Y, vfeas, state); break;
         case BAMGPU_MDL_MIXTURE: {
             int r = mixture_apply(o, n, X, ldx, fullTheta, Y, dparModel);
             if (r < 0) return 1;
@@ -1429,9 +1434,16 @@ static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const
         if (!vfeas[t]) {
             all = 0;
             for (int y = 0; y < o->nY; ++y) Y[t + (size_t)y * ldy] = o->unfeas;
+            if (state)
+                for (int y = 0; y < o->nState; ++y) state[t + (size_t)y * ldy] = o->unfeas; /* :427-431 */
         }
     *feas = all;
     return 0;
+}
+
+static int apply_model(const oracle_t* o, int n, const double* X, int ldx, const double* fullTheta, double* Y,
+                       int ldy, double* dparModel, int32_t* vfeas, int* feas) {
+    return apply_model_s(o, n, X, ldx, fullTheta, Y, ldy, dparModel, vfeas, feas, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1868,7 +1880,15 @@ done:
 }
 
 /* GetSim_calibration (src/BaM_tools.f90:3619-3680): Xtrue (n x nX) and Ysim (n x nY) for one vector */
+int oracle_calibration_run_states(const oracle_t* o, const double* x, double* Xtrue, double* Ysim, double* state,
+                                  int32_t* feas_out, char* mess);
 int oracle_calibration_run(const oracle_t* o, const double* x, double* Xtrue, double* Ysim, int32_t* feas_out, char* mess) {
+    return oracle_calibration_run_states(o, x, Xtrue, Ysim, NULL, feas_out, mess);
+}
+
+/* GetSim_calibration (src/BaM_tools.f90:3619-3680) with the state variables; VAR parameters: states are not returned */
+int oracle_calibration_run_states(const oracle_t* o, const double* x, double* Xtrue, double* Ysim, double* state,
+                                  int32_t* feas_out, char* mess) {
     int n = o->n, nX = o->nX;
     if (mess) mess[0] = 0;
     double* xt = (double*)malloc(((size_t)n * nX + 1) * 8);
@@ -1884,7 +1904,13 @@ int oracle_calibration_run(const oracle_t* o, const double* x, double* Xtrue, do
     int32_t* vfeas = (int32_t*)malloc(((size_t)n + 1) * 4);
     int feas = 1;
     for (size_t q = 0; q < (size_t)n * o->nY; ++q) Ysim[q] = o->unfeas;
-    int e = apply_model_bam(o, xt, x, Ysim, dpar, vfeas, &feas);
+    int e;
+    if (state && o->nState > 0 && o->nVar == 0) {
+        double full[256];
+        for (size_t q = 0; q < (size_t)n * o->nState; ++q) state[q] = o->unfeas;
+        full_theta(o, x, 0, full);
+        e = apply_model_s(o, n, xt, n, full, Ysim, n, dpar, vfeas, &feas, state);
+    } else e = apply_model_bam(o, xt, x, Ysim, dpar, vfeas, &feas);
     *feas_out = feas;
     free(xt); free(dpar); free(vfeas);
     if (e > 0) setmess(mess, "oracle: ApplyModel failed");
@@ -2021,23 +2047,42 @@ void oracle_envelope(const double* col, int64_t nrep, double unfeas, double* env
     free(arr);
 }
 
+static int predict_impl(const oracle_t* o, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                        const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
+                        uint64_t seed, int t0, int t1, double* env, double* spag_out, int nthreads, char* mess, int nS);
+
 int oracle_predict(const oracle_t* o, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
                    const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
                    uint64_t seed, int t0, int t1, double* env, double* spag_out, int nthreads, char* mess) {
+    return predict_impl(o, Nrep, mc, mode, nobs_pred, xspag, nspag, doParametric, doRemnant, seed, t0, t1, env, spag_out,
+                        nthreads, mess, 0);
+}
+
+/* with the state spaghetti (src/BaM_tools.f90:1071-1075,1121-1132): nState extra outputs after the nY outputs */
+int oracle_predict_states(const oracle_t* o, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                          const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
+                          uint64_t seed, int t0, int t1, double* env, double* spag_out, int nthreads, char* mess) {
+    return predict_impl(o, Nrep, mc, mode, nobs_pred, xspag, nspag, doParametric, doRemnant, seed, t0, t1, env, spag_out,
+                        nthreads, mess, o->nState);
+}
+
+static int predict_impl(const oracle_t* o, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                        const double* const* xspag, const int32_t* nspag, int doParametric, const int32_t* doRemnant,
+                        uint64_t seed, int t0, int t1, double* env, double* spag_out, int nthreads, char* mess, int nS) {
     if (mess) mess[0] = 0;
     if (o->nVar) { setmess(mess, "oracle: BaM_Prediction: VAR parameters not allowed (BaM_Message 13)"); return 1; }
-    int nT = t1 - t0, nX = o->nX, nY = o->nY;
+    int nT = t1 - t0, nX = o->nX, nY = o->nY, nOut = nY + nS;
     if (nT <= 0 || Nrep <= 0) return 0;
     int anyRem = 0;
     for (int y = 0; y < nY; ++y) anyRem |= doRemnant[y];
     if ((doParametric || anyRem) && !mc) { setmess(mess, "oracle: BaM_Prediction: mcmc matrix required"); return 1; }
-    double* spag = spag_out ? spag_out : (double*)malloc((size_t)Nrep * nT * nY * 8);
+    double* spag = spag_out ? spag_out : (double*)malloc((size_t)Nrep * nT * nOut * 8);
     int err = 0;
     if (nthreads < 1) nthreads = 1;
 #pragma omp parallel for num_threads(nthreads) schedule(static)
     for (int64_t rep = 0; rep < Nrep; ++rep) { /* the rep loop, :1034-1108 */
         double* X = (double*)malloc(((size_t)nT * nX + 1) * 8);
-        double* Ys = (double*)malloc(((size_t)nT * nY + 1) * 8);
+        double* Ys = (double*)malloc(((size_t)nT * nOut + 1) * 8);
         int32_t* vf = (int32_t*)malloc(((size_t)nT + 1) * 4);
         double theta[256], full[256], dmod[MAXCONTROL + 64];
         for (int i = 0; i < nX; ++i) { /* indx = modulo(rep, nspag), 1-based rep (:1049) */
@@ -2047,7 +2092,8 @@ int oracle_predict(const oracle_t* o, int64_t Nrep, const double* mc, const doub
         for (int k = 0; k < o->nFit; ++k) theta[k] = doParametric ? mc[rep + (size_t)k * Nrep] : mode[k];
         full_theta(o, theta, 0, full);
         int feas;
-        int e = apply_model(o, nT, X, nT, full, Ys, nT, dmod, vf, &feas);
+        for (size_t q = (size_t)nT * nY; q < (size_t)nT * nOut; ++q) Ys[q] = o->unfeas;
+        int e = apply_model_s(o, nT, X, nT, full, Ys, nT, dmod, vf, &feas, nS ? Ys + (size_t)nT * nY : NULL);
         if (e > 0) {
 #pragma omp critical
             err = e;
@@ -2067,11 +2113,13 @@ int oracle_predict(const oracle_t* o, int64_t Nrep, const double* mc, const doub
             }
             for (int t = 0; t < nT; ++t) spag[(size_t)y * Nrep * nT + (size_t)t * Nrep + rep] = Ys[t + (size_t)y * nT];
         }
+        for (int y = nY; y < nOut; ++y) /* states: written before the structural error is added, never perturbed (:1071-1075) */
+            for (int t = 0; t < nT; ++t) spag[(size_t)y * Nrep * nT + (size_t)t * Nrep + rep] = Ys[t + (size_t)y * nT];
         free(X); free(Ys); free(vf);
     }
     if (env && Nrep >= 2) {
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 8)
-        for (int64_t q = 0; q < (int64_t)nT * nY; ++q) {
+        for (int64_t q = 0; q < (int64_t)nT * nOut; ++q) {
             int y = (int)(q / nT), t = (int)(q % nT);
             double e7[BAMGPU_NENV];
             oracle_envelope(spag + (size_t)y * Nrep * nT + (size_t)t * Nrep, Nrep, o->unfeas, e7);

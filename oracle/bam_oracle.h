@@ -39,6 +39,9 @@ int oracle_logpost(const oracle_t* o, const double* x, double* fx, double* prior
 
 /* GetSim_calibration (src/BaM_tools.f90:3619-3680) */
 int oracle_calibration_run(const oracle_t* o, const double* x, double* Xtrue, double* Ysim, int32_t* feas, char* mess);
+/* with the state variables (n x nState), same arguments as bamgpu_calibration_run_states */
+int oracle_calibration_run_states(const oracle_t* o, const double* x, double* Xtrue, double* Ysim, double* state,
+                                  int32_t* feas, char* mess);
 
 /* K vectors (P x K), nthreads OpenMP threads over vectors (1 = the serial reference analogue). */
 int oracle_logpost_batch(const oracle_t* o, int K, const double* x, double* fx, int32_t* feas, int32_t* isnull,
@@ -55,6 +58,11 @@ int oracle_predict(const oracle_t* o, int64_t Nrep, const double* mc, const doub
                    const double* const* xspag, const int32_t* nspag, int doParametric,
                    const int32_t* doRemnant, uint64_t seed, int t0, int t1, double* env, double* spag,
                    int nthreads, char* mess);
+/* with the state spaghetti: nState extra outputs after the nY outputs (same arguments as bamgpu_predict_states) */
+int oracle_predict_states(const oracle_t* o, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
+                          const double* const* xspag, const int32_t* nspag, int doParametric,
+                          const int32_t* doRemnant, uint64_t seed, int t0, int t1, double* env, double* spag,
+                          int nthreads, char* mess);
 
 /* the 7 envelope statistics of one column of nrep values (src/BaM_tools.f90:1393-1421) */
 void oracle_envelope(const double* col, int64_t nrep, double unfeas_flag, double* env7);

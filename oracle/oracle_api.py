@@ -41,7 +41,9 @@ def load():
     lib.oracle_logpost_batch.argtypes = [H, ci, _dp, _dp, _ip, _ip, _dp, ci, cp]
     lib.oracle_apply_model.argtypes = [H, ci, _dp, _dp, _dp, _dp, _ip, cp]
     lib.oracle_calibration_run.argtypes = [H, _dp, _dp, _dp, _ip, cp]
+    lib.oracle_calibration_run_states.argtypes = [H, _dp, _dp, _dp, _dp, _ip, cp]
     lib.oracle_predict.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, ci, _ip, u64, ci, ci, _dp, _dp, ci, cp]
+    lib.oracle_predict_states.argtypes = lib.oracle_predict.argtypes
     lib.oracle_envelope.argtypes = [_dp, i64, d, _dp]
     lib.oracle_envelope.restype = None
     lib.oracle_fit.argtypes = [H, ci, _dp, _dp, ci, ci, d, d, d, d, u64, ci, ci, _dp, C.POINTER(i64), _dp, _dp, i64, cp]
@@ -134,6 +136,18 @@ class Oracle:
         _check(self.lib.oracle_calibration_run(self.h, _ptr_d(x), _ptr_d(Xtrue), _ptr_d(Ysim), C.byref(feas), mess), mess)
         return Xtrue, Ysim, bool(feas.value)
 
+    def calibration_run_states(self, x):
+        pr = self.problem
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        Xtrue = np.empty((pr.nobs, pr.nX), order="F")
+        Ysim = np.empty((pr.nobs, pr.nY), order="F")
+        state = np.empty((pr.nobs, self.sizes.nState), order="F")
+        feas = C.c_int32(0)
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(self.lib.oracle_calibration_run_states(self.h, _ptr_d(x), _ptr_d(Xtrue), _ptr_d(Ysim), _ptr_d(state),
+                                                      C.byref(feas), mess), mess)
+        return Xtrue, Ysim, state, bool(feas.value)
+
     def apply_model(self, X, theta_fit):
         X = np.asarray(X, dtype=np.float64)
         if X.ndim == 1:
@@ -150,7 +164,7 @@ class Oracle:
         return Y, feas, dpar
 
     def predict(self, mc, mode, xspag, doParametric, doRemnant, seed=1, t0=0, t1=None, want_env=True,
-                want_spag=False, nthreads=1):
+                want_spag=False, nthreads=1, states=False):
         from bam_b200.capi import BamGpu
 
         nobs_pred = np.asarray(xspag[0]).shape[0]
@@ -163,11 +177,11 @@ class Oracle:
             Nrep = 1
         mode = None if mode is None else np.ascontiguousarray(mode, dtype=np.float64)
         dr = np.asarray(doRemnant, dtype=np.int32)
-        nT, nY = t1 - t0, self.problem.nY
+        nT, nY = t1 - t0, self.problem.nY + (self.sizes.nState if states else 0)
         env = np.empty((nY, NENV, nT)) if want_env else None
         spag = np.empty((nY, nT, Nrep)) if want_spag else None
         mess = C.create_string_buffer(MESS_LEN)
-        _check(self.lib.oracle_predict(self.h, Nrep, _ptr_d(mc), _ptr_d(mode), nobs_pred, ptrs, _ptr_i(nspag),
+        _check((self.lib.oracle_predict_states if states else self.lib.oracle_predict)(self.h, Nrep, _ptr_d(mc), _ptr_d(mode), nobs_pred, ptrs, _ptr_i(nspag),
                                        int(doParametric), _ptr_i(dr), seed, t0, t1,
                                        _ptr_d(env) if want_env else C.cast(None, _dp),
                                        _ptr_d(spag) if want_spag else C.cast(None, _dp), nthreads, mess), mess)

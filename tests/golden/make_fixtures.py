@@ -160,6 +160,11 @@ def load_workspace(cfg_name):
     elif model_id == "TextFile":
         with open(path(ws, f_xtra)) as f:
             xtra_text = f.read()
+    elif model_id == "SFD":  # SFD_XtraRead (StageFallDischarge_model.f90:191-247): ID, 5 Newton options, maxiter
+        s = read_lines(path(ws, f_xtra))
+        assert items(s[0])[0] == "SFD_Val_General"
+        xtra_d = [fnum(items(s[i])[0]) for i in range(1, 6)]
+        xtra_i = [1, int(items(s[6])[0])]
     elif model_id == "Mixture":  # Mixture_XtraRead (Mixture_model.f90:137-190): nS, nEvt, nElt, missingSource
         s = read_lines(path(ws, f_xtra))
         xtra_i = [int(items(s[i])[0]) for i in range(3)] + [1 if items(s[3])[0].strip(".").lower().startswith("t") else 0]
@@ -207,6 +212,7 @@ WORKSPACES = {
     "sediment_mpm_x2": "Config_BaM_Sediment.txt",
     "textfile_inputuncertainty": "Config_BaM_TextFile_InputUncertainty.txt",
     "mixture": "Config_BaM_Mixture.txt",
+    "sfd": "Config_BaM_SFD.txt",
 }
 
 

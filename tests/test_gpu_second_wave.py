@@ -150,6 +150,28 @@ def test_sfd():
     isv = np.isclose(det[0, ok, 0], qv[ok], rtol=1e-9)
     isc = np.isclose(det[0, ok, 0], qc[ok], rtol=1e-9)
     assert (isv | isc).all() and isv.any() and isc.any()
+    # state spaghetti (BaM_Prediction :1071-1075): kappa follows the output, no structural-error noise on it; rows that
+    # never solve for kappa keep undefRN, infeasible rows carry the unfeasible flag
+    h1[9] = truth[1] - 0.5  # below h0: Q = 0, kappa stays undefRN (:126,148)
+    envs, spags = g.predict(mc, truth, [h1, h2], 1, [1], seed=4, want_spag=True, states=True)
+    oenvs, ospags = o.predict(mc, truth, [h1, h2], 1, [1], seed=4, want_spag=True, nthreads=8, states=True)
+    assert spags.shape == (2, 80, 200) and envs.shape == (2, 7, 80)
+    cmp_spag(spags, ospags)
+    cmp_env(envs, oenvs)
+    assert (spags[1, 5] == -666.666).all() and (spags[1, 9] == -999999999.0).all()
+    kap = spags[1][(spags[1] != -666.666) & (spags[1] != -999999999.0)]
+    assert kap.size > 0.9 * 78 * 200 and (kap > 1.93).all() and (kap < 20.0).all()
+    # the discharge switches regime exactly at kappa: rows with h1 <= kappa follow the variable-slope law
+    _, dets = g.predict(None, truth, [h1, h2], 0, [0], want_env=False, want_spag=True, states=True)
+    q, kp = dets[0, :, 0], dets[1, :, 0]
+    okk = (kp != -666.666) & (kp != -999999999.0)
+    assert np.allclose(q[okk & (h1 <= kp)], qv[okk & (h1 <= kp)], rtol=1e-9) and np.allclose(q[okk & (h1 > kp)], qc[okk & (h1 > kp)], rtol=1e-9)
+    # residual run with the state column (GetSim_calibration)
+    Xt, Ys, St, feas = g.calibration_run_states(truth)
+    oXt, oYs, oSt, ofeas = o.calibration_run_states(truth)
+    assert feas == ofeas and np.allclose(Ys, oYs, rtol=1e-12, atol=1e-300) and St.shape == (400, 1)
+    assert ((St == -999999999.0) == (oSt == -999999999.0)).all() and ((St == -666.666) == (oSt == -666.666)).all()
+    assert np.allclose(St, oSt, rtol=1e-12, atol=0)
 
 
 @pytest.mark.parametrize("missing,shuffle", [(True, True), (False, True), (True, False)])

@@ -14,7 +14,7 @@ from tests.workspace_writer import write_workspace
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "bam_b200", "bam_gpu")
 FIXTURES = ["baratin", "baratin_spd", "regression_x2y2", "sediment_camenen_x4", "sediment_mpm_x2",
-            "textfile_inputuncertainty", "mixture"]
+            "textfile_inputuncertainty", "mixture", "sfd"]
 DIST = {"Gaussian": 1, "Uniform": 2, "Triangle": 3, "LogNormal": 4, "Exponential": 5, "FlatPrior": 6, "FlatPrior+": 7,
         "FlatPrior-": 8}
 SIG = {"Constant": 1, "Linear": 2, "Proportional": 3, "Power": 4, "Exponential": 5, "Gaussian": 6}
@@ -75,7 +75,7 @@ def test_config_reader_roundtrip(name, tmp_path):
 @pytest.mark.parametrize("cfg,name", [("Config_BaM_BaRatin.txt", "baratin"), ("Config_BaM_BaRatin_SPD.txt", "baratin_spd"),
                                       ("Config_BaM_Regression_X2Y2.txt", "regression_x2y2"),
                                       ("Config_BaM_TextFile_InputUncertainty.txt", "textfile_inputuncertainty"),
-                                      ("Config_BaM_Mixture.txt", "mixture")])
+                                      ("Config_BaM_Mixture.txt", "mixture"), ("Config_BaM_SFD.txt", "sfd")])
 def test_config_reader_on_shipped_workspaces(cfg, name):
     """the reference's own example workspaces, Windows path separators included"""
     compare_d = dump_ref(cfg)
@@ -247,3 +247,41 @@ def test_onerun_dontrun_saveprior_modes(tmp_path):
     hp, pri = read_table(os.path.join(ws, "PriorSample.txt"))
     assert hp[:3] == ["k1", "a1", "c1"] and pri.shape == (30, 8)
     assert abs(pri[:, 1].mean() - 53.0) < 10.0  # a1 ~ N(53, 10) in Config_Model of tests/BaM_BaRatin
+
+
+@pytest.mark.gpu
+def test_state_variable_files(tmp_path):
+    """SFD (tests/BaM_SFD): the state variable kappa goes to its own spaghetti / envelope files (BaM_Prediction
+    :1071-1075,1121-1132, Config_Read_Pred :2808-2826) and to the TransitionStage column of the residual file."""
+    from oracle.oracle_api import Oracle
+    from tests.helpers import problem_from_fixture
+
+    fx = load_fixture("sfd")
+    h1 = np.linspace(1.0, 7.0, 30)
+    h2 = np.full(30, 1.93)
+    cfg, ws = write_workspace(fx, str(tmp_path), name="ST", nAdapt=10, nCycles=4, do_pred=True, do_residual=True,
+                              pred=[dict(Xs=[h1, h2], doParametric=True, doRemnant=True, state=True),
+                                    dict(Xs=[h1, h2], doParametric=False, doRemnant=False, state=True),
+                                    dict(Xs=[h1, h2], doParametric=True, doRemnant=False)])
+    r = subprocess.run([EXE, "-cf", cfg, "-sd", "11", "--chains", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    _, cooked = read_table(os.path.join(ws, "Results_MCMC_Cooked.txt"))
+    nrep = cooked.shape[0]
+    S = np.loadtxt(os.path.join(ws, "S_1.spag"))
+    Y = np.loadtxt(os.path.join(ws, "Y_1.spag"))
+    assert S.shape == (30, nrep) and Y.shape == (30, nrep)
+    head, env = read_table(os.path.join(ws, "S_1.env"))
+    assert head[0] == "Median" and env.shape == (30, 7)
+    assert os.path.exists(os.path.join(ws, "Y_3.spag")) and not os.path.exists(os.path.join(ws, "S_3.spag"))
+    # maxpost run: the state column equals the oracle's kappa at the written maxpost (7 digits in the file)
+    prob, _ = problem_from_fixture("sfd")
+    o = Oracle(prob)
+    k = int(np.argmax(cooked[:, o.P]))
+    mp = cooked[k, :o.P]
+    _, ospag = o.predict(None, mp, [h1, h2], 0, [0], want_env=False, want_spag=True, states=True)
+    S2 = np.loadtxt(os.path.join(ws, "S_2.spag"))
+    assert S2.shape == (30,) and np.allclose(S2, ospag[1, :, 0], rtol=1e-4)
+    head, res = read_table(os.path.join(ws, "Results_Residuals.txt"))
+    assert head[-1] == "TransitionStage" and res.shape == (68, 2 * 2 + 5 * 1 + 1)
+    _, _, oSt, _ = o.calibration_run_states(mp)
+    assert np.allclose(res[:, -1], oSt[:, 0], rtol=1e-4)

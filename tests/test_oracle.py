@@ -347,3 +347,24 @@ def test_mixture_row_pairing(missing):
         bad = th.copy()
         bad[0], bad[1] = 0.7, 0.6
         assert not Oracle(prob).apply_model(X, bad)[1].any()
+
+
+def test_sfd_state_variable():
+    """the transition stage kappa (SFD's state) solves fNewton_Val_General = 0 (StageFallDischarge_model.f90:253-283)
+    and is undefRN on the rows that never solve for it (:126,148)"""
+    from bam_b200 import synth
+
+    prob, truth = synth.sfd(nobs=120)
+    o = Oracle(prob)
+    assert o.sizes.nState == 1
+    Xt, Ys, St, feas = o.calibration_run_states(truth)
+    th = truth[:8]
+    k = St[:, 0]
+    solved = (k != -999999999.0) & (k != -666.666)
+    assert solved.sum() > 60
+    h2 = np.asarray(prob.X)[:, 1]
+    lhs = th[0] * (k[solved] - th[1]) ** th[2] * np.sqrt((k[solved] - h2[solved] - th[6]) / th[3])
+    rhs = th[5] * (k[solved] - th[4]) ** th[7]
+    assert np.max(np.abs(lhs - rhs) / rhs) < 1e-10
+    h1 = np.asarray(prob.X)[:, 0]
+    assert ((h1 - th[1] <= 0) | (h2 - th[4] <= 0) | (h1 - h2 - th[6] <= 0))[~solved].all()

@@ -98,6 +98,9 @@ def write_workspace(fx: dict, root: str, name: str = "WS", nAdapt=None, nCycles=
             "\n" + ",".join(repr(float(v)) for v in fx["xtra_d"]) + "\n")
     elif fx["model_id"] == "TextFile":
         open(os.path.join(ws, xf), "w").write(fx["xtra_text"])
+    elif fx["model_id"] == "SFD":
+        xd = fx["xtra_d"]
+        open(os.path.join(ws, xf), "w").write('"SFD_Val_General"\n' + "\n".join(repr(float(v)) for v in xd) + f"\n{fx['xtra_i'][1]}\n")
     elif fx["model_id"] == "Mixture":
         xi = fx["xtra_i"]
         open(os.path.join(ws, xf), "w").write(f"{xi[0]} ! nS\n{xi[1]} ! nEvt\n{xi[2]} ! nElt\n{'.true.' if xi[3] else '.false.'} ! missing source\n")
@@ -126,16 +129,30 @@ def write_workspace(fx: dict, root: str, name: str = "WS", nAdapt=None, nCycles=
         for i, pc in enumerate(pred):
             pf = f"Config_Pred_{i + 1}.txt"
             plines.append(f"'{pf}'")
-            X = np.atleast_2d(np.asarray(pc["X"], dtype=float))
-            if X.shape[0] == 1 and X.shape[1] > 1 and pc.get("column", True):
-                X = X.T
-            xfile = f"Xpred_{i + 1}.txt"
-            np.savetxt(os.path.join(ws, xfile), X, fmt="%.17g")
             tf = lambda b: ".true." if b else ".false."  # noqa: E731
-            open(os.path.join(ws, pf), "w").write("\n".join([
-                f"'{name}{sep}{xfile}'", str(X.shape[0]), str(X.shape[1]), tf(pc["doParametric"]), tf(pc["doRemnant"]),
-                str(pc.get("nsim", -1)), f"'Y_{i + 1}.spag'", tf(pc.get("transpose", True)), ".true.", f"'Y_{i + 1}.env'",
-                ".false.", ".false."]) + "\n")
+            if "Xs" in pc:  # one series per input variable
+                cols = [np.asarray(c, dtype=float).reshape(-1, 1) for c in pc["Xs"]]
+                xfiles = []
+                for j, c in enumerate(cols):
+                    xfiles.append(f"Xpred_{i + 1}_{j + 1}.txt")
+                    np.savetxt(os.path.join(ws, xfiles[-1]), c, fmt="%.17g")
+                nobs, nsp = cols[0].shape[0], ",".join("1" for _ in cols)
+                xlist = ",".join(f"'{name}{sep}{f}'" for f in xfiles)
+            else:
+                X = np.atleast_2d(np.asarray(pc["X"], dtype=float))
+                if X.shape[0] == 1 and X.shape[1] > 1 and pc.get("column", True):
+                    X = X.T
+                xfile = f"Xpred_{i + 1}.txt"
+                np.savetxt(os.path.join(ws, xfile), X, fmt="%.17g")
+                nobs, nsp, xlist = X.shape[0], str(X.shape[1]), f"'{name}{sep}{xfile}'"
+            lines = [xlist, str(nobs), nsp, tf(pc["doParametric"]), tf(pc["doRemnant"]),
+                     str(pc.get("nsim", -1)), f"'Y_{i + 1}.spag'", tf(pc.get("transpose", True)), ".true.", f"'Y_{i + 1}.env'",
+                     ".false."]
+            if pc.get("state") is not None:  # state section (Config_Read_Pred :2808-2826)
+                lines += [tf(pc["state"]), f"'S_{i + 1}.spag'", tf(pc.get("transpose", True)), ".true.", f"'S_{i + 1}.env'"]
+            else:
+                lines += [".false."]
+            open(os.path.join(ws, pf), "w").write("\n".join(lines) + "\n")
     open(os.path.join(ws, "Config_Pred_Master.txt"), "w").write("\n".join(plines) + "\n")
 
     cfg = os.path.join(root, f"Config_BaM_{name}.txt")
