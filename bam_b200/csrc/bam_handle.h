@@ -47,6 +47,7 @@ struct bamgpu_handle {
     bool noPartial = false;     // tests / measurement: always re-evaluate every observation in the sampler
     bool noSelect3 = false;     // tests: skip the 2-read envelope selection
     bool forceGeneric = false;  // tests: disable the specialised fast kernels  // global index of local chain 0 (multi-GPU sharding; RNG streams)
+    bool noFastSweep = false;   // option "no_fast_sweep": keep the generic latent sweep (tests compare the two)
 
     // ---- sampler state ----
     double *d_std = nullptr, *d_delta = nullptr, *d_fxcur = nullptr, *d_dparcur = nullptr;

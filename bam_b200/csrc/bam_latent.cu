@@ -127,9 +127,158 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3l fast path (cfg 3): Linear model, every input cell latent, no biases, no missing Y, one sigma function -- the
+// eligibility of logpost_linear_latent.  Same sweep, same Philox streams, same accept rule; what changes is the cost:
+//   * every load of the thread (state, jump scales, observation tables) is issued before the first use;
+//   * the posterior of one observation is  const - T/2,  T = sum_j [log v_j + r_j^2 / v_j] + sum_k z_k^2  (the constants
+//     cancel in candidate - current); NY == 2 shares one log and one reciprocal through v_0 v_1;
+//   * table-driven log / sqrt / cos for the Box-Muller normal and the log of the acceptance uniform (libdevice where
+//     the table log loses relative accuracy, u within 2^-10 of 1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double log_unit_fast(double u, unsigned lt) {  // log(u), u in (0, 1)
+    return ((unsigned)__double2hiint(u) >= 0x3fefff80u) ? log(u) : tlog_pos(u, lt);
+}
+
+template <int NX, int NY, int SIGF>
+__device__ __forceinline__ bool linear_T(const double* xt, const double* xo, const double* hr, const double* yo,
+                                         const double* yu2, const double* __restrict__ th, const double* __restrict__ gm,
+                                         unsigned lt, double& T) {
+    double v[NY], r2[NY];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+        double yh = 0.0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) yh = yh + xt[k] * th[j * NX + k];
+        double sig;
+        if (SIGF == BAMGPU_SIG_CONSTANT) sig = gm[j];
+        else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(gm[2 * j + 1], fabs(yh), gm[2 * j]);
+        else sig = gm[j] * fabs(yh);
+        ok &= sig > 0.0;
+        v[j] = fma(sig, sig, yu2[j]);
+        ok &= ((unsigned)__double2hiint(v[j]) - 0x00100000u < 0x7fe00000u);
+        const double r = yo[j] - yh;
+        r2[j] = r * r;
+    }
+    double t;
+    if (NY == 2) {
+        const double vp = v[0] * v[1];
+        if ((unsigned)__double2hiint(vp) - 0x00100000u < 0x7fe00000u)
+            t = fma(fma(r2[0], v[1], r2[1] * v[0]), trcp(vp), tlog_pos(vp, lt));
+        else t = fma(r2[0], trcp(v[0]), tlog_pos(v[0], lt)) + fma(r2[1], trcp(v[1]), tlog_pos(v[1], lt));
+    } else {
+        t = 0.0;
+#pragma unroll
+        for (int j = 0; j < NY; ++j) t += fma(r2[j], trcp(v[j]), tlog_pos(v[j], lt));
+    }
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+        const double z = (xo[k] - xt[k]) * hr[k];
+        t = fma(z, z, t);
+    }
+    T = t;
+    return ok && t == t;
+}
+
+template <int NX, int NY, int SIGF>
+__global__ void __launch_bounds__(BAM_BLOCK) latent_sweep_linear(DevProblem p, int K, unsigned long long seed,
+                                                                 long long chainOffset, unsigned it, double* __restrict__ x,
+                                                                 const double* __restrict__ sd, int* __restrict__ moves,
+                                                                 const double* __restrict__ tab) {
+    constexpr int NG = (SIGF == BAMGPU_SIG_LINEAR) ? 2 : 1;
+    extern __shared__ __align__(16) double lsm[];  // [log table (4 KB) | theta | gamma]
+    double2* sLogT = reinterpret_cast<double2*>(lsm);
+    double* sth = lsm + 2 * BAM_LOGTAB_N;
+    double* sgm = sth + NX * NY;
+    const int c = blockIdx.y;
+    for (int q = threadIdx.x; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
+    if (threadIdx.x < NX * NY) sth[threadIdx.x] = tab[(size_t)c * p.tabStride + p.tabCombo + threadIdx.x];
+    if (threadIdx.x < NG * NY)
+        sgm[threadIdx.x] = tab[(size_t)c * p.tabStride + p.tabGamma + p.gamOff[threadIdx.x / NG] + threadIdx.x % NG];
+    __syncthreads();
+    const unsigned lt = smem_addr(sLogT);
+    const int n = p.n;
+    const int i = blockIdx.x * BAM_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const size_t base = (size_t)c * p.P + (size_t)p.nFit + p.nGamma;  // cell (i, j) at base + j n + i
+    double xt[NX], sdv[NX], xo[NX], hr[NX], yo[NY], yu2[NY], th[NX * NY], gm[NG * NY];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        xt[j] = x[base + (size_t)j * n + i];
+        sdv[j] = sd[base + (size_t)j * n + i];
+        xo[j] = p.X[i + (size_t)j * n];
+        hr[j] = p.XuInv[i + (size_t)j * n];
+    }
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+        yo[j] = p.Y[i + (size_t)j * n];
+        const double yu = p.Yu[i + (size_t)j * n];
+        yu2[j] = yu * yu;
+    }
+#pragma unroll
+    for (int q = 0; q < NX * NY; ++q) th[q] = sth[q];
+#pragma unroll
+    for (int q = 0; q < NG * NY; ++q) gm[q] = sgm[q];
+    double cur;
+    if (!linear_T<NX, NY, SIGF>(xt, xo, hr, yo, yu2, th, gm, lt, cur)) return;  // cannot happen for a feasible state
+    const unsigned long long gc = (unsigned long long)(chainOffset + c);
+    const unsigned compBase = (unsigned)(p.nFit + p.nGamma);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const unsigned comp = compBase + (unsigned)j * (unsigned)n + (unsigned)i;
+        // philox_normal(seed, gc, it, 2 comp): sqrt(-2 log u1) cos(2 pi u2) with 53-bit uniforms
+        uint32_t c0 = (uint32_t)gc, c1 = (uint32_t)(gc >> 32), c2 = it, c3 = 2u * comp;
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double u1 = u53(c0, c1), u2 = u53(c2, c3);
+        double sn, cs;
+        tsincospi(2.0 * u2, sn, cs);
+        const double zn = tsqrt_pos(-2.0 * log_unit_fast(u1, lt)) * cs;
+        const double old = xt[j];
+        xt[j] = fma(sdv[j], zn, old);
+        double cand;
+        bool acc = false;
+        if (linear_T<NX, NY, SIGF>(xt, xo, hr, yo, yu2, th, gm, lt, cand)) {
+            uint32_t d0 = (uint32_t)gc, d1 = (uint32_t)(gc >> 32), d2 = it, d3 = 2u * comp + 1u;
+            philox4x32_10(d0, d1, d2, d3, (uint32_t)seed, (uint32_t)(seed >> 32));
+            acc = log_unit_fast(u53(d0, d1), lt) < -0.5 * (cand - cur);
+        }
+        if (acc) {
+            cur = cand;
+            x[base + (size_t)j * n + i] = xt[j];
+            moves[base + (size_t)j * n + i] += 1;
+        } else xt[j] = old;
+    }
+}
+
 }  // namespace
 
 namespace bam {
+template <int NX, int NY>
+static LatentKernel pick_sweep_linear_sig(int sigf) {
+    switch (sigf) {
+        case BAMGPU_SIG_CONSTANT: return latent_sweep_linear<NX, NY, BAMGPU_SIG_CONSTANT>;
+        case BAMGPU_SIG_LINEAR: return latent_sweep_linear<NX, NY, BAMGPU_SIG_LINEAR>;
+        case BAMGPU_SIG_PROPORTIONAL: return latent_sweep_linear<NX, NY, BAMGPU_SIG_PROPORTIONAL>;
+    }
+    return nullptr;
+}
+// same eligibility as the log-posterior fast path of cfg 3 (bam_logpost.cu: pick_latent)
+LatentKernel pick_latent_sweep_linear(const bamgpu_handle* h) {
+    const DevProblem& p = h->dp;
+    const HostLayout& L = h->L;
+    if (h->forceGeneric || p.model != BAMGPU_MDL_LINEAR || !p.hasLatent || p.n < 1 || !p.XuInv) return nullptr;
+    if ((long long)L.nLatent != (long long)p.n * p.nX || p.n != L.n) return nullptr;
+    if (p.hasXbias || p.hasYbias || p.hasMissing || p.hyperInfeasible || p.nCombo != 1) return nullptr;
+    for (int j = 1; j < p.nY; ++j)
+        if (p.sigfunc[j] != p.sigfunc[0]) return nullptr;
+    if (p.nX == 1 && p.nY == 1) return pick_sweep_linear_sig<1, 1>(p.sigfunc[0]);
+    if (p.nX == 2 && p.nY == 1) return pick_sweep_linear_sig<2, 1>(p.sigfunc[0]);
+    if (p.nX == 1 && p.nY == 2) return pick_sweep_linear_sig<1, 2>(p.sigfunc[0]);
+    if (p.nX == 2 && p.nY == 2) return pick_sweep_linear_sig<2, 2>(p.sigfunc[0]);
+    return nullptr;
+}
+
 LatentKernel pick_latent_sweep(int model, int nX, int nY) {
 #define X(M, A, B) \
     if (model == M && nX == A && nY == B) return latent_sweep<M, A, B>;

@@ -155,6 +155,8 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
     // components visited with one launch set per proposal: everything except the latent inputs when the one-launch
     // sweep applies (vector order: theta | gamma | latent inputs | X biases | Y biases, Packer :4202-4242)
     LatentKernel lk = (p.hasLatent && !h->forceGeneric) ? pick_latent_sweep(p.model, p.nX, p.nY) : nullptr;
+    if (lk && !h->noFastSweep)
+        if (LatentKernel fastSweep = pick_latent_sweep_linear(h)) lk = fastSweep;
     const int latBeg = p.nFit + p.nGamma, latEnd = latBeg + p.nLatent;
     // fast path (BaRatin, many chains): per-combination likelihood sums of the current state are kept, so that a
     // proposal on a VAR parameter only re-evaluates the observations of the combinations it touches

@@ -16,10 +16,13 @@ struct WarpSamplerArgs {
     int* moves;
 };
 
+struct bamgpu_handle;
+
 namespace bam {
 using WarpSamplerKernel = void (*)(DevProblem, WarpSamplerArgs);
 WarpSamplerKernel pick_warp_sampler(int model, int nX, int nY);  // bam_sampler_warp.cu
 using LatentKernel = void (*)(DevProblem, int, unsigned long long, long long, unsigned, double*, const double*, int*,
                               const double*);
 LatentKernel pick_latent_sweep(int model, int nX, int nY);       // bam_latent.cu
+LatentKernel pick_latent_sweep_linear(const bamgpu_handle* h);   // bam_latent.cu: cfg-3 fast path or nullptr
 }  // namespace bam

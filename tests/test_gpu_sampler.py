@@ -163,6 +163,34 @@ def test_latent_sweep_equals_full_posterior_oaat():
     assert g.launch_count() < g2.launch_count() / 5
 
 
+def test_latent_fast_paths_follow_the_oracle():
+    """cfg 3 shape (Linear 2x2, EVERY input cell latent, no biases): the specialised log-posterior kernel
+    (logpost_linear_latent) and the specialised sweep (latent_sweep_linear, table-driven Box-Muller and log u) give the
+    oracle's chains, and the generic sweep's."""
+    prob, truth = synth.linear_latent(nobs=300)
+    K = 6
+    s = np.tile(truth, (K, 1))
+    sd = np.tile(np.concatenate([0.01 * np.abs(truth[:8]), np.full(600, 0.1)]), (K, 1))
+    g, o = BamGpu(prob), Oracle(prob)
+    rows = g.fit(s, sd, nAdapt=5, nCycles=3, seed=23)
+    orow, _, _ = o.fit(s, sd, nAdapt=5, nCycles=3, seed=23)
+    P = truth.size
+    assert np.allclose(rows[:, :, :P], orow[:, :, :P], rtol=1e-10, atol=1e-12)
+    assert np.allclose(rows[:, :, P], orow[:, :, P], rtol=1e-10)
+    assert (rows[:, -1, 8:P] != s[:, 8:]).mean() > 0.5
+    g2 = BamGpu(prob)
+    g2.set_option("no_fast_sweep", 1)
+    rows2 = g2.fit(s, sd, nAdapt=5, nCycles=3, seed=23)
+    assert np.allclose(rows, rows2, rtol=1e-10, atol=1e-12)
+    # log-posterior of perturbed vectors: fast kernel against the oracle, flags included (a negative gamma1)
+    rng = np.random.default_rng(2)
+    x = s + 0.02 * rng.standard_normal(s.shape)
+    x[2, 4] = -5.0  # gamma1 of output 1 outside its Uniform(0,100) prior -> null
+    x[3, 5] = -50.0  # gamma2 so negative that sigma <= 0 on every row -> infeasible likelihood
+    from tests.test_gpu_logpost import check_parity
+    check_parity(prob, x)
+
+
 def test_latent_sweep_textfile_and_moments():
     prob, truth = synth.textfile_latent(nobs=300)
     K = 8
