@@ -181,8 +181,11 @@ __device__ __forceinline__ bool linear_T(const double* xt, const double* xo, con
     return ok && t == t;
 }
 
+#ifndef LS_MINB
+#define LS_MINB 4
+#endif
 template <int NX, int NY, int SIGF>
-__global__ void __launch_bounds__(BAM_BLOCK) latent_sweep_linear(DevProblem p, int K, unsigned long long seed,
+__global__ void __launch_bounds__(BAM_BLOCK, LS_MINB) latent_sweep_linear(DevProblem p, int K, unsigned long long seed,
                                                                  long long chainOffset, unsigned it, double* __restrict__ x,
                                                                  const double* __restrict__ sd, int* __restrict__ moves,
                                                                  const double* __restrict__ tab) {
