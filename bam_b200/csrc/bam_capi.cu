@@ -299,6 +299,7 @@ int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s) {
 int bamgpu_set_option(bamgpu_t* h, const char* name, int value) {
     if (!strcmp(name, "force_generic")) { h->forceGeneric = value != 0; return 0; }
     if (!strcmp(name, "no_select3")) { h->noSelect3 = value != 0; return 0; }
+    if (!strcmp(name, "only_radix")) { h->onlyRadix = value != 0; return 0; }
     if (!strcmp(name, "no_partial")) { h->noPartial = value != 0; return 0; }
     if (!strcmp(name, "no_fast_sweep")) { h->noFastSweep = value != 0; return 0; }
     return 1;

@@ -45,6 +45,7 @@ struct bamgpu_handle {
     bool lkCvalid = false;
     long long chainOffset = 0;
     bool noPartial = false;     // tests / measurement: always re-evaluate every observation in the sampler
+    bool onlyRadix = false;     // tests: every large column through envelope_radix
     bool noSelect3 = false;     // tests: skip the 2-read envelope selection
     bool forceGeneric = false;  // tests: disable the specialised fast kernels  // global index of local chain 0 (multi-GPU sharding; RNG streams)
     bool noFastSweep = false;   // option "no_fast_sweep": keep the generic latent sweep (tests compare the two)

@@ -14,7 +14,7 @@
 //   envelope_*  per prediction input: drop infeasible / NaN values when they are < 75 %, exact
 //               empirical quantiles (0.5, 0.025, 0.975, 0.16, 0.84), mean, standard deviation.
 //               Small Nrep: the column is sorted in shared memory (bitonic).  Large Nrep: exact
-//               selection by multi-level linear histograms over the HBM tile (no full sort).
+//               selection by histograms over the HBM tile (2-read, 4-read, then MSB-first radix; no full sort).
 #include <algorithm>
 #include <cfloat>
 
@@ -495,207 +495,180 @@ __global__ void __launch_bounds__(BAM_BLOCK) envelope_smem(long long Nrep, int n
     }
 }
 
-// ---- large Nrep: exact selection with two levels of linear histograms + a final gather ------------
-//
-// Level 0: min / max / count of good values.  Level 1: NB equal-width bins on [min,max]; for each of
-// the 10 order statistics needed (two neighbours per quantile) find its bin and the rank inside it.
-// Level 2: the same inside each selected bin.  Final: gather the (few) values that fall in the selected
-// level-2 bins, sort them in shared memory, pick the order statistics.  bin(v) is a monotone function of
-// v, so the selection is exact; ties and degenerate ranges are handled by the width==0 shortcut.
-#define SEL_NB 1024
+// ---- large Nrep: exact selection kernels ------------------------------------------------------------------------
 #define SEL_NT 10
-#define SEL_GATHER 2048
 
-struct SelState {
-    double lo[SEL_NT], hi[SEL_NT];   // current value interval of each target
-    long long rank[SEL_NT];          // 0-based rank of the target inside the interval
-    long long below[SEL_NT];
-};
-
-__device__ __forceinline__ int lin_bin(double v, double lo, double scale) {
-    int b = (int)((v - lo) * scale);
-    return b < 0 ? 0 : (b >= SEL_NB ? SEL_NB - 1 : b);
+// ---- large Nrep, last resort: MSB-first radix selection of all 10 order statistics at once --------------------------
+//
+// For the columns the histogram kernels give up on (heavy ties next to other values: a growth index that is exactly
+// zero for most replications, a discharge that is zero below the activation stage for a part of the sample).  The
+// order-preserving 64-bit key of a double is resolved 11 bits at a time (11,11,11,11,11,9): per pass one histogram per
+// DISTINCT prefix among the 10 targets, then every target walks into its digit.  Exact whatever the data look like,
+// 6 reads of the column + 1 for the sum of squares (the multi-level linear histograms it replaces needed >= 2 passes
+// per target and level: 22+ reads on such columns).
+#define RX_THREADS 512
+#define RX_NB 2048
+__device__ __forceinline__ unsigned long long rx_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);  // -0.0 -> +0.0
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double rx_val(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
 }
 
-__global__ void __launch_bounds__(BAM_BLOCK) envelope_select(long long Nrep, int nT, double unfeas,
+__global__ void __launch_bounds__(RX_THREADS) envelope_radix(long long Nrep, int nT, double unfeas,
                                                              const double* __restrict__ V, double* __restrict__ env,
                                                              const int* __restrict__ only) {
-    if (only != nullptr && only[blockIdx.x] == 0) return;  // second chance for the columns envelope_select2 gave up
-    __shared__ unsigned hist[SEL_NB];
+    if (only != nullptr && only[blockIdx.x] == 0) return;
+    extern __shared__ unsigned rxh[];  // [SEL_NT][RX_NB]
     __shared__ double scratch[32];
-    __shared__ double gath[SEL_GATHER];
-    __shared__ SelState st;
-    __shared__ double sMin, sMax;
-    __shared__ long long sBad;
-    __shared__ int sCnt, sOverflow;
-    const int tid = threadIdx.x;
+    __shared__ unsigned long long sPrefix[SEL_NT], sGPrefix[SEL_NT];
+    __shared__ long long sRank[SEL_NT];
+    __shared__ int sGroupOf[SEL_NT], sNG;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int colId = blockIdx.x;
-    const double* col = V + (size_t)colId * Nrep;
+    const double* __restrict__ col = V + (size_t)colId * Nrep;
     const int y = colId / nT, t = colId % nT;
     double* out = env + (size_t)y * BAMGPU_NENV * nT + t;
+    const int width[6] = {11, 11, 11, 11, 11, 9};
+    const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
 
-    // level 0: min, max, #bad, sum
-    double mn = INFINITY, mx = -INFINITY, sum = 0.0;
-    long long nb = 0;
-    for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
-        const double v = col[r];
-        if (v == unfeas || v != v) { ++nb; continue; }
-        mn = fmin(mn, v); mx = fmax(mx, v); sum += v;
+    if (tid == 0) { sNG = 1; sGPrefix[0] = 0ull; }
+    if (tid < SEL_NT) { sPrefix[tid] = 0ull; sGroupOf[tid] = 0; sRank[tid] = 0; }
+    long long m = 0;
+    double mean = 0.0;
+    int shift = 64;
+    for (int pass = 0; pass < 6; ++pass) {
+        const int w = width[pass], nb = 1 << w;
+        shift -= w;
+        __syncthreads();
+        const int nG = sNG;
+        for (int b = tid; b < nG * RX_NB; b += RX_THREADS) rxh[b] = 0u;
+        __syncthreads();
+        double sum = 0.0;
+        long long nbadLoc = 0;
+        for (long long base = 0; base < Nrep; base += 4 * RX_THREADS) {  // block-uniform trip count (warp collectives inside)
+            const long long r0 = base + tid;
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long r = r0 + (long long)q * RX_THREADS;
+                v[q] = (r < Nrep) ? __ldcs(col + r) : unfeas;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long r = r0 + (long long)q * RX_THREADS;
+                const bool inside = r < Nrep;
+                const bool good = inside && !(v[q] == unfeas || v[q] != v[q]);
+                if (pass == 0 && inside && !good) ++nbadLoc;
+                const unsigned long long key = rx_key(v[q]);
+                const unsigned digit = (unsigned)(key >> shift) & (unsigned)(nb - 1);
+                if (pass == 0) {
+                    if (good) sum += v[q];
+                    // tie-heavy columns: a whole warp usually hits one bin
+                    const unsigned act = __ballot_sync(0xffffffffu, good);
+                    if (act) {
+                        const int lead = __ffs(act) - 1;
+                        const unsigned d0 = __shfl_sync(0xffffffffu, digit, lead);
+                        const bool same = __all_sync(0xffffffffu, !good || digit == d0);
+                        if (same) { if (lane == lead) atomicAdd(&rxh[d0], (unsigned)__popc(act)); }
+                        else if (good) atomicAdd(&rxh[digit], 1u);
+                    }
+                } else if (good) {
+                    const unsigned long long hi = key >> (shift + w);
+                    for (int g = 0; g < nG; ++g)
+                        if (hi == sGPrefix[g]) atomicAdd(&rxh[g * RX_NB + digit], 1u);
+                }
+            }
+        }
+        if (pass == 0) {
+            const double nbd = block_sum((double)nbadLoc, scratch);
+            const long long nbad = (long long)nbd;
+            const bool drop = (double)nbad / (double)Nrep < 0.75;
+            if ((!drop && nbad > 0) || nbad == Nrep) {
+                if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
+                return;
+            }
+            m = Nrep - nbad;
+            mean = block_sum(sum, scratch) / (double)m;
+            if (tid == 0)
+                for (int q = 0; q < 5; ++q) {  // the 10 target ranks (0-based): i-1 and i of each Hazen quantile
+                    const double hh = pr[q] * (double)m + 0.5;
+                    long long i0, i1;
+                    if (hh <= 1.0) i0 = i1 = 0;
+                    else if (hh >= (double)m) i0 = i1 = m - 1;
+                    else { const long long i = (long long)floor(hh); i0 = i - 1; i1 = i; }
+                    sRank[2 * q] = i0; sRank[2 * q + 1] = i1;
+                }
+        }
+        __syncthreads();
+        // every target walks into its digit: warp k serves target k
+        if (warp < SEL_NT) {
+            const unsigned* hg = rxh + sGroupOf[warp] * RX_NB;
+            const int per = nb / 32;
+            long long rank = sRank[warp];
+            long long mine = 0;
+            for (int b = 0; b < per; ++b) mine += hg[lane * per + b];
+            long long incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const long long o = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += o;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
+            const int L = hit ? (__ffs(hit) - 1) : 31;
+            int digit = 0;
+            long long newRank = 0;
+            if (lane == L) {
+                long long acc = incl - mine;
+                int b = 0;
+                for (; b < per - 1; ++b) {
+                    const long long c = hg[lane * per + b];
+                    if (acc + c > rank) break;
+                    acc += c;
+                }
+                digit = lane * per + b;
+                newRank = rank - acc;
+            }
+            digit = __shfl_sync(0xffffffffu, digit, L);
+            newRank = __shfl_sync(0xffffffffu, newRank, L);
+            if (lane == 0) {
+                sPrefix[warp] = (sPrefix[warp] << w) | (unsigned long long)digit;
+                sRank[warp] = newRank;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {  // distinct prefixes -> groups of the next pass
+            int ng = 0;
+            for (int k = 0; k < SEL_NT; ++k) {
+                int g = -1;
+                for (int q = 0; q < ng && g < 0; ++q)
+                    if (sGPrefix[q] == sPrefix[k]) g = q;
+                if (g < 0) { g = ng; sGPrefix[ng++] = sPrefix[k]; }
+                sGroupOf[k] = g;
+            }
+            sNG = ng;
+        }
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        nb += __shfl_xor_sync(0xffffffffu, nb, off);
-    }
-    if ((tid & 31) == 0) { scratch[tid >> 5] = mn; }
     __syncthreads();
-    if (tid == 0) { double v = INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmin(v, scratch[i]); sMin = v; }
-    __syncthreads();
-    if ((tid & 31) == 0) { scratch[tid >> 5] = mx; }
-    __syncthreads();
-    if (tid == 0) { double v = -INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmax(v, scratch[i]); sMax = v; }
-    __syncthreads();
-    if ((tid & 31) == 0) { scratch[tid >> 5] = (double)nb; }
-    __syncthreads();
-    if (tid == 0) { double v = 0; for (int i = 0; i < BAM_BLOCK / 32; ++i) v += scratch[i]; sBad = (long long)v; }
-    __syncthreads();
-    const long long nbad = sBad;
-    const bool drop = (double)nbad / (double)Nrep < 0.75;
-    if ((!drop && nbad > 0) || nbad == Nrep) {
-        if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
-        return;
-    }
-    const long long m = Nrep - nbad;
-    const double mean = block_sum(sum, scratch) / (double)m;
     double part = 0.0;
-    for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
-        const double v = col[r];
+    for (long long r = tid; r < Nrep; r += RX_THREADS) {
+        const double v = __ldcs(col + r);
         if (v == unfeas || v != v) continue;
         const double d = v - mean;
         part += d * d;
     }
     const double ss = block_sum(part, scratch);
-
-    // the 10 target ranks (0-based): i-1 and i of each Hazen quantile
-    const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
     if (tid == 0) {
         for (int q = 0; q < 5; ++q) {
-            const double hh = pr[q] * (double)m + 0.5;
-            long long i0, i1;
-            if (hh <= 1.0) i0 = i1 = 0;
-            else if (hh >= (double)m) i0 = i1 = m - 1;
-            else { const long long i = (long long)floor(hh); i0 = i - 1; i1 = i; }
-            st.rank[2 * q] = i0; st.rank[2 * q + 1] = i1;
-            for (int k = 0; k < 2; ++k) { st.lo[2 * q + k] = sMin; st.hi[2 * q + k] = sMax; }
-        }
-    }
-    __syncthreads();
-    double result[SEL_NT];
-    for (int k = 0; k < SEL_NT; ++k) {
-        // targets are processed one at a time; an interval shared with the previous target is re-used
-        double lo = st.lo[k], hi = st.hi[k];
-        long long rank = st.rank[k];
-        double val = lo;
-        for (int level = 0; level < 64; ++level) {
-            if (!(hi > lo)) { val = lo; break; }
-            const double scale = (double)SEL_NB / (hi - lo);
-            for (int b = tid; b < SEL_NB; b += BAM_BLOCK) hist[b] = 0;
-            if (tid == 0) { sCnt = 0; sOverflow = 0; }
-            __syncthreads();
-            // count values inside [lo,hi] per bin
-            for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
-                const double v = col[r];
-                if (v == unfeas || v != v) continue;
-                if (v < lo || v > hi) continue;
-                atomicAdd(&hist[lin_bin(v, lo, scale)], 1u);
-            }
-            __syncthreads();
-            // locate the bin of `rank` (serial scan by thread 0: 1024 steps)
-            __shared__ int sBin;
-            __shared__ long long sBefore, sInBin;
-            if (tid == 0) {
-                long long acc = 0;
-                int b = 0;
-                for (; b < SEL_NB; ++b) {
-                    if (acc + hist[b] > rank) break;
-                    acc += hist[b];
-                }
-                if (b >= SEL_NB) b = SEL_NB - 1;
-                sBin = b; sBefore = acc; sInBin = hist[b];
-            }
-            __syncthreads();
-            const int bsel = sBin;
-            const long long inBin = sInBin;
-            rank -= sBefore;
-            if (inBin <= SEL_GATHER) {
-                // gather the bin, sort, pick
-                for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
-                    const double v = col[r];
-                    if (v == unfeas || v != v) continue;
-                    if (v < lo || v > hi) continue;
-                    if (lin_bin(v, lo, scale) == bsel) {
-                        const int pos = atomicAdd(&sCnt, 1);
-                        if (pos < SEL_GATHER) gath[pos] = v;
-                    }
-                }
-                __syncthreads();
-                const int cnt = min(sCnt, SEL_GATHER);
-                int npad = 1;
-                while (npad < cnt) npad <<= 1;
-                for (int i = cnt + tid; i < npad; i += BAM_BLOCK) gath[i] = INFINITY;
-                __syncthreads();
-                for (int kk = 2; kk <= npad; kk <<= 1)
-                    for (int j = kk >> 1; j > 0; j >>= 1) {
-                        for (int i = tid; i < npad; i += BAM_BLOCK) {
-                            const int ixj = i ^ j;
-                            if (ixj > i) {
-                                const double a = gath[i], b = gath[ixj];
-                                const bool up = ((i & kk) == 0);
-                                if ((a > b) == up) { gath[i] = b; gath[ixj] = a; }
-                            }
-                        }
-                        __syncthreads();
-                    }
-                val = gath[rank < cnt ? rank : cnt - 1];
-                __syncthreads();
-                break;
-            }
-            // refine: new interval = value range of the selected bin (computed exactly from the data)
-            double bmn = INFINITY, bmx = -INFINITY;
-            for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
-                const double v = col[r];
-                if (v == unfeas || v != v) continue;
-                if (v < lo || v > hi) continue;
-                if (lin_bin(v, lo, scale) == bsel) { bmn = fmin(bmn, v); bmx = fmax(bmx, v); }
-            }
-            for (int off = 16; off > 0; off >>= 1) {
-                bmn = fmin(bmn, __shfl_xor_sync(0xffffffffu, bmn, off));
-                bmx = fmax(bmx, __shfl_xor_sync(0xffffffffu, bmx, off));
-            }
-            __syncthreads();
-            if ((tid & 31) == 0) scratch[tid >> 5] = bmn;
-            __syncthreads();
-            if (tid == 0) { double v = INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmin(v, scratch[i]); sMin = v; }
-            __syncthreads();
-            if ((tid & 31) == 0) scratch[tid >> 5] = bmx;
-            __syncthreads();
-            if (tid == 0) { double v = -INFINITY; for (int i = 0; i < BAM_BLOCK / 32; ++i) v = fmax(v, scratch[i]); sMax = v; }
-            __syncthreads();
-            lo = sMin; hi = sMax;
-            val = lo;
-            __syncthreads();
-        }
-        result[k] = val;
-    }
-    if (tid == 0) {
-        for (int q = 0; q < 5; ++q) {
+            const double a = rx_val(sPrefix[2 * q]), b = rx_val(sPrefix[2 * q + 1]);
             const double hh = pr[q] * (double)m + 0.5;
             double qv;
-            if (hh <= 1.0 || hh >= (double)m) qv = result[2 * q];
+            if (hh <= 1.0 || hh >= (double)m) qv = a;
             else {
                 const long long i = (long long)floor(hh);
                 const double frac = hh - (double)i;
-                qv = result[2 * q] + frac * (result[2 * q + 1] - result[2 * q]);
+                qv = a + frac * (b - a);
             }
             out[(size_t)q * nT] = qv;
         }
@@ -711,7 +684,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) envelope_select(long long Nrep, int
 // pass C  1024-bin sub-histogram inside every selected bin (<= 10)  (1 read)   -> sub-bin and residual rank
 // pass D  gather the members of the selected sub-bins (<= 256 each), sort, pick (1 read)
 // A target whose sub-bin still holds more than 256 values (heavy ties / pathological clustering) is resolved by
-// the multi-level routine of envelope_select on its own (rare).  bin functions are monotone in v => exact.
+// envelope_radix on its own (rare).  bin functions are monotone in v => exact.
 #define S2_NB1 2048
 #define S2_NB2 1024
 #define S2_CAP 256
@@ -1317,6 +1290,8 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     if (smallN && smemEnv > 48 * 1024)
         BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEnv));
 
+    const size_t smemRadix = sizeof(unsigned) * SEL_NT * RX_NB;
+    BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRadix));
     const size_t smemSel2 = sizeof(unsigned) * SEL_NT * S2_NB2 + sizeof(double) * SEL_NT * S2_CAP;
     // the 2-read selection resolves bins of <= CAP members: worth trying while the densest of its 16384 bins stays below
     // that (a Gaussian column peaks at ~1.1e-4 Nrep per bin); two instantiations, see envelope_select3
@@ -1377,7 +1352,9 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             double* envTile = nullptr;
             BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nOut, s));
             if (smallN) envelope_smem<<<nT * nOut, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
-            else {
+            else if (h->onlyRadix) {  // tests: every column through the last-resort kernel
+                envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, nullptr);
+            } else {
                 int *need3 = nullptr, *needSlow = nullptr;
                 BAM_CUDA(cudaMallocAsync(&needSlow, sizeof(int) * (size_t)nT * nOut, s));
                 if (trySel3) {
@@ -1387,7 +1364,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                     h->launches += 1;
                 }
                 envelope_select2<<<nT * nOut, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow, need3);
-                envelope_select<<<nT * nOut, BAM_BLOCK, 0, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
+                envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
                 BAM_CUDA(cudaFreeAsync(needSlow, s));
                 if (need3) BAM_CUDA(cudaFreeAsync(need3, s));
                 h->launches += 1;

@@ -234,6 +234,12 @@ def test_two_read_selection_ties_zeros_and_fallbacks():
         q, q4 = env[0, :5], env4[0, :5]
         assert (q == q4).all()  # order statistics are exact on both paths
         assert np.allclose(env[0, 5:], env4[0, 5:], rtol=1e-12, atol=1e-300)
+        # ... and from the last-resort MSB-first radix selection alone (exact order statistics whatever the data)
+        gr = BamGpu(prob)
+        gr.set_option("only_radix", 1)
+        envr, _ = gr.predict(mc, mode, [Hs], 1, dor, seed=13)
+        assert (envr[0, :5] == q).all()
+        assert np.allclose(envr[0, 5:], env[0, 5:], rtol=1e-12, atol=1e-300)
     # clustered values with a few far outliers (the subsample's range does not cover the column)
     mc2 = np.tile(mode, (50000, 1))
     mc2[:, 1] *= 1.0 + 1e-9 * np.arange(50000)
@@ -241,6 +247,26 @@ def test_two_read_selection_ties_zeros_and_fallbacks():
     env, _ = g.predict(mc2, mode, [Hs], 1, [0])
     oenv, _ = o.predict(mc2, mode, [Hs], 1, [0], nthreads=8)
     cmp_env(env, oenv)
+    gr = BamGpu(prob)
+    gr.set_option("only_radix", 1)
+    envr, _ = gr.predict(mc2, mode, [Hs], 1, [0])
+    cmp_env(envr, oenv)
+    # negative values, mixed signs and -0.0 / +0.0 through the order-preserving key: Linear model y = x * theta
+    from bam_b200.capi import Problem
+    rng = np.random.default_rng(8)
+    pl = Problem("Linear", np.ones((5, 1)), np.zeros(5), partype=[0], priors_theta=[("FlatPrior", [])],
+                 sigma_func=["Constant"], priors_gamma=[("FlatPrior+", [])])
+    th = rng.standard_normal(40000) * np.where(rng.random(40000) < 0.3, 0.0, 1.0)  # 30 % exact zeros, both signs elsewhere
+    th[::7] = -0.0
+    mcl = np.column_stack([th, np.ones(40000)])
+    xs = [np.array([1.0, -1.0, 1e-30, -1e3, 0.0])]
+    gl, ol = BamGpu(pl), Oracle(pl)
+    gl.set_option("only_radix", 1)
+    envl, _ = gl.predict(mcl, np.array([0.5, 1.0]), xs, 1, [0])
+    oenvl, _ = ol.predict(mcl, np.array([0.5, 1.0]), xs, 1, [0], nthreads=8)
+    cmp_env(envl[:, :5], oenvl[:, :5])  # order statistics
+    sd = oenvl[0, 6]
+    assert np.allclose(envl[0, 6], sd, rtol=1e-12) and (np.abs(envl[0, 5] - oenvl[0, 5]) <= 1e-12 * sd + 1e-300).all()  # zero-mean columns
 
 
 @pytest.mark.parametrize("formula,css", [("Camenen", "Soulsby"), ("MPM", "SoulsbyWhitehouse"), ("Nielsen", "Soulsby"),
