@@ -502,7 +502,7 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
                 }
             }
             L.nDparModel = temporal ? 1 : L.vegNYear + 1;
-            L.nDer = temporal ? 3 : 1 + 6 * L.vegNYear;
+            L.nDer = temporal ? 4 : 2 + 6 * L.vegNYear;  // last slot: (B U_chi)^chi, the parameter-only factor of gamma2
             break;
         }
     }

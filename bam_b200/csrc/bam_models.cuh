@@ -363,6 +363,7 @@ __device__ inline bool vegetation_prepare(const DevProblem& p, const double* th,
     bool badg = false;
     for (int i = 0; i < nGmax; ++i) badg |= gmax[i] < 0.0;
     if (B <= 0.0 || S0 <= 0.0 || n1 <= 0.0 || c1 <= 0.0 || chi < -2.0 || chi > 0.0 || U_chi <= 0.0 || badg) return false;
+    der[temporal ? 3 : 1 + 6 * p.vegNYear] = pow(B, chi) * pow(U_chi, chi);  // gamma2 = B^chi y^chi U_chi^chi (:216-218)
     if (temporal) {  // :395-419
         const double t0 = par[0], ti = par[1], tmax = par[2];
         if (t0 <= 0.0 || ti <= 0.0 || tmax <= 0.0 || t0 >= 1.0 || ti >= 1.0 || tmax >= 1.0 || t0 >= ti || ti >= tmax) return false;
@@ -428,13 +429,17 @@ __device__ inline bool vegetation_prepare(const DevProblem& p, const double* th,
     return true;
 }
 
-// Vegetation_fNewton (:536-569)
+// Vegetation_fNewton (:536-569).  x^chi once per evaluation, as exp(chi log x) (x^(1+chi) = x x^chi): the reference's two
+// pow() calls per evaluation dominate the per-observation cost; x = 0 (only the bracket's lower end) keeps pow()'s
+// limits x^chi = +inf (chi < 0) or 1 (chi = 0) and x^(1+chi) through pow() itself.
 __device__ __forceinline__ void veg_fnewton(double x, double Q0, double gam, double gam2, double chi, double& f, double& df) {
-    double m = pow(x, chi) / gam2;
+    const bool pos = x > 0.0;
+    const double px = pos ? exp(chi * log(x)) : pow(x, chi);
+    double m = px / gam2;
     if (1.0 < m) m = 1.0;
     f = x * x + (gam * (x * x) * m) - Q0 * Q0;
     if (m == 1.0) df = 2.0 * x * (1.0 + gam);
-    else df = 2.0 * x + (gam / gam2 * (2.0 + chi) * pow(x, 1.0 + chi));
+    else df = 2.0 * x + (gam / gam2 * (2.0 + chi) * (pos ? x * px : pow(x, 1.0 + chi)));
 }
 
 // znewton on [0, Q0]: declared convention (miniDMSL is un-vendored), identical to oracle/bam_oracle.c:veg_znewton
@@ -486,8 +491,9 @@ __device__ inline bool vegetation_apply(const DevProblem& p, const double* in, c
         const double tt = time - floor(time);
         if (tt >= t0 && tt <= tf) g0 = (pow((tt - t0) / (tmax - t0), alf)) * (tf - tt) / (tf - tmax);
         else g0 = 0.0;
-        cosg = cos(g0 * BAM_VEG_PI);
-        sing = (tt <= tmax) ? sin(g0 * BAM_VEG_PI) : -1.0 * sin(g0 * BAM_VEG_PI);
+        double sn;
+        sincos(g0 * BAM_VEG_PI, &sn, &cosg);
+        sing = (tt <= tmax) ? sn : -1.0 * sn;
         g = th[10] * g0;
     } else {
         const int nYear = p.vegNYear;
@@ -499,8 +505,9 @@ __device__ inline bool vegetation_apply(const DevProblem& p, const double* in, c
             if (yr[4] != 0.0 || time <= time_b || time >= time_f) g0 = 0.0;
             else g0 = pow((time - time_b) / (time_e - time_b), alpha) * (time_f - time) / (time_f - time_e);
             g = g0 * th[11 + i];
-            cosg = cos(g0 * BAM_VEG_PI);
-            sing = (time <= time_e) ? sin(g0 * BAM_VEG_PI) : -1.0 * sin(g0 * BAM_VEG_PI);
+            double sn;
+            sincos(g0 * BAM_VEG_PI, &sn, &cosg);
+            sing = (time <= time_e) ? sn : -1.0 * sn;
         } else g = g0 = cosg = sing = BAMGPU_UNDEF_RN;  // a point outside every year keeps the initial undefRN (:380)
     }
     if (NY > 1) out[1] = g;
@@ -509,11 +516,12 @@ __device__ inline bool vegetation_apply(const DevProblem& p, const double* in, c
     if (NY > 4) out[4] = g0;
     const double y = h - th[3];
     if (y <= 0.0) { out[0] = 0.0; return true; }
-    const double Q0 = der[0] * pow(y, th[4]);
+    const double ly = log(y);  // y > 0: the three powers of y share one logarithm
+    const double Q0 = der[0] * exp(th[4] * ly);
     if (g <= 0.0) { out[0] = Q0; return true; }
     const double chi = th[5];
-    const double gam = (g * pow(y, 1.0 / 3.0)) / (8.0 * BAM_VEG_GRAVITY * (th[2] * th[2]));
-    const double gam2 = pow(th[0], chi) * pow(y, chi) * pow(th[6], chi);
+    const double gam = (g * cbrt(y)) / (8.0 * BAM_VEG_GRAVITY * (th[2] * th[2]));
+    const double gam2 = der[(p.vegGrowth == BAMGPU_VEG_YIN1_TEMPORAL) ? 3 : 1 + 6 * p.vegNYear] * exp(chi * ly);
     double q;
     if (!veg_root(p, Q0, gam, gam2, chi, q)) return false;
     out[0] = q;

@@ -319,6 +319,40 @@ def sediment_prediction_leg(device, hbm_peak, Nrep=10_000_000, steps=2):
             "finite": bool(np.isfinite(g.predict_download()).all())}
 
 
+def vegetation_prediction_leg(device, Nrep=2_000_000, nobs=1095, steps=1):
+    """configs[3], second law: Vegetation (Growth_Yin3, 3 years of daily inputs, 5 outputs: Q, g, cos, sin, g0), posterior
+    sample propagated through the per-observation Newton solve, remnant noise on Q, exact envelopes of all outputs.
+    Generic kernels (pred_main, libdevice pow); the tie-heavy growth-index columns (exactly zero off season) exercise the
+    4-read and the radix selection.  Bounded sample of the 10^7-sample experiment (host RAM of the bench process)."""
+    from bam_b200 import synth
+    from bam_b200.capi import BamGpu
+
+    prob, truth = synth.vegetation(nobs=nobs, growth="Growth_Yin3", nY=5)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.002 * rng.standard_normal((Nrep, truth.size)))
+    X = [np.asarray(prob.X)[:, j].copy() for j in range(prob.nX)]
+    g = BamGpu(prob, device)
+    g.predict_upload(mc, truth, X)
+    dor = [1, 0, 0, 0, 0]
+    g.predict_resident(1, dor, seed=1)
+    g.sync()
+    g.step_times(); g.kernel_times()
+    for _ in range(steps):
+        g.step_begin()
+        g.predict_resident(1, dor, seed=1)
+        g.step_end()
+    g.sync()
+    ms, km = g.step_times(), g.kernel_times()
+    pairs = Nrep * nobs
+    return {"metric": "prediction samples x inputs/sec", "value": pairs / (ms.mean() * 1e-3), "unit": "sample*input/s",
+            "ms_per_step": float(ms.mean()),
+            "workload": f"Vegetation Growth_Yin3, {Nrep} samples x {nobs} inputs x 5 outputs, parametric + remnant noise on Q, "
+                        f"exact envelopes ({8 * 5 * pairs / 1e9:.0f} GB of spaghetti materialised in tiles; configs[3], bounded sample)",
+            "kernels": {"propagation": {"kernel": "pred_main<Vegetation,4,5>", "ms": float(km[0::2].sum()) / steps},
+                        "envelopes": {"kernel": "envelope_select3 / envelope_select2 / envelope_radix", "ms": float(km[1::2].sum()) / steps}},
+            "finite": bool(np.isfinite(g.predict_download()).all())}
+
+
 def small_sampler_leg(device):
     """configs[0]: the reference's own tests/BaM_BaRatin workspace (38 gaugings, P = 8), adaptive Metropolis with the
     persistent warp-per-chain kernel; K = 1 is like-for-like with the reference's single chain."""
@@ -679,6 +713,10 @@ def main():
             line["prediction_sediment"] = sediment_prediction_leg(device, hbm_peak)
         except Exception as e:
             line["prediction_sediment"] = {"error": str(e)}
+        try:
+            line["prediction_vegetation"] = vegetation_prediction_leg(device)
+        except Exception as e:
+            line["prediction_vegetation"] = {"error": str(e)}
         try:
             line["sampler_cfg2"] = cfg2_sampler_leg(g, x, K, n)
         except Exception as e:
