@@ -213,3 +213,25 @@ __device__ __forceinline__ void normal_quad_fast(uint64_t seed, uint64_t rep, ui
     box_muller_fast(c0, c1, lt, z[0], z[1]);
     box_muller_fast(c2, c3, lt, z[2], z[3]);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The sampler's draws (philox_normal / philox_uniform of bam_device.cuh: 53-bit uniforms, z = sqrt(-2 ln u1) cos(2 pi u2),
+// accept iff ln u < delta) with the table-driven functions.  Values agree with the libdevice formulation to ~1e-15.
+// ---------------------------------------------------------------------------------------------------------------
+// log(u), u in (0,1): the table log has ABSOLUTE error ~1e-16, so libdevice takes over within 2^-10 of 1
+__device__ __forceinline__ double tlog_unit(double u, unsigned lt) {
+    return ((unsigned)__double2hiint(u) >= 0x3fefff80u) ? log(u) : tlog_pos(u, lt);
+}
+__device__ __forceinline__ double philox_normal_fast(uint64_t seed, uint64_t a, uint32_t b, uint32_t c, unsigned lt) {
+    uint32_t c0 = (uint32_t)a, c1 = (uint32_t)(a >> 32), c2 = b, c3 = c;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = u53(c0, c1), u2 = u53(c2, c3);
+    double sn, cs;
+    tsincospi(2.0 * u2, sn, cs);
+    return tsqrt_pos(-2.0 * tlog_unit(u1, lt)) * cs;
+}
+__device__ __forceinline__ double philox_log_uniform_fast(uint64_t seed, uint64_t a, uint32_t b, uint32_t c, unsigned lt) {
+    uint32_t c0 = (uint32_t)a, c1 = (uint32_t)(a >> 32), c2 = b, c3 = c;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return tlog_unit(u53(c0, c1), lt);
+}

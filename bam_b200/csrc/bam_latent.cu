@@ -136,10 +136,6 @@ __global__ void __launch_bounds__(BAM_BLOCK) latent_sweep(DevProblem p, int K, u
 //   * table-driven log / sqrt / cos for the Box-Muller normal and the log of the acceptance uniform (libdevice where
 //     the table log loses relative accuracy, u within 2^-10 of 1).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double log_unit_fast(double u, unsigned lt) {  // log(u), u in (0, 1)
-    return ((unsigned)__double2hiint(u) >= 0x3fefff80u) ? log(u) : tlog_pos(u, lt);
-}
-
 template <int NX, int NY, int SIGF>
 __device__ __forceinline__ bool linear_T(const double* xt, const double* xo, const double* hr, const double* yo,
                                          const double* yu2, const double* __restrict__ th, const double* __restrict__ gm,
@@ -230,21 +226,13 @@ __global__ void __launch_bounds__(BAM_BLOCK, LS_MINB) latent_sweep_linear(DevPro
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
         const unsigned comp = compBase + (unsigned)j * (unsigned)n + (unsigned)i;
-        // philox_normal(seed, gc, it, 2 comp): sqrt(-2 log u1) cos(2 pi u2) with 53-bit uniforms
-        uint32_t c0 = (uint32_t)gc, c1 = (uint32_t)(gc >> 32), c2 = it, c3 = 2u * comp;
-        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const double u1 = u53(c0, c1), u2 = u53(c2, c3);
-        double sn, cs;
-        tsincospi(2.0 * u2, sn, cs);
-        const double zn = tsqrt_pos(-2.0 * log_unit_fast(u1, lt)) * cs;
+        const double zn = philox_normal_fast(seed, gc, it, 2u * comp, lt);
         const double old = xt[j];
         xt[j] = fma(sdv[j], zn, old);
         double cand;
         bool acc = false;
         if (linear_T<NX, NY, SIGF>(xt, xo, hr, yo, yu2, th, gm, lt, cand)) {
-            uint32_t d0 = (uint32_t)gc, d1 = (uint32_t)(gc >> 32), d2 = it, d3 = 2u * comp + 1u;
-            philox4x32_10(d0, d1, d2, d3, (uint32_t)seed, (uint32_t)(seed >> 32));
-            acc = log_unit_fast(u53(d0, d1), lt) < -0.5 * (cand - cur);
+            acc = philox_log_uniform_fast(seed, gc, it, 2u * comp + 1u, lt) < -0.5 * (cand - cur);
         }
         if (acc) {
             cur = cand;

@@ -5,6 +5,7 @@
 
 #define WS_WARPS 4       /* chains per block */
 #define WS_MAXP 64       /* vector length limit of this path (no latent inputs) */
+#define WS_TABLES (2 * BAM_LOGTAB_N + BAM_EXPTAB_N) /* doubles of shared memory in front of the per-warp areas: log / exp tables */
 
 struct WarpSamplerArgs {
     int K, nIterChunk, nAdapt;

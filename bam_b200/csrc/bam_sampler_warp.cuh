@@ -26,9 +26,58 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// BaRatin with the table-driven log / exp of bam_fastmath.cuh (the libdevice pow / log / exp of baratin_prepare and
+// baratin_apply are ~3/4 of a proposal's instructions on the reference's own 38-gauging workspace).  Same operation
+// order and the same exits as ApplyContinuity (:330-396) and BaRatin_computeQ (:194-252); x^c = texp(c tlog(x)) keeps
+// pow()'s limits for x = 0 (0 or +inf by the sign of c).
+__device__ inline bool baratin_prepare_t(const DevProblem& p, const double* th, double* b, unsigned lt, unsigned et) {
+    const int nc = p.ncontrol;
+    if (th[1] <= 0.0 || th[2] == 0.0) return false;
+    b[0] = th[0];
+    for (int j = 1; j < nc; ++j) {
+        const double kj = th[3 * j], aj = th[3 * j + 1], cj = th[3 * j + 2];
+        if (kj <= th[3 * (j - 1)]) return false;
+        for (int i = 0; i < j; ++i)
+            if (kj < b[i]) return false;
+        if (aj <= 0.0 || cj == 0.0) return false;
+        double som = 0.0;
+        for (int i = 0; i < j; ++i) {
+            const int d = (int)((p.ctrlMask >> ((j - 1) * 8 + i)) & 1ull) - (int)((p.ctrlMask >> (j * 8 + i)) & 1ull);
+            som = som + (double)d * th[3 * i + 1] * texp(th[3 * i + 2] * tlog(kj - b[i], lt), et);
+        }
+        if (som < 0.0) return false;
+        b[j] = kj - texp(tlog((1.0 / aj) * som, lt) * (1.0 / cj), et);
+    }
+    for (int i = 0; i < nc; ++i) b[nc + i] = tlog_pos(th[3 * i + 1], lt);
+    return true;
+}
+
+__device__ __forceinline__ bool baratin_apply_t(const DevProblem& p, double H, const double* __restrict__ th,
+                                                const double* __restrict__ b, double& Q, unsigned lt, unsigned et) {
+    const int nc = p.ncontrol;
+    int range = nc;
+    for (int i = 0; i < nc; ++i)
+        if (H < th[3 * i]) { range = i; break; }
+    double q = 0.0;
+    bool ok = true;
+    if (range > 0) {
+        const unsigned row = (unsigned)((p.ctrlMask >> ((range - 1) * 8)) & 0xffull);
+        for (int i = 0; i < range; ++i) {
+            const double d = H - b[i];
+            if ((row >> i) & 1u) {
+                if (d < 0.0) { q = 0.0; break; }
+                q = q + texp(fma(th[3 * i + 2], tlog(d, lt), b[nc + i]), et);
+            } else if (d < 0.0) { ok = false; break; }
+        }
+    }
+    Q = q;
+    return ok;
+}
+
 // log-posterior of the vector xs (shared memory) for one chain, computed by one warp.  Returns status bits.
 template <int MODEL, int NX, int NY>
-__device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, double* vcop, double& fx) {
+__device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, double* vcop, double& fx, unsigned lt,
+                            unsigned et) {
     const int lane = threadIdx.x & 31;
     int st = 0;
     // ---- prior (GetPriorLogPdf :3006-3138): parameters spread over lanes
@@ -83,7 +132,8 @@ __device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, 
             cr[i] = th[i];
         }
         for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
-        if (!model_prepare(p, th, der, xc, p.n)) st |= ST_LKH_INFEAS;
+        const bool okp = (MODEL == BAMGPU_MDL_BARATIN) ? baratin_prepare_t(p, th, der, lt, et) : model_prepare(p, th, der, xc, p.n);
+        if (!okp) st |= ST_LKH_INFEAS;
         for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
     }
     st = __reduce_or_sync(0xffffffffu, st);
@@ -107,7 +157,9 @@ __device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, 
             }
             const int combo = (p.nCombo > 1) ? p.comboOf[i] : 0;
             const double* th = tab + p.tabCombo + (size_t)combo * p.comboStride;
-            if (!model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh)) { bad = true; continue; }
+            const bool oka = (MODEL == BAMGPU_MDL_BARATIN) ? baratin_apply_t(p, xt[0], th, th + p.ntheta, yh[0], lt, et)
+                                                           : model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh);
+            if (!oka) { bad = true; continue; }
 #pragma unroll
             for (int j = 0; j < NY; ++j) {
                 const size_t q = i + (size_t)j * n;
@@ -121,7 +173,7 @@ __device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, 
                     const int bi = p.Ybindx[q];
                     if (bi != 0) mu = yh[j] + p.Yb[q] * tab[p.tabOffYb[j] + bi - 1];
                 }
-                lk += gauss_logpdf_var(yo, mu, fma(yu, yu, sig * sig));
+                lk += gauss_logpdf_var_t(yo, mu, fma(yu, yu, sig * sig), lt);
             }
         }
         if (__any_sync(0xffffffffu, bad)) st |= ST_LKH_INFEAS;
@@ -134,13 +186,19 @@ __device__ int warp_logpost(const DevProblem& p, const double* xs, double* tab, 
 
 template <int MODEL, int NX, int NY>
 __global__ void __launch_bounds__(32 * WS_WARPS) sampler_warp(DevProblem p, WarpSamplerArgs a) {
-    extern __shared__ double wsm[];
+    extern __shared__ __align__(16) double wsm[];  // [log table | exp table | per warp: xs | sd | tab | copula v]
+    double2* sLogT = reinterpret_cast<double2*>(wsm);
+    double* sExpT = wsm + 2 * BAM_LOGTAB_N;
+    for (int q = threadIdx.x; q < BAM_LOGTAB_N; q += 32 * WS_WARPS) sLogT[q] = p.logTab[q];
+    for (int q = threadIdx.x; q < BAM_EXPTAB_N; q += 32 * WS_WARPS) sExpT[q] = p.expTab[q];
+    __syncthreads();
+    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * WS_WARPS + w;
     if (c >= a.K) return;
     const int P = p.P, nD = p.nDpar;
     const int perWarp = 2 * P + p.tabStride + p.kM + 2;  // xs | sd | tab | copula v
-    double* xs = wsm + (size_t)w * perWarp;
+    double* xs = wsm + WS_TABLES + (size_t)w * perWarp;
     double* sd = xs + P;
     double* tab = sd + P;
     double* vcop = tab + p.tabStride;
@@ -154,17 +212,14 @@ __global__ void __launch_bounds__(32 * WS_WARPS) sampler_warp(DevProblem p, Warp
         const long long it = a.it0 + itl;
         for (int i = 0; i < P; ++i) {
             const double old = xs[i];
-            const double delta = sd[i] * philox_normal(a.seed, gc, (unsigned)it, 2u * (unsigned)i);
+            const double delta = sd[i] * philox_normal_fast(a.seed, gc, (unsigned)it, 2u * (unsigned)i, lt);
             __syncwarp();
             if (lane == 0) xs[i] = old + delta;
             __syncwarp();
             double fc;
-            const int st = warp_logpost<MODEL, NX, NY>(p, xs, tab, vcop, fc);
+            const int st = warp_logpost<MODEL, NX, NY>(p, xs, tab, vcop, fc, lt, et);
             bool acc = false;
-            if (st == 0) {
-                const double u = philox_uniform(a.seed, gc, (unsigned)it, 2u * (unsigned)i + 1u);
-                acc = log(u) < fc - fxc;
-            }
+            if (st == 0) acc = philox_log_uniform_fast(a.seed, gc, (unsigned)it, 2u * (unsigned)i + 1u, lt) < fc - fxc;
             if (acc) {
                 fxc = fc;
                 if (lane == (i & 31)) { if (i < 32) ++mv0; else ++mv1; }
