@@ -212,6 +212,13 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
                 lt[2 * i + 1] = (double)(-logl((long double)lt[2 * i]));
             }
             for (int j = 0; j < BAM_EXPTAB_N; ++j) et[j] = (double)exp2l(j / (long double)BAM_EXPTAB_N);
+            std::vector<double> sc(2 * BAM_SCTAB_N);
+            for (int j = 0; j < BAM_SCTAB_N; ++j) {
+                const long double ang = 2.0L * 3.141592653589793238462643383279502884L * (j + 0.5L) / (long double)BAM_SCTAB_N;
+                sc[2 * j] = (double)cosl(ang);
+                sc[2 * j + 1] = (double)sinl(ang);
+            }
+            d.scTab = reinterpret_cast<const double2*>(upload(h, sc.data(), sc.size()));
             d.logTab = reinterpret_cast<const double2*>(upload(h, lt.data(), lt.size()));
             d.expTab = upload(h, et.data(), et.size());
         }

@@ -22,6 +22,7 @@
 #define BAM_VMSTACK 24
 #define BAM_LOGTAB_N 256  /* table-driven log: reciprocal table entries (bam_fastmath.cuh) */
 #define BAM_EXPTAB_N 256  /* table-driven exp: 2^(j/N) entries */
+#define BAM_SCTAB_N 256   /* table-driven sin / cos of 2 pi u: (cos, sin) at the bin centres 2 pi (j + 0.5) / N */
 
 // chain status bits (priority order of the reference's early exits, GetPostLogPdf :3310-3382)
 #define ST_PRIOR_INFEAS 1
@@ -41,6 +42,7 @@ struct DevProblem {
     const int* comboStart;  // nCombo+1 : observations are stored sorted by combination; combo v = [start[v], start[v+1])
     const double2* logTab;  // BAM_LOGTAB_N x (1/c_i, -log(1/c_i)), c_i = 1 + (i+0.5)/N : table-driven log (bam_fastmath.cuh)
     const double* expTab;   // BAM_EXPTAB_N x 2^(j/N)                                    : table-driven exp
+    const double2* scTab;   // BAM_SCTAB_N x (cos, sin)(2 pi (j + 0.5) / N)              : Box-Muller angle of the noise
     const int* comboSrc;  // nCombo x ntheta : position in the parameter vector, or -1 for FIX
     const int* latIdx;    // n x nX : position of the latent "true input" in the vector, or -1
     const double* XuInv;  // n x nX : 1 / Xu          } only when EVERY input cell is latent (logpost_linear_latent),

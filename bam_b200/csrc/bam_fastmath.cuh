@@ -185,33 +185,56 @@ __device__ __forceinline__ void tsincospi(double a, double& s, double& c) {
     c = __hiloint2double((int)((unsigned)__double2hiint(c0) ^ (cneg << 30)), __double2loint(c0));
 }
 
-// the Box-Muller pair (z_even, z_odd) from two Philox words; `lt` = shared log table
-__device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, unsigned lt, double& z0, double& z1) {
-    const double n1 = u32_plus_half(wa), n2 = u32_plus_half(wb);
+// sin / cos of the Box-Muller angle 2 pi (w + 0.5) 2^-32 from the 32-bit word itself: the top 8 bits select the bin
+// centre a_j = 2 pi (j + 0.5) / 256 of a (cos, sin) table in shared memory (`st`), the low 24 bits give the residual
+// |r| <= pi/256, where sin r and cos r - 1 need 2 and 3 Taylor terms (truncation < 1e-17).  15 FP64 instructions and six
+// constants (1/2, 1/6, 1/24 are shared with texp) against 23 and thirteen for the quadrant-reduced minimax kernels:
+// with those, the constants of the propagation loop no longer fit the uniform register file and every use cost an
+// extra LDC.  ABSOLUTE error ~2e-16 (the result multiplies sqrt(-2 ln u1) <= 6.7).
+// [0] 2 pi 2^-32, [1] 2^52 + 2^23, [2] 1/120, [3] 1/720, [4] pi 2^-32 (the +0.5 of the word, scaled)
+__constant__ double kFS[5] = {1.4629180792671596e-09, 4503599635759104.0, 1.0 / 120.0, 1.0 / 720.0, 7.314590396335798e-10};
+__device__ __forceinline__ void tsincos2pi_word(uint32_t w, unsigned st, double& s, double& c) {
+    const double2 cs = lds_f64x2(st + ((w >> 20) & 0xff0u));  // (cos a_j, sin a_j), 16 B per entry
+    // r = 2 pi 2^-32 ((w & 0xffffff) - 2^23 + 0.5): the integer part through a magic-number subtract (exact)
+    const double r = fma(__hiloint2double(0x43300000, (int)(w & 0x00ffffffu)) - kFS[1], kFS[0], kFS[4]);
+    const double r2 = r * r;
+    const double sr = fma(r, r2 * fma(r2, kFS[2], -kFM[9]), r);            // sin r
+    const double cm = r2 * fma(fma(r2, -kFS[3], kFM[8]), r2, -kFM[10]);    // cos r - 1
+    s = cs.y + fma(cs.y, cm, cs.x * sr);
+    c = cs.x + fma(cs.x, cm, -(cs.y * sr));
+}
+
+// libdevice log() behind a call: it serves one draw in a thousand, and inlined into the unrolled noise code its ~60
+// instructions and live registers were paid for (spills at the 64-register cap) by every other draw
+static __device__ __noinline__ double log_rare(double x) { return log(x); }
+
+// the Box-Muller pair (z_even, z_odd) from two Philox words; `lt` = shared log table, `st` = shared (cos, sin) table
+__device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, unsigned lt, unsigned st, double& z0, double& z1) {
+    const double n1 = u32_plus_half(wa);
     // u1 = n1 * 2^-32 through the exponent field (integer subtract, exact)
     const double u1 = __hiloint2double(__double2hiint(n1) - (32 << 20), __double2loint(n1));
     double L;
     if (wa >= 0xFFC00000u) {
         // u1 within 2^-10 of 1 (probability 1e-3): the table-driven log has ABSOLUTE error ~1e-16, not enough
         // relative accuracy when log(u1) -> 0
-        L = log(u1);
+        L = log_rare(u1);
     } else {
         L = tlog_pos(u1, lt);  // |L| >= 9.7e-4
     }
     const double r = tsqrt_pos(-2.0 * L);
     double s, c;
-    tsincospi(n2 * (2.0 / 4294967296.0), s, c);
+    tsincos2pi_word(wb, st, s, c);
     z0 = r * c;
     z1 = r * s;
 }
 
 // the four normals z(4q), z(4q+1), z(4q+2), z(4q+3) of (seed, rep, quad q = t>>2, y)
 __device__ __forceinline__ void normal_quad_fast(uint64_t seed, uint64_t rep, uint32_t quad, uint32_t y, unsigned lt,
-                                                 double z[4]) {
+                                                 unsigned st, double z[4]) {
     uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = quad, c3 = y;
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-    box_muller_fast(c0, c1, lt, z[0], z[1]);
-    box_muller_fast(c2, c3, lt, z[2], z[3]);
+    box_muller_fast(c0, c1, lt, st, z[0], z[1]);
+    box_muller_fast(c2, c3, lt, st, z[2], z[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
 #ifndef PF_MINB
 #define PF_MINB 4
 #endif
-#define PF_SMEM (sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + PF_TT))
+#define PF_SMEM (sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 2 * BAM_SCTAB_N + PF_TT))
 template <int NC, int SIGF, bool NOISE>
 __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProblem p, PredArgs a, const double* __restrict__ tab,
                                                                   const int* __restrict__ status,
@@ -135,11 +135,14 @@ __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProbl
     extern __shared__ __align__(16) double pfsm[];
     double2* sLogT = reinterpret_cast<double2*>(pfsm);
     double* sExpT = pfsm + 2 * BAM_LOGTAB_N;
-    double* sH = sExpT + BAM_EXPTAB_N;
+    double2* sScT = reinterpret_cast<double2*>(sExpT + BAM_EXPTAB_N);
+    double* sH = sExpT + BAM_EXPTAB_N + 2 * BAM_SCTAB_N;
     const int tid = threadIdx.x;
     const int tBeg = blockIdx.y * PF_TT, nt = min(PF_TT, a.nT - tBeg);
     for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) sLogT[i] = p.logTab[i];
     for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExpT[i] = p.expTab[i];
+    if (NOISE)
+        for (int i = tid; i < BAM_SCTAB_N; i += BAM_BLOCK) sScT[i] = p.scTab[i];
     if (nspag == 1)
         for (int i = tid; i < nt; i += BAM_BLOCK) sH[i] = xs[a.t0 + tBeg + i];
     __syncthreads();
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProbl
     unsigned mask4 = 0;
 #pragma unroll
     for (int r = 1; r <= NC; ++r) mask4 |= ((unsigned)(p.ctrlMask >> ((r - 1) * 8)) & 0xfu) << (4 * r);
-    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT), ht = smem_addr(sH);
+    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT), ht = smem_addr(sH), st = smem_addr(sScT);
     const double* __restrict__ xcol = xs + (size_t)(rep % nspag) * a.nobsPred + a.t0 + tBeg;
     const bool shared = nspag == 1;
 
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProbl
     double z[4] = {0.0, 0.0, 0.0, 0.0};
     auto single = [&](int t) {  // head / tail of a tile that does not start or end on a multiple of four inputs
         const unsigned tg = tg0 + (unsigned)t;
-        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, tg >> 2, 0u, lt, z);
+        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, tg >> 2, 0u, lt, st, z);
         const double h = stage(t);
         const double zz = (tg & 2u) ? ((tg & 1u) ? z[3] : z[2]) : ((tg & 1u) ? z[1] : z[0]);
         finish(t, q_checked(h, amask(h)), zz);
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProbl
     int t = 0;
     for (; t < nt && ((tg0 + (unsigned)t) & 3u); ++t) single(t);
     for (; t + 3 < nt; t += 4) {  // four inputs share one Philox block, two share one log and one sqrt
-        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 2, 0u, lt, z);
+        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 2, 0u, lt, st, z);
         two(t, z[0], z[1]);
         two(t + 2, z[2], z[3]);
     }
@@ -323,11 +326,13 @@ __global__ void __launch_bounds__(BAM_BLOCK, 4) pred_sediment_fast(DevProblem p,
     extern __shared__ __align__(16) double pfsm[];
     double2* sLogT = reinterpret_cast<double2*>(pfsm);
     double* sExpT = pfsm + 2 * BAM_LOGTAB_N;
-    SedObs* sObs = reinterpret_cast<SedObs*>(sExpT + BAM_EXPTAB_N);
+    double2* sScT = reinterpret_cast<double2*>(sExpT + BAM_EXPTAB_N);
+    SedObs* sObs = reinterpret_cast<SedObs*>(sExpT + BAM_EXPTAB_N + 2 * BAM_SCTAB_N);
     const int tid = threadIdx.x;
     const int tBeg = blockIdx.y * PF_TT, nt = min(PF_TT, a.nT - tBeg);
     for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) sLogT[i] = p.logTab[i];
     for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExpT[i] = p.expTab[i];
+    for (int i = tid; i < BAM_SCTAB_N; i += BAM_BLOCK) sScT[i] = p.scTab[i];
     for (int i = tid; i < nt; i += BAM_BLOCK) sObs[i] = obs[a.t0 - a.tBase + tBeg + i];
     __syncthreads();
     const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, 4) pred_sediment_fast(DevProblem p,
         g1 = mc[rep + (size_t)p.nFit * a.Nrep];
         if (SIGF == BAMGPU_SIG_LINEAR) g2 = mc[rep + (size_t)(p.nFit + 1) * a.Nrep];
     }
-    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT);
+    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT), st = smem_addr(sScT);
     const unsigned tg0 = (unsigned)(a.t0 + tBeg);
     double z[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned lastQuad = 0xffffffffu;
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, 4) pred_sediment_fast(DevProblem p,
         const unsigned tg = tg0 + (unsigned)t;
         if (NOISE && (tg >> 2) != lastQuad) {
             lastQuad = tg >> 2;
-            normal_quad_fast(a.seed, (uint64_t)rep, lastQuad, 0u, lt, z);
+            normal_quad_fast(a.seed, (uint64_t)rep, lastQuad, 0u, lt, st, z);
         }
         double v;
         if (o.st == 2.0) v = p.unfeas;
@@ -1334,7 +1339,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         cudaEvent_t kp0 = mark();
         if (sedK) {
             dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + PF_TT - 1) / PF_TT);
-            sedK<<<grid, BAM_BLOCK, sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N) + sizeof(SedObs) * PF_TT, s>>>(
+            sedK<<<grid, BAM_BLOCK, sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 2 * BAM_SCTAB_N) + sizeof(SedObs) * PF_TT, s>>>(
                 p, a, h->d_mc, h->d_mode, d_sedObs, h->d_V);
         } else if (fastK) {
             dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + PF_TT - 1) / PF_TT);
