@@ -151,7 +151,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         for (int i = 0; i < L.n; ++i) xsrc[i] = i;
         const bool mixture = L.model == BAMGPU_MDL_MIXTURE && L.n > 0;
         if (mixture && bam::mixture_rows(L.n, pb->X, L.modelOpt[1], L.modelOpt[2], xsrc, xelt, m)) { setmess(mess, m); delete h; return 1; }
-        if (!L.hasLatent && nDev > 1 && L.model != BAMGPU_MDL_VEGETATION && !mixture)  // Vegetation: the series order matters
+        if (!L.hasLatent && nDev > 1 && L.model != BAMGPU_MDL_VEGETATION && !mixture && !L.isSeries)  // Vegetation: the series order matters
             std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
                 if (L.comboOf[a] != L.comboOf[b]) return L.comboOf[a] < L.comboOf[b];
                 return pb->X[a] < pb->X[b];
@@ -188,6 +188,11 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
                     xd[i] = (double)(perm[i] / L.modelOpt[2] + 1);
                     xd[i + (size_t)nDev] = (double)xelt[perm[i]];
                 }
+            if (L.isSeries) {  // time-recursive model: the kernels see the row index, the series pass sees the inputs
+                for (int i = 0; i < nDev; ++i) xd[i] = (double)perm[i];
+                d.seriesX = upload(h, pb->X, (size_t)L.n * L.nX);
+                d.isSeries = 1; d.seriesN = L.n;
+            }
             d.X = upload(h, xd.data(), sxd);
         }
         d.Xu = upload(h, permXD(pb->Xu, L.nX).data(), sxd);
@@ -282,6 +287,7 @@ void bamgpu_destroy(bamgpu_t* h) {
     fr(h->d_x); fr(h->d_tab); fr(h->d_part); fr(h->d_prior); fr(h->d_lkh); fr(h->d_hyper); fr(h->d_fx); fr(h->d_dpar);
     fr(h->d_status); fr(h->d_delta); fr(h->d_std); fr(h->d_fxcur); fr(h->d_dparcur); fr(h->d_moves); fr(h->d_mcount);
     fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_env);
+    fr(h->d_series); fr(h->d_seriesXpred);
     fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0); fr(h->d_lkCcur); fr(h->d_lkCcand);
     for (auto*& q : h->d_compTiles) fr(q);
     for (auto*& q : h->d_compAffected) fr(q);
@@ -530,12 +536,23 @@ int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const dou
             if (nspag[0] != 1) throw bam::CudaError{"bamgpu: Mixture: the event column of a prediction must be a single series (nspag = 1)"};
             if (bam::mixture_rows(nobs_pred, xspag[0], p.modelOpt[1], p.modelOpt[2], msrc, melt, m)) throw bam::CudaError{m};
         }
+        if (p.isSeries) {  // time-recursive model: one input series (kept in series order for the series pass)
+            for (int i = 0; i < p.nX; ++i)
+                if (nspag[i] != 1) throw bam::CudaError{"bamgpu: a time-recursive model needs single input series in a prediction (nspag = 1)"};
+            if (h->d_seriesXpred) cudaFree(h->d_seriesXpred);
+            BAM_CUDA(cudaMalloc(&h->d_seriesXpred, sizeof(double) * (size_t)nobs_pred * p.nX));
+            for (int i = 0; i < p.nX; ++i)
+                BAM_CUDA(cudaMemcpyAsync(h->d_seriesXpred + (size_t)i * nobs_pred, xspag[i], sizeof(double) * nobs_pred,
+                                         cudaMemcpyHostToDevice, h->stream));
+            mbuf.resize(nobs_pred);
+            for (int r = 0; r < nobs_pred; ++r) mbuf[r] = (double)r;  // column 0 of the pointwise kernels = row index
+        }
         for (int i = 0; i < p.nX; ++i) {
             if (nspag[i] < 1) throw bam::CudaError{"BaM_ReadSpag: nspag must be >= 1"};
             double* d = nullptr;
             const size_t cnt = (size_t)nobs_pred * nspag[i];
             BAM_CUDA(cudaMalloc(&d, sizeof(double) * cnt));
-            const double* srcp = xspag[i];
+            const double* srcp = (p.isSeries && i == 0) ? mbuf.data() : xspag[i];
             if (mixture) {
                 mbuf.resize(cnt);
                 for (int c = 0; c < nspag[i]; ++c)
@@ -549,7 +566,7 @@ int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const dou
                 BAM_CUDA(cudaStreamSynchronize(h->stream));  // mbuf is reused for the next column
             }
             BAM_CUDA(cudaMemcpyAsync(d, srcp, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
-            if (mixture) BAM_CUDA(cudaStreamSynchronize(h->stream));
+            if (mixture || p.isSeries) BAM_CUDA(cudaStreamSynchronize(h->stream));
             h->d_xspag.push_back(d);
             h->predNspag.push_back(nspag[i]);
             ptrs[i] = d;

@@ -72,6 +72,12 @@ struct DevProblem {
     double modelOptD;
     const double* hcsTab;  // HydraulicControl_section: 4 x hcsN (h | A | w | h + A/(2w))
     int hcsN;
+    // time-recursive models (row f4): the model output of every vector is produced by one sequential pass over the series
+    // (series_run) into seriesY[(y * seriesN + t) * seriesK + vector]; for those models column 0 of X holds the row index t
+    // and der[0] of a vector its own index, so the pointwise kernels just look the value up (model_apply)
+    int isSeries, seriesN, seriesK;
+    const double* seriesX;  // seriesN x nX, the real inputs in series order
+    double* seriesY;
     // Vegetation
     int vegGrowth, vegNYear, vegItmax;
     double vegXscale, vegFscale, vegTolX, vegTolF;

@@ -72,6 +72,9 @@ struct bamgpu_handle {
     size_t vCap = 0;
     double* d_env = nullptr;   // nT x 7 x nY of the last resident prediction
     int predT0 = 0, predT1 = 0;
+    double* d_series = nullptr;  // time-recursive models: outputs of all vectors [y][t][vector]
+    size_t seriesCap = 0;
+    double* d_seriesXpred = nullptr;  // prediction inputs of a time-recursive model (series order)
     int predNout = 0;  // outputs (+ state variables) of the last prediction: rows of d_env
     size_t envCap = 0;
 
@@ -109,6 +112,8 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
 bool fast_path_keeps_combo_sums(const bamgpu_handle* h, int K);
 
 void launch_table(bamgpu_handle* h, int K, const double* d_x);
+void ensure_series_capacity(bamgpu_handle* h, size_t count);
+void launch_series(bamgpu_handle* h, const DevProblem& p, int K, const double* tab, int stride, int thOff, int* status, int nOut);
 int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const double* d_xtrue, const int* d_combo,
                            double* d_ysim, double* d_state /* n x nState, may be null */);
 

@@ -33,6 +33,7 @@ int model_from_name(const char* name) {
     if (s == "BaRatinBAC") return BAMGPU_MDL_BARATINBAC;
     if (s == "SFD") return BAMGPU_MDL_SFD;
     if (s == "Mixture") return BAMGPU_MDL_MIXTURE;
+    if (s == "SFDTidal_Qmec") return BAMGPU_MDL_SFDTIDAL_QMEC;
     return 0;
 }
 
@@ -547,6 +548,12 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             L.modelOptD = p.xtra_d[0];                                   // upper bound of the search interval
             L.nState = 1;
             break;
+        case BAMGPU_MDL_SFDTIDAL_QMEC:  // SFDTidal_Qmec_GetParNumber (:31-59); nothing to read (ModelLibrary_tools.f90:506-507)
+            if (nt != 12 || nX != 2 || nY != 1) { mess = "SFDTidal_Qmec_Apply: wrong size [theta], nX or nY"; return 1; }
+            if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: SFDTidal_Qmec is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
+            L.nState = 3;  // pressure, friction, advection (:672-676)
+            L.isSeries = true;
+            break;
         case BAMGPU_MDL_MIXTURE: {  // Mixture_XtraRead (:137-190), Mixture_GetParNumber (:33-72)
             if (p.n_xtra_i != 4) { mess = "Mixture_XtraRead:problem reading xtra"; return 1; }
             const int nS = p.xtra_i[0], nEvt = p.xtra_i[1], nElt = p.xtra_i[2], miss = p.xtra_i[3] != 0;
@@ -580,6 +587,7 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
     else if (L.model == BAMGPU_MDL_BARATINBAC) L.nDer = 2 * L.ncontrol;  // k_i and ktype_i
     else if (L.model == BAMGPU_MDL_SEGMENTATION) L.nDer = std::max(L.modelOpt[0] - 1, 0);  // the shift times tau
     else if (L.model == BAMGPU_MDL_ORTHO) L.nDer = 22;           // Dpar + the two focal lengths in pixels
+    else if (L.isSeries) L.nDer = 1;                                     // the vector's own index into the series buffer
     else if (L.model != BAMGPU_MDL_VEGETATION) L.nDer = L.nDparModel;
 
     // VAR combinations in order of first appearance (:346-379); L(t,i) = offset_i + indx_i(t) (:326-334)

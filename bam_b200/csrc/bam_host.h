@@ -57,6 +57,7 @@ struct HostLayout {
     double modelOptD = 0.0;          // Segmentation: tmin
     std::vector<double> hcsTab;      // HydraulicControl_section: h | A | w | h + A/(2w), p rows each
     int nDer = 0;  // derived values per (parameter set, combination) kept in the device table
+    bool isSeries = false;  // time-recursive model: one sequential pass over the series per parameter vector (row f4)
 };
 
 // Mixture (Mixture_model.f90:119-123): output row (j-1)*nElt+e is built from the e-th input row whose event column

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* 
         }
         for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
         const bool ok = model_prepare(p, th, der, xc, p.n);
+        if (p.isSeries) der[0] = (double)c;  // this vector's column of the series buffer (model_apply looks it up)
         if (!ok) st |= ST_LKH_INFEAS;
         for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
         if (dpar != nullptr)
@@ -128,6 +129,19 @@ __global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* 
     }
     prior_out[c] = prior;
     status[c] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1s: time-recursive models (row f4).  thread <-> parameter vector: one sequential pass over the series, outputs (and
+// state variables when nOut > nY) written to seriesY[(y * n + t) * K + vector] -- consecutive lanes = consecutive
+// vectors, so every step of the recursion is one coalesced store.  An infeasible vector raises ST_LKH_INFEAS.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) series_run(DevProblem p, int K, const double* __restrict__ tab, int stride, int thOff,
+                                                  int* __restrict__ status, int nOut) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    if (status[c] != 0) return;
+    if (!model_series(p, tab + (size_t)c * stride + thOff, p.seriesY + c, (size_t)K, nOut)) atomicOr(&status[c], ST_LKH_INFEAS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -932,6 +946,18 @@ static void ensure_comp_tiles(bamgpu_handle* h, int comp) {
     h->compTileCnt[comp] = (int)tiles.size();
 }
 
+void ensure_series_capacity(bamgpu_handle* h, size_t count) {
+    if (count <= h->seriesCap) return;
+    if (h->d_series) cudaFree(h->d_series);
+    BAM_CUDA(cudaMalloc(&h->d_series, sizeof(double) * count));
+    h->seriesCap = count;
+}
+
+void launch_series(bamgpu_handle* h, const DevProblem& p, int K, const double* tab, int stride, int thOff, int* status, int nOut) {
+    series_run<<<(K + 127) / 128, 128, 0, h->stream>>>(p, K, tab, stride, thOff, status, nOut);
+    h->launches += 1;
+}
+
 cudaEvent_t take_event(bamgpu_handle* h) {
     if (!h->evPool.empty()) { cudaEvent_t e = h->evPool.back(); h->evPool.pop_back(); return e; }
     cudaEvent_t e;
@@ -983,11 +1009,25 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
     p.X = d_xtrue;
     p.n = n;
     logpost_prep<<<1, 128, 0, h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
+    double* d_idx = nullptr;
+    if (p.isSeries) {  // the series of this one vector (outputs + states), then the lookup kernel on the row indices
+        const int nOut = p.nY + model_nstate(p.model);
+        ensure_series_capacity(h, (size_t)n * nOut);
+        p.seriesX = d_xtrue; p.seriesN = n; p.seriesK = 1; p.seriesY = h->d_series;
+        series_run<<<1, 128, 0, h->stream>>>(p, 1, tab, p.tabStride, p.tabCombo, status, nOut);
+        std::vector<double> idx((size_t)n * p.nX, 0.0);
+        for (int i = 0; i < n; ++i) idx[i] = (double)i;
+        BAM_CUDA(cudaMalloc(&d_idx, sizeof(double) * idx.size()));
+        BAM_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(double) * idx.size(), cudaMemcpyHostToDevice, h->stream));
+        BAM_CUDA(cudaStreamSynchronize(h->stream));
+        d_xtrue = d_idx;
+    }
     kern<<<(n + BAM_BLOCK - 1) / BAM_BLOCK, BAM_BLOCK, 0, h->stream>>>(p, n, d_xtrue, d_combo, tab, d_ysim, d_state, status + 1);
     int st[2] = {0, 0};
     BAM_CUDA(cudaMemcpyAsync(st, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     BAM_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(tab); cudaFree(prior); cudaFree(dpar); cudaFree(status);
+    if (d_idx) cudaFree(d_idx);
     h->launches += 2;
     BAM_CUDA(cudaGetLastError());
     return (st[0] & ST_LKH_INFEAS) ? -1 : st[1];
@@ -1008,6 +1048,14 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     FastKernel fast = (p.n > 0 && !h->forceGeneric) ? pick_fast(p, K) : nullptr;
     logpost_prep<<<(K + 127) / 128, 128, 0, h->stream>>>(p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status,
                                                          h->d_dpar);
+    DevProblem pser = p;
+    if (p.isSeries && p.n > 0) {  // time-recursive model: the outputs of all K vectors, then the generic likelihood kernel
+        ensure_series_capacity(h, (size_t)p.seriesN * p.nY * K);
+        pser.seriesY = h->d_series;
+        pser.seriesK = K;
+        series_run<<<(K + 127) / 128, 128, 0, h->stream>>>(pser, K, h->d_tab, p.tabStride, p.tabCombo, h->d_status, p.nY);
+        h->launches += 1;
+    }
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     if (timeMain) {
         BAM_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -1048,7 +1096,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     } else if (p.n > 0) {
         if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);
-        kern<<<grid, BAM_BLOCK, pl.smem, h->stream>>>(p, d_x, K, pl.CT, pl.TX, h->d_tab, h->d_status, h->d_part, h->d_status,
+        kern<<<grid, BAM_BLOCK, pl.smem, h->stream>>>(pser, d_x, K, pl.CT, pl.TX, h->d_tab, h->d_status, h->d_part, h->d_status,
                                                        comp, d_delta, pl.logOff);
     }
     if (timeMain) {

@@ -799,6 +799,86 @@ __device__ __forceinline__ bool mixture_apply(const DevProblem& p, const double*
 }
 
 // -------------------------------------------------------------------------------------------
+// SFDTidal_Qmec (SFDTidal_Qmec_model.f90:61-197), time-recursive: Q(m) = Q(m-1) + dt (pg + bf + ad), first-order step
+// for the second point, second-order Adams-Bashforth afterwards.  One thread walks the whole series of one parameter
+// vector; values of the last three points live in registers.  Explicitly rounded operations (no FMA contraction): the
+// recursion feeds every rounding back into itself, so the operation sequence is the reference's (and the oracle's).
+// out[(y * n + t) * K]: y = 0 discharge, 1..3 = dt pg, dt bf, dt ad (the three state variables).
+// -------------------------------------------------------------------------------------------
+__device__ inline bool sfdtidal_qmec_series(int n, const double* __restrict__ h1, const double* __restrict__ h2,
+                                            const double* __restrict__ th, double* __restrict__ out, size_t K, int nOut) {
+    const double y0 = th[0], A0 = th[1], be = th[2], delta = th[3], phi = th[4], d1 = th[5], d2 = th[6], c = th[7],
+                 g = th[8], Q0 = th[9], dx = th[10], dt = th[11];
+    if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return false;
+    const double width = __ddiv_rn(A0, __dsub_rn(y0, be));
+    const double R0 = __ddiv_rn(A0, __dadd_rn(width, __dmul_rn(2.0, __dsub_rn(y0, be))));
+    const double ne = sqrt(__dmul_rn(__dmul_rn(__dmul_rn(phi, __ddiv_rn(1.0, __dmul_rn(8.0, g))), A0), pow(R0, c)));
+    const double ne2 = __dmul_rn(ne, ne);
+    auto geom = [&](int m, double& dy, double& ym, double& Ae, double& Rhe) -> bool {
+        const double y1 = __dadd_rn(h1[m], d1), y2 = __dadd_rn(h2[m], d2);
+        dy = __dsub_rn(y2, y1);
+        ym = __ddiv_rn(__dadd_rn(y1, y2), 2.0);
+        Ae = __dmul_rn(width, __dsub_rn(ym, be));
+        const double Pe = __dadd_rn(width, __dmul_rn(2.0, __dsub_rn(ym, be)));
+        Rhe = __ddiv_rn(Ae, Pe);
+        return !(Ae < 0.0 || Pe < 0.0 || Rhe < 0.0);
+    };
+    bool ok = true;
+    for (int m = 0; m < n; ++m) {  // the geometry check covers the whole series before anything is run (:131-133)
+        double a, b2, c2, d;
+        ok &= geom(m, a, b2, c2, d);
+    }
+    if (!ok) return false;
+    auto put = [&](int m, double q, double s1, double s2, double s3) {
+        out[(size_t)m * K] = q;
+        if (nOut > 1) {
+            out[((size_t)n + m) * K] = s1;
+            out[((size_t)2 * n + m) * K] = s2;
+            out[((size_t)3 * n + m) * K] = s3;
+        }
+    };
+    // point m-1 (suffix 1), m-2 (suffix 2), m-3 (ym only)
+    double dy1, ym1, Ae1, Rh1, dy2 = 0.0, ym2 = 0.0, Ae2 = 0.0, Rh2 = 0.0, ym3 = 0.0, Q1 = Q0, Q2 = 0.0;
+    if (n > 0) { geom(0, dy1, ym1, Ae1, Rh1); put(0, Q0, 0.0, 0.0, 0.0); }
+    auto pgf = [&](double Ae, double dy) { return __ddiv_rn(__dmul_rn(__dmul_rn(-g, Ae), __dadd_rn(dy, delta)), dx); };
+    auto bff = [&](double Rh, double Q, double Ae) {
+        return __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(-g, __ddiv_rn(ne2, pow(Rh, c))), Q), fabs(Q)), Ae);
+    };
+    auto adf = [&](double Q, double Ae, double dydt) { return __dmul_rn(__dmul_rn(__dmul_rn(2.0, __ddiv_rn(Q, Ae)), width), dydt); };
+    for (int m = 1; m < n; ++m) {
+        double dy0, ym0, Ae0, Rh0;
+        geom(m, dy0, ym0, Ae0, Rh0);
+        double pg, bf, ad;
+        if (m == 1) {
+            const double dydt1 = __ddiv_rn(__dsub_rn(ym0, ym1), dt);
+            pg = -__dmul_rn(g, __ddiv_rn(__dmul_rn(Ae1, __dadd_rn(dy1, delta)), dx));  // -g*(Ae*(dy+delta)/dx) (:147)
+            bf = bff(Rh1, Q1, Ae1);
+            ad = adf(Q1, Ae1, dydt1);
+        } else {
+            const double dydt1 = __ddiv_rn(__dsub_rn(ym0, ym2), __dmul_rn(2.0, dt));
+            const double dydt2 = (m == 2) ? __ddiv_rn(__dsub_rn(ym1, ym2), dt) : __ddiv_rn(__dsub_rn(ym1, ym3), __dmul_rn(2.0, dt));
+            pg = __dsub_rn(__dmul_rn(1.5, pgf(Ae1, dy1)), __dmul_rn(0.5, pgf(Ae2, dy2)));
+            bf = __dsub_rn(__dmul_rn(1.5, bff(Rh1, Q1, Ae1)), __dmul_rn(0.5, bff(Rh2, Q2, Ae2)));
+            ad = __dsub_rn(__dmul_rn(1.5, adf(Q1, Ae1, dydt1)), __dmul_rn(0.5, adf(Q2, Ae2, dydt2)));
+        }
+        const double Qm = __dadd_rn(Q1, __dmul_rn(dt, __dadd_rn(__dadd_rn(pg, bf), ad)));
+        put(m, Qm, __dmul_rn(dt, pg), __dmul_rn(dt, bf), __dmul_rn(dt, ad));
+        ym3 = ym2;
+        dy2 = dy1; ym2 = ym1; Ae2 = Ae1; Rh2 = Rh1; Q2 = Q1;
+        dy1 = dy0; ym1 = ym0; Ae1 = Ae0; Rh1 = Rh0; Q1 = Qm;
+    }
+    return true;
+}
+
+// one sequential pass of a time-recursive model for one parameter vector; false = infeasible vector
+__device__ inline bool model_series(const DevProblem& p, const double* __restrict__ th, double* __restrict__ out, size_t K,
+                                    int nOut) {
+    if (p.model == BAMGPU_MDL_SFDTIDAL_QMEC)
+        return sfdtidal_qmec_series(p.seriesN, p.seriesX, p.seriesX + p.seriesN, th, out, K, nOut);
+    return false;
+}
+
+// -------------------------------------------------------------------------------------------
 // dispatch
 // -------------------------------------------------------------------------------------------
 
@@ -855,6 +935,11 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return segmentation_apply(p, x[0], th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_MIXTURE) {
         return mixture_apply<NX>(p, x, th, der, y[0]);
+    } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC) {  // time-recursive: produced by series_run, looked up here
+#pragma unroll
+        for (int k = 0; k < NY; ++k)
+            y[k] = p.seriesY[((size_t)k * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];
+        return true;
     } else {
         bool ok = true;
 #pragma unroll
@@ -864,12 +949,19 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
 }
 
 // state variables (ModelLibrary_tools.f90 XtraSetup: model%nState): only SFD has one on this path (kappa)
-__host__ __device__ constexpr int model_nstate(int model) { return model == BAMGPU_MDL_SFD ? 1 : 0; }
+__host__ __device__ constexpr int model_nstate(int model) {
+    return model == BAMGPU_MDL_SFD ? 1 : (model == BAMGPU_MDL_SFDTIDAL_QMEC ? 3 : 0);
+}
 
 // model_apply + the state variables of the observation (st[model_nstate(MODEL)])
 template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool model_apply_s(const DevProblem& p, const double* x, const double* __restrict__ th,
                                               const double* __restrict__ der, double* y, double* st) {
     if (MODEL == BAMGPU_MDL_SFD) return sfd_apply(p, x, th, y[0], st);
+    if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC) {
+#pragma unroll
+        for (int k = 0; k < model_nstate(MODEL); ++k)
+            st[k] = p.seriesY[((size_t)(NY + k) * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];
+    }
     return model_apply<MODEL, NX, NY>(p, x, th, der, y);
 }

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const
     const double* xc[BAM_MAXX];
     for (int j = 0; j < p.nX; ++j) xc[j] = xspag[j] + (size_t)(rep % nspag[j]) * a.nobsPred;
     const bool ok = model_prepare(p, th, der, xc, a.nobsPred);
+    if (p.isSeries) der[0] = (double)rep;  // this replication's column of the series buffer
     for (int d = 0; d < p.nDer; ++d) row[p.nGamma + p.ntheta + d] = der[d];
     status[rep] = ok ? 0 : 1;
 }
@@ -1285,6 +1286,15 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     pred_prep<<<(unsigned)((Nrep + 127) / 128), 128, 0, s>>>(p, a, h->d_mc, h->d_mode, h->d_xspagPtrs, h->d_nspag, h->d_ptab,
                                                              h->d_pstatus);
     h->launches += 1;
+    DevProblem pser = p;
+    if (p.isSeries) {  // time-recursive model: every replication's whole series (outputs + states) first, then the generic
+                       // kernel looks the values up, adds the structural error and fills the tile
+        const int nOutS = nY + model_nstate(p.model);
+        if ((double)h->predNobs * nOutS * (double)Nrep * 8.0 > 64e9) throw CudaError{"bamgpu: time-recursive prediction too large for one series buffer"};
+        ensure_series_capacity(h, (size_t)h->predNobs * nOutS * (size_t)Nrep);
+        pser.seriesX = h->d_seriesXpred; pser.seriesN = h->predNobs; pser.seriesK = (int)Nrep; pser.seriesY = h->d_series;
+        launch_series(h, pser, (int)Nrep, h->d_ptab, a.stride, p.nGamma, h->d_pstatus, nOutS);
+    }
     const size_t smemMain = a.stage ? sizeof(double) * (size_t)a.stride * BAM_BLOCK : 0;
     if (smemMain > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMain));
 
@@ -1346,7 +1356,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
             fastK<<<grid, BAM_BLOCK, PF_SMEM, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspag[0], h->predNspag[0], h->d_V);
         } else {
             dim3 grid((unsigned)((Nrep + BAM_BLOCK - 1) / BAM_BLOCK), (nT + 31) / 32);
-            kern<<<grid, BAM_BLOCK, smemMain, s>>>(p, a, h->d_ptab, h->d_pstatus, h->d_xspagPtrs, h->d_nspag, h->d_V);
+            kern<<<grid, BAM_BLOCK, smemMain, s>>>(pser, a, h->d_ptab, h->d_pstatus, h->d_xspagPtrs, h->d_nspag, h->d_V);
         }
         h->launches += 1;
         cudaEvent_t kp1 = mark();

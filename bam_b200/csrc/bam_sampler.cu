@@ -125,7 +125,7 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
     // small data sets: the persistent warp-per-chain sampler (one launch per cycle)
     WarpSamplerKernel wk = pick_warp_sampler(p.model, p.nX, p.nY);
     const size_t wsSmem = sizeof(double) * (WS_TABLES + WS_WARPS * (size_t)(2 * P + p.tabStride + p.kM + 2));
-    if (wk && !h->forceGeneric && !p.hasLatent && P <= WS_MAXP && p.n <= 4096 && wsSmem <= 200 * 1024) {
+    if (wk && !h->forceGeneric && !p.hasLatent && !p.isSeries && P <= WS_MAXP && p.n <= 4096 && wsSmem <= 200 * 1024) {
         if (wsSmem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsSmem));
         WarpSamplerArgs a;
         a.K = K; a.nAdapt = nAdapt; a.burn = burn; a.keepEvery = keepEvery; a.nKeep = nKeep;

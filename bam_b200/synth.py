@@ -418,6 +418,50 @@ def mixture(nS: int = 3, nEvt: int = 6, nElt: int = 9, missing: bool = True, shu
     return prob, np.concatenate([th, [0.02, 0.01]])
 
 
+def sfdtidal_qmec(nobs: int = 600, seed: int = SEED + 12, missing_every: int = 3):
+    """SFDTidal_Qmec (time-recursive momentum balance between two tide gauges, SFDTidal_Qmec_model.f90:61-197):
+    theta = (y0, A0, be, delta, phi, d1, d2, c, g, Q0, dx, dt).  Two synthetic tidal stage series at a 60 s step; the
+    discharge "observations" are the model's own output plus noise, with gaps (most of a real record is ungauged).
+    Returns (Problem, truth)."""
+    rng = np.random.default_rng(seed)
+    th = np.array([2.0, 1800.0, -6.0, 0.02, 4e-6, 0.0, 0.05, 4.0 / 3.0, 9.81, 300.0, 4000.0, 60.0])
+    t = np.arange(nobs) * th[11]
+    h1 = 1.5 * np.sin(2 * np.pi * t / 44700.0) + 0.3 * np.sin(2 * np.pi * t / 7000.0)
+    h2 = 1.5 * np.sin(2 * np.pi * (t - 600.0) / 44700.0) + 0.3 * np.sin(2 * np.pi * (t - 500.0) / 7000.0) - 0.03
+    y0, A0, be, delta, phi, d1, d2, c, g, Q0, dx, dt = th
+    width = A0 / (y0 - be)
+    R0 = A0 / (width + 2 * (y0 - be))
+    ne2 = phi / (8 * g) * A0 * R0**c
+    y1, y2 = h1 + d1, h2 + d2
+    dy, ym = y2 - y1, (y1 + y2) / 2
+    Ae = width * (ym - be)
+    Rhe = Ae / (width + 2 * (ym - be))
+    Q = np.zeros(nobs)
+    Q[0] = Q0
+    pgf = lambda m: -g * Ae[m] * (dy[m] + delta) / dx  # noqa: E731
+    bff = lambda m: -g * (ne2 / Rhe[m] ** c) * Q[m] * abs(Q[m]) / Ae[m]  # noqa: E731
+    for m in range(1, nobs):
+        if m == 1:
+            f = pgf(0) + bff(0) + 2 * (Q[0] / Ae[0]) * width * (ym[1] - ym[0]) / dt
+        else:
+            d1t = (ym[m] - ym[m - 2]) / (2 * dt)
+            d2t = (ym[m - 1] - ym[m - 2]) / dt if m == 2 else (ym[m - 1] - ym[m - 3]) / (2 * dt)
+            f = (1.5 * pgf(m - 1) - 0.5 * pgf(m - 2) + 1.5 * bff(m - 1) - 0.5 * bff(m - 2) +
+                 1.5 * 2 * (Q[m - 1] / Ae[m - 1]) * width * d1t - 0.5 * 2 * (Q[m - 2] / Ae[m - 2]) * width * d2t)
+        Q[m] = Q[m - 1] + dt * f
+    uq = 0.03 * np.abs(Q) + 5.0
+    Y = Q + rng.standard_normal(nobs) * np.sqrt(uq**2 + (10.0 + 0.02 * np.abs(Q)) ** 2)
+    if missing_every > 1:
+        Y[np.arange(nobs) % missing_every != 0] = -9999.0
+    pri = [("Gaussian", [v, 0.05 * abs(v) + 0.01]) for v in th]
+    partype = [-1, 0, 0, 0, 0, -1, -1, -1, -1, 0, -1, -1]  # y0, datums, exponent, gravity, dx, dt fixed by the user (:96-107)
+    prob = Problem("SFDTidal_Qmec", np.column_stack([h1, h2]), Y, Yu=uq, partype=partype,
+                   priors_theta=[pri[i] for i in range(12) if partype[i] == 0], fix_value=[v if partype[i] == -1 else 0.0 for i, v in enumerate(th)],
+                   sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000])] * 2)
+    truth = np.concatenate([[th[i] for i in range(12) if partype[i] == 0], [10.0, 0.02]])
+    return prob, truth
+
+
 def baratin_bac(nobs: int = 300, seed: int = SEED + 8, hmax: float = 6.0):
     """BaRatinBAC: the 3-control matrix of tests/BaM_BaRatinBAC (control 2 REPLACES control 1, control 3 is ADDED),
     theta = (b, a, c) per control.  Returns (Problem, truth)."""

@@ -48,8 +48,12 @@ enum bamgpu_model {
     BAMGPU_MDL_BARATINBAC = 13,   /* BaRatinBAC_model.f90:96-666: BaRatin in the b-a-c parameterisation */
     BAMGPU_MDL_SFD = 14,          /* StageFallDischarge_model.f90:80-283 (SFD_Val_General); the transition stage kappa is
                                      the model's state variable (bamgpu_predict_states, bamgpu_calibration_run_states) */
-    BAMGPU_MDL_MIXTURE = 15       /* Mixture_model.f90:74-135: per-event weighted sum of source concentrations; output
+    BAMGPU_MDL_MIXTURE = 15,      /* Mixture_model.f90:74-135: per-event weighted sum of source concentrations; output
                                      rows are event x element blocks (row (j-1)*nElt+e = e-th input row of event j) */
+    /* time-recursive models: one sequential pass over the series per parameter vector */
+    BAMGPU_MDL_SFDTIDAL_QMEC = 16 /* SFDTidal_Qmec_model.f90:61-197: tidal discharge from two stage series by a momentum
+                                     balance (Adams-Bashforth in time); 12 parameters, states = pressure gradient, bottom
+                                     friction, advection */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */

@@ -1376,6 +1376,65 @@ static int mixture_apply(const oracle_t* o, int n, const double* X, int ldx, con
     return 1;
 }
 
+/* SFDTidal_Qmec_Apply, SFDTidal_Qmec_model.f90:61-197: Q(m) = Q(m-1) + dt (pg + bf + ad), first-order step for m = 2,
+   second-order Adams-Bashforth afterwards.  state (nullable, ld = lds): pressure_gradient, bottom_friction, advection.
+   Returns 0 when the parameter set (or the geometry of the series) is infeasible. */
+static int sfdtidal_qmec_apply(int nm, const double* h1, const double* h2, const double* theta, double* Q, double* state,
+                               int lds) {
+    double y0 = theta[0], A0 = theta[1], be = theta[2], delta = theta[3], phi = theta[4], d1 = theta[5], d2 = theta[6],
+           c = theta[7], g = theta[8], Q0 = theta[9], dx = theta[10], dt = theta[11];
+    for (int m = 0; m < nm; ++m) Q[m] = BAMGPU_UNDEF_RN;
+    if (state)
+        for (int s = 0; s < 3; ++s)
+            for (int m = 0; m < nm; ++m) state[m + (size_t)s * lds] = BAMGPU_UNDEF_RN;
+    if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return 0;
+    double width = A0 / (y0 - be);
+    double R0 = A0 / (width + 2.0 * (y0 - be));
+    double ne = sqrt(phi * (1.0 / (8.0 * g)) * A0 * pow(R0, c));
+    double* dy = (double*)malloc(((size_t)nm + 1) * 8 * 4);
+    double *ym = dy + nm, *Ae = ym + nm, *Rhe = Ae + nm;
+    int ok = 1;
+    for (int m = 0; m < nm; ++m) {
+        double y1 = h1[m] + d1, y2 = h2[m] + d2;
+        dy[m] = y2 - y1;
+        ym[m] = (y1 + y2) / 2.0;
+        Ae[m] = width * (ym[m] - be);
+        double Pe = width + 2.0 * (ym[m] - be);
+        Rhe[m] = Ae[m] / Pe;
+        if (Ae[m] < 0.0 || Pe < 0.0 || Rhe[m] < 0.0) ok = 0;
+    }
+    if (!ok) { free(dy); return 0; }
+    if (nm > 0) {
+        Q[0] = Q0;
+        if (state) for (int s = 0; s < 3; ++s) state[(size_t)s * lds] = 0.0;
+    }
+    for (int m = 1; m < nm; ++m) {
+        double pg, bf, ad;
+        if (m == 1) {
+            double dydt1 = (ym[m] - ym[m - 1]) / (dt);
+            pg = -g * (Ae[m - 1] * (dy[m - 1] + delta) / dx);
+            bf = -g * ((ne * ne) / (pow(Rhe[m - 1], c))) * Q[m - 1] * fabs(Q[m - 1]) / Ae[m - 1];
+            ad = 2.0 * (Q[m - 1] / Ae[m - 1]) * width * dydt1;
+        } else {
+            double dydt1 = (ym[m] - ym[m - 2]) / (2 * dt), dydt2;
+            if (m == 2) dydt2 = (ym[m - 1] - ym[m - 2]) / dt;
+            else dydt2 = (ym[m - 1] - ym[m - 3]) / (2 * dt);
+            pg = (1.5) * (-g * Ae[m - 1] * (dy[m - 1] + delta) / dx) - (0.5) * (-g * Ae[m - 2] * (dy[m - 2] + delta) / dx);
+            bf = (1.5) * (-g * ((ne * ne) / (pow(Rhe[m - 1], c))) * Q[m - 1] * fabs(Q[m - 1]) / Ae[m - 1]) -
+                 (0.5) * (-g * ((ne * ne) / (pow(Rhe[m - 2], c))) * Q[m - 2] * fabs(Q[m - 2]) / Ae[m - 2]);
+            ad = (1.5) * (2.0 * (Q[m - 1] / Ae[m - 1]) * width * dydt1) - (0.5) * (2.0 * (Q[m - 2] / Ae[m - 2]) * width * dydt2);
+        }
+        Q[m] = Q[m - 1] + dt * (pg + bf + ad);
+        if (state) {
+            state[m] = dt * pg;
+            state[m + (size_t)lds] = dt * bf;
+            state[m + (size_t)2 * lds] = dt * ad;
+        }
+    }
+    free(dy);
+    return 1;
+}
+
 /* TxtMdl_Apply, TextFile_model.f90:1035-1098 */
 static void textfile_apply(const oracle_t* o, int n, const double* IN, int ldx, const double* theta, double* OUT,
                            int ldy, int32_t* vfeas) {
@@ -1416,6 +1475,10 @@ static int apply_model_s(const oracle_t* o, int n, const double* X, int ldx, con
         case BAMGPU_MDL_HCS: hcs_apply(o, n, X, fullTheta, Y, vfeas); break;
         case BAMGPU_MDL_BARATINBAC: baratinbac_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
         case BAMGPU_MDL_SFD: sfd_apply(o, n, X, ldx, fullTheta, Y, vfeas, state); break;
+        case BAMGPU_MDL_SFDTIDAL_QMEC:
+            if (!sfdtidal_qmec_apply(n, X, X + (size_t)ldx, fullTheta, Y, state, ldy))
+                for (int t = 0; t < n; ++t) vfeas[t] = 0;
+            break;
         case BAMGPU_MDL_MIXTURE: {
             int r = mixture_apply(o, n, X, ldx, fullTheta, Y, dparModel);
             if (r < 0) return 1;
@@ -1468,6 +1531,7 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "BaRatinBAC")) return BAMGPU_MDL_BARATINBAC;
     if (!strcmp(name, "SFD")) return BAMGPU_MDL_SFD;
     if (!strcmp(name, "Mixture")) return BAMGPU_MDL_MIXTURE;
+    if (!strcmp(name, "SFDTidal_Qmec")) return BAMGPU_MDL_SFDTIDAL_QMEC;
     return 0;
 }
 
@@ -1626,6 +1690,10 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
         case BAMGPU_MDL_HCS:
             o->hcs_n = p->n_xtra_d / 3;
             if (o->hcs_n < 3 || p->n_xtra_d != 3 * o->hcs_n || nt != 2 || nX != 1 || nY != 1) { setmess(mess, "oracle: HydraulicControl_section: bad xtra or sizes"); return 1; }
+            break;
+        case BAMGPU_MDL_SFDTIDAL_QMEC: /* SFDTidal_Qmec_GetParNumber (:31-59): 12; XtraSetup (ModelLibrary_tools.f90:672-676) */
+            if (nt != 12 || nX != 2 || nY != 1) { setmess(mess, "oracle: SFDTidal_Qmec: bad sizes"); return 1; }
+            o->nState = 3;
             break;
         case BAMGPU_MDL_MIXTURE: { /* Mixture_GetParNumber (:33-72), XtraSetup (ModelLibrary_tools.f90:580-586) */
             if (p->n_xtra_i != 4) { setmess(mess, "oracle: Mixture: bad xtra"); return 1; }

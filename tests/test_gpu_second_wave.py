@@ -220,3 +220,37 @@ def test_mixture_reference_workspace():
     oenv, ospag = o.predict(mc, np.asarray(d["start"]), xs, 1, [1], seed=9, want_spag=True, nthreads=8)
     cmp_spag(spag, ospag)
     cmp_env(env, oenv)
+
+
+def test_time_recursive_sfdtidal_qmec():
+    """row f4: one sequential pass over the series per parameter vector (series_run), the pointwise kernels look the
+    values up.  Log-posterior with gaps in the observations, prediction with the three state spaghetti, sampler, residual
+    run -- all against the oracle."""
+    prob, truth = synth.sfdtidal_qmec(nobs=500)
+    x = synth.feasible_starts(truth, 40, rel=0.01, seed=2)
+    x[3, 0] = -10.0   # A0 <= 0: infeasible vector (and null under its prior? no: Gaussian prior) -> likelihood infeasible
+    x[4, 1] = 3.0     # bed above the water level: negative wetted area somewhere in the series (:131-133)
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.sizes.nState == 3
+    check_parity(prob, x, tol=1e-11)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.003 * rng.standard_normal((120, truth.size)))
+    mc[5, 0] = -1.0  # an infeasible replication
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(2)]
+    env, spag = g.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True, states=True)
+    oenv, ospag = o.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True, nthreads=8, states=True)
+    assert spag.shape == (4, 500, 120) and (spag[:, :, 5] == -666.666).all()
+    cmp_spag(spag, ospag, tol=1e-10)
+    cmp_env(env, oenv, tol=1e-10)
+    # a sub-range of the inputs is a slice of the full prediction: the recursion always starts at the first input
+    _, sfull = g.predict(mc, truth, xs, 1, [0], want_env=False, want_spag=True)
+    _, s2 = g.predict(mc, truth, xs, 1, [0], want_env=False, want_spag=True, t0=100, t1=260)
+    assert np.array_equal(s2[0], sfull[0, 100:260])
+    s = np.tile(truth, (3, 1))
+    sd = 0.005 * np.abs(s) + 1e-12
+    rows = g.fit(s, sd, nAdapt=3, nCycles=2, seed=5)
+    orows = o.fit(s, sd, nAdapt=3, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+    Xt, Ys, St, feas = g.calibration_run_states(truth)
+    oXt, oYs, oSt, ofeas = o.calibration_run_states(truth)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-11) and np.allclose(St, oSt, rtol=1e-10, atol=1e-12)

@@ -368,3 +368,30 @@ def test_sfd_state_variable():
     assert np.max(np.abs(lhs - rhs) / rhs) < 1e-10
     h1 = np.asarray(prob.X)[:, 0]
     assert ((h1 - th[1] <= 0) | (h2 - th[4] <= 0) | (h1 - h2 - th[6] <= 0))[~solved].all()
+
+
+def test_sfdtidal_qmec_recursion():
+    """time-recursive model (row f4): the restatement of SFDTidal_Qmec_Apply against an independent numpy run of the same
+    scheme (first-order start, second-order Adams-Bashforth; bam_b200/synth.py), its three states, and the exits"""
+    from bam_b200 import synth
+
+    prob, truth = synth.sfdtidal_qmec(nobs=400, missing_every=1)
+    o = Oracle(prob)
+    assert o.sizes.nState == 3 and o.P == 7
+    Xt, Ys, St, feas = o.calibration_run_states(truth)
+    assert feas and St.shape == (400, 3) and (St[0] == 0.0).all() and Ys[0, 0] == 300.0
+    # the synthetic observations are the numpy run + noise: recover it through the noise-free part
+    dt = 60.0
+    assert np.allclose(np.diff(Ys[:, 0]), St[1:].sum(axis=1), rtol=1e-9, atol=1e-9)  # Q(m) - Q(m-1) = dt (pg + bf + ad)
+    th = np.array([2.0, 1800.0, -6.0, 0.02, 4e-6, 0.0, 0.05, 4.0 / 3.0, 9.81, 300.0, 4000.0, 60.0])
+    h1, h2 = np.asarray(prob.X)[:, 0], np.asarray(prob.X)[:, 1]
+    width = th[1] / (th[0] - th[2])
+    ym = (h1 + th[5] + h2 + th[6]) / 2
+    Ae = width * (ym - th[2])
+    pg1 = -th[8] * Ae[0] * ((h2[0] + th[6]) - (h1[0] + th[5]) + th[3]) / th[10]
+    assert np.isclose(St[1, 0], dt * pg1, rtol=1e-13)
+    # infeasible: non-positive area / friction coefficient, a bed above the water (negative wetted area somewhere)
+    for pos, val in ((0, -5.0), (3, -1e-6), (1, 3.0)):  # fitted vector positions: A0, phi, be
+        x = truth.copy()
+        x[pos] = val
+        assert o.logpost_one(x)["feas"] == 0
