@@ -845,26 +845,35 @@ __device__ inline bool sfdtidal_qmec_series(int n, const double* __restrict__ h1
         return __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(-g, __ddiv_rn(ne2, pow(Rh, c))), Q), fabs(Q)), Ae);
     };
     auto adf = [&](double Q, double Ae, double dydt) { return __dmul_rn(__dmul_rn(__dmul_rn(2.0, __ddiv_rn(Q, Ae)), width), dydt); };
+    // The "m-2" terms of step m are the "m-1" terms of step m-1, operand for operand: pgf(Ae(m-2), dy(m-2)),
+    // bff(Rhe(m-2), Q(m-2), Ae(m-2)) and adf(Q(m-2), Ae(m-2), dydt2) with dydt2(m) = dydt1(m-1) -- also at m = 2, 3, where
+    // the reference switches between the one-sided and the centred difference (:160-172).  They are carried over
+    // instead of being recomputed (one pow and ~10 divisions per step), bit for bit the same values.
+    double pgP = 0.0, bfP = 0.0, adP = 0.0;  // pgf / bff / adf of the previous step's point m-1
+    (void)dy2; (void)Ae2; (void)Rh2; (void)Q2; (void)ym3;
     for (int m = 1; m < n; ++m) {
         double dy0, ym0, Ae0, Rh0;
         geom(m, dy0, ym0, Ae0, Rh0);
         double pg, bf, ad;
+        const double pgC = pgf(Ae1, dy1), bfC = bff(Rh1, Q1, Ae1);
+        double adC;
         if (m == 1) {
             const double dydt1 = __ddiv_rn(__dsub_rn(ym0, ym1), dt);
-            pg = -__dmul_rn(g, __ddiv_rn(__dmul_rn(Ae1, __dadd_rn(dy1, delta)), dx));  // -g*(Ae*(dy+delta)/dx) (:147)
-            bf = bff(Rh1, Q1, Ae1);
-            ad = adf(Q1, Ae1, dydt1);
+            adC = adf(Q1, Ae1, dydt1);
+            pg = -__dmul_rn(g, __ddiv_rn(__dmul_rn(Ae1, __dadd_rn(dy1, delta)), dx));  // -g*(Ae*(dy+delta)/dx) (:165)
+            bf = bfC;
+            ad = adC;
         } else {
             const double dydt1 = __ddiv_rn(__dsub_rn(ym0, ym2), __dmul_rn(2.0, dt));
-            const double dydt2 = (m == 2) ? __ddiv_rn(__dsub_rn(ym1, ym2), dt) : __ddiv_rn(__dsub_rn(ym1, ym3), __dmul_rn(2.0, dt));
-            pg = __dsub_rn(__dmul_rn(1.5, pgf(Ae1, dy1)), __dmul_rn(0.5, pgf(Ae2, dy2)));
-            bf = __dsub_rn(__dmul_rn(1.5, bff(Rh1, Q1, Ae1)), __dmul_rn(0.5, bff(Rh2, Q2, Ae2)));
-            ad = __dsub_rn(__dmul_rn(1.5, adf(Q1, Ae1, dydt1)), __dmul_rn(0.5, adf(Q2, Ae2, dydt2)));
+            adC = adf(Q1, Ae1, dydt1);
+            pg = __dsub_rn(__dmul_rn(1.5, pgC), __dmul_rn(0.5, pgP));
+            bf = __dsub_rn(__dmul_rn(1.5, bfC), __dmul_rn(0.5, bfP));
+            ad = __dsub_rn(__dmul_rn(1.5, adC), __dmul_rn(0.5, adP));
         }
         const double Qm = __dadd_rn(Q1, __dmul_rn(dt, __dadd_rn(__dadd_rn(pg, bf), ad)));
         put(m, Qm, __dmul_rn(dt, pg), __dmul_rn(dt, bf), __dmul_rn(dt, ad));
-        ym3 = ym2;
-        dy2 = dy1; ym2 = ym1; Ae2 = Ae1; Rh2 = Rh1; Q2 = Q1;
+        pgP = pgC; bfP = bfC; adP = adC;
+        ym2 = ym1;
         dy1 = dy0; ym1 = ym0; Ae1 = Ae0; Rh1 = Rh0; Q1 = Qm;
     }
     return true;
