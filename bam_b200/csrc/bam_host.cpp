@@ -34,6 +34,7 @@ int model_from_name(const char* name) {
     if (s == "SFD") return BAMGPU_MDL_SFD;
     if (s == "Mixture") return BAMGPU_MDL_MIXTURE;
     if (s == "SFDTidal_Qmec") return BAMGPU_MDL_SFDTIDAL_QMEC;
+    if (s == "SFDTidal_Qmec2") return BAMGPU_MDL_SFDTIDAL_QMEC2;
     return 0;
 }
 
@@ -548,8 +549,9 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             L.modelOptD = p.xtra_d[0];                                   // upper bound of the search interval
             L.nState = 1;
             break;
-        case BAMGPU_MDL_SFDTIDAL_QMEC:  // SFDTidal_Qmec_GetParNumber (:31-59); nothing to read (ModelLibrary_tools.f90:506-507)
-            if (nt != 12 || nX != 2 || nY != 1) { mess = "SFDTidal_Qmec_Apply: wrong size [theta], nX or nY"; return 1; }
+        case BAMGPU_MDL_SFDTIDAL_QMEC:   // SFDTidal_Qmec_GetParNumber (:31-59); nothing to read (ModelLibrary_tools.f90:506-509)
+        case BAMGPU_MDL_SFDTIDAL_QMEC2:  // SFDTidal_Qmec2_GetParNumber: 11
+            if (nt != (L.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 11 : 12) || nX != 2 || nY != 1) { mess = "SFDTidal_Qmec_Apply: wrong size [theta], nX or nY"; return 1; }
             if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: SFDTidal_Qmec is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
             L.nState = 3;  // pressure, friction, advection (:672-676)
             L.isSeries = true;

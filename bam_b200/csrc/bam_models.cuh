@@ -805,14 +805,23 @@ __device__ __forceinline__ bool mixture_apply(const DevProblem& p, const double*
 // recursion feeds every rounding back into itself, so the operation sequence is the reference's (and the oracle's).
 // out[(y * n + t) * K]: y = 0 discharge, 1..3 = dt pg, dt bf, dt ad (the three state variables).
 // -------------------------------------------------------------------------------------------
-__device__ inline bool sfdtidal_qmec_series(int n, const double* __restrict__ h1, const double* __restrict__ h2,
+// variant 2 = SFDTidal_Qmec2 (SFDTidal_Qmec2_model.f90:61-187): theta = (Be, bevs, delta, ne, d1, d2, c, g, Q0, dx, dt), the
+// effective width and the Manning coefficient are parameters instead of being derived from (y0, A0, be, phi).
+__device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __restrict__ h1, const double* __restrict__ h2,
                                             const double* __restrict__ th, double* __restrict__ out, size_t K, int nOut) {
-    const double y0 = th[0], A0 = th[1], be = th[2], delta = th[3], phi = th[4], d1 = th[5], d2 = th[6], c = th[7],
-                 g = th[8], Q0 = th[9], dx = th[10], dt = th[11];
-    if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return false;
-    const double width = __ddiv_rn(A0, __dsub_rn(y0, be));
-    const double R0 = __ddiv_rn(A0, __dadd_rn(width, __dmul_rn(2.0, __dsub_rn(y0, be))));
-    const double ne = sqrt(__dmul_rn(__dmul_rn(__dmul_rn(phi, __ddiv_rn(1.0, __dmul_rn(8.0, g))), A0), pow(R0, c)));
+    double be, delta, d1, d2, c, g, Q0, dx, dt, width, ne;
+    if (variant == 2) {
+        width = th[0]; be = th[1]; delta = th[2]; ne = th[3]; d1 = th[4]; d2 = th[5]; c = th[6]; g = th[7]; Q0 = th[8];
+        dx = th[9]; dt = th[10];
+        if (width <= 0.0 || ne <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return false;
+    } else {
+        const double y0 = th[0], A0 = th[1], phi = th[4];
+        be = th[2]; delta = th[3]; d1 = th[5]; d2 = th[6]; c = th[7]; g = th[8]; Q0 = th[9]; dx = th[10]; dt = th[11];
+        if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return false;
+        width = __ddiv_rn(A0, __dsub_rn(y0, be));
+        const double R0 = __ddiv_rn(A0, __dadd_rn(width, __dmul_rn(2.0, __dsub_rn(y0, be))));
+        ne = sqrt(__dmul_rn(__dmul_rn(__dmul_rn(phi, __ddiv_rn(1.0, __dmul_rn(8.0, g))), A0), pow(R0, c)));
+    }
     const double ne2 = __dmul_rn(ne, ne);
     auto geom = [&](int m, double& dy, double& ym, double& Ae, double& Rhe) -> bool {
         const double y1 = __dadd_rn(h1[m], d1), y2 = __dadd_rn(h2[m], d2);
@@ -882,8 +891,9 @@ __device__ inline bool sfdtidal_qmec_series(int n, const double* __restrict__ h1
 // one sequential pass of a time-recursive model for one parameter vector; false = infeasible vector
 __device__ inline bool model_series(const DevProblem& p, const double* __restrict__ th, double* __restrict__ out, size_t K,
                                     int nOut) {
-    if (p.model == BAMGPU_MDL_SFDTIDAL_QMEC)
-        return sfdtidal_qmec_series(p.seriesN, p.seriesX, p.seriesX + p.seriesN, th, out, K, nOut);
+    if (p.model == BAMGPU_MDL_SFDTIDAL_QMEC || p.model == BAMGPU_MDL_SFDTIDAL_QMEC2)
+        return sfdtidal_qmec_series(p.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : 1, p.seriesN, p.seriesX, p.seriesX + p.seriesN, th,
+                                    out, K, nOut);
     return false;
 }
 
@@ -944,7 +954,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return segmentation_apply(p, x[0], th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_MIXTURE) {
         return mixture_apply<NX>(p, x, th, der, y[0]);
-    } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC) {  // time-recursive: produced by series_run, looked up here
+    } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2) {  // time-recursive: produced by series_run, looked up here
 #pragma unroll
         for (int k = 0; k < NY; ++k)
             y[k] = p.seriesY[((size_t)k * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];
@@ -959,7 +969,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
 
 // state variables (ModelLibrary_tools.f90 XtraSetup: model%nState): only SFD has one on this path (kappa)
 __host__ __device__ constexpr int model_nstate(int model) {
-    return model == BAMGPU_MDL_SFD ? 1 : (model == BAMGPU_MDL_SFDTIDAL_QMEC ? 3 : 0);
+    return model == BAMGPU_MDL_SFD ? 1 : ((model == BAMGPU_MDL_SFDTIDAL_QMEC || model == BAMGPU_MDL_SFDTIDAL_QMEC2) ? 3 : 0);
 }
 
 // model_apply + the state variables of the observation (st[model_nstate(MODEL)])
@@ -967,7 +977,7 @@ template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool model_apply_s(const DevProblem& p, const double* x, const double* __restrict__ th,
                                               const double* __restrict__ der, double* y, double* st) {
     if (MODEL == BAMGPU_MDL_SFD) return sfd_apply(p, x, th, y[0], st);
-    if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC) {
+    if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2) {
 #pragma unroll
         for (int k = 0; k < model_nstate(MODEL); ++k)
             st[k] = p.seriesY[((size_t)(NY + k) * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];

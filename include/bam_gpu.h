@@ -51,9 +51,11 @@ enum bamgpu_model {
     BAMGPU_MDL_MIXTURE = 15,      /* Mixture_model.f90:74-135: per-event weighted sum of source concentrations; output
                                      rows are event x element blocks (row (j-1)*nElt+e = e-th input row of event j) */
     /* time-recursive models: one sequential pass over the series per parameter vector */
-    BAMGPU_MDL_SFDTIDAL_QMEC = 16 /* SFDTidal_Qmec_model.f90:61-197: tidal discharge from two stage series by a momentum
+    BAMGPU_MDL_SFDTIDAL_QMEC = 16, /* SFDTidal_Qmec_model.f90:61-197: tidal discharge from two stage series by a momentum
                                      balance (Adams-Bashforth in time); 12 parameters, states = pressure gradient, bottom
                                      friction, advection */
+    BAMGPU_MDL_SFDTIDAL_QMEC2 = 17 /* SFDTidal_Qmec2_model.f90: the same recursion parameterised by (Be, bevs, delta, ne, d1,
+                                      d2, c, g, Q0, dx, dt) -- effective width and Manning coefficient given directly */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */

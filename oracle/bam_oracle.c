@@ -1379,18 +1379,28 @@ static int mixture_apply(const oracle_t* o, int n, const double* X, int ldx, con
 /* SFDTidal_Qmec_Apply, SFDTidal_Qmec_model.f90:61-197: Q(m) = Q(m-1) + dt (pg + bf + ad), first-order step for m = 2,
    second-order Adams-Bashforth afterwards.  state (nullable, ld = lds): pressure_gradient, bottom_friction, advection.
    Returns 0 when the parameter set (or the geometry of the series) is infeasible. */
-static int sfdtidal_qmec_apply(int nm, const double* h1, const double* h2, const double* theta, double* Q, double* state,
-                               int lds) {
-    double y0 = theta[0], A0 = theta[1], be = theta[2], delta = theta[3], phi = theta[4], d1 = theta[5], d2 = theta[6],
-           c = theta[7], g = theta[8], Q0 = theta[9], dx = theta[10], dt = theta[11];
+static int sfdtidal_qmec_apply(int variant, int nm, const double* h1, const double* h2, const double* theta, double* Q,
+                               double* state, int lds) {
+    /* variant 1: SFDTidal_Qmec (y0, A0, be, delta, phi, d1, d2, c, g, Q0, dx, dt);
+       variant 2: SFDTidal_Qmec2_model.f90:61-187 (Be, bevs, delta, ne, d1, d2, c, g, Q0, dx, dt): width = Be, be = bevs */
+    double be, delta, d1, d2, c, g, Q0, dx, dt, width, ne;
     for (int m = 0; m < nm; ++m) Q[m] = BAMGPU_UNDEF_RN;
     if (state)
         for (int s = 0; s < 3; ++s)
             for (int m = 0; m < nm; ++m) state[m + (size_t)s * lds] = BAMGPU_UNDEF_RN;
-    if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return 0;
-    double width = A0 / (y0 - be);
-    double R0 = A0 / (width + 2.0 * (y0 - be));
-    double ne = sqrt(phi * (1.0 / (8.0 * g)) * A0 * pow(R0, c));
+    if (variant == 2) {
+        width = theta[0]; be = theta[1]; delta = theta[2]; ne = theta[3]; d1 = theta[4]; d2 = theta[5]; c = theta[6];
+        g = theta[7]; Q0 = theta[8]; dx = theta[9]; dt = theta[10];
+        if (width <= 0.0 || ne <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return 0;
+    } else {
+        double y0 = theta[0], A0 = theta[1], phi = theta[4];
+        be = theta[2]; delta = theta[3]; d1 = theta[5]; d2 = theta[6]; c = theta[7]; g = theta[8]; Q0 = theta[9];
+        dx = theta[10]; dt = theta[11];
+        if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return 0;
+        width = A0 / (y0 - be);
+        double R0 = A0 / (width + 2.0 * (y0 - be));
+        ne = sqrt(phi * (1.0 / (8.0 * g)) * A0 * pow(R0, c));
+    }
     double* dy = (double*)malloc(((size_t)nm + 1) * 8 * 4);
     double *ym = dy + nm, *Ae = ym + nm, *Rhe = Ae + nm;
     int ok = 1;
@@ -1476,7 +1486,8 @@ static int apply_model_s(const oracle_t* o, int n, const double* X, int ldx, con
         case BAMGPU_MDL_BARATINBAC: baratinbac_apply(o, n, X, fullTheta, Y, dparModel, vfeas); break;
         case BAMGPU_MDL_SFD: sfd_apply(o, n, X, ldx, fullTheta, Y, vfeas, state); break;
         case BAMGPU_MDL_SFDTIDAL_QMEC:
-            if (!sfdtidal_qmec_apply(n, X, X + (size_t)ldx, fullTheta, Y, state, ldy))
+        case BAMGPU_MDL_SFDTIDAL_QMEC2:
+            if (!sfdtidal_qmec_apply(o->model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : 1, n, X, X + (size_t)ldx, fullTheta, Y, state, ldy))
                 for (int t = 0; t < n; ++t) vfeas[t] = 0;
             break;
         case BAMGPU_MDL_MIXTURE: {
@@ -1532,6 +1543,7 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "SFD")) return BAMGPU_MDL_SFD;
     if (!strcmp(name, "Mixture")) return BAMGPU_MDL_MIXTURE;
     if (!strcmp(name, "SFDTidal_Qmec")) return BAMGPU_MDL_SFDTIDAL_QMEC;
+    if (!strcmp(name, "SFDTidal_Qmec2")) return BAMGPU_MDL_SFDTIDAL_QMEC2;
     return 0;
 }
 
@@ -1692,7 +1704,8 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             if (o->hcs_n < 3 || p->n_xtra_d != 3 * o->hcs_n || nt != 2 || nX != 1 || nY != 1) { setmess(mess, "oracle: HydraulicControl_section: bad xtra or sizes"); return 1; }
             break;
         case BAMGPU_MDL_SFDTIDAL_QMEC: /* SFDTidal_Qmec_GetParNumber (:31-59): 12; XtraSetup (ModelLibrary_tools.f90:672-676) */
-            if (nt != 12 || nX != 2 || nY != 1) { setmess(mess, "oracle: SFDTidal_Qmec: bad sizes"); return 1; }
+        case BAMGPU_MDL_SFDTIDAL_QMEC2: /* SFDTidal_Qmec2_GetParNumber: 11; XtraSetup (:677-681) */
+            if (nt != (o->model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 11 : 12) || nX != 2 || nY != 1) { setmess(mess, "oracle: SFDTidal_Qmec: bad sizes"); return 1; }
             o->nState = 3;
             break;
         case BAMGPU_MDL_MIXTURE: { /* Mixture_GetParNumber (:33-72), XtraSetup (ModelLibrary_tools.f90:580-586) */

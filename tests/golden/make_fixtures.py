@@ -81,7 +81,7 @@ def read_par_block(lines, k):
     return name, init, dist, rest
 
 
-def load_workspace(cfg_name):
+def load_workspace(cfg_name, max_rows=None):
     cfg = read_lines(os.path.join(TESTS, cfg_name))
     ws = os.path.join(TESTS, items(cfg[0])[0].replace("\\", "/"))
     f_model, f_xtra, f_data = (items(cfg[i])[0] for i in (2, 3, 4))
@@ -97,6 +97,8 @@ def load_workspace(cfg_name):
     header = raw[:nhead]
     W = np.array([[fnum(v) for v in re.split(r"[\s,;]+", ln.strip())[:ncol]] for ln in raw[nhead:nhead + nobs]])
     assert W.shape == (nobs, ncol), (W.shape, nobs, ncol)
+    if max_rows is not None and nobs > max_rows:  # a prefix of a long time series keeps the fixture small
+        W, nobs = W[:max_rows], max_rows
 
     def extract(c):  # Wextract (:4181-4198)
         return np.column_stack([np.zeros(nobs) if j == 0 else W[:, j - 1] for j in c])
@@ -213,7 +215,9 @@ WORKSPACES = {
     "textfile_inputuncertainty": "Config_BaM_TextFile_InputUncertainty.txt",
     "mixture": "Config_BaM_Mixture.txt",
     "sfd": "Config_BaM_SFD.txt",
+    "sfdtidal_qmec2": "Config_BaM_SFDTidal_Qmec2.txt",  # first 8000 of its 14401 time steps: the gauged window starts at step 7745 (MAX_ROWS)
 }
+MAX_ROWS = {"sfdtidal_qmec2": 8000}
 
 
 def synth_cfg(ws_name, remnant=("Config_RemnantSigma.txt",), xtra="Config_Options.txt"):
@@ -234,7 +238,7 @@ def main():
                 f.write("\n".join(synth_cfg("BaM_Sediment_Camenen_X4")) + "\n")
             # load_workspace joins TESTS with cfg_name: give it a relative path out of TESTS
             cfg = os.path.relpath(tmp, TESTS)
-        fx = load_workspace(cfg)
+        fx = load_workspace(cfg, MAX_ROWS.get(key))
         if key.startswith("sediment"):
             fx["source"] = "tests/BaM_Sediment_Camenen_X4" if key.endswith("x4") else fx["source"]
         with open(os.path.join(OUT, key + ".json"), "w") as f:

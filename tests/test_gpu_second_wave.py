@@ -254,3 +254,19 @@ def test_time_recursive_sfdtidal_qmec():
     Xt, Ys, St, feas = g.calibration_run_states(truth)
     oXt, oYs, oSt, ofeas = o.calibration_run_states(truth)
     assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-11) and np.allclose(St, oSt, rtol=1e-10, atol=1e-12)
+
+
+def test_sfdtidal_qmec2_reference_workspace():
+    """tests/BaM_SFDTidal_Qmec2 (8000-step prefix, 128 gauged steps, 5 of 11 parameters fixed): the 8000-step recursion
+    on the device against the oracle"""
+    from tests.helpers import perturbed_vectors, problem_from_fixture
+
+    prob, d = problem_from_fixture("sfdtidal_qmec2")
+    x = perturbed_vectors(d["start"], 48, rel=0.01, seed=1)
+    x[5, 0] = -3.0  # Be <= 0
+    check_parity(prob, x, tol=1e-10)
+    g, o = BamGpu(prob), Oracle(prob)
+    x0 = np.asarray(d["start"])
+    Xt, Ys, St, feas = g.calibration_run_states(x0)
+    oXt, oYs, oSt, ofeas = o.calibration_run_states(x0)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-10, atol=1e-8) and np.allclose(St, oSt, rtol=1e-9, atol=1e-8)

@@ -395,3 +395,22 @@ def test_sfdtidal_qmec_recursion():
         x = truth.copy()
         x[pos] = val
         assert o.logpost_one(x)["feas"] == 0
+
+
+def test_sfdtidal_qmec2_on_the_reference_workspace():
+    """tests/BaM_SFDTidal_Qmec2 (first 8000 of 14401 one-minute steps, 128 gauged): the workspace ships no simulated
+    column, but its ADCP discharges give a physical check of the restatement -- run at the configured initial guesses, the
+    recursion started 7745 steps earlier arrives at the gauged tidal discharge within a factor 1.6"""
+    prob, d = problem_from_fixture("sfdtidal_qmec2")
+    o = Oracle(prob)
+    assert (prob.nobs, prob.ntheta, o.P, o.sizes.nState) == (8000, 11, 6, 3)
+    x0 = np.asarray(d["start"])
+    Xt, Ys, St, feas = o.calibration_run_states(x0)
+    Y = np.asarray(d["Y"])
+    ok = Y != -9999
+    assert feas and ok.sum() == 128
+    ratio = Ys[ok, 0] / Y[ok]  # same sign and magnitude over the gauged window (prior guesses, not a fit)
+    assert ratio.min() > 0.5 and ratio.max() < 1.6
+    assert np.allclose(np.diff(Ys[:, 0]), St[1:].sum(axis=1), rtol=1e-9, atol=1e-6)
+    r = o.logpost_one(x0)
+    assert r["feas"] == 1 and np.isfinite(r["fx"])
