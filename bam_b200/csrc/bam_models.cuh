@@ -832,12 +832,10 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
         Rhe = __ddiv_rn(Ae, Pe);
         return !(Ae < 0.0 || Pe < 0.0 || Rhe < 0.0);
     };
+    // The reference checks the geometry of the whole series before it runs anything (:131-133).  Here the check rides
+    // along with the recursion: a vector with a bad point returns false at the end, and what it wrote is never read
+    // (the likelihood, prediction and residual kernels skip flagged vectors).
     bool ok = true;
-    for (int m = 0; m < n; ++m) {  // the geometry check covers the whole series before anything is run (:131-133)
-        double a, b2, c2, d;
-        ok &= geom(m, a, b2, c2, d);
-    }
-    if (!ok) return false;
     auto put = [&](int m, double q, double s1, double s2, double s3) {
         out[(size_t)m * K] = q;
         if (nOut > 1) {
@@ -848,7 +846,7 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
     };
     // point m-1 (suffix 1), m-2 (suffix 2), m-3 (ym only)
     double dy1, ym1, Ae1, Rh1, dy2 = 0.0, ym2 = 0.0, Ae2 = 0.0, Rh2 = 0.0, ym3 = 0.0, Q1 = Q0, Q2 = 0.0;
-    if (n > 0) { geom(0, dy1, ym1, Ae1, Rh1); put(0, Q0, 0.0, 0.0, 0.0); }
+    if (n > 0) { ok &= geom(0, dy1, ym1, Ae1, Rh1); put(0, Q0, 0.0, 0.0, 0.0); }
     auto pgf = [&](double Ae, double dy) { return __ddiv_rn(__dmul_rn(__dmul_rn(-g, Ae), __dadd_rn(dy, delta)), dx); };
     auto bff = [&](double Rh, double Q, double Ae) {
         return __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(-g, __ddiv_rn(ne2, pow(Rh, c))), Q), fabs(Q)), Ae);
@@ -862,7 +860,7 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
     (void)dy2; (void)Ae2; (void)Rh2; (void)Q2; (void)ym3;
     for (int m = 1; m < n; ++m) {
         double dy0, ym0, Ae0, Rh0;
-        geom(m, dy0, ym0, Ae0, Rh0);
+        ok &= geom(m, dy0, ym0, Ae0, Rh0);
         double pg, bf, ad;
         const double pgC = pgf(Ae1, dy1), bfC = bff(Rh1, Q1, Ae1);
         double adC;
@@ -885,7 +883,7 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
         ym2 = ym1;
         dy1 = dy0; ym1 = ym0; Ae1 = Ae0; Rh1 = Rh0; Q1 = Qm;
     }
-    return true;
+    return ok;
 }
 
 // one sequential pass of a time-recursive model for one parameter vector; false = infeasible vector
