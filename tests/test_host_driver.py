@@ -109,6 +109,20 @@ def test_config_reader_on_shipped_second_wave_workspace():
     assert (d["model_id"], d["nobs"]) == ("Segmentation", 110) and list(d["xtra_i"]) == [2, 2, 1]
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference workspaces only exist in the build container")
+def test_config_reader_on_shipped_time_recursive_workspace():
+    """tests/BaM_SFDTidal_Qmec2 (14 401 steps; the fixture keeps the first 8000): same inputs, FIX pattern and start"""
+    d = dump_ref("Config_BaM_SFDTidal_Qmec2.txt")
+    fx = load_fixture("sfdtidal_qmec2")
+    assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == ("SFDTidal_Qmec2", 14401, 2, 1)
+    assert list(d["partype"]) == list(fx["partype"]) and np.array_equal(np.asarray(d["start"]), np.asarray(fx["start"]))
+    X = np.asarray(d["X"]).reshape(2, 14401)
+    Xf = np.asarray(fx["X"]).reshape(2, 8000)
+    assert np.array_equal(X[:, :8000], Xf)
+    Y = np.asarray(d["Y"])
+    assert np.array_equal(Y[:8000], np.asarray(fx["Y"])) and (Y != -9999.0).sum() == 264
+
+
 def dump_ref(cfg):
     out = "/tmp/_dump_" + cfg.replace("/", "_") + ".json"
     r = subprocess.run([EXE, "-cf", os.path.join("/root/reference/tests", cfg), "--dump-problem", out],
@@ -285,3 +299,31 @@ def test_state_variable_files(tmp_path):
     assert head[-1] == "TransitionStage" and res.shape == (68, 2 * 2 + 5 * 1 + 1)
     _, _, oSt, _ = o.calibration_run_states(mp)
     assert np.allclose(res[:, -1], oSt[:, 0], rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_time_recursive_workspace_end_to_end(tmp_path):
+    """tests/BaM_SFDTidal_Qmec2 (8000-step prefix) through the driver: MCMC on the 6 free parameters (5 are FIX), cooked
+    sample, residual file with the three state columns of the model (pressure, friction, advection)"""
+    from oracle.oracle_api import Oracle
+    from tests.helpers import problem_from_fixture
+
+    fx = load_fixture("sfdtidal_qmec2")
+    cfg, ws = write_workspace(fx, str(tmp_path), name="TR", nAdapt=5, nCycles=2, do_residual=True)
+    compare(dump(cfg), fx)  # the written workspace reads back as the fixture (FIX parameters included)
+    r = subprocess.run([EXE, "-cf", cfg, "-sd", "5", "--chains", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    head, rows = read_table(os.path.join(ws, "Results_MCMC.txt"))
+    assert head[:6] == ["Be", "bevs", "delta", "ne", "Q0", "Y1_gamma1"][:6] or head[4] == "Q0"
+    assert rows.shape[0] == 10 and np.isfinite(rows).all()
+    hr, res = read_table(os.path.join(ws, "Results_Residuals.txt"))
+    assert hr[-3:] == ["pressure", "friction", "advection"] and res.shape == (8000, 2 * 2 + 5 * 1 + 3)
+    _, cooked = read_table(os.path.join(ws, "Results_MCMC_Cooked.txt"))
+    prob, _ = problem_from_fixture("sfdtidal_qmec2")
+    o = Oracle(prob)
+    k = int(np.argmax(cooked[:, o.P]))
+    _, oYs, oSt, ofeas = o.calibration_run_states(cooked[k, :o.P])
+    assert ofeas
+    # the cooked file holds 7 digits of every parameter and the recursion integrates over 8000 steps: loose comparison
+    assert np.allclose(res[:, 6], oYs[:, 0], rtol=5e-3, atol=5.0)
+    assert np.allclose(res[1:, -3:].sum(axis=1), np.diff(res[:, 6]), rtol=1e-4, atol=0.1)  # Q(m) - Q(m-1) = sum of the states (7 digits in the file)
