@@ -31,6 +31,15 @@ __constant__ double kFM[12] = {0.2,
                                0.5,
                                6755399441055744.0};
 
+// Coefficients whose low 32 bits are zero are encoded by ptxas as 32-bit immediates of DFMA / DMUL: they need neither a
+// uniform register nor a constant load.  -1/2, -1/4 are exact; for 1/5 (log1p), 1/24 (exp), 1/120 and 1/720 (sin / cos
+// of the residual angle) the value rounded to 20 mantissa bits is enough: they multiply r^5, r^4, r^5 and r^6 with
+// |r| < 2^-9, ln2/512 and pi/256, so the coefficient error (5e-7 relative) contributes < 1e-19 (tests/test_fastmath.py).
+#define FM_C5 0x1.9999ap-3    /* 1/5   */
+#define FM_C24 0x1.55555p-5   /* 1/24  */
+#define FM_C120 0x1.11111p-7  /* 1/120 */
+#define FM_C720 0x1.6c16cp-10 /* 1/720 */
+
 // The tables live in shared memory and are addressed with 32-bit shared-window addresses (ld.shared): pointer
 // arithmetic on generic pointers made ptxas rebuild the shared base (S2UR/ULEA) in every loop iteration.
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -52,9 +61,9 @@ __device__ __forceinline__ double tlog_pos(double x, unsigned lt) {
     const double2 t = lds_f64x2(lt + ((hi >> 8) & 0xff0));                   // entry (hi >> 12) & 255, 16 B each
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);  // mantissa in [1,2)
     const double r = fma(m, t.x, -1.0);                                       // |r| < 2^-9
-    double q = fma(kFM[0], r, kFM[1]);                                        // log1p(r), degree 5
+    double q = fma(FM_C5, r, -0.25);                                          // log1p(r), degree 5
     q = fma(q, r, kFM[2]);
-    q = fma(q, r, kFM[3]);
+    q = fma(q, r, -0.5);
     const double pr = fma(q, r * r, r);
     const double s = fma((double)((hi >> 20) - 1023), kFM[4], t.y);
     return s + pr;
@@ -75,8 +84,8 @@ __device__ __forceinline__ double texp_inrange(double x, unsigned et) {
     double r = fma(kd, kFM[6], x);
     r = fma(kd, kFM[7], r);
     const double T = lds_f64(et + ((ki << 3) & 0x7f8));
-    double q = fma(kFM[8], r, kFM[9]);
-    q = fma(q, r, kFM[10]);
+    double q = fma(FM_C24, r, kFM[9]);
+    q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     const double res = fma(T, q * r, T);
     return __hiloint2double(__double2hiint(res) + ((ki << 12) & 0xfff00000), __double2loint(res));
@@ -91,8 +100,8 @@ __device__ __forceinline__ double texp(double x, unsigned et) {
     double r = fma(kd, kFM[6], x);             // ln2/256 split hi (26 bits) / lo
     r = fma(kd, kFM[7], r);
     const double T = lds_f64(et + ((ki << 3) & 0x7f8));
-    double q = fma(kFM[8], r, kFM[9]);         // e^r - 1, degree 4, |r| <= ln2/512
-    q = fma(q, r, kFM[10]);
+    double q = fma(FM_C24, r, kFM[9]);         // e^r - 1, degree 4, |r| <= ln2/512
+    q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     double res = fma(T, q * r, T);
     res = __hiloint2double(__double2hiint(res) + ((ki << 12) & 0xfff00000), __double2loint(res));  // * 2^(ki >> 8)
@@ -198,8 +207,8 @@ __device__ __forceinline__ void tsincos2pi_word(uint32_t w, unsigned st, double&
     // r = 2 pi 2^-32 ((w & 0xffffff) - 2^23 + 0.5): the integer part through a magic-number subtract (exact)
     const double r = fma(__hiloint2double(0x43300000, (int)(w & 0x00ffffffu)) - kFS[1], kFS[0], kFS[4]);
     const double r2 = r * r;
-    const double sr = fma(r, r2 * fma(r2, kFS[2], -kFM[9]), r);            // sin r
-    const double cm = r2 * fma(fma(r2, -kFS[3], kFM[8]), r2, -kFM[10]);    // cos r - 1
+    const double sr = fma(r, r2 * fma(r2, FM_C120, -kFM[9]), r);           // sin r
+    const double cm = r2 * fma(fma(r2, -FM_C720, kFM[8]), r2, -0.5);       // cos r - 1
     s = cs.y + fma(cs.y, cm, cs.x * sr);
     c = cs.x + fma(cs.x, cm, -(cs.y * sr));
 }

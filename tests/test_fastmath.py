@@ -10,6 +10,8 @@ LN2 = 0.693147180559945309417232
 C_EXP = 369.32993046757463        # 256 / ln2
 C_HI, C_LO = -0.0027076061523985118, -2.1663774597568432e-11  # -ln2/256 split
 MAGIC = 6755399441055744.0        # 1.5 * 2^52
+# coefficients rounded to 20 mantissa bits (32-bit immediates of DFMA): FM_C5, FM_C24, FM_C120, FM_C720
+C5, C24, C120, C720 = float.fromhex("0x1.9999ap-3"), float.fromhex("0x1.55555p-5"), float.fromhex("0x1.11111p-7"), float.fromhex("0x1.6c16cp-10")
 
 
 def fma(a, b, c):
@@ -35,7 +37,7 @@ def tlog_pos(x):
     idx = (hi >> 12) & 255
     m = ((bits & np.uint64(0x000FFFFFFFFFFFFF)) | np.uint64(0x3FF0000000000000)).view(np.float64)
     r = fma(m, INV[idx], -1.0)
-    q = fma(0.2, r, -0.25)
+    q = fma(C5, r, -0.25)
     q = fma(q, r, 1.0 / 3.0)
     q = fma(q, r, -0.5)
     pr = fma(q, r * r, r)
@@ -50,7 +52,7 @@ def texp(x):
     r = fma(kd, C_HI, x)
     r = fma(kd, C_LO, r)
     T = EXPT[ki & 255]
-    q = fma(1.0 / 24.0, r, 1.0 / 6.0)
+    q = fma(C24, r, 1.0 / 6.0)
     q = fma(q, r, 0.5)
     q = fma(q, r, 1.0)
     res = fma(T, q * r, T)
@@ -62,8 +64,8 @@ def tsincos2pi_word(w):
     low = (w & np.uint64(0xFFFFFF)).astype(np.float64)
     r = fma(low - 2.0**23, 1.4629180792671596e-09, 7.314590396335798e-10)
     r2 = r * r
-    sr = fma(r, r2 * fma(r2, 1.0 / 120.0, -1.0 / 6.0), r)
-    cm = r2 * fma(fma(r2, -1.0 / 720.0, 1.0 / 24.0), r2, -0.5)
+    sr = fma(r, r2 * fma(r2, C120, -1.0 / 6.0), r)
+    cm = r2 * fma(fma(r2, -C720, 1.0 / 24.0), r2, -0.5)
     C, S = COST[j], SINT[j]
     return S + fma(S, cm, C * sr), C + fma(C, cm, -(S * sr))
 
