@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final_combo(DevPro
 #define BAM_CB_MINB 2
 #endif
 #ifndef BAM_CB_ILP
-#define BAM_CB_ILP 4
+#define BAM_CB_ILP 5  /* observations per loop iteration: 3 / 4 / 5 / 6 measured 1.535 / 1.496 / 1.467 / 1.491 ms (cfg 2) */
 #endif
 template <int NC, int SIGF>
 __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(DevProblem p, int K, int TOBS, const int* __restrict__ tStart,
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(Dev
         // non-positive sigma makes the vector infeasible (:3210): flagged through the sign of (high word - 1), the
         // (garbage) contribution is still accumulated because the sum of an infeasible vector is never read.
         int badAcc = 0;
-        // The sum of the log-variances is accumulated as ONE product of mantissas (four independent chains, one per
+        // The sum of the log-variances is accumulated as ONE product of mantissas (BAM_CB_ILP independent chains, one per
         // observation slot of the unrolled loop) plus an integer sum of exponents: log(prod m_i) + ln2 * sum e_i costs
         // one DMUL and three integer instructions per observation instead of the eight FP64 instructions of a
         // table-driven log.  A mantissa product grows by < 2 per factor, i.e. < 2^64 per chain and tile: no overflow.
