@@ -25,6 +25,7 @@
 #include "bam_fastmath.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
+#include "bam_baratin_fast.cuh"
 
 namespace {
 
@@ -35,84 +36,94 @@ __device__ __forceinline__ double xval(const double* __restrict__ x, size_t base
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: prior + per-chain table
+// K2: prior + per-chain table.  ONE WARP PER VECTOR: lanes stride over the parameters (priors, copula scores), over the
+// copula's columns, over the table entries and over the VAR combinations (one model pre-pass per lane).  With one thread
+// per vector this kernel was a serial chain of ~4500 instructions (19 log-densities, 19 quantiles + a 19 x 19 product,
+// five continuity pre-passes with two pow each for cfg 2): 55 us of a 1.5 ms step at K = 4096 and 80 us of a 0.11 ms
+// step for a single chain.
+// The reference evaluates the priors in sequence and leaves at the first parameter that is infeasible or has zero
+// density (GetPriorLogPdf :3062-3112: remnant parameters, then theta, then the copula); the flag of a vector is
+// therefore that of its FIRST failing parameter in that order, found here with a warp minimum over (order, kind).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* __restrict__ x, int K, int comp,
-                                                    const double* __restrict__ delta, double* __restrict__ tab,
-                                                    double* __restrict__ prior_out, int* __restrict__ status,
-                                                    double* __restrict__ dpar) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+#define PREP_WARPS 4
+__global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, const double* __restrict__ x, int K, int comp,
+                                                                const double* __restrict__ delta, double* __restrict__ tab,
+                                                                double* __restrict__ prior_out, int* __restrict__ status,
+                                                                double* __restrict__ dpar) {
+    extern __shared__ double psm[];  // PREP_WARPS x kM copula scores
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * PREP_WARPS + w;
     if (c >= K) return;
+    double* vcop = psm + (size_t)w * max(p.kM, 1);
     const size_t base = (size_t)c * p.P;
     const double dl = (comp >= 0) ? delta[c] : 0.0;
-    int st = 0;
-    double prior = 0.0, lp;
-    bool feas = true, isnull = false;
-
-    // GetPriorLogPdf (:3006-3138): remnant parameters first, then theta
-    for (int j = 0; j < p.nY && !st; ++j) {
-        double s = 0.0;
-        for (int m = 0; m < p.nrem[j]; ++m) {
-            const int g = p.gamOff[j] + m;
-            dist_logpdf(p.pgDist[g], p.pgPar + (size_t)g * BAMGPU_PRIOR_NPAR, xval(x, base, p.nFit + g, comp, dl), lp,
-                        feas, isnull);
-            if (!feas) { st = ST_PRIOR_INFEAS; break; }
-            if (isnull) { st = ST_PRIOR_NULL; break; }
-            s = s + lp;
+    const int npar = p.nFit + p.nGamma;
+    // ---- priors: order index of a parameter = its place in the reference's sequence (gamma first, then theta)
+    double pr = 0.0;
+    unsigned fail = 0xffffffffu;  // (order << 1) | kind, kind 0 = infeasible, 1 = null; minimum over the warp = first failure
+    for (int q = lane; q < npar; q += 32) {
+        double lp;
+        bool feas, isnull;
+        int order;
+        if (q < p.nGamma) {
+            dist_logpdf(p.pgDist[q], p.pgPar + (size_t)q * BAMGPU_PRIOR_NPAR, xval(x, base, p.nFit + q, comp, dl), lp, feas, isnull);
+            order = q;
+        } else {
+            const int k = q - p.nGamma;
+            dist_logpdf(p.ptDist[k], p.ptPar + (size_t)k * BAMGPU_PRIOR_NPAR, xval(x, base, k, comp, dl), lp, feas, isnull);
+            order = q;
         }
-        prior = prior + s;
+        if (!feas) fail = min(fail, ((unsigned)order << 1));
+        else if (isnull) fail = min(fail, ((unsigned)order << 1) | 1u);
+        else pr += lp;
     }
-    if (!st) {
-        double s = 0.0;
-        for (int k = 0; k < p.nFit; ++k) {
-            dist_logpdf(p.ptDist[k], p.ptPar + (size_t)k * BAMGPU_PRIOR_NPAR, xval(x, base, k, comp, dl), lp, feas,
-                        isnull);
-            if (!feas) { st = ST_PRIOR_INFEAS; break; }
-            if (isnull) { st = ST_PRIOR_NULL; break; }
-            s = s + lp;
-        }
-        prior = prior + s;
-    }
-    if (!st && p.priorM != nullptr) {  // Gaussian copula (:3080-3112), v = qnorm(cdf(x)) (Gcop_getV :4246)
-        double v[BAM_MAXCOPULA];
+    fail = __reduce_min_sync(0xffffffffu, fail);
+    if (fail == 0xffffffffu && p.priorM != nullptr) {  // Gaussian copula (:3080-3112), v = qnorm(cdf(x)) (Gcop_getV :4246)
         const int k = p.kM;
-        for (int i = 0; i < k && !st; ++i) {
+        unsigned cfail = 0xffffffffu;
+        for (int i = lane; i < k; i += 32) {
             double u;
             bool f;
             if (i < p.nFit) dist_cdf(p.ptDist[i], p.ptPar + (size_t)i * BAMGPU_PRIOR_NPAR, xval(x, base, i, comp, dl), u, f);
-            else dist_cdf(p.pgDist[i - p.nFit], p.pgPar + (size_t)(i - p.nFit) * BAMGPU_PRIOR_NPAR,
-                          xval(x, base, i, comp, dl), u, f);
-            if (!f || !(u > 0.0 && u < 1.0)) { st = ST_PRIOR_INFEAS; break; }
-            v[i] = normcdfinv(u);
+            else dist_cdf(p.pgDist[i - p.nFit], p.pgPar + (size_t)(i - p.nFit) * BAMGPU_PRIOR_NPAR, xval(x, base, i, comp, dl), u, f);
+            if (!f || !(u > 0.0 && u < 1.0)) { cfail = 0u; vcop[i] = 0.0; }
+            else vcop[i] = normcdfinv(u);
         }
-        if (!st) {
-            double q = 0.0;
-            for (int cc = 0; cc < k; ++cc) {
-                double w = 0.0;
-                for (int r = 0; r < k; ++r) w = w + v[r] * p.priorM[r + (size_t)cc * k];
-                q = q + w * v[cc];
+        cfail = __reduce_min_sync(0xffffffffu, cfail);
+        __syncwarp();
+        if (cfail == 0u) fail = ((unsigned)npar << 1);  // after every prior: infeasible
+        else {
+            double qf = 0.0;
+            for (int cc = lane; cc < k; cc += 32) {
+                double wv = 0.0;
+                for (int r = 0; r < k; ++r) wv = wv + vcop[r] * p.priorM[r + (size_t)cc * k];
+                qf += wv * vcop[cc];
             }
-            prior = prior - 0.5 * q;
+            pr -= 0.5 * qf;
         }
     }
-    if (!st) {  // N(0,1) priors of the input / output biases (:3116-3135)
-        for (int j = 0; j < p.nX; ++j)
-            for (int i = 0; i < p.nXb[j]; ++i) prior = prior + gauss_logpdf(xval(x, base, p.offXb[j] + i, comp, dl), 0.0, 1.0);
-        for (int j = 0; j < p.nY; ++j)
-            for (int i = 0; i < p.nYb[j]; ++i) prior = prior + gauss_logpdf(xval(x, base, p.offYb[j] + i, comp, dl), 0.0, 1.0);
-    }
-
-    // per-chain table
-    double* row = tab + (size_t)c * p.tabStride;
-    for (int g = 0; g < p.nGamma; ++g) row[p.tabGamma + g] = xval(x, base, p.nFit + g, comp, dl);
+    // N(0,1) priors of the input / output biases (:3116-3135): never fail
     for (int j = 0; j < p.nX; ++j)
-        for (int i = 0; i < p.nXb[j]; ++i) row[p.tabOffXb[j] + i] = xval(x, base, p.offXb[j] + i, comp, dl);
+        for (int i = lane; i < p.nXb[j]; i += 32) pr += gauss_logpdf(xval(x, base, p.offXb[j] + i, comp, dl), 0.0, 1.0);
     for (int j = 0; j < p.nY; ++j)
-        for (int i = 0; i < p.nYb[j]; ++i) row[p.tabOffYb[j] + i] = xval(x, base, p.offYb[j] + i, comp, dl);
-    double th[BAM_MAXTHETA], der[BAM_MAXDER];
-    const double* xc[BAM_MAXX];
-    for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
-    for (int k = 0; k < p.nCombo; ++k) {  // ApplyModel_BaM theta expansion (:4133-4159), once per combination
+        for (int i = lane; i < p.nYb[j]; i += 32) pr += gauss_logpdf(xval(x, base, p.offYb[j] + i, comp, dl), 0.0, 1.0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, off);
+    int st = 0;
+    if (fail != 0xffffffffu) st = (fail & 1u) ? ST_PRIOR_NULL : ST_PRIOR_INFEAS;
+
+    // ---- per-chain table
+    double* row = tab + (size_t)c * p.tabStride;
+    for (int g = lane; g < p.nGamma; g += 32) row[p.tabGamma + g] = xval(x, base, p.nFit + g, comp, dl);
+    for (int j = 0; j < p.nX; ++j)
+        for (int i = lane; i < p.nXb[j]; i += 32) row[p.tabOffXb[j] + i] = xval(x, base, p.offXb[j] + i, comp, dl);
+    for (int j = 0; j < p.nY; ++j)
+        for (int i = lane; i < p.nYb[j]; i += 32) row[p.tabOffYb[j] + i] = xval(x, base, p.offYb[j] + i, comp, dl);
+    int stl = 0;
+    for (int k = lane; k < p.nCombo; k += 32) {  // ApplyModel_BaM theta expansion (:4133-4159), one combination per lane
+        double th[BAM_MAXTHETA], der[BAM_MAXDER];
+        const double* xc[BAM_MAXX];
+        for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
         double* cr = row + p.tabCombo + (size_t)k * p.comboStride;
         for (int i = 0; i < p.ntheta; ++i) {
             const int src = p.comboSrc[(size_t)k * p.ntheta + i];
@@ -122,13 +133,16 @@ __global__ void __launch_bounds__(128) logpost_prep(DevProblem p, const double* 
         for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
         const bool ok = model_prepare(p, th, der, xc, p.n);
         if (p.isSeries) der[0] = (double)c;  // this vector's column of the series buffer (model_apply looks it up)
-        if (!ok) st |= ST_LKH_INFEAS;
+        if (!ok) stl |= ST_LKH_INFEAS;
         for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
         if (dpar != nullptr)
             for (int d = 0; d < p.nDparModel; ++d) dpar[(size_t)c * p.nDpar + k * p.nDparModel + d] = ok ? der[d] : p.unfeas;
     }
-    prior_out[c] = prior;
-    status[c] = st;
+    st |= __reduce_or_sync(0xffffffffu, stl);
+    if (lane == 0) {
+        prior_out[c] = pr;
+        status[c] = st;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -159,10 +173,13 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
     double* red = sm + (size_t)CT * tabStride;  // [2][warpsPerRow][CT]
     int* sst = (int*)(red + 2 * warpsPerRow * CT);  // CT chain status
     double2* sLogT = reinterpret_cast<double2*>(sm + smemLogOff);  // table of the table-driven log (16-byte aligned)
+    double* sExpT = sm + smemLogOff + 2 * BAM_LOGTAB_N;            // and of the table-driven exp (BaRatin)
 
     const int tid = threadIdx.x;
     for (int q = tid; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
-    const unsigned lt = smem_addr(sLogT);
+    if (MODEL == BAMGPU_MDL_BARATIN)
+        for (int q = tid; q < BAM_EXPTAB_N; q += BAM_BLOCK) sExpT[q] = p.expTab[q];
+    const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT);
     const int tx = tid % TX, ty = tid / TX, TY = BAM_BLOCK / TX;
     const int lane = tid & 31, wrow = tx >> 5;
     const int c0 = blockIdx.y * CT;
@@ -247,7 +264,10 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
             }
             const double* __restrict__ th = row + p.tabCombo + (size_t)combo * p.comboStride;
             double yh[NY];
-            const bool ok = model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh);
+            // BaRatin (few chains on many gaugings never reach the chain-parallel fast path): same exits as
+            // baratin_apply, a (H-b)^c through the table-driven functions instead of libdevice log + exp
+            const bool ok = (MODEL == BAMGPU_MDL_BARATIN) ? baratin_apply_t(p, xt[0], th, th + p.ntheta, yh[0], lt, et)
+                                                          : model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh);
             if (!ok) bad = true;
             else {
 #pragma unroll
@@ -883,7 +903,7 @@ static void make_plan(bamgpu_handle* h, int K) {
     // [chain tables | cross-warp partials | chain status (int)] then, 16-byte aligned, the 4 KB log table
     const size_t head = ((size_t)ct * stride + 2 * (pl.TX / 32) * ct) * 8 + (size_t)ct * 4;
     pl.logOff = (int)((head + 15) / 16 * 2);  // in doubles
-    pl.smem = (size_t)pl.logOff * 8 + sizeof(double) * 2 * BAM_LOGTAB_N;
+    pl.smem = (size_t)pl.logOff * 8 + sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N);
 }
 
 #define BAM_FP_MAXCOMBO 64
@@ -1008,7 +1028,7 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
     DevProblem p = p0;
     p.X = d_xtrue;
     p.n = n;
-    logpost_prep<<<1, 128, 0, h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
+    logpost_prep<<<1, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
     double* d_idx = nullptr;
     if (p.isSeries) {  // the series of this one vector (outputs + states), then the lookup kernel on the row indices
         const int nOut = p.nY + model_nstate(p.model);
@@ -1035,7 +1055,8 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
 
 // only K2: the per-chain tables (gamma, biases, expanded theta + derived values) of the vectors at d_x
 void launch_table(bamgpu_handle* h, int K, const double* d_x) {
-    logpost_prep<<<(K + 127) / 128, 128, 0, h->stream>>>(h->dp, d_x, K, -1, nullptr, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
+    logpost_prep<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(h->dp.kM, 1), h->stream>>>(
+        h->dp, d_x, K, -1, nullptr, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
     h->launches += 1;
     BAM_CUDA(cudaGetLastError());
 }
@@ -1046,8 +1067,8 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     MainKernel kern = pick_main(p.model, p.nX, p.nY);
     if (!kern) throw CudaError{"bamgpu: no kernel instantiated for this (model, nX, nY)"};
     FastKernel fast = (p.n > 0 && !h->forceGeneric) ? pick_fast(p, K) : nullptr;
-    logpost_prep<<<(K + 127) / 128, 128, 0, h->stream>>>(p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status,
-                                                         h->d_dpar);
+    logpost_prep<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(
+        p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
     DevProblem pser = p;
     if (p.isSeries && p.n > 0) {  // time-recursive model: the outputs of all K vectors, then the generic likelihood kernel
         ensure_series_capacity(h, (size_t)p.seriesN * p.nY * K);
