@@ -187,7 +187,9 @@ int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s);
    streams are keyed by the GLOBAL chain index, so results do not depend on the GPU count) */
 int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset);
 /* tuning / test switches: "force_generic" (1 = never use the specialised fast kernels), "no_select3" (1 = skip the
-   2-read envelope selection), "no_partial" (1 = the sampler re-evaluates every observation for every proposal).  err=1 if unknown. */
+   2-read envelope selection), "only_radix" (1 = every large column through the last-resort radix selection),
+   "no_partial" (1 = the sampler re-evaluates every observation for every proposal), "no_fast_sweep" (1 = the generic
+   one-launch sweep over latent inputs instead of the Linear-specialised one).  err=1 if unknown. */
 int bamgpu_set_option(bamgpu_t* h, const char* name, int value);
 
 /* name -> enum helpers (return 0 when the name is unknown) */
