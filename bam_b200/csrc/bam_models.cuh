@@ -844,8 +844,8 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
             out[((size_t)3 * n + m) * K] = s3;
         }
     };
-    // point m-1 (suffix 1), m-2 (suffix 2), m-3 (ym only)
-    double dy1, ym1, Ae1, Rh1, dy2 = 0.0, ym2 = 0.0, Ae2 = 0.0, Rh2 = 0.0, ym3 = 0.0, Q1 = Q0, Q2 = 0.0;
+    // point m-1 (suffix 1); of point m-2 only ym is still needed (see below)
+    double dy1 = 0.0, ym1 = 0.0, Ae1 = 0.0, Rh1 = 0.0, ym2 = 0.0, Q1 = Q0;
     if (n > 0) { ok &= geom(0, dy1, ym1, Ae1, Rh1); put(0, Q0, 0.0, 0.0, 0.0); }
     auto pgf = [&](double Ae, double dy) { return __ddiv_rn(__dmul_rn(__dmul_rn(-g, Ae), __dadd_rn(dy, delta)), dx); };
     auto bff = [&](double Rh, double Q, double Ae) {
@@ -857,7 +857,6 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
     // the reference switches between the one-sided and the centred difference (:160-172).  They are carried over
     // instead of being recomputed (one pow and ~10 divisions per step), bit for bit the same values.
     double pgP = 0.0, bfP = 0.0, adP = 0.0;  // pgf / bff / adf of the previous step's point m-1
-    (void)dy2; (void)Ae2; (void)Rh2; (void)Q2; (void)ym3;
     for (int m = 1; m < n; ++m) {
         double dy0, ym0, Ae0, Rh0;
         ok &= geom(m, dy0, ym0, Ae0, Rh0);
