@@ -97,3 +97,32 @@ def test_prediction_single_replication_and_subranges():
     ef, sf = g.predict(mc, mode, [Hs], 1, [1], seed=9, want_spag=True)
     e, s = g.predict(mc, mode, [Hs], 1, [1], seed=9, t0=3, t1=50, want_spag=True)
     assert np.array_equal(s, sf[:, 3:50]) and np.array_equal(e, ef[:, :, 3:50])
+
+
+def test_first_failing_prior_decides_the_flag():
+    """GetPriorLogPdf leaves at the FIRST parameter (remnant parameters, then theta) that is infeasible (invalid prior
+    parameters) or has zero density: a null gamma before an infeasible theta prior is "null", an infeasible gamma prior
+    before a null theta is "infeasible".  The warp-parallel prior kernel reproduces the order."""
+    prob0, truth = synth.baratin_2c(nobs=50)
+    X, Y, Yu = np.asarray(prob0.X), np.asarray(prob0.Y), np.asarray(prob0.Yu)
+    good = [("Gaussian", [-0.5, 0.25]), ("Gaussian", [53, 10]), ("Gaussian", [1.5, 0.025]), ("Uniform", [0.5, 2.5]),
+            ("Gaussian", [144, 45]), ("Gaussian", [1.67, 0.025])]
+    bad_theta = list(good)
+    bad_theta[4] = ("Gaussian", [144, -1.0])  # invalid standard deviation: infeasible whatever the value
+    x = synth.feasible_starts(truth, 6, rel=0.001, seed=1)
+    x[1, 6] = -1.0   # gamma1 outside Uniform(0,1000): null, and gamma comes first
+    x[2, 3] = 9.0    # k2 outside its Uniform prior: null at theta 4 (before the invalid prior of theta 5)
+    for priors_theta, priors_gamma in ((bad_theta, [("Uniform", [0, 1000])] * 2),
+                                       (good, [("Gaussian", [1.0, -2.0]), ("Uniform", [0, 1000])])):
+        p = Problem("BaRatin", X, Y, Yu=Yu, partype=[0] * 6, priors_theta=priors_theta, sigma_func=["Linear"],
+                    priors_gamma=priors_gamma, xtra_i=[1, 0, 0, 1])
+        g, o = BamGpu(p), Oracle(p)
+        fx, feas, isnull = g.logpost(x)
+        ofx, ofeas, oisnull = o.logpost(x)
+        assert (feas == ofeas).all() and (isnull == oisnull).all()
+        assert (fx == -999999999.0).all()
+    # first problem: vector 1 null (gamma first), vector 2 null (theta 4 before theta 5), the others infeasible
+    p = Problem("BaRatin", X, Y, Yu=Yu, partype=[0] * 6, priors_theta=bad_theta, sigma_func=["Linear"],
+                priors_gamma=[("Uniform", [0, 1000])] * 2, xtra_i=[1, 0, 0, 1])
+    fx, feas, isnull = BamGpu(p).logpost(x)
+    assert list(isnull) == [0, 1, 1, 0, 0, 0] and list(feas) == [0, 1, 1, 0, 0, 0]
