@@ -267,3 +267,14 @@ __device__ __forceinline__ double philox_log_uniform_fast(uint64_t seed, uint64_
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
     return tlog_unit(u53(c0, c1), lt);
 }
+
+// one normal of the prediction noise stream (bam_device.cuh:philox_normal_pred) with the table-driven functions: for the
+// generic prediction kernel, which visits (replication, input, output) one at a time
+__device__ __forceinline__ double philox_normal_pred_fast(uint64_t seed, uint64_t rep, uint32_t t, uint32_t y, unsigned lt,
+                                                          unsigned st) {
+    uint32_t c0 = (uint32_t)rep, c1 = (uint32_t)(rep >> 32), c2 = t >> 2, c3 = y;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    double z0, z1;
+    box_muller_fast((t & 2u) ? c2 : c0, (t & 2u) ? c3 : c1, lt, st, z0, z1);
+    return (t & 1u) ? z1 : z0;
+}

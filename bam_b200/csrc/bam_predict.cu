@@ -67,14 +67,21 @@ template <int MODEL, int NX, int NY>
 __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a, const double* __restrict__ tab,
                                                        const int* __restrict__ status, double* const* __restrict__ xspag,
                                                        const int* __restrict__ nspag, double* __restrict__ V) {
-    extern __shared__ double sm[];  // [stride][BAM_BLOCK] : parameter k of thread t at sm[k*BLOCK + t]
+    extern __shared__ __align__(16) double sm[];  // [log table | (cos, sin) table | [stride][BAM_BLOCK] : parameter k of thread t at sm[k*BLOCK + t]]
+    double2* sLogT = reinterpret_cast<double2*>(sm);
+    double2* sScT = reinterpret_cast<double2*>(sm + 2 * BAM_LOGTAB_N);
+    for (int q = threadIdx.x; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
+    for (int q = threadIdx.x; q < BAM_SCTAB_N; q += BAM_BLOCK) sScT[q] = p.scTab[q];
+    __syncthreads();
+    const unsigned lt = smem_addr(sLogT), sct = smem_addr(sScT);
+    double* const smT = sm + 2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N;
     const int tid = threadIdx.x;
     const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
     const bool act = rep < a.Nrep;
     const int stride = a.stride;
     // a.stage == 0 (stride too large for shared memory, e.g. Mixture with its 148 weights): read the table row directly
     if (act && a.stage)
-        for (int k = 0; k < stride; ++k) sm[k * BAM_BLOCK + tid] = tab[(size_t)rep * stride + k];
+        for (int k = 0; k < stride; ++k) smT[k * BAM_BLOCK + tid] = tab[(size_t)rep * stride + k];
     const bool setOk = act ? (status[rep] == 0) : false;
     const int tBeg = blockIdx.y * 32, tEnd = min(a.nT, tBeg + 32);
     const double* xp[NX];
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
     // this replication's full theta + derived values: private copy, loaded once for all inputs of the tile
     double loc[BAM_MAXTHETA + BAM_MAXDER];
     const int np = p.ntheta + p.nDer;
-    if (a.stage) for (int k = 0; k < np; ++k) loc[k] = sm[(p.nGamma + k) * BAM_BLOCK + tid];
+    if (a.stage) for (int k = 0; k < np; ++k) loc[k] = smT[(p.nGamma + k) * BAM_BLOCK + tid];
     else for (int k = 0; k < np; ++k) loc[k] = tab[(size_t)rep * stride + p.nGamma + k];
     for (int t = tBeg; t < tEnd; ++t) {
         constexpr int NS = model_nstate(MODEL);
@@ -105,9 +112,9 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
             if (a.doRemnant[j] && v != p.unfeas) {
                 double gam[3];
                 for (int m = 0; m < p.nrem[j] && m < 3; ++m)
-                    gam[m] = a.stage ? sm[(p.gamOff[j] + m) * BAM_BLOCK + tid] : tab[(size_t)rep * stride + p.gamOff[j] + m];
+                    gam[m] = a.stage ? smT[(p.gamOff[j] + m) * BAM_BLOCK + tid] : tab[(size_t)rep * stride + p.gamOff[j] + m];
                 const double sig = sigmafunk(p.sigfunc[j], gam, v);
-                if (sig > 0.0) v = v + sig * philox_normal_pred(a.seed, (uint64_t)rep, (unsigned)(a.t0 + t), (unsigned)j);
+                if (sig > 0.0) v = v + sig * philox_normal_pred_fast(a.seed, (uint64_t)rep, (unsigned)(a.t0 + t), (unsigned)j, lt, sct);
             }
             V[((size_t)j * a.nT + t) * a.Nrep + rep] = v;
         }
@@ -1295,7 +1302,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         pser.seriesX = h->d_seriesXpred; pser.seriesN = h->predNobs; pser.seriesK = (int)Nrep; pser.seriesY = h->d_series;
         launch_series(h, pser, (int)Nrep, h->d_ptab, a.stride, p.nGamma, h->d_pstatus, nOutS);
     }
-    const size_t smemMain = a.stage ? sizeof(double) * (size_t)a.stride * BAM_BLOCK : 0;
+    const size_t smemMain = sizeof(double) * (2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N) + (a.stage ? sizeof(double) * (size_t)a.stride * BAM_BLOCK : 0);
     if (smemMain > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMain));
 
     int npad = 1;
