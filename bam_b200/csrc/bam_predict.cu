@@ -449,11 +449,11 @@ __global__ void __launch_bounds__(BAM_BLOCK) envelope_smem(long long Nrep, int n
                                                            const double* __restrict__ V, double* __restrict__ env) {
     extern __shared__ double s[];  // npad values + 32 scratch
     double* scratch = s + npad;
-    __shared__ int nbadS, mS;
+    __shared__ int nbadS;
     const int tid = threadIdx.x;
     const int colId = blockIdx.x;  // y*nT + t
     const double* col = V + (size_t)colId * Nrep;
-    if (tid == 0) { nbadS = 0; mS = 0; }
+    if (tid == 0) nbadS = 0;
     __syncthreads();
     int nb = 0;
     for (long long r = tid; r < Nrep; r += BAM_BLOCK) {
@@ -736,8 +736,8 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
     double* gath = reinterpret_cast<double*>(s2raw + sizeof(unsigned) * SEL_NT * S2_NB2);  // 10 x CAP doubles = 20 KB
     __shared__ double scratch[40];
     __shared__ short slotOfBin[S2_NB1];
-    __shared__ long long tRank[SEL_NT], tBefore[SEL_NT];
-    __shared__ int tBin1[SEL_NT], tSlot[SEL_NT], tBin2[SEL_NT], tList[SEL_NT], nSlots, nLists, gCount[SEL_NT], listSlot[SEL_NT],
+    __shared__ long long tRank[SEL_NT];
+    __shared__ int tBin1[SEL_NT], tSlot[SEL_NT], tBin2[SEL_NT], tList[SEL_NT], nLists, listSlot[SEL_NT],
         listBin2[SEL_NT];
     __shared__ double slotLo[SEL_NT], slotScale[SEL_NT], tVal[SEL_NT];
     __shared__ unsigned prefix[S2_THREADS];
@@ -825,7 +825,6 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
             if ((long long)hist[mid] <= rk) lo = mid; else hi = mid - 1;
         }
         tBin1[tid] = lo;
-        tBefore[tid] = hist[lo];
         tRank[tid] = rk - hist[lo];
     }
     __syncthreads();
@@ -845,7 +844,6 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
             }
             tSlot[k] = sl;
         }
-        nSlots = ns;
     }
     __syncthreads();
     const bool degenerate = !(mx > mn);
@@ -871,7 +869,6 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
             if (b >= S2_NB2) b = S2_NB2 - 1;
             tBin2[tid] = b;
             tRank[tid] -= acc;
-            gCount[tid] = (int)min((unsigned)0x7fffffff, hsl[b]);  // members of the selected sub-bin
         }
         __syncthreads();
         if (tid == 0) {  // distinct (slot, sub-bin) -> gather lists
