@@ -623,6 +623,9 @@ __global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final_combo(DevPro
 #ifndef BAM_CB_MINB
 #define BAM_CB_MINB 2
 #endif
+#ifndef BAM_CB_TOBS
+#define BAM_CB_TOBS 256  /* observations per tile (halved while the grid would leave SMs idle); 160 / 256 / 320 / 640: 1.467 / 1.464 / 1.460 / 1.482 ms */
+#endif
 #ifndef BAM_CB_ILP
 #define BAM_CB_ILP 5  /* observations per loop iteration: 3 / 4 / 5 / 6 measured 1.535 / 1.496 / 1.467 / 1.491 ms (cfg 2) */
 #endif
@@ -1087,7 +1090,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     const int* d_affected = nullptr;
     if (fast) {
         // observations per block: large tiles amortise the staging, but keep >= ~6 blocks per SM in flight
-        int tobs = 256;
+        int tobs = BAM_CB_TOBS;
         const int chainBlocks = (K + BAM_BLOCK - 1) / BAM_BLOCK;
         while (tobs > 128 && (long long)chainBlocks * ((p.n + tobs - 1) / tobs) < 148 * 6) tobs >>= 1;
         ensure_fast_tiles(h, tobs);
