@@ -192,6 +192,49 @@ def test_full_size_properties_cfg2():
     assert (np.abs(fx_all[:4] - ofx) <= 1e-12 * np.abs(ofx)).all()
 
 
+def test_full_size_properties_cfg3():
+    """BASELINE configs[2] size (10^6 observations, every input latent: P = 2 000 008): size-independent properties of
+    the cfg-3 fast path.  (1) the specialised kernel equals the generic one on the same vectors (parts included);
+    (2) bitwise repeatability and batch independence; (3) moving ONE latent input changes the posterior by exactly the
+    local term of its observation (the factorisation the latent sweep relies on); (4) spot parity against the oracle."""
+    n, K = 1_000_000, 8
+    prob, truth = synth.linear_latent(nobs=n)
+    rng = np.random.default_rng(5)
+    x = np.tile(truth, (K, 1))
+    x[:, :8] *= 1.0 + 0.01 * rng.standard_normal((K, 8))
+    x[:, 8:] += 0.05 * rng.standard_normal((K, 2 * n))
+    g = BamGpu(prob)
+    pr, lk, hy, feas, isnull = g.logpost_parts(x)
+    assert feas.all() and not isnull.any()
+    gg = BamGpu(prob)
+    gg.set_option("force_generic", 1)
+    pr2, lk2, hy2, _, _ = gg.logpost_parts(x)
+    assert (pr == pr2).all() and np.allclose(lk, lk2, rtol=1e-12, atol=0) and np.allclose(hy, hy2, rtol=1e-12, atol=0)
+    fx = g.logpost(x)[0]
+    assert (g.logpost(x)[0] == fx).all() and (g.logpost(x[:3])[0] == fx[:3]).all()
+    # (3) one latent input of observation i: f changes by [lkh_i + hyper_i](new) - [lkh_i + hyper_i](old)
+    i, d = 123_457, 0.07
+    y = x[:2].copy()
+    y[:, 8 + i] += d  # first input column of observation i
+    fy = g.logpost(y)[0]
+    X, Y, Yu, Xu = (np.asarray(a) for a in (prob.X, prob.Y, prob.Yu, prob.Xu))
+
+    def local(v):
+        th = v[:4].reshape(2, 2, order="F")
+        xt = np.array([v[8 + i], v[8 + n + i]])
+        yh = xt @ th
+        sig = v[[4, 6]] + v[[5, 7]] * np.abs(yh)
+        var = Yu[i] ** 2 + sig**2
+        lkh = np.sum(-0.5 * np.log(2 * np.pi * var) - 0.5 * (Y[i] - yh) ** 2 / var)
+        hyp = np.sum(-0.5 * np.log(2 * np.pi * Xu[i] ** 2) - 0.5 * ((X[i] - xt) / Xu[i]) ** 2)
+        return lkh + hyp
+
+    for k in range(2):
+        assert abs((fy[k] - fx[k]) - (local(y[k]) - local(x[k]))) <= 1e-9 * abs(fx[k]) * 1e-3 + 1e-6
+    ofx = Oracle(prob).logpost(x[:2], nthreads=2)[0]
+    assert (np.abs(fx[:2] - ofx) <= 1e-12 * np.abs(ofx)).all()
+
+
 @pytest.mark.parametrize("name,copula", [("baratin", False), ("baratin_spd", True), ("baratin_spd", False)])
 def test_chain_parallel_fast_path(name, copula):
     """K >= 128 BaRatin problems without latent inputs / biases run the chain-parallel kernel with the
