@@ -101,9 +101,9 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         if (e) { setmess(mess, m); delete h; return e; }
         const bam::HostLayout& L = h->L;
         if (L.nX > BAM_MAXX || L.nY > BAM_MAXY || L.ntheta > BAM_MAXTHETA || L.nGamma > BAM_MAXGAMMA ||
-            (pb->priorM && L.nFit + L.nGamma > BAM_MAXCOPULA) || L.vmMaxStack > BAM_VMSTACK) {
+            (pb->priorM && L.nFit + L.nGamma > BAM_MAXCOPULA) || L.vmMaxStack > BAM_VMSTACK || L.nDer > BAM_MAXDER) {
             delete h;
-            throw bam::CudaError{"bamgpu_create: problem exceeds the compiled limits (nX,nY<=8, ntheta<=160, copula<=96)"};
+            throw bam::CudaError{"bamgpu_create: problem exceeds the compiled limits (nX,nY<=8, ntheta<=160, derived values<=64, copula<=96)"};
         }
         h->device = device;
         BAM_CUDA(cudaSetDevice(device));
@@ -119,6 +119,9 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         }
         BAM_CUDA(cudaEventCreate(&h->ev0));
         BAM_CUDA(cudaEventCreate(&h->ev1));
+        BAM_CUDA(cudaDeviceGetAttribute(&h->smCount, cudaDevAttrMultiProcessorCount, device));
+        for (size_t i = 0; i < (size_t)L.n * L.nY; ++i)
+            if (!(std::fabs(pb->Yu[i]) <= 0x1p86)) h->fpYuOk = false;
 
         DevProblem& d = h->dp;
         memset(&d, 0, sizeof d);
@@ -181,8 +184,13 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
             return v;
         };
         const size_t sxd = (size_t)nDev * L.nX, syd = (size_t)nDev * L.nY;
+        double x0lo = 0.0, x0hi = 0.0;  // range of the first input (BaRatin: the stage), for the window of the joint log table
         {
             std::vector<double> xd = permXD(pb->X, L.nX);
+            for (int i = 0; i < nDev && L.nX > 0; ++i) {
+                if (i == 0) x0lo = x0hi = xd[0];
+                x0lo = std::min(x0lo, xd[i]); x0hi = std::max(x0hi, xd[i]);
+            }
             if (mixture)
                 for (int i = 0; i < nDev; ++i) {  // exact integers: event of the output block, position within the event
                     xd[i] = (double)(perm[i] / L.modelOpt[2] + 1);
@@ -226,6 +234,32 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
             d.scTab = reinterpret_cast<const double2*>(upload(h, sc.data(), sc.size()));
             d.logTab = reinterpret_cast<const double2*>(upload(h, lt.data(), lt.size()));
             d.expTab = upload(h, et.data(), et.size());
+            {
+                // joint (exponent, mantissa) log table + index-compensated exp table of the BaRatin fast path
+                // (bam_baratin_cb2.cuh).  Window: 16 binades ending 3 binades above the scale of the stage data, so that
+                // H - b is inside for every offset b within a few data ranges of the gaugings.
+                double S = std::max(std::max(std::fabs(x0lo), std::fabs(x0hi)), x0hi - x0lo);
+                if (!(S > 0.0) || !std::isfinite(S)) S = 1.0;
+                const int eTop = std::min(std::max(std::ilogb(S) + 3 + 1023, BAM_LOG2_NB + 1), 2046);  // biased, exclusive
+                const int E0 = eTop - BAM_LOG2_NB;
+                std::vector<double> lt2(2 * (size_t)BAM_LOG2_N), et2(BAM_EXPTAB_N);
+                for (int e = E0; e < eTop; ++e)
+                    for (int i = 0; i < 256; ++i) {
+                        const size_t slot = (size_t)(e & (BAM_LOG2_NB - 1)) * 256 + i;
+                        const double inv = std::ldexp(lt[2 * i], -(e - 1023));     // exact scaling of 1/c_i
+                        lt2[2 * slot] = inv;
+                        lt2[2 * slot + 1] = (double)((long double)(e - 1023) * 0.693147180559945309417232121458L - logl((long double)lt[2 * i]));
+                    }
+                for (int j = 0; j < BAM_EXPTAB_N; ++j) {
+                    uint64_t bits;
+                    std::memcpy(&bits, &et[j], 8);
+                    bits -= (uint64_t)j << (12 + 32);
+                    std::memcpy(&et2[j], &bits, 8);
+                }
+                d.logTab2 = reinterpret_cast<const double2*>(upload(h, lt2.data(), lt2.size()));
+                d.expTab2 = upload(h, et2.data(), et2.size());
+                d.logBaseHi = E0 << 20;
+            }
         }
         d.comboSrc = upload(h, L.comboSrc.data(), L.comboSrc.size());
         d.latIdx = L.hasLatent ? upload(h, permXI(L.latIdx.data(), L.nX).data(), L.latIdx.size()) : nullptr;  // hasLatent: perm is the identity

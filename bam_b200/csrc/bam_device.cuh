@@ -22,6 +22,8 @@
 #define BAM_VMSTACK 24
 #define BAM_LOGTAB_N 256  /* table-driven log: reciprocal table entries (bam_fastmath.cuh) */
 #define BAM_EXPTAB_N 256  /* table-driven exp: 2^(j/N) entries */
+#define BAM_LOG2_NB 16    /* joint (exponent, mantissa) log table of the BaRatin fast path: binades in the window */
+#define BAM_LOG2_N (BAM_LOG2_NB * 256)
 #define BAM_SCTAB_N 256   /* table-driven sin / cos of 2 pi u: (cos, sin) at the bin centres 2 pi (j + 0.5) / N */
 
 // chain status bits (priority order of the reference's early exits, GetPostLogPdf :3310-3382)
@@ -42,6 +44,9 @@ struct DevProblem {
     const int* comboStart;  // nCombo+1 : observations are stored sorted by combination; combo v = [start[v], start[v+1])
     const double2* logTab;  // BAM_LOGTAB_N x (1/c_i, -log(1/c_i)), c_i = 1 + (i+0.5)/N : table-driven log (bam_fastmath.cuh)
     const double* expTab;   // BAM_EXPTAB_N x 2^(j/N)                                    : table-driven exp
+    const double2* logTab2; // BAM_LOG2_N x (1/c, log c), c = 2^e (1 + (i+0.5)/256), slot (e mod 16, i): window [logBaseHi, +16 binades)
+    const double* expTab2;  // BAM_EXPTAB_N x 2^(j/N) with (j << 12) subtracted from the high word (bam_baratin_cb2.cuh)
+    int logBaseHi;          // high word of the window's lower bound 2^(E0-1023)
     const double2* scTab;   // BAM_SCTAB_N x (cos, sin)(2 pi (j + 0.5) / N)              : Box-Muller angle of the noise
     const int* comboSrc;  // nCombo x ntheta : position in the parameter vector, or -1 for FIX
     const int* latIdx;    // n x nX : position of the latent "true input" in the vector, or -1

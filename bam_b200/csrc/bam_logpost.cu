@@ -27,7 +27,12 @@
 #include "bam_models.cuh"
 #include "bam_baratin_fast.cuh"
 
+#ifndef BAM_CB_GEN
+#define BAM_CB_GEN 2  /* generation of the BaRatin fast path: 1 = logpost_baratin_cb, 2 = logpost_baratin_cb2 (persistent) */
+#endif
+
 namespace {
+#include "bam_baratin_cb2.cuh"
 
 // value q of vector c, with the optional single-component candidate shift
 __device__ __forceinline__ double xval(const double* __restrict__ x, size_t base, int q, int comp, double dl) {
@@ -810,6 +815,17 @@ FastKernel pick_fast(const DevProblem& p, int K) {
     return nullptr;
 }
 
+Fast2Kernel pick_fast2(const DevProblem& p, int K) {
+    if (!pick_fast(p, K) || !p.logTab2) return nullptr;
+    switch (p.ncontrol) {
+        case 1: return pick_fast2_sig<1>(p.sigfunc[0]);
+        case 2: return pick_fast2_sig<2>(p.sigfunc[0]);
+        case 3: return pick_fast2_sig<3>(p.sigfunc[0]);
+        case 4: return pick_fast2_sig<4>(p.sigfunc[0]);
+    }
+    return nullptr;
+}
+
 using MainKernel = void (*)(DevProblem, const double*, int, int, int, const double*, const int*, double*, int*, int,
                             const double*, int);
 
@@ -915,6 +931,22 @@ bool fast_path_keeps_combo_sums(const bamgpu_handle* h, int K) {
     return !h->forceGeneric && h->dp.n > 0 && pick_fast(h->dp, K) != nullptr && h->dp.nCombo <= BAM_FP_MAXCOMBO;
 }
 
+// Tile size of the persistent fast path: items = tiles x chain blocks are dealt round-robin to `slots` resident blocks, so
+// the cost is rounds x (tile + fixed per-item work); tiles are multiples of the group size, between 64 and BAM_CB_TOBS.
+static int pick_tile_size(const bamgpu_handle* h, int chainBlocks, int slots) {
+    const int nCombo = h->dp.nCombo;
+    int best = BAM_CB_TOBS / BAM_CB2_ILP * BAM_CB2_ILP;
+    double bestCost = 1e300;
+    for (int tobs = best; tobs >= 64; tobs -= BAM_CB2_ILP) {
+        long long tiles = 0;
+        for (int v = 0; v < nCombo; ++v) tiles += (h->comboStartHost[v + 1] - h->comboStartHost[v] + tobs - 1) / tobs;
+        const long long rounds = (tiles * chainBlocks + slots - 1) / slots;
+        const double cost = (double)rounds * (tobs + 3);
+        if (cost < bestCost * 0.995) { bestCost = cost; best = tobs; }
+    }
+    return best;
+}
+
 // tiles of at most `tobs` observations that never straddle two VAR combinations (observations are stored sorted by
 // combination): tile table on the device, tile range of every combination on host and device
 static void ensure_fast_tiles(bamgpu_handle* h, int tobs) {
@@ -998,7 +1030,7 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     make_plan(h, K);
     BAM_CUDA(cudaMalloc(&h->d_x, sizeof(double) * (size_t)K * p.P));
     BAM_CUDA(cudaMalloc(&h->d_tab, sizeof(double) * (size_t)K * p.tabStride));
-    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * (std::max(std::max(h->plan.nTiles, (h->dp.n + 127) / 128), 1) + p.nCombo)));
+    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * (std::max(std::max(h->plan.nTiles, (h->dp.n + 63) / 64), 1) + p.nCombo)));
     if (p.nCombo <= BAM_FP_MAXCOMBO) {
         BAM_CUDA(cudaMalloc(&h->d_lkCcur, sizeof(double) * (size_t)K * p.nCombo));
         BAM_CUDA(cudaMalloc(&h->d_lkCcand, sizeof(double) * (size_t)K * p.nCombo));
@@ -1089,10 +1121,18 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     bool comboFinal = false;
     const int* d_affected = nullptr;
     if (fast) {
+        const int chainBlocks = (K + BAM_BLOCK - 1) / BAM_BLOCK;
+        const int slots = BAM_CB2_MINB * h->smCount;  // persistent blocks
+#if BAM_CB_GEN == 2
+        Fast2Kernel fast2 = h->fpYuOk ? pick_fast2(p, K) : nullptr;
+        int tobs = BAM_CB_TOBS;
+        if (fast2) tobs = pick_tile_size(h, chainBlocks, slots);
+#else
+        Fast2Kernel fast2 = nullptr;
         // observations per block: large tiles amortise the staging, but keep >= ~6 blocks per SM in flight
         int tobs = BAM_CB_TOBS;
-        const int chainBlocks = (K + BAM_BLOCK - 1) / BAM_BLOCK;
         while (tobs > 128 && (long long)chainBlocks * ((p.n + tobs - 1) / tobs) < 148 * 6) tobs >>= 1;
+#endif
         ensure_fast_tiles(h, tobs);
         nTiles = h->fpTiles;
         comboFinal = p.nCombo <= BAM_FP_MAXCOMBO;
@@ -1108,11 +1148,26 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
                 d_affected = h->d_compAffected[comp];
             }
         }
-        const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 3 * (size_t)tobs);
-        dim3 grid(std::max(launchTiles, 1), chainBlocks);
-        if (launchTiles > 0)
-            fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_fpStart, h->d_fpEnd, h->d_fpCombo, d_tiles, h->d_tab,
-                                                       h->d_status, h->d_part, h->d_status);
+        if (fast2) {
+            const int groups = (tobs + BAM_CB2_ILP - 1) / BAM_CB2_ILP;
+            const size_t smem = sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + (size_t)groups * CB2_GS);
+            if (!h->fp2Attr) {
+                // every instantiation that may be picked later for this handle is this one (model options are fixed)
+                BAM_CUDA(cudaFuncSetAttribute((const void*)fast2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + (size_t)(BAM_CB_TOBS / BAM_CB2_ILP + 2) * CB2_GS))));
+                h->fp2Attr = true;
+            }
+            const int nItems = launchTiles * chainBlocks;
+            if (nItems > 0)
+                fast2<<<std::min(nItems, slots), BAM_BLOCK, smem, h->stream>>>(p, K, nItems, chainBlocks, h->d_fpStart, h->d_fpEnd, h->d_fpCombo,
+                                                                            d_tiles, h->d_tab, h->d_status, h->d_part, h->d_status);
+        } else {
+            const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 3 * (size_t)tobs);
+            dim3 grid(std::max(launchTiles, 1), chainBlocks);
+            if (launchTiles > 0)
+                fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_fpStart, h->d_fpEnd, h->d_fpCombo, d_tiles, h->d_tab,
+                                                           h->d_status, h->d_part, h->d_status);
+        }
     } else if (LatentLogpostKernel lk = pick_latent(h, comp)) {
         nTiles = (p.n + BAM_BLOCK * LL_OPT - 1) / (BAM_BLOCK * LL_OPT);
         dim3 grid((K + LL_CT - 1) / LL_CT, nTiles);
