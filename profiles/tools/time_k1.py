@@ -1,6 +1,6 @@
 import sys, os; sys.path.insert(0, '.')
 import numpy as np
-from bam_b200 import synth
+from workloads import synth
 from bam_b200.capi import BamGpu, load_library
 LIB = load_library(os.environ['BAM_LIB']) if os.environ.get('BAM_LIB') else None
 Ks = [int(k) for k in os.environ.get('BAM_K', '4096').split(',')]

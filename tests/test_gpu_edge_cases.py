@@ -3,7 +3,7 @@ chains / single replications, sub-ranges of a prediction."""
 import numpy as np
 import pytest
 
-from bam_b200 import synth
+from workloads import synth
 from bam_b200.capi import BamGpu, Problem
 from oracle.oracle_api import Oracle
 from tests.helpers import perturbed_vectors, problem_from_fixture

@@ -9,7 +9,7 @@ Feasibility / null flags (integer work) must be identical.
 import numpy as np
 import pytest
 
-from bam_b200 import synth
+from workloads import synth
 from bam_b200.capi import BamGpu
 from oracle.oracle_api import Oracle
 from tests.helpers import perturbed_vectors, problem_from_fixture

@@ -7,7 +7,7 @@ The structural-error noise is a pure function of (seed, rep, t, y) on both sides
 import numpy as np
 import pytest
 
-from bam_b200 import synth
+from workloads import synth
 from bam_b200.capi import BamGpu
 from oracle.oracle_api import Oracle
 from tests.helpers import load_fixture, problem_from_fixture

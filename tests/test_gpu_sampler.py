@@ -6,7 +6,7 @@ component), short runs can also be compared trajectory by trajectory."""
 import numpy as np
 import pytest
 
-from bam_b200 import synth
+from workloads import synth
 from bam_b200.capi import BamGpu
 from oracle.oracle_api import Oracle
 from tests.helpers import problem_from_fixture

@@ -5,7 +5,7 @@ envelopes 1e-12, short sampler runs trajectory-identical."""
 import numpy as np
 import pytest
 
-from bam_b200 import synth
+from workloads import synth
 from bam_b200.capi import BamGpu
 from oracle.oracle_api import Oracle
 from tests.test_gpu_logpost import check_parity

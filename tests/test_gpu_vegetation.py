@@ -7,7 +7,7 @@ log-posterior and on every output column; row feasibility (integer work) must be
 import numpy as np
 import pytest
 
-from bam_b200 import synth
+from workloads import synth
 from bam_b200.capi import VEG_GROWTH, BamGpu, Problem
 from oracle.oracle_api import Oracle
 from tests.helpers import load_fixture

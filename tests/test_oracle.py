@@ -226,7 +226,7 @@ def test_vegetation_known_answer_columns():
 
 def test_vegetation_newton_root_is_the_root():
     """bending branch (chi < 0): the restated znewton returns the root of Vegetation_fNewton (:559) to rounding"""
-    from bam_b200 import synth
+    from workloads import synth
 
     prob, truth = synth.vegetation(nobs=300, growth="Growth_Yin1_temporal")
     o = Oracle(prob)
@@ -335,7 +335,7 @@ def test_mixture_on_the_reference_workspace():
 @pytest.mark.parametrize("missing", [True, False])
 def test_mixture_row_pairing(missing):
     """rows interleaved across events: output row (j-1)*nElt+e is the e-th INPUT row of event j (pack order)"""
-    from bam_b200 import synth
+    from workloads import synth
 
     prob, truth = synth.mixture(nS=3, nEvt=5, nElt=7, missing=missing, shuffle=True)
     X = np.asarray(prob.X)
@@ -352,7 +352,7 @@ def test_mixture_row_pairing(missing):
 def test_sfd_state_variable():
     """the transition stage kappa (SFD's state) solves fNewton_Val_General = 0 (StageFallDischarge_model.f90:253-283)
     and is undefRN on the rows that never solve for it (:126,148)"""
-    from bam_b200 import synth
+    from workloads import synth
 
     prob, truth = synth.sfd(nobs=120)
     o = Oracle(prob)
@@ -373,7 +373,7 @@ def test_sfd_state_variable():
 def test_sfdtidal_qmec_recursion():
     """time-recursive model (row f4): the restatement of SFDTidal_Qmec_Apply against an independent numpy run of the same
     scheme (first-order start, second-order Adams-Bashforth; bam_b200/synth.py), its three states, and the exits"""
-    from bam_b200 import synth
+    from workloads import synth
 
     prob, truth = synth.sfdtidal_qmec(nobs=400, missing_every=1)
     o = Oracle(prob)

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .capi import PARTYPE, SED_CO, SED_CSS, SED_FORMULA, SED_PPO, VEG_GROWTH, Problem
+from bam_b200.capi import PARTYPE, SED_CO, SED_CSS, SED_FORMULA, SED_PPO, VEG_GROWTH, Problem
 
 SEED = 20261019
 
