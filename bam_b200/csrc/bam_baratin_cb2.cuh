@@ -23,6 +23,21 @@
 //  * persistent blocks (2 per SM) loop over (tile, chain block) items: the 66 KB of tables are staged once per block,
 //    and small chain counts (512 per GPU in the strong-scaling configuration) still fill every SM with small tiles.
 //
+//  * generation 3, TAYLOR SUB-TILES.  The gaugings of a tile are sorted by stage, so a sub-tile of 80 consecutive gaugings
+//    spans a short stage interval [Hf, Hl] around its centre H0.  When no activation stage of the chain falls inside it,
+//    the rating curve  Q(H) = sum_{j active} a_j (H - b_j)^c_j  is analytic there and
+//        Q(H0 + d) = sum_m T_m d^m,   T_m = sum_j a_j (H0-b_j)^c_j binom(c_j, m) (H0-b_j)^-m :
+//    ONE degree-8 Horner evaluation (8 DFMA, whatever the number of active controls) replaces one table-driven power per
+//    active control (18 FP64 each).  The coefficients cost one power + a 4-instruction recurrence step per degree and
+//    control, once per (sub-tile, chain).  Lagrange remainder of control j, relative to its value at H0, for 0 < c <= D+1:
+//        |R_j| <= |binom(c_j, D+1)| rho_j^(D+1),   rho_j = max|d| / (Hf - b_j)
+//    (the smallest argument of the sub-tile in the denominator); a thread takes the expansion only if that bound is
+//    <= 2^-51 for every active control, rho <= 1/8, and the power at H0 is inside both tables.  The decision is per THREAD
+//    (a chain's value must not depend on its warp mates); neighbouring chains agree except next to a threshold, where
+//    the warp runs both paths.  A thread that declines runs the group path on the same sub-tile.  d = H - H0 is chain
+//    independent and staged next to the gaugings.  Sub-tiles start every TSUB groups from the start of a VAR combination,
+//    whatever the tile size, so the expansion points do not depend on the tile plan.
+//
 // Anything the group path cannot prove safe -- a stage boundary inside the group, H - b outside the table window,
 // |c log(H-b) + log a| >= 44, a chain whose remnant parameters fail the gate -- goes gauging by gauging through
 // cb2_obs_checked (table functions with every test), which itself hands values outside the table window to
@@ -40,6 +55,16 @@
 #ifndef BAM_CB2_EXP1C
 #define BAM_CB2_EXP1C 0 /* 1: one-constant argument reduction of exp (8 FP64, relative error |x| 1.1e-16) */
 #endif
+#ifndef BAM_CB2_TAYLOR
+#define BAM_CB2_TAYLOR 1 /* 1: Taylor sub-tile path (generation 3), see below */
+#endif
+#ifndef BAM_CB2_TDEG
+#define BAM_CB2_TDEG 8   /* degree of the per-(sub-tile, chain) expansion of the rating curve */
+#endif
+#ifndef BAM_CB2_TSUB
+#define BAM_CB2_TSUB 16  /* groups per sub-tile (x BAM_CB2_ILP gaugings) */
+#endif
+#define CB2_TEPS 0x1p-51                            /* bound on the relative truncation error of one control's power */
 #define CB2_GS ((3 * BAM_CB2_ILP + 1) & ~1)        /* doubles per staged group (multiple of 16 bytes) */
 #define CB2_XX_OOR 0x40460000u                      /* high word of 44.0 */
 #define CB2_WIN ((unsigned)BAM_LOG2_NB << 20)       /* width of the log window in high-word units */
@@ -110,55 +135,159 @@ __device__ __noinline__ Cb2Obs cb2_obs_slow(const double* __restrict__ cr, unsig
     return o;
 }
 
+// ---- staging: packed tiles in global memory, moved by the TMA engine (cp.async.bulk + mbarrier), double buffered ----
+// A tile of the plan is stored once per plan (cb2_pack_tiles) exactly as the kernel wants it in shared memory:
+//   [ {int nt, int combo, 0, 0} | G groups {H[ILP], Y[ILP], uQ^2[ILP], pad} | G groups {H - H0, Y, uQ^2, pad} | nSub x {H0, max|H-H0|, Hf, Hl} ]
+// with G = ceil(nt / ILP) and nSub = ceil(floor(nt / ILP) / TSUB), so staging is ONE bulk copy issued by one thread while
+// the block still works on the previous item, and the block needs one barrier per item instead of two.
+#define CB2_HDR 2 /* doubles in front of the groups */
+__host__ __device__ inline int cb2_tile_doubles(int nt) {
+    const int G = (nt + BAM_CB2_ILP - 1) / BAM_CB2_ILP, nSub = (nt / BAM_CB2_ILP + BAM_CB2_TSUB - 1) / BAM_CB2_TSUB;
+    return CB2_HDR + 2 * G * CB2_GS + 4 * nSub;
+}
+
+static __global__ void cb2_pack_tiles(DevProblem p, int nTiles, const int* __restrict__ tStart, const int* __restrict__ tEnd,
+                                      const int* __restrict__ tCombo, const long long* __restrict__ tOff, double* __restrict__ out) {
+    constexpr int ILP = BAM_CB2_ILP, TSUB = BAM_CB2_TSUB;
+    const int tile = blockIdx.x;
+    if (tile >= nTiles) return;
+    const int i0 = tStart[tile], nt = tEnd[tile] - i0;
+    const int G = (nt + ILP - 1) / ILP, ngAll = nt / ILP;
+    double* base = out + tOff[tile];
+    double* sObs = base + CB2_HDR;
+    double* sTay = sObs + (size_t)G * CB2_GS;
+    double* sMeta = sTay + (size_t)G * CB2_GS;
+    if (threadIdx.x == 0) {
+        int* hd = reinterpret_cast<int*>(base);
+        hd[0] = nt; hd[1] = tCombo[tile]; hd[2] = 0; hd[3] = 0;
+    }
+    for (int i = threadIdx.x; i < G * CB2_GS; i += blockDim.x) { sObs[i] = 0.0; sTay[i] = 0.0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        const int g = i / ILP, u = i - g * ILP;
+        const double yu = p.Yu[i0 + i], hh = p.X[i0 + i], yy = p.Y[i0 + i];
+        double* grp = sObs + (size_t)g * CB2_GS;
+        grp[u] = hh;
+        grp[ILP + u] = yy;
+        grp[2 * ILP + u] = yu * yu;
+        if (g < ngAll) {
+            const int sb = g / TSUB;
+            const int s0 = sb * TSUB * ILP, s1 = min((sb + 1) * TSUB, ngAll) * ILP;
+            const double hf = p.X[i0 + s0], hl = p.X[i0 + s1 - 1];
+            const double h0 = 0.5 * (hf + hl);
+            double* tg = sTay + (size_t)g * CB2_GS;
+            tg[u] = hh - h0;
+            tg[ILP + u] = yy;
+            tg[2 * ILP + u] = yu * yu;
+            if (i == s0) {
+                double* me = sMeta + 4 * sb;
+                me[0] = h0; me[1] = fmax(h0 - hf, hl - h0); me[2] = hf; me[3] = hl;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void cb2_mbar_init(unsigned bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void cb2_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void cb2_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CB2_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CB2_DONE;\n"
+        "bra CB2_WAIT;\n"
+        "CB2_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
+// sched[0] = next item to hand out (beyond the first one of every block), sched[1] = blocks that left the loop; the last
+// block to leave re-arms both, so the counters are zero again when the kernel ends.
 template <int NC, int SIGF>
-__global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(DevProblem p, int K, int nItems, int chainBlocks,
-                                                                         const int* __restrict__ tStart, const int* __restrict__ tEnd,
-                                                                         const int* __restrict__ tCombo, const int* __restrict__ tileIds,
+__global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(DevProblem p, int K, int nItems, int chainBlocks, int maxDoubles,
+                                                                         const double* __restrict__ packed, const long long* __restrict__ tOff,
+                                                                         const int* __restrict__ tBytes, const int* __restrict__ tileIds,
                                                                          const double* __restrict__ tab, const int* status,
-                                                                         double* __restrict__ part, int* statusOut) {
+                                                                         double* __restrict__ part, int* statusOut, int* sched) {
     constexpr int ILP = BAM_CB2_ILP;
     constexpr int CH = (SIGF == BAMGPU_SIG_PROPORTIONAL) ? (ILP < 4 ? ILP : 4) : (ILP < 5 ? ILP : 5);  // variances per product
+    constexpr int TD = BAM_CB2_TDEG, TSUB = BAM_CB2_TSUB;
     extern __shared__ __align__(16) double sm[];
     double2* sLog = reinterpret_cast<double2*>(sm);  // BAM_LOG2_N x 16 B
     double* sExp = sm + 2 * BAM_LOG2_N;
-    double* sObs = sExp + BAM_EXPTAB_N;              // groups of CB2_GS doubles
+    double* sCtl = sExp + BAM_EXPTAB_N;              // 2 mbarriers, 2 item ids
+    double* sBuf = sCtl + 4;                         // 2 x maxDoubles: packed tiles
 
     const int tid = threadIdx.x;
     for (int i = tid; i < BAM_LOG2_N; i += BAM_BLOCK) sLog[i] = p.logTab2[i];
     for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExp[i] = p.expTab2[i];
-    const unsigned lt = smem_addr(sLog), et = smem_addr(sExp), ot = smem_addr(sObs);
+    const unsigned lt = smem_addr(sLog), et = smem_addr(sExp);
+    const unsigned bar0 = smem_addr(sCtl), buf0 = smem_addr(sBuf);
+    volatile int* sItem = reinterpret_cast<volatile int*>(sCtl + 2);
     const unsigned baseHi = (unsigned)p.logBaseHi;
     // control matrix as nibbles: nibble r = row r-1 (nibble 0 = no control: H below every activation stage)
     unsigned mask4 = 0;
 #pragma unroll
     for (int r = 1; r <= NC; ++r) mask4 |= ((unsigned)(p.ctrlMask >> ((r - 1) * 8)) & 0xfu) << (4 * r);
 
-    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+    auto issue = [&](int item, int slot) {  // thread 0: the bulk copy of `item`'s tile into buffer `slot`
+        const int tsel = item / chainBlocks;
+        const int tile = tileIds ? tileIds[tsel] : tsel;
+        cb2_bulk_load(buf0 + (unsigned)slot * (unsigned)maxDoubles * 8u, packed + tOff[tile], (unsigned)tBytes[tile], bar0 + 8u * slot);
+    };
+    if (tid == 0) {
+        cb2_mbar_init(bar0);
+        cb2_mbar_init(bar0 + 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sItem[0] = blockIdx.x;
+        if ((int)blockIdx.x < nItems) issue(blockIdx.x, 0);
+    }
+    __syncthreads();
+    unsigned parity = 0;  // bit s = phase of buffer s
+    for (int cur = 0;; cur ^= 1) {
+        const int item = sItem[cur];
+        if (item >= nItems) break;
+        if (tid == 0) {  // hand out and prefetch the next item; its buffer was released by the barrier that ended the previous round
+            const int nxt = atomicAdd(&sched[0], 1) + (int)gridDim.x;
+            sItem[cur ^ 1] = nxt;
+            if (nxt < nItems) issue(nxt, cur ^ 1);
+        }
         const int tsel = item / chainBlocks, cb = item - tsel * chainBlocks;
         const int tile = tileIds ? tileIds[tsel] : tsel;
-        const int i0 = tStart[tile];
-        const int nt = tEnd[tile] - i0;
-        __syncthreads();  // the previous item's gaugings are no longer read
-        for (int i = tid; i < nt; i += BAM_BLOCK) {
-            const int g = i / ILP, u = i - g * ILP;
-            const double yu = p.Yu[i0 + i];
-            double* grp = sObs + (size_t)g * CB2_GS;
-            grp[u] = p.X[i0 + i];
-            grp[ILP + u] = p.Y[i0 + i];
-            grp[2 * ILP + u] = yu * yu;
-        }
-        __syncthreads();
+        cb2_mbar_wait(bar0 + 8u * cur, (parity >> cur) & 1u);
+        parity ^= 1u << cur;
+        const unsigned hb = buf0 + (unsigned)cur * (unsigned)maxDoubles * 8u;
+        int nt, combo;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(nt), "=r"(combo) : "r"(hb));
+        const int ngAll = nt / ILP;  // full groups
+        const unsigned ot = hb + 8u * CB2_HDR;
+        const unsigned tt = ot + (unsigned)((nt + ILP - 1) / ILP) * (CB2_GS * 8);
+        const unsigned mt = tt + (unsigned)((nt + ILP - 1) / ILP) * (CB2_GS * 8);
         const int c = cb * BAM_BLOCK + tid;
-        if (c >= K) continue;
-        const size_t o = ((size_t)tile * K + c) * 2;
-        part[o + 1] = 0.0;
-        if (status[c] != 0) { part[o] = 0.0; continue; }
-        const double* __restrict__ row = tab + (size_t)c * p.tabStride;
-        const double g1 = row[p.tabGamma], g2 = (SIGF == BAMGPU_SIG_LINEAR) ? row[p.tabGamma + 1] : 0.0;
-        const double* __restrict__ cr = row + p.tabCombo + (size_t)tCombo[tile] * p.comboStride;
+        // dead lanes (beyond K, or a vector whose prior already failed) stay in the loop for the barrier
+        const bool live = c < K && status[c] == 0;
+        const size_t o = ((size_t)tile * K + (c < K ? c : 0)) * 2;
+        if (c < K) {
+            part[o + 1] = 0.0;
+            if (!live) part[o] = 0.0;
+        }
+        const double* __restrict__ row = tab + (size_t)(live ? c : 0) * p.tabStride;
+        const double* __restrict__ cr = row + p.tabCombo + (size_t)combo * p.comboStride;
+        double g1 = 1.0, g2 = 0.0;
         double k[NC], b[NC], cc[NC], la[NC];
 #pragma unroll
-        for (int j = 0; j < NC; ++j) { k[j] = cr[3 * j]; cc[j] = cr[3 * j + 2]; b[j] = cr[3 * NC + j]; la[j] = cr[4 * NC + j]; }
+        for (int j = 0; j < NC; ++j) { k[j] = 0.0; cc[j] = 1.0; b[j] = 0.0; la[j] = 0.0; }
+        if (live) {
+            g1 = row[p.tabGamma];
+            if (SIGF == BAMGPU_SIG_LINEAR) g2 = row[p.tabGamma + 1];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) { k[j] = cr[3 * j]; cc[j] = cr[3 * j + 2]; b[j] = cr[3 * NC + j]; la[j] = cr[4 * NC + j]; }
+        }
         // gate: remnant parameters inside [2^-60, 2^20] (g2 may also be 0) bound every variance of the group path
         bool gate;
         {
@@ -225,13 +354,33 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
                 add_var(var);
             }
         };
-
-        const int ngFull = gate ? nt / ILP : 0;
-        if (ngFull > 0) {
-            int r = range(lds_f64(ot));
+        // Gaussian log-density of a group given its Q (GetLogLikelihood :3208-3225) in variance form; sigma > 0 by the gate
+        auto group_tail = [&](const double (&qq)[ILP], const double* yv, const double* vv) {
+            double var[ILP];
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                double sig;
+                if (SIGF == BAMGPU_SIG_CONSTANT) sig = g1;
+                else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(g2, fabs(qq[u]), g1);
+                else sig = g1 * fabs(qq[u]);
+                var[u] = fma(sig, sig, vv[u]);
+                const double res = yv[u] - qq[u];
+                s2 = fma(res * res, trcp(var[u]), s2);
+            }
+#pragma unroll
+            for (int u0 = 0; u0 < ILP; u0 += CH) {
+                double pc = var[u0];
+#pragma unroll
+                for (int u = u0 + 1; u < u0 + CH && u < ILP; ++u) pc *= var[u];
+                add_var(pc);
+            }
+        };
+        // the group path on groups [gA, gB): one table-driven power per (gauging, active control)
+        auto direct_groups = [&](int gA, int gB) {
+            int r = range(lds_f64(ot + (unsigned)gA * (CB2_GS * 8)));
             unsigned m = (mask4 >> (4 * r)) & 0xfu;
             double knext = next_stage(r);
-            for (int g = 0; g < ngFull; ++g) {
+            for (int g = gA; g < gB; ++g) {
                 double w[CB2_GS];
                 const unsigned ga = ot + (unsigned)g * (CB2_GS * 8);
 #pragma unroll
@@ -277,42 +426,118 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
                     }
                     continue;
                 }
-                // Gaussian log-density given Q (GetLogLikelihood :3208-3225) in variance form; sigma > 0 by the gate
-                double var[ILP];
+                group_tail(qq, &w[ILP], &w[2 * ILP]);
+            }
+        };
+        auto checked_groups = [&](int gA, int gB) {  // a chain whose remnant parameters fail the gate
+#pragma unroll 1
+            for (int i = gA * ILP; i < gB * ILP; ++i) {
+                const int g = i / ILP, u = i - g * ILP;
+                const unsigned ga = ot + (unsigned)g * (CB2_GS * 8);
+                obs_checked(lds_f64(ga + 8 * u), lds_f64(ga + 8 * (ILP + u)), lds_f64(ga + 8 * (2 * ILP + u)));
+            }
+        };
+
+#if BAM_CB2_TAYLOR
+        for (int sb = 0; sb * TSUB < ngAll; ++sb) {
+            const int gA = sb * TSUB, gB = min(gA + TSUB, ngAll);
+            // ---- expansion of the rating curve about the centre of the sub-tile, and the proof that it may be used
+            double T[TD + 1];
 #pragma unroll
-                for (int u = 0; u < ILP; ++u) {
-                    double sig;
-                    if (SIGF == BAMGPU_SIG_CONSTANT) sig = g1;
-                    else if (SIGF == BAMGPU_SIG_LINEAR) sig = fma(g2, fabs(qq[u]), g1);
-                    else sig = g1 * fabs(qq[u]);
-                    var[u] = fma(sig, sig, w[2 * ILP + u]);
-                    const double res = w[ILP + u] - qq[u];
-                    s2 = fma(res * res, trcp(var[u]), s2);
+            for (int q2 = 0; q2 <= TD; ++q2) T[q2] = 0.0;
+            bool el = live && gate;
+            if (el) {
+                const double2 m01 = lds_f64x2(mt + 32 * sb), m23 = lds_f64x2(mt + 32 * sb + 16);
+                const double H0 = m01.x, dmax = m01.y, Hf = m23.x, Hl = m23.y;
+                const int r = range(Hf);
+                el = !(Hl >= next_stage(r));  // the same stage range from the first to the last gauging
+                const unsigned m = (mask4 >> (4 * r)) & 0xfu;
+                if (SIGF == BAMGPU_SIG_PROPORTIONAL) el = el && m != 0;
+#pragma unroll
+                for (int j = 0; j < NC; ++j)
+                    if ((m >> j) & 1u) {
+                        const double x0 = H0 - b[j], xmin = Hf - b[j];
+                        double ty, pr;
+                        tlog2_parts(x0, lt, ty, pr);
+                        const double xx = fma(cc[j], pr, fma(cc[j], ty, la[j]));
+                        const double w0 = texp2_acc(xx, 0.0, et);  // a (H0 - b)^c
+                        const double inv = trcp(x0);
+                        const double rho = dmax * trcp(xmin);
+                        double t = w0, bn = 1.0;
+                        T[0] += t;
+#pragma unroll
+                        for (int q2 = 1; q2 <= TD; ++q2) {
+                            const double gq = fma(cc[j], 1.0 / q2, -(double)(q2 - 1) / q2);  // (c - q + 1) / q
+                            bn *= gq;
+                            t *= gq * inv;
+                            T[q2] += t;
+                        }
+                        bn *= fma(cc[j], 1.0 / (TD + 1), -(double)TD / (TD + 1));
+                        double rp = rho;  // rho^(TD+1)
+#pragma unroll
+                        for (int q2 = 1; q2 < TD + 1; ++q2) rp *= rho;
+                        const bool okj = ((unsigned)__double2hiint(x0) - baseHi < CB2_WIN) & (((unsigned)__double2hiint(xx) & 0x7fffffffu) < CB2_XX_OOR) &
+                                         (xmin > 0.0) & (rho <= 0.125) & (cc[j] > 0.0) & (cc[j] <= (double)(TD + 1)) & (fabs(bn) * rp <= CB2_TEPS);
+                        el = el && okj;
+                    }
+            }
+            if (!live) continue;
+            if (!el) {  // per THREAD: a chain's value never depends on the chains that share its warp
+                if (gate) direct_groups(gA, gB);
+                else checked_groups(gA, gB);
+                continue;
+            }
+            for (int g = gA; g < gB; ++g) {
+                double w[CB2_GS];
+                const unsigned ga = tt + (unsigned)g * (CB2_GS * 8);
+#pragma unroll
+                for (int q2 = 0; q2 < CB2_GS / 2; ++q2) {
+                    const double2 v = lds_f64x2(ga + 16 * q2);
+                    w[2 * q2] = v.x;
+                    w[2 * q2 + 1] = v.y;
                 }
+                double qq[ILP];
 #pragma unroll
-                for (int u0 = 0; u0 < ILP; u0 += CH) {
-                    double pc = var[u0];
+                for (int u = 0; u < ILP; ++u) qq[u] = fma(T[TD], w[u], T[TD - 1]);
 #pragma unroll
-                    for (int u = u0 + 1; u < u0 + CH && u < ILP; ++u) pc *= var[u];
-                    add_var(pc);
-                }
+                for (int q2 = TD - 2; q2 >= 0; --q2)
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u) qq[u] = fma(qq[u], w[u], T[q2]);
+                group_tail(qq, &w[ILP], &w[2 * ILP]);
             }
         }
-#pragma unroll 1
-        for (int i = ngFull * ILP; i < nt; ++i) {
-            const int g = i / ILP, u = i - g * ILP;
-            const unsigned ga = ot + (unsigned)g * (CB2_GS * 8);
-            obs_checked(lds_f64(ga + 8 * u), lds_f64(ga + 8 * (ILP + u)), lds_f64(ga + 8 * (2 * ILP + u)));
+#else
+        if (live) {
+            if (gate) direct_groups(0, ngAll);
+            else checked_groups(0, ngAll);
         }
-        // sum_i log N(y_i; q_i, sqrt(var_i)) = -n log sqrt(2 pi) - 0.5 [ sum log var_i + sum res_i^2 / var_i ]
-        const double lsum = fma((double)pe, kFM[4], log(pm));
-        part[o] = fma(-0.5, lsum + s2, -BAM_LOG_SQRT_2PI * (double)nt);
-        if (bad) atomicOr(&statusOut[c], ST_LKH_INFEAS);
+#endif
+        if (live) {
+#pragma unroll 1
+            for (int i = ngAll * ILP; i < nt; ++i) {
+                const int g = i / ILP, u = i - g * ILP;
+                const unsigned ga = ot + (unsigned)g * (CB2_GS * 8);
+                obs_checked(lds_f64(ga + 8 * u), lds_f64(ga + 8 * (ILP + u)), lds_f64(ga + 8 * (2 * ILP + u)));
+            }
+            // sum_i log N(y_i; q_i, sqrt(var_i)) = -n log sqrt(2 pi) - 0.5 [ sum log var_i + sum res_i^2 / var_i ]
+            const double lsum = fma((double)pe, kFM[4], log(pm));
+            part[o] = fma(-0.5, lsum + s2, -BAM_LOG_SQRT_2PI * (double)nt);
+            if (bad) atomicOr(&statusOut[c], ST_LKH_INFEAS);
+        }
+        __syncthreads();  // this item's tile is no longer read: its buffer may be refilled; the next item id is visible
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {  // every block has fetched its last item
+            sched[0] = 0;
+            sched[1] = 0;
+            __threadfence();
+        }
     }
 }
 
-using Fast2Kernel = void (*)(DevProblem, int, int, int, const int*, const int*, const int*, const int*, const double*, const int*,
-                             double*, int*);
+using Fast2Kernel = void (*)(DevProblem, int, int, int, int, const double*, const long long*, const int*, const int*, const double*,
+                             const int*, double*, int*, int*);
 
 template <int NC>
 Fast2Kernel pick_fast2_sig(int sigf) {

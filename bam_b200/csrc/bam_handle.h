@@ -41,6 +41,12 @@ struct bamgpu_handle {
     bool fp2Attr = false;  // dynamic shared-memory limit of the picked logpost_baratin_cb2 instantiation raised
     int smCount = 148;
     int *d_fpStart = nullptr, *d_fpEnd = nullptr, *d_fpCombo = nullptr, *d_fpComboTile0 = nullptr;
+    // packed tiles of logpost_baratin_cb2 (bam_baratin_cb2.cuh): one bulk copy per tile; offsets in doubles, sizes in bytes
+    double* d_fpPacked = nullptr;
+    long long* d_fpOff = nullptr;
+    int* d_fpBytes = nullptr;
+    int* d_fpSched = nullptr;  // {next item, blocks done}: re-armed by the kernel itself
+    int fpMaxDoubles = 0;
     std::vector<int> comboStartHost, fpComboTile0;
     double *d_lkCcur = nullptr, *d_lkCcand = nullptr;  // nCombo x Kcap: per-combination log-likelihood of the current / candidate state
     std::vector<int*> d_compTiles, d_compAffected;      // per vector component: tile ids / 0-1 flag per combination (lazy)

@@ -931,18 +931,18 @@ bool fast_path_keeps_combo_sums(const bamgpu_handle* h, int K) {
     return !h->forceGeneric && h->dp.n > 0 && pick_fast(h->dp, K) != nullptr && h->dp.nCombo <= BAM_FP_MAXCOMBO;
 }
 
-// Tile size of the persistent fast path: items = tiles x chain blocks are dealt round-robin to `slots` resident blocks, so
-// the cost is rounds x (tile + fixed per-item work); tiles are multiples of the group size, between 64 and BAM_CB_TOBS.
+// Tile size of the persistent fast path: a whole number of Taylor sub-tiles (BAM_CB2_TSUB groups of BAM_CB2_ILP gaugings).
+// Items = tiles x chain blocks are handed out dynamically to `slots` resident blocks, so the idle tail at the end of the
+// launch is about half an item per block: large tiles amortise the per-item work (parameter loads, barrier, final log)
+// when there are many rounds, small tiles keep the tail short when chains are few (512 per GPU in the sharded cfg 2).
 static int pick_tile_size(const bamgpu_handle* h, int chainBlocks, int slots) {
     const int nCombo = h->dp.nCombo;
-    int best = BAM_CB_TOBS / BAM_CB2_ILP * BAM_CB2_ILP;
-    double bestCost = 1e300;
-    for (int tobs = best; tobs >= 64; tobs -= BAM_CB2_ILP) {
+    const int sub = BAM_CB2_TSUB * BAM_CB2_ILP;
+    int best = sub;
+    for (int tobs = (BAM_CB_TOBS / sub) * sub; tobs >= sub; tobs -= sub) {
         long long tiles = 0;
         for (int v = 0; v < nCombo; ++v) tiles += (h->comboStartHost[v + 1] - h->comboStartHost[v] + tobs - 1) / tobs;
-        const long long rounds = (tiles * chainBlocks + slots - 1) / slots;
-        const double cost = (double)rounds * (tobs + 3);
-        if (cost < bestCost * 0.995) { bestCost = cost; best = tobs; }
+        if (tiles * chainBlocks >= 8LL * slots || tobs == sub) { best = tobs; break; }
     }
     return best;
 }
@@ -952,7 +952,7 @@ static int pick_tile_size(const bamgpu_handle* h, int chainBlocks, int slots) {
 static void ensure_fast_tiles(bamgpu_handle* h, int tobs) {
     if (h->fpTobs == tobs && h->d_fpStart) return;
     auto fr = [](auto*& q) { if (q) cudaFree(q); q = nullptr; };
-    fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0);
+    fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0); fr(h->d_fpPacked); fr(h->d_fpOff); fr(h->d_fpBytes);
     for (auto*& q : h->d_compTiles) fr(q);
     for (auto*& q : h->d_compAffected) fr(q);
     h->d_compTiles.clear(); h->d_compAffected.clear(); h->compTileCnt.clear();
@@ -973,6 +973,33 @@ static void ensure_fast_tiles(bamgpu_handle* h, int tobs) {
         BAM_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, h->stream));
     };
     up(h->d_fpStart, ts); up(h->d_fpEnd, te); up(h->d_fpCombo, tc); up(h->d_fpComboTile0, h->fpComboTile0);
+#if BAM_CB_GEN == 2
+    {   // the tiles as logpost_baratin_cb2 stages them (one bulk copy each)
+        std::vector<long long> off(ts.size() + 1, 0);
+        std::vector<int> bytes(ts.size(), 0);
+        int mx = 0;
+        for (size_t t = 0; t < ts.size(); ++t) {
+            const int d = cb2_tile_doubles(te[t] - ts[t]);
+            bytes[t] = d * 8;
+            off[t + 1] = off[t] + d;
+            mx = std::max(mx, d);
+        }
+        h->fpMaxDoubles = mx;
+        BAM_CUDA(cudaMalloc(&h->d_fpPacked, sizeof(double) * std::max<long long>(off.back(), 2)));
+        BAM_CUDA(cudaMalloc(&h->d_fpOff, sizeof(long long) * off.size()));
+        BAM_CUDA(cudaMalloc(&h->d_fpBytes, sizeof(int) * std::max<size_t>(bytes.size(), 1)));
+        BAM_CUDA(cudaMemcpyAsync(h->d_fpOff, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, h->stream));
+        BAM_CUDA(cudaMemcpyAsync(h->d_fpBytes, bytes.data(), sizeof(int) * bytes.size(), cudaMemcpyHostToDevice, h->stream));
+        if (!h->d_fpSched) {
+            BAM_CUDA(cudaMalloc(&h->d_fpSched, 2 * sizeof(int)));
+            BAM_CUDA(cudaMemsetAsync(h->d_fpSched, 0, 2 * sizeof(int), h->stream));
+        }
+        if (!ts.empty())
+            cb2_pack_tiles<<<(int)ts.size(), 128, 0, h->stream>>>(h->dp, (int)ts.size(), h->d_fpStart, h->d_fpEnd, h->d_fpCombo, h->d_fpOff,
+                                                                  h->d_fpPacked);
+        BAM_CUDA(cudaGetLastError());
+    }
+#endif
     BAM_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
     h->lkCvalid = false;
 }
@@ -1149,18 +1176,20 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
             }
         }
         if (fast2) {
-            const int groups = (tobs + BAM_CB2_ILP - 1) / BAM_CB2_ILP;
-            const size_t smem = sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + (size_t)groups * CB2_GS);
+            // tables + {2 mbarriers, 2 item ids} + two packed-tile buffers
+            auto smem_for = [](int tileDoubles) { return sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + 4 + 2 * (size_t)tileDoubles); };
+            const size_t smem = smem_for(h->fpMaxDoubles);
             if (!h->fp2Attr) {
                 // every instantiation that may be picked later for this handle is this one (model options are fixed)
                 BAM_CUDA(cudaFuncSetAttribute((const void*)fast2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)(sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + (size_t)(BAM_CB_TOBS / BAM_CB2_ILP + 2) * CB2_GS))));
+                                              (int)smem_for(cb2_tile_doubles(BAM_CB_TOBS + BAM_CB2_ILP))));
                 h->fp2Attr = true;
             }
             const int nItems = launchTiles * chainBlocks;
             if (nItems > 0)
-                fast2<<<std::min(nItems, slots), BAM_BLOCK, smem, h->stream>>>(p, K, nItems, chainBlocks, h->d_fpStart, h->d_fpEnd, h->d_fpCombo,
-                                                                            d_tiles, h->d_tab, h->d_status, h->d_part, h->d_status);
+                fast2<<<std::min(nItems, slots), BAM_BLOCK, smem, h->stream>>>(p, K, nItems, chainBlocks, h->fpMaxDoubles, h->d_fpPacked, h->d_fpOff,
+                                                                            h->d_fpBytes, d_tiles, h->d_tab, h->d_status, h->d_part, h->d_status,
+                                                                            h->d_fpSched);
         } else {
             const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 3 * (size_t)tobs);
             dim3 grid(std::max(launchTiles, 1), chainBlocks);
