@@ -18,7 +18,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "g++"]
 LIB_SOURCES = ["bam_capi.cu", "bam_logpost.cu", "bam_sampler.cu", "bam_sampler_warp_a.cu", "bam_sampler_warp_b.cu",
-               "bam_sampler_warp_c.cu", "bam_latent.cu", "bam_predict.cu", "bam_host.cpp"]
+               "bam_sampler_warp_c.cu", "bam_latent.cu", "bam_predict.cu", "bam_comm.cu", "bam_host.cpp"]
 
 
 def _newer(src_list, target):
@@ -63,7 +63,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             logs = list(ex.map(_run, jobs))
     so = os.path.join(HERE, "libbam_gpu.so")
     if jobs or not os.path.exists(so):
-        _run([NVCC] + ARCH + ["-shared", "-o", so] + objs + ["-lcudart"])
+        _run([NVCC] + ARCH + ["-shared", "-o", so] + objs + ["-lcudart", "-ldl"])
     if verbose:
         print("\n".join(logs))
     return so

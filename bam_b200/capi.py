@@ -308,6 +308,15 @@ def load_library(path: Optional[str] = None):
                                _dp, C.POINTER(i64), cp]
     lib.bamgpu_moments.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, ci, cp]
     lib.bamgpu_rhat.argtypes = [ci, ci, _dp, _dp, _dp, _dp, cp]
+    lib.bamgpu_comm_unique_id.argtypes = [cp, cp]
+    lib.bamgpu_comm_init_rank.argtypes = [C.POINTER(H), ci, ci, cp, ci, cp]
+    lib.bamgpu_comm_init_all.argtypes = [C.POINTER(H), ci, _ip, cp]
+    lib.bamgpu_comm_destroy.argtypes = [H]
+    lib.bamgpu_comm_destroy.restype = None
+    lib.bamgpu_comm_info.argtypes = [H, _ip, _ip, _ip]
+    lib.bamgpu_moments_allgather.argtypes = [H, H, _dp, _dp, _dp, _dp, _dp, cp]
+    lib.bamgpu_envelope_allgather.argtypes = [H, H, ci, _dp, _dp, cp]
+    lib.bamgpu_comm_allreduce_sum.argtypes = [H, C.c_void_p, C.c_size_t, ci, C.c_void_p, cp]
     lib.bamgpu_predict.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, ci, _ip, u64, ci, ci, _dp, _dp, cp]
     lib.bamgpu_predict_states.argtypes = lib.bamgpu_predict.argtypes
     lib.bamgpu_predict_upload.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, cp]
@@ -593,6 +602,24 @@ class BamGpu:
         if self.lib.bamgpu_set_option(self.h, name.encode(), int(value)) != 0:
             raise ValueError(f"unknown option {name}")
 
+    # -- multi-GPU exchanges (NCCL inside the library) ---------------------------------------
+    def moments_allgather(self, comm: "Comm"):
+        """R-hat over the chains of all ranks; returns (rhat[P], ms of the collective)"""
+        out = np.empty(self.P)
+        ms = np.zeros(1)
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(self.lib.bamgpu_moments_allgather(self.h, comm.c, _ptr_d(out), None, None, None, _ptr_d(ms), mess), mess)
+        return out, float(ms[0])
+
+    def envelope_allgather(self, comm: "Comm", nobs_pred: int, n_out: Optional[int] = None):
+        """envelopes of the whole prediction from the per-rank slices; returns (env[nOut, 7, nobs_pred], ms)"""
+        n_out = n_out or self.problem.nY
+        env = np.empty((n_out, 7, nobs_pred))
+        ms = np.zeros(1)
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(self.lib.bamgpu_envelope_allgather(self.h, comm.c, nobs_pred, _ptr_d(env), _ptr_d(ms), mess), mess)
+        return env, float(ms[0])
+
     def set_chain_offset(self, off: int):
         self.lib.bamgpu_set_chain_offset(self.h, off)
 
@@ -601,3 +628,38 @@ class BamGpu:
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.bamgpu_last_kernel_ms(self.h))
+
+
+class Comm:
+    """One NCCL communicator rank (bamgpu_comm_t).  `unique_id()` on rank 0, broadcast the 128 bytes, `Comm(n, r, id, dev)`."""
+
+    def __init__(self, nranks: int, rank: int, uid: bytes, device: int, lib=None):
+        self.lib = lib or load_library()
+        self.c = C.c_void_p()
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(self.lib.bamgpu_comm_init_rank(C.byref(self.c), nranks, rank, uid, device, mess), mess)
+        self.nranks, self.rank = nranks, rank
+
+    @staticmethod
+    def unique_id(lib=None) -> bytes:
+        lib = lib or load_library()
+        buf = C.create_string_buffer(128)
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(lib.bamgpu_comm_unique_id(buf, mess), mess)
+        return buf.raw
+
+    def nccl_version(self) -> int:
+        v = np.zeros(1, dtype=np.int32)
+        self.lib.bamgpu_comm_info(self.c, None, None, v.ctypes.data_as(C.POINTER(C.c_int32)))
+        return int(v[0])
+
+    def close(self):
+        if self.c:
+            self.lib.bamgpu_comm_destroy(self.c)
+            self.c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

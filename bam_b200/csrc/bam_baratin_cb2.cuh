@@ -43,6 +43,8 @@
 // cb2_obs_checked (table functions with every test), which itself hands values outside the table window to
 // cb2_obs_slow (libdevice, out of line).  All three tiers evaluate the same formulas; they agree to ~1e-15.
 #pragma once
+#include <type_traits>
+
 #include "bam_fastmath.cuh"
 #include "bam_handle.h"
 
@@ -59,12 +61,13 @@
 #define BAM_CB2_TAYLOR 1 /* 1: Taylor sub-tile path (generation 3), see below */
 #endif
 #ifndef BAM_CB2_TDEG
-#define BAM_CB2_TDEG 8   /* degree of the per-(sub-tile, chain) expansion of the rating curve */
+#define BAM_CB2_TDEG 16  /* highest degree of the per-(sub-tile, chain) expansion of the rating curve */
 #endif
+#define CB2_TDMIN 4      /* lowest degree (the remainder bound needs c <= degree + 1) */
 #ifndef BAM_CB2_TSUB
 #define BAM_CB2_TSUB 16  /* groups per sub-tile (x BAM_CB2_ILP gaugings) */
 #endif
-#define CB2_TEPS 0x1p-51                            /* bound on the relative truncation error of one control's power */
+#define CB2_TEPS 0x1p-52                            /* bound on the relative truncation error of one control's power */
 #define CB2_GS ((3 * BAM_CB2_ILP + 1) & ~1)        /* doubles per staged group (multiple of 16 bytes) */
 #define CB2_XX_OOR 0x40460000u                      /* high word of 44.0 */
 #define CB2_WIN ((unsigned)BAM_LOG2_NB << 20)       /* width of the log window in high-word units */
@@ -206,6 +209,14 @@ __device__ __forceinline__ void cb2_mbar_wait(unsigned bar, unsigned parity) {
         : "memory");
 }
 
+#ifdef BAM_CB2_TRACE
+__device__ long long g_cb2Trace[4 * 1024 + 2 * 16384];
+__device__ unsigned long long g_cb2Cnt[8];
+#define CB2_COUNT(i) atomicAdd(&g_cb2Cnt[i], 1ull)
+__device__ __forceinline__ long long cb2_gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#else
+#define CB2_COUNT(i)
+#endif
 // sched[0] = next item to hand out (beyond the first one of every block), sched[1] = blocks that left the loop; the last
 // block to leave re-arms both, so the counters are zero again when the kernel ends.
 template <int NC, int SIGF>
@@ -220,13 +231,19 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
     extern __shared__ __align__(16) double sm[];
     double2* sLog = reinterpret_cast<double2*>(sm);  // BAM_LOG2_N x 16 B
     double* sExp = sm + 2 * BAM_LOG2_N;
-    double* sCtl = sExp + BAM_EXPTAB_N;              // 2 mbarriers, 2 item ids
+    double* sLog1 = sExp + BAM_EXPTAB_N;             // BAM_LOGTAB_N x 16 B: exponent-free log table for arguments outside the window
+    double* sCtl = sLog1 + 2 * BAM_LOGTAB_N;         // 2 mbarriers, 2 item ids
     double* sBuf = sCtl + 4;                         // 2 x maxDoubles: packed tiles
 
     const int tid = threadIdx.x;
+#ifdef BAM_CB2_TRACE
+    int trItems = 0;
+    if (tid == 0 && blockIdx.x < 1024) { g_cb2Trace[4 * blockIdx.x] = cb2_gtime(); unsigned sid; asm("mov.u32 %0, %smid;" : "=r"(sid)); g_cb2Trace[4 * blockIdx.x + 3] = sid; }
+#endif
     for (int i = tid; i < BAM_LOG2_N; i += BAM_BLOCK) sLog[i] = p.logTab2[i];
     for (int i = tid; i < BAM_EXPTAB_N; i += BAM_BLOCK) sExp[i] = p.expTab2[i];
-    const unsigned lt = smem_addr(sLog), et = smem_addr(sExp);
+    for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) reinterpret_cast<double2*>(sLog1)[i] = p.logTab[i];
+    const unsigned lt = smem_addr(sLog), et = smem_addr(sExp), lt1 = smem_addr(sLog1);
     const unsigned bar0 = smem_addr(sCtl), buf0 = smem_addr(sBuf);
     volatile int* sItem = reinterpret_cast<volatile int*>(sCtl + 2);
     const unsigned baseHi = (unsigned)p.logBaseHi;
@@ -259,6 +276,9 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
         }
         const int tsel = item / chainBlocks, cb = item - tsel * chainBlocks;
         const int tile = tileIds ? tileIds[tsel] : tsel;
+#ifdef BAM_CB2_TRACE
+        if (tid == 0 && item < 16384) { g_cb2Trace[4096 + 2 * item] = cb2_gtime(); }
+#endif
         cb2_mbar_wait(bar0 + 8u * cur, (parity >> cur) & 1u);
         parity ^= 1u << cur;
         const unsigned hb = buf0 + (unsigned)cur * (unsigned)maxDoubles * 8u;
@@ -321,6 +341,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
         // one gauging, table functions with every test (BaRatin_computeQ :236-249 for a set that passed ApplyContinuity:
         // the "H-b<0" exits are dead, see the first-generation kernel)
         auto obs_checked = [&](double h, double y, double v2) {
+            CB2_COUNT(0);
             const unsigned m = (mask4 >> (4 * range(h))) & 0xfu;
             double q = 0.0;
             bool oor = false;
@@ -328,10 +349,13 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
             for (int j = 0; j < NC; ++j)
                 if ((m >> j) & 1u) {
                     const double x = h - b[j];
-                    double ty, pr;
-                    tlog2_parts(x, lt, ty, pr);
+                    const unsigned xh = (unsigned)__double2hiint(x);
+                    double ty = 0.0, pr = 0.0;
+                    if (xh - baseHi < CB2_WIN) tlog2_parts(x, lt, ty, pr);
+                    else if (xh - 0x00100000u < 0x7fe00000u) ty = tlog_pos(x, lt1);  // positive and normal, outside the window (just above an activation stage)
+                    else oor = true;                                                  // zero, denormal, negative, inf, NaN
                     const double xx = fma(cc[j], pr, fma(cc[j], ty, la[j]));
-                    oor |= ((unsigned)__double2hiint(x) - baseHi >= CB2_WIN) | (((unsigned)__double2hiint(xx) & 0x7fffffffu) >= CB2_XX_OOR);
+                    oor |= (((unsigned)__double2hiint(xx) & 0x7fffffffu) >= BAM_EXP_OOR);
                     q = texp2_acc(xx, q, et);
                 }
             double sig;
@@ -341,6 +365,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
             const double var = fma(sig, sig, v2);
             const unsigned vh = (unsigned)__double2hiint(var);
             if (oor || !gate || __double2hiint(sig) < 0x00100000 || vh - 0x00100000u >= 0x7fe00000u) {
+                CB2_COUNT(1);
                 const Cb2Obs so = cb2_obs_slow<NC, SIGF>(cr, mask4, g1, g2, h, y, v2);
                 bad |= so.bad;
                 s2 += so.s2;
@@ -417,8 +442,41 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
                     regular = (oorA < CB2_WIN) & (oorB < CB2_XX_OOR);
                 }
                 if (!regular) {  // rare: stage boundary inside the group, value outside a table
+                    CB2_COUNT(2);
+                    // The five gaugings together, each with its own control mask and the exponent-free log table (any
+                    // positive normal argument): one such group costs ~0.3 us of dependent latency instead of ~2 us for
+                    // five serial obs_checked calls -- and every lane meets its stage boundaries in groups of its own,
+                    // so a warp pays for each of them separately.
+                    bool hard = false;
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u) qq[u] = 0.0;
+                    unsigned mu[ILP];
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u) {
+                        mu[u] = (mask4 >> (4 * range(w[u]))) & 0xfu;
+                        if (SIGF == BAMGPU_SIG_PROPORTIONAL) hard |= mu[u] == 0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        double xx[ILP];
+#pragma unroll
+                        for (int u = 0; u < ILP; ++u) {
+                            const bool act = (mu[u] >> j) & 1u;
+                            const double x = w[u] - b[j];
+                            const bool okx = (unsigned)__double2hiint(x) - 0x00100000u < 0x7fe00000u;  // positive and normal
+                            xx[u] = fma(cc[j], tlog_pos((act && okx) ? x : 1.0, lt1), la[j]);
+                            hard |= act && (!okx || ((unsigned)__double2hiint(xx[u]) & 0x7fffffffu) >= CB2_XX_OOR);
+                        }
+#pragma unroll
+                        for (int u = 0; u < ILP; ++u) {
+                            const double e = texp2_acc(xx[u], 0.0, et);
+                            qq[u] += ((mu[u] >> j) & 1u) ? e : 0.0;
+                        }
+                    }
+                    if (!hard) group_tail(qq, &w[ILP], &w[2 * ILP]);
+                    else
 #pragma unroll 1
-                    for (int u = 0; u < ILP; ++u) obs_checked(lds_f64(ga + 8 * u), lds_f64(ga + 8 * (ILP + u)), lds_f64(ga + 8 * (2 * ILP + u)));
+                        for (int u = 0; u < ILP; ++u) obs_checked(lds_f64(ga + 8 * u), lds_f64(ga + 8 * (ILP + u)), lds_f64(ga + 8 * (2 * ILP + u)));
                     if (w[ILP - 1] >= knext) {
                         r = range(w[ILP - 1]);
                         m = (mask4 >> (4 * r)) & 0xfu;
@@ -446,6 +504,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
 #pragma unroll
             for (int q2 = 0; q2 <= TD; ++q2) T[q2] = 0.0;
             bool el = live && gate;
+            int deg = CB2_TDMIN;
             if (el) {
                 const double2 m01 = lds_f64x2(mt + 32 * sb), m23 = lds_f64x2(mt + 32 * sb + 16);
                 const double H0 = m01.x, dmax = m01.y, Hf = m23.x, Hl = m23.y;
@@ -463,48 +522,65 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
                         const double w0 = texp2_acc(xx, 0.0, et);  // a (H0 - b)^c
                         const double inv = trcp(x0);
                         const double rho = dmax * trcp(xmin);
-                        double t = w0, bn = 1.0;
+                        // t_q = w0 binom(c,q) / x0^q (coefficient), s_q = w0 binom(c,q) rho^q (remainder bound if the series
+                        // stops before q); the expansion of this control ends at the first q > TDMIN with |s_q| <= eps w0
+                        double t = w0, sq = w0;
+                        const double thr = CB2_TEPS * w0;
+                        int dj = TD + 1;
                         T[0] += t;
 #pragma unroll
-                        for (int q2 = 1; q2 <= TD; ++q2) {
+                        for (int q2 = 1; q2 <= TD + 1; ++q2) {
                             const double gq = fma(cc[j], 1.0 / q2, -(double)(q2 - 1) / q2);  // (c - q + 1) / q
-                            bn *= gq;
-                            t *= gq * inv;
-                            T[q2] += t;
+                            sq *= gq * rho;
+                            if (q2 > CB2_TDMIN && fabs(sq) <= thr) { dj = q2 - 1; break; }
+                            if (q2 <= TD) {
+                                t *= gq * inv;
+                                T[q2] += t;
+                            }
                         }
-                        bn *= fma(cc[j], 1.0 / (TD + 1), -(double)TD / (TD + 1));
-                        double rp = rho;  // rho^(TD+1)
-#pragma unroll
-                        for (int q2 = 1; q2 < TD + 1; ++q2) rp *= rho;
                         const bool okj = ((unsigned)__double2hiint(x0) - baseHi < CB2_WIN) & (((unsigned)__double2hiint(xx) & 0x7fffffffu) < CB2_XX_OOR) &
-                                         (xmin > 0.0) & (rho <= 0.125) & (cc[j] > 0.0) & (cc[j] <= (double)(TD + 1)) & (fabs(bn) * rp <= CB2_TEPS);
+                                         (xmin > 0.0) & (rho <= 0.25) & (cc[j] > 0.0) & (cc[j] <= (double)(CB2_TDMIN + 1)) & (dj <= TD);
                         el = el && okj;
+                        deg = max(deg, dj);
                     }
             }
+            // degree class of the WARP: coefficients above a lane's own degree are exact zeros, so evaluating at a
+            // higher degree returns the same bits -- the lanes of a warp can share one loop without depending on each other
+            const int degw = __reduce_max_sync(0xffffffffu, el ? deg : 0);
             if (!live) continue;
+            CB2_COUNT(el ? 3 : 4);
             if (!el) {  // per THREAD: a chain's value never depends on the chains that share its warp
                 if (gate) direct_groups(gA, gB);
                 else checked_groups(gA, gB);
                 continue;
             }
-            for (int g = gA; g < gB; ++g) {
-                double w[CB2_GS];
-                const unsigned ga = tt + (unsigned)g * (CB2_GS * 8);
+            // Horner evaluation at the smallest compiled degree that covers `deg` (higher coefficients are exact zeros)
+            auto taylor_groups = [&](auto DEG) {
+                constexpr int D = decltype(DEG)::value;
+                for (int g = gA; g < gB; ++g) {
+                    double w[CB2_GS];
+                    const unsigned ga = tt + (unsigned)g * (CB2_GS * 8);
 #pragma unroll
-                for (int q2 = 0; q2 < CB2_GS / 2; ++q2) {
-                    const double2 v = lds_f64x2(ga + 16 * q2);
-                    w[2 * q2] = v.x;
-                    w[2 * q2 + 1] = v.y;
+                    for (int q2 = 0; q2 < CB2_GS / 2; ++q2) {
+                        const double2 v = lds_f64x2(ga + 16 * q2);
+                        w[2 * q2] = v.x;
+                        w[2 * q2 + 1] = v.y;
+                    }
+                    double qq[ILP];
+#pragma unroll
+                    for (int u = 0; u < ILP; ++u) qq[u] = fma(T[D], w[u], T[D - 1]);
+#pragma unroll
+                    for (int q2 = D - 2; q2 >= 0; --q2)
+#pragma unroll
+                        for (int u = 0; u < ILP; ++u) qq[u] = fma(qq[u], w[u], T[q2]);
+                    group_tail(qq, &w[ILP], &w[2 * ILP]);
                 }
-                double qq[ILP];
-#pragma unroll
-                for (int u = 0; u < ILP; ++u) qq[u] = fma(T[TD], w[u], T[TD - 1]);
-#pragma unroll
-                for (int q2 = TD - 2; q2 >= 0; --q2)
-#pragma unroll
-                    for (int u = 0; u < ILP; ++u) qq[u] = fma(qq[u], w[u], T[q2]);
-                group_tail(qq, &w[ILP], &w[2 * ILP]);
-            }
+            };
+            if (degw <= 5) taylor_groups(std::integral_constant<int, 5>{});
+            else if (degw <= 6) taylor_groups(std::integral_constant<int, 6>{});
+            else if (degw <= 8) taylor_groups(std::integral_constant<int, 8>{});
+            else if (TD >= 12 && degw <= 12) taylor_groups(std::integral_constant<int, (TD >= 12 ? 12 : TD)>{});
+            else taylor_groups(std::integral_constant<int, TD>{});
         }
 #else
         if (live) {
@@ -525,7 +601,14 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
             if (bad) atomicOr(&statusOut[c], ST_LKH_INFEAS);
         }
         __syncthreads();  // this item's tile is no longer read: its buffer may be refilled; the next item id is visible
+#ifdef BAM_CB2_TRACE
+        ++trItems;
+        if (tid == 0 && item < 16384) { g_cb2Trace[4096 + 2 * item + 1] = cb2_gtime(); }
+#endif
     }
+#ifdef BAM_CB2_TRACE
+    if (tid == 0 && blockIdx.x < 1024) { g_cb2Trace[4 * blockIdx.x + 1] = cb2_gtime(); g_cb2Trace[4 * blockIdx.x + 2] = trItems; }
+#endif
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {  // every block has fetched its last item

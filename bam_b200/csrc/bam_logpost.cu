@@ -1177,7 +1177,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         }
         if (fast2) {
             // tables + {2 mbarriers, 2 item ids} + two packed-tile buffers
-            auto smem_for = [](int tileDoubles) { return sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + 4 + 2 * (size_t)tileDoubles); };
+            auto smem_for = [](int tileDoubles) { return sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + 2 * BAM_LOGTAB_N + 4 + 2 * (size_t)tileDoubles); };
             const size_t smem = smem_for(h->fpMaxDoubles);
             if (!h->fp2Attr) {
                 // every instantiation that may be picked later for this handle is this one (model options are fixed)
@@ -1223,3 +1223,14 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
 }
 
 }  // namespace bam
+
+#ifdef BAM_CB2_TRACE
+extern "C" int bamgpu_debug_cb2_trace(long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, g_cb2Trace, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+extern "C" int bamgpu_debug_cb2_counts(unsigned long long* out, int reset) {
+    int e = cudaMemcpyFromSymbol(out, g_cb2Cnt, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : 1;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_cb2Cnt, z, sizeof(z)); }
+    return e;
+}
+#endif

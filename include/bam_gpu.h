@@ -277,6 +277,35 @@ int bamgpu_predict_resident(bamgpu_t* h, int doParametric, const int32_t* doRemn
                             int t1, char* mess);
 int bamgpu_predict_download(bamgpu_t* h, double* env, char* mess);
 
+/* ---- multi-GPU: the two exchanges of the path on an NCCL communicator ------------------------------
+   Chains shard across GPUs (observations replicated), prediction inputs shard across GPUs (samples replicated): no
+   collective on the data path.  One communicator rank per GPU.  NCCL (libnccl.so.2) is loaded at the first call. */
+#define BAMGPU_COMM_ID_BYTES 128
+typedef struct bamgpu_comm bamgpu_comm_t;
+/* one process per GPU: rank 0 creates the id, the host broadcasts the 128 bytes (MPI_Bcast, a file, ...), every rank
+   joins with its own `device` */
+int bamgpu_comm_unique_id(char* id128, char* mess);
+int bamgpu_comm_init_rank(bamgpu_comm_t** c, int nranks, int rank, const char* id128, int device, char* mess);
+/* one process, ndev GPUs (ncclCommInitAll): comms[i] is the rank-i communicator on devices[i] (NULL: 0..ndev-1); the
+   per-rank calls below must then be issued concurrently from one host thread per GPU */
+int bamgpu_comm_init_all(bamgpu_comm_t** comms, int ndev, const int* devices, char* mess);
+void bamgpu_comm_destroy(bamgpu_comm_t* c);
+int bamgpu_comm_info(const bamgpu_comm_t* c, int* nranks, int* rank, int* nccl_version);
+/* Gelman-Rubin across ALL chains of ALL ranks after bamgpu_fit (every rank holds the same number of chains): the
+   per-chain moments {count, mean[P], M2[P]} are packed into one message, all-gathered (one ncclAllGather) and the
+   statistic is computed redundantly on every rank.  rhat[P]; count_all[Ktot], mean_all / m2_all [P x Ktot] may be NULL;
+   *ms (may be NULL) = device time of the collective. */
+int bamgpu_moments_allgather(bamgpu_t* h, bamgpu_comm_t* c, double* rhat, double* count_all, double* mean_all,
+                             double* m2_all, double* ms, char* mess);
+/* prediction inputs sharded as t in [rank*per, min(nobs_pred,(rank+1)*per)), per = ceil(nobs_pred / nranks): after
+   bamgpu_predict_resident on that slice, gathers the envelope slices of all ranks; env_all is nobs_pred x 7 x nOut
+   column-major per output (the layout bamgpu_predict returns for t0 = 0, t1 = nobs_pred), on every rank. */
+int bamgpu_envelope_allgather(bamgpu_t* h, bamgpu_comm_t* c, int nobs_pred, double* env_all, double* ms, char* mess);
+/* in-place sum over ranks of a DEVICE buffer of `count` doubles (is_double != 0) or uint64 (the per-input histograms
+   of the sample-sharded envelope selection); on `cuda_stream` (asynchronous) or, if NULL, on the communicator's own
+   stream followed by a synchronisation */
+int bamgpu_comm_allreduce_sum(bamgpu_comm_t* c, void* dev_buf, size_t count, int is_double, void* cuda_stream, char* mess);
+
 /* ---- measurement helpers ---------------------------------------------------------------- */
 
 /* number of kernel launches issued by this handle since creation, and the device time (ms) of the
