@@ -57,6 +57,9 @@
 #ifndef BAM_CB2_EXP1C
 #define BAM_CB2_EXP1C 0 /* 1: one-constant argument reduction of exp (8 FP64, relative error |x| 1.1e-16) */
 #endif
+#ifndef BAM_CB2_COFACTOR
+#define BAM_CB2_COFACTOR 1 /* 1: one reciprocal per group of gaugings (common denominator) */
+#endif
 #ifndef BAM_CB2_TAYLOR
 #define BAM_CB2_TAYLOR 1 /* 1: Taylor sub-tile path (generation 3), see below */
 #endif
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
         };
         // Gaussian log-density of a group given its Q (GetLogLikelihood :3208-3225) in variance form; sigma > 0 by the gate
         auto group_tail = [&](const double (&qq)[ILP], const double* yv, const double* vv) {
-            double var[ILP];
+            double var[ILP], r2[ILP];
 #pragma unroll
             for (int u = 0; u < ILP; ++u) {
                 double sig;
@@ -390,14 +393,36 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
                 else sig = g1 * fabs(qq[u]);
                 var[u] = fma(sig, sig, vv[u]);
                 const double res = yv[u] - qq[u];
-                s2 = fma(res * res, trcp(var[u]), s2);
+                r2[u] = res * res;
             }
+            if (CH == ILP && ILP >= 3 && BAM_CB2_COFACTOR) {
+                // ONE reciprocal per group: sum_u r2_u / v_u = [sum_u r2_u prod_{w != u} v_w] / prod_w v_w.  The prefix products
+                // are the ones the log-variance sum needs anyway; suffix products and cofactors cost 2 (ILP - 2) + 1 more
+                // multiplications against 3 (ILP - 1) saved reciprocal steps.  The gate bounds every variance to
+                // [2^-120, 2^172], the data check |Y| <= 2^100 bounds r2, so no product leaves the normal range.
+                double pre[ILP], suf[ILP];
+                pre[0] = var[0];
 #pragma unroll
-            for (int u0 = 0; u0 < ILP; u0 += CH) {
-                double pc = var[u0];
+                for (int u = 1; u < ILP; ++u) pre[u] = pre[u - 1] * var[u];
+                suf[ILP - 1] = var[ILP - 1];
 #pragma unroll
-                for (int u = u0 + 1; u < u0 + CH && u < ILP; ++u) pc *= var[u];
-                add_var(pc);
+                for (int u = ILP - 2; u >= 1; --u) suf[u] = suf[u + 1] * var[u];
+                double num = r2[0] * suf[1];
+#pragma unroll
+                for (int u = 1; u < ILP - 1; ++u) num = fma(r2[u], pre[u - 1] * suf[u + 1], num);
+                num = fma(r2[ILP - 1], pre[ILP - 2], num);
+                s2 = fma(num, trcp(pre[ILP - 1]), s2);
+                add_var(pre[ILP - 1]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) s2 = fma(r2[u], trcp(var[u]), s2);
+#pragma unroll
+                for (int u0 = 0; u0 < ILP; u0 += CH) {
+                    double pc = var[u0];
+#pragma unroll
+                    for (int u = u0 + 1; u < u0 + CH && u < ILP; ++u) pc *= var[u];
+                    add_var(pc);
+                }
             }
         };
         // the group path on groups [gA, gB): one table-driven power per (gauging, active control)

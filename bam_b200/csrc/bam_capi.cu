@@ -121,7 +121,7 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         BAM_CUDA(cudaEventCreate(&h->ev1));
         BAM_CUDA(cudaDeviceGetAttribute(&h->smCount, cudaDevAttrMultiProcessorCount, device));
         for (size_t i = 0; i < (size_t)L.n * L.nY; ++i)
-            if (!(std::fabs(pb->Yu[i]) <= 0x1p86)) h->fpYuOk = false;
+            if (!(std::fabs(pb->Yu[i]) <= 0x1p86) || !(std::fabs(pb->Y[i]) <= 0x1p100)) h->fpYuOk = false;
 
         DevProblem& d = h->dp;
         memset(&d, 0, sizeof d);

@@ -37,7 +37,7 @@ struct bamgpu_handle {
     // fast-path tiling: tiles never straddle VAR combinations, so per-combination likelihood sums exist and a
     // proposal on a VAR parameter only re-evaluates the tiles of the combinations it touches (bam_logpost.cu)
     int fpTobs = 0, fpTiles = 0;
-    bool fpYuOk = true;    // every Yu <= 2^86: the group path of logpost_baratin_cb2 multiplies up to five variances
+    bool fpYuOk = true;    // every Yu <= 2^86 and |Y| <= 2^100: the group path of logpost_baratin_cb2 multiplies up to five variances (and residuals)
     bool fp2Attr = false;  // dynamic shared-memory limit of the picked logpost_baratin_cb2 instantiation raised
     int smCount = 148;
     int *d_fpStart = nullptr, *d_fpEnd = nullptr, *d_fpCombo = nullptr, *d_fpComboTile0 = nullptr;
