@@ -308,6 +308,7 @@ def load_library(path: Optional[str] = None):
                                _dp, C.POINTER(i64), cp]
     lib.bamgpu_moments.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, ci, cp]
     lib.bamgpu_rhat.argtypes = [ci, ci, _dp, _dp, _dp, _dp, cp]
+    lib.bamgpu_phase_times.argtypes = [H, _dp, _dp, ci]
     lib.bamgpu_comm_unique_id.argtypes = [cp, cp]
     lib.bamgpu_comm_init_rank.argtypes = [C.POINTER(H), ci, ci, cp, ci, cp]
     lib.bamgpu_comm_init_all.argtypes = [C.POINTER(H), ci, _ip, cp]
@@ -622,6 +623,11 @@ class BamGpu:
 
     def set_chain_offset(self, off: int):
         self.lib.bamgpu_set_chain_offset(self.h, off)
+
+    def phase_times(self, cap: int = 8192):
+        a, b = np.zeros(cap), np.zeros(cap)
+        n = self.lib.bamgpu_phase_times(self.h, _ptr_d(a), _ptr_d(b), cap)
+        return a[:n].copy(), b[:n].copy()
 
     def launch_count(self) -> int:
         return int(self.lib.bamgpu_launch_count(self.h))

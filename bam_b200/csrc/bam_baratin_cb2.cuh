@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
                                                                          const double* __restrict__ packed, const long long* __restrict__ tOff,
                                                                          const int* __restrict__ tBytes, const int* __restrict__ tileIds,
                                                                          const double* __restrict__ tab, const int* status,
-                                                                         double* __restrict__ part, int* statusOut, int* sched) {
+                                                                         double* __restrict__ part, int* statusOut, int* sched,
+                                                                         const int* __restrict__ order, float* __restrict__ cost) {
     constexpr int ILP = BAM_CB2_ILP;
     constexpr int CH = (SIGF == BAMGPU_SIG_PROPORTIONAL) ? (ILP < 4 ? ILP : 4) : (ILP < 5 ? ILP : 5);  // variances per product
     constexpr int TD = BAM_CB2_TDEG, TSUB = BAM_CB2_TSUB;
@@ -248,42 +249,70 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
     for (int i = tid; i < BAM_LOGTAB_N; i += BAM_BLOCK) reinterpret_cast<double2*>(sLog1)[i] = p.logTab[i];
     const unsigned lt = smem_addr(sLog), et = smem_addr(sExp), lt1 = smem_addr(sLog1);
     const unsigned bar0 = smem_addr(sCtl), buf0 = smem_addr(sBuf);
-    volatile int* sItem = reinterpret_cast<volatile int*>(sCtl + 2);
+    volatile int* sItem = reinterpret_cast<volatile int*>(sCtl + 2);  // item id of each buffer (-1: end of the queue)
+    int* sCnt = reinterpret_cast<int*>(sCtl + 3);                     // warps that have left each buffer
     const unsigned baseHi = (unsigned)p.logBaseHi;
     // control matrix as nibbles: nibble r = row r-1 (nibble 0 = no control: H below every activation stage)
     unsigned mask4 = 0;
 #pragma unroll
     for (int r = 1; r <= NC; ++r) mask4 |= ((unsigned)(p.ctrlMask >> ((r - 1) * 8)) & 0xfu) << (4 * r);
 
-    auto issue = [&](int item, int slot) {  // thread 0: the bulk copy of `item`'s tile into buffer `slot`
-        const int tsel = item / chainBlocks;
+    // queue position -> item (profile-guided order: expensive items first, see cb2_reorder) -> (chain block, tile): chain
+    // block major, so that a block that takes consecutive items mostly keeps its 256 chains and their VAR combination
+    const int nTilesLaunch = nItems / chainBlocks;
+    auto item_of = [&](int q) -> int { return order ? order[q] : q; };
+    auto issue = [&](int item, int slot) {  // one thread: the bulk copy of `item`'s tile into buffer `slot`
+        const int tsel = item % nTilesLaunch;
         const int tile = tileIds ? tileIds[tsel] : tsel;
         cb2_bulk_load(buf0 + (unsigned)slot * (unsigned)maxDoubles * 8u, packed + tOff[tile], (unsigned)tBytes[tile], bar0 + 8u * slot);
+    };
+    // hand out the next queue position into `slot`: item id for the consumers, then the copy (or, at the end of the queue,
+    // a plain arrival that completes the phase with the sentinel -1 in place)
+    auto produce = [&](int slot) {
+        const int q = atomicAdd(&sched[0], 1) + (int)gridDim.x;
+        if (q < nItems) {
+            const int it = item_of(q);
+            sItem[slot] = it;
+            issue(it, slot);
+        } else {
+            sItem[slot] = -1;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * slot) : "memory");
+        }
     };
     if (tid == 0) {
         cb2_mbar_init(bar0);
         cb2_mbar_init(bar0 + 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sItem[0] = blockIdx.x;
-        if ((int)blockIdx.x < nItems) issue(blockIdx.x, 0);
+        sCnt[0] = 0;
+        sCnt[1] = 0;
+        const int it0 = item_of(blockIdx.x);  // grid <= nItems
+        sItem[0] = it0;
+        issue(it0, 0);
+        produce(1);
     }
     __syncthreads();
     unsigned parity = 0;  // bit s = phase of buffer s
+    // chain parameters of the current (chain block, VAR combination): reloaded only when either changes
+    int curCb = -1, curCombo = -1;
+    bool live = false, gate = false;
+    double g1 = 1.0, g2 = 0.0;
+    double k[NC], b[NC], cc[NC], la[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) { k[j] = 0.0; cc[j] = 1.0; b[j] = 0.0; la[j] = 0.0; }
+    const double* cr = tab;
     for (int cur = 0;; cur ^= 1) {
+        // the warps of a block are coupled only through the two tile buffers: a warp that is done with an item goes on
+        // to the next one (already staged); the LAST warp to leave a buffer refills it (arrival counter in shared memory)
+        cb2_mbar_wait(bar0 + 8u * cur, (parity >> cur) & 1u);
+        parity ^= 1u << cur;
         const int item = sItem[cur];
-        if (item >= nItems) break;
-        if (tid == 0) {  // hand out and prefetch the next item; its buffer was released by the barrier that ended the previous round
-            const int nxt = atomicAdd(&sched[0], 1) + (int)gridDim.x;
-            sItem[cur ^ 1] = nxt;
-            if (nxt < nItems) issue(nxt, cur ^ 1);
-        }
-        const int tsel = item / chainBlocks, cb = item - tsel * chainBlocks;
+        if (item < 0) break;
+        const long long tItem0 = clock64();
+        const int cb = item / nTilesLaunch, tsel = item - cb * nTilesLaunch;
         const int tile = tileIds ? tileIds[tsel] : tsel;
 #ifdef BAM_CB2_TRACE
         if (tid == 0 && item < 16384) { g_cb2Trace[4096 + 2 * item] = cb2_gtime(); }
 #endif
-        cb2_mbar_wait(bar0 + 8u * cur, (parity >> cur) & 1u);
-        parity ^= 1u << cur;
         const unsigned hb = buf0 + (unsigned)cur * (unsigned)maxDoubles * 8u;
         int nt, combo;
         asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(nt), "=r"(combo) : "r"(hb));
@@ -292,31 +321,28 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
         const unsigned tt = ot + (unsigned)((nt + ILP - 1) / ILP) * (CB2_GS * 8);
         const unsigned mt = tt + (unsigned)((nt + ILP - 1) / ILP) * (CB2_GS * 8);
         const int c = cb * BAM_BLOCK + tid;
-        // dead lanes (beyond K, or a vector whose prior already failed) stay in the loop for the barrier
-        const bool live = c < K && status[c] == 0;
         const size_t o = ((size_t)tile * K + (c < K ? c : 0)) * 2;
-        if (c < K) {
-            part[o + 1] = 0.0;
-            if (!live) part[o] = 0.0;
-        }
-        const double* __restrict__ row = tab + (size_t)(live ? c : 0) * p.tabStride;
-        const double* __restrict__ cr = row + p.tabCombo + (size_t)combo * p.comboStride;
-        double g1 = 1.0, g2 = 0.0;
-        double k[NC], b[NC], cc[NC], la[NC];
+        if (cb != curCb || combo != curCombo) {
+            curCb = cb; curCombo = combo;
+            // dead lanes (beyond K, or a vector whose prior already failed) stay in the loop for the arrival counter
+            live = c < K && status[c] == 0;
+            const double* __restrict__ row = tab + (size_t)(live ? c : 0) * p.tabStride;
+            cr = row + p.tabCombo + (size_t)combo * p.comboStride;
+            g1 = 1.0; g2 = 0.0;
+            if (live) {
+                g1 = row[p.tabGamma];
+                if (SIGF == BAMGPU_SIG_LINEAR) g2 = row[p.tabGamma + 1];
 #pragma unroll
-        for (int j = 0; j < NC; ++j) { k[j] = 0.0; cc[j] = 1.0; b[j] = 0.0; la[j] = 0.0; }
-        if (live) {
-            g1 = row[p.tabGamma];
-            if (SIGF == BAMGPU_SIG_LINEAR) g2 = row[p.tabGamma + 1];
-#pragma unroll
-            for (int j = 0; j < NC; ++j) { k[j] = cr[3 * j]; cc[j] = cr[3 * j + 2]; b[j] = cr[3 * NC + j]; la[j] = cr[4 * NC + j]; }
-        }
-        // gate: remnant parameters inside [2^-60, 2^20] (g2 may also be 0) bound every variance of the group path
-        bool gate;
-        {
+                for (int j = 0; j < NC; ++j) { k[j] = cr[3 * j]; cc[j] = cr[3 * j + 2]; b[j] = cr[3 * NC + j]; la[j] = cr[4 * NC + j]; }
+            }
+            // gate: remnant parameters inside [2^-60, 2^20] (g2 may also be 0) bound every variance of the group path
             const int h1 = __double2hiint(g1), h2 = __double2hiint(g2);
             gate = h1 >= CB2_G_LO && h1 < CB2_G_HI;
             if (SIGF == BAMGPU_SIG_LINEAR) gate = gate && ((h2 >= CB2_G_LO && h2 < CB2_G_HI) || g2 == 0.0);
+        }
+        if (c < K) {
+            part[o + 1] = 0.0;
+            if (!live) part[o] = 0.0;
         }
 
         double s2 = 0.0;  // sum of squared standardised residuals
@@ -625,12 +651,20 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
             part[o] = fma(-0.5, lsum + s2, -BAM_LOG_SQRT_2PI * (double)nt);
             if (bad) atomicOr(&statusOut[c], ST_LKH_INFEAS);
         }
-        __syncthreads();  // this item's tile is no longer read: its buffer may be refilled; the next item id is visible
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            if (atomicAdd(&sCnt[cur], 1) == BAM_BLOCK / 32 - 1) {  // the last warp out: nobody reads this buffer any more
+                sCnt[cur] = 0;
+                if (cost) cost[item] = (float)(clock64() - tItem0);
+                produce(cur);
+            }
+        }
 #ifdef BAM_CB2_TRACE
         ++trItems;
         if (tid == 0 && item < 16384) { g_cb2Trace[4096 + 2 * item + 1] = cb2_gtime(); }
 #endif
     }
+    __syncthreads();
 #ifdef BAM_CB2_TRACE
     if (tid == 0 && blockIdx.x < 1024) { g_cb2Trace[4 * blockIdx.x + 1] = cb2_gtime(); g_cb2Trace[4 * blockIdx.x + 2] = trItems; }
 #endif
@@ -644,8 +678,35 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
     }
 }
 
+// Profile-guided queue order: every launch records what each item cost (clock cycles of the last warp to leave it); from
+// time to time this kernel sorts the items by that cost, most expensive first, so that the end of the queue -- where a
+// late 200 us item would leave 295 blocks waiting -- is made of cheap, uniform items.  The order never changes a value
+// (one partial per (tile, chain), summed in fixed order afterwards).  One block, bitonic sort in shared memory.
+static __global__ void __launch_bounds__(1024) cb2_reorder(const float* __restrict__ cost, int n, int* __restrict__ order) {
+    extern __shared__ unsigned long long sk[];
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+        sk[i] = i < n ? (((unsigned long long)__float_as_uint(fmaxf(cost[i], 0.f)) << 32) | (unsigned)(0x7fffffff - i)) : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = (i & size) == 0;
+                    const unsigned long long a = sk[i], bq = sk[j];
+                    if ((a < bq) == desc) { sk[i] = bq; sk[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) order[i] = 0x7fffffff - (int)(unsigned)(sk[i] & 0xffffffffu);
+}
+#define CB2_REORDER_MAX 16384
+
 using Fast2Kernel = void (*)(DevProblem, int, int, int, int, const double*, const long long*, const int*, const int*, const double*,
-                             const int*, double*, int*, int*);
+                             const int*, double*, int*, int*, const int*, float*);
 
 template <int NC>
 Fast2Kernel pick_fast2_sig(int sigf) {

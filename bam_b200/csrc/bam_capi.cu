@@ -323,7 +323,7 @@ void bamgpu_destroy(bamgpu_t* h) {
     fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_env);
     fr(h->d_series); fr(h->d_seriesXpred);
     fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0); fr(h->d_lkCcur); fr(h->d_lkCcand);
-    fr(h->d_fpPacked); fr(h->d_fpOff); fr(h->d_fpBytes); fr(h->d_fpSched);
+    fr(h->d_fpPacked); fr(h->d_fpOff); fr(h->d_fpBytes); fr(h->d_fpSched); fr(h->d_fpOrder); fr(h->d_fpCost);
     for (auto*& q : h->d_compTiles) fr(q);
     for (auto*& q : h->d_compAffected) fr(q);
     free_prediction(h);
@@ -331,6 +331,8 @@ void bamgpu_destroy(bamgpu_t* h) {
     for (auto e : h->evPool) cudaEventDestroy(e);
     for (auto& pr : h->stepEv) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : h->kernEv) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : h->prepEv) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : h->finalEv) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -707,6 +709,10 @@ static int drain(bamgpu_t* h, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& 
 
 int bamgpu_step_times(bamgpu_t* h, double* ms, int cap) { return drain(h, h->stepEv, ms, cap); }
 int bamgpu_kernel_times(bamgpu_t* h, double* ms, int cap) { return drain(h, h->kernEv, ms, cap); }
+int bamgpu_phase_times(bamgpu_t* h, double* prep_ms, double* final_ms, int cap) {
+    const int a = drain(h, h->prepEv, prep_ms, cap), b = drain(h, h->finalEv, final_ms, cap);
+    return a < b ? a : b;
+}
 
 int bamgpu_flush_l2(bamgpu_t* h, size_t bytes) {
     if (bytes > h->flushCap) {

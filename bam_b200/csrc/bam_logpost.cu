@@ -968,6 +968,7 @@ static void ensure_fast_tiles(bamgpu_handle* h, int tobs) {
     h->fpComboTile0[nCombo] = (int)ts.size();
     h->fpTiles = (int)ts.size();
     h->fpTobs = tobs;
+    h->fpOrderItems = 0; h->fpOrderValid = false;
     auto up = [&](int*& d, const std::vector<int>& v) {
         BAM_CUDA(cudaMalloc(&d, sizeof(int) * std::max<size_t>(v.size(), 1)));
         BAM_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, h->stream));
@@ -1129,8 +1130,11 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     MainKernel kern = pick_main(p.model, p.nX, p.nY);
     if (!kern) throw CudaError{"bamgpu: no kernel instantiated for this (model, nX, nY)"};
     FastKernel fast = (p.n > 0 && !h->forceGeneric) ? pick_fast(p, K) : nullptr;
+    cudaEvent_t p0 = nullptr;
+    if (timeMain && h->recordKernels && h->prepEv.size() < 8192) { p0 = take_event(h); BAM_CUDA(cudaEventRecord(p0, h->stream)); }
     logpost_prep<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(
         p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
+    if (p0) { cudaEvent_t p1 = take_event(h); BAM_CUDA(cudaEventRecord(p1, h->stream)); h->prepEv.emplace_back(p0, p1); }
     DevProblem pser = p;
     if (p.isSeries && p.n > 0) {  // time-recursive model: the outputs of all K vectors, then the generic likelihood kernel
         ensure_series_capacity(h, (size_t)p.seriesN * p.nY * K);
@@ -1176,7 +1180,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
             }
         }
         if (fast2) {
-            // tables + {2 mbarriers, 2 item ids} + two packed-tile buffers
+            // tables + {2 mbarriers, 2 item ids, 2 arrival counters} + two packed-tile buffers
             auto smem_for = [](int tileDoubles) { return sizeof(double) * (2 * (size_t)BAM_LOG2_N + BAM_EXPTAB_N + 2 * BAM_LOGTAB_N + 4 + 2 * (size_t)tileDoubles); };
             const size_t smem = smem_for(h->fpMaxDoubles);
             if (!h->fp2Attr) {
@@ -1186,10 +1190,34 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
                 h->fp2Attr = true;
             }
             const int nItems = launchTiles * chainBlocks;
+            // profile-guided queue order of the FULL launch (partial re-evaluations are short: natural order)
+            const int* d_order = nullptr;
+            float* d_cost = nullptr;
+            const bool full = d_tiles == nullptr;
+            if (full && nItems <= CB2_REORDER_MAX && nItems > 2 * slots) {
+                if (h->fpOrderItems != nItems) {
+                    auto fr2 = [](auto*& q) { if (q) cudaFree(q); q = nullptr; };
+                    fr2(h->d_fpOrder); fr2(h->d_fpCost);
+                    BAM_CUDA(cudaMalloc(&h->d_fpOrder, sizeof(int) * nItems));
+                    BAM_CUDA(cudaMalloc(&h->d_fpCost, sizeof(float) * nItems));
+                    h->fpOrderItems = nItems; h->fpOrderValid = false; h->fpFullLaunches = 0;
+                }
+                // re-sort after the first launch of a plan, then every 32 launches (chains move slowly in a sampler)
+                if (h->fpFullLaunches == 1 || (h->fpFullLaunches > 1 && h->fpFullLaunches % 32 == 0)) {
+                    int m = 1;
+                    while (m < nItems) m <<= 1;
+                    if (m * 8 > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)cb2_reorder, cudaFuncAttributeMaxDynamicSharedMemorySize, m * 8));
+                    cb2_reorder<<<1, 1024, (size_t)m * 8, h->stream>>>(h->d_fpCost, nItems, h->d_fpOrder);
+                    h->fpOrderValid = true;
+                }
+                d_order = h->fpOrderValid ? h->d_fpOrder : nullptr;
+                d_cost = h->d_fpCost;
+                ++h->fpFullLaunches;
+            }
             if (nItems > 0)
                 fast2<<<std::min(nItems, slots), BAM_BLOCK, smem, h->stream>>>(p, K, nItems, chainBlocks, h->fpMaxDoubles, h->d_fpPacked, h->d_fpOff,
                                                                             h->d_fpBytes, d_tiles, h->d_tab, h->d_status, h->d_part, h->d_status,
-                                                                            h->d_fpSched);
+                                                                            h->d_fpSched, d_order, d_cost);
         } else {
             const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 3 * (size_t)tobs);
             dim3 grid(std::max(launchTiles, 1), chainBlocks);
@@ -1211,6 +1239,8 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         BAM_CUDA(cudaEventRecord(h->ev1, h->stream));
         if (k1) { BAM_CUDA(cudaEventRecord(k1, h->stream)); h->kernEv.emplace_back(k0, k1); }
     }
+    cudaEvent_t f0 = nullptr;
+    if (p0) { f0 = take_event(h); BAM_CUDA(cudaEventRecord(f0, h->stream)); }
     if (comboFinal)
         logpost_final_combo<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, h->d_fpComboTile0, h->d_part, h->d_prior,
                                                                                  h->d_status, d_affected, h->d_lkCcur, h->d_lkCcand,
@@ -1218,6 +1248,11 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     else
         logpost_final<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, p.n > 0 ? nTiles : 0, h->d_part, h->d_prior,
                                                                            h->d_status, h->d_lkh, h->d_hyper, h->d_fx);
+    if (f0) {
+        cudaEvent_t f1 = take_event(h);
+        BAM_CUDA(cudaEventRecord(f1, h->stream));
+        h->finalEv.emplace_back(f0, f1);
+    }
     h->launches += (p.n > 0) ? 3 : 2;
     BAM_CUDA(cudaGetLastError());
 }

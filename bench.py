@@ -458,6 +458,51 @@ def latent_sampler_leg(device, n=1_000_000, K=64, iters=4):
                     "full log-posterior (n observations) per component, the sweep kernel needs O(1) per latent input"}
 
 
+def timed_resident_logpost(g, steps, flush=True):
+    """`steps` resident log-posterior evaluations, each bracketed by CUDA events, with the three kernels of a step timed
+    separately: parameter table (priors, copula, continuity pre-pass), dominant kernel, fixed-order final sum."""
+    g.sync(); g.step_times(); g.kernel_times(); g.phase_times()
+    for _ in range(steps):
+        if flush:
+            g.flush_l2(256 << 20)
+        g.step_begin(); g.logpost_resident(); g.step_end()
+    g.sync()
+    ms, km = g.step_times(), g.kernel_times()
+    pm, fm = g.phase_times()
+    return ms, km, pm, fm
+
+
+def strong_scaling_leg(device, rank, world, dist, torch, total_chains, n, steps, prob, truth):
+    """BASELINE configs[1] as written: 4096 chains x 100 000 gaugings SHARDED over the GPUs (total_chains / world per GPU,
+    observations replicated, no collective on the data path).  value = total chain x obs / max-over-ranks step time; the
+    per-kernel breakdown names what limits the curve."""
+    from workloads import synth
+    from bam_b200.capi import BamGpu
+
+    Kloc = total_chains // world
+    xall = synth.feasible_starts(truth, total_chains, seed=synth.SEED + 1, check=synth.spd_start_check)
+    g = BamGpu(prob, device)
+    g.set_chain_offset(rank * Kloc)
+    g.chains_upload(xall[rank * Kloc:(rank + 1) * Kloc])
+    for _ in range(3):
+        g.logpost_resident()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms, km, pm, fm = timed_resident_logpost(g, steps)
+    fx, feas, _ = g.chains_download()
+    t = torch.tensor([float(ms.sum()), float(km.sum()), float(pm.sum()), float(fm.sum())], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tt = [float(v) / steps for v in t.tolist()]
+    return {"scaling": "strong", "workload": f"BaRatin_SPD {total_chains} chains x {n} gaugings sharded over {world} GPU(s): "
+            f"{Kloc} chains per GPU (configs[1] as written)", "chains_per_gpu": Kloc,
+            "value": total_chains * n / (tt[0] * 1e-3), "unit": UNIT, "ms_per_step": tt[0],
+            "breakdown_ms": {"parameter_table": tt[2], "likelihood_kernel": tt[1], "final_sum": tt[3],
+                             "launch_gaps": max(tt[0] - tt[1] - tt[2] - tt[3], 0.0)},
+            "feasible": bool(feas.all()), "timing": "CUDA events per step, L2 flushed between steps, max over ranks"}
+
+
 def multi_gpu_legs(device, rank, world, dist, torch):
     """N > 1: the two places where the path exchanges data, through NCCL over NVLink.
     (1) prediction inputs shard across ranks ([t0,t1) slices, samples replicated); every rank owns whole columns, so
@@ -543,6 +588,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-prediction", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="which leg is the headline `value` (the other one is reported beside it)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -600,7 +648,7 @@ def main():
     while sampler.n() < 20 and time.perf_counter() - t_ramp < 2.0:
         g.logpost_resident()
         g.sync()
-    g.step_times(); g.kernel_times()
+    g.step_times(); g.kernel_times(); g.phase_times()
     launches0 = g.launch_count()
     barrier()
     wall0 = time.perf_counter()
@@ -625,6 +673,16 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_total = float(tt.item())
     value = world * K * n * args.steps / t_total
+
+    pm_ms, fm_ms = g.phase_times()
+    # ---- configs[1] as written: 4096 chains in total, sharded (strong scaling) ----
+    strong = None
+    if args.chains % world == 0 and not args.no_strong:
+        try:
+            strong = strong_scaling_leg(device, rank, world, dist if world > 1 else None, torch, args.chains, n,
+                                        max(args.steps, 10), prob, truth)
+        except Exception as e:
+            strong = {"error": str(e)}
 
     # ---- e2e path: host buffers through the C ABI ----
     xh = np.ascontiguousarray(x)
@@ -717,6 +775,13 @@ def main():
                 "path": "bamgpu_logpost (C ABI) with pinned host buffers, wall clock around the blocking calls"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "wall_s_timed_region": wall,
     }
+    line["breakdown_ms"] = {"parameter_table": float(pm_ms.mean()) if pm_ms.size else None, "likelihood_kernel": k_ms,
+                            "final_sum": float(fm_ms.mean()) if fm_ms.size else None}
+    if strong is not None:
+        line["strong"] = strong
+        if args.scaling == "strong" and "value" in strong:  # the sharded configuration as the headline, the weak one beside it
+            line["weak"] = {"value": line["value"], "ms_per_step": line["ms_per_step"], "chains_per_gpu": K}
+            line.update({"value": strong["value"], "ms_per_step": strong["ms_per_step"], "scaling": "strong"})
     if multi is not None:
         line["multi_gpu"] = multi
     if not args.no_prediction and world == 1:

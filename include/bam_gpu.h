@@ -319,6 +319,9 @@ int bamgpu_step_begin(bamgpu_t* h);
 int bamgpu_step_end(bamgpu_t* h);
 int bamgpu_step_times(bamgpu_t* h, double* ms, int cap);
 int bamgpu_kernel_times(bamgpu_t* h, double* ms, int cap);
+/* the other two kernels of a resident log-posterior evaluation: the per-vector parameter table (priors, copula, derived
+   values) before the dominant kernel and the fixed-order sum of the tile partials after it */
+int bamgpu_phase_times(bamgpu_t* h, double* prep_ms, double* final_ms, int cap);
 /* write `bytes` of scratch HBM on the handle's stream (L2 flush between timed iterations) */
 int bamgpu_flush_l2(bamgpu_t* h, size_t bytes);
 /* FP64 DFMA peak micro-benchmark (register-resident FMA chains), TFLOP/s counting 2 flop per DFMA */
