@@ -52,26 +52,6 @@ struct bamgpu_handle {
     int fpOrderItems = 0;        // items the two arrays describe (0: none)
     bool fpOrderValid = false;
     long long fpFullLaunches = 0;
-    int smCount = 148;
-    int *d_fpStart = nullptr, *d_fpEnd = nullptr, *d_fpCombo = nullptr, *d_fpComboTile0 = nullptr;
-    // packed tiles of logpost_baratin_cb2 (bam_baratin_cb2.cuh): one bulk copy per tile; offsets in doubles, sizes in bytes
-    double* d_fpPacked = nullptr;
-    long long* d_fpOff = nullptr;
-    int* d_fpBytes = nullptr;
-    int* d_fpSched = nullptr;  // {next item, blocks done}: re-armed by the kernel itself
-    int fpMaxDoubles = 0;
-    int* d_fpOrder = nullptr;    // queue order of the full launch (most expensive items first), or unused
-    float* d_fpCost = nullptr;   // measured cost of every item of the last full launch
-    int fpOrderItems = 0;        // items the two arrays describe (0: none)
-    bool fpOrderValid = false;
-    long long fpFullLaunches = 0;
-    // generation 4 (bam_baratin_cb4.cuh): chunks of <= 80 gaugings packed one by one, per-chain-group queues
-    double* d_fp4Packed = nullptr;
-    long long* d_fp4Off = nullptr;
-    int *d_fp4Bytes = nullptr, *d_fp4TileChunk0 = nullptr, *d_fp4Sched = nullptr;
-    int fp4SchedCap = 0;
-    bool fp4Attr = false;
-    int cbGen = 4;  // option "cb_gen": 4 = warp-autonomous kernel, 3 = block-cooperative kernel of generation 3
     std::vector<int> comboStartHost, fpComboTile0;
     double *d_lkCcur = nullptr, *d_lkCcand = nullptr;  // nCombo x Kcap: per-combination log-likelihood of the current / candidate state
     std::vector<int*> d_compTiles, d_compAffected;      // per vector component: tile ids / 0-1 flag per combination (lazy)
