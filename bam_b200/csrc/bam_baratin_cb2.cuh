@@ -501,14 +501,16 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
                     bool hard = false;
 #pragma unroll
                     for (int u = 0; u < ILP; ++u) qq[u] = 0.0;
-                    unsigned mu[ILP];
+                    unsigned mu[ILP], mall = 0;
 #pragma unroll
                     for (int u = 0; u < ILP; ++u) {
                         mu[u] = (mask4 >> (4 * range(w[u]))) & 0xfu;
+                        mall |= mu[u];
                         if (SIGF == BAMGPU_SIG_PROPORTIONAL) hard |= mu[u] == 0;
                     }
 #pragma unroll
-                    for (int j = 0; j < NC; ++j) {
+                    for (int j = 0; j < NC; ++j)
+                      if ((mall >> j) & 1u) {  // controls no gauging of the group uses are skipped
                         double xx[ILP];
 #pragma unroll
                         for (int u = 0; u < ILP; ++u) {
@@ -687,7 +689,9 @@ static __global__ void __launch_bounds__(1024) cb2_reorder(const float* __restri
     int m = 1;
     while (m < n) m <<= 1;
     for (int i = threadIdx.x; i < m; i += blockDim.x)
-        sk[i] = i < n ? (((unsigned long long)__float_as_uint(fmaxf(cost[i], 0.f)) << 32) | (unsigned)(0x7fffffff - i)) : 0ull;
+        // key = power-of-two cost class, then the natural (chain block, tile) order: a block that takes consecutive items of
+        // a class mostly keeps its chains and their VAR combination (no parameter reload)
+        sk[i] = i < n ? (((unsigned long long)(__float_as_uint(fmaxf(cost[i], 1.f)) >> 23) << 32) | (unsigned)(0x7fffffff - i)) : 0ull;
     __syncthreads();
     for (int size = 2; size <= m; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
