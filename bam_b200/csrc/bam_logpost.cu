@@ -50,7 +50,10 @@ __device__ __forceinline__ double xval(const double* __restrict__ x, size_t base
 // density (GetPriorLogPdf :3062-3112: remnant parameters, then theta, then the copula); the flag of a vector is
 // therefore that of its FIRST failing parameter in that order, found here with a warp minimum over (order, kind).
 // ------------------------------------------------------------------------------------------------
+// SPEC = a model id compiles the pre-pass of that model only (the generic instance carries the pre-passes of every model:
+// 13 000 instructions, and at 512 vectors per GPU the kernel was 25 us of instruction-cache misses), 0 = any model.
 #define PREP_WARPS 4
+template <int SPEC>
 __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, const double* __restrict__ x, int K, int comp,
                                                                 const double* __restrict__ delta, double* __restrict__ tab,
                                                                 double* __restrict__ prior_out, int* __restrict__ status,
@@ -69,15 +72,12 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
     for (int q = lane; q < npar; q += 32) {
         double lp;
         bool feas, isnull;
-        int order;
-        if (q < p.nGamma) {
-            dist_logpdf(p.pgDist[q], p.pgPar + (size_t)q * BAMGPU_PRIOR_NPAR, xval(x, base, p.nFit + q, comp, dl), lp, feas, isnull);
-            order = q;
-        } else {
-            const int k = q - p.nGamma;
-            dist_logpdf(p.ptDist[k], p.ptPar + (size_t)k * BAMGPU_PRIOR_NPAR, xval(x, base, k, comp, dl), lp, feas, isnull);
-            order = q;
-        }
+        const int order = q;
+        // one call site (the distribution switch is ~1000 instructions): remnant parameters first, then theta
+        const bool isG = q < p.nGamma;
+        const int k = isG ? q : q - p.nGamma;
+        dist_logpdf(isG ? p.pgDist[k] : p.ptDist[k], (isG ? p.pgPar : p.ptPar) + (size_t)k * BAMGPU_PRIOR_NPAR,
+                    xval(x, base, isG ? p.nFit + k : k, comp, dl), lp, feas, isnull);
         if (!feas) fail = min(fail, ((unsigned)order << 1));
         else if (isnull) fail = min(fail, ((unsigned)order << 1) | 1u);
         else pr += lp;
@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
         for (int i = lane; i < k; i += 32) {
             double u;
             bool f;
-            if (i < p.nFit) dist_cdf(p.ptDist[i], p.ptPar + (size_t)i * BAMGPU_PRIOR_NPAR, xval(x, base, i, comp, dl), u, f);
-            else dist_cdf(p.pgDist[i - p.nFit], p.pgPar + (size_t)(i - p.nFit) * BAMGPU_PRIOR_NPAR, xval(x, base, i, comp, dl), u, f);
+            const bool isT = i < p.nFit;
+            const int kk = isT ? i : i - p.nFit;
+            dist_cdf(isT ? p.ptDist[kk] : p.pgDist[kk], (isT ? p.ptPar : p.pgPar) + (size_t)kk * BAMGPU_PRIOR_NPAR, xval(x, base, i, comp, dl), u, f);
             if (!f || !(u > 0.0 && u < 1.0)) { cfail = 0u; vcop[i] = 0.0; }
             else vcop[i] = normcdfinv(u);
         }
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
         for (int i = lane; i < p.nYb[j]; i += 32) row[p.tabOffYb[j] + i] = xval(x, base, p.offYb[j] + i, comp, dl);
     int stl = 0;
     for (int k = lane; k < p.nCombo; k += 32) {  // ApplyModel_BaM theta expansion (:4133-4159), one combination per lane
-        double th[BAM_MAXTHETA], der[BAM_MAXDER];
+        constexpr int MT = (SPEC == BAMGPU_MDL_BARATIN) ? 12 : BAM_MAXTHETA, MD = (SPEC == BAMGPU_MDL_BARATIN) ? 8 : BAM_MAXDER;
+        double th[MT], der[MD];
         const double* xc[BAM_MAXX];
         for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
         double* cr = row + p.tabCombo + (size_t)k * p.comboStride;
@@ -136,8 +138,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
             cr[i] = th[i];
         }
         for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
-        const bool ok = model_prepare(p, th, der, xc, p.n);
-        if (p.isSeries) der[0] = (double)c;  // this vector's column of the series buffer (model_apply looks it up)
+        const bool ok = (SPEC == BAMGPU_MDL_BARATIN) ? baratin_prepare(p, th, der) : model_prepare(p, th, der, xc, p.n);
+        if (SPEC == 0 && p.isSeries) der[0] = (double)c;  // this vector's column of the series buffer (model_apply looks it up)
         if (!ok) stl |= ST_LKH_INFEAS;
         for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
         if (dpar != nullptr)
@@ -148,6 +150,12 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
         prior_out[c] = pr;
         status[c] = st;
     }
+}
+
+using PrepKernel = void (*)(DevProblem, const double*, int, int, const double*, double*, double*, int*, double*);
+static PrepKernel pick_prep(const DevProblem& p) {
+    if (p.model == BAMGPU_MDL_BARATIN && p.ncontrol <= 4 && p.ntheta <= 12 && p.nDer <= 8) return logpost_prep<BAMGPU_MDL_BARATIN>;
+    return logpost_prep<0>;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,34 +584,55 @@ __global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final_combo(DevPro
                                                                     const int* __restrict__ affected,
                                                                     const double* __restrict__ lkCcur, double* __restrict__ lkCcand,
                                                                     double* __restrict__ lkh, double* __restrict__ hyper,
-                                                                    double* __restrict__ fx) {
+                                                                    double* __restrict__ fx, int* __restrict__ arrive) {
+    // grid = (32-chain groups, VAR combinations): one block sums the tiles of ONE combination (FINAL_STRIPES warps, every
+    // FINAL_STRIPES-th tile each, four loads in flight, fixed-order combine); the last block of a chain group to finish
+    // adds the combinations in order.  With one block per chain group looping over the combinations the kernel was a
+    // chain of dependent L2 loads on 16 blocks when chains are few (512 per GPU: 25 us of a 180 us step).
     __shared__ double sa[FINAL_STRIPES][32];
+    __shared__ int sLast;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
-    double total = 0.0;
-    for (int v = 0; v < p.nCombo; ++v) {
-        const bool redo = affected == nullptr || affected[v] != 0;  // uniform over the block
-        if (redo) {
-            double a = 0.0;
-            if (c < K)
-                for (int t = comboTile0[v] + w; t < comboTile0[v + 1]; t += FINAL_STRIPES) a += part[((size_t)t * K + c) * 2];
-            sa[w][lane] = a;
-            __syncthreads();
-            if (w == 0 && c < K) {
-                double s = 0.0;
-#pragma unroll
-                for (int q = 0; q < FINAL_STRIPES; ++q) s += sa[q][lane];
-                lkCcand[(size_t)v * K + c] = s;
-                total += s;
+    const int v = blockIdx.y;
+    const bool redo = affected == nullptr || affected[v] != 0;  // uniform over the block
+    if (redo) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (c < K) {
+            const int t1 = comboTile0[v + 1];
+            int t = comboTile0[v] + w;
+            // a fixed association: stripe w adds its tiles four at a time into four chains, then (a0 + a1) + (a2 + a3)
+            for (; t + 3 * FINAL_STRIPES < t1; t += 4 * FINAL_STRIPES) {
+                a0 += part[((size_t)t * K + c) * 2];
+                a1 += part[((size_t)(t + FINAL_STRIPES) * K + c) * 2];
+                a2 += part[((size_t)(t + 2 * FINAL_STRIPES) * K + c) * 2];
+                a3 += part[((size_t)(t + 3 * FINAL_STRIPES) * K + c) * 2];
             }
-            __syncthreads();
-        } else if (w == 0 && c < K) {
-            const double s = lkCcur[(size_t)v * K + c];
-            lkCcand[(size_t)v * K + c] = s;
-            total += s;
+            for (; t < t1; t += FINAL_STRIPES) a0 += part[((size_t)t * K + c) * 2];
         }
+        sa[w][lane] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (w == 0 && c < K) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < FINAL_STRIPES; ++q) s += sa[q][lane];
+            lkCcand[(size_t)v * K + c] = s;
+        }
+    } else if (w == 0 && c < K) {
+        lkCcand[(size_t)v * K + c] = lkCcur[(size_t)v * K + c];
     }
-    if (w != 0 || c >= K) return;
+    // last block of this chain group: total over the combinations, in order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(&arrive[blockIdx.x], 1);
+        sLast = (old == (int)gridDim.y - 1);
+        if (sLast) arrive[blockIdx.x] = 0;  // re-armed for the next launch
+    }
+    __syncthreads();
+    if (!sLast || w != 0 || c >= K) return;
+    __threadfence();
+    double total = 0.0;
+    for (int q = 0; q < p.nCombo; ++q) total += __ldcg(&lkCcand[(size_t)q * K + c]);
     int st = status[c];
     if (!st && !(total == total)) st |= ST_LKH_INFEAS;
     status[c] = st;
@@ -1052,7 +1081,7 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     if (K <= h->Kcap) { make_plan(h, K); return; }
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(h->d_x); fr(h->d_tab); fr(h->d_part); fr(h->d_prior); fr(h->d_lkh); fr(h->d_hyper); fr(h->d_fx); fr(h->d_dpar);
-    fr(h->d_status); fr(h->d_delta); fr(h->d_lkCcur); fr(h->d_lkCcand);
+    fr(h->d_status); fr(h->d_delta); fr(h->d_lkCcur); fr(h->d_lkCcand); fr(h->d_finalArrive);
     h->lkCvalid = false;
     const DevProblem& p = h->dp;
     make_plan(h, K);
@@ -1070,6 +1099,8 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     BAM_CUDA(cudaMalloc(&h->d_dpar, sizeof(double) * (size_t)K * std::max(p.nDpar, 1)));
     BAM_CUDA(cudaMalloc(&h->d_status, sizeof(int) * K));
     BAM_CUDA(cudaMalloc(&h->d_delta, sizeof(double) * K));
+    BAM_CUDA(cudaMalloc(&h->d_finalArrive, sizeof(int) * ((K + 31) / 32)));
+    BAM_CUDA(cudaMemsetAsync(h->d_finalArrive, 0, sizeof(int) * ((K + 31) / 32), h->stream));
     h->Kcap = K;
 }
 
@@ -1091,7 +1122,7 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
     DevProblem p = p0;
     p.X = d_xtrue;
     p.n = n;
-    logpost_prep<<<1, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
+    pick_prep(p)<<<1, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
     double* d_idx = nullptr;
     if (p.isSeries) {  // the series of this one vector (outputs + states), then the lookup kernel on the row indices
         const int nOut = p.nY + model_nstate(p.model);
@@ -1118,7 +1149,7 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
 
 // only K2: the per-chain tables (gamma, biases, expanded theta + derived values) of the vectors at d_x
 void launch_table(bamgpu_handle* h, int K, const double* d_x) {
-    logpost_prep<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(h->dp.kM, 1), h->stream>>>(
+    pick_prep(h->dp)<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(h->dp.kM, 1), h->stream>>>(
         h->dp, d_x, K, -1, nullptr, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
     h->launches += 1;
     BAM_CUDA(cudaGetLastError());
@@ -1132,7 +1163,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     FastKernel fast = (p.n > 0 && !h->forceGeneric) ? pick_fast(p, K) : nullptr;
     cudaEvent_t p0 = nullptr;
     if (timeMain && h->recordKernels && h->prepEv.size() < 8192) { p0 = take_event(h); BAM_CUDA(cudaEventRecord(p0, h->stream)); }
-    logpost_prep<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(
+    pick_prep(p)<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(
         p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
     if (p0) { cudaEvent_t p1 = take_event(h); BAM_CUDA(cudaEventRecord(p1, h->stream)); h->prepEv.emplace_back(p0, p1); }
     DevProblem pser = p;
@@ -1242,9 +1273,10 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     cudaEvent_t f0 = nullptr;
     if (p0) { f0 = take_event(h); BAM_CUDA(cudaEventRecord(f0, h->stream)); }
     if (comboFinal)
-        logpost_final_combo<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, h->d_fpComboTile0, h->d_part, h->d_prior,
-                                                                                 h->d_status, d_affected, h->d_lkCcur, h->d_lkCcand,
-                                                                                 h->d_lkh, h->d_hyper, h->d_fx);
+        logpost_final_combo<<<dim3((K + 31) / 32, p.nCombo), 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, h->d_fpComboTile0, h->d_part, h->d_prior,
+                                                                                                  h->d_status, d_affected, h->d_lkCcur,
+                                                                                                  h->d_lkCcand, h->d_lkh, h->d_hyper, h->d_fx,
+                                                                                                  h->d_finalArrive);
     else
         logpost_final<<<(K + 31) / 32, 32 * FINAL_STRIPES, 0, h->stream>>>(p, K, p.n > 0 ? nTiles : 0, h->d_part, h->d_prior,
                                                                            h->d_status, h->d_lkh, h->d_hyper, h->d_fx);

@@ -733,7 +733,7 @@ def main():
     ach = NOMINAL_FLOPS_PER_UNIT * units / (k_ms * 1e-3) / 1e12
     roof = {
         "bound": "fp64",
-        "kernel": "logpost_baratin_cb2<3,Linear> (BaRatin fast path, generation 2)",
+        "kernel": "logpost_baratin_cb2<3,Linear> (BaRatin fast path, generation 3.5: Taylor sub-tiles)",
         "unit": "TFLOP/s",
         # ALGORITHMIC (nominal) flops per chain x obs -- +,-,*,/,compare and each pow/log/exp count 1 --
         # x units per launch / the kernel's CUDA-event time; independent of how the kernel is written
