@@ -80,7 +80,7 @@ def build_driver(force: bool = False) -> str | None:
     so = os.path.join(HERE, "libbam_gpu.so")
     if force or _newer(srcs + _headers() + [so], exe):
         _run(["g++", "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), "-I", CSRC, "-o", exe] + srcs +
-             ["-L", HERE, "-lbam_gpu", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+             ["-L", HERE, "-lbam_gpu", "-pthread", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
     return exe
 
 

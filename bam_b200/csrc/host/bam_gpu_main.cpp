@@ -19,6 +19,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bam_config.h"
@@ -130,7 +131,7 @@ static std::string state_name(const std::string& modelID, int i) {
 int main(int argc, char** argv) {
     std::string cfg = "Config_BaM.txt", dump, priorFile, yFile;
     unsigned long long seed = 20261019ull;
-    int K = 1, device = 0;
+    int K = 1, device = 0, gpus = 1;
     bool savePrior = false, earlyStop = false, oneRun = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -146,17 +147,20 @@ int main(int argc, char** argv) {
         else if (a == "-or" || a == "--onerun") { oneRun = true; yFile = need("a file name"); }
         else if (a == "--chains") K = atoi(need("a number of chains").c_str());
         else if (a == "--device") device = atoi(need("a device ordinal").c_str());
+        else if (a == "--gpus") gpus = atoi(need("a number of GPUs").c_str());
         else if (a == "--dump-problem") dump = need("a file name");
         else if (a == "-v" || a == "--version") { printf(" version: %s\n", kVersion); return 0; }
         else if (a == "-h" || a == "--help") {
-            printf("usage: bam_gpu [-cf Config_BaM.txt] [-sd seed | -rd] [-sp priorfile] [-dr] [-or Yfile] [--chains K] [--device d]\n"
+            printf("usage: bam_gpu [-cf Config_BaM.txt] [-sd seed | -rd] [-sp priorfile] [-dr] [-or Yfile] [--chains K] [--device d] [--gpus N]\n"
                    "               [--dump-problem file.json] [-v] [-h]\n"
                    "  -cf, --config     main configuration file (default Config_BaM.txt)\n"
                    "  -sd, --seed       seed of the random streams;  -rd, --random: seed from the clock\n"
                    "  -sp, --saveprior  save the prior sample of prior-prediction experiments in this file (workspace-relative)\n"
                    "  -dr, --dontrun    read the configuration, write INFO_BaM.txt and stop\n"
                    "  -or, --onerun     run the model once at the initial parameter values on an input file, write Y to Yfile\n"
-                   "  --chains K        number of MCMC chains run in lockstep on the GPU (the reference runs 1)\n");
+                   "  --chains K        number of MCMC chains run in lockstep on the GPU (the reference runs 1)\n"
+                   "  --gpus N          shard the K chains (and the prediction inputs) over GPUs 0..N-1 of this box: one host thread per\n"
+                   "                    GPU, NCCL (ncclCommInitAll) all-gather of the per-chain moments for Results_Rhat.txt\n");
             return 0;
         } else { fprintf(stderr, "Unrecognized command-line option: %s\n", a.c_str()); return 1; }
     }
@@ -216,6 +220,44 @@ int main(int argc, char** argv) {
             const long long N = (long long)w.mcmc.nAdapt * w.mcmc.nCycles;
             std::vector<double> rows((size_t)K * N * rowlen);
             int64_t nKeep = 0;
+            std::vector<double> rhatAll;  // filled by the multi-GPU path
+            if (gpus > 1) {
+                // chains shard over the GPUs of the box (observations replicated, no collective on the data path); the RNG
+                // streams are keyed by the GLOBAL chain index, so the rows equal those of a one-GPU run of the same K
+                if (K % gpus) throw std::runtime_error("--gpus: the number of chains must be a multiple of the number of GPUs");
+                const int Kloc = K / gpus;
+                std::vector<bamgpu_t*> hs(gpus, nullptr);
+                std::vector<bamgpu_comm_t*> comms(gpus, nullptr);
+                std::vector<std::string> errs(gpus);
+                hs[0] = h;
+                for (int g = 1; g < gpus; ++g) check(bamgpu_create(&hs[g], &pb, g, mess), mess);
+                check(bamgpu_comm_init_all(comms.data(), gpus, nullptr, mess), mess);
+                std::vector<std::vector<double>> rh(gpus, std::vector<double>(P));
+                std::vector<std::thread> th;
+                for (int g = 0; g < gpus; ++g)
+                    th.emplace_back([&, g] {
+                        char m[BAMGPU_MESS_LEN];
+                        int64_t nk = 0;
+                        bamgpu_set_chain_offset(hs[g], (int64_t)g * Kloc);
+                        int e = bamgpu_fit(hs[g], Kloc, start.data() + (size_t)g * Kloc * P, sd.data() + (size_t)g * Kloc * P, w.mcmc.nAdapt,
+                                           w.mcmc.nCycles, w.mcmc.minMoveRate, w.mcmc.maxMoveRate, w.mcmc.downMult, w.mcmc.upMult, seed, 0, 1,
+                                           rows.data() + (size_t)g * Kloc * N * rowlen, &nk, m);
+                        if (e > 0) errs[g] = m;
+                        // every rank must enter the collective, failed or not
+                        double ms = 0.0;
+                        e = bamgpu_moments_allgather(hs[g], comms[g], rh[g].data(), nullptr, nullptr, nullptr, &ms, m);
+                        if (e > 0 && errs[g].empty()) errs[g] = m;
+                    });
+                for (auto& t : th) t.join();
+                for (int g = 0; g < gpus; ++g) bamgpu_comm_destroy(comms[g]);
+                for (int g = 1; g < gpus; ++g) bamgpu_destroy(hs[g]);
+                for (auto& e : errs)
+                    if (!e.empty()) throw std::runtime_error(e);
+                for (int g = 1; g < gpus; ++g)
+                    if (rh[g] != rh[0]) throw std::runtime_error("--gpus: the ranks disagree on the Gelman-Rubin statistic");
+                rhatAll = rh[0];
+                nKeep = N;
+            } else
             check(bamgpu_fit(h, K, start.data(), sd.data(), w.mcmc.nAdapt, w.mcmc.nCycles, w.mcmc.minMoveRate, w.mcmc.maxMoveRate,
                              w.mcmc.downMult, w.mcmc.upMult, seed, 0, 1, rows.data(), &nKeep, mess), mess);
             write_monitor(w.dir + w.fMCMC + ".monitor", N, N);
@@ -231,8 +273,11 @@ int main(int argc, char** argv) {
             write_table(cookPath, w.headers, cooked, nCooked, rowlen);
             if (K > 1) {
                 std::vector<double> cnt(K), mean((size_t)K * P), m2((size_t)K * P), rhat(P);
-                check(bamgpu_moments(h, cnt.data(), mean.data(), m2.data(), 0, mess), mess);
-                check(bamgpu_rhat(K, P, cnt.data(), mean.data(), m2.data(), rhat.data(), mess), mess);
+                if (!rhatAll.empty()) rhat = rhatAll;  // all-gathered across the GPUs (bamgpu_moments_allgather)
+                else {
+                    check(bamgpu_moments(h, cnt.data(), mean.data(), m2.data(), 0, mess), mess);
+                    check(bamgpu_rhat(K, P, cnt.data(), mean.data(), m2.data(), rhat.data(), mess), mess);
+                }
                 std::vector<std::string> hd(w.headers.begin(), w.headers.begin() + P);
                 write_table(w.dir + "Results_Rhat.txt", hd, rhat, 1, P);
             }

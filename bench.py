@@ -504,26 +504,34 @@ def strong_scaling_leg(device, rank, world, dist, torch, total_chains, n, steps,
 
 
 def multi_gpu_legs(device, rank, world, dist, torch):
-    """N > 1: the two places where the path exchanges data, through NCCL over NVLink.
+    """N > 1: the two places where the path exchanges data, through NCCL over NVLink INSIDE the
+    library (bam_b200/csrc/bam_comm.cu; torch.distributed only carries the 128-byte communicator id between the ranks).
     (1) prediction inputs shard across ranks ([t0,t1) slices, samples replicated); every rank owns whole columns, so
-        the exact quantiles need no exchange; the envelope slices are all-gathered.  STRONG scaling: the experiment is
-        fixed (10^6 samples x 10^5 inputs), time = max over ranks (CUDA events) + the gather.
-    (2) chains shard across ranks; per-chain moments {count, mean, M2} are all-gathered from DEVICE buffers filled by
-        bamgpu_moments(dev_ptrs=1) and the Gelman-Rubin statistic is computed redundantly on every rank."""
+        the exact quantiles need no exchange; the envelope slices are all-gathered (bamgpu_envelope_allgather).
+        STRONG scaling: the experiment is fixed (10^6 samples x 10^5 inputs), time = max over ranks (CUDA events) + the
+        gather.
+    (2) chains shard across ranks; per-chain moments {count, mean, M2} are packed into one message, all-gathered and
+        the Gelman-Rubin statistic is computed redundantly on every rank (bamgpu_moments_allgather)."""
     from workloads import synth
-    from bam_b200.capi import BamGpu
+    from bam_b200.capi import BamGpu, Comm
     from tests.helpers import problem_from_fixture
 
-    out = {}
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    comm = Comm(world, rank, bytes(uid.cpu().numpy().tobytes()), device)
+    out = {"nccl_version": comm.nccl_version()}
     # ---- (1) sharded prediction
     Nrep, nobs = 1_000_000, 100_000
     prob, _ = synth.baratin_2c(nobs=38)
     mc, mode, Hs = synth.baratin_spaghetti(Nrep=Nrep, nobs=nobs)
     per = (nobs + world - 1) // world
-    t0, t1 = rank * per, min(nobs, (rank + 1) * per)
+    t0, t1 = min(rank * per, nobs), min(nobs, (rank + 1) * per)
     g = BamGpu(prob, device)
     g.predict_upload(mc, mode, [Hs])
     g.predict_resident(1, [1], seed=1, t0=t0, t1=t1)
+    g.envelope_allgather(comm, nobs)  # warm-up: NCCL channels, buffers
     g.sync(); g.step_times(); g.kernel_times()
     dist.barrier(); torch.cuda.synchronize()
     g.step_begin()
@@ -531,23 +539,14 @@ def multi_gpu_legs(device, rank, world, dist, torch):
     g.step_end()
     g.sync()
     ms = float(g.step_times()[-1])
-    env = torch.from_numpy(np.ascontiguousarray(g.predict_download()[0].T)).cuda()  # (t1-t0) x 7
-    pad = torch.zeros(per, 7, dtype=torch.float64, device="cuda")
-    pad[: t1 - t0] = env
-    gathered = torch.empty(world * per, 7, dtype=torch.float64, device="cuda")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    dist.all_gather_into_tensor(gathered, pad)
-    e1.record()
-    torch.cuda.synchronize()
-    tt = torch.tensor([ms, e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    full, ms_gather = g.envelope_allgather(comm, nobs)
+    tt = torch.tensor([ms, ms_gather], device="cuda", dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    full = gathered[:nobs].cpu().numpy()
     out["prediction"] = {"metric": "prediction samples x inputs/sec", "value": Nrep * nobs / ((tt[0].item() + tt[1].item()) * 1e-3),
                          "unit": "sample*input/s", "scaling": "strong", "ms_compute_max_over_ranks": tt[0].item(),
                          "ms_envelope_allgather_nccl": tt[1].item(),
                          "workload": f"BaRatin spaghetti {Nrep} samples x {nobs} inputs sharded by input over {world} GPUs",
-                         "finite": bool(np.isfinite(full).all()), "median_checksum": float(full[:, 0].sum())}
+                         "finite": bool(np.isfinite(full).all()), "median_checksum": float(full[0, 0].sum())}
     del g
     # ---- (2) sharded sampler + NCCL all-gather of the moments
     prob, d = problem_from_fixture("baratin")
@@ -556,24 +555,15 @@ def multi_gpu_legs(device, rank, world, dist, torch):
     g.set_chain_offset(rank * K)
     s0 = np.tile(np.asarray(d["start"]), (K, 1))
     g.fit(s0, 0.1 * np.abs(s0), nAdapt=100, nCycles=20, seed=3, want_rows=False)
-    P = g.P
-    cnt = torch.empty(K, dtype=torch.float64, device="cuda")
-    mean = torch.empty(K, P, dtype=torch.float64, device="cuda")
-    m2 = torch.empty(K, P, dtype=torch.float64, device="cuda")
-    g.moments_device(cnt.data_ptr(), mean.data_ptr(), m2.data_ptr())
-    gc = torch.empty(world * K, dtype=torch.float64, device="cuda")
-    gm = torch.empty(world * K, P, dtype=torch.float64, device="cuda")
-    g2 = torch.empty(world * K, P, dtype=torch.float64, device="cuda")
-    e0.record()
-    dist.all_gather_into_tensor(gc, cnt)
-    dist.all_gather_into_tensor(gm, mean)
-    dist.all_gather_into_tensor(g2, m2)
-    e1.record()
-    torch.cuda.synchronize()
-    rhat = g.rhat(gc.cpu().numpy(), gm.cpu().numpy(), g2.cpu().numpy())
+    g.moments_allgather(comm)  # warm-up
+    dist.barrier(); torch.cuda.synchronize()
+    rhat, ms_m = g.moments_allgather(comm)
+    tm = torch.tensor([ms_m], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     out["sampler"] = {"workload": f"tests/BaM_BaRatin, {K} chains per GPU x 2000 iterations, chains sharded over {world} GPUs",
-                      "ms_fit_loop": float(g.step_times()[-1]), "ms_moments_allgather_nccl": e0.elapsed_time(e1),
+                      "ms_fit_loop": float(g.step_times()[-1]), "ms_moments_allgather_nccl": tm.item(),
                       "chains_total": world * K, "rhat_max": float(np.nanmax(rhat))}
+    comm.close()
     return out
 
 
