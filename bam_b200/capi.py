@@ -307,6 +307,7 @@ def load_library(path: Optional[str] = None):
     lib.bamgpu_fit.argtypes = [H, ci, _dp, _dp, ci, ci, C.c_double, C.c_double, C.c_double, C.c_double, u64, ci, ci,
                                _dp, C.POINTER(i64), cp]
     lib.bamgpu_moments.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, ci, cp]
+    lib.bamgpu_moments_window.argtypes = [H, i64, ci, cp]
     lib.bamgpu_rhat.argtypes = [ci, ci, _dp, _dp, _dp, _dp, cp]
     lib.bamgpu_phase_times.argtypes = [H, _dp, _dp, ci]
     lib.bamgpu_comm_unique_id.argtypes = [cp, cp]
@@ -504,6 +505,11 @@ class BamGpu:
         mess = C.create_string_buffer(MESS_LEN)
         _check(self.lib.bamgpu_moments(self.h, count.ctypes.data, mean.ctypes.data, m2.ctypes.data, 0, mess), mess)
         return count, mean, m2
+
+    def moments_window(self, first: int, every: int = 1):
+        """moments over rows first, first+every, ... of the last fit (the cooked sample)"""
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(self.lib.bamgpu_moments_window(self.h, first, every, mess), mess)
 
     def moments_device(self, count_ptr: int, mean_ptr: int, m2_ptr: int):
         mess = C.create_string_buffer(MESS_LEN)

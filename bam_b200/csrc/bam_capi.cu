@@ -89,6 +89,7 @@ int bamgpu_rhat(int K, int P, const double* count, const double* mean, const dou
 }
 
 int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* mess) {
+    if (!out || !pb) { if (mess) snprintf(mess, BAMGPU_MESS_LEN, "bamgpu_create: null argument"); return 1; }
     *out = nullptr;
     return guarded(mess, [&]() -> int {
         int ndev = 0;
@@ -141,11 +142,16 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         // shared-memory table reads become broadcasts) and on the stage range of BaRatin (no divergent pow counts).
         // Not done when latent inputs exist: their per-chain values are read coalesced in the original order.
         // With a single output and no latent inputs, an observation whose Y is the missing-value code contributes
-        // nothing to the posterior (:3207): it is dropped from the device tables (nDev <= n) instead of being tested
-        // in the inner loop.
+        // nothing to the likelihood (:3207): it is dropped from the device tables (nDev <= n) instead of being tested
+        // in the inner loop -- but ONLY for models whose rows cannot be infeasible once the parameter set is feasible
+        // (BaRatin: the "H - b < 0" exits are dead after ApplyContinuity; Linear: no test at all).  ApplyModel takes
+        // feas = all(vfeas) over ALL rows (ModelLibrary_tools.f90:421-423), so for every other pointwise model a row with
+        // missing Y can still make the vector infeasible, and whole-series models (Segmentation: segment sizes and tmax
+        // from the full time vector, Segmentation_model.f90:138,147; Vegetation; the time-recursive ones) need every row.
+        const bool canDrop = L.nY == 1 && !L.hasLatent && (L.model == BAMGPU_MDL_BARATIN || L.model == BAMGPU_MDL_LINEAR);
         std::vector<int> perm;
         for (int i = 0; i < L.n; ++i)
-            if (!(L.nY == 1 && !L.hasLatent && pb->Y[i] == pb->mv)) perm.push_back(i);
+            if (!(canDrop && pb->Y[i] == pb->mv)) perm.push_back(i);
         const int nDev = (int)perm.size();
         const bool dropped = nDev != L.n;
         // Mixture: output row r is built from input row xsrc[r] (pack order of its event, bam::mixture_rows); pairing the
@@ -340,6 +346,7 @@ void bamgpu_destroy(bamgpu_t* h) {
 }
 
 int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s) {
+    if (!h || !s) return 1;
     const bam::HostLayout& L = h->L;
     s->nFit = L.nFit; s->nGamma = L.nGamma; s->nLatent = L.nLatent; s->nXbias = L.nXbTot; s->nYbias = L.nYbTot;
     s->nInfer = L.P; s->nDpar = L.nDpar; s->nCombo = L.nCombo; s->nState = L.nState;
@@ -347,6 +354,7 @@ int bamgpu_get_sizes(const bamgpu_t* h, bamgpu_sizes* s) {
 }
 
 int bamgpu_set_option(bamgpu_t* h, const char* name, int value) {
+    if (!h || !name) return 1;
     if (!strcmp(name, "force_generic")) { h->forceGeneric = value != 0; return 0; }
     if (!strcmp(name, "no_select3")) { h->noSelect3 = value != 0; return 0; }
     if (!strcmp(name, "only_radix")) { h->onlyRadix = value != 0; return 0; }
@@ -356,6 +364,7 @@ int bamgpu_set_option(bamgpu_t* h, const char* name, int value) {
 }
 
 int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset) {
+    if (!h) return 1;
     h->chainOffset = offset;
     return 0;
 }
@@ -364,6 +373,7 @@ int bamgpu_set_chain_offset(bamgpu_t* h, int64_t offset) {
 
 int bamgpu_chains_upload(bamgpu_t* h, int K, const double* x, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         if (K < 1) throw bam::CudaError{"bamgpu: K must be >= 1"};
         BAM_CUDA(cudaSetDevice(h->device));
         bam::ensure_chain_capacity(h, K);
@@ -375,6 +385,7 @@ int bamgpu_chains_upload(bamgpu_t* h, int K, const double* x, char* mess) {
 
 int bamgpu_logpost_resident(bamgpu_t* h, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         if (h->K < 1) throw bam::CudaError{"bamgpu: no resident chains (call bamgpu_chains_upload first)"};
         BAM_CUDA(cudaSetDevice(h->device));
         bam::launch_logpost(h, h->K, h->d_x, -1, nullptr, true);
@@ -384,6 +395,7 @@ int bamgpu_logpost_resident(bamgpu_t* h, char* mess) {
 
 int bamgpu_sync(bamgpu_t* h, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         BAM_CUDA(cudaStreamSynchronize(h->stream));
         float ms = 0.f;
         if (cudaEventQuery(h->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->lastMs = ms;
@@ -410,6 +422,7 @@ static void download_flags(bamgpu_t* h, int K, int32_t* feas, int32_t* isnull) {
 
 int bamgpu_chains_download(bamgpu_t* h, double* fx, int32_t* feas, int32_t* isnull, double* dpar, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         const int K = h->K;
         BAM_CUDA(cudaSetDevice(h->device));
         if (fx) BAM_CUDA(cudaMemcpyAsync(fx, h->d_fx, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
@@ -422,6 +435,7 @@ int bamgpu_chains_download(bamgpu_t* h, double* fx, int32_t* feas, int32_t* isnu
 
 int bamgpu_logpost(bamgpu_t* h, int K, const double* x, double* fx, int32_t* feas, int32_t* isnull, double* dpar,
                    char* mess) {
+    if (!h) { if (mess) snprintf(mess, BAMGPU_MESS_LEN, "bamgpu: null handle"); return 1; }
     int e = bamgpu_chains_upload(h, K, x, mess);
     if (e) return e;
     e = bamgpu_logpost_resident(h, mess);
@@ -431,6 +445,7 @@ int bamgpu_logpost(bamgpu_t* h, int K, const double* x, double* fx, int32_t* fea
 
 int bamgpu_logpost_parts(bamgpu_t* h, int K, const double* x, double* prior, double* lkh, double* hyper, int32_t* feas,
                          int32_t* isnull, char* mess) {
+    if (!h) { if (mess) snprintf(mess, BAMGPU_MESS_LEN, "bamgpu: null handle"); return 1; }
     int e = bamgpu_chains_upload(h, K, x, mess);
     if (e) return e;
     e = bamgpu_logpost_resident(h, mess);
@@ -452,6 +467,7 @@ int bamgpu_calibration_run(bamgpu_t* h, const bamgpu_problem* pb, const double* 
 int bamgpu_calibration_run_states(bamgpu_t* h, const bamgpu_problem* pb, const double* x, double* Xtrue, double* Ysim,
                                   double* state, int32_t* feas, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         BAM_CUDA(cudaSetDevice(h->device));
         const bam::HostLayout& L = h->L;
         const int n = L.n, nX = L.nX, nY = L.nY;
@@ -511,6 +527,7 @@ int bamgpu_calibration_run_states(bamgpu_t* h, const bamgpu_problem* pb, const d
 int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std, int nAdapt, int nCycles,
                double MinMoveRate, double MaxMoveRate, double DownMult, double UpMult, uint64_t seed, int burn,
                int keep_every, double* out_rows, int64_t* n_keep, char* mess) {
+    if (!h) { if (mess) snprintf(mess, BAMGPU_MESS_LEN, "bamgpu: null handle"); return 1; }
     int e = bamgpu_chains_upload(h, K, start, mess);
     if (e) return e;
     return guarded(mess, [&]() -> int {
@@ -524,6 +541,7 @@ int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std,
         BAM_CUDA(cudaMemcpyAsync(h->d_std, start_std, sizeof(double) * (size_t)K * h->dp.P, cudaMemcpyHostToDevice, h->stream));
         bam::launch_fit(h, K, nAdapt, nCycles, MinMoveRate, MaxMoveRate, DownMult, UpMult, seed, burn, keep_every,
                         out_rows != nullptr, nKeep);
+        h->rowsKept = out_rows ? nKeep : 0;
         if (out_rows && nKeep > 0)
             BAM_CUDA(cudaMemcpyAsync(out_rows, h->d_rows, sizeof(double) * (size_t)K * nKeep * (h->dp.P + 1 + h->dp.nDpar),
                                      cudaMemcpyDeviceToHost, h->stream));
@@ -532,8 +550,21 @@ int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std,
     });
 }
 
+int bamgpu_moments_window(bamgpu_t* h, int64_t first, int every, char* mess) {
+    return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
+        if (!h->haveMoments || h->rowsKept < 1) throw bam::CudaError{"bamgpu_moments_window: run bamgpu_fit with out_rows first"};
+        if (first < 0 || every < 1) throw bam::CudaError{"bamgpu_moments_window: bad window"};
+        BAM_CUDA(cudaSetDevice(h->device));
+        bam::launch_window_moments(h, h->K, h->rowsKept, first, every);
+        BAM_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    });
+}
+
 int bamgpu_moments(bamgpu_t* h, double* count, double* mean, double* m2, int dev_ptrs, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         if (!h->haveMoments) throw bam::CudaError{"bamgpu_moments: run bamgpu_fit first"};
         const size_t K = h->K, KP = K * h->dp.P;
         const cudaMemcpyKind kind = dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -550,6 +581,7 @@ int bamgpu_moments(bamgpu_t* h, double* count, double* mean, double* m2, int dev
 int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const double* mode, int nobs_pred,
                           const double* const* xspag, const int32_t* nspag, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         BAM_CUDA(cudaSetDevice(h->device));
         if (Nrep < 1 || nobs_pred < 1) throw bam::CudaError{"BaM_Prediction: empty prediction"};
         free_prediction(h);
@@ -620,6 +652,7 @@ int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const dou
 int bamgpu_predict_resident(bamgpu_t* h, int doParametric, const int32_t* doRemnant, uint64_t seed, int t0, int t1,
                             char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         BAM_CUDA(cudaSetDevice(h->device));
         if (h->predNrep < 1) throw bam::CudaError{"bamgpu_predict_resident: call bamgpu_predict_upload first"};
         if (t0 < 0 || t1 > h->predNobs || t0 >= t1) throw bam::CudaError{"bamgpu_predict: bad input range [t0,t1)"};
@@ -630,6 +663,7 @@ int bamgpu_predict_resident(bamgpu_t* h, int doParametric, const int32_t* doRemn
 
 int bamgpu_predict_download(bamgpu_t* h, double* env, char* mess) {
     return guarded(mess, [&]() -> int {
+        if (!h) throw bam::CudaError{"bamgpu: null handle"};
         const size_t cnt = (size_t)(h->predT1 - h->predT0) * BAMGPU_NENV * (h->predNout > 0 ? h->predNout : h->dp.nY);
         if (h->predNrep >= 2)
             BAM_CUDA(cudaMemcpyAsync(env, h->d_env, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
@@ -670,10 +704,11 @@ int bamgpu_predict_states(bamgpu_t* h, int64_t Nrep, const double* mc, const dou
 
 // ---- measurement --------------------------------------------------------------------------------------
 
-int64_t bamgpu_launch_count(const bamgpu_t* h) { return h->launches; }
-double bamgpu_last_kernel_ms(const bamgpu_t* h) { return h->lastMs; }
+int64_t bamgpu_launch_count(const bamgpu_t* h) { return h ? h->launches : 0; }
+double bamgpu_last_kernel_ms(const bamgpu_t* h) { return h ? h->lastMs : 0.0; }
 
 int bamgpu_step_begin(bamgpu_t* h) {
+    if (!h) return 1;
     try {
         h->recordKernels = true;
         h->stepOpen = bam::take_event(h);
@@ -682,6 +717,7 @@ int bamgpu_step_begin(bamgpu_t* h) {
 }
 
 int bamgpu_step_end(bamgpu_t* h) {
+    if (!h) return 1;
     try {
         if (!h->stepOpen) return 1;
         cudaEvent_t e = bam::take_event(h);
@@ -707,14 +743,16 @@ static int drain(bamgpu_t* h, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& 
     return n < cap ? n : cap;
 }
 
-int bamgpu_step_times(bamgpu_t* h, double* ms, int cap) { return drain(h, h->stepEv, ms, cap); }
-int bamgpu_kernel_times(bamgpu_t* h, double* ms, int cap) { return drain(h, h->kernEv, ms, cap); }
+int bamgpu_step_times(bamgpu_t* h, double* ms, int cap) { return h ? drain(h, h->stepEv, ms, cap) : 0; }
+int bamgpu_kernel_times(bamgpu_t* h, double* ms, int cap) { return h ? drain(h, h->kernEv, ms, cap) : 0; }
 int bamgpu_phase_times(bamgpu_t* h, double* prep_ms, double* final_ms, int cap) {
+    if (!h) return 0;
     const int a = drain(h, h->prepEv, prep_ms, cap), b = drain(h, h->finalEv, final_ms, cap);
     return a < b ? a : b;
 }
 
 int bamgpu_flush_l2(bamgpu_t* h, size_t bytes) {
+    if (!h) return 1;
     if (bytes > h->flushCap) {
         if (h->d_flush) cudaFree(h->d_flush);
         if (cudaMalloc(&h->d_flush, bytes) != cudaSuccess) { h->d_flush = nullptr; h->flushCap = 0; return 1; }

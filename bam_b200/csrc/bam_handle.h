@@ -72,6 +72,7 @@ struct bamgpu_handle {
     double* d_rows = nullptr;
     size_t rowsCap = 0;
     bool haveMoments = false;
+    long long rowsKept = 0;  // rows per chain the last fit left in d_rows (0: none stored)
 
     // ---- prediction workspace ----
     long long predNrep = 0;
@@ -135,6 +136,8 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
 
 void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, double maxMR, double downMult,
                 double upMult, unsigned long long seed, int burn, int keepEvery, bool storeRows, long long nKeep);
+
+void launch_window_moments(bamgpu_handle* h, int K, long long nKeep, long long first, int every);
 
 void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, unsigned long long seed, int t0, int t1,
                     double* h_spag /* host, may be null */, bool withStates = false);

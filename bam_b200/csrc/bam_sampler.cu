@@ -79,6 +79,27 @@ __global__ void record_kernel(int K, int P, int nDpar, long long keepIdx, long l
     }
 }
 
+// moments of the rows [first, nKeep) taken every `every`-th (the cooked sample: burn-in dropped, slimmed), from the rows a
+// fit left on the device; one thread per (chain, component), Welford in the order of the rows
+__global__ void window_moments_kernel(int K, int P, int rowlen, long long nKeep, long long first, int every,
+                                      const double* __restrict__ rows, double* __restrict__ mcount, double* __restrict__ mmean,
+                                      double* __restrict__ mm2) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)K * P) return;
+    const int c = (int)(q / P), j = (int)(q % P);
+    double cnt = 0.0, m = 0.0, s2 = 0.0;
+    for (long long r = first; r < nKeep; r += every) {
+        const double v = rows[((size_t)c * nKeep + r) * rowlen + j];
+        cnt += 1.0;
+        const double d = v - m;
+        m += d / cnt;
+        s2 += d * (v - m);
+    }
+    mmean[q] = m;
+    mm2[q] = s2;
+    if (j == 0) mcount[c] = cnt;
+}
+
 __global__ void adapt_kernel(int K, int P, int nAdapt, double minMR, double maxMR, double downMult, double upMult,
                              double* __restrict__ sd, int* __restrict__ moves) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,6 +197,11 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
     long long it = 0, kept = 0;
     cudaEvent_t f0 = take_event(h), f1 = take_event(h);  // the iterations as one timed "step" (bamgpu_step_times)
     BAM_CUDA(cudaEventRecord(f0, s));
+    const size_t lkSmem = sizeof(double) * ((size_t)p.tabStride + 2 * BAM_LOGTAB_N);
+    if (lk) {  // the sweep stages the chain's table row: with many VAR combinations it outgrows the default 48 KB
+        if (lkSmem > 227 * 1024) throw CudaError{"bamgpu_fit: the per-chain parameter table of this problem does not fit the shared memory of the latent sweep"};
+        if (lkSmem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)lk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lkSmem));
+    }
     for (int cyc = 0; cyc < nCycles; ++cyc) {
         for (int a = 0; a < nAdapt; ++a, ++it) {
             for (int i = 0; i < (lk ? latBeg : P); ++i) propose_one(i, it);
@@ -184,7 +210,7 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
                 // full log-posterior of the swept state becomes the current one
                 launch_table(h, K, h->d_x);
                 dim3 grid((p.n + BAM_BLOCK - 1) / BAM_BLOCK, K);
-                lk<<<grid, BAM_BLOCK, sizeof(double) * (p.tabStride + 2 * BAM_LOGTAB_N), s>>>(p, K, seed, h->chainOffset, (unsigned)it, h->d_x,
+                lk<<<grid, BAM_BLOCK, lkSmem, s>>>(p, K, seed, h->chainOffset, (unsigned)it, h->d_x,
                                                                         h->d_std, h->d_moves, h->d_tab);
                 launch_logpost(h, K, h->d_x, -1, nullptr, false);
                 BAM_CUDA(cudaMemcpyAsync(h->d_fxcur, h->d_fx, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
@@ -215,4 +241,15 @@ void launch_fit(bamgpu_handle* h, int K, int nAdapt, int nCycles, double minMR, 
     h->haveMoments = true;
 }
 
+}  // namespace bam
+
+namespace bam {
+void launch_window_moments(bamgpu_handle* h, int K, long long nKeep, long long first, int every) {
+    const DevProblem& p = h->dp;
+    const long long q = (long long)K * p.P;
+    window_moments_kernel<<<(unsigned)((q + 255) / 256), 256, 0, h->stream>>>(K, p.P, p.P + 1 + p.nDpar, nKeep, first, every, h->d_rows,
+                                                                             h->d_mcount, h->d_mmean, h->d_mm2);
+    h->launches += 1;
+    BAM_CUDA(cudaGetLastError());
+}
 }  // namespace bam

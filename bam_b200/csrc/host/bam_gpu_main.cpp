@@ -221,6 +221,7 @@ int main(int argc, char** argv) {
             std::vector<double> rows((size_t)K * N * rowlen);
             int64_t nKeep = 0;
             std::vector<double> rhatAll;  // filled by the multi-GPU path
+            const long long nburnAll = std::llround((double)N * w.burnFactor);  // BaM_LoadMCMC :672-677
             if (gpus > 1) {
                 // chains shard over the GPUs of the box (observations replicated, no collective on the data path); the RNG
                 // streams are keyed by the GLOBAL chain index, so the rows equal those of a one-GPU run of the same K
@@ -243,6 +244,7 @@ int main(int argc, char** argv) {
                                            w.mcmc.nCycles, w.mcmc.minMoveRate, w.mcmc.maxMoveRate, w.mcmc.downMult, w.mcmc.upMult, seed, 0, 1,
                                            rows.data() + (size_t)g * Kloc * N * rowlen, &nk, m);
                         if (e > 0) errs[g] = m;
+                        else if (bamgpu_moments_window(hs[g], nburnAll, std::max(1, w.nSlim), m) > 0) errs[g] = m;  // the cooked sample
                         // every rank must enter the collective, failed or not
                         double ms = 0.0;
                         e = bamgpu_moments_allgather(hs[g], comms[g], rh[g].data(), nullptr, nullptr, nullptr, &ms, m);
@@ -275,6 +277,8 @@ int main(int argc, char** argv) {
                 std::vector<double> cnt(K), mean((size_t)K * P), m2((size_t)K * P), rhat(P);
                 if (!rhatAll.empty()) rhat = rhatAll;  // all-gathered across the GPUs (bamgpu_moments_allgather)
                 else {
+                    // Gelman-Rubin on the COOKED sample (burn-in dropped, slimmed): the sample that is summarised and propagated
+                    check(bamgpu_moments_window(h, nburnAll, std::max(1, w.nSlim), mess), mess);
                     check(bamgpu_moments(h, cnt.data(), mean.data(), m2.data(), 0, mess), mess);
                     check(bamgpu_rhat(K, P, cnt.data(), mean.data(), m2.data(), rhat.data(), mess), mess);
                 }

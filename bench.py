@@ -244,6 +244,47 @@ def run_reference(args):
     return 0
 
 
+def prediction_e2e(g, lib, mc, mode, xspag, doRemnant, pairs, calls=2):
+    """the prediction metric through the C-ABI call a host makes (bamgpu_predict): HOST sample matrix and inputs in,
+    envelopes out, copies inside the timed region (wall clock around the blocking call)"""
+    mcf = np.asfortranarray(mc)
+    lib.bamgpu_pin(mcf.ctypes.data, mcf.nbytes)
+    try:
+        g.predict(mcf, mode, xspag, 1, doRemnant, seed=1)  # warm-up (allocations)
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            env, _ = g.predict(mcf, mode, xspag, 1, doRemnant, seed=1)
+        dt = (time.perf_counter() - t0) / calls
+    finally:
+        lib.bamgpu_unpin(mcf.ctypes.data)
+    return {"value": pairs / dt, "unit": "sample*input/s", "ms_per_call": 1e3 * dt,
+            "h2d_bytes_per_step": int(mcf.nbytes + sum(np.asarray(x).nbytes for x in xspag)), "d2h_bytes_per_step": int(env.nbytes),
+            "path": "bamgpu_predict (C ABI): pinned host sample matrix + inputs in, envelopes out, wall clock"}
+
+
+def prediction_cpu_baseline(prob, mc, mode, xspag, doRemnant, nY_pred, seconds_target=10.0):
+    """oracle (port) on all host cores, OpenMP over prediction inputs, on a bounded sample of the same experiment"""
+    from oracle.oracle_api import Oracle
+
+    o = Oracle(prob)
+    cores = os.cpu_count() or 1
+    nrep = min(mc.shape[0], 20_000)
+    nobs = min(np.asarray(xspag[0]).shape[0], 64 * cores)
+    xs = [np.asarray(x)[:nobs] for x in xspag]
+    t0 = time.perf_counter()
+    o.predict(mc[:nrep], mode, xs, 1, doRemnant, seed=1, nthreads=cores)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    scale = int(max(1, min(np.asarray(xspag[0]).shape[0] // nobs, round(seconds_target / dt))))
+    nobs2 = nobs * scale
+    xs = [np.asarray(x)[:nobs2] for x in xspag]
+    t0 = time.perf_counter()
+    o.predict(mc[:nrep], mode, xs, 1, doRemnant, seed=1, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": nrep * nobs2 * nY_pred / dt, "unit": "sample*input/s", "cores": cores, "kind": "port", "seconds": dt,
+            "sample": f"{nrep} samples x {nobs2} inputs of the same experiment, oracle/bam_oracle.c (propagation + noise + "
+                      f"sorted-column envelopes), OpenMP"}
+
+
 def prediction_leg(device, fp64_peak, hbm_peak, steps=2):
     """BASELINE's second metric on configs[4] (BaRatin spaghetti + structural-error noise), bounded size.
 
@@ -277,6 +318,12 @@ def prediction_leg(device, fp64_peak, hbm_peak, steps=2):
            f"remnant noise, exact envelopes (configs[4], full size: {8 * Nrep * nobs / 1e9:.0f} GB of spaghetti materialised in "
            f"tiles of <= 48 GiB, far larger than L2)",
            "finite": ok}
+    try:
+        from bam_b200.capi import load_library
+        out["e2e"] = prediction_e2e(g, load_library(), mc, mode, [Hs], [1], pairs)
+        out["cpu_baseline"] = prediction_cpu_baseline(prob, mc, mode, [Hs], [1], 1)
+    except Exception as e:
+        out["e2e_error"] = str(e)
     if km.size >= 2 * steps:
         kp, ke = float(km[0::2].sum()) / steps, float(km[1::2].sum()) / steps  # summed over the tiles of a step
         ipu = fp64_inst_per_unit().get("pred_baratin_fast")
@@ -317,7 +364,14 @@ def sediment_prediction_leg(device, hbm_peak, Nrep=10_000_000, steps=2):
     km = g.kernel_times()
     pairs = Nrep * nobs
     kp, ke = float(km[0::2].sum()) / steps, float(km[1::2].sum()) / steps
-    return {"metric": "prediction samples x inputs/sec", "value": pairs / (ms.mean() * 1e-3), "unit": "sample*input/s",
+    extra = {}
+    try:
+        from bam_b200.capi import load_library
+        extra["e2e"] = prediction_e2e(g, load_library(), mc, truth, X, [1], pairs)
+        extra["cpu_baseline"] = prediction_cpu_baseline(prob, mc, truth, X, [1], 1)
+    except Exception as e:
+        extra["e2e_error"] = str(e)
+    return {**extra, "metric": "prediction samples x inputs/sec", "value": pairs / (ms.mean() * 1e-3), "unit": "sample*input/s",
             "ms_per_step": float(ms.mean()),
             "workload": f"Sediment Camenen+Soulsby, {Nrep} samples x {nobs} inputs, parametric + remnant noise, exact envelopes "
                         f"(configs[3], full size; {8 * pairs / 1e9:.0f} GB of spaghetti materialised in tiles, inputs larger than L2)",
@@ -329,17 +383,20 @@ def sediment_prediction_leg(device, hbm_peak, Nrep=10_000_000, steps=2):
             "finite": bool(np.isfinite(g.predict_download()).all())}
 
 
-def vegetation_prediction_leg(device, Nrep=2_000_000, nobs=1095, steps=1):
+def vegetation_prediction_leg(device, Nrep=10_000_000, nobs=1095, steps=1):
     """configs[3], second law: Vegetation (Growth_Yin3, 3 years of daily inputs, 5 outputs: Q, g, cos, sin, g0), posterior
     sample propagated through the per-observation Newton solve, remnant noise on Q, exact envelopes of all outputs.
     Generic kernels (pred_main, libdevice pow); the tie-heavy growth-index columns (exactly zero off season) exercise the
-    4-read and the radix selection.  Bounded sample of the 10^7-sample experiment (host RAM of the bench process)."""
+    4-read and the radix selection.  Full size: 10^7 samples."""
     from workloads import synth
     from bam_b200.capi import BamGpu
 
     prob, truth = synth.vegetation(nobs=nobs, growth="Growth_Yin3", nY=5)
     rng = np.random.default_rng(3)
-    mc = truth * (1.0 + 0.002 * rng.standard_normal((Nrep, truth.size)))
+    mc = rng.standard_normal((Nrep, truth.size))  # in place: 10^7 x P doubles once
+    mc *= 0.002
+    mc += 1.0
+    mc *= truth
     X = [np.asarray(prob.X)[:, j].copy() for j in range(prob.nX)]
     g = BamGpu(prob, device)
     g.predict_upload(mc, truth, X)
@@ -357,7 +414,7 @@ def vegetation_prediction_leg(device, Nrep=2_000_000, nobs=1095, steps=1):
     return {"metric": "prediction samples x inputs/sec", "value": pairs / (ms.mean() * 1e-3), "unit": "sample*input/s",
             "ms_per_step": float(ms.mean()),
             "workload": f"Vegetation Growth_Yin3, {Nrep} samples x {nobs} inputs x 5 outputs, parametric + remnant noise on Q, "
-                        f"exact envelopes ({8 * 5 * pairs / 1e9:.0f} GB of spaghetti materialised in tiles; configs[3], bounded sample)",
+                        f"exact envelopes ({8 * 5 * pairs / 1e9:.0f} GB of spaghetti materialised in tiles; configs[3], full size)",
             "kernels": {"propagation": {"kernel": "pred_main<Vegetation,4,5>", "ms": float(km[0::2].sum()) / steps},
                         "envelopes": {"kernel": "envelope_select3 / envelope_select2 / envelope_radix", "ms": float(km[1::2].sum()) / steps}},
             "finite": bool(np.isfinite(g.predict_download()).all())}

@@ -111,9 +111,128 @@ interface
         import; type(c_ptr), value :: h; real(c_double), intent(out) :: cnt(*), mean(*), m2(*)
         integer(c_int), value :: dev_ptrs; character(kind=c_char) :: mess(*)
     end function
+    integer(c_int) function bamgpu_moments_window(h, first, every, mess) bind(C, name='bamgpu_moments_window')
+        import; type(c_ptr), value :: h; integer(c_int64_t), value :: first; integer(c_int), value :: every
+        character(kind=c_char) :: mess(*)
+    end function
     integer(c_int) function bamgpu_rhat(K, P, cnt, mean, m2, rhat, mess) bind(C, name='bamgpu_rhat')
         import; integer(c_int), value :: K, P; real(c_double), intent(in) :: cnt(*), mean(*), m2(*)
         real(c_double), intent(out) :: rhat(*); character(kind=c_char) :: mess(*)
+    end function
+    ! ---- the remaining entry points of include/bam_gpu.h, in header order -------------------------------------------
+    integer(c_int) function bamgpu_set_chain_offset(h, offset) bind(C, name='bamgpu_set_chain_offset')
+        import; type(c_ptr), value :: h; integer(c_int64_t), value :: offset
+    end function
+    integer(c_int) function bamgpu_set_option(h, name, val) bind(C, name='bamgpu_set_option')
+        import; type(c_ptr), value :: h; character(kind=c_char) :: name(*); integer(c_int), value :: val
+    end function
+    integer(c_int) function bamgpu_dist_npar(dist) bind(C, name='bamgpu_dist_npar')
+        import; integer(c_int), value :: dist
+    end function
+    integer(c_int) function bamgpu_sigmafunc_npar(f) bind(C, name='bamgpu_sigmafunc_npar')
+        import; integer(c_int), value :: f
+    end function
+    integer(c_int) function bamgpu_model_id(name) bind(C, name='bamgpu_model_id')
+        import; character(kind=c_char) :: name(*)
+    end function
+    integer(c_int) function bamgpu_prior_corr_to_M(k, C, M, mess) bind(C, name='bamgpu_prior_corr_to_M')
+        import; integer(c_int), value :: k; real(c_double), intent(in) :: C(*); real(c_double), intent(out) :: M(*)
+        character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_chains_upload(h, K, x, mess) bind(C, name='bamgpu_chains_upload')
+        import; type(c_ptr), value :: h; integer(c_int), value :: K; real(c_double), intent(in) :: x(*)
+        character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_logpost_resident(h, mess) bind(C, name='bamgpu_logpost_resident')
+        import; type(c_ptr), value :: h; character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_chains_download(h, fx, feas, isnull, dpar, mess) bind(C, name='bamgpu_chains_download')
+        import; type(c_ptr), value :: h; real(c_double), intent(out) :: fx(*); integer(c_int), intent(out) :: feas(*), isnull(*)
+        type(c_ptr), value :: dpar; character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_sync(h, mess) bind(C, name='bamgpu_sync')
+        import; type(c_ptr), value :: h; character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_predict_upload(h, Nrep, mc, mode, nobs_pred, xspag, nspag, mess) bind(C, name='bamgpu_predict_upload')
+        import; type(c_ptr), value :: h; integer(c_int64_t), value :: Nrep; type(c_ptr), value :: mc, mode
+        integer(c_int), value :: nobs_pred; type(c_ptr), intent(in) :: xspag(*); integer(c_int), intent(in) :: nspag(*)
+        character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_predict_resident(h, doParametric, doRemnant, seed, t0, t1, mess) bind(C, name='bamgpu_predict_resident')
+        import; type(c_ptr), value :: h; integer(c_int), value :: doParametric, t0, t1; integer(c_int), intent(in) :: doRemnant(*)
+        integer(c_int64_t), value :: seed; character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_predict_download(h, env, mess) bind(C, name='bamgpu_predict_download')
+        import; type(c_ptr), value :: h; real(c_double), intent(out) :: env(*); character(kind=c_char) :: mess(*)
+    end function
+    ! multi-GPU: one communicator rank per GPU (MPI hosts broadcast the 128-byte id with MPI_Bcast)
+    integer(c_int) function bamgpu_comm_unique_id(id128, mess) bind(C, name='bamgpu_comm_unique_id')
+        import; character(kind=c_char) :: id128(128), mess(*)
+    end function
+    integer(c_int) function bamgpu_comm_init_rank(c, nranks, rank, id128, device, mess) bind(C, name='bamgpu_comm_init_rank')
+        import; type(c_ptr), intent(out) :: c; integer(c_int), value :: nranks, rank, device
+        character(kind=c_char), intent(in) :: id128(128); character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_comm_init_all(comms, ndev, devices, mess) bind(C, name='bamgpu_comm_init_all')
+        import; type(c_ptr), intent(out) :: comms(*); integer(c_int), value :: ndev; type(c_ptr), value :: devices
+        character(kind=c_char) :: mess(*)
+    end function
+    subroutine bamgpu_comm_destroy(c) bind(C, name='bamgpu_comm_destroy')
+        import; type(c_ptr), value :: c
+    end subroutine
+    integer(c_int) function bamgpu_comm_info(c, nranks, rank, nccl_version) bind(C, name='bamgpu_comm_info')
+        import; type(c_ptr), value :: c; integer(c_int), intent(out) :: nranks, rank, nccl_version
+    end function
+    integer(c_int) function bamgpu_moments_allgather(h, c, rhat, count_all, mean_all, m2_all, ms, mess) &
+                                                     bind(C, name='bamgpu_moments_allgather')
+        import; type(c_ptr), value :: h, c; real(c_double), intent(out) :: rhat(*); type(c_ptr), value :: count_all, mean_all, m2_all, ms
+        character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_envelope_allgather(h, c, nobs_pred, env_all, ms, mess) bind(C, name='bamgpu_envelope_allgather')
+        import; type(c_ptr), value :: h, c; integer(c_int), value :: nobs_pred; real(c_double), intent(out) :: env_all(*)
+        type(c_ptr), value :: ms; character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_comm_allreduce_sum(c, dev_buf, count, is_double, cuda_stream, mess) &
+                                                      bind(C, name='bamgpu_comm_allreduce_sum')
+        import; type(c_ptr), value :: c, dev_buf, cuda_stream; integer(c_size_t), value :: count; integer(c_int), value :: is_double
+        character(kind=c_char) :: mess(*)
+    end function
+    ! measurement helpers
+    integer(c_int64_t) function bamgpu_launch_count(h) bind(C, name='bamgpu_launch_count')
+        import; type(c_ptr), value :: h
+    end function
+    real(c_double) function bamgpu_last_kernel_ms(h) bind(C, name='bamgpu_last_kernel_ms')
+        import; type(c_ptr), value :: h
+    end function
+    integer(c_int) function bamgpu_step_begin(h) bind(C, name='bamgpu_step_begin')
+        import; type(c_ptr), value :: h
+    end function
+    integer(c_int) function bamgpu_step_end(h) bind(C, name='bamgpu_step_end')
+        import; type(c_ptr), value :: h
+    end function
+    integer(c_int) function bamgpu_step_times(h, ms, cap) bind(C, name='bamgpu_step_times')
+        import; type(c_ptr), value :: h; real(c_double), intent(out) :: ms(*); integer(c_int), value :: cap
+    end function
+    integer(c_int) function bamgpu_kernel_times(h, ms, cap) bind(C, name='bamgpu_kernel_times')
+        import; type(c_ptr), value :: h; real(c_double), intent(out) :: ms(*); integer(c_int), value :: cap
+    end function
+    integer(c_int) function bamgpu_phase_times(h, prep_ms, final_ms, cap) bind(C, name='bamgpu_phase_times')
+        import; type(c_ptr), value :: h; real(c_double), intent(out) :: prep_ms(*), final_ms(*); integer(c_int), value :: cap
+    end function
+    integer(c_int) function bamgpu_flush_l2(h, bytes) bind(C, name='bamgpu_flush_l2')
+        import; type(c_ptr), value :: h; integer(c_size_t), value :: bytes
+    end function
+    integer(c_int) function bamgpu_fp64_peak(device, tflops, mess) bind(C, name='bamgpu_fp64_peak')
+        import; integer(c_int), value :: device; real(c_double), intent(out) :: tflops; character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_pin(ptr, bytes) bind(C, name='bamgpu_pin')
+        import; type(c_ptr), value :: ptr; integer(c_size_t), value :: bytes
+    end function
+    integer(c_int) function bamgpu_unpin(ptr) bind(C, name='bamgpu_unpin')
+        import; type(c_ptr), value :: ptr
+    end function
+    type(c_ptr) function bamgpu_version() bind(C, name='bamgpu_version')
+        import
     end function
 end interface
 

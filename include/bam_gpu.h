@@ -246,6 +246,10 @@ int bamgpu_fit(bamgpu_t* h, int K, const double* start, const double* start_std,
 /* per-chain moments of the kept rows: count[K], mean[P x K], m2[P x K] (sum of squared deviations).
    If dev_ptrs != 0 the three pointers are DEVICE pointers (for an NCCL all-gather across ranks). */
 int bamgpu_moments(bamgpu_t* h, double* count, double* mean, double* m2, int dev_ptrs, char* mess);
+/* re-accumulate the per-chain moments over the COOKED sample (BaM_LoadMCMC burn / slim, src/BaM_tools.f90:672-677): rows
+   first, first+every, ... of the rows the last bamgpu_fit kept (needs out_rows != NULL in that call), so that the
+   Gelman-Rubin statistic describes the sample that is summarised and propagated, not the burn-in transient */
+int bamgpu_moments_window(bamgpu_t* h, int64_t first, int every, char* mess);
 /* Gelman-Rubin potential scale reduction from (gathered) per-chain moments; host arrays. */
 int bamgpu_rhat(int K, int P, const double* count, const double* mean, const double* m2, double* rhat,
                 char* mess);

@@ -126,3 +126,40 @@ def test_first_failing_prior_decides_the_flag():
                 priors_gamma=[("Uniform", [0, 1000])] * 2, xtra_i=[1, 0, 0, 1])
     fx, feas, isnull = BamGpu(p).logpost(x)
     assert list(isnull) == [0, 1, 1, 0, 0, 0] and list(feas) == [0, 1, 1, 0, 0, 0]
+
+
+def test_missing_output_rows_keep_their_feasibility_test():
+    """ApplyModel takes feas = all(vfeas) over ALL rows (ModelLibrary_tools.f90:421-423): a row whose Y is missing still
+    makes the vector infeasible when the model is infeasible there (Sediment: an input <= 0, :155), although it adds no
+    likelihood term (:3207).  Only BaRatin / Linear rows -- which cannot be infeasible -- are dropped from the device."""
+    import copy
+
+    prob, truth = synth.sediment_camenen(nobs=60)
+    ok_prob = copy.deepcopy(prob)
+    ok_prob.Y[[5, 17], 0] = -9999.0
+    bad_prob = copy.deepcopy(ok_prob)
+    bad_prob.X[17, 0] = -0.1  # water depth <= 0 in a row with missing Y
+    x = synth.feasible_starts(truth, 5, rel=0.01, seed=6)
+    for p, expect in ((ok_prob, 1), (bad_prob, 0)):
+        g, o = BamGpu(p), Oracle(p)
+        fx, feas, isnull = g.logpost(x)
+        ofx, ofeas, oisnull = o.logpost(x)
+        assert (feas == ofeas).all() and (isnull == oisnull).all() and (feas == expect).all()
+        if expect:
+            assert np.allclose(fx, ofx, rtol=1e-12)
+
+
+def test_derived_value_limit_is_checked_at_creation():
+    """Segmentation with nS = 70 segments has 69 derived values: beyond the compiled limit (64), refused loudly"""
+    from bam_b200.capi import BamError
+
+    nS, n = 70, 400
+    t = np.arange(n, dtype=np.float64)
+    y = np.zeros(n)
+    theta_pri = [("Gaussian", [0, 10])] * nS + [("Uniform", [0, float(n)])] * (nS - 1)
+    p = Problem("Segmentation", t.reshape(n, 1), y.reshape(n, 1), Yu=np.full((n, 1), 0.1), partype=[0] * (2 * nS - 1),
+                priors_theta=theta_pri, sigma_func=["Constant"], priors_gamma=[("Uniform", [0, 100])],
+                xtra_i=[nS, 1, 1], xtra_d=[1.0])
+    with pytest.raises(BamError) as e:
+        BamGpu(p)
+    assert "compiled limits" in str(e.value)
