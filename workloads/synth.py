@@ -283,7 +283,7 @@ def vegetation(nobs: int = 600, growth: str = "Growth_Yin1_temporal", nyear: int
 def second_wave(model: str, nobs: int = 400, seed: int = SEED + 7, **kw):
     """Synthetic problems for the second-wave pointwise models.
     Returns (Problem, truth vector)."""
-    from .capi import ORTHO_DISTO, SWOT_ID
+    from bam_b200.capi import ORTHO_DISTO, SWOT_ID
 
     rng = np.random.default_rng(seed)
     flat = lambda k: [("FlatPrior", [])] * k  # noqa: E731
