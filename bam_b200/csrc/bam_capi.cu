@@ -329,7 +329,7 @@ void bamgpu_destroy(bamgpu_t* h) {
     fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_env);
     fr(h->d_series); fr(h->d_seriesXpred);
     fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0); fr(h->d_lkCcur); fr(h->d_lkCcand);
-    fr(h->d_finalArrive); fr(h->d_fpPacked); fr(h->d_fpOff); fr(h->d_fpBytes); fr(h->d_fpSched); fr(h->d_fpOrder); fr(h->d_fpCost);
+    fr(h->d_finalArrive); fr(h->d_sedObs); fr(h->d_fpPacked); fr(h->d_fpOff); fr(h->d_fpBytes); fr(h->d_fpSched); fr(h->d_fpOrder); fr(h->d_fpCost);
     for (auto*& q : h->d_compTiles) fr(q);
     for (auto*& q : h->d_compAffected) fr(q);
     free_prediction(h);

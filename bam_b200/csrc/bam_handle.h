@@ -33,6 +33,7 @@ struct bamgpu_handle {
     double* d_part = nullptr;   // 2 x K x nTiles
     double *d_prior = nullptr, *d_lkh = nullptr, *d_hyper = nullptr, *d_fx = nullptr, *d_dpar = nullptr;
     int* d_status = nullptr;
+    void* d_sedObs = nullptr;      // Sediment fast path: per-row invariants (SedObs[n]) of the calibration inputs
     int* d_finalArrive = nullptr;  // logpost_final_combo: blocks of a 32-chain group that have finished (re-armed by the kernel)
     LogpostPlan plan;
     // fast-path tiling: tiles never straddle VAR combinations, so per-combination likelihood sums exist and a

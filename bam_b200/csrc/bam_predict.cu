@@ -20,6 +20,7 @@
 
 #include "bam_dispatch.cuh"
 #include "bam_fastmath.cuh"
+#include "bam_sediment_fast.cuh"
 #include "bam_handle.h"
 #include "bam_models.cuh"
 
@@ -279,54 +280,6 @@ PredFastKernel pick_pred_fast(const DevProblem& p, bool noise, long long Nrep) {
 // (SedimentTransport_model.f90:155-187,290-304); `pred_sediment_fast` then spends one table-driven exp per
 // (replication, input) instead of three pow, two exp, a cube root and a square root: ~330 -> ~12 FP64 instructions
 // for the model (plus ~24 for the noise).
-struct SedObs { double B, L1, L2, st; };  // st: 0 normal, 1 -> value 0 (tau <= css), 2 infeasible row
-
-template <int NX>
-__global__ void sed_obs_prep(DevProblem p, int nobsPred, int t0, int nT, double* const* __restrict__ xspag,
-                             SedObs* __restrict__ obs) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nT) return;
-    double in[NX];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) in[j] = xspag[j][t0 + t];
-    SedObs o{0.0, 0.0, 0.0, 2.0};
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < NX; ++j) ok &= in[j] > 0.0;
-    double pseudo[4];
-    int kin = 2;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (p.sedPpo[i] == BAMGPU_PPO_FIX) pseudo[i] = p.sedPseudo[i];
-        else { pseudo[i] = (kin < NX) ? in[kin < NX ? kin : 0] : 0.0; ++kin; }
-    }
-    const double d = pseudo[0], s = pseudo[1], v = pseudo[2], g = pseudo[3];
-    ok = ok && d > 0.0 && s > 0.0 && v > 0.0 && g > 0.0 && s > 1.0;
-    if (ok) {
-        const double SD = pow(g * (s - 1.0) / (v * v), 1.0 / 3.0) * d;
-        const double css = (p.sedCss == BAMGPU_CSS_SOULSBY) ? (0.3 / (1.0 + 1.2 * SD)) * 0.055 * (1.0 - exp(-1.0 * 0.02 * SD))
-                                                           : (0.24 / SD) * 0.055 * (1.0 - exp(-1.0 * 0.02 * SD));
-        const double tau = (in[0] * in[1]) / ((s - 1.0) * d);
-        if (tau > 0.0) {
-            if (tau <= css) o.st = 1.0;
-            else {
-                const double dim = sqrt(g * (s - 1.0) * (d * d * d));
-                o.st = 0.0;
-                switch (p.sedFormula) {
-                    case BAMGPU_SED_MPM: o.B = dim; o.L1 = log(tau - css); break;
-                    case BAMGPU_SED_CAMENEN: o.B = dim; o.L1 = log(tau); o.L2 = -1.0 * (css / tau); break;
-                    case BAMGPU_SED_NIELSEN: o.B = dim * (tau - css); o.L1 = log(tau); break;
-                    default:
-                        o.B = dim * pow(s - 1.0, 1.0 / 6.0) * pow(d, 1.0 / 6.0) * pow(g, -0.5) * (tau - css);
-                        o.L1 = log(in[1]); o.L2 = log(tau);
-                        break;
-                }
-            }
-        }
-    }
-    obs[t] = o;
-}
-
 template <int SIGF, bool NOISE>
 __global__ void __launch_bounds__(BAM_BLOCK, 4) pred_sediment_fast(DevProblem p, PredArgs a, const double* __restrict__ mc,
                                                                    const double* __restrict__ mode,
@@ -393,23 +346,12 @@ __global__ void __launch_bounds__(BAM_BLOCK, 4) pred_sediment_fast(DevProblem p,
 }
 
 using SedFastKernel = void (*)(DevProblem, PredArgs, const double*, const double*, const SedObs*, double*);
-using SedPrepKernel = void (*)(DevProblem, int, int, int, double* const*, SedObs*);
 
 SedFastKernel pick_sed_fast(int sigf, bool noise) {
     switch (sigf) {
         case BAMGPU_SIG_CONSTANT: return noise ? pred_sediment_fast<BAMGPU_SIG_CONSTANT, true> : pred_sediment_fast<BAMGPU_SIG_CONSTANT, false>;
         case BAMGPU_SIG_LINEAR: return noise ? pred_sediment_fast<BAMGPU_SIG_LINEAR, true> : pred_sediment_fast<BAMGPU_SIG_LINEAR, false>;
         case BAMGPU_SIG_PROPORTIONAL: return noise ? pred_sediment_fast<BAMGPU_SIG_PROPORTIONAL, true> : pred_sediment_fast<BAMGPU_SIG_PROPORTIONAL, false>;
-    }
-    return nullptr;
-}
-SedPrepKernel pick_sed_prep(int nX) {
-    switch (nX) {
-        case 2: return sed_obs_prep<2>;
-        case 3: return sed_obs_prep<3>;
-        case 4: return sed_obs_prep<4>;
-        case 5: return sed_obs_prep<5>;
-        case 6: return sed_obs_prep<6>;
     }
     return nullptr;
 }

@@ -493,6 +493,59 @@ def latent_logpost_leg(device, hbm_peak, n=1_000_000, K=64, steps=10):
                        "frac": algo / (k_ms * 1e-3) / 1e9 / hbm_peak}}
 
 
+def other_models_leg(device, fp64_peak, hbm_peak, steps=10):
+    """log-posterior of the other starred models at their BASELINE shapes: Sediment Camenen (812 rows of the reference's
+    workspace shape) x 4096 chains, the TextFile twin of configs[2] (a*T+b with a latent T per observation, 10^6
+    observations) x 64 chains, Vegetation (1095 daily rows) x 4096 chains.  Each with the roofline that bounds it: nominal
+    flops per chain x obs / kernel time / DFMA peak, or algorithmic bytes / kernel time / HBM peak."""
+    from workloads import synth
+    from bam_b200.capi import BamGpu
+
+    out = {}
+
+    def run(name, prob, x, nominal_flops, algo_bytes_per_unit, kernel):
+        g = BamGpu(prob, device)
+        K, n = x.shape[0], prob.nobs
+        g.chains_upload(x)
+        for _ in range(3):
+            g.logpost_resident()
+        ms, km, pm, fm = timed_resident_logpost(g, steps)
+        fx, feas, _ = g.chains_download()
+        k_ms = float(km.mean())
+        units = K * n
+        e = {"workload": f"{name}: {K} chains x {n} observations", "value": units / (float(ms.mean()) * 1e-3), "unit": UNIT,
+             "ms_per_step": float(ms.mean()), "feasible": bool(feas.all()),
+             "breakdown_ms": {"parameter_table": float(pm.mean()), "likelihood_kernel": k_ms, "final_sum": float(fm.mean())},
+             "kernel": {"name": kernel, "ms": k_ms, "nominal_flops_per_unit": nominal_flops,
+                        "fp64": {"achieved": nominal_flops * units / (k_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                                 "frac": nominal_flops * units / (k_ms * 1e-3) / 1e12 / fp64_peak},
+                        "hbm": {"achieved": algo_bytes_per_unit * units / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": algo_bytes_per_unit * units / (k_ms * 1e-3) / 1e9 / hbm_peak}}}
+        out[name] = e
+
+    try:
+        prob, truth = synth.sediment_camenen(nobs=812)
+        x = synth.feasible_starts(truth, 4096, rel=0.01, seed=synth.SEED + 21)
+        run("sediment_camenen", prob, x, 27 + 14, 0.0, "logpost_sediment_cb<Linear> (per-row invariants hoisted)")
+    except Exception as e:
+        out["sediment_camenen"] = {"error": str(e)}
+    try:
+        prob, truth = synth.textfile_latent(nobs=1_000_000)
+        rng = np.random.default_rng(2)
+        x = np.tile(truth, (64, 1))
+        x[:, :4] *= 1.0 + 0.01 * rng.standard_normal((64, 4))
+        run("textfile_twin", prob, x, 2 + 14 + 7, 8.0, "logpost_main<TextFile,1,1>")
+    except Exception as e:
+        out["textfile_twin"] = {"error": str(e)}
+    try:
+        prob, truth = synth.vegetation(nobs=1095, growth="Growth_Yin3", nY=5)
+        x = synth.feasible_starts(truth, 4096, rel=0.002, seed=synth.SEED + 22)
+        run("vegetation_yin3", prob, x, 60 + 5 * 14, 0.0, "logpost_main<Vegetation,4,5>")
+    except Exception as e:
+        out["vegetation_yin3"] = {"error": str(e)}
+    return out
+
+
 def latent_sampler_leg(device, n=1_000_000, K=64, iters=4):
     """configs[2] (Regression with input uncertainty): adaptive Metropolis over theta, gamma AND 2n latent inputs per
     chain; the latent inputs are swept by one kernel launch with O(1) local posterior differences.  Bounded size."""
@@ -860,6 +913,10 @@ def main():
             line["latent_sampler"] = latent_sampler_leg(device)
         except Exception as e:
             line["latent_sampler"] = {"error": str(e)}
+        try:
+            line["logpost_other_models"] = other_models_leg(device, fp64_peak, hbm_peak)
+        except Exception as e:
+            line["logpost_other_models"] = {"error": str(e)}
     if not args.no_cpu and world == 1:  # last: the OpenMP team of the oracle must not compete with the launch thread above
         line["cpu_baseline"] = cpu_baseline(prob, x)
     print(json.dumps(line))

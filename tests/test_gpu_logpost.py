@@ -279,3 +279,43 @@ def test_fast_path_edge_observations():
         x = perturbed_vectors(np.concatenate([theta, gam]), 200, rel=0.01, seed=nc)
         x[0] = np.concatenate([theta, gam])  # exact k: H == k rows hit the boundary bit-exactly
         check_parity(prob, x)
+
+
+@pytest.mark.parametrize("formula,css", [("Camenen", "Soulsby"), ("MPM", "SoulsbyWhitehouse"), ("Nielsen", "Soulsby"), ("Smart", "Soulsby")])
+def test_sediment_fast_logpost_against_oracle(formula, css):
+    """the chain-parallel Sediment kernel (per-row invariants hoisted, one table-driven exp per chain x row) at a batch
+    that takes it (K >= 128): parity with the oracle, which keeps Sediment_Apply's own formulation
+    (SedimentTransport_model.f90:100-192), and with the generic kernel; rows with tau* <= css (Q = 0), a missing output,
+    vectors with a null prior / sigma <= 0, and a data set with an infeasible row included"""
+    from bam_b200.capi import SED_CO, SED_CSS, SED_FORMULA, SED_PPO, Problem
+
+    prob0, _ = synth.sediment_camenen(nobs=300)
+    base = {"Camenen": [12.0, 1.5, 4.5], "MPM": [8.0, 1.5], "Nielsen": [12.0, 0.5], "Smart": [4.0, 0.6, 0.5]}[formula]
+    nbase = len(base)
+    X, Y = np.asarray(prob0.X).copy(), np.asarray(prob0.Y).copy()
+    X[:12, 0] *= 1e-4   # very shallow rows: tau* <= css -> Q = 0
+    Y[7, 0] = -9999.0   # a missing output
+
+    def make(Xm):
+        return Problem("Sediment", Xm, Y, partype=[0] * nbase, priors_theta=[("Gaussian", [b, 0.5 * b]) for b in base],
+                       sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1]), ("Uniform", [0, 10])],
+                       xtra_i=[SED_FORMULA[formula], SED_CSS[css], SED_CO["FIX"], SED_PPO["IN"], SED_PPO["IN"], SED_PPO["FIX"],
+                               SED_PPO["FIX"]], xtra_d=[5.06e-4, 2.65, 1e-6, 9.81])
+
+    prob = make(X)
+    truth = np.array(base + [1e-4, 0.1])
+    x = synth.feasible_starts(truth, 200, rel=0.02, seed=31)
+    x[9, nbase] = -0.5      # gamma1 outside its Uniform prior: null density
+    x[11, nbase] = 0.0      # gamma1 = 0 with Q = 0 rows: sigma = 0 -> infeasible (:3211)
+    x[11, nbase + 1] = 0.05
+    check_parity(prob, x)
+    g, g2 = BamGpu(prob), BamGpu(prob)
+    g2.set_option("force_generic", 1)
+    fx, fg = g.logpost(x)[0], g2.logpost(x)[0]
+    ok = fx != -999999999.0
+    assert (ok == (fg != -999999999.0)).all() and ok.sum() >= 190
+    assert np.allclose(fx[ok], fg[ok], rtol=1e-12)
+    X2 = X.copy()
+    X2[40, 1] = -1e-3       # a non-positive input: the row, hence every vector, is infeasible
+    gb, ob = BamGpu(make(X2)), Oracle(make(X2))
+    assert (gb.logpost(x)[1] == ob.logpost(x)[1]).all() and not gb.logpost(x)[1][[0, 1, 2]].any()
