@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Extract the handful of ncu metrics DESIGN.md / bench.py rely on from a .ncu-rep (run HERE, no GPU).
 
-    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep [units_per_launch] > profiles/<name>.json
+    python profiles/tools/summarize_ncu.py gpurun_out/prof.ncu-rep [units_per_launch] > profiles/<name>.json
 """
 import csv
 import json
