@@ -658,6 +658,37 @@ def multi_gpu_legs(device, rank, world, dist, torch):
                          "workload": f"BaRatin spaghetti {Nrep} samples x {nobs} inputs sharded by input over {world} GPUs",
                          "finite": bool(np.isfinite(full).all()), "median_checksum": float(full[0, 0].sum())}
     del g
+    # ---- (1b) configs[3]: Sediment, 10^7 samples x 812 inputs, inputs sharded (101 columns per GPU at N = 8)
+    try:
+        Nrep, nobs = 10_000_000, 812
+        prob, truth = synth.sediment_camenen(nobs=nobs)
+        mc = synth.sediment_posterior(Nrep)
+        X = [np.asarray(prob.X)[:, j].copy() for j in range(4)]
+        per = (nobs + world - 1) // world
+        t0, t1 = min(rank * per, nobs), min(nobs, (rank + 1) * per)
+        g = BamGpu(prob, device)
+        g.predict_upload(mc, truth, X)
+        g.predict_resident(1, [1], seed=1, t0=t0, t1=t1)
+        g.envelope_allgather(comm, nobs)
+        g.sync(); g.step_times(); g.kernel_times()
+        dist.barrier(); torch.cuda.synchronize()
+        g.step_begin()
+        g.predict_resident(1, [1], seed=1, t0=t0, t1=t1)
+        g.step_end()
+        g.sync()
+        ms = float(g.step_times()[-1])
+        full, ms_gather = g.envelope_allgather(comm, nobs)
+        tt = torch.tensor([ms, ms_gather], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        out["prediction_sediment"] = {"metric": "prediction samples x inputs/sec", "value": Nrep * nobs / ((tt[0].item() + tt[1].item()) * 1e-3),
+                                      "unit": "sample*input/s", "scaling": "strong", "ms_compute_max_over_ranks": tt[0].item(),
+                                      "ms_envelope_allgather_nccl": tt[1].item(),
+                                      "workload": f"Sediment Camenen {Nrep} samples x {nobs} inputs sharded by input over {world} GPUs "
+                                                  f"({per} columns per GPU)", "finite": bool(np.isfinite(full).all()),
+                                      "median_checksum": float(full[0, 0].sum())}
+        del g, mc
+    except Exception as e:
+        out["prediction_sediment"] = {"error": str(e)}
     # ---- (2) sharded sampler + NCCL all-gather of the moments
     prob, d = problem_from_fixture("baratin")
     K = 4096
