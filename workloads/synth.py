@@ -1,4 +1,4 @@
-"""Synthetic workloads of the BASELINE.json configs, seed 20261019.
+"""Synthetic workloads of the BASELINE.json configs: std::mt19937_64, seed 20261019.
 
 These only build *inputs* (numpy); they contain no compute path.  Used by bench.py and by the
 tests (so that the parity tests and the bench run the same shapes).
@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from workloads.mt64 import default_rng  # std::mt19937_64, the generator SURVEY.md 8(d) names
 from bam_b200.capi import PARTYPE, SED_CO, SED_CSS, SED_FORMULA, SED_PPO, VEG_GROWTH, Problem
 
 SEED = 20261019
@@ -39,7 +40,7 @@ def baratin_spd(nobs: int = 100_000, copula: bool = False, seed: int = SEED):
     """cfg 2: BaRatin, 3 controls, 5 periods, VAR k1 and k2 (multi-period rating curves).
 
     Returns (Problem, truth vector of length 19)."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     nper = 5
     period = 1 + (nper * np.arange(nobs)) // max(nobs, 1)
     H = rng.uniform(-0.5, 3.0, nobs)
@@ -82,7 +83,7 @@ def baratin_spd(nobs: int = 100_000, copula: bool = False, seed: int = SEED):
 
 def feasible_starts(truth, K: int, rel: float = 0.01, seed: int = SEED + 1, check=None):
     """K starting vectors = truth * (1 + rel * N(0,1)), redrawn until `check(x)` says feasible."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     truth = np.asarray(truth, dtype=np.float64)
     x = truth * (1.0 + rel * rng.standard_normal((K, truth.size)))
     if check is not None:
@@ -102,7 +103,7 @@ def spd_start_check(x):
 
 def linear_latent(nobs: int = 1_000_000, seed: int = SEED):
     """cfg 3: Linear nX=nY=2 with input uncertainty on every cell -> 2*nobs latent inputs."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     Xtrue = rng.standard_normal((nobs, 2))
     Xu = np.full((nobs, 2), 0.1)
     Xobs = Xtrue + rng.standard_normal((nobs, 2)) * Xu
@@ -120,7 +121,7 @@ def linear_latent(nobs: int = 1_000_000, seed: int = SEED):
 
 def textfile_latent(nobs: int = 100_000, seed: int = SEED):
     """cfg 3 twin: TextFile 'a*T+b' with input uncertainty (tests/BaM_TextFile_InputUncertainty shape)."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     T = rng.uniform(5.0, 50.0, nobs)
     Tu = np.full(nobs, 1.0)
     Tobs = T + rng.standard_normal(nobs) * Tu
@@ -138,7 +139,7 @@ def textfile_latent(nobs: int = 100_000, seed: int = SEED):
 
 def sediment_camenen(nobs: int = 812, seed: int = SEED):
     """cfg 4: Sediment Camenen + Soulsby, d and s as inputs (tests/BaM_Sediment_Camenen_X4 options)."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     h = rng.uniform(0.02, 0.5, nobs)
     S0 = rng.uniform(1e-3, 8e-3, nobs)
     d = rng.choice([3.05e-4, 5.06e-4, 1.0e-3], nobs)
@@ -164,7 +165,7 @@ def sediment_camenen(nobs: int = 812, seed: int = SEED):
 
 def sediment_posterior(Nrep: int, seed: int = SEED + 4):
     """cfg 4 posterior sample: theta ~ N((12,1.5,4.5), diag(1,0.05,0.3)^2) truncated > 0, gamma ~ |N|."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     th = np.abs(np.array([12.0, 1.5, 4.5]) + rng.standard_normal((Nrep, 3)) * np.array([1.0, 0.05, 0.3]))
     gm = np.abs(np.array([1e-4, 0.1]) + rng.standard_normal((Nrep, 2)) * np.array([2e-5, 0.01]))
     return np.column_stack([th, gm])
@@ -172,7 +173,7 @@ def sediment_posterior(Nrep: int, seed: int = SEED + 4):
 
 def baratin_2c(nobs: int = 38, seed: int = SEED):
     """cfg 1/5 model: 2-control BaRatin with the priors of tests/BaM_BaRatin; synthetic gaugings."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     H = rng.uniform(-0.3, 4.0, nobs)
     k, a, c = [-0.5, 1.5], [53.0, 144.0], [1.5, 1.67]
     Q = _baratin_q(H, k, a, c, [[1, 0], [0, 1]])
@@ -190,7 +191,7 @@ def baratin_2c(nobs: int = 38, seed: int = SEED):
 def baratin_spaghetti(Nrep: int = 1_000_000, nobs: int = 100_000, nspag: int = 1, seed: int = SEED + 5):
     """cfg 5: Nrep posterior rows ~ N(maxpost, (2 % of value)^2), feasibility filtered; stage series
     H_t = 0.5 + 1.5 sin^2(pi t / 5000) + 0.05 N(0,1); optionally nspag noisy copies."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     maxpost = np.array([-0.5, 53.0, 1.5, 1.5, 144.0, 1.67, 1.0, 0.1])
     mc = maxpost * (1.0 + 0.02 * rng.standard_normal((Nrep, maxpost.size)))
     mc[:, 6:] = np.abs(mc[:, 6:])
@@ -208,7 +209,7 @@ def vegetation(nobs: int = 600, growth: str = "Growth_Yin1_temporal", nyear: int
     """Vegetation-affected rating curve (tests/BaM_Vegetation_static shape; theta with U_chi as the CODE expects,
     Vegetation_model.f90:40-41,156-181).  Inputs: time (years), stage [, raw and smoothed temperature].
     Outputs: Q (observed with noise), g / cos / sin / g0 (g observed, the rest missing).  Returns (Problem, truth)."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     temporal = growth == "Growth_Yin1_temporal"
     time = np.sort(rng.uniform(0.0, nyear, nobs))
     for y in range(nyear):  # make sure every year starts and ends with a point
@@ -285,7 +286,7 @@ def second_wave(model: str, nobs: int = 400, seed: int = SEED + 7, **kw):
     Returns (Problem, truth vector)."""
     from bam_b200.capi import ORTHO_DISTO, SWOT_ID
 
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     flat = lambda k: [("FlatPrior", [])] * k  # noqa: E731
     if model == "SuspendedLoad":  # Qs = t1 (h-t2)^t3 / (h-t4)^t5
         th = np.array([2.0, 0.2, 2.5, -0.5, 1.2])
@@ -385,7 +386,7 @@ def mixture(nS: int = 3, nEvt: int = 6, nElt: int = 9, missing: bool = True, shu
     """Mixture (Mixture_model.f90): nEvt events x nElt elements, nS sources; rows optionally interleaved across events so
     that the reference's pack() pairing (e-th input row of event j -> output row (j-1)*nElt+e) is exercised.
     Returns (Problem, truth)."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     n = nEvt * nElt
     evt = np.repeat(np.arange(1, nEvt + 1), nElt)
     elt = np.tile(np.arange(1, nElt + 1), nEvt)
@@ -423,7 +424,7 @@ def sfdtidal_qmec(nobs: int = 600, seed: int = SEED + 12, missing_every: int = 3
     theta = (y0, A0, be, delta, phi, d1, d2, c, g, Q0, dx, dt).  Two synthetic tidal stage series at a 60 s step; the
     discharge "observations" are the model's own output plus noise, with gaps (most of a real record is ungauged).
     Returns (Problem, truth)."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     th = np.array([2.0, 1800.0, -6.0, 0.02, 4e-6, 0.0, 0.05, 4.0 / 3.0, 9.81, 300.0, 4000.0, 60.0])
     t = np.arange(nobs) * th[11]
     h1 = 1.5 * np.sin(2 * np.pi * t / 44700.0) + 0.3 * np.sin(2 * np.pi * t / 7000.0)
@@ -465,7 +466,7 @@ def sfdtidal_qmec(nobs: int = 600, seed: int = SEED + 12, missing_every: int = 3
 def baratin_bac(nobs: int = 300, seed: int = SEED + 8, hmax: float = 6.0):
     """BaRatinBAC: the 3-control matrix of tests/BaM_BaRatinBAC (control 2 REPLACES control 1, control 3 is ADDED),
     theta = (b, a, c) per control.  Returns (Problem, truth)."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     M = [[1, 0, 0], [0, 1, 0], [0, 1, 1]]
     b, a, c = [-0.6, -0.1, 1.2], [14.17, 26.52, 31.82], [1.5, 1.67, 1.67]
     # activation stages: k1 = b1; k2 solves a1 (k-b1)^c1 = a2 (k-b2)^c2 (replacement); k3 = b3 (addition)
@@ -492,7 +493,7 @@ def baratin_bac(nobs: int = 300, seed: int = SEED + 8, hmax: float = 6.0):
 
 def sfd(nobs: int = 300, seed: int = SEED + 9):
     """SFD (twin-gauge stage-fall-discharge, SFD_Val_General) with the parameter values of tests/BaM_SFD."""
-    rng = np.random.default_rng(seed)
+    rng = default_rng(seed)
     th = np.array([6000.0, -5.0, 1.6667, 3900.0, -5.0, 171.0, -0.01, 1.6667])
     h2 = rng.uniform(1.0, 3.0, nobs)
     h1 = h2 + rng.uniform(0.02, 1.5, nobs)
