@@ -319,6 +319,7 @@ def load_library(path: Optional[str] = None):
     lib.bamgpu_moments_allgather.argtypes = [H, H, _dp, _dp, _dp, _dp, _dp, cp]
     lib.bamgpu_envelope_allgather.argtypes = [H, H, ci, _dp, _dp, cp]
     lib.bamgpu_comm_allreduce_sum.argtypes = [H, C.c_void_p, C.c_size_t, ci, C.c_void_p, cp]
+    lib.bamgpu_predict_sample_sharded.argtypes = [H, H, i64, i64, ci, _ip, u64, ci, ci, cp]
     lib.bamgpu_predict.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, ci, _ip, u64, ci, ci, _dp, _dp, cp]
     lib.bamgpu_predict_states.argtypes = lib.bamgpu_predict.argtypes
     lib.bamgpu_predict_upload.argtypes = [H, i64, _dp, _dp, ci, C.POINTER(_dp), _ip, cp]
@@ -626,6 +627,14 @@ class BamGpu:
         mess = C.create_string_buffer(MESS_LEN)
         _check(self.lib.bamgpu_envelope_allgather(self.h, comm.c, nobs_pred, _ptr_d(env), _ptr_d(ms), mess), mess)
         return env, float(ms[0])
+
+    def predict_sample_sharded(self, comm: "Comm", rep_base: int, nrep_total: int, doParametric, doRemnant, seed=1, t0=0, t1=None):
+        """after predict_upload of THIS rank's rows of the sample: envelopes of [t0, t1) over the rows of all ranks"""
+        t1 = self._pred_n if t1 is None else t1
+        dr = np.asarray(doRemnant, dtype=np.int32)
+        mess = C.create_string_buffer(MESS_LEN)
+        _check(self.lib.bamgpu_predict_sample_sharded(self.h, comm.c, rep_base, nrep_total, int(doParametric), _ptr_i(dr), seed, t0, t1, mess), mess)
+        self._pred_nT = t1 - t0
 
     def set_chain_offset(self, off: int):
         self.lib.bamgpu_set_chain_offset(self.h, off)

@@ -270,12 +270,30 @@ int bamgpu_envelope_allgather(bamgpu_t* h, bamgpu_comm_t* c, int nobs_pred, doub
     });
 }
 
-int bamgpu_comm_allreduce_sum(bamgpu_comm_t* c, void* dev_buf, size_t count, int is_double, void* cuda_stream, char* mess) {
+int bamgpu_comm_allreduce_sum(bamgpu_comm_t* c, void* dev_buf, size_t count, int type, void* cuda_stream, char* mess) {
     return guarded(mess, [&]() -> int {
         if (!c) throw bam::CudaError{"bamgpu_comm_allreduce_sum: null communicator"};
-        BAM_NCCL(nccl().AllReduce(dev_buf, dev_buf, count, is_double ? ncclDouble : ncclUint64, ncclSum, c->comm,
-                                  cuda_stream ? (cudaStream_t)cuda_stream : c->stream));
+        const ncclDataType_t dt = type == 1 ? ncclDouble : (type == 2 ? ncclUint32 : ncclUint64);
+        BAM_NCCL(nccl().AllReduce(dev_buf, dev_buf, count, dt, ncclSum, c->comm, cuda_stream ? (cudaStream_t)cuda_stream : c->stream));
         if (!cuda_stream) BAM_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    });
+}
+
+int bamgpu_predict_sample_sharded(bamgpu_t* h, bamgpu_comm_t* c, int64_t rep_base, int64_t nrep_total, int doParametric,
+                                  const int32_t* doRemnant, uint64_t seed, int t0, int t1, char* mess) {
+    return guarded(mess, [&]() -> int {
+        if (!h || !c) throw bam::CudaError{"bamgpu_predict_sample_sharded: null handle"};
+        if (h->predNrep < 1) throw bam::CudaError{"bamgpu_predict_sample_sharded: no uploaded prediction (bamgpu_predict_upload with this rank's rows of the sample first)"};
+        if (t0 < 0 || t1 > h->predNobs || t0 >= t1) throw bam::CudaError{"bamgpu_predict_sample_sharded: bad input range [t0,t1)"};
+        if (rep_base < 0 || nrep_total < rep_base + h->predNrep) throw bam::CudaError{"bamgpu_predict_sample_sharded: the shard does not fit the total"};
+        BAM_CUDA(cudaSetDevice(h->device));
+        h->shardComm = c; h->shardRepBase = rep_base; h->shardNrepTotal = nrep_total;
+        try {
+            bam::launch_predict(h, doParametric, doRemnant, seed, t0, t1, nullptr);
+            BAM_CUDA(cudaStreamSynchronize(h->stream));
+        } catch (...) { h->shardComm = nullptr; throw; }
+        h->shardComm = nullptr;
         return 0;
     });
 }

@@ -11,6 +11,8 @@
 
 #define BAM_BLOCK 256
 
+struct bamgpu_comm;
+
 struct LogpostPlan {
     int TX = 256, TY = 1;  // block = TX observation lanes x TY chain rows
     int CT = 32;           // chains per block tile
@@ -92,6 +94,8 @@ struct bamgpu_handle {
     double* d_series = nullptr;  // time-recursive models: outputs of all vectors [y][t][vector]
     size_t seriesCap = 0;
     double* d_seriesXpred = nullptr;  // prediction inputs of a time-recursive model (series order)
+    struct bamgpu_comm* shardComm = nullptr;  // sample-sharded prediction in progress (bamgpu_predict_sample_sharded)
+    long long shardRepBase = 0, shardNrepTotal = 0;
     int predNout = 0;  // outputs (+ state variables) of the last prediction: rows of d_env
     size_t envCap = 0;
 

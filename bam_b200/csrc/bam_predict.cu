@@ -36,6 +36,7 @@ struct PredArgs {
     int stride;                 // doubles per replication in the table: [gamma | full theta | derived]
     int nStateOut;              // state variables written after the nY outputs (0 | model_nstate)
     int stage;                  // pred_main: stage the table rows of the block in shared memory (stride * 2 KB fits)
+    long long repBase;          // global index of local replication 0 (sample-sharded prediction; keys the noise and the input spaghetti)
 };
 
 __global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const double* __restrict__ mc,
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(128) pred_prep(DevProblem p, PredArgs a, const
     for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
     // whole-series models scan the complete input series of this replication (column rep mod nspag, :1049)
     const double* xc[BAM_MAXX];
-    for (int j = 0; j < p.nX; ++j) xc[j] = xspag[j] + (size_t)(rep % nspag[j]) * a.nobsPred;
+    for (int j = 0; j < p.nX; ++j) xc[j] = xspag[j] + (size_t)((rep + a.repBase) % nspag[j]) * a.nobsPred;
     const bool ok = model_prepare(p, th, der, xc, a.nobsPred);
     if (p.isSeries) der[0] = (double)rep;  // this replication's column of the series buffer
     for (int d = 0; d < p.nDer; ++d) row[p.nGamma + p.ntheta + d] = der[d];
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
     const double* xp[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
-        const int col = act ? (int)(rep % nspag[j]) : 0;  // indx = modulo(rep, nspag) with 1-based rep (:1049)
+        const int col = act ? (int)((rep + a.repBase) % nspag[j]) : 0;  // indx = modulo(rep, nspag) with 1-based rep (:1049)
         xp[j] = xspag[j] + (size_t)col * a.nobsPred + a.t0;
     }
     if (!act) return;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
                 for (int m = 0; m < p.nrem[j] && m < 3; ++m)
                     gam[m] = a.stage ? smT[(p.gamOff[j] + m) * BAM_BLOCK + tid] : tab[(size_t)rep * stride + p.gamOff[j] + m];
                 const double sig = sigmafunk(p.sigfunc[j], gam, v);
-                if (sig > 0.0) v = v + sig * philox_normal_pred_fast(a.seed, (uint64_t)rep, (unsigned)(a.t0 + t), (unsigned)j, lt, sct);
+                if (sig > 0.0) v = v + sig * philox_normal_pred_fast(a.seed, (uint64_t)(rep + a.repBase), (unsigned)(a.t0 + t), (unsigned)j, lt, sct);
             }
             V[((size_t)j * a.nT + t) * a.Nrep + rep] = v;
         }
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProbl
 #pragma unroll
     for (int r = 1; r <= NC; ++r) mask4 |= ((unsigned)(p.ctrlMask >> ((r - 1) * 8)) & 0xfu) << (4 * r);
     const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT), ht = smem_addr(sH), st = smem_addr(sScT);
-    const double* __restrict__ xcol = xs + (size_t)(rep % nspag) * a.nobsPred + a.t0 + tBeg;
+    const double* __restrict__ xcol = xs + (size_t)((rep + a.repBase) % nspag) * a.nobsPred + a.t0 + tBeg;
     const bool shared = nspag == 1;
 
     auto stage = [&](int t) -> double { return shared ? lds_f64(ht + 8u * (unsigned)t) : __ldg(xcol + t); };
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProbl
     double z[4] = {0.0, 0.0, 0.0, 0.0};
     auto single = [&](int t) {  // head / tail of a tile that does not start or end on a multiple of four inputs
         const unsigned tg = tg0 + (unsigned)t;
-        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, tg >> 2, 0u, lt, st, z);
+        if (NOISE) normal_quad_fast(a.seed, (uint64_t)(rep + a.repBase), tg >> 2, 0u, lt, st, z);
         const double h = stage(t);
         const double zz = (tg & 2u) ? ((tg & 1u) ? z[3] : z[2]) : ((tg & 1u) ? z[1] : z[0]);
         finish(t, q_checked(h, amask(h)), zz);
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, PF_MINB) pred_baratin_fast(DevProbl
     int t = 0;
     for (; t < nt && ((tg0 + (unsigned)t) & 3u); ++t) single(t);
     for (; t + 3 < nt; t += 4) {  // four inputs share one Philox block, two share one log and one sqrt
-        if (NOISE) normal_quad_fast(a.seed, (uint64_t)rep, (tg0 + (unsigned)t) >> 2, 0u, lt, st, z);
+        if (NOISE) normal_quad_fast(a.seed, (uint64_t)(rep + a.repBase), (tg0 + (unsigned)t) >> 2, 0u, lt, st, z);
         two(t, z[0], z[1]);
         two(t + 2, z[2], z[3]);
     }
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, 4) pred_sediment_fast(DevProblem p,
         const unsigned tg = tg0 + (unsigned)t;
         if (NOISE && (tg >> 2) != lastQuad) {
             lastQuad = tg >> 2;
-            normal_quad_fast(a.seed, (uint64_t)rep, lastQuad, 0u, lt, st, z);
+            normal_quad_fast(a.seed, (uint64_t)(rep + a.repBase), lastQuad, 0u, lt, st, z);
         }
         double v;
         if (o.st == 2.0) v = p.unfeas;
@@ -630,6 +631,222 @@ __global__ void __launch_bounds__(RX_THREADS) envelope_radix(long long Nrep, int
         out[(size_t)5 * nT] = mean;
         out[(size_t)6 * nT] = (m > 1) ? sqrt(ss / (double)(m - 1)) : unfeas;
     }
+}
+
+// ---- sample-sharded envelopes (few prediction inputs, many samples) ---------------------------------
+//
+// Every rank holds Nloc of the Nrep replications of EVERY column.  The order statistics of a column are then selected by
+// the same MSB-first radix walk as envelope_radix, cut at the histogram: per pass a rank counts the digits of ITS values
+// (one histogram per distinct prefix among the 10 targets), the histograms are summed over the ranks (one all-reduce of
+// unsigned counts per pass), and every rank walks the summed histograms -- identically, so the selection state never has
+// to be exchanged.  After 6 passes the 64-bit keys of the 10 order statistics are known: EXACT quantiles whatever the
+// data, 7 reads of the local shard.  Count of bad values, sum and sum of squared deviations travel the same way (one
+// all-reduce of doubles each; the sums are fixed trees per rank, the cross-rank order is NCCL's).
+struct RxsState {
+    unsigned long long prefix[SEL_NT], gprefix[SEL_NT];
+    long long rank[SEL_NT];
+    int groupOf[SEL_NT];
+    int nG, flagged;
+    long long m;
+    double mean;
+};
+
+__global__ void rxs_init(RxsState* __restrict__ st, int ncol) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    RxsState z;
+    for (int k = 0; k < SEL_NT; ++k) { z.prefix[k] = 0ull; z.gprefix[k] = 0ull; z.rank[k] = 0; z.groupOf[k] = 0; }
+    z.nG = 1; z.flagged = 0; z.m = 0; z.mean = 0.0;
+    st[c] = z;
+}
+
+__global__ void __launch_bounds__(RX_THREADS) rxs_hist(long long Nloc, double unfeas, const double* __restrict__ V,
+                                                       const RxsState* __restrict__ st, int pass, unsigned* __restrict__ hist,
+                                                       double* __restrict__ acc) {
+    extern __shared__ unsigned rxh[];  // [SEL_NT][RX_NB]
+    __shared__ double scratch[32];
+    __shared__ unsigned long long sG[SEL_NT];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int colId = blockIdx.x;
+    const double* __restrict__ col = V + (size_t)colId * Nloc;
+    unsigned* __restrict__ hout = hist + (size_t)colId * SEL_NT * RX_NB;
+    const int nG = st[colId].nG;
+    const bool flagged = st[colId].flagged != 0;
+    if (tid < SEL_NT) sG[tid] = st[colId].gprefix[tid];
+    for (int b = tid; b < SEL_NT * RX_NB; b += RX_THREADS) rxh[b] = 0u;
+    __syncthreads();
+    const int width[6] = {11, 11, 11, 11, 11, 9};
+    int shift = 64;
+    for (int q = 0; q <= pass; ++q) shift -= width[q];
+    const int w = width[pass], nb = 1 << w;
+    double sum = 0.0;
+    long long nbadLoc = 0;
+    if (!flagged)
+        for (long long base = 0; base < Nloc; base += 4 * RX_THREADS) {
+            const long long r0 = base + tid;
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long r = r0 + (long long)q * RX_THREADS;
+                v[q] = (r < Nloc) ? __ldcs(col + r) : unfeas;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long r = r0 + (long long)q * RX_THREADS;
+                const bool inside = r < Nloc;
+                const bool good = inside && !(v[q] == unfeas || v[q] != v[q]);
+                if (pass == 0 && inside && !good) ++nbadLoc;
+                const unsigned long long key = rx_key(v[q]);
+                const unsigned digit = (unsigned)(key >> shift) & (unsigned)(nb - 1);
+                if (pass == 0) {
+                    if (good) sum += v[q];
+                    const unsigned act = __ballot_sync(0xffffffffu, good);
+                    if (act) {
+                        const int lead = __ffs(act) - 1;
+                        const unsigned d0 = __shfl_sync(0xffffffffu, digit, lead);
+                        const bool same = __all_sync(0xffffffffu, !good || digit == d0);
+                        if (same) { if (lane == lead) atomicAdd(&rxh[d0], (unsigned)__popc(act)); }
+                        else if (good) atomicAdd(&rxh[digit], 1u);
+                    }
+                } else if (good) {
+                    const unsigned long long hi = key >> (shift + w);
+                    for (int g = 0; g < nG; ++g)
+                        if (hi == sG[g]) atomicAdd(&rxh[g * RX_NB + digit], 1u);
+                }
+            }
+        }
+    __syncthreads();
+    for (int b = tid; b < SEL_NT * RX_NB; b += RX_THREADS) hout[b] = rxh[b];
+    if (pass == 0) {
+        const double nbd = block_sum((double)nbadLoc, scratch);
+        const double sm = block_sum(sum, scratch);
+        if (tid == 0) { acc[2 * colId] = nbd; acc[2 * colId + 1] = sm; }
+    }
+}
+
+// every target walks into its digit of the SUMMED histograms: warp k serves target k (identical on every rank)
+__global__ void __launch_bounds__(32 * SEL_NT) rxs_walk(long long Nrep, RxsState* __restrict__ stAll, const unsigned* __restrict__ hist,
+                                                        const double* __restrict__ acc, int pass) {
+    __shared__ RxsState st;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int colId = blockIdx.x;
+    if (tid == 0) st = stAll[colId];
+    __syncthreads();
+    const int width[6] = {11, 11, 11, 11, 11, 9};
+    const int w = width[pass], nb = 1 << w;
+    if (pass == 0 && tid == 0) {
+        const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
+        const long long nbad = (long long)acc[2 * colId];
+        const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
+        if ((!drop && nbad > 0) || nbad == Nrep) st.flagged = 1;
+        else {
+            st.m = Nrep - nbad;
+            st.mean = acc[2 * colId + 1] / (double)st.m;
+            for (int q = 0; q < 5; ++q) {  // the 10 target ranks (0-based): i-1 and i of each Hazen quantile
+                const double hh = pr[q] * (double)st.m + 0.5;
+                long long i0, i1;
+                if (hh <= 1.0) i0 = i1 = 0;
+                else if (hh >= (double)st.m) i0 = i1 = st.m - 1;
+                else { const long long i = (long long)floor(hh); i0 = i - 1; i1 = i; }
+                st.rank[2 * q] = i0; st.rank[2 * q + 1] = i1;
+            }
+        }
+    }
+    __syncthreads();
+    if (!st.flagged) {
+        const unsigned* hg = hist + ((size_t)colId * SEL_NT + st.groupOf[warp]) * RX_NB;
+        const int per = nb / 32;
+        const long long rank = st.rank[warp];
+        long long mine = 0;
+        for (int b = 0; b < per; ++b) mine += hg[lane * per + b];
+        long long incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
+        const int L = hit ? (__ffs(hit) - 1) : 31;
+        int digit = 0;
+        long long newRank = 0;
+        if (lane == L) {
+            long long a = incl - mine;
+            int b = 0;
+            for (; b < per - 1; ++b) {
+                const long long c = hg[lane * per + b];
+                if (a + c > rank) break;
+                a += c;
+            }
+            digit = lane * per + b;
+            newRank = rank - a;
+        }
+        digit = __shfl_sync(0xffffffffu, digit, L);
+        newRank = __shfl_sync(0xffffffffu, newRank, L);
+        __syncthreads();
+        if (lane == 0) {
+            st.prefix[warp] = (st.prefix[warp] << w) | (unsigned long long)digit;
+            st.rank[warp] = newRank;
+        }
+        __syncthreads();
+        if (tid == 0) {  // distinct prefixes -> groups of the next pass
+            int ng = 0;
+            for (int k = 0; k < SEL_NT; ++k) {
+                int g = -1;
+                for (int q = 0; q < ng && g < 0; ++q)
+                    if (st.gprefix[q] == st.prefix[k]) g = q;
+                if (g < 0) { g = ng; st.gprefix[ng++] = st.prefix[k]; }
+                st.groupOf[k] = g;
+            }
+            st.nG = ng;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) stAll[colId] = st;
+}
+
+__global__ void __launch_bounds__(RX_THREADS) rxs_ss(long long Nloc, double unfeas, const double* __restrict__ V,
+                                                     const RxsState* __restrict__ st, double* __restrict__ ss) {
+    __shared__ double scratch[32];
+    const int tid = threadIdx.x, colId = blockIdx.x;
+    const double* __restrict__ col = V + (size_t)colId * Nloc;
+    const double mean = st[colId].mean;
+    double part = 0.0;
+    if (!st[colId].flagged)
+        for (long long r = tid; r < Nloc; r += RX_THREADS) {
+            const double v = __ldcs(col + r);
+            if (v == unfeas || v != v) continue;
+            const double d = v - mean;
+            part += d * d;
+        }
+    const double t = block_sum(part, scratch);
+    if (tid == 0) ss[colId] = t;
+}
+
+__global__ void rxs_finish(int ncol, int nT, double unfeas, const RxsState* __restrict__ stAll, const double* __restrict__ ss,
+                           double* __restrict__ env) {
+    const int colId = blockIdx.x * blockDim.x + threadIdx.x;
+    if (colId >= ncol) return;
+    const RxsState& st = stAll[colId];
+    const int y = colId / nT, t = colId % nT;
+    double* out = env + (size_t)y * BAMGPU_NENV * nT + t;
+    if (st.flagged) {
+        for (int q = 0; q < BAMGPU_NENV; ++q) out[(size_t)q * nT] = unfeas;
+        return;
+    }
+    const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
+    for (int q = 0; q < 5; ++q) {
+        const double a = rx_val(st.prefix[2 * q]), b = rx_val(st.prefix[2 * q + 1]);
+        const double hh = pr[q] * (double)st.m + 0.5;
+        double qv;
+        if (hh <= 1.0 || hh >= (double)st.m) qv = a;
+        else {
+            const long long i = (long long)floor(hh);
+            qv = a + (hh - (double)i) * (b - a);
+        }
+        out[(size_t)q * nT] = qv;
+    }
+    out[(size_t)5 * nT] = st.mean;
+    out[(size_t)6 * nT] = (st.m > 1) ? sqrt(ss[colId] / (double)(st.m - 1)) : unfeas;
 }
 
 // ---- large Nrep, fast path: all 10 order statistics with 4 reads of the column ---------------------------------
@@ -1198,6 +1415,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     for (int y = 0; y < BAM_MAXY; ++y) a.doRemnant[y] = (y < nY) ? doRemnant[y] : 0;
     a.stride = p.nGamma + p.ntheta + p.nDer;
     a.nStateOut = nS;
+    a.repBase = h->shardComm ? h->shardRepBase : 0;
     h->predNout = nOut;
     a.stage = sizeof(double) * (size_t)a.stride * BAM_BLOCK <= 96 * 1024;
 
@@ -1222,6 +1440,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     long long tileT = (long long)(budget / (sizeof(double) * (size_t)Nrep * nOut));
     tileT = std::max<long long>(32, std::min<long long>(tileT / 32 * 32, ((long long)nTall + 31) / 32 * 32));
     if (h_spag) tileT = std::max<long long>(tileT, 32);
+    if (h->shardComm) tileT = std::min<long long>(tileT, std::max<long long>(32, (1024 / nOut) / 32 * 32));  // 80 KB of histograms per column
     const size_t vNeed = (size_t)tileT * Nrep * nOut;
     if (vNeed > h->vCap) {
         if (h->d_V) cudaFree(h->d_V);
@@ -1253,6 +1472,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
 
     const size_t smemRadix = sizeof(unsigned) * SEL_NT * RX_NB;
     BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRadix));
+    if (h->shardComm) BAM_CUDA(cudaFuncSetAttribute((const void*)rxs_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemRadix));
     const size_t smemSel2 = sizeof(unsigned) * SEL_NT * S2_NB2 + sizeof(double) * SEL_NT * S2_CAP;
     // the 2-read selection resolves bins of <= CAP members: worth trying while the densest of its 16384 bins stays below
     // that (a Gaussian column peaks at ~1.1e-4 Nrep per bin); two instantiations, see envelope_select3
@@ -1307,12 +1527,38 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         h->launches += 1;
         cudaEvent_t kp1 = mark();
         if (kp0 && kp1) h->kernEv.emplace_back(kp0, kp1);
-        if (Nrep >= 2) {
+        if (Nrep >= 2 || (h->shardComm && h->shardNrepTotal >= 2)) {
             cudaEvent_t ke0 = mark();
             // envelopes of this tile go to a compact [y][7][nT] scratch, then into the full [y][7][nTall] array
             double* envTile = nullptr;
             BAM_CUDA(cudaMallocAsync(&envTile, sizeof(double) * (size_t)nT * BAMGPU_NENV * nOut, s));
-            if (smallN) envelope_smem<<<nT * nOut, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
+            if (h->shardComm) {  // sample-sharded: radix walk over histograms summed across the ranks
+                const int ncol = nT * nOut;
+                RxsState* st = nullptr;
+                unsigned* hist = nullptr;
+                double *acc = nullptr, *ssq = nullptr;
+                BAM_CUDA(cudaMallocAsync(&st, sizeof(RxsState) * ncol, s));
+                BAM_CUDA(cudaMallocAsync(&hist, sizeof(unsigned) * (size_t)ncol * SEL_NT * RX_NB, s));
+                BAM_CUDA(cudaMallocAsync(&acc, sizeof(double) * 2 * ncol, s));
+                BAM_CUDA(cudaMallocAsync(&ssq, sizeof(double) * ncol, s));
+                rxs_init<<<(ncol + 127) / 128, 128, 0, s>>>(st, ncol);
+                char cm[BAMGPU_MESS_LEN];
+                auto reduce = [&](void* buf, size_t count, int type) {
+                    if (bamgpu_comm_allreduce_sum(h->shardComm, buf, count, type, (void*)s, cm) != 0) throw CudaError{std::string(cm)};
+                };
+                for (int pass = 0; pass < 6; ++pass) {
+                    rxs_hist<<<ncol, RX_THREADS, smemRadix, s>>>(Nrep, p.unfeas, h->d_V, st, pass, hist, acc);
+                    reduce(hist, (size_t)ncol * SEL_NT * RX_NB, 2);
+                    if (pass == 0) reduce(acc, (size_t)2 * ncol, 1);
+                    rxs_walk<<<ncol, 32 * SEL_NT, 0, s>>>(h->shardNrepTotal, st, hist, acc, pass);
+                    h->launches += 2;
+                }
+                rxs_ss<<<ncol, RX_THREADS, 0, s>>>(Nrep, p.unfeas, h->d_V, st, ssq);
+                reduce(ssq, (size_t)ncol, 1);
+                rxs_finish<<<(ncol + 127) / 128, 128, 0, s>>>(ncol, nT, p.unfeas, st, ssq, envTile);
+                h->launches += 3;
+                BAM_CUDA(cudaFreeAsync(st, s)); BAM_CUDA(cudaFreeAsync(hist, s)); BAM_CUDA(cudaFreeAsync(acc, s)); BAM_CUDA(cudaFreeAsync(ssq, s));
+            } else if (smallN) envelope_smem<<<nT * nOut, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
             else if (h->onlyRadix) {  // tests: every column through the last-resort kernel
                 envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, nullptr);
             } else {

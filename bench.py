@@ -689,6 +689,34 @@ def multi_gpu_legs(device, rank, world, dist, torch):
         del g, mc
     except Exception as e:
         out["prediction_sediment"] = {"error": str(e)}
+    # ---- (1c) few inputs, many samples: SAMPLES sharded, exact quantiles from digit histograms summed over the ranks
+    try:
+        Nrep, nobs = 8_000_000, 181  # the 181-point stage grid of tests/BaM_BaRatin (Hgrid.txt)
+        prob, _ = synth.baratin_2c(nobs=38)
+        mc, mode, _ = synth.baratin_spaghetti(Nrep=Nrep, nobs=8)
+        Hgrid = np.linspace(-1.0, 8.0, nobs)
+        per = Nrep // world
+        lo, hi = rank * per, (Nrep if rank == world - 1 else (rank + 1) * per)
+        g = BamGpu(prob, device)
+        g.predict_upload(mc[lo:hi], mode, [Hgrid])
+        g.predict_sample_sharded(comm, lo, Nrep, 1, [1], seed=1)  # warm-up
+        g.sync(); g.step_times(); g.kernel_times()
+        dist.barrier(); torch.cuda.synchronize()
+        g.step_begin()
+        g.predict_sample_sharded(comm, lo, Nrep, 1, [1], seed=1)
+        g.step_end()
+        g.sync()
+        tt = torch.tensor([float(g.step_times()[-1])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        env = g.predict_download()
+        out["prediction_sample_sharded"] = {"metric": "prediction samples x inputs/sec", "value": Nrep * nobs / (tt[0].item() * 1e-3),
+                                            "unit": "sample*input/s", "scaling": "strong", "ms_max_over_ranks": tt[0].item(),
+                                            "workload": f"BaRatin {Nrep} samples x {nobs}-point stage grid, SAMPLES sharded over {world} GPUs "
+                                                        f"(6 all-reduces of digit histograms + 3 of sums inside the timed region)",
+                                            "finite": bool(np.isfinite(env).all()), "median_checksum": float(env[0, 0].sum())}
+        del g, mc
+    except Exception as e:
+        out["prediction_sample_sharded"] = {"error": str(e)}
     # ---- (2) sharded sampler + NCCL all-gather of the moments
     prob, d = problem_from_fixture("baratin")
     K = 4096

@@ -192,10 +192,15 @@ interface
         import; type(c_ptr), value :: h, c; integer(c_int), value :: nobs_pred; real(c_double), intent(out) :: env_all(*)
         type(c_ptr), value :: ms; character(kind=c_char) :: mess(*)
     end function
-    integer(c_int) function bamgpu_comm_allreduce_sum(c, dev_buf, count, is_double, cuda_stream, mess) &
+    integer(c_int) function bamgpu_comm_allreduce_sum(c, dev_buf, count, dtype, cuda_stream, mess) &
                                                       bind(C, name='bamgpu_comm_allreduce_sum')
-        import; type(c_ptr), value :: c, dev_buf, cuda_stream; integer(c_size_t), value :: count; integer(c_int), value :: is_double
+        import; type(c_ptr), value :: c, dev_buf, cuda_stream; integer(c_size_t), value :: count; integer(c_int), value :: dtype
         character(kind=c_char) :: mess(*)
+    end function
+    integer(c_int) function bamgpu_predict_sample_sharded(h, c, rep_base, nrep_total, doParametric, doRemnant, seed, t0, t1, mess) &
+                                                          bind(C, name='bamgpu_predict_sample_sharded')
+        import; type(c_ptr), value :: h, c; integer(c_int64_t), value :: rep_base, nrep_total, seed
+        integer(c_int), value :: doParametric, t0, t1; integer(c_int), intent(in) :: doRemnant(*); character(kind=c_char) :: mess(*)
     end function
     ! measurement helpers
     integer(c_int64_t) function bamgpu_launch_count(h) bind(C, name='bamgpu_launch_count')

@@ -305,10 +305,18 @@ int bamgpu_moments_allgather(bamgpu_t* h, bamgpu_comm_t* c, double* rhat, double
    bamgpu_predict_resident on that slice, gathers the envelope slices of all ranks; env_all is nobs_pred x 7 x nOut
    column-major per output (the layout bamgpu_predict returns for t0 = 0, t1 = nobs_pred), on every rank. */
 int bamgpu_envelope_allgather(bamgpu_t* h, bamgpu_comm_t* c, int nobs_pred, double* env_all, double* ms, char* mess);
-/* in-place sum over ranks of a DEVICE buffer of `count` doubles (is_double != 0) or uint64 (the per-input histograms
-   of the sample-sharded envelope selection); on `cuda_stream` (asynchronous) or, if NULL, on the communicator's own
-   stream followed by a synchronisation */
-int bamgpu_comm_allreduce_sum(bamgpu_comm_t* c, void* dev_buf, size_t count, int is_double, void* cuda_stream, char* mess);
+/* in-place sum over ranks of a DEVICE buffer of `count` elements; type: 0 = uint64, 1 = double, 2 = uint32 (the per-input
+   histograms of the sample-sharded envelope selection); on `cuda_stream` (asynchronous) or, if NULL, on the communicator's
+   own stream followed by a synchronisation */
+int bamgpu_comm_allreduce_sum(bamgpu_comm_t* c, void* dev_buf, size_t count, int type, void* cuda_stream, char* mess);
+/* SAMPLE-sharded prediction, for few inputs and many samples (a 41-point stage grid, 10^7 samples): every rank uploads ITS
+   rows of the sample matrix (bamgpu_predict_upload with Nrep = this rank's count, all the inputs) and propagates them;
+   rep_base = global index of the rank's first row (keys the structural-error noise and the input spaghetti exactly as a
+   single-GPU run would), nrep_total = rows of all ranks.  The quantiles are selected exactly by a radix walk over digit
+   histograms that are summed across the ranks (6 all-reduces of counts per tile of inputs), count / sum / sum of squares
+   by all-reduces of doubles.  Every rank ends with the full envelopes of [t0, t1) (bamgpu_predict_download). */
+int bamgpu_predict_sample_sharded(bamgpu_t* h, bamgpu_comm_t* c, int64_t rep_base, int64_t nrep_total, int doParametric,
+                                  const int32_t* doRemnant, uint64_t seed, int t0, int t1, char* mess);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 

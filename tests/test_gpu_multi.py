@@ -63,6 +63,14 @@ def test_one_rank_communicator():
     env = g2.predict_download()
     env_all, _ = g2.envelope_allgather(comm, H.size)
     assert (env_all == env).all()
+    # sample-sharded selection with a single rank: the radix walk over (trivially) summed histograms
+    g3 = BamGpu(prob)
+    g3.predict_upload(mc, mode, [H])
+    g3.predict_sample_sharded(comm, 0, mc.shape[0], 1, [1], seed=3)
+    env_s = g3.predict_download()
+    assert (env_s[:, :5] == env[:, :5]).all()  # order statistics are exact on every path
+    sd = env[:, 6]
+    assert np.allclose(env_s[:, 6], sd, rtol=1e-12) and (np.abs(env_s[:, 5] - env[:, 5]) <= 1e-12 * np.maximum(sd, np.abs(env[:, 5]))).all()
     comm.close()
 
 
@@ -84,10 +92,19 @@ def _rank(rank, world, uid, q):
         g2.predict_upload(mc, mode, [H])
         g2.predict_resident(1, [1], seed=3, t0=min(rank * pt, n), t1=min((rank + 1) * pt, n))
         env_all, _ = g2.envelope_allgather(comm, n)
+        # the same prediction with the SAMPLES sharded instead: this rank's rows, every input
+        half = mc.shape[0] // world
+        lo, hi = rank * half, (mc.shape[0] if rank == world - 1 else (rank + 1) * half)
+        mc_bad = mc.copy()
+        mc_bad[37, 3] = -2.0  # an infeasible replication (k2 < k1) in rank 0's shard: dropped by the < 75 % rule
+        g3 = BamGpu(prob, rank)
+        g3.predict_upload(mc_bad[lo:hi], mode, [H])
+        g3.predict_sample_sharded(comm, lo, mc.shape[0], 1, [1], seed=3)
+        env_s = g3.predict_download()
         comm.close()
-        q.put((rank, rows, rhat, env_all, None))
+        q.put((rank, rows, rhat, env_all, None, env_s))
     except Exception as e:  # the parent must not wait for ever
-        q.put((rank, None, None, None, repr(e)))
+        q.put((rank, None, None, None, repr(e), None))
 
 
 @pytest.mark.skipif(gpu_count() < 2, reason="needs 2 GPUs")
@@ -116,6 +133,15 @@ def test_two_ranks_one_process_per_gpu():
     g2 = BamGpu(prob)
     env, _ = g2.predict(mc, mode, [H], 1, [1], seed=3)
     assert (res[0][3] == env).all() and (res[1][3] == env).all()
+    # sample-sharded: exact order statistics, mean / sd to rounding (the cross-rank order of the sums is NCCL's)
+    mc_bad = mc.copy()
+    mc_bad[37, 3] = -2.0
+    envb, _ = g2.predict(mc_bad, mode, [H], 1, [1], seed=3)
+    for r in range(world):
+        es = res[r][5]
+        assert (es[:, :5] == envb[:, :5]).all()
+        sd = envb[:, 6]
+        assert np.allclose(es[:, 6], sd, rtol=1e-12) and (np.abs(es[:, 5] - envb[:, 5]) <= 1e-12 * np.maximum(sd, np.abs(envb[:, 5]))).all()
 
 
 def read_table(path):
