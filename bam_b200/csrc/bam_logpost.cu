@@ -1037,6 +1037,9 @@ bool fast_path_keeps_combo_sums(const bamgpu_handle* h, int K) {
 // Items = tiles x chain blocks are handed out dynamically to `slots` resident blocks, so the idle tail at the end of the
 // launch is about half an item per block: large tiles amortise the per-item work (parameter loads, barrier, final log)
 // when there are many rounds, small tiles keep the tail short when chains are few (512 per GPU in the sharded cfg 2).
+#ifndef BAM_CB2_ROUNDS
+#define BAM_CB2_ROUNDS 8 /* items per resident block below which the tiles get smaller */
+#endif
 static int pick_tile_size(const bamgpu_handle* h, int chainBlocks, int slots) {
     const int nCombo = h->dp.nCombo;
     const int sub = BAM_CB2_TSUB * BAM_CB2_ILP;
@@ -1044,7 +1047,7 @@ static int pick_tile_size(const bamgpu_handle* h, int chainBlocks, int slots) {
     for (int tobs = (BAM_CB_TOBS / sub) * sub; tobs >= sub; tobs -= sub) {
         long long tiles = 0;
         for (int v = 0; v < nCombo; ++v) tiles += (h->comboStartHost[v + 1] - h->comboStartHost[v] + tobs - 1) / tobs;
-        if (tiles * chainBlocks >= 8LL * slots || tobs == sub) { best = tobs; break; }
+        if (tiles * chainBlocks >= (long long)BAM_CB2_ROUNDS * slots || tobs == sub) { best = tobs; break; }
     }
     return best;
 }
