@@ -11,6 +11,19 @@
 
 namespace bam {
 
+// AlgaeBiomass_Apply's input checks (AlgaeBiomass_model.f90:79-99): a fatal error (err = 1), not an infeasible vector
+const char* algae_input_error(int n, const double* X) {
+    for (int i = 0; i < n; ++i) {
+        if (X[i + (size_t)1 * n] < 0.0) return "AlgaeBiomass_Apply:Irradiance<0 impossible";
+        if (X[i + (size_t)2 * n] < 0.0) return "AlgaeBiomass_Apply:depth<0 impossible";
+        if (X[i + (size_t)3 * n] < 0.0) return "AlgaeBiomass_Apply:turbidity<0 impossible";
+        if (X[i + (size_t)4 * n] < 0.0) return "AlgaeBiomass_Apply:removal<0 impossible";
+        if (X[i + (size_t)4 * n] > 1.0) return "AlgaeBiomass_Apply:removal>1 impossible";
+    }
+    return nullptr;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // catalogues
 // ------------------------------------------------------------------------------------------------
@@ -35,6 +48,7 @@ int model_from_name(const char* name) {
     if (s == "Mixture") return BAMGPU_MDL_MIXTURE;
     if (s == "SFDTidal_Qmec") return BAMGPU_MDL_SFDTIDAL_QMEC;
     if (s == "SFDTidal_Qmec2") return BAMGPU_MDL_SFDTIDAL_QMEC2;
+    if (s == "AlgaeBiomass") return BAMGPU_MDL_ALGAE;
     return 0;
 }
 
@@ -554,6 +568,13 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             if (nt != (L.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 11 : 12) || nX != 2 || nY != 1) { mess = "SFDTidal_Qmec_Apply: wrong size [theta], nX or nY"; return 1; }
             if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: SFDTidal_Qmec is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
             L.nState = 3;  // pressure, friction, advection (:672-676)
+            L.isSeries = true;
+            break;
+        case BAMGPU_MDL_ALGAE:  // AlgaeBiomass_GetParNumber: 18 (AlgaeBiomass_model.f90:46-51); XtraSetup: 5 states (ModelLibrary_tools.f90:697-702)
+            if (nt != 18 || nX != 5 || nY != 2) { mess = "AlgaeBiomass_Apply: wrong size [theta], nX or nY"; return 1; }
+            if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: AlgaeBiomass is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
+            if (const char* bad = bam::algae_input_error(p.nobs, p.X)) { mess = bad; return 1; }  // err = 1 in the reference (:79-99)
+            L.nState = 5;
             L.isSeries = true;
             break;
         case BAMGPU_MDL_MIXTURE: {  // Mixture_XtraRead (:137-190), Mixture_GetParNumber (:33-72)

@@ -885,12 +885,66 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
     return ok;
 }
 
+// -------------------------------------------------------------------------------------------
+// AlgaeBiomass (AlgaeBiomass_model.f90:55-197), time-recursive: b(t) = b(t-1) + mu0 Fb Ft Fi Fn b dt - (Rsen + removal + Rhyd)
+// (b - bmin) dt, clamped to [bmin, bmax].  Inputs (series order): temperature, irradiance, depth, turbidity, removal.
+// Explicitly rounded operations in the reference's order (the recursion feeds every rounding back into itself); pow / exp
+// are libdevice's (1-2 ulp from libm: the logistic recursion is contractive, the difference does not grow).
+// out[(y * n + t) * K]: y = 0 biomass, 1 biomass / bmax, then the states Fb, Ft, Fi, Fn, Rhyd.
+// -------------------------------------------------------------------------------------------
+#define BAM_EPSRE 2.2204460492503131e-16 /* DMSL epsRe (un-vendored): declared = epsilon(1._mrk) */
+__device__ inline bool algae_series(int n, const double* __restrict__ X, const double* __restrict__ th, double* __restrict__ out,
+                                    size_t K, int nOut) {
+    const double dt = th[0], b0 = th[1], bmin = th[2], bmax = th[3], mu0 = th[4], Tmin = th[5], Topt = th[6], Tmax = th[7],
+                 Iopt = th[8], katt = th[9], kcw = th[10], Rsen = th[11], g = th[12], rho = th[13], J = th[14], tau0 = th[15],
+                 bHyd = th[16], cHyd = th[17];
+    if (dt <= 0.0 || bmin < 0.0 || b0 < bmin || b0 > bmax || bmin >= bmax || mu0 < 0.0 || Tmin >= Tmax || Topt >= Tmax ||
+        Topt <= Tmin || Iopt <= 0.0 || katt < 0.0 || kcw < 0.0 || Rsen < 0.0 || g < 0.0 || rho < 0.0 || J < 0.0 || tau0 <= 0.0 ||
+        bHyd < 0.0 || cHyd < 0.0)
+        return false;  // :140-146
+    const double Texp = __ddiv_rn(__dsub_rn(Topt, Tmin), __dsub_rn(Tmax, Topt));
+    const double *temp = X, *irr = X + n, *depth = X + 2 * (size_t)n, *turb = X + 3 * (size_t)n, *rem = X + 4 * (size_t)n;
+    double bt = b0;
+    for (int t = 0; t < n; ++t) {
+        const double Fb = __dsub_rn(1.0, __ddiv_rn(bt, bmax));
+        double Ft = 0.0;
+        const double T = temp[t];
+        if (!(T <= Tmin || T >= Tmax)) {
+            Ft = __dmul_rn(__ddiv_rn(__dsub_rn(Tmax, T), __dsub_rn(Tmax, Topt)), pow(__ddiv_rn(__dsub_rn(T, Tmin), __dsub_rn(Topt, Tmin)), Texp));
+            if (Ft <= BAM_EPSRE) Ft = 0.0;
+        }
+        const double iz = __dmul_rn(irr[t], exp(__dmul_rn(-__dadd_rn(__dmul_rn(katt, turb[t]), kcw), depth[t])));
+        const double Ir = __ddiv_rn(iz, Iopt);
+        const double Fi = __dmul_rn(Ir, exp(__dsub_rn(1.0, Ir)));
+        const double Fn = 1.0;
+        const double tau = __dmul_rn(__dmul_rn(__dmul_rn(depth[t], g), J), rho);
+        const double Rh = (tau <= tau0) ? 0.0 : __dmul_rn(cHyd, pow(__ddiv_rn(__dsub_rn(tau, tau0), tau0), bHyd));
+        const double grow = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(mu0, Fb), Ft), Fi), Fn), bt), dt);
+        const double loss = __dmul_rn(__dmul_rn(__dadd_rn(__dadd_rn(Rsen, rem[t]), Rh), __dsub_rn(bt, bmin)), dt);
+        double b = __dsub_rn(__dadd_rn(bt, grow), loss);
+        b = fmin(b, bmax);
+        b = fmax(b, bmin);
+        bt = b;
+        out[(size_t)t * K] = b;
+        if (nOut > 1) out[((size_t)n + t) * K] = __ddiv_rn(b, bmax);
+        if (nOut > 2) {
+            out[((size_t)2 * n + t) * K] = Fb;
+            out[((size_t)3 * n + t) * K] = Ft;
+            out[((size_t)4 * n + t) * K] = Fi;
+            out[((size_t)5 * n + t) * K] = Fn;
+            out[((size_t)6 * n + t) * K] = Rh;
+        }
+    }
+    return true;
+}
+
 // one sequential pass of a time-recursive model for one parameter vector; false = infeasible vector
 __device__ inline bool model_series(const DevProblem& p, const double* __restrict__ th, double* __restrict__ out, size_t K,
                                     int nOut) {
     if (p.model == BAMGPU_MDL_SFDTIDAL_QMEC || p.model == BAMGPU_MDL_SFDTIDAL_QMEC2)
         return sfdtidal_qmec_series(p.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : 1, p.seriesN, p.seriesX, p.seriesX + p.seriesN, th,
                                     out, K, nOut);
+    if (p.model == BAMGPU_MDL_ALGAE) return algae_series(p.seriesN, p.seriesX, th, out, K, nOut);
     return false;
 }
 
@@ -951,7 +1005,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return segmentation_apply(p, x[0], th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_MIXTURE) {
         return mixture_apply<NX>(p, x, th, der, y[0]);
-    } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2) {  // time-recursive: produced by series_run, looked up here
+    } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE) {  // time-recursive: produced by series_run, looked up here
 #pragma unroll
         for (int k = 0; k < NY; ++k)
             y[k] = p.seriesY[((size_t)k * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];
@@ -966,7 +1020,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
 
 // state variables (ModelLibrary_tools.f90 XtraSetup: model%nState): only SFD has one on this path (kappa)
 __host__ __device__ constexpr int model_nstate(int model) {
-    return model == BAMGPU_MDL_SFD ? 1 : ((model == BAMGPU_MDL_SFDTIDAL_QMEC || model == BAMGPU_MDL_SFDTIDAL_QMEC2) ? 3 : 0);
+    return model == BAMGPU_MDL_SFD ? 1 : ((model == BAMGPU_MDL_SFDTIDAL_QMEC || model == BAMGPU_MDL_SFDTIDAL_QMEC2) ? 3 : (model == BAMGPU_MDL_ALGAE ? 5 : 0));
 }
 
 // model_apply + the state variables of the observation (st[model_nstate(MODEL)])
@@ -974,7 +1028,7 @@ template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool model_apply_s(const DevProblem& p, const double* x, const double* __restrict__ th,
                                               const double* __restrict__ der, double* y, double* st) {
     if (MODEL == BAMGPU_MDL_SFD) return sfd_apply(p, x, th, y[0], st);
-    if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2) {
+    if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE) {
 #pragma unroll
         for (int k = 0; k < model_nstate(MODEL); ++k)
             st[k] = p.seriesY[((size_t)(NY + k) * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];

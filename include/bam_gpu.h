@@ -54,8 +54,12 @@ enum bamgpu_model {
     BAMGPU_MDL_SFDTIDAL_QMEC = 16, /* SFDTidal_Qmec_model.f90:61-197: tidal discharge from two stage series by a momentum
                                      balance (Adams-Bashforth in time); 12 parameters, states = pressure gradient, bottom
                                      friction, advection */
-    BAMGPU_MDL_SFDTIDAL_QMEC2 = 17 /* SFDTidal_Qmec2_model.f90: the same recursion parameterised by (Be, bevs, delta, ne, d1,
+    BAMGPU_MDL_SFDTIDAL_QMEC2 = 17, /* SFDTidal_Qmec2_model.f90: the same recursion parameterised by (Be, bevs, delta, ne, d1,
                                       d2, c, g, Q0, dx, dt) -- effective width and Manning coefficient given directly */
+    BAMGPU_MDL_ALGAE = 18          /* AlgaeBiomass_model.f90:55-197 ("AlgaeBiomass"): daily biomass recursion (logistic growth
+                                      limited by temperature and light, senescence, grazing / removal, hydraulic scour);
+                                      5 inputs (temperature, irradiance, depth, turbidity, removal), 18 parameters, outputs
+                                      biomass and biomass / bmax, states Fb, Ft, Fi, Fn, Rhyd */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -104,7 +108,8 @@ enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YI
  */
 typedef struct bamgpu_problem {
     const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
-                             "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC" | "SFD"
+                             "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC" | "SFD" |
+                             "Mixture" | "SFDTidal_Qmec" | "SFDTidal_Qmec2" | "AlgaeBiomass"
                              (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 

@@ -1376,6 +1376,50 @@ static int mixture_apply(const oracle_t* o, int n, const double* X, int ldx, con
     return 1;
 }
 
+/* AlgaeBiomass_Apply, AlgaeBiomass_model.f90:55-197: daily biomass recursion; X = (temperature, irradiance, depth, turbidity,
+   removal), ld = ldx; Y(:,1) = biomass, Y(:,2) = biomass / bmax (ld = ldy); state (nullable, ld = ldy): Fb, Ft, Fi, Fn, Rhyd.
+   Returns 0 when the parameter set is infeasible (:140-146), -1 on the input errors of :79-99 (err = 1 in the reference).
+   epsRe is DMSL's (un-vendored): declared = epsilon(1._mrk). */
+static int algae_apply(int n, const double* X, int ldx, const double* th, double* Y, int ldy, double* state) {
+    const double *temp = X, *irr = X + (size_t)ldx, *depth = X + 2 * (size_t)ldx, *turb = X + 3 * (size_t)ldx, *rem = X + 4 * (size_t)ldx;
+    for (int t = 0; t < n; ++t) {
+        Y[t] = BAMGPU_UNDEF_RN; Y[t + (size_t)ldy] = BAMGPU_UNDEF_RN;
+        if (state) for (int s = 0; s < 5; ++s) state[t + (size_t)s * ldy] = BAMGPU_UNDEF_RN;
+    }
+    for (int t = 0; t < n; ++t)
+        if (irr[t] < 0.0 || depth[t] < 0.0 || turb[t] < 0.0 || rem[t] < 0.0 || rem[t] > 1.0) return -1;
+    double dt = th[0], b0 = th[1], bmin = th[2], bmax = th[3], mu0 = th[4], Tmin = th[5], Topt = th[6], Tmax = th[7], Iopt = th[8],
+           katt = th[9], kcw = th[10], Rsen = th[11], g = th[12], rho = th[13], J = th[14], tau0 = th[15], bHyd = th[16], cHyd = th[17];
+    if (dt <= 0.0 || bmin < 0.0 || b0 < bmin || b0 > bmax || bmin >= bmax || mu0 < 0.0 || Tmin >= Tmax || Topt >= Tmax ||
+        Topt <= Tmin || Iopt <= 0.0 || katt < 0.0 || kcw < 0.0 || Rsen < 0.0 || g < 0.0 || rho < 0.0 || J < 0.0 || tau0 <= 0.0 ||
+        bHyd < 0.0 || cHyd < 0.0)
+        return 0;
+    double Texp = (Topt - Tmin) / (Tmax - Topt);
+    double bt = b0;
+    for (int t = 0; t < n; ++t) {
+        double Fb = 1.0 - bt / bmax, Ft, Fi, Fn, Rhyd, iz, Iratio, tau, b;
+        if (temp[t] <= Tmin || temp[t] >= Tmax) Ft = 0.0;
+        else {
+            Ft = ((Tmax - temp[t]) / (Tmax - Topt)) * pow((temp[t] - Tmin) / (Topt - Tmin), Texp);
+            if (Ft <= 2.2204460492503131e-16) Ft = 0.0;
+        }
+        iz = irr[t] * exp(-(katt * turb[t] + kcw) * depth[t]);
+        Iratio = iz / Iopt;
+        Fi = Iratio * exp(1.0 - Iratio);
+        Fn = 1.0;
+        tau = depth[t] * g * J * rho;
+        Rhyd = (tau <= tau0) ? 0.0 : cHyd * pow((tau - tau0) / tau0, bHyd);
+        b = bt + (mu0 * Fb * Ft * Fi * Fn) * bt * dt - (Rsen + rem[t] + Rhyd) * (bt - bmin) * dt;
+        b = b < bmax ? b : bmax;
+        b = b > bmin ? b : bmin;
+        bt = b;
+        Y[t] = b;
+        Y[t + (size_t)ldy] = b / bmax;
+        if (state) { state[t] = Fb; state[t + (size_t)ldy] = Ft; state[t + 2 * (size_t)ldy] = Fi; state[t + 3 * (size_t)ldy] = Fn; state[t + 4 * (size_t)ldy] = Rhyd; }
+    }
+    return 1;
+}
+
 /* SFDTidal_Qmec_Apply, SFDTidal_Qmec_model.f90:61-197: Q(m) = Q(m-1) + dt (pg + bf + ad), first-order step for m = 2,
    second-order Adams-Bashforth afterwards.  state (nullable, ld = lds): pressure_gradient, bottom_friction, advection.
    Returns 0 when the parameter set (or the geometry of the series) is infeasible. */
@@ -1490,6 +1534,13 @@ static int apply_model_s(const oracle_t* o, int n, const double* X, int ldx, con
             if (!sfdtidal_qmec_apply(o->model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : 1, n, X, X + (size_t)ldx, fullTheta, Y, state, ldy))
                 for (int t = 0; t < n; ++t) vfeas[t] = 0;
             break;
+        case BAMGPU_MDL_ALGAE: {
+            int r = algae_apply(n, X, ldx, fullTheta, Y, ldy, state);
+            if (r < 0) return 1;
+            if (!r)
+                for (int t = 0; t < n; ++t) vfeas[t] = 0;
+            break;
+        }
         case BAMGPU_MDL_MIXTURE: {
             int r = mixture_apply(o, n, X, ldx, fullTheta, Y, dparModel);
             if (r < 0) return 1;
@@ -1544,6 +1595,7 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "Mixture")) return BAMGPU_MDL_MIXTURE;
     if (!strcmp(name, "SFDTidal_Qmec")) return BAMGPU_MDL_SFDTIDAL_QMEC;
     if (!strcmp(name, "SFDTidal_Qmec2")) return BAMGPU_MDL_SFDTIDAL_QMEC2;
+    if (!strcmp(name, "AlgaeBiomass")) return BAMGPU_MDL_ALGAE;
     return 0;
 }
 
@@ -1707,6 +1759,10 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
         case BAMGPU_MDL_SFDTIDAL_QMEC2: /* SFDTidal_Qmec2_GetParNumber: 11; XtraSetup (:677-681) */
             if (nt != (o->model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 11 : 12) || nX != 2 || nY != 1) { setmess(mess, "oracle: SFDTidal_Qmec: bad sizes"); return 1; }
             o->nState = 3;
+            break;
+        case BAMGPU_MDL_ALGAE: /* AlgaeBiomass_GetParNumber: 18; XtraSetup: 5 state variables (ModelLibrary_tools.f90:697-702) */
+            if (nt != 18 || nX != 5 || nY != 2) { setmess(mess, "oracle: AlgaeBiomass: bad sizes"); return 1; }
+            o->nState = 5;
             break;
         case BAMGPU_MDL_MIXTURE: { /* Mixture_GetParNumber (:33-72), XtraSetup (ModelLibrary_tools.f90:580-586) */
             if (p->n_xtra_i != 4) { setmess(mess, "oracle: Mixture: bad xtra"); return 1; }

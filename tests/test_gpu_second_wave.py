@@ -270,3 +270,42 @@ def test_sfdtidal_qmec2_reference_workspace():
     Xt, Ys, St, feas = g.calibration_run_states(x0)
     oXt, oYs, oSt, ofeas = o.calibration_run_states(x0)
     assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-10, atol=1e-8) and np.allclose(St, oSt, rtol=1e-9, atol=1e-8)
+
+
+def test_time_recursive_algae_biomass():
+    """row f4: AlgaeBiomass on series_run (5 input series, 18 parameters, 2 outputs, 5 state variables): log-posterior with
+    gaps in both outputs, prediction with the state spaghetti, sampler, residual run -- all against the oracle; input
+    errors are refused at creation with the reference's message"""
+    import copy
+
+    from bam_b200.capi import BamError
+
+    prob, truth = synth.algae_biomass(nobs=400)
+    x = synth.feasible_starts(truth, 40, rel=0.01, seed=2)
+    x[3, 0] = 2.0     # b0 > bmax: infeasible parameter set
+    x[4, 4] = 40.0    # Topt >= Tmax
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.sizes.nState == 5
+    check_parity(prob, x, tol=1e-11)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.003 * rng.standard_normal((120, truth.size)))
+    mc[5, 0] = 2.0  # an infeasible replication
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(5)]
+    env, spag = g.predict(mc, truth, xs, 1, [1, 0], seed=4, want_spag=True, states=True)
+    oenv, ospag = o.predict(mc, truth, xs, 1, [1, 0], seed=4, want_spag=True, nthreads=8, states=True)
+    assert spag.shape == (7, 400, 120) and (spag[:, :, 5] == -666.666).all()
+    cmp_spag(spag, ospag, tol=1e-10)
+    cmp_env(env, oenv, tol=1e-10)
+    s = np.tile(truth, (3, 1))
+    sd = 0.005 * np.abs(s) + 1e-12
+    rows = g.fit(s, sd, nAdapt=3, nCycles=2, seed=5)
+    orows = o.fit(s, sd, nAdapt=3, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+    Xt, Ys, St, feas = g.calibration_run_states(truth)
+    oXt, oYs, oSt, ofeas = o.calibration_run_states(truth)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-11) and np.allclose(St, oSt, rtol=1e-10, atol=1e-13)
+    bad = copy.deepcopy(prob)
+    bad.X[7, 1] = -1.0  # irradiance < 0
+    with pytest.raises(BamError) as e:
+        BamGpu(bad)
+    assert "Irradiance<0" in str(e.value)

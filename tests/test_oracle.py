@@ -414,3 +414,42 @@ def test_sfdtidal_qmec2_on_the_reference_workspace():
     assert np.allclose(np.diff(Ys[:, 0]), St[1:].sum(axis=1), rtol=1e-9, atol=1e-6)
     r = o.logpost_one(x0)
     assert r["feas"] == 1 and np.isfinite(r["fx"])
+
+
+def test_algae_biomass_recursion():
+    """time-recursive model (row f4): the restatement of AlgaeBiomass_Apply (AlgaeBiomass_model.f90:55-197) against an
+    independent numpy run of the same daily budget (workloads/synth.py), its five state variables, the clamps and the
+    exits.  The shipped workspace (tests/BaM_AlgaeBiomass: 17 parameters, one output) predates the code (18 parameters:
+    katt + kcw instead of one attenuation; two outputs), so nothing in the reference pins this model beyond its source."""
+    from workloads import synth
+
+    prob, truth = synth.algae_biomass(nobs=500, missing_every=1)
+    o = Oracle(prob)
+    assert o.sizes.nState == 5 and o.P == 15
+    Xt, Ys, St, feas = o.calibration_run_states(truth)
+    assert feas and St.shape == (500, 5) and Ys.shape == (500, 2)
+    th = np.array([1.0, 0.3, 0.001, 1.0, 0.12, 6.0, 16.5, 30.0, 150.0, 0.02, 0.5, 0.02, 9.81, 1000.0, 1e-4, 0.8, 1.5, 0.05])
+    X = np.asarray(prob.X)
+    assert np.allclose(Ys[:, 1], Ys[:, 0] / th[3], rtol=1e-15)
+    assert (St[:, 3] == 1.0).all()                                      # Fn
+    assert np.allclose(St[1:, 0], 1.0 - Ys[:-1, 0] / th[3], rtol=1e-14)  # Fb(t) = 1 - b(t-1) / bmax
+    assert St[0, 0] == 1.0 - th[1] / th[3]
+    tau = X[:, 2] * th[12] * th[14] * th[13]
+    assert ((St[:, 4] > 0) == (tau > th[15])).all() and (St[:, 4] > 0).any()   # scour only above the critical shear stress
+    cold = (X[:, 0] <= th[5]) | (X[:, 0] >= th[7])
+    assert (St[cold, 1] == 0.0).all() and cold.any() and (St[~cold, 1] > 0).all()
+    # the budget itself, step by step
+    b_prev = np.concatenate([[th[1]], Ys[:-1, 0]])
+    want = b_prev + th[4] * St[:, 0] * St[:, 1] * St[:, 2] * b_prev * th[0] - (th[11] + X[:, 4] + St[:, 4]) * (b_prev - th[2]) * th[0]
+    assert np.allclose(Ys[:, 0], np.clip(want, th[2], th[3]), rtol=1e-13)
+    # infeasible parameter sets (:140-146): b0 > bmax, Topt outside (Tmin, Tmax), tau0 <= 0
+    for pos, val in ((0, 2.0), (4, 40.0), (10, -0.1)):  # fitted positions: b0, Topt, tau0
+        x = truth.copy()
+        x[pos] = val
+        assert o.logpost_one(x)["feas"] == 0
+    # input errors are fatal, as in the reference (err = 1, :79-99)
+    import copy
+    bad = copy.deepcopy(prob)
+    bad.X[7, 4] = 1.5  # removal > 1
+    with pytest.raises(Exception):
+        Oracle(bad).logpost_one(truth)

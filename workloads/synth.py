@@ -508,3 +508,45 @@ def sfd(nobs: int = 300, seed: int = SEED + 9):
     prob = Problem("SFD", np.column_stack([h1, h2]), Y, Yu=uq, partype=[0] * 8, priors_theta=pri, sigma_func=["Linear"],
                    priors_gamma=[("Uniform", [0, 10000])] * 2, xtra_i=[1, 100], xtra_d=[20.0, 5.0, 1000.0, 1e-5, 1e-10])
     return prob, np.concatenate([th, [10.0, 0.05]])
+
+
+def algae_biomass(nobs: int = 730, seed: int = SEED + 14, missing_every: int = 4):
+    """AlgaeBiomass (time-recursive daily biomass budget, AlgaeBiomass_model.f90:55-197): 5 input series (temperature,
+    irradiance, depth, turbidity, removal), 18 parameters, outputs biomass and biomass / bmax.  Synthetic two-year record
+    with a few floods (hydraulic scour) and cuts (removal); the "observations" are the model's own output plus noise,
+    with gaps.  Returns (Problem, truth)."""
+    rng = default_rng(seed)
+    day = np.arange(nobs, dtype=np.float64)
+    temp = 14.0 - 10.0 * np.cos(2 * np.pi * (day - 20.0) / 365.0) + 1.5 * rng.standard_normal(nobs)
+    irr = np.maximum(140.0 - 110.0 * np.cos(2 * np.pi * (day - 10.0) / 365.0) + 25.0 * rng.standard_normal(nobs), 1.0)
+    depth = 0.6 + 0.15 * np.sin(2 * np.pi * day / 90.0) ** 2
+    flood = (rng.uniform(0.0, 1.0, nobs) < 0.02)
+    depth = depth + np.convolve(flood.astype(float), np.array([1.2, 0.8, 0.4, 0.2]), mode="full")[:nobs]
+    turb = np.maximum(5.0 + 40.0 * (depth - 0.6), 0.0)
+    rem = np.where(rng.uniform(0.0, 1.0, nobs) < 0.01, 0.4, 0.0)
+    th = np.array([1.0, 0.3, 0.001, 1.0, 0.12, 6.0, 16.5, 30.0, 150.0, 0.02, 0.5, 0.02, 9.81, 1000.0, 1e-4, 0.8, 1.5, 0.05])
+    dt, b0, bmin, bmax, mu0, Tmin, Topt, Tmax, Iopt, katt, kcw, Rsen, g, rho, J, tau0, bHyd, cHyd = th
+    Texp = (Topt - Tmin) / (Tmax - Topt)
+    b = np.zeros(nobs)
+    bt = b0
+    for t in range(nobs):
+        Fb = 1.0 - bt / bmax
+        Ft = 0.0 if (temp[t] <= Tmin or temp[t] >= Tmax) else ((Tmax - temp[t]) / (Tmax - Topt)) * ((temp[t] - Tmin) / (Topt - Tmin)) ** Texp
+        Ir = irr[t] * np.exp(-(katt * turb[t] + kcw) * depth[t]) / Iopt
+        Fi = Ir * np.exp(1.0 - Ir)
+        tau = depth[t] * g * J * rho
+        Rh = 0.0 if tau <= tau0 else cHyd * ((tau - tau0) / tau0) ** bHyd
+        bt = min(max(bt + mu0 * Fb * Ft * Fi * bt * dt - (Rsen + rem[t] + Rh) * (bt - bmin) * dt, bmin), bmax)
+        b[t] = bt
+    Y = np.column_stack([b, b / bmax]) + 0.02 * rng.standard_normal((nobs, 2))
+    if missing_every > 1:
+        Y[np.arange(nobs) % missing_every != 0, :] = -9999.0
+    Y[:, 0] = np.where(np.arange(nobs) % 2 == 0, -9999.0, Y[:, 0])  # the second output is the better observed one
+    partype = [-1, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, -1, -1, 0, 0, 0]  # dt, bmin, g, rho, J fixed (Config_Model_FIX.txt)
+    pri = [("Gaussian", [v, 0.05 * abs(v) + 1e-3]) for v in th]
+    prob = Problem("AlgaeBiomass", np.column_stack([temp, irr, depth, turb, rem]), Y, Yu=np.full((nobs, 2), 0.01), partype=partype,
+                   priors_theta=[pri[i] for i in range(18) if partype[i] == 0],
+                   fix_value=[v if partype[i] == -1 else 0.0 for i, v in enumerate(th)], sigma_func=["Constant", "Constant"],
+                   priors_gamma=[("Uniform", [0, 10]), ("Uniform", [0, 10])])
+    truth = np.concatenate([[th[i] for i in range(18) if partype[i] == 0], [0.02, 0.02]])
+    return prob, truth
