@@ -322,3 +322,44 @@ def test_sediment_fast_logpost_against_oracle(formula, css):
     X2[40, 1] = -1e-3       # a non-positive input: the row, hence every vector, is infeasible
     gb, ob = BamGpu(make(X2)), Oracle(make(X2))
     assert (gb.logpost(x)[1] == ob.logpost(x)[1]).all() and not gb.logpost(x)[1][[0, 1, 2]].any()
+
+
+def test_taylor_subtile_paths_of_the_fast_kernel():
+    """generation 3 of the BaRatin fast path: dense, stage-sorted gaugings make most (chain, sub-tile) pairs take the
+    Taylor expansion; this data set is built to visit every branch around it -- degree classes 5 .. 16 (sub-tiles close
+    to an offset b need the high degrees), the group path (arguments H - b too small for any degree, exponents outside
+    (0, 5]), stage boundaries inside a sub-tile and inside a group of five, chains that fail the remnant gate, a partial
+    last chain block, infeasible chains in the middle of a warp, three sigma functions -- against the oracle (which
+    evaluates one libm pow per gauging and control, BaRatin_model.f90:229-250) and against the generic kernel."""
+    from bam_b200.capi import Problem
+
+    rng = np.random.default_rng(12)
+    n = 30_000
+    k = np.array([-0.4, 0.9, 1.6])
+    a = np.array([18.0, 30.0, 42.0])
+    c = np.array([1.5, 1.67, 2.2])
+    M = np.array([[1, 0, 0], [0, 1, 0], [0, 1, 1]], dtype=np.int32)
+    # dense stages, with a cluster right above the third activation stage (tiny H - b3) and a sparse upper tail
+    H = np.concatenate([rng.uniform(-0.39, 2.4, n - 3000), 1.6 + np.abs(rng.standard_normal(2000)) * 2e-3, rng.uniform(2.4, 30.0, 1000)])
+    theta = np.column_stack([k, a, c]).ravel()
+    for funk, gam in (("Linear", [0.6, 0.08]), ("Constant", [1.5]), ("Proportional", [0.2])):
+        Y = np.abs(rng.standard_normal(n)) * 40 + 2.0
+        prob = Problem("BaRatin", H, Y, Yu=0.05 * Y, partype=[0] * 9,
+                       priors_theta=[("Gaussian", [t, abs(t) * 0.5 + 0.1]) for t in theta], sigma_func=[funk],
+                       priors_gamma=[("Uniform", [0, 1e7])] * len(gam), xtra_i=M.flatten(order="F"))
+        x = perturbed_vectors(np.concatenate([theta, gam]), 300, rel=0.02, seed=5)
+        x[3, 3] = -1.0            # k2 < k1: infeasible vector inside a warp
+        x[40, 2] = 6.5            # c1 outside (0, 5]: no expansion for that chain, group path with c = 6.5
+        x[41, 5] = -0.8           # a negative exponent: (H - b)^c grows without bound next to the offset
+        x[77, 9] = 3e6            # gamma1 beyond the gate of the group path (2^20): every gauging through the checked path
+        x[78, 9] = 1e-19          # ... and below it
+        x[130, 0] = -0.3999999    # k1 a hair above the lowest stages: the first group straddles the activation stage
+        err = check_parity(prob, x, tol=1e-12, floor=float(n) * 1e-3)
+        g, g2 = BamGpu(prob), BamGpu(prob)
+        g2.set_option("force_generic", 1)
+        fx, fg = g.logpost(x), g2.logpost(x)
+        assert (fx[1] == fg[1]).all() and (fx[2] == fg[2]).all()
+        ok = fx[1] == 1
+        assert ok.sum() >= 200
+        assert (np.abs(fx[0][ok] - fg[0][ok]) <= 1e-12 * np.maximum(np.abs(fg[0][ok]), n * 1e-3)).all()
+        assert (g.logpost(x)[0] == fx[0]).all()  # bitwise repeatable (dynamic item order, fixed-order sums)
