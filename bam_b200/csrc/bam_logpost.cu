@@ -191,9 +191,11 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
 
     const int tid = threadIdx.x;
     for (int q = tid; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
-    if (MODEL == BAMGPU_MDL_BARATIN)
+    constexpr bool FM = MODEL == BAMGPU_MDL_VEGETATION || MODEL == BAMGPU_MDL_TEXTFILE;  // table-driven log / exp inside the model
+    if (MODEL == BAMGPU_MDL_BARATIN || FM)
         for (int q = tid; q < BAM_EXPTAB_N; q += BAM_BLOCK) sExpT[q] = p.expTab[q];
     const unsigned lt = smem_addr(sLogT), et = smem_addr(sExpT);
+    const FmTab fm = FM ? FmTab{lt, et} : FmTab{0u, 0u};
     const int tx = tid % TX, ty = tid / TX, TY = BAM_BLOCK / TX;
     const int lane = tid & 31, wrow = tx >> 5;
     const int c0 = blockIdx.y * CT;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) logpost_main(DevProblem p, const do
             // BaRatin (few chains on many gaugings never reach the chain-parallel fast path): same exits as
             // baratin_apply, a (H-b)^c through the table-driven functions instead of libdevice log + exp
             const bool ok = (MODEL == BAMGPU_MDL_BARATIN) ? baratin_apply_t(p, xt[0], th, th + p.ntheta, yh[0], lt, et)
-                                                          : model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh);
+                                                          : model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh, fm);
             if (!ok) bad = true;
             else {
 #pragma unroll

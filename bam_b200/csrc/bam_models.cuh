@@ -6,6 +6,24 @@
 // model_prepare(), write the nY outputs and return row feasibility.
 #pragma once
 #include "bam_device.cuh"
+#include "bam_fastmath.cuh"
+
+// ---- table-driven log / exp for the generic kernels ------------------------------------------------------------
+// Shared-memory addresses of the 256-entry log and exp tables of bam_fastmath.cuh (0, 0: not staged -> libdevice).  The
+// models whose per-observation cost is dominated by libdevice pow / log / exp (Vegetation: ~10 evaluations of x^chi inside
+// the bracketed Newton, three powers of the water depth; the TextFile VM's ^, exp, log opcodes) take them through these
+// wrappers: tlog is within 5.4e-16 (absolute), texp within 2.5e-16 (relative) of libm (tests/test_fastmath.py).
+struct FmTab {
+    unsigned lt, et;
+};
+__device__ __forceinline__ double fm_log(double x, FmTab t) {  // x > 0 expected by the caller's own domain test
+    return (t.lt != 0u && (unsigned)__double2hiint(x) - 0x00100000u < 0x7fe00000u) ? tlog_pos(x, t.lt) : log(x);
+}
+__device__ __forceinline__ double fm_exp(double x, FmTab t) { return t.et != 0u ? texp(x, t.et) : exp(x); }
+__device__ __forceinline__ double fm_pow(double b, double e, FmTab t) {  // pow() itself outside b > 0 (signs, zeros, infinities)
+    return (t.lt != 0u && t.et != 0u && (unsigned)__double2hiint(b) - 0x00100000u < 0x7fe00000u) ? texp(e * tlog_pos(b, t.lt), t.et) : pow(b, e);
+}
+
 
 // -------------------------------------------------------------------------------------------
 // BaRatin (BaRatin_model.f90).  theta = (k_i, a_i, c_i) per control; der = offsets b_i.
@@ -277,7 +295,7 @@ enum { VM_IMMED = 1, VM_NEG, VM_ADD, VM_SUB, VM_MUL, VM_DIV, VM_POW, VM_ABS, VM_
 
 template <int NX>
 __device__ inline bool textfile_eval(const DevProblem& p, int k, const double* in, const double* __restrict__ th,
-                                     double& res) {
+                                     double& res, FmTab fm = FmTab{0u, 0u}) {
     double st[BAM_VMSTACK];
     int sp = -1;
     const int* __restrict__ code = p.vmCode + p.vmCodeOff[k];
@@ -295,15 +313,15 @@ __device__ inline bool textfile_eval(const DevProblem& p, int k, const double* i
             case VM_DIV:
                 if (st[sp] == 0.0) return false;
                 st[sp - 1] = st[sp - 1] / st[sp]; --sp; break;
-            case VM_POW: st[sp - 1] = pow(st[sp - 1], st[sp]); --sp; break;
+            case VM_POW: st[sp - 1] = fm_pow(st[sp - 1], st[sp], fm); --sp; break;
             case VM_ABS: st[sp] = fabs(st[sp]); break;
-            case VM_EXP: st[sp] = exp(st[sp]); break;
+            case VM_EXP: st[sp] = fm_exp(st[sp], fm); break;
             case VM_LOG10:
                 if (st[sp] <= 0.0) return false;
                 st[sp] = log10(st[sp]); break;
             case VM_LOG:
                 if (st[sp] <= 0.0) return false;
-                st[sp] = log(st[sp]); break;
+                st[sp] = fm_log(st[sp], fm); break;
             case VM_SQRT:
                 if (st[sp] < 0.0) return false;
                 st[sp] = sqrt(st[sp]); break;
@@ -432,9 +450,10 @@ __device__ inline bool vegetation_prepare(const DevProblem& p, const double* th,
 // Vegetation_fNewton (:536-569).  x^chi once per evaluation, as exp(chi log x) (x^(1+chi) = x x^chi): the reference's two
 // pow() calls per evaluation dominate the per-observation cost; x = 0 (only the bracket's lower end) keeps pow()'s
 // limits x^chi = +inf (chi < 0) or 1 (chi = 0) and x^(1+chi) through pow() itself.
-__device__ __forceinline__ void veg_fnewton(double x, double Q0, double gam, double gam2, double chi, double& f, double& df) {
+__device__ __forceinline__ void veg_fnewton(double x, double Q0, double gam, double gam2, double chi, double& f, double& df,
+                                            FmTab fm = FmTab{0u, 0u}) {
     const bool pos = x > 0.0;
-    const double px = pos ? exp(chi * log(x)) : pow(x, chi);
+    const double px = pos ? fm_exp(chi * fm_log(x, fm), fm) : pow(x, chi);
     double m = px / gam2;
     if (1.0 < m) m = 1.0;
     f = x * x + (gam * (x * x) * m) - Q0 * Q0;
@@ -443,18 +462,19 @@ __device__ __forceinline__ void veg_fnewton(double x, double Q0, double gam, dou
 }
 
 // znewton on [0, Q0]: declared convention (miniDMSL is un-vendored), identical to oracle/bam_oracle.c:veg_znewton
-__device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, double gam2, double chi, double& root) {
+__device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, double gam2, double chi, double& root,
+                                FmTab fm = FmTab{0u, 0u}) {
     double fl, fh, df, f, xl, xh;
     const double x1 = 0.0, x2 = Q0;
-    veg_fnewton(x1, Q0, gam, gam2, chi, fl, df);
-    veg_fnewton(x2, Q0, gam, gam2, chi, fh, df);
+    veg_fnewton(x1, Q0, gam, gam2, chi, fl, df, fm);
+    veg_fnewton(x2, Q0, gam, gam2, chi, fh, df, fm);
     int fcalls = 2;
     if (fl == 0.0) { root = x1; return fcalls <= p.vegItmax; }
     if (fh == 0.0) { root = x2; return fcalls <= p.vegItmax; }
     if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) return false;
     if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
     double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
-    veg_fnewton(rts, Q0, gam, gam2, chi, f, df);
+    veg_fnewton(rts, Q0, gam, gam2, chi, f, df, fm);
     ++fcalls;
     for (int j = 0; j < p.vegItmax; ++j) {
         if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
@@ -463,7 +483,7 @@ __device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, doub
             dxold = dx; dx = f / df; rts = rts - dx;
         }
         const bool convx = fabs(dx) <= p.vegTolX * p.vegXscale;
-        veg_fnewton(rts, Q0, gam, gam2, chi, f, df);
+        veg_fnewton(rts, Q0, gam, gam2, chi, f, df, fm);
         ++fcalls;
         if (f < 0.0) xl = rts; else xh = rts;
         if (convx || fabs(f) <= p.vegTolF * p.vegFscale) break;
@@ -474,7 +494,7 @@ __device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, doub
         xn = fmin(fmax(xn, lo), hi);
         if (xn == rts) break;
         rts = xn;
-        veg_fnewton(rts, Q0, gam, gam2, chi, f, df);
+        veg_fnewton(rts, Q0, gam, gam2, chi, f, df, fm);
         if (f < 0.0) xl = rts; else xh = rts;
     }
     root = rts;
@@ -483,13 +503,13 @@ __device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, doub
 
 template <int NX, int NY>
 __device__ inline bool vegetation_apply(const DevProblem& p, const double* in, const double* __restrict__ th,
-                                        const double* __restrict__ der, double* out) {
+                                        const double* __restrict__ der, double* out, FmTab fm = FmTab{0u, 0u}) {
     const double time = in[0], h = in[1];
     double g, g0, cosg, sing;
     if (p.vegGrowth == BAMGPU_VEG_YIN1_TEMPORAL) {
         const double t0 = th[7], tmax = th[9], alf = der[1], tf = der[2];
         const double tt = time - floor(time);
-        if (tt >= t0 && tt <= tf) g0 = (pow((tt - t0) / (tmax - t0), alf)) * (tf - tt) / (tf - tmax);
+        if (tt >= t0 && tt <= tf) g0 = (fm_pow((tt - t0) / (tmax - t0), alf, fm)) * (tf - tt) / (tf - tmax);
         else g0 = 0.0;
         double sn;
         sincos(g0 * BAM_VEG_PI, &sn, &cosg);
@@ -503,7 +523,7 @@ __device__ inline bool vegetation_apply(const DevProblem& p, const double* in, c
             const double* yr = der + 1 + nYear + 5 * i;
             const double time_b = yr[0], time_e = yr[1], time_f = yr[2], alpha = yr[3];
             if (yr[4] != 0.0 || time <= time_b || time >= time_f) g0 = 0.0;
-            else g0 = pow((time - time_b) / (time_e - time_b), alpha) * (time_f - time) / (time_f - time_e);
+            else g0 = fm_pow((time - time_b) / (time_e - time_b), alpha, fm) * (time_f - time) / (time_f - time_e);
             g = g0 * th[11 + i];
             double sn;
             sincos(g0 * BAM_VEG_PI, &sn, &cosg);
@@ -516,14 +536,14 @@ __device__ inline bool vegetation_apply(const DevProblem& p, const double* in, c
     if (NY > 4) out[4] = g0;
     const double y = h - th[3];
     if (y <= 0.0) { out[0] = 0.0; return true; }
-    const double ly = log(y);  // y > 0: the three powers of y share one logarithm
-    const double Q0 = der[0] * exp(th[4] * ly);
+    const double ly = fm_log(y, fm);  // y > 0: the three powers of y share one logarithm
+    const double Q0 = der[0] * fm_exp(th[4] * ly, fm);
     if (g <= 0.0) { out[0] = Q0; return true; }
     const double chi = th[5];
-    const double gam = (g * cbrt(y)) / (8.0 * BAM_VEG_GRAVITY * (th[2] * th[2]));
-    const double gam2 = der[(p.vegGrowth == BAMGPU_VEG_YIN1_TEMPORAL) ? 3 : 1 + 6 * p.vegNYear] * exp(chi * ly);
+    const double gam = (g * (fm.et != 0u ? texp(ly * (1.0 / 3.0), fm.et) : cbrt(y))) / (8.0 * BAM_VEG_GRAVITY * (th[2] * th[2]));
+    const double gam2 = der[(p.vegGrowth == BAMGPU_VEG_YIN1_TEMPORAL) ? 3 : 1 + 6 * p.vegNYear] * fm_exp(chi * ly, fm);
     double q;
-    if (!veg_root(p, Q0, gam, gam2, chi, q)) return false;
+    if (!veg_root(p, Q0, gam, gam2, chi, q, fm)) return false;
     out[0] = q;
     return true;
 }
@@ -975,7 +995,7 @@ __device__ inline bool model_prepare(const DevProblem& p, const double* th, doub
 // one observation.  y[NY]; returns row feasibility (ApplyModel's vfeas, ModelLibrary_tools.f90:419-432)
 template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x, const double* __restrict__ th,
-                                            const double* __restrict__ der, double* y) {
+                                            const double* __restrict__ der, double* y, FmTab fm = FmTab{0u, 0u}) {
     if (MODEL == BAMGPU_MDL_BARATIN) {
         return baratin_apply(p, x[0], th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_LINEAR) {
@@ -984,7 +1004,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
     } else if (MODEL == BAMGPU_MDL_SEDIMENT) {
         return sediment_apply<NX>(p, x, th, y[0]);
     } else if (MODEL == BAMGPU_MDL_VEGETATION) {
-        return vegetation_apply<NX, NY>(p, x, th, der, y);
+        return vegetation_apply<NX, NY>(p, x, th, der, y, fm);
     } else if (MODEL == BAMGPU_MDL_SUSPENDEDLOAD) {
         return suspendedload_apply(x[0], th, y[0]);
     } else if (MODEL == BAMGPU_MDL_SWOT) {
@@ -1013,7 +1033,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
     } else {
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < NY; ++k) ok = textfile_eval<NX>(p, k, x, th, y[k]) && ok;
+        for (int k = 0; k < NY; ++k) ok = textfile_eval<NX>(p, k, x, th, y[k], fm) && ok;
         return ok;
     }
 }
@@ -1026,12 +1046,12 @@ __host__ __device__ constexpr int model_nstate(int model) {
 // model_apply + the state variables of the observation (st[model_nstate(MODEL)])
 template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool model_apply_s(const DevProblem& p, const double* x, const double* __restrict__ th,
-                                              const double* __restrict__ der, double* y, double* st) {
+                                              const double* __restrict__ der, double* y, double* st, FmTab fm = FmTab{0u, 0u}) {
     if (MODEL == BAMGPU_MDL_SFD) return sfd_apply(p, x, th, y[0], st);
     if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE) {
 #pragma unroll
         for (int k = 0; k < model_nstate(MODEL); ++k)
             st[k] = p.seriesY[((size_t)(NY + k) * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];
     }
-    return model_apply<MODEL, NX, NY>(p, x, th, der, y);
+    return model_apply<MODEL, NX, NY>(p, x, th, der, y, fm);
 }

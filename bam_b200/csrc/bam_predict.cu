@@ -69,14 +69,19 @@ template <int MODEL, int NX, int NY>
 __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a, const double* __restrict__ tab,
                                                        const int* __restrict__ status, double* const* __restrict__ xspag,
                                                        const int* __restrict__ nspag, double* __restrict__ V) {
-    extern __shared__ __align__(16) double sm[];  // [log table | (cos, sin) table | [stride][BAM_BLOCK] : parameter k of thread t at sm[k*BLOCK + t]]
+    extern __shared__ __align__(16) double sm[];  // [log table | (cos, sin) table | exp table | [stride][BAM_BLOCK] : parameter k of thread t at sm[k*BLOCK + t]]
     double2* sLogT = reinterpret_cast<double2*>(sm);
     double2* sScT = reinterpret_cast<double2*>(sm + 2 * BAM_LOGTAB_N);
+    double* sExpT = sm + 2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N;
+    constexpr bool FM = MODEL == BAMGPU_MDL_VEGETATION || MODEL == BAMGPU_MDL_TEXTFILE;  // table-driven log / exp inside the model
     for (int q = threadIdx.x; q < BAM_LOGTAB_N; q += BAM_BLOCK) sLogT[q] = p.logTab[q];
     for (int q = threadIdx.x; q < BAM_SCTAB_N; q += BAM_BLOCK) sScT[q] = p.scTab[q];
+    if (FM)
+        for (int q = threadIdx.x; q < BAM_EXPTAB_N; q += BAM_BLOCK) sExpT[q] = p.expTab[q];
     __syncthreads();
     const unsigned lt = smem_addr(sLogT), sct = smem_addr(sScT);
-    double* const smT = sm + 2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N;
+    const FmTab fm = FM ? FmTab{lt, smem_addr(sExpT)} : FmTab{0u, 0u};
+    double* const smT = sm + 2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N + BAM_EXPTAB_N;
     const int tid = threadIdx.x;
     const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
     const bool act = rep < a.Nrep;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
 #pragma unroll
         for (int j = 0; j < NX; ++j) xin[j] = xp[j][t];
         bool ok = setOk;
-        if (ok) ok = model_apply_s<MODEL, NX, NY>(p, xin, loc, loc + p.ntheta, y, st);
+        if (ok) ok = model_apply_s<MODEL, NX, NY>(p, xin, loc, loc + p.ntheta, y, st, fm);
         if (NS > 0 && a.nStateOut > 0)
 #pragma unroll
             for (int j = 0; j < NS; ++j) V[((size_t)(NY + j) * a.nT + t) * a.Nrep + rep] = ok ? st[j] : p.unfeas;
@@ -1468,7 +1473,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         pser.seriesX = h->d_seriesXpred; pser.seriesN = h->predNobs; pser.seriesK = (int)Nrep; pser.seriesY = h->d_series;
         launch_series(h, pser, (int)Nrep, h->d_ptab, a.stride, p.nGamma, h->d_pstatus, nOutS);
     }
-    const size_t smemMain = sizeof(double) * (2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N) + (a.stage ? sizeof(double) * (size_t)a.stride * BAM_BLOCK : 0);
+    const size_t smemMain = sizeof(double) * (2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N + BAM_EXPTAB_N) + (a.stage ? sizeof(double) * (size_t)a.stride * BAM_BLOCK : 0);
     if (smemMain > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMain));
 
     int npad = 1;
