@@ -86,9 +86,13 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
     const long long rep = (long long)blockIdx.x * BAM_BLOCK + tid;
     const bool act = rep < a.Nrep;
     const int stride = a.stride;
-    // a.stage == 0 (stride too large for shared memory, e.g. Mixture with its 148 weights): read the table row directly
+    // a.stage: the block's table rows in shared memory, ONE ROW PER THREAD with an odd stride (conflict-free when the lanes
+    // read the same entry of their own rows): the model reads its parameters straight from there.  A private local-memory
+    // copy (up to 224 doubles per thread, dynamically indexed by the growth / VM code) cost more than the model's arithmetic.
+    // a.stage == 0 (stride too large for shared memory, e.g. Mixture with its 148 weights): private copy from the table row.
+    const int strideP = stride | 1;
     if (act && a.stage)
-        for (int k = 0; k < stride; ++k) smT[k * BAM_BLOCK + tid] = tab[(size_t)rep * stride + k];
+        for (int k = 0; k < stride; ++k) smT[(size_t)tid * strideP + k] = tab[(size_t)rep * stride + k];
     const bool setOk = act ? (status[rep] == 0) : false;
     const int tBeg = blockIdx.y * 32, tEnd = min(a.nT, tBeg + 32);
     const double* xp[NX];
@@ -98,11 +102,11 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
         xp[j] = xspag[j] + (size_t)col * a.nobsPred + a.t0;
     }
     if (!act) return;
-    // this replication's full theta + derived values: private copy, loaded once for all inputs of the tile
-    double loc[BAM_MAXTHETA + BAM_MAXDER];
+    double locBuf[BAM_MAXTHETA + BAM_MAXDER];
     const int np = p.ntheta + p.nDer;
-    if (a.stage) for (int k = 0; k < np; ++k) loc[k] = smT[(p.nGamma + k) * BAM_BLOCK + tid];
-    else for (int k = 0; k < np; ++k) loc[k] = tab[(size_t)rep * stride + p.nGamma + k];
+    const double* loc = locBuf;
+    if (a.stage) loc = smT + (size_t)tid * strideP + p.nGamma;
+    else for (int k = 0; k < np; ++k) locBuf[k] = tab[(size_t)rep * stride + p.nGamma + k];
     for (int t = tBeg; t < tEnd; ++t) {
         constexpr int NS = model_nstate(MODEL);
         double xin[NX], y[NY], st[NS > 0 ? NS : 1];
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) pred_main(DevProblem p, PredArgs a,
             if (a.doRemnant[j] && v != p.unfeas) {
                 double gam[3];
                 for (int m = 0; m < p.nrem[j] && m < 3; ++m)
-                    gam[m] = a.stage ? smT[(p.gamOff[j] + m) * BAM_BLOCK + tid] : tab[(size_t)rep * stride + p.gamOff[j] + m];
+                    gam[m] = a.stage ? smT[(size_t)tid * strideP + p.gamOff[j] + m] : tab[(size_t)rep * stride + p.gamOff[j] + m];
                 const double sig = sigmafunk(p.sigfunc[j], gam, v);
                 if (sig > 0.0) v = v + sig * philox_normal_pred_fast(a.seed, (uint64_t)(rep + a.repBase), (unsigned)(a.t0 + t), (unsigned)j, lt, sct);
             }
@@ -1430,7 +1434,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     a.nStateOut = nS;
     a.repBase = h->shardComm ? h->shardRepBase : 0;
     h->predNout = nOut;
-    a.stage = sizeof(double) * (size_t)a.stride * BAM_BLOCK <= 96 * 1024;
+    a.stage = sizeof(double) * (size_t)(a.stride | 1) * BAM_BLOCK <= 96 * 1024;
 
     // table + envelope output
     if (!h->d_ptab) {
@@ -1473,7 +1477,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         pser.seriesX = h->d_seriesXpred; pser.seriesN = h->predNobs; pser.seriesK = (int)Nrep; pser.seriesY = h->d_series;
         launch_series(h, pser, (int)Nrep, h->d_ptab, a.stride, p.nGamma, h->d_pstatus, nOutS);
     }
-    const size_t smemMain = sizeof(double) * (2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N + BAM_EXPTAB_N) + (a.stage ? sizeof(double) * (size_t)a.stride * BAM_BLOCK : 0);
+    const size_t smemMain = sizeof(double) * (2 * BAM_LOGTAB_N + 2 * BAM_SCTAB_N + BAM_EXPTAB_N) + (a.stage ? sizeof(double) * (size_t)(a.stride | 1) * BAM_BLOCK : 0);
     if (smemMain > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMain));
 
     int npad = 1;
