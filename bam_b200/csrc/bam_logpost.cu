@@ -127,24 +127,23 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
     for (int j = 0; j < p.nY; ++j)
         for (int i = lane; i < p.nYb[j]; i += 32) row[p.tabOffYb[j] + i] = xval(x, base, p.offYb[j] + i, comp, dl);
     int stl = 0;
-    for (int k = lane; k < p.nCombo; k += 32) {  // ApplyModel_BaM theta expansion (:4133-4159), one combination per lane
-        constexpr int MT = (SPEC == BAMGPU_MDL_BARATIN) ? 12 : BAM_MAXTHETA, MD = (SPEC == BAMGPU_MDL_BARATIN) ? 8 : BAM_MAXDER;
-        double th[MT], der[MD];
-        const double* xc[BAM_MAXX];
-        for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
-        double* cr = row + p.tabCombo + (size_t)k * p.comboStride;
-        for (int i = 0; i < p.ntheta; ++i) {
-            const int src = p.comboSrc[(size_t)k * p.ntheta + i];
-            th[i] = (src < 0) ? p.fixv[i] : xval(x, base, src, comp, dl);
-            cr[i] = th[i];
+    if (SPEC != 0) {  // the generic instance leaves the model pre-pass to logpost_prep_model (thread per vector x combination)
+        for (int k = lane; k < p.nCombo; k += 32) {  // ApplyModel_BaM theta expansion (:4133-4159), one combination per lane
+            constexpr int MT = (SPEC == BAMGPU_MDL_BARATIN) ? 12 : BAM_MAXTHETA, MD = (SPEC == BAMGPU_MDL_BARATIN) ? 8 : BAM_MAXDER;
+            double th[MT], der[MD];
+            double* cr = row + p.tabCombo + (size_t)k * p.comboStride;
+            for (int i = 0; i < p.ntheta; ++i) {
+                const int src = p.comboSrc[(size_t)k * p.ntheta + i];
+                th[i] = (src < 0) ? p.fixv[i] : xval(x, base, src, comp, dl);
+                cr[i] = th[i];
+            }
+            for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
+            const bool ok = baratin_prepare(p, th, der);
+            if (!ok) stl |= ST_LKH_INFEAS;
+            for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
+            if (dpar != nullptr)
+                for (int d = 0; d < p.nDparModel; ++d) dpar[(size_t)c * p.nDpar + k * p.nDparModel + d] = ok ? der[d] : p.unfeas;
         }
-        for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
-        const bool ok = (SPEC == BAMGPU_MDL_BARATIN) ? baratin_prepare(p, th, der) : model_prepare(p, th, der, xc, p.n);
-        if (SPEC == 0 && p.isSeries) der[0] = (double)c;  // this vector's column of the series buffer (model_apply looks it up)
-        if (!ok) stl |= ST_LKH_INFEAS;
-        for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
-        if (dpar != nullptr)
-            for (int d = 0; d < p.nDparModel; ++d) dpar[(size_t)c * p.nDpar + k * p.nDparModel + d] = ok ? der[d] : p.unfeas;
     }
     st |= __reduce_or_sync(0xffffffffu, stl);
     if (lane == 0) {
@@ -153,10 +152,56 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
     }
 }
 
+// K2m: model pre-pass of the generic path, THREAD per (vector, VAR combination), consecutive lanes = consecutive vectors
+// of one combination.  Inside logpost_prep (one warp per vector, lanes over the combinations) a model with a single
+// combination ran its pre-pass on one lane of the warp: the per-year degree-day scan of Vegetation (2 x 1095 rows) was
+// 72 000 warp-instructions per vector, 0.80 ms of a 1.2 ms step at 4096 vectors.  Runs after logpost_prep on the same
+// stream: ORs its flag into the status word written there.
+#define PREPM_BLOCK 64
+__global__ void __launch_bounds__(PREPM_BLOCK) logpost_prep_model(DevProblem p, const double* __restrict__ x, int K, int comp,
+                                                                  const double* __restrict__ delta, double* __restrict__ tab,
+                                                                  int* __restrict__ status, double* __restrict__ dpar) {
+    const long long t = (long long)blockIdx.x * PREPM_BLOCK + threadIdx.x;
+    if (t >= (long long)K * p.nCombo) return;
+    const int c = (int)(t % K), k = (int)(t / K);
+    const size_t base = (size_t)c * p.P;
+    const double dl = (comp >= 0) ? delta[c] : 0.0;
+    double th[BAM_MAXTHETA], der[BAM_MAXDER];
+    const double* xc[BAM_MAXX];
+    for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
+    double* cr = tab + (size_t)c * p.tabStride + p.tabCombo + (size_t)k * p.comboStride;
+    for (int i = 0; i < p.ntheta; ++i) {  // ApplyModel_BaM theta expansion (:4133-4159)
+        const int src = p.comboSrc[(size_t)k * p.ntheta + i];
+        th[i] = (src < 0) ? p.fixv[i] : xval(x, base, src, comp, dl);
+        cr[i] = th[i];
+    }
+    for (int d = 0; d < p.nDer; ++d) der[d] = p.unfeas;
+    const bool ok = model_prepare(p, th, der, xc, p.n);
+    if (p.isSeries) der[0] = (double)c;  // this vector's column of the series buffer (model_apply looks it up)
+    if (!ok) atomicOr(&status[c], ST_LKH_INFEAS);
+    for (int d = 0; d < p.nDer; ++d) cr[p.ntheta + d] = der[d];
+    if (dpar != nullptr)
+        for (int d = 0; d < p.nDparModel; ++d) dpar[(size_t)c * p.nDpar + k * p.nDparModel + d] = ok ? der[d] : p.unfeas;
+}
+
 using PrepKernel = void (*)(DevProblem, const double*, int, int, const double*, double*, double*, int*, double*);
 static PrepKernel pick_prep(const DevProblem& p) {
     if (p.model == BAMGPU_MDL_BARATIN && p.ncontrol <= 4 && p.ntheta <= 12 && p.nDer <= 8) return logpost_prep<BAMGPU_MDL_BARATIN>;
     return logpost_prep<0>;
+}
+// K2 (+ K2m for the generic instance); returns the number of launches
+static int launch_prep_on(cudaStream_t stream, const DevProblem& p, int K, const double* d_x, int comp, const double* d_delta,
+                          double* tab, double* prior, int* status, double* dpar) {
+    PrepKernel k = pick_prep(p);
+    k<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), stream>>>(
+        p, d_x, K, comp, d_delta, tab, prior, status, dpar);
+    if (k != logpost_prep<0>) return 1;
+    const long long nt = (long long)K * p.nCombo;
+    logpost_prep_model<<<(unsigned)((nt + PREPM_BLOCK - 1) / PREPM_BLOCK), PREPM_BLOCK, 0, stream>>>(p, d_x, K, comp, d_delta, tab, status, dpar);
+    return 2;
+}
+static int launch_prep(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta) {
+    return launch_prep_on(h->stream, h->dp, K, d_x, comp, d_delta, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1165,7 +1210,7 @@ void ensure_chain_capacity(bamgpu_handle* h, int K) {
     make_plan(h, K);
     BAM_CUDA(cudaMalloc(&h->d_x, sizeof(double) * (size_t)K * p.P));
     BAM_CUDA(cudaMalloc(&h->d_tab, sizeof(double) * (size_t)K * p.tabStride));
-    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * (std::max(std::max(h->plan.nTiles, (h->dp.n + 63) / 64), 1) + p.nCombo)));
+    BAM_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * (size_t)K * (std::max(std::max(std::max(h->plan.nTiles, (h->dp.n + 63) / 64), logpost_chain_tiles(h->dp.n)), 1) + p.nCombo)));
     if (p.nCombo <= BAM_FP_MAXCOMBO) {
         BAM_CUDA(cudaMalloc(&h->d_lkCcur, sizeof(double) * (size_t)K * p.nCombo));
         BAM_CUDA(cudaMalloc(&h->d_lkCcand, sizeof(double) * (size_t)K * p.nCombo));
@@ -1200,7 +1245,7 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
     DevProblem p = p0;
     p.X = d_xtrue;
     p.n = n;
-    pick_prep(p)<<<1, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(p, d_x1, 1, -1, nullptr, tab, prior, status, dpar);
+    launch_prep_on(h->stream, p, 1, d_x1, -1, nullptr, tab, prior, status, dpar);
     double* d_idx = nullptr;
     if (p.isSeries) {  // the series of this one vector (outputs + states), then the lookup kernel on the row indices
         const int nOut = p.nY + model_nstate(p.model);
@@ -1227,9 +1272,7 @@ int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const do
 
 // only K2: the per-chain tables (gamma, biases, expanded theta + derived values) of the vectors at d_x
 void launch_table(bamgpu_handle* h, int K, const double* d_x) {
-    pick_prep(h->dp)<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(h->dp.kM, 1), h->stream>>>(
-        h->dp, d_x, K, -1, nullptr, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
-    h->launches += 1;
+    h->launches += launch_prep(h, K, d_x, -1, nullptr);
     BAM_CUDA(cudaGetLastError());
 }
 
@@ -1241,8 +1284,7 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
     FastKernel fast = (p.n > 0 && !h->forceGeneric) ? pick_fast(p, K) : nullptr;
     cudaEvent_t p0 = nullptr;
     if (timeMain && h->recordKernels && h->prepEv.size() < 8192) { p0 = take_event(h); BAM_CUDA(cudaEventRecord(p0, h->stream)); }
-    pick_prep(p)<<<(K + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, sizeof(double) * PREP_WARPS * std::max(p.kM, 1), h->stream>>>(
-        p, d_x, K, comp, d_delta, h->d_tab, h->d_prior, h->d_status, h->d_dpar);
+    h->launches += launch_prep(h, K, d_x, comp, d_delta) - 1;  // (the first launch is counted with the step below)
     if (p0) { cudaEvent_t p1 = take_event(h); BAM_CUDA(cudaEventRecord(p1, h->stream)); h->prepEv.emplace_back(p0, p1); }
     DevProblem pser = p;
     if (p.isSeries && p.n > 0) {  // time-recursive model: the outputs of all K vectors, then the generic likelihood kernel
@@ -1354,6 +1396,8 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         nTiles = (p.n + BAM_BLOCK * LL_OPT - 1) / (BAM_BLOCK * LL_OPT);
         dim3 grid((K + LL_CT - 1) / LL_CT, nTiles);
         lk<<<grid, BAM_BLOCK, 0, h->stream>>>(p, d_x, K, h->d_tab, h->d_status, h->d_part, h->d_status);
+    } else if (int ct = launch_logpost_chain(h, pser, K, comp)) {
+        nTiles = ct;
     } else if (p.n > 0) {
         if (pl.smem > 48 * 1024) BAM_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         dim3 grid(pl.nTiles, (K + pl.CT - 1) / pl.CT);

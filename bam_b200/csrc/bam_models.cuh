@@ -394,56 +394,131 @@ __device__ inline bool vegetation_prepare(const DevProblem& p, const double* th,
     for (int i = 0; i < nYear; ++i) der[1 + i] = BAMGPU_UNDEF_RN;
     if (Te <= Tb) return false;
     const double *time = xc[0], *Traw = xc[2], *Tsmooth = xc[3];
+    // The reference scans the whole series once per year (Apply_growth :420-532).  Here ONE sweep serves all years: the
+    // running state of the year being visited (degree-day sum, previous time, first crossings) lives in registers and is
+    // parked in that year's der slots when the series moves to another year, so every year still sees its own rows in
+    // order of appearance with the same arithmetic -- nser iterations instead of nYear x nser.
+    // parked state of year i: yr[0] t_b, yr[1] t_e, yr[2] degree-day sum, yr[3] previous time (= last time once the year has
+    // a row), yr[4] flags (1 crossed T_b, 2 crossed T_e, 4 crossed T_m, 8 has rows), der[1+i] t_m
     for (int i = 0; i < nYear; ++i) {
-        // pass 1: degree-day sum in order of appearance; first crossings of T_b, T_e (and of T_m for Yin1)
-        double cumul = 0.0, prev = (double)i, time_b = 0.0, time_e = 0.0, time_m = 0.0, last = 0.0;
-        bool gotB = false, gotE = false, gotM = false;
-        int m = 0;
-        for (int j = 0; j < nser; ++j) {
-            const double tj = time[j];
-            if (floor(tj) != (double)i) continue;
-            const double tr = Traw[j];
+        double* yr = der + 1 + nYear + 5 * i;
+        yr[0] = 0.0; yr[1] = 0.0; yr[2] = 0.0; yr[3] = (double)i; yr[4] = 0.0;
+        der[1 + i] = 0.0;
+    }
+    const bool yin1 = p.vegGrowth == BAMGPU_VEG_YIN1;
+    {
+        int cy = -1;
+        double cumul = 0.0, prev = 0.0, time_b = 0.0, time_e = 0.0, time_m = 0.0;
+        unsigned fl = 0u;
+        const double Tm1 = yin1 ? par[3] : 0.0;
+        // one row of the year in registers: the loop-carried chain is the degree-day sum alone (one fused add per row)
+        auto step = [&](double tj, double tr, double ts) {
             if (tr >= Tmin) cumul = cumul + 365.0 * (tj - prev) * (tr - Tmin);
             prev = tj;
-            last = tj;
-            ++m;
-            if (!gotB && cumul >= Tb) { gotB = true; time_b = tj; }
-            if (!gotE && cumul >= Te) { gotE = true; time_e = tj; }
-            if (p.vegGrowth == BAMGPU_VEG_YIN1 && !gotM && Tsmooth[j] >= par[3]) { gotM = true; time_m = tj; }
+            fl |= 8u;
+            if (!(fl & 1u) && cumul >= Tb) { fl |= 1u; time_b = tj; }
+            if (!(fl & 2u) && cumul >= Te) { fl |= 2u; time_e = tj; }
+            if (yin1 && !(fl & 4u) && ts >= Tm1) { fl |= 4u; time_m = tj; }
+        };
+        auto row = [&](double tj, double tr, double ts) {  // any row: switch the register state to its year first
+            const double fy = floor(tj);
+            if (!(fy >= 0.0 && fy < (double)nYear)) return;
+            const int iy = (int)fy;
+            if (iy != cy) {
+                if (cy >= 0) {
+                    double* yr = der + 1 + nYear + 5 * cy;
+                    yr[0] = time_b; yr[1] = time_e; yr[2] = cumul; yr[3] = prev; yr[4] = (double)fl;
+                    der[1 + cy] = time_m;
+                }
+                const double* yr = der + 1 + nYear + 5 * iy;
+                time_b = yr[0]; time_e = yr[1]; cumul = yr[2]; prev = yr[3]; fl = (unsigned)yr[4];
+                time_m = der[1 + iy];
+                cy = iy;
+            }
+            step(tj, tr, ts);
+        };
+        int j = 0;
+        // four rows per trip: the loads and the year tests of the four are independent, so their latencies overlap; rows
+        // of the year already in registers (the usual case: a series in time order) skip the state switch
+        for (; j + 4 <= nser; j += 4) {
+            const double t0 = time[j], t1 = time[j + 1], t2 = time[j + 2], t3 = time[j + 3];
+            const double r0 = Traw[j], r1 = Traw[j + 1], r2 = Traw[j + 2], r3 = Traw[j + 3];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (yin1) { s0 = Tsmooth[j]; s1 = Tsmooth[j + 1]; s2 = Tsmooth[j + 2]; s3 = Tsmooth[j + 3]; }
+            const double cyd = (double)cy;
+            if (cy >= 0 && floor(t0) == cyd && floor(t1) == cyd && floor(t2) == cyd && floor(t3) == cyd) {
+                step(t0, r0, s0); step(t1, r1, s1); step(t2, r2, s2); step(t3, r3, s3);
+            } else {
+                row(t0, r0, s0); row(t1, r1, s1); row(t2, r2, s2); row(t3, r3, s3);
+            }
         }
-        if (m == 0) return false;  // "empty year": an error in the reference (:432-436); checked on the host where possible
-        if (!gotE) return false;
+        for (; j < nser; ++j) row(time[j], Traw[j], yin1 ? Tsmooth[j] : 0.0);
+        if (cy >= 0) {
+            double* yr = der + 1 + nYear + 5 * cy;
+            yr[0] = time_b; yr[1] = time_e; yr[2] = cumul; yr[3] = prev; yr[4] = (double)fl;
+            der[1 + cy] = time_m;
+        }
+    }
+    // per year, in year order with the reference's exits: growth-curve constants; t_m parked in der[1+i] for the second sweep
+    unsigned need = 0u;
+    bool ok = true;
+    for (int i = 0; i < nYear && ok; ++i) {
         double* yr = der + 1 + nYear + 5 * i;
-        yr[0] = time_b; yr[1] = time_e; yr[2] = 0.0; yr[3] = 0.0; yr[4] = gotB ? 0.0 : 1.0;
+        const double time_b = yr[0], time_e = yr[1], last = yr[3];
+        const unsigned fl = (unsigned)yr[4];
+        double time_m = der[1 + i];
+        der[1 + i] = BAMGPU_UNDEF_RN;
+        if (!(fl & 8u)) { ok = false; break; }  // "empty year": an error in the reference (:432-436); checked on the host where possible
+        if (!(fl & 2u)) { ok = false; break; }
+        const bool gotB = (fl & 1u) != 0u;
+        yr[2] = 0.0; yr[3] = 0.0; yr[4] = gotB ? 0.0 : 1.0;
         if (!gotB) continue;  // no growth this year
         double alpha, time_f;
-        if (p.vegGrowth == BAMGPU_VEG_YIN1) {
-            if (!gotM) return false;
+        if (yin1) {
+            if (!(fl & 4u)) { ok = false; break; }
             if (time_m <= time_b) time_m = time_b;
-            if (time_m >= time_e) return false;
+            if (time_m >= time_e) { ok = false; break; }
             alpha = (time_e - time_b) / (time_e - time_m);
             time_f = 2.0 * time_e - time_m;
         } else if (p.vegGrowth == BAMGPU_VEG_YIN2) {
-            if (par[3] <= 0.0) return false;
+            if (par[3] <= 0.0) { ok = false; break; }
             alpha = par[3];
             time_f = time_e + (time_e - time_b) / alpha;
             time_m = ((alpha - 1.0) * time_f + 2.0 * time_b) / (alpha + 1.0);
         } else {
-            if (par[3] <= 0.0) return false;
+            if (par[3] <= 0.0) { ok = false; break; }
             time_f = time_e + par[3];
             alpha = (time_e - time_b) / (time_f - time_e);
             time_m = ((alpha - 1.0) * time_f + 2.0 * time_b) / (alpha + 1.0);
         }
         if (time_m < time_b) time_m = time_b;
-        if (alpha <= 0.0 || time_m >= time_e || time_f > last) return false;
+        if (alpha <= 0.0 || time_m >= time_e || time_f > last) { ok = false; break; }
         yr[2] = time_f; yr[3] = alpha;
-        // pass 2: optimal temperature = smoothed temperature at the first point with time >= t_m
-        for (int j = 0; j < nser; ++j) {
-            const double tj = time[j];
-            if (floor(tj) != (double)i) continue;
-            if (tj >= time_m) { der[1 + i] = Tsmooth[j]; break; }
-        }
+        der[1 + i] = time_m;
+        need |= 1u << i;
     }
+    if (!ok) {
+        for (int i = 0; i < nYear; ++i)
+            if ((need >> i) & 1u) der[1 + i] = BAMGPU_UNDEF_RN;
+        return false;
+    }
+    // second sweep: optimal temperature = smoothed temperature at the first point of the year with time >= t_m
+    {
+        auto look = [&](double tj, int j) {
+            const double fy = floor(tj);
+            if (!(fy >= 0.0 && fy < (double)nYear)) return;
+            const int iy = (int)fy;
+            if (((need >> iy) & 1u) && tj >= der[1 + iy]) { der[1 + iy] = Tsmooth[j]; need &= ~(1u << iy); }
+        };
+        int j = 0;
+        for (; j + 4 <= nser && need != 0u; j += 4) {
+            const double t0 = time[j], t1 = time[j + 1], t2 = time[j + 2], t3 = time[j + 3];
+            look(t0, j); look(t1, j + 1); look(t2, j + 2); look(t3, j + 3);
+        }
+        for (; j < nser && need != 0u; ++j) look(time[j], j);
+    }
+    for (int i = 0; i < nYear; ++i)
+        if ((need >> i) & 1u) der[1 + i] = BAMGPU_UNDEF_RN;
     return true;
 }
 

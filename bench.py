@@ -540,7 +540,7 @@ def other_models_leg(device, fp64_peak, hbm_peak, steps=10):
     try:
         prob, truth = synth.vegetation(nobs=1095, growth="Growth_Yin3", nY=5)
         x = synth.feasible_starts(truth, 4096, rel=0.002, seed=synth.SEED + 22)
-        run("vegetation_yin3", prob, x, 60 + 5 * 14, 0.0, "logpost_main<Vegetation,4,5>")
+        run("vegetation_yin3", prob, x, 60 + 5 * 14, 0.0, "logpost_chain<Vegetation,4,5> (thread = chain)")
     except Exception as e:
         out["vegetation_yin3"] = {"error": str(e)}
     return out

@@ -309,3 +309,93 @@ def test_time_recursive_algae_biomass():
     with pytest.raises(BamError) as e:
         BamGpu(bad)
     assert "Irradiance<0" in str(e.value)
+
+
+def _bias_problem():
+    """Linear model, 2 inputs x 2 outputs, X and Y biases, missing Y values, no latent inputs."""
+    from bam_b200.capi import Problem
+
+    rng = np.random.default_rng(8)
+    n = 333
+    X = rng.uniform(1.0, 5.0, (n, 2))
+    th = np.array([1.5, -0.7, 0.4, 2.0])
+    Y = np.column_stack([X @ th[:2], X @ th[2:]]) + 0.1 * rng.standard_normal((n, 2))
+    Y[5, 1] = -9999.0
+    Y[300, 0] = -9999.0
+    Xbindx = rng.integers(0, 3, (n, 2))
+    Xb = np.where(Xbindx > 0, 0.02, 0.0)
+    Ybindx = rng.integers(0, 3, (n, 2))
+    Yb = np.where(Ybindx > 0, 0.05, 0.0)
+    prob = Problem("Linear", X, Y, Yu=np.full((n, 2), 0.05), Xb=Xb, Xbindx=Xbindx, Yb=Yb, Ybindx=Ybindx, partype=[0] * 4,
+                   priors_theta=[("Gaussian", [t, 1.0]) for t in th], sigma_func=["Linear", "Constant"],
+                   priors_gamma=[("Uniform", [0, 10]), ("Uniform", [0, 10]), ("Uniform", [0, 10])])
+    o = Oracle(prob)
+    start = np.concatenate([th, [0.1, 0.02, 0.1], np.zeros(o.P - 7)])
+    return prob, start
+
+
+CHAIN_CASES = ["vegetation", "vegetation_var", "bias", "SWOT", "SuspendedLoad", "Orthorectification", "textfile", "sfdtidal",
+               "mixture", "baratin_spd_yu0"]
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES)
+def test_chain_parallel_generic_kernel(case):
+    """logpost_chain (thread <-> chain, K >= 1024, no latent inputs): against the oracle, against the observation-parallel
+    kernel, ragged last block, infeasible chains, and a chain's value independent of the chains it is launched with."""
+    K = 1100
+    tol = 1e-12
+    if case == "vegetation":
+        prob, truth = synth.vegetation(nobs=400, growth="Growth_Yin3", nY=5)
+        x = synth.feasible_starts(truth, K, rel=0.002, seed=3)
+    elif case == "vegetation_var":
+        prob, truth = synth.vegetation(nobs=400, var_gmax=True)
+        x = synth.feasible_starts(truth, K, rel=0.002, seed=3)
+    elif case == "bias":
+        prob, start = _bias_problem()
+        rng = np.random.default_rng(6)
+        x = np.tile(start, (K, 1)) * (1.0 + 0.01 * rng.standard_normal((K, start.size)))
+        x[:, 7:] = 0.3 * rng.standard_normal((K, start.size - 7))
+        x[9, 4] = -0.5  # gamma1 < 0 under a Uniform(0, 10) prior: null prior
+    elif case == "textfile":
+        from bam_b200.capi import Problem
+
+        rng = np.random.default_rng(12)
+        n = 450
+        T, S = rng.uniform(5.0, 50.0, n), rng.uniform(0.5, 2.0, n)
+        a, b, c = 2.0, 0.3, 1.4
+        Yh = a * T**c + b * np.exp(-S) * np.log(T)
+        Y = Yh * (1.0 + 0.05 * rng.standard_normal(n))
+        text = "2\nT,S\n3\na,b,c\n1\na*T^c+b*exp(-S)*log(T)\n"
+        prob = Problem("TextFile", np.column_stack([T, S]), Y, Yu=np.full(n, 0.5), partype=[0, 0, 0],
+                       priors_theta=[("Gaussian", [0, 10])] * 3, sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 100])] * 2,
+                       xtra_text=text)
+        x = synth.feasible_starts(np.array([a, b, c, 0.5, 0.05]), K, rel=0.01, seed=3)
+    elif case == "sfdtidal":
+        prob, truth = synth.sfdtidal_qmec(nobs=300)
+        x = synth.feasible_starts(truth, K, rel=0.01, seed=3)
+        x[4, 1] = 3.0
+        tol = 1e-11
+    elif case == "mixture":
+        prob, truth = synth.mixture()
+        x = synth.feasible_starts(truth, K, rel=0.01, seed=3)
+    elif case == "baratin_spd_yu0":
+        prob, truth = synth.baratin_spd(nobs=700)
+        prob.Yu[3, 0] = 0.0  # a zero Yu keeps the BaRatin fast path out: generic kernels
+        x = synth.feasible_starts(truth, K, rel=0.01, seed=3, check=synth.spd_start_check)
+    else:
+        kw = dict(variant="SWOT_hSB") if case == "SWOT" else (dict(disto_npar=2) if case == "Orthorectification" else {})
+        prob, truth = synth.second_wave(case, nobs=500, **kw)
+        x = synth.feasible_starts(truth, K, rel=0.01, seed=3)
+    if case not in ("bias", "mixture"):
+        x[3, 0] = -abs(x[3, 0]) - 1.0
+    check_parity(prob, x, tol=tol, floor=float(prob.nobs) * 1e-3)
+    g, g2 = BamGpu(prob), BamGpu(prob)
+    g2.set_option("force_generic", 1)
+    a, b = g.logpost(x), g2.logpost(x)
+    assert (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    ok = (a[1] == 1) & (a[2] == 0)
+    assert (np.abs(a[0][ok] - b[0][ok]) <= tol * np.maximum(np.abs(b[0][ok]), prob.nobs * 1e-3)).all()
+    # batch independence: the tiling depends on the number of observations only
+    sub = g.logpost(x[40:40 + 1024])
+    assert (sub[0] == a[0][40:40 + 1024]).all()
+    assert (g.logpost(x)[0] == a[0]).all()
