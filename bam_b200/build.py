@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "build")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "g++"]
-LIB_SOURCES = ["bam_capi.cu", "bam_logpost.cu", "bam_logpost_chain.cu", "bam_sampler.cu", "bam_sampler_warp_a.cu", "bam_sampler_warp_b.cu",
+LIB_SOURCES = ["bam_capi.cu", "bam_logpost.cu", "bam_logpost_chain.cu", "bam_logpost_tile.cu", "bam_sampler.cu", "bam_sampler_warp_a.cu", "bam_sampler_warp_b.cu",
                "bam_sampler_warp_c.cu", "bam_latent.cu", "bam_predict.cu", "bam_comm.cu", "bam_host.cpp"]
 
 

@@ -269,11 +269,12 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         }
         d.comboSrc = upload(h, L.comboSrc.data(), L.comboSrc.size());
         d.latIdx = L.hasLatent ? upload(h, permXI(L.latIdx.data(), L.nX).data(), L.latIdx.size()) : nullptr;  // hasLatent: perm is the identity
-        if (L.hasLatent && (long long)L.nLatent == (long long)L.n * L.nX) {  // chain-independent parts of the hyper term
-            std::vector<double> inv((size_t)L.n * L.nX), hc(L.n, 0.0);
+        if (L.hasLatent && !L.hyperInfeasible) {  // chain-independent parts of the hyper term (cells with Xu = 0 have none)
+            std::vector<double> inv((size_t)L.n * L.nX, 0.0), hc(L.n, 0.0);
             for (int j = 0; j < L.nX; ++j)
                 for (int i = 0; i < L.n; ++i) {
                     const double xu = pb->Xu[xsrc[i] + (size_t)j * L.n];
+                    if (!(xu > 0.0)) continue;
                     inv[i + (size_t)j * L.n] = 1.0 / xu;
                     hc[i] += -BAM_LOG_SQRT_2PI - std::log(xu);
                 }

@@ -50,8 +50,8 @@ struct DevProblem {
     const double2* scTab;   // BAM_SCTAB_N x (cos, sin)(2 pi (j + 0.5) / N)              : Box-Muller angle of the noise
     const int* comboSrc;  // nCombo x ntheta : position in the parameter vector, or -1 for FIX
     const int* latIdx;    // n x nX : position of the latent "true input" in the vector, or -1
-    const double* XuInv;  // n x nX : 1 / Xu          } only when EVERY input cell is latent (logpost_linear_latent),
-    const double* hyC;    // n : sum_j -log sqrt(2 pi) - log Xu(i,j)  } else nullptr
+    const double* XuInv;  // n x nX : 1 / Xu (0 where Xu = 0)                    } problems with latent inputs and no negative Xu,
+    const double* hyC;    // n : sum over the cells with Xu > 0 of -log sqrt(2 pi) - log Xu  } else nullptr
     double fixv[BAM_MAXTHETA];
     int hasLatent, hasXbias, hasYbias, hyperInfeasible, hasMissing;
     int Xerror[BAM_MAXX], nXb[BAM_MAXX], offXb[BAM_MAXX], tabOffXb[BAM_MAXX];

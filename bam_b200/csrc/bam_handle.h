@@ -42,6 +42,7 @@ struct bamgpu_handle {
     // proposal on a VAR parameter only re-evaluates the tiles of the combinations it touches (bam_logpost.cu)
     int fpTobs = 0, fpTiles = 0;
     bool fpYuOk = true;    // every Yu <= 2^86 and |Y| <= 2^100: the group path of logpost_baratin_cb2 multiplies up to five variances (and residuals)
+    size_t tileAttr = 0;   // same for logpost_tile
     size_t chainAttr = 0;  // dynamic shared-memory limit raised for the picked logpost_chain instantiation (bytes)
     bool fp2Attr = false;  // dynamic shared-memory limit of the picked logpost_baratin_cb2 instantiation raised
     int smCount = 148;
@@ -138,6 +139,8 @@ void launch_table(bamgpu_handle* h, int K, const double* d_x);
 // chain-parallel generic likelihood kernel (bam_logpost_chain.cu): tiles written to d_part, 0 = not eligible
 int launch_logpost_chain(bamgpu_handle* h, const DevProblem& p, int K, int comp);
 int logpost_chain_tiles(int n);
+// latent inputs on many observations (bam_logpost_tile.cu): tiles written to d_part, 0 = not eligible
+int launch_logpost_tile(bamgpu_handle* h, const DevProblem& p, int K, const double* d_x, int comp);
 void ensure_series_capacity(bamgpu_handle* h, size_t count);
 void launch_series(bamgpu_handle* h, const DevProblem& p, int K, const double* tab, int stride, int thOff, int* status, int nOut);
 int launch_calibration_run(bamgpu_handle* h, const double* d_x1, int n, const double* d_xtrue, const int* d_combo,

@@ -1396,6 +1396,8 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         nTiles = (p.n + BAM_BLOCK * LL_OPT - 1) / (BAM_BLOCK * LL_OPT);
         dim3 grid((K + LL_CT - 1) / LL_CT, nTiles);
         lk<<<grid, BAM_BLOCK, 0, h->stream>>>(p, d_x, K, h->d_tab, h->d_status, h->d_part, h->d_status);
+    } else if (int tt = launch_logpost_tile(h, pser, K, d_x, comp)) {
+        nTiles = tt;
     } else if (int ct = launch_logpost_chain(h, pser, K, comp)) {
         nTiles = ct;
     } else if (p.n > 0) {

@@ -534,7 +534,7 @@ def other_models_leg(device, fp64_peak, hbm_peak, steps=10):
         rng = np.random.default_rng(2)
         x = np.tile(truth, (64, 1))
         x[:, :4] *= 1.0 + 0.01 * rng.standard_normal((64, 4))
-        run("textfile_twin", prob, x, 2 + 14 + 7, 8.0, "logpost_main<TextFile,1,1>")
+        run("textfile_twin", prob, x, 2 + 14 + 7, 8.0, "logpost_tile<TextFile,1,1> (register-resident sums over observation tiles)")
     except Exception as e:
         out["textfile_twin"] = {"error": str(e)}
     try:

@@ -363,3 +363,65 @@ def test_taylor_subtile_paths_of_the_fast_kernel():
         assert ok.sum() >= 200
         assert (np.abs(fx[0][ok] - fg[0][ok]) <= 1e-12 * np.maximum(np.abs(fg[0][ok]), n * 1e-3)).all()
         assert (g.logpost(x)[0] == fx[0]).all()  # bitwise repeatable (dynamic item order, fixed-order sums)
+
+
+def _baratin_latent_bias(n, seed=5):
+    """BaRatin with X random error on half the gaugings (latent stages), X bias, Y bias, one missing Y."""
+    from bam_b200.capi import Problem
+
+    rng = np.random.default_rng(seed)
+    prob0, truth = synth.baratin_2c(nobs=n, seed=11)
+    Xu = np.where(rng.random(n) < 0.5, 0.02, 0.0).reshape(-1, 1)
+    Xbindx = rng.integers(0, 3, n).reshape(-1, 1)
+    Xb = np.where(Xbindx > 0, 0.01, 0.0)
+    Ybindx = rng.integers(0, 4, n).reshape(-1, 1)
+    Yb = np.where(Ybindx > 0, 0.05 * np.abs(prob0.Y), 0.0)
+    Y = prob0.Y.copy()
+    Y[7, 0] = -9999.0
+    prob = Problem("BaRatin", prob0.X, Y, Yu=prob0.Yu, Xu=Xu, Xb=Xb, Xbindx=Xbindx, Yb=Yb, Ybindx=Ybindx,
+                   partype=[0] * 6, priors_theta=[("Gaussian", [t, abs(t) * 0.2 + 0.1]) for t in truth[:6]],
+                   sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000]), ("LogNormal", [-2.0, 1.0])],
+                   xtra_i=[1, 0, 0, 1])
+    start = np.concatenate([truth, prob0.X[Xu[:, 0] > 0, 0], np.zeros(5)])
+    return prob, start
+
+
+@pytest.mark.parametrize("case", ["textfile", "baratin_bias", "linear_partial"])
+def test_latent_tile_kernel(case):
+    """logpost_tile (latent inputs, n >= 16384: register-resident per-chain sums over a tile of observations) against the
+    oracle and against logpost_main; K = 10 leaves a ragged chain tile; an infeasible and a null vector."""
+    n, K = 20000, 10
+    rng = np.random.default_rng(3)
+    if case == "textfile":
+        prob, truth = synth.textfile_latent(nobs=n)
+        x = perturbed_vectors(truth, K, rel=0.005, seed=10)
+        x[4, 2] = -1.0  # gamma1 < 0: outside its Uniform(0, 100) prior
+    elif case == "baratin_bias":
+        prob, start = _baratin_latent_bias(n)
+        x = perturbed_vectors(start, K, rel=0.01, seed=6)
+        x[:, -5:] = 0.3 * rng.standard_normal((K, 5))
+        x[4, 3] = x[4, 0] - 1.0  # k2 < k1: infeasible rating curve
+    else:
+        from bam_b200.capi import Problem
+
+        X = rng.uniform(1.0, 5.0, (n, 2))
+        Xu = np.column_stack([np.where(rng.random(n) < 0.3, 0.05, 0.0), np.full(n, 0.1)])  # column 0 partly latent
+        th = np.array([1.5, -0.7, 0.4, 2.0])
+        Y = np.column_stack([X @ th[:2], X @ th[2:]]) + 0.1 * rng.standard_normal((n, 2))
+        Y[11, 1] = -9999.0
+        prob = Problem("Linear", X, Y, Yu=np.full((n, 2), 0.05), Xu=Xu, partype=[0] * 4,
+                       priors_theta=[("Gaussian", [t, 1.0]) for t in th], sigma_func=["Constant", "Proportional"],
+                       priors_gamma=[("Uniform", [0, 10]), ("Uniform", [0, 10])])
+        lat = np.concatenate([X[Xu[:, 0] > 0, 0], X[:, 1]])
+        x = perturbed_vectors(np.concatenate([th, [0.1, 0.05], lat]), K, rel=0.01, seed=7)
+        x[4, 4] = -0.5
+    check_parity(prob, x, floor=float(n) * 1e-3)
+    g, g2 = BamGpu(prob), BamGpu(prob)
+    g2.set_option("force_generic", 1)
+    a, b = g.logpost_parts(x), g2.logpost_parts(x)
+    assert (a[3] == b[3]).all() and (a[4] == b[4]).all()
+    ok = (a[3] == 1) & (a[4] == 0)
+    assert ok.sum() >= K - 2
+    for u, v in ((a[1], b[1]), (a[2], b[2])):  # likelihood, hyper
+        assert (np.abs(u[ok] - v[ok]) <= 1e-12 * np.maximum(np.abs(v[ok]), n * 1e-3)).all()
+    assert (g.logpost(x[3:9])[0] == g.logpost(x)[0][3:9]).all()  # a chain's value does not depend on its tile mates
