@@ -420,7 +420,7 @@ def vegetation_prediction_leg(device, Nrep=10_000_000, nobs=1095, steps=1):
             "finite": bool(np.isfinite(g.predict_download()).all())}
 
 
-def small_sampler_leg(device):
+def small_sampler_leg(device, cpu=True):
     """configs[0]: the reference's own tests/BaM_BaRatin workspace (38 gaugings, P = 8), adaptive Metropolis with the
     persistent warp-per-chain kernel; K = 1 is like-for-like with the reference's single chain."""
     from bam_b200.capi import BamGpu
@@ -439,6 +439,35 @@ def small_sampler_leg(device):
         nprop = K * 100 * nC * g.P
         out[f"K{K}"] = {"iterations": 100 * nC, "ms": ms, "proposals_per_s": nprop / (ms * 1e-3),
                         "chain_obs_per_s": nprop * prob.nobs / (ms * 1e-3)}
+    if cpu:  # the same single chain through the oracle on ONE host core (the reference's own mode of operation)
+        import time
+        from oracle.oracle_api import Oracle
+
+        o = Oracle(prob)
+        s = np.tile(np.asarray(d["start"]), (1, 1))
+        sd = 0.1 * np.abs(s)
+        t0 = time.perf_counter()
+        o.fit(s, sd, nAdapt=100, nCycles=50, seed=3)
+        dt = time.perf_counter() - t0
+        v = 100 * 50 * o.P / dt
+        out["cpu_1core"] = {"kind": "port", "proposals_per_s": v, "seconds": dt,
+                            "note": "38 gaugings per evaluation: a single GPU chain is a serial latency chain and does NOT beat a "
+                                    "CPU core here; the GPU's case is many chains (K4096) or many observations (small_k)"}
+        out["K1"]["vs_cpu_1core"] = out["K1"]["proposals_per_s"] / v
+        out["K4096"]["vs_cpu_1core"] = out["K4096"]["proposals_per_s"] / v
+    return out
+
+
+def small_k_leg(g, x, n, steps=10):
+    """configs[1] problem (100 000 gaugings) with FEW chains: one resident log-posterior step at K = 1, 8, 64 (launch
+    latency and tail bound; the headline configuration is K = 4096)."""
+    out = {"workload": f"BaRatin_SPD log-posterior, {n} gaugings, K = 1 / 8 / 64 chains (resident, L2 flushed between steps)"}
+    for K in (1, 8, 64):
+        g.chains_upload(x[:K])
+        for _ in range(3):
+            g.logpost_resident()
+        ms, km, pm, fm = timed_resident_logpost(g, steps)
+        out[f"K{K}"] = {"ms_per_step": float(ms.mean()), "value": K * n / (float(ms.mean()) * 1e-3), "unit": UNIT}
     return out
 
 
@@ -961,9 +990,14 @@ def main():
         except Exception as e:
             line["sampler_cfg2"] = {"error": str(e)}
         try:
-            line["sampler_small"] = small_sampler_leg(device)
+            line["sampler_small"] = small_sampler_leg(device, cpu=not args.no_cpu)
         except Exception as e:
             line["sampler_small"] = {"error": str(e)}
+        try:
+            line["small_k"] = small_k_leg(g, x, n)
+            g.chains_upload(x)
+        except Exception as e:
+            line["small_k"] = {"error": str(e)}
         try:
             line["latent_logpost"] = latent_logpost_leg(device, hbm_peak)
         except Exception as e:
@@ -978,6 +1012,11 @@ def main():
             line["logpost_other_models"] = {"error": str(e)}
     if not args.no_cpu and world == 1:  # last: the OpenMP team of the oracle must not compete with the launch thread above
         line["cpu_baseline"] = cpu_baseline(prob, x)
+        v1 = line["cpu_baseline"].get("value_1core")
+        if v1 and isinstance(line.get("small_k"), dict):
+            for kk, e in line["small_k"].items():
+                if isinstance(e, dict) and "value" in e:
+                    e["vs_cpu_1core"] = e["value"] / v1
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
