@@ -614,10 +614,10 @@ int bamgpu_predict_upload(bamgpu_t* h, int64_t Nrep, const double* mc, const dou
             for (int i = 0; i < p.nX; ++i)
                 BAM_CUDA(cudaMemcpyAsync(h->d_seriesXpred + (size_t)i * nobs_pred, xspag[i], sizeof(double) * nobs_pred,
                                          cudaMemcpyHostToDevice, h->stream));
-            if (p.model == BAMGPU_MDL_ALGAE) {  // AlgaeBiomass_Apply's input checks: a fatal error, as in the reference (:79-99)
+            if (p.model == BAMGPU_MDL_ALGAE || p.model == BAMGPU_MDL_DYNVEG) {  // AlgaeBiomass_Apply's input checks: a fatal error, as in the reference (:79-99)
                 std::vector<double> all((size_t)nobs_pred * p.nX);
                 for (int i = 0; i < p.nX; ++i) std::copy(xspag[i], xspag[i] + nobs_pred, all.begin() + (size_t)i * nobs_pred);
-                if (const char* bad = bam::algae_input_error(nobs_pred, all.data())) throw bam::CudaError{bad};
+                if (const char* bad = bam::algae_input_error(nobs_pred, all.data(), p.model == BAMGPU_MDL_ALGAE)) throw bam::CudaError{bad};
             }
             mbuf.resize(nobs_pred);
             for (int r = 0; r < nobs_pred; ++r) mbuf[r] = (double)r;  // column 0 of the pointwise kernels = row index

@@ -12,10 +12,11 @@
 namespace bam {
 
 // AlgaeBiomass_Apply's input checks (AlgaeBiomass_model.f90:79-99): a fatal error (err = 1), not an infeasible vector
-const char* algae_input_error(int n, const double* X) {
+// (checkDepth = false for DynamicVegetation, whose third input is a stage: the depth handed on is max(stage - b1, 0))
+const char* algae_input_error(int n, const double* X, bool checkDepth) {
     for (int i = 0; i < n; ++i) {
         if (X[i + (size_t)1 * n] < 0.0) return "AlgaeBiomass_Apply:Irradiance<0 impossible";
-        if (X[i + (size_t)2 * n] < 0.0) return "AlgaeBiomass_Apply:depth<0 impossible";
+        if (checkDepth && X[i + (size_t)2 * n] < 0.0) return "AlgaeBiomass_Apply:depth<0 impossible";
         if (X[i + (size_t)3 * n] < 0.0) return "AlgaeBiomass_Apply:turbidity<0 impossible";
         if (X[i + (size_t)4 * n] < 0.0) return "AlgaeBiomass_Apply:removal<0 impossible";
         if (X[i + (size_t)4 * n] > 1.0) return "AlgaeBiomass_Apply:removal>1 impossible";
@@ -49,6 +50,7 @@ int model_from_name(const char* name) {
     if (s == "SFDTidal_Qmec") return BAMGPU_MDL_SFDTIDAL_QMEC;
     if (s == "SFDTidal_Qmec2") return BAMGPU_MDL_SFDTIDAL_QMEC2;
     if (s == "AlgaeBiomass") return BAMGPU_MDL_ALGAE;
+    if (s == "DynamicVegetation") return BAMGPU_MDL_DYNVEG;
     return 0;
 }
 
@@ -574,6 +576,16 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             if (nt != 18 || nX != 5 || nY != 2) { mess = "AlgaeBiomass_Apply: wrong size [theta], nX or nY"; return 1; }
             if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: AlgaeBiomass is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
             if (const char* bad = bam::algae_input_error(p.nobs, p.X)) { mess = bad; return 1; }  // err = 1 in the reference (:79-99)
+            L.nState = 5;
+            L.isSeries = true;
+            break;
+        case BAMGPU_MDL_DYNVEG:  // DynamicVegetation_GetParNumber: 18 + 4 + 2 (DynamicVegetation_model.f90:27-30,68-71); XtraRead :193-247; 5 states (ModelLibrary_tools.f90:703-707)
+            if (p.n_xtra_i != 1 || p.n_xtra_d != 4) { mess = "DynamicVegetation_XtraRead:problem reading xtra"; return 1; }
+            if (nt != 24 || nX != 5 || nY != 3) { mess = "DynamicVegetation_Apply: wrong size [theta], nX or nY"; return 1; }
+            if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: DynamicVegetation is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
+            if (const char* bad = bam::algae_input_error(p.nobs, p.X, false)) { mess = bad; return 1; }
+            L.vegItmax = p.xtra_i[0];
+            for (int i = 0; i < 4; ++i) L.vegOpt[i] = p.xtra_d[i];  // xscale, fscale, tolX, tolF
             L.nState = 5;
             L.isSeries = true;
             break;

@@ -78,7 +78,7 @@ int sigmafunc_npar(int f);
 int prior_corr_to_M(int k, const double* C, double* M, std::string& mess);
 
 // Gelman-Rubin from per-chain moments
-const char* algae_input_error(int n, const double* X);  // n x 5 column-major; NULL = fine
+const char* algae_input_error(int n, const double* X, bool checkDepth = true);  // n x 5 column-major; NULL = fine
 void rhat_from_moments(int K, int P, const double* count, const double* mean, const double* m2, double* rhat);
 
 }  // namespace bam

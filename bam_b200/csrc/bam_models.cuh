@@ -988,8 +988,13 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
 // out[(y * n + t) * K]: y = 0 biomass, 1 biomass / bmax, then the states Fb, Ft, Fi, Fn, Rhyd.
 // -------------------------------------------------------------------------------------------
 #define BAM_EPSRE 2.2204460492503131e-16 /* DMSL epsRe (un-vendored): declared = epsilon(1._mrk) */
-__device__ inline bool algae_series(int n, const double* __restrict__ X, const double* __restrict__ th, double* __restrict__ out,
-                                    size_t K, int nOut) {
+// DYN: DynamicVegetation_Apply (DynamicVegetation_model.f90:74-191) = the same recursion on depth = max(stage - b1, 0)
+// (:137-138) with the discharge of the vegetation-affected rating curve in front of the outputs (:147-189): rows Q,
+// biomass, biomass / bmax, then the states.  A time step whose Newton search fails is an infeasible ROW (feas(t), :171-182),
+// stored as NaN and turned back into a row flag by model_apply.
+template <bool DYN>
+__device__ inline bool algae_series(const DevProblem& p, int n, const double* __restrict__ X, const double* __restrict__ th,
+                                    double* __restrict__ out, size_t K, int nOut) {
     const double dt = th[0], b0 = th[1], bmin = th[2], bmax = th[3], mu0 = th[4], Tmin = th[5], Topt = th[6], Tmax = th[7],
                  Iopt = th[8], katt = th[9], kcw = th[10], Rsen = th[11], g = th[12], rho = th[13], J = th[14], tau0 = th[15],
                  bHyd = th[16], cHyd = th[17];
@@ -998,9 +1003,19 @@ __device__ inline bool algae_series(int n, const double* __restrict__ X, const d
         bHyd < 0.0 || cHyd < 0.0)
         return false;  // :140-146
     const double Texp = __ddiv_rn(__dsub_rn(Topt, Tmin), __dsub_rn(Tmax, Topt));
-    const double *temp = X, *irr = X + n, *depth = X + 2 * (size_t)n, *turb = X + 3 * (size_t)n, *rem = X + 4 * (size_t)n;
+    const double *temp = X, *irr = X + n, *depthIn = X + 2 * (size_t)n, *turb = X + 3 * (size_t)n, *rem = X + 4 * (size_t)n;
+    constexpr int Y0 = DYN ? 1 : 0, NYS = DYN ? 3 : 2;  // first biomass row, first state row
+    const double B = DYN ? th[18] : 0.0, n1 = DYN ? th[19] : 0.0, b1 = DYN ? th[20] : 0.0, c1 = DYN ? th[21] : 0.0,
+                 chi = DYN ? th[22] : 0.0, U_chi = DYN ? th[23] : 0.0;
+    const double kQ0 = DYN ? (B * sqrt(J)) / n1 : 0.0;                       // S0 = theta(iS0) = the slope J of the biomass budget (:30,:131)
+    const double kG2 = DYN ? pow(B, chi) * pow(U_chi, chi) : 0.0;           // parameter-only factor of gamma2
     double bt = b0;
     for (int t = 0; t < n; ++t) {
+        double dep = depthIn[t];
+        if (DYN) {
+            dep = __dsub_rn(dep, b1);
+            if (dep <= 0.0) dep = 0.0;
+        }
         const double Fb = __dsub_rn(1.0, __ddiv_rn(bt, bmax));
         double Ft = 0.0;
         const double T = temp[t];
@@ -1008,11 +1023,11 @@ __device__ inline bool algae_series(int n, const double* __restrict__ X, const d
             Ft = __dmul_rn(__ddiv_rn(__dsub_rn(Tmax, T), __dsub_rn(Tmax, Topt)), pow(__ddiv_rn(__dsub_rn(T, Tmin), __dsub_rn(Topt, Tmin)), Texp));
             if (Ft <= BAM_EPSRE) Ft = 0.0;
         }
-        const double iz = __dmul_rn(irr[t], exp(__dmul_rn(-__dadd_rn(__dmul_rn(katt, turb[t]), kcw), depth[t])));
+        const double iz = __dmul_rn(irr[t], exp(__dmul_rn(-__dadd_rn(__dmul_rn(katt, turb[t]), kcw), dep)));
         const double Ir = __ddiv_rn(iz, Iopt);
         const double Fi = __dmul_rn(Ir, exp(__dsub_rn(1.0, Ir)));
         const double Fn = 1.0;
-        const double tau = __dmul_rn(__dmul_rn(__dmul_rn(depth[t], g), J), rho);
+        const double tau = __dmul_rn(__dmul_rn(__dmul_rn(dep, g), J), rho);
         const double Rh = (tau <= tau0) ? 0.0 : __dmul_rn(cHyd, pow(__ddiv_rn(__dsub_rn(tau, tau0), tau0), bHyd));
         const double grow = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(mu0, Fb), Ft), Fi), Fn), bt), dt);
         const double loss = __dmul_rn(__dmul_rn(__dadd_rn(__dadd_rn(Rsen, rem[t]), Rh), __dsub_rn(bt, bmin)), dt);
@@ -1020,14 +1035,28 @@ __device__ inline bool algae_series(int n, const double* __restrict__ X, const d
         b = fmin(b, bmax);
         b = fmax(b, bmin);
         bt = b;
-        out[(size_t)t * K] = b;
-        if (nOut > 1) out[((size_t)n + t) * K] = __ddiv_rn(b, bmax);
-        if (nOut > 2) {
-            out[((size_t)2 * n + t) * K] = Fb;
-            out[((size_t)3 * n + t) * K] = Ft;
-            out[((size_t)4 * n + t) * K] = Fi;
-            out[((size_t)5 * n + t) * K] = Fn;
-            out[((size_t)6 * n + t) * K] = Rh;
+        if (DYN) {  // discharge of this time step (:147-189)
+            double Q;
+            if (dep <= 0.0) Q = 0.0;
+            else {
+                const double Q0 = kQ0 * pow(dep, c1);
+                if (b <= 0.0) Q = Q0;
+                else {
+                    const double gam = (b * cbrt(dep)) / (8.0 * g * (n1 * n1));
+                    const double gam2 = kG2 * pow(dep, chi);
+                    if (!veg_root(p, Q0, gam, gam2, chi, Q)) Q = CUDART_NAN;
+                }
+            }
+            out[(size_t)t * K] = Q;
+        }
+        out[((size_t)Y0 * n + t) * K] = b;
+        if (nOut > Y0 + 1) out[((size_t)(Y0 + 1) * n + t) * K] = __ddiv_rn(b, bmax);
+        if (nOut > NYS) {
+            out[((size_t)NYS * n + t) * K] = Fb;
+            out[((size_t)(NYS + 1) * n + t) * K] = Ft;
+            out[((size_t)(NYS + 2) * n + t) * K] = Fi;
+            out[((size_t)(NYS + 3) * n + t) * K] = Fn;
+            out[((size_t)(NYS + 4) * n + t) * K] = Rh;
         }
     }
     return true;
@@ -1039,7 +1068,8 @@ __device__ inline bool model_series(const DevProblem& p, const double* __restric
     if (p.model == BAMGPU_MDL_SFDTIDAL_QMEC || p.model == BAMGPU_MDL_SFDTIDAL_QMEC2)
         return sfdtidal_qmec_series(p.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : 1, p.seriesN, p.seriesX, p.seriesX + p.seriesN, th,
                                     out, K, nOut);
-    if (p.model == BAMGPU_MDL_ALGAE) return algae_series(p.seriesN, p.seriesX, th, out, K, nOut);
+    if (p.model == BAMGPU_MDL_ALGAE) return algae_series<false>(p, p.seriesN, p.seriesX, th, out, K, nOut);
+    if (p.model == BAMGPU_MDL_DYNVEG) return algae_series<true>(p, p.seriesN, p.seriesX, th, out, K, nOut);
     return false;
 }
 
@@ -1100,11 +1130,12 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
         return segmentation_apply(p, x[0], th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_MIXTURE) {
         return mixture_apply<NX>(p, x, th, der, y[0]);
-    } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE) {  // time-recursive: produced by series_run, looked up here
+    } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE ||
+               MODEL == BAMGPU_MDL_DYNVEG) {  // time-recursive: produced by series_run, looked up here
 #pragma unroll
         for (int k = 0; k < NY; ++k)
             y[k] = p.seriesY[((size_t)k * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];
-        return true;
+        return MODEL != BAMGPU_MDL_DYNVEG || y[0] == y[0];  // DynamicVegetation: a failed Newton search is an infeasible row
     } else {
         bool ok = true;
 #pragma unroll
@@ -1115,7 +1146,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
 
 // state variables (ModelLibrary_tools.f90 XtraSetup: model%nState): only SFD has one on this path (kappa)
 __host__ __device__ constexpr int model_nstate(int model) {
-    return model == BAMGPU_MDL_SFD ? 1 : ((model == BAMGPU_MDL_SFDTIDAL_QMEC || model == BAMGPU_MDL_SFDTIDAL_QMEC2) ? 3 : (model == BAMGPU_MDL_ALGAE ? 5 : 0));
+    return model == BAMGPU_MDL_SFD ? 1 : ((model == BAMGPU_MDL_SFDTIDAL_QMEC || model == BAMGPU_MDL_SFDTIDAL_QMEC2) ? 3 : ((model == BAMGPU_MDL_ALGAE || model == BAMGPU_MDL_DYNVEG) ? 5 : 0));
 }
 
 // model_apply + the state variables of the observation (st[model_nstate(MODEL)])
@@ -1123,7 +1154,7 @@ template <int MODEL, int NX, int NY>
 __device__ __forceinline__ bool model_apply_s(const DevProblem& p, const double* x, const double* __restrict__ th,
                                               const double* __restrict__ der, double* y, double* st, FmTab fm = FmTab{0u, 0u}) {
     if (MODEL == BAMGPU_MDL_SFD) return sfd_apply(p, x, th, y[0], st);
-    if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE) {
+    if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE || MODEL == BAMGPU_MDL_DYNVEG) {
 #pragma unroll
         for (int k = 0; k < model_nstate(MODEL); ++k)
             st[k] = p.seriesY[((size_t)(NY + k) * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];

@@ -273,6 +273,10 @@ static void read_xtra(Workspace& w) {
         w.xtraI.push_back(s.integer());                          // nYear
         for (int k = 0; k < 4; ++k) w.xtraD.push_back(s.num());  // Newton xscale, fscale, tolX, tolF (one per line)
         w.xtraI.push_back(s.integer());                          // Newton itmax
+    } else if (w.modelID == "DynamicVegetation") {  // DynamicVegetation_XtraRead (DynamicVegetation_model.f90:193-247)
+        Cursor s(xf);
+        for (int k = 0; k < 4; ++k) w.xtraD.push_back(s.num());  // Newton xscale, fscale, xtol, ftol (one per line)
+        w.xtraI.push_back(s.integer());                          // Newton maxiter
     } else if (w.modelID == "SFD") {  // SFD_XtraRead (StageFallDischarge_model.f90:191-247)
         Cursor s(xf);
         const std::string id = s.str();

@@ -125,7 +125,7 @@ static bool prior_draw(const Prior& pr, std::mt19937_64& g, double& x, double& m
 static std::string state_name(const std::string& modelID, int i) {
     if (modelID == "SFD" && i == 0) return "TransitionStage";
     if ((modelID == "SFDTidal_Qmec" || modelID == "SFDTidal_Qmec2") && i < 3) return std::string(i == 0 ? "pressure" : (i == 1 ? "friction" : "advection"));  // :676
-    if (modelID == "AlgaeBiomass" && i < 5) { static const char* nm[5] = {"Fb", "Ft", "Fi", "Fn", "Rhyd"}; return nm[i]; }  // ModelLibrary_tools.f90:702
+    if ((modelID == "AlgaeBiomass" || modelID == "DynamicVegetation") && i < 5) { static const char* nm[5] = {"Fb", "Ft", "Fi", "Fn", "Rhyd"}; return nm[i]; }  // ModelLibrary_tools.f90:702
     return "State" + std::to_string(i + 1);
 }
 

@@ -56,10 +56,15 @@ enum bamgpu_model {
                                      friction, advection */
     BAMGPU_MDL_SFDTIDAL_QMEC2 = 17, /* SFDTidal_Qmec2_model.f90: the same recursion parameterised by (Be, bevs, delta, ne, d1,
                                       d2, c, g, Q0, dx, dt) -- effective width and Manning coefficient given directly */
-    BAMGPU_MDL_ALGAE = 18          /* AlgaeBiomass_model.f90:55-197 ("AlgaeBiomass"): daily biomass recursion (logistic growth
+    BAMGPU_MDL_ALGAE = 18,         /* AlgaeBiomass_model.f90:55-197 ("AlgaeBiomass"): daily biomass recursion (logistic growth
                                       limited by temperature and light, senescence, grazing / removal, hydraulic scour);
                                       5 inputs (temperature, irradiance, depth, turbidity, removal), 18 parameters, outputs
                                       biomass and biomass / bmax, states Fb, Ft, Fi, Fn, Rhyd */
+    BAMGPU_MDL_DYNVEG = 19         /* DynamicVegetation_model.f90:74-191 ("DynamicVegetation"): the AlgaeBiomass recursion on
+                                      depth = max(stage - b1, 0) feeds the vegetation-affected rating curve (Newton per time
+                                      step, Vegetation_fNewton); 5 inputs (temperature, irradiance, stage, turbidity, removal),
+                                      18 + 6 parameters (B, n1, b1, c1, chi, U_chi), outputs Q, biomass, biomass / bmax, the five
+                                      AlgaeBiomass states; xtra_d = Newton xscale, fscale, tolX, tolF, xtra_i = itmax */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -109,7 +114,7 @@ enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YI
 typedef struct bamgpu_problem {
     const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
                              "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC" | "SFD" |
-                             "Mixture" | "SFDTidal_Qmec" | "SFDTidal_Qmec2" | "AlgaeBiomass"
+                             "Mixture" | "SFDTidal_Qmec" | "SFDTidal_Qmec2" | "AlgaeBiomass" | "DynamicVegetation"
                              (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 

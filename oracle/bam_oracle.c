@@ -1380,8 +1380,8 @@ static int mixture_apply(const oracle_t* o, int n, const double* X, int ldx, con
    removal), ld = ldx; Y(:,1) = biomass, Y(:,2) = biomass / bmax (ld = ldy); state (nullable, ld = ldy): Fb, Ft, Fi, Fn, Rhyd.
    Returns 0 when the parameter set is infeasible (:140-146), -1 on the input errors of :79-99 (err = 1 in the reference).
    epsRe is DMSL's (un-vendored): declared = epsilon(1._mrk). */
-static int algae_apply(int n, const double* X, int ldx, const double* th, double* Y, int ldy, double* state) {
-    const double *temp = X, *irr = X + (size_t)ldx, *depth = X + 2 * (size_t)ldx, *turb = X + 3 * (size_t)ldx, *rem = X + 4 * (size_t)ldx;
+static int algae_apply_depth(int n, const double* X, int ldx, const double* depthArg, const double* th, double* Y, int ldy, double* state) {
+    const double *temp = X, *irr = X + (size_t)ldx, *depth = depthArg ? depthArg : X + 2 * (size_t)ldx, *turb = X + 3 * (size_t)ldx, *rem = X + 4 * (size_t)ldx;
     for (int t = 0; t < n; ++t) {
         Y[t] = BAMGPU_UNDEF_RN; Y[t + (size_t)ldy] = BAMGPU_UNDEF_RN;
         if (state) for (int s = 0; s < 5; ++s) state[t + (size_t)s * ldy] = BAMGPU_UNDEF_RN;
@@ -1417,6 +1417,45 @@ static int algae_apply(int n, const double* X, int ldx, const double* th, double
         Y[t + (size_t)ldy] = b / bmax;
         if (state) { state[t] = Fb; state[t + (size_t)ldy] = Ft; state[t + 2 * (size_t)ldy] = Fi; state[t + 3 * (size_t)ldy] = Fn; state[t + 4 * (size_t)ldy] = Rhyd; }
     }
+    return 1;
+}
+static int algae_apply(int n, const double* X, int ldx, const double* th, double* Y, int ldy, double* state) {
+    return algae_apply_depth(n, X, ldx, NULL, th, Y, ldy, state);
+}
+
+/* DynamicVegetation_Apply, DynamicVegetation_model.f90:74-191: X = (temperature, irradiance, stage, turbidity, removal);
+   theta = 18 AlgaeBiomass parameters, then B, n1, b1, c1, chi, U_chi; gravity and slope are AlgaeBiomass's g = theta(13) and
+   J = theta(15) (:30).  Y(:,1) = Q, Y(:,2) = biomass, Y(:,3) = biomass / bmax; state = Fb, Ft, Fi, Fn, Rhyd.
+   The biomass budget runs on depth = max(stage - b1, 0) (:137-138); per time step the discharge solves Vegetation_fNewton on
+   [0, Q0] (:147-189), a failed search flags the ROW (feas(t)).  Returns as algae_apply. */
+static int veg_znewton(double Q0, double gam, double gam2, double chi, double x1, double x2, double tolX, double tolF,
+                       double xscale, double fscale, int itmax, double* xroot, int* fcalls);
+static int dynveg_apply(const oracle_t* o, int n, const double* X, int ldx, const double* th, double* Y, int ldy, double* state,
+                        int32_t* vfeas) {
+    const double B = th[18], n1 = th[19], b1 = th[20], c1 = th[21], chi = th[22], U_chi = th[23], S0 = th[14], g = th[12];
+    const double* stage = X + 2 * (size_t)ldx;
+    double* depth = (double*)malloc(((size_t)n + 1) * sizeof(double));
+    for (int t = 0; t < n; ++t) {
+        depth[t] = stage[t] - b1;
+        if (depth[t] <= 0.0) depth[t] = 0.0;
+        Y[t] = BAMGPU_UNDEF_RN;
+    }
+    int r = algae_apply_depth(n, X, ldx, depth, th, Y + (size_t)ldy, ldy, state);
+    if (r <= 0) { free(depth); return r; }
+    for (int t = 0; t < n; ++t) {
+        double y = depth[t], Q;
+        if (y <= 0.0) { Y[t] = 0.0; continue; }
+        double Q0 = ((B * sqrt(S0)) / n1) * pow(y, c1);
+        double bio = Y[t + (size_t)ldy];
+        if (bio <= 0.0) { Y[t] = Q0; continue; }
+        double gam = (bio * pow(y, 1.0 / 3.0)) / (8.0 * g * (n1 * n1));
+        double gam2 = pow(B, chi) * pow(y, chi) * pow(U_chi, chi);
+        int fcalls = 0;
+        int e = veg_znewton(Q0, gam, gam2, chi, 0.0, Q0, o->veg_tolx, o->veg_tolf, o->veg_xscale, o->veg_fscale, o->veg_itmax, &Q, &fcalls);
+        if (e > 0 || fcalls > o->veg_itmax) { vfeas[t] = 0; continue; }
+        Y[t] = Q;
+    }
+    free(depth);
     return 1;
 }
 
@@ -1541,6 +1580,13 @@ static int apply_model_s(const oracle_t* o, int n, const double* X, int ldx, con
                 for (int t = 0; t < n; ++t) vfeas[t] = 0;
             break;
         }
+        case BAMGPU_MDL_DYNVEG: {
+            int r = dynveg_apply(o, n, X, ldx, fullTheta, Y, ldy, state, vfeas);
+            if (r < 0) return 1;
+            if (!r)
+                for (int t = 0; t < n; ++t) vfeas[t] = 0;
+            break;
+        }
         case BAMGPU_MDL_MIXTURE: {
             int r = mixture_apply(o, n, X, ldx, fullTheta, Y, dparModel);
             if (r < 0) return 1;
@@ -1596,6 +1642,7 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "SFDTidal_Qmec")) return BAMGPU_MDL_SFDTIDAL_QMEC;
     if (!strcmp(name, "SFDTidal_Qmec2")) return BAMGPU_MDL_SFDTIDAL_QMEC2;
     if (!strcmp(name, "AlgaeBiomass")) return BAMGPU_MDL_ALGAE;
+    if (!strcmp(name, "DynamicVegetation")) return BAMGPU_MDL_DYNVEG;
     return 0;
 }
 
@@ -1762,6 +1809,13 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
             break;
         case BAMGPU_MDL_ALGAE: /* AlgaeBiomass_GetParNumber: 18; XtraSetup: 5 state variables (ModelLibrary_tools.f90:697-702) */
             if (nt != 18 || nX != 5 || nY != 2) { setmess(mess, "oracle: AlgaeBiomass: bad sizes"); return 1; }
+            o->nState = 5;
+            break;
+        case BAMGPU_MDL_DYNVEG: /* DynamicVegetation_GetParNumber: 18 + 4 + 2; XtraRead (:193-247); 5 states (ModelLibrary_tools.f90:703-707) */
+            if (p->n_xtra_i != 1 || p->n_xtra_d != 4) { setmess(mess, "oracle: DynamicVegetation: bad xtra"); return 1; }
+            if (nt != 24 || nX != 5 || nY != 3) { setmess(mess, "oracle: DynamicVegetation: bad sizes"); return 1; }
+            o->veg_itmax = p->xtra_i[0];
+            o->veg_xscale = p->xtra_d[0]; o->veg_fscale = p->xtra_d[1]; o->veg_tolx = p->xtra_d[2]; o->veg_tolf = p->xtra_d[3];
             o->nState = 5;
             break;
         case BAMGPU_MDL_MIXTURE: { /* Mixture_GetParNumber (:33-72), XtraSetup (ModelLibrary_tools.f90:580-586) */

@@ -399,3 +399,40 @@ def test_chain_parallel_generic_kernel(case):
     sub = g.logpost(x[40:40 + 1024])
     assert (sub[0] == a[0][40:40 + 1024]).all()
     assert (g.logpost(x)[0] == a[0]).all()
+
+
+def test_time_recursive_dynamic_vegetation():
+    """row f4: DynamicVegetation on series_run (AlgaeBiomass budget on the clamped depth + a Newton solve per time step):
+    log-posterior with gaps, prediction with the state spaghetti, sampler, residual run -- against the oracle; a Newton
+    budget that cannot converge flags rows, which makes the vector infeasible on both sides."""
+    import copy
+
+    prob, truth = synth.dynamic_vegetation(nobs=400)
+    x = synth.feasible_starts(truth, 40, rel=0.01, seed=2)
+    x[3, 0] = 2.0     # b0 > bmax: infeasible parameter set
+    x[4, 15] = 5.0    # b1 above every stage: depth 0 everywhere, Q = 0
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.sizes.nState == 5
+    check_parity(prob, x, tol=1e-11)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.003 * rng.standard_normal((120, truth.size)))
+    mc[5, 0] = 2.0  # an infeasible replication
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(5)]
+    env, spag = g.predict(mc, truth, xs, 1, [1, 1, 0], seed=4, want_spag=True, states=True)
+    oenv, ospag = o.predict(mc, truth, xs, 1, [1, 1, 0], seed=4, want_spag=True, nthreads=8, states=True)
+    assert spag.shape == (8, 400, 120) and (spag[:, :, 5] == -666.666).all()
+    cmp_spag(spag, ospag, tol=1e-10)
+    cmp_env(env, oenv, tol=1e-10)
+    s = np.tile(truth, (3, 1))
+    sd = 0.005 * np.abs(s) + 1e-12
+    rows = g.fit(s, sd, nAdapt=3, nCycles=2, seed=5)
+    orows = o.fit(s, sd, nAdapt=3, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+    Xt, Ys, St, feas = g.calibration_run_states(truth)
+    oXt, oYs, oSt, ofeas = o.calibration_run_states(truth)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-10, atol=1e-13) and np.allclose(St, oSt, rtol=1e-10, atol=1e-13)
+    tight = copy.deepcopy(prob)
+    tight.xtra_i[0] = 2  # two evaluations: the bracket ends only
+    fx, feas1, _ = BamGpu(tight).logpost(x[:8])[:3]
+    ofx, ofeas1, _ = Oracle(tight).logpost(x[:8])[:3]
+    assert (feas1 == ofeas1).all() and feas1[0] == 0 and feas1[4] == 1  # the all-dry vector needs no Newton solve

@@ -453,3 +453,47 @@ def test_algae_biomass_recursion():
     bad.X[7, 4] = 1.5  # removal > 1
     with pytest.raises(Exception):
         Oracle(bad).logpost_one(truth)
+
+
+def test_dynamic_vegetation():
+    """row f4: DynamicVegetation_Apply (DynamicVegetation_model.f90:74-191) = AlgaeBiomass on depth = max(stage - b1, 0) plus,
+    per time step, the root of Vegetation_fNewton on [0, Q0].  Checked against the pieces: the biomass rows equal an
+    AlgaeBiomass run on the clamped depth, the discharge satisfies the Newton equation, the special cases (:150-153)."""
+    from bam_b200.capi import Problem
+    from workloads import synth
+
+    prob, truth = synth.dynamic_vegetation(nobs=400, missing_every=1)
+    o = Oracle(prob)
+    assert o.sizes.nState == 5 and o.P == 19 + 4
+    Xt, Ys, St, feas = o.calibration_run_states(truth)
+    assert feas and Ys.shape == (400, 3) and St.shape == (400, 5)
+    X = np.asarray(prob.X)
+    B, n1, b1, c1, chi, U = truth[13:19]
+    g, S0 = 9.81, 1e-4
+    depth = np.maximum(X[:, 2] - b1, 0.0)
+    # biomass rows = AlgaeBiomass on the clamped depth
+    pa, ta = synth.algae_biomass(nobs=400, missing_every=1)
+    Xa = X.copy(); Xa[:, 2] = depth
+    pa2 = Problem("AlgaeBiomass", Xa, np.zeros((400, 2)), Yu=np.full((400, 2), 0.01), partype=[int(v) for v in pa.partype],
+                  priors_theta=[("Gaussian", [0, 1])] * 13, fix_value=pa.fix_value, sigma_func=["Constant", "Constant"],
+                  priors_gamma=[("Uniform", [0, 10])] * 2)
+    _, Ya, Sa, fa = Oracle(pa2).calibration_run_states(np.concatenate([truth[:13], [0.02, 0.02]]))
+    assert fa and np.array_equal(Ya, Ys[:, 1:]) and np.array_equal(Sa, St)
+    # discharge: 0 on a dry bed, Q0 without biomass (none here: bmin > 0), else the root of Vegetation_fNewton
+    dry = depth <= 0.0
+    assert dry.sum() >= 5 and (Ys[dry, 0] == 0.0).all()
+    y = depth[~dry]
+    Q0 = (B * np.sqrt(S0) / n1) * y**c1
+    gam = Ys[~dry, 1] * y ** (1.0 / 3.0) / (8.0 * g * n1**2)
+    gam2 = (B * y * U) ** chi
+    Q = Ys[~dry, 0]
+    assert ((Q > 0) & (Q < Q0)).all()
+    m = np.minimum(Q**chi / gam2, 1.0)
+    assert np.max(np.abs(Q**2 * (1.0 + gam * m) - Q0**2) / Q0**2) < 1e-9
+    # a Newton budget of 2 evaluations cannot converge: every wet row is infeasible -> infeasible vector
+    tight = Problem("DynamicVegetation", X, np.asarray(prob.Y), Yu=np.asarray(prob.Yu), partype=[int(v) for v in prob.partype],
+                    priors_theta=[("Gaussian", [0, 1])] * 19, fix_value=prob.fix_value, sigma_func=["Linear", "Constant", "Constant"],
+                    priors_gamma=[("Uniform", [0, 10])] * 4, xtra_d=[1.0, 1.0, 1e-10, 1e-12], xtra_i=[2])
+    assert Oracle(tight).logpost_one(truth)["feas"] == 0
+    x = truth.copy(); x[0] = 2.0  # b0 > bmax (AlgaeBiomass :140-146)
+    assert o.logpost_one(x)["feas"] == 0

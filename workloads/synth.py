@@ -550,3 +550,42 @@ def algae_biomass(nobs: int = 730, seed: int = SEED + 14, missing_every: int = 4
                    priors_gamma=[("Uniform", [0, 10]), ("Uniform", [0, 10])])
     truth = np.concatenate([[th[i] for i in range(18) if partype[i] == 0], [0.02, 0.02]])
     return prob, truth
+
+
+def dynamic_vegetation(nobs: int = 730, seed: int = SEED + 15, missing_every: int = 3):
+    """DynamicVegetation (DynamicVegetation_model.f90:74-191): the AlgaeBiomass budget on depth = max(stage - b1, 0) drives
+    the vegetation-affected rating curve.  5 input series (temperature, irradiance, STAGE, turbidity, removal), 18 + 6
+    parameters, outputs Q, biomass, biomass / bmax.  The "observations" come from the oracle's own run of the model (the
+    generator needs the Newton solve) plus noise; a dry spell puts some stages below b1.  Returns (Problem, truth)."""
+    from oracle.oracle_api import Oracle
+
+    rng = default_rng(seed)
+    day = np.arange(nobs, dtype=np.float64)
+    temp = 14.0 - 10.0 * np.cos(2 * np.pi * (day - 20.0) / 365.0) + 1.5 * rng.standard_normal(nobs)
+    irr = np.maximum(140.0 - 110.0 * np.cos(2 * np.pi * (day - 10.0) / 365.0) + 25.0 * rng.standard_normal(nobs), 1.0)
+    stage = 0.9 + 0.15 * np.sin(2 * np.pi * day / 90.0) ** 2
+    flood = (rng.uniform(0.0, 1.0, nobs) < 0.02)
+    stage = stage + np.convolve(flood.astype(float), np.array([1.2, 0.8, 0.4, 0.2]), mode="full")[:nobs]
+    stage[200:206] = 0.25  # dry spell: stage below b1 -> depth 0, Q = 0
+    turb = np.maximum(5.0 + 40.0 * (stage - 0.9), 0.0)
+    rem = np.where(rng.uniform(0.0, 1.0, nobs) < 0.01, 0.4, 0.0)
+    alg = [1.0, 0.3, 0.001, 1.0, 0.12, 6.0, 16.5, 30.0, 150.0, 0.02, 0.5, 0.02, 9.81, 1000.0, 1e-4, 0.8, 1.5, 0.05]
+    th = np.array(alg + [12.0, 0.03, 0.3, 1.67, -0.8, 0.5])  # B, n1, b1, c1, chi, U_chi
+    partype = [-1, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, -1, -1, 0, 0, 0] + [0] * 6
+    pri = [("Gaussian", [v, 0.05 * abs(v) + 1e-3]) for v in th]
+    X = np.column_stack([temp, irr, stage, turb, rem])
+
+    def make(Y):
+        return Problem("DynamicVegetation", X, Y, Yu=np.column_stack([np.full(nobs, 0.002), np.full((nobs, 2), 0.01)]),
+                       partype=partype, priors_theta=[pri[i] for i in range(24) if partype[i] == 0],
+                       fix_value=[v if partype[i] == -1 else 0.0 for i, v in enumerate(th)],
+                       sigma_func=["Linear", "Constant", "Constant"],
+                       priors_gamma=[("Uniform", [0, 10])] * 4, xtra_d=[1.0, 1.0, 1e-10, 1e-12], xtra_i=[100])
+
+    truth = np.concatenate([[th[i] for i in range(24) if partype[i] == 0], [0.001, 0.03, 0.02, 0.02]])
+    _, Ys, feas = Oracle(make(np.zeros((nobs, 3)))).calibration_run(truth)
+    assert feas
+    Y = Ys * (1.0 + 0.03 * rng.standard_normal((nobs, 3))) + 0.002 * rng.standard_normal((nobs, 3))
+    if missing_every > 1:
+        Y[np.arange(nobs) % missing_every != 0, 1:] = -9999.0
+    return make(Y), truth
