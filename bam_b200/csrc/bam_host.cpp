@@ -51,6 +51,8 @@ int model_from_name(const char* name) {
     if (s == "SFDTidal_Qmec2") return BAMGPU_MDL_SFDTIDAL_QMEC2;
     if (s == "AlgaeBiomass") return BAMGPU_MDL_ALGAE;
     if (s == "DynamicVegetation") return BAMGPU_MDL_DYNVEG;
+    if (s == "SFDTidal_Qmec0") return BAMGPU_MDL_SFDTIDAL_QMEC0;
+    if (s == "SFDTidal_QmecMS") return BAMGPU_MDL_SFDTIDAL_QMECMS;
     return 0;
 }
 
@@ -570,6 +572,12 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             if (nt != (L.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 11 : 12) || nX != 2 || nY != 1) { mess = "SFDTidal_Qmec_Apply: wrong size [theta], nX or nY"; return 1; }
             if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: SFDTidal_Qmec is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
             L.nState = 3;  // pressure, friction, advection (:672-676)
+            L.isSeries = true;
+            break;
+        case BAMGPU_MDL_SFDTIDAL_QMEC0:   // SFDTidal_Qmec0_GetParNumber: 11; no state variables (ModelLibrary_tools.f90:668-671)
+        case BAMGPU_MDL_SFDTIDAL_QMECMS:  // SFDTidal_QmecMS_GetParNumber: 10 (:60); no state variables (:682-685)
+            if (nt != (L.model == BAMGPU_MDL_SFDTIDAL_QMEC0 ? 11 : 10) || nX != 2 || nY != 1) { mess = "SFDTidal_Qmec_Apply: wrong size [theta], nX or nY"; return 1; }
+            if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: SFDTidal_Qmec is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
             L.isSeries = true;
             break;
         case BAMGPU_MDL_ALGAE:  // AlgaeBiomass_GetParNumber: 18 (AlgaeBiomass_model.f90:46-51); XtraSetup: 5 states (ModelLibrary_tools.f90:697-702)

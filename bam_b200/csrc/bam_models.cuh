@@ -904,14 +904,25 @@ __device__ __forceinline__ bool mixture_apply(const DevProblem& p, const double*
 // effective width and the Manning coefficient are parameters instead of being derived from (y0, A0, be, phi).
 __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __restrict__ h1, const double* __restrict__ h2,
                                             const double* __restrict__ th, double* __restrict__ out, size_t K, int nOut) {
+    // variant 3 = SFDTidal_Qmec0 (SFDTidal_Qmec0_model.f90:61-178): theta = (Be, he, dzeta, ne, d1, d2, c, g, Q0, dx, dt), stages
+    //   MINUS datums and Ae = Be (he + hm): variant 2 with be = -he and the datums negated (x - (-y) and x + (-y) are the exact
+    //   sum / difference), its own feasibility conditions (:96-98), no state variables;
+    // variant 4 = SFDTidal_QmecMS (SFDTidal_QmecMS_model.f90:62-154): theta = (y0, A0, be, delta, phi, d1, d2, c, g, dx); the
+    //   Manning-Strickler discharge of every point on its own, sign from the water-surface slope (:149-152)
     double be, delta, d1, d2, c, g, Q0, dx, dt, width, ne;
-    if (variant == 2) {
+    if (variant == 2 || variant == 3) {
         width = th[0]; be = th[1]; delta = th[2]; ne = th[3]; d1 = th[4]; d2 = th[5]; c = th[6]; g = th[7]; Q0 = th[8];
         dx = th[9]; dt = th[10];
         if (width <= 0.0 || ne <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return false;
+        if (variant == 3) {
+            if (be <= 0.0 || delta >= 0.0) return false;  // he <= 0, dzeta >= 0
+            be = -be; d1 = -d1; d2 = -d2;
+        }
     } else {
         const double y0 = th[0], A0 = th[1], phi = th[4];
-        be = th[2]; delta = th[3]; d1 = th[5]; d2 = th[6]; c = th[7]; g = th[8]; Q0 = th[9]; dx = th[10]; dt = th[11];
+        be = th[2]; delta = th[3]; d1 = th[5]; d2 = th[6]; c = th[7]; g = th[8];
+        if (variant == 4) { Q0 = 0.0; dx = th[9]; dt = 1.0; }
+        else { Q0 = th[9]; dx = th[10]; dt = th[11]; }
         if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return false;
         width = __ddiv_rn(A0, __dsub_rn(y0, be));
         const double R0 = __ddiv_rn(A0, __dadd_rn(width, __dmul_rn(2.0, __dsub_rn(y0, be))));
@@ -939,6 +950,18 @@ __device__ inline bool sfdtidal_qmec_series(int variant, int n, const double* __
             out[((size_t)3 * n + m) * K] = s3;
         }
     };
+    if (variant == 4) {  // Q(m) = (1/ne) Rhe^(c/2) Ae sqrt(|(dy + delta) / dx|), negative when the surface rises downstream
+        const double rne = __ddiv_rn(1.0, ne), hc = __dmul_rn(0.5, c);
+        for (int m = 0; m < n; ++m) {
+            double dy0, ym0, Ae0, Rh0;
+            ok &= geom(m, dy0, ym0, Ae0, Rh0);
+            const double sl = __dadd_rn(dy0, delta);
+            double q = __dmul_rn(__dmul_rn(__dmul_rn(rne, pow(Rh0, hc)), Ae0), sqrt(fabs(__ddiv_rn(sl, dx))));
+            if (sl > 0.0) q = -q;
+            put(m, q, 0.0, 0.0, 0.0);
+        }
+        return ok;
+    }
     // point m-1 (suffix 1); of point m-2 only ym is still needed (see below)
     double dy1 = 0.0, ym1 = 0.0, Ae1 = 0.0, Rh1 = 0.0, ym2 = 0.0, Q1 = Q0;
     if (n > 0) { ok &= geom(0, dy1, ym1, Ae1, Rh1); put(0, Q0, 0.0, 0.0, 0.0); }
@@ -1065,9 +1088,10 @@ __device__ inline bool algae_series(const DevProblem& p, int n, const double* __
 // one sequential pass of a time-recursive model for one parameter vector; false = infeasible vector
 __device__ inline bool model_series(const DevProblem& p, const double* __restrict__ th, double* __restrict__ out, size_t K,
                                     int nOut) {
-    if (p.model == BAMGPU_MDL_SFDTIDAL_QMEC || p.model == BAMGPU_MDL_SFDTIDAL_QMEC2)
-        return sfdtidal_qmec_series(p.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : 1, p.seriesN, p.seriesX, p.seriesX + p.seriesN, th,
-                                    out, K, nOut);
+    if (p.model == BAMGPU_MDL_SFDTIDAL_QMEC || p.model == BAMGPU_MDL_SFDTIDAL_QMEC2 || p.model == BAMGPU_MDL_SFDTIDAL_QMEC0 ||
+        p.model == BAMGPU_MDL_SFDTIDAL_QMECMS)
+        return sfdtidal_qmec_series(p.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : (p.model == BAMGPU_MDL_SFDTIDAL_QMEC0 ? 3 : (p.model == BAMGPU_MDL_SFDTIDAL_QMECMS ? 4 : 1)),
+                                    p.seriesN, p.seriesX, p.seriesX + p.seriesN, th, out, K, nOut);
     if (p.model == BAMGPU_MDL_ALGAE) return algae_series<false>(p, p.seriesN, p.seriesX, th, out, K, nOut);
     if (p.model == BAMGPU_MDL_DYNVEG) return algae_series<true>(p, p.seriesN, p.seriesX, th, out, K, nOut);
     return false;
@@ -1131,7 +1155,7 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
     } else if (MODEL == BAMGPU_MDL_MIXTURE) {
         return mixture_apply<NX>(p, x, th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE ||
-               MODEL == BAMGPU_MDL_DYNVEG) {  // time-recursive: produced by series_run, looked up here
+               MODEL == BAMGPU_MDL_DYNVEG || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC0 || MODEL == BAMGPU_MDL_SFDTIDAL_QMECMS) {  // time-recursive: produced by series_run, looked up here
 #pragma unroll
         for (int k = 0; k < NY; ++k)
             y[k] = p.seriesY[((size_t)k * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];

@@ -60,11 +60,16 @@ enum bamgpu_model {
                                       limited by temperature and light, senescence, grazing / removal, hydraulic scour);
                                       5 inputs (temperature, irradiance, depth, turbidity, removal), 18 parameters, outputs
                                       biomass and biomass / bmax, states Fb, Ft, Fi, Fn, Rhyd */
-    BAMGPU_MDL_DYNVEG = 19         /* DynamicVegetation_model.f90:74-191 ("DynamicVegetation"): the AlgaeBiomass recursion on
+    BAMGPU_MDL_DYNVEG = 19,        /* DynamicVegetation_model.f90:74-191 ("DynamicVegetation"): the AlgaeBiomass recursion on
                                       depth = max(stage - b1, 0) feeds the vegetation-affected rating curve (Newton per time
                                       step, Vegetation_fNewton); 5 inputs (temperature, irradiance, stage, turbidity, removal),
                                       18 + 6 parameters (B, n1, b1, c1, chi, U_chi), outputs Q, biomass, biomass / bmax, the five
                                       AlgaeBiomass states; xtra_d = Newton xscale, fscale, tolX, tolF, xtra_i = itmax */
+    BAMGPU_MDL_SFDTIDAL_QMEC0 = 20, /* SFDTidal_Qmec0_model.f90:61-178: the original Qmec parameterisation (Be, he, dzeta, ne, d1,
+                                      d2, c, g, Q0, dx, dt), stages MINUS datums, no state variables */
+    BAMGPU_MDL_SFDTIDAL_QMECMS = 21 /* SFDTidal_QmecMS_model.f90:62-154: Manning-Strickler (steady) version of Qmec, theta =
+                                      (y0, A0, be, delta, phi, d1, d2, c, g, dx); pointwise in time but the geometry of the
+                                      WHOLE series decides feasibility, so it runs with the time-recursive models */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -114,7 +119,8 @@ enum bamgpu_veg_growth { BAMGPU_VEG_YIN1 = 1, BAMGPU_VEG_YIN2 = 2, BAMGPU_VEG_YI
 typedef struct bamgpu_problem {
     const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
                              "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC" | "SFD" |
-                             "Mixture" | "SFDTidal_Qmec" | "SFDTidal_Qmec2" | "AlgaeBiomass" | "DynamicVegetation"
+                             "Mixture" | "SFDTidal_Qmec" | "SFDTidal_Qmec2" | "AlgaeBiomass" | "DynamicVegetation" |
+                             "SFDTidal_Qmec0" | "SFDTidal_QmecMS"
                              (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 

@@ -1471,14 +1471,22 @@ static int sfdtidal_qmec_apply(int variant, int nm, const double* h1, const doub
     if (state)
         for (int s = 0; s < 3; ++s)
             for (int m = 0; m < nm; ++m) state[m + (size_t)s * lds] = BAMGPU_UNDEF_RN;
-    if (variant == 2) {
+    /* variant 3: SFDTidal_Qmec0_model.f90:61-178 (Be, he, dzeta, ne, d1, d2, c, g, Q0, dx, dt): y = h - d, Ae = Be (he + hm);
+       variant 4: SFDTidal_QmecMS_model.f90:62-154 (y0, A0, be, delta, phi, d1, d2, c, g, dx): steady Manning-Strickler discharge */
+    double he = 0.0;
+    if (variant == 2 || variant == 3) {
         width = theta[0]; be = theta[1]; delta = theta[2]; ne = theta[3]; d1 = theta[4]; d2 = theta[5]; c = theta[6];
         g = theta[7]; Q0 = theta[8]; dx = theta[9]; dt = theta[10];
         if (width <= 0.0 || ne <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return 0;
+        if (variant == 3) {
+            he = be;
+            if (he <= 0.0 || delta >= 0.0) return 0;
+        }
     } else {
         double y0 = theta[0], A0 = theta[1], phi = theta[4];
-        be = theta[2]; delta = theta[3]; d1 = theta[5]; d2 = theta[6]; c = theta[7]; g = theta[8]; Q0 = theta[9];
-        dx = theta[10]; dt = theta[11];
+        be = theta[2]; delta = theta[3]; d1 = theta[5]; d2 = theta[6]; c = theta[7]; g = theta[8];
+        if (variant == 4) { Q0 = 0.0; dx = theta[9]; dt = 1.0; }
+        else { Q0 = theta[9]; dx = theta[10]; dt = theta[11]; }
         if (A0 <= 0.0 || (y0 - be) <= 0.0 || phi <= 0.0 || c <= 0.0 || g <= 0.0 || dx <= 0.0 || dt <= 0.0) return 0;
         width = A0 / (y0 - be);
         double R0 = A0 / (width + 2.0 * (y0 - be));
@@ -1488,15 +1496,24 @@ static int sfdtidal_qmec_apply(int variant, int nm, const double* h1, const doub
     double *ym = dy + nm, *Ae = ym + nm, *Rhe = Ae + nm;
     int ok = 1;
     for (int m = 0; m < nm; ++m) {
-        double y1 = h1[m] + d1, y2 = h2[m] + d2;
+        double y1 = (variant == 3) ? h1[m] - d1 : h1[m] + d1, y2 = (variant == 3) ? h2[m] - d2 : h2[m] + d2;
         dy[m] = y2 - y1;
         ym[m] = (y1 + y2) / 2.0;
-        Ae[m] = width * (ym[m] - be);
-        double Pe = width + 2.0 * (ym[m] - be);
+        double depth = (variant == 3) ? he + ym[m] : ym[m] - be;
+        Ae[m] = width * depth;
+        double Pe = width + 2.0 * depth;
         Rhe[m] = Ae[m] / Pe;
         if (Ae[m] < 0.0 || Pe < 0.0 || Rhe[m] < 0.0) ok = 0;
     }
     if (!ok) { free(dy); return 0; }
+    if (variant == 4) { /* :149-152 */
+        for (int m = 0; m < nm; ++m) {
+            Q[m] = (1.0 / ne) * pow(Rhe[m], 0.5 * c) * Ae[m] * sqrt(fabs((dy[m] + delta) / dx));
+            if ((dy[m] + delta) > 0.0) Q[m] = -1.0 * Q[m];
+        }
+        free(dy);
+        return 1;
+    }
     if (nm > 0) {
         Q[0] = Q0;
         if (state) for (int s = 0; s < 3; ++s) state[(size_t)s * lds] = 0.0;
@@ -1570,7 +1587,10 @@ static int apply_model_s(const oracle_t* o, int n, const double* X, int ldx, con
         case BAMGPU_MDL_SFD: sfd_apply(o, n, X, ldx, fullTheta, Y, vfeas, state); break;
         case BAMGPU_MDL_SFDTIDAL_QMEC:
         case BAMGPU_MDL_SFDTIDAL_QMEC2:
-            if (!sfdtidal_qmec_apply(o->model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : 1, n, X, X + (size_t)ldx, fullTheta, Y, state, ldy))
+        case BAMGPU_MDL_SFDTIDAL_QMEC0:
+        case BAMGPU_MDL_SFDTIDAL_QMECMS:
+            if (!sfdtidal_qmec_apply(o->model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : (o->model == BAMGPU_MDL_SFDTIDAL_QMEC0 ? 3 : (o->model == BAMGPU_MDL_SFDTIDAL_QMECMS ? 4 : 1)),
+                                     n, X, X + (size_t)ldx, fullTheta, Y, o->nState ? state : NULL, ldy))
                 for (int t = 0; t < n; ++t) vfeas[t] = 0;
             break;
         case BAMGPU_MDL_ALGAE: {
@@ -1643,6 +1663,8 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "SFDTidal_Qmec2")) return BAMGPU_MDL_SFDTIDAL_QMEC2;
     if (!strcmp(name, "AlgaeBiomass")) return BAMGPU_MDL_ALGAE;
     if (!strcmp(name, "DynamicVegetation")) return BAMGPU_MDL_DYNVEG;
+    if (!strcmp(name, "SFDTidal_Qmec0")) return BAMGPU_MDL_SFDTIDAL_QMEC0;
+    if (!strcmp(name, "SFDTidal_QmecMS")) return BAMGPU_MDL_SFDTIDAL_QMECMS;
     return 0;
 }
 
@@ -1806,6 +1828,10 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
         case BAMGPU_MDL_SFDTIDAL_QMEC2: /* SFDTidal_Qmec2_GetParNumber: 11; XtraSetup (:677-681) */
             if (nt != (o->model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 11 : 12) || nX != 2 || nY != 1) { setmess(mess, "oracle: SFDTidal_Qmec: bad sizes"); return 1; }
             o->nState = 3;
+            break;
+        case BAMGPU_MDL_SFDTIDAL_QMEC0:  /* SFDTidal_Qmec0_GetParNumber: 11; no states (ModelLibrary_tools.f90:668-671) */
+        case BAMGPU_MDL_SFDTIDAL_QMECMS: /* SFDTidal_QmecMS_GetParNumber: 10; no states (:682-685) */
+            if (nt != (o->model == BAMGPU_MDL_SFDTIDAL_QMEC0 ? 11 : 10) || nX != 2 || nY != 1) { setmess(mess, "oracle: SFDTidal_Qmec: bad sizes"); return 1; }
             break;
         case BAMGPU_MDL_ALGAE: /* AlgaeBiomass_GetParNumber: 18; XtraSetup: 5 state variables (ModelLibrary_tools.f90:697-702) */
             if (nt != 18 || nX != 5 || nY != 2) { setmess(mess, "oracle: AlgaeBiomass: bad sizes"); return 1; }

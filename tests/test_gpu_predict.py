@@ -35,7 +35,10 @@ def cmp_spag(a, b, tol=1e-12):
         assert rel.max() <= tol, ("per-value relative error", rel.max())
     if small.any():
         ab = d[small] / colscale[small]
-        assert ab.max() <= 4e-15, ("cancelled values, error in units of the column scale", ab.max())
+        # (a caller that loosens tol -- the time-recursive models, whose rounding accumulates along the series and whose
+        # discharge crosses zero with the tide -- gets the same factor 1e-2 x tol in absolute terms)
+        lim = 4e-15 if tol <= 1e-12 else 1e-2 * tol
+        assert ab.max() <= lim, ("cancelled values, error in units of the column scale", ab.max())
 
 
 def cmp_env(a, b, tol=1e-12):

@@ -436,3 +436,37 @@ def test_time_recursive_dynamic_vegetation():
     fx, feas1, _ = BamGpu(tight).logpost(x[:8])[:3]
     ofx, ofeas1, _ = Oracle(tight).logpost(x[:8])[:3]
     assert (feas1 == ofeas1).all() and feas1[0] == 0 and feas1[4] == 1  # the all-dry vector needs no Newton solve
+
+
+@pytest.mark.parametrize("model", ["SFDTidal_Qmec0", "SFDTidal_QmecMS"])
+def test_time_recursive_sfdtidal_variants(model):
+    """row f4: the original Qmec parameterisation and the steady Manning-Strickler version on series_run: log-posterior with
+    gaps, prediction, sampler, residual run against the oracle; infeasible parameter sets and infeasible geometry."""
+    prob, truth = synth.sfdtidal_variant(model, nobs=500)
+    x = synth.feasible_starts(truth, 40, rel=0.01, seed=2)
+    if model == "SFDTidal_Qmec0":
+        x[3, 2] = 0.01   # dzeta >= 0
+        x[4, 1] = 0.5    # effective depth so small that the wetted area turns negative at low tide
+    else:
+        x[3, 0] = -5.0   # A0 <= 0
+        x[4, 1] = 3.0    # bed above the water level
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.sizes.nState == 0
+    check_parity(prob, x, tol=1e-11)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.003 * rng.standard_normal((120, truth.size)))
+    mc[5, 0] = -1.0  # an infeasible replication
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(2)]
+    env, spag = g.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True)
+    oenv, ospag = o.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True, nthreads=8)
+    assert spag.shape == (1, 500, 120) and (spag[:, :, 5] == -666.666).all()
+    cmp_spag(spag, ospag, tol=1e-10)
+    cmp_env(env, oenv, tol=1e-10)
+    s = np.tile(truth, (3, 1))
+    sd = 0.005 * np.abs(s) + 1e-12
+    rows = g.fit(s, sd, nAdapt=3, nCycles=2, seed=5)
+    orows = o.fit(s, sd, nAdapt=3, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+    Xt, Ys, feas = g.calibration_run(truth)
+    oXt, oYs, ofeas = o.calibration_run(truth)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-11)

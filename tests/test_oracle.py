@@ -497,3 +497,49 @@ def test_dynamic_vegetation():
     assert Oracle(tight).logpost_one(truth)["feas"] == 0
     x = truth.copy(); x[0] = 2.0  # b0 > bmax (AlgaeBiomass :140-146)
     assert o.logpost_one(x)["feas"] == 0
+
+
+def test_sfdtidal_qmec0_and_qmecms():
+    """row f4: SFDTidal_Qmec0 (SFDTidal_Qmec0_model.f90:61-178) is SFDTidal_Qmec2's recursion with stages MINUS datums and
+    Ae = Be (he + hm): the two restatements must agree bit for bit under that change of variables; SFDTidal_QmecMS
+    (SFDTidal_QmecMS_model.f90:62-154) against its closed form in numpy; the exits of both."""
+    from bam_b200.capi import Problem
+    from workloads import synth
+
+    prob, truth = synth.sfdtidal_variant("SFDTidal_Qmec0", nobs=500, missing_every=1)
+    o = Oracle(prob)
+    assert o.sizes.nState == 0 and o.P == 5 + 2
+    _, Ys, feas = o.calibration_run(truth)
+    assert feas and np.isfinite(Ys).all() and np.ptp(Ys[:, 0]) > 100.0
+    Be, he, dzeta, ne, Q0 = truth[:5]
+    fix = np.asarray(prob.fix_value)
+    th2 = [Be, -he, dzeta, ne, -fix[4], -fix[5], fix[6], fix[7], Q0, fix[9], fix[10]]  # Qmec2: (Be, bevs, delta, ne, d1, d2, c, g, Q0, dx, dt)
+    p2 = Problem("SFDTidal_Qmec2", np.asarray(prob.X), np.asarray(prob.Y), Yu=np.asarray(prob.Yu), partype=[-1] * 11, priors_theta=[],
+                 fix_value=th2, sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000])] * 2)
+    _, Y2, f2 = Oracle(p2).calibration_run(np.array([10.0, 0.02]))
+    assert f2 and np.array_equal(Y2, Ys)
+    for pos, val in ((1, -1.0), (2, 0.01), (3, 0.0)):  # he <= 0, dzeta >= 0, ne <= 0 (:96-98)
+        x = truth.copy(); x[pos] = val
+        assert o.logpost_one(x)["feas"] == 0
+    x = truth.copy(); x[1] = 0.5  # he so small that the wetted area turns negative at low tide (:113-115)
+    assert o.logpost_one(x)["feas"] == 0
+
+    prob, truth = synth.sfdtidal_variant("SFDTidal_QmecMS", nobs=500, missing_every=1)
+    o = Oracle(prob)
+    assert o.sizes.nState == 0 and o.P == 4 + 2
+    _, Ys, feas = o.calibration_run(truth)
+    A0, be, delta, phi = truth[:4]
+    fix = np.asarray(prob.fix_value)
+    y0, d1, d2, c, g, dx = fix[0], fix[5], fix[6], fix[7], fix[8], fix[9]
+    X = np.asarray(prob.X)
+    width = A0 / (y0 - be)
+    R0 = A0 / (width + 2 * (y0 - be))
+    ne = np.sqrt(phi / (8 * g) * A0 * R0**c)
+    y1, y2 = X[:, 0] + d1, X[:, 1] + d2
+    Ae = width * ((y1 + y2) / 2 - be)
+    Rh = Ae / (width + 2 * ((y1 + y2) / 2 - be))
+    sl = (y2 - y1) + delta
+    want = np.where(sl > 0, -1.0, 1.0) * (1 / ne) * Rh ** (0.5 * c) * Ae * np.sqrt(np.abs(sl / dx))
+    assert feas and np.allclose(Ys[:, 0], want, rtol=1e-13) and (want > 0).any() and (want < 0).any()
+    x = truth.copy(); x[0] = -5.0  # A0 <= 0
+    assert o.logpost_one(x)["feas"] == 0

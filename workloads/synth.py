@@ -589,3 +589,41 @@ def dynamic_vegetation(nobs: int = 730, seed: int = SEED + 15, missing_every: in
     if missing_every > 1:
         Y[np.arange(nobs) % missing_every != 0, 1:] = -9999.0
     return make(Y), truth
+
+
+def sfdtidal_variant(model: str, nobs: int = 600, seed: int = SEED + 16, missing_every: int = 3):
+    """SFDTidal_Qmec0 (original Qmec parameterisation: Be, he, dzeta, ne, d1, d2, c, g, Q0, dx, dt; stages minus datums) and
+    SFDTidal_QmecMS (steady Manning-Strickler version: y0, A0, be, delta, phi, d1, d2, c, g, dx) on the two synthetic tidal
+    stage series of sfdtidal_qmec.  The discharge "observations" are the oracle's own run plus noise.  Returns (Problem, truth)."""
+    from oracle.oracle_api import Oracle
+
+    rng = default_rng(seed)
+    t = np.arange(nobs) * 60.0
+    h1 = 1.5 * np.sin(2 * np.pi * t / 44700.0) + 0.3 * np.sin(2 * np.pi * t / 7000.0)
+    h2 = 1.5 * np.sin(2 * np.pi * (t - 600.0) / 44700.0) + 0.3 * np.sin(2 * np.pi * (t - 500.0) / 7000.0) - 0.03
+    if model == "SFDTidal_Qmec0":
+        th = np.array([225.0, 8.0, -0.02, 0.03, 0.0, -0.05, 4.0 / 3.0, 9.81, 300.0, 4000.0, 60.0])
+        partype = [0, 0, 0, 0, -1, -1, -1, -1, 0, -1, -1]
+    elif model == "SFDTidal_QmecMS":
+        th = np.array([2.0, 1800.0, -6.0, 0.02, 4e-6, 0.0, 0.05, 4.0 / 3.0, 9.81, 4000.0])
+        partype = [-1, 0, 0, 0, 0, -1, -1, -1, -1, -1]
+    else:
+        raise ValueError(model)
+    nt = th.size
+    pri = [("Gaussian", [v, 0.05 * abs(v) + 0.01]) for v in th]
+
+    def make(Y, uq):
+        return Problem(model, np.column_stack([h1, h2]), Y, Yu=uq, partype=partype,
+                       priors_theta=[pri[i] for i in range(nt) if partype[i] == 0],
+                       fix_value=[v if partype[i] == -1 else 0.0 for i, v in enumerate(th)],
+                       sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000])] * 2)
+
+    truth = np.concatenate([[th[i] for i in range(nt) if partype[i] == 0], [10.0, 0.02]])
+    _, Ys, feas = Oracle(make(np.zeros(nobs), np.ones(nobs))).calibration_run(truth)
+    assert feas
+    Q = Ys[:, 0]
+    uq = 0.03 * np.abs(Q) + 5.0
+    Y = Q + rng.standard_normal(nobs) * np.sqrt(uq**2 + (10.0 + 0.02 * np.abs(Q)) ** 2)
+    if missing_every > 1:
+        Y[np.arange(nobs) % missing_every != 0] = -9999.0
+    return make(Y, uq), truth
