@@ -1238,7 +1238,34 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     const double lo = smp[ns / 200], hi = smp[ns - 1 - ns / 200], pivot = smp[ns / 2];
     __syncthreads();
     if (!(hi > lo) || !(hi - lo < INFINITY)) {
-        if (tid == 0) needSlow[colId] = (hi == lo && Nrep > 6000000) ? 2 : 1;  // 99 % of the subsample is one value: ties
+        if (hi == lo) {
+            // 99 % of the subsample is ONE value.  Often the whole column is (a growth index outside the season for every
+            // replication, cos(pi g0) = 1 there, Q = 0 on a dry bed): one read decides, and a constant column needs no
+            // selection at all -- instead of the 7 reads of the radix walk (Vegetation 10^7 x 1095 x 5: a third of the columns)
+            const double v0 = lo;
+            double nb = 0.0, nd = 0.0;
+            s3_for_each<NTHR>(col, Nrep, [&](double v) {
+                if (v == unfeas || v != v) nb += 1.0;
+                else if (v != v0) nd += 1.0;
+            });
+            const long long nbad = (long long)s3_block_sum<NTHR>(nb, scratch);
+            const long long ndiff = (long long)s3_block_sum<NTHR>(nd, scratch);
+            if (ndiff == 0) {
+                const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
+                const long long m = Nrep - nbad;
+                if (tid == 0) {
+                    if ((!drop && nbad > 0) || nbad == Nrep) {
+                        for (int k = 0; k < BAMGPU_NENV; ++k) out[(size_t)k * nT] = unfeas;
+                    } else {
+                        for (int k = 0; k < 6; ++k) out[(size_t)k * nT] = v0;  // five quantiles and the mean
+                        out[(size_t)6 * nT] = (m > 1) ? 0.0 : unfeas;
+                    }
+                    needSlow[colId] = 0;
+                }
+                return;
+            }
+        }
+        if (tid == 0) needSlow[colId] = (hi == lo && Nrep > 6000000) ? 2 : 1;  // ties next to other values
         return;
     }
     const double scale = (double)(S3_NB - 2) / (hi - lo);
