@@ -1132,6 +1132,8 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
 // below the first activation stage); anything else is flagged for the 4-read kernel envelope_select2.
 #define S3_NB 16384
 #define S3_SAMPLE 2048
+#define S3_ATOMS 2   /* atoms per column handled by envelope_select3 */
+#define S3_RUN 8     /* run length in the sorted subsample that makes a value an atom */
 
 __device__ __forceinline__ int s3_bin(double v, double lo, double scale) {
     if (v < lo) return 0;
@@ -1200,6 +1202,13 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     __shared__ int tBin[SEL_NT], tList[SEL_NT], listBin[SEL_NT], listCnt[SEL_NT], listOver[SEL_NT], gCnt[SEL_NT], nLists, nGood;
     __shared__ unsigned long long listMin[SEL_NT], listMax[SEL_NT];
     __shared__ double tVal[SEL_NT];
+    // ATOMS: values the subsample holds S3_RUN or more times (0.4 % of the column: far more than a gather list takes) -- a
+    // growth index that is exactly 0 before the season, cos(pi g0) = -1 at its peak, Q = 0 below an activation stage.  They are
+    // counted, not gathered: the bin that holds one keeps its place in the prefix sums, its list holds the OTHER values of
+    // the bin, and a rank inside the bin is resolved against (sorted list + c copies of the atom).
+    __shared__ double atomV[S3_ATOMS];
+    __shared__ long long atomC[S3_ATOMS];
+    __shared__ int nAtomRaw, listAtoms[SEL_NT];
     const int tid = threadIdx.x;
     const int colId = blockIdx.x;
     const double* col = V + (size_t)colId * Nrep;
@@ -1235,38 +1244,70 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
         if (tid == 0) needSlow[colId] = 1;
         return;
     }
-    const double lo = smp[ns / 200], hi = smp[ns - 1 - ns / 200], pivot = smp[ns / 2];
+    double lo = smp[ns / 200], hi = smp[ns - 1 - ns / 200];
+    const double pivot = smp[ns / 2], smin = smp[0], smax = smp[ns - 1];
+    if (tid == 0) nAtomRaw = 0;
+    __syncthreads();
+    for (int i = tid; i + S3_RUN <= ns; i += NTHR) {  // start of a run of >= S3_RUN equal values
+        const double v = smp[i];
+        if (v == smp[i + S3_RUN - 1] && (i == 0 || smp[i - 1] != v)) {
+            const int a = atomicAdd(&nAtomRaw, 1);
+            if (a < S3_ATOMS) atomV[a] = v;
+        }
+    }
+    __syncthreads();
+    // more runs than slots: which ones got a slot depends on the atomics' order, so use none (the answers never depend on
+    // the atoms, only the path does; this keeps the path itself repeatable)
+    const int nAtom = (nAtomRaw <= S3_ATOMS) ? nAtomRaw : 0;
+    double at0 = (nAtom > 0) ? atomV[0] : NAN, at1 = (nAtom > 1) ? atomV[1] : NAN;
+    if (nAtom == 2 && at1 < at0) { const double t = at0; at0 = at1; at1 = t; }
     __syncthreads();
     if (!(hi > lo) || !(hi - lo < INFINITY)) {
-        if (hi == lo) {
-            // 99 % of the subsample is ONE value.  Often the whole column is (a growth index outside the season for every
-            // replication, cos(pi g0) = 1 there, Q = 0 on a dry bed): one read decides, and a constant column needs no
-            // selection at all -- instead of the 7 reads of the radix walk (Vegetation 10^7 x 1095 x 5: a third of the columns)
+        if (hi == lo && smin == smax) {
+            // the whole subsample is ONE value v0.  One read counts the values below / above / equal and their moments: when
+            // every target rank falls inside the block of v0 (always, for a constant column: a growth index outside the
+            // season for every replication, cos(pi g0) = 1 there, Q = 0 on a dry bed) no selection is needed at all --
+            // instead of the 7 reads of the radix walk (Vegetation 10^7 x 1095 x 5: a third of the columns)
             const double v0 = lo;
-            double nb = 0.0, nd = 0.0;
+            double nb = 0.0, nl = 0.0, ng = 0.0, s1 = 0.0, s2 = 0.0;
             s3_for_each<NTHR>(col, Nrep, [&](double v) {
-                if (v == unfeas || v != v) nb += 1.0;
-                else if (v != v0) nd += 1.0;
+                if (v == unfeas || v != v) { nb += 1.0; return; }
+                if (v == v0) return;
+                if (v < v0) nl += 1.0; else ng += 1.0;
+                const double d = v - v0;
+                s1 += d;
+                s2 = fma(d, d, s2);
             });
             const long long nbad = (long long)s3_block_sum<NTHR>(nb, scratch);
-            const long long ndiff = (long long)s3_block_sum<NTHR>(nd, scratch);
-            if (ndiff == 0) {
-                const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
-                const long long m = Nrep - nbad;
+            const long long nless = (long long)s3_block_sum<NTHR>(nl, scratch), ngreat = (long long)s3_block_sum<NTHR>(ng, scratch);
+            const double S1 = s3_block_sum<NTHR>(s1, scratch), S2 = s3_block_sum<NTHR>(s2, scratch);
+            const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
+            const long long m = Nrep - nbad;
+            if ((!drop && nbad > 0) || nbad == Nrep) {
+                if (tid < BAMGPU_NENV) out[(size_t)tid * nT] = unfeas;
+                if (tid == 0) needSlow[colId] = 0;
+                return;
+            }
+            // lowest and highest target rank (Hazen positions of 2.5 % and 97.5 %, both neighbours)
+            const double hLo = 0.025 * (double)m + 0.5, hHi = 0.975 * (double)m + 0.5;
+            const long long rLo = (hLo <= 1.0) ? 0 : ((hLo >= (double)m) ? m - 1 : (long long)floor(hLo) - 1);
+            const long long rHi = (hHi <= 1.0) ? 0 : ((hHi >= (double)m) ? m - 1 : (long long)floor(hHi));
+            if (rLo >= nless && rHi < m - ngreat) {
                 if (tid == 0) {
-                    if ((!drop && nbad > 0) || nbad == Nrep) {
-                        for (int k = 0; k < BAMGPU_NENV; ++k) out[(size_t)k * nT] = unfeas;
-                    } else {
-                        for (int k = 0; k < 6; ++k) out[(size_t)k * nT] = v0;  // five quantiles and the mean
-                        out[(size_t)6 * nT] = (m > 1) ? 0.0 : unfeas;
-                    }
+                    for (int k = 0; k < 5; ++k) out[(size_t)k * nT] = v0;
+                    out[(size_t)5 * nT] = v0 + S1 / (double)m;
+                    out[(size_t)6 * nT] = (m > 1) ? sqrt(fmax(S2 - S1 * (S1 / (double)m), 0.0) / (double)(m - 1)) : unfeas;
                     needSlow[colId] = 0;
                 }
                 return;
             }
         }
-        if (tid == 0) needSlow[colId] = (hi == lo && Nrep > 6000000) ? 2 : 1;  // ties next to other values
-        return;
+        if (smax > smin && smax - smin < INFINITY && nAtom > 0) {
+            lo = smin; hi = smax;  // 99 % of the subsample is one value (an atom): bin the full range of the subsample instead
+        } else {
+            if (tid == 0) needSlow[colId] = (hi == lo && Nrep > 6000000) ? 2 : 1;  // ties next to other values
+            return;
+        }
     }
     const double scale = (double)(S3_NB - 2) / (hi - lo);
 
@@ -1274,14 +1315,26 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     for (int b = tid; b < S3_NB; b += NTHR) hist[b] = 0;
     for (int b = tid; b < S3_NB / 32; b += NTHR) bitmap[b] = 0;
     __syncthreads();
-    double s1 = 0.0, s2 = 0.0, nb = 0.0;
+    double s1 = 0.0, s2 = 0.0, nb = 0.0, ca0 = 0.0, ca1 = 0.0;
     s3_for_each<NTHR>(col, Nrep, [&](double v) {
         if (v == unfeas || v != v) { nb += 1.0; return; }
         const double d = v - pivot;
         s1 += d;
         s2 = fma(d, d, s2);
+        if (v == at0) { ca0 += 1.0; return; }
+        if (v == at1) { ca1 += 1.0; return; }
         atomicAdd(&hist[s3_bin(v, lo, scale)], 1u);
     });
+    if (nAtom > 0) {  // the atoms' bins count them all the same
+        const long long c0 = (long long)s3_block_sum<NTHR>(ca0, scratch), c1 = (long long)s3_block_sum<NTHR>(ca1, scratch);
+        if (tid == 0) {
+            atomV[0] = at0; atomC[0] = c0;
+            atomV[1] = at1; atomC[1] = (nAtom > 1) ? c1 : 0;
+            hist[s3_bin(at0, lo, scale)] += (unsigned)c0;
+            if (nAtom > 1) hist[s3_bin(at1, lo, scale)] += (unsigned)c1;
+        }
+        __syncthreads();
+    }
     const long long nbad = (long long)s3_block_sum<NTHR>(nb, scratch);
     const bool drop = (double)nbad / (double)Nrep < 0.75;  // maxMVrate (:1306,1395)
     if ((!drop && nbad > 0) || nbad == Nrep) {
@@ -1337,7 +1390,12 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
                 li = nl++;
                 listBin[li] = tBin[k];
                 listCnt[li] = 0;
-                listOver[li] = gCnt[k] > CAP;
+                int am = 0;
+                long long others = gCnt[k];
+                for (int a = 0; a < nAtom; ++a)
+                    if (s3_bin(atomV[a], lo, scale) == tBin[k]) { am |= 1 << a; others -= atomC[a]; }
+                listAtoms[li] = am;
+                listOver[li] = others > CAP;
                 listMin[li] = 0xffffffffffffffffull;
                 listMax[li] = 0ull;
                 bitmap[tBin[k] >> 5] |= 1u << (tBin[k] & 31);
@@ -1352,6 +1410,7 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     const int nl = nLists;
     s3_for_each<NTHR>(col, Nrep, [&](double v) {
         if (v == unfeas || v != v) return;
+        if (v == at0 || v == at1) return;
         const int b = s3_bin(v, lo, scale);
         if (!((bitmap[b >> 5] >> (b & 31)) & 1u)) return;
         for (int j = 0; j < nl; ++j)
@@ -1390,8 +1449,26 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     }
     if (tid < SEL_NT) {
         const int j = tList[tid];
-        if (!listOver[j]) tVal[tid] = gath[j * CAP + (int)tRank[tid]];
-        else if (listMin[j] == listMax[j]) {  // every member of the bin is the same value
+        if (!listOver[j] && listAtoms[j] == 0) tVal[tid] = gath[j * CAP + (int)tRank[tid]];
+        else if (!listOver[j]) {  // rank inside (sorted other values of the bin) merged with the bin's atoms, ascending
+            const double* g = gath + j * CAP;
+            const int cnt = listCnt[j];
+            long long r = tRank[tid], before = 0;  // before = atom copies that precede the answer
+            double ans = NAN;
+            bool done = false;
+            for (int a = 0; a < nAtom && !done; ++a) {
+                if (!((listAtoms[j] >> a) & 1)) continue;
+                const double av = atomV[a];
+                int l0 = 0, l1 = cnt;  // number of list values below the atom
+                while (l0 < l1) { const int mid = (l0 + l1) >> 1; if (g[mid] < av) l0 = mid + 1; else l1 = mid; }
+                const long long first = (long long)l0 + before;
+                if (r < first) { ans = g[r - before]; done = true; }
+                else if (r < first + atomC[a]) { ans = av; done = true; }
+                else before += atomC[a];
+            }
+            if (!done) ans = (r - before < cnt) ? g[r - before] : NAN;
+            tVal[tid] = ans;
+        } else if (listMin[j] == listMax[j] && listAtoms[j] == 0) {  // every member of the bin is the same value
             const unsigned long long kx = listMin[j];
             const unsigned long long bits = (kx >> 63) ? (kx ^ 0x8000000000000000ull) : ~kx;
             tVal[tid] = __longlong_as_double((long long)bits);

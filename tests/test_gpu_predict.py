@@ -336,3 +336,45 @@ def test_two_read_selection_large_sample():
         assert np.allclose(env[0, 5:], env4[0, 5:], rtol=1e-11, atol=1e-300)
         q = env[0]
         assert (q[1] <= q[3]).all() and (q[3] <= q[0]).all() and (q[0] <= q[4]).all() and (q[4] <= q[2]).all()
+
+
+def test_two_read_selection_atoms():
+    """envelope_select3 with ATOMS (values that fill far more than a gather list): exact zeros for 30 % of the sample next to
+    a continuum, two atoms in one column, an atom that holds every target rank with a few other values around it, and a
+    column of 99.9 % one value with outliers on both sides -- against the oracle's sort and the radix walk."""
+    from bam_b200.capi import Problem
+
+    rng = np.random.default_rng(18)
+    N = 60000
+    pl = Problem("Linear", np.ones((5, 1)), np.zeros(5), partype=[0], priors_theta=[("FlatPrior", [])],
+                 sigma_func=["Constant"], priors_gamma=[("FlatPrior+", [])])
+    cases = []
+    th = rng.standard_normal(N); th[rng.random(N) < 0.3] = 0.0
+    cases.append(th)                                              # one atom inside the continuum
+    th = rng.standard_normal(N); u = rng.random(N); th[u < 0.3] = 0.0; th[u > 0.8] = 0.001
+    cases.append(th)                                              # two atoms, probably in one bin or neighbours
+    th = np.full(N, 2.5); th[:700] = rng.standard_normal(700) + 2.5
+    cases.append(rng.permutation(th))                             # 98.8 % one value: every target rank inside the atom
+    th = np.full(N, -1.0); th[:30] = 50.0; th[30:80] = -70.0
+    cases.append(rng.permutation(th))                             # the subsample may be ONE value: the counting shortcut
+    th = np.full(N, 1.0); th[: N // 20] = rng.uniform(0.0, 1.0, N // 20)
+    cases.append(rng.permutation(th))                             # 95 % atom at the upper end (cos(pi g0) = 1 with a tail)
+    xs = [np.array([1.0, -1.0, 3.0])]
+    for th in cases:
+        mc = np.column_stack([th, np.ones(N)])
+        mc_bad = mc.copy()
+        g, o, gr = BamGpu(pl), Oracle(pl), BamGpu(pl)
+        gr.set_option("only_radix", 1)
+        env, _ = g.predict(mc, np.array([0.5, 1.0]), xs, 1, [0])
+        oenv, _ = o.predict(mc, np.array([0.5, 1.0]), xs, 1, [0], nthreads=8)
+        envr, _ = gr.predict(mc, np.array([0.5, 1.0]), xs, 1, [0])
+        assert (env[0, :5] == envr[0, :5]).all()                  # exact order statistics on both paths
+        cmp_env(env[:, :5], oenv[:, :5])
+        # mean and sd against a long-double evaluation: the oracle (like the reference) adds the squared deviations in sorted
+        # order in plain doubles, and 59 000 IDENTICAL tiny addends round the same way every time (1.2e-12 on the third case)
+        col = th.astype(np.longdouble)[None, :] * np.asarray(xs[0], dtype=np.longdouble)[:, None]
+        sd = np.std(col, axis=1, ddof=1).astype(np.float64)
+        mean = col.mean(axis=1).astype(np.float64)
+        assert np.allclose(env[0, 6], sd, rtol=1e-12, atol=1e-300) and np.allclose(oenv[0, 6], sd, rtol=1e-11, atol=1e-300)
+        assert (np.abs(env[0, 5] - mean) <= 1e-12 * np.maximum(sd, np.abs(mean)) + 1e-300).all()
+        assert (np.abs(oenv[0, 5] - mean) <= 1e-12 * np.maximum(sd, np.abs(mean)) + 1e-300).all()
