@@ -14,7 +14,7 @@
 // UnfoldParVector's un-biasing of the inputs (:3429-3452).  The tiling depends on n only, so a chain's value does not
 // depend on how many chains share the launch.
 // Eligible (launch_logpost): K >= 1024, no latent inputs (their hyper term and per-chain cells stay with logpost_main),
-// no single-component shift (comp < 0), rows fit in shared memory.
+// rows fit in shared memory.  Proposals of the launch-per-proposal sampler (one shifted component) take it as well.
 #include <algorithm>
 
 #include "bam_dispatch.cuh"
@@ -121,7 +121,10 @@ int logpost_chain_tiles(int n) {
 
 // returns the number of observation tiles written to h->d_part, or 0 when the launch is not eligible (caller falls back)
 int launch_logpost_chain(bamgpu_handle* h, const DevProblem& p, int K, int comp) {
-    if (h->forceGeneric || K < 1024 || p.n < 1 || p.hasLatent || comp >= 0) return 0;
+    // (a single-component shift `comp` needs nothing here: without latent inputs every component is a theta, a gamma or a
+    // bias, and logpost_prep has already written the shifted value into the chain's table row)
+    (void)comp;
+    if (h->forceGeneric || K < 1024 || p.n < 1 || p.hasLatent) return 0;
     const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + (size_t)LC_BLOCK * (p.tabStride | 1));
     if (smem > 200 * 1024) return 0;
     ChainKernel kern = pick_chain(p.model, p.nX, p.nY);

@@ -231,3 +231,23 @@ def test_partial_reevaluation_of_var_parameters():
     fx, feas, isnull = g.chains_download()
     fx2, _, _ = BamGpu(prob).logpost(rows[:, -1, :P])
     assert np.allclose(fx, fx2, rtol=1e-13) and feas.all()
+
+
+def test_launch_per_proposal_sampler_on_the_chain_parallel_kernel():
+    """n > 4096 keeps a pointwise model out of the persistent warp sampler; with K >= 1024 chains every proposal is then
+    evaluated by logpost_chain (thread = chain): same chains as with the observation-parallel kernel, and the first chains
+    follow the oracle."""
+    from workloads import synth
+
+    prob, truth = synth.second_wave("SWOT", nobs=5000, variant="SWOT_hSB")
+    K = 1024
+    s = synth.feasible_starts(truth, K, rel=0.005, seed=4)
+    sd = 0.002 * np.abs(s) + 1e-9
+    g, g2 = BamGpu(prob), BamGpu(prob)
+    g2.set_option("force_generic", 1)
+    rows = g.fit(s, sd, nAdapt=3, nCycles=1, seed=6)
+    rows2 = g2.fit(s, sd, nAdapt=3, nCycles=1, seed=6)
+    assert rows.shape == rows2.shape and np.allclose(rows, rows2, rtol=1e-9, atol=1e-12)
+    o = Oracle(prob)
+    orows = o.fit(s[:4], sd[:4], nAdapt=3, nCycles=1, seed=6)[0]
+    assert np.allclose(rows[:4], orows, rtol=1e-9, atol=1e-12)
