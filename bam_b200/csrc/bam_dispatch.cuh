@@ -24,5 +24,6 @@
     X(BAMGPU_MDL_MIXTURE, 4, 1) X(BAMGPU_MDL_MIXTURE, 5, 1) X(BAMGPU_MDL_MIXTURE, 6, 1)                     \
     X(BAMGPU_MDL_MIXTURE, 7, 1) X(BAMGPU_MDL_MIXTURE, 8, 1)                                                 \
     X(BAMGPU_MDL_SFDTIDAL_QMEC, 2, 1) X(BAMGPU_MDL_SFDTIDAL_QMEC2, 2, 1) X(BAMGPU_MDL_ALGAE, 5, 2) \
-    X(BAMGPU_MDL_DYNVEG, 5, 3) X(BAMGPU_MDL_SFDTIDAL_QMEC0, 2, 1) X(BAMGPU_MDL_SFDTIDAL_QMECMS, 2, 1)
+    X(BAMGPU_MDL_DYNVEG, 5, 3) X(BAMGPU_MDL_SFDTIDAL_QMEC0, 2, 1) X(BAMGPU_MDL_SFDTIDAL_QMECMS, 2, 1) \
+    X(BAMGPU_MDL_SFDTIDAL_LAG, 2, 1) X(BAMGPU_MDL_SFDTIDAL_LAG, 3, 1)
 #define BAM_FOR_EACH_INSTANCE(X) BAM_INSTANCES_A(X) BAM_INSTANCES_B(X) BAM_INSTANCES_C(X)

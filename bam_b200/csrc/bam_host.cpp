@@ -53,6 +53,7 @@ int model_from_name(const char* name) {
     if (s == "DynamicVegetation") return BAMGPU_MDL_DYNVEG;
     if (s == "SFDTidal_Qmec0") return BAMGPU_MDL_SFDTIDAL_QMEC0;
     if (s == "SFDTidal_QmecMS") return BAMGPU_MDL_SFDTIDAL_QMECMS;
+    if (s == "SFDTidal" || s == "SFDTidal2" || s == "SFDTidal4" || s == "SFDTidalJones") return BAMGPU_MDL_SFDTIDAL_LAG;
     return 0;
 }
 
@@ -580,6 +581,16 @@ int build_layout(const bamgpu_problem& p, HostLayout& L, std::string& mess) {
             if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: SFDTidal_Qmec is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }
             L.isSeries = true;
             break;
+        case BAMGPU_MDL_SFDTIDAL_LAG: {  // SFDTidal / SFDTidal2 / SFDTidal4 / SFDTidalJones: 8 parameters each, no xtra, no states (ModelLibrary_tools.f90:647-667)
+            std::string id = p.model_id ? p.model_id : "";
+            if (id.rfind("MDL_", 0) == 0) id = id.substr(4);
+            const int variant = id == "SFDTidal" ? 1 : (id == "SFDTidal2" ? 2 : (id == "SFDTidal4" ? 3 : 4));
+            if (nt != 8 || nX != (variant == 4 ? 3 : 2) || nY != 1) { mess = "SFDTidal_Apply: wrong size [theta], nX or nY"; return 1; }
+            if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: SFDTidal reads lagged rows of the input series: VAR parameters and input errors are not supported"; return 1; }
+            L.modelOpt[0] = variant;
+            L.isSeries = true;
+            break;
+        }
         case BAMGPU_MDL_ALGAE:  // AlgaeBiomass_GetParNumber: 18 (AlgaeBiomass_model.f90:46-51); XtraSetup: 5 states (ModelLibrary_tools.f90:697-702)
             if (nt != 18 || nX != 5 || nY != 2) { mess = "AlgaeBiomass_Apply: wrong size [theta], nX or nY"; return 1; }
             if (L.nVar || L.hasLatent || L.hasXbias) { mess = "bamgpu: AlgaeBiomass is a time-recursive model: VAR parameters and input errors are not supported"; return 1; }

@@ -1085,6 +1085,83 @@ __device__ inline bool algae_series(const DevProblem& p, int n, const double* __
     return true;
 }
 
+// SFDTidal / SFDTidal2 / SFDTidal4 / SFDTidalJones (variant 1..4): stage-fall-discharge curves for tidal rivers whose slope
+// term reads the stages at the lagged step tlag = clamp(t - Dt, 1, n), Dt = int(theta1) (SFDTidal_model.f90:110-118 and the
+// same lines of the other three).  Not recursive, but an output needs OTHER rows of the input series, so they run on
+// series_run with the time-recursive models.  Products are rounded operation by operation in the reference's order.
+__device__ inline bool sfdtidal_lag_series(int variant, int n, const double* __restrict__ X, const double* __restrict__ th,
+                                           double* __restrict__ out, size_t K) {
+    const double* h1 = X;
+    const double* h2 = X + n;
+    const double* dhdt = X + 2 * (size_t)n;  // Jones only
+    const long long Dt = (long long)th[0];   // Fortran real -> integer assignment truncates
+    auto lag = [&](int t) -> int {           // 0-based
+        const long long q = (long long)t - Dt;
+        return (q < 0) ? 0 : ((q > n - 1) ? n - 1 : (int)q);
+    };
+    auto sgn = [](double x) { return (x < 0.0 || (x == 0.0 && signbit(x))) ? -1.0 : 1.0; };  // sign(1._mrk, x)
+    if (variant == 1) {  // Dt, K, B1, B2, h0, M, L, deltaz
+        const double Kc = th[1], B1 = th[2], B2 = th[3], h0 = th[4], M = th[5], L = th[6], dz = th[7];
+        if (Kc <= 0.0 || B1 <= 0.0 || B2 <= 0.0 || M <= 0.0 || L <= 0.0) return false;
+        for (int t = 0; t < n; ++t) {
+            const int tl = lag(t);
+            const double fall = __dsub_rn(__dsub_rn(h1[tl], h2[tl]), dz);
+            double q = __ddiv_rn(__dmul_rn(__dmul_rn(sgn(fall), Kc), __dadd_rn(B2, B1)), 2.0);
+            q = __dmul_rn(q, sqrt(__ddiv_rn(fabs(fall), L)));
+            q = __dmul_rn(q, pow(__dsub_rn(__ddiv_rn(__dadd_rn(h1[tl], h2[tl]), 2.0), h0), M));
+            if (__dsub_rn(h1[t], h0) <= 0.0) q = 0.0;
+            out[(size_t)t * K] = q;
+        }
+        return true;
+    }
+    const double Kc = th[1], B = th[2], h0 = th[3], M = th[4], L = th[5], delta = th[6];
+    if (variant == 2) {  // ..., alpha in (0, 1)
+        const double alpha = th[7];
+        if (Kc <= 0.0 || B <= 0.0 || M <= 0.0 || L <= 0.0 || alpha <= 0.0 || alpha >= 1.0) return false;
+        for (int t = 0; t < n; ++t) {
+            double q = 0.0;
+            if (__dsub_rn(h1[t], h0) > 0.0) {
+                const double fall = __dsub_rn(__dsub_rn(h1[t], __dmul_rn(alpha, h2[lag(t)])), delta);
+                q = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(sgn(fall), Kc), B), sqrt(__ddiv_rn(fabs(fall), L))), pow(__dsub_rn(h1[t], h0), M));
+            }
+            out[(size_t)t * K] = q;
+        }
+        return true;
+    }
+    if (variant == 3) {  // ..., P = int(theta8): half-width of the window the slope is averaged over
+        const long long P = (long long)th[7];
+        if (Kc <= 0.0 || B <= 0.0 || M <= 0.0 || L <= 0.0 || P < 0) return false;
+        auto Sf = [&](int t) { const int tl = lag(t); return __ddiv_rn(__dsub_rn(__dsub_rn(h1[tl], h2[tl]), delta), L); };
+        for (int t = 0; t < n; ++t) {
+            long long t1 = t, t2 = t;
+            if (!((long long)t - P < 0 || (long long)t - P > n - 1 || (long long)t + P < 0 || (long long)t + P > n - 1)) { t1 = t - P; t2 = t + P; }
+            double sum = 0.0;
+            for (long long u = t1; u <= t2; ++u) sum = __dadd_rn(sum, Sf((int)u));
+            const double Sm = __ddiv_rn(sum, (double)(t2 - t1 + 1));
+            double q = 0.0;
+            if (__dsub_rn(h1[t], h0) > 0.0)
+                q = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(sgn(Sm), Kc), B), sqrt(fabs(Sm))), pow(__dsub_rn(h1[t], h0), M));
+            out[(size_t)t * K] = q;
+        }
+        return true;
+    }
+    {   // Jones: ..., alpha > 0; third input dh/dt
+        const double alpha = th[7];
+        if (Kc <= 0.0 || B <= 0.0 || M <= 0.0 || L <= 0.0 || alpha <= 0.0) return false;
+        for (int t = 0; t < n; ++t) {
+            double q = 0.0;
+            if (__dsub_rn(h1[t], h0) > 0.0) {
+                const int tl = lag(t);
+                const double Sf = __ddiv_rn(__dsub_rn(__dsub_rn(h1[tl], h2[tl]), delta), L);
+                const double rad = __dmul_rn(fabs(Sf), __dsub_rn(1.0, __dmul_rn(alpha, dhdt[t])));
+                q = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(sgn(Sf), Kc), B), sqrt(rad)), pow(__dsub_rn(h1[t], h0), M));
+            }
+            out[(size_t)t * K] = q;
+        }
+        return true;
+    }
+}
+
 // one sequential pass of a time-recursive model for one parameter vector; false = infeasible vector
 __device__ inline bool model_series(const DevProblem& p, const double* __restrict__ th, double* __restrict__ out, size_t K,
                                     int nOut) {
@@ -1092,6 +1169,7 @@ __device__ inline bool model_series(const DevProblem& p, const double* __restric
         p.model == BAMGPU_MDL_SFDTIDAL_QMECMS)
         return sfdtidal_qmec_series(p.model == BAMGPU_MDL_SFDTIDAL_QMEC2 ? 2 : (p.model == BAMGPU_MDL_SFDTIDAL_QMEC0 ? 3 : (p.model == BAMGPU_MDL_SFDTIDAL_QMECMS ? 4 : 1)),
                                     p.seriesN, p.seriesX, p.seriesX + p.seriesN, th, out, K, nOut);
+    if (p.model == BAMGPU_MDL_SFDTIDAL_LAG) return sfdtidal_lag_series(p.modelOpt[0], p.seriesN, p.seriesX, th, out, K);
     if (p.model == BAMGPU_MDL_ALGAE) return algae_series<false>(p, p.seriesN, p.seriesX, th, out, K, nOut);
     if (p.model == BAMGPU_MDL_DYNVEG) return algae_series<true>(p, p.seriesN, p.seriesX, th, out, K, nOut);
     return false;
@@ -1155,7 +1233,8 @@ __device__ __forceinline__ bool model_apply(const DevProblem& p, const double* x
     } else if (MODEL == BAMGPU_MDL_MIXTURE) {
         return mixture_apply<NX>(p, x, th, der, y[0]);
     } else if (MODEL == BAMGPU_MDL_SFDTIDAL_QMEC || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC2 || MODEL == BAMGPU_MDL_ALGAE ||
-               MODEL == BAMGPU_MDL_DYNVEG || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC0 || MODEL == BAMGPU_MDL_SFDTIDAL_QMECMS) {  // time-recursive: produced by series_run, looked up here
+               MODEL == BAMGPU_MDL_DYNVEG || MODEL == BAMGPU_MDL_SFDTIDAL_QMEC0 || MODEL == BAMGPU_MDL_SFDTIDAL_QMECMS ||
+               MODEL == BAMGPU_MDL_SFDTIDAL_LAG) {  // time-recursive: produced by series_run, looked up here
 #pragma unroll
         for (int k = 0; k < NY; ++k)
             y[k] = p.seriesY[((size_t)k * p.seriesN + (size_t)x[0]) * p.seriesK + (size_t)der[0]];

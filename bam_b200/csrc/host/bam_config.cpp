@@ -326,7 +326,8 @@ static void read_xtra(Workspace& w) {
         w.xtraI = {nS, nEvt, nElt, c0 == 't' ? 1 : 0};
     } else if (w.modelID == "Linear" || w.modelID == "SuspendedLoad" || w.modelID == "SGD" || w.modelID == "Recession_h" ||
                w.modelID == "SFDTidal_Qmec" || w.modelID == "SFDTidal_Qmec2" || w.modelID == "SFDTidal_Qmec0" ||
-               w.modelID == "SFDTidal_QmecMS" || w.modelID == "AlgaeBiomass") {  // nothing to read (ModelLibrary_tools.f90:506-507)
+               w.modelID == "SFDTidal_QmecMS" || w.modelID == "AlgaeBiomass" || w.modelID == "SFDTidal" || w.modelID == "SFDTidal2" ||
+               w.modelID == "SFDTidal4" || w.modelID == "SFDTidalJones") {  // nothing to read (ModelLibrary_tools.f90:506-507)
     } else {
         fail("ApplyModel: Fatal: Unavailable [model%ID] '" + w.modelID + "' (not on the GPU hot path yet)");
     }

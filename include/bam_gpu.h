@@ -67,9 +67,14 @@ enum bamgpu_model {
                                       AlgaeBiomass states; xtra_d = Newton xscale, fscale, tolX, tolF, xtra_i = itmax */
     BAMGPU_MDL_SFDTIDAL_QMEC0 = 20, /* SFDTidal_Qmec0_model.f90:61-178: the original Qmec parameterisation (Be, he, dzeta, ne, d1,
                                       d2, c, g, Q0, dx, dt), stages MINUS datums, no state variables */
-    BAMGPU_MDL_SFDTIDAL_QMECMS = 21 /* SFDTidal_QmecMS_model.f90:62-154: Manning-Strickler (steady) version of Qmec, theta =
+    BAMGPU_MDL_SFDTIDAL_QMECMS = 21, /* SFDTidal_QmecMS_model.f90:62-154: Manning-Strickler (steady) version of Qmec, theta =
                                       (y0, A0, be, delta, phi, d1, d2, c, g, dx); pointwise in time but the geometry of the
                                       WHOLE series decides feasibility, so it runs with the time-recursive models */
+    BAMGPU_MDL_SFDTIDAL_LAG = 22    /* the stage-fall-discharge curves for tidal rivers that read the stages at a LAGGED time
+                                      step, tlag = clamp(t - int(theta1), 1, n): "SFDTidal" (SFDTidal_model.f90:65-141),
+                                      "SFDTidal2" (SFDTidal2_model.f90), "SFDTidal4" (slope averaged over t-P..t+P,
+                                      SFDTidal4_model.f90) and "SFDTidalJones" (third input dh/dt, SFDTidalJones_model.f90);
+                                      8 parameters each, no state variables; the four names share this id */
 };
 
 /* Prior / distribution families (BMSL Distribution_tools names). */
@@ -120,7 +125,7 @@ typedef struct bamgpu_problem {
     const char* model_id; /* "BaRatin" | "Linear" | "Sediment" | "TextFile" | "Vegetation" | "SuspendedLoad" | "SWOT" | "SGD" |
                              "Orthorectification" | "Recession_h" | "HydraulicControl_section" | "Segmentation" | "BaRatinBAC" | "SFD" |
                              "Mixture" | "SFDTidal_Qmec" | "SFDTidal_Qmec2" | "AlgaeBiomass" | "DynamicVegetation" |
-                             "SFDTidal_Qmec0" | "SFDTidal_QmecMS"
+                             "SFDTidal_Qmec0" | "SFDTidal_QmecMS" | "SFDTidal" | "SFDTidal2" | "SFDTidal4" | "SFDTidalJones"
                              (optionally "MDL_"-prefixed) */
     int32_t nobs, nX, nY, ntheta;
 

@@ -1459,6 +1459,68 @@ static int dynveg_apply(const oracle_t* o, int n, const double* X, int ldx, cons
     return 1;
 }
 
+/* SFDTidal_Apply (SFDTidal_model.f90:65-141), SFDTidal2_Apply, SFDTidal4_Apply, SFDTidalJones_Apply (same lines of their
+   files): variant 1..4.  tlag = clamp(t - Dt, 1, n) with Dt = int(theta(1)); IN = (h1, h2[, dh/dt]), ld = ldx.
+   Returns 0 when the parameter set is infeasible. */
+static double f_sign1(double x) { return (x < 0.0 || (x == 0.0 && signbit(x))) ? -1.0 : 1.0; } /* sign(1._mrk, x) */
+static int sfdtidal_lag_apply(int variant, int n, const double* IN, int ldx, const double* th, double* OUT) {
+    const double *h1 = IN, *h2 = IN + (size_t)ldx, *dhdt = IN + 2 * (size_t)ldx;
+    long long Dt = (long long)th[0];
+    for (int t = 0; t < n; ++t) OUT[t] = BAMGPU_UNDEF_RN;
+#define TLAG(t) ((long long)(t) - Dt < 0 ? 0 : ((long long)(t) - Dt > n - 1 ? n - 1 : (int)((long long)(t) - Dt)))
+    if (variant == 1) {
+        double K = th[1], B1 = th[2], B2 = th[3], h0 = th[4], M = th[5], L = th[6], dz = th[7];
+        if (K <= 0.0 || B1 <= 0.0 || B2 <= 0.0 || M <= 0.0 || L <= 0.0) return 0;
+        for (int t = 0; t < n; ++t) {
+            int tl = TLAG(t);
+            OUT[t] = f_sign1(h1[tl] - h2[tl] - dz) * K * (B2 + B1) / 2 * sqrt(fabs(h1[tl] - h2[tl] - dz) / L) *
+                     pow((h1[tl] + h2[tl]) / 2 - h0, M);
+            if (h1[t] - h0 <= 0.0) OUT[t] = 0.0;
+        }
+        return 1;
+    }
+    double K = th[1], B = th[2], h0 = th[3], M = th[4], L = th[5], delta = th[6];
+    if (variant == 2) {
+        double alpha = th[7];
+        if (K <= 0.0 || B <= 0.0 || M <= 0.0 || L <= 0.0 || alpha <= 0.0 || alpha >= 1.0) return 0;
+        for (int t = 0; t < n; ++t) {
+            int tl = TLAG(t);
+            if (h1[t] - h0 <= 0.0) { OUT[t] = 0.0; continue; }
+            OUT[t] = f_sign1(h1[t] - alpha * h2[tl] - delta) * K * B * sqrt(fabs(h1[t] - alpha * h2[tl] - delta) / L) * pow(h1[t] - h0, M);
+        }
+        return 1;
+    }
+    if (variant == 3) {
+        long long P = (long long)th[7];
+        if (K <= 0.0 || B <= 0.0 || M <= 0.0 || L <= 0.0 || P < 0) return 0;
+        double* Sf = (double*)malloc(((size_t)n + 1) * sizeof(double));
+        for (int t = 0; t < n; ++t) { int tl = TLAG(t); Sf[t] = (h1[tl] - h2[tl] - delta) / L; }
+        for (int t = 0; t < n; ++t) {
+            long long t1 = t, t2 = t;
+            if (!((long long)t - P < 0 || (long long)t - P > n - 1 || (long long)t + P < 0 || (long long)t + P > n - 1)) { t1 = t - P; t2 = t + P; }
+            double sum = 0.0;
+            for (long long u = t1; u <= t2; ++u) sum += Sf[u];
+            double Sm = sum / (double)(t2 - t1 + 1);
+            if (h1[t] - h0 <= 0.0) { OUT[t] = 0.0; continue; }
+            OUT[t] = f_sign1(Sm) * K * B * sqrt(fabs(Sm)) * pow(h1[t] - h0, M);
+        }
+        free(Sf);
+        return 1;
+    }
+    {
+        double alpha = th[7];
+        if (K <= 0.0 || B <= 0.0 || M <= 0.0 || L <= 0.0 || alpha <= 0.0) return 0;
+        for (int t = 0; t < n; ++t) {
+            int tl = TLAG(t);
+            if (h1[t] - h0 <= 0.0) { OUT[t] = 0.0; continue; }
+            double Sf = (h1[tl] - h2[tl] - delta) / L;
+            OUT[t] = f_sign1(Sf) * K * B * sqrt(fabs(Sf) * (1 - (alpha * dhdt[t]))) * pow(h1[t] - h0, M);
+        }
+        return 1;
+    }
+#undef TLAG
+}
+
 /* SFDTidal_Qmec_Apply, SFDTidal_Qmec_model.f90:61-197: Q(m) = Q(m-1) + dt (pg + bf + ad), first-order step for m = 2,
    second-order Adams-Bashforth afterwards.  state (nullable, ld = lds): pressure_gradient, bottom_friction, advection.
    Returns 0 when the parameter set (or the geometry of the series) is infeasible. */
@@ -1593,6 +1655,10 @@ static int apply_model_s(const oracle_t* o, int n, const double* X, int ldx, con
                                      n, X, X + (size_t)ldx, fullTheta, Y, o->nState ? state : NULL, ldy))
                 for (int t = 0; t < n; ++t) vfeas[t] = 0;
             break;
+        case BAMGPU_MDL_SFDTIDAL_LAG:
+            if (!sfdtidal_lag_apply(o->model_opt[0], n, X, ldx, fullTheta, Y))
+                for (int t = 0; t < n; ++t) vfeas[t] = 0;
+            break;
         case BAMGPU_MDL_ALGAE: {
             int r = algae_apply(n, X, ldx, fullTheta, Y, ldy, state);
             if (r < 0) return 1;
@@ -1665,6 +1731,8 @@ static int model_from_name(const char* name) {
     if (!strcmp(name, "DynamicVegetation")) return BAMGPU_MDL_DYNVEG;
     if (!strcmp(name, "SFDTidal_Qmec0")) return BAMGPU_MDL_SFDTIDAL_QMEC0;
     if (!strcmp(name, "SFDTidal_QmecMS")) return BAMGPU_MDL_SFDTIDAL_QMECMS;
+    if (!strcmp(name, "SFDTidal") || !strcmp(name, "SFDTidal2") || !strcmp(name, "SFDTidal4") || !strcmp(name, "SFDTidalJones"))
+        return BAMGPU_MDL_SFDTIDAL_LAG;
     return 0;
 }
 
@@ -1833,6 +1901,14 @@ int oracle_create(oracle_t** out, const bamgpu_problem* p, char* mess) {
         case BAMGPU_MDL_SFDTIDAL_QMECMS: /* SFDTidal_QmecMS_GetParNumber: 10; no states (:682-685) */
             if (nt != (o->model == BAMGPU_MDL_SFDTIDAL_QMEC0 ? 11 : 10) || nX != 2 || nY != 1) { setmess(mess, "oracle: SFDTidal_Qmec: bad sizes"); return 1; }
             break;
+        case BAMGPU_MDL_SFDTIDAL_LAG: { /* 8 parameters each, no xtra, no states (ModelLibrary_tools.f90:647-667) */
+            const char* id = p->model_id;
+            if (!strncmp(id, "MDL_", 4)) id += 4;
+            int variant = !strcmp(id, "SFDTidal") ? 1 : (!strcmp(id, "SFDTidal2") ? 2 : (!strcmp(id, "SFDTidal4") ? 3 : 4));
+            if (nt != 8 || nX != (variant == 4 ? 3 : 2) || nY != 1) { setmess(mess, "oracle: SFDTidal: bad sizes"); return 1; }
+            o->model_opt[0] = variant;
+            break;
+        }
         case BAMGPU_MDL_ALGAE: /* AlgaeBiomass_GetParNumber: 18; XtraSetup: 5 state variables (ModelLibrary_tools.f90:697-702) */
             if (nt != 18 || nX != 5 || nY != 2) { setmess(mess, "oracle: AlgaeBiomass: bad sizes"); return 1; }
             o->nState = 5;

@@ -470,3 +470,36 @@ def test_time_recursive_sfdtidal_variants(model):
     Xt, Ys, feas = g.calibration_run(truth)
     oXt, oYs, ofeas = o.calibration_run(truth)
     assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-11)
+
+
+@pytest.mark.parametrize("model", ["SFDTidal", "SFDTidal2", "SFDTidal4", "SFDTidalJones"])
+def test_sfdtidal_lagged_family(model):
+    """row f4: the stage-fall-discharge curves that read the stages at a lagged time step (one device model id, four
+    variants) on series_run: log-posterior with gaps, prediction, sampler, residual run against the oracle."""
+    prob, truth = synth.sfdtidal_lag(model, nobs=500)
+    x = synth.feasible_starts(truth, 40, rel=0.01, seed=2)
+    x[3, 0] = -1.0                                  # K <= 0: infeasible parameter set
+    x[4, 3 if model == "SFDTidal" else 2] = 10.0    # bed above every stage: Q = 0 everywhere, feasible
+    g, o = BamGpu(prob), Oracle(prob)
+    assert g.sizes.nState == 0
+    check_parity(prob, x, tol=1e-12)
+    rng = np.random.default_rng(3)
+    mc = truth * (1.0 + 0.003 * rng.standard_normal((120, truth.size)))
+    mc[5, 0] = -1.0  # an infeasible replication
+    xs = [np.asarray(prob.X)[:, j].copy() for j in range(prob.nX)]
+    env, spag = g.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True)
+    oenv, ospag = o.predict(mc, truth, xs, 1, [1], seed=4, want_spag=True, nthreads=8)
+    assert spag.shape == (1, 500, 120) and (spag[:, :, 5] == -666.666).all()
+    cmp_spag(spag, ospag)
+    cmp_env(env, oenv)
+    _, s2 = g.predict(mc, truth, xs, 1, [0], want_env=False, want_spag=True, t0=100, t1=260)
+    _, sfull = g.predict(mc, truth, xs, 1, [0], want_env=False, want_spag=True)
+    assert np.array_equal(s2[0], sfull[0, 100:260])  # a sub-range still reads the lagged rows of the WHOLE series
+    s = np.tile(truth, (3, 1))
+    sd = 0.005 * np.abs(s) + 1e-12
+    rows = g.fit(s, sd, nAdapt=3, nCycles=2, seed=5)
+    orows = o.fit(s, sd, nAdapt=3, nCycles=2, seed=5)[0]
+    assert np.allclose(rows, orows, rtol=1e-9, atol=1e-12)
+    Xt, Ys, feas = g.calibration_run(truth)
+    oXt, oYs, ofeas = o.calibration_run(truth)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-12)

@@ -543,3 +543,50 @@ def test_sfdtidal_qmec0_and_qmecms():
     assert feas and np.allclose(Ys[:, 0], want, rtol=1e-13) and (want > 0).any() and (want < 0).any()
     x = truth.copy(); x[0] = -5.0  # A0 <= 0
     assert o.logpost_one(x)["feas"] == 0
+
+
+def test_sfdtidal_lagged_family():
+    """row f4: SFDTidal / SFDTidal2 / SFDTidal4 / SFDTidalJones against vectorised numpy restatements of their formulas
+    (the lag clamp, SFDTidal4's window rule at the ends of the series, the dry-bed zero) and their parameter exits."""
+    from workloads import synth
+
+    def lagged(a, Dt):
+        n = a.size
+        return a[np.clip(np.arange(n) - Dt, 0, n - 1)]
+
+    for model in ("SFDTidal", "SFDTidal2", "SFDTidal4", "SFDTidalJones"):
+        prob, truth = synth.sfdtidal_lag(model, nobs=500, missing_every=1)
+        o = Oracle(prob)
+        assert o.sizes.nState == 0
+        _, Ys, feas = o.calibration_run(truth)
+        X, fix = np.asarray(prob.X), np.asarray(prob.fix_value)
+        h1, h2 = X[:, 0], X[:, 1]
+        Dt = int(fix[0])
+        sg = lambda x: np.where(x < 0, -1.0, 1.0)  # noqa: E731
+        if model == "SFDTidal":
+            K, B1, B2, h0, M, dz = truth[:6]; L = fix[6]
+            fall = lagged(h1, Dt) - lagged(h2, Dt) - dz
+            want = sg(fall) * K * (B2 + B1) / 2 * np.sqrt(np.abs(fall) / L) * ((lagged(h1, Dt) + lagged(h2, Dt)) / 2 - h0) ** M
+            bad = (1, -1.0)
+        elif model == "SFDTidal2":
+            K, B, h0, M, delta, alpha = truth[:6]; L = fix[5]
+            fall = h1 - alpha * lagged(h2, Dt) - delta
+            want = sg(fall) * K * B * np.sqrt(np.abs(fall) / L) * (h1 - h0) ** M
+            bad = (5, 1.0)   # alpha >= 1
+        elif model == "SFDTidal4":
+            K, B, h0, M, delta = truth[:5]; L, P = fix[5], int(fix[7])
+            Sf = (lagged(h1, Dt) - lagged(h2, Dt) - delta) / L
+            Sm = np.array([Sf[t - P:t + P + 1].mean() if (t - P >= 0 and t + P <= 499) else Sf[t] for t in range(500)])
+            want = sg(Sm) * K * B * np.sqrt(np.abs(Sm)) * (h1 - h0) ** M
+            bad = (0, 0.0)   # K <= 0
+        else:
+            K, B, h0, M, delta, alpha = truth[:6]; L = fix[5]
+            Sf = (lagged(h1, Dt) - lagged(h2, Dt) - delta) / L
+            want = sg(Sf) * K * B * np.sqrt(np.abs(Sf) * (1 - alpha * X[:, 2])) * (h1 - h0) ** M
+            bad = (5, -1.0)  # alpha <= 0
+        assert feas and np.allclose(Ys[:, 0], want, rtol=1e-12) and (want > 0).any() and (want < 0).any()
+        x = truth.copy(); x[bad[0]] = bad[1]
+        assert o.logpost_one(x)["feas"] == 0
+        x = truth.copy(); x[2 if model != "SFDTidal" else 3] = 10.0  # bed above every stage: Q = 0 everywhere, still feasible
+        _, Y0, f0 = o.calibration_run(x)
+        assert f0 and (Y0 == 0.0).all()

@@ -627,3 +627,49 @@ def sfdtidal_variant(model: str, nobs: int = 600, seed: int = SEED + 16, missing
     if missing_every > 1:
         Y[np.arange(nobs) % missing_every != 0] = -9999.0
     return make(Y, uq), truth
+
+
+def sfdtidal_lag(model: str, nobs: int = 600, seed: int = SEED + 17, missing_every: int = 3):
+    """SFDTidal / SFDTidal2 / SFDTidal4 / SFDTidalJones: stage-fall-discharge curves for tidal rivers that read the stages
+    at a lagged time step (8 parameters each; the lag and SFDTidal4's averaging half-width are integers carried in real
+    parameters, fixed by the user).  Two synthetic tidal stage series (+ dh/dt for Jones); the discharge "observations"
+    are the oracle's own run plus noise.  Returns (Problem, truth)."""
+    from oracle.oracle_api import Oracle
+
+    rng = default_rng(seed)
+    t = np.arange(nobs) * 60.0
+    h1 = 2.0 + 1.5 * np.sin(2 * np.pi * t / 44700.0) + 0.3 * np.sin(2 * np.pi * t / 7000.0)
+    h2 = 2.0 + 1.5 * np.sin(2 * np.pi * (t - 600.0) / 44700.0) + 0.3 * np.sin(2 * np.pi * (t - 500.0) / 7000.0) - 0.03
+    X = [h1, h2]
+    if model == "SFDTidal":        # Dt, K, B1, B2, h0, M, L, deltaz
+        th = np.array([7.0, 30.0, 200.0, 240.0, -5.0, 1.67, 4000.0, 0.02])
+        partype = [-1, 0, 0, 0, 0, 0, -1, 0]
+    elif model == "SFDTidal2":     # Dt, K, B, h0, M, L, delta, alpha
+        th = np.array([7.0, 30.0, 220.0, -5.0, 1.67, 4000.0, 0.05, 0.97])
+        partype = [-1, 0, 0, 0, 0, -1, 0, 0]
+    elif model == "SFDTidal4":     # Dt, K, B, h0, M, L, delta, P
+        th = np.array([7.0, 30.0, 220.0, -5.0, 1.67, 4000.0, 0.02, 5.0])
+        partype = [-1, 0, 0, 0, 0, -1, 0, -1]
+    elif model == "SFDTidalJones":  # Dt, K, B, h0, M, L, delta, alpha; third input dh/dt
+        th = np.array([7.0, 30.0, 220.0, -5.0, 1.67, 4000.0, 0.02, 800.0])
+        partype = [-1, 0, 0, 0, 0, -1, 0, 0]
+        X.append(np.gradient(h1, 60.0))
+    else:
+        raise ValueError(model)
+    pri = [("Gaussian", [v, 0.05 * abs(v) + 0.01]) for v in th]
+
+    def make(Y, uq):
+        return Problem(model, np.column_stack(X), Y, Yu=uq, partype=partype,
+                       priors_theta=[pri[i] for i in range(8) if partype[i] == 0],
+                       fix_value=[v if partype[i] == -1 else 0.0 for i, v in enumerate(th)],
+                       sigma_func=["Linear"], priors_gamma=[("Uniform", [0, 1000])] * 2)
+
+    truth = np.concatenate([[th[i] for i in range(8) if partype[i] == 0], [10.0, 0.02]])
+    _, Ys, feas = Oracle(make(np.zeros(nobs), np.ones(nobs))).calibration_run(truth)
+    assert feas
+    Q = Ys[:, 0]
+    uq = 0.03 * np.abs(Q) + 5.0
+    Y = Q + rng.standard_normal(nobs) * np.sqrt(uq**2 + (10.0 + 0.02 * np.abs(Q)) ** 2)
+    if missing_every > 1:
+        Y[np.arange(nobs) % missing_every != 0] = -9999.0
+    return make(Y, uq), truth
