@@ -109,6 +109,15 @@ int bamgpu_create(bamgpu_t** out, const bamgpu_problem* pb, int device, char* me
         h->device = device;
         BAM_CUDA(cudaSetDevice(device));
         BAM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        {   // the stream-ordered scratch of the prediction tiles (cudaMallocAsync) stays in the device's default pool across
+            // synchronisations instead of being unmapped at each one and mapped again by the next call (milliseconds per tile)
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        }
         {   // stream-ordered scratch (cudaMallocAsync in the prediction loop): keep freed blocks in the pool across
             // synchronisations instead of returning them to the driver (default threshold 0 -> re-mapping every step)
             cudaMemPool_t pool;
