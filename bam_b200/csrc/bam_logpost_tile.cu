@@ -97,22 +97,49 @@ __global__ void __launch_bounds__(LT_BLOCK) logpost_tile(DevProblem p, const dou
             if (p.hasYbias) { yb[j] = p.Yb[q]; ybi[j] = p.Ybindx[q]; }
         }
         hyConst += p.hyC[i];
+        // UnfoldParVector for the LT_CT chains: latent cell from the vector, else un-bias the observed input
+        double xt[LT_CT][NX], yhAll[LT_CT][NY];
+        unsigned okMask = 0u;
 #pragma unroll
         for (int cc = 0; cc < LT_CT; ++cc) {
-            if (!live[cc]) continue;  // uniform over the block
             const double* __restrict__ row = rows + (size_t)cc * stride;
-            double xt[NX], yh[NY];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) {  // UnfoldParVector: latent cell from the vector, else un-bias the observed input
+            for (int j = 0; j < NX; ++j) {
                 double v = xo[j];
                 if (lat[j] >= 0) v = xl[cc][j];
                 else if (p.hasXbias && xbi[j] > 0) v = xo[j] - xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
-                xt[j] = v;
+                xt[cc][j] = v;
             }
-            const double* __restrict__ th = row + p.tabCombo + (size_t)combo * p.comboStride;
-            const bool ok = (MODEL == BAMGPU_MDL_BARATIN) ? baratin_apply_t(p, xt[0], th, th + p.ntheta, yh[0], lt, et)
-                                                          : model_apply<MODEL, NX, NY>(p, xt, th, th + p.ntheta, yh, fm);
-            if (!ok) { badMask |= 1u << cc; continue; }
+        }
+        if (MODEL == BAMGPU_MDL_TEXTFILE) {  // one pass of the bytecode interpreter serves the LT_CT chains
+            const double* thp[LT_CT];
+#pragma unroll
+            for (int cc = 0; cc < LT_CT; ++cc) thp[cc] = rows + (size_t)cc * stride + p.tabCombo + (size_t)combo * p.comboStride;
+            unsigned fail = 0u;
+#pragma unroll
+            for (int k = 0; k < NY; ++k) {
+                double r[LT_CT];
+                fail |= textfile_eval_multi<NX, LT_CT>(p, k, xt, thp, r, fm);
+#pragma unroll
+                for (int cc = 0; cc < LT_CT; ++cc) yhAll[cc][k] = r[cc];
+            }
+            okMask = ~fail;
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < LT_CT; ++cc) {
+                if (!live[cc]) continue;  // uniform over the block
+                const double* __restrict__ th = rows + (size_t)cc * stride + p.tabCombo + (size_t)combo * p.comboStride;
+                const bool ok = (MODEL == BAMGPU_MDL_BARATIN) ? baratin_apply_t(p, xt[cc][0], th, th + p.ntheta, yhAll[cc][0], lt, et)
+                                                              : model_apply<MODEL, NX, NY>(p, xt[cc], th, th + p.ntheta, yhAll[cc], fm);
+                if (ok) okMask |= 1u << cc;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < LT_CT; ++cc) {
+            if (!live[cc]) continue;
+            if (!((okMask >> cc) & 1u)) { badMask |= 1u << cc; continue; }
+            const double* __restrict__ row = rows + (size_t)cc * stride;
+            const double* yh = yhAll[cc];
             double l = 0.0;
 #pragma unroll
             for (int j = 0; j < NY; ++j) {
@@ -128,8 +155,8 @@ __global__ void __launch_bounds__(LT_BLOCK) logpost_tile(DevProblem p, const dou
             double H = 0.0;
 #pragma unroll
             for (int j = 0; j < NX; ++j) {  // cells without input error have hr = 0: no term
-                double mu = xt[j];
-                if (p.hasXbias && xbi[j] != 0) mu = xt[j] + xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
+                double mu = xt[cc][j];
+                if (p.hasXbias && xbi[j] != 0) mu = xt[cc][j] + xb[j] * row[p.tabOffXb[j] + xbi[j] - 1];
                 const double z = (xo[j] - mu) * hr[j];
                 H = fma(z, z, H);
             }

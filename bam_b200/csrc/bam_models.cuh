@@ -360,6 +360,72 @@ __device__ inline bool textfile_eval(const DevProblem& p, int k, const double* i
     return !(res != res);
 }
 
+// The same program for V parameter sets at once (the chains of a logpost_tile thread): one opcode fetch and one dispatch per
+// V evaluations instead of per evaluation -- with a 5-opcode formula the interpreter's own bookkeeping (fetch, jump table,
+// stack pointer) is 2/3 of the instructions.  Each set has its own inputs (latent cells differ per chain) and parameters.
+// Returns the mask of sets whose evaluation FAILED (the error exits of textfile_eval, or a NaN result); the arithmetic per
+// set is that of textfile_eval, operation for operation.
+template <int NX, int V>
+__device__ inline unsigned textfile_eval_multi(const DevProblem& p, int k, const double (*in)[NX], const double* const* th,
+                                               double* res, FmTab fm = FmTab{0u, 0u}) {
+    double st[BAM_VMSTACK][V];
+    int sp = -1;
+    unsigned fail = 0u;
+    const int* __restrict__ code = p.vmCode + p.vmCodeOff[k];
+    const double* __restrict__ imm = p.vmImmed + p.vmImmedOff[k];
+    int dp = 0;
+    const int ncode = p.vmNcode[k];
+#define VM_EACH(expr) _Pragma("unroll") for (int v = 0; v < V; ++v) { expr; }
+    for (int ip = 0; ip < ncode; ++ip) {
+        const int op = __ldg(code + ip);
+        switch (op) {
+            case VM_IMMED: { const double c = __ldg(imm + dp); ++dp; ++sp; VM_EACH(st[sp][v] = c) break; }
+            case VM_NEG: VM_EACH(st[sp][v] = -st[sp][v]) break;
+            case VM_ADD: VM_EACH(st[sp - 1][v] = st[sp - 1][v] + st[sp][v]) --sp; break;
+            case VM_SUB: VM_EACH(st[sp - 1][v] = st[sp - 1][v] - st[sp][v]) --sp; break;
+            case VM_MUL: VM_EACH(st[sp - 1][v] = st[sp - 1][v] * st[sp][v]) --sp; break;
+            case VM_DIV: VM_EACH(if (st[sp][v] == 0.0) fail |= 1u << v; st[sp - 1][v] = st[sp - 1][v] / st[sp][v]) --sp; break;
+            case VM_POW: VM_EACH(st[sp - 1][v] = fm_pow(st[sp - 1][v], st[sp][v], fm)) --sp; break;
+            case VM_ABS: VM_EACH(st[sp][v] = fabs(st[sp][v])) break;
+            case VM_EXP: VM_EACH(st[sp][v] = fm_exp(st[sp][v], fm)) break;
+            case VM_LOG10: VM_EACH(if (st[sp][v] <= 0.0) fail |= 1u << v; st[sp][v] = log10(st[sp][v])) break;
+            case VM_LOG: VM_EACH(if (st[sp][v] <= 0.0) { fail |= 1u << v; st[sp][v] = 1.0; } st[sp][v] = fm_log(st[sp][v], fm)) break;
+            case VM_SQRT: VM_EACH(if (st[sp][v] < 0.0) fail |= 1u << v; st[sp][v] = sqrt(st[sp][v])) break;
+            case VM_SINH: VM_EACH(st[sp][v] = sinh(st[sp][v])) break;
+            case VM_COSH: VM_EACH(st[sp][v] = cosh(st[sp][v])) break;
+            case VM_TANH: VM_EACH(st[sp][v] = tanh(st[sp][v])) break;
+            case VM_SIN: VM_EACH(st[sp][v] = sin(st[sp][v])) break;
+            case VM_COS: VM_EACH(st[sp][v] = cos(st[sp][v])) break;
+            case VM_TAN: VM_EACH(st[sp][v] = tan(st[sp][v])) break;
+            case VM_ASIN: VM_EACH(if (st[sp][v] < -1.0 || st[sp][v] > 1.0) fail |= 1u << v; st[sp][v] = asin(st[sp][v])) break;
+            case VM_ACOS: VM_EACH(if (st[sp][v] < -1.0 || st[sp][v] > 1.0) fail |= 1u << v; st[sp][v] = acos(st[sp][v])) break;
+            case VM_ATAN: VM_EACH(st[sp][v] = atan(st[sp][v])) break;
+            case VM_IS0: VM_EACH(st[sp][v] = (st[sp][v] == 0.0) ? 1.0 : 0.0) break;
+            case VM_ISPOS: VM_EACH(st[sp][v] = (st[sp][v] >= 0.0) ? 1.0 : 0.0) break;
+            case VM_ISNEG: VM_EACH(st[sp][v] = (st[sp][v] <= 0.0) ? 1.0 : 0.0) break;
+            case VM_ISSPOS: VM_EACH(st[sp][v] = (st[sp][v] > 0.0) ? 1.0 : 0.0) break;
+            case VM_ISSNEG: VM_EACH(st[sp][v] = (st[sp][v] < 0.0) ? 1.0 : 0.0) break;
+            default: {
+                const int q = op - VM_VARBEGIN;
+                ++sp;
+                if (q < NX) {
+                    VM_EACH(double val = 0.0; _Pragma("unroll") for (int i = 0; i < NX; ++i) if (i == q) val = in[v][i]; st[sp][v] = val)
+                } else {
+                    VM_EACH(st[sp][v] = th[v][q - NX])
+                }
+                break;
+            }
+        }
+    }
+#undef VM_EACH
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        res[v] = st[0][v];
+        if (res[v] != res[v]) fail |= 1u << v;
+    }
+    return fail;
+}
+
 // -------------------------------------------------------------------------------------------
 // Vegetation (Vegetation_model.f90:87-569).  theta = (B,S0,n1,b1,c1 | chi,U_chi | growth pars | gmax).
 // Per parameter set (vegetation_prepare): feasibility + growth-curve constants; for the temperature-driven
