@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
         const unsigned tt = ot + (unsigned)((nt + ILP - 1) / ILP) * (CB2_GS * 8);
         const unsigned mt = tt + (unsigned)((nt + ILP - 1) / ILP) * (CB2_GS * 8);
         const int c = cb * BAM_BLOCK + tid;
-        const size_t o = ((size_t)tile * K + (c < K ? c : 0)) * 2;
+        const size_t o = ((size_t)tile * K + (c < K ? c : 0)) * (p.partPacked ? 1 : 2);
         if (cb != curCb || combo != curCombo) {
             curCb = cb; curCombo = combo;
             // dead lanes (beyond K, or a vector whose prior already failed) stay in the loop for the arrival counter
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB2_MINB) logpost_baratin_cb2(D
             if (SIGF == BAMGPU_SIG_LINEAR) gate = gate && ((h2 >= CB2_G_LO && h2 < CB2_G_HI) || g2 == 0.0);
         }
         if (c < K) {
-            part[o + 1] = 0.0;
+            if (!p.partPacked) part[o + 1] = 0.0;
             if (!live) part[o] = 0.0;
         }
 

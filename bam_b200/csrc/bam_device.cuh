@@ -73,6 +73,7 @@ struct DevProblem {
     const double* vmImmed;
     int vmNcode[BAM_MAXY], vmCodeOff[BAM_MAXY], vmImmedOff[BAM_MAXY], vmNin, vmNpar;
     // SWOT {variant}, Orthorectification {distortion id, npar}, Segmentation {nS, nmin, option}, Mixture {nS, nEvt, nElt, missing}
+    int partPacked;  // BaRatin fast paths: 1 = one double per (tile, chain) partial (logpost_final_combo reads nothing else), 0 = {lkh, hyper} pairs
     int modelOpt[4];
     double modelOptD;
     const double* hcsTab;  // HydraulicControl_section: 4 x hcsN (h | A | w | h + A/(2w))

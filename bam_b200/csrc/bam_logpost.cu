@@ -650,12 +650,12 @@ __global__ void __launch_bounds__(32 * FINAL_STRIPES) logpost_final_combo(DevPro
             int t = comboTile0[v] + w;
             // a fixed association: stripe w adds its tiles four at a time into four chains, then (a0 + a1) + (a2 + a3)
             for (; t + 3 * FINAL_STRIPES < t1; t += 4 * FINAL_STRIPES) {
-                a0 += part[((size_t)t * K + c) * 2];
-                a1 += part[((size_t)(t + FINAL_STRIPES) * K + c) * 2];
-                a2 += part[((size_t)(t + 2 * FINAL_STRIPES) * K + c) * 2];
-                a3 += part[((size_t)(t + 3 * FINAL_STRIPES) * K + c) * 2];
+                a0 += part[((size_t)t * K + c)];
+                a1 += part[((size_t)(t + FINAL_STRIPES) * K + c)];
+                a2 += part[((size_t)(t + 2 * FINAL_STRIPES) * K + c)];
+                a3 += part[((size_t)(t + 3 * FINAL_STRIPES) * K + c)];
             }
-            for (; t < t1; t += FINAL_STRIPES) a0 += part[((size_t)t * K + c) * 2];
+            for (; t < t1; t += FINAL_STRIPES) a0 += part[((size_t)t * K + c)];
         }
         sa[w][lane] = (a0 + a1) + (a2 + a3);
         __syncthreads();
@@ -740,8 +740,8 @@ __global__ void __launch_bounds__(BAM_BLOCK, BAM_CB_MINB) logpost_baratin_cb(Dev
     __syncthreads();
     const int c = blockIdx.y * BAM_BLOCK + tid;
     if (c >= K) return;
-    const size_t o = ((size_t)tile * K + c) * 2;
-    part[o + 1] = 0.0;
+    const size_t o = ((size_t)tile * K + c) * (p.partPacked ? 1 : 2);
+    if (!p.partPacked) part[o + 1] = 0.0;
     if (status[c] != 0) { part[o] = 0.0; return; }
     const double* __restrict__ row = tab + (size_t)c * p.tabStride;
     const double g1 = row[p.tabGamma], g2 = (SIGF == BAMGPU_SIG_LINEAR) ? row[p.tabGamma + 1] : 0.0;
@@ -1318,6 +1318,8 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
         ensure_fast_tiles(h, tobs);
         nTiles = h->fpTiles;
         comboFinal = p.nCombo <= BAM_FP_MAXCOMBO;
+        DevProblem pf = p;
+        pf.partPacked = comboFinal ? 1 : 0;  // logpost_final_combo reads one double per (tile, chain)
         // a proposal that touches only some VAR combinations re-evaluates only their tiles (the cached sums of the
         // current state cover the rest); needs the cache to describe the CURRENT state: the sampler guarantees it
         const int* d_tiles = nullptr;
@@ -1366,14 +1368,14 @@ void launch_logpost(bamgpu_handle* h, int K, const double* d_x, int comp, const 
                 ++h->fpFullLaunches;
             }
             if (nItems > 0)
-                fast2<<<std::min(nItems, slots), BAM_BLOCK, smem, h->stream>>>(p, K, nItems, chainBlocks, h->fpMaxDoubles, h->d_fpPacked, h->d_fpOff,
+                fast2<<<std::min(nItems, slots), BAM_BLOCK, smem, h->stream>>>(pf, K, nItems, chainBlocks, h->fpMaxDoubles, h->d_fpPacked, h->d_fpOff,
                                                                             h->d_fpBytes, d_tiles, h->d_tab, h->d_status, h->d_part, h->d_status,
                                                                             h->d_fpSched, d_order, d_cost);
         } else {
             const size_t smem = sizeof(double) * (2 * BAM_LOGTAB_N + BAM_EXPTAB_N + 3 * (size_t)tobs);
             dim3 grid(std::max(launchTiles, 1), chainBlocks);
             if (launchTiles > 0)
-                fast<<<grid, BAM_BLOCK, smem, h->stream>>>(p, K, tobs, h->d_fpStart, h->d_fpEnd, h->d_fpCombo, d_tiles, h->d_tab,
+                fast<<<grid, BAM_BLOCK, smem, h->stream>>>(pf, K, tobs, h->d_fpStart, h->d_fpEnd, h->d_fpCombo, d_tiles, h->d_tab,
                                                            h->d_status, h->d_part, h->d_status);
         }
     } else if (SedLogpostKernel sk = (h->forceGeneric || comp >= p.nFit + p.nGamma) ? nullptr : pick_sed_logpost(p, K)) {
