@@ -589,53 +589,61 @@ __device__ inline bool vegetation_prepare(const DevProblem& p, const double* th,
 }
 
 // Vegetation_fNewton (:536-569).  x^chi once per evaluation, as exp(chi log x) (x^(1+chi) = x x^chi): the reference's two
-// pow() calls per evaluation dominate the per-observation cost; x = 0 (only the bracket's lower end) keeps pow()'s
-// limits x^chi = +inf (chi < 0) or 1 (chi = 0) and x^(1+chi) through pow() itself.
-__device__ __forceinline__ void veg_fnewton(double x, double Q0, double gam, double gam2, double chi, double& f, double& df,
-                                            FmTab fm = FmTab{0u, 0u}) {
-    const bool pos = x > 0.0;
-    const double px = pos ? fm_exp(chi * fm_log(x, fm), fm) : pow(x, chi);
-    double m = px / gam2;
+// pow() calls per evaluation dominate the per-observation cost.
+// The loop invariants of a solve are computed once (veg_root): Q0^2, 1 / gamma2 and gamma / gamma2 (2 + chi) -- the reference
+// divides by gamma2 twice in EVERY evaluation, and an FP64 division is ~30 instructions here; x^chi / gamma2 becomes a product
+// (<= 1 ulp from the quotient: the iterates move by that much, the polished root does not).
+struct VegNewton { double Q0sq, gam, rg2, k3, chi; };
+__device__ __forceinline__ void veg_fnewton(double x, const VegNewton& w, double& f, double& df, FmTab fm = FmTab{0u, 0u}) {
+    // x > 0 (the bracket's lower end x = 0 is evaluated in closed form by veg_root)
+    const double px = fm_exp(w.chi * fm_log(x, fm), fm);
+    double m = px * w.rg2;
     if (1.0 < m) m = 1.0;
-    f = x * x + (gam * (x * x) * m) - Q0 * Q0;
-    if (m == 1.0) df = 2.0 * x * (1.0 + gam);
-    else df = 2.0 * x + (gam / gam2 * (2.0 + chi) * (pos ? x * px : pow(x, 1.0 + chi)));
+    f = x * x + (w.gam * (x * x) * m) - w.Q0sq;
+    if (m == 1.0) df = 2.0 * x * (1.0 + w.gam);
+    else df = 2.0 * x + (w.k3 * (x * px));
 }
 
-// znewton on [0, Q0]: declared convention (miniDMSL is un-vendored), identical to oracle/bam_oracle.c:veg_znewton
+// znewton on [0, Q0]: declared convention (miniDMSL is un-vendored), the algorithm of oracle/bam_oracle.c:veg_znewton
 __device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, double gam2, double chi, double& root,
                                 FmTab fm = FmTab{0u, 0u}) {
     double fl, fh, df, f, xl, xh;
     const double x1 = 0.0, x2 = Q0;
-    veg_fnewton(x1, Q0, gam, gam2, chi, fl, df, fm);
-    veg_fnewton(x2, Q0, gam, gam2, chi, fh, df, fm);
+    VegNewton w;
+    w.Q0sq = Q0 * Q0; w.gam = gam; w.rg2 = 1.0 / gam2; w.k3 = gam / gam2 * (2.0 + chi); w.chi = chi;
+    // f(0) = 0 + gamma 0 m - Q0^2 with m = min(0^chi / gamma2, 1) in (0, 1]: no power needed (a NaN gamma still gives NaN)
+    fl = 0.0 + (gam * 0.0) - w.Q0sq;
     int fcalls = 2;
-    if (fl == 0.0) { root = x1; return fcalls <= p.vegItmax; }
+    if (fl == 0.0) { root = x1; return fcalls <= p.vegItmax; }  // Q0 = 0
+    if (!(Q0 > 0.0)) return false;                              // negative or NaN Q0: no bracket (f(Q0) was NaN)
+    veg_fnewton(x2, w, fh, df, fm);
     if (fh == 0.0) { root = x2; return fcalls <= p.vegItmax; }
     if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) return false;
     if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
     double rts = 0.5 * (x1 + x2), dxold = fabs(x2 - x1), dx = dxold;
-    veg_fnewton(rts, Q0, gam, gam2, chi, f, df, fm);
+    veg_fnewton(rts, w, f, df, fm);
     ++fcalls;
+    const double tolx = p.vegTolX * p.vegXscale, tolf = p.vegTolF * p.vegFscale;
     for (int j = 0; j < p.vegItmax; ++j) {
         if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
             dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
         } else {
             dxold = dx; dx = f / df; rts = rts - dx;
         }
-        const bool convx = fabs(dx) <= p.vegTolX * p.vegXscale;
-        veg_fnewton(rts, Q0, gam, gam2, chi, f, df, fm);
+        const bool convx = fabs(dx) <= tolx;
+        if (!(rts > 0.0)) return false;  // cannot happen inside a bracket (0, Q0] with f(0) < 0; guards the closed-form f(0)
+        veg_fnewton(rts, w, f, df, fm);
         ++fcalls;
         if (f < 0.0) xl = rts; else xh = rts;
-        if (convx || fabs(f) <= p.vegTolF * p.vegFscale) break;
+        if (convx || fabs(f) <= tolf) break;
     }
     for (int j = 0; j < 3 && f != 0.0 && df > 0.0; ++j) {  // polish to the root itself
         const double lo = fmin(xl, xh), hi = fmax(xl, xh);
         double xn = rts - f / df;
         xn = fmin(fmax(xn, lo), hi);
-        if (xn == rts) break;
+        if (xn == rts || !(xn > 0.0)) break;
         rts = xn;
-        veg_fnewton(rts, Q0, gam, gam2, chi, f, df, fm);
+        veg_fnewton(rts, w, f, df, fm);
         if (f < 0.0) xl = rts; else xh = rts;
     }
     root = rts;
