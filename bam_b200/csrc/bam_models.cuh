@@ -594,6 +594,12 @@ __device__ inline bool vegetation_prepare(const DevProblem& p, const double* th,
 // divides by gamma2 twice in EVERY evaluation, and an FP64 division is ~30 instructions here; x^chi / gamma2 becomes a product
 // (<= 1 ulp from the quotient: the iterates move by that much, the polished root does not).
 struct VegNewton { double Q0sq, gam, rg2, k3, chi; };
+// Newton step f / df: reciprocal (MUFU seed + one cubic correction, <= 1 ulp) times f for a derivative in the normal range,
+// the IEEE quotient otherwise
+__device__ __forceinline__ double veg_quot(double f, double df) {
+    const unsigned hi = (unsigned)__double2hiint(df);
+    return (hi - 0x00200000u < 0x7fb00000u) ? f * trcp(df) : f / df;
+}
 __device__ __forceinline__ void veg_fnewton(double x, const VegNewton& w, double& f, double& df, FmTab fm = FmTab{0u, 0u}) {
     // x > 0 (the bracket's lower end x = 0 is evaluated in closed form by veg_root)
     const double px = fm_exp(w.chi * fm_log(x, fm), fm);
@@ -628,7 +634,7 @@ __device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, doub
         if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
             dxold = dx; dx = 0.5 * (xh - xl); rts = xl + dx;
         } else {
-            dxold = dx; dx = f / df; rts = rts - dx;
+            dxold = dx; dx = veg_quot(f, df); rts = rts - dx;
         }
         const bool convx = fabs(dx) <= tolx;
         if (!(rts > 0.0)) return false;  // cannot happen inside a bracket (0, Q0] with f(0) < 0; guards the closed-form f(0)
@@ -639,7 +645,7 @@ __device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, doub
     }
     for (int j = 0; j < 3 && f != 0.0 && df > 0.0; ++j) {  // polish to the root itself
         const double lo = fmin(xl, xh), hi = fmax(xl, xh);
-        double xn = rts - f / df;
+        double xn = rts - veg_quot(f, df);
         xn = fmin(fmax(xn, lo), hi);
         if (xn == rts || !(xn > 0.0)) break;
         rts = xn;
