@@ -1130,15 +1130,16 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
 // pass C   gather the members of the <= 10 selected bins (<= S3_CAP each), sort, pick       (1 read)
 // A selected bin with more than S3_CAP members is still resolved when all its members are equal (ties: e.g. Q = 0
 // below the first activation stage); anything else is flagged for the 4-read kernel envelope_select2.
-#define S3_NB 16384
+// (bins of envelope_select3: 32 per thread of its block, see the kernel)
 #define S3_SAMPLE 2048
 #define S3_ATOMS 2   /* atoms per column handled by envelope_select3 */
 #define S3_RUN 8     /* run length in the sorted subsample that makes a value an atom */
 
+template <int NB>
 __device__ __forceinline__ int s3_bin(double v, double lo, double scale) {
     if (v < lo) return 0;
     const double f = (v - lo) * scale;
-    return (f >= (double)(S3_NB - 2)) ? S3_NB - 1 : 1 + (int)f;
+    return (f >= (double)(NB - 2)) ? NB - 1 : 1 + (int)f;
 }
 
 __device__ __forceinline__ unsigned long long s3_key(double v) {  // order-preserving map double -> uint64
@@ -1191,12 +1192,15 @@ template <int CAP, int NTHR>
 __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT, double unfeas,
                                                                const double* __restrict__ V, double* __restrict__ env,
                                                                int* __restrict__ needSlow) {
+    // bins: 32 per thread of the block -- 16384 for <512, 512>, 32768 for <2048, 1024>, whose 10^7-value columns put more than
+    // CAP values into the densest bins of a 16384-bin histogram (no ties needed: 8 % of Vegetation's columns went to the radix walk)
+    constexpr int NB = 32 * NTHR;
     extern __shared__ __align__(16) unsigned char s3raw[];  // 64 KB: sample (16 KB) -> histogram (64 KB) -> gather lists (40 KB)
     double* smp = reinterpret_cast<double*>(s3raw);
     unsigned* hist = reinterpret_cast<unsigned*>(s3raw);
     double* gath = reinterpret_cast<double*>(s3raw);
     __shared__ double scratch[40];
-    __shared__ unsigned bitmap[S3_NB / 32];
+    __shared__ unsigned bitmap[NB / 32];
     __shared__ unsigned prefix[NTHR];
     __shared__ long long tRank[SEL_NT];
     __shared__ int tBin[SEL_NT], tList[SEL_NT], listBin[SEL_NT], listCnt[SEL_NT], listOver[SEL_NT], gCnt[SEL_NT], nLists, nGood;
@@ -1309,11 +1313,11 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
             return;
         }
     }
-    const double scale = (double)(S3_NB - 2) / (hi - lo);
+    const double scale = (double)(NB - 2) / (hi - lo);
 
     // ---- pass B
-    for (int b = tid; b < S3_NB; b += NTHR) hist[b] = 0;
-    for (int b = tid; b < S3_NB / 32; b += NTHR) bitmap[b] = 0;
+    for (int b = tid; b < NB; b += NTHR) hist[b] = 0;
+    for (int b = tid; b < NB / 32; b += NTHR) bitmap[b] = 0;
     __syncthreads();
     double s1 = 0.0, s2 = 0.0, nb = 0.0, ca0 = 0.0, ca1 = 0.0;
     s3_for_each<NTHR>(col, Nrep, [&](double v) {
@@ -1323,15 +1327,15 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
         s2 = fma(d, d, s2);
         if (v == at0) { ca0 += 1.0; return; }
         if (v == at1) { ca1 += 1.0; return; }
-        atomicAdd(&hist[s3_bin(v, lo, scale)], 1u);
+        atomicAdd(&hist[s3_bin<NB>(v, lo, scale)], 1u);
     });
     if (nAtom > 0) {  // the atoms' bins count them all the same
         const long long c0 = (long long)s3_block_sum<NTHR>(ca0, scratch), c1 = (long long)s3_block_sum<NTHR>(ca1, scratch);
         if (tid == 0) {
             atomV[0] = at0; atomC[0] = c0;
             atomV[1] = at1; atomC[1] = (nAtom > 1) ? c1 : 0;
-            hist[s3_bin(at0, lo, scale)] += (unsigned)c0;
-            if (nAtom > 1) hist[s3_bin(at1, lo, scale)] += (unsigned)c1;
+            hist[s3_bin<NB>(at0, lo, scale)] += (unsigned)c0;
+            if (nAtom > 1) hist[s3_bin<NB>(at1, lo, scale)] += (unsigned)c1;
         }
         __syncthreads();
     }
@@ -1347,7 +1351,7 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     const double mean = pivot + S1 / (double)m;
     const double ss = fmax(S2 - S1 * (S1 / (double)m), 0.0);
     {   // exclusive prefix over the bins: 32 consecutive bins per thread + scan of the 512 partials
-        constexpr int PER = S3_NB / NTHR;
+        constexpr int PER = NB / NTHR;
         unsigned acc = 0;
         for (int q = 0; q < PER; ++q) acc += hist[tid * PER + q];
         prefix[tid] = acc;
@@ -1370,14 +1374,14 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
         if (hh <= 1.0) rk = 0;
         else if (hh >= (double)m) rk = m - 1;
         else rk = (long long)floor(hh) - 1 + (tid & 1);
-        int a0 = 0, a1 = S3_NB - 1;  // largest bin b with hist[b] <= rk
+        int a0 = 0, a1 = NB - 1;  // largest bin b with hist[b] <= rk
         while (a0 < a1) {
             const int mid = (a0 + a1 + 1) >> 1;
             if ((long long)hist[mid] <= rk) a0 = mid; else a1 = mid - 1;
         }
         tBin[tid] = a0;
         tRank[tid] = rk - hist[a0];
-        gCnt[tid] = (int)(((a0 + 1 < S3_NB) ? hist[a0 + 1] : (unsigned)m) - hist[a0]);
+        gCnt[tid] = (int)(((a0 + 1 < NB) ? hist[a0 + 1] : (unsigned)m) - hist[a0]);
     }
     __syncthreads();
     if (tid == 0) {
@@ -1393,7 +1397,7 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
                 int am = 0;
                 long long others = gCnt[k];
                 for (int a = 0; a < nAtom; ++a)
-                    if (s3_bin(atomV[a], lo, scale) == tBin[k]) { am |= 1 << a; others -= atomC[a]; }
+                    if (s3_bin<NB>(atomV[a], lo, scale) == tBin[k]) { am |= 1 << a; others -= atomC[a]; }
                 listAtoms[li] = am;
                 listOver[li] = others > CAP;
                 listMin[li] = 0xffffffffffffffffull;
@@ -1411,7 +1415,7 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     s3_for_each<NTHR>(col, Nrep, [&](double v) {
         if (v == unfeas || v != v) return;
         if (v == at0 || v == at1) return;
-        const int b = s3_bin(v, lo, scale);
+        const int b = s3_bin<NB>(v, lo, scale);
         if (!((bitmap[b >> 5] >> (b & 31)) & 1u)) return;
         for (int j = 0; j < nl; ++j)
             if (listBin[j] == b) {
@@ -1598,7 +1602,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     // the 2-read selection resolves bins of <= CAP members: worth trying while the densest of its 16384 bins stays below
     // that (a Gaussian column peaks at ~1.1e-4 Nrep per bin); two instantiations, see envelope_select3
     const bool sel3Big = Nrep > 3000000;
-    const size_t smemSel3 = std::max(sizeof(unsigned) * S3_NB, sizeof(double) * SEL_NT * (sel3Big ? 2048 : 512));
+    const size_t smemSel3 = std::max(sizeof(unsigned) * 32 * (sel3Big ? 1024 : 512), sizeof(double) * SEL_NT * (sel3Big ? 2048 : 512));
     const bool trySel3 = !smallN && Nrep <= 12000000 && !h->noSelect3;
     if (!smallN) {
         BAM_CUDA(cudaFuncSetAttribute((const void*)envelope_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemSel2));
