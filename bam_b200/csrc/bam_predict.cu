@@ -1203,7 +1203,7 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     __shared__ unsigned bitmap[NB / 32];
     __shared__ unsigned prefix[NTHR];
     __shared__ long long tRank[SEL_NT];
-    __shared__ int tBin[SEL_NT], tList[SEL_NT], listBin[SEL_NT], listCnt[SEL_NT], listOver[SEL_NT], gCnt[SEL_NT], nLists, nGood;
+    __shared__ int tBin[SEL_NT], tList[SEL_NT], listBin[SEL_NT], listCnt[SEL_NT], listOver[SEL_NT], listOff[SEL_NT], gCnt[SEL_NT], nLists, nGood;
     __shared__ unsigned long long listMin[SEL_NT], listMax[SEL_NT];
     __shared__ double tVal[SEL_NT];
     // ATOMS: values the subsample holds S3_RUN or more times (0.4 % of the column: far more than a gather list takes) -- a
@@ -1399,12 +1399,25 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
                 for (int a = 0; a < nAtom; ++a)
                     if (s3_bin<NB>(atomV[a], lo, scale) == tBin[k]) { am |= 1 << a; others -= atomC[a]; }
                 listAtoms[li] = am;
-                listOver[li] = others > CAP;
+                listCnt[li] = (int)min(others, (long long)(SEL_NT * CAP + 1));  // members to gather (set to 0 again below)
                 listMin[li] = 0xffffffffffffffffull;
                 listMax[li] = 0ull;
                 bitmap[tBin[k] >> 5] |= 1u << (tBin[k] & 31);
             }
             tList[k] = li;
+        }
+        // the SEL_NT x CAP doubles are ONE pool: every list gets the power of two (the sort pads to one) that holds its
+        // members, in list order, while the pool lasts -- the ten targets usually share five bins, so a dense bin of a
+        // peaked column may take several times CAP
+        int used = 0;
+        for (int j = 0; j < nl; ++j) {
+            int cap = 2;
+            while (cap < listCnt[j] && cap < SEL_NT * CAP) cap <<= 1;
+            const bool fits = listCnt[j] <= cap && used + cap <= SEL_NT * CAP;
+            listOver[j] = !fits;
+            listOff[j] = used;
+            if (fits) used += cap;
+            listCnt[j] = 0;
         }
         nLists = nl;
     }
@@ -1425,7 +1438,7 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
                     atomicMax(&listMax[j], key);
                 } else {
                     const int pos = atomicAdd(&listCnt[j], 1);
-                    gath[j * CAP + pos] = v;
+                    gath[listOff[j] + pos] = v;
                 }
             }
     });
@@ -1435,7 +1448,7 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
         const int cnt = listCnt[j];
         int npad = 2;
         while (npad < cnt) npad <<= 1;
-        double* g = gath + j * CAP;
+        double* g = gath + listOff[j];
         for (int i = cnt + tid; i < npad; i += NTHR) g[i] = INFINITY;
         __syncthreads();
         for (int kk = 2; kk <= npad; kk <<= 1)
@@ -1453,9 +1466,9 @@ __global__ void __launch_bounds__(NTHR) envelope_select3(long long Nrep, int nT,
     }
     if (tid < SEL_NT) {
         const int j = tList[tid];
-        if (!listOver[j] && listAtoms[j] == 0) tVal[tid] = gath[j * CAP + (int)tRank[tid]];
+        if (!listOver[j] && listAtoms[j] == 0) tVal[tid] = gath[listOff[j] + (int)tRank[tid]];
         else if (!listOver[j]) {  // rank inside (sorted other values of the bin) merged with the bin's atoms, ascending
-            const double* g = gath + j * CAP;
+            const double* g = gath + listOff[j];
             const int cnt = listCnt[j];
             long long r = tRank[tid], before = 0;  // before = atom copies that precede the answer
             double ans = NAN;
