@@ -1125,7 +1125,7 @@ __global__ void __launch_bounds__(S2_THREADS) envelope_select2(long long Nrep, i
 //          (the targets are the 2.5 % .. 97.5 % quantiles and their neighbours), pivot = its median.  Values outside
 //          [lo,hi] are CLAMPED into the two edge bins: the bin function stays monotone, so the selection stays exact
 //          whatever the subsample looks like; a bad subsample only costs a fallback.
-// pass B   16384-bin histogram in shared memory + #bad + sum (v-pivot) + sum (v-pivot)^2     (1 read)
+// pass B   histogram (32 bins per thread) in shared memory + #bad + sum (v-pivot) + sum (v-pivot)^2     (1 read)
 //          -> m, mean, variance (shifted-data formula), bin and residual rank of every target
 // pass C   gather the members of the <= 10 selected bins (<= S3_CAP each), sort, pick       (1 read)
 // A selected bin with more than S3_CAP members is still resolved when all its members are equal (ties: e.g. Q = 0
