@@ -336,7 +336,7 @@ void bamgpu_destroy(bamgpu_t* h) {
     auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(h->d_x); fr(h->d_tab); fr(h->d_part); fr(h->d_prior); fr(h->d_lkh); fr(h->d_hyper); fr(h->d_fx); fr(h->d_dpar);
     fr(h->d_status); fr(h->d_delta); fr(h->d_std); fr(h->d_fxcur); fr(h->d_dparcur); fr(h->d_moves); fr(h->d_mcount);
-    fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_env);
+    fr(h->d_mmean); fr(h->d_mm2); fr(h->d_rows); fr(h->d_V); fr(h->d_side); fr(h->d_env);
     fr(h->d_series); fr(h->d_seriesXpred);
     fr(h->d_fpStart); fr(h->d_fpEnd); fr(h->d_fpCombo); fr(h->d_fpComboTile0); fr(h->d_lkCcur); fr(h->d_lkCcand);
     fr(h->d_finalArrive); fr(h->d_sedObs); fr(h->d_fpPacked); fr(h->d_fpOff); fr(h->d_fpBytes); fr(h->d_fpSched); fr(h->d_fpOrder); fr(h->d_fpCost);

@@ -91,6 +91,8 @@ struct bamgpu_handle {
     int* d_pstatus = nullptr;
     double* d_V = nullptr;     // materialised spaghetti tile: Nrep x tileT per output
     size_t vCap = 0;
+    double* d_side = nullptr;  // side buffer of the columns deferred to one radix launch after the last tile (bam_predict.cu)
+    size_t sideCap = 0;        // ... in doubles
     double* d_env = nullptr;   // nT x 7 x nY of the last resident prediction
     int predT0 = 0, predT1 = 0;
     double* d_series = nullptr;  // time-recursive models: outputs of all vectors [y][t][vector]

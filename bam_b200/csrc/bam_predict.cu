@@ -481,10 +481,14 @@ __device__ __forceinline__ double rx_val(unsigned long long k) {
     return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
 }
 
+// colMap != nullptr: DEFERRED columns.  Block b works on column b of the side buffer V and writes the envelope of
+// (output colMap[2b], input colMap[2b+1]) into an array of nT inputs per statistic; blocks at or beyond *colCount leave.
 __global__ void __launch_bounds__(RX_THREADS) envelope_radix(long long Nrep, int nT, double unfeas,
                                                              const double* __restrict__ V, double* __restrict__ env,
-                                                             const int* __restrict__ only) {
+                                                             const int* __restrict__ only, const int* __restrict__ colMap = nullptr,
+                                                             const int* __restrict__ colCount = nullptr) {
     if (only != nullptr && only[blockIdx.x] == 0) return;
+    if (colMap != nullptr && (int)blockIdx.x >= *colCount) return;
     extern __shared__ unsigned rxh[];  // [SEL_NT][RX_NB]
     __shared__ double scratch[32];
     __shared__ unsigned long long sPrefix[SEL_NT], sGPrefix[SEL_NT];
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(RX_THREADS) envelope_radix(long long Nrep, int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int colId = blockIdx.x;
     const double* __restrict__ col = V + (size_t)colId * Nrep;
-    const int y = colId / nT, t = colId % nT;
+    const int y = colMap ? colMap[2 * colId] : colId / nT, t = colMap ? colMap[2 * colId + 1] : colId % nT;
     double* out = env + (size_t)y * BAMGPU_NENV * nT + t;
     const int width[6] = {11, 11, 11, 11, 11, 9};
     const double pr[5] = {0.5, 0.025, 0.975, 0.16, 0.84};
@@ -640,6 +644,37 @@ __global__ void __launch_bounds__(RX_THREADS) envelope_radix(long long Nrep, int
         out[(size_t)5 * nT] = mean;
         out[(size_t)6 * nT] = (m > 1) ? sqrt(ss / (double)(m - 1)) : unfeas;
     }
+}
+
+// Columns the histogram kernels gave up on are few (1 % of Vegetation's 5475) but the radix walk reads each of them 7 times
+// with ONE block, at the ~30 GB/s a single SM pulls: inside a tile the few blocks of that launch held up everything behind
+// them (190 ms of a 920 ms prediction for 60 columns).  They are copied to a side buffer instead (slot handed out by an
+// atomic counter; the flag is cleared so the in-tile launch skips the column) and walked together after the last tile,
+// one block per column, all at once.  A column that finds the buffer full keeps its flag and is walked in its tile.
+__global__ void __launch_bounds__(256) stash_slow_columns(long long Nrep, int nT, int tile0, const double* __restrict__ V,
+                                                         int* __restrict__ needSlow, double* __restrict__ side, int sideCap,
+                                                         int* __restrict__ count, int* __restrict__ colMap) {
+    const int colId = blockIdx.x;
+    if (needSlow[colId] == 0) return;
+    __shared__ int sSlot;
+    if (threadIdx.x == 0) {
+        const int slot = atomicAdd(count, 1);
+        if (slot < sideCap) {
+            colMap[2 * slot] = colId / nT;
+            colMap[2 * slot + 1] = tile0 + colId % nT;
+            needSlow[colId] = 0;
+            sSlot = slot;
+        } else {
+            atomicSub(count, 1);
+            sSlot = -1;
+        }
+    }
+    __syncthreads();
+    const int slot = sSlot;
+    if (slot < 0) return;
+    const double* __restrict__ src = V + (size_t)colId * Nrep;
+    double* __restrict__ dst = side + (size_t)slot * Nrep;
+    for (long long r = threadIdx.x; r < Nrep; r += 256) dst[r] = __ldcs(src + r);
 }
 
 // ---- sample-sharded envelopes (few prediction inputs, many samples) ---------------------------------
@@ -1579,6 +1614,19 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     tileT = std::max<long long>(32, std::min<long long>(tileT / 32 * 32, ((long long)nTall + 31) / 32 * 32));
     if (h_spag) tileT = std::max<long long>(tileT, 32);
     if (h->shardComm) tileT = std::min<long long>(tileT, std::max<long long>(32, (1024 / nOut) / 32 * 32));  // 80 KB of histograms per column
+    else if (Nrep > 16384 && tileT < nTall) {
+        // the selection kernels run one block per column, 1 (large-sample instantiation, 160 KB of shared memory) or 3 per SM:
+        // cut the tile so that its columns fill whole waves (128 inputs x 5 outputs = 640 blocks were 4.3 waves on 148 SMs)
+        const long long slots = (long long)h->smCount * (Nrep > 3000000 ? 1 : 3);
+        long long best = tileT;
+        double bestEff = 0.0;
+        for (long long t = tileT; t >= std::max<long long>(32, tileT * 7 / 10); --t) {
+            const double w = (double)(t * nOut) / (double)slots;
+            const double eff = w / std::ceil(w);
+            if (eff > bestEff + 1e-9) { bestEff = eff; best = t; }
+        }
+        tileT = best;
+    }
     const size_t vNeed = (size_t)tileT * Nrep * nOut;
     if (vNeed > h->vCap) {
         if (h->d_V) cudaFree(h->d_V);
@@ -1586,6 +1634,31 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         h->vCap = vNeed;
     }
 
+    // side buffer of the deferred radix columns (stash_slow_columns): at most 256 columns / a sixteenth of the free memory
+    // (64 columns when memory allows: kept with the handle like the tile buffer, released with it)
+    int sideCap = 0;
+    int *d_sideCount = nullptr, *d_sideMap = nullptr;
+    if (Nrep > 16384 && !h->shardComm && !h->onlyRadix) {
+        const size_t want = 64;
+        if (h->sideCap < want * (size_t)Nrep) {
+            size_t fb = 0, tb = 0;
+            BAM_CUDA(cudaMemGetInfo(&fb, &tb));
+            const size_t cols = std::min<size_t>(want, (fb / 16) / (sizeof(double) * (size_t)Nrep));
+            if (cols >= 4 && cols * (size_t)Nrep > h->sideCap) {
+                if (h->d_side) cudaFree(h->d_side);
+                h->d_side = nullptr; h->sideCap = 0;
+                BAM_CUDA(cudaMalloc(&h->d_side, sizeof(double) * cols * (size_t)Nrep));
+                h->sideCap = cols * (size_t)Nrep;
+            }
+        }
+        sideCap = (int)std::min<size_t>(want, h->sideCap / (size_t)Nrep);
+        if (sideCap < 4) sideCap = 0;
+        if (sideCap) {
+            BAM_CUDA(cudaMallocAsync(&d_sideCount, sizeof(int), s));
+            BAM_CUDA(cudaMallocAsync(&d_sideMap, sizeof(int) * 2 * sideCap, s));
+            BAM_CUDA(cudaMemsetAsync(d_sideCount, 0, sizeof(int), s));
+        }
+    }
     pred_prep<<<(unsigned)((Nrep + 127) / 128), 128, 0, s>>>(p, a, h->d_mc, h->d_mode, h->d_xspagPtrs, h->d_nspag, h->d_ptab,
                                                              h->d_pstatus);
     h->launches += 1;
@@ -1709,6 +1782,10 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                     h->launches += 1;
                 }
                 envelope_select2<<<nT * nOut, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow, need3);
+                if (sideCap) {
+                    stash_slow_columns<<<nT * nOut, 256, 0, s>>>(Nrep, nT, tt, h->d_V, needSlow, h->d_side, sideCap, d_sideCount, d_sideMap);
+                    h->launches += 1;
+                }
                 envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
                 BAM_CUDA(cudaFreeAsync(needSlow, s));
                 if (need3) BAM_CUDA(cudaFreeAsync(need3, s));
@@ -1729,6 +1806,16 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                                          sizeof(double) * (size_t)nT * Nrep, cudaMemcpyDeviceToHost, s));
             BAM_CUDA(cudaStreamSynchronize(s));
         }
+    }
+    if (sideCap) {  // the deferred columns, all at once, straight into the full envelope array
+        // (accounted with the envelope kernels: an empty propagation interval keeps the [propagation, envelopes] pairing;
+        // four distinct events, every event belongs to one interval)
+        cudaEvent_t ka = mark(), kb = mark(), kd0 = mark();
+        envelope_radix<<<sideCap, RX_THREADS, smemRadix, s>>>(Nrep, nTall, p.unfeas, h->d_side, h->d_env, nullptr, d_sideMap, d_sideCount);
+        cudaEvent_t kd1 = mark();
+        if (ka && kb && kd0 && kd1) { h->kernEv.emplace_back(ka, kb); h->kernEv.emplace_back(kd0, kd1); }
+        h->launches += 1;
+        BAM_CUDA(cudaFreeAsync(d_sideCount, s)); BAM_CUDA(cudaFreeAsync(d_sideMap, s));
     }
     if (d_sedObs) BAM_CUDA(cudaFreeAsync(d_sedObs, s));
     BAM_CUDA(cudaEventRecord(h->ev1, s));
