@@ -1638,7 +1638,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
     // (64 columns when memory allows: kept with the handle like the tile buffer, released with it)
     int sideCap = 0;
     int *d_sideCount = nullptr, *d_sideMap = nullptr;
-    if (Nrep > 16384 && !h->shardComm && !h->onlyRadix) {
+    if (Nrep > 16384 && !h->shardComm) {
         const size_t want = 64;
         if (h->sideCap < want * (size_t)Nrep) {
             size_t fb = 0, tb = 0;
@@ -1770,8 +1770,17 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                 h->launches += 3;
                 BAM_CUDA(cudaFreeAsync(st, s)); BAM_CUDA(cudaFreeAsync(hist, s)); BAM_CUDA(cudaFreeAsync(acc, s)); BAM_CUDA(cudaFreeAsync(ssq, s));
             } else if (smallN) envelope_smem<<<nT * nOut, BAM_BLOCK, smemEnv, s>>>(Nrep, npad, nT, p.unfeas, h->d_V, envTile);
-            else if (h->onlyRadix) {  // tests: every column through the last-resort kernel
-                envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, nullptr);
+            else if (h->onlyRadix) {  // tests: every column through the last-resort kernel -- the first ones by way of the
+                                      // side buffer (deferred launch), the rest inside their tile
+                int* all = nullptr;
+                BAM_CUDA(cudaMallocAsync(&all, sizeof(int) * (size_t)nT * nOut, s));
+                BAM_CUDA(cudaMemsetAsync(all, 1, sizeof(int) * (size_t)nT * nOut, s));  // 0x01010101: "needs the slow path"
+                if (sideCap) {
+                    stash_slow_columns<<<nT * nOut, 256, 0, s>>>(Nrep, nT, tt, h->d_V, all, h->d_side, sideCap, d_sideCount, d_sideMap);
+                    h->launches += 1;
+                }
+                envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, all);
+                BAM_CUDA(cudaFreeAsync(all, s));
             } else {
                 int *need3 = nullptr, *needSlow = nullptr;
                 BAM_CUDA(cudaMallocAsync(&needSlow, sizeof(int) * (size_t)nT * nOut, s));
