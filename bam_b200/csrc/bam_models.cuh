@@ -622,7 +622,10 @@ __device__ inline bool veg_root(const DevProblem& p, double Q0, double gam, doub
     int fcalls = 2;
     if (fl == 0.0) { root = x1; return fcalls <= p.vegItmax; }  // Q0 = 0
     if (!(Q0 > 0.0)) return false;                              // negative or NaN Q0: no bracket (f(Q0) was NaN)
-    veg_fnewton(x2, w, fh, df, fm);
+    // f(Q0) = gamma Q0^2 m(Q0) with m in (0, 1]: positive for a positive finite gamma and gamma2 -- only its sign is needed
+    // (a value that rounds to zero made the reference return Q0; the iteration below arrives there to rounding)
+    if (gam > 0.0 && gam < CUDART_INF && gam2 > 0.0 && gam2 < CUDART_INF && w.Q0sq < CUDART_INF) fh = 1.0;
+    else veg_fnewton(x2, w, fh, df, fm);
     if (fh == 0.0) { root = x2; return fcalls <= p.vegItmax; }
     if ((fl > 0.0) == (fh > 0.0) || fl != fl || fh != fh) return false;
     if (fl < 0.0) { xl = x1; xh = x2; } else { xl = x2; xh = x1; }
