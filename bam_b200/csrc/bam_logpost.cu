@@ -160,15 +160,27 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) logpost_prep(DevProblem p, co
 #define PREPM_BLOCK 64
 __global__ void __launch_bounds__(PREPM_BLOCK) logpost_prep_model(DevProblem p, const double* __restrict__ x, int K, int comp,
                                                                   const double* __restrict__ delta, double* __restrict__ tab,
-                                                                  int* __restrict__ status, double* __restrict__ dpar) {
+                                                                  int* __restrict__ status, double* __restrict__ dpar, int stageSeries) {
+    extern __shared__ double pms[];  // stageSeries: the three series the degree-day scan of Vegetation walks
     const long long t = (long long)blockIdx.x * PREPM_BLOCK + threadIdx.x;
+    const double* xc[BAM_MAXX];
+    for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
+    if (stageSeries) {
+        // every thread of the block walks the SAME series four rows (one 32-byte sector) per trip: from global memory each
+        // trip waited for an L2 round trip (~300 cycles x 274 trips x 2 sweeps = most of the kernel's 0.22 ms)
+        for (int i = threadIdx.x; i < p.n; i += PREPM_BLOCK) {
+            pms[i] = xc[0][i];
+            pms[p.n + i] = xc[2][i];
+            pms[2 * (size_t)p.n + i] = xc[3][i];
+        }
+        __syncthreads();
+        xc[0] = pms; xc[2] = pms + p.n; xc[3] = pms + 2 * (size_t)p.n;
+    }
     if (t >= (long long)K * p.nCombo) return;
     const int c = (int)(t % K), k = (int)(t / K);
     const size_t base = (size_t)c * p.P;
     const double dl = (comp >= 0) ? delta[c] : 0.0;
     double th[BAM_MAXTHETA], der[BAM_MAXDER];
-    const double* xc[BAM_MAXX];
-    for (int j = 0; j < p.nX; ++j) xc[j] = p.X + (size_t)j * p.n;
     double* cr = tab + (size_t)c * p.tabStride + p.tabCombo + (size_t)k * p.comboStride;
     for (int i = 0; i < p.ntheta; ++i) {  // ApplyModel_BaM theta expansion (:4133-4159)
         const int src = p.comboSrc[(size_t)k * p.ntheta + i];
@@ -197,7 +209,17 @@ static int launch_prep_on(cudaStream_t stream, const DevProblem& p, int K, const
         p, d_x, K, comp, d_delta, tab, prior, status, dpar);
     if (k != logpost_prep<0>) return 1;
     const long long nt = (long long)K * p.nCombo;
-    logpost_prep_model<<<(unsigned)((nt + PREPM_BLOCK - 1) / PREPM_BLOCK), PREPM_BLOCK, 0, stream>>>(p, d_x, K, comp, d_delta, tab, status, dpar);
+    size_t smem = 0;
+    if (p.model == BAMGPU_MDL_VEGETATION && p.vegGrowth != BAMGPU_VEG_YIN1_TEMPORAL && p.nX >= 4 && p.n > 0) {
+        smem = sizeof(double) * 3 * (size_t)p.n;
+        if (smem > 200 * 1024) smem = 0;
+        else if (smem > 48 * 1024) {
+            static size_t attr = 0;  // raised once per process (and again for a longer series)
+            if (attr < smem) { cudaFuncSetAttribute((const void*)logpost_prep_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+        }
+    }
+    logpost_prep_model<<<(unsigned)((nt + PREPM_BLOCK - 1) / PREPM_BLOCK), PREPM_BLOCK, smem, stream>>>(p, d_x, K, comp, d_delta, tab, status, dpar,
+                                                                                                     smem ? 1 : 0);
     return 2;
 }
 static int launch_prep(bamgpu_handle* h, int K, const double* d_x, int comp, const double* d_delta) {
