@@ -513,7 +513,10 @@ __device__ inline bool vegetation_prepare(const DevProblem& p, const double* th,
             if (yin1) { s0 = Tsmooth[j]; s1 = Tsmooth[j + 1]; s2 = Tsmooth[j + 2]; s3 = Tsmooth[j + 3]; }
             const double cyd = (double)cy;
             if (cy >= 0 && floor(t0) == cyd && floor(t1) == cyd && floor(t2) == cyd && floor(t3) == cyd) {
-                step(t0, r0, s0); step(t1, r1, s1); step(t2, r2, s2); step(t3, r3, s3);
+                // once every crossing of the year is found, its later rows only move "the last time of the year"
+                const unsigned all = 1u | 2u | 8u | (yin1 ? 4u : 0u);
+                if ((fl & all) == all) prev = t3;
+                else { step(t0, r0, s0); step(t1, r1, s1); step(t2, r2, s2); step(t3, r3, s3); }
             } else {
                 row(t0, r0, s0); row(t1, r1, s1); row(t2, r2, s2); row(t3, r3, s3);
             }
