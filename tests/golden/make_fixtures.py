@@ -216,6 +216,9 @@ WORKSPACES = {
     "mixture": "Config_BaM_Mixture.txt",
     "sfd": "Config_BaM_SFD.txt",
     "sfdtidal_qmec2": "Config_BaM_SFDTidal_Qmec2.txt",  # first 8000 of its 14401 time steps: the gauged window starts at step 7745 (MAX_ROWS)
+    "sfdtidal2": "Config_BaM_SFDTidal2.txt",            # Saigon, 1372 steps: the lagged stage-fall-discharge curves whose
+    "sfdtidal4": "Config_BaM_SFDTidal4.txt",            # shipped workspaces match the code (8 parameters); Seine, 2881 steps
+    "sfdtidal_jones": "Config_BaM_SFDTidal_Jones.txt",  # third input dh/dt
 }
 MAX_ROWS = {"sfdtidal_qmec2": 8000}
 

@@ -503,3 +503,20 @@ def test_sfdtidal_lagged_family(model):
     Xt, Ys, feas = g.calibration_run(truth)
     oXt, oYs, ofeas = o.calibration_run(truth)
     assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["sfdtidal2", "sfdtidal4", "sfdtidal_jones"])
+def test_lagged_sfdtidal_reference_workspaces(name):
+    """tests/BaM_SFDTidal2, BaM_SFDTidal4, BaM_SFDTidal_Jones (the shipped workspaces whose parameter lists match the code):
+    log-posterior around the configured starting point and the residual run on the device against the oracle"""
+    from tests.helpers import perturbed_vectors, problem_from_fixture
+
+    prob, d = problem_from_fixture(name)
+    x = perturbed_vectors(d["start"], 48, rel=0.01, seed=1)
+    x[5, 1] = -3.0  # K <= 0
+    check_parity(prob, x, tol=1e-12)
+    g, o = BamGpu(prob), Oracle(prob)
+    x0 = np.asarray(d["start"])
+    Xt, Ys, feas = g.calibration_run(x0)
+    oXt, oYs, ofeas = o.calibration_run(x0)
+    assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-12, atol=1e-300)

@@ -327,3 +327,17 @@ def test_time_recursive_workspace_end_to_end(tmp_path):
     # the cooked file holds 7 digits of every parameter and the recursion integrates over 8000 steps: loose comparison
     assert np.allclose(res[:, 6], oYs[:, 0], rtol=5e-3, atol=5.0)
     assert np.allclose(res[1:, -3:].sum(axis=1), np.diff(res[:, 6]), rtol=1e-4, atol=0.1)  # Q(m) - Q(m-1) = sum of the states (7 digits in the file)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference workspaces only exist in the build container")
+@pytest.mark.parametrize("cfg,name,model,n,nX", [("Config_BaM_SFDTidal2.txt", "sfdtidal2", "SFDTidal2", 1372, 2),
+                                                 ("Config_BaM_SFDTidal4.txt", "sfdtidal4", "SFDTidal4", 2881, 2),
+                                                 ("Config_BaM_SFDTidal_Jones.txt", "sfdtidal_jones", "SFDTidalJones", 1372, 3)])
+def test_config_reader_on_the_lagged_sfdtidal_workspaces(cfg, name, model, n, nX):
+    """the C++ config reader and the independent Python fixture reader agree on the shipped workspaces of the lagged
+    stage-fall-discharge models"""
+    d = dump_ref(cfg)
+    fx = load_fixture(name)
+    assert (d["model_id"], d["nobs"], d["nX"], d["nY"]) == (model, n, nX, 1)
+    assert list(d["partype"]) == list(fx["partype"]) and np.array_equal(np.asarray(d["start"]), np.asarray(fx["start"]))
+    assert np.array_equal(np.asarray(d["X"]), np.asarray(fx["X"])) and np.array_equal(np.asarray(d["Y"]), np.asarray(fx["Y"]))

@@ -590,3 +590,49 @@ def test_sfdtidal_lagged_family():
         x = truth.copy(); x[2 if model != "SFDTidal" else 3] = 10.0  # bed above every stage: Q = 0 everywhere, still feasible
         _, Y0, f0 = o.calibration_run(x)
         assert f0 and (Y0 == 0.0).all()
+
+
+def test_lagged_sfdtidal_on_the_reference_workspaces():
+    """tests/BaM_SFDTidal2 (Saigon, 1372 steps, 70 gauged), BaM_SFDTidal4 (Seine, 2881 steps, 78 gauged) and
+    BaM_SFDTidal_Jones (Saigon + dh/dt): the shipped workspaces whose parameter lists match the code.  At the configured
+    initial guesses the restatement is feasible, equals a vectorised numpy evaluation of the formulas, and follows the
+    ADCP discharges (correlation; prior guesses, not a fit)."""
+    def lagged(a, Dt):
+        n = a.size
+        return a[np.clip(np.arange(n) - Dt, 0, n - 1)]
+
+    sg = lambda x: np.where(x < 0, -1.0, 1.0)  # noqa: E731
+    for name, nobs, gauged, mincorr in (("sfdtidal2", 1372, 70, 0.2), ("sfdtidal4", 2881, 78, 0.8), ("sfdtidal_jones", 1372, 70, 0.8)):
+        prob, d = problem_from_fixture(name)
+        o = Oracle(prob)
+        x0 = np.asarray(d["start"])
+        assert (prob.nobs, prob.ntheta, o.sizes.nState) == (nobs, 8, 0)
+        _, Ys, feas = o.calibration_run(x0)
+        Y = np.asarray(d["Y"]); ok = Y != -9999
+        assert feas and ok.sum() == gauged and np.isfinite(Ys).all()
+        r = o.logpost_one(x0)
+        assert r["feas"] == 1 and np.isfinite(r["fx"])
+        assert np.corrcoef(Ys[ok, 0], Y[ok])[0, 1] > mincorr
+        # full theta (FIX values merged) and the formulas
+        th, k = np.asarray(prob.fix_value, dtype=float).copy(), 0
+        for i, pt in enumerate(prob.partype):
+            if pt == 0:
+                th[i] = x0[k]; k += 1
+        X = np.asarray(prob.X)
+        h1, h2, Dt = X[:, 0], X[:, 1], int(th[0])
+        K, B, h0, M, L, delta = th[1:7]
+        wet = h1 - h0 > 0
+        with np.errstate(invalid="ignore"):
+            if name == "sfdtidal2":
+                fall = h1 - th[7] * lagged(h2, Dt) - delta
+                want = sg(fall) * K * B * np.sqrt(np.abs(fall) / L) * (h1 - h0) ** M
+            elif name == "sfdtidal4":
+                P = int(th[7])
+                Sf = (lagged(h1, Dt) - lagged(h2, Dt) - delta) / L
+                Sm = np.array([Sf[t - P:t + P + 1].sum() / (2 * P + 1) if (t - P >= 0 and t + P <= nobs - 1) else Sf[t] for t in range(nobs)])
+                want = sg(Sm) * K * B * np.sqrt(np.abs(Sm)) * (h1 - h0) ** M
+            else:
+                Sf = (lagged(h1, Dt) - lagged(h2, Dt) - delta) / L
+                want = sg(Sf) * K * B * np.sqrt(np.abs(Sf) * (1 - th[7] * X[:, 2])) * (h1 - h0) ** M
+        want = np.where(wet, want, 0.0)
+        assert np.allclose(Ys[:, 0], want, rtol=1e-12, atol=1e-300)
