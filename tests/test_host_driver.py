@@ -75,7 +75,11 @@ def test_config_reader_roundtrip(name, tmp_path):
 @pytest.mark.parametrize("cfg,name", [("Config_BaM_BaRatin.txt", "baratin"), ("Config_BaM_BaRatin_SPD.txt", "baratin_spd"),
                                       ("Config_BaM_Regression_X2Y2.txt", "regression_x2y2"),
                                       ("Config_BaM_TextFile_InputUncertainty.txt", "textfile_inputuncertainty"),
-                                      ("Config_BaM_Mixture.txt", "mixture"), ("Config_BaM_SFD.txt", "sfd")])
+                                      ("Config_BaM_Mixture.txt", "mixture"), ("Config_BaM_SFD.txt", "sfd"),
+                                      ("Config_BaM_HydraulicControl_section.txt", "hydraulic_control_section"),
+                                      ("Config_BaM_Orthorectification.txt", "orthorectification"),
+                                      ("Config_BaM_Regression_X2Y1.txt", "regression_x2y1"), ("Config_BaM_Sediment.txt", "sediment"),
+                                      ("Config_BaM_TextFileModel.txt", "textfilemodel")])
 def test_config_reader_on_shipped_workspaces(cfg, name):
     """the reference's own example workspaces, Windows path separators included"""
     compare_d = dump_ref(cfg)

@@ -636,3 +636,16 @@ def test_lagged_sfdtidal_on_the_reference_workspaces():
                 want = sg(Sf) * K * B * np.sqrt(np.abs(Sf) * (1 - th[7] * X[:, 2])) * (h1 - h0) ** M
         want = np.where(wet, want, 0.0)
         assert np.allclose(Ys[:, 0], want, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("name,P", [("hydraulic_control_section", 3), ("orthorectification", 9), ("regression_x2y1", 4), ("sediment", 5),
+                                    ("textfilemodel", 8)])
+def test_remaining_shipped_workspaces_run(name, P):
+    """the other shipped workspaces of models on the device (tests/BaM_HydraulicControl_section, BaM_Orthorectification,
+    BaM_Regression_X2Y1, BaM_Sediment, BaM_TextFileModel) through the fixture reader and the oracle: feasible with a finite
+    log-posterior at the configured starting point"""
+    prob, d = problem_from_fixture(name)
+    o = Oracle(prob)
+    assert o.P == P
+    r = o.logpost_one(np.asarray(d["start"]))
+    assert r["feas"] == 1 and r["isnull"] == 0 and np.isfinite(r["fx"])
