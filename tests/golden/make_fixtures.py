@@ -154,6 +154,12 @@ def load_workspace(cfg_name, max_rows=None):
         nc = len(rows)
         M = np.array([r[:nc] for r in rows])
         xtra_i = [int(v) for v in M.flatten(order="F")]
+    elif model_id == "BaRatinBAC":  # BaRatinBAC_XtraRead (BaRatinBAC_model.f90:150-180): control matrix rows, then hmax
+        rows = [[fnum(v) for v in items(ln)] for ln in read_lines(path(ws, f_xtra)) if items(ln)]
+        nc = len(rows) - 1
+        M = np.array([[int(round(v)) for v in r[:nc]] for r in rows[:nc]])
+        xtra_i = [int(v) for v in M.flatten(order="F")]
+        xtra_d = [rows[nc][0]]
     elif model_id == "Sediment":
         s = read_lines(path(ws, f_xtra))
         ppo = items(s[3])[:4]
@@ -237,6 +243,12 @@ WORKSPACES = {
     "regression_x2y1": "Config_BaM_Regression_X2Y1.txt",
     "sediment": "Config_BaM_Sediment.txt",
     "textfilemodel": "Config_BaM_TextFileModel.txt",
+    # workspaces without a top-level Config_BaM_*.txt: (directory, xtra file, remnant files) -> an equivalent config in /tmp
+    "baratin_qbias": ("BaM_BaRatin_Qbias", "Config_ControlMatrix.txt", ("Config_RemnantSigma.txt",)),            # Y biases
+    "baratin_qbiashbias": ("BaM_BaRatin_QbiasHbias", "Config_ControlMatrix.txt", ("Config_RemnantSigma.txt",)),  # X errors, X and Y biases
+    "baratinbac": ("BaM_BaRatinBAC", "Config_ControlMatrix.txt", ("Config_RemnantSigma.txt",)),
+    "baratinbac_spd": ("BaM_BaRatinBAC_SPD", "Config_ControlMatrix.txt", ("Config_RemnantSigma.txt",)),          # VAR offsets
+    "suspendedload": ("BaM_SuspendedLoad", "", ("Config_RemnantSigma.txt",)),
     # (Config_BaM_Vegetation.txt -- the Ladhof workspace -- lists 18 parameters where Growth_Yin2 with 8 years takes 19: the
     #  reference itself refuses it; Vegetation is pinned by tests/BaM_Vegetation/SyntheticData.txt, make_vegetation_fixture.py)
 }
@@ -255,10 +267,11 @@ def main():
     global TESTS
     made = []
     for key, cfg in WORKSPACES.items():
-        if cfg is None:
+        if cfg is None or isinstance(cfg, tuple):
             tmp = f"/tmp/_cfg_{key}.txt"
             with open(tmp, "w") as f:
-                f.write("\n".join(synth_cfg("BaM_Sediment_Camenen_X4")) + "\n")
+                lines = synth_cfg("BaM_Sediment_Camenen_X4") if cfg is None else synth_cfg(cfg[0], remnant=cfg[2], xtra=cfg[1])
+                f.write("\n".join(lines) + "\n")
             # load_workspace joins TESTS with cfg_name: give it a relative path out of TESTS
             cfg = os.path.relpath(tmp, TESTS)
         fx = load_workspace(cfg, MAX_ROWS.get(key))

@@ -522,12 +522,14 @@ def test_lagged_sfdtidal_reference_workspaces(name):
     assert feas == ofeas == 1 and np.allclose(Ys, oYs, rtol=1e-12, atol=1e-300)
 
 
-@pytest.mark.parametrize("name", ["hydraulic_control_section", "orthorectification", "regression_x2y1", "sediment", "textfilemodel"])
+@pytest.mark.parametrize("name", ["hydraulic_control_section", "orthorectification", "regression_x2y1", "sediment", "textfilemodel",
+                                  "baratin_qbias", "baratin_qbiashbias", "baratinbac", "baratinbac_spd", "suspendedload"])
 def test_remaining_shipped_workspaces(name):
     """the other shipped workspaces of models on the device, on the device against the oracle around their configured
     starting points"""
     from tests.helpers import perturbed_vectors, problem_from_fixture
 
     prob, d = problem_from_fixture(name)
-    x = perturbed_vectors(d["start"], 48, rel=0.01, seed=1)
+    # (the b-a-c parameterisation with period-specific offsets is feasible in a narrow band around its starting point only)
+    x = perturbed_vectors(d["start"], 48, rel=0.0005 if name == "baratinbac_spd" else 0.01, seed=1)
     check_parity(prob, x, tol=1e-12, floor=float(prob.nobs) * 1e-3)
