@@ -7,6 +7,7 @@
 #define BAM_INSTANCES_A(X)                                                                                  \
     X(BAMGPU_MDL_BARATIN, 1, 1)                                                                             \
     X(BAMGPU_MDL_LINEAR, 1, 1) X(BAMGPU_MDL_LINEAR, 2, 1) X(BAMGPU_MDL_LINEAR, 3, 1) X(BAMGPU_MDL_LINEAR, 4, 1)   \
+    X(BAMGPU_MDL_LINEAR, 5, 1) X(BAMGPU_MDL_LINEAR, 6, 1) \
     X(BAMGPU_MDL_LINEAR, 1, 2) X(BAMGPU_MDL_LINEAR, 2, 2) X(BAMGPU_MDL_LINEAR, 3, 2) X(BAMGPU_MDL_LINEAR, 4, 2)   \
     X(BAMGPU_MDL_SEDIMENT, 2, 1) X(BAMGPU_MDL_SEDIMENT, 3, 1) X(BAMGPU_MDL_SEDIMENT, 4, 1)                   \
     X(BAMGPU_MDL_SEDIMENT, 5, 1) X(BAMGPU_MDL_SEDIMENT, 6, 1)

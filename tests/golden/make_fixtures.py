@@ -184,6 +184,10 @@ def load_workspace(cfg_name, max_rows=None):
     elif model_id == "HydraulicControl_section":  # h-A-w table, one row per line, stored column-major (:114-150)
         rows = [[fnum(v) for v in items(ln)[:3]] for ln in read_lines(path(ws, f_xtra)) if items(ln)]
         xtra_d = [r[c] for c in range(3) for r in rows]
+    elif model_id == "Segmentation":  # Segmentation_XtraRead (Segmentation_model.f90:142-180): nS, tmin, nmin, option
+        s = read_lines(path(ws, f_xtra))
+        xtra_i = [int(items(s[0])[0]), int(items(s[2])[0]), int(items(s[3])[0])]
+        xtra_d = [fnum(items(s[1])[0])]
     elif model_id == "Mixture":  # Mixture_XtraRead (Mixture_model.f90:137-190): nS, nEvt, nElt, missingSource
         s = read_lines(path(ws, f_xtra))
         xtra_i = [int(items(s[i])[0]) for i in range(3)] + [1 if items(s[3])[0].strip(".").lower().startswith("t") else 0]
@@ -249,6 +253,11 @@ WORKSPACES = {
     "baratinbac": ("BaM_BaRatinBAC", "Config_ControlMatrix.txt", ("Config_RemnantSigma.txt",)),
     "baratinbac_spd": ("BaM_BaRatinBAC_SPD", "Config_ControlMatrix.txt", ("Config_RemnantSigma.txt",)),          # VAR offsets
     "suspendedload": ("BaM_SuspendedLoad", "", ("Config_RemnantSigma.txt",)),
+    "sediment_camenen_x2": ("BaM_Sediment_Camenen_X2", "Config_Options.txt", ("Config_RemnantSigma.txt",)),
+    "regression_catchments": ("BaM_Regression_Catchments", "", ("Config_RemnantSigma.txt",)),
+    "regression_x6": ("BaM_Emeline", "", ("Config_RemnantSigma.txt",)),
+    # (BaM_Vegetation_static lists a parameter set of an older version of Growth_Yin1_temporal: the reference refuses it)
+    "segmentation": "BaM_Segmentation/Config_BaM.txt",
     # (Config_BaM_Vegetation.txt -- the Ladhof workspace -- lists 18 parameters where Growth_Yin2 with 8 years takes 19: the
     #  reference itself refuses it; Vegetation is pinned by tests/BaM_Vegetation/SyntheticData.txt, make_vegetation_fixture.py)
 }

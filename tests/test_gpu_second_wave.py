@@ -523,7 +523,8 @@ def test_lagged_sfdtidal_reference_workspaces(name):
 
 
 @pytest.mark.parametrize("name", ["hydraulic_control_section", "orthorectification", "regression_x2y1", "sediment", "textfilemodel",
-                                  "baratin_qbias", "baratin_qbiashbias", "baratinbac", "baratinbac_spd", "suspendedload"])
+                                  "baratin_qbias", "baratin_qbiashbias", "baratinbac", "baratinbac_spd", "suspendedload",
+                                  "sediment_camenen_x2", "regression_catchments", "regression_x6", "segmentation"])
 def test_remaining_shipped_workspaces(name):
     """the other shipped workspaces of models on the device, on the device against the oracle around their configured
     starting points"""

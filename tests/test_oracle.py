@@ -640,11 +640,13 @@ def test_lagged_sfdtidal_on_the_reference_workspaces():
 
 @pytest.mark.parametrize("name,P", [("hydraulic_control_section", 3), ("orthorectification", 9), ("regression_x2y1", 4), ("sediment", 5),
                                     ("textfilemodel", 8), ("baratin_qbias", 9), ("baratin_qbiashbias", 10), ("baratinbac", 11),
-                                    ("baratinbac_spd", 19), ("suspendedload", 5)])
+                                    ("baratinbac_spd", 19), ("suspendedload", 5), ("sediment_camenen_x2", 6), ("regression_catchments", 5),
+                                    ("regression_x6", 7), ("segmentation", 4)])
 def test_remaining_shipped_workspaces_run(name, P):
     """the other shipped workspaces of models on the device (tests/BaM_HydraulicControl_section, BaM_Orthorectification,
     BaM_Regression_X2Y1, BaM_Sediment, BaM_TextFileModel, BaM_BaRatin_Qbias, BaM_BaRatin_QbiasHbias with its X and Y
-    biases, BaM_BaRatinBAC, BaM_BaRatinBAC_SPD with VAR offsets, BaM_SuspendedLoad) through the fixture reader and the
+    biases, BaM_BaRatinBAC, BaM_BaRatinBAC_SPD with VAR offsets, BaM_SuspendedLoad, BaM_Sediment_Camenen_X2,
+    BaM_Regression_Catchments, BaM_Emeline (6 inputs), BaM_Segmentation) through the fixture reader and the
     oracle: feasible with a finite log-posterior at the configured starting point"""
     prob, d = problem_from_fixture(name)
     o = Oracle(prob)
