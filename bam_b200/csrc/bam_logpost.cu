@@ -213,10 +213,8 @@ static int launch_prep_on(cudaStream_t stream, const DevProblem& p, int K, const
     if (p.model == BAMGPU_MDL_VEGETATION && p.vegGrowth != BAMGPU_VEG_YIN1_TEMPORAL && p.nX >= 4 && p.n > 0) {
         smem = sizeof(double) * 3 * (size_t)p.n;
         if (smem > 200 * 1024) smem = 0;
-        else if (smem > 48 * 1024) {
-            static size_t attr = 0;  // raised once per process (and again for a longer series)
-            if (attr < smem) { cudaFuncSetAttribute((const void*)logpost_prep_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-        }
+        else if (smem > 48 * 1024)  // (per device and cheap: set on every launch that needs it -- bam_gpu --gpus N drives several devices)
+            cudaFuncSetAttribute((const void*)logpost_prep_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     logpost_prep_model<<<(unsigned)((nt + PREPM_BLOCK - 1) / PREPM_BLOCK), PREPM_BLOCK, smem, stream>>>(p, d_x, K, comp, d_delta, tab, status, dpar,
                                                                                                      smem ? 1 : 0);
