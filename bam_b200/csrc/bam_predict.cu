@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) envelope_smem(long long Nrep, int n
 // per target and level: 22+ reads on such columns).
 #define RX_THREADS 512
 #define RX_NB 2048
+#define RX_UNROLL 8
 __device__ __forceinline__ unsigned long long rx_key(double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);  // -0.0 -> +0.0
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
@@ -516,16 +517,16 @@ __global__ void __launch_bounds__(RX_THREADS) envelope_radix(long long Nrep, int
         __syncthreads();
         double sum = 0.0;
         long long nbadLoc = 0;
-        for (long long base = 0; base < Nrep; base += 4 * RX_THREADS) {  // block-uniform trip count (warp collectives inside)
+        for (long long base = 0; base < Nrep; base += RX_UNROLL * RX_THREADS) {  // block-uniform trip count (warp collectives inside)
             const long long r0 = base + tid;
-            double v[4];
+            double v[RX_UNROLL];  // RX_UNROLL independent loads in flight per thread: one block walks a column alone
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < RX_UNROLL; ++q) {
                 const long long r = r0 + (long long)q * RX_THREADS;
                 v[q] = (r < Nrep) ? __ldcs(col + r) : unfeas;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < RX_UNROLL; ++q) {
                 const long long r = r0 + (long long)q * RX_THREADS;
                 const bool inside = r < Nrep;
                 const bool good = inside && !(v[q] == unfeas || v[q] != v[q]);
