@@ -652,30 +652,43 @@ __global__ void __launch_bounds__(RX_THREADS) envelope_radix(long long Nrep, int
 // them (190 ms of a 920 ms prediction for 60 columns).  They are copied to a side buffer instead (slot handed out by an
 // atomic counter; the flag is cleared so the in-tile launch skips the column) and walked together after the last tile,
 // one block per column, all at once.  A column that finds the buffer full keeps its flag and is walked in its tile.
-__global__ void __launch_bounds__(256) stash_slow_columns(long long Nrep, int nT, int tile0, const double* __restrict__ V,
-                                                         int* __restrict__ needSlow, double* __restrict__ side, int sideCap,
-                                                         int* __restrict__ count, int* __restrict__ colMap) {
-    const int colId = blockIdx.x;
-    if (needSlow[colId] == 0) return;
-    __shared__ int sSlot;
-    if (threadIdx.x == 0) {
-        const int slot = atomicAdd(count, 1);
+// Two kernels: slots first (one thread per column), then the copy with several blocks per column.
+__global__ void __launch_bounds__(256) stash_assign(int ncol, int nT, int tile0, int* __restrict__ needSlow, int sideCap,
+                                                   int* __restrict__ count, int* __restrict__ colMap, int* __restrict__ slotOf) {
+    const int colId = blockIdx.x * 256 + threadIdx.x;
+    if (colId >= ncol) return;
+    int slot = -1;
+    if (needSlow[colId] != 0) {
+        slot = atomicAdd(count, 1);
         if (slot < sideCap) {
             colMap[2 * slot] = colId / nT;
             colMap[2 * slot + 1] = tile0 + colId % nT;
             needSlow[colId] = 0;
-            sSlot = slot;
         } else {
             atomicSub(count, 1);
-            sSlot = -1;
+            slot = -1;
         }
     }
-    __syncthreads();
-    const int slot = sSlot;
+    slotOf[colId] = slot;
+}
+// the copy: STASH_SPLIT blocks per column (a single block moves ~10 GB/s; 45 columns of 80 MB took 8 ms per tile)
+#define STASH_SPLIT 16
+__global__ void __launch_bounds__(256) stash_copy(long long Nrep, const double* __restrict__ V, const int* __restrict__ slotOf,
+                                                 double* __restrict__ side) {
+    const int colId = blockIdx.x, slot = slotOf[colId];
     if (slot < 0) return;
     const double* __restrict__ src = V + (size_t)colId * Nrep;
     double* __restrict__ dst = side + (size_t)slot * Nrep;
-    for (long long r = threadIdx.x; r < Nrep; r += 256) dst[r] = __ldcs(src + r);
+    const long long per = (Nrep + STASH_SPLIT - 1) / STASH_SPLIT;
+    const long long r0 = (long long)blockIdx.y * per, r1 = min(Nrep, r0 + per);
+    for (long long r = r0 + threadIdx.x; r < r1; r += 4 * 256) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (r + q * 256 < r1) ? __ldcs(src + r + q * 256) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (r + q * 256 < r1) dst[r + q * 256] = v[q];
+    }
 }
 
 // ---- sample-sharded envelopes (few prediction inputs, many samples) ---------------------------------
@@ -1635,7 +1648,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         h->vCap = vNeed;
     }
 
-    // side buffer of the deferred radix columns (stash_slow_columns): at most 256 columns / a sixteenth of the free memory
+    // side buffer of the deferred radix columns (stash_assign, stash_copy): at most 64 columns / a sixteenth of the free memory
     // (64 columns when memory allows: kept with the handle like the tile buffer, released with it)
     int sideCap = 0;
     int *d_sideCount = nullptr, *d_sideMap = nullptr;
@@ -1721,6 +1734,14 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
         BAM_CUDA(cudaEventRecord(e, s));
         return e;
     };
+    auto stash = [&](int* flags, int ncol, int nT, int tile0) {  // slow columns of this tile -> side buffer (see stash_assign)
+        int* slotOf = nullptr;
+        BAM_CUDA(cudaMallocAsync(&slotOf, sizeof(int) * (size_t)ncol, s));
+        stash_assign<<<(ncol + 255) / 256, 256, 0, s>>>(ncol, nT, tile0, flags, sideCap, d_sideCount, d_sideMap, slotOf);
+        stash_copy<<<dim3(ncol, STASH_SPLIT), 256, 0, s>>>(Nrep, h->d_V, slotOf, h->d_side);
+        BAM_CUDA(cudaFreeAsync(slotOf, s));
+        h->launches += 2;
+    };
     for (int tt = 0; tt < nTall; tt += (int)tileT) {
         const int nT = std::min<long long>(tileT, nTall - tt);
         a.t0 = t0 + tt; a.nT = nT;
@@ -1777,8 +1798,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                 BAM_CUDA(cudaMallocAsync(&all, sizeof(int) * (size_t)nT * nOut, s));
                 BAM_CUDA(cudaMemsetAsync(all, 1, sizeof(int) * (size_t)nT * nOut, s));  // 0x01010101: "needs the slow path"
                 if (sideCap) {
-                    stash_slow_columns<<<nT * nOut, 256, 0, s>>>(Nrep, nT, tt, h->d_V, all, h->d_side, sideCap, d_sideCount, d_sideMap);
-                    h->launches += 1;
+                    stash(all, nT * nOut, nT, tt);
                 }
                 envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, all);
                 BAM_CUDA(cudaFreeAsync(all, s));
@@ -1793,8 +1813,7 @@ void launch_predict(bamgpu_handle* h, int doParametric, const int* doRemnant, un
                 }
                 envelope_select2<<<nT * nOut, S2_THREADS, smemSel2, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow, need3);
                 if (sideCap) {
-                    stash_slow_columns<<<nT * nOut, 256, 0, s>>>(Nrep, nT, tt, h->d_V, needSlow, h->d_side, sideCap, d_sideCount, d_sideMap);
-                    h->launches += 1;
+                    stash(needSlow, nT * nOut, nT, tt);
                 }
                 envelope_radix<<<nT * nOut, RX_THREADS, smemRadix, s>>>(Nrep, nT, p.unfeas, h->d_V, envTile, needSlow);
                 BAM_CUDA(cudaFreeAsync(needSlow, s));
