@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(BAM_BLOCK) envelope_smem(long long Nrep, int n
 // DISTINCT prefix among the 10 targets, then every target walks into its digit.  Exact whatever the data look like,
 // 6 reads of the column + 1 for the sum of squares (the multi-level linear histograms it replaces needed >= 2 passes
 // per target and level: 22+ reads on such columns).
-#define RX_THREADS 512
+#define RX_THREADS 1024
 #define RX_NB 2048
 #define RX_UNROLL 8
 __device__ __forceinline__ unsigned long long rx_key(double v) {
